@@ -1,0 +1,62 @@
+"""CPU-only: libb200media.so builds, loads and exports every symbol include/*.h declares."""
+import ctypes as C
+import re
+from pathlib import Path
+
+import kvazzup_b200
+from kvazzup_b200 import capi as libmod
+
+ROOT = Path(__file__).resolve().parent.parent
+
+DECL = re.compile(r"^\s*(?:const\s+)?[A-Za-z_][\w\s\*]*?\b(\w+)\s*\(", re.M)
+
+
+def declared_symbols():
+    names = set()
+    for hdr in sorted((ROOT / "include").glob("*.h")):
+        text = re.sub(r"/\*.*?\*/", "", hdr.read_text(), flags=re.S)
+        text = re.sub(r"//.*", "", text)
+        text = re.sub(r"^\s*#.*(?:\\\n.*)*", "", text, flags=re.M)
+        text = re.sub(r"typedef\s+struct\s+\w*\s*\{.*?\}\s*\w+\s*;", "", text, flags=re.S)
+        text = re.sub(r"struct\s+\w+\s*\{.*?\}\s*;", "", text, flags=re.S)
+        for m in re.finditer(r"\b(\w+)\s*\([^;{}]*\)\s*;", text):
+            name = m.group(1)
+            if name not in ("defined", "sizeof"):
+                names.add(name)
+    return names
+
+
+def test_library_builds_and_exports_every_declared_symbol():
+    l = kvazzup_b200.load()
+    syms = declared_symbols()
+    assert "b200_yuv420_to_rgb32" in syms and "b200_ConvertToI420" in syms
+    missing = [s for s in sorted(syms) if not hasattr(l, s)]
+    assert not missing, f"declared in include/*.h but not exported: {missing}"
+
+
+def test_runtime_queries_do_not_need_a_gpu():
+    l = kvazzup_b200.lib()
+    assert l.b200_device_count() >= 0
+    assert b"sm_100a" in l.b200_version()
+    assert l.b200_frame_bytes(libmod.FOURCC["YUYV"], 640, 480) == 640 * 480 * 2
+    assert l.b200_frame_bytes(2, 640, 480) == 0
+
+
+def test_product_never_imports_the_oracle():
+    for py in (ROOT / "kvazzup_b200").rglob("*.py"):
+        src = py.read_text()
+        assert "import oracle" not in src and "from oracle" not in src, py
+    for cu in (ROOT / "kvazzup_b200" / "csrc").glob("*"):
+        if cu.is_file():
+            assert "oracle/" not in cu.read_text().replace("// oracle/", ""), cu
+
+
+def test_compute_fails_loudly_without_gpu():
+    l = kvazzup_b200.lib()
+    if l.b200_device_count() > 0:
+        return
+    import numpy as np
+    a = np.zeros(2 * 2 * 3 // 2, np.uint8)
+    o = np.zeros(16, np.uint8)
+    rc = l.b200_yuv420_to_rgb32(C.c_void_p(a.ctypes.data), C.c_void_p(o.ctypes.data), 2, 2)
+    assert rc < 0 and b"no CPU fallback" in l.b200_last_error()
