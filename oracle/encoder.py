@@ -1,0 +1,67 @@
+"""TEST INFRASTRUCTURE ONLY: Python wrapper of the oracle HEVC encoder (oracle/hevc_enc.c)."""
+from __future__ import annotations
+
+import ctypes as C
+
+import numpy as np
+
+from .binding import load
+from .sigs import OrcCu, OrcEncCfg
+
+CU_DTYPE = np.dtype([("mvx", "<i2"), ("mvy", "<i2"), ("log2_size", "u1"), ("pred_mode", "u1"),
+                     ("intra_mode", "u1"), ("cbf", "u1"), ("skip", "u1"), ("merge_idx", "u1"),
+                     ("mvp_idx", "u1"), ("pad", "u1")])
+assert CU_DTYPE.itemsize == C.sizeof(OrcCu) == 12
+
+
+class OracleEncoder:
+    def __init__(self, w, h, qp=32, intra_period=64, search_range=8, deblock=1, hash_sei=0):
+        self.lib = load()
+        self.w, self.h = w, h
+        cfg = OrcEncCfg(w, h, qp, intra_period, search_range, deblock, hash_sei)
+        self.h_enc = self.lib.orc_enc_open(C.byref(cfg))
+        if not self.h_enc:
+            raise ValueError("orc_enc_open rejected the configuration")
+        self.out = np.empty(w * h * 3 + 65536, np.uint8)
+
+    def encode(self, i420: np.ndarray) -> bytes:
+        assert i420.dtype == np.uint8 and i420.size == self.w * self.h * 3 // 2
+        frame = np.ascontiguousarray(i420)
+        n = self.lib.orc_enc_encode(self.h_enc, C.c_void_p(frame.ctypes.data), C.c_void_p(self.out.ctypes.data),
+                                    self.out.size)
+        if n < 0:
+            raise RuntimeError(f"orc_enc_encode failed ({n})")
+        return self.out[:n].tobytes()
+
+    def _view(self, ptr, dtype, count):
+        t = (C.c_uint8 * (count * np.dtype(dtype).itemsize)).from_address(ptr)
+        return np.frombuffer(t, dtype=dtype, count=count).copy()
+
+    def recon(self):
+        return self._view(self.lib.orc_enc_recon(self.h_enc), np.uint8, self.w * self.h * 3 // 2)
+
+    def recon_predeblock(self):
+        return self._view(self.lib.orc_enc_recon_predeblock(self.h_enc), np.uint8, self.w * self.h * 3 // 2)
+
+    def levels(self):
+        return self._view(self.lib.orc_enc_levels(self.h_enc), np.int16, self.w * self.h * 3 // 2)
+
+    def cu_map(self):
+        return self._view(self.lib.orc_enc_cu_map(self.h_enc), CU_DTYPE, (self.w // 8) * (self.h // 8))
+
+    def last_was_idr(self):
+        return bool(self.lib.orc_enc_last_was_idr(self.h_enc))
+
+    def bins(self):
+        return int(self.lib.orc_enc_bins(self.h_enc))
+
+    def close(self):
+        if self.h_enc:
+            self.lib.orc_enc_close(self.h_enc)
+            self.h_enc = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass

@@ -1,0 +1,962 @@
+/* TEST INFRASTRUCTURE ONLY -- see hevc_enc.h.
+ *
+ * Encoder structure (the algorithm the CUDA encoder mirrors):
+ *   I pictures  CTUs in raster order, CUs of 16x16 (8x8 where 16 does not fit) in z-order;
+ *               35-mode SAD + lambda*bits search on reconstructed neighbours; chroma = DM.
+ *   P pictures  1 reference (previous reconstruction), 2Nx2N inter CUs of 32/16/8:
+ *               exhaustive full-sample search (+-range) at 8x8 granularity with SADs summed
+ *               to 16x16 / 32x32, bottom-up partition decision, half- then quarter-sample
+ *               refinement, residual DCT/quant/recon with TU = CU, then deblocking.
+ *               merge / skip / AMVP are resolved at entropy-coding time from the final
+ *               motion field, so no reconstruction step depends on a neighbouring CU.
+ *   Entropy     CABAC, one substream per CTU row (WPP, entropy_coding_sync), one slice.
+ *
+ * Reference call sites this stands in for: kvz_api encoder_encode as used at
+ * /root/reference/src/media/processing/kvazaarfilter.cpp:435-449 (one AU per call, in order).
+ */
+#include "hevc_enc.h"
+#include "hevc_cabac.h"
+#include "hevc_prims.h"
+#include "hevc_tables.h"
+
+#include <limits.h>
+#include <stdlib.h>
+#include <string.h>
+
+#define CTB_LOG2 6
+#define CTB 64
+#define PAD 48                 /* luma padding of the reference planes */
+#define CU_OVERHEAD_BITS 3
+#define MAX_MERGE 5
+
+static const uint16_t lambda_q4_tab[52] = {   /* round(16*sqrt(0.57*2^((qp-12)/3))) */
+  3, 3, 4, 4, 5, 5, 6, 7, 8, 9, 10, 11, 12, 14, 15, 17, 19, 22, 24, 27, 30, 34, 38, 43, 48, 54, 61, 68,
+  77, 86, 97, 108, 122, 137, 153, 172, 193, 217, 244, 273, 307, 344, 387, 434, 487, 547, 614, 689, 773,
+  868, 974, 1093};
+
+struct orc_encoder {
+  orc_enc_cfg_t cfg;
+  int w, h, cw, ch, w8, h8, ctb_cols, ctb_rows;
+  int frame_idx, poc, is_idr;
+  int lambda_q4;
+  const uint8_t *src;
+  uint8_t *rec, *rec_pre;        /* packed I420 */
+  uint8_t *refpad[3];            /* padded previous reconstruction */
+  int refstride[3];
+  orc_cu_t *cu;
+  int16_t *levels;               /* I420-shaped */
+  uint8_t *done;                 /* per 8x8 unit: reconstructed (intra availability) */
+  uint8_t *sub;                  /* substream scratch */
+  size_t sub_cap;
+  unsigned long long bins;
+};
+
+static inline int imin(int a, int b) { return a < b ? a : b; }
+static inline int imax(int a, int b) { return a > b ? a : b; }
+static inline int clip3i(int lo, int hi, int v) { return v < lo ? lo : (v > hi ? hi : v); }
+
+static uint8_t *plane(uint8_t *base, int w, int h, int c)
+{
+  return c == 0 ? base : base + (size_t)w * h + (c == 2 ? (size_t)(w / 2) * (h / 2) : 0);
+}
+static int16_t *lplane(int16_t *base, int w, int h, int c)
+{
+  return c == 0 ? base : base + (size_t)w * h + (c == 2 ? (size_t)(w / 2) * (h / 2) : 0);
+}
+
+orc_encoder_t *orc_enc_open(const orc_enc_cfg_t *cfg)
+{
+  if (!cfg || cfg->width <= 0 || cfg->height <= 0 || (cfg->width & 7) || (cfg->height & 7)) return NULL;
+  if (cfg->qp < 0 || cfg->qp > 51 || cfg->search_range < 1 || cfg->search_range > 32) return NULL;
+  orc_encoder_t *e = (orc_encoder_t *)calloc(1, sizeof(*e));
+  if (!e) return NULL;
+  e->cfg = *cfg;
+  e->w = cfg->width; e->h = cfg->height; e->cw = e->w / 2; e->ch = e->h / 2;
+  e->w8 = e->w / 8; e->h8 = e->h / 8;
+  e->ctb_cols = (e->w + CTB - 1) / CTB; e->ctb_rows = (e->h + CTB - 1) / CTB;
+  e->lambda_q4 = lambda_q4_tab[cfg->qp];
+  size_t fsz = (size_t)e->w * e->h * 3 / 2;
+  e->rec = (uint8_t *)calloc(fsz, 1);
+  e->rec_pre = (uint8_t *)calloc(fsz, 1);
+  for (int c = 0; c < 3; c++) {
+    int pw = c ? e->cw : e->w, ph = c ? e->ch : e->h, pad = c ? PAD / 2 : PAD;
+    e->refstride[c] = pw + 2 * pad;
+    e->refpad[c] = (uint8_t *)calloc((size_t)e->refstride[c] * (ph + 2 * pad), 1);
+  }
+  e->cu = (orc_cu_t *)calloc((size_t)e->w8 * e->h8, sizeof(orc_cu_t));
+  e->levels = (int16_t *)calloc(fsz, sizeof(int16_t));
+  e->done = (uint8_t *)calloc((size_t)e->w8 * e->h8, 1);
+  e->sub_cap = fsz * 2 + 65536;
+  e->sub = (uint8_t *)malloc(e->sub_cap);
+  return e;
+}
+
+void orc_enc_close(orc_encoder_t *e)
+{
+  if (!e) return;
+  free(e->rec); free(e->rec_pre);
+  for (int c = 0; c < 3; c++) free(e->refpad[c]);
+  free(e->cu); free(e->levels); free(e->done); free(e->sub);
+  free(e);
+}
+
+const uint8_t *orc_enc_recon(const orc_encoder_t *e) { return e->rec; }
+const uint8_t *orc_enc_recon_predeblock(const orc_encoder_t *e) { return e->rec_pre; }
+const orc_cu_t *orc_enc_cu_map(const orc_encoder_t *e) { return e->cu; }
+const int16_t *orc_enc_levels(const orc_encoder_t *e) { return e->levels; }
+int orc_enc_last_was_idr(const orc_encoder_t *e) { return e->is_idr; }
+unsigned long long orc_enc_bins(const orc_encoder_t *e) { return e->bins; }
+
+/* ------------------------------------------------------------------------------------------ */
+/* residual path shared by intra and inter: src - pred -> DCT -> Q -> (IQ -> IDCT) -> recon     */
+
+static int recon_tb(orc_encoder_t *e, int c, int x0, int y0, int log2n, const uint8_t *pred)
+{
+  const int n = 1 << log2n;
+  const int pw = c ? e->cw : e->w, ph = c ? e->ch : e->h;
+  const uint8_t *src = plane((uint8_t *)e->src, e->w, e->h, c);
+  uint8_t *rec = plane(e->rec, e->w, e->h, c);
+  int16_t *lv = lplane(e->levels, e->w, e->h, c);
+  int16_t resid[32 * 32], coef[32 * 32], level[32 * 32];
+  const int qp = c ? orc_chroma_qp(e->cfg.qp) : e->cfg.qp;
+  (void)ph;
+  for (int y = 0; y < n; y++)
+    for (int x = 0; x < n; x++)
+      resid[y * n + x] = (int16_t)((int)src[(size_t)(y0 + y) * pw + x0 + x] - (int)pred[y * n + x]);
+  orc_fdct(resid, coef, log2n);
+  int nz = orc_quant(coef, level, log2n, qp, e->is_idr);
+  for (int y = 0; y < n; y++) memcpy(lv + (size_t)(y0 + y) * pw + x0, level + y * n, n * sizeof(int16_t));
+  if (nz) {
+    orc_dequant(level, coef, log2n, qp);
+    orc_idct(coef, resid, log2n);
+    for (int y = 0; y < n; y++)
+      for (int x = 0; x < n; x++)
+        rec[(size_t)(y0 + y) * pw + x0 + x] = (uint8_t)clip3i(0, 255, pred[y * n + x] + resid[y * n + x]);
+  } else {
+    for (int y = 0; y < n; y++) memcpy(rec + (size_t)(y0 + y) * pw + x0, pred + y * n, n);
+  }
+  return nz != 0;
+}
+
+static void set_cu(orc_encoder_t *e, int x0, int y0, int log2, const orc_cu_t *v)
+{
+  int n8 = 1 << (log2 - 3);
+  for (int j = 0; j < n8; j++)
+    for (int i = 0; i < n8; i++) e->cu[(size_t)(y0 / 8 + j) * e->w8 + x0 / 8 + i] = *v;
+}
+
+/* ------------------------------------------------------------------------------------------ */
+/* intra                                                                                          */
+
+/* luma-coordinate availability: inside the picture and already reconstructed */
+static int avail_luma(const orc_encoder_t *e, int x, int y)
+{
+  if (x < 0 || y < 0 || x >= e->w || y >= e->h) return 0;
+  return e->done[(size_t)(y >> 3) * e->w8 + (x >> 3)];
+}
+
+/* 8.4.4.2.2: gather the 4N+1 neighbours (layout of orc_intra_predict) with substitution */
+static void gather_refs(const orc_encoder_t *e, int c, int x0, int y0, int n, uint8_t *refs)
+{
+  const int pw = c ? e->cw : e->w;
+  const int sh = c ? 1 : 0;
+  const uint8_t *rec = plane(e->rec, e->w, e->h, c);
+  uint8_t av[4 * 32 + 1];
+  int any = 0;
+  for (int k = 0; k < 2 * n; k++) {
+    int x = x0 - 1, y = y0 + 2 * n - 1 - k;
+    av[k] = (uint8_t)avail_luma(e, x << sh, y << sh);
+    if (av[k]) refs[k] = rec[(size_t)y * pw + x];
+  }
+  av[2 * n] = (uint8_t)avail_luma(e, (x0 - 1) << sh, (y0 - 1) << sh);
+  if (av[2 * n]) refs[2 * n] = rec[(size_t)(y0 - 1) * pw + x0 - 1];
+  for (int k = 0; k < 2 * n; k++) {
+    int x = x0 + k, y = y0 - 1;
+    av[2 * n + 1 + k] = (uint8_t)avail_luma(e, x << sh, y << sh);
+    if (av[2 * n + 1 + k]) refs[2 * n + 1 + k] = rec[(size_t)y * pw + x];
+  }
+  for (int k = 0; k <= 4 * n; k++) any |= av[k];
+  if (!any) { memset(refs, 128, 4 * n + 1); return; }
+  if (!av[0]) {
+    int k = 1;
+    while (!av[k]) k++;
+    refs[0] = refs[k];
+  }
+  for (int k = 1; k <= 4 * n; k++)
+    if (!av[k]) refs[k] = refs[k - 1];
+}
+
+/* 8.4.2: most probable modes of the luma block at (x0,y0) */
+static void mpm_list(const orc_encoder_t *e, int x0, int y0, int cand[3])
+{
+  int a = 1, b = 1;   /* INTRA_DC when unavailable / not intra */
+  if (avail_luma(e, x0 - 1, y0)) {
+    const orc_cu_t *n = &e->cu[(size_t)(y0 >> 3) * e->w8 + ((x0 - 1) >> 3)];
+    if (n->pred_mode == 1) a = n->intra_mode;
+  }
+  if (avail_luma(e, x0, y0 - 1) && (y0 - 1) >= ((y0 >> CTB_LOG2) << CTB_LOG2)) {
+    const orc_cu_t *n = &e->cu[(size_t)((y0 - 1) >> 3) * e->w8 + (x0 >> 3)];
+    if (n->pred_mode == 1) b = n->intra_mode;
+  }
+  if (a == b) {
+    if (a < 2) { cand[0] = 0; cand[1] = 1; cand[2] = 26; }
+    else { cand[0] = a; cand[1] = 2 + ((a + 29) % 32); cand[2] = 2 + ((a - 2 + 1) % 32); }
+  } else {
+    cand[0] = a; cand[1] = b;
+    if (a != 0 && b != 0) cand[2] = 0;
+    else if (a != 1 && b != 1) cand[2] = 1;
+    else cand[2] = 26;
+  }
+}
+
+static void intra_cu(orc_encoder_t *e, int x0, int y0, int log2)
+{
+  const int n = 1 << log2;
+  uint8_t refs[4 * 32 + 1], pred[32 * 32], best_pred[32 * 32];
+  const uint8_t *src = e->src;
+  int cand[3];
+  mpm_list(e, x0, y0, cand);
+  gather_refs(e, 0, x0, y0, n, refs);
+  uint32_t best_cost = UINT_MAX;
+  int best_mode = 0;
+  for (int mode = 0; mode < 35; mode++) {
+    orc_intra_predict(refs, log2, mode, 0, pred, n);
+    uint32_t sad = orc_sad(src + (size_t)y0 * e->w + x0, e->w, pred, n, n, n);
+    int bits = mode == cand[0] ? 2 : (mode == cand[1] || mode == cand[2]) ? 3 : 6;
+    uint32_t cost = sad + (uint32_t)((e->lambda_q4 * bits) >> 4);
+    if (cost < best_cost) { best_cost = cost; best_mode = mode; memcpy(best_pred, pred, (size_t)n * n); }
+  }
+  orc_cu_t cu;
+  memset(&cu, 0, sizeof(cu));
+  cu.log2_size = (uint8_t)log2; cu.pred_mode = 1; cu.intra_mode = (uint8_t)best_mode; cu.merge_idx = 0xff;
+  cu.cbf = (uint8_t)recon_tb(e, 0, x0, y0, log2, best_pred);
+  for (int c = 1; c < 3; c++) {
+    gather_refs(e, c, x0 / 2, y0 / 2, n / 2, refs);
+    orc_intra_predict(refs, log2 - 1, best_mode, c, pred, n / 2);     /* intra_chroma_pred_mode 4 (DM) */
+    cu.cbf |= (uint8_t)(recon_tb(e, c, x0 / 2, y0 / 2, log2 - 1, pred) << c);
+  }
+  set_cu(e, x0, y0, log2, &cu);
+  for (int j = 0; j < n / 8; j++)
+    for (int i = 0; i < n / 8; i++) e->done[(size_t)(y0 / 8 + j) * e->w8 + x0 / 8 + i] = 1;
+}
+
+static void intra_quadtree(orc_encoder_t *e, int x0, int y0, int log2)
+{
+  if (x0 >= e->w || y0 >= e->h) return;
+  int n = 1 << log2;
+  if (x0 + n > e->w || y0 + n > e->h || log2 > 4) {
+    int hn = n / 2;
+    intra_quadtree(e, x0, y0, log2 - 1);
+    intra_quadtree(e, x0 + hn, y0, log2 - 1);
+    intra_quadtree(e, x0, y0 + hn, log2 - 1);
+    intra_quadtree(e, x0 + hn, y0 + hn, log2 - 1);
+  } else {
+    intra_cu(e, x0, y0, log2);
+  }
+}
+
+/* ------------------------------------------------------------------------------------------ */
+/* inter                                                                                          */
+
+/* HM TComRdCost::xGetComponentBits: exp-Golomb-like length of one mvd component */
+static int mv_comp_bits(int v)
+{
+  int len = 1;
+  unsigned t = v <= 0 ? ((unsigned)(-v) << 1) + 1 : (unsigned)v << 1;
+  while (t != 1) { t >>= 1; len += 2; }
+  return len;
+}
+static inline uint32_t mv_penalty(const orc_encoder_t *e, int mvx, int mvy)
+{
+  return (uint32_t)((e->lambda_q4 * (mv_comp_bits(mvx) + mv_comp_bits(mvy))) >> 4);
+}
+
+static void pad_reference(orc_encoder_t *e)
+{
+  for (int c = 0; c < 3; c++) {
+    int pw = c ? e->cw : e->w, ph = c ? e->ch : e->h, pad = c ? PAD / 2 : PAD, st = e->refstride[c];
+    const uint8_t *s = plane(e->rec, e->w, e->h, c);
+    for (int y = -pad; y < ph + pad; y++) {
+      const uint8_t *row = s + (size_t)clip3i(0, ph - 1, y) * pw;
+      uint8_t *d = e->refpad[c] + (size_t)(y + pad) * st;
+      memset(d, row[0], pad);
+      memcpy(d + pad, row, pw);
+      memset(d + pad + pw, row[pw - 1], pad);
+    }
+  }
+}
+
+static void mc_luma(const orc_encoder_t *e, int x0, int y0, int n, int mvx, int mvy, uint8_t *dst)
+{
+  orc_mc_luma(e->refpad[0], e->refstride[0], e->w + 2 * PAD, e->h + 2 * PAD, x0 + PAD, y0 + PAD, n, n, mvx, mvy, dst, n);
+}
+static void mc_chroma(const orc_encoder_t *e, int c, int x0, int y0, int n, int mvx, int mvy, uint8_t *dst)
+{
+  orc_mc_chroma(e->refpad[c], e->refstride[c], e->cw + PAD, e->ch + PAD, x0 + PAD / 2, y0 + PAD / 2, n, n, mvx, mvy, dst, n);
+}
+
+typedef struct { uint32_t cost; int dx, dy; } me_best_t;
+
+/* full-sample exhaustive search of one CTU at 8x8 granularity, partition decision, cu-map fill */
+static void me_ctu(orc_encoder_t *e, int cx, int cy)
+{
+  const int R = e->cfg.search_range;
+  const uint8_t *src = e->src;
+  const uint8_t *ref = e->refpad[0];
+  const int rs = e->refstride[0];
+  me_best_t b8[8][8], b16[4][4], b32[2][2];
+  for (int j = 0; j < 8; j++) for (int i = 0; i < 8; i++) b8[j][i].cost = UINT_MAX;
+  for (int j = 0; j < 4; j++) for (int i = 0; i < 4; i++) b16[j][i].cost = UINT_MAX;
+  for (int j = 0; j < 2; j++) for (int i = 0; i < 2; i++) b32[j][i].cost = UINT_MAX;
+  for (int dy = -R; dy <= R; dy++)
+    for (int dx = -R; dx <= R; dx++) {
+      uint32_t pen = mv_penalty(e, dx * 4, dy * 4);
+      uint32_t s8[8][8];
+      for (int j = 0; j < 8; j++)
+        for (int i = 0; i < 8; i++) {
+          int x = cx + 8 * i, y = cy + 8 * j;
+          if (x >= e->w || y >= e->h) { s8[j][i] = 0; continue; }
+          s8[j][i] = orc_sad(src + (size_t)y * e->w + x, e->w, ref + (size_t)(y + PAD + dy) * rs + x + PAD + dx, rs, 8, 8);
+          uint32_t cost = s8[j][i] + pen;
+          if (cost < b8[j][i].cost) { b8[j][i].cost = cost; b8[j][i].dx = dx; b8[j][i].dy = dy; }
+        }
+      uint32_t s16[4][4];
+      for (int j = 0; j < 4; j++)
+        for (int i = 0; i < 4; i++) {
+          s16[j][i] = s8[2 * j][2 * i] + s8[2 * j][2 * i + 1] + s8[2 * j + 1][2 * i] + s8[2 * j + 1][2 * i + 1];
+          if (cx + 16 * i + 16 > e->w || cy + 16 * j + 16 > e->h) continue;
+          uint32_t cost = s16[j][i] + pen;
+          if (cost < b16[j][i].cost) { b16[j][i].cost = cost; b16[j][i].dx = dx; b16[j][i].dy = dy; }
+        }
+      for (int j = 0; j < 2; j++)
+        for (int i = 0; i < 2; i++) {
+          if (cx + 32 * i + 32 > e->w || cy + 32 * j + 32 > e->h) continue;
+          uint32_t s = s16[2 * j][2 * i] + s16[2 * j][2 * i + 1] + s16[2 * j + 1][2 * i] + s16[2 * j + 1][2 * i + 1];
+          uint32_t cost = s + pen;
+          if (cost < b32[j][i].cost) { b32[j][i].cost = cost; b32[j][i].dx = dx; b32[j][i].dy = dy; }
+        }
+    }
+  /* bottom-up partition decision */
+  const uint32_t ovh = (uint32_t)((e->lambda_q4 * CU_OVERHEAD_BITS) >> 4);
+  uint32_t eff16[4][4];
+  uint8_t use16[4][4];
+  for (int j = 0; j < 4; j++)
+    for (int i = 0; i < 4; i++) {
+      uint32_t sum8 = 0;
+      for (int q = 0; q < 4; q++) {
+        int jj = 2 * j + (q >> 1), ii = 2 * i + (q & 1);
+        if (b8[jj][ii].cost != UINT_MAX) sum8 += b8[jj][ii].cost + ovh;
+      }
+      use16[j][i] = b16[j][i].cost != UINT_MAX && b16[j][i].cost + ovh <= sum8;
+      eff16[j][i] = use16[j][i] ? b16[j][i].cost + ovh : sum8;
+    }
+  for (int j = 0; j < 2; j++)
+    for (int i = 0; i < 2; i++) {
+      uint32_t sum16 = 0;
+      for (int q = 0; q < 4; q++) sum16 += eff16[2 * j + (q >> 1)][2 * i + (q & 1)];
+      int use32 = b32[j][i].cost != UINT_MAX && b32[j][i].cost + ovh <= sum16;
+      orc_cu_t cu;
+      memset(&cu, 0, sizeof(cu));
+      cu.merge_idx = 0xff;
+      if (use32) {
+        cu.log2_size = 5; cu.mvx = (int16_t)(b32[j][i].dx * 4); cu.mvy = (int16_t)(b32[j][i].dy * 4);
+        set_cu(e, cx + 32 * i, cy + 32 * j, 5, &cu);
+        continue;
+      }
+      for (int q = 0; q < 4; q++) {
+        int jj = 2 * j + (q >> 1), ii = 2 * i + (q & 1);
+        if (use16[jj][ii]) {
+          cu.log2_size = 4; cu.mvx = (int16_t)(b16[jj][ii].dx * 4); cu.mvy = (int16_t)(b16[jj][ii].dy * 4);
+          set_cu(e, cx + 16 * ii, cy + 16 * jj, 4, &cu);
+          continue;
+        }
+        for (int r = 0; r < 4; r++) {
+          int j8 = 2 * jj + (r >> 1), i8 = 2 * ii + (r & 1);
+          if (b8[j8][i8].cost == UINT_MAX) continue;
+          cu.log2_size = 3; cu.mvx = (int16_t)(b8[j8][i8].dx * 4); cu.mvy = (int16_t)(b8[j8][i8].dy * 4);
+          set_cu(e, cx + 8 * i8, cy + 8 * j8, 3, &cu);
+        }
+      }
+    }
+}
+
+/* half- then quarter-sample refinement of one CU, then prediction + residual + reconstruction */
+static void inter_cu(orc_encoder_t *e, int x0, int y0, int log2)
+{
+  static const int8_t off[8][2] = {{-1, -1}, {0, -1}, {1, -1}, {-1, 0}, {1, 0}, {-1, 1}, {0, 1}, {1, 1}};
+  const int n = 1 << log2;
+  orc_cu_t cu = e->cu[(size_t)(y0 / 8) * e->w8 + x0 / 8];
+  const uint8_t *src = e->src + (size_t)y0 * e->w + x0;
+  uint8_t pred[32 * 32], best_pred[32 * 32];
+  int bx = cu.mvx, by = cu.mvy;
+  mc_luma(e, x0, y0, n, bx, by, best_pred);
+  uint32_t best = orc_sad(src, e->w, best_pred, n, n, n) + mv_penalty(e, bx, by);
+  for (int step = 2; step >= 1; step--) {
+    int cxm = bx, cym = by;
+    for (int k = 0; k < 8; k++) {
+      int mx = cxm + off[k][0] * step, my = cym + off[k][1] * step;
+      mc_luma(e, x0, y0, n, mx, my, pred);
+      uint32_t cost = orc_sad(src, e->w, pred, n, n, n) + mv_penalty(e, mx, my);
+      if (cost < best) { best = cost; bx = mx; by = my; memcpy(best_pred, pred, (size_t)n * n); }
+    }
+  }
+  cu.mvx = (int16_t)bx; cu.mvy = (int16_t)by;
+  cu.cbf = (uint8_t)recon_tb(e, 0, x0, y0, log2, best_pred);
+  for (int c = 1; c < 3; c++) {
+    mc_chroma(e, c, x0 / 2, y0 / 2, n / 2, bx, by, pred);
+    cu.cbf |= (uint8_t)(recon_tb(e, c, x0 / 2, y0 / 2, log2 - 1, pred) << c);
+  }
+  set_cu(e, x0, y0, log2, &cu);
+}
+
+static void inter_frame(orc_encoder_t *e)
+{
+  for (int cy = 0; cy < e->h; cy += CTB)
+    for (int cx = 0; cx < e->w; cx += CTB) me_ctu(e, cx, cy);
+  for (int y8 = 0; y8 < e->h8; y8++)
+    for (int x8 = 0; x8 < e->w8; x8++) {
+      const orc_cu_t *cu = &e->cu[(size_t)y8 * e->w8 + x8];
+      int n8 = 1 << (cu->log2_size - 3);
+      if ((x8 & (n8 - 1)) == 0 && (y8 & (n8 - 1)) == 0) inter_cu(e, x8 * 8, y8 * 8, cu->log2_size);
+    }
+}
+
+/* ------------------------------------------------------------------------------------------ */
+/* deblocking (8.7.2): all vertical edges of the picture, then all horizontal edges             */
+
+static int edge_bs(const orc_cu_t *p, const orc_cu_t *q)
+{
+  if (p->pred_mode == 1 || q->pred_mode == 1) return 2;
+  if ((p->cbf & 1) || (q->cbf & 1)) return 1;          /* TU edge == CU edge (TU = CU) */
+  return abs(p->mvx - q->mvx) >= 4 || abs(p->mvy - q->mvy) >= 4;
+}
+
+static void deblock_frame(orc_encoder_t *e)
+{
+  uint8_t *Y = e->rec, *U = plane(e->rec, e->w, e->h, 1), *V = plane(e->rec, e->w, e->h, 2);
+  const int qp = e->cfg.qp;
+  for (int dir = 0; dir < 2; dir++)                    /* 0: vertical edges, 1: horizontal edges */
+    for (int y8 = 0; y8 < e->h8; y8++)
+      for (int x8 = 0; x8 < e->w8; x8++) {
+        const orc_cu_t *q = &e->cu[(size_t)y8 * e->w8 + x8];
+        int n8 = 1 << (q->log2_size - 3);
+        if (dir == 0 ? (x8 == 0 || (x8 & (n8 - 1))) : (y8 == 0 || (y8 & (n8 - 1)))) continue;
+        const orc_cu_t *p = dir == 0 ? q - 1 : q - e->w8;
+        int bs = edge_bs(p, q);
+        if (!bs) continue;
+        int x = x8 * 8, y = y8 * 8;
+        for (int seg = 0; seg < 2; seg++) {
+          if (dir == 0) orc_deblock_luma_segment(Y + (size_t)(y + 4 * seg) * e->w + x, 1, e->w, bs, qp);
+          else          orc_deblock_luma_segment(Y + (size_t)y * e->w + x + 4 * seg, e->w, 1, bs, qp);
+        }
+        if (bs == 2 && (dir == 0 ? (x & 15) == 0 : (y & 15) == 0)) {
+          int xc = x / 2, yc = y / 2;
+          if (dir == 0) {
+            orc_deblock_chroma_segment(U + (size_t)yc * e->cw + xc, 1, e->cw, qp, 4);
+            orc_deblock_chroma_segment(V + (size_t)yc * e->cw + xc, 1, e->cw, qp, 4);
+          } else {
+            orc_deblock_chroma_segment(U + (size_t)yc * e->cw + xc, e->cw, 1, qp, 4);
+            orc_deblock_chroma_segment(V + (size_t)yc * e->cw + xc, e->cw, 1, qp, 4);
+          }
+        }
+      }
+}
+
+/* ------------------------------------------------------------------------------------------ */
+/* entropy coding                                                                                 */
+
+typedef struct { int16_t x, y; } mv_t;
+
+static unsigned zorder8(int x8, int y8)      /* z-scan index of an 8x8 unit inside its CTB */
+{
+  unsigned z = 0;
+  for (int b = 0; b < 3; b++) z |= (unsigned)((x8 >> b) & 1) << (2 * b) | (unsigned)((y8 >> b) & 1) << (2 * b + 1);
+  return z;
+}
+static unsigned coding_order(const orc_encoder_t *e, int x, int y)
+{
+  return (unsigned)((y >> CTB_LOG2) * e->ctb_cols + (x >> CTB_LOG2)) * 64 + zorder8((x >> 3) & 7, (y >> 3) & 7);
+}
+/* 6.4.2: neighbouring prediction block available for inter candidates */
+static const orc_cu_t *inter_nb(const orc_encoder_t *e, int xc, int yc, int xn, int yn)
+{
+  if (xn < 0 || yn < 0 || xn >= e->w || yn >= e->h) return NULL;
+  if (coding_order(e, xn, yn) >= coding_order(e, xc, yc)) return NULL;
+  const orc_cu_t *n = &e->cu[(size_t)(yn >> 3) * e->w8 + (xn >> 3)];
+  return n->pred_mode == 0 ? n : NULL;
+}
+static inline int same_mv(const orc_cu_t *a, const orc_cu_t *b) { return a->mvx == b->mvx && a->mvy == b->mvy; }
+
+/* 8.5.3.2.2-8.5.3.2.4 merge candidate list, P slice, one reference picture, no TMVP */
+static int merge_candidates(const orc_encoder_t *e, int x0, int y0, int n, mv_t out[MAX_MERGE])
+{
+  const orc_cu_t *a1 = inter_nb(e, x0, y0, x0 - 1, y0 + n - 1);
+  const orc_cu_t *b1 = inter_nb(e, x0, y0, x0 + n - 1, y0 - 1);
+  const orc_cu_t *b0 = inter_nb(e, x0, y0, x0 + n, y0 - 1);
+  const orc_cu_t *a0 = inter_nb(e, x0, y0, x0 - 1, y0 + n);
+  const orc_cu_t *b2 = inter_nb(e, x0, y0, x0 - 1, y0 - 1);
+  int cnt = 0;
+  if (b1 && a1 && same_mv(b1, a1)) b1 = NULL;
+  const orc_cu_t *b1o = inter_nb(e, x0, y0, x0 + n - 1, y0 - 1);   /* comparisons use the unpruned B1 */
+  if (b0 && b1o && same_mv(b0, b1o)) b0 = NULL;
+  if (a0 && a1 && same_mv(a0, a1)) a0 = NULL;
+  if (b2 && ((a1 && same_mv(b2, a1)) || (b1o && same_mv(b2, b1o)))) b2 = NULL;
+  if (a1) { out[cnt].x = a1->mvx; out[cnt++].y = a1->mvy; }
+  if (b1) { out[cnt].x = b1->mvx; out[cnt++].y = b1->mvy; }
+  if (b0) { out[cnt].x = b0->mvx; out[cnt++].y = b0->mvy; }
+  if (a0) { out[cnt].x = a0->mvx; out[cnt++].y = a0->mvy; }
+  if (b2 && cnt < 4) { out[cnt].x = b2->mvx; out[cnt++].y = b2->mvy; }
+  while (cnt < MAX_MERGE) { out[cnt].x = 0; out[cnt++].y = 0; }
+  return cnt;
+}
+
+/* 8.5.3.2.6-7 AMVP list for one reference picture, no TMVP */
+static void amvp_candidates(const orc_encoder_t *e, int x0, int y0, int n, mv_t out[2])
+{
+  const orc_cu_t *a = inter_nb(e, x0, y0, x0 - 1, y0 + n);          /* A0 */
+  if (!a) a = inter_nb(e, x0, y0, x0 - 1, y0 + n - 1);             /* A1 */
+  const orc_cu_t *b = inter_nb(e, x0, y0, x0 + n, y0 - 1);          /* B0 */
+  if (!b) b = inter_nb(e, x0, y0, x0 + n - 1, y0 - 1);             /* B1 */
+  if (!b) b = inter_nb(e, x0, y0, x0 - 1, y0 - 1);                 /* B2 */
+  int cnt = 0;
+  if (a) { out[cnt].x = a->mvx; out[cnt++].y = a->mvy; }
+  if (b && !(a && same_mv(a, b))) { out[cnt].x = b->mvx; out[cnt++].y = b->mvy; }
+  while (cnt < 2) { out[cnt].x = 0; out[cnt++].y = 0; }
+}
+
+static void code_mvd(orc_cabac_t *c, int dx, int dy)
+{
+  int ax = abs(dx), ay = abs(dy);
+  orc_cabac_bin(c, CTX_MVD_GT0, ax > 0);
+  orc_cabac_bin(c, CTX_MVD_GT0, ay > 0);
+  if (ax) orc_cabac_bin(c, CTX_MVD_GT1, ax > 1);
+  if (ay) orc_cabac_bin(c, CTX_MVD_GT1, ay > 1);
+  for (int k = 0; k < 2; k++) {
+    int a = k ? ay : ax, d = k ? dy : dx;
+    if (!a) continue;
+    if (a > 1) {                         /* abs_mvd_minus2: EG1 */
+      int v = a - 2, kk = 1;
+      while (v >= (1 << kk)) { orc_cabac_bypass(c, 1); v -= 1 << kk; kk++; }
+      orc_cabac_bypass(c, 0);
+      orc_cabac_bypass_bits(c, (uint32_t)v, kk);
+    }
+    orc_cabac_bypass(c, d < 0);
+  }
+}
+
+static int scan_idx_for(int pred_mode, int intra_mode, int log2n, int cidx)
+{
+  if (pred_mode != 1) return 0;
+  if (!(log2n == 2 || (log2n == 3 && cidx == 0))) return 0;
+  if (intra_mode >= 6 && intra_mode <= 14) return 2;
+  if (intra_mode >= 22 && intra_mode <= 30) return 1;
+  return 0;
+}
+
+static void code_transform_unit(orc_encoder_t *e, orc_cabac_t *c, int x0, int y0, int log2, const orc_cu_t *cu)
+{
+  /* transform_tree at depth 0 with no split (7.3.8.8): cbf_cb, cbf_cr, cbf_luma */
+  int cb = (cu->cbf >> 1) & 1, cr = (cu->cbf >> 2) & 1, lu = cu->cbf & 1;
+  orc_cabac_bin(c, CTX_CBF_CHROMA + 0, cb);
+  orc_cabac_bin(c, CTX_CBF_CHROMA + 0, cr);
+  if (cu->pred_mode == 1 || cb || cr) orc_cabac_bin(c, CTX_CBF_LUMA + 1, lu);
+  if (lu)
+    orc_code_residual(c, e->levels + (size_t)y0 * e->w + x0, e->w, log2, 0,
+                      scan_idx_for(cu->pred_mode, cu->intra_mode, log2, 0));
+  for (int k = 1; k < 3; k++)
+    if ((cu->cbf >> k) & 1)
+      orc_code_residual(c, lplane(e->levels, e->w, e->h, k) + (size_t)(y0 / 2) * e->cw + x0 / 2, e->cw, log2 - 1, k,
+                        scan_idx_for(cu->pred_mode, cu->intra_mode, log2 - 1, k));
+}
+
+static void code_cu(orc_encoder_t *e, orc_cabac_t *c, int x0, int y0, int log2)
+{
+  orc_cu_t *cu = &e->cu[(size_t)(y0 >> 3) * e->w8 + (x0 >> 3)];
+  const int n = 1 << log2;
+  orc_cu_t upd = *cu;
+  if (!e->is_idr) {
+    mv_t mc[MAX_MERGE], ac[2];
+    merge_candidates(e, x0, y0, n, mc);
+    int midx = -1;
+    for (int i = 0; i < MAX_MERGE && midx < 0; i++)
+      if (mc[i].x == cu->mvx && mc[i].y == cu->mvy) midx = i;
+    int skip = midx >= 0 && cu->cbf == 0;
+    int ctx = 0;
+    if (x0 > 0) ctx += e->cu[(size_t)(y0 >> 3) * e->w8 + ((x0 - 1) >> 3)].skip;
+    if (y0 > 0) ctx += e->cu[(size_t)((y0 - 1) >> 3) * e->w8 + (x0 >> 3)].skip;
+    orc_cabac_bin(c, CTX_SKIP + ctx, skip);
+    upd.skip = (uint8_t)skip;
+    upd.merge_idx = (uint8_t)(midx >= 0 ? midx : 0xff);
+    if (midx >= 0) {
+      if (!skip) {
+        orc_cabac_bin(c, CTX_PRED_MODE, 0);
+        orc_cabac_bin(c, CTX_PART_MODE, 1);
+        orc_cabac_bin(c, CTX_MERGE_FLAG, 1);
+      }
+      orc_cabac_bin(c, CTX_MERGE_IDX, midx > 0);                 /* TR, cMax 4: first bin coded */
+      for (int i = 1; i < MAX_MERGE - 1 && midx >= i; i++) orc_cabac_bypass(c, midx > i);
+      if (!skip) code_transform_unit(e, c, x0, y0, log2, cu);    /* rqt_root_cbf inferred 1 */
+    } else {
+      orc_cabac_bin(c, CTX_PRED_MODE, 0);
+      orc_cabac_bin(c, CTX_PART_MODE, 1);
+      orc_cabac_bin(c, CTX_MERGE_FLAG, 0);
+      amvp_candidates(e, x0, y0, n, ac);
+      int b0 = mv_comp_bits(cu->mvx - ac[0].x) + mv_comp_bits(cu->mvy - ac[0].y);
+      int b1 = mv_comp_bits(cu->mvx - ac[1].x) + mv_comp_bits(cu->mvy - ac[1].y);
+      int pi = b1 < b0;
+      upd.mvp_idx = (uint8_t)pi;
+      code_mvd(c, cu->mvx - ac[pi].x, cu->mvy - ac[pi].y);
+      orc_cabac_bin(c, CTX_MVP_IDX, pi);
+      orc_cabac_bin(c, CTX_RQT_ROOT_CBF, cu->cbf != 0);
+      if (cu->cbf) code_transform_unit(e, c, x0, y0, log2, cu);
+    }
+  } else {
+    if (log2 == 3) orc_cabac_bin(c, CTX_PART_MODE, 1);           /* PART_2Nx2N */
+    /* intra mode: availability for the MPM derivation follows coding order, and every
+     * unit coded so far is reconstructed, so e->done (all ones now) must not be used here */
+    int cand[3];
+    {
+      int a = 1, b = 1;
+      if (x0 > 0) a = e->cu[(size_t)(y0 >> 3) * e->w8 + ((x0 - 1) >> 3)].intra_mode;
+      if (y0 > 0 && (y0 & (CTB - 1))) b = e->cu[(size_t)((y0 - 1) >> 3) * e->w8 + (x0 >> 3)].intra_mode;
+      if (a == b) {
+        if (a < 2) { cand[0] = 0; cand[1] = 1; cand[2] = 26; }
+        else { cand[0] = a; cand[1] = 2 + ((a + 29) % 32); cand[2] = 2 + ((a - 2 + 1) % 32); }
+      } else {
+        cand[0] = a; cand[1] = b;
+        cand[2] = (a != 0 && b != 0) ? 0 : ((a != 1 && b != 1) ? 1 : 26);
+      }
+    }
+    int mode = cu->intra_mode, mpm = -1;
+    for (int i = 0; i < 3; i++) if (cand[i] == mode) mpm = i;
+    orc_cabac_bin(c, CTX_PREV_INTRA_LUMA, mpm >= 0);
+    if (mpm >= 0) {
+      orc_cabac_bypass(c, mpm > 0);
+      if (mpm > 0) orc_cabac_bypass(c, mpm > 1);
+    } else {
+      if (cand[0] > cand[1]) { int t = cand[0]; cand[0] = cand[1]; cand[1] = t; }
+      if (cand[0] > cand[2]) { int t = cand[0]; cand[0] = cand[2]; cand[2] = t; }
+      if (cand[1] > cand[2]) { int t = cand[1]; cand[1] = cand[2]; cand[2] = t; }
+      int rem = mode;
+      for (int i = 2; i >= 0; i--) if (rem > cand[i]) rem--;
+      orc_cabac_bypass_bits(c, (uint32_t)rem, 5);
+    }
+    orc_cabac_bin(c, CTX_INTRA_CHROMA, 0);                        /* intra_chroma_pred_mode = 4 */
+    code_transform_unit(e, c, x0, y0, log2, cu);
+  }
+  set_cu(e, x0, y0, log2, &upd);
+}
+
+static void code_quadtree(orc_encoder_t *e, orc_cabac_t *c, int x0, int y0, int log2, int depth)
+{
+  if (x0 >= e->w || y0 >= e->h) return;
+  const int n = 1 << log2;
+  const orc_cu_t *cu = &e->cu[(size_t)(y0 >> 3) * e->w8 + (x0 >> 3)];
+  int split;
+  if (x0 + n <= e->w && y0 + n <= e->h && log2 > 3) {
+    split = cu->log2_size < log2;
+    int ctx = 0;
+    if (x0 > 0) ctx += (CTB_LOG2 - e->cu[(size_t)(y0 >> 3) * e->w8 + ((x0 - 1) >> 3)].log2_size) > depth;
+    if (y0 > 0) ctx += (CTB_LOG2 - e->cu[(size_t)((y0 - 1) >> 3) * e->w8 + (x0 >> 3)].log2_size) > depth;
+    orc_cabac_bin(c, CTX_SPLIT_CU + ctx, split);
+  } else {
+    split = log2 > 3;
+  }
+  if (split) {
+    int hn = n / 2;
+    code_quadtree(e, c, x0, y0, log2 - 1, depth + 1);
+    code_quadtree(e, c, x0 + hn, y0, log2 - 1, depth + 1);
+    code_quadtree(e, c, x0, y0 + hn, log2 - 1, depth + 1);
+    code_quadtree(e, c, x0 + hn, y0 + hn, log2 - 1, depth + 1);
+  } else {
+    code_cu(e, c, x0, y0, log2);
+  }
+}
+
+/* ---- parameter sets and slice header ------------------------------------------------------ */
+
+static void put_ptl(orc_bits_t *b, int level_idc)
+{
+  orc_bits_put(b, 0, 2);            /* general_profile_space */
+  orc_bits_put(b, 0, 1);            /* general_tier_flag */
+  orc_bits_put(b, 1, 5);            /* general_profile_idc = Main */
+  orc_bits_put(b, 0x60000000u, 32); /* compatibility flags: Main (1) and Main 10 (2) */
+  orc_bits_put(b, 1, 1);            /* progressive_source */
+  orc_bits_put(b, 0, 1);            /* interlaced_source */
+  orc_bits_put(b, 0, 1);            /* non_packed_constraint */
+  orc_bits_put(b, 1, 1);            /* frame_only_constraint */
+  orc_bits_put(b, 0, 32); orc_bits_put(b, 0, 11);   /* 43 reserved zero bits */
+  orc_bits_put(b, 0, 1);            /* general_inbld_flag / reserved */
+  orc_bits_put(b, (uint32_t)level_idc, 8);
+}
+
+static int level_for(int w, int h)
+{
+  long px = (long)w * h;
+  return px <= 552960 ? 93 : px <= 983040 ? 120 : px <= 2228224 ? 123 : px <= 8912896 ? 153 : 183;
+}
+
+static size_t write_nal(uint8_t *out, size_t cap, int type, const uint8_t *rbsp, size_t n)
+{
+  if (cap < 6) return n + 6 + n / 2;
+  out[0] = 0; out[1] = 0; out[2] = 0; out[3] = 1;
+  out[4] = (uint8_t)(type << 1); out[5] = 1;
+  return 6 + orc_nal_escape(rbsp, n, out + 6, cap - 6);
+}
+
+static size_t write_parameter_sets(const orc_encoder_t *e, uint8_t *out, size_t cap)
+{
+  uint8_t tmp[256];
+  orc_bits_t b;
+  size_t o = 0;
+  int level = level_for(e->w, e->h);
+  /* VPS (7.3.2.1) */
+  orc_bits_init(&b, tmp, sizeof(tmp));
+  orc_bits_put(&b, 0, 4); orc_bits_put(&b, 1, 1); orc_bits_put(&b, 1, 1);
+  orc_bits_put(&b, 0, 6); orc_bits_put(&b, 0, 3); orc_bits_put(&b, 1, 1);
+  orc_bits_put(&b, 0xffff, 16);
+  put_ptl(&b, level);
+  orc_bits_put(&b, 0, 1);             /* vps_sub_layer_ordering_info_present_flag */
+  orc_bits_ue(&b, 1); orc_bits_ue(&b, 0); orc_bits_ue(&b, 0);
+  orc_bits_put(&b, 0, 6);             /* vps_max_layer_id */
+  orc_bits_ue(&b, 0);                 /* vps_num_layer_sets_minus1 */
+  orc_bits_put(&b, 0, 1);             /* vps_timing_info_present_flag */
+  orc_bits_put(&b, 0, 1);             /* vps_extension_flag */
+  orc_bits_trailing(&b);
+  o += write_nal(out + o, cap - o, 32, tmp, orc_bits_bytes(&b));
+  /* SPS (7.3.2.2) */
+  orc_bits_init(&b, tmp, sizeof(tmp));
+  orc_bits_put(&b, 0, 4); orc_bits_put(&b, 0, 3); orc_bits_put(&b, 1, 1);
+  put_ptl(&b, level);
+  orc_bits_ue(&b, 0);                 /* sps_seq_parameter_set_id */
+  orc_bits_ue(&b, 1);                 /* chroma_format_idc 4:2:0 */
+  orc_bits_ue(&b, (uint32_t)e->w); orc_bits_ue(&b, (uint32_t)e->h);
+  orc_bits_put(&b, 0, 1);             /* conformance_window_flag */
+  orc_bits_ue(&b, 0); orc_bits_ue(&b, 0);       /* bit depths - 8 */
+  orc_bits_ue(&b, 4);                 /* log2_max_pic_order_cnt_lsb_minus4 -> 8 bits */
+  orc_bits_put(&b, 0, 1);             /* sps_sub_layer_ordering_info_present_flag */
+  orc_bits_ue(&b, 1); orc_bits_ue(&b, 0); orc_bits_ue(&b, 0);
+  orc_bits_ue(&b, 0);                 /* log2_min_luma_coding_block_size_minus3 -> 8 */
+  orc_bits_ue(&b, 3);                 /* log2_diff_max_min -> 64 */
+  orc_bits_ue(&b, 0);                 /* log2_min_luma_transform_block_size_minus2 -> 4 */
+  orc_bits_ue(&b, 3);                 /* log2_diff_max_min transform -> 32 */
+  orc_bits_ue(&b, 0); orc_bits_ue(&b, 0);       /* max_transform_hierarchy_depth_inter / intra */
+  orc_bits_put(&b, 0, 1);             /* scaling_list_enabled_flag */
+  orc_bits_put(&b, 0, 1);             /* amp_enabled_flag */
+  orc_bits_put(&b, 0, 1);             /* sample_adaptive_offset_enabled_flag */
+  orc_bits_put(&b, 0, 1);             /* pcm_enabled_flag */
+  orc_bits_ue(&b, 1);                 /* num_short_term_ref_pic_sets */
+  orc_bits_ue(&b, 1); orc_bits_ue(&b, 0);       /* num_negative_pics = 1, num_positive_pics = 0 */
+  orc_bits_ue(&b, 0); orc_bits_put(&b, 1, 1);   /* delta_poc_s0_minus1 = 0, used_by_curr_pic_s0 */
+  orc_bits_put(&b, 0, 1);             /* long_term_ref_pics_present_flag */
+  orc_bits_put(&b, 0, 1);             /* sps_temporal_mvp_enabled_flag */
+  orc_bits_put(&b, 0, 1);             /* strong_intra_smoothing_enabled_flag */
+  orc_bits_put(&b, 0, 1);             /* vui_parameters_present_flag */
+  orc_bits_put(&b, 0, 1);             /* sps_extension_present_flag */
+  orc_bits_trailing(&b);
+  o += write_nal(out + o, cap - o, 33, tmp, orc_bits_bytes(&b));
+  /* PPS (7.3.2.3) */
+  orc_bits_init(&b, tmp, sizeof(tmp));
+  orc_bits_ue(&b, 0); orc_bits_ue(&b, 0);
+  orc_bits_put(&b, 0, 1);             /* dependent_slice_segments_enabled_flag */
+  orc_bits_put(&b, 0, 1);             /* output_flag_present_flag */
+  orc_bits_put(&b, 0, 3);             /* num_extra_slice_header_bits */
+  orc_bits_put(&b, 0, 1);             /* sign_data_hiding_enabled_flag */
+  orc_bits_put(&b, 0, 1);             /* cabac_init_present_flag */
+  orc_bits_ue(&b, 0); orc_bits_ue(&b, 0);       /* num_ref_idx_l0/l1_default_active_minus1 */
+  orc_bits_se(&b, 0);                 /* init_qp_minus26 */
+  orc_bits_put(&b, 0, 1);             /* constrained_intra_pred_flag */
+  orc_bits_put(&b, 0, 1);             /* transform_skip_enabled_flag */
+  orc_bits_put(&b, 0, 1);             /* cu_qp_delta_enabled_flag */
+  orc_bits_se(&b, 0); orc_bits_se(&b, 0);       /* pps_cb_qp_offset, pps_cr_qp_offset */
+  orc_bits_put(&b, 0, 1);             /* pps_slice_chroma_qp_offsets_present_flag */
+  orc_bits_put(&b, 0, 1);             /* weighted_pred_flag */
+  orc_bits_put(&b, 0, 1);             /* weighted_bipred_flag */
+  orc_bits_put(&b, 0, 1);             /* transquant_bypass_enabled_flag */
+  orc_bits_put(&b, 0, 1);             /* tiles_enabled_flag */
+  orc_bits_put(&b, 1, 1);             /* entropy_coding_sync_enabled_flag (WPP) */
+  orc_bits_put(&b, 1, 1);             /* pps_loop_filter_across_slices_enabled_flag */
+  if (e->cfg.deblock) {
+    orc_bits_put(&b, 0, 1);           /* deblocking_filter_control_present_flag */
+  } else {
+    orc_bits_put(&b, 1, 1);
+    orc_bits_put(&b, 0, 1);           /* deblocking_filter_override_enabled_flag */
+    orc_bits_put(&b, 1, 1);           /* pps_deblocking_filter_disabled_flag */
+  }
+  orc_bits_put(&b, 0, 1);             /* pps_scaling_list_data_present_flag */
+  orc_bits_put(&b, 0, 1);             /* lists_modification_present_flag */
+  orc_bits_ue(&b, 0);                 /* log2_parallel_merge_level_minus2 */
+  orc_bits_put(&b, 0, 1);             /* slice_segment_header_extension_present_flag */
+  orc_bits_put(&b, 0, 1);             /* pps_extension_present_flag */
+  orc_bits_trailing(&b);
+  o += write_nal(out + o, cap - o, 34, tmp, orc_bits_bytes(&b));
+  return o;
+}
+
+/* ---- minimal MD5 for the decoded picture hash SEI (test use) ------------------------------ */
+
+typedef struct { uint32_t s[4]; uint64_t len; uint8_t buf[64]; int fill; } md5_t;
+static void md5_block(uint32_t s[4], const uint8_t *p)
+{
+  static const uint8_t r[64] = {7, 12, 17, 22, 7, 12, 17, 22, 7, 12, 17, 22, 7, 12, 17, 22, 5, 9, 14, 20, 5, 9, 14, 20,
+    5, 9, 14, 20, 5, 9, 14, 20, 4, 11, 16, 23, 4, 11, 16, 23, 4, 11, 16, 23, 4, 11, 16, 23, 6, 10, 15, 21, 6, 10, 15, 21,
+    6, 10, 15, 21, 6, 10, 15, 21};
+  static const uint32_t k[64] = {
+    0xd76aa478, 0xe8c7b756, 0x242070db, 0xc1bdceee, 0xf57c0faf, 0x4787c62a, 0xa8304613, 0xfd469501,
+    0x698098d8, 0x8b44f7af, 0xffff5bb1, 0x895cd7be, 0x6b901122, 0xfd987193, 0xa679438e, 0x49b40821,
+    0xf61e2562, 0xc040b340, 0x265e5a51, 0xe9b6c7aa, 0xd62f105d, 0x02441453, 0xd8a1e681, 0xe7d3fbc8,
+    0x21e1cde6, 0xc33707d6, 0xf4d50d87, 0x455a14ed, 0xa9e3e905, 0xfcefa3f8, 0x676f02d9, 0x8d2a4c8a,
+    0xfffa3942, 0x8771f681, 0x6d9d6122, 0xfde5380c, 0xa4beea44, 0x4bdecfa9, 0xf6bb4b60, 0xbebfbc70,
+    0x289b7ec6, 0xeaa127fa, 0xd4ef3085, 0x04881d05, 0xd9d4d039, 0xe6db99e5, 0x1fa27cf8, 0xc4ac5665,
+    0xf4292244, 0x432aff97, 0xab9423a7, 0xfc93a039, 0x655b59c3, 0x8f0ccc92, 0xffeff47d, 0x85845dd1,
+    0x6fa87e4f, 0xfe2ce6e0, 0xa3014314, 0x4e0811a1, 0xf7537e82, 0xbd3af235, 0x2ad7d2bb, 0xeb86d391};
+  uint32_t w[16], a = s[0], b = s[1], c = s[2], d = s[3];
+  for (int i = 0; i < 16; i++) w[i] = p[4 * i] | (p[4 * i + 1] << 8) | (p[4 * i + 2] << 16) | ((uint32_t)p[4 * i + 3] << 24);
+  for (int i = 0; i < 64; i++) {
+    uint32_t f; int g;
+    if (i < 16) { f = (b & c) | (~b & d); g = i; }
+    else if (i < 32) { f = (d & b) | (~d & c); g = (5 * i + 1) & 15; }
+    else if (i < 48) { f = b ^ c ^ d; g = (3 * i + 5) & 15; }
+    else { f = c ^ (b | ~d); g = (7 * i) & 15; }
+    uint32_t t = d; d = c; c = b;
+    uint32_t x = a + f + k[i] + w[g];
+    b = b + ((x << r[i]) | (x >> (32 - r[i])));
+    a = t;
+  }
+  s[0] += a; s[1] += b; s[2] += c; s[3] += d;
+}
+static void md5_init(md5_t *m) { m->s[0] = 0x67452301; m->s[1] = 0xefcdab89; m->s[2] = 0x98badcfe; m->s[3] = 0x10325476; m->len = 0; m->fill = 0; }
+static void md5_update(md5_t *m, const uint8_t *p, size_t n)
+{
+  m->len += n;
+  while (n) {
+    size_t k = 64 - (size_t)m->fill; if (k > n) k = n;
+    memcpy(m->buf + m->fill, p, k); m->fill += (int)k; p += k; n -= k;
+    if (m->fill == 64) { md5_block(m->s, m->buf); m->fill = 0; }
+  }
+}
+static void md5_final(md5_t *m, uint8_t out[16])
+{
+  uint64_t bits = m->len * 8; uint8_t pad = 0x80, z = 0;
+  md5_update(m, &pad, 1);
+  while (m->fill != 56) md5_update(m, &z, 1);
+  uint8_t l[8]; for (int i = 0; i < 8; i++) l[i] = (uint8_t)(bits >> (8 * i));
+  md5_update(m, l, 8);
+  for (int i = 0; i < 4; i++) for (int j = 0; j < 4; j++) out[4 * i + j] = (uint8_t)(m->s[i] >> (8 * j));
+}
+
+static size_t write_hash_sei(const orc_encoder_t *e, uint8_t *out, size_t cap)
+{
+  uint8_t rbsp[64]; size_t n = 0;
+  rbsp[n++] = 132;            /* payloadType decoded picture hash */
+  rbsp[n++] = 1 + 3 * 16;     /* payloadSize */
+  rbsp[n++] = 0;              /* hash_type MD5 */
+  for (int c = 0; c < 3; c++) {
+    md5_t m; md5_init(&m);
+    int pw = c ? e->cw : e->w, ph = c ? e->ch : e->h;
+    md5_update(&m, plane(e->rec, e->w, e->h, c), (size_t)pw * ph);
+    md5_final(&m, rbsp + n); n += 16;
+  }
+  rbsp[n++] = 0x80;           /* rbsp_trailing_bits */
+  return write_nal(out, cap, 40, rbsp, n);     /* SUFFIX_SEI_NUT */
+}
+
+/* ---- slice ------------------------------------------------------------------------------------ */
+
+static int encode_slice(orc_encoder_t *e, uint8_t *out, size_t cap, size_t *written)
+{
+  const int rows = e->ctb_rows, cols = e->ctb_cols;
+  size_t *sub_len = (size_t *)calloc((size_t)rows, sizeof(size_t));
+  size_t *sub_esc = (size_t *)calloc((size_t)rows, sizeof(size_t));
+  orc_cabac_t cab, saved;
+  memset(&cab, 0, sizeof(cab));
+  memset(&saved, 0, sizeof(saved));
+  size_t pos = 0;
+  e->bins = 0;
+  for (int r = 0; r < rows; r++) {
+    orc_bits_t bits;
+    orc_bits_init(&bits, e->sub + pos, e->sub_cap - pos);
+    if (r == 0 || cols < 2) orc_cabac_init_contexts(&cab, e->is_idr ? 0 : 1, e->cfg.qp);
+    else memcpy(cab.ctx, saved.ctx, sizeof(cab.ctx));            /* WPP sync from CTU 1 of the row above */
+    orc_cabac_start(&cab, &bits);
+    for (int cidx = 0; cidx < cols; cidx++) {
+      code_quadtree(e, &cab, cidx * CTB, r * CTB, CTB_LOG2, 0);
+      if (cidx == 1) memcpy(saved.ctx, cab.ctx, sizeof(cab.ctx));
+      int last_in_slice = r == rows - 1 && cidx == cols - 1;
+      orc_cabac_terminate(&cab, last_in_slice);                  /* end_of_slice_segment_flag */
+      if (cidx == cols - 1 && !last_in_slice) orc_cabac_terminate(&cab, 1);   /* end_of_subset_one_bit */
+    }
+    orc_cabac_finish(&cab);
+    if (bits.overflow) { free(sub_len); free(sub_esc); return -1; }
+    sub_len[r] = orc_bits_bytes(&bits);
+    /* emulation prevention bytes this substream will receive inside the NAL */
+    sub_esc[r] = orc_nal_escape(e->sub + pos, sub_len[r], NULL, 0);
+    pos += sub_len[r];
+    e->bins += cab.bins; cab.bins = 0;
+  }
+  /* slice segment header (7.3.6.1) */
+  uint8_t hdr[4096];
+  orc_bits_t b;
+  orc_bits_init(&b, hdr, sizeof(hdr));
+  orc_bits_put(&b, 1, 1);                               /* first_slice_segment_in_pic_flag */
+  if (e->is_idr) orc_bits_put(&b, 0, 1);                /* no_output_of_prior_pics_flag */
+  orc_bits_ue(&b, 0);                                   /* slice_pic_parameter_set_id */
+  orc_bits_ue(&b, e->is_idr ? 2 : 1);                   /* slice_type */
+  if (!e->is_idr) {
+    orc_bits_put(&b, (uint32_t)(e->poc & 255), 8);      /* slice_pic_order_cnt_lsb */
+    orc_bits_put(&b, 1, 1);                             /* short_term_ref_pic_set_sps_flag */
+    orc_bits_put(&b, 0, 1);                             /* num_ref_idx_active_override_flag */
+    orc_bits_ue(&b, 5 - MAX_MERGE);                     /* five_minus_max_num_merge_cand */
+  }
+  orc_bits_se(&b, e->cfg.qp - 26);                      /* slice_qp_delta */
+  if (e->cfg.deblock) orc_bits_put(&b, 1, 1);           /* slice_loop_filter_across_slices_enabled_flag */
+  orc_bits_ue(&b, (uint32_t)(rows - 1));                /* num_entry_point_offsets */
+  if (rows > 1) {
+    size_t mx = 1;
+    for (int r = 0; r < rows - 1; r++) if (sub_esc[r] > mx) mx = sub_esc[r];
+    int len = 1;
+    while (((mx - 1) >> len) > 0) len++;
+    orc_bits_ue(&b, (uint32_t)(len - 1));               /* offset_len_minus1 */
+    for (int r = 0; r < rows - 1; r++) orc_bits_put(&b, (uint32_t)(sub_esc[r] - 1), len);
+  }
+  orc_bits_trailing(&b);                                /* byte_alignment() */
+  size_t hl = orc_bits_bytes(&b);
+  /* assemble the NAL: header + substreams, escaped as one RBSP */
+  uint8_t *rbsp = (uint8_t *)malloc(hl + pos);
+  memcpy(rbsp, hdr, hl);
+  memcpy(rbsp + hl, e->sub, pos);
+  size_t n = write_nal(out, cap, e->is_idr ? 19 : 1, rbsp, hl + pos);
+  free(rbsp); free(sub_len); free(sub_esc);
+  *written = n;
+  return n <= cap ? 0 : -1;
+}
+
+int orc_enc_encode(orc_encoder_t *e, const uint8_t *i420, uint8_t *out, int cap)
+{
+  if (!e || !i420 || !out || cap <= 0) return -1;
+  const size_t fsz = (size_t)e->w * e->h * 3 / 2;
+  e->src = i420;
+  e->is_idr = e->frame_idx == 0 || (e->cfg.intra_period > 0 && e->frame_idx % e->cfg.intra_period == 0);
+  if (e->is_idr) e->poc = 0;
+  memset(e->levels, 0, fsz * sizeof(int16_t));
+  if (e->is_idr) {
+    memset(e->done, 0, (size_t)e->w8 * e->h8);
+    for (int cy = 0; cy < e->h; cy += CTB)
+      for (int cx = 0; cx < e->w; cx += CTB) intra_quadtree(e, cx, cy, CTB_LOG2);
+  } else {
+    inter_frame(e);
+  }
+  memcpy(e->rec_pre, e->rec, fsz);
+  if (e->cfg.deblock) deblock_frame(e);
+  size_t o = 0, n = 0;
+  if (e->is_idr) o += write_parameter_sets(e, out, (size_t)cap);
+  if (o > (size_t)cap) return -1;
+  if (encode_slice(e, out + o, (size_t)cap - o, &n) != 0) return -1;
+  o += n;
+  if (e->cfg.hash_sei) o += write_hash_sei(e, out + o, (size_t)cap - o);
+  if (o > (size_t)cap) return -1;
+  pad_reference(e);
+  e->frame_idx++;
+  e->poc++;
+  return (int)o;
+}

@@ -1,0 +1,47 @@
+/* TEST INFRASTRUCTURE ONLY -- CPU oracle of the B200 HEVC encoder: the same decision
+ * algorithm the CUDA encoder runs, written as plain sequential C directly from the
+ * H.265 text, so that (a) its streams can be validated by an independent decoder and
+ * (b) the GPU's cu-map, coefficients, reconstruction and bitstream can be compared
+ * with it bit for bit.  See hevc_tables.h for scope and pinning status. */
+#ifndef ORACLE_HEVC_ENC_H_
+#define ORACLE_HEVC_ENC_H_
+#include <stdint.h>
+
+/* One entry per 8x8 luma unit (all units of a CU carry the same values). */
+typedef struct {
+  int16_t mvx, mvy;        /* quarter-sample motion vector (inter) */
+  uint8_t log2_size;       /* CU size: 3..6 */
+  uint8_t pred_mode;       /* 0 inter, 1 intra */
+  uint8_t intra_mode;      /* luma intra prediction mode 0..34 */
+  uint8_t cbf;             /* bit0 Y, bit1 Cb, bit2 Cr */
+  uint8_t skip;            /* filled by the entropy stage */
+  uint8_t merge_idx;       /* 0xff = not merged */
+  uint8_t mvp_idx;
+  uint8_t pad;
+} orc_cu_t;
+
+typedef struct {
+  int width, height;       /* multiples of 8 */
+  int qp;                  /* constant QP, 0..51 */
+  int intra_period;        /* IDR every n frames; 0 = first frame only */
+  int search_range;        /* full-sample search range (+-), 1..32 */
+  int deblock;             /* 1 = in-loop deblocking on */
+  int hash_sei;            /* 1 = append MD5 decoded-picture-hash SEI (test use) */
+} orc_enc_cfg_t;
+
+typedef struct orc_encoder orc_encoder_t;
+
+orc_encoder_t *orc_enc_open(const orc_enc_cfg_t *cfg);
+void orc_enc_close(orc_encoder_t *e);
+/* Encode one packed I420 frame; writes one Annex-B access unit (4-byte start codes;
+ * VPS+SPS+PPS precede every IDR).  Returns the AU size in bytes or <0 (-needed if cap is short). */
+int orc_enc_encode(orc_encoder_t *e, const uint8_t *i420, uint8_t *out, int cap);
+
+const uint8_t *orc_enc_recon(const orc_encoder_t *e);            /* packed I420, after deblocking */
+const uint8_t *orc_enc_recon_predeblock(const orc_encoder_t *e); /* packed I420, before deblocking */
+const orc_cu_t *orc_enc_cu_map(const orc_encoder_t *e);          /* (w/8)*(h/8) entries, raster */
+const int16_t *orc_enc_levels(const orc_encoder_t *e);           /* quantised levels, I420-shaped int16 */
+int orc_enc_last_was_idr(const orc_encoder_t *e);
+unsigned long long orc_enc_bins(const orc_encoder_t *e);         /* CABAC bins of the last frame */
+
+#endif

@@ -20,3 +20,42 @@ def bind(lib) -> None:
             continue
         fn.restype = res
         fn.argtypes = args
+
+
+class OrcCu(C.Structure):
+    _fields_ = [("mvx", C.c_int16), ("mvy", C.c_int16), ("log2_size", C.c_uint8), ("pred_mode", C.c_uint8),
+                ("intra_mode", C.c_uint8), ("cbf", C.c_uint8), ("skip", C.c_uint8), ("merge_idx", C.c_uint8),
+                ("mvp_idx", C.c_uint8), ("pad", C.c_uint8)]
+
+
+class OrcEncCfg(C.Structure):
+    _fields_ = [("width", i), ("height", i), ("qp", i), ("intra_period", i), ("search_range", i),
+                ("deblock", i), ("hash_sei", i)]
+
+
+SIGS.update({
+    "orc_enc_open": (v, [C.POINTER(OrcEncCfg)]),
+    "orc_enc_close": (None, [v]),
+    "orc_enc_encode": (i, [v, v, v, i]),
+    "orc_enc_recon": (v, [v]),
+    "orc_enc_recon_predeblock": (v, [v]),
+    "orc_enc_cu_map": (v, [v]),
+    "orc_enc_levels": (v, [v]),
+    "orc_enc_last_was_idr": (i, [v]),
+    "orc_enc_bins": (C.c_ulonglong, [v]),
+    "orc_sad": (C.c_uint32, [v, i, v, i, i, i]),
+    "orc_satd": (C.c_uint32, [v, i, v, i, i, i]),
+    "orc_fdct": (None, [v, v, i]),
+    "orc_idct": (None, [v, v, i]),
+    "orc_fdst4": (None, [v, v]),
+    "orc_idst4": (None, [v, v]),
+    "orc_quant": (i, [v, v, i, i, i]),
+    "orc_dequant": (None, [v, v, i, i]),
+    "orc_chroma_qp": (i, [i]),
+    "orc_intra_predict": (None, [v, i, i, i, v, i]),
+    "orc_mc_luma": (None, [v, i, i, i, i, i, i, i, i, i, v, i]),
+    "orc_mc_chroma": (None, [v, i, i, i, i, i, i, i, i, i, v, i]),
+    "orc_deblock_luma_segment": (None, [v, i, i, i, i]),
+    "orc_deblock_chroma_segment": (None, [v, i, i, i, i]),
+    "orc_dct_coef": (i, [i, i, i]),
+})

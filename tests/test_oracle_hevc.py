@@ -1,0 +1,232 @@
+"""CPU-only: pin the HEVC oracle.
+
+* normative parts: the oracle encoder's streams are decoded by FFmpeg's native HEVC decoder
+  (independent implementation) and must equal the oracle's own reconstruction bit for bit;
+  the MD5 picture-hash SEI must verify under err_detect=crccheck+explode.
+* primitives: known-answer tests (DC block, impulse, spec worked values).
+"""
+import ctypes as C
+
+import numpy as np
+import pytest
+
+from kvazzup_b200 import synth
+from oracle.encoder import OracleEncoder
+from tests import ffhevc
+from tests.helpers import ptr
+
+needs_ff = pytest.mark.skipif(not ffhevc.available(), reason="FFmpeg libavcodec (cv2 wheel) not present")
+
+
+def frames_of(kind, w, h, n):
+    out = []
+    for t in range(n):
+        if kind == "noise":
+            out.append(synth.noise(100 + t, w * h * 3 // 2))
+        elif kind == "screen":
+            out.append(synth.screen_i420(w, h, t * 5))
+        else:
+            out.append(synth.camera_i420(w, h, t))
+    return out
+
+
+def encode_all(frames, w, h, **kw):
+    enc = OracleEncoder(w, h, **kw)
+    aus, recs = [], []
+    for f in frames:
+        aus.append(enc.encode(f))
+        recs.append(enc.recon())
+    enc.close()
+    return aus, recs
+
+
+@needs_ff
+@pytest.mark.parametrize("kind,w,h,n,qp,kw", [
+    ("camera", 64, 64, 1, 32, {}),                       # one CTU, I picture
+    ("camera", 192, 136, 4, 32, {}),                     # partial CTUs (8-high bottom row), WPP, P pictures
+    ("camera", 72, 200, 2, 27, {"deblock": 0}),          # deblocking disabled via PPS
+    ("noise", 128, 72, 3, 0, {}),                        # QP 0: escape-coded levels
+    ("noise", 128, 72, 3, 10, {}),
+    ("noise", 128, 72, 3, 45, {}),
+    ("camera", 128, 72, 3, 51, {}),                      # QP 51: mostly skip
+    ("camera", 416, 240, 5, 27, {"hash_sei": 1}),        # MD5 SEI verified by the decoder
+    ("screen", 416, 240, 5, 32, {}),                     # static content: merge / skip paths
+    ("camera", 200, 200, 7, 30, {"intra_period": 3}),    # periodic IDR, POC reset
+    ("camera", 256, 128, 4, 22, {"search_range": 16}),
+    ("camera", 64, 8, 3, 37, {}),                        # single row of 8x8 CUs
+])
+def test_oracle_streams_decode_bit_exactly_in_ffmpeg(kind, w, h, n, qp, kw):
+    frames = frames_of(kind, w, h, n)
+    aus, recs = encode_all(frames, w, h, qp=qp, **({"intra_period": 0} | kw))
+    dec, errs = ffhevc.decode_stream(aus)
+    assert errs == 0 and len(dec) == n
+    for i, (fr, fw, fh) in enumerate(dec):
+        assert (fw, fh) == (w, h)
+        assert np.array_equal(fr, recs[i]), f"frame {i}: decoder output differs from encoder reconstruction"
+
+
+@needs_ff
+def test_corrupted_hash_is_detected():
+    """Guards the guard: the decoder really does check the MD5 SEI."""
+    w, h = 64, 64
+    aus, _ = encode_all(frames_of("camera", w, h, 1), w, h, qp=30, intra_period=0, hash_sei=1)
+    bad = bytearray(aus[0])
+    bad[-5] ^= 0xFF
+    _, errs = ffhevc.decode_stream([bytes(bad)], quiet=True)
+    assert errs > 0
+
+
+def test_rate_and_quality_move_with_qp():
+    w, h = 128, 72
+    frames = frames_of("camera", w, h, 2)
+    sizes, psnrs = [], []
+    for qp in (22, 32, 42):
+        aus, recs = encode_all(frames, w, h, qp=qp, intra_period=0)
+        sizes.append(sum(map(len, aus)))
+        psnrs.append(synth.psnr(frames[1][:w * h], recs[1][:w * h]))
+    assert sizes[0] > sizes[1] > sizes[2] and psnrs[0] > psnrs[1] > psnrs[2]
+
+
+def test_stream_structure():
+    w, h = 128, 72
+    aus, _ = encode_all(frames_of("camera", w, h, 2), w, h, qp=32, intra_period=0)
+
+    def nal_types(au):
+        t, i = [], 0
+        while True:
+            i = au.find(b"\0\0\0\1", i)
+            if i < 0:
+                return t
+            t.append((au[i + 4] >> 1) & 63)
+            i += 4
+    assert nal_types(aus[0]) == [32, 33, 34, 19]        # VPS SPS PPS IDR_W_RADL (filter.h:52-53)
+    assert nal_types(aus[1]) == [1]                     # TRAIL_R
+    assert all(au[4] >> 7 == 0 for au in aus)
+
+
+# ---- primitives -----------------------------------------------------------------------------
+
+def i16(a):
+    return np.ascontiguousarray(a, dtype=np.int16)
+
+
+def test_dct_matrix_matches_the_standard_rows(oracle_lib):
+    assert [oracle_lib.orc_dct_coef(4, 1, n) for n in range(4)] == [83, 36, -36, -83]
+    assert [oracle_lib.orc_dct_coef(8, 1, n) for n in range(8)] == [89, 75, 50, 18, -18, -50, -75, -89]
+    assert [oracle_lib.orc_dct_coef(16, 1, n) for n in range(8)] == [90, 87, 80, 70, 57, 43, 25, 9]
+    assert [oracle_lib.orc_dct_coef(32, 1, n) for n in range(16)] == [90, 90, 88, 85, 82, 78, 73, 67, 61, 54, 46, 38, 31, 22, 13, 4]
+    assert [oracle_lib.orc_dct_coef(32, 31, n) for n in range(4)] == [4, -13, 22, -31]
+    for N in (4, 8, 16, 32):
+        assert all(oracle_lib.orc_dct_coef(N, 0, n) == 64 for n in range(N))
+        M = np.array([[oracle_lib.orc_dct_coef(N, k, n) for n in range(N)] for k in range(N)], np.int64)
+        G = M @ M.T                                        # near-orthogonal: diagonal ~ 64*64*N
+        assert np.all(np.abs(np.diag(G) - 4096 * N) <= 4096 * N * 0.01)
+
+
+@pytest.mark.parametrize("log2n", [2, 3, 4, 5])
+def test_dct_known_answers_and_roundtrip(oracle_lib, log2n):
+    n = 1 << log2n
+    coef = np.zeros(n * n, np.int16)
+    res = np.zeros(n * n, np.int16)
+    dc = i16(np.full(n * n, 100))
+    oracle_lib.orc_fdct(ptr(dc), ptr(coef), log2n)
+    # DC gain of the two forward passes: 64*N >> (log2N-1), then *64*N >> (log2N+6)
+    assert coef[0] == (((100 * 64 * n) >> (log2n - 1)) * 64 * n) >> (log2n + 6)
+    assert not coef[1:].any()
+    oracle_lib.orc_idct(ptr(coef), ptr(res), log2n)
+    assert np.abs(res.astype(int) - 100).max() <= 1
+    rng = np.random.default_rng(log2n)
+    x = i16(rng.integers(-255, 256, n * n))
+    oracle_lib.orc_fdct(ptr(x), ptr(coef), log2n)
+    oracle_lib.orc_idct(ptr(coef), ptr(res), log2n)
+    assert np.abs(res.astype(int) - x).max() <= 6            # integer DCT pair is near-lossless (not exactly orthogonal)
+    imp = np.zeros(n * n, np.int16)
+    imp[0] = 64                                              # inverse of a DC-only block is flat
+    oracle_lib.orc_idct(ptr(imp), ptr(res), log2n)
+    assert len(set(res.tolist())) == 1 and res[0] == (((64 * 64 + 64) >> 7) * 64 + 2048) >> 12
+
+
+def test_dst_roundtrip(oracle_lib):
+    rng = np.random.default_rng(7)
+    x = i16(rng.integers(-255, 256, 16))
+    c = np.zeros(16, np.int16)
+    r = np.zeros(16, np.int16)
+    oracle_lib.orc_fdst4(ptr(x), ptr(c))
+    oracle_lib.orc_idst4(ptr(c), ptr(r))
+    assert np.abs(r.astype(int) - x).max() <= 2
+
+
+def test_quant_dequant_known_answers(oracle_lib):
+    c = i16([1000, -1000, 10, 0] * 4)
+    lv = np.zeros(16, np.int16)
+    # qp 22: per 3, rem 4 -> scale 16384; log2n 2: qbits = 14+3+5 = 22; inter offset 85<<13
+    nz = oracle_lib.orc_quant(ptr(c), ptr(lv), 2, 22, 0)
+    exp = (1000 * 16384 + (85 << 13)) >> 22
+    assert lv[0] == exp and lv[1] == -exp and lv[2] == 0 and nz == 8
+    d = np.zeros(16, np.int16)
+    oracle_lib.orc_dequant(ptr(lv), ptr(d), 2, 22)
+    assert d[0] == ((exp * 16 * 64 << 3) + 16) >> 5 and d[1] == -d[0]
+    assert [oracle_lib.orc_chroma_qp(q) for q in (29, 30, 35, 43, 44, 51)] == [29, 29, 33, 37, 38, 45]
+
+
+def test_sad_satd_known_answers(oracle_lib):
+    a = np.zeros(64, np.uint8)
+    b = np.full(64, 3, np.uint8)
+    assert oracle_lib.orc_sad(ptr(a), 8, ptr(b), 8, 8, 8) == 192
+    # constant difference d on 8x8: only the DC Hadamard term = 64*d -> (64*3+2)>>2
+    assert oracle_lib.orc_satd(ptr(a), 8, ptr(b), 8, 8, 8) == (64 * 3 + 2) >> 2
+    assert oracle_lib.orc_satd(ptr(a), 8, ptr(b), 8, 4, 4) == (16 * 3 + 1) >> 1
+    assert oracle_lib.orc_satd(ptr(a), 8, ptr(a), 8, 8, 8) == 0
+
+
+def test_intra_known_answers(oracle_lib):
+    n, log2n = 8, 3
+    refs = np.full(4 * n + 1, 77, np.uint8)
+    out = np.zeros(n * n, np.uint8)
+    for mode in range(35):                                   # flat neighbours predict a flat block
+        oracle_lib.orc_intra_predict(ptr(refs), log2n, mode, 0, ptr(out), n)
+        assert (out == 77).all(), mode
+    refs = np.arange(4 * n + 1, dtype=np.uint8) * 3
+    oracle_lib.orc_intra_predict(ptr(refs), log2n, 26, 1, ptr(out), n)      # pure vertical, chroma: copy top row
+    top = refs[2 * n + 1:2 * n + 1 + n]
+    assert np.array_equal(out.reshape(n, n), np.tile(top, (n, 1)))
+    oracle_lib.orc_intra_predict(ptr(refs), log2n, 10, 1, ptr(out), n)      # pure horizontal: copy left column
+    left = refs[2 * n - 1::-1][:n]
+    assert np.array_equal(out.reshape(n, n), np.tile(left[:, None], (1, n)))
+
+
+def test_mc_known_answers(oracle_lib):
+    w = h = 32
+    ref = synth.noise(9, w * h)
+    out = np.zeros(64, np.uint8)
+    oracle_lib.orc_mc_luma(ptr(ref), w, w, h, 8, 8, 8, 8, 4 * 2, -4 * 3, ptr(out), 8)    # integer mv = copy
+    assert np.array_equal(out.reshape(8, 8), ref.reshape(h, w)[5:13, 10:18])
+    flat = np.full(w * h, 200, np.uint8)
+    for mv in ((1, 0), (0, 2), (3, 3), (-5, 7)):                                           # filters have unit DC gain
+        oracle_lib.orc_mc_luma(ptr(flat), w, w, h, 8, 8, 8, 8, mv[0], mv[1], ptr(out), 8)
+        assert (out == 200).all()
+        oracle_lib.orc_mc_chroma(ptr(flat), w, w, h, 8, 8, 8, 8, mv[0], mv[1], ptr(out), 8)
+        assert (out == 200).all()
+    # half-sample horizontal: (-1,4,-11,40,40,-11,4,-1) on a step edge
+    row = np.array([0] * 16 + [255] * 16, np.uint8)
+    img = np.tile(row, (h, 1)).ravel().copy()
+    oracle_lib.orc_mc_luma(ptr(img), w, w, h, 12, 8, 8, 8, 2, 0, ptr(out), 8)
+    taps = [-1, 4, -11, 40, 40, -11, 4, -1]
+    exp = [min(255, max(0, (sum(t * int(row[12 + x + k - 3]) for k, t in enumerate(taps)) + 32) >> 6)) for x in range(8)]
+    assert out[:8].tolist() == exp
+
+
+def test_deblock_known_answers(oracle_lib):
+    # flat step of 10 across a vertical edge at QP 37, bS 2 -> strong filter smooths, bounded by 2*tc
+    img = np.zeros((4, 16), np.uint8)
+    img[:, :8] = 100
+    img[:, 8:] = 110
+    buf = img.ravel().copy()
+    oracle_lib.orc_deblock_luma_segment(C.c_void_p(buf.ctypes.data + 8), 1, 16, 2, 37)
+    r = buf.reshape(4, 16)
+    assert (r[:, 7] > 100).all() and (r[:, 8] < 110).all() and (r[:, :5] == 100).all() and (r[:, 11:] == 110).all()
+    # a large step is a real edge: untouched
+    img[:, 8:] = 200
+    buf = img.ravel().copy()
+    oracle_lib.orc_deblock_luma_segment(C.c_void_p(buf.ctypes.data + 8), 1, 16, 2, 37)
+    assert np.array_equal(buf.reshape(4, 16), img)
