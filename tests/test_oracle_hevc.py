@@ -225,8 +225,9 @@ def test_deblock_known_answers(oracle_lib):
     oracle_lib.orc_deblock_luma_segment(C.c_void_p(buf.ctypes.data + 8), 1, 16, 2, 37)
     r = buf.reshape(4, 16)
     assert (r[:, 7] > 100).all() and (r[:, 8] < 110).all() and (r[:, :5] == 100).all() and (r[:, 11:] == 110).all()
-    # a large step is a real edge: untouched
-    img[:, 8:] = 200
+    # a large step is a real edge (|delta| >= 10*tc): untouched
+    img[:, :8] = 0
+    img[:, 8:] = 255
     buf = img.ravel().copy()
     oracle_lib.orc_deblock_luma_segment(C.c_void_p(buf.ctypes.data + 8), 1, 16, 2, 37)
     assert np.array_equal(buf.reshape(4, 16), img)
