@@ -1,0 +1,40 @@
+/*
+ * b200_hevc.h -- plain-argument C ABI of the B200 HEVC encoder / decoder engines.
+ *
+ * These are the engines underneath the reference-shaped boundaries (kvz_api in b200_kvazaar.h,
+ * libOpenHevc* in b200_openhevc.h).  They exist so that the benchmark can keep frames resident
+ * in HBM and so that the parity tests can read intermediate state (cu map, levels,
+ * reconstruction) and compare it with the CPU oracle stage by stage.
+ */
+#ifndef B200_HEVC_H_
+#define B200_HEVC_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+/* Encoder: constant QP, low-delay P (each picture references the previous reconstruction),
+ * IDR every intra_period pictures (0 = first only), one slice, WPP substreams.
+ * width/height multiples of 8 (reference requirement: camerafilter.cpp:330-331).
+ * Returns NULL on error (see b200_last_error()). */
+void *b200_enc_open(int width, int height, int qp, int intra_period, int search_range, int deblock, int debug);
+void  b200_enc_close(void *enc);
+/* Encode one packed I420 picture from host / device memory; writes one Annex-B access unit
+ * (VPS+SPS+PPS precede every IDR).  Returns its size, or <0 (-needed when cap is short). */
+int   b200_enc_encode(void *enc, const uint8_t *i420, uint8_t *out, int cap);
+int   b200_enc_encode_dev(void *enc, const uint8_t *d_i420, uint8_t *out, int cap);
+int   b200_enc_last_was_idr(void *enc);
+unsigned long long b200_enc_last_bins(void *enc);
+
+/* Test hooks.  what: 0 reconstruction after deblocking, 1 before deblocking (debug=1),
+ * 2 cu map (12 bytes per 8x8 unit), 3 quantised levels (int16, I420-shaped). */
+int   b200_enc_debug_read(void *enc, int what, void *dst, size_t bytes);
+int   b200_enc_debug_set_reference(void *enc, const uint8_t *i420);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

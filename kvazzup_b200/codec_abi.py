@@ -3,7 +3,19 @@ from __future__ import annotations
 
 import ctypes as C
 
-SIGNATURES: dict = {}
+v = C.c_void_p
+i = C.c_int
+
+SIGNATURES: dict = {
+    "b200_enc_open": (v, [i, i, i, i, i, i, i]),
+    "b200_enc_close": (None, [v]),
+    "b200_enc_encode": (i, [v, v, v, i]),
+    "b200_enc_encode_dev": (i, [v, v, v, i]),
+    "b200_enc_last_was_idr": (i, [v]),
+    "b200_enc_last_bins": (C.c_ulonglong, [v]),
+    "b200_enc_debug_read": (i, [v, i, v, C.c_size_t]),
+    "b200_enc_debug_set_reference": (i, [v, v]),
+}
 
 
 def bind(l) -> None:

@@ -1,0 +1,562 @@
+// CABAC entropy coding of the B200 HEVC encoder (sm_100a); SURVEY.md 8a-K row K8.
+//
+// One WPP substream (CTU row) per warp, all rows of the picture in flight at once.  Arithmetic
+// coding is serial by nature, so the warp runs the coder redundantly in all 32 lanes (uniform
+// control flow costs the same as one lane) and uses the lanes only where they differ: the
+// cooperative, coalesced staging of each transform block's levels from HBM into shared memory.
+// Lane 0 alone stores output bytes.  Rows synchronise once: row r starts from the context
+// tables row r-1 published after its second CTU (H.265 9.3.1, entropy_coding_sync_enabled).
+// All mode decisions (merge / skip / AMVP index) were taken by k_inter_modes; this kernel only
+// serialises syntax.  Output bytes are escaped on the fly (emulation_prevention_three_byte),
+// which is exact because every substream starts after a non-zero byte.
+#include "hevc_device.cuh"
+#include "hevc_kernels.h"
+
+namespace b200 {
+
+namespace {
+
+struct Coder {
+  uint32_t low, range;
+  int bits_left, num_buffered, buffered_byte;
+  uint8_t *out;
+  uint32_t pos, cap;
+  int zeros;
+  uint8_t *ctx;               // shared memory, this lane's private table: entry i at ctx[i * 32]
+  unsigned long long bins;
+  bool writer;                // lane 0
+};
+
+__device__ __forceinline__ void emit(Coder &c, uint32_t byte)
+{
+  byte &= 0xff;
+  if (c.zeros >= 2 && byte <= 3) {
+    if (c.writer && c.pos < c.cap) c.out[c.pos] = 3;
+    c.pos++;
+    c.zeros = 0;
+  }
+  if (c.writer && c.pos < c.cap) c.out[c.pos] = (uint8_t)byte;
+  c.pos++;
+  c.zeros = byte == 0 ? c.zeros + 1 : 0;
+}
+
+__device__ __forceinline__ void coder_start(Coder &c)
+{
+  c.low = 0; c.range = 510; c.bits_left = 23; c.num_buffered = 0; c.buffered_byte = 0xff;
+}
+
+__device__ __forceinline__ void write_out(Coder &c)
+{
+  uint32_t lead = c.low >> (24 - c.bits_left);
+  c.bits_left += 8;
+  c.low &= 0xffffffffu >> c.bits_left;
+  if (lead == 0xff) {
+    c.num_buffered++;
+  } else if (c.num_buffered > 0) {
+    uint32_t carry = lead >> 8;
+    uint32_t byte = (uint32_t)c.buffered_byte + carry;
+    c.buffered_byte = (int)(lead & 0xff);
+    emit(c, byte);
+    byte = (0xff + carry) & 0xff;
+    while (c.num_buffered > 1) { emit(c, byte); c.num_buffered--; }
+  } else {
+    c.num_buffered = 1;
+    c.buffered_byte = (int)lead;
+  }
+}
+
+__device__ __forceinline__ void enc_bin(Coder &c, int ctx_idx, int bin)
+{
+  uint32_t s = c.ctx[ctx_idx * 32];
+  uint32_t st = s >> 1, mps = s & 1;
+  uint32_t lps = (c_range_lps[st] >> (((c.range >> 6) & 3) * 8)) & 0xff;
+  c.bins++;
+  c.range -= lps;
+  if ((uint32_t)bin != mps) {
+    int nb = __clz(lps) - 23;                     // shifts until lps >= 256
+    c.low = (c.low + c.range) << nb;
+    c.range = lps << nb;
+    if (st == 0) mps ^= 1;
+    st = c_trans_lps[st];
+    c.bits_left -= nb;
+  } else {
+    if (st < 62) st++;
+    if (c.range < 256) { c.low <<= 1; c.range <<= 1; c.bits_left--; }
+  }
+  c.ctx[ctx_idx * 32] = (uint8_t)((st << 1) | mps);
+  if (c.bits_left < 12) write_out(c);
+}
+
+__device__ __forceinline__ void enc_bypass(Coder &c, int bin)
+{
+  c.bins++;
+  c.low <<= 1;
+  if (bin) c.low += c.range;
+  c.bits_left--;
+  if (c.bits_left < 12) write_out(c);
+}
+
+__device__ __forceinline__ void enc_bypass_bits(Coder &c, uint32_t bins, int n)
+{
+  for (int i = n - 1; i >= 0; i--) enc_bypass(c, (bins >> i) & 1);
+}
+
+__device__ __forceinline__ void enc_terminate(Coder &c, int bin)
+{
+  c.bins++;
+  c.range -= 2;
+  if (bin) {
+    c.low += c.range;
+    c.low <<= 7;
+    c.range = 2 << 7;
+    c.bits_left -= 7;
+  } else if (c.range >= 256) {
+    return;
+  } else {
+    c.low <<= 1;
+    c.range <<= 1;
+    c.bits_left--;
+  }
+  if (c.bits_left < 12) write_out(c);
+}
+
+// flush (9.3.4.5) + rbsp_stop_one_bit / alignment bit + zero bits up to the byte boundary
+__device__ __forceinline__ void coder_finish(Coder &c)
+{
+  if (c.low >> (32 - c.bits_left)) {
+    emit(c, (uint32_t)(c.buffered_byte + 1));
+    while (c.num_buffered > 1) { emit(c, 0x00); c.num_buffered--; }
+    c.low -= 1u << (32 - c.bits_left);
+  } else {
+    if (c.num_buffered > 0) emit(c, (uint32_t)c.buffered_byte);
+    while (c.num_buffered > 1) { emit(c, 0xff); c.num_buffered--; }
+  }
+  int nb = 24 - c.bits_left;                      // 1..12 bits of (low >> 8), then the stop bit
+  uint32_t v = (((c.low >> 8) & ((1u << nb) - 1)) << 1) | 1u;
+  nb += 1;
+  int pad = (8 - (nb & 7)) & 7;
+  v <<= pad; nb += pad;
+  for (int i = nb - 8; i >= 0; i -= 8) emit(c, v >> i);
+}
+
+// Every lane keeps a private copy of the context table (entry i of lane l at s_ctx[i*32 + l]):
+// the lanes run the same coder redundantly, and private tables make that independent of warp
+// reconvergence timing.
+__device__ __forceinline__ void init_contexts(uint8_t *ctx, int init_type, int qp)
+{
+  qp = clip3(0, 51, qp);
+  for (int i = 0; i < CTX_COUNT; i++) {
+    int iv = c_ctx_init[init_type][i];
+    int m = (iv >> 4) * 5 - 45, n = ((iv & 15) << 3) - 16;
+    int pre = clip3(1, 126, ((m * qp) >> 4) + n);
+    int mps = pre <= 63 ? 0 : 1;
+    int st = mps ? pre - 64 : 63 - pre;
+    ctx[i * 32] = (uint8_t)((st << 1) | mps);
+  }
+}
+
+// ---- residual_coding (7.3.8.11) ---------------------------------------------------------------
+
+__device__ __forceinline__ void scan_pos(int scan_idx, int blk_log2, int i, int &x, int &y)
+{
+  int n = 1 << blk_log2;
+  if (scan_idx == 1) { x = i & (n - 1); y = i >> blk_log2; return; }
+  if (scan_idx == 2) { x = i >> blk_log2; y = i & (n - 1); return; }
+  int v = blk_log2 == 2 ? c_diag4[i] : (blk_log2 == 1 ? c_diag2[i] : (blk_log2 == 3 ? c_diag8[i] : 0));
+  x = v & 15; y = v >> 4;
+}
+
+__device__ __forceinline__ void code_last_prefix(Coder &c, int pos, int log2n, int cidx, int base)
+{
+  int offset, shift;
+  if (cidx == 0) { offset = 3 * (log2n - 2) + ((log2n - 1) >> 2); shift = (log2n + 1) >> 2; }
+  else { offset = 15; shift = log2n - 2; }
+  int prefix = pos < 4 ? pos : ((pos < 8) ? 4 + ((pos - 4) >> 1) : (pos < 16 ? 6 + ((pos - 8) >> 2) : 8 + ((pos - 16) >> 3)));
+  int cmax = (log2n << 1) - 1;
+  for (int i = 0; i < prefix; i++) enc_bin(c, base + offset + (i >> shift), 1);
+  if (prefix < cmax) enc_bin(c, base + offset + (prefix >> shift), 0);
+}
+__device__ __forceinline__ void code_last_suffix(Coder &c, int pos)
+{
+  if (pos < 4) return;
+  int g = (pos < 8) ? 4 + ((pos - 4) >> 1) : (pos < 16 ? 6 + ((pos - 8) >> 2) : 8 + ((pos - 16) >> 3));
+  int nb = (g >> 1) - 1;
+  int min_in_group = (2 + (g & 1)) << nb;
+  enc_bypass_bits(c, (uint32_t)(pos - min_in_group), nb);
+}
+
+__device__ __forceinline__ void code_remaining(Coder &c, int value, int rice)
+{
+  if (value < (3 << rice)) {
+    int len = value >> rice;
+    enc_bypass_bits(c, (1u << (len + 1)) - 2, len + 1);
+    enc_bypass_bits(c, (uint32_t)value & ((1u << rice) - 1), rice);
+  } else {
+    int len = rice;
+    value -= 3 << rice;
+    while (value >= (1 << len)) { value -= 1 << len; len++; }
+    int pre = 3 + len + 1 - rice;
+    for (int i = 0; i < pre - 1; i++) enc_bypass(c, 1);
+    enc_bypass(c, 0);
+    enc_bypass_bits(c, (uint32_t)value, len);
+  }
+}
+
+// lv: N x N levels in shared memory, row pitch n
+__device__ void code_residual(Coder &c, const int16_t *lv, int log2n, int cidx, int scan_idx)
+{
+  const int n = 1 << log2n, sb_log2 = log2n - 2, nsb = 1 << (2 * sb_log2);
+  int last_sb = -1, last_pos = -1, last_x = 0, last_y = 0;
+  for (int i = nsb - 1; i >= 0 && last_sb < 0; i--) {
+    int xs, ys;
+    scan_pos(scan_idx, sb_log2, i, xs, ys);
+    for (int p = 15; p >= 0; p--) {
+      int xp, yp;
+      scan_pos(scan_idx, 2, p, xp, yp);
+      if (lv[(ys * 4 + yp) * n + xs * 4 + xp]) { last_sb = i; last_pos = p; last_x = xs * 4 + xp; last_y = ys * 4 + yp; break; }
+    }
+  }
+  if (last_sb < 0) return;
+  {
+    int px = last_x, py = last_y;
+    if (scan_idx == 2) { int tt = px; px = py; py = tt; }
+    code_last_prefix(c, px, log2n, cidx, CTX_LAST_X);
+    code_last_prefix(c, py, log2n, cidx, CTX_LAST_Y);
+    code_last_suffix(c, px);
+    code_last_suffix(c, py);
+  }
+  unsigned long long csbf = 0;                  // bit (ys*8 + xs)
+  int c1 = 1;
+  for (int i = last_sb; i >= 0; i--) {
+    int xs, ys;
+    scan_pos(scan_idx, sb_log2, i, xs, ys);
+    int right = xs + 1 < (1 << sb_log2) ? (int)((csbf >> (ys * 8 + xs + 1)) & 1) : 0;
+    int below = ys + 1 < (1 << sb_log2) ? (int)((csbf >> ((ys + 1) * 8 + xs)) & 1) : 0;
+    int prev_csbf = right | (below << 1);
+    int absv[16];
+    unsigned sig = 0, neg = 0;
+#pragma unroll
+    for (int p = 0; p < 16; p++) {
+      int xp, yp;
+      scan_pos(scan_idx, 2, p, xp, yp);
+      int v = lv[(ys * 4 + yp) * n + xs * 4 + xp];
+      if (i == last_sb && p > last_pos) v = 0;
+      absv[p] = abs(v);
+      if (v) sig |= 1u << p;
+      if (v < 0) neg |= 1u << p;
+    }
+    int any = sig != 0, infer_dc = 0;
+    if (i < last_sb && i > 0) {
+      enc_bin(c, CTX_CSBF + (prev_csbf ? 1 : 0) + (cidx ? 2 : 0), any);
+      infer_dc = 1;
+    } else {
+      any = 1;
+    }
+    if (any) csbf |= 1ull << (ys * 8 + xs);
+    if (!any) continue;
+    int start = (i == last_sb) ? last_pos - 1 : 15;
+    for (int p = start; p >= 0; p--) {
+      if (p == 0 && infer_dc) break;
+      int xp, yp;
+      scan_pos(scan_idx, 2, p, xp, yp);
+      int xc = xs * 4 + xp, yc = ys * 4 + yp, sctx;
+      if (log2n == 2) sctx = c_sig_ctx_4x4[(yc << 2) + xc];
+      else if (xc + yc == 0) sctx = 0;
+      else {
+        if (prev_csbf == 0) sctx = (xp + yp == 0) ? 2 : (xp + yp < 3) ? 1 : 0;
+        else if (prev_csbf == 1) sctx = yp == 0 ? 2 : (yp == 1 ? 1 : 0);
+        else if (prev_csbf == 2) sctx = xp == 0 ? 2 : (xp == 1 ? 1 : 0);
+        else sctx = 2;
+        if (cidx == 0) {
+          if (xs || ys) sctx += 3;
+          sctx += log2n == 3 ? (scan_idx == 0 ? 9 : 15) : 21;
+        } else {
+          sctx += log2n == 3 ? 9 : 12;
+        }
+      }
+      int s = (sig >> p) & 1;
+      enc_bin(c, CTX_SIG + (cidx == 0 ? sctx : 27 + sctx), s);
+      if (s) infer_dc = 0;
+    }
+    int ctx_set = (i > 0 && cidx == 0) ? 2 : 0;
+    if (c1 == 0) ctx_set++;
+    c1 = 1;
+    int num_g1 = 0, first_g1 = -1;
+    unsigned g1 = 0;
+    for (int p = 15; p >= 0; p--) {
+      if (!((sig >> p) & 1) || num_g1 >= 8) continue;
+      int f = absv[p] > 1;
+      enc_bin(c, CTX_GT1 + (cidx ? 16 : 0) + 4 * ctx_set + c1, f);
+      if (f) { g1 |= 1u << p; c1 = 0; if (first_g1 < 0) first_g1 = p; }
+      else if (c1 < 3 && c1 > 0) c1++;
+      num_g1++;
+    }
+    int g2 = 0;
+    if (first_g1 >= 0) {
+      g2 = absv[first_g1] > 2;
+      enc_bin(c, CTX_GT2 + (cidx ? 4 : 0) + ctx_set, g2);
+    }
+    for (int p = 15; p >= 0; p--)
+      if ((sig >> p) & 1) enc_bypass(c, (neg >> p) & 1);
+    int num_sig = 0, rice = 0;
+    for (int p = 15; p >= 0; p--) {
+      if (!((sig >> p) & 1)) continue;
+      int base = 1 + (num_sig < 8 ? (int)((g1 >> p) & 1) : 0) + (p == first_g1 ? g2 : 0);
+      int thresh = num_sig < 8 ? (p == first_g1 ? 3 : 2) : 1;
+      if (base == thresh) {
+        code_remaining(c, absv[p] - base, rice);
+        if (absv[p] > (3 << rice)) rice = min(rice + 1, 4);
+      }
+      num_sig++;
+    }
+  }
+}
+
+// ---- coding quadtree ------------------------------------------------------------------------------
+
+struct RowCtx {
+  const FrameParams *fp;
+  const CuInfo *cu;
+  const int16_t *levels;
+  int16_t *s_lv;              // 32 x 32 staging tile in shared memory
+  int lane;
+};
+
+__device__ __forceinline__ unsigned coding_order_c(const FrameParams &fp, int x, int y)
+{
+  return (unsigned)((y >> kCtbLog2) * fp.ctb_cols + (x >> kCtbLog2)) * 64u + (unsigned)xy_to_z((x >> 3) & 7, (y >> 3) & 7);
+}
+struct NbMv { bool ok; int mvx, mvy; };
+__device__ __forceinline__ NbMv nb_mv(const FrameParams &fp, const CuInfo *cu, unsigned cur, int xn, int yn)
+{
+  NbMv n{false, 0, 0};
+  if (xn < 0 || yn < 0 || xn >= fp.w || yn >= fp.h) return n;
+  if (coding_order_c(fp, xn, yn) >= cur) return n;
+  const CuInfo *c = &cu[(size_t)(yn >> 3) * fp.w8 + (xn >> 3)];
+  if (c->pred_mode != 0) return n;
+  n.ok = true; n.mvx = c->mvx; n.mvy = c->mvy;
+  return n;
+}
+
+__device__ __forceinline__ int scan_idx_for(int pred_mode, int intra_mode, int log2n, int cidx)
+{
+  if (pred_mode != 1) return 0;
+  if (!(log2n == 2 || (log2n == 3 && cidx == 0))) return 0;
+  if (intra_mode >= 6 && intra_mode <= 14) return 2;
+  if (intra_mode >= 22 && intra_mode <= 30) return 1;
+  return 0;
+}
+
+// stage one transform block of levels into shared memory (all lanes), then code it
+__device__ void code_tb(Coder &c, const RowCtx &rc, const int16_t *plane, int pw, int x0, int y0, int log2n, int cidx,
+                        int scan_idx)
+{
+  const int n = 1 << log2n;
+  __syncwarp();
+  for (int i = rc.lane; i < n * n; i += 32) rc.s_lv[i] = plane[(size_t)(y0 + (i >> log2n)) * pw + x0 + (i & (n - 1))];
+  __syncwarp();
+  code_residual(c, rc.s_lv, log2n, cidx, scan_idx);
+}
+
+__device__ void code_transform_unit(Coder &c, const RowCtx &rc, int x0, int y0, int log2, const CuInfo &cu)
+{
+  const FrameParams &fp = *rc.fp;
+  const size_t ysz = (size_t)fp.w * fp.h;
+  int cb = (cu.cbf >> 1) & 1, cr = (cu.cbf >> 2) & 1, lu = cu.cbf & 1;
+  enc_bin(c, CTX_CBF_CHROMA, cb);
+  enc_bin(c, CTX_CBF_CHROMA, cr);
+  if (cu.pred_mode == 1 || cb || cr) enc_bin(c, CTX_CBF_LUMA + 1, lu);
+  if (lu) code_tb(c, rc, rc.levels, fp.w, x0, y0, log2, 0, scan_idx_for(cu.pred_mode, cu.intra_mode, log2, 0));
+  if (cb) code_tb(c, rc, rc.levels + ysz, fp.w >> 1, x0 >> 1, y0 >> 1, log2 - 1, 1, scan_idx_for(cu.pred_mode, cu.intra_mode, log2 - 1, 1));
+  if (cr) code_tb(c, rc, rc.levels + ysz + ysz / 4, fp.w >> 1, x0 >> 1, y0 >> 1, log2 - 1, 2, scan_idx_for(cu.pred_mode, cu.intra_mode, log2 - 1, 2));
+}
+
+__device__ void code_mvd(Coder &c, int dx, int dy)
+{
+  int ax = abs(dx), ay = abs(dy);
+  enc_bin(c, CTX_MVD_GT0, ax > 0);
+  enc_bin(c, CTX_MVD_GT0, ay > 0);
+  if (ax) enc_bin(c, CTX_MVD_GT1, ax > 1);
+  if (ay) enc_bin(c, CTX_MVD_GT1, ay > 1);
+  for (int k = 0; k < 2; k++) {
+    int a = k ? ay : ax, d = k ? dy : dx;
+    if (!a) continue;
+    if (a > 1) {
+      int v = a - 2, kk = 1;
+      while (v >= (1 << kk)) { enc_bypass(c, 1); v -= 1 << kk; kk++; }
+      enc_bypass(c, 0);
+      enc_bypass_bits(c, (uint32_t)v, kk);
+    }
+    enc_bypass(c, d < 0);
+  }
+}
+
+__device__ void code_cu(Coder &c, const RowCtx &rc, int x0, int y0, int log2)
+{
+  const FrameParams &fp = *rc.fp;
+  const CuInfo cu = rc.cu[(size_t)(y0 >> 3) * fp.w8 + (x0 >> 3)];
+  const int n = 1 << log2;
+  if (!fp.is_idr) {
+    int ctx = 0;
+    if (x0 > 0) ctx += rc.cu[(size_t)(y0 >> 3) * fp.w8 + ((x0 - 1) >> 3)].skip;
+    if (y0 > 0) ctx += rc.cu[(size_t)((y0 - 1) >> 3) * fp.w8 + (x0 >> 3)].skip;
+    enc_bin(c, CTX_SKIP + ctx, cu.skip);
+    if (cu.merge_idx != 0xff) {
+      int midx = cu.merge_idx;
+      if (!cu.skip) {
+        enc_bin(c, CTX_PRED_MODE, 0);
+        enc_bin(c, CTX_PART_MODE, 1);
+        enc_bin(c, CTX_MERGE_FLAG, 1);
+      }
+      enc_bin(c, CTX_MERGE_IDX, midx > 0);
+      for (int i = 1; i < kMaxMerge - 1 && midx >= i; i++) enc_bypass(c, midx > i);
+      if (!cu.skip) code_transform_unit(c, rc, x0, y0, log2, cu);
+    } else {
+      enc_bin(c, CTX_PRED_MODE, 0);
+      enc_bin(c, CTX_PART_MODE, 1);
+      enc_bin(c, CTX_MERGE_FLAG, 0);
+      // AMVP predictor (8.5.3.2.6-7): first available of (A0,A1), first of (B0,B1,B2), zero padding
+      unsigned cur = coding_order_c(fp, x0, y0);
+      NbMv a = nb_mv(fp, rc.cu, cur, x0 - 1, y0 + n);
+      if (!a.ok) a = nb_mv(fp, rc.cu, cur, x0 - 1, y0 + n - 1);
+      NbMv b = nb_mv(fp, rc.cu, cur, x0 + n, y0 - 1);
+      if (!b.ok) b = nb_mv(fp, rc.cu, cur, x0 + n - 1, y0 - 1);
+      if (!b.ok) b = nb_mv(fp, rc.cu, cur, x0 - 1, y0 - 1);
+      int px[2], py[2], k = 0;
+      if (a.ok) { px[k] = a.mvx; py[k++] = a.mvy; }
+      if (b.ok && !(a.ok && a.mvx == b.mvx && a.mvy == b.mvy)) { px[k] = b.mvx; py[k++] = b.mvy; }
+      while (k < 2) { px[k] = 0; py[k++] = 0; }
+      int pi = cu.mvp_idx;
+      code_mvd(c, cu.mvx - px[pi], cu.mvy - py[pi]);
+      enc_bin(c, CTX_MVP_IDX, pi);
+      enc_bin(c, CTX_RQT_ROOT_CBF, cu.cbf != 0);
+      if (cu.cbf) code_transform_unit(c, rc, x0, y0, log2, cu);
+    }
+  } else {
+    if (log2 == 3) enc_bin(c, CTX_PART_MODE, 1);
+    int cand[3];
+    int a = 1, b = 1;
+    if (x0 > 0) a = rc.cu[(size_t)(y0 >> 3) * fp.w8 + ((x0 - 1) >> 3)].intra_mode;
+    if (y0 > 0 && (y0 & (kCtb - 1))) b = rc.cu[(size_t)((y0 - 1) >> 3) * fp.w8 + (x0 >> 3)].intra_mode;
+    if (a == b) {
+      if (a < 2) { cand[0] = 0; cand[1] = 1; cand[2] = 26; }
+      else { cand[0] = a; cand[1] = 2 + ((a + 29) % 32); cand[2] = 2 + ((a - 2 + 1) % 32); }
+    } else {
+      cand[0] = a; cand[1] = b;
+      cand[2] = (a != 0 && b != 0) ? 0 : ((a != 1 && b != 1) ? 1 : 26);
+    }
+    int mode = cu.intra_mode, mpm = -1;
+    for (int i = 0; i < 3; i++) if (cand[i] == mode) mpm = i;
+    enc_bin(c, CTX_PREV_INTRA_LUMA, mpm >= 0);
+    if (mpm >= 0) {
+      enc_bypass(c, mpm > 0);
+      if (mpm > 0) enc_bypass(c, mpm > 1);
+    } else {
+      if (cand[0] > cand[1]) { int tt = cand[0]; cand[0] = cand[1]; cand[1] = tt; }
+      if (cand[0] > cand[2]) { int tt = cand[0]; cand[0] = cand[2]; cand[2] = tt; }
+      if (cand[1] > cand[2]) { int tt = cand[1]; cand[1] = cand[2]; cand[2] = tt; }
+      int rem = mode;
+      for (int i = 2; i >= 0; i--) if (rem > cand[i]) rem--;
+      enc_bypass_bits(c, (uint32_t)rem, 5);
+    }
+    enc_bin(c, CTX_INTRA_CHROMA, 0);
+    code_transform_unit(c, rc, x0, y0, log2, cu);
+  }
+}
+
+// split_cu_flag (7.3.8.4): coded when the block fits the picture and is larger than the minimum CU
+__device__ __forceinline__ int code_split(Coder &c, const RowCtx &rc, int x0, int y0, int log2, int depth)
+{
+  const FrameParams &fp = *rc.fp;
+  const int n = 1 << log2;
+  if (!(x0 + n <= fp.w && y0 + n <= fp.h && log2 > 3)) return log2 > 3;
+  int split = rc.cu[(size_t)(y0 >> 3) * fp.w8 + (x0 >> 3)].log2_size < log2;
+  int ctx = 0;
+  if (x0 > 0) ctx += (kCtbLog2 - rc.cu[(size_t)(y0 >> 3) * fp.w8 + ((x0 - 1) >> 3)].log2_size) > depth;
+  if (y0 > 0) ctx += (kCtbLog2 - rc.cu[(size_t)((y0 - 1) >> 3) * fp.w8 + (x0 >> 3)].log2_size) > depth;
+  enc_bin(c, CTX_SPLIT_CU + ctx, split);
+  return split;
+}
+
+// coding_quadtree of one CTU, depth-first in z-order, written without recursion
+__device__ void code_ctu(Coder &c, const RowCtx &rc, int cx, int cy)
+{
+  const FrameParams &fp = *rc.fp;
+  if (!code_split(c, rc, cx, cy, 6, 0)) { code_cu(c, rc, cx, cy, 6); return; }
+  for (int a = 0; a < 4; a++) {
+    int x5 = cx + 32 * (a & 1), y5 = cy + 32 * (a >> 1);
+    if (x5 >= fp.w || y5 >= fp.h) continue;
+    if (!code_split(c, rc, x5, y5, 5, 1)) { code_cu(c, rc, x5, y5, 5); continue; }
+    for (int b = 0; b < 4; b++) {
+      int x4 = x5 + 16 * (b & 1), y4 = y5 + 16 * (b >> 1);
+      if (x4 >= fp.w || y4 >= fp.h) continue;
+      if (!code_split(c, rc, x4, y4, 4, 2)) { code_cu(c, rc, x4, y4, 4); continue; }
+      for (int d = 0; d < 4; d++) {
+        int x3 = x4 + 8 * (d & 1), y3 = y4 + 8 * (d >> 1);
+        if (x3 >= fp.w || y3 >= fp.h) continue;
+        code_cu(c, rc, x3, y3, 3);
+      }
+    }
+  }
+}
+
+__global__ void __launch_bounds__(32)
+k_cabac_rows(FrameParams fp, const CuInfo *__restrict__ cu, const int16_t *__restrict__ levels, uint8_t *rows,
+             uint32_t row_cap, uint32_t *row_len, uint8_t *sync_ctx, int *sync_flag, unsigned long long *bins)
+{
+  __shared__ uint8_t s_ctx[CTX_COUNT * 32];
+  __shared__ int16_t s_lv[32 * 32];
+  const int r = blockIdx.x, lane = threadIdx.x;
+  Coder c;
+  c.out = rows + (size_t)r * row_cap; c.pos = 0; c.cap = row_cap; c.zeros = 0; c.ctx = s_ctx + lane; c.bins = 0;
+  c.writer = lane == 0;
+  RowCtx rc{&fp, cu, levels, s_lv, lane};
+  if (r == 0 || fp.ctb_cols < 2) {
+    init_contexts(c.ctx, fp.is_idr ? 0 : 1, fp.qp);
+  } else {
+    if (lane == 0) {
+      volatile int *f = sync_flag;
+      while (f[r - 1] == 0) __nanosleep(100);
+      __threadfence();
+    }
+    __syncwarp();
+    for (int i = 0; i < CTX_COUNT; i++) c.ctx[i * 32] = __ldcg(sync_ctx + (size_t)(r - 1) * CTX_COUNT + i);
+  }
+  __syncwarp();
+  coder_start(c);
+  for (int col = 0; col < fp.ctb_cols; col++) {
+    code_ctu(c, rc, col * kCtb, r * kCtb);
+    if (col == 1 && r + 1 < fp.ctb_rows) {
+      __syncwarp();
+      if (lane == 0)
+        for (int i = 0; i < CTX_COUNT; i++) sync_ctx[(size_t)r * CTX_COUNT + i] = c.ctx[i * 32];
+      __threadfence();
+      __syncwarp();
+      if (lane == 0) atomicExch(&sync_flag[r], 1);
+    }
+    bool last = r == fp.ctb_rows - 1 && col == fp.ctb_cols - 1;
+    enc_terminate(c, last);
+    if (col == fp.ctb_cols - 1 && !last) enc_terminate(c, 1);
+  }
+  coder_finish(c);
+  if (lane == 0) {
+    row_len[r] = c.pos <= c.cap ? c.pos : 0xffffffffu;
+    atomicAdd(bins, c.bins);
+  }
+}
+
+}  // namespace
+
+cudaError_t launch_cabac(const FrameParams &fp, const CuInfo *cu, const int16_t *levels, uint8_t *rows,
+                         uint32_t row_cap, uint32_t *row_len, uint8_t *sync_ctx, int *sync_flag,
+                         unsigned long long *bins, cudaStream_t s)
+{
+  cudaError_t e = cudaMemsetAsync(sync_flag, 0, sizeof(int) * fp.ctb_rows, s);
+  if (e != cudaSuccess) return e;
+  e = cudaMemsetAsync(bins, 0, sizeof(unsigned long long), s);
+  if (e != cudaSuccess) return e;
+  k_cabac_rows<<<fp.ctb_rows, 32, 0, s>>>(fp, cu, levels, rows, row_cap, row_len, sync_ctx, sync_flag, bins);
+  return cudaGetLastError();
+}
+
+}  // namespace b200

@@ -1,0 +1,56 @@
+// Shared host/device definitions of the B200 HEVC codec (internal header).
+//
+// Data layout in HBM (per encoder / decoder instance), all picture-shaped so that every
+// kernel addresses it with coalesced row segments:
+//   frame planes   packed I420 (Y w*h, Cb, Cr), uint8
+//   levels         quantised transform levels, int16, same I420 geometry: the level of the
+//                  coefficient (u,v) of the TU whose top-left sample is (x0,y0) lives at
+//                  plane[(y0+v)*stride + x0+u]
+//   cu map         one 12-byte CuInfo per 8x8 luma unit, raster order, every unit of a CU
+//                  carries the CU's values (what the entropy coder, the deblocking filter
+//                  and the decoder's reconstruction all index by sample position)
+//   substreams     one byte buffer per CTU row (WPP substream), already escaped
+#pragma once
+#include <stdint.h>
+
+namespace b200 {
+
+constexpr int kCtbLog2 = 6;
+constexpr int kCtb = 64;
+constexpr int kMaxMerge = 5;
+constexpr int kCuOverheadBits = 3;
+
+struct CuInfo {
+  int16_t mvx, mvy;     // quarter-sample motion vector
+  uint8_t log2_size;    // CU size 3..6 (0 = outside the picture / not yet decided)
+  uint8_t pred_mode;    // 0 inter, 1 intra
+  uint8_t intra_mode;   // 0..34
+  uint8_t cbf;          // bit0 Y, bit1 Cb, bit2 Cr
+  uint8_t skip;
+  uint8_t merge_idx;    // 0xff = not merged
+  uint8_t mvp_idx;
+  uint8_t pad;
+};
+static_assert(sizeof(CuInfo) == 12, "CuInfo layout is part of the test ABI");
+
+// CABAC context layout (one flat table per substream)
+enum CtxOffset {
+  CTX_SPLIT_CU = 0, CTX_SKIP = 3, CTX_MERGE_FLAG = 6, CTX_MERGE_IDX = 7, CTX_PART_MODE = 8,
+  CTX_PRED_MODE = 12, CTX_PREV_INTRA_LUMA = 13, CTX_INTRA_CHROMA = 14, CTX_MVD_GT0 = 15,
+  CTX_MVD_GT1 = 16, CTX_MVP_IDX = 17, CTX_RQT_ROOT_CBF = 18, CTX_SPLIT_TRANSFORM = 19,
+  CTX_CBF_LUMA = 22, CTX_CBF_CHROMA = 24, CTX_LAST_X = 28, CTX_LAST_Y = 46, CTX_CSBF = 64,
+  CTX_SIG = 68, CTX_GT1 = 110, CTX_GT2 = 134, CTX_COUNT = 140
+};
+
+struct FrameParams {
+  int w, h;             // luma size, multiples of 8
+  int w8, h8;           // size in 8x8 units
+  int ctb_cols, ctb_rows;
+  int qp, qp_c;         // luma / chroma QP
+  int lambda_q4;        // 16 * sqrt(lambda) for SAD-domain costs
+  int search_range;
+  int is_idr;           // quantiser rounding offset and CABAC init type follow the slice type
+  int deblock;
+};
+
+}  // namespace b200

@@ -1,0 +1,266 @@
+// Device-side building blocks shared by the encoder and decoder kernels (sm_100a).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "hevc_common.h"
+#include "hevc_tables.cuh"
+
+namespace b200 {
+
+__device__ __forceinline__ int clip3(int lo, int hi, int v) { return min(max(v, lo), hi); }
+__device__ __forceinline__ int clip8(int v) { return min(max(v, 0), 255); }
+
+// sum of absolute differences of four packed bytes, accumulated (one VABSDIFF4)
+__device__ __forceinline__ unsigned sad4_acc(unsigned a, unsigned b, unsigned acc)
+{
+  unsigned d;
+  asm("vabsdiff4.u32.u32.u32.add %0, %1, %2, %3;" : "=r"(d) : "r"(a), "r"(b), "r"(acc));
+  return d;
+}
+
+// dot product of four unsigned bytes (a) with four signed bytes (b), accumulated
+__device__ __forceinline__ int dp4a_us(unsigned a, unsigned b, int c)
+{
+  int d;
+  asm("dp4a.u32.s32 %0, %1, %2, %3;" : "=r"(d) : "r"(a), "r"(b), "r"(c));
+  return d;
+}
+
+__device__ __forceinline__ unsigned pack4(const int8_t *p)
+{
+  return (unsigned)(uint8_t)p[0] | ((unsigned)(uint8_t)p[1] << 8) | ((unsigned)(uint8_t)p[2] << 16) |
+         ((unsigned)(uint8_t)p[3] << 24);
+}
+
+// HM xGetComponentBits: exp-Golomb-like length of one mvd component
+__device__ __forceinline__ int mv_comp_bits(int v)
+{
+  unsigned t = v <= 0 ? ((unsigned)(-v) << 1) + 1 : (unsigned)v << 1;
+  return 2 * (31 - __clz(t)) + 1;
+}
+__device__ __forceinline__ unsigned mv_penalty(int lambda_q4, int mvx, int mvy)
+{
+  return (unsigned)((lambda_q4 * (mv_comp_bits(mvx) + mv_comp_bits(mvy))) >> 4);
+}
+
+// z-order index of an 8x8 unit inside its CTB <-> unit coordinates
+__device__ __forceinline__ int z_to_x(int z) { return (z & 1) | ((z >> 1) & 2) | ((z >> 2) & 4); }
+__device__ __forceinline__ int z_to_y(int z) { return ((z >> 1) & 1) | ((z >> 2) & 2) | ((z >> 3) & 4); }
+__device__ __forceinline__ int xy_to_z(int x, int y)
+{
+  return (x & 1) | ((y & 1) << 1) | ((x & 2) << 1) | ((y & 2) << 2) | ((x & 4) << 2) | ((y & 4) << 3);
+}
+
+// Load a (ws x ws) window of a plane into shared memory as bytes, edge-clamped (8.5.3.3.3.1).
+// Window pixel (wx,wy) = plane(clamp(x0+wx), clamp(y0+wy)).  x0 must be a multiple of 4 and
+// the row pitch of the window (wsw words) >= ws/4.
+__device__ __forceinline__ void load_window(const uint8_t *__restrict__ plane, int pw, int ph, int x0, int y0,
+                                            int ws, int wsw, uint32_t *s_win)
+{
+  const int words = (ws + 3) >> 2;
+  for (int i = threadIdx.x; i < ws * words; i += blockDim.x) {
+    int wy = i / words, wi = i - wy * words;
+    int y = clip3(0, ph - 1, y0 + wy), x = x0 + 4 * wi;
+    const uint8_t *row = plane + (size_t)y * pw;
+    uint32_t v;
+    if (x >= 0 && x + 3 < pw) {
+      v = __ldg((const uint32_t *)(row + x));
+    } else {
+      v = (uint32_t)row[clip3(0, pw - 1, x)] | ((uint32_t)row[clip3(0, pw - 1, x + 1)] << 8) |
+          ((uint32_t)row[clip3(0, pw - 1, x + 2)] << 16) | ((uint32_t)row[clip3(0, pw - 1, x + 3)] << 24);
+    }
+    s_win[wy * wsw + wi] = v;
+  }
+}
+
+// ---- luma motion compensation: 2 columns x 8 rows at window position (xi,yi), fractional
+// phase (fx,fy).  Separable 8-tap, rows first (8.5.3.3.3); exact for zero phases as well
+// because the zero-phase filter is {0,0,0,64,0,0,0,0}.  out[r] = pixel(col0) | pixel(col1) << 8.
+__device__ __forceinline__ void mc_luma_2x8(const uint32_t *s_win, int wsw, int xi, int yi, int fx, int fy,
+                                            unsigned out[8])
+{
+  const unsigned tl = pack4(c_luma_filter[fx]), th = pack4(c_luma_filter[fx] + 4);
+  const int x0 = xi - 3;
+  const int xw = x0 >> 2, sh = (x0 & 3) * 8;
+  int h0[15], h1[15];
+#pragma unroll
+  for (int r = 0; r < 15; r++) {
+    const uint32_t *row = s_win + (yi - 3 + r) * wsw + xw;
+    unsigned a = row[0], b = row[1], c = row[2];
+    unsigned p0 = __funnelshift_r(a, b, sh), p1 = __funnelshift_r(b, c, sh), p2 = c >> sh;
+    unsigned q0 = __funnelshift_r(p0, p1, 8), q1 = __funnelshift_r(p1, p2, 8);
+    h0[r] = dp4a_us(p0, tl, dp4a_us(p1, th, 0));
+    h1[r] = dp4a_us(q0, tl, dp4a_us(q1, th, 0));
+  }
+  int f[8];
+#pragma unroll
+  for (int t = 0; t < 8; t++) f[t] = c_luma_filter[fy][t];
+#pragma unroll
+  for (int r = 0; r < 8; r++) {
+    int v0 = 0, v1 = 0;
+#pragma unroll
+    for (int t = 0; t < 8; t++) { v0 += f[t] * h0[r + t]; v1 += f[t] * h1[r + t]; }
+    v0 = clip8(((v0 >> 6) + 32) >> 6);
+    v1 = clip8(((v1 >> 6) + 32) >> 6);
+    out[r] = (unsigned)v0 | ((unsigned)v1 << 8);
+  }
+}
+
+// ---- chroma motion compensation: 1 column x 4 rows, 4-tap, eighth-sample phases.
+__device__ __forceinline__ void mc_chroma_1x4(const uint32_t *s_win, int wsw, int xi, int yi, int fx, int fy,
+                                              unsigned out[4])
+{
+  const unsigned tp = pack4(c_chroma_filter[fx]);
+  const int x0 = xi - 1;
+  const int xw = x0 >> 2, sh = (x0 & 3) * 8;
+  int hv[7];
+#pragma unroll
+  for (int r = 0; r < 7; r++) {
+    const uint32_t *row = s_win + (yi - 1 + r) * wsw + xw;
+    hv[r] = dp4a_us(__funnelshift_r(row[0], row[1], sh), tp, 0);
+  }
+#pragma unroll
+  for (int r = 0; r < 4; r++) {
+    int v = 0;
+#pragma unroll
+    for (int t = 0; t < 4; t++) v += c_chroma_filter[fy][t] * hv[r + t];
+    out[r] = (unsigned)clip8(((v >> 6) + 32) >> 6);
+  }
+}
+
+// ---- transform / quantisation pipeline over a CTU-shaped tile held in shared memory ---------
+//
+// Geometry: the tile is T x T samples (T = 64 luma, 32 chroma), row pitch T.  unit_log2 is the
+// size of one cu-map unit in this plane (3 luma, 2 chroma).  s_org[z] is the z-index of the
+// origin unit of the CU covering unit z (0xff = outside the picture); s_log2[z] the CU size
+// (luma log2).  The transform block of every CU is the CU itself (luma) / half of it (chroma).
+//
+// Stage order (each `sync` is a __syncthreads):
+//   resid = src - pred | sync | H pass | sync | V pass + quant (+ dequant into s_a) | sync |
+//   inverse V | sync | inverse H + reconstruction
+struct TileGeom {
+  int T;            // tile width (64 / 32)
+  int tlog2;        // log2(T)
+  int unit_log2;    // 3 / 2
+  int chroma;       // 0 / 1: transform size = CU size >> chroma
+};
+
+struct TqParams {
+  int qp;           // QP of this plane
+  int is_idr;       // quantiser offset 171 (I slices) / 85
+};
+
+// dct coefficient of the N-point transform: c[k][n]
+__device__ __forceinline__ int dctc(const int8_t (*s_dct)[32], int nshift, int k, int n) { return s_dct[k << nshift][n]; }
+
+// One sample position (x,y) of the tile -> its transform block; returns false outside the picture.
+struct TbPos { int ox, oy, n, log2n, org; };
+__device__ __forceinline__ bool tb_at(const TileGeom &g, const uint8_t *s_org, const uint8_t *s_log2, int x, int y, TbPos &tb)
+{
+  int z = xy_to_z(x >> g.unit_log2, y >> g.unit_log2);
+  int o = s_org[z];
+  if (o == 0xff) return false;
+  tb.org = o;
+  tb.log2n = s_log2[o] - g.chroma;
+  tb.n = 1 << tb.log2n;
+  tb.ox = z_to_x(o) << g.unit_log2;
+  tb.oy = z_to_y(o) << g.unit_log2;
+  return true;
+}
+
+// Forward path.  s_src/s_pred: uint8 tiles.  s_a, s_b: int16 scratch tiles.  On return s_lvl
+// (aliasing s_b) holds the levels, s_a the dequantised coefficients, s_nz[org] != 0 where the
+// block has a non-zero level.  Caller must have zeroed s_nz and synchronised.
+__device__ __forceinline__ void forward_tq(const TileGeom g, const TqParams q, const uint8_t *s_src, const uint8_t *s_pred,
+                                           const uint8_t *s_org, const uint8_t *s_log2, const int8_t (*s_dct)[32],
+                                           const int8_t (*s_dctT)[32], int16_t *s_a, int16_t *s_b, int *s_nz)
+{
+  const int T = g.T, total = T * T;
+  for (int p = threadIdx.x; p < total; p += blockDim.x) s_a[p] = (int16_t)((int)s_src[p] - (int)s_pred[p]);
+  __syncthreads();
+  // horizontal pass: tmp[j][k] = (sum_i c[k][i] * resid[j][i] + rnd) >> (log2n - 1)
+  for (int p = threadIdx.x; p < total; p += blockDim.x) {
+    int y = p >> g.tlog2, x = p & (T - 1);
+    TbPos tb;
+    if (!tb_at(g, s_org, s_log2, x, y, tb)) continue;
+    int k = x - tb.ox, nshift = 5 - tb.log2n;
+    const int16_t *row = s_a + y * T + tb.ox;
+    const int kk = k << nshift;            // transposed table: lanes read consecutive bytes
+    int acc = 0;
+    for (int i = 0; i < tb.n; i++) acc += s_dctT[i][kk] * row[i];
+    int s1 = tb.log2n - 1;
+    s_b[p] = (int16_t)((acc + (1 << (s1 - 1))) >> s1);
+  }
+  __syncthreads();
+  // vertical pass + quantisation + dequantisation
+  const int qper = q.qp / 6, qrem = q.qp % 6;
+  const int scale = c_quant_scale[qrem], dscale = 16 * c_level_scale[qrem];
+  int16_t vals[16];
+  int cnt = 0;
+  for (int p = threadIdx.x; p < total; p += blockDim.x, cnt++) {
+    int y = p >> g.tlog2, x = p & (T - 1);
+    TbPos tb;
+    vals[cnt] = 0;
+    if (!tb_at(g, s_org, s_log2, x, y, tb)) continue;
+    int v = y - tb.oy, nshift = 5 - tb.log2n;
+    const int16_t *col = s_b + tb.oy * T + x;
+    const int8_t *c = s_dct[v << nshift];
+    int acc = 0;
+    for (int j = 0; j < tb.n; j++) acc += c[j] * col[j * T];
+    int s2 = tb.log2n + 6;
+    int coef = (acc + (1 << (s2 - 1))) >> s2;
+    int qbits = 14 + qper + (7 - tb.log2n);
+    unsigned add = (unsigned)(q.is_idr ? 171 : 85) << (qbits - 9);
+    unsigned a = ((unsigned)abs(coef) * (unsigned)scale + add) >> qbits;    // < 2^32: |coef| <= 2^15, scale < 2^15
+    int lvl = (int)min(a, 32767u);
+    if (coef < 0) lvl = -lvl;
+    vals[cnt] = (int16_t)lvl;
+    if (lvl) s_nz[tb.org] = 1;
+    int bd = tb.log2n + 3;
+    long long d = (((long long)lvl * dscale) << qper);
+    d = (d + (1LL << (bd - 1))) >> bd;
+    s_a[p] = (int16_t)max(-32768LL, min(32767LL, d));
+  }
+  __syncthreads();     // all reads of s_b (tmp) are done; levels may now overwrite it
+  cnt = 0;
+  for (int p = threadIdx.x; p < total; p += blockDim.x, cnt++) s_b[p] = vals[cnt];
+  __syncthreads();
+}
+
+// Inverse path: s_a holds dequantised coefficients; result: reconstructed samples written
+// to s_rec (uint8 tile).  s_t is an int16 scratch tile.  Blocks with s_nz[org]==0 copy the prediction.
+__device__ __forceinline__ void inverse_recon(const TileGeom g, const uint8_t *s_pred, const uint8_t *s_org,
+                                              const uint8_t *s_log2, const int8_t (*s_dct)[32], const int16_t *s_a,
+                                              int16_t *s_t, const int *s_nz, uint8_t *s_rec)
+{
+  const int T = g.T, total = T * T;
+  for (int p = threadIdx.x; p < total; p += blockDim.x) {
+    int y = p >> g.tlog2, x = p & (T - 1);
+    TbPos tb;
+    if (!tb_at(g, s_org, s_log2, x, y, tb) || !s_nz[tb.org]) continue;
+    int yy = y - tb.oy, nshift = 5 - tb.log2n;
+    const int16_t *col = s_a + tb.oy * T + x;
+    int acc = 0;
+    for (int k = 0; k < tb.n; k++) acc += s_dct[k << nshift][yy] * col[k * T];
+    s_t[p] = (int16_t)clip3(-32768, 32767, (acc + 64) >> 7);
+  }
+  __syncthreads();
+  for (int p = threadIdx.x; p < total; p += blockDim.x) {
+    int y = p >> g.tlog2, x = p & (T - 1);
+    TbPos tb;
+    if (!tb_at(g, s_org, s_log2, x, y, tb)) continue;
+    int pr = s_pred[p];
+    if (s_nz[tb.org]) {
+      int xx = x - tb.ox, nshift = 5 - tb.log2n;
+      const int16_t *row = s_t + y * T + tb.ox;
+      int acc = 0;
+      for (int k = 0; k < tb.n; k++) acc += s_dct[k << nshift][xx] * row[k];
+      pr = clip8(pr + clip3(-32768, 32767, (acc + 2048) >> 12));
+    }
+    s_rec[p] = (uint8_t)pr;
+  }
+  __syncthreads();
+}
+
+}  // namespace b200

@@ -1,0 +1,424 @@
+// P-picture kernels of the B200 HEVC encoder (sm_100a).
+//
+//   k_me_ctu        one CTA per CTU: exhaustive full-sample search at 8x8 granularity with the
+//                   SADs summed to 16x16 / 32x32 in registers (warp shuffles), bottom-up
+//                   partition decision, half- then quarter-sample refinement.  Source block in
+//                   registers, reference window staged in shared memory, SAD by VABSDIFF4,
+//                   interpolation by DP4A.  Replaces Kvazaar's search_inter / kvz_sad /
+//                   kvz_filter_inter path.
+//   k_inter_recon   one CTA per CTU: motion compensation (luma 8-tap, chroma 4-tap), residual,
+//                   forward DCT, quantisation, dequantisation, inverse DCT, reconstruction
+//                   (rows K3, K5, K6).
+//   k_inter_modes   one thread per 8x8 unit: merge candidates, skip decision, AMVP predictor
+//                   choice from the final motion field (row K10) -- keeps the entropy coder
+//                   free of any decision logic.
+#include "hevc_device.cuh"
+#include "hevc_kernels.h"
+
+namespace b200 {
+
+namespace {
+
+constexpr int kThreads = 256;
+
+__device__ __forceinline__ int window_margin(int range) { return (range + 4 + 3) & ~3; }
+
+struct MeShared {
+  unsigned key8[64], key16[16], key32[4];
+  unsigned eff16[16];
+  uint8_t use16[16], use32[4];
+  uint8_t org[64], log2[64];       // per unit (z-order): origin unit of its CU, CU log2 size
+  short mvx[64], mvy[64];          // per origin unit: best mv so far (quarter samples)
+  short cmx[64], cmy[64];          // per origin unit: centre of the current refinement step
+  unsigned best[64];               // per origin unit: best cost so far
+  unsigned acc[64];                // per origin unit: SAD accumulator of the candidate in flight
+};
+
+__global__ void __launch_bounds__(kThreads)
+k_me_ctu(FrameParams fp, const uint8_t *__restrict__ src, const uint8_t *__restrict__ ref, CuInfo *__restrict__ cu)
+{
+  extern __shared__ uint32_t s_dyn[];
+  __shared__ MeShared sh;
+  const int R = fp.search_range;
+  const int M = window_margin(R);
+  const int WS = kCtb + 2 * M, WSW = (WS >> 2) + 1;
+  uint32_t *s_ref = s_dyn;                     // WS rows x WSW words
+  uint32_t *s_src = s_dyn + WS * WSW;          // 64 rows x 16 words
+  const int ctb_x = blockIdx.x % fp.ctb_cols, ctb_y = blockIdx.x / fp.ctb_cols;
+  const int cx = ctb_x * kCtb, cy = ctb_y * kCtb;
+  const int t = threadIdx.x;
+
+  load_window(ref, fp.w, fp.h, cx - M, cy - M, WS, WSW, s_ref);
+  for (int i = t; i < 64 * 16; i += kThreads) {
+    int y = cy + (i >> 4), x = cx + 4 * (i & 15);
+    s_src[i] = (y < fp.h && x < fp.w) ? __ldg((const uint32_t *)(src + (size_t)y * fp.w + x)) : 0u;
+  }
+  if (t < 64) { sh.key8[t] = 0xffffffffu; sh.acc[t] = 0; }
+  if (t < 16) sh.key16[t] = 0xffffffffu;
+  if (t < 4) sh.key32[t] = 0xffffffffu;
+  __syncthreads();
+
+  // ---- full-sample search: lane <-> 8x8 block (z-order), warp pair <-> candidate subset ----
+  {
+    const int lane = t & 31, wid = t >> 5;
+    const int z = ((wid & 1) << 5) | lane;          // z-order index of this thread's 8x8 block
+    const int q = wid >> 1;                         // candidates q, q+4, q+8, ...
+    const int bx = z_to_x(z), by = z_to_y(z);
+    const bool v8 = cx + 8 * bx < fp.w && cy + 8 * by < fp.h;
+    const bool v16 = cx + 16 * (bx >> 1) + 16 <= fp.w && cy + 16 * (by >> 1) + 16 <= fp.h;
+    const bool v32 = cx + 32 * (bx >> 2) + 32 <= fp.w && cy + 32 * (by >> 2) + 32 <= fp.h;
+    uint32_t s[16];
+#pragma unroll
+    for (int r = 0; r < 8; r++) { s[2 * r] = s_src[(by * 8 + r) * 16 + bx * 2]; s[2 * r + 1] = s_src[(by * 8 + r) * 16 + bx * 2 + 1]; }
+    const int side = 2 * R + 1, ncand = side * side;
+    unsigned k8 = 0xffffffffu, k16 = 0xffffffffu, k32 = 0xffffffffu;
+    for (int c = q; c < ncand; c += 4) {
+      int dy = c / side - R, dx = c - (dy + R) * side - R;
+      unsigned pen = mv_penalty(fp.lambda_q4, dx * 4, dy * 4);
+      int x = M + bx * 8 + dx, xw = x >> 2, shf = (x & 3) * 8;
+      const uint32_t *row = s_ref + (M + by * 8 + dy) * WSW + xw;
+      unsigned sad = 0;
+#pragma unroll
+      for (int r = 0; r < 8; r++) {
+        unsigned a = row[0], b = row[1], cc = row[2];
+        sad = sad4_acc(s[2 * r], __funnelshift_r(a, b, shf), sad);
+        sad = sad4_acc(s[2 * r + 1], __funnelshift_r(b, cc, shf), sad);
+        row += WSW;
+      }
+      if (!v8) sad = 0;
+      unsigned s16 = sad + __shfl_xor_sync(0xffffffffu, sad, 1);
+      s16 += __shfl_xor_sync(0xffffffffu, s16, 2);
+      unsigned s32 = s16 + __shfl_xor_sync(0xffffffffu, s16, 4);
+      s32 += __shfl_xor_sync(0xffffffffu, s32, 8);
+      if (v8) k8 = min(k8, ((sad + pen) << 13) | (unsigned)c);
+      if (v16) k16 = min(k16, ((s16 + pen) << 13) | (unsigned)c);
+      if (v32) k32 = min(k32, ((s32 + pen) << 13) | (unsigned)c);
+    }
+    atomicMin(&sh.key8[z], k8);
+    if ((lane & 3) == 0) atomicMin(&sh.key16[z >> 2], k16);
+    if ((lane & 15) == 0) atomicMin(&sh.key32[z >> 4], k32);
+  }
+  __syncthreads();
+
+  // ---- bottom-up partition decision ----
+  const unsigned ovh = (unsigned)((fp.lambda_q4 * kCuOverheadBits) >> 4);
+  if (t < 16) {
+    unsigned sum8 = 0;
+    for (int i = 0; i < 4; i++) {
+      unsigned k = sh.key8[4 * t + i];
+      if (k != 0xffffffffu) sum8 += (k >> 13) + ovh;
+    }
+    unsigned k16 = sh.key16[t];
+    bool use = k16 != 0xffffffffu && (k16 >> 13) + ovh <= sum8;
+    sh.use16[t] = use;
+    sh.eff16[t] = use ? (k16 >> 13) + ovh : sum8;
+  }
+  __syncthreads();
+  if (t < 4) {
+    unsigned sum16 = sh.eff16[4 * t] + sh.eff16[4 * t + 1] + sh.eff16[4 * t + 2] + sh.eff16[4 * t + 3];
+    unsigned k32 = sh.key32[t];
+    sh.use32[t] = k32 != 0xffffffffu && (k32 >> 13) + ovh <= sum16;
+  }
+  __syncthreads();
+  if (t < 64) {
+    unsigned key;
+    int org, l2;
+    if (sh.use32[t >> 4]) { key = sh.key32[t >> 4]; org = t & ~15; l2 = 5; }
+    else if (sh.use16[t >> 2]) { key = sh.key16[t >> 2]; org = t & ~3; l2 = 4; }
+    else { key = sh.key8[t]; org = t; l2 = 3; }
+    if (key == 0xffffffffu) { org = 0xff; l2 = 0; }
+    sh.org[t] = (uint8_t)org;
+    sh.log2[t] = (uint8_t)l2;
+    if (org == t) {
+      const int side = 2 * R + 1;
+      int c = (int)(key & 8191u);
+      int dy = c / side - R, dx = c - (dy + R) * side - R;
+      sh.mvx[t] = (short)(dx * 4); sh.mvy[t] = (short)(dy * 4);
+      sh.cmx[t] = (short)(dx * 4); sh.cmy[t] = (short)(dy * 4);
+      sh.best[t] = key >> 13;                    // SAD at the full-sample mv + its mv penalty
+    }
+  }
+  __syncthreads();
+
+  // ---- half- then quarter-sample refinement: 4 threads per 8x8 unit, 2 columns x 8 rows each ----
+  {
+    const int z = t >> 2, qc = t & 3;
+    const int ux = z_to_x(z), uy = z_to_y(z);
+    const int org = sh.org[z];
+    const uint8_t *srcb = (const uint8_t *)s_src;
+    for (int step = 2; step >= 1; step--) {
+      for (int k = 0; k < 8; k++) {
+        const int ox = (k < 3 ? k - 1 : (k == 3 ? -1 : (k == 4 ? 1 : k - 6)));
+        const int oy = k < 3 ? -1 : (k < 5 ? 0 : 1);
+        if (org != 0xff) {
+          int mx = sh.cmx[org] + ox * step, my = sh.cmy[org] + oy * step;
+          unsigned pr[8];
+          mc_luma_2x8(s_ref, WSW, M + ux * 8 + 2 * qc + (mx >> 2), M + uy * 8 + (my >> 2), mx & 3, my & 3, pr);
+          unsigned sad = 0;
+#pragma unroll
+          for (int r = 0; r < 8; r++) {
+            const uint8_t *sp = srcb + (uy * 8 + r) * 64 + ux * 8 + 2 * qc;
+            unsigned sv = (unsigned)sp[0] | ((unsigned)sp[1] << 8);
+            sad = sad4_acc(sv, pr[r], sad);
+          }
+          atomicAdd(&sh.acc[org], sad);
+        }
+        __syncthreads();
+        if (t < 64 && sh.org[t] == t) {
+          int mx = sh.cmx[t] + ox * step, my = sh.cmy[t] + oy * step;
+          unsigned cost = sh.acc[t] + mv_penalty(fp.lambda_q4, mx, my);
+          if (cost < sh.best[t]) { sh.best[t] = cost; sh.mvx[t] = (short)mx; sh.mvy[t] = (short)my; }
+          sh.acc[t] = 0;
+        }
+        __syncthreads();
+      }
+      if (t < 64 && sh.org[t] == t) { sh.cmx[t] = sh.mvx[t]; sh.cmy[t] = sh.mvy[t]; }
+      __syncthreads();
+    }
+  }
+
+  // ---- cu map ----
+  if (t < 64) {
+    int ux = z_to_x(t), uy = z_to_y(t);
+    int x8 = (cx >> 3) + ux, y8 = (cy >> 3) + uy;
+    int org = sh.org[t];
+    if (org != 0xff && x8 < fp.w8 && y8 < fp.h8) {
+      CuInfo ci;
+      ci.mvx = sh.mvx[org]; ci.mvy = sh.mvy[org];
+      ci.log2_size = sh.log2[t]; ci.pred_mode = 0; ci.intra_mode = 0; ci.cbf = 0;
+      ci.skip = 0; ci.merge_idx = 0xff; ci.mvp_idx = 0; ci.pad = 0;
+      cu[(size_t)y8 * fp.w8 + x8] = ci;
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+
+struct ReconShared {
+  uint8_t org[64], log2[64];
+  short mvx[64], mvy[64];
+  int nz[64];
+  uint8_t cbf[64];
+  int8_t dct[32][32], dctT[32][32];
+};
+
+__device__ __forceinline__ int chroma_margin(int range) { return (((range + 1) >> 1) + 2 + 3) & ~3; }
+
+__global__ void __launch_bounds__(kThreads)
+k_inter_recon(FrameParams fp, const uint8_t *__restrict__ src, const uint8_t *__restrict__ ref,
+              uint8_t *__restrict__ rec, int16_t *__restrict__ levels, CuInfo *__restrict__ cu)
+{
+  extern __shared__ uint32_t s_dyn[];
+  __shared__ ReconShared sh;
+  const int R = fp.search_range;
+  const int M = window_margin(R), WS = kCtb + 2 * M, WSW = (WS >> 2) + 1;
+  uint32_t *s_ref = s_dyn;                                   // luma window; reused for chroma windows
+  uint8_t *s_src = (uint8_t *)(s_dyn + WS * WSW);            // 64 x 64
+  uint8_t *s_pred = s_src + 4096;                            // 64 x 64
+  uint8_t *s_rec = s_pred + 4096;                            // 64 x 64
+  int16_t *s_a = (int16_t *)(s_rec + 4096);                  // 64 x 64
+  int16_t *s_b = s_a + 4096;                                 // 64 x 64
+  const int ctb_x = blockIdx.x % fp.ctb_cols, ctb_y = blockIdx.x / fp.ctb_cols;
+  const int cx = ctb_x * kCtb, cy = ctb_y * kCtb;
+  const int t = threadIdx.x;
+  const size_t ysz = (size_t)fp.w * fp.h;
+
+  for (int i = t; i < 1024; i += kThreads) {
+    ((int8_t *)sh.dct)[i] = c_dct32[i >> 5][i & 31];
+    ((int8_t *)sh.dctT)[i] = c_dct32[i & 31][i >> 5];
+  }
+  if (t < 64) {
+    int ux = z_to_x(t), uy = z_to_y(t);
+    int x8 = (cx >> 3) + ux, y8 = (cy >> 3) + uy;
+    int org = 0xff, l2 = 0;
+    if (x8 < fp.w8 && y8 < fp.h8) {
+      CuInfo ci = cu[(size_t)y8 * fp.w8 + x8];
+      l2 = ci.log2_size;
+      int n8 = 1 << (l2 - 3);
+      org = xy_to_z(ux & ~(n8 - 1), uy & ~(n8 - 1));
+      sh.mvx[t] = ci.mvx; sh.mvy[t] = ci.mvy;
+    }
+    sh.org[t] = (uint8_t)org; sh.log2[t] = (uint8_t)l2;
+    sh.cbf[t] = 0;
+  }
+  __syncthreads();
+
+  for (int c = 0; c < 3; c++) {
+    const int cs = c ? 1 : 0;                                // chroma shift
+    const int T = kCtb >> cs, pw = fp.w >> cs, ph = fp.h >> cs;
+    const uint8_t *psrc = src + (c == 0 ? 0 : ysz + (c == 2 ? ysz / 4 : 0));
+    const uint8_t *pref = ref + (c == 0 ? 0 : ysz + (c == 2 ? ysz / 4 : 0));
+    uint8_t *prec = rec + (c == 0 ? 0 : ysz + (c == 2 ? ysz / 4 : 0));
+    int16_t *plev = levels + (c == 0 ? 0 : ysz + (c == 2 ? ysz / 4 : 0));
+    const int Mc = c ? chroma_margin(R) : M;
+    const int ws = T + 2 * Mc, wsw = (ws >> 2) + 1;
+    const int px0 = cx >> cs, py0 = cy >> cs;
+    load_window(pref, pw, ph, px0 - Mc, py0 - Mc, ws, wsw, s_ref);
+    for (int i = t; i < T * T / 4; i += kThreads) {
+      int y = i / (T / 4), xw = i - y * (T / 4);
+      int gy = py0 + y, gx = px0 + 4 * xw;
+      ((uint32_t *)s_src)[i] = (gy < ph && gx < pw) ? __ldg((const uint32_t *)(psrc + (size_t)gy * pw + gx)) : 0u;
+    }
+    if (t < 64) sh.nz[t] = 0;
+    __syncthreads();
+    // motion compensation: 4 threads per unit
+    {
+      const int z = t >> 2, qc = t & 3;
+      const int ux = z_to_x(z), uy = z_to_y(z);
+      const int org = sh.org[z];
+      if (org != 0xff) {
+        int mx = sh.mvx[z], my = sh.mvy[z];
+        if (c == 0) {
+          unsigned pr[8];
+          mc_luma_2x8(s_ref, wsw, Mc + ux * 8 + 2 * qc + (mx >> 2), Mc + uy * 8 + (my >> 2), mx & 3, my & 3, pr);
+#pragma unroll
+          for (int r = 0; r < 8; r++) {
+            uint8_t *d = s_pred + (uy * 8 + r) * 64 + ux * 8 + 2 * qc;
+            d[0] = (uint8_t)(pr[r] & 0xff); d[1] = (uint8_t)(pr[r] >> 8);
+          }
+        } else {
+          unsigned pr[4];
+          mc_chroma_1x4(s_ref, wsw, Mc + ux * 4 + qc + (mx >> 3), Mc + uy * 4 + (my >> 3), mx & 7, my & 7, pr);
+#pragma unroll
+          for (int r = 0; r < 4; r++) s_pred[(uy * 4 + r) * 32 + ux * 4 + qc] = (uint8_t)pr[r];
+        }
+      }
+    }
+    __syncthreads();
+    TileGeom g{T, c ? 5 : 6, c ? 2 : 3, cs};
+    TqParams q{c ? fp.qp_c : fp.qp, fp.is_idr};
+    forward_tq(g, q, s_src, s_pred, sh.org, sh.log2, sh.dct, sh.dctT, s_a, s_b, sh.nz);
+    // levels (s_b) -> HBM, 4 per thread; s_b then becomes the scratch tile of the inverse path
+    for (int i = t; i < T * T / 4; i += kThreads) {
+      int y = i / (T / 4), xw = i - y * (T / 4);
+      int gy = py0 + y, gx = px0 + 4 * xw;
+      if (gy < ph && gx < pw) *(uint2 *)(plev + (size_t)gy * pw + gx) = ((const uint2 *)s_b)[i];
+    }
+    __syncthreads();
+    inverse_recon(g, s_pred, sh.org, sh.log2, sh.dct, s_a, s_b, sh.nz, s_rec);
+    for (int i = t; i < T * T / 4; i += kThreads) {
+      int y = i / (T / 4), xw = i - y * (T / 4);
+      int gy = py0 + y, gx = px0 + 4 * xw;
+      if (gy < ph && gx < pw) *(uint32_t *)(prec + (size_t)gy * pw + gx) = ((const uint32_t *)s_rec)[i];
+    }
+    if (t < 64 && sh.org[t] == t && sh.nz[t]) sh.cbf[t] |= (uint8_t)(1 << c);
+    __syncthreads();
+  }
+  if (t < 64) {
+    int ux = z_to_x(t), uy = z_to_y(t);
+    int x8 = (cx >> 3) + ux, y8 = (cy >> 3) + uy;
+    int org = sh.org[t];
+    if (org != 0xff) cu[(size_t)y8 * fp.w8 + x8].cbf = sh.cbf[org];
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// merge / skip / AMVP decisions from the final motion field (H.265 8.5.3.2.2-8.5.3.2.7, P slice,
+// one reference picture, no temporal candidates).  One thread per 8x8 unit; every unit of a CU
+// computes the CU's result and writes its own entry.
+
+__device__ __forceinline__ unsigned coding_order(const FrameParams &fp, int x, int y)
+{
+  return (unsigned)((y >> kCtbLog2) * fp.ctb_cols + (x >> kCtbLog2)) * 64u + (unsigned)xy_to_z((x >> 3) & 7, (y >> 3) & 7);
+}
+
+struct Nb { bool ok; int mvx, mvy; };
+__device__ __forceinline__ Nb inter_nb(const FrameParams &fp, const CuInfo *cu, unsigned cur_order, int xn, int yn)
+{
+  Nb n{false, 0, 0};
+  if (xn < 0 || yn < 0 || xn >= fp.w || yn >= fp.h) return n;
+  if (coding_order(fp, xn, yn) >= cur_order) return n;
+  const CuInfo *c = &cu[(size_t)(yn >> 3) * fp.w8 + (xn >> 3)];
+  if (c->pred_mode != 0) return n;
+  n.ok = true; n.mvx = c->mvx; n.mvy = c->mvy;
+  return n;
+}
+__device__ __forceinline__ bool same_mv(const Nb &a, const Nb &b) { return a.mvx == b.mvx && a.mvy == b.mvy; }
+
+__global__ void __launch_bounds__(kThreads)
+k_inter_modes(FrameParams fp, CuInfo *__restrict__ cu)
+{
+  int u = blockIdx.x * blockDim.x + threadIdx.x;
+  if (u >= fp.w8 * fp.h8) return;
+  int x8 = u % fp.w8, y8 = u / fp.w8;
+  CuInfo me = cu[u];
+  if (me.pred_mode != 0 || me.log2_size < 3) return;
+  const int n = 1 << me.log2_size;
+  const int x0 = (x8 * 8) & ~(n - 1), y0 = (y8 * 8) & ~(n - 1);
+  const unsigned cur = coding_order(fp, x0, y0);
+  Nb a1 = inter_nb(fp, cu, cur, x0 - 1, y0 + n - 1);
+  Nb b1 = inter_nb(fp, cu, cur, x0 + n - 1, y0 - 1);
+  Nb b0 = inter_nb(fp, cu, cur, x0 + n, y0 - 1);
+  Nb a0 = inter_nb(fp, cu, cur, x0 - 1, y0 + n);
+  Nb b2 = inter_nb(fp, cu, cur, x0 - 1, y0 - 1);
+  // merge list with the standard's pairwise pruning (comparisons use availability, not the pruned flags)
+  int mvx[kMaxMerge], mvy[kMaxMerge], cnt = 0;
+  bool use_b1 = b1.ok && !(a1.ok && same_mv(b1, a1));
+  bool use_b0 = b0.ok && !(b1.ok && same_mv(b0, b1));
+  bool use_a0 = a0.ok && !(a1.ok && same_mv(a0, a1));
+  bool use_b2 = b2.ok && !(a1.ok && same_mv(b2, a1)) && !(b1.ok && same_mv(b2, b1));
+  if (a1.ok) { mvx[cnt] = a1.mvx; mvy[cnt++] = a1.mvy; }
+  if (use_b1) { mvx[cnt] = b1.mvx; mvy[cnt++] = b1.mvy; }
+  if (use_b0) { mvx[cnt] = b0.mvx; mvy[cnt++] = b0.mvy; }
+  if (use_a0) { mvx[cnt] = a0.mvx; mvy[cnt++] = a0.mvy; }
+  if (use_b2 && cnt < 4) { mvx[cnt] = b2.mvx; mvy[cnt++] = b2.mvy; }
+  while (cnt < kMaxMerge) { mvx[cnt] = 0; mvy[cnt++] = 0; }
+  int midx = -1;
+  for (int i = kMaxMerge - 1; i >= 0; i--)
+    if (mvx[i] == me.mvx && mvy[i] == me.mvy) midx = i;
+  me.merge_idx = (uint8_t)(midx >= 0 ? midx : 0xff);
+  me.skip = (uint8_t)(midx >= 0 && me.cbf == 0);
+  me.mvp_idx = 0;
+  if (midx < 0) {
+    Nb a = a0.ok ? a0 : a1;
+    Nb b = b0.ok ? b0 : (b1.ok ? b1 : b2);
+    int cx[2], cy[2], k = 0;
+    if (a.ok) { cx[k] = a.mvx; cy[k++] = a.mvy; }
+    if (b.ok && !(a.ok && same_mv(a, b))) { cx[k] = b.mvx; cy[k++] = b.mvy; }
+    while (k < 2) { cx[k] = 0; cy[k++] = 0; }
+    int bits0 = mv_comp_bits(me.mvx - cx[0]) + mv_comp_bits(me.mvy - cy[0]);
+    int bits1 = mv_comp_bits(me.mvx - cx[1]) + mv_comp_bits(me.mvy - cy[1]);
+    me.mvp_idx = (uint8_t)(bits1 < bits0);
+    // the predictor itself is re-derived by the entropy coder; stash the mvd for it instead
+  }
+  cu[u] = me;
+}
+
+}  // namespace
+
+static size_t me_smem(int range)
+{
+  int M = (range + 4 + 3) & ~3, WS = kCtb + 2 * M, WSW = (WS >> 2) + 1;
+  return (size_t)(WS * WSW + 64 * 16) * 4;
+}
+static size_t recon_smem(int range)
+{
+  int M = (range + 4 + 3) & ~3, WS = kCtb + 2 * M, WSW = (WS >> 2) + 1;
+  return (size_t)WS * WSW * 4 + 3 * 4096 + 2 * 4096 * 2;
+}
+
+cudaError_t launch_inter_me(const FrameParams &fp, const uint8_t *src, const uint8_t *ref, CuInfo *cu, cudaStream_t s)
+{
+  size_t sm = me_smem(fp.search_range);
+  cudaFuncSetAttribute(k_me_ctu, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm);
+  k_me_ctu<<<fp.ctb_cols * fp.ctb_rows, kThreads, sm, s>>>(fp, src, ref, cu);
+  return cudaGetLastError();
+}
+
+cudaError_t launch_inter_recon(const FrameParams &fp, const uint8_t *src, const uint8_t *ref, uint8_t *rec,
+                               int16_t *levels, CuInfo *cu, cudaStream_t s)
+{
+  size_t sm = recon_smem(fp.search_range);
+  cudaFuncSetAttribute(k_inter_recon, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm);
+  k_inter_recon<<<fp.ctb_cols * fp.ctb_rows, kThreads, sm, s>>>(fp, src, ref, rec, levels, cu);
+  return cudaGetLastError();
+}
+
+cudaError_t launch_inter_modes(const FrameParams &fp, CuInfo *cu, cudaStream_t s)
+{
+  int units = fp.w8 * fp.h8;
+  k_inter_modes<<<(units + kThreads - 1) / kThreads, kThreads, 0, s>>>(fp, cu);
+  return cudaGetLastError();
+}
+
+}  // namespace b200

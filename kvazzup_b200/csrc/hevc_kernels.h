@@ -1,0 +1,30 @@
+// Launchers of the HEVC kernels (internal header).  Every launcher enqueues on `s` and returns
+// the launch status; each counts as one kernel launch for b200_launch_count().
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "hevc_common.h"
+
+namespace b200 {
+
+// P pictures
+cudaError_t launch_inter_me(const FrameParams &fp, const uint8_t *src, const uint8_t *ref, CuInfo *cu, cudaStream_t s);
+cudaError_t launch_inter_recon(const FrameParams &fp, const uint8_t *src, const uint8_t *ref, uint8_t *rec,
+                               int16_t *levels, CuInfo *cu, cudaStream_t s);
+cudaError_t launch_inter_modes(const FrameParams &fp, CuInfo *cu, cudaStream_t s);
+
+// I pictures: wavefront over CTUs. `progress` = ctb_rows ints, `ticket` = 1 int, both zeroed by the launcher.
+cudaError_t launch_intra_frame(const FrameParams &fp, const uint8_t *src, uint8_t *rec, int16_t *levels, CuInfo *cu,
+                               int *progress, int *ticket, cudaStream_t s);
+
+// in-loop deblocking, in place on `rec` (vertical edges of the whole picture, then horizontal)
+cudaError_t launch_deblock(const FrameParams &fp, uint8_t *rec, const CuInfo *cu, cudaStream_t s);
+
+// CABAC: one substream per CTU row.  rows[r*row_cap ..] receives the escaped bytes of row r,
+// row_len[r] its length (0xffffffff on overflow).  sync = ctb_rows * (CTX_COUNT + pad) bytes + flags.
+cudaError_t launch_cabac(const FrameParams &fp, const CuInfo *cu, const int16_t *levels, uint8_t *rows,
+                         uint32_t row_cap, uint32_t *row_len, uint8_t *sync_ctx, int *sync_flag,
+                         unsigned long long *bins, cudaStream_t s);
+
+}  // namespace b200

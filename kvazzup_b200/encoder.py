@@ -1,0 +1,80 @@
+"""Python handle on the B200 HEVC encoder engine (include/b200_hevc.h).
+
+The reference-shaped boundary is kvz_api (kvazzup_b200/kvazaar.py); this thinner wrapper is what the
+parity tests and the benchmark use to keep frames in HBM and to read intermediate state.
+"""
+from __future__ import annotations
+
+import ctypes as C
+
+import numpy as np
+
+from .capi import B200Error, lib
+
+CU_DTYPE = np.dtype([("mvx", "<i2"), ("mvy", "<i2"), ("log2_size", "u1"), ("pred_mode", "u1"),
+                     ("intra_mode", "u1"), ("cbf", "u1"), ("skip", "u1"), ("merge_idx", "u1"),
+                     ("mvp_idx", "u1"), ("pad", "u1")])
+
+
+class GpuEncoder:
+    def __init__(self, w, h, qp=32, intra_period=64, search_range=8, deblock=1, debug=0):
+        self.l = lib()
+        self.w, self.h = w, h
+        self.h_enc = self.l.b200_enc_open(w, h, qp, intra_period, search_range, deblock, debug)
+        if not self.h_enc:
+            raise B200Error("b200_enc_open failed: " + self.l.b200_last_error().decode())
+        self.out = np.empty(w * h * 3 + 65536, np.uint8)
+
+    def _ret(self, n):
+        if n < 0:
+            raise B200Error(f"encode failed ({n}): " + self.l.b200_last_error().decode())
+        return self.out[:n].tobytes()
+
+    def encode(self, i420: np.ndarray) -> bytes:
+        assert i420.dtype == np.uint8 and i420.size == self.w * self.h * 3 // 2
+        f = np.ascontiguousarray(i420)
+        return self._ret(self.l.b200_enc_encode(self.h_enc, C.c_void_p(f.ctypes.data), C.c_void_p(self.out.ctypes.data), self.out.size))
+
+    def encode_dev(self, d_i420) -> bytes:
+        return self._ret(self.l.b200_enc_encode_dev(self.h_enc, C.c_void_p(d_i420.data_ptr()), C.c_void_p(self.out.ctypes.data), self.out.size))
+
+    def _read(self, what, dtype, count):
+        a = np.empty(count, dtype)
+        rc = self.l.b200_enc_debug_read(self.h_enc, what, C.c_void_p(a.ctypes.data), a.nbytes)
+        if rc != 0:
+            raise B200Error(f"debug_read({what}) failed: " + self.l.b200_last_error().decode())
+        return a
+
+    def recon(self):
+        return self._read(0, np.uint8, self.w * self.h * 3 // 2)
+
+    def recon_predeblock(self):
+        return self._read(1, np.uint8, self.w * self.h * 3 // 2)
+
+    def cu_map(self):
+        return self._read(2, CU_DTYPE, (self.w // 8) * (self.h // 8))
+
+    def levels(self):
+        return self._read(3, np.int16, self.w * self.h * 3 // 2)
+
+    def set_reference(self, i420: np.ndarray):
+        f = np.ascontiguousarray(i420)
+        if self.l.b200_enc_debug_set_reference(self.h_enc, C.c_void_p(f.ctypes.data)) != 0:
+            raise B200Error("set_reference failed")
+
+    def last_was_idr(self):
+        return bool(self.l.b200_enc_last_was_idr(self.h_enc))
+
+    def bins(self):
+        return int(self.l.b200_enc_last_bins(self.h_enc))
+
+    def close(self):
+        if self.h_enc:
+            self.l.b200_enc_close(self.h_enc)
+            self.h_enc = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
