@@ -19,13 +19,23 @@ extern "C" {
 /* Encoder: constant QP, low-delay P (each picture references the previous reconstruction),
  * IDR every intra_period pictures (0 = first only), one slice, WPP substreams.
  * width/height multiples of 8 (reference requirement: camerafilter.cpp:330-331).
+ * depth = pictures in flight (Kvazaar's owf + 1): with depth > 1 the access unit of picture n is
+ * returned by the call that submits picture n + depth - 1 (0 = nothing ready yet) and the tail is
+ * drained with b200_enc_flush(), exactly like kvz_api's encoder_encode(pic = NULL).
  * Returns NULL on error (see b200_last_error()). */
-void *b200_enc_open(int width, int height, int qp, int intra_period, int search_range, int deblock, int debug);
+void *b200_enc_open(int width, int height, int qp, int intra_period, int search_range, int deblock, int debug,
+                    int depth);
 void  b200_enc_close(void *enc);
 /* Encode one packed I420 picture from host / device memory; writes one Annex-B access unit
  * (VPS+SPS+PPS precede every IDR).  Returns its size, or <0 (-needed when cap is short). */
 int   b200_enc_encode(void *enc, const uint8_t *i420, uint8_t *out, int cap);
 int   b200_enc_encode_dev(void *enc, const uint8_t *d_i420, uint8_t *out, int cap);
+int   b200_enc_flush(void *enc, uint8_t *out, int cap);   /* next pending access unit, 0 when drained */
+int   b200_enc_pending(void *enc);
+/* Per-kernel device time measured with CUDA events on the launching stream.  Kernel ids:
+ * 0 intra, 1 motion search, 2 inter reconstruction, 3 merge/skip modes, 4 deblocking, 5 CABAC, 6 pack. */
+int   b200_enc_set_profile(void *enc, int on);
+int   b200_enc_get_profile(void *enc, double *ms, unsigned long long *count, int n);
 int   b200_enc_last_was_idr(void *enc);
 unsigned long long b200_enc_last_bins(void *enc);
 

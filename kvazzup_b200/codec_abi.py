@@ -7,7 +7,11 @@ v = C.c_void_p
 i = C.c_int
 
 SIGNATURES: dict = {
-    "b200_enc_open": (v, [i, i, i, i, i, i, i]),
+    "b200_enc_open": (v, [i, i, i, i, i, i, i, i]),
+    "b200_enc_flush": (i, [v, v, i]),
+    "b200_enc_pending": (i, [v]),
+    "b200_enc_set_profile": (i, [v, i]),
+    "b200_enc_get_profile": (i, [v, v, v, i]),
     "b200_enc_close": (None, [v]),
     "b200_enc_encode": (i, [v, v, v, i]),
     "b200_enc_encode_dev": (i, [v, v, v, i]),

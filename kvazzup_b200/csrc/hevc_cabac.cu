@@ -545,7 +545,53 @@ k_cabac_rows(FrameParams fp, const CuInfo *__restrict__ cu, const int16_t *__res
   }
 }
 
+// Gather the substreams into one contiguous buffer (normally mapped pinned host memory, so the
+// bytes cross PCIe exactly once and the host needs a single event wait per picture).
+// hdr[0] = total bytes, hdr[1..rows] = row lengths (0xffffffff marks an overflowed row).
+__global__ void __launch_bounds__(128)
+k_pack_rows(int rows, const uint8_t *__restrict__ src, uint32_t row_cap, const uint32_t *__restrict__ row_len,
+            uint8_t *dst, uint32_t dst_cap, uint32_t *hdr)
+{
+  __shared__ uint32_t s_off, s_len, s_total;
+  const int r = blockIdx.x;
+  if (threadIdx.x == 0) {
+    uint32_t off = 0, total = 0;
+    bool bad = false;
+    for (int i = 0; i < rows; i++) {
+      uint32_t l = row_len[i];
+      if (l == 0xffffffffu) { bad = true; l = 0; }
+      if (i < r) off += l;
+      total += l;
+    }
+    if (bad || total > dst_cap) total = 0xffffffffu;
+    s_off = off; s_len = row_len[r] == 0xffffffffu ? 0 : row_len[r]; s_total = total;
+    if (r == 0) hdr[0] = total;
+    hdr[1 + r] = row_len[r];
+  }
+  __syncthreads();
+  if (s_total == 0xffffffffu) return;
+  const uint8_t *s = src + (size_t)r * row_cap;
+  uint8_t *d = dst + s_off;
+  const uint32_t n = s_len;
+  // align the destination to 4 bytes, then move words (source alignment handled by byte gathers)
+  uint32_t head = min(n, (uint32_t)((4 - ((uintptr_t)d & 3)) & 3));
+  for (uint32_t i = threadIdx.x; i < head; i += blockDim.x) d[i] = s[i];
+  const uint32_t words = (n - head) >> 2;
+  for (uint32_t i = threadIdx.x; i < words; i += blockDim.x) {
+    const uint8_t *q = s + head + 4 * i;
+    ((uint32_t *)(d + head))[i] = (uint32_t)q[0] | ((uint32_t)q[1] << 8) | ((uint32_t)q[2] << 16) | ((uint32_t)q[3] << 24);
+  }
+  for (uint32_t i = head + 4 * words + threadIdx.x; i < n; i += blockDim.x) d[i] = s[i];
+}
+
 }  // namespace
+
+cudaError_t launch_pack_rows(int rows, const uint8_t *src, uint32_t row_cap, const uint32_t *row_len, uint8_t *dst,
+                             uint32_t dst_cap, uint32_t *hdr, cudaStream_t s)
+{
+  k_pack_rows<<<rows, 128, 0, s>>>(rows, src, row_cap, row_len, dst, dst_cap, hdr);
+  return cudaGetLastError();
+}
 
 cudaError_t launch_cabac(const FrameParams &fp, const CuInfo *cu, const int16_t *levels, uint8_t *rows,
                          uint32_t row_cap, uint32_t *row_len, uint8_t *sync_ctx, int *sync_flag,

@@ -103,19 +103,28 @@ Encoder::~Encoder() { release(); }
 
 void Encoder::release()
 {
-  if (d_src) cudaFree(d_src);
+  if (stream) cudaStreamSynchronize(stream);
+  for (FrameSlot &s : slots) {
+    if (s.stream) cudaStreamSynchronize(s.stream);
+    if (s.d_cu) cudaFree(s.d_cu);
+    if (s.d_levels) cudaFree(s.d_levels);
+    if (s.d_rows) cudaFree(s.d_rows);
+    if (s.d_small) cudaFree(s.d_small);
+    if (s.d_src) cudaFree(s.d_src);
+    if (s.h_src) cudaFreeHost(s.h_src);
+    if (s.h_pack) cudaFreeHost(s.h_pack);
+    if (s.h_hdr) cudaFreeHost(s.h_hdr);
+    for (cudaEvent_t &e : s.pev) if (e) cudaEventDestroy(e);
+    if (s.ev_pred) cudaEventDestroy(s.ev_pred);
+    if (s.ev_done) cudaEventDestroy(s.ev_done);
+    if (s.stream) cudaStreamDestroy(s.stream);
+  }
+  slots.clear();
+  inflight.clear();
   for (int i = 0; i < 2; i++) if (d_rec[i]) cudaFree(d_rec[i]);
   if (d_rec_pre) cudaFree(d_rec_pre);
-  if (d_cu) cudaFree(d_cu);
-  if (d_levels) cudaFree(d_levels);
-  if (d_rows) cudaFree(d_rows);
-  if (d_small) cudaFree(d_small);
-  if (h_src) cudaFreeHost(h_src);
-  if (h_rows) cudaFreeHost(h_rows);
-  if (h_small) cudaFreeHost(h_small);
   if (stream) cudaStreamDestroy(stream);
-  d_src = d_rec[0] = d_rec[1] = d_rec_pre = d_rows = nullptr;
-  d_cu = nullptr; d_levels = nullptr; d_small = nullptr; h_src = h_rows = nullptr; h_small = nullptr; stream = nullptr;
+  d_rec[0] = d_rec[1] = d_rec_pre = nullptr; stream = nullptr;
 }
 
 bool Encoder::open(const EncoderConfig &c)
@@ -123,6 +132,7 @@ bool Encoder::open(const EncoderConfig &c)
   if (c.width <= 0 || c.height <= 0 || (c.width & 7) || (c.height & 7)) { set_error("encoder: width/height must be positive multiples of 8 (got %dx%d)", c.width, c.height); return false; }
   if (c.qp < 0 || c.qp > 51) { set_error("encoder: qp %d out of range 0..51", c.qp); return false; }
   if (c.search_range < 1 || c.search_range > 32) { set_error("encoder: search range %d out of range 1..32", c.search_range); return false; }
+  if (c.depth < 1 || c.depth > 64) { set_error("encoder: depth %d out of range 1..64", c.depth); return false; }
   if (b200_device_count() <= 0) { set_error("no CUDA device: the B200 encoder has no CPU fallback"); return false; }
   cfg = c;
   fp.w = c.width; fp.h = c.height; fp.w8 = c.width / 8; fp.h8 = c.height / 8;
@@ -132,25 +142,33 @@ bool Encoder::open(const EncoderConfig &c)
   fp.search_range = c.search_range; fp.is_idr = 1; fp.deblock = c.deblock;
   frame_bytes = (size_t)fp.w * fp.h * 3 / 2;
   row_cap = (uint32_t)fp.w * kCtb * 4 + 4096;
+  pack_cap = (uint32_t)std::min<size_t>((size_t)row_cap * fp.ctb_rows, frame_bytes * 3 + 65536);
   ENC_CHECK(cudaStreamCreateWithFlags(&stream, cudaStreamNonBlocking), "cudaStreamCreate");
-  ENC_CHECK(cudaMalloc((void **)&d_src, frame_bytes), "cudaMalloc src");
   ENC_CHECK(cudaMalloc((void **)&d_rec[0], frame_bytes), "cudaMalloc rec0");
   ENC_CHECK(cudaMalloc((void **)&d_rec[1], frame_bytes), "cudaMalloc rec1");
-  ENC_CHECK(cudaMalloc((void **)&d_rec_pre, frame_bytes), "cudaMalloc rec_pre");
-  ENC_CHECK(cudaMalloc((void **)&d_cu, sizeof(CuInfo) * fp.w8 * fp.h8), "cudaMalloc cu");
-  ENC_CHECK(cudaMalloc((void **)&d_levels, frame_bytes * sizeof(int16_t)), "cudaMalloc levels");
-  ENC_CHECK(cudaMalloc((void **)&d_rows, (size_t)row_cap * fp.ctb_rows), "cudaMalloc rows");
+  if (c.debug) ENC_CHECK(cudaMalloc((void **)&d_rec_pre, frame_bytes), "cudaMalloc rec_pre");
   // small state: row_len[rows] | sync_flag[rows] | progress[rows] | ticket | bins(8) | sync_ctx[rows*CTX_COUNT]
   off_flag = sizeof(int) * fp.ctb_rows; off_prog = 2 * off_flag; off_ticket = 3 * off_flag;
   off_bins = (off_ticket + sizeof(int) + 7) & ~(size_t)7; off_ctx = off_bins + 8;
   small_bytes = off_ctx + (size_t)fp.ctb_rows * CTX_COUNT;
-  ENC_CHECK(cudaMalloc((void **)&d_small, small_bytes), "cudaMalloc small");
-  ENC_CHECK(cudaMemset(d_small, 0, small_bytes), "memset small");
-  ENC_CHECK(cudaMemset(d_cu, 0, sizeof(CuInfo) * fp.w8 * fp.h8), "memset cu");
-  ENC_CHECK(cudaMallocHost((void **)&h_src, frame_bytes), "cudaMallocHost src");
-  ENC_CHECK(cudaMallocHost((void **)&h_rows, (size_t)row_cap * fp.ctb_rows), "cudaMallocHost rows");
-  ENC_CHECK(cudaMallocHost((void **)&h_small, sizeof(uint32_t) * (fp.ctb_rows + 4)), "cudaMallocHost small");
-  frame_idx = 0; poc = 0; cur = 0;
+  slots.resize(c.depth);
+  for (FrameSlot &s : slots) {
+    ENC_CHECK(cudaMalloc((void **)&s.d_cu, sizeof(CuInfo) * fp.w8 * fp.h8), "cudaMalloc cu");
+    ENC_CHECK(cudaMemset(s.d_cu, 0, sizeof(CuInfo) * fp.w8 * fp.h8), "memset cu");
+    ENC_CHECK(cudaMalloc((void **)&s.d_levels, frame_bytes * sizeof(int16_t)), "cudaMalloc levels");
+    ENC_CHECK(cudaMalloc((void **)&s.d_rows, (size_t)row_cap * fp.ctb_rows), "cudaMalloc rows");
+    ENC_CHECK(cudaMalloc((void **)&s.d_small, small_bytes), "cudaMalloc small");
+    ENC_CHECK(cudaMemset(s.d_small, 0, small_bytes), "memset small");
+    ENC_CHECK(cudaMalloc((void **)&s.d_src, frame_bytes), "cudaMalloc src");
+    ENC_CHECK(cudaMallocHost((void **)&s.h_src, frame_bytes), "cudaMallocHost src");
+    ENC_CHECK(cudaHostAlloc((void **)&s.h_pack, pack_cap, cudaHostAllocMapped), "cudaHostAlloc pack");
+    ENC_CHECK(cudaHostAlloc((void **)&s.h_hdr, sizeof(uint32_t) * (fp.ctb_rows + 2), cudaHostAllocMapped), "cudaHostAlloc hdr");
+    ENC_CHECK(cudaStreamCreateWithFlags(&s.stream, cudaStreamNonBlocking), "cudaStreamCreate slot");
+    ENC_CHECK(cudaEventCreateWithFlags(&s.ev_pred, cudaEventDisableTiming), "cudaEventCreate");
+    ENC_CHECK(cudaEventCreateWithFlags(&s.ev_done, cudaEventDisableTiming), "cudaEventCreate");
+    for (cudaEvent_t &e : s.pev) ENC_CHECK(cudaEventCreate(&e), "cudaEventCreate");
+  }
+  frame_idx = 0; poc = 0; cur = 0; cur_qp = c.qp;
   return true;
 }
 
@@ -216,21 +234,22 @@ void Encoder::write_parameter_sets(std::vector<uint8_t> &out) const
   }
 }
 
-void Encoder::write_slice(std::vector<uint8_t> &out, bool idr, const uint32_t *row_len) const
+void Encoder::write_slice(std::vector<uint8_t> &out, const FrameSlot &s) const
 {
   const int rows = fp.ctb_rows;
+  const uint32_t *row_len = s.h_hdr + 1;
   BitWriter b;
   b.put(1, 1);
-  if (idr) b.put(0, 1);
+  if (s.idr) b.put(0, 1);
   b.ue(0);
-  b.ue(idr ? 2 : 1);
-  if (!idr) {
-    b.put((uint32_t)(poc & 255), 8);
+  b.ue(s.idr ? 2 : 1);
+  if (!s.idr) {
+    b.put((uint32_t)(s.poc & 255), 8);
     b.put(1, 1);
     b.put(0, 1);
     b.ue(5 - kMaxMerge);
   }
-  b.se(cfg.qp - 26);
+  b.se(s.qp - 26);
   if (cfg.deblock) b.put(1, 1);
   b.ue((uint32_t)(rows - 1));
   if (rows > 1) {
@@ -242,57 +261,129 @@ void Encoder::write_slice(std::vector<uint8_t> &out, bool idr, const uint32_t *r
     for (int r = 0; r < rows - 1; r++) b.put(row_len[r] - 1, len);
   }
   b.trailing();
-  start_nal(out, idr ? 19 : 1);
+  start_nal(out, s.idr ? 19 : 1);
   append_escaped(out, b.bytes.data(), b.bytes.size());
-  for (int r = 0; r < rows; r++) out.insert(out.end(), h_rows + (size_t)r * row_cap, h_rows + (size_t)r * row_cap + row_len[r]);
+  out.insert(out.end(), s.h_pack, s.h_pack + s.h_hdr[0]);      // substreams are already escaped
 }
 
-bool Encoder::encode_device(const uint8_t *d_i420, std::vector<uint8_t> &au)
+// Enqueue everything for one picture; returns without waiting for the GPU.
+bool Encoder::submit(FrameSlot &s, const uint8_t *d_i420)
 {
   const bool idr = frame_idx == 0 || (cfg.intra_period > 0 && frame_idx % cfg.intra_period == 0);
   if (idr) poc = 0;
-  fp.is_idr = idr ? 1 : 0;
+  s.idr = idr; s.poc = poc; s.qp = cur_qp; s.seq = frame_idx;
+  FrameParams p = fp;
+  p.is_idr = idr ? 1 : 0;
+  p.qp = cur_qp; p.qp_c = kChromaQp[cur_qp]; p.lambda_q4 = kLambdaQ4[cur_qp];
   uint8_t *rec = d_rec[cur], *ref = d_rec[cur ^ 1];
-  ENC_CHECK(cudaMemsetAsync(d_levels, 0, frame_bytes * sizeof(int16_t), stream), "memset levels");
+  uint32_t *row_len = (uint32_t *)s.d_small;
+  int *sync_flag = (int *)(s.d_small + off_flag), *progress = (int *)(s.d_small + off_prog), *ticket = (int *)(s.d_small + off_ticket);
+  unsigned long long *bins = (unsigned long long *)(s.d_small + off_bins);
+  s.prof_mask = 0;
+#define PROF_BEGIN(id, st) do { if (profile) { ENC_CHECK(cudaEventRecord(s.pev[2 * (id)], st), "prof event"); s.prof_mask |= 1u << (id); } } while (0)
+#define PROF_END(id, st) do { if (profile) ENC_CHECK(cudaEventRecord(s.pev[2 * (id) + 1], st), "prof event"); } while (0)
+  // prediction chain, main stream, picture order
+  ENC_CHECK(cudaMemsetAsync(s.d_levels, 0, frame_bytes * sizeof(int16_t), stream), "memset levels");
   if (idr) {
-    ENC_CHECK(launch_intra_frame(fp, d_i420, rec, d_levels, d_cu, d_progress(), d_ticket(), stream), "intra launch");
+    PROF_BEGIN(K_INTRA, stream);
+    ENC_CHECK(launch_intra_frame(p, d_i420, rec, s.d_levels, s.d_cu, progress, ticket, stream), "intra launch");
+    PROF_END(K_INTRA, stream);
     count_launch(1);
   } else {
-    ENC_CHECK(launch_inter_me(fp, d_i420, ref, d_cu, stream), "me launch");
-    ENC_CHECK(launch_inter_recon(fp, d_i420, ref, rec, d_levels, d_cu, stream), "recon launch");
-    ENC_CHECK(launch_inter_modes(fp, d_cu, stream), "modes launch");
+    PROF_BEGIN(K_ME, stream);
+    ENC_CHECK(launch_inter_me(p, d_i420, ref, s.d_cu, stream), "me launch");
+    PROF_END(K_ME, stream);
+    PROF_BEGIN(K_RECON, stream);
+    ENC_CHECK(launch_inter_recon(p, d_i420, ref, rec, s.d_levels, s.d_cu, stream), "recon launch");
+    PROF_END(K_RECON, stream);
+    PROF_BEGIN(K_MODES, stream);
+    ENC_CHECK(launch_inter_modes(p, s.d_cu, stream), "modes launch");
+    PROF_END(K_MODES, stream);
     count_launch(3);
   }
   if (cfg.debug) ENC_CHECK(cudaMemcpyAsync(d_rec_pre, rec, frame_bytes, cudaMemcpyDeviceToDevice, stream), "copy pre-deblock");
+  ENC_CHECK(cudaEventRecord(s.ev_pred, stream), "event record");
   if (cfg.deblock) {
-    ENC_CHECK(launch_deblock(fp, rec, d_cu, stream), "deblock launch");
+    PROF_BEGIN(K_DEBLOCK, stream);
+    ENC_CHECK(launch_deblock(p, rec, s.d_cu, stream), "deblock launch");
+    PROF_END(K_DEBLOCK, stream);
     count_launch(2);
   }
-  ENC_CHECK(launch_cabac(fp, d_cu, d_levels, d_rows, row_cap, d_row_len(), d_sync_ctx(), d_sync_flag(), d_bins(), stream),
-            "cabac launch");
-  count_launch(1);
-  ENC_CHECK(cudaMemcpyAsync(h_small, d_row_len(), sizeof(uint32_t) * fp.ctb_rows, cudaMemcpyDeviceToHost, stream), "D2H row_len");
-  ENC_CHECK(cudaStreamSynchronize(stream), "sync after cabac");
-  for (int r = 0; r < fp.ctb_rows; r++) {
-    if (h_small[r] == 0xffffffffu || h_small[r] == 0) { set_error("encoder: substream %d overflowed its %u-byte buffer", r, row_cap); return false; }
-    ENC_CHECK(cudaMemcpyAsync(h_rows + (size_t)r * row_cap, d_rows + (size_t)r * row_cap, h_small[r], cudaMemcpyDeviceToHost, stream), "D2H row");
-  }
-  ENC_CHECK(cudaStreamSynchronize(stream), "sync rows");
-  au.clear();
-  if (idr) write_parameter_sets(au);
-  write_slice(au, idr, h_small);
-  last_idr = idr;
+  // entropy coding, slot stream: needs the cu map and the levels, not the deblocked picture
+  ENC_CHECK(cudaStreamWaitEvent(s.stream, s.ev_pred, 0), "stream wait");
+  PROF_BEGIN(K_CABAC, s.stream);
+  ENC_CHECK(launch_cabac(p, s.d_cu, s.d_levels, s.d_rows, row_cap, row_len, s.d_small + off_ctx, sync_flag, bins, s.stream), "cabac launch");
+  PROF_END(K_CABAC, s.stream);
+  PROF_BEGIN(K_PACK, s.stream);
+  ENC_CHECK(launch_pack_rows(p.ctb_rows, s.d_rows, row_cap, row_len, s.h_pack, pack_cap, s.h_hdr, s.stream), "pack launch");
+  PROF_END(K_PACK, s.stream);
+#undef PROF_BEGIN
+#undef PROF_END
+  count_launch(2);
+  ENC_CHECK(cudaEventRecord(s.ev_done, s.stream), "event record");
   cur ^= 1;
   frame_idx++;
   poc++;
   return true;
 }
 
-bool Encoder::encode_host(const uint8_t *i420, std::vector<uint8_t> &au)
+// Wait for a submitted picture and assemble its access unit.
+bool Encoder::collect(FrameSlot &s, std::vector<uint8_t> &out)
 {
-  memcpy(h_src, i420, frame_bytes);
-  ENC_CHECK(cudaMemcpyAsync(d_src, h_src, frame_bytes, cudaMemcpyHostToDevice, stream), "H2D frame");
-  return encode_device(d_src, au);
+  ENC_CHECK(cudaEventSynchronize(s.ev_done), "wait for picture");
+  if (s.prof_mask) {
+    cudaStreamSynchronize(stream);                 // the deblocking of this picture may still be running
+    for (int k = 0; k < K_COUNT; k++) {
+      if (!(s.prof_mask & (1u << k))) continue;
+      float ms = 0;
+      if (cudaEventElapsedTime(&ms, s.pev[2 * k], s.pev[2 * k + 1]) == cudaSuccess) { prof_ms[k] += ms; prof_cnt[k]++; }
+    }
+    s.prof_mask = 0;
+  }
+  if (s.h_hdr[0] == 0xffffffffu || s.h_hdr[0] == 0) {
+    set_error("encoder: a substream overflowed its %u-byte buffer (picture %lld)", row_cap, s.seq);
+    return false;
+  }
+  out.clear();
+  if (s.idr) write_parameter_sets(out);
+  write_slice(out, s);
+  last_idr = s.idr; last_qp = s.qp; last_poc = s.poc;
+  return true;
+}
+
+void Encoder::set_qp(int qp) { cur_qp = std::min(std::max(qp, 0), 51); }
+
+bool Encoder::encode_device(const uint8_t *d_i420, std::vector<uint8_t> &out)
+{
+  out.clear();
+  const int slot = (int)(frame_idx % cfg.depth);
+  FrameSlot &s = slots[slot];
+  // the slot is free: its previous picture was collected when the pipeline was full.
+  // Take a private copy so that the caller may reuse its buffer as soon as this call returns
+  // (the caller orders its producer before this call; the copy is ~1 us of HBM time).
+  if (d_i420 != s.d_src) ENC_CHECK(cudaMemcpyAsync(s.d_src, d_i420, frame_bytes, cudaMemcpyDeviceToDevice, stream), "D2D frame");
+  if (!submit(s, s.d_src)) return false;
+  inflight.push_back(slot);
+  last_slot = slot;
+  if ((int)inflight.size() >= cfg.depth) return flush(out);
+  return true;
+}
+
+bool Encoder::encode_host(const uint8_t *i420, std::vector<uint8_t> &out)
+{
+  FrameSlot &s = slots[frame_idx % cfg.depth];
+  memcpy(s.h_src, i420, frame_bytes);
+  ENC_CHECK(cudaMemcpyAsync(s.d_src, s.h_src, frame_bytes, cudaMemcpyHostToDevice, stream), "H2D frame");
+  return encode_device(s.d_src, out);
+}
+
+bool Encoder::flush(std::vector<uint8_t> &out)
+{
+  out.clear();
+  if (inflight.empty()) return true;
+  int slot = inflight.front();
+  inflight.pop_front();
+  return collect(slots[slot], out);
 }
 
 }  // namespace b200
@@ -304,12 +395,12 @@ using b200::EncoderConfig;
 
 extern "C" {
 
-void *b200_enc_open(int width, int height, int qp, int intra_period, int search_range, int deblock, int debug)
+void *b200_enc_open(int width, int height, int qp, int intra_period, int search_range, int deblock, int debug, int depth)
 {
   Encoder *e = new Encoder();
   EncoderConfig c;
   c.width = width; c.height = height; c.qp = qp; c.intra_period = intra_period; c.search_range = search_range;
-  c.deblock = deblock; c.debug = debug;
+  c.deblock = deblock; c.debug = debug; c.depth = depth;
   if (!e->open(c)) { delete e; return nullptr; }
   return e;
 }
@@ -318,6 +409,7 @@ void b200_enc_close(void *h) { delete (Encoder *)h; }
 
 static int finish_au(Encoder *e, uint8_t *out, int cap)
 {
+  if (e->au.empty()) return 0;
   if ((size_t)cap < e->au.size()) { b200::set_error("b200_enc_encode: output buffer too small (%zu needed)", e->au.size()); return -(int)e->au.size(); }
   memcpy(out, e->au.data(), e->au.size());
   return (int)e->au.size();
@@ -340,22 +432,55 @@ int b200_enc_encode_dev(void *h, const uint8_t *d_i420, uint8_t *out, int cap)
   return finish_au(e, out, cap);
 }
 
+int b200_enc_flush(void *h, uint8_t *out, int cap)
+{
+  Encoder *e = (Encoder *)h;
+  if (!e || !out) { b200::set_error("b200_enc_flush: bad arguments"); return B200_ERR_ARG; }
+  if (!e->flush(e->au)) return B200_ERR_CUDA;
+  return finish_au(e, out, cap);
+}
+
+int b200_enc_pending(void *h) { return h ? ((Encoder *)h)->pending() : 0; }
+
+// Per-kernel device time from CUDA events on the launching stream.  Kernel ids: 0 intra, 1 me,
+// 2 inter recon, 3 modes, 4 deblock (both passes), 5 cabac, 6 pack.
+int b200_enc_set_profile(void *h, int on)
+{
+  Encoder *e = (Encoder *)h;
+  if (!e) return B200_ERR_ARG;
+  e->profile = on;
+  for (int k = 0; k < Encoder::K_COUNT; k++) { e->prof_ms[k] = 0; e->prof_cnt[k] = 0; }
+  return B200_OK;
+}
+
+int b200_enc_get_profile(void *h, double *ms, unsigned long long *count, int n)
+{
+  Encoder *e = (Encoder *)h;
+  if (!e || !ms || !count) return B200_ERR_ARG;
+  int k = 0;
+  for (; k < n && k < Encoder::K_COUNT; k++) { ms[k] = e->prof_ms[k]; count[k] = e->prof_cnt[k]; }
+  return k;
+}
+
 // what: 0 reconstruction (after deblocking), 1 reconstruction before deblocking (debug=1 only),
-//       2 cu map, 3 levels, 4 reference picture the NEXT frame will use (== 0)
+//       2 cu map, 3 levels -- of the most recently submitted picture (waits for it)
 int b200_enc_debug_read(void *h, int what, void *dst, size_t bytes)
 {
   Encoder *e = (Encoder *)h;
   if (!e || !dst) return B200_ERR_ARG;
+  const b200::FrameSlot &s = e->slots[e->last_slot];
+  B200_CHECK(cudaStreamSynchronize(e->stream), "debug sync");
+  B200_CHECK(cudaStreamSynchronize(s.stream), "debug sync");
   const void *src = nullptr;
   size_t n = 0;
   switch (what) {
-  case 0: case 4: src = e->d_rec[e->cur ^ 1]; n = e->frame_bytes; break;
+  case 0: src = e->d_rec[e->cur ^ 1]; n = e->frame_bytes; break;
   case 1: src = e->d_rec_pre; n = e->frame_bytes; break;
-  case 2: src = e->d_cu; n = sizeof(b200::CuInfo) * e->fp.w8 * e->fp.h8; break;
-  case 3: src = e->d_levels; n = e->frame_bytes * sizeof(int16_t); break;
+  case 2: src = s.d_cu; n = sizeof(b200::CuInfo) * e->fp.w8 * e->fp.h8; break;
+  case 3: src = s.d_levels; n = e->frame_bytes * sizeof(int16_t); break;
   default: return B200_ERR_ARG;
   }
-  if (bytes < n) return B200_ERR_ARG;
+  if (bytes < n || !src) return B200_ERR_ARG;
   B200_CHECK(cudaMemcpy(dst, src, n, cudaMemcpyDeviceToHost), "debug read");
   return (int)B200_OK;
 }
@@ -366,6 +491,7 @@ int b200_enc_debug_set_reference(void *h, const uint8_t *i420)
 {
   Encoder *e = (Encoder *)h;
   if (!e || !i420) return B200_ERR_ARG;
+  B200_CHECK(cudaStreamSynchronize(e->stream), "debug sync");
   B200_CHECK(cudaMemcpy(e->d_rec[e->cur ^ 1], i420, e->frame_bytes, cudaMemcpyHostToDevice), "set reference");
   return B200_OK;
 }
@@ -374,7 +500,10 @@ unsigned long long b200_enc_last_bins(void *h)
 {
   Encoder *e = (Encoder *)h;
   unsigned long long v = 0;
-  if (e) cudaMemcpy(&v, e->d_bins(), sizeof(v), cudaMemcpyDeviceToHost);
+  if (!e) return 0;
+  const b200::FrameSlot &s = e->slots[e->last_slot];
+  cudaStreamSynchronize(s.stream);
+  cudaMemcpy(&v, s.d_small + e->off_bins, sizeof(v), cudaMemcpyDeviceToHost);
   return v;
 }
 

@@ -3,6 +3,7 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 
+#include <deque>
 #include <vector>
 
 #include "hevc_common.h"
@@ -16,45 +17,74 @@ struct EncoderConfig {
   int search_range = 8;      // full-sample motion search range (+-)
   int deblock = 1;
   int debug = 0;             // keep a copy of the reconstruction before deblocking
+  int depth = 1;             // pictures in flight (Kvazaar's owf + 1): output of picture n is
+                             // returned by the call that submits picture n + depth - 1
+};
+
+// Everything one in-flight picture owns.  The prediction chain (ME, reconstruction, deblocking)
+// runs on the encoder's main stream in picture order; entropy coding of a finished picture runs
+// on the slot's own stream, overlapping the next pictures' prediction chain.
+struct FrameSlot {
+  CuInfo *d_cu = nullptr;
+  int16_t *d_levels = nullptr;
+  uint8_t *d_rows = nullptr;       // per-row substreams
+  uint8_t *d_small = nullptr;      // row_len | sync flags | progress | ticket | bins | sync contexts
+  uint8_t *d_src = nullptr;        // device copy of a host-supplied picture
+  uint8_t *h_src = nullptr;        // pinned staging of the input
+  uint8_t *h_pack = nullptr;       // mapped pinned: packed substreams
+  uint32_t *h_hdr = nullptr;       // mapped pinned: {total, row_len[rows]}
+  cudaStream_t stream = nullptr;
+  cudaEvent_t ev_pred = nullptr, ev_done = nullptr;
+  cudaEvent_t pev[14] = {};        // profiling: begin/end event per kernel slot (kernel ids below)
+  unsigned prof_mask = 0;          // which kernel ids were recorded for the picture in this slot
+  bool idr = false;
+  int poc = 0, qp = 0;
+  long long seq = 0;
 };
 
 class Encoder {
  public:
   ~Encoder();
   bool open(const EncoderConfig &c);
-  // Encode one packed I420 picture (host / device resident).  `au` receives one Annex-B access unit.
+  // Submit one packed I420 picture (host / device resident).  Returns false on error.  `au`
+  // receives the next finished access unit in submission order, or stays empty while the
+  // pipeline is filling.
   bool encode_host(const uint8_t *i420, std::vector<uint8_t> &au);
   bool encode_device(const uint8_t *d_i420, std::vector<uint8_t> &au);
+  // Drain: returns the next pending access unit (empty when none is left).
+  bool flush(std::vector<uint8_t> &au);
+  int pending() const { return (int)inflight.size(); }
+  // QP of the pictures submitted from now on (frame-level rate control hook)
+  void set_qp(int qp);
+  int qp() const { return cur_qp; }
 
   EncoderConfig cfg;
   FrameParams fp{};
   size_t frame_bytes = 0;
-  uint32_t row_cap = 0;
-  int frame_idx = 0, poc = 0, cur = 0, last_idr = 0;
+  uint32_t row_cap = 0, pack_cap = 0;
+  int frame_idx = 0, poc = 0, cur = 0, last_idr = 0, last_qp = 0, last_poc = 0, cur_qp = 32;
+  unsigned long long last_bins = 0;
   std::vector<uint8_t> au;
 
-  // HBM-resident state
-  uint8_t *d_src = nullptr, *d_rec[2] = {nullptr, nullptr}, *d_rec_pre = nullptr, *d_rows = nullptr;
-  CuInfo *d_cu = nullptr;
-  int16_t *d_levels = nullptr;
-  uint8_t *d_small = nullptr;
+  uint8_t *d_rec[2] = {nullptr, nullptr}, *d_rec_pre = nullptr;
+  std::vector<FrameSlot> slots;
+  std::deque<int> inflight;          // slot indices, oldest first
+  int last_slot = 0;
   size_t small_bytes = 0, off_flag = 0, off_prog = 0, off_ticket = 0, off_bins = 0, off_ctx = 0;
-  // pinned host staging
-  uint8_t *h_src = nullptr, *h_rows = nullptr;
-  uint32_t *h_small = nullptr;
-  cudaStream_t stream = nullptr;
+  cudaStream_t stream = nullptr;     // main (prediction chain) stream
 
-  uint32_t *d_row_len() const { return (uint32_t *)d_small; }
-  int *d_sync_flag() const { return (int *)(d_small + off_flag); }
-  int *d_progress() const { return (int *)(d_small + off_prog); }
-  int *d_ticket() const { return (int *)(d_small + off_ticket); }
-  unsigned long long *d_bins() const { return (unsigned long long *)(d_small + off_bins); }
-  uint8_t *d_sync_ctx() const { return d_small + off_ctx; }
+  // per-kernel device time, measured with CUDA events on the launching stream (profile != 0)
+  enum { K_INTRA = 0, K_ME, K_RECON, K_MODES, K_DEBLOCK, K_CABAC, K_PACK, K_COUNT };
+  int profile = 0;
+  double prof_ms[K_COUNT] = {};
+  unsigned long long prof_cnt[K_COUNT] = {};
 
  private:
   void release();
+  bool submit(FrameSlot &s, const uint8_t *d_i420);
+  bool collect(FrameSlot &s, std::vector<uint8_t> &au);
   void write_parameter_sets(std::vector<uint8_t> &out) const;
-  void write_slice(std::vector<uint8_t> &out, bool idr, const uint32_t *row_len) const;
+  void write_slice(std::vector<uint8_t> &out, const FrameSlot &s) const;
 };
 
 }  // namespace b200

@@ -27,4 +27,8 @@ cudaError_t launch_cabac(const FrameParams &fp, const CuInfo *cu, const int16_t 
                          uint32_t row_cap, uint32_t *row_len, uint8_t *sync_ctx, int *sync_flag,
                          unsigned long long *bins, cudaStream_t s);
 
+// substreams -> one contiguous buffer + header {total, row_len[rows]} (dst/hdr may be mapped host memory)
+cudaError_t launch_pack_rows(int rows, const uint8_t *src, uint32_t row_cap, const uint32_t *row_len, uint8_t *dst,
+                             uint32_t dst_cap, uint32_t *hdr, cudaStream_t s);
+
 }  // namespace b200

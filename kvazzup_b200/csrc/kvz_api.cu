@@ -1,0 +1,333 @@
+// kvz_api boundary (include/b200_kvazaar.h): the C ABI KvazaarFilter binds
+// (reference src/media/processing/kvazaarfilter.cpp:145-318, 374-484), implemented on the B200
+// encoder engine.  Option names follow Kvazaar's config_parse; presets map to the search range.
+#include <stdio.h>
+#include <stdlib.h>
+#include <string.h>
+
+#include <deque>
+#include <new>
+
+#include "../../include/b200_kvazaar.h"
+#include "hevc_encoder.h"
+#include "runtime.h"
+
+using b200::Encoder;
+using b200::EncoderConfig;
+
+struct kvz_encoder {
+  Encoder eng;
+  kvz_config cfg;
+  std::deque<int64_t> pts;              // presentation timestamps of the pictures in flight
+  // frame-level rate control (target_bitrate != 0): leaky bucket on the produced bits
+  double bits_per_frame = 0, bucket = 0;
+  int rc_window = 0;
+  std::vector<uint8_t> au;
+};
+
+namespace {
+
+struct Preset { const char *name; int me_range; };
+const Preset kPresets[] = {{"ultrafast", 8}, {"superfast", 8}, {"veryfast", 12}, {"faster", 12}, {"fast", 16},
+                           {"medium", 16}, {"slow", 24}, {"slower", 24}, {"veryslow", 32}, {"placebo", 32}};
+
+int parse_int(const char *v, int *out)
+{
+  if (!v || !*v) return 0;
+  char *end = nullptr;
+  long x = strtol(v, &end, 10);
+  if (*end) return 0;
+  *out = (int)x;
+  return 1;
+}
+
+int parse_bool(const char *v, int *out)
+{
+  if (!v || !*v) { *out = 1; return 1; }
+  if (!strcmp(v, "1") || !strcmp(v, "true") || !strcmp(v, "on") || !strcmp(v, "yes")) { *out = 1; return 1; }
+  if (!strcmp(v, "0") || !strcmp(v, "false") || !strcmp(v, "off") || !strcmp(v, "no")) { *out = 0; return 1; }
+  return 0;
+}
+
+kvz_config *config_alloc(void) { return (kvz_config *)calloc(1, sizeof(kvz_config)); }
+
+int config_destroy(kvz_config *cfg) { free(cfg); return 1; }
+
+int config_init(kvz_config *cfg)
+{
+  if (!cfg) return 0;
+  memset(cfg, 0, sizeof(*cfg));
+  cfg->framerate_num = 25; cfg->framerate_denom = 1;
+  cfg->qp = 22;                    // Kvazaar's default; the reference always overrides it (:219)
+  cfg->intra_period = 64; cfg->vps_period = 0;
+  cfg->wpp = 1; cfg->owf = 0; cfg->threads = 0;
+  cfg->deblock_enable = 1; cfg->sao_type = 0;
+  cfg->tiles_width_count = 1; cfg->tiles_height_count = 1;
+  cfg->gop_lowdelay = 1; cfg->gop_len = 4;
+  cfg->me_range = 12; cfg->device = -1;
+  snprintf(cfg->preset, sizeof(cfg->preset), "veryfast");
+  return 1;
+}
+
+// Options Kvazaar knows that do not change what this encoder does: accepted so that the
+// reference's "parameters" array (kvazaarfilter.cpp:351-371) does not log spurious warnings.
+const char *const kIgnored[] = {"rd", "rdoq", "rdoq-skip", "signhide", "smp", "amp", "subme", "me", "me-steps",
+  "pu-depth-inter", "pu-depth-intra", "tr-depth-intra", "bipred", "ref", "transform-skip", "full-intra-search",
+  "cu-split-termination", "me-early-termination", "intra-rdo-et", "early-skip", "fast-residual-cost", "max-merge",
+  "cqmfile", "erp-aqp", "level", "force-level", "high-tier", "implicit-rdpcm", "mrl", "tmvp", "open-gop",
+  "input-bitdepth", "input-format", "aud", "psnr", "info", "cpuid", "roi", "fastrd-sampling", "fastrd-accuracy-check",
+  "intra-qp-offset", "intra-bits", "clip-neighbour", "partial-coding", "zero-coeff-rdo", "combine-intra-cus", NULL};
+
+int config_parse(kvz_config *cfg, const char *name, const char *value)
+{
+  if (!cfg || !name) return 0;
+  int v = 0;
+  if (!strncmp(name, "--", 2)) name += 2;
+  if (!strcmp(name, "preset")) {
+    for (const Preset &p : kPresets)
+      if (value && !strcmp(value, p.name)) { cfg->me_range = p.me_range; snprintf(cfg->preset, sizeof(cfg->preset), "%s", p.name); return 1; }
+    return 0;
+  }
+  if (!strcmp(name, "input-res")) {
+    int w = 0, h = 0;
+    if (!value || sscanf(value, "%dx%d", &w, &h) != 2 || w <= 0 || h <= 0) return 0;
+    cfg->width = w; cfg->height = h;
+    return 1;
+  }
+  if (!strcmp(name, "input-fps")) {
+    int n = 0, d = 1;
+    if (!value) return 0;
+    if (sscanf(value, "%d/%d", &n, &d) == 2 && n > 0 && d > 0) { cfg->framerate_num = n; cfg->framerate_denom = d; return 1; }
+    double f = atof(value);
+    if (f <= 0) return 0;
+    cfg->framerate_num = (int)(f * 1000 + 0.5); cfg->framerate_denom = 1000;
+    return 1;
+  }
+  if (!strcmp(name, "qp")) { if (!parse_int(value, &v) || v < 0 || v > 51) return 0; cfg->qp = v; return 1; }
+  if (!strcmp(name, "period")) { if (!parse_int(value, &v) || v < 0) return 0; cfg->intra_period = v; return 1; }
+  if (!strcmp(name, "vps-period")) { if (!parse_int(value, &v) || v < 0) return 0; cfg->vps_period = v; return 1; }
+  if (!strcmp(name, "threads")) { if (value && !strcmp(value, "auto")) { cfg->threads = -1; return 1; } if (!parse_int(value, &v) || v < 0) return 0; cfg->threads = v; return 1; }
+  if (!strcmp(name, "owf")) { if (value && !strcmp(value, "auto")) { cfg->owf = 3; return 1; } if (!parse_int(value, &v) || v < 0 || v > 63) return 0; cfg->owf = v; return 1; }
+  if (!strcmp(name, "wpp")) { if (!parse_bool(value, &v)) return 0; cfg->wpp = v; return 1; }
+  if (!strcmp(name, "no-wpp")) { cfg->wpp = 0; return 1; }
+  if (!strcmp(name, "tiles")) {
+    int c = 0, r = 0;
+    if (!value || sscanf(value, "%dx%d", &c, &r) != 2) return 0;
+    if (c != 1 || r != 1) return 0;            // tile columns are a planned multi-GPU split, not built yet
+    cfg->tiles_width_count = c; cfg->tiles_height_count = r;
+    return 1;
+  }
+  if (!strcmp(name, "slices")) { return 0; }   // one slice per picture (the reference notes slices break uvgRTP, :204)
+  if (!strcmp(name, "bitrate")) { if (!parse_int(value, &v) || v < 0) return 0; cfg->target_bitrate = v; return 1; }
+  if (!strcmp(name, "rc-algorithm")) {
+    if (!value) return 0;
+    if (!strcmp(value, "no-rc")) { cfg->rc_algorithm = KVZ_NO_RC; return 1; }
+    if (!strcmp(value, "lambda")) { cfg->rc_algorithm = KVZ_LAMBDA; return 1; }
+    if (!strcmp(value, "oba")) { cfg->rc_algorithm = KVZ_OBA; return 1; }
+    return 0;
+  }
+  if (!strcmp(name, "gop")) {
+    // low-delay P only: "lp-g<len>d<depth>t<layers>" (the reference hard-codes lp-g4d3t1, :233) or 0
+    if (!value) return 0;
+    if (!strcmp(value, "0")) { cfg->gop_lowdelay = 1; return 1; }
+    if (!strncmp(value, "lp-", 3)) { cfg->gop_lowdelay = 1; int g = 4; sscanf(value, "lp-g%d", &g); cfg->gop_len = g; return 1; }
+    return 0;
+  }
+  if (!strcmp(name, "scaling-list")) { if (value && !strcmp(value, "off")) { cfg->scaling_list = 0; return 1; } return 0; }
+  if (!strcmp(name, "mv-constraint")) {
+    if (!value || !*value || !strcmp(value, "none")) { cfg->mv_constraint = KVZ_MV_CONSTRAIN_NONE; return 1; }
+    if (!strcmp(value, "frame")) { cfg->mv_constraint = KVZ_MV_CONSTRAIN_FRAME; return 1; }
+    if (!strcmp(value, "tile")) { cfg->mv_constraint = KVZ_MV_CONSTRAIN_TILE; return 1; }
+    if (!strcmp(value, "frametile")) { cfg->mv_constraint = KVZ_MV_CONSTRAIN_FRAME_AND_TILE; return 1; }
+    if (!strcmp(value, "frametilemargin")) { cfg->mv_constraint = KVZ_MV_CONSTRAIN_FRAME_AND_TILE_MARGIN; return 1; }
+    return 0;
+  }
+  if (!strcmp(name, "vaq")) { if (!parse_int(value, &v) || v < 0 || v > 20) return 0; cfg->vaq = v; return 1; }
+  if (!strcmp(name, "deblock")) {
+    if (!value || !*value) { cfg->deblock_enable = 1; return 1; }
+    if (parse_bool(value, &v)) { cfg->deblock_enable = v; return 1; }
+    int b = 0, t = 0;
+    if (sscanf(value, "%d:%d", &b, &t) == 2 && b == 0 && t == 0) { cfg->deblock_enable = 1; return 1; }
+    return 0;
+  }
+  if (!strcmp(name, "no-deblock")) { cfg->deblock_enable = 0; return 1; }
+  if (!strcmp(name, "sao")) { cfg->sao_type = 0; return value != NULL; }
+  if (!strcmp(name, "no-sao")) { cfg->sao_type = 0; return 1; }
+  if (!strcmp(name, "lossless")) { if (!parse_bool(value, &v)) return 0; cfg->lossless = v; return 1; }
+  if (!strcmp(name, "hash")) {
+    if (!value) return 0;
+    if (!strcmp(value, "none")) { cfg->hash = KVZ_HASH_NONE; return 1; }
+    return 0;
+  }
+  if (!strcmp(name, "set-qp-in-cu")) { if (!parse_bool(value, &v)) return 0; cfg->set_qp_in_cu = v; return 1; }
+  if (!strcmp(name, "b200-me-range")) { if (!parse_int(value, &v) || v < 1 || v > 32) return 0; cfg->me_range = v; return 1; }
+  if (!strcmp(name, "b200-recon")) { if (!parse_bool(value, &v)) return 0; cfg->return_recon = v; return 1; }
+  if (!strcmp(name, "b200-device")) { if (!parse_int(value, &v)) return 0; cfg->device = v; return 1; }
+  for (int i = 0; kIgnored[i]; i++)
+    if (!strcmp(name, kIgnored[i])) return 1;
+  return 0;
+}
+
+kvz_picture *picture_alloc_csp(enum kvz_chroma_format csp, int32_t w, int32_t h)
+{
+  if (csp != KVZ_CSP_420 || w <= 0 || h <= 0 || (w & 1) || (h & 1)) return NULL;
+  kvz_picture *p = (kvz_picture *)calloc(1, sizeof(kvz_picture));
+  if (!p) return NULL;
+  size_t ysz = (size_t)w * h;
+  p->fulldata_buf = (kvz_pixel *)malloc(ysz + ysz / 2);
+  if (!p->fulldata_buf) { free(p); return NULL; }
+  p->fulldata = p->fulldata_buf;
+  p->y = p->data[0] = p->fulldata;
+  p->u = p->data[1] = p->fulldata + ysz;
+  p->v = p->data[2] = p->fulldata + ysz + ysz / 4;
+  p->width = w; p->height = h; p->stride = w;
+  p->refcount = 1; p->chroma_format = csp;
+  return p;
+}
+
+kvz_picture *picture_alloc(int32_t w, int32_t h) { return picture_alloc_csp(KVZ_CSP_420, w, h); }
+
+void picture_free(kvz_picture *p)
+{
+  if (!p) return;
+  if (--p->refcount > 0) return;
+  free(p->fulldata_buf);
+  free(p);
+}
+
+void chunk_free(kvz_data_chunk *c)
+{
+  while (c) { kvz_data_chunk *n = c->next; free(c); c = n; }
+}
+
+kvz_data_chunk *to_chunks(const std::vector<uint8_t> &au)
+{
+  kvz_data_chunk *head = NULL, **tail = &head;
+  for (size_t off = 0; off < au.size(); off += KVZ_DATA_CHUNK_SIZE) {
+    kvz_data_chunk *c = (kvz_data_chunk *)malloc(sizeof(kvz_data_chunk));
+    if (!c) { chunk_free(head); return NULL; }
+    c->len = (uint32_t)std::min<size_t>(KVZ_DATA_CHUNK_SIZE, au.size() - off);
+    memcpy(c->data, au.data() + off, c->len);
+    c->next = NULL;
+    *tail = c;
+    tail = &c->next;
+  }
+  return head;
+}
+
+kvz_encoder *encoder_open(const kvz_config *cfg)
+{
+  if (!cfg) { b200::set_error("encoder_open: NULL config"); return NULL; }
+  if (cfg->lossless) { b200::set_error("encoder_open: lossless coding is not supported"); return NULL; }
+  if (cfg->tiles_width_count != 1 || cfg->tiles_height_count != 1) { b200::set_error("encoder_open: tiles are not supported yet"); return NULL; }
+  if (cfg->device >= 0 && cudaSetDevice(cfg->device) != cudaSuccess) { b200::set_error("encoder_open: cannot select CUDA device %d", cfg->device); return NULL; }
+  kvz_encoder *e = new (std::nothrow) kvz_encoder();
+  if (!e) return NULL;
+  e->cfg = *cfg;
+  EncoderConfig c;
+  c.width = cfg->width; c.height = cfg->height; c.qp = cfg->qp; c.intra_period = cfg->intra_period;
+  c.search_range = cfg->me_range > 0 ? cfg->me_range : 12;
+  c.deblock = cfg->deblock_enable; c.debug = 0; c.depth = cfg->owf + 1;
+  if (!e->eng.open(c)) { delete e; return NULL; }
+  if (cfg->target_bitrate > 0 && cfg->framerate_num > 0) {
+    e->bits_per_frame = (double)cfg->target_bitrate * cfg->framerate_denom / cfg->framerate_num;
+  }
+  return e;
+}
+
+void encoder_close(kvz_encoder *e) { delete e; }
+
+int encoder_headers(kvz_encoder *e, kvz_data_chunk **data_out, uint32_t *len_out)
+{
+  // parameter sets travel in-band before every IDR (vps-period 1 in the reference, :221)
+  (void)e;
+  if (data_out) *data_out = NULL;
+  if (len_out) *len_out = 0;
+  return 1;
+}
+
+// frame-level rate control: nudge the QP of future pictures so that the produced bits track the
+// target (a restatement of the intent of Kvazaar's rate control, not of its lambda / OBA models)
+void rate_control_update(kvz_encoder *e, size_t au_bytes, bool idr)
+{
+  if (e->bits_per_frame <= 0) return;
+  double bits = 8.0 * au_bytes;
+  e->bucket += bits - e->bits_per_frame;
+  if (idr) return;                                // let the bucket absorb the intra picture over the GOP
+  if (++e->rc_window < 2) return;
+  e->rc_window = 0;
+  int qp = e->eng.qp();
+  const double hi = 4.0 * e->bits_per_frame, lo = -4.0 * e->bits_per_frame;
+  if (e->bucket > hi || bits > 1.5 * e->bits_per_frame) qp++;
+  else if (e->bucket < lo || bits < 0.6 * e->bits_per_frame) qp--;
+  e->eng.set_qp(std::min(std::max(qp, 10), 51));
+}
+
+int encoder_encode(kvz_encoder *e, kvz_picture *pic_in, kvz_data_chunk **data_out, uint32_t *len_out,
+                   kvz_picture **pic_recon, kvz_picture **pic_src, kvz_frame_info *info_out)
+{
+  if (data_out) *data_out = NULL;
+  if (len_out) *len_out = 0;
+  if (pic_recon) *pic_recon = NULL;
+  if (pic_src) *pic_src = NULL;
+  if (!e) { b200::set_error("encoder_encode: NULL encoder"); return 0; }
+  bool ok;
+  if (pic_in) {
+    if (pic_in->width != e->cfg.width || pic_in->height != e->cfg.height || !pic_in->y || !pic_in->u || !pic_in->v) {
+      b200::set_error("encoder_encode: picture does not match the configured %dx%d", e->cfg.width, e->cfg.height);
+      return 0;
+    }
+    const size_t ysz = (size_t)e->cfg.width * e->cfg.height;
+    if (pic_in->u == pic_in->y + ysz && pic_in->v == pic_in->u + ysz / 4 && pic_in->stride == pic_in->width) {
+      ok = e->eng.encode_host(pic_in->y, e->au);
+    } else {
+      std::vector<uint8_t> tmp(ysz + ysz / 2);
+      for (int r = 0; r < pic_in->height; r++) memcpy(&tmp[(size_t)r * pic_in->width], pic_in->y + (size_t)r * pic_in->stride, pic_in->width);
+      for (int r = 0; r < pic_in->height / 2; r++) {
+        memcpy(&tmp[ysz + (size_t)r * (pic_in->width / 2)], pic_in->u + (size_t)r * (pic_in->stride / 2), pic_in->width / 2);
+        memcpy(&tmp[ysz + ysz / 4 + (size_t)r * (pic_in->width / 2)], pic_in->v + (size_t)r * (pic_in->stride / 2), pic_in->width / 2);
+      }
+      ok = e->eng.encode_host(tmp.data(), e->au);
+    }
+    e->pts.push_back(pic_in->pts);
+  } else {
+    ok = e->eng.flush(e->au);
+  }
+  if (!ok) return 0;
+  if (e->au.empty()) return 1;                      // pipeline still filling / nothing left to drain
+  rate_control_update(e, e->au.size(), e->eng.last_idr != 0);
+  if (data_out) {
+    *data_out = to_chunks(e->au);
+    if (!*data_out) { b200::set_error("encoder_encode: out of memory"); return 0; }
+  }
+  if (len_out) *len_out = (uint32_t)e->au.size();
+  if (info_out) {
+    memset(info_out, 0, sizeof(*info_out));
+    info_out->poc = e->eng.last_poc;
+    info_out->qp = (int8_t)e->eng.last_qp;
+    info_out->nal_unit_type = e->eng.last_idr ? KVZ_NAL_IDR_W_RADL : KVZ_NAL_TRAIL_R;
+    info_out->slice_type = e->eng.last_idr ? KVZ_SLICE_I : KVZ_SLICE_P;
+    if (!e->eng.last_idr) { info_out->ref_list_len[0] = 1; info_out->ref_list[0][0] = e->eng.last_poc - 1; }
+  }
+  if (!e->pts.empty()) e->pts.pop_front();
+  if (pic_recon && e->cfg.return_recon && e->eng.cfg.depth == 1) {
+    kvz_picture *r = picture_alloc(e->cfg.width, e->cfg.height);
+    if (r) {
+      cudaStreamSynchronize(e->eng.stream);
+      cudaMemcpy(r->y, e->eng.d_rec[e->eng.cur ^ 1], e->eng.frame_bytes, cudaMemcpyDeviceToHost);
+      *pic_recon = r;
+    }
+  }
+  return 1;
+}
+
+const kvz_api kApi = {config_alloc, config_destroy, config_init, config_parse, picture_alloc, picture_free,
+                      chunk_free, encoder_open, encoder_close, encoder_headers, encoder_encode, picture_alloc_csp};
+
+}  // namespace
+
+extern "C" const kvz_api *kvz_api_get(int bit_depth)
+{
+  if (bit_depth != 8) { b200::set_error("kvz_api_get: only 8-bit video is supported (asked for %d)", bit_depth); return NULL; }
+  return &kApi;
+}

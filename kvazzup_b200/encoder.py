@@ -17,10 +17,10 @@ CU_DTYPE = np.dtype([("mvx", "<i2"), ("mvy", "<i2"), ("log2_size", "u1"), ("pred
 
 
 class GpuEncoder:
-    def __init__(self, w, h, qp=32, intra_period=64, search_range=8, deblock=1, debug=0):
+    def __init__(self, w, h, qp=32, intra_period=64, search_range=8, deblock=1, debug=0, depth=1):
         self.l = lib()
         self.w, self.h = w, h
-        self.h_enc = self.l.b200_enc_open(w, h, qp, intra_period, search_range, deblock, debug)
+        self.h_enc = self.l.b200_enc_open(w, h, qp, intra_period, search_range, deblock, debug, depth)
         if not self.h_enc:
             raise B200Error("b200_enc_open failed: " + self.l.b200_last_error().decode())
         self.out = np.empty(w * h * 3 + 65536, np.uint8)
@@ -37,6 +37,25 @@ class GpuEncoder:
 
     def encode_dev(self, d_i420) -> bytes:
         return self._ret(self.l.b200_enc_encode_dev(self.h_enc, C.c_void_p(d_i420.data_ptr()), C.c_void_p(self.out.ctypes.data), self.out.size))
+
+    def flush(self) -> bytes:
+        """Next pending access unit (b'' when the pipeline is drained)."""
+        return self._ret(self.l.b200_enc_flush(self.h_enc, C.c_void_p(self.out.ctypes.data), self.out.size))
+
+    def pending(self) -> int:
+        return int(self.l.b200_enc_pending(self.h_enc))
+
+    KERNELS = ("intra", "me", "recon", "modes", "deblock", "cabac", "pack")
+
+    def set_profile(self, on: bool):
+        self.l.b200_enc_set_profile(self.h_enc, int(on))
+
+    def profile(self) -> dict:
+        """{kernel: (total_ms, launches)} measured with CUDA events on the launching streams."""
+        ms = (C.c_double * 7)()
+        cnt = (C.c_ulonglong * 7)()
+        self.l.b200_enc_get_profile(self.h_enc, ms, cnt, 7)
+        return {k: (ms[i], int(cnt[i])) for i, k in enumerate(self.KERNELS)}
 
     def _read(self, what, dtype, count):
         a = np.empty(count, dtype)

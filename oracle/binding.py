@@ -32,6 +32,10 @@ def load():
         _lib = C.CDLL(str(LIB), mode=C.RTLD_LOCAL)
         from . import sigs
         sigs.bind(_lib)
+        try:
+            _lib.orc_set_threads(1)        # deterministic default; bench.py raises it explicitly
+        except AttributeError:
+            pass
     return _lib
 
 

@@ -100,6 +100,27 @@ void orc_enc_close(orc_encoder_t *e)
   free(e);
 }
 
+#ifdef _OPENMP
+#include <omp.h>
+#endif
+/* Threads used by the parallel loops of this library (cpu_baseline / reference arm of bench.py). */
+void orc_set_threads(int n)
+{
+#ifdef _OPENMP
+  omp_set_num_threads(n < 1 ? 1 : n);
+#else
+  (void)n;
+#endif
+}
+int orc_max_threads(void)
+{
+#ifdef _OPENMP
+  return omp_get_num_procs();
+#else
+  return 1;
+#endif
+}
+
 const uint8_t *orc_enc_recon(const orc_encoder_t *e) { return e->rec; }
 const uint8_t *orc_enc_recon_predeblock(const orc_encoder_t *e) { return e->rec_pre; }
 const orc_cu_t *orc_enc_cu_map(const orc_encoder_t *e) { return e->cu; }
@@ -409,10 +430,14 @@ static void inter_cu(orc_encoder_t *e, int x0, int y0, int log2)
   set_cu(e, x0, y0, log2, &cu);
 }
 
+/* P pictures have no intra-picture dependency before the entropy stage, so both loops are
+ * plain parallel-for over CTUs / CUs (threads set by orc_set_threads; 1 by default). */
 static void inter_frame(orc_encoder_t *e)
 {
-  for (int cy = 0; cy < e->h; cy += CTB)
-    for (int cx = 0; cx < e->w; cx += CTB) me_ctu(e, cx, cy);
+  const int nctb = e->ctb_cols * e->ctb_rows;
+#pragma omp parallel for schedule(dynamic, 1)
+  for (int i = 0; i < nctb; i++) me_ctu(e, (i % e->ctb_cols) * CTB, (i / e->ctb_cols) * CTB);
+#pragma omp parallel for schedule(dynamic, 4)
   for (int y8 = 0; y8 < e->h8; y8++)
     for (int x8 = 0; x8 < e->w8; x8++) {
       const orc_cu_t *cu = &e->cu[(size_t)y8 * e->w8 + x8];
@@ -436,6 +461,7 @@ static void deblock_frame(orc_encoder_t *e)
   uint8_t *Y = e->rec, *U = plane(e->rec, e->w, e->h, 1), *V = plane(e->rec, e->w, e->h, 2);
   const int qp = e->cfg.qp;
   for (int dir = 0; dir < 2; dir++)                    /* 0: vertical edges, 1: horizontal edges */
+#pragma omp parallel for schedule(static)
     for (int y8 = 0; y8 < e->h8; y8++)
       for (int x8 = 0; x8 < e->w8; x8++) {
         const orc_cu_t *q = &e->cu[(size_t)y8 * e->w8 + x8];

@@ -31,6 +31,9 @@ typedef struct {
 
 typedef struct orc_encoder orc_encoder_t;
 
+void orc_set_threads(int n);      /* OpenMP threads for the P-picture loops (default: 1 via binding) */
+int orc_max_threads(void);
+
 orc_encoder_t *orc_enc_open(const orc_enc_cfg_t *cfg);
 void orc_enc_close(orc_encoder_t *e);
 /* Encode one packed I420 frame; writes one Annex-B access unit (4-byte start codes;

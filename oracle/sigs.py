@@ -36,6 +36,8 @@ class OrcEncCfg(C.Structure):
 SIGS.update({
     "orc_enc_open": (v, [C.POINTER(OrcEncCfg)]),
     "orc_enc_close": (None, [v]),
+    "orc_set_threads": (None, [i]),
+    "orc_max_threads": (i, []),
     "orc_enc_encode": (i, [v, v, v, i]),
     "orc_enc_recon": (v, [v]),
     "orc_enc_recon_predeblock": (v, [v]),

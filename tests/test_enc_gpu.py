@@ -85,6 +85,26 @@ def test_device_resident_input_gives_the_same_stream():
         assert a.encode(f) == b.encode_dev(d)
 
 
+def test_pipelined_encoder_returns_the_same_access_units_in_order():
+    """depth > 1 (Kvazaar's owf): outputs lag by depth-1 submissions, bytes identical to depth 1."""
+    w, h = 192, 136
+    frames = frames_of("camera", w, h, 9)
+    a = GpuEncoder(w, h, qp=30, intra_period=4)
+    ref = [a.encode(f) for f in frames]
+    for depth in (2, 4):
+        b = GpuEncoder(w, h, qp=30, intra_period=4, depth=depth)
+        got = []
+        for i, f in enumerate(frames):
+            au = b.encode(f)
+            assert (au == b"") == (i < depth - 1)
+            if au:
+                got.append(au)
+        while b.pending():
+            got.append(b.flush())
+        assert b.flush() == b""
+        assert got == ref
+
+
 def test_full_hd_two_frames_match_oracle():
     """BASELINE config 2 size (1080p, partial bottom CTU row): I + P picture, bit-identical stream."""
     w, h = 1920, 1080
@@ -102,3 +122,83 @@ def test_encoder_rejects_bad_configuration():
     for bad in ((100, 64, 30), (64, 64, 52), (0, 0, 30)):
         with pytest.raises(B200Error):
             GpuEncoder(bad[0], bad[1], qp=bad[2])
+
+
+# ---- the reference-shaped boundary: kvz_api through the KvazaarFilter mirror ----------------------
+
+def test_kvazaar_filter_default_settings_stream_equals_engine_and_decodes():
+    """uvgComm.ini defaults at config-1 size; kvz_api output == engine output == oracle output."""
+    from kvazzup_b200.kvazaar import KvazaarFilter
+    w, h, n = 640, 480, 4
+    frames = frames_of("camera", w, h, n)
+    f = KvazaarFilter({"video/ResolutionWidth": w, "video/ResolutionHeight": h, "video/Preset": "ultrafast",
+                       "video/QP": 32, "parameters": [("rd", "0"), ("no-such-option", "1")]})
+    assert f.init()
+    assert f.warnings == [("no-such-option", "1")]            # config_parse != 1 is only a warning (:363-369)
+    aus = []
+    for fr in frames:
+        got = f.feed_input(fr)
+        assert len(got) == 1
+        aus += got
+    f.close()
+    o = OracleEncoder(w, h, qp=32, intra_period=64, search_range=8)
+    assert aus == [o.encode(fr) for fr in frames]
+    if ffhevc.available():
+        dec, errs = ffhevc.decode_stream(aus)
+        assert errs == 0 and len(dec) == n and np.array_equal(dec[-1][0], o.recon())
+
+
+def test_kvazaar_filter_owf_pipeline_and_drain():
+    from kvazzup_b200.kvazaar import KvazaarFilter
+    w, h, n = 192, 136, 7
+    frames = frames_of("camera", w, h, n)
+    base = {"video/ResolutionWidth": w, "video/ResolutionHeight": h, "video/QP": 30, "video/Intra": 4}
+    a = KvazaarFilter(base)
+    assert a.init()
+    ref = [a.feed_input(fr)[0] for fr in frames]
+    a.close()
+    b = KvazaarFilter(base | {"video/OWF": 2})
+    assert b.init()
+    got, counts = [], []
+    for fr in frames:
+        out = b.feed_input(fr)
+        counts.append(len(out))
+        got += out
+    assert counts[:2] == [0, 0] and all(c == 1 for c in counts[2:])
+    got += b.flush()
+    b.close()
+    assert got == ref
+
+
+def test_kvz_api_error_behaviour():
+    from kvazzup_b200 import kvazaar as kz
+    assert kz.kvz_api_get(10) is None                         # only 8-bit (kvazaarfilter.cpp:145)
+    api = kz.kvz_api_get(8)
+    cfg = api.config_alloc()
+    api.config_init(cfg)
+    assert api.config_parse(cfg, b"qp", b"99") == 0
+    assert api.config_parse(cfg, b"preset", b"warp9") == 0
+    assert api.config_parse(cfg, b"input-res", b"100x64") == 1
+    assert not api.encoder_open(cfg)                          # width not a multiple of 8 -> NULL, like a failed open
+    api.picture_free(None)                                    # must accept NULL (:476)
+    api.chunk_free(None)
+    api.config_destroy(cfg)
+
+
+def test_rate_control_tracks_the_target_bitrate():
+    from kvazzup_b200.kvazaar import KvazaarFilter
+    w, h, n = 416, 240, 40
+    frames = frames_of("camera", w, h, n)
+    sizes = {}
+    for kbps in (300, 1500):
+        f = KvazaarFilter({"video/ResolutionWidth": w, "video/ResolutionHeight": h, "video/bitrate": kbps * 1000,
+                           "video/QP": 32})
+        assert f.init()
+        aus = [f.feed_input(fr)[0] for fr in frames]
+        f.close()
+        sizes[kbps] = sum(len(a) for a in aus[8:]) * 8 / (n - 8) * 30 / 1000      # kbit/s after the intra picture
+        if ffhevc.available():
+            dec, errs = ffhevc.decode_stream(aus)
+            assert errs == 0 and len(dec) == n
+    assert sizes[300] < sizes[1500]
+    assert 0.4 * 1500 < sizes[1500] < 2.0 * 1500
