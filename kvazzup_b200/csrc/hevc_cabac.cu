@@ -101,6 +101,23 @@ __device__ __forceinline__ void enc_bypass_bits(Coder &c, uint32_t bins, int n)
   for (int i = n - 1; i >= 0; i--) enc_bypass(c, (bins >> i) & 1);
 }
 
+// n <= 16 bypass bins at once (HM encodeBinsEP): low = low * 2^n + range * value, eight at a time
+__device__ __forceinline__ void enc_bypass_group(Coder &c, uint32_t v, int n)
+{
+  c.bins += n;
+  if (n > 8) {
+    n -= 8;
+    uint32_t pat = v >> n;
+    c.low = (c.low << 8) + c.range * pat;
+    v -= pat << n;
+    c.bits_left -= 8;
+    if (c.bits_left < 12) write_out(c);
+  }
+  c.low = (c.low << n) + c.range * v;
+  c.bits_left -= n;
+  if (c.bits_left < 12) write_out(c);
+}
+
 __device__ __forceinline__ void enc_terminate(Coder &c, int bin)
 {
   c.bins++;
@@ -185,53 +202,74 @@ __device__ __forceinline__ void code_last_suffix(Coder &c, int pos)
   enc_bypass_bits(c, (uint32_t)(pos - min_in_group), nb);
 }
 
-__device__ __forceinline__ void code_remaining(Coder &c, int value, int rice)
+// ---- two-phase residual coding -------------------------------------------------------------------
+//
+// Phase A (parallel): every lane binarises whole 4x4 sub-blocks.  All context indices of
+// residual_coding are pure functions of the levels (the greater1 context set depends on the
+// previous coded sub-block only through "did it contain a level > 1 among its first eight"),
+// so each sub-block's bins can be produced independently as a list of records in shared memory:
+//     bit31 = 0 : context-coded bin,  bits 15..1 context index, bit 0 value
+//     bit31 = 1 : bypass group,       bits 28..24 count (1..16), bits 15..0 value
+// Phase B (serial, lane-redundant): the arithmetic coder walks the records in coding order.
+constexpr int kRecSlot = 80;          // records per sub-block: 1 + 16 + 8 + 1 + 1 + up to 3 per remaining level
+
+struct ResidualShared {
+  uint32_t rec[64][kRecSlot];
+  uint8_t cnt[64];
+  uint8_t any[64], hasg1[64], lastp[64];
+  uint8_t csbf_pos[64];               // coded_sub_block_flag by position (ys * 8 + xs)
+};
+
+__device__ __forceinline__ void push_bits(uint32_t *rec, int &k, unsigned long long bits, int n)
 {
-  if (value < (3 << rice)) {
-    int len = value >> rice;
-    enc_bypass_bits(c, (1u << (len + 1)) - 2, len + 1);
-    enc_bypass_bits(c, (uint32_t)value & ((1u << rice) - 1), rice);
-  } else {
-    int len = rice;
-    value -= 3 << rice;
-    while (value >= (1 << len)) { value -= 1 << len; len++; }
-    int pre = 3 + len + 1 - rice;
-    for (int i = 0; i < pre - 1; i++) enc_bypass(c, 1);
-    enc_bypass(c, 0);
-    enc_bypass_bits(c, (uint32_t)value, len);
+  while (n > 0) {
+    int m = n > 16 ? 16 : n;
+    uint32_t v = (uint32_t)((bits >> (n - m)) & ((1u << m) - 1));
+    rec[k++] = 0x80000000u | ((uint32_t)m << 24) | v;
+    n -= m;
   }
 }
 
-// lv: N x N levels in shared memory, row pitch n
-__device__ void code_residual(Coder &c, const int16_t *lv, int log2n, int cidx, int scan_idx)
+__device__ void code_residual(Coder &c, ResidualShared &rs, const int16_t *lv, int log2n, int cidx, int scan_idx, int lane)
 {
-  const int n = 1 << log2n, sb_log2 = log2n - 2, nsb = 1 << (2 * sb_log2);
-  int last_sb = -1, last_pos = -1, last_x = 0, last_y = 0;
-  for (int i = nsb - 1; i >= 0 && last_sb < 0; i--) {
+  const int n = 1 << log2n, sb_log2 = log2n - 2, nsb = 1 << (2 * sb_log2), sbw = 1 << sb_log2;
+  // ---- A1: per sub-block summary ----
+  for (int i = lane; i < nsb; i += 32) {
     int xs, ys;
     scan_pos(scan_idx, sb_log2, i, xs, ys);
+    int lastp = -1, g1seen = 0, nsig = 0;
     for (int p = 15; p >= 0; p--) {
       int xp, yp;
       scan_pos(scan_idx, 2, p, xp, yp);
-      if (lv[(ys * 4 + yp) * n + xs * 4 + xp]) { last_sb = i; last_pos = p; last_x = xs * 4 + xp; last_y = ys * 4 + yp; break; }
+      int v = lv[(ys * 4 + yp) * n + xs * 4 + xp];
+      if (v) {
+        if (lastp < 0) lastp = p;
+        if (nsig < 8 && (v > 1 || v < -1)) g1seen = 1;
+        nsig++;
+      }
     }
+    rs.any[i] = nsig != 0; rs.hasg1[i] = (uint8_t)g1seen; rs.lastp[i] = (uint8_t)(lastp < 0 ? 0 : lastp);
   }
-  if (last_sb < 0) return;
-  {
-    int px = last_x, py = last_y;
-    if (scan_idx == 2) { int tt = px; px = py; py = tt; }
-    code_last_prefix(c, px, log2n, cidx, CTX_LAST_X);
-    code_last_prefix(c, py, log2n, cidx, CTX_LAST_Y);
-    code_last_suffix(c, px);
-    code_last_suffix(c, py);
-  }
-  unsigned long long csbf = 0;                  // bit (ys*8 + xs)
-  int c1 = 1;
-  for (int i = last_sb; i >= 0; i--) {
+  __syncwarp();
+  int last_sb = -1;
+  for (int i = nsb - 1; i >= 0; i--)
+    if (rs.any[i]) { last_sb = i; break; }
+  if (last_sb < 0) return;                       // uniform: every lane sees the same flags
+  const int last_pos = rs.lastp[last_sb];
+  for (int i = lane; i < nsb; i += 32) {
     int xs, ys;
     scan_pos(scan_idx, sb_log2, i, xs, ys);
-    int right = xs + 1 < (1 << sb_log2) ? (int)((csbf >> (ys * 8 + xs + 1)) & 1) : 0;
-    int below = ys + 1 < (1 << sb_log2) ? (int)((csbf >> ((ys + 1) * 8 + xs)) & 1) : 0;
+    rs.csbf_pos[ys * 8 + xs] = i > last_sb ? 0 : ((i == last_sb || i == 0) ? 1 : rs.any[i]);
+  }
+  __syncwarp();
+  // ---- A2: records of every sub-block up to the last one ----
+  for (int i = lane; i <= last_sb; i += 32) {
+    uint32_t *rec = rs.rec[i];
+    int k = 0;
+    int xs, ys;
+    scan_pos(scan_idx, sb_log2, i, xs, ys);
+    int right = xs + 1 < sbw ? rs.csbf_pos[ys * 8 + xs + 1] : 0;
+    int below = ys + 1 < sbw ? rs.csbf_pos[(ys + 1) * 8 + xs] : 0;
     int prev_csbf = right | (below << 1);
     int absv[16];
     unsigned sig = 0, neg = 0;
@@ -247,96 +285,165 @@ __device__ void code_residual(Coder &c, const int16_t *lv, int log2n, int cidx, 
     }
     int any = sig != 0, infer_dc = 0;
     if (i < last_sb && i > 0) {
-      enc_bin(c, CTX_CSBF + (prev_csbf ? 1 : 0) + (cidx ? 2 : 0), any);
+      rec[k++] = (uint32_t)((CTX_CSBF + (prev_csbf ? 1 : 0) + (cidx ? 2 : 0)) << 1) | (uint32_t)any;
       infer_dc = 1;
     } else {
       any = 1;
     }
-    if (any) csbf |= 1ull << (ys * 8 + xs);
-    if (!any) continue;
-    int start = (i == last_sb) ? last_pos - 1 : 15;
-    for (int p = start; p >= 0; p--) {
-      if (p == 0 && infer_dc) break;
-      int xp, yp;
-      scan_pos(scan_idx, 2, p, xp, yp);
-      int xc = xs * 4 + xp, yc = ys * 4 + yp, sctx;
-      if (log2n == 2) sctx = c_sig_ctx_4x4[(yc << 2) + xc];
-      else if (xc + yc == 0) sctx = 0;
-      else {
-        if (prev_csbf == 0) sctx = (xp + yp == 0) ? 2 : (xp + yp < 3) ? 1 : 0;
-        else if (prev_csbf == 1) sctx = yp == 0 ? 2 : (yp == 1 ? 1 : 0);
-        else if (prev_csbf == 2) sctx = xp == 0 ? 2 : (xp == 1 ? 1 : 0);
-        else sctx = 2;
-        if (cidx == 0) {
-          if (xs || ys) sctx += 3;
-          sctx += log2n == 3 ? (scan_idx == 0 ? 9 : 15) : 21;
-        } else {
-          sctx += log2n == 3 ? 9 : 12;
+    if (any) {
+      int start = (i == last_sb) ? last_pos - 1 : 15;
+      for (int p = start; p >= 0; p--) {
+        if (p == 0 && infer_dc) break;
+        int xp, yp;
+        scan_pos(scan_idx, 2, p, xp, yp);
+        int xc = xs * 4 + xp, yc = ys * 4 + yp, sctx;
+        if (log2n == 2) sctx = c_sig_ctx_4x4[(yc << 2) + xc];
+        else if (xc + yc == 0) sctx = 0;
+        else {
+          if (prev_csbf == 0) sctx = (xp + yp == 0) ? 2 : (xp + yp < 3) ? 1 : 0;
+          else if (prev_csbf == 1) sctx = yp == 0 ? 2 : (yp == 1 ? 1 : 0);
+          else if (prev_csbf == 2) sctx = xp == 0 ? 2 : (xp == 1 ? 1 : 0);
+          else sctx = 2;
+          if (cidx == 0) {
+            if (xs || ys) sctx += 3;
+            sctx += log2n == 3 ? (scan_idx == 0 ? 9 : 15) : 21;
+          } else {
+            sctx += log2n == 3 ? 9 : 12;
+          }
         }
+        int sbit = (sig >> p) & 1;
+        rec[k++] = (uint32_t)((CTX_SIG + (cidx == 0 ? sctx : 27 + sctx)) << 1) | (uint32_t)sbit;
+        if (sbit) infer_dc = 0;
       }
-      int s = (sig >> p) & 1;
-      enc_bin(c, CTX_SIG + (cidx == 0 ? sctx : 27 + sctx), s);
-      if (s) infer_dc = 0;
-    }
-    int ctx_set = (i > 0 && cidx == 0) ? 2 : 0;
-    if (c1 == 0) ctx_set++;
-    c1 = 1;
-    int num_g1 = 0, first_g1 = -1;
-    unsigned g1 = 0;
-    for (int p = 15; p >= 0; p--) {
-      if (!((sig >> p) & 1) || num_g1 >= 8) continue;
-      int f = absv[p] > 1;
-      enc_bin(c, CTX_GT1 + (cidx ? 16 : 0) + 4 * ctx_set + c1, f);
-      if (f) { g1 |= 1u << p; c1 = 0; if (first_g1 < 0) first_g1 = p; }
-      else if (c1 < 3 && c1 > 0) c1++;
-      num_g1++;
-    }
-    int g2 = 0;
-    if (first_g1 >= 0) {
-      g2 = absv[first_g1] > 2;
-      enc_bin(c, CTX_GT2 + (cidx ? 4 : 0) + ctx_set, g2);
-    }
-    for (int p = 15; p >= 0; p--)
-      if ((sig >> p) & 1) enc_bypass(c, (neg >> p) & 1);
-    int num_sig = 0, rice = 0;
-    for (int p = 15; p >= 0; p--) {
-      if (!((sig >> p) & 1)) continue;
-      int base = 1 + (num_sig < 8 ? (int)((g1 >> p) & 1) : 0) + (p == first_g1 ? g2 : 0);
-      int thresh = num_sig < 8 ? (p == first_g1 ? 3 : 2) : 1;
-      if (base == thresh) {
-        code_remaining(c, absv[p] - base, rice);
-        if (absv[p] > (3 << rice)) rice = min(rice + 1, 4);
+      // greater1 context set: carried from the previous sub-block that had coefficients
+      int ctx_set = (i > 0 && cidx == 0) ? 2 : 0;
+      for (int j = i + 1; j <= last_sb; j++)
+        if (rs.any[j]) { if (rs.hasg1[j]) ctx_set++; break; }
+      int c1 = 1, num_g1 = 0, first_g1 = -1;
+      unsigned g1 = 0;
+      for (int p = 15; p >= 0; p--) {
+        if (!((sig >> p) & 1) || num_g1 >= 8) continue;
+        int f = absv[p] > 1;
+        rec[k++] = (uint32_t)((CTX_GT1 + (cidx ? 16 : 0) + 4 * ctx_set + c1) << 1) | (uint32_t)f;
+        if (f) { g1 |= 1u << p; c1 = 0; if (first_g1 < 0) first_g1 = p; }
+        else if (c1 < 3 && c1 > 0) c1++;
+        num_g1++;
       }
-      num_sig++;
+      int g2 = 0;
+      if (first_g1 >= 0) {
+        g2 = absv[first_g1] > 2;
+        rec[k++] = (uint32_t)((CTX_GT2 + (cidx ? 4 : 0) + ctx_set) << 1) | (uint32_t)g2;
+      }
+      {
+        unsigned long long sb = 0;
+        int ns = 0;
+        for (int p = 15; p >= 0; p--)
+          if ((sig >> p) & 1) { sb = (sb << 1) | ((neg >> p) & 1); ns++; }
+        push_bits(rec, k, sb, ns);
+      }
+      int num_sig = 0, rice = 0;
+      for (int p = 15; p >= 0; p--) {
+        if (!((sig >> p) & 1)) continue;
+        int base = 1 + (num_sig < 8 ? (int)((g1 >> p) & 1) : 0) + (p == first_g1 ? g2 : 0);
+        int thresh = num_sig < 8 ? (p == first_g1 ? 3 : 2) : 1;
+        if (base == thresh) {
+          int value = absv[p] - base;
+          if (value < (3 << rice)) {
+            int len = value >> rice;
+            unsigned long long bits = ((((1ull << (len + 1)) - 2) << rice) | (unsigned)(value & ((1 << rice) - 1)));
+            push_bits(rec, k, bits, len + 1 + rice);
+          } else {
+            int len = rice, vv = value - (3 << rice);
+            while (vv >= (1 << len)) { vv -= 1 << len; len++; }
+            int pre = 3 + len + 1 - rice;
+            unsigned long long bits = ((((1ull << pre) - 2) << len) | (unsigned)vv);
+            push_bits(rec, k, bits, pre + len);
+          }
+          if (absv[p] > (3 << rice)) rice = min(rice + 1, 4);
+        }
+        num_sig++;
+      }
+    }
+    rs.cnt[i] = (uint8_t)k;
+  }
+  __syncwarp();
+  // ---- B: serial arithmetic coding ----
+  {
+    int xs, ys, xp, yp;
+    scan_pos(scan_idx, sb_log2, last_sb, xs, ys);
+    scan_pos(scan_idx, 2, last_pos, xp, yp);
+    int px = xs * 4 + xp, py = ys * 4 + yp;
+    if (scan_idx == 2) { int tt = px; px = py; py = tt; }
+    code_last_prefix(c, px, log2n, cidx, CTX_LAST_X);
+    code_last_prefix(c, py, log2n, cidx, CTX_LAST_Y);
+    code_last_suffix(c, px);
+    code_last_suffix(c, py);
+  }
+  for (int i = last_sb; i >= 0; i--) {
+    const uint32_t *rec = rs.rec[i];
+    const int cnt = rs.cnt[i];
+    for (int k = 0; k < cnt; k++) {
+      uint32_t r = rec[k];
+      if (r & 0x80000000u) enc_bypass_group(c, r & 0xffffu, (int)((r >> 24) & 31));
+      else enc_bin(c, (int)(r >> 1), (int)(r & 1));
     }
   }
+  __syncwarp();
 }
 
 // ---- coding quadtree ------------------------------------------------------------------------------
+
+__device__ __forceinline__ unsigned coding_order_c(const FrameParams &fp, int x, int y)
+{
+  return (unsigned)((y >> kCtbLog2) * fp.ctb_cols + (x >> kCtbLog2)) * 64u + (unsigned)xy_to_z((x >> 3) & 7, (y >> 3) & 7);
+}
 
 struct RowCtx {
   const FrameParams *fp;
   const CuInfo *cu;
   const int16_t *levels;
   int16_t *s_lv;              // 32 x 32 staging tile in shared memory
+  ResidualShared *rs;
+  const CuInfo *s_cu;         // cu map of the current CTU plus a one-unit halo: 9 rows x 10 columns
+  int hx8, hy8;               // unit coordinates of the CTU origin
   int lane;
 };
 
-__device__ __forceinline__ unsigned coding_order_c(const FrameParams &fp, int x, int y)
+// cu-map entry covering luma sample (x,y): served from the shared-memory halo tile
+__device__ __forceinline__ const CuInfo &cu_at(const RowCtx &rc, int x, int y)
 {
-  return (unsigned)((y >> kCtbLog2) * fp.ctb_cols + (x >> kCtbLog2)) * 64u + (unsigned)xy_to_z((x >> 3) & 7, (y >> 3) & 7);
+  return rc.s_cu[((y >> 3) - rc.hy8 + 1) * 10 + ((x >> 3) - rc.hx8 + 1)];
 }
+
+__device__ void load_halo(RowCtx &rc, CuInfo *s_cu, int cx, int cy)
+{
+  const FrameParams &fp = *rc.fp;
+  __syncwarp();
+  uint32_t *dst = (uint32_t *)s_cu;
+  for (int i = rc.lane; i < 90 * 3; i += 32) {
+    int e = i / 3, wd = i - e * 3;
+    int ry = e / 10, rx = e - ry * 10;
+    int x8 = (cx >> 3) + rx - 1, y8 = (cy >> 3) + ry - 1;
+    uint32_t v = 0;
+    if (x8 >= 0 && y8 >= 0 && x8 < fp.w8 && y8 < fp.h8) v = __ldg((const uint32_t *)(rc.cu + (size_t)y8 * fp.w8 + x8) + wd);
+    dst[i] = v;
+  }
+  rc.hx8 = cx >> 3; rc.hy8 = cy >> 3;
+  __syncwarp();
+}
+
 struct NbMv { bool ok; int mvx, mvy; };
-__device__ __forceinline__ NbMv nb_mv(const FrameParams &fp, const CuInfo *cu, unsigned cur, int xn, int yn)
+__device__ __forceinline__ NbMv nb_mv(const FrameParams &fp, const RowCtx &rc, unsigned cur, int xn, int yn)
 {
   NbMv n{false, 0, 0};
   if (xn < 0 || yn < 0 || xn >= fp.w || yn >= fp.h) return n;
   if (coding_order_c(fp, xn, yn) >= cur) return n;
-  const CuInfo *c = &cu[(size_t)(yn >> 3) * fp.w8 + (xn >> 3)];
+  const CuInfo *c = &cu_at(rc, xn, yn);
   if (c->pred_mode != 0) return n;
   n.ok = true; n.mvx = c->mvx; n.mvy = c->mvy;
   return n;
 }
+
 
 __device__ __forceinline__ int scan_idx_for(int pred_mode, int intra_mode, int log2n, int cidx)
 {
@@ -355,7 +462,7 @@ __device__ void code_tb(Coder &c, const RowCtx &rc, const int16_t *plane, int pw
   __syncwarp();
   for (int i = rc.lane; i < n * n; i += 32) rc.s_lv[i] = plane[(size_t)(y0 + (i >> log2n)) * pw + x0 + (i & (n - 1))];
   __syncwarp();
-  code_residual(c, rc.s_lv, log2n, cidx, scan_idx);
+  code_residual(c, *rc.rs, rc.s_lv, log2n, cidx, scan_idx, rc.lane);
 }
 
 __device__ void code_transform_unit(Coder &c, const RowCtx &rc, int x0, int y0, int log2, const CuInfo &cu)
@@ -394,12 +501,12 @@ __device__ void code_mvd(Coder &c, int dx, int dy)
 __device__ void code_cu(Coder &c, const RowCtx &rc, int x0, int y0, int log2)
 {
   const FrameParams &fp = *rc.fp;
-  const CuInfo cu = rc.cu[(size_t)(y0 >> 3) * fp.w8 + (x0 >> 3)];
+  const CuInfo cu = cu_at(rc, x0, y0);
   const int n = 1 << log2;
   if (!fp.is_idr) {
     int ctx = 0;
-    if (x0 > 0) ctx += rc.cu[(size_t)(y0 >> 3) * fp.w8 + ((x0 - 1) >> 3)].skip;
-    if (y0 > 0) ctx += rc.cu[(size_t)((y0 - 1) >> 3) * fp.w8 + (x0 >> 3)].skip;
+    if (x0 > 0) ctx += cu_at(rc, x0 - 1, y0).skip;
+    if (y0 > 0) ctx += cu_at(rc, x0, y0 - 1).skip;
     enc_bin(c, CTX_SKIP + ctx, cu.skip);
     if (cu.merge_idx != 0xff) {
       int midx = cu.merge_idx;
@@ -417,11 +524,11 @@ __device__ void code_cu(Coder &c, const RowCtx &rc, int x0, int y0, int log2)
       enc_bin(c, CTX_MERGE_FLAG, 0);
       // AMVP predictor (8.5.3.2.6-7): first available of (A0,A1), first of (B0,B1,B2), zero padding
       unsigned cur = coding_order_c(fp, x0, y0);
-      NbMv a = nb_mv(fp, rc.cu, cur, x0 - 1, y0 + n);
-      if (!a.ok) a = nb_mv(fp, rc.cu, cur, x0 - 1, y0 + n - 1);
-      NbMv b = nb_mv(fp, rc.cu, cur, x0 + n, y0 - 1);
-      if (!b.ok) b = nb_mv(fp, rc.cu, cur, x0 + n - 1, y0 - 1);
-      if (!b.ok) b = nb_mv(fp, rc.cu, cur, x0 - 1, y0 - 1);
+      NbMv a = nb_mv(fp, rc, cur, x0 - 1, y0 + n);
+      if (!a.ok) a = nb_mv(fp, rc, cur, x0 - 1, y0 + n - 1);
+      NbMv b = nb_mv(fp, rc, cur, x0 + n, y0 - 1);
+      if (!b.ok) b = nb_mv(fp, rc, cur, x0 + n - 1, y0 - 1);
+      if (!b.ok) b = nb_mv(fp, rc, cur, x0 - 1, y0 - 1);
       int px[2], py[2], k = 0;
       if (a.ok) { px[k] = a.mvx; py[k++] = a.mvy; }
       if (b.ok && !(a.ok && a.mvx == b.mvx && a.mvy == b.mvy)) { px[k] = b.mvx; py[k++] = b.mvy; }
@@ -436,8 +543,8 @@ __device__ void code_cu(Coder &c, const RowCtx &rc, int x0, int y0, int log2)
     if (log2 == 3) enc_bin(c, CTX_PART_MODE, 1);
     int cand[3];
     int a = 1, b = 1;
-    if (x0 > 0) a = rc.cu[(size_t)(y0 >> 3) * fp.w8 + ((x0 - 1) >> 3)].intra_mode;
-    if (y0 > 0 && (y0 & (kCtb - 1))) b = rc.cu[(size_t)((y0 - 1) >> 3) * fp.w8 + (x0 >> 3)].intra_mode;
+    if (x0 > 0) a = cu_at(rc, x0 - 1, y0).intra_mode;
+    if (y0 > 0 && (y0 & (kCtb - 1))) b = cu_at(rc, x0, y0 - 1).intra_mode;
     if (a == b) {
       if (a < 2) { cand[0] = 0; cand[1] = 1; cand[2] = 26; }
       else { cand[0] = a; cand[1] = 2 + ((a + 29) % 32); cand[2] = 2 + ((a - 2 + 1) % 32); }
@@ -470,10 +577,10 @@ __device__ __forceinline__ int code_split(Coder &c, const RowCtx &rc, int x0, in
   const FrameParams &fp = *rc.fp;
   const int n = 1 << log2;
   if (!(x0 + n <= fp.w && y0 + n <= fp.h && log2 > 3)) return log2 > 3;
-  int split = rc.cu[(size_t)(y0 >> 3) * fp.w8 + (x0 >> 3)].log2_size < log2;
+  int split = cu_at(rc, x0, y0).log2_size < log2;
   int ctx = 0;
-  if (x0 > 0) ctx += (kCtbLog2 - rc.cu[(size_t)(y0 >> 3) * fp.w8 + ((x0 - 1) >> 3)].log2_size) > depth;
-  if (y0 > 0) ctx += (kCtbLog2 - rc.cu[(size_t)((y0 - 1) >> 3) * fp.w8 + (x0 >> 3)].log2_size) > depth;
+  if (x0 > 0) ctx += (kCtbLog2 - cu_at(rc, x0 - 1, y0).log2_size) > depth;
+  if (y0 > 0) ctx += (kCtbLog2 - cu_at(rc, x0, y0 - 1).log2_size) > depth;
   enc_bin(c, CTX_SPLIT_CU + ctx, split);
   return split;
 }
@@ -506,11 +613,13 @@ k_cabac_rows(FrameParams fp, const CuInfo *__restrict__ cu, const int16_t *__res
 {
   __shared__ uint8_t s_ctx[CTX_COUNT * 32];
   __shared__ int16_t s_lv[32 * 32];
+  __shared__ ResidualShared s_rs;
+  __shared__ CuInfo s_cu[90];
   const int r = blockIdx.x, lane = threadIdx.x;
   Coder c;
   c.out = rows + (size_t)r * row_cap; c.pos = 0; c.cap = row_cap; c.zeros = 0; c.ctx = s_ctx + lane; c.bins = 0;
   c.writer = lane == 0;
-  RowCtx rc{&fp, cu, levels, s_lv, lane};
+  RowCtx rc{&fp, cu, levels, s_lv, &s_rs, s_cu, 0, 0, lane};
   if (r == 0 || fp.ctb_cols < 2) {
     init_contexts(c.ctx, fp.is_idr ? 0 : 1, fp.qp);
   } else {
@@ -525,6 +634,7 @@ k_cabac_rows(FrameParams fp, const CuInfo *__restrict__ cu, const int16_t *__res
   __syncwarp();
   coder_start(c);
   for (int col = 0; col < fp.ctb_cols; col++) {
+    load_halo(rc, s_cu, col * kCtb, r * kCtb);
     code_ctu(c, rc, col * kCtb, r * kCtb);
     if (col == 1 && r + 1 < fp.ctb_rows) {
       __syncwarp();
