@@ -42,7 +42,7 @@ QP = 27
 PRESET = "veryfast"
 ME_RANGE = 12                      # what "veryfast" maps to (kvz_api.cu kPresets)
 DEPTH = 16                         # pictures in flight (owf = 15)
-KERNELS = ("intra", "me", "recon", "modes", "deblock", "cabac", "pack")
+KERNELS = ("intra", "me", "recon", "modes", "deblock", "binarise", "arith", "pack")
 
 
 def env_int(name, default):
@@ -232,7 +232,8 @@ def run_b200(args):
         "recon": px * 1.5 * 2 + px * 1.5 + px * 3.0 + (px / 64) * 12,   # src+ref read, recon + levels written, cu map
         "modes": (px / 64) * 12 * 2,
         "deblock": 2 * (px * 1.0 * 2),                        # two passes, luma read + written
-        "cabac": px * 3.0 + (px / 64) * 12,                   # levels + cu map read (bitstream written is small)
+        "binarise": px * 3.0 + (px / 64) * 12 + 4.0 * 8 * out_bytes[0] / GOP,   # levels + cu map read, ~1 record (4 B) per bin written
+        "arith": 4.0 * 8 * out_bytes[0] / GOP + out_bytes[0] / GOP,              # records read, bitstream written
         "pack": 2.0 * out_bytes[0] / GOP,
     }
     total_ms = sum(v[0] for v in prof.values()) or 1.0

@@ -33,7 +33,8 @@ int   b200_enc_encode_dev(void *enc, const uint8_t *d_i420, uint8_t *out, int ca
 int   b200_enc_flush(void *enc, uint8_t *out, int cap);   /* next pending access unit, 0 when drained */
 int   b200_enc_pending(void *enc);
 /* Per-kernel device time measured with CUDA events on the launching stream.  Kernel ids:
- * 0 intra, 1 motion search, 2 inter reconstruction, 3 merge/skip modes, 4 deblocking, 5 CABAC, 6 pack. */
+ * 0 intra, 1 motion search, 2 inter reconstruction, 3 merge/skip modes, 4 deblocking, 5 binarisation,
+ * 6 arithmetic coding, 7 pack. */
 int   b200_enc_set_profile(void *enc, int on);
 int   b200_enc_get_profile(void *enc, double *ms, unsigned long long *count, int n);
 int   b200_enc_last_was_idr(void *enc);

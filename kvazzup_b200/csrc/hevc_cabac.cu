@@ -1,14 +1,22 @@
 // CABAC entropy coding of the B200 HEVC encoder (sm_100a); SURVEY.md 8a-K row K8.
 //
-// One WPP substream (CTU row) per warp, all rows of the picture in flight at once.  Arithmetic
-// coding is serial by nature, so the warp runs the coder redundantly in all 32 lanes (uniform
-// control flow costs the same as one lane) and uses the lanes only where they differ: the
-// cooperative, coalesced staging of each transform block's levels from HBM into shared memory.
-// Lane 0 alone stores output bytes.  Rows synchronise once: row r starts from the context
-// tables row r-1 published after its second CTU (H.265 9.3.1, entropy_coding_sync_enabled).
-// All mode decisions (merge / skip / AMVP index) were taken by k_inter_modes; this kernel only
-// serialises syntax.  Output bytes are escaped on the fly (emulation_prevention_three_byte),
-// which is exact because every substream starts after a non-zero byte.
+// Arithmetic coding is serial per substream, binarisation is not, so the work is split in two
+// kernels that meet in a record buffer in HBM (hevc_common.h kRecUnitCap):
+//
+//   k_binarise     one warp per CU, every CU of the picture at once.  Writes the CU's complete
+//                  syntax as a list of bin RECORDS (context index + value, a group of <= 16 bypass
+//                  bins, or a terminate bin).  All context indices of HEVC's coding_unit /
+//                  residual_coding syntax are functions of the cu map and the levels only -- never
+//                  of the arithmetic coder's state -- so the whole picture binarises in parallel;
+//                  inside a transform block every lane binarises whole 4x4 sub-blocks.
+//   k_arith_rows   one warp per WPP substream (CTU row), all rows in flight.  Streams the record
+//                  lists of its CUs with coalesced 32-record loads (one per lane, broadcast by
+//                  shuffle, next chunk prefetched) and runs the range coder; every lane runs it
+//                  redundantly on a private context table, lane 0 stores the bytes, escaped on the
+//                  fly (exact: each substream starts after a non-zero byte).  Row r starts from
+//                  the tables row r-1 published after its second CTU (H.265 9.3.1).
+//
+// The only serial work left per bin is the range coder update itself.
 #include "hevc_device.cuh"
 #include "hevc_kernels.h"
 
@@ -87,20 +95,6 @@ __device__ __forceinline__ void enc_bin(Coder &c, int ctx_idx, int bin)
   if (c.bits_left < 12) write_out(c);
 }
 
-__device__ __forceinline__ void enc_bypass(Coder &c, int bin)
-{
-  c.bins++;
-  c.low <<= 1;
-  if (bin) c.low += c.range;
-  c.bits_left--;
-  if (c.bits_left < 12) write_out(c);
-}
-
-__device__ __forceinline__ void enc_bypass_bits(Coder &c, uint32_t bins, int n)
-{
-  for (int i = n - 1; i >= 0; i--) enc_bypass(c, (bins >> i) & 1);
-}
-
 // n <= 16 bypass bins at once (HM encodeBinsEP): low = low * 2^n + range * value, eight at a time
 __device__ __forceinline__ void enc_bypass_group(Coder &c, uint32_t v, int n)
 {
@@ -172,6 +166,24 @@ __device__ __forceinline__ void init_contexts(uint8_t *ctx, int init_type, int q
   }
 }
 
+// ---- bin records ------------------------------------------------------------------------------------
+//   bit31 = 0, bit30 = 0 : context-coded bin,  bits 15..1 context index, bit 0 value
+//   bit31 = 1            : bypass group,       bits 28..24 count (1..16), bits 15..0 value
+
+struct Syn { uint32_t *r; int k; };      // syntax-element record list (shared memory; lanes write identical values)
+
+__device__ __forceinline__ void put_ctx(Syn &s, int ctx, int bin) { s.r[s.k++] = ((uint32_t)ctx << 1) | (uint32_t)(bin & 1); }
+__device__ __forceinline__ void put_byp(uint32_t *rec, int &k, unsigned long long bits, int n)
+{
+  while (n > 0) {
+    int m = n > 16 ? 16 : n;
+    uint32_t v = (uint32_t)((bits >> (n - m)) & ((1u << m) - 1));
+    rec[k++] = 0x80000000u | ((uint32_t)m << 24) | v;
+    n -= m;
+  }
+}
+__device__ __forceinline__ void put_byp(Syn &s, unsigned long long bits, int n) { put_byp(s.r, s.k, bits, n); }
+
 // ---- residual_coding (7.3.8.11) ---------------------------------------------------------------
 
 __device__ __forceinline__ void scan_pos(int scan_idx, int blk_log2, int i, int &x, int &y)
@@ -183,34 +195,30 @@ __device__ __forceinline__ void scan_pos(int scan_idx, int blk_log2, int i, int 
   x = v & 15; y = v >> 4;
 }
 
-__device__ __forceinline__ void code_last_prefix(Coder &c, int pos, int log2n, int cidx, int base)
+__device__ __forceinline__ void put_last_prefix(Syn &s, int pos, int log2n, int cidx, int base)
 {
   int offset, shift;
   if (cidx == 0) { offset = 3 * (log2n - 2) + ((log2n - 1) >> 2); shift = (log2n + 1) >> 2; }
   else { offset = 15; shift = log2n - 2; }
   int prefix = pos < 4 ? pos : ((pos < 8) ? 4 + ((pos - 4) >> 1) : (pos < 16 ? 6 + ((pos - 8) >> 2) : 8 + ((pos - 16) >> 3)));
   int cmax = (log2n << 1) - 1;
-  for (int i = 0; i < prefix; i++) enc_bin(c, base + offset + (i >> shift), 1);
-  if (prefix < cmax) enc_bin(c, base + offset + (prefix >> shift), 0);
+  for (int i = 0; i < prefix; i++) put_ctx(s, base + offset + (i >> shift), 1);
+  if (prefix < cmax) put_ctx(s, base + offset + (prefix >> shift), 0);
 }
-__device__ __forceinline__ void code_last_suffix(Coder &c, int pos)
+__device__ __forceinline__ void put_last_suffix(Syn &s, int pos)
 {
   if (pos < 4) return;
   int g = (pos < 8) ? 4 + ((pos - 4) >> 1) : (pos < 16 ? 6 + ((pos - 8) >> 2) : 8 + ((pos - 16) >> 3));
   int nb = (g >> 1) - 1;
   int min_in_group = (2 + (g & 1)) << nb;
-  enc_bypass_bits(c, (uint32_t)(pos - min_in_group), nb);
+  put_byp(s, (unsigned)(pos - min_in_group), nb);
 }
 
-// ---- two-phase residual coding -------------------------------------------------------------------
-//
 // Phase A (parallel): every lane binarises whole 4x4 sub-blocks.  All context indices of
 // residual_coding are pure functions of the levels (the greater1 context set depends on the
 // previous coded sub-block only through "did it contain a level > 1 among its first eight"),
-// so each sub-block's bins can be produced independently as a list of records in shared memory:
-//     bit31 = 0 : context-coded bin,  bits 15..1 context index, bit 0 value
-//     bit31 = 1 : bypass group,       bits 28..24 count (1..16), bits 15..0 value
-// Phase B (serial, lane-redundant): the arithmetic coder walks the records in coding order.
+// so each sub-block's bins are produced independently.  Phase B (serial, lane-redundant): the
+// arithmetic coder walks the record lists in coding order.
 constexpr int kRecSlot = 80;          // records per sub-block: 1 + 16 + 8 + 1 + 1 + up to 3 per remaining level
 
 struct ResidualShared {
@@ -220,20 +228,11 @@ struct ResidualShared {
   uint8_t csbf_pos[64];               // coded_sub_block_flag by position (ys * 8 + xs)
 };
 
-__device__ __forceinline__ void push_bits(uint32_t *rec, int &k, unsigned long long bits, int n)
-{
-  while (n > 0) {
-    int m = n > 16 ? 16 : n;
-    uint32_t v = (uint32_t)((bits >> (n - m)) & ((1u << m) - 1));
-    rec[k++] = 0x80000000u | ((uint32_t)m << 24) | v;
-    n -= m;
-  }
-}
-
-__device__ void code_residual(Coder &c, ResidualShared &rs, const int16_t *lv, int log2n, int cidx, int scan_idx, int lane)
+// Returns the index of the last sub-block (-1: block is all zero); the last-position syntax is
+// appended to `syn`, the per-sub-block records are left in rs.rec / rs.cnt.
+__device__ int binarise_residual(Syn &syn, ResidualShared &rs, const int16_t *lv, int log2n, int cidx, int scan_idx, int lane)
 {
   const int n = 1 << log2n, sb_log2 = log2n - 2, nsb = 1 << (2 * sb_log2), sbw = 1 << sb_log2;
-  // ---- A1: per sub-block summary ----
   for (int i = lane; i < nsb; i += 32) {
     int xs, ys;
     scan_pos(scan_idx, sb_log2, i, xs, ys);
@@ -251,10 +250,11 @@ __device__ void code_residual(Coder &c, ResidualShared &rs, const int16_t *lv, i
     rs.any[i] = nsig != 0; rs.hasg1[i] = (uint8_t)g1seen; rs.lastp[i] = (uint8_t)(lastp < 0 ? 0 : lastp);
   }
   __syncwarp();
-  int last_sb = -1;
-  for (int i = nsb - 1; i >= 0; i--)
-    if (rs.any[i]) { last_sb = i; break; }
-  if (last_sb < 0) return;                       // uniform: every lane sees the same flags
+  // last sub-block in scan order: ballot over the (at most two) sub-blocks each lane owns
+  unsigned lo = __ballot_sync(0xffffffffu, lane < nsb && rs.any[lane]);
+  unsigned hi = __ballot_sync(0xffffffffu, lane + 32 < nsb && rs.any[lane + 32]);
+  int last_sb = hi ? 63 - __clz(hi) : (lo ? 31 - __clz(lo) : -1);
+  if (last_sb < 0) return -1;
   const int last_pos = rs.lastp[last_sb];
   for (int i = lane; i < nsb; i += 32) {
     int xs, ys;
@@ -262,7 +262,6 @@ __device__ void code_residual(Coder &c, ResidualShared &rs, const int16_t *lv, i
     rs.csbf_pos[ys * 8 + xs] = i > last_sb ? 0 : ((i == last_sb || i == 0) ? 1 : rs.any[i]);
   }
   __syncwarp();
-  // ---- A2: records of every sub-block up to the last one ----
   for (int i = lane; i <= last_sb; i += 32) {
     uint32_t *rec = rs.rec[i];
     int k = 0;
@@ -273,7 +272,7 @@ __device__ void code_residual(Coder &c, ResidualShared &rs, const int16_t *lv, i
     int prev_csbf = right | (below << 1);
     int absv[16];
     unsigned sig = 0, neg = 0;
-#pragma unroll
+#pragma unroll 1
     for (int p = 0; p < 16; p++) {
       int xp, yp;
       scan_pos(scan_idx, 2, p, xp, yp);
@@ -339,7 +338,7 @@ __device__ void code_residual(Coder &c, ResidualShared &rs, const int16_t *lv, i
         int ns = 0;
         for (int p = 15; p >= 0; p--)
           if ((sig >> p) & 1) { sb = (sb << 1) | ((neg >> p) & 1); ns++; }
-        push_bits(rec, k, sb, ns);
+        put_byp(rec, k, sb, ns);
       }
       int num_sig = 0, rice = 0;
       for (int p = 15; p >= 0; p--) {
@@ -351,13 +350,13 @@ __device__ void code_residual(Coder &c, ResidualShared &rs, const int16_t *lv, i
           if (value < (3 << rice)) {
             int len = value >> rice;
             unsigned long long bits = ((((1ull << (len + 1)) - 2) << rice) | (unsigned)(value & ((1 << rice) - 1)));
-            push_bits(rec, k, bits, len + 1 + rice);
+            put_byp(rec, k, bits, len + 1 + rice);
           } else {
             int len = rice, vv = value - (3 << rice);
             while (vv >= (1 << len)) { vv -= 1 << len; len++; }
             int pre = 3 + len + 1 - rice;
             unsigned long long bits = ((((1ull << pre) - 2) << len) | (unsigned)vv);
-            push_bits(rec, k, bits, pre + len);
+            put_byp(rec, k, bits, pre + len);
           }
           if (absv[p] > (3 << rice)) rice = min(rice + 1, 4);
         }
@@ -366,29 +365,19 @@ __device__ void code_residual(Coder &c, ResidualShared &rs, const int16_t *lv, i
     }
     rs.cnt[i] = (uint8_t)k;
   }
-  __syncwarp();
-  // ---- B: serial arithmetic coding ----
   {
     int xs, ys, xp, yp;
     scan_pos(scan_idx, sb_log2, last_sb, xs, ys);
     scan_pos(scan_idx, 2, last_pos, xp, yp);
     int px = xs * 4 + xp, py = ys * 4 + yp;
     if (scan_idx == 2) { int tt = px; px = py; py = tt; }
-    code_last_prefix(c, px, log2n, cidx, CTX_LAST_X);
-    code_last_prefix(c, py, log2n, cidx, CTX_LAST_Y);
-    code_last_suffix(c, px);
-    code_last_suffix(c, py);
-  }
-  for (int i = last_sb; i >= 0; i--) {
-    const uint32_t *rec = rs.rec[i];
-    const int cnt = rs.cnt[i];
-    for (int k = 0; k < cnt; k++) {
-      uint32_t r = rec[k];
-      if (r & 0x80000000u) enc_bypass_group(c, r & 0xffffu, (int)((r >> 24) & 31));
-      else enc_bin(c, (int)(r >> 1), (int)(r & 1));
-    }
+    put_last_prefix(syn, px, log2n, cidx, CTX_LAST_X);
+    put_last_prefix(syn, py, log2n, cidx, CTX_LAST_Y);
+    put_last_suffix(syn, px);
+    put_last_suffix(syn, py);
   }
   __syncwarp();
+  return last_sb;
 }
 
 // ---- coding quadtree ------------------------------------------------------------------------------
@@ -398,52 +387,25 @@ __device__ __forceinline__ unsigned coding_order_c(const FrameParams &fp, int x,
   return (unsigned)((y >> kCtbLog2) * fp.ctb_cols + (x >> kCtbLog2)) * 64u + (unsigned)xy_to_z((x >> 3) & 7, (y >> 3) & 7);
 }
 
-struct RowCtx {
+// cu-map access for the binariser (straight from HBM / L2: thousands of warps hide the latency)
+struct CuView {
   const FrameParams *fp;
   const CuInfo *cu;
-  const int16_t *levels;
-  int16_t *s_lv;              // 32 x 32 staging tile in shared memory
-  ResidualShared *rs;
-  const CuInfo *s_cu;         // cu map of the current CTU plus a one-unit halo: 9 rows x 10 columns
-  int hx8, hy8;               // unit coordinates of the CTU origin
-  int lane;
 };
-
-// cu-map entry covering luma sample (x,y): served from the shared-memory halo tile
-__device__ __forceinline__ const CuInfo &cu_at(const RowCtx &rc, int x, int y)
-{
-  return rc.s_cu[((y >> 3) - rc.hy8 + 1) * 10 + ((x >> 3) - rc.hx8 + 1)];
-}
-
-__device__ void load_halo(RowCtx &rc, CuInfo *s_cu, int cx, int cy)
-{
-  const FrameParams &fp = *rc.fp;
-  __syncwarp();
-  uint32_t *dst = (uint32_t *)s_cu;
-  for (int i = rc.lane; i < 90 * 3; i += 32) {
-    int e = i / 3, wd = i - e * 3;
-    int ry = e / 10, rx = e - ry * 10;
-    int x8 = (cx >> 3) + rx - 1, y8 = (cy >> 3) + ry - 1;
-    uint32_t v = 0;
-    if (x8 >= 0 && y8 >= 0 && x8 < fp.w8 && y8 < fp.h8) v = __ldg((const uint32_t *)(rc.cu + (size_t)y8 * fp.w8 + x8) + wd);
-    dst[i] = v;
-  }
-  rc.hx8 = cx >> 3; rc.hy8 = cy >> 3;
-  __syncwarp();
-}
+__device__ __forceinline__ const CuInfo &cu_at(const CuView &v, int x, int y) { return v.cu[(size_t)(y >> 3) * v.fp->w8 + (x >> 3)]; }
 
 struct NbMv { bool ok; int mvx, mvy; };
-__device__ __forceinline__ NbMv nb_mv(const FrameParams &fp, const RowCtx &rc, unsigned cur, int xn, int yn)
+__device__ __forceinline__ NbMv nb_mv(const CuView &v, unsigned cur, int xn, int yn)
 {
+  const FrameParams &fp = *v.fp;
   NbMv n{false, 0, 0};
   if (xn < 0 || yn < 0 || xn >= fp.w || yn >= fp.h) return n;
   if (coding_order_c(fp, xn, yn) >= cur) return n;
-  const CuInfo *c = &cu_at(rc, xn, yn);
+  const CuInfo *c = &cu_at(v, xn, yn);
   if (c->pred_mode != 0) return n;
   n.ok = true; n.mvx = c->mvx; n.mvy = c->mvy;
   return n;
 }
-
 
 __device__ __forceinline__ int scan_idx_for(int pred_mode, int intra_mode, int log2n, int cidx)
 {
@@ -454,97 +416,87 @@ __device__ __forceinline__ int scan_idx_for(int pred_mode, int intra_mode, int l
   return 0;
 }
 
-// stage one transform block of levels into shared memory (all lanes), then code it
-__device__ void code_tb(Coder &c, const RowCtx &rc, const int16_t *plane, int pw, int x0, int y0, int log2n, int cidx,
-                        int scan_idx)
-{
-  const int n = 1 << log2n;
-  __syncwarp();
-  for (int i = rc.lane; i < n * n; i += 32) rc.s_lv[i] = plane[(size_t)(y0 + (i >> log2n)) * pw + x0 + (i & (n - 1))];
-  __syncwarp();
-  code_residual(c, *rc.rs, rc.s_lv, log2n, cidx, scan_idx, rc.lane);
-}
-
-__device__ void code_transform_unit(Coder &c, const RowCtx &rc, int x0, int y0, int log2, const CuInfo &cu)
-{
-  const FrameParams &fp = *rc.fp;
-  const size_t ysz = (size_t)fp.w * fp.h;
-  int cb = (cu.cbf >> 1) & 1, cr = (cu.cbf >> 2) & 1, lu = cu.cbf & 1;
-  enc_bin(c, CTX_CBF_CHROMA, cb);
-  enc_bin(c, CTX_CBF_CHROMA, cr);
-  if (cu.pred_mode == 1 || cb || cr) enc_bin(c, CTX_CBF_LUMA + 1, lu);
-  if (lu) code_tb(c, rc, rc.levels, fp.w, x0, y0, log2, 0, scan_idx_for(cu.pred_mode, cu.intra_mode, log2, 0));
-  if (cb) code_tb(c, rc, rc.levels + ysz, fp.w >> 1, x0 >> 1, y0 >> 1, log2 - 1, 1, scan_idx_for(cu.pred_mode, cu.intra_mode, log2 - 1, 1));
-  if (cr) code_tb(c, rc, rc.levels + ysz + ysz / 4, fp.w >> 1, x0 >> 1, y0 >> 1, log2 - 1, 2, scan_idx_for(cu.pred_mode, cu.intra_mode, log2 - 1, 2));
-}
-
-__device__ void code_mvd(Coder &c, int dx, int dy)
+__device__ __forceinline__ void put_mvd(Syn &s, int dx, int dy)
 {
   int ax = abs(dx), ay = abs(dy);
-  enc_bin(c, CTX_MVD_GT0, ax > 0);
-  enc_bin(c, CTX_MVD_GT0, ay > 0);
-  if (ax) enc_bin(c, CTX_MVD_GT1, ax > 1);
-  if (ay) enc_bin(c, CTX_MVD_GT1, ay > 1);
+  put_ctx(s, CTX_MVD_GT0, ax > 0);
+  put_ctx(s, CTX_MVD_GT0, ay > 0);
+  if (ax) put_ctx(s, CTX_MVD_GT1, ax > 1);
+  if (ay) put_ctx(s, CTX_MVD_GT1, ay > 1);
   for (int k = 0; k < 2; k++) {
     int a = k ? ay : ax, d = k ? dy : dx;
     if (!a) continue;
-    if (a > 1) {
-      int v = a - 2, kk = 1;
-      while (v >= (1 << kk)) { enc_bypass(c, 1); v -= 1 << kk; kk++; }
-      enc_bypass(c, 0);
-      enc_bypass_bits(c, (uint32_t)v, kk);
+    if (a > 1) {                                   // abs_mvd_minus2: EG1
+      int v = a - 2, kk = 1, ones = 0;
+      while (v >= (1 << kk)) { ones++; v -= 1 << kk; kk++; }
+      unsigned long long bits = ((((1ull << (ones + 1)) - 2) << kk) | (unsigned)v);
+      put_byp(s, bits, ones + 1 + kk);
     }
-    enc_bypass(c, d < 0);
+    put_byp(s, d < 0, 1);
   }
 }
 
-__device__ void code_cu(Coder &c, const RowCtx &rc, int x0, int y0, int log2)
+// split_cu_flag (7.3.8.4): coded when the block fits the picture and is larger than the minimum CU
+__device__ __forceinline__ void put_split(Syn &s, const CuView &v, int x0, int y0, int log2, int depth, int split)
 {
-  const FrameParams &fp = *rc.fp;
-  const CuInfo cu = cu_at(rc, x0, y0);
+  const FrameParams &fp = *v.fp;
   const int n = 1 << log2;
+  if (!(x0 + n <= fp.w && y0 + n <= fp.h && log2 > 3)) return;       // inferred
+  int ctx = 0;
+  if (x0 > 0) ctx += (kCtbLog2 - cu_at(v, x0 - 1, y0).log2_size) > depth;
+  if (y0 > 0) ctx += (kCtbLog2 - cu_at(v, x0, y0 - 1).log2_size) > depth;
+  put_ctx(s, CTX_SPLIT_CU + ctx, split);
+}
+
+// coding_unit header (7.3.8.5-7.3.8.9) up to and including the cbf flags; returns the cbf mask
+// of the transform blocks whose residual follows (0 = none).
+__device__ __forceinline__ int put_cu_header(Syn &s, const CuView &v, const CuInfo &cu, int x0, int y0, int log2)
+{
+  const FrameParams &fp = *v.fp;
+  const int n = 1 << log2;
+  bool tu = false;
   if (!fp.is_idr) {
     int ctx = 0;
-    if (x0 > 0) ctx += cu_at(rc, x0 - 1, y0).skip;
-    if (y0 > 0) ctx += cu_at(rc, x0, y0 - 1).skip;
-    enc_bin(c, CTX_SKIP + ctx, cu.skip);
+    if (x0 > 0) ctx += cu_at(v, x0 - 1, y0).skip;
+    if (y0 > 0) ctx += cu_at(v, x0, y0 - 1).skip;
+    put_ctx(s, CTX_SKIP + ctx, cu.skip);
     if (cu.merge_idx != 0xff) {
       int midx = cu.merge_idx;
       if (!cu.skip) {
-        enc_bin(c, CTX_PRED_MODE, 0);
-        enc_bin(c, CTX_PART_MODE, 1);
-        enc_bin(c, CTX_MERGE_FLAG, 1);
+        put_ctx(s, CTX_PRED_MODE, 0);
+        put_ctx(s, CTX_PART_MODE, 1);
+        put_ctx(s, CTX_MERGE_FLAG, 1);
       }
-      enc_bin(c, CTX_MERGE_IDX, midx > 0);
-      for (int i = 1; i < kMaxMerge - 1 && midx >= i; i++) enc_bypass(c, midx > i);
-      if (!cu.skip) code_transform_unit(c, rc, x0, y0, log2, cu);
+      put_ctx(s, CTX_MERGE_IDX, midx > 0);
+      for (int i = 1; i < kMaxMerge - 1 && midx >= i; i++) put_byp(s, midx > i, 1);
+      tu = !cu.skip;                                // rqt_root_cbf inferred 1
     } else {
-      enc_bin(c, CTX_PRED_MODE, 0);
-      enc_bin(c, CTX_PART_MODE, 1);
-      enc_bin(c, CTX_MERGE_FLAG, 0);
+      put_ctx(s, CTX_PRED_MODE, 0);
+      put_ctx(s, CTX_PART_MODE, 1);
+      put_ctx(s, CTX_MERGE_FLAG, 0);
       // AMVP predictor (8.5.3.2.6-7): first available of (A0,A1), first of (B0,B1,B2), zero padding
       unsigned cur = coding_order_c(fp, x0, y0);
-      NbMv a = nb_mv(fp, rc, cur, x0 - 1, y0 + n);
-      if (!a.ok) a = nb_mv(fp, rc, cur, x0 - 1, y0 + n - 1);
-      NbMv b = nb_mv(fp, rc, cur, x0 + n, y0 - 1);
-      if (!b.ok) b = nb_mv(fp, rc, cur, x0 + n - 1, y0 - 1);
-      if (!b.ok) b = nb_mv(fp, rc, cur, x0 - 1, y0 - 1);
+      NbMv a = nb_mv(v, cur, x0 - 1, y0 + n);
+      if (!a.ok) a = nb_mv(v, cur, x0 - 1, y0 + n - 1);
+      NbMv b = nb_mv(v, cur, x0 + n, y0 - 1);
+      if (!b.ok) b = nb_mv(v, cur, x0 + n - 1, y0 - 1);
+      if (!b.ok) b = nb_mv(v, cur, x0 - 1, y0 - 1);
       int px[2], py[2], k = 0;
       if (a.ok) { px[k] = a.mvx; py[k++] = a.mvy; }
       if (b.ok && !(a.ok && a.mvx == b.mvx && a.mvy == b.mvy)) { px[k] = b.mvx; py[k++] = b.mvy; }
       while (k < 2) { px[k] = 0; py[k++] = 0; }
       int pi = cu.mvp_idx;
-      code_mvd(c, cu.mvx - px[pi], cu.mvy - py[pi]);
-      enc_bin(c, CTX_MVP_IDX, pi);
-      enc_bin(c, CTX_RQT_ROOT_CBF, cu.cbf != 0);
-      if (cu.cbf) code_transform_unit(c, rc, x0, y0, log2, cu);
+      put_mvd(s, cu.mvx - px[pi], cu.mvy - py[pi]);
+      put_ctx(s, CTX_MVP_IDX, pi);
+      put_ctx(s, CTX_RQT_ROOT_CBF, cu.cbf != 0);
+      tu = cu.cbf != 0;
     }
   } else {
-    if (log2 == 3) enc_bin(c, CTX_PART_MODE, 1);
+    if (log2 == 3) put_ctx(s, CTX_PART_MODE, 1);
     int cand[3];
     int a = 1, b = 1;
-    if (x0 > 0) a = cu_at(rc, x0 - 1, y0).intra_mode;
-    if (y0 > 0 && (y0 & (kCtb - 1))) b = cu_at(rc, x0, y0 - 1).intra_mode;
+    if (x0 > 0) a = cu_at(v, x0 - 1, y0).intra_mode;
+    if (y0 > 0 && (y0 & (kCtb - 1))) b = cu_at(v, x0, y0 - 1).intra_mode;
     if (a == b) {
       if (a < 2) { cand[0] = 0; cand[1] = 1; cand[2] = 26; }
       else { cand[0] = a; cand[1] = 2 + ((a + 29) % 32); cand[2] = 2 + ((a - 2 + 1) % 32); }
@@ -554,72 +506,112 @@ __device__ void code_cu(Coder &c, const RowCtx &rc, int x0, int y0, int log2)
     }
     int mode = cu.intra_mode, mpm = -1;
     for (int i = 0; i < 3; i++) if (cand[i] == mode) mpm = i;
-    enc_bin(c, CTX_PREV_INTRA_LUMA, mpm >= 0);
+    put_ctx(s, CTX_PREV_INTRA_LUMA, mpm >= 0);
     if (mpm >= 0) {
-      enc_bypass(c, mpm > 0);
-      if (mpm > 0) enc_bypass(c, mpm > 1);
+      put_byp(s, mpm > 0, 1);
+      if (mpm > 0) put_byp(s, mpm > 1, 1);
     } else {
       if (cand[0] > cand[1]) { int tt = cand[0]; cand[0] = cand[1]; cand[1] = tt; }
       if (cand[0] > cand[2]) { int tt = cand[0]; cand[0] = cand[2]; cand[2] = tt; }
       if (cand[1] > cand[2]) { int tt = cand[1]; cand[1] = cand[2]; cand[2] = tt; }
       int rem = mode;
       for (int i = 2; i >= 0; i--) if (rem > cand[i]) rem--;
-      enc_bypass_bits(c, (uint32_t)rem, 5);
+      put_byp(s, (unsigned)rem, 5);
     }
-    enc_bin(c, CTX_INTRA_CHROMA, 0);
-    code_transform_unit(c, rc, x0, y0, log2, cu);
+    put_ctx(s, CTX_INTRA_CHROMA, 0);
+    tu = true;
   }
+  if (!tu) return 0;
+  // transform_tree at depth 0 with no split (7.3.8.8): cbf_cb, cbf_cr, cbf_luma
+  int cb = (cu.cbf >> 1) & 1, cr = (cu.cbf >> 2) & 1, lu = cu.cbf & 1;
+  put_ctx(s, CTX_CBF_CHROMA, cb);
+  put_ctx(s, CTX_CBF_CHROMA, cr);
+  if (cu.pred_mode == 1 || cb || cr) put_ctx(s, CTX_CBF_LUMA + 1, lu);
+  return cu.cbf;
 }
 
-// split_cu_flag (7.3.8.4): coded when the block fits the picture and is larger than the minimum CU
-__device__ __forceinline__ int code_split(Coder &c, const RowCtx &rc, int x0, int y0, int log2, int depth)
-{
-  const FrameParams &fp = *rc.fp;
-  const int n = 1 << log2;
-  if (!(x0 + n <= fp.w && y0 + n <= fp.h && log2 > 3)) return log2 > 3;
-  int split = cu_at(rc, x0, y0).log2_size < log2;
-  int ctx = 0;
-  if (x0 > 0) ctx += (kCtbLog2 - cu_at(rc, x0 - 1, y0).log2_size) > depth;
-  if (y0 > 0) ctx += (kCtbLog2 - cu_at(rc, x0, y0 - 1).log2_size) > depth;
-  enc_bin(c, CTX_SPLIT_CU + ctx, split);
-  return split;
-}
+// Record region of the CU whose first unit is (ctu, z): fixed address, no prefix sums needed.
+// Word 0 = record count | log2 CU size << 24; records follow.
+__device__ __forceinline__ uint32_t *cu_region(uint32_t *recs, int ctu, int z) { return recs + ((size_t)ctu * 64 + z) * kRecUnitCap; }
 
-// coding_quadtree of one CTU, depth-first in z-order, written without recursion
-__device__ void code_ctu(Coder &c, const RowCtx &rc, int cx, int cy)
+constexpr int kBinWarps = 2;           // warps (CUs) per CTA of the binariser
+
+struct BinWarpShared {
+  int16_t lv[32 * 32];
+  ResidualShared rs;
+  uint32_t syn[128];
+};
+
+__global__ void __launch_bounds__(32 * kBinWarps)
+k_binarise(FrameParams fp, const CuInfo *__restrict__ cu, const int16_t *__restrict__ levels, uint32_t *__restrict__ recs)
 {
-  const FrameParams &fp = *rc.fp;
-  if (!code_split(c, rc, cx, cy, 6, 0)) { code_cu(c, rc, cx, cy, 6); return; }
-  for (int a = 0; a < 4; a++) {
-    int x5 = cx + 32 * (a & 1), y5 = cy + 32 * (a >> 1);
-    if (x5 >= fp.w || y5 >= fp.h) continue;
-    if (!code_split(c, rc, x5, y5, 5, 1)) { code_cu(c, rc, x5, y5, 5); continue; }
-    for (int b = 0; b < 4; b++) {
-      int x4 = x5 + 16 * (b & 1), y4 = y5 + 16 * (b >> 1);
-      if (x4 >= fp.w || y4 >= fp.h) continue;
-      if (!code_split(c, rc, x4, y4, 4, 2)) { code_cu(c, rc, x4, y4, 4); continue; }
-      for (int d = 0; d < 4; d++) {
-        int x3 = x4 + 8 * (d & 1), y3 = y4 + 8 * (d >> 1);
-        if (x3 >= fp.w || y3 >= fp.h) continue;
-        code_cu(c, rc, x3, y3, 3);
+  __shared__ BinWarpShared s_all[kBinWarps];
+  const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
+  const int unit = blockIdx.x * kBinWarps + wib;           // CTU-major, z-order inside the CTU
+  const int ctu = unit >> 6, z = unit & 63;
+  if (ctu >= fp.ctb_cols * fp.ctb_rows) return;
+  const int cx = (ctu % fp.ctb_cols) * kCtb, cy = (ctu / fp.ctb_cols) * kCtb;
+  const int x0 = cx + 8 * z_to_x(z), y0 = cy + 8 * z_to_y(z);
+  if (x0 >= fp.w || y0 >= fp.h) return;
+  CuView v{&fp, cu};
+  const CuInfo cur = cu_at(v, x0, y0);
+  const int log2 = cur.log2_size;
+  if (z & ((1 << (2 * (log2 - 3))) - 1)) return;            // not the first unit of its CU
+  BinWarpShared &sh = s_all[wib];
+  Syn syn{sh.syn, 0};
+  uint32_t *out = cu_region(recs, ctu, z);
+  int o = 1;                                                // word 0 is the header
+  // split flags of every ancestor block that starts at this unit, top down, then this CU's own
+  for (int L = 6; L > 3; L--) {
+    if (L < log2) break;
+    if (z & ((1 << (2 * (L - 3))) - 1)) continue;
+    put_split(syn, v, x0, y0, L, 6 - L, L > log2);
+  }
+  const int cbf = put_cu_header(syn, v, cur, x0, y0, log2);
+  __syncwarp();
+  for (int i = lane; i < syn.k; i += 32) out[o + i] = syn.r[i];
+  o += syn.k;
+  const size_t ysz = (size_t)fp.w * fp.h;
+  for (int k = 0; k < 3; k++) {
+    if (!((cbf >> k) & 1)) continue;
+    const int sft = k ? 1 : 0, l2 = log2 - sft, n = 1 << l2, pw = fp.w >> sft;
+    const int16_t *plane = levels + (k == 0 ? 0 : ysz + (k == 2 ? ysz / 4 : 0)) + (size_t)(y0 >> sft) * pw + (x0 >> sft);
+    __syncwarp();
+    for (int i = lane; i < n * n; i += 32) sh.lv[i] = plane[(size_t)(i >> l2) * pw + (i & (n - 1))];
+    __syncwarp();
+    syn.k = 0;
+    const int last_sb = binarise_residual(syn, sh.rs, sh.lv, l2, k, scan_idx_for(cur.pred_mode, cur.intra_mode, l2, k), lane);
+    if (last_sb < 0) continue;
+    for (int i = lane; i < syn.k; i += 32) out[o + i] = syn.r[i];      // last significant position
+    o += syn.k;
+    // sub-block record lists, concatenated in coding order (last_sb down to 0): exclusive scan of the counts
+    for (int base = last_sb; base >= 0; base -= 32) {
+      const int i = base - lane;                                       // lane 0 owns the first sub-block in coding order
+      const int cnt = i >= 0 ? sh.rs.cnt[i] : 0;
+      int pre = cnt;
+#pragma unroll
+      for (int d = 1; d < 32; d <<= 1) {
+        int t = __shfl_up_sync(0xffffffffu, pre, d);
+        if (lane >= d) pre += t;
       }
+      const int total = __shfl_sync(0xffffffffu, pre, 31);
+      const int start = o + pre - cnt;
+      for (int j = 0; j < cnt; j++) out[start + j] = sh.rs.rec[i][j];
+      o += total;
     }
   }
+  if (lane == 0) out[0] = (uint32_t)(o - 1) | ((uint32_t)log2 << 24);
 }
 
 __global__ void __launch_bounds__(32)
-k_cabac_rows(FrameParams fp, const CuInfo *__restrict__ cu, const int16_t *__restrict__ levels, uint8_t *rows,
-             uint32_t row_cap, uint32_t *row_len, uint8_t *sync_ctx, int *sync_flag, unsigned long long *bins)
+k_arith_rows(FrameParams fp, const uint32_t *__restrict__ recs, uint8_t *rows, uint32_t row_cap, uint32_t *row_len,
+             uint8_t *sync_ctx, int *sync_flag, unsigned long long *bins)
 {
   __shared__ uint8_t s_ctx[CTX_COUNT * 32];
-  __shared__ int16_t s_lv[32 * 32];
-  __shared__ ResidualShared s_rs;
-  __shared__ CuInfo s_cu[90];
   const int r = blockIdx.x, lane = threadIdx.x;
   Coder c;
   c.out = rows + (size_t)r * row_cap; c.pos = 0; c.cap = row_cap; c.zeros = 0; c.ctx = s_ctx + lane; c.bins = 0;
   c.writer = lane == 0;
-  RowCtx rc{&fp, cu, levels, s_lv, &s_rs, s_cu, 0, 0, lane};
   if (r == 0 || fp.ctb_cols < 2) {
     init_contexts(c.ctx, fp.is_idr ? 0 : 1, fp.qp);
   } else {
@@ -634,8 +626,28 @@ k_cabac_rows(FrameParams fp, const CuInfo *__restrict__ cu, const int16_t *__res
   __syncwarp();
   coder_start(c);
   for (int col = 0; col < fp.ctb_cols; col++) {
-    load_halo(rc, s_cu, col * kCtb, r * kCtb);
-    code_ctu(c, rc, col * kCtb, r * kCtb);
+    const int ctu = r * fp.ctb_cols + col;
+    const int cx = col * kCtb, cy = r * kCtb;
+    for (int z = 0; z < 64;) {
+      if (cx + 8 * z_to_x(z) >= fp.w || cy + 8 * z_to_y(z) >= fp.h) { z++; continue; }
+      const uint32_t *reg = recs + ((size_t)ctu * 64 + z) * kRecUnitCap;
+      const uint32_t hdr = __ldg(reg);
+      const int cnt = (int)(hdr & 0xffffffu), log2 = (int)(hdr >> 24);
+      // stream the CU's records: one coalesced 32-record load per chunk, the next one in flight
+      uint32_t nxt = lane < cnt ? __ldg(reg + 1 + lane) : 0;
+      for (int base = 0; base < cnt; base += 32) {
+        const uint32_t curv = nxt;
+        const int nb = base + 32;
+        nxt = nb + lane < cnt ? __ldg(reg + 1 + nb + lane) : 0;
+        const int m = min(32, cnt - base);
+        for (int k = 0; k < m; k++) {
+          const uint32_t v = __shfl_sync(0xffffffffu, curv, k);
+          if (v & 0x80000000u) enc_bypass_group(c, v & 0xffffu, (int)((v >> 24) & 31));
+          else enc_bin(c, (int)(v >> 1), (int)(v & 1));
+        }
+      }
+      z += 1 << (2 * (log2 - 3));
+    }
     if (col == 1 && r + 1 < fp.ctb_rows) {
       __syncwarp();
       if (lane == 0)
@@ -644,9 +656,9 @@ k_cabac_rows(FrameParams fp, const CuInfo *__restrict__ cu, const int16_t *__res
       __syncwarp();
       if (lane == 0) atomicExch(&sync_flag[r], 1);
     }
-    bool last = r == fp.ctb_rows - 1 && col == fp.ctb_cols - 1;
-    enc_terminate(c, last);
-    if (col == fp.ctb_cols - 1 && !last) enc_terminate(c, 1);
+    const bool last = r == fp.ctb_rows - 1 && col == fp.ctb_cols - 1;
+    enc_terminate(c, last);                                           // end_of_slice_segment_flag
+    if (col == fp.ctb_cols - 1 && !last) enc_terminate(c, 1);         // end_of_subset_one_bit
   }
   coder_finish(c);
   if (lane == 0) {
@@ -703,15 +715,21 @@ cudaError_t launch_pack_rows(int rows, const uint8_t *src, uint32_t row_cap, con
   return cudaGetLastError();
 }
 
-cudaError_t launch_cabac(const FrameParams &fp, const CuInfo *cu, const int16_t *levels, uint8_t *rows,
-                         uint32_t row_cap, uint32_t *row_len, uint8_t *sync_ctx, int *sync_flag,
-                         unsigned long long *bins, cudaStream_t s)
+cudaError_t launch_binarise(const FrameParams &fp, const CuInfo *cu, const int16_t *levels, uint32_t *recs, cudaStream_t s)
+{
+  const int units = fp.ctb_cols * fp.ctb_rows * 64;
+  k_binarise<<<(units + kBinWarps - 1) / kBinWarps, 32 * kBinWarps, 0, s>>>(fp, cu, levels, recs);
+  return cudaGetLastError();
+}
+
+cudaError_t launch_arith(const FrameParams &fp, const uint32_t *recs, uint8_t *rows, uint32_t row_cap, uint32_t *row_len,
+                         uint8_t *sync_ctx, int *sync_flag, unsigned long long *bins, cudaStream_t s)
 {
   cudaError_t e = cudaMemsetAsync(sync_flag, 0, sizeof(int) * fp.ctb_rows, s);
   if (e != cudaSuccess) return e;
   e = cudaMemsetAsync(bins, 0, sizeof(unsigned long long), s);
   if (e != cudaSuccess) return e;
-  k_cabac_rows<<<fp.ctb_rows, 32, 0, s>>>(fp, cu, levels, rows, row_cap, row_len, sync_ctx, sync_flag, bins);
+  k_arith_rows<<<fp.ctb_rows, 32, 0, s>>>(fp, recs, rows, row_cap, row_len, sync_ctx, sync_flag, bins);
   return cudaGetLastError();
 }
 

@@ -19,6 +19,10 @@ constexpr int kCtbLog2 = 6;
 constexpr int kCtb = 64;
 constexpr int kMaxMerge = 5;
 constexpr int kCuOverheadBits = 3;
+// Bin-record buffer: kRecUnitCap 32-bit words per 8x8 luma unit (CTU-major, z-order inside the
+// CTU), so the record list of a CU starts at a fixed address and owns the capacity of all its
+// units.  Worst case of an 8x8 CU: 6 sub-blocks x 75 records + CU header + 3 last positions < 640.
+constexpr int kRecUnitCap = 640;
 
 struct CuInfo {
   int16_t mvx, mvy;     // quarter-sample motion vector

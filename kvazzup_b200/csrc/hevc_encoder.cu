@@ -109,6 +109,7 @@ void Encoder::release()
     if (s.d_cu) cudaFree(s.d_cu);
     if (s.d_levels) cudaFree(s.d_levels);
     if (s.d_rows) cudaFree(s.d_rows);
+    if (s.d_recs) cudaFree(s.d_recs);
     if (s.d_small) cudaFree(s.d_small);
     if (s.d_src) cudaFree(s.d_src);
     if (s.h_src) cudaFreeHost(s.h_src);
@@ -157,6 +158,7 @@ bool Encoder::open(const EncoderConfig &c)
     ENC_CHECK(cudaMemset(s.d_cu, 0, sizeof(CuInfo) * fp.w8 * fp.h8), "memset cu");
     ENC_CHECK(cudaMalloc((void **)&s.d_levels, frame_bytes * sizeof(int16_t)), "cudaMalloc levels");
     ENC_CHECK(cudaMalloc((void **)&s.d_rows, (size_t)row_cap * fp.ctb_rows), "cudaMalloc rows");
+    ENC_CHECK(cudaMalloc((void **)&s.d_recs, (size_t)fp.ctb_cols * fp.ctb_rows * 64 * kRecUnitCap * sizeof(uint32_t)), "cudaMalloc recs");
     ENC_CHECK(cudaMalloc((void **)&s.d_small, small_bytes), "cudaMalloc small");
     ENC_CHECK(cudaMemset(s.d_small, 0, small_bytes), "memset small");
     ENC_CHECK(cudaMalloc((void **)&s.d_src, frame_bytes), "cudaMalloc src");
@@ -311,12 +313,16 @@ bool Encoder::submit(FrameSlot &s, const uint8_t *d_i420)
   }
   // entropy coding, slot stream: needs the cu map and the levels, not the deblocked picture
   ENC_CHECK(cudaStreamWaitEvent(s.stream, s.ev_pred, 0), "stream wait");
-  PROF_BEGIN(K_CABAC, s.stream);
-  ENC_CHECK(launch_cabac(p, s.d_cu, s.d_levels, s.d_rows, row_cap, row_len, s.d_small + off_ctx, sync_flag, bins, s.stream), "cabac launch");
-  PROF_END(K_CABAC, s.stream);
+  PROF_BEGIN(K_BINARISE, s.stream);
+  ENC_CHECK(launch_binarise(p, s.d_cu, s.d_levels, s.d_recs, s.stream), "binarise launch");
+  PROF_END(K_BINARISE, s.stream);
+  PROF_BEGIN(K_ARITH, s.stream);
+  ENC_CHECK(launch_arith(p, s.d_recs, s.d_rows, row_cap, row_len, s.d_small + off_ctx, sync_flag, bins, s.stream), "arith launch");
+  PROF_END(K_ARITH, s.stream);
   PROF_BEGIN(K_PACK, s.stream);
   ENC_CHECK(launch_pack_rows(p.ctb_rows, s.d_rows, row_cap, row_len, s.h_pack, pack_cap, s.h_hdr, s.stream), "pack launch");
   PROF_END(K_PACK, s.stream);
+  count_launch(1);                                 // launch_cabac is two kernels
 #undef PROF_BEGIN
 #undef PROF_END
   count_launch(2);
@@ -443,7 +449,7 @@ int b200_enc_flush(void *h, uint8_t *out, int cap)
 int b200_enc_pending(void *h) { return h ? ((Encoder *)h)->pending() : 0; }
 
 // Per-kernel device time from CUDA events on the launching stream.  Kernel ids: 0 intra, 1 me,
-// 2 inter recon, 3 modes, 4 deblock (both passes), 5 cabac, 6 pack.
+// 2 inter recon, 3 modes, 4 deblock (both passes), 5 binarise, 6 arithmetic coder, 7 pack.
 int b200_enc_set_profile(void *h, int on)
 {
   Encoder *e = (Encoder *)h;

@@ -28,6 +28,7 @@ struct FrameSlot {
   CuInfo *d_cu = nullptr;
   int16_t *d_levels = nullptr;
   uint8_t *d_rows = nullptr;       // per-row substreams
+  uint32_t *d_recs = nullptr;      // bin records (binariser -> arithmetic coder)
   uint8_t *d_small = nullptr;      // row_len | sync flags | progress | ticket | bins | sync contexts
   uint8_t *d_src = nullptr;        // device copy of a host-supplied picture
   uint8_t *h_src = nullptr;        // pinned staging of the input
@@ -35,7 +36,7 @@ struct FrameSlot {
   uint32_t *h_hdr = nullptr;       // mapped pinned: {total, row_len[rows]}
   cudaStream_t stream = nullptr;
   cudaEvent_t ev_pred = nullptr, ev_done = nullptr;
-  cudaEvent_t pev[14] = {};        // profiling: begin/end event per kernel slot (kernel ids below)
+  cudaEvent_t pev[16] = {};        // profiling: begin/end event per kernel slot (kernel ids below)
   unsigned prof_mask = 0;          // which kernel ids were recorded for the picture in this slot
   bool idr = false;
   int poc = 0, qp = 0;
@@ -74,7 +75,7 @@ class Encoder {
   cudaStream_t stream = nullptr;     // main (prediction chain) stream
 
   // per-kernel device time, measured with CUDA events on the launching stream (profile != 0)
-  enum { K_INTRA = 0, K_ME, K_RECON, K_MODES, K_DEBLOCK, K_CABAC, K_PACK, K_COUNT };
+  enum { K_INTRA = 0, K_ME, K_RECON, K_MODES, K_DEBLOCK, K_BINARISE, K_ARITH, K_PACK, K_COUNT };
   int profile = 0;
   double prof_ms[K_COUNT] = {};
   unsigned long long prof_cnt[K_COUNT] = {};

@@ -45,16 +45,16 @@ class GpuEncoder:
     def pending(self) -> int:
         return int(self.l.b200_enc_pending(self.h_enc))
 
-    KERNELS = ("intra", "me", "recon", "modes", "deblock", "cabac", "pack")
+    KERNELS = ("intra", "me", "recon", "modes", "deblock", "binarise", "arith", "pack")
 
     def set_profile(self, on: bool):
         self.l.b200_enc_set_profile(self.h_enc, int(on))
 
     def profile(self) -> dict:
         """{kernel: (total_ms, launches)} measured with CUDA events on the launching streams."""
-        ms = (C.c_double * 7)()
-        cnt = (C.c_ulonglong * 7)()
-        self.l.b200_enc_get_profile(self.h_enc, ms, cnt, 7)
+        ms = (C.c_double * 8)()
+        cnt = (C.c_ulonglong * 8)()
+        self.l.b200_enc_get_profile(self.h_enc, ms, cnt, 8)
         return {k: (ms[i], int(cnt[i])) for i, k in enumerate(self.KERNELS)}
 
     def _read(self, what, dtype, count):
