@@ -1,0 +1,87 @@
+/*
+ * b200_openhevc.h -- libOpenHevc-shaped C ABI of the B200 HEVC decoder.
+ *
+ * SOURCE-compatible stand-in for gpac's openHevcWrapper.h (the header the reference copies next to
+ * its OpenHEVC build, /root/reference/dependencies/openhevc.cmake:24-25) for everything
+ * src/media/processing/openhevcfilter.cpp touches:
+ *   libOpenHevcInit(threads, thread_type)                  :38-46
+ *   libOpenHevcStartDecoder                                :49
+ *   libOpenHevcSetTemporalLayer_id / SetActiveDecoders / SetViewLayers   :54-56
+ *   libOpenHevcVersion                                     :64
+ *   libOpenHevcDecode(h, buf, len, pts)                    :145   (<0 error, 0 no picture, >0 picture ready)
+ *   libOpenHevcGetOutput(h, got, &frame)                   :195
+ *   libOpenHevcGetPictureInfo(h, &frame.frameInfo)         :199
+ *   libOpenHevcFlush / libOpenHevcClose                    :81-82
+ * Struct members read by the reference: OpenHevc_Frame::{pvY,pvU,pvV,frameInfo},
+ * frameInfo.{nWidth,nHeight,nYPitch,nUPitch,frameRate.num,frameRate.den}   :201-233
+ *
+ * Decoding scope this round: streams of the B200 encoder's syntax family:
+ * Main profile 8-bit 4:2:0, 64x64 CTUs, 2Nx2N CUs with one TU, I and P slices with one reference
+ * picture, WPP entry points, deblocking; no SAO / PCM / AMP / scaling lists / transform skip /
+ * sign hiding / cu_qp_delta / TMVP / tiles.  Anything else makes libOpenHevcDecode return -1 with
+ * the reason in b200_last_error() -- never a silently wrong picture.
+ */
+#ifndef B200_OPENHEVC_H_
+#define B200_OPENHEVC_H_
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef void *OpenHevc_Handle;
+
+typedef struct OpenHevc_Rational {
+  int num;
+  int den;
+} OpenHevc_Rational;
+
+typedef struct OpenHevc_FrameInfo {
+  int nYPitch;
+  int nUPitch;
+  int nVPitch;
+  int nBitDepth;
+  int nWidth;
+  int nHeight;
+  int chromat_format;
+  OpenHevc_Rational sample_aspect_ratio;
+  OpenHevc_Rational frameRate;
+  int display_picture_number;
+  int flag;
+  int64_t nTimeStamp;
+} OpenHevc_FrameInfo;
+
+typedef struct OpenHevc_Frame {
+  void *pvY;                 /* decoder-owned, valid until the next libOpenHevcDecode call */
+  void *pvU;
+  void *pvV;
+  OpenHevc_FrameInfo frameInfo;
+} OpenHevc_Frame;
+
+/* thread_type: 1 frame, 2 slice, 4 frame+slice (openhevcfilter.cpp:11); accepted and ignored --
+ * parallelism comes from the WPP substreams on the GPU. */
+OpenHevc_Handle libOpenHevcInit(int nb_pthreads, int thread_type);
+int  libOpenHevcStartDecoder(OpenHevc_Handle h);            /* -1 on failure (no CUDA device) */
+/* buff: one or more NAL units, each with a 3- or 4-byte start code (the reference passes one NAL
+ * per call, openhevcfilter.cpp:145).  Returns 1 when a picture became available, 0 when not, -1 on
+ * error. */
+int  libOpenHevcDecode(OpenHevc_Handle h, const unsigned char *buff, int nal_len, int64_t pts);
+int  libOpenHevcGetOutput(OpenHevc_Handle h, int got_picture, OpenHevc_Frame *frame);   /* >0: frame filled */
+void libOpenHevcGetPictureInfo(OpenHevc_Handle h, OpenHevc_FrameInfo *info);
+void libOpenHevcSetTemporalLayer_id(OpenHevc_Handle h, int id);
+void libOpenHevcSetActiveDecoders(OpenHevc_Handle h, int n);
+void libOpenHevcSetViewLayers(OpenHevc_Handle h, int n);
+void libOpenHevcSetDebugMode(OpenHevc_Handle h, int level);
+void libOpenHevcSetCheckMD5(OpenHevc_Handle h, int on);
+const char *libOpenHevcVersion(OpenHevc_Handle h);
+void libOpenHevcFlush(OpenHevc_Handle h);
+void libOpenHevcClose(OpenHevc_Handle h);
+
+/* B200 extension: copy of the last decoded picture as packed I420 (w*h*3/2 bytes). */
+int  b200_dec_last_picture(OpenHevc_Handle h, uint8_t *dst, int cap);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* B200_OPENHEVC_H_ */

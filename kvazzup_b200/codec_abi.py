@@ -19,6 +19,20 @@ SIGNATURES: dict = {
     "b200_enc_last_bins": (C.c_ulonglong, [v]),
     "b200_enc_debug_read": (i, [v, i, v, C.c_size_t]),
     "b200_enc_debug_set_reference": (i, [v, v]),
+    "libOpenHevcInit": (v, [i, i]),
+    "libOpenHevcStartDecoder": (i, [v]),
+    "libOpenHevcDecode": (i, [v, v, i, C.c_int64]),
+    "libOpenHevcGetOutput": (i, [v, i, v]),
+    "libOpenHevcGetPictureInfo": (None, [v, v]),
+    "libOpenHevcSetTemporalLayer_id": (None, [v, i]),
+    "libOpenHevcSetActiveDecoders": (None, [v, i]),
+    "libOpenHevcSetViewLayers": (None, [v, i]),
+    "libOpenHevcSetDebugMode": (None, [v, i]),
+    "libOpenHevcSetCheckMD5": (None, [v, i]),
+    "libOpenHevcVersion": (C.c_char_p, [v]),
+    "libOpenHevcFlush": (None, [v]),
+    "libOpenHevcClose": (None, [v]),
+    "b200_dec_last_picture": (i, [v, v, i]),
 }
 
 

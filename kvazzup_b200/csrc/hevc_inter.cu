@@ -204,6 +204,9 @@ struct ReconShared {
 
 __device__ __forceinline__ int chroma_margin(int range) { return (((range + 1) >> 1) + 2 + 3) & ~3; }
 
+// kDecode = false: encoder (source given, levels and cbf produced).
+// kDecode = true : decoder (levels and cbf given by the parser; `src` unused).
+template <bool kDecode>
 __global__ void __launch_bounds__(kThreads)
 k_inter_recon(FrameParams fp, const uint8_t *__restrict__ src, const uint8_t *__restrict__ ref,
               uint8_t *__restrict__ rec, int16_t *__restrict__ levels, CuInfo *__restrict__ cu)
@@ -237,9 +240,12 @@ k_inter_recon(FrameParams fp, const uint8_t *__restrict__ src, const uint8_t *__
       int n8 = 1 << (l2 - 3);
       org = xy_to_z(ux & ~(n8 - 1), uy & ~(n8 - 1));
       sh.mvx[t] = ci.mvx; sh.mvy[t] = ci.mvy;
+      sh.cbf[t] = kDecode ? ci.cbf : 0;
+      if (kDecode && ci.pred_mode != 0) org = 0xff;        // not an inter CU: left to the intra path
+    } else {
+      sh.cbf[t] = 0;
     }
     sh.org[t] = (uint8_t)org; sh.log2[t] = (uint8_t)l2;
-    sh.cbf[t] = 0;
   }
   __syncthreads();
 
@@ -254,12 +260,14 @@ k_inter_recon(FrameParams fp, const uint8_t *__restrict__ src, const uint8_t *__
     const int ws = T + 2 * Mc, wsw = (ws >> 2) + 1;
     const int px0 = cx >> cs, py0 = cy >> cs;
     load_window(pref, pw, ph, px0 - Mc, py0 - Mc, ws, wsw, s_ref);
-    for (int i = t; i < T * T / 4; i += kThreads) {
-      int y = i / (T / 4), xw = i - y * (T / 4);
-      int gy = py0 + y, gx = px0 + 4 * xw;
-      ((uint32_t *)s_src)[i] = (gy < ph && gx < pw) ? __ldg((const uint32_t *)(psrc + (size_t)gy * pw + gx)) : 0u;
+    if (!kDecode) {
+      for (int i = t; i < T * T / 4; i += kThreads) {
+        int y = i / (T / 4), xw = i - y * (T / 4);
+        int gy = py0 + y, gx = px0 + 4 * xw;
+        ((uint32_t *)s_src)[i] = (gy < ph && gx < pw) ? __ldg((const uint32_t *)(psrc + (size_t)gy * pw + gx)) : 0u;
+      }
     }
-    if (t < 64) sh.nz[t] = 0;
+    if (t < 64) sh.nz[t] = kDecode ? ((sh.cbf[t] >> c) & 1) : 0;
     __syncthreads();
     // motion compensation: 4 threads per unit
     {
@@ -287,24 +295,51 @@ k_inter_recon(FrameParams fp, const uint8_t *__restrict__ src, const uint8_t *__
     __syncthreads();
     TileGeom g{T, c ? 5 : 6, c ? 2 : 3, cs};
     TqParams q{c ? fp.qp_c : fp.qp, fp.is_idr};
-    forward_tq(g, q, s_src, s_pred, sh.org, sh.log2, sh.dct, sh.dctT, s_a, s_b, sh.nz);
-    // levels (s_b) -> HBM, 4 per thread; s_b then becomes the scratch tile of the inverse path
-    for (int i = t; i < T * T / 4; i += kThreads) {
-      int y = i / (T / 4), xw = i - y * (T / 4);
-      int gy = py0 + y, gx = px0 + 4 * xw;
-      if (gy < ph && gx < pw) *(uint2 *)(plev + (size_t)gy * pw + gx) = ((const uint2 *)s_b)[i];
+    if (!kDecode) {
+      forward_tq(g, q, s_src, s_pred, sh.org, sh.log2, sh.dct, sh.dctT, s_a, s_b, sh.nz);
+      // levels (s_b) -> HBM, 4 per thread; s_b then becomes the scratch tile of the inverse path
+      for (int i = t; i < T * T / 4; i += kThreads) {
+        int y = i / (T / 4), xw = i - y * (T / 4);
+        int gy = py0 + y, gx = px0 + 4 * xw;
+        if (gy < ph && gx < pw) *(uint2 *)(plev + (size_t)gy * pw + gx) = ((const uint2 *)s_b)[i];
+      }
+    } else {
+      // dequantise the parsed levels (H.265 8.6.3) straight into the coefficient tile
+      const int qper = q.qp / 6, dscale = 16 * c_level_scale[q.qp % 6];
+      for (int p = t; p < T * T; p += kThreads) {
+        int y = p >> g.tlog2, x = p & (T - 1);
+        TbPos tb;
+        int16_t v = 0;
+        if (tb_at(g, sh.org, sh.log2, x, y, tb) && sh.nz[tb.org]) {
+          int lvl = plev[(size_t)(py0 + y) * pw + px0 + x];
+          int bd = tb.log2n + 3;
+          long long d = (((long long)lvl * dscale) << qper);
+          d = (d + (1LL << (bd - 1))) >> bd;
+          v = (int16_t)max(-32768LL, min(32767LL, d));
+        }
+        s_a[p] = v;
+      }
     }
     __syncthreads();
     inverse_recon(g, s_pred, sh.org, sh.log2, sh.dct, s_a, s_b, sh.nz, s_rec);
-    for (int i = t; i < T * T / 4; i += kThreads) {
-      int y = i / (T / 4), xw = i - y * (T / 4);
-      int gy = py0 + y, gx = px0 + 4 * xw;
-      if (gy < ph && gx < pw) *(uint32_t *)(prec + (size_t)gy * pw + gx) = ((const uint32_t *)s_rec)[i];
+    if (!kDecode) {
+      for (int i = t; i < T * T / 4; i += kThreads) {
+        int y = i / (T / 4), xw = i - y * (T / 4);
+        int gy = py0 + y, gx = px0 + 4 * xw;
+        if (gy < ph && gx < pw) *(uint32_t *)(prec + (size_t)gy * pw + gx) = ((const uint32_t *)s_rec)[i];
+      }
+    } else {
+      // only inter CUs own their samples here (a decoder may meet intra CUs in later revisions)
+      for (int p = t; p < T * T; p += kThreads) {
+        int y = p >> g.tlog2, x = p & (T - 1);
+        TbPos tb;
+        if (tb_at(g, sh.org, sh.log2, x, y, tb)) prec[(size_t)(py0 + y) * pw + px0 + x] = s_rec[p];
+      }
     }
-    if (t < 64 && sh.org[t] == t && sh.nz[t]) sh.cbf[t] |= (uint8_t)(1 << c);
+    if (!kDecode && t < 64 && sh.org[t] == t && sh.nz[t]) sh.cbf[t] |= (uint8_t)(1 << c);
     __syncthreads();
   }
-  if (t < 64) {
+  if (!kDecode && t < 64) {
     int ux = z_to_x(t), uy = z_to_y(t);
     int x8 = (cx >> 3) + ux, y8 = (cy >> 3) + uy;
     int org = sh.org[t];
@@ -409,8 +444,20 @@ cudaError_t launch_inter_recon(const FrameParams &fp, const uint8_t *src, const 
                                int16_t *levels, CuInfo *cu, cudaStream_t s)
 {
   size_t sm = recon_smem(fp.search_range);
-  cudaFuncSetAttribute(k_inter_recon, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm);
-  k_inter_recon<<<fp.ctb_cols * fp.ctb_rows, kThreads, sm, s>>>(fp, src, ref, rec, levels, cu);
+  cudaFuncSetAttribute(k_inter_recon<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm);
+  k_inter_recon<false><<<fp.ctb_cols * fp.ctb_rows, kThreads, sm, s>>>(fp, src, ref, rec, levels, cu);
+  return cudaGetLastError();
+}
+
+// Decoder reconstruction of a P picture: motion compensation + dequantisation + inverse transform.
+// fp.search_range must cover the largest motion vector of the picture (in full samples).
+cudaError_t launch_inter_decode(const FrameParams &fp, const uint8_t *ref, uint8_t *rec, const int16_t *levels,
+                                const CuInfo *cu, cudaStream_t s)
+{
+  size_t sm = recon_smem(fp.search_range);
+  if (sm > 200 * 1024) return cudaErrorInvalidValue;
+  cudaFuncSetAttribute(k_inter_recon<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm);
+  k_inter_recon<true><<<fp.ctb_cols * fp.ctb_rows, kThreads, sm, s>>>(fp, nullptr, ref, rec, (int16_t *)levels, (CuInfo *)cu);
   return cudaGetLastError();
 }
 

@@ -1,12 +1,17 @@
-// I-picture kernel of the B200 HEVC encoder (sm_100a).
+// I-picture kernels of the B200 HEVC encoder (sm_100a).
 //
-// Intra prediction needs the reconstructed left / above / above-right neighbours, so CTUs run
-// as a wavefront: one CTA per CTU, CTU indices handed out in raster order by an atomic ticket
-// (so every CTU a CTA waits for is already running or done -- no deadlock), a per-row progress
-// counter published with a release fence.  Inside a CTU the CUs (16x16, or 8x8 where 16 does
-// not fit the picture) are coded in z-order by all 256 threads: one thread per sample for the
-// 35-mode SAD search (H.265 8.4.4.2, rows K4/K10 of SURVEY.md 8a-K), then the transform /
-// quantisation / reconstruction of the chosen mode (rows K5, K6) with chroma in derived mode.
+//   k_intra_modes   mode decision for every CU of the picture at once: one CTA per 16x16 block
+//                   (8x8 CUs where 16 does not fit the picture), one thread per sample, 35-mode
+//                   SAD search (H.265 8.4.4.2) predicted from the
+//                   SOURCE picture's neighbours with the standard's availability / substitution /
+//                   smoothing rules.  No dependency on any reconstruction, so fully parallel.
+//   k_intra_frame   reconstruction wavefront: intra prediction needs the reconstructed left /
+//                   above / above-right neighbours, so CTUs run as a wavefront -- one CTA per CTU,
+//                   CTU indices handed out in raster order by an atomic ticket (every CTU a CTA
+//                   waits for is already running or done: no deadlock), a per-row progress counter
+//                   published with a release fence.  Inside a CTU the CUs are coded in z-order;
+//                   the three planes of a CU go through prediction, DCT, quantisation, inverse and
+//                   reconstruction (rows K5, K6) concurrently: 256 + 64 + 64 threads.
 #include "hevc_device.cuh"
 #include "hevc_kernels.h"
 
@@ -14,16 +19,11 @@ namespace b200 {
 
 namespace {
 
-constexpr int kThreads = 256;
+constexpr int kModeThreads = 256;     // k_intra_modes: one thread per luma sample of a 16x16 CU
+constexpr int kReconThreads = 384;    // k_intra_frame: 256 luma + 64 Cb + 64 Cr samples of a 16x16 CU
 
-struct IntraShared {
-  uint8_t raw[132], sub[132], filt[132], av[132];
-  unsigned sad[36];
-  int best_mode, dc, ctu, cand[3];
-  int8_t dct[32][32], dctT[32][32];
-  uint8_t src[256], pred[256];
-  int16_t a[256], b[256];
-};
+// neighbour samples of one block: raw gather, substituted, [1 2 1]-filtered, availability
+struct RefSet { uint8_t raw[68], sub[68], filt[68], av[68]; int dc; };
 
 __device__ __forceinline__ unsigned coding_order_i(const FrameParams &fp, int x, int y)
 {
@@ -75,126 +75,73 @@ __device__ __forceinline__ int intra_pixel(const uint8_t *u, const uint8_t *f, i
 #undef TOP
 }
 
-// Gather + substitute (8.4.4.2.2) + filter (8.4.4.2.3) the neighbours of the n x n block at
-// (x0,y0) of plane c.  Result in sh.sub / sh.filt, DC value in sh.dc.
-__device__ void prepare_refs(IntraShared &sh, const FrameParams &fp, const uint8_t *rec_plane, int pw, int c,
-                             int x0, int y0, int n, unsigned cur_order)
+// Gather (8.4.4.2.2) the 4n+1 neighbours of the n x n block at (x0,y0) of `plane` (plane c of the
+// picture; c > 0 is 4:2:0 chroma) into rs.raw / rs.av.  `first` = index of the first thread of
+// the group of >= 4n+1 threads doing this block.  Caller synchronises, then calls finish_refs.
+__device__ __forceinline__ void gather_refs(RefSet &rs, const FrameParams &fp, const uint8_t *plane, int pw, int c,
+                                            int x0, int y0, int n, unsigned cur_order, int t)
 {
-  const int t = threadIdx.x, cnt = 4 * n + 1, sft = c ? 1 : 0;
-  if (t < cnt) {
+  const int cnt = 4 * n + 1, sft = c ? 1 : 0;
+  if (t >= 0 && t < cnt) {
     int x, y;
     if (t < 2 * n) { x = x0 - 1; y = y0 + 2 * n - 1 - t; }
     else if (t == 2 * n) { x = x0 - 1; y = y0 - 1; }
     else { x = x0 + (t - 2 * n - 1); y = y0 - 1; }
     int lx = x << sft, ly = y << sft;
     bool ok = lx >= 0 && ly >= 0 && lx < fp.w && ly < fp.h && coding_order_i(fp, lx, ly) < cur_order;
-    sh.av[t] = ok;
-    sh.raw[t] = ok ? __ldcg(rec_plane + (size_t)y * pw + x) : 0;
+    rs.av[t] = ok;
+    rs.raw[t] = ok ? __ldcg(plane + (size_t)y * pw + x) : 0;
   }
-  __syncthreads();
-  if (t < cnt) {
-    int j = t;
-    while (j >= 0 && !sh.av[j]) j--;
-    if (j < 0) { j = t + 1; while (j < cnt && !sh.av[j]) j++; }
-    sh.sub[t] = j < cnt ? sh.raw[j] : 128;
-  }
-  __syncthreads();
-  if (t < cnt)
-    sh.filt[t] = (t == 0 || t == cnt - 1) ? sh.sub[t] : (uint8_t)((sh.sub[t - 1] + 2 * sh.sub[t] + sh.sub[t + 1] + 2) >> 2);
-  if (t == 0) {
-    int s = n;
-    for (int i = 0; i < n; i++) s += sh.sub[2 * n + 1 + i] + sh.sub[2 * n - 1 - i];
-    sh.dc = s >> (31 - __clz(n) + 1);
-  }
-  __syncthreads();
 }
-
-// residual -> DCT -> Q -> IQ -> IDCT -> reconstruction of one n x n block held in sh.src / sh.pred.
-// Writes levels and reconstruction to HBM; returns (to all threads) whether any level is non-zero.
-__device__ int tq_block(IntraShared &sh, const FrameParams &fp, int log2n, int qp, int16_t *lev_plane,
-                        uint8_t *rec_plane, int pw, int x0, int y0)
+// substitution (8.4.4.2.2) by thread t of the group; caller synchronises afterwards
+__device__ __forceinline__ void substitute_refs(RefSet &rs, int n, int t)
 {
-  const int n = 1 << log2n, nn = n * n, t = threadIdx.x, nshift = 5 - log2n;
-  const int y = t >> log2n, x = t & (n - 1);
-  const bool act = t < nn;
-  if (act) sh.a[t] = (int16_t)((int)sh.src[t] - (int)sh.pred[t]);
-  __syncthreads();
-  if (act) {
-    int acc = 0, kk = x << nshift;
-    for (int i = 0; i < n; i++) acc += sh.dctT[i][kk] * sh.a[y * n + i];
-    int s1 = log2n - 1;
-    sh.b[t] = (int16_t)((acc + (1 << (s1 - 1))) >> s1);
+  const int cnt = 4 * n + 1;
+  if (t >= 0 && t < cnt) {
+    int j = t;
+    while (j >= 0 && !rs.av[j]) j--;
+    if (j < 0) { j = t + 1; while (j < cnt && !rs.av[j]) j++; }
+    rs.sub[t] = j < cnt ? rs.raw[j] : 128;
   }
-  __syncthreads();
-  int lvl = 0;
-  if (act) {
-    int acc = 0;
-    const int8_t *c = sh.dct[y << nshift];
-    for (int j = 0; j < n; j++) acc += c[j] * sh.b[j * n + x];
-    int s2 = log2n + 6;
-    int coef = (acc + (1 << (s2 - 1))) >> s2;
-    int qper = qp / 6, qrem = qp % 6;
-    int qbits = 14 + qper + (7 - log2n);
-    unsigned add = (unsigned)(fp.is_idr ? 171 : 85) << (qbits - 9);
-    unsigned a = ((unsigned)abs(coef) * (unsigned)c_quant_scale[qrem] + add) >> qbits;
-    lvl = (int)min(a, 32767u);
-    if (coef < 0) lvl = -lvl;
-    lev_plane[(size_t)(y0 + y) * pw + x0 + x] = (int16_t)lvl;
-    int bd = log2n + 3;
-    long long d = ((long long)lvl * (16 * c_level_scale[qrem])) << qper;
-    d = (d + (1LL << (bd - 1))) >> bd;
-    sh.a[t] = (int16_t)max(-32768LL, min(32767LL, d));
+}
+// [1 2 1] smoothing (8.4.4.2.3) and the DC value; caller synchronises afterwards
+__device__ __forceinline__ void filter_refs(RefSet &rs, int n, int t)
+{
+  const int cnt = 4 * n + 1;
+  if (t >= 0 && t < cnt)
+    rs.filt[t] = (t == 0 || t == cnt - 1) ? rs.sub[t] : (uint8_t)((rs.sub[t - 1] + 2 * rs.sub[t] + rs.sub[t + 1] + 2) >> 2);
+  if (t == cnt) {                      // one spare thread of the group sums the DC value
+    int s = n;
+    for (int i = 0; i < n; i++) s += rs.sub[2 * n + 1 + i] + rs.sub[2 * n - 1 - i];
+    rs.dc = s >> (31 - __clz(n) + 1);
   }
-  int nz = __syncthreads_or(lvl != 0);
-  if (nz) {
-    if (act) {
-      int acc = 0;
-      for (int k = 0; k < n; k++) acc += sh.dct[k << nshift][y] * sh.a[k * n + x];
-      sh.b[t] = (int16_t)clip3(-32768, 32767, (acc + 64) >> 7);
-    }
-    __syncthreads();
-  }
-  if (act) {
-    int pr = sh.pred[t];
-    if (nz) {
-      int acc = 0;
-      for (int k = 0; k < n; k++) acc += sh.dct[k << nshift][x] * sh.b[y * n + k];
-      pr = clip8(pr + clip3(-32768, 32767, (acc + 2048) >> 12));
-    }
-    __stcg(rec_plane + (size_t)(y0 + y) * pw + x0 + x, (uint8_t)pr);
-  }
-  __syncthreads();
-  return nz;
 }
 
-__device__ void intra_cu(IntraShared &sh, const FrameParams &fp, const uint8_t *src, uint8_t *rec, int16_t *levels,
-                         CuInfo *cu, int x0, int y0, int log2)
+// ---- mode decision, whole picture in parallel ----------------------------------------------------
+
+struct ModeShared {
+  RefSet rs;
+  unsigned sad[36];
+  uint8_t src[256];
+};
+
+__device__ void decide_cu(ModeShared &sh, const FrameParams &fp, const uint8_t *src, CuInfo *cu, int x0, int y0, int log2)
 {
   const int n = 1 << log2, t = threadIdx.x;
-  const size_t ysz = (size_t)fp.w * fp.h;
   const unsigned cur = coding_order_i(fp, x0, y0);
-  // most probable modes (8.4.2) -> mode signalling cost
-  if (t == 0) {
-    int a = 1, b = 1;
-    if (x0 > 0) { const CuInfo *nb = &cu[(size_t)(y0 >> 3) * fp.w8 + ((x0 - 1) >> 3)]; if (__ldcg(&nb->pred_mode) == 1) a = __ldcg(&nb->intra_mode); }
-    if (y0 > 0 && (y0 & (kCtb - 1))) { const CuInfo *nb = &cu[(size_t)((y0 - 1) >> 3) * fp.w8 + (x0 >> 3)]; if (__ldcg(&nb->pred_mode) == 1) b = __ldcg(&nb->intra_mode); }
-    if (a == b) {
-      if (a < 2) { sh.cand[0] = 0; sh.cand[1] = 1; sh.cand[2] = 26; }
-      else { sh.cand[0] = a; sh.cand[1] = 2 + ((a + 29) % 32); sh.cand[2] = 2 + ((a - 2 + 1) % 32); }
-    } else {
-      sh.cand[0] = a; sh.cand[1] = b;
-      sh.cand[2] = (a != 0 && b != 0) ? 0 : ((a != 1 && b != 1) ? 1 : 26);
-    }
-  }
-  if (t < 36) sh.sad[t] = 0;
   const int y = t >> log2, x = t & (n - 1);
   const bool act = t < n * n;
+  if (t < 36) sh.sad[t] = 0;
   if (act) sh.src[t] = __ldg(src + (size_t)(y0 + y) * fp.w + x0 + x);
-  prepare_refs(sh, fp, rec, fp.w, 0, x0, y0, n, cur);
-  // 35-mode search, one thread per sample
+  gather_refs(sh.rs, fp, src, fp.w, 0, x0, y0, n, cur, t);
+  __syncthreads();
+  substitute_refs(sh.rs, n, t);
+  __syncthreads();
+  filter_refs(sh.rs, n, t);
+  __syncthreads();
   for (int mode = 0; mode < 35; mode++) {
     unsigned d = 0;
-    if (act) d = (unsigned)abs((int)sh.src[t] - intra_pixel(sh.sub, sh.filt, n, log2, mode, 0, sh.dc, x, y));
+    if (act) d = (unsigned)abs((int)sh.src[t] - intra_pixel(sh.rs.sub, sh.rs.filt, n, log2, mode, 0, sh.rs.dc, x, y));
     d = __reduce_add_sync(0xffffffffu, d);
     if ((t & 31) == 0 && d) atomicAdd(&sh.sad[mode], d);
   }
@@ -203,68 +150,161 @@ __device__ void intra_cu(IntraShared &sh, const FrameParams &fp, const uint8_t *
     unsigned best = 0xffffffffu;
     int bm = 0;
     for (int mode = 0; mode < 35; mode++) {
-      int bits = mode == sh.cand[0] ? 2 : ((mode == sh.cand[1] || mode == sh.cand[2]) ? 3 : 6);
+      int bits = (mode == 0 || mode == 1 || mode == 26) ? 2 : 6;     // fixed prior: the MPM list is unknown here
       unsigned cost = sh.sad[mode] + (unsigned)((fp.lambda_q4 * bits) >> 4);
       if (cost < best) { best = cost; bm = mode; }
     }
-    sh.best_mode = bm;
-  }
-  __syncthreads();
-  const int mode = sh.best_mode;
-  if (act) sh.pred[t] = (uint8_t)intra_pixel(sh.sub, sh.filt, n, log2, mode, 0, sh.dc, x, y);
-  __syncthreads();
-  int cbf = tq_block(sh, fp, log2, fp.qp, levels, rec, fp.w, x0, y0) ? 1 : 0;
-  // chroma, derived mode
-  const int nc = n >> 1, lc = log2 - 1, cw = fp.w >> 1;
-  for (int c = 1; c < 3; c++) {
-    const size_t off = ysz + (c == 2 ? ysz / 4 : 0);
-    const int yc = t >> lc, xc = t & (nc - 1);
-    const bool actc = t < nc * nc;
-    if (actc) sh.src[t] = __ldg(src + off + (size_t)(y0 / 2 + yc) * cw + x0 / 2 + xc);
-    prepare_refs(sh, fp, rec + off, cw, c, x0 / 2, y0 / 2, nc, cur);
-    if (actc) sh.pred[t] = (uint8_t)intra_pixel(sh.sub, sh.filt, nc, lc, mode, c, sh.dc, xc, yc);
-    __syncthreads();
-    if (tq_block(sh, fp, lc, fp.qp_c, levels + off, rec + off, cw, x0 / 2, y0 / 2)) cbf |= 1 << c;
-  }
-  const int n8 = n >> 3;
-  if (t < n8 * n8) {
     CuInfo ci;
-    ci.mvx = 0; ci.mvy = 0; ci.log2_size = (uint8_t)log2; ci.pred_mode = 1; ci.intra_mode = (uint8_t)mode;
-    ci.cbf = (uint8_t)cbf; ci.skip = 0; ci.merge_idx = 0xff; ci.mvp_idx = 0; ci.pad = 0;
-    CuInfo *dst = &cu[(size_t)((y0 >> 3) + t / n8) * fp.w8 + (x0 >> 3) + t % n8];
-    uint32_t *d32 = (uint32_t *)dst;
-    const uint32_t *s32 = (const uint32_t *)&ci;
-    __stcg(d32, s32[0]); __stcg(d32 + 1, s32[1]); __stcg(d32 + 2, s32[2]);
+    ci.mvx = 0; ci.mvy = 0; ci.log2_size = (uint8_t)log2; ci.pred_mode = 1; ci.intra_mode = (uint8_t)bm;
+    ci.cbf = 0; ci.skip = 0; ci.merge_idx = 0xff; ci.mvp_idx = 0; ci.pad = 0;
+    const int n8 = n >> 3;
+    for (int j = 0; j < n8; j++)
+      for (int i = 0; i < n8; i++) cu[(size_t)((y0 >> 3) + j) * fp.w8 + (x0 >> 3) + i] = ci;
+  }
+  __syncthreads();
+}
+
+__global__ void __launch_bounds__(kModeThreads)
+k_intra_modes(FrameParams fp, const uint8_t *__restrict__ src, CuInfo *__restrict__ cu)
+{
+  __shared__ ModeShared sh;
+  const int bw = (fp.w + 15) >> 4;
+  const int x0 = (blockIdx.x % bw) * 16, y0 = (blockIdx.x / bw) * 16;
+  if (x0 + 16 <= fp.w && y0 + 16 <= fp.h) {
+    decide_cu(sh, fp, src, cu, x0, y0, 4);
+  } else {
+    for (int q = 0; q < 4; q++) {
+      int x1 = x0 + 8 * (q & 1), y1 = y0 + 8 * (q >> 1);
+      if (x1 < fp.w && y1 < fp.h) decide_cu(sh, fp, src, cu, x1, y1, 3);
+    }
+  }
+}
+
+// ---- reconstruction wavefront ----------------------------------------------------------------------
+
+struct ReconSharedI {
+  RefSet rs[3];
+  int nz[3], ctu;
+  int8_t dct[32][32], dctT[32][32];
+  uint8_t pred[384];
+  int16_t a[384], b[384];
+};
+
+// One CU: the three planes side by side.  Thread t: plane p (0: t < 256, 1: 256..319, 2: 320..383
+// for a 16x16 CU), sample (x,y) of that plane's n_p x n_p block.
+template <bool kDecode>
+__device__ void recon_cu(ReconSharedI &sh, const FrameParams &fp, const uint8_t *src, uint8_t *rec, int16_t *levels,
+                         CuInfo *cu, int x0, int y0, int log2)
+{
+  const int t = threadIdx.x;
+  const size_t ysz = (size_t)fp.w * fp.h;
+  const unsigned cur = coding_order_i(fp, x0, y0);
+  const int nl = 1 << log2, nc = nl >> 1, ll = nl * nl, lc = nc * nc;
+  // plane of this thread
+  int p, li;
+  if (t < ll) { p = 0; li = t; }
+  else if (t < ll + lc) { p = 1; li = t - ll; }
+  else if (t < ll + 2 * lc) { p = 2; li = t - ll - lc; }
+  else { p = -1; li = 0; }
+  const int l2 = p == 0 ? log2 : log2 - 1, n = 1 << l2;
+  const int y = li >> l2, x = li & (n - 1);
+  const int pw = p == 0 ? fp.w : fp.w >> 1;
+  const size_t poff = p <= 0 ? 0 : ysz + (p == 2 ? ysz / 4 : 0);
+  const int bx = p == 0 ? x0 : x0 >> 1, by = p == 0 ? y0 : y0 >> 1;
+  const int qp = p == 0 ? fp.qp : fp.qp_c;
+  const int mode = __ldcg(&cu[(size_t)(y0 >> 3) * fp.w8 + (x0 >> 3)].intra_mode);
+  // neighbours: groups of 128 threads gather one plane each (4n+1 <= 65 samples, +1 for the DC sum)
+  {
+    const int g = t >> 7, gt = t & 127;                    // g = plane whose neighbours this thread helps with
+    const int gn = g == 0 ? nl : nc;
+    const size_t goff = g == 0 ? 0 : ysz + (g == 2 ? ysz / 4 : 0);
+    const int gpw = g == 0 ? fp.w : fp.w >> 1;
+    const int gx = g == 0 ? x0 : x0 >> 1, gy = g == 0 ? y0 : y0 >> 1;
+    if (t < 3) sh.nz[t] = kDecode ? ((__ldcg(&cu[(size_t)(y0 >> 3) * fp.w8 + (x0 >> 3)].cbf) >> t) & 1) : 0;
+    gather_refs(sh.rs[g], fp, rec + goff, gpw, g, gx, gy, gn, cur, gt);
+    __syncthreads();
+    substitute_refs(sh.rs[g], gn, gt);
+    __syncthreads();
+    filter_refs(sh.rs[g], gn, gt);
+    __syncthreads();
+  }
+  const int nshift = 5 - l2;
+  int16_t *a = sh.a + (p <= 0 ? 0 : ll + (p == 2 ? lc : 0));
+  int16_t *b = sh.b + (p <= 0 ? 0 : ll + (p == 2 ? lc : 0));
+  int pr = 0;
+  if (p >= 0) pr = intra_pixel(sh.rs[p].sub, sh.rs[p].filt, n, l2, mode, p, sh.rs[p].dc, x, y);
+  if (!kDecode) {
+    if (p >= 0) {
+      int s = __ldg(src + poff + (size_t)(by + y) * pw + bx + x);
+      a[li] = (int16_t)(s - pr);
+    }
+    __syncthreads();
+    if (p >= 0) {
+      int acc = 0, kk = x << nshift;
+      for (int i = 0; i < n; i++) acc += sh.dctT[i][kk] * a[y * n + i];
+      int s1 = l2 - 1;
+      b[li] = (int16_t)((acc + (1 << (s1 - 1))) >> s1);
+    }
+    __syncthreads();
+  }
+  if (p >= 0) {
+    const int qper = qp / 6, qrem = qp % 6;
+    int lvl;
+    if (!kDecode) {
+      int acc = 0;
+      const int8_t *c = sh.dct[y << nshift];
+      for (int j = 0; j < n; j++) acc += c[j] * b[j * n + x];
+      int s2 = l2 + 6;
+      int coef = (acc + (1 << (s2 - 1))) >> s2;
+      int qbits = 14 + qper + (7 - l2);
+      unsigned add = (unsigned)(fp.is_idr ? 171 : 85) << (qbits - 9);
+      unsigned av = ((unsigned)abs(coef) * (unsigned)c_quant_scale[qrem] + add) >> qbits;
+      lvl = (int)min(av, 32767u);
+      if (coef < 0) lvl = -lvl;
+      levels[poff + (size_t)(by + y) * pw + bx + x] = (int16_t)lvl;
+      if (lvl) sh.nz[p] = 1;
+    } else {
+      lvl = sh.nz[p] ? levels[poff + (size_t)(by + y) * pw + bx + x] : 0;
+    }
+    int bd = l2 + 3;
+    long long d = ((long long)lvl * (16 * c_level_scale[qrem])) << qper;
+    d = (d + (1LL << (bd - 1))) >> bd;
+    a[li] = (int16_t)max(-32768LL, min(32767LL, d));
+  }
+  __syncthreads();
+  const int nz = p >= 0 ? sh.nz[p] : 0;
+  if (nz) {
+    int acc = 0;
+    for (int k = 0; k < n; k++) acc += sh.dct[k << nshift][y] * a[k * n + x];
+    b[li] = (int16_t)clip3(-32768, 32767, (acc + 64) >> 7);
+  }
+  __syncthreads();
+  if (p >= 0) {
+    int v = pr;
+    if (nz) {
+      int acc = 0;
+      for (int k = 0; k < n; k++) acc += sh.dct[k << nshift][x] * b[y * n + k];
+      v = clip8(pr + clip3(-32768, 32767, (acc + 2048) >> 12));
+    }
+    __stcg(rec + poff + (size_t)(by + y) * pw + bx + x, (uint8_t)v);
+  }
+  const int n8 = nl >> 3;
+  if (!kDecode && t < n8 * n8) {
+    int cbf = (sh.nz[0] ? 1 : 0) | (sh.nz[1] ? 2 : 0) | (sh.nz[2] ? 4 : 0);
+    __stcg(&cu[(size_t)((y0 >> 3) + t / n8) * fp.w8 + (x0 >> 3) + t % n8].cbf, (uint8_t)cbf);
   }
   __threadfence();
   __syncthreads();
 }
 
-__device__ void intra_tree(IntraShared &sh, const FrameParams &fp, const uint8_t *src, uint8_t *rec, int16_t *levels,
-                           CuInfo *cu, int cx, int cy)
-{
-  // z-order walk over the sixteen 16x16 positions of the CTU; 16x16 that cross the picture edge fall to 8x8
-  for (int z16 = 0; z16 < 16; z16++) {
-    int x0 = cx + 16 * ((z16 & 1) | ((z16 >> 1) & 2)), y0 = cy + 16 * (((z16 >> 1) & 1) | ((z16 >> 2) & 2));
-    if (x0 >= fp.w || y0 >= fp.h) continue;
-    if (x0 + 16 <= fp.w && y0 + 16 <= fp.h) {
-      intra_cu(sh, fp, src, rec, levels, cu, x0, y0, 4);
-    } else {
-      for (int q = 0; q < 4; q++) {
-        int x1 = x0 + 8 * (q & 1), y1 = y0 + 8 * (q >> 1);
-        if (x1 < fp.w && y1 < fp.h) intra_cu(sh, fp, src, rec, levels, cu, x1, y1, 3);
-      }
-    }
-  }
-}
-
-__global__ void __launch_bounds__(kThreads)
+template <bool kDecode>
+__global__ void __launch_bounds__(kReconThreads)
 k_intra_frame(FrameParams fp, const uint8_t *__restrict__ src, uint8_t *rec, int16_t *levels, CuInfo *cu,
               int *progress, int *ticket)
 {
-  __shared__ IntraShared sh;
+  __shared__ ReconSharedI sh;
   const int t = threadIdx.x;
-  for (int i = t; i < 1024; i += kThreads) {
+  for (int i = t; i < 1024; i += kReconThreads) {
     ((int8_t *)sh.dct)[i] = c_dct32[i >> 5][i & 31];
     ((int8_t *)sh.dctT)[i] = c_dct32[i & 31][i >> 5];
   }
@@ -275,15 +315,28 @@ k_intra_frame(FrameParams fp, const uint8_t *__restrict__ src, uint8_t *rec, int
   if (t == 0) {
     // left CTU of this row, and the above-right CTU of the row above
     volatile int *p = progress;
-    while (col > 0 && p[row] < col) __nanosleep(64);
+    while (col > 0 && p[row] < col) __nanosleep(32);
     if (row > 0) {
       int need = min(col + 2, fp.ctb_cols);
-      while (p[row - 1] < need) __nanosleep(64);
+      while (p[row - 1] < need) __nanosleep(32);
     }
     __threadfence();
   }
   __syncthreads();
-  intra_tree(sh, fp, src, rec, levels, cu, col * kCtb, row * kCtb);
+  const int cx = col * kCtb, cy = row * kCtb;
+  // z-order walk over the sixteen 16x16 positions of the CTU; 16x16 that cross the picture edge fall to 8x8
+  for (int z16 = 0; z16 < 16; z16++) {
+    int x0 = cx + 16 * ((z16 & 1) | ((z16 >> 1) & 2)), y0 = cy + 16 * (((z16 >> 1) & 1) | ((z16 >> 2) & 2));
+    if (x0 >= fp.w || y0 >= fp.h) continue;
+    if (x0 + 16 <= fp.w && y0 + 16 <= fp.h) {
+      recon_cu<kDecode>(sh, fp, src, rec, levels, cu, x0, y0, 4);
+    } else {
+      for (int q = 0; q < 4; q++) {
+        int x1 = x0 + 8 * (q & 1), y1 = y0 + 8 * (q >> 1);
+        if (x1 < fp.w && y1 < fp.h) recon_cu<kDecode>(sh, fp, src, rec, levels, cu, x1, y1, 3);
+      }
+    }
+  }
   __threadfence();
   __syncthreads();
   if (t == 0) atomicExch(&progress[row], col + 1);
@@ -298,7 +351,22 @@ cudaError_t launch_intra_frame(const FrameParams &fp, const uint8_t *src, uint8_
   if (e != cudaSuccess) return e;
   e = cudaMemsetAsync(ticket, 0, sizeof(int), s);
   if (e != cudaSuccess) return e;
-  k_intra_frame<<<fp.ctb_cols * fp.ctb_rows, kThreads, 0, s>>>(fp, src, rec, levels, cu, progress, ticket);
+  const int blocks16 = ((fp.w + 15) >> 4) * ((fp.h + 15) >> 4);
+  k_intra_modes<<<blocks16, kModeThreads, 0, s>>>(fp, src, cu);
+  k_intra_frame<false><<<fp.ctb_cols * fp.ctb_rows, kReconThreads, 0, s>>>(fp, src, rec, levels, cu, progress, ticket);
+  return cudaGetLastError();
+}
+
+// Decoder reconstruction of an I picture (modes, cbf and levels from the parser).  Intra CUs must
+// be 16x16 or 8x8 (what the parser accepts for I slices produced by this encoder family).
+cudaError_t launch_intra_decode(const FrameParams &fp, uint8_t *rec, const int16_t *levels, const CuInfo *cu,
+                                int *progress, int *ticket, cudaStream_t s)
+{
+  cudaError_t e = cudaMemsetAsync(progress, 0, sizeof(int) * fp.ctb_rows, s);
+  if (e != cudaSuccess) return e;
+  e = cudaMemsetAsync(ticket, 0, sizeof(int), s);
+  if (e != cudaSuccess) return e;
+  k_intra_frame<true><<<fp.ctb_cols * fp.ctb_rows, kReconThreads, 0, s>>>(fp, nullptr, rec, (int16_t *)levels, (CuInfo *)cu, progress, ticket);
   return cudaGetLastError();
 }
 

@@ -18,6 +18,16 @@ cudaError_t launch_inter_modes(const FrameParams &fp, CuInfo *cu, cudaStream_t s
 cudaError_t launch_intra_frame(const FrameParams &fp, const uint8_t *src, uint8_t *rec, int16_t *levels, CuInfo *cu,
                                int *progress, int *ticket, cudaStream_t s);
 
+// decoder-side reconstruction (levels / modes / motion from the parser)
+cudaError_t launch_inter_decode(const FrameParams &fp, const uint8_t *ref, uint8_t *rec, const int16_t *levels,
+                                const CuInfo *cu, cudaStream_t s);
+cudaError_t launch_intra_decode(const FrameParams &fp, uint8_t *rec, const int16_t *levels, const CuInfo *cu,
+                                int *progress, int *ticket, cudaStream_t s);
+// CABAC parse: one warp per substream.  data = unescaped slice data, bases[r] = offset of row r
+// (bases[rows] = end).  status[0] = first error (0 ok), status[1] = largest |mv| component.
+cudaError_t launch_parse(const FrameParams &fp, const uint8_t *data, const uint32_t *bases, CuInfo *cu, int16_t *levels,
+                         uint8_t *sync_ctx, int *sync_flag, int *progress, int *status, cudaStream_t s);
+
 // in-loop deblocking, in place on `rec` (vertical edges of the whole picture, then horizontal)
 cudaError_t launch_deblock(const FrameParams &fp, uint8_t *rec, const CuInfo *cu, cudaStream_t s);
 

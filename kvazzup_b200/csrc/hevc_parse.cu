@@ -1,0 +1,535 @@
+// CABAC parsing of the B200 HEVC decoder (sm_100a); SURVEY.md 8a row a7 (OpenHEVC replacement).
+//
+// One warp per WPP substream (CTU row); the entry points of the slice header give every row its
+// own byte range, so all rows of a picture parse concurrently, each two CTUs behind the row above
+// (context hand-over after the second CTU, H.265 9.3.1, and the above / above-right neighbours
+// that merge / AMVP derivation reads).  Parsing cannot be split from arithmetic decoding -- what
+// to read next depends on what was just decoded -- so the warp runs the parser redundantly in all
+// lanes on private context tables; lane 0 stores the cu map entries and the non-zero levels.
+//
+// Scope: the syntax subset the B200 encoder (and any encoder with the same parameter sets)
+// produces -- 2Nx2N CUs 8..64, one TU per CU, I and P slices, one reference picture, no SAO /
+// PCM / AMP / scaling lists / transform skip / sign hiding / cu_qp_delta / TMVP.  Anything else is
+// reported through `status` and the picture is rejected by the host.
+#include "hevc_device.cuh"
+#include "hevc_kernels.h"
+
+namespace b200 {
+
+namespace {
+
+struct Reader {
+  const uint8_t *p, *end;
+  uint32_t range, value;
+  int bits_needed;
+  uint8_t *ctx;          // this lane's private context table, entry i at ctx[i * 32]
+  int err;
+};
+
+__device__ __forceinline__ uint32_t next_byte(Reader &r)
+{
+  return r.p < r.end ? *r.p++ : 0u;
+}
+
+__device__ __forceinline__ void reader_start(Reader &r)
+{
+  r.range = 510;
+  r.bits_needed = -8;
+  r.value = next_byte(r) << 8;
+  r.value |= next_byte(r);
+}
+
+__device__ __forceinline__ int dec_bin(Reader &r, int ctx_idx)
+{
+  uint32_t s = r.ctx[ctx_idx * 32];
+  uint32_t st = s >> 1, mps = s & 1;
+  uint32_t lps = (c_range_lps[st] >> (((r.range >> 6) & 3) * 8)) & 0xff;
+  r.range -= lps;
+  uint32_t scaled = r.range << 7;
+  int bin;
+  if (r.value < scaled) {
+    bin = (int)mps;
+    if (st < 62) st++;
+    if (scaled < (256u << 7)) {
+      r.range = scaled >> 6;
+      r.value += r.value;
+      if (++r.bits_needed == 0) { r.bits_needed = -8; r.value += next_byte(r); }
+    }
+  } else {
+    bin = (int)(mps ^ 1);
+    int nb = __clz(lps) - 23;
+    r.value = (r.value - scaled) << nb;
+    r.range = lps << nb;
+    if (st == 0) mps ^= 1;
+    st = c_trans_lps[st];
+    r.bits_needed += nb;
+    if (r.bits_needed >= 0) { r.value += next_byte(r) << r.bits_needed; r.bits_needed -= 8; }
+  }
+  r.ctx[ctx_idx * 32] = (uint8_t)((st << 1) | mps);
+  return bin;
+}
+
+__device__ __forceinline__ int dec_bypass(Reader &r)
+{
+  r.value += r.value;
+  if (++r.bits_needed >= 0) { r.bits_needed = -8; r.value += next_byte(r); }
+  uint32_t scaled = r.range << 7;
+  if (r.value >= scaled) { r.value -= scaled; return 1; }
+  return 0;
+}
+
+__device__ __forceinline__ uint32_t dec_bypass_bits(Reader &r, int n)
+{
+  uint32_t v = 0;
+  for (int i = 0; i < n; i++) v = (v << 1) | (uint32_t)dec_bypass(r);
+  return v;
+}
+
+__device__ __forceinline__ int dec_terminate(Reader &r)
+{
+  r.range -= 2;
+  uint32_t scaled = r.range << 7;
+  if (r.value >= scaled) return 1;
+  if (scaled < (256u << 7)) {
+    r.range = scaled >> 6;
+    r.value += r.value;
+    if (++r.bits_needed == 0) { r.bits_needed = -8; r.value += next_byte(r); }
+  }
+  return 0;
+}
+
+__device__ __forceinline__ void init_contexts_d(uint8_t *ctx, int init_type, int qp)
+{
+  qp = clip3(0, 51, qp);
+  for (int i = 0; i < CTX_COUNT; i++) {
+    int iv = c_ctx_init[init_type][i];
+    int m = (iv >> 4) * 5 - 45, n = ((iv & 15) << 3) - 16;
+    int pre = clip3(1, 126, ((m * qp) >> 4) + n);
+    int mps = pre <= 63 ? 0 : 1;
+    int st = mps ? pre - 64 : 63 - pre;
+    ctx[i * 32] = (uint8_t)((st << 1) | mps);
+  }
+}
+
+__device__ __forceinline__ void scan_pos_d(int scan_idx, int blk_log2, int i, int &x, int &y)
+{
+  int n = 1 << blk_log2;
+  if (scan_idx == 1) { x = i & (n - 1); y = i >> blk_log2; return; }
+  if (scan_idx == 2) { x = i >> blk_log2; y = i & (n - 1); return; }
+  int v = blk_log2 == 2 ? c_diag4[i] : (blk_log2 == 1 ? c_diag2[i] : (blk_log2 == 3 ? c_diag8[i] : 0));
+  x = v & 15; y = v >> 4;
+}
+// inverse scan: index of position (x,y) in the scan of a (1<<blk_log2)^2 array
+__device__ __forceinline__ int scan_index_d(int scan_idx, int blk_log2, int x, int y)
+{
+  int n = 1 << blk_log2;
+  if (scan_idx == 1) return y * n + x;
+  if (scan_idx == 2) return x * n + y;
+  for (int i = 0; i < n * n; i++) {
+    int xx, yy;
+    scan_pos_d(0, blk_log2, i, xx, yy);
+    if (xx == x && yy == y) return i;
+  }
+  return 0;
+}
+
+struct ParseCtx {
+  FrameParams fp;
+  CuInfo *cu;            // global cu map (written by lane 0, read back with ld.cg)
+  int16_t *levels;       // zeroed by the host before the launch; only non-zero levels are stored
+  int lane;
+  int max_mv;            // largest |mv component| seen (quarter samples)
+};
+
+__device__ __forceinline__ CuInfo load_cu(const ParseCtx &pc, int x, int y)
+{
+  const uint32_t *s = (const uint32_t *)(pc.cu + (size_t)(y >> 3) * pc.fp.w8 + (x >> 3));
+  uint32_t w0 = __ldcg(s), w1 = __ldcg(s + 1), w2 = __ldcg(s + 2);
+  CuInfo c;
+  uint32_t *d = (uint32_t *)&c;
+  d[0] = w0; d[1] = w1; d[2] = w2;
+  return c;
+}
+
+__device__ __forceinline__ unsigned coding_order_p(const FrameParams &fp, int x, int y)
+{
+  return (unsigned)((y >> kCtbLog2) * fp.ctb_cols + (x >> kCtbLog2)) * 64u + (unsigned)xy_to_z((x >> 3) & 7, (y >> 3) & 7);
+}
+
+struct NbP { bool ok; int mvx, mvy; };
+__device__ __forceinline__ NbP nb_p(const ParseCtx &pc, unsigned cur, int xn, int yn)
+{
+  NbP n{false, 0, 0};
+  const FrameParams &fp = pc.fp;
+  if (xn < 0 || yn < 0 || xn >= fp.w || yn >= fp.h) return n;
+  if (coding_order_p(fp, xn, yn) >= cur) return n;
+  CuInfo c = load_cu(pc, xn, yn);
+  if (c.pred_mode != 0) return n;
+  n.ok = true; n.mvx = c.mvx; n.mvy = c.mvy;
+  return n;
+}
+__device__ __forceinline__ bool same_p(const NbP &a, const NbP &b) { return a.mvx == b.mvx && a.mvy == b.mvy; }
+
+// residual_coding (7.3.8.11): decoded levels go straight to the picture-shaped level plane
+__device__ void parse_residual(Reader &r, const ParseCtx &pc, int16_t *plane, int pw, int x0, int y0, int log2n, int cidx,
+                               int scan_idx)
+{
+  const int sb_log2 = log2n - 2, sbw = 1 << sb_log2;
+  int offset, shift;
+  if (cidx == 0) { offset = 3 * (log2n - 2) + ((log2n - 1) >> 2); shift = (log2n + 1) >> 2; }
+  else { offset = 15; shift = log2n - 2; }
+  const int cmax = (log2n << 1) - 1;
+  int pre[2];
+  for (int d = 0; d < 2; d++) {
+    int base = d ? CTX_LAST_Y : CTX_LAST_X, k = 0;
+    while (k < cmax && dec_bin(r, base + offset + (k >> shift))) k++;
+    pre[d] = k;
+  }
+  int last[2];
+  for (int d = 0; d < 2; d++) {
+    int g = pre[d];
+    if (g > 3) {
+      int nb = (g >> 1) - 1;
+      last[d] = ((2 + (g & 1)) << nb) + (int)dec_bypass_bits(r, nb);
+    } else {
+      last[d] = g;
+    }
+  }
+  int last_x = last[0], last_y = last[1];
+  if (scan_idx == 2) { int t = last_x; last_x = last_y; last_y = t; }
+  const int last_sb = scan_index_d(scan_idx, sb_log2, last_x >> 2, last_y >> 2);
+  const int last_pos = scan_index_d(scan_idx, 2, last_x & 3, last_y & 3);
+  unsigned long long csbf = 0;
+  int c1 = 1;
+  for (int i = last_sb; i >= 0; i--) {
+    int xs, ys;
+    scan_pos_d(scan_idx, sb_log2, i, xs, ys);
+    int right = xs + 1 < sbw ? (int)((csbf >> (ys * 8 + xs + 1)) & 1) : 0;
+    int below = ys + 1 < sbw ? (int)((csbf >> ((ys + 1) * 8 + xs)) & 1) : 0;
+    int prev_csbf = right | (below << 1);
+    int coded = 1, infer_dc = 0;
+    if (i < last_sb && i > 0) {
+      coded = dec_bin(r, CTX_CSBF + (prev_csbf ? 1 : 0) + (cidx ? 2 : 0));
+      infer_dc = 1;
+    }
+    if (!coded) continue;
+    csbf |= 1ull << (ys * 8 + xs);
+    unsigned sig = 0;
+    int start = 15;
+    if (i == last_sb) { sig = 1u << last_pos; start = last_pos - 1; }
+    for (int p = start; p >= 0; p--) {
+      if (p == 0 && infer_dc) { sig |= 1u; break; }
+      int xp, yp;
+      scan_pos_d(scan_idx, 2, p, xp, yp);
+      int xc = xs * 4 + xp, yc = ys * 4 + yp, sctx;
+      if (log2n == 2) sctx = c_sig_ctx_4x4[(yc << 2) + xc];
+      else if (xc + yc == 0) sctx = 0;
+      else {
+        if (prev_csbf == 0) sctx = (xp + yp == 0) ? 2 : (xp + yp < 3) ? 1 : 0;
+        else if (prev_csbf == 1) sctx = yp == 0 ? 2 : (yp == 1 ? 1 : 0);
+        else if (prev_csbf == 2) sctx = xp == 0 ? 2 : (xp == 1 ? 1 : 0);
+        else sctx = 2;
+        if (cidx == 0) {
+          if (xs || ys) sctx += 3;
+          sctx += log2n == 3 ? (scan_idx == 0 ? 9 : 15) : 21;
+        } else {
+          sctx += log2n == 3 ? 9 : 12;
+        }
+      }
+      if (dec_bin(r, CTX_SIG + (cidx == 0 ? sctx : 27 + sctx))) { sig |= 1u << p; infer_dc = 0; }
+    }
+    if (!sig) continue;
+    int ctx_set = (i > 0 && cidx == 0) ? 2 : 0;
+    if (c1 == 0) ctx_set++;
+    c1 = 1;
+    int num_g1 = 0, first_g1 = -1;
+    unsigned g1 = 0;
+    for (int p = 15; p >= 0; p--) {
+      if (!((sig >> p) & 1) || num_g1 >= 8) continue;
+      int f = dec_bin(r, CTX_GT1 + (cidx ? 16 : 0) + 4 * ctx_set + c1);
+      if (f) { g1 |= 1u << p; c1 = 0; if (first_g1 < 0) first_g1 = p; }
+      else if (c1 < 3 && c1 > 0) c1++;
+      num_g1++;
+    }
+    int g2 = 0;
+    if (first_g1 >= 0) g2 = dec_bin(r, CTX_GT2 + (cidx ? 4 : 0) + ctx_set);
+    unsigned neg = 0;
+    for (int p = 15; p >= 0; p--)
+      if ((sig >> p) & 1) neg |= (unsigned)dec_bypass(r) << p;
+    int num_sig = 0, rice = 0;
+    for (int p = 15; p >= 0; p--) {
+      if (!((sig >> p) & 1)) continue;
+      int base = 1 + (num_sig < 8 ? (int)((g1 >> p) & 1) : 0) + (p == first_g1 ? g2 : 0);
+      int thresh = num_sig < 8 ? (p == first_g1 ? 3 : 2) : 1;
+      int absv = base;
+      if (base == thresh) {
+        // coeff_abs_level_remaining: TR prefix (<= 4 ones) + rice suffix, or EG(rice+1) escape
+        int q = 0;
+        while (q < 4 && dec_bypass(r)) q++;
+        int rem;
+        if (q < 4) {
+          rem = (q << rice) + (int)dec_bypass_bits(r, rice);
+        } else {
+          int k = rice + 1, v = 0;
+          while (k < 32 && dec_bypass(r)) { v += 1 << k; k++; }
+          if (k >= 32) { r.err = 1; return; }
+          v += (int)dec_bypass_bits(r, k);
+          rem = (4 << rice) + v;
+        }
+        absv = base + rem;
+        if (absv > (3 << rice)) rice = min(rice + 1, 4);
+      }
+      num_sig++;
+      int xp, yp;
+      scan_pos_d(scan_idx, 2, p, xp, yp);
+      if (pc.lane == 0) {
+        int v = min(absv, 32767);
+        plane[(size_t)(y0 + ys * 4 + yp) * pw + x0 + xs * 4 + xp] = (int16_t)(((neg >> p) & 1) ? -v : v);
+      }
+    }
+  }
+}
+
+__device__ __forceinline__ int scan_idx_for_d(int pred_mode, int intra_mode, int log2n, int cidx)
+{
+  if (pred_mode != 1) return 0;
+  if (!(log2n == 2 || (log2n == 3 && cidx == 0))) return 0;
+  if (intra_mode >= 6 && intra_mode <= 14) return 2;
+  if (intra_mode >= 22 && intra_mode <= 30) return 1;
+  return 0;
+}
+
+__device__ void parse_cu(Reader &r, ParseCtx &pc, int x0, int y0, int log2)
+{
+  const FrameParams &fp = pc.fp;
+  const int n = 1 << log2;
+  CuInfo cu;
+  cu.mvx = 0; cu.mvy = 0; cu.log2_size = (uint8_t)log2; cu.pred_mode = 0; cu.intra_mode = 1; cu.cbf = 0;
+  cu.skip = 0; cu.merge_idx = 0xff; cu.mvp_idx = 0; cu.pad = 0;
+  bool tu = false;
+  if (!fp.is_idr) {
+    int ctx = 0;
+    if (x0 > 0) ctx += load_cu(pc, x0 - 1, y0).skip;
+    if (y0 > 0) ctx += load_cu(pc, x0, y0 - 1).skip;
+    cu.skip = (uint8_t)dec_bin(r, CTX_SKIP + ctx);
+    int merge = cu.skip;
+    if (!cu.skip) {
+      if (dec_bin(r, CTX_PRED_MODE)) { r.err = 2; return; }            // intra CU in a P slice: not supported
+      if (!dec_bin(r, CTX_PART_MODE)) { r.err = 3; return; }           // only PART_2Nx2N
+      merge = dec_bin(r, CTX_MERGE_FLAG);
+    }
+    const unsigned cur = coding_order_p(fp, x0, y0);
+    NbP a1 = nb_p(pc, cur, x0 - 1, y0 + n - 1), b1 = nb_p(pc, cur, x0 + n - 1, y0 - 1);
+    NbP b0 = nb_p(pc, cur, x0 + n, y0 - 1), a0 = nb_p(pc, cur, x0 - 1, y0 + n), b2 = nb_p(pc, cur, x0 - 1, y0 - 1);
+    if (merge) {
+      int midx = 0;
+      if (dec_bin(r, CTX_MERGE_IDX)) {
+        midx = 1;
+        while (midx < kMaxMerge - 1 && dec_bypass(r)) midx++;
+      }
+      int mvx[kMaxMerge], mvy[kMaxMerge], cnt = 0;
+      bool use_b1 = b1.ok && !(a1.ok && same_p(b1, a1));
+      bool use_b0 = b0.ok && !(b1.ok && same_p(b0, b1));
+      bool use_a0 = a0.ok && !(a1.ok && same_p(a0, a1));
+      bool use_b2 = b2.ok && !(a1.ok && same_p(b2, a1)) && !(b1.ok && same_p(b2, b1));
+      if (a1.ok) { mvx[cnt] = a1.mvx; mvy[cnt++] = a1.mvy; }
+      if (use_b1) { mvx[cnt] = b1.mvx; mvy[cnt++] = b1.mvy; }
+      if (use_b0) { mvx[cnt] = b0.mvx; mvy[cnt++] = b0.mvy; }
+      if (use_a0) { mvx[cnt] = a0.mvx; mvy[cnt++] = a0.mvy; }
+      if (use_b2 && cnt < 4) { mvx[cnt] = b2.mvx; mvy[cnt++] = b2.mvy; }
+      while (cnt < kMaxMerge) { mvx[cnt] = 0; mvy[cnt++] = 0; }
+      cu.mvx = (int16_t)mvx[midx]; cu.mvy = (int16_t)mvy[midx];
+      cu.merge_idx = (uint8_t)midx;
+      tu = !cu.skip;
+    } else {
+      // mvd_coding (7.3.8.9)
+      int gt0[2], gt1[2] = {0, 0}, mvd[2] = {0, 0};
+      gt0[0] = dec_bin(r, CTX_MVD_GT0);
+      gt0[1] = dec_bin(r, CTX_MVD_GT0);
+      if (gt0[0]) gt1[0] = dec_bin(r, CTX_MVD_GT1);
+      if (gt0[1]) gt1[1] = dec_bin(r, CTX_MVD_GT1);
+      for (int k = 0; k < 2; k++) {
+        if (!gt0[k]) continue;
+        int a = 1;
+        if (gt1[k]) {
+          int kk = 1, v = 0;
+          while (kk < 32 && dec_bypass(r)) { v += 1 << kk; kk++; }
+          if (kk >= 32) { r.err = 4; return; }
+          v += (int)dec_bypass_bits(r, kk);
+          a = v + 2;
+        }
+        mvd[k] = dec_bypass(r) ? -a : a;
+      }
+      int pi = dec_bin(r, CTX_MVP_IDX);
+      NbP a = a0.ok ? a0 : a1;
+      NbP b = b0.ok ? b0 : (b1.ok ? b1 : b2);
+      int px[2], py[2], k = 0;
+      if (a.ok) { px[k] = a.mvx; py[k++] = a.mvy; }
+      if (b.ok && !(a.ok && same_p(a, b))) { px[k] = b.mvx; py[k++] = b.mvy; }
+      while (k < 2) { px[k] = 0; py[k++] = 0; }
+      cu.mvx = (int16_t)(px[pi] + mvd[0]); cu.mvy = (int16_t)(py[pi] + mvd[1]);
+      cu.mvp_idx = (uint8_t)pi;
+      tu = dec_bin(r, CTX_RQT_ROOT_CBF) != 0;
+    }
+    pc.max_mv = max(pc.max_mv, max(abs((int)cu.mvx), abs((int)cu.mvy)));
+  } else {
+    cu.pred_mode = 1;
+    {
+      // the intra reconstruction kernel handles 16x16 CUs, and 8x8 only where 16x16 crosses the picture edge
+      const int bx = x0 & ~15, by = y0 & ~15;
+      const bool fits16 = bx + 16 <= fp.w && by + 16 <= fp.h;
+      if (!((log2 == 4 && fits16) || (log2 == 3 && !fits16))) { r.err = 10; return; }
+    }
+    if (log2 == 3 && !dec_bin(r, CTX_PART_MODE)) { r.err = 5; return; }   // PART_NxN: not supported
+    int prev = dec_bin(r, CTX_PREV_INTRA_LUMA);
+    int a = 1, b = 1;
+    if (x0 > 0) a = load_cu(pc, x0 - 1, y0).intra_mode;
+    if (y0 > 0 && (y0 & (kCtb - 1))) b = load_cu(pc, x0, y0 - 1).intra_mode;
+    int cand[3];
+    if (a == b) {
+      if (a < 2) { cand[0] = 0; cand[1] = 1; cand[2] = 26; }
+      else { cand[0] = a; cand[1] = 2 + ((a + 29) % 32); cand[2] = 2 + ((a - 2 + 1) % 32); }
+    } else {
+      cand[0] = a; cand[1] = b;
+      cand[2] = (a != 0 && b != 0) ? 0 : ((a != 1 && b != 1) ? 1 : 26);
+    }
+    int mode;
+    if (prev) {
+      int idx = 0;
+      if (dec_bypass(r)) idx = dec_bypass(r) ? 2 : 1;
+      mode = cand[idx];
+    } else {
+      if (cand[0] > cand[1]) { int t = cand[0]; cand[0] = cand[1]; cand[1] = t; }
+      if (cand[0] > cand[2]) { int t = cand[0]; cand[0] = cand[2]; cand[2] = t; }
+      if (cand[1] > cand[2]) { int t = cand[1]; cand[1] = cand[2]; cand[2] = t; }
+      mode = (int)dec_bypass_bits(r, 5);
+      for (int i = 0; i < 3; i++) if (mode >= cand[i]) mode++;
+    }
+    cu.intra_mode = (uint8_t)mode;
+    if (dec_bin(r, CTX_INTRA_CHROMA)) { r.err = 6; return; }              // only intra_chroma_pred_mode 4 (derived)
+    tu = true;
+  }
+  if (tu) {
+    if (log2 > 5) { r.err = 7; return; }                                   // a 64x64 CU with residual needs a split transform tree
+    int cb = dec_bin(r, CTX_CBF_CHROMA), cr = dec_bin(r, CTX_CBF_CHROMA), lu = 1;
+    if (cu.pred_mode == 1 || cb || cr) lu = dec_bin(r, CTX_CBF_LUMA + 1);
+    cu.cbf = (uint8_t)(lu | (cb << 1) | (cr << 2));
+  }
+  // publish the cu map entry before any later CU reads it
+  if (pc.lane == 0) {
+    const uint32_t *s = (const uint32_t *)&cu;
+    const int n8 = n >> 3;
+    for (int j = 0; j < n8; j++)
+      for (int i = 0; i < n8; i++) {
+        uint32_t *d = (uint32_t *)(pc.cu + (size_t)((y0 >> 3) + j) * fp.w8 + (x0 >> 3) + i);
+        __stcg(d, s[0]); __stcg(d + 1, s[1]); __stcg(d + 2, s[2]);
+      }
+  }
+  __syncwarp();
+  const size_t ysz = (size_t)fp.w * fp.h;
+  for (int k = 0; k < 3 && !r.err; k++) {
+    if (!((cu.cbf >> k) & 1)) continue;
+    const int sft = k ? 1 : 0;
+    int16_t *plane = pc.levels + (k == 0 ? 0 : ysz + (k == 2 ? ysz / 4 : 0));
+    parse_residual(r, pc, plane, fp.w >> sft, x0 >> sft, y0 >> sft, log2 - sft, k, scan_idx_for_d(cu.pred_mode, cu.intra_mode, log2 - sft, k));
+  }
+}
+
+// bases[r] = byte offset of substream r inside `data`, bases[rows] = end.  status[0] receives the
+// first error code (0 = ok), status[1] the largest |mv| component.
+__global__ void __launch_bounds__(32)
+k_parse_rows(FrameParams fp, const uint8_t *__restrict__ data, const uint32_t *__restrict__ bases, CuInfo *cu,
+             int16_t *levels, uint8_t *sync_ctx, int *sync_flag, int *progress, int *status)
+{
+  __shared__ uint8_t s_ctx[CTX_COUNT * 32];
+  const int row = blockIdx.x, lane = threadIdx.x;
+  Reader r;
+  r.p = data + bases[row]; r.end = data + bases[row + 1]; r.ctx = s_ctx + lane; r.err = 0;
+  ParseCtx pc{fp, cu, levels, lane, 0};
+  if (row == 0 || fp.ctb_cols < 2) {
+    init_contexts_d(r.ctx, fp.is_idr ? 0 : 1, fp.qp);
+  } else {
+    if (lane == 0) {
+      volatile int *f = sync_flag;
+      while (f[row - 1] == 0) __nanosleep(100);
+      __threadfence();
+    }
+    __syncwarp();
+    for (int i = 0; i < CTX_COUNT; i++) r.ctx[i * 32] = __ldcg(sync_ctx + (size_t)(row - 1) * CTX_COUNT + i);
+  }
+  __syncwarp();
+  reader_start(r);
+  for (int col = 0; col < fp.ctb_cols && !r.err; col++) {
+    if (row > 0) {                       // above and above-right CTUs must be parsed (cu map reads)
+      if (lane == 0) {
+        volatile int *p = progress;
+        int need = min(col + 2, fp.ctb_cols);
+        while (p[row - 1] < need && p[row - 1] >= 0) __nanosleep(64);
+        __threadfence();
+      }
+      __syncwarp();
+    }
+    const int cx = col * kCtb, cy = row * kCtb;
+    for (int z = 0; z < 64 && !r.err;) {
+      int x0 = cx + 8 * z_to_x(z), y0 = cy + 8 * z_to_y(z);
+      if (x0 >= fp.w || y0 >= fp.h) { z++; continue; }
+      int log2 = 3;
+      for (int L = 6; L > 3; L--) {
+        if (z & ((1 << (2 * (L - 3))) - 1)) continue;
+        const int nn = 1 << L;
+        int split;
+        if (x0 + nn <= fp.w && y0 + nn <= fp.h) {
+          int ctx = 0, depth = 6 - L;
+          if (x0 > 0) ctx += (kCtbLog2 - load_cu(pc, x0 - 1, y0).log2_size) > depth;
+          if (y0 > 0) ctx += (kCtbLog2 - load_cu(pc, x0, y0 - 1).log2_size) > depth;
+          split = dec_bin(r, CTX_SPLIT_CU + ctx);
+        } else {
+          split = 1;
+        }
+        if (!split) { log2 = L; break; }
+      }
+      parse_cu(r, pc, x0, y0, log2);
+      z += 1 << (2 * (log2 - 3));
+    }
+    if (col == 1 && row + 1 < fp.ctb_rows) {
+      __syncwarp();
+      if (lane == 0)
+        for (int i = 0; i < CTX_COUNT; i++) sync_ctx[(size_t)row * CTX_COUNT + i] = r.ctx[i * 32];
+      __threadfence();
+      __syncwarp();
+      if (lane == 0) atomicExch(&sync_flag[row], 1);
+    }
+    const bool last = row == fp.ctb_rows - 1 && col == fp.ctb_cols - 1;
+    int eos = dec_terminate(r);                                        // end_of_slice_segment_flag
+    if (eos != (last ? 1 : 0)) r.err = 8;
+    if (col == fp.ctb_cols - 1 && !last && !dec_terminate(r)) r.err = 9;   // end_of_subset_one_bit
+    __threadfence();
+    __syncwarp();
+    if (lane == 0) atomicExch(&progress[row], r.err ? -1 : col + 1);
+  }
+  if (lane == 0) {
+    if (r.err) {
+      atomicCAS(&status[0], 0, r.err);
+      atomicExch(&progress[row], -1);          // release the rows below
+      atomicExch(&sync_flag[row], 1);
+    }
+    atomicMax(&status[1], pc.max_mv);
+  }
+}
+
+}  // namespace
+
+cudaError_t launch_parse(const FrameParams &fp, const uint8_t *data, const uint32_t *bases, CuInfo *cu, int16_t *levels,
+                         uint8_t *sync_ctx, int *sync_flag, int *progress, int *status, cudaStream_t s)
+{
+  cudaError_t e = cudaMemsetAsync(sync_flag, 0, sizeof(int) * fp.ctb_rows, s);
+  if (e != cudaSuccess) return e;
+  e = cudaMemsetAsync(progress, 0, sizeof(int) * fp.ctb_rows, s);
+  if (e != cudaSuccess) return e;
+  e = cudaMemsetAsync(status, 0, sizeof(int) * 2, s);
+  if (e != cudaSuccess) return e;
+  k_parse_rows<<<fp.ctb_rows, 32, 0, s>>>(fp, data, bases, cu, levels, sync_ctx, sync_flag, progress, status);
+  return cudaGetLastError();
+}
+
+}  // namespace b200

@@ -177,11 +177,11 @@ static int avail_luma(const orc_encoder_t *e, int x, int y)
 }
 
 /* 8.4.4.2.2: gather the 4N+1 neighbours (layout of orc_intra_predict) with substitution */
-static void gather_refs(const orc_encoder_t *e, int c, int x0, int y0, int n, uint8_t *refs)
+static void gather_refs_from(const orc_encoder_t *e, const uint8_t *frame, int c, int x0, int y0, int n, uint8_t *refs)
 {
   const int pw = c ? e->cw : e->w;
   const int sh = c ? 1 : 0;
-  const uint8_t *rec = plane(e->rec, e->w, e->h, c);
+  const uint8_t *rec = plane((uint8_t *)frame, e->w, e->h, c);
   uint8_t av[4 * 32 + 1];
   int any = 0;
   for (int k = 0; k < 2 * n; k++) {
@@ -207,27 +207,9 @@ static void gather_refs(const orc_encoder_t *e, int c, int x0, int y0, int n, ui
     if (!av[k]) refs[k] = refs[k - 1];
 }
 
-/* 8.4.2: most probable modes of the luma block at (x0,y0) */
-static void mpm_list(const orc_encoder_t *e, int x0, int y0, int cand[3])
+static void gather_refs(const orc_encoder_t *e, int c, int x0, int y0, int n, uint8_t *refs)
 {
-  int a = 1, b = 1;   /* INTRA_DC when unavailable / not intra */
-  if (avail_luma(e, x0 - 1, y0)) {
-    const orc_cu_t *n = &e->cu[(size_t)(y0 >> 3) * e->w8 + ((x0 - 1) >> 3)];
-    if (n->pred_mode == 1) a = n->intra_mode;
-  }
-  if (avail_luma(e, x0, y0 - 1) && (y0 - 1) >= ((y0 >> CTB_LOG2) << CTB_LOG2)) {
-    const orc_cu_t *n = &e->cu[(size_t)((y0 - 1) >> 3) * e->w8 + (x0 >> 3)];
-    if (n->pred_mode == 1) b = n->intra_mode;
-  }
-  if (a == b) {
-    if (a < 2) { cand[0] = 0; cand[1] = 1; cand[2] = 26; }
-    else { cand[0] = a; cand[1] = 2 + ((a + 29) % 32); cand[2] = 2 + ((a - 2 + 1) % 32); }
-  } else {
-    cand[0] = a; cand[1] = b;
-    if (a != 0 && b != 0) cand[2] = 0;
-    else if (a != 1 && b != 1) cand[2] = 1;
-    else cand[2] = 26;
-  }
+  gather_refs_from(e, e->rec, c, x0, y0, n, refs);
 }
 
 static void intra_cu(orc_encoder_t *e, int x0, int y0, int log2)
@@ -235,18 +217,23 @@ static void intra_cu(orc_encoder_t *e, int x0, int y0, int log2)
   const int n = 1 << log2;
   uint8_t refs[4 * 32 + 1], pred[32 * 32], best_pred[32 * 32];
   const uint8_t *src = e->src;
-  int cand[3];
-  mpm_list(e, x0, y0, cand);
-  gather_refs(e, 0, x0, y0, n, refs);
+  /* Mode decision on SOURCE neighbours (same availability and substitution rules as the real
+   * prediction): it does not depend on any reconstruction, so the GPU takes it for every CU of the
+   * picture in one parallel pass and the reconstruction wavefront only predicts the chosen mode.
+   * Cost = SAD + lambda * bits with a fixed prior (planar / DC / vertical cheap) because the
+   * neighbours' modes -- hence the MPM list -- are not known in a parallel pass. */
+  gather_refs_from(e, e->src, 0, x0, y0, n, refs);
   uint32_t best_cost = UINT_MAX;
   int best_mode = 0;
   for (int mode = 0; mode < 35; mode++) {
     orc_intra_predict(refs, log2, mode, 0, pred, n);
     uint32_t sad = orc_sad(src + (size_t)y0 * e->w + x0, e->w, pred, n, n, n);
-    int bits = mode == cand[0] ? 2 : (mode == cand[1] || mode == cand[2]) ? 3 : 6;
+    int bits = (mode == 0 || mode == 1 || mode == 26) ? 2 : 6;
     uint32_t cost = sad + (uint32_t)((e->lambda_q4 * bits) >> 4);
-    if (cost < best_cost) { best_cost = cost; best_mode = mode; memcpy(best_pred, pred, (size_t)n * n); }
+    if (cost < best_cost) { best_cost = cost; best_mode = mode; }
   }
+  gather_refs(e, 0, x0, y0, n, refs);
+  orc_intra_predict(refs, log2, best_mode, 0, best_pred, n);
   orc_cu_t cu;
   memset(&cu, 0, sizeof(cu));
   cu.log2_size = (uint8_t)log2; cu.pred_mode = 1; cu.intra_mode = (uint8_t)best_mode; cu.merge_idx = 0xff;

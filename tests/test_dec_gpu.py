@@ -1,0 +1,123 @@
+"""GPU parity: the CUDA HEVC decoder (through the libOpenHevc* C ABI, driven like OpenHEVCFilter)
+must reproduce, bit for bit, the reconstruction of the encoder that produced the stream -- which
+the oracle tests pin to FFmpeg's independent decoder.  Streams come from the CPU oracle encoder and
+from the GPU encoder."""
+import numpy as np
+import pytest
+
+from kvazzup_b200.encoder import GpuEncoder
+from kvazzup_b200.openhevc import OpenHEVCFilter, split_nals
+from oracle.encoder import OracleEncoder
+from tests import ffhevc
+from tests.test_oracle_hevc import frames_of
+
+pytestmark = pytest.mark.gpu
+
+
+def decode_all(aus):
+    f = OpenHEVCFilter()
+    assert f.init()
+    out = []
+    for i, au in enumerate(aus):
+        for nal in split_nals(au):
+            got = f.process(nal, pts=i)
+            if got is not None:
+                out.append(got)
+    f.close()
+    return out
+
+
+@pytest.mark.parametrize("kind,w,h,n,qp,kw", [
+    ("camera", 64, 64, 2, 32, {}),
+    ("camera", 192, 136, 4, 32, {}),
+    ("camera", 72, 200, 3, 27, {"deblock": 0}),
+    ("noise", 128, 72, 3, 0, {}),
+    ("noise", 128, 72, 3, 10, {}),
+    ("noise", 128, 72, 3, 45, {}),
+    ("camera", 128, 72, 3, 51, {}),
+    ("camera", 416, 240, 5, 27, {}),
+    ("screen", 416, 240, 5, 32, {}),
+    ("camera", 200, 200, 7, 30, {"intra_period": 3}),
+    ("camera", 256, 128, 4, 22, {"search_range": 16}),
+    ("camera", 64, 8, 3, 37, {}),
+    ("camera", 640, 480, 3, 32, {}),
+])
+def test_decoder_reproduces_oracle_reconstruction(kind, w, h, n, qp, kw):
+    frames = frames_of(kind, w, h, n)
+    enc = OracleEncoder(w, h, qp=qp, **({"intra_period": 0} | kw))
+    aus, recs = [], []
+    for f in frames:
+        aus.append(enc.encode(f))
+        recs.append(enc.recon())
+    dec = decode_all(aus)
+    assert len(dec) == n
+    for i, (pic, pw, ph) in enumerate(dec):
+        assert (pw, ph) == (w, h)
+        bad = np.flatnonzero(pic != recs[i])
+        assert bad.size == 0, f"picture {i}: {bad.size} samples differ, first at {bad[:6]}"
+
+
+def test_decoder_on_gpu_encoder_stream_1080p_and_ffmpeg_agreement():
+    w, h, n = 1920, 1080, 3
+    frames = frames_of("camera", w, h, n)
+    g = GpuEncoder(w, h, qp=27, intra_period=0, search_range=12)
+    aus, recs = [], []
+    for f in frames:
+        aus.append(g.encode(f))
+        recs.append(g.recon())
+    dec = decode_all(aus)
+    assert len(dec) == n
+    for i in range(n):
+        assert np.array_equal(dec[i][0], recs[i]), i
+    if ffhevc.available():
+        ff, errs = ffhevc.decode_stream(aus)
+        assert errs == 0
+        for i in range(n):
+            assert np.array_equal(dec[i][0], ff[i][0]), i
+
+
+def test_filter_gates_on_parameter_sets_and_reports_picture_info():
+    w, h = 192, 136
+    enc = OracleEncoder(w, h, qp=30, intra_period=0)
+    aus = [enc.encode(f) for f in frames_of("camera", w, h, 2)]
+    f = OpenHEVCFilter()
+    assert f.init() and "b200" in f.version()
+    nals = split_nals(aus[0])
+    assert [n[4] >> 1 for n in nals] == [32, 33, 34, 19]
+    assert f.process(nals[3]) is None and f.discarded == 1      # VCL before VPS/SPS/PPS is discarded (:116-182)
+    for nal in nals[:3]:
+        assert f.process(nal) is None
+    pic = f.process(nals[3])
+    assert pic is not None and pic[1:] == (w, h)
+    f.close()
+
+
+def test_decoder_rejects_what_it_cannot_decode():
+    from kvazzup_b200.capi import B200Error
+    w, h = 64, 64
+    enc = OracleEncoder(w, h, qp=30, intra_period=0)
+    au = enc.encode(frames_of("camera", w, h, 1)[0])
+    nals = split_nals(au)
+    f = OpenHEVCFilter()
+    assert f.init()
+    sps = bytearray(nals[1])
+    sps[-3] ^= 0x10                      # flip a tool flag near the end of the SPS (SAO / PCM / ... region)
+    f.process(nals[0])
+    with pytest.raises(B200Error):
+        f.process(bytes(sps))
+        f.process(nals[2])
+        f.process(nals[3])
+    f.close()
+    # corrupt slice data: must fail or at least never crash; a wrong picture must not be reported as an error-free decode
+    g = OpenHEVCFilter()
+    assert g.init()
+    for nal in nals[:3]:
+        g.process(nal)
+    bad = bytearray(nals[3])
+    for k in range(40, min(len(bad), 200), 7):
+        bad[k] ^= 0x5A
+    try:
+        g.process(bytes(bad))
+    except B200Error:
+        pass
+    g.close()
