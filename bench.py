@@ -41,7 +41,7 @@ GOP = 64
 QP = 27
 PRESET = "veryfast"
 ME_RANGE = 12                      # what "veryfast" maps to (kvz_api.cu kPresets)
-DEPTH = 16                         # pictures in flight (owf = 15)
+DEPTH = 48                         # pictures in flight (owf = 47): an IDR's entropy coding overlaps ~40 P pictures
 KERNELS = ("intra", "me", "recon", "modes", "deblock", "binarise", "arith", "pack")
 
 

@@ -625,40 +625,53 @@ k_arith_rows(FrameParams fp, const uint32_t *__restrict__ recs, uint8_t *rows, u
   }
   __syncwarp();
   coder_start(c);
-  for (int col = 0; col < fp.ctb_cols; col++) {
-    const int ctu = r * fp.ctb_cols + col;
-    const int cx = col * kCtb, cy = r * kCtb;
-    for (int z = 0; z < 64;) {
-      if (cx + 8 * z_to_x(z) >= fp.w || cy + 8 * z_to_y(z) >= fp.h) { z++; continue; }
-      const uint32_t *reg = recs + ((size_t)ctu * 64 + z) * kRecUnitCap;
-      const uint32_t hdr = __ldg(reg);
-      const int cnt = (int)(hdr & 0xffffffu), log2 = (int)(hdr >> 24);
-      // stream the CU's records: one coalesced 32-record load per chunk, the next one in flight
-      uint32_t nxt = lane < cnt ? __ldg(reg + 1 + lane) : 0;
-      for (int base = 0; base < cnt; base += 32) {
-        const uint32_t curv = nxt;
-        const int nb = base + 32;
-        nxt = nb + lane < cnt ? __ldg(reg + 1 + nb + lane) : 0;
-        const int m = min(32, cnt - base);
-        for (int k = 0; k < m; k++) {
-          const uint32_t v = __shfl_sync(0xffffffffu, curv, k);
-          if (v & 0x80000000u) enc_bypass_group(c, v & 0xffffu, (int)((v >> 24) & 31));
-          else enc_bin(c, (int)(v >> 1), (int)(v & 1));
-        }
+  // Flat walk over the CUs of the row.  The address of the next CU's record list is known as
+  // soon as the current header is read, so its header and first 32 records are fetched while the
+  // current list is being coded (a lone warp has nothing else to hide the ~1 us load latency).
+  const int cy = r * kCtb;
+  auto first_unit = [&](int col, int z) -> int {          // first z >= given whose unit lies inside the picture, 64 if none
+    while (z < 64 && (col * kCtb + 8 * z_to_x(z) >= fp.w || cy + 8 * z_to_y(z) >= fp.h)) z++;
+    return z;
+  };
+  int col = 0, z = first_unit(0, 0);
+  const uint32_t *reg = recs + ((size_t)(r * fp.ctb_cols) * 64 + z) * kRecUnitCap;
+  uint32_t hdr = __ldg(reg);
+  uint32_t first = __ldg(reg + 1 + lane);
+  while (col < fp.ctb_cols) {
+    const int cnt = (int)(hdr & 0xffffffu), log2 = (int)(hdr >> 24);
+    // cursor of the CU after this one
+    int ncol = col, nz = first_unit(col, z + (1 << (2 * (log2 - 3))));
+    if (nz >= 64) { ncol = col + 1; nz = ncol < fp.ctb_cols ? first_unit(ncol, 0) : 64; }
+    const uint32_t *nreg = recs + ((size_t)(r * fp.ctb_cols + ncol) * 64 + nz) * kRecUnitCap;
+    uint32_t nhdr = 0, nfirst = 0;
+    if (ncol < fp.ctb_cols) { nhdr = __ldg(nreg); nfirst = __ldg(nreg + 1 + lane); }
+    // code this CU
+    uint32_t curv = first;
+    for (int base = 0; base < cnt; base += 32) {
+      const int nb = base + 32;
+      uint32_t nxt = nb + lane < cnt ? __ldg(reg + 1 + nb + lane) : 0;
+      const int m = min(32, cnt - base);
+      for (int k = 0; k < m; k++) {
+        const uint32_t v = __shfl_sync(0xffffffffu, curv, k);
+        if (v & 0x80000000u) enc_bypass_group(c, v & 0xffffu, (int)((v >> 24) & 31));
+        else enc_bin(c, (int)(v >> 1), (int)(v & 1));
       }
-      z += 1 << (2 * (log2 - 3));
+      curv = nxt;
     }
-    if (col == 1 && r + 1 < fp.ctb_rows) {
-      __syncwarp();
-      if (lane == 0)
-        for (int i = 0; i < CTX_COUNT; i++) sync_ctx[(size_t)r * CTX_COUNT + i] = c.ctx[i * 32];
-      __threadfence();
-      __syncwarp();
-      if (lane == 0) atomicExch(&sync_flag[r], 1);
+    if (ncol != col) {                                    // the CTU is complete
+      if (col == 1 && r + 1 < fp.ctb_rows) {
+        __syncwarp();
+        if (lane == 0)
+          for (int i = 0; i < CTX_COUNT; i++) sync_ctx[(size_t)r * CTX_COUNT + i] = c.ctx[i * 32];
+        __threadfence();
+        __syncwarp();
+        if (lane == 0) atomicExch(&sync_flag[r], 1);
+      }
+      const bool last = r == fp.ctb_rows - 1 && col == fp.ctb_cols - 1;
+      enc_terminate(c, last);                                           // end_of_slice_segment_flag
+      if (col == fp.ctb_cols - 1 && !last) enc_terminate(c, 1);         // end_of_subset_one_bit
     }
-    const bool last = r == fp.ctb_rows - 1 && col == fp.ctb_cols - 1;
-    enc_terminate(c, last);                                           // end_of_slice_segment_flag
-    if (col == fp.ctb_cols - 1 && !last) enc_terminate(c, 1);         // end_of_subset_one_bit
+    col = ncol; z = nz; reg = nreg; hdr = nhdr; first = nfirst;
   }
   coder_finish(c);
   if (lane == 0) {
