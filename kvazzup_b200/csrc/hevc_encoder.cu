@@ -338,7 +338,9 @@ bool Encoder::collect(FrameSlot &s, std::vector<uint8_t> &out)
 {
   ENC_CHECK(cudaEventSynchronize(s.ev_done), "wait for picture");
   if (s.prof_mask) {
-    cudaStreamSynchronize(stream);                 // the deblocking of this picture may still be running
+    // the deblocking of this picture (main stream) may still be running: wait for ITS end event
+    // only -- synchronising the whole main stream would drain the pictures submitted after it
+    if (s.prof_mask & (1u << K_DEBLOCK)) cudaEventSynchronize(s.pev[2 * K_DEBLOCK + 1]);
     for (int k = 0; k < K_COUNT; k++) {
       if (!(s.prof_mask & (1u << k))) continue;
       float ms = 0;
