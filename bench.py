@@ -33,6 +33,8 @@ from pathlib import Path
 
 ROOT = Path(__file__).resolve().parent
 sys.path.insert(0, str(ROOT))
+# one hardware work queue per stream: must be set before the CUDA context exists (see runtime.cu)
+os.environ.setdefault("CUDA_DEVICE_MAX_CONNECTIONS", "32")
 
 import numpy as np  # noqa: E402
 
@@ -41,7 +43,7 @@ GOP = 64
 QP = 27
 PRESET = "veryfast"
 ME_RANGE = 12                      # what "veryfast" maps to (kvz_api.cu kPresets)
-DEPTH = 48                         # pictures in flight (owf = 47): an IDR's entropy coding overlaps ~40 P pictures
+DEPTH = 96                         # pictures in flight (owf = 95): an IDR's serial entropy coding (~30 ms) overlaps the next GOP's prediction chain
 KERNELS = ("intra", "me", "recon", "modes", "deblock", "binarise", "arith", "pack")
 
 
@@ -146,17 +148,24 @@ def run_b200(args):
     enc = GpuEncoder(W, H, qp=QP, intra_period=GOP, search_range=ME_RANGE, depth=DEPTH)
     out_bytes = [0]
 
+    # A step submits one GOP (64 pictures); the pipeline stays full across steps (like a live
+    # stream) and is drained once, inside the timed region, after the last step.
     def step_engine(e):
         n = 0
         for d in d_frames:
             au = e.encode_dev(d)
             n += len(au)
+        return n
+
+    def drain(e):
+        n = 0
         while e.pending():
             n += len(e.flush())
-        out_bytes[0] = n
+        return n
 
     for _ in range(args.warmup):
         step_engine(enc)
+    drain(enc)
     enc.set_profile(True)
     sampler = ClockSampler(local)
     sampler.start()
@@ -165,8 +174,11 @@ def run_b200(args):
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
     t0 = time.perf_counter()
+    produced = 0
     for _ in range(args.steps):
-        step_engine(enc)
+        produced += step_engine(enc)
+    produced += drain(enc)
+    out_bytes[0] = produced / args.steps
     e1.record()
     barrier()
     wall = time.perf_counter() - t0
@@ -195,19 +207,21 @@ def run_b200(args):
     def step_e2e():
         n = 0
         for f in frames:
-            for au in filt.feed_input(f):
+            for au in filt.feed_input(f, drain=False):
                 n += len(au)
-        for au in filt.flush():
-            n += len(au)
-        d2h[0] = n
+        return n
 
     for _ in range(max(1, args.warmup // 2)):
         step_e2e()
+    filt.flush()
     barrier()
     e2e_steps = max(1, args.steps // 2)
     t0 = time.perf_counter()
+    nb = 0
     for _ in range(e2e_steps):
-        step_e2e()
+        nb += step_e2e()
+    nb += sum(len(a) for a in filt.flush())
+    d2h[0] = nb // e2e_steps
     torch.cuda.synchronize()
     e2e_s = time.perf_counter() - t0
     if world > 1:

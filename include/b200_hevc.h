@@ -37,6 +37,8 @@ int   b200_enc_pending(void *enc);
  * 6 arithmetic coding, 7 pack. */
 int   b200_enc_set_profile(void *enc, int on);
 int   b200_enc_get_profile(void *enc, double *ms, unsigned long long *count, int n);
+/* begin/end (ms since open) of each kernel id of the last returned picture: out[2*id], out[2*id+1] */
+int   b200_enc_get_timeline(void *enc, float *out, int n);
 int   b200_enc_last_was_idr(void *enc);
 unsigned long long b200_enc_last_bins(void *enc);
 

@@ -12,6 +12,7 @@ SIGNATURES: dict = {
     "b200_enc_pending": (i, [v]),
     "b200_enc_set_profile": (i, [v, i]),
     "b200_enc_get_profile": (i, [v, v, v, i]),
+    "b200_enc_get_timeline": (i, [v, v, i]),
     "b200_enc_close": (None, [v]),
     "b200_enc_encode": (i, [v, v, v, i]),
     "b200_enc_encode_dev": (i, [v, v, v, i]),

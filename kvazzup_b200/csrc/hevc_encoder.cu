@@ -124,8 +124,9 @@ void Encoder::release()
   inflight.clear();
   for (int i = 0; i < 2; i++) if (d_rec[i]) cudaFree(d_rec[i]);
   if (d_rec_pre) cudaFree(d_rec_pre);
+  if (ev_base) cudaEventDestroy(ev_base);
   if (stream) cudaStreamDestroy(stream);
-  d_rec[0] = d_rec[1] = d_rec_pre = nullptr; stream = nullptr;
+  d_rec[0] = d_rec[1] = d_rec_pre = nullptr; stream = nullptr; ev_base = nullptr;
 }
 
 bool Encoder::open(const EncoderConfig &c)
@@ -133,7 +134,7 @@ bool Encoder::open(const EncoderConfig &c)
   if (c.width <= 0 || c.height <= 0 || (c.width & 7) || (c.height & 7)) { set_error("encoder: width/height must be positive multiples of 8 (got %dx%d)", c.width, c.height); return false; }
   if (c.qp < 0 || c.qp > 51) { set_error("encoder: qp %d out of range 0..51", c.qp); return false; }
   if (c.search_range < 1 || c.search_range > 32) { set_error("encoder: search range %d out of range 1..32", c.search_range); return false; }
-  if (c.depth < 1 || c.depth > 64) { set_error("encoder: depth %d out of range 1..64", c.depth); return false; }
+  if (c.depth < 1 || c.depth > 128) { set_error("encoder: depth %d out of range 1..128", c.depth); return false; }
   if (b200_device_count() <= 0) { set_error("no CUDA device: the B200 encoder has no CPU fallback"); return false; }
   cfg = c;
   fp.w = c.width; fp.h = c.height; fp.w8 = c.width / 8; fp.h8 = c.height / 8;
@@ -144,7 +145,14 @@ bool Encoder::open(const EncoderConfig &c)
   frame_bytes = (size_t)fp.w * fp.h * 3 / 2;
   row_cap = (uint32_t)fp.w * kCtb * 4 + 4096;
   pack_cap = (uint32_t)std::min<size_t>((size_t)row_cap * fp.ctb_rows, frame_bytes * 3 + 65536);
-  ENC_CHECK(cudaStreamCreateWithFlags(&stream, cudaStreamNonBlocking), "cudaStreamCreate");
+  // Stream priorities: the entropy-coding kernels are tiny (one warp per CTU row) but long-running
+  // and need all their rows resident to make progress, while the motion-search / reconstruction
+  // CTAs fill every register of an SM.  Entropy streams therefore get the HIGH priority, so that
+  // whenever a prediction CTA retires, pending entropy CTAs are placed first; the prediction chain
+  // runs at the low priority.
+  int prio_lo = 0, prio_hi = 0;
+  cudaDeviceGetStreamPriorityRange(&prio_lo, &prio_hi);
+  ENC_CHECK(cudaStreamCreateWithPriority(&stream, cudaStreamNonBlocking, prio_lo), "cudaStreamCreate");
   ENC_CHECK(cudaMalloc((void **)&d_rec[0], frame_bytes), "cudaMalloc rec0");
   ENC_CHECK(cudaMalloc((void **)&d_rec[1], frame_bytes), "cudaMalloc rec1");
   if (c.debug) ENC_CHECK(cudaMalloc((void **)&d_rec_pre, frame_bytes), "cudaMalloc rec_pre");
@@ -165,11 +173,13 @@ bool Encoder::open(const EncoderConfig &c)
     ENC_CHECK(cudaMallocHost((void **)&s.h_src, frame_bytes), "cudaMallocHost src");
     ENC_CHECK(cudaHostAlloc((void **)&s.h_pack, pack_cap, cudaHostAllocMapped), "cudaHostAlloc pack");
     ENC_CHECK(cudaHostAlloc((void **)&s.h_hdr, sizeof(uint32_t) * (fp.ctb_rows + 2), cudaHostAllocMapped), "cudaHostAlloc hdr");
-    ENC_CHECK(cudaStreamCreateWithFlags(&s.stream, cudaStreamNonBlocking), "cudaStreamCreate slot");
+    ENC_CHECK(cudaStreamCreateWithPriority(&s.stream, cudaStreamNonBlocking, prio_hi), "cudaStreamCreate slot");
     ENC_CHECK(cudaEventCreateWithFlags(&s.ev_pred, cudaEventDisableTiming), "cudaEventCreate");
     ENC_CHECK(cudaEventCreateWithFlags(&s.ev_done, cudaEventDisableTiming), "cudaEventCreate");
     for (cudaEvent_t &e : s.pev) ENC_CHECK(cudaEventCreate(&e), "cudaEventCreate");
   }
+  ENC_CHECK(cudaEventCreate(&ev_base), "cudaEventCreate");
+  ENC_CHECK(cudaEventRecord(ev_base, stream), "event record");
   frame_idx = 0; poc = 0; cur = 0; cur_qp = c.qp;
   return true;
 }
@@ -345,6 +355,8 @@ bool Encoder::collect(FrameSlot &s, std::vector<uint8_t> &out)
       if (!(s.prof_mask & (1u << k))) continue;
       float ms = 0;
       if (cudaEventElapsedTime(&ms, s.pev[2 * k], s.pev[2 * k + 1]) == cudaSuccess) { prof_ms[k] += ms; prof_cnt[k]++; }
+      cudaEventElapsedTime(&timeline[2 * k], ev_base, s.pev[2 * k]);
+      cudaEventElapsedTime(&timeline[2 * k + 1], ev_base, s.pev[2 * k + 1]);
     }
     s.prof_mask = 0;
   }
@@ -459,6 +471,16 @@ int b200_enc_set_profile(void *h, int on)
   e->profile = on;
   for (int k = 0; k < Encoder::K_COUNT; k++) { e->prof_ms[k] = 0; e->prof_cnt[k] = 0; }
   return B200_OK;
+}
+
+// begin/end times (ms since the encoder was opened) of each kernel of the last collected picture
+int b200_enc_get_timeline(void *h, float *out, int n)
+{
+  Encoder *e = (Encoder *)h;
+  if (!e || !out) return B200_ERR_ARG;
+  int k = 0;
+  for (; k < n && k < 2 * Encoder::K_COUNT; k++) out[k] = e->timeline[k];
+  return k;
 }
 
 int b200_enc_get_profile(void *h, double *ms, unsigned long long *count, int n)

@@ -77,6 +77,8 @@ class Encoder {
   // per-kernel device time, measured with CUDA events on the launching stream (profile != 0)
   enum { K_INTRA = 0, K_ME, K_RECON, K_MODES, K_DEBLOCK, K_BINARISE, K_ARITH, K_PACK, K_COUNT };
   int profile = 0;
+  cudaEvent_t ev_base = nullptr;      // time origin of the timeline below
+  float timeline[2 * K_COUNT] = {};  // begin/end (ms since ev_base) of each kernel of the last collected picture
   double prof_ms[K_COUNT] = {};
   unsigned long long prof_cnt[K_COUNT] = {};
 

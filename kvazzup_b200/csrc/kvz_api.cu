@@ -107,7 +107,7 @@ int config_parse(kvz_config *cfg, const char *name, const char *value)
   if (!strcmp(name, "period")) { if (!parse_int(value, &v) || v < 0) return 0; cfg->intra_period = v; return 1; }
   if (!strcmp(name, "vps-period")) { if (!parse_int(value, &v) || v < 0) return 0; cfg->vps_period = v; return 1; }
   if (!strcmp(name, "threads")) { if (value && !strcmp(value, "auto")) { cfg->threads = -1; return 1; } if (!parse_int(value, &v) || v < 0) return 0; cfg->threads = v; return 1; }
-  if (!strcmp(name, "owf")) { if (value && !strcmp(value, "auto")) { cfg->owf = 3; return 1; } if (!parse_int(value, &v) || v < 0 || v > 63) return 0; cfg->owf = v; return 1; }
+  if (!strcmp(name, "owf")) { if (value && !strcmp(value, "auto")) { cfg->owf = 3; return 1; } if (!parse_int(value, &v) || v < 0 || v > 127) return 0; cfg->owf = v; return 1; }
   if (!strcmp(name, "wpp")) { if (!parse_bool(value, &v)) return 0; cfg->wpp = v; return 1; }
   if (!strcmp(name, "no-wpp")) { cfg->wpp = 0; return 1; }
   if (!strcmp(name, "tiles")) {

@@ -7,7 +7,20 @@
 #include <stdio.h>
 #include <string.h>
 
+#include <stdlib.h>
+
 namespace b200 {
+
+// The encoder keeps one CUDA stream per picture in flight next to its main stream.  With the
+// default of 8 hardware work queues, unrelated streams share a queue and a 3 ms entropy-coding
+// kernel then blocks the next picture's motion search behind it.  Ask for the maximum (32)
+// unless the application chose a value; this only has an effect when the library is loaded
+// before the CUDA context is created (bench.py also sets it before importing torch).
+namespace {
+struct ConnectionsInit {
+  ConnectionsInit() { setenv("CUDA_DEVICE_MAX_CONNECTIONS", "32", 0); }
+} g_connections_init;
+}  // namespace
 
 static thread_local char t_err[512] = "";
 std::atomic<unsigned long long> g_launches{0};

@@ -57,6 +57,12 @@ class GpuEncoder:
         self.l.b200_enc_get_profile(self.h_enc, ms, cnt, 8)
         return {k: (ms[i], int(cnt[i])) for i, k in enumerate(self.KERNELS)}
 
+    def timeline(self) -> dict:
+        """{kernel: (begin_ms, end_ms)} of the last returned picture, since the encoder was opened."""
+        t = (C.c_float * 16)()
+        self.l.b200_enc_get_timeline(self.h_enc, t, 16)
+        return {k: (t[2 * i], t[2 * i + 1]) for i, k in enumerate(self.KERNELS)}
+
     def _read(self, what, dtype, count):
         a = np.empty(count, dtype)
         rc = self.l.b200_enc_debug_read(self.h_enc, what, C.c_void_p(a.ctypes.data), a.nbytes)

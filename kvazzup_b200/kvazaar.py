@@ -179,7 +179,7 @@ class KvazaarFilter:
         self.input_pics = []
         self.api = None
 
-    def _drain(self, pic):
+    def _drain(self, pic, drain=True):
         api = self.api
         out = []
         data_out = _chunkp()
@@ -190,6 +190,8 @@ class KvazaarFilter:
             raise B200Error("encoder_encode failed: " + lib().b200_last_error().decode())
         while data_out:
             out.append(self._parse_encoded_frame(data_out, len_out.value, recon))
+            if not drain:
+                break                     # poll, do not drain, to keep owf pictures in flight
             data_out = _chunkp()
             recon = _picp()
             if api.encoder_encode(self.enc, None, C.byref(data_out), C.byref(len_out), C.byref(recon), None, C.byref(info)) != 1:
@@ -197,8 +199,10 @@ class KvazaarFilter:
         return out
 
     # kvazaarfilter.cpp:374-450
-    def feed_input(self, i420: np.ndarray):
-        """Returns the list of access units that became available (0 or more)."""
+    def feed_input(self, i420: np.ndarray, drain: bool = True):
+        """Returns the list of access units that became available (0 or more).  drain=True is the
+        reference's loop (encoder_encode(pic=NULL) after every output, kvazaarfilter.cpp:440-449);
+        drain=False is the one-line variant of INTEGRATION.md that keeps the pipeline full."""
         c = self.config.contents
         w, h = c.width, c.height
         assert i420.size == w * h * 3 // 2
@@ -210,7 +214,7 @@ class KvazaarFilter:
         C.memmove(pic.contents.v, src.ctypes.data + w * h + w * h // 4, w * h // 4)
         pic.contents.pts = self.pts
         self.pts += 1
-        return self._drain(pic)
+        return self._drain(pic, drain)
 
     def flush(self):
         """Drain the frames still in flight (owf > 0): encoder_encode(pic = NULL) until empty."""
