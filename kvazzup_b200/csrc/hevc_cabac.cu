@@ -73,22 +73,25 @@ __device__ __forceinline__ void write_out(Coder &c)
   }
 }
 
-__device__ __forceinline__ void enc_bin(Coder &c, int ctx_idx, int bin)
+// One 64-bit shared-memory entry per pStateIdx: .x = rangeTabLps row (4 bytes), .y = state after
+// an LPS (transIdxLps) | (valMps flips) << 6 -- a single load feeds the whole update.
+__device__ __forceinline__ void enc_bin(Coder &c, const uint2 *tab, int ctx_idx, int bin)
 {
   uint32_t s = c.ctx[ctx_idx * 32];
   uint32_t st = s >> 1, mps = s & 1;
-  uint32_t lps = (c_range_lps[st] >> (((c.range >> 6) & 3) * 8)) & 0xff;
+  const uint2 e = tab[st];
+  uint32_t lps = (e.x >> (((c.range >> 6) & 3) * 8)) & 0xff;
   c.bins++;
   c.range -= lps;
   if ((uint32_t)bin != mps) {
     int nb = __clz(lps) - 23;                     // shifts until lps >= 256
     c.low = (c.low + c.range) << nb;
     c.range = lps << nb;
-    if (st == 0) mps ^= 1;
-    st = c_trans_lps[st];
+    mps ^= e.y >> 6;
+    st = e.y & 63;
     c.bits_left -= nb;
   } else {
-    if (st < 62) st++;
+    st = min(st + 1, 62u);
     if (c.range < 256) { c.low <<= 1; c.range <<= 1; c.bits_left--; }
   }
   c.ctx[ctx_idx * 32] = (uint8_t)((st << 1) | mps);
@@ -608,7 +611,10 @@ k_arith_rows(FrameParams fp, const uint32_t *__restrict__ recs, uint8_t *rows, u
              uint8_t *sync_ctx, int *sync_flag, unsigned long long *bins)
 {
   __shared__ uint8_t s_ctx[CTX_COUNT * 32];
+  __shared__ uint2 s_tab[64];
+  __shared__ uint32_t s_chunk[2][32];
   const int r = blockIdx.x, lane = threadIdx.x;
+  for (int i = lane; i < 64; i += 32) s_tab[i] = make_uint2(c_range_lps[i], (uint32_t)c_trans_lps[i] | (i == 0 ? 64u : 0u));
   Coder c;
   c.out = rows + (size_t)r * row_cap; c.pos = 0; c.cap = row_cap; c.zeros = 0; c.ctx = s_ctx + lane; c.bins = 0;
   c.writer = lane == 0;
@@ -645,18 +651,26 @@ k_arith_rows(FrameParams fp, const uint32_t *__restrict__ recs, uint8_t *rows, u
     const uint32_t *nreg = recs + ((size_t)(r * fp.ctb_cols + ncol) * 64 + nz) * kRecUnitCap;
     uint32_t nhdr = 0, nfirst = 0;
     if (ncol < fp.ctb_cols) { nhdr = __ldg(nreg); nfirst = __ldg(nreg + 1 + lane); }
-    // code this CU
+    // code this CU: each 32-record chunk is staged in shared memory (double buffered) so that the
+    // next record's load is independent of the coder state and can be issued early
     uint32_t curv = first;
+    int buf = 0;
     for (int base = 0; base < cnt; base += 32) {
       const int nb = base + 32;
       uint32_t nxt = nb + lane < cnt ? __ldg(reg + 1 + nb + lane) : 0;
+      s_chunk[buf][lane] = curv;
+      __syncwarp();
       const int m = min(32, cnt - base);
+      const uint32_t *ch = s_chunk[buf];
+      uint32_t vn = ch[0];
       for (int k = 0; k < m; k++) {
-        const uint32_t v = __shfl_sync(0xffffffffu, curv, k);
+        const uint32_t v = vn;
+        vn = ch[min(k + 1, 31)];
         if (v & 0x80000000u) enc_bypass_group(c, v & 0xffffu, (int)((v >> 24) & 31));
-        else enc_bin(c, (int)(v >> 1), (int)(v & 1));
+        else enc_bin(c, s_tab, (int)(v >> 1), (int)(v & 1));
       }
       curv = nxt;
+      buf ^= 1;
     }
     if (ncol != col) {                                    // the CTU is complete
       if (col == 1 && r + 1 < fp.ctb_rows) {
