@@ -432,10 +432,25 @@ static size_t recon_smem(int range)
   return (size_t)WS * WSW * 4 + 3 * 4096 + 2 * 4096 * 2;
 }
 
+// The opt-in limit of dynamic shared memory is a per-function, process-wide attribute: set it once
+// to the largest size any stream may ask for (several encoders / decoders with different search
+// ranges launch these kernels concurrently from different host threads).
+constexpr int kMaxDynSmem = 200 * 1024;
+static void allow_big_smem()
+{
+  static const bool once = [] {
+    cudaFuncSetAttribute(k_me_ctu, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxDynSmem);
+    cudaFuncSetAttribute(k_inter_recon<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxDynSmem);
+    cudaFuncSetAttribute(k_inter_recon<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxDynSmem);
+    return true;
+  }();
+  (void)once;
+}
+
 cudaError_t launch_inter_me(const FrameParams &fp, const uint8_t *src, const uint8_t *ref, CuInfo *cu, cudaStream_t s)
 {
   size_t sm = me_smem(fp.search_range);
-  cudaFuncSetAttribute(k_me_ctu, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm);
+  allow_big_smem();
   k_me_ctu<<<fp.ctb_cols * fp.ctb_rows, kThreads, sm, s>>>(fp, src, ref, cu);
   return cudaGetLastError();
 }
@@ -444,7 +459,7 @@ cudaError_t launch_inter_recon(const FrameParams &fp, const uint8_t *src, const 
                                int16_t *levels, CuInfo *cu, cudaStream_t s)
 {
   size_t sm = recon_smem(fp.search_range);
-  cudaFuncSetAttribute(k_inter_recon<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm);
+  allow_big_smem();
   k_inter_recon<false><<<fp.ctb_cols * fp.ctb_rows, kThreads, sm, s>>>(fp, src, ref, rec, levels, cu);
   return cudaGetLastError();
 }
@@ -455,8 +470,8 @@ cudaError_t launch_inter_decode(const FrameParams &fp, const uint8_t *ref, uint8
                                 const CuInfo *cu, cudaStream_t s)
 {
   size_t sm = recon_smem(fp.search_range);
-  if (sm > 200 * 1024) return cudaErrorInvalidValue;
-  cudaFuncSetAttribute(k_inter_recon<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm);
+  if (sm > (size_t)kMaxDynSmem) return cudaErrorInvalidValue;
+  allow_big_smem();
   k_inter_recon<true><<<fp.ctb_cols * fp.ctb_rows, kThreads, sm, s>>>(fp, nullptr, ref, rec, (int16_t *)levels, (CuInfo *)cu);
   return cudaGetLastError();
 }
