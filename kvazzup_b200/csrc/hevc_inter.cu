@@ -31,7 +31,7 @@ struct MeShared {
   short mvx[64], mvy[64];          // per origin unit: best mv so far (quarter samples)
   short cmx[64], cmy[64];          // per origin unit: centre of the current refinement step
   unsigned best[64];               // per origin unit: best cost so far
-  unsigned acc[64];                // per origin unit: SAD accumulator of the candidate in flight
+  unsigned acc8[64][8];            // per origin unit: SAD accumulators of the eight candidates of a step
 };
 
 __global__ void __launch_bounds__(kThreads)
@@ -53,7 +53,7 @@ k_me_ctu(FrameParams fp, const uint8_t *__restrict__ src, const uint8_t *__restr
     int y = cy + (i >> 4), x = cx + 4 * (i & 15);
     s_src[i] = (y < fp.h && x < fp.w) ? __ldg((const uint32_t *)(src + (size_t)y * fp.w + x)) : 0u;
   }
-  if (t < 64) { sh.key8[t] = 0xffffffffu; sh.acc[t] = 0; }
+  if (t < 64) { sh.key8[t] = 0xffffffffu; for (int k = 0; k < 8; k++) sh.acc8[t][k] = 0; }
   if (t < 16) sh.key16[t] = 0xffffffffu;
   if (t < 4) sh.key32[t] = 0xffffffffu;
   __syncthreads();
@@ -70,29 +70,48 @@ k_me_ctu(FrameParams fp, const uint8_t *__restrict__ src, const uint8_t *__restr
     uint32_t s[16];
 #pragma unroll
     for (int r = 0; r < 8; r++) { s[2 * r] = s_src[(by * 8 + r) * 16 + bx * 2]; s[2 * r + 1] = s_src[(by * 8 + r) * 16 + bx * 2 + 1]; }
-    const int side = 2 * R + 1, ncand = side * side;
+    // Candidates are taken four at a time along x, starting on a 4-byte boundary of the window:
+    // the three words loaded per row then serve all four (byte shifts 0..3 are compile-time), so a
+    // row costs 3 LDS + 6 SHF + 8 VABSDIFF4 for four candidates.  dx runs from -Rr (R rounded up to
+    // a multiple of 4); candidates beyond +R are masked out.
+    const int side = 2 * R + 1, Rr = (R + 3) & ~3, groups = (Rr + R) / 4 + 1, items = side * groups;
     unsigned k8 = 0xffffffffu, k16 = 0xffffffffu, k32 = 0xffffffffu;
-    for (int c = q; c < ncand; c += 4) {
-      int dy = c / side - R, dx = c - (dy + R) * side - R;
-      unsigned pen = mv_penalty(fp.lambda_q4, dx * 4, dy * 4);
-      int x = M + bx * 8 + dx, xw = x >> 2, shf = (x & 3) * 8;
-      const uint32_t *row = s_ref + (M + by * 8 + dy) * WSW + xw;
-      unsigned sad = 0;
+    for (int it = q; it < items; it += 4) {
+      const int dyi = it / groups, g = it - dyi * groups;
+      const int dy = dyi - R, dx0 = 4 * g - Rr;
+      const uint32_t *row = s_ref + (M + by * 8 + dy) * WSW + ((M + bx * 8 + dx0) >> 2);
+      unsigned sad0 = 0, sad1 = 0, sad2 = 0, sad3 = 0;
 #pragma unroll
       for (int r = 0; r < 8; r++) {
-        unsigned a = row[0], b = row[1], cc = row[2];
-        sad = sad4_acc(s[2 * r], __funnelshift_r(a, b, shf), sad);
-        sad = sad4_acc(s[2 * r + 1], __funnelshift_r(b, cc, shf), sad);
+        const unsigned a = row[0], b = row[1], cc = row[2];
+        const unsigned s0 = s[2 * r], s1 = s[2 * r + 1];
+        sad0 = sad4_acc(s0, a, sad0);
+        sad0 = sad4_acc(s1, b, sad0);
+        sad1 = sad4_acc(s0, __funnelshift_r(a, b, 8), sad1);
+        sad1 = sad4_acc(s1, __funnelshift_r(b, cc, 8), sad1);
+        sad2 = sad4_acc(s0, __funnelshift_r(a, b, 16), sad2);
+        sad2 = sad4_acc(s1, __funnelshift_r(b, cc, 16), sad2);
+        sad3 = sad4_acc(s0, __funnelshift_r(a, b, 24), sad3);
+        sad3 = sad4_acc(s1, __funnelshift_r(b, cc, 24), sad3);
         row += WSW;
       }
-      if (!v8) sad = 0;
-      unsigned s16 = sad + __shfl_xor_sync(0xffffffffu, sad, 1);
-      s16 += __shfl_xor_sync(0xffffffffu, s16, 2);
-      unsigned s32 = s16 + __shfl_xor_sync(0xffffffffu, s16, 4);
-      s32 += __shfl_xor_sync(0xffffffffu, s32, 8);
-      if (v8) k8 = min(k8, ((sad + pen) << 13) | (unsigned)c);
-      if (v16) k16 = min(k16, ((s16 + pen) << 13) | (unsigned)c);
-      if (v32) k32 = min(k32, ((s32 + pen) << 13) | (unsigned)c);
+      const unsigned sads[4] = {sad0, sad1, sad2, sad3};
+#pragma unroll
+      for (int j = 0; j < 4; j++) {
+        const int dx = dx0 + j;
+        const bool in_range = dx >= -R && dx <= R;          // uniform across the warp
+        unsigned sad = v8 ? sads[j] : 0;
+        unsigned s16 = sad + __shfl_xor_sync(0xffffffffu, sad, 1);
+        s16 += __shfl_xor_sync(0xffffffffu, s16, 2);
+        unsigned s32 = s16 + __shfl_xor_sync(0xffffffffu, s16, 4);
+        s32 += __shfl_xor_sync(0xffffffffu, s32, 8);
+        if (!in_range) continue;
+        const unsigned c = (unsigned)((dy + R) * side + dx + R);
+        const unsigned pen = mv_penalty(fp.lambda_q4, dx * 4, dy * 4);
+        if (v8) k8 = min(k8, ((sad + pen) << 13) | c);
+        if (v16) k16 = min(k16, ((s16 + pen) << 13) | c);
+        if (v32) k32 = min(k32, ((s32 + pen) << 13) | c);
+      }
     }
     atomicMin(&sh.key8[z], k8);
     if ((lane & 3) == 0) atomicMin(&sh.key16[z >> 2], k16);
@@ -140,39 +159,48 @@ k_me_ctu(FrameParams fp, const uint8_t *__restrict__ src, const uint8_t *__restr
   }
   __syncthreads();
 
-  // ---- half- then quarter-sample refinement: 4 threads per 8x8 unit, 2 columns x 8 rows each ----
+  // ---- half- then quarter-sample refinement: 4 threads per 8x8 unit, 2 columns x 8 rows each.
+  // The eight candidates of a step share one centre, so they are evaluated back to back into
+  // eight accumulators per CU and compared once per step (same result as comparing one by one:
+  // the first strictly smaller cost in candidate order wins).
   {
     const int z = t >> 2, qc = t & 3;
     const int ux = z_to_x(z), uy = z_to_y(z);
     const int org = sh.org[z];
     const uint8_t *srcb = (const uint8_t *)s_src;
+    unsigned sv[8];
+#pragma unroll
+    for (int r = 0; r < 8; r++) {
+      const uint8_t *sp = srcb + (uy * 8 + r) * 64 + ux * 8 + 2 * qc;
+      sv[r] = (unsigned)sp[0] | ((unsigned)sp[1] << 8);
+    }
     for (int step = 2; step >= 1; step--) {
-      for (int k = 0; k < 8; k++) {
-        const int ox = (k < 3 ? k - 1 : (k == 3 ? -1 : (k == 4 ? 1 : k - 6)));
-        const int oy = k < 3 ? -1 : (k < 5 ? 0 : 1);
-        if (org != 0xff) {
-          int mx = sh.cmx[org] + ox * step, my = sh.cmy[org] + oy * step;
+      if (org != 0xff) {
+        const int cmx = sh.cmx[org], cmy = sh.cmy[org];
+        for (int k = 0; k < 8; k++) {
+          const int ox = (k < 3 ? k - 1 : (k == 3 ? -1 : (k == 4 ? 1 : k - 6)));
+          const int oy = k < 3 ? -1 : (k < 5 ? 0 : 1);
+          const int mx = cmx + ox * step, my = cmy + oy * step;
           unsigned pr[8];
           mc_luma_2x8(s_ref, WSW, M + ux * 8 + 2 * qc + (mx >> 2), M + uy * 8 + (my >> 2), mx & 3, my & 3, pr);
           unsigned sad = 0;
 #pragma unroll
-          for (int r = 0; r < 8; r++) {
-            const uint8_t *sp = srcb + (uy * 8 + r) * 64 + ux * 8 + 2 * qc;
-            unsigned sv = (unsigned)sp[0] | ((unsigned)sp[1] << 8);
-            sad = sad4_acc(sv, pr[r], sad);
-          }
-          atomicAdd(&sh.acc[org], sad);
+          for (int r = 0; r < 8; r++) sad = sad4_acc(sv[r], pr[r], sad);
+          atomicAdd(&sh.acc8[org][k], sad);
         }
-        __syncthreads();
-        if (t < 64 && sh.org[t] == t) {
-          int mx = sh.cmx[t] + ox * step, my = sh.cmy[t] + oy * step;
-          unsigned cost = sh.acc[t] + mv_penalty(fp.lambda_q4, mx, my);
-          if (cost < sh.best[t]) { sh.best[t] = cost; sh.mvx[t] = (short)mx; sh.mvy[t] = (short)my; }
-          sh.acc[t] = 0;
-        }
-        __syncthreads();
       }
-      if (t < 64 && sh.org[t] == t) { sh.cmx[t] = sh.mvx[t]; sh.cmy[t] = sh.mvy[t]; }
+      __syncthreads();
+      if (t < 64 && sh.org[t] == t) {
+        for (int k = 0; k < 8; k++) {
+          const int ox = (k < 3 ? k - 1 : (k == 3 ? -1 : (k == 4 ? 1 : k - 6)));
+          const int oy = k < 3 ? -1 : (k < 5 ? 0 : 1);
+          const int mx = sh.cmx[t] + ox * step, my = sh.cmy[t] + oy * step;
+          unsigned cost = sh.acc8[t][k] + mv_penalty(fp.lambda_q4, mx, my);
+          if (cost < sh.best[t]) { sh.best[t] = cost; sh.mvx[t] = (short)mx; sh.mvy[t] = (short)my; }
+          sh.acc8[t][k] = 0;
+        }
+        sh.cmx[t] = sh.mvx[t]; sh.cmy[t] = sh.mvy[t];
+      }
       __syncthreads();
     }
   }
