@@ -82,6 +82,7 @@ struct Decoder {
   size_t frame_bytes = 0;
   cudaStream_t stream = nullptr;
   uint8_t *d_rec[2] = {nullptr, nullptr}, *d_data = nullptr, *d_small = nullptr;
+  int *d_order = nullptr;
   CuInfo *d_cu = nullptr;
   int16_t *d_levels = nullptr;
   uint8_t *h_out = nullptr, *h_data = nullptr;
@@ -97,6 +98,8 @@ struct Decoder {
   {
     if (stream) cudaStreamSynchronize(stream);
     for (int i = 0; i < 2; i++) if (d_rec[i]) cudaFree(d_rec[i]);
+    if (d_order) cudaFree(d_order);
+    d_order = nullptr;
     if (d_data) cudaFree(d_data);
     if (d_small) cudaFree(d_small);
     if (d_cu) cudaFree(d_cu);
@@ -130,6 +133,12 @@ struct Decoder {
     if (!cuda_ok(cudaMalloc((void **)&d_small, small_bytes), "cudaMalloc")) return false;
     if (!cuda_ok(cudaMalloc((void **)&d_cu, sizeof(CuInfo) * fp.w8 * fp.h8), "cudaMalloc")) return false;
     if (!cuda_ok(cudaMalloc((void **)&d_levels, frame_bytes * sizeof(int16_t)), "cudaMalloc")) return false;
+    {
+      std::vector<int> order((size_t)fp.ctb_cols * fp.ctb_rows);
+      intra_wavefront_order(fp.ctb_cols, fp.ctb_rows, order.data());
+      if (!cuda_ok(cudaMalloc((void **)&d_order, order.size() * sizeof(int)), "cudaMalloc")) return false;
+      if (!cuda_ok(cudaMemcpy(d_order, order.data(), order.size() * sizeof(int), cudaMemcpyHostToDevice), "H2D order")) return false;
+    }
     if (!cuda_ok(cudaMallocHost((void **)&h_out, frame_bytes), "cudaMallocHost")) return false;
     if (!cuda_ok(cudaMallocHost((void **)&h_data, data_cap), "cudaMallocHost")) return false;
     if (!cuda_ok(cudaMallocHost((void **)&h_bases, sizeof(uint32_t) * (rows + 1)), "cudaMallocHost")) return false;
@@ -320,7 +329,7 @@ struct Decoder {
       return -1;
     }
     if (fp.is_idr) {
-      DEC_CHECK(launch_intra_decode(fp, rec, d_levels, d_cu, progress, ticket, stream), "intra decode launch");
+      DEC_CHECK(launch_intra_decode(fp, rec, d_levels, d_cu, progress, ticket, d_order, stream), "intra decode launch");
       count_launch(1);
     } else {
       fp.search_range = std::max(1, (h_status[1] + 3) / 4 + 1);

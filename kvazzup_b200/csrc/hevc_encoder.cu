@@ -122,11 +122,17 @@ void Encoder::release()
   }
   slots.clear();
   inflight.clear();
-  for (int i = 0; i < 2; i++) if (d_rec[i]) cudaFree(d_rec[i]);
+  if (intra_stream) cudaStreamSynchronize(intra_stream);
+  for (int i = 0; i < kRecRing; i++) { if (d_rec[i]) cudaFree(d_rec[i]); if (ev_ring[i]) cudaEventDestroy(ev_ring[i]); d_rec[i] = nullptr; ev_ring[i] = nullptr; }
+  if (d_order) cudaFree(d_order);
+  d_order = nullptr;
+  if (ev_intra) cudaEventDestroy(ev_intra);
+  if (intra_stream) cudaStreamDestroy(intra_stream);
+  ev_intra = nullptr; intra_stream = nullptr;
   if (d_rec_pre) cudaFree(d_rec_pre);
   if (ev_base) cudaEventDestroy(ev_base);
   if (stream) cudaStreamDestroy(stream);
-  d_rec[0] = d_rec[1] = d_rec_pre = nullptr; stream = nullptr; ev_base = nullptr;
+  d_rec_pre = nullptr; stream = nullptr; ev_base = nullptr;
 }
 
 bool Encoder::open(const EncoderConfig &c)
@@ -153,8 +159,18 @@ bool Encoder::open(const EncoderConfig &c)
   int prio_lo = 0, prio_hi = 0;
   cudaDeviceGetStreamPriorityRange(&prio_lo, &prio_hi);
   ENC_CHECK(cudaStreamCreateWithPriority(&stream, cudaStreamNonBlocking, prio_lo), "cudaStreamCreate");
-  ENC_CHECK(cudaMalloc((void **)&d_rec[0], frame_bytes), "cudaMalloc rec0");
-  ENC_CHECK(cudaMalloc((void **)&d_rec[1], frame_bytes), "cudaMalloc rec1");
+  ENC_CHECK(cudaStreamCreateWithPriority(&intra_stream, cudaStreamNonBlocking, prio_hi), "cudaStreamCreate intra");
+  ENC_CHECK(cudaEventCreateWithFlags(&ev_intra, cudaEventDisableTiming), "cudaEventCreate");
+  {
+    std::vector<int> order((size_t)fp.ctb_cols * fp.ctb_rows);
+    intra_wavefront_order(fp.ctb_cols, fp.ctb_rows, order.data());
+    ENC_CHECK(cudaMalloc((void **)&d_order, order.size() * sizeof(int)), "cudaMalloc order");
+    ENC_CHECK(cudaMemcpy(d_order, order.data(), order.size() * sizeof(int), cudaMemcpyHostToDevice), "H2D order");
+  }
+  for (int i = 0; i < kRecRing; i++) {
+    ENC_CHECK(cudaMalloc((void **)&d_rec[i], frame_bytes), "cudaMalloc rec");
+    ENC_CHECK(cudaEventCreateWithFlags(&ev_ring[i], cudaEventDisableTiming), "cudaEventCreate");
+  }
   if (c.debug) ENC_CHECK(cudaMalloc((void **)&d_rec_pre, frame_bytes), "cudaMalloc rec_pre");
   // small state: row_len[rows] | sync_flag[rows] | progress[rows] | ticket | bins(8) | sync_ctx[rows*CTX_COUNT]
   off_flag = sizeof(int) * fp.ctb_rows; off_prog = 2 * off_flag; off_ticket = 3 * off_flag;
@@ -287,21 +303,32 @@ bool Encoder::submit(FrameSlot &s, const uint8_t *d_i420)
   FrameParams p = fp;
   p.is_idr = idr ? 1 : 0;
   p.qp = cur_qp; p.qp_c = kChromaQp[cur_qp]; p.lambda_q4 = kLambdaQ4[cur_qp];
-  uint8_t *rec = d_rec[cur], *ref = d_rec[cur ^ 1];
+  uint8_t *rec = d_rec[frame_idx % kRecRing], *ref = d_rec[(frame_idx + kRecRing - 1) % kRecRing];
   uint32_t *row_len = (uint32_t *)s.d_small;
   int *sync_flag = (int *)(s.d_small + off_flag), *progress = (int *)(s.d_small + off_prog), *ticket = (int *)(s.d_small + off_ticket);
   unsigned long long *bins = (unsigned long long *)(s.d_small + off_bins);
   s.prof_mask = 0;
 #define PROF_BEGIN(id, st) do { if (profile) { ENC_CHECK(cudaEventRecord(s.pev[2 * (id)], st), "prof event"); s.prof_mask |= 1u << (id); } } while (0)
 #define PROF_END(id, st) do { if (profile) ENC_CHECK(cudaEventRecord(s.pev[2 * (id) + 1], st), "prof event"); } while (0)
-  // prediction chain, main stream, picture order
-  ENC_CHECK(cudaMemsetAsync(s.d_levels, 0, frame_bytes * sizeof(int16_t), stream), "memset levels");
   if (idr) {
-    PROF_BEGIN(K_INTRA, stream);
-    ENC_CHECK(launch_intra_frame(p, d_i420, rec, s.d_levels, s.d_cu, progress, ticket, stream), "intra launch");
-    PROF_END(K_INTRA, stream);
-    count_launch(1);
+    // An IDR depends on no other picture: it runs on its own stream, concurrently with the P
+    // pictures still queued on the main stream.  Its buffer ring[n % R] was last read (as a
+    // reference) by picture n - R + 1, so that is the only thing to wait for (the input copy of
+    // an IDR is enqueued on the intra stream as well, see input_stream()).
+    cudaStream_t is = cfg.overlap_idr ? intra_stream : stream;
+    if (cfg.overlap_idr && frame_idx >= kRecRing - 1) ENC_CHECK(cudaStreamWaitEvent(is, ev_ring[(frame_idx + 1) % kRecRing], 0), "stream wait");
+    ENC_CHECK(cudaMemsetAsync(s.d_levels, 0, frame_bytes * sizeof(int16_t), is), "memset levels");
+    PROF_BEGIN(K_INTRA, is);
+    ENC_CHECK(launch_intra_frame(p, d_i420, rec, s.d_levels, s.d_cu, progress, ticket, d_order, is), "intra launch");
+    PROF_END(K_INTRA, is);
+    if (cfg.overlap_idr) {
+      ENC_CHECK(cudaEventRecord(ev_intra, is), "event record");
+      ENC_CHECK(cudaStreamWaitEvent(stream, ev_intra, 0), "stream wait");     // the prediction chain continues after it
+    }
+    count_launch(2);
   } else {
+    // prediction chain, main stream, picture order
+    ENC_CHECK(cudaMemsetAsync(s.d_levels, 0, frame_bytes * sizeof(int16_t), stream), "memset levels");
     PROF_BEGIN(K_ME, stream);
     ENC_CHECK(launch_inter_me(p, d_i420, ref, s.d_cu, stream), "me launch");
     PROF_END(K_ME, stream);
@@ -313,6 +340,7 @@ bool Encoder::submit(FrameSlot &s, const uint8_t *d_i420)
     PROF_END(K_MODES, stream);
     count_launch(3);
   }
+  ENC_CHECK(cudaEventRecord(ev_ring[frame_idx % kRecRing], stream), "event record");   // done reading the reference
   if (cfg.debug) ENC_CHECK(cudaMemcpyAsync(d_rec_pre, rec, frame_bytes, cudaMemcpyDeviceToDevice, stream), "copy pre-deblock");
   ENC_CHECK(cudaEventRecord(s.ev_pred, stream), "event record");
   if (cfg.deblock) {
@@ -337,7 +365,6 @@ bool Encoder::submit(FrameSlot &s, const uint8_t *d_i420)
 #undef PROF_END
   count_launch(2);
   ENC_CHECK(cudaEventRecord(s.ev_done, s.stream), "event record");
-  cur ^= 1;
   frame_idx++;
   poc++;
   return true;
@@ -373,6 +400,13 @@ bool Encoder::collect(FrameSlot &s, std::vector<uint8_t> &out)
 
 void Encoder::set_qp(int qp) { cur_qp = std::min(std::max(qp, 0), 51); }
 
+// stream that consumes the next picture's input: the intra stream for an IDR, else the main stream
+cudaStream_t Encoder::input_stream() const
+{
+  const bool idr = frame_idx == 0 || (cfg.intra_period > 0 && frame_idx % cfg.intra_period == 0);
+  return (idr && cfg.overlap_idr) ? intra_stream : stream;
+}
+
 bool Encoder::encode_device(const uint8_t *d_i420, std::vector<uint8_t> &out)
 {
   out.clear();
@@ -381,7 +415,7 @@ bool Encoder::encode_device(const uint8_t *d_i420, std::vector<uint8_t> &out)
   // the slot is free: its previous picture was collected when the pipeline was full.
   // Take a private copy so that the caller may reuse its buffer as soon as this call returns
   // (the caller orders its producer before this call; the copy is ~1 us of HBM time).
-  if (d_i420 != s.d_src) ENC_CHECK(cudaMemcpyAsync(s.d_src, d_i420, frame_bytes, cudaMemcpyDeviceToDevice, stream), "D2D frame");
+  if (d_i420 != s.d_src) ENC_CHECK(cudaMemcpyAsync(s.d_src, d_i420, frame_bytes, cudaMemcpyDeviceToDevice, input_stream()), "D2D frame");
   if (!submit(s, s.d_src)) return false;
   inflight.push_back(slot);
   last_slot = slot;
@@ -393,7 +427,7 @@ bool Encoder::encode_host(const uint8_t *i420, std::vector<uint8_t> &out)
 {
   FrameSlot &s = slots[frame_idx % cfg.depth];
   memcpy(s.h_src, i420, frame_bytes);
-  ENC_CHECK(cudaMemcpyAsync(s.d_src, s.h_src, frame_bytes, cudaMemcpyHostToDevice, stream), "H2D frame");
+  ENC_CHECK(cudaMemcpyAsync(s.d_src, s.h_src, frame_bytes, cudaMemcpyHostToDevice, input_stream()), "H2D frame");
   return encode_device(s.d_src, out);
 }
 
@@ -504,7 +538,7 @@ int b200_enc_debug_read(void *h, int what, void *dst, size_t bytes)
   const void *src = nullptr;
   size_t n = 0;
   switch (what) {
-  case 0: src = e->d_rec[e->cur ^ 1]; n = e->frame_bytes; break;
+  case 0: src = e->last_rec(); n = e->frame_bytes; break;
   case 1: src = e->d_rec_pre; n = e->frame_bytes; break;
   case 2: src = s.d_cu; n = sizeof(b200::CuInfo) * e->fp.w8 * e->fp.h8; break;
   case 3: src = s.d_levels; n = e->frame_bytes * sizeof(int16_t); break;
@@ -522,7 +556,7 @@ int b200_enc_debug_set_reference(void *h, const uint8_t *i420)
   Encoder *e = (Encoder *)h;
   if (!e || !i420) return B200_ERR_ARG;
   B200_CHECK(cudaStreamSynchronize(e->stream), "debug sync");
-  B200_CHECK(cudaMemcpy(e->d_rec[e->cur ^ 1], i420, e->frame_bytes, cudaMemcpyHostToDevice), "set reference");
+  B200_CHECK(cudaMemcpy(e->last_rec(), i420, e->frame_bytes, cudaMemcpyHostToDevice), "set reference");
   return B200_OK;
 }
 

@@ -17,6 +17,9 @@ struct EncoderConfig {
   int search_range = 8;      // full-sample motion search range (+-)
   int deblock = 1;
   int debug = 0;             // keep a copy of the reconstruction before deblocking
+  int overlap_idr = 0;       // 1 = run an IDR on its own stream, concurrently with the P pictures queued before it.
+                             // Measured slower on B200 (the latency-bound wavefront loses its issue slots to the
+                             // motion-search CTAs it shares SMs with: 8 ms alone, 30 ms overlapped), so off.
   int depth = 1;             // pictures in flight (Kvazaar's owf + 1): output of picture n is
                              // returned by the call that submits picture n + depth - 1
 };
@@ -67,7 +70,16 @@ class Encoder {
   unsigned long long last_bins = 0;
   std::vector<uint8_t> au;
 
-  uint8_t *d_rec[2] = {nullptr, nullptr}, *d_rec_pre = nullptr;
+  // Reconstruction ring: picture n is written to ring[n % kRecRing] and predicts from
+  // ring[(n-1) % kRecRing].  More than two buffers let an IDR (which depends on nothing) run on
+  // its own stream concurrently with the P pictures queued before it.
+  static constexpr int kRecRing = 32;
+  uint8_t *d_rec[kRecRing] = {}, *d_rec_pre = nullptr;
+  cudaEvent_t ev_ring[kRecRing] = {};    // "picture n finished reading its reference" (main stream)
+  cudaStream_t intra_stream = nullptr;
+  int *d_order = nullptr;                // CTU indices in wavefront order (intra kernel tickets)
+  cudaEvent_t ev_intra = nullptr;
+  uint8_t *last_rec() const { return d_rec[(frame_idx + kRecRing - 1) % kRecRing]; }
   std::vector<FrameSlot> slots;
   std::deque<int> inflight;          // slot indices, oldest first
   int last_slot = 0;
@@ -84,6 +96,7 @@ class Encoder {
 
  private:
   void release();
+  cudaStream_t input_stream() const;
   bool submit(FrameSlot &s, const uint8_t *d_i420);
   bool collect(FrameSlot &s, std::vector<uint8_t> &au);
   void write_parameter_sets(std::vector<uint8_t> &out) const;

@@ -12,6 +12,8 @@
 //                   published with a release fence.  Inside a CTU the CUs are coded in z-order;
 //                   the three planes of a CU go through prediction, DCT, quantisation, inverse and
 //                   reconstruction (rows K5, K6) concurrently: 256 + 64 + 64 threads.
+#include <algorithm>
+
 #include "hevc_device.cuh"
 #include "hevc_kernels.h"
 
@@ -78,8 +80,12 @@ __device__ __forceinline__ int intra_pixel(const uint8_t *u, const uint8_t *f, i
 // Gather (8.4.4.2.2) the 4n+1 neighbours of the n x n block at (x0,y0) of `plane` (plane c of the
 // picture; c > 0 is 4:2:0 chroma) into rs.raw / rs.av.  `first` = index of the first thread of
 // the group of >= 4n+1 threads doing this block.  Caller synchronises, then calls finish_refs.
+// `tile` (may be NULL): the current CTU's reconstruction of this plane in shared memory, T x T
+// samples whose top-left is plane sample (tx0,ty0); neighbours inside it are read from there
+// (no L2 round trip on the wavefront's critical path), the others from HBM / L2.
 __device__ __forceinline__ void gather_refs(RefSet &rs, const FrameParams &fp, const uint8_t *plane, int pw, int c,
-                                            int x0, int y0, int n, unsigned cur_order, int t)
+                                            int x0, int y0, int n, unsigned cur_order, int t,
+                                            const uint8_t *tile = nullptr, int T = 0, int tx0 = 0, int ty0 = 0)
 {
   const int cnt = 4 * n + 1, sft = c ? 1 : 0;
   if (t >= 0 && t < cnt) {
@@ -90,7 +96,13 @@ __device__ __forceinline__ void gather_refs(RefSet &rs, const FrameParams &fp, c
     int lx = x << sft, ly = y << sft;
     bool ok = lx >= 0 && ly >= 0 && lx < fp.w && ly < fp.h && coding_order_i(fp, lx, ly) < cur_order;
     rs.av[t] = ok;
-    rs.raw[t] = ok ? __ldcg(plane + (size_t)y * pw + x) : 0;
+    uint8_t v = 0;
+    if (ok) {
+      const int lx2 = x - tx0, ly2 = y - ty0;
+      if (tile && lx2 >= 0 && ly2 >= 0 && lx2 < T && ly2 < T) v = tile[ly2 * T + lx2];
+      else v = __ldcg(plane + (size_t)y * pw + x);
+    }
+    rs.raw[t] = v;
   }
 }
 // substitution (8.4.4.2.2) by thread t of the group; caller synchronises afterwards
@@ -183,6 +195,8 @@ k_intra_modes(FrameParams fp, const uint8_t *__restrict__ src, CuInfo *__restric
 // ---- reconstruction wavefront ----------------------------------------------------------------------
 
 struct ReconSharedI {
+  uint8_t rec_y[64 * 64], rec_c[2][32 * 32];      // reconstruction of the current CTU
+  uint8_t src_y[64 * 64], src_c[2][32 * 32];      // source samples of the current CTU
   RefSet rs[3];
   int nz[3], ctu;
   int8_t dct[32][32], dctT[32][32];
@@ -194,7 +208,7 @@ struct ReconSharedI {
 // for a 16x16 CU), sample (x,y) of that plane's n_p x n_p block.
 template <bool kDecode>
 __device__ void recon_cu(ReconSharedI &sh, const FrameParams &fp, const uint8_t *src, uint8_t *rec, int16_t *levels,
-                         CuInfo *cu, int x0, int y0, int log2)
+                         CuInfo *cu, int cx, int cy, int x0, int y0, int log2)
 {
   const int t = threadIdx.x;
   const size_t ysz = (size_t)fp.w * fp.h;
@@ -221,7 +235,8 @@ __device__ void recon_cu(ReconSharedI &sh, const FrameParams &fp, const uint8_t 
     const int gpw = g == 0 ? fp.w : fp.w >> 1;
     const int gx = g == 0 ? x0 : x0 >> 1, gy = g == 0 ? y0 : y0 >> 1;
     if (t < 3) sh.nz[t] = kDecode ? ((__ldcg(&cu[(size_t)(y0 >> 3) * fp.w8 + (x0 >> 3)].cbf) >> t) & 1) : 0;
-    gather_refs(sh.rs[g], fp, rec + goff, gpw, g, gx, gy, gn, cur, gt);
+    const uint8_t *tile = g == 0 ? sh.rec_y : sh.rec_c[g - 1];
+    gather_refs(sh.rs[g], fp, rec + goff, gpw, g, gx, gy, gn, cur, gt, tile, g == 0 ? 64 : 32, g == 0 ? cx : cx >> 1, g == 0 ? cy : cy >> 1);
     __syncthreads();
     substitute_refs(sh.rs[g], gn, gt);
     __syncthreads();
@@ -235,7 +250,9 @@ __device__ void recon_cu(ReconSharedI &sh, const FrameParams &fp, const uint8_t 
   if (p >= 0) pr = intra_pixel(sh.rs[p].sub, sh.rs[p].filt, n, l2, mode, p, sh.rs[p].dc, x, y);
   if (!kDecode) {
     if (p >= 0) {
-      int s = __ldg(src + poff + (size_t)(by + y) * pw + bx + x);
+      const int T = p == 0 ? 64 : 32;
+      const uint8_t *st = p == 0 ? sh.src_y : sh.src_c[p - 1];
+      int s = st[(by + y - (p == 0 ? cy : cy >> 1)) * T + bx + x - (p == 0 ? cx : cx >> 1)];
       a[li] = (int16_t)(s - pr);
     }
     __syncthreads();
@@ -287,20 +304,24 @@ __device__ void recon_cu(ReconSharedI &sh, const FrameParams &fp, const uint8_t 
       v = clip8(pr + clip3(-32768, 32767, (acc + 2048) >> 12));
     }
     __stcg(rec + poff + (size_t)(by + y) * pw + bx + x, (uint8_t)v);
+    const int T = p == 0 ? 64 : 32;
+    uint8_t *rt = p == 0 ? sh.rec_y : sh.rec_c[p - 1];
+    rt[(by + y - (p == 0 ? cy : cy >> 1)) * T + bx + x - (p == 0 ? cx : cx >> 1)] = (uint8_t)v;
   }
   const int n8 = nl >> 3;
   if (!kDecode && t < n8 * n8) {
     int cbf = (sh.nz[0] ? 1 : 0) | (sh.nz[1] ? 2 : 0) | (sh.nz[2] ? 4 : 0);
     __stcg(&cu[(size_t)((y0 >> 3) + t / n8) * fp.w8 + (x0 >> 3) + t % n8].cbf, (uint8_t)cbf);
   }
-  __threadfence();
+  // no device-scope fence here: later CUs of this CTU read these samples from the shared-memory
+  // tile (ordered by the barrier); other CTUs only after the fence + progress update at CTU end
   __syncthreads();
 }
 
 template <bool kDecode>
-__global__ void __launch_bounds__(kReconThreads)
+__global__ void __launch_bounds__(kReconThreads, 2)     // <= 85 registers: a CTA then fits beside two motion-search CTAs
 k_intra_frame(FrameParams fp, const uint8_t *__restrict__ src, uint8_t *rec, int16_t *levels, CuInfo *cu,
-              int *progress, int *ticket)
+              int *progress, int *ticket, const int *__restrict__ order)
 {
   __shared__ ReconSharedI sh;
   const int t = threadIdx.x;
@@ -308,44 +329,87 @@ k_intra_frame(FrameParams fp, const uint8_t *__restrict__ src, uint8_t *rec, int
     ((int8_t *)sh.dct)[i] = c_dct32[i >> 5][i & 31];
     ((int8_t *)sh.dctT)[i] = c_dct32[i & 31][i >> 5];
   }
-  if (t == 0) sh.ctu = atomicAdd(ticket, 1);
-  __syncthreads();
-  const int ctu = sh.ctu;
-  const int row = ctu / fp.ctb_cols, col = ctu - row * fp.ctb_cols;
-  if (t == 0) {
-    // left CTU of this row, and the above-right CTU of the row above
-    volatile int *p = progress;
-    while (col > 0 && p[row] < col) __nanosleep(32);
-    if (row > 0) {
-      int need = min(col + 2, fp.ctb_cols);
-      while (p[row - 1] < need) __nanosleep(32);
+  // Persistent CTAs: the wavefront is at most min(rows, ceil(cols/2)) CTUs wide, so a small grid
+  // that keeps taking tickets does the same work as one CTA per CTU without parking hundreds of
+  // waiting CTAs (384 threads x ~150 registers each) on SMs that other streams' kernels could use.
+  const int nctu = fp.ctb_cols * fp.ctb_rows;
+  for (;;) {
+    __syncthreads();
+    if (t == 0) sh.ctu = atomicAdd(ticket, 1);
+    __syncthreads();
+    if (sh.ctu >= nctu) break;
+    // tickets follow the wavefront (anti-diagonals c + 2r), not raster order, so that the CTUs a
+    // small resident grid holds at any time are the ones that can actually run concurrently;
+    // every dependency (left, above-right) still has a smaller ticket
+    const int ctu = order[sh.ctu];
+    const int row = ctu / fp.ctb_cols, col = ctu - row * fp.ctb_cols;
+    if (t == 0) {
+      // left CTU of this row, and the above-right CTU of the row above
+      volatile int *p = progress;
+      while (col > 0 && p[row] < col) __nanosleep(32);
+      if (row > 0) {
+        int need = min(col + 2, fp.ctb_cols);
+        while (p[row - 1] < need) __nanosleep(32);
+      }
+      __threadfence();
     }
-    __threadfence();
-  }
-  __syncthreads();
-  const int cx = col * kCtb, cy = row * kCtb;
-  // z-order walk over the sixteen 16x16 positions of the CTU; 16x16 that cross the picture edge fall to 8x8
-  for (int z16 = 0; z16 < 16; z16++) {
-    int x0 = cx + 16 * ((z16 & 1) | ((z16 >> 1) & 2)), y0 = cy + 16 * (((z16 >> 1) & 1) | ((z16 >> 2) & 2));
-    if (x0 >= fp.w || y0 >= fp.h) continue;
-    if (x0 + 16 <= fp.w && y0 + 16 <= fp.h) {
-      recon_cu<kDecode>(sh, fp, src, rec, levels, cu, x0, y0, 4);
-    } else {
-      for (int q = 0; q < 4; q++) {
-        int x1 = x0 + 8 * (q & 1), y1 = y0 + 8 * (q >> 1);
-        if (x1 < fp.w && y1 < fp.h) recon_cu<kDecode>(sh, fp, src, rec, levels, cu, x1, y1, 3);
+    __syncthreads();
+    const int cx = col * kCtb, cy = row * kCtb;
+    if (!kDecode) {
+      const size_t ysz = (size_t)fp.w * fp.h;
+      for (int i = t; i < 64 * 16; i += kReconThreads) {
+        int y = cy + (i >> 4), x = cx + 4 * (i & 15);
+        ((uint32_t *)sh.src_y)[i] = (y < fp.h && x < fp.w) ? __ldg((const uint32_t *)(src + (size_t)y * fp.w + x)) : 0u;
+      }
+      for (int i = t; i < 2 * 32 * 8; i += kReconThreads) {
+        int c = i >> 8, j = i & 255;
+        int y = (cy >> 1) + (j >> 3), x = (cx >> 1) + 4 * (j & 7);
+        const uint8_t *pl = src + ysz + (c ? ysz / 4 : 0);
+        ((uint32_t *)sh.src_c[c])[j] = (y < (fp.h >> 1) && x < (fp.w >> 1)) ? __ldg((const uint32_t *)(pl + (size_t)y * (fp.w >> 1) + x)) : 0u;
+      }
+      __syncthreads();
+    }
+    // z-order walk over the sixteen 16x16 positions of the CTU; 16x16 that cross the picture edge fall to 8x8
+    for (int z16 = 0; z16 < 16; z16++) {
+      int x0 = cx + 16 * ((z16 & 1) | ((z16 >> 1) & 2)), y0 = cy + 16 * (((z16 >> 1) & 1) | ((z16 >> 2) & 2));
+      if (x0 >= fp.w || y0 >= fp.h) continue;
+      if (x0 + 16 <= fp.w && y0 + 16 <= fp.h) {
+        recon_cu<kDecode>(sh, fp, src, rec, levels, cu, cx, cy, x0, y0, 4);
+      } else {
+        for (int q = 0; q < 4; q++) {
+          int x1 = x0 + 8 * (q & 1), y1 = y0 + 8 * (q >> 1);
+          if (x1 < fp.w && y1 < fp.h) recon_cu<kDecode>(sh, fp, src, rec, levels, cu, cx, cy, x1, y1, 3);
+        }
       }
     }
+    __threadfence();
+    __syncthreads();
+    if (t == 0) atomicExch(&progress[row], col + 1);
   }
-  __threadfence();
-  __syncthreads();
-  if (t == 0) atomicExch(&progress[row], col + 1);
 }
 
 }  // namespace
 
+// CTU indices in wavefront order: sorted by (col + 2*row, row).  n = cols*rows entries.
+void intra_wavefront_order(int cols, int rows, int *out)
+{
+  int k = 0;
+  for (int w = 0; w <= (cols - 1) + 2 * (rows - 1); w++)
+    for (int r = 0; r < rows; r++) {
+      int c = w - 2 * r;
+      if (c >= 0 && c < cols) out[k++] = r * cols + c;
+    }
+}
+
+// wavefront width + slack, never more CTAs than CTUs
+static int intra_grid(const FrameParams &fp)
+{
+  int width = std::min(fp.ctb_rows, (fp.ctb_cols + 1) / 2) + 3;
+  return std::max(1, std::min(width, fp.ctb_cols * fp.ctb_rows));
+}
+
 cudaError_t launch_intra_frame(const FrameParams &fp, const uint8_t *src, uint8_t *rec, int16_t *levels, CuInfo *cu,
-                               int *progress, int *ticket, cudaStream_t s)
+                               int *progress, int *ticket, const int *order, cudaStream_t s)
 {
   cudaError_t e = cudaMemsetAsync(progress, 0, sizeof(int) * fp.ctb_rows, s);
   if (e != cudaSuccess) return e;
@@ -353,20 +417,20 @@ cudaError_t launch_intra_frame(const FrameParams &fp, const uint8_t *src, uint8_
   if (e != cudaSuccess) return e;
   const int blocks16 = ((fp.w + 15) >> 4) * ((fp.h + 15) >> 4);
   k_intra_modes<<<blocks16, kModeThreads, 0, s>>>(fp, src, cu);
-  k_intra_frame<false><<<fp.ctb_cols * fp.ctb_rows, kReconThreads, 0, s>>>(fp, src, rec, levels, cu, progress, ticket);
+  k_intra_frame<false><<<intra_grid(fp), kReconThreads, 0, s>>>(fp, src, rec, levels, cu, progress, ticket, order);
   return cudaGetLastError();
 }
 
 // Decoder reconstruction of an I picture (modes, cbf and levels from the parser).  Intra CUs must
 // be 16x16 or 8x8 (what the parser accepts for I slices produced by this encoder family).
 cudaError_t launch_intra_decode(const FrameParams &fp, uint8_t *rec, const int16_t *levels, const CuInfo *cu,
-                                int *progress, int *ticket, cudaStream_t s)
+                                int *progress, int *ticket, const int *order, cudaStream_t s)
 {
   cudaError_t e = cudaMemsetAsync(progress, 0, sizeof(int) * fp.ctb_rows, s);
   if (e != cudaSuccess) return e;
   e = cudaMemsetAsync(ticket, 0, sizeof(int), s);
   if (e != cudaSuccess) return e;
-  k_intra_frame<true><<<fp.ctb_cols * fp.ctb_rows, kReconThreads, 0, s>>>(fp, nullptr, rec, (int16_t *)levels, (CuInfo *)cu, progress, ticket);
+  k_intra_frame<true><<<intra_grid(fp), kReconThreads, 0, s>>>(fp, nullptr, rec, (int16_t *)levels, (CuInfo *)cu, progress, ticket, order);
   return cudaGetLastError();
 }
 

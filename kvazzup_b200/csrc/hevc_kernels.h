@@ -15,14 +15,15 @@ cudaError_t launch_inter_recon(const FrameParams &fp, const uint8_t *src, const 
 cudaError_t launch_inter_modes(const FrameParams &fp, CuInfo *cu, cudaStream_t s);
 
 // I pictures: wavefront over CTUs. `progress` = ctb_rows ints, `ticket` = 1 int, both zeroed by the launcher.
+void intra_wavefront_order(int cols, int rows, int *out);      // host: CTU indices sorted by (col + 2*row, row)
 cudaError_t launch_intra_frame(const FrameParams &fp, const uint8_t *src, uint8_t *rec, int16_t *levels, CuInfo *cu,
-                               int *progress, int *ticket, cudaStream_t s);
+                               int *progress, int *ticket, const int *order, cudaStream_t s);
 
 // decoder-side reconstruction (levels / modes / motion from the parser)
 cudaError_t launch_inter_decode(const FrameParams &fp, const uint8_t *ref, uint8_t *rec, const int16_t *levels,
                                 const CuInfo *cu, cudaStream_t s);
 cudaError_t launch_intra_decode(const FrameParams &fp, uint8_t *rec, const int16_t *levels, const CuInfo *cu,
-                                int *progress, int *ticket, cudaStream_t s);
+                                int *progress, int *ticket, const int *order, cudaStream_t s);
 // CABAC parse: one warp per substream.  data = unescaped slice data, bases[r] = offset of row r
 // (bases[rows] = end).  status[0] = first error (0 ok), status[1] = largest |mv| component.
 cudaError_t launch_parse(const FrameParams &fp, const uint8_t *data, const uint32_t *bases, CuInfo *cu, int16_t *levels,

@@ -314,7 +314,7 @@ int encoder_encode(kvz_encoder *e, kvz_picture *pic_in, kvz_data_chunk **data_ou
     kvz_picture *r = picture_alloc(e->cfg.width, e->cfg.height);
     if (r) {
       cudaStreamSynchronize(e->eng.stream);
-      cudaMemcpy(r->y, e->eng.d_rec[e->eng.cur ^ 1], e->eng.frame_bytes, cudaMemcpyDeviceToHost);
+      cudaMemcpy(r->y, e->eng.last_rec(), e->eng.frame_bytes, cudaMemcpyDeviceToHost);
       *pic_recon = r;
     }
   }
