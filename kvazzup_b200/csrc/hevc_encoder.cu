@@ -7,6 +7,7 @@
 #include "hevc_encoder.h"
 
 #include <stdio.h>
+#include <stdlib.h>
 #include <string.h>
 
 #include <algorithm>
@@ -128,6 +129,9 @@ void Encoder::release()
   d_order = nullptr;
   if (ev_intra) cudaEventDestroy(ev_intra);
   if (intra_stream) cudaStreamDestroy(intra_stream);
+  if (upload_stream) { cudaStreamSynchronize(upload_stream); cudaStreamDestroy(upload_stream); }
+  if (ev_upload) cudaEventDestroy(ev_upload);
+  upload_stream = nullptr; ev_upload = nullptr;
   ev_intra = nullptr; intra_stream = nullptr;
   if (d_rec_pre) cudaFree(d_rec_pre);
   if (ev_base) cudaEventDestroy(ev_base);
@@ -143,6 +147,7 @@ bool Encoder::open(const EncoderConfig &c)
   if (c.depth < 1 || c.depth > 128) { set_error("encoder: depth %d out of range 1..128", c.depth); return false; }
   if (b200_device_count() <= 0) { set_error("no CUDA device: the B200 encoder has no CPU fallback"); return false; }
   cfg = c;
+  if (const char *ev = getenv("B200_OVERLAP_IDR")) cfg.overlap_idr = atoi(ev);
   fp.w = c.width; fp.h = c.height; fp.w8 = c.width / 8; fp.h8 = c.height / 8;
   fp.ctb_cols = (c.width + kCtb - 1) / kCtb; fp.ctb_rows = (c.height + kCtb - 1) / kCtb;
   fp.qp = c.qp; fp.qp_c = kChromaQp[std::min(std::max(c.qp, 0), 57)];
@@ -161,6 +166,8 @@ bool Encoder::open(const EncoderConfig &c)
   ENC_CHECK(cudaStreamCreateWithPriority(&stream, cudaStreamNonBlocking, prio_lo), "cudaStreamCreate");
   ENC_CHECK(cudaStreamCreateWithPriority(&intra_stream, cudaStreamNonBlocking, prio_hi), "cudaStreamCreate intra");
   ENC_CHECK(cudaEventCreateWithFlags(&ev_intra, cudaEventDisableTiming), "cudaEventCreate");
+  ENC_CHECK(cudaStreamCreateWithPriority(&upload_stream, cudaStreamNonBlocking, prio_hi), "cudaStreamCreate upload");
+  ENC_CHECK(cudaEventCreateWithFlags(&ev_upload, cudaEventDisableTiming), "cudaEventCreate");
   {
     std::vector<int> order((size_t)fp.ctb_cols * fp.ctb_rows);
     intra_wavefront_order(fp.ctb_cols, fp.ctb_rows, order.data());
@@ -423,11 +430,19 @@ bool Encoder::encode_device(const uint8_t *d_i420, std::vector<uint8_t> &out)
   return true;
 }
 
-bool Encoder::encode_host(const uint8_t *i420, std::vector<uint8_t> &out)
+bool Encoder::encode_host(const uint8_t *i420, std::vector<uint8_t> &out, bool pinned)
 {
   FrameSlot &s = slots[frame_idx % cfg.depth];
-  memcpy(s.h_src, i420, frame_bytes);
-  ENC_CHECK(cudaMemcpyAsync(s.d_src, s.h_src, frame_bytes, cudaMemcpyHostToDevice, input_stream()), "H2D frame");
+  const uint8_t *from = i420;
+  if (!pinned) {
+    memcpy(s.h_src, i420, frame_bytes);
+    from = s.h_src;
+  }
+  // the upload runs on its own stream so that the copy engine works while the previous picture's
+  // kernels execute; the consuming stream waits for it
+  ENC_CHECK(cudaMemcpyAsync(s.d_src, from, frame_bytes, cudaMemcpyHostToDevice, upload_stream), "H2D frame");
+  ENC_CHECK(cudaEventRecord(ev_upload, upload_stream), "event record");
+  ENC_CHECK(cudaStreamWaitEvent(input_stream(), ev_upload, 0), "stream wait");
   return encode_device(s.d_src, out);
 }
 

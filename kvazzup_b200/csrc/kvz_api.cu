@@ -174,7 +174,16 @@ kvz_picture *picture_alloc_csp(enum kvz_chroma_format csp, int32_t w, int32_t h)
   kvz_picture *p = (kvz_picture *)calloc(1, sizeof(kvz_picture));
   if (!p) return NULL;
   size_t ysz = (size_t)w * h;
-  p->fulldata_buf = (kvz_pixel *)malloc(ysz + ysz / 2);
+  // page-locked when a CUDA device is present, so that encoder_encode can upload the picture in
+  // place (the reference keeps a ring of owf + 1 pictures and does not touch a picture again before
+  // its access unit came back, kvazaarfilter.cpp:76-88,299); plain memory otherwise
+  p->base_image = NULL;
+  if (cudaHostAlloc((void **)&p->fulldata_buf, ysz + ysz / 2, cudaHostAllocDefault) == cudaSuccess) {
+    p->base_image = p;                         // marks "page-locked, allocated by us"
+  } else {
+    cudaGetLastError();
+    p->fulldata_buf = (kvz_pixel *)malloc(ysz + ysz / 2);
+  }
   if (!p->fulldata_buf) { free(p); return NULL; }
   p->fulldata = p->fulldata_buf;
   p->y = p->data[0] = p->fulldata;
@@ -191,7 +200,8 @@ void picture_free(kvz_picture *p)
 {
   if (!p) return;
   if (--p->refcount > 0) return;
-  free(p->fulldata_buf);
+  if (p->base_image == p) cudaFreeHost(p->fulldata_buf);
+  else free(p->fulldata_buf);
   free(p);
 }
 
@@ -279,7 +289,7 @@ int encoder_encode(kvz_encoder *e, kvz_picture *pic_in, kvz_data_chunk **data_ou
     }
     const size_t ysz = (size_t)e->cfg.width * e->cfg.height;
     if (pic_in->u == pic_in->y + ysz && pic_in->v == pic_in->u + ysz / 4 && pic_in->stride == pic_in->width) {
-      ok = e->eng.encode_host(pic_in->y, e->au);
+      ok = e->eng.encode_host(pic_in->y, e->au, pic_in->base_image == pic_in);
     } else {
       std::vector<uint8_t> tmp(ysz + ysz / 2);
       for (int r = 0; r < pic_in->height; r++) memcpy(&tmp[(size_t)r * pic_in->width], pic_in->y + (size_t)r * pic_in->stride, pic_in->width);

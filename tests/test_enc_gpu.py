@@ -205,3 +205,40 @@ def test_rate_control_tracks_the_target_bitrate():
             assert errs == 0 and len(dec) == n
     assert sizes[300] < sizes[1500]
     assert 0.4 * 1500 < sizes[1500] < 2.0 * 1500
+
+
+# ---- BASELINE full sizes through size-independent properties -------------------------------------
+
+@pytest.mark.parametrize("kind,w,h,qp", [("camera", 3840, 2160, 32), ("screen", 2560, 1440, 27), ("camera", 1280, 720, 22)])
+def test_full_size_roundtrip_properties(kind, w, h, qp):
+    """Sizes of BASELINE configs 3, 5 and 4: the encoder's reconstruction must equal what two
+    independent decoders (ours, FFmpeg's) make of its stream, and pipelined == synchronous."""
+    from kvazzup_b200.openhevc import OpenHEVCFilter, split_nals
+    n = 3
+    frames = frames_of(kind, w, h, n)
+    a = GpuEncoder(w, h, qp=qp, intra_period=0, search_range=12)
+    b = GpuEncoder(w, h, qp=qp, intra_period=0, search_range=12, depth=3)
+    aus, recs, piped = [], [], []
+    for f in frames:
+        aus.append(a.encode(f))
+        recs.append(a.recon())
+        au = b.encode(f)
+        if au:
+            piped.append(au)
+    while b.pending():
+        piped.append(b.flush())
+    assert piped == aus
+    dec = OpenHEVCFilter()
+    assert dec.init()
+    got = []
+    for au in aus:
+        for nal in split_nals(au):
+            pic = dec.process(nal)
+            if pic is not None:
+                got.append(pic[0])
+    dec.close()
+    assert len(got) == n and all(np.array_equal(g, r) for g, r in zip(got, recs))
+    if ffhevc.available():
+        ff, errs = ffhevc.decode_stream(aus)
+        assert errs == 0 and all(np.array_equal(f[0], r) for f, r in zip(ff, recs))
+    assert synth.psnr(frames[-1][:w * h], recs[-1][:w * h]) > 30.0
