@@ -131,14 +131,20 @@ __device__ __forceinline__ void mc_chroma_1x4(const uint32_t *s_win, int wsw, in
 
 // ---- transform / quantisation pipeline over a CTU-shaped tile held in shared memory ---------
 //
-// Geometry: the tile is T x T samples (T = 64 luma, 32 chroma), row pitch T.  unit_log2 is the
-// size of one cu-map unit in this plane (3 luma, 2 chroma).  s_org[z] is the z-index of the
-// origin unit of the CU covering unit z (0xff = outside the picture); s_log2[z] the CU size
-// (luma log2).  The transform block of every CU is the CU itself (luma) / half of it (chroma).
+// Geometry: the tile is T x T samples (T = 64 luma, 32 chroma).  unit_log2 is the size of one
+// cu-map unit in this plane (3 luma, 2 chroma).  s_org[z] is the z-index of the origin unit of the
+// CU covering unit z (0xff = outside the picture); s_log2[z] the CU size (luma log2).  The
+// transform block of every CU is the CU itself (luma) / half of it (chroma).
 //
-// Stage order (each `sync` is a __syncthreads):
-//   resid = src - pred | sync | H pass | sync | V pass + quant (+ dequant into s_a) | sync |
-//   inverse V | sync | inverse H + reconstruction
+// All four 1-D passes are written as  out[a][b] = sum_i M[b][i] * in[a][i]  with the contraction
+// index i contiguous in shared memory, so that two int16 samples and four int8 coefficients go
+// through one DP2A: the int16 tiles have a row pitch of T+2 (33 words: column accesses hit 32
+// different banks), every pass stores its result in the orientation the next pass contracts
+// over, and lanes always run along the matrix index b, which makes the data reads broadcasts and
+// the coefficient-word reads consecutive.
+//
+//   forward:  resid[y][x] --H--> tmpT[k][j] --V--> coef[v][k] -> level (natural) , deqT[k][v]
+//   inverse:  deqT[x][v] --V--> tmp2[y][x] --H--> residual[y][x] -> reconstruction
 struct TileGeom {
   int T;            // tile width (64 / 32)
   int tlog2;        // log2(T)
@@ -151,8 +157,42 @@ struct TqParams {
   int is_idr;       // quantiser offset 171 (I slices) / 85
 };
 
-// dct coefficient of the N-point transform: c[k][n]
-__device__ __forceinline__ int dctc(const int8_t (*s_dct)[32], int nshift, int k, int n) { return s_dct[k << nshift][n]; }
+// Coefficient words.  wc[q][r] = { c32[r][4q .. 4q+3] }: row r of the 32-point matrix; the N-point
+// transform uses rows k << (5 - log2 N) and q < N/4.  wct holds, per transform size, the words of
+// the TRANSPOSED N-point matrix: wct[off(N) + q*N + y] = { C_N[4q .. 4q+3][y] }.
+struct DctWords {
+  uint32_t wc[8][32];
+  uint32_t wct[4 + 16 + 64 + 256];
+};
+__device__ __forceinline__ int wct_offset(int log2n) { return log2n == 2 ? 0 : (log2n == 3 ? 4 : (log2n == 4 ? 20 : 84)); }
+
+__device__ __forceinline__ void build_dct_words(DctWords &w)
+{
+  for (int i = threadIdx.x; i < 8 * 32; i += blockDim.x) {
+    int q = i >> 5, r = i & 31;
+    w.wc[q][r] = pack4(&c_dct32[r][4 * q]);
+  }
+  for (int i = threadIdx.x; i < 340; i += blockDim.x) {
+    int log2n = i < 4 ? 2 : (i < 20 ? 3 : (i < 84 ? 4 : 5));
+    int j = i - wct_offset(log2n), n = 1 << log2n, nshift = 5 - log2n;
+    int q = j / n, y = j - q * n;
+    int8_t c[4];
+    for (int t = 0; t < 4; t++) c[t] = c_dct32[(4 * q + t) << nshift][y];
+    w.wct[i] = pack4(c);
+  }
+}
+
+// sum over n int16 samples (pairs in `data`, 4-byte aligned) times the coefficient words cw[q * stride]
+__device__ __forceinline__ int dot_dp2a(const uint32_t *data, const uint32_t *cw, int stride, int n)
+{
+  int acc = 0;
+  for (int q = 0; q < (n >> 2); q++) {
+    const int c = (int)cw[q * stride];
+    acc = __dp2a_lo((int)data[2 * q], c, acc);
+    acc = __dp2a_hi((int)data[2 * q + 1], c, acc);
+  }
+  return acc;
+}
 
 // One sample position (x,y) of the tile -> its transform block; returns false outside the picture.
 struct TbPos { int ox, oy, n, log2n, org; };
@@ -169,93 +209,102 @@ __device__ __forceinline__ bool tb_at(const TileGeom &g, const uint8_t *s_org, c
   return true;
 }
 
-// Forward path.  s_src/s_pred: uint8 tiles.  s_a, s_b: int16 scratch tiles.  On return s_lvl
-// (aliasing s_b) holds the levels, s_a the dequantised coefficients, s_nz[org] != 0 where the
-// block has a non-zero level.  Caller must have zeroed s_nz and synchronised.
-__device__ __forceinline__ void forward_tq(const TileGeom g, const TqParams q, const uint8_t *s_src, const uint8_t *s_pred,
-                                           const uint8_t *s_org, const uint8_t *s_log2, const int8_t (*s_dct)[32],
-                                           const int8_t (*s_dctT)[32], int16_t *s_a, int16_t *s_b, int *s_nz)
+__device__ __forceinline__ int16_t dequant_level(int lvl, int log2n, int qper, int dscale)
 {
-  const int T = g.T, total = T * T;
-  for (int p = threadIdx.x; p < total; p += blockDim.x) s_a[p] = (int16_t)((int)s_src[p] - (int)s_pred[p]);
+  const int bd = log2n + 3;
+  long long d = (((long long)lvl * dscale) << qper);
+  d = (d + (1LL << (bd - 1))) >> bd;
+  return (int16_t)max(-32768LL, min(32767LL, d));
+}
+
+// Forward path.  s_src / s_pred: uint8 tiles (pitch T).  s_a, s_b: int16 tiles of pitch T+2.
+// On return s_b holds the levels (natural orientation), s_a the dequantised coefficients
+// TRANSPOSED inside each block, s_nz[org] != 0 where the block has a non-zero level.  The caller
+// must have zeroed s_nz and synchronised.
+__device__ __forceinline__ void forward_tq(const TileGeom g, const TqParams q, const uint8_t *s_src, const uint8_t *s_pred,
+                                           const uint8_t *s_org, const uint8_t *s_log2, const DctWords &w,
+                                           int16_t *s_a, int16_t *s_b, int *s_nz)
+{
+  const int T = g.T, P = T + 2, total = T * T;
+  for (int p = threadIdx.x; p < total; p += blockDim.x) {
+    int y = p >> g.tlog2, x = p & (T - 1);
+    s_a[y * P + x] = (int16_t)((int)s_src[p] - (int)s_pred[p]);
+  }
   __syncthreads();
-  // horizontal pass: tmp[j][k] = (sum_i c[k][i] * resid[j][i] + rnd) >> (log2n - 1)
+  // horizontal pass, lanes along k: tmpT[k][j] = (sum_i C[k][i] * resid[j][i] + rnd) >> (log2n - 1)
   for (int p = threadIdx.x; p < total; p += blockDim.x) {
     int y = p >> g.tlog2, x = p & (T - 1);
     TbPos tb;
     if (!tb_at(g, s_org, s_log2, x, y, tb)) continue;
-    int k = x - tb.ox, nshift = 5 - tb.log2n;
-    const int16_t *row = s_a + y * T + tb.ox;
-    const int kk = k << nshift;            // transposed table: lanes read consecutive bytes
-    int acc = 0;
-    for (int i = 0; i < tb.n; i++) acc += s_dctT[i][kk] * row[i];
-    int s1 = tb.log2n - 1;
-    s_b[p] = (int16_t)((acc + (1 << (s1 - 1))) >> s1);
+    const int k = x - tb.ox, j = y - tb.oy, nshift = 5 - tb.log2n;
+    const uint32_t *row = (const uint32_t *)(s_a + y * P + tb.ox);
+    int acc = dot_dp2a(row, &w.wc[0][k << nshift], 32, tb.n);
+    const int s1 = tb.log2n - 1;
+    s_b[(tb.oy + k) * P + tb.ox + j] = (int16_t)((acc + (1 << (s1 - 1))) >> s1);
   }
   __syncthreads();
-  // vertical pass + quantisation + dequantisation
+  // vertical pass, lanes along v: coef[v][k] = (sum_j C[v][j] * tmpT[k][j] + rnd) >> (log2n + 6), then Q and IQ
   const int qper = q.qp / 6, qrem = q.qp % 6;
   const int scale = c_quant_scale[qrem], dscale = 16 * c_level_scale[qrem];
   int16_t vals[16];
   int cnt = 0;
   for (int p = threadIdx.x; p < total; p += blockDim.x, cnt++) {
-    int y = p >> g.tlog2, x = p & (T - 1);
+    int x = p >> g.tlog2, y = p & (T - 1);           // transposed enumeration: consecutive lanes run down a column
     TbPos tb;
     vals[cnt] = 0;
     if (!tb_at(g, s_org, s_log2, x, y, tb)) continue;
-    int v = y - tb.oy, nshift = 5 - tb.log2n;
-    const int16_t *col = s_b + tb.oy * T + x;
-    const int8_t *c = s_dct[v << nshift];
-    int acc = 0;
-    for (int j = 0; j < tb.n; j++) acc += c[j] * col[j * T];
-    int s2 = tb.log2n + 6;
-    int coef = (acc + (1 << (s2 - 1))) >> s2;
-    int qbits = 14 + qper + (7 - tb.log2n);
-    unsigned add = (unsigned)(q.is_idr ? 171 : 85) << (qbits - 9);
-    unsigned a = ((unsigned)abs(coef) * (unsigned)scale + add) >> qbits;    // < 2^32: |coef| <= 2^15, scale < 2^15
+    const int v = y - tb.oy, k = x - tb.ox, nshift = 5 - tb.log2n;
+    const uint32_t *row = (const uint32_t *)(s_b + (tb.oy + k) * P + tb.ox);
+    int acc = dot_dp2a(row, &w.wc[0][v << nshift], 32, tb.n);
+    const int s2 = tb.log2n + 6;
+    const int coef = (acc + (1 << (s2 - 1))) >> s2;
+    const int qbits = 14 + qper + (7 - tb.log2n);
+    const unsigned add = (unsigned)(q.is_idr ? 171 : 85) << (qbits - 9);
+    const unsigned a = ((unsigned)abs(coef) * (unsigned)scale + add) >> qbits;    // < 2^32: |coef| <= 2^15, scale < 2^15
     int lvl = (int)min(a, 32767u);
     if (coef < 0) lvl = -lvl;
     vals[cnt] = (int16_t)lvl;
     if (lvl) s_nz[tb.org] = 1;
-    int bd = tb.log2n + 3;
-    long long d = (((long long)lvl * dscale) << qper);
-    d = (d + (1LL << (bd - 1))) >> bd;
-    s_a[p] = (int16_t)max(-32768LL, min(32767LL, d));
+    s_a[(tb.oy + k) * P + tb.ox + v] = dequant_level(lvl, tb.log2n, qper, dscale);   // deqT[k][v]
   }
-  __syncthreads();     // all reads of s_b (tmp) are done; levels may now overwrite it
+  __syncthreads();     // all reads of s_b (tmpT) are done; the levels may now overwrite it
   cnt = 0;
-  for (int p = threadIdx.x; p < total; p += blockDim.x, cnt++) s_b[p] = vals[cnt];
+  for (int p = threadIdx.x; p < total; p += blockDim.x, cnt++) {
+    int x = p >> g.tlog2, y = p & (T - 1);
+    s_b[y * P + x] = vals[cnt];
+  }
   __syncthreads();
 }
 
-// Inverse path: s_a holds dequantised coefficients; result: reconstructed samples written
-// to s_rec (uint8 tile).  s_t is an int16 scratch tile.  Blocks with s_nz[org]==0 copy the prediction.
+// Inverse path: s_a holds dequantised coefficients transposed inside each block (deqT[x][v]);
+// the reconstruction goes to s_rec (uint8 tile, pitch T).  s_t is an int16 scratch tile (pitch T+2).
+// Blocks with s_nz[org]==0 copy the prediction.
 __device__ __forceinline__ void inverse_recon(const TileGeom g, const uint8_t *s_pred, const uint8_t *s_org,
-                                              const uint8_t *s_log2, const int8_t (*s_dct)[32], const int16_t *s_a,
+                                              const uint8_t *s_log2, const DctWords &w, const int16_t *s_a,
                                               int16_t *s_t, const int *s_nz, uint8_t *s_rec)
 {
-  const int T = g.T, total = T * T;
+  const int T = g.T, P = T + 2, total = T * T;
+  // vertical pass, lanes along y: tmp2[y][x] = clip16((sum_v C[v][y] * deqT[x][v] + 64) >> 7)
   for (int p = threadIdx.x; p < total; p += blockDim.x) {
-    int y = p >> g.tlog2, x = p & (T - 1);
+    int x = p >> g.tlog2, y = p & (T - 1);
     TbPos tb;
     if (!tb_at(g, s_org, s_log2, x, y, tb) || !s_nz[tb.org]) continue;
-    int yy = y - tb.oy, nshift = 5 - tb.log2n;
-    const int16_t *col = s_a + tb.oy * T + x;
-    int acc = 0;
-    for (int k = 0; k < tb.n; k++) acc += s_dct[k << nshift][yy] * col[k * T];
-    s_t[p] = (int16_t)clip3(-32768, 32767, (acc + 64) >> 7);
+    const int yy = y - tb.oy, xx = x - tb.ox;
+    const uint32_t *row = (const uint32_t *)(s_a + (tb.oy + xx) * P + tb.ox);
+    int acc = dot_dp2a(row, &w.wct[wct_offset(tb.log2n) + yy], tb.n, tb.n);
+    s_t[y * P + x] = (int16_t)clip3(-32768, 32767, (acc + 64) >> 7);
   }
   __syncthreads();
+  // horizontal pass, lanes along x: res[y][x] = (sum_k C[k][x] * tmp2[y][k] + 2048) >> 12
   for (int p = threadIdx.x; p < total; p += blockDim.x) {
     int y = p >> g.tlog2, x = p & (T - 1);
     TbPos tb;
     if (!tb_at(g, s_org, s_log2, x, y, tb)) continue;
     int pr = s_pred[p];
     if (s_nz[tb.org]) {
-      int xx = x - tb.ox, nshift = 5 - tb.log2n;
-      const int16_t *row = s_t + y * T + tb.ox;
-      int acc = 0;
-      for (int k = 0; k < tb.n; k++) acc += s_dct[k << nshift][xx] * row[k];
+      const int xx = x - tb.ox;
+      const uint32_t *row = (const uint32_t *)(s_t + y * P + tb.ox);
+      int acc = dot_dp2a(row, &w.wct[wct_offset(tb.log2n) + xx], tb.n, tb.n);
       pr = clip8(pr + clip3(-32768, 32767, (acc + 2048) >> 12));
     }
     s_rec[p] = (uint8_t)pr;

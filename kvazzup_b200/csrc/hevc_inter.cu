@@ -227,7 +227,7 @@ struct ReconShared {
   short mvx[64], mvy[64];
   int nz[64];
   uint8_t cbf[64];
-  int8_t dct[32][32], dctT[32][32];
+  DctWords w;
 };
 
 __device__ __forceinline__ int chroma_margin(int range) { return (((range + 1) >> 1) + 2 + 3) & ~3; }
@@ -247,17 +247,14 @@ k_inter_recon(FrameParams fp, const uint8_t *__restrict__ src, const uint8_t *__
   uint8_t *s_src = (uint8_t *)(s_dyn + WS * WSW);            // 64 x 64
   uint8_t *s_pred = s_src + 4096;                            // 64 x 64
   uint8_t *s_rec = s_pred + 4096;                            // 64 x 64
-  int16_t *s_a = (int16_t *)(s_rec + 4096);                  // 64 x 64
-  int16_t *s_b = s_a + 4096;                                 // 64 x 64
+  int16_t *s_a = (int16_t *)(s_rec + 4096);                  // 64 rows, pitch 66
+  int16_t *s_b = s_a + 64 * 66;                              // 64 rows, pitch 66
   const int ctb_x = blockIdx.x % fp.ctb_cols, ctb_y = blockIdx.x / fp.ctb_cols;
   const int cx = ctb_x * kCtb, cy = ctb_y * kCtb;
   const int t = threadIdx.x;
   const size_t ysz = (size_t)fp.w * fp.h;
 
-  for (int i = t; i < 1024; i += kThreads) {
-    ((int8_t *)sh.dct)[i] = c_dct32[i >> 5][i & 31];
-    ((int8_t *)sh.dctT)[i] = c_dct32[i & 31][i >> 5];
-  }
+  build_dct_words(sh.w);
   if (t < 64) {
     int ux = z_to_x(t), uy = z_to_y(t);
     int x8 = (cx >> 3) + ux, y8 = (cy >> 3) + uy;
@@ -324,32 +321,31 @@ k_inter_recon(FrameParams fp, const uint8_t *__restrict__ src, const uint8_t *__
     TileGeom g{T, c ? 5 : 6, c ? 2 : 3, cs};
     TqParams q{c ? fp.qp_c : fp.qp, fp.is_idr};
     if (!kDecode) {
-      forward_tq(g, q, s_src, s_pred, sh.org, sh.log2, sh.dct, sh.dctT, s_a, s_b, sh.nz);
+      forward_tq(g, q, s_src, s_pred, sh.org, sh.log2, sh.w, s_a, s_b, sh.nz);
       // levels (s_b) -> HBM, 4 per thread; s_b then becomes the scratch tile of the inverse path
       for (int i = t; i < T * T / 4; i += kThreads) {
         int y = i / (T / 4), xw = i - y * (T / 4);
         int gy = py0 + y, gx = px0 + 4 * xw;
-        if (gy < ph && gx < pw) *(uint2 *)(plev + (size_t)gy * pw + gx) = ((const uint2 *)s_b)[i];
+        if (gy < ph && gx < pw) {
+          const uint32_t *lp = (const uint32_t *)(s_b + y * (T + 2) + 4 * xw);      // pitch T+2: 4-byte aligned only
+          *(uint2 *)(plev + (size_t)gy * pw + gx) = make_uint2(lp[0], lp[1]);
+        }
       }
     } else {
-      // dequantise the parsed levels (H.265 8.6.3) straight into the coefficient tile
+      // dequantise the parsed levels (H.265 8.6.3) straight into the coefficient tile, transposed
+      // inside each block (what the inverse vertical pass contracts over)
       const int qper = q.qp / 6, dscale = 16 * c_level_scale[q.qp % 6];
       for (int p = t; p < T * T; p += kThreads) {
         int y = p >> g.tlog2, x = p & (T - 1);
         TbPos tb;
-        int16_t v = 0;
         if (tb_at(g, sh.org, sh.log2, x, y, tb) && sh.nz[tb.org]) {
           int lvl = plev[(size_t)(py0 + y) * pw + px0 + x];
-          int bd = tb.log2n + 3;
-          long long d = (((long long)lvl * dscale) << qper);
-          d = (d + (1LL << (bd - 1))) >> bd;
-          v = (int16_t)max(-32768LL, min(32767LL, d));
+          s_a[(tb.oy + (x - tb.ox)) * (T + 2) + tb.ox + (y - tb.oy)] = dequant_level(lvl, tb.log2n, qper, dscale);
         }
-        s_a[p] = v;
       }
     }
     __syncthreads();
-    inverse_recon(g, s_pred, sh.org, sh.log2, sh.dct, s_a, s_b, sh.nz, s_rec);
+    inverse_recon(g, s_pred, sh.org, sh.log2, sh.w, s_a, s_b, sh.nz, s_rec);
     if (!kDecode) {
       for (int i = t; i < T * T / 4; i += kThreads) {
         int y = i / (T / 4), xw = i - y * (T / 4);
@@ -457,7 +453,7 @@ static size_t me_smem(int range)
 static size_t recon_smem(int range)
 {
   int M = (range + 4 + 3) & ~3, WS = kCtb + 2 * M, WSW = (WS >> 2) + 1;
-  return (size_t)WS * WSW * 4 + 3 * 4096 + 2 * 4096 * 2;
+  return (size_t)WS * WSW * 4 + 3 * 4096 + 2 * 64 * 66 * 2;
 }
 
 // The opt-in limit of dynamic shared memory is a per-function, process-wide attribute: set it once
