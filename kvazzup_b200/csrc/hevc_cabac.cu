@@ -545,65 +545,72 @@ struct BinWarpShared {
   uint32_t syn[128];
 };
 
+// One warp per 32x32 quadrant of a CTU; the warp walks the (1..16) CUs that start inside it.
+// (One warp per 8x8 unit would launch 16k CTAs of which three quarters exit at once.)
 __global__ void __launch_bounds__(32 * kBinWarps)
 k_binarise(FrameParams fp, const CuInfo *__restrict__ cu, const int16_t *__restrict__ levels, uint32_t *__restrict__ recs)
 {
   __shared__ BinWarpShared s_all[kBinWarps];
   const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
-  const int unit = blockIdx.x * kBinWarps + wib;           // CTU-major, z-order inside the CTU
-  const int ctu = unit >> 6, z = unit & 63;
+  const int quad = blockIdx.x * kBinWarps + wib;            // CTU-major, four quadrants per CTU
+  const int ctu = quad >> 2;
   if (ctu >= fp.ctb_cols * fp.ctb_rows) return;
   const int cx = (ctu % fp.ctb_cols) * kCtb, cy = (ctu / fp.ctb_cols) * kCtb;
-  const int x0 = cx + 8 * z_to_x(z), y0 = cy + 8 * z_to_y(z);
-  if (x0 >= fp.w || y0 >= fp.h) return;
   CuView v{&fp, cu};
-  const CuInfo cur = cu_at(v, x0, y0);
-  const int log2 = cur.log2_size;
-  if (z & ((1 << (2 * (log2 - 3))) - 1)) return;            // not the first unit of its CU
   BinWarpShared &sh = s_all[wib];
-  Syn syn{sh.syn, 0};
-  uint32_t *out = cu_region(recs, ctu, z);
-  int o = 1;                                                // word 0 is the header
-  // split flags of every ancestor block that starts at this unit, top down, then this CU's own
-  for (int L = 6; L > 3; L--) {
-    if (L < log2) break;
-    if (z & ((1 << (2 * (L - 3))) - 1)) continue;
-    put_split(syn, v, x0, y0, L, 6 - L, L > log2);
-  }
-  const int cbf = put_cu_header(syn, v, cur, x0, y0, log2);
-  __syncwarp();
-  for (int i = lane; i < syn.k; i += 32) out[o + i] = syn.r[i];
-  o += syn.k;
   const size_t ysz = (size_t)fp.w * fp.h;
-  for (int k = 0; k < 3; k++) {
-    if (!((cbf >> k) & 1)) continue;
-    const int sft = k ? 1 : 0, l2 = log2 - sft, n = 1 << l2, pw = fp.w >> sft;
-    const int16_t *plane = levels + (k == 0 ? 0 : ysz + (k == 2 ? ysz / 4 : 0)) + (size_t)(y0 >> sft) * pw + (x0 >> sft);
+  for (int z = (quad & 3) * 16; z < (quad & 3) * 16 + 16;) {
+    const int x0 = cx + 8 * z_to_x(z), y0 = cy + 8 * z_to_y(z);
+    if (x0 >= fp.w || y0 >= fp.h) { z++; continue; }
+    const CuInfo cur = cu_at(v, x0, y0);
+    const int log2 = cur.log2_size;
+    const int units = 1 << (2 * (log2 - 3));
+    if (z & (units - 1)) { z++; continue; }                  // inside a CU that started in another quadrant (64x64)
     __syncwarp();
-    for (int i = lane; i < n * n; i += 32) sh.lv[i] = plane[(size_t)(i >> l2) * pw + (i & (n - 1))];
-    __syncwarp();
-    syn.k = 0;
-    const int last_sb = binarise_residual(syn, sh.rs, sh.lv, l2, k, scan_idx_for(cur.pred_mode, cur.intra_mode, l2, k), lane);
-    if (last_sb < 0) continue;
-    for (int i = lane; i < syn.k; i += 32) out[o + i] = syn.r[i];      // last significant position
-    o += syn.k;
-    // sub-block record lists, concatenated in coding order (last_sb down to 0): exclusive scan of the counts
-    for (int base = last_sb; base >= 0; base -= 32) {
-      const int i = base - lane;                                       // lane 0 owns the first sub-block in coding order
-      const int cnt = i >= 0 ? sh.rs.cnt[i] : 0;
-      int pre = cnt;
-#pragma unroll
-      for (int d = 1; d < 32; d <<= 1) {
-        int t = __shfl_up_sync(0xffffffffu, pre, d);
-        if (lane >= d) pre += t;
-      }
-      const int total = __shfl_sync(0xffffffffu, pre, 31);
-      const int start = o + pre - cnt;
-      for (int j = 0; j < cnt; j++) out[start + j] = sh.rs.rec[i][j];
-      o += total;
+    Syn syn{sh.syn, 0};
+    uint32_t *out = cu_region(recs, ctu, z);
+    int o = 1;                                                // word 0 is the header
+    // split flags of every ancestor block that starts at this unit, top down, then this CU's own
+    for (int L = 6; L > 3; L--) {
+      if (L < log2) break;
+      if (z & ((1 << (2 * (L - 3))) - 1)) continue;
+      put_split(syn, v, x0, y0, L, 6 - L, L > log2);
     }
+    const int cbf = put_cu_header(syn, v, cur, x0, y0, log2);
+    __syncwarp();
+    for (int i = lane; i < syn.k; i += 32) out[o + i] = syn.r[i];
+    o += syn.k;
+    for (int k = 0; k < 3; k++) {
+      if (!((cbf >> k) & 1)) continue;
+      const int sft = k ? 1 : 0, l2 = log2 - sft, n = 1 << l2, pw = fp.w >> sft;
+      const int16_t *plane = levels + (k == 0 ? 0 : ysz + (k == 2 ? ysz / 4 : 0)) + (size_t)(y0 >> sft) * pw + (x0 >> sft);
+      __syncwarp();
+      for (int i = lane; i < n * n; i += 32) sh.lv[i] = plane[(size_t)(i >> l2) * pw + (i & (n - 1))];
+      __syncwarp();
+      syn.k = 0;
+      const int last_sb = binarise_residual(syn, sh.rs, sh.lv, l2, k, scan_idx_for(cur.pred_mode, cur.intra_mode, l2, k), lane);
+      if (last_sb < 0) continue;
+      for (int i = lane; i < syn.k; i += 32) out[o + i] = syn.r[i];      // last significant position
+      o += syn.k;
+      // sub-block record lists, concatenated in coding order (last_sb down to 0): exclusive scan of the counts
+      for (int base = last_sb; base >= 0; base -= 32) {
+        const int i = base - lane;                                       // lane 0 owns the first sub-block in coding order
+        const int cnt = i >= 0 ? sh.rs.cnt[i] : 0;
+        int pre = cnt;
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) {
+          int t = __shfl_up_sync(0xffffffffu, pre, d);
+          if (lane >= d) pre += t;
+        }
+        const int total = __shfl_sync(0xffffffffu, pre, 31);
+        const int start = o + pre - cnt;
+        for (int j = 0; j < cnt; j++) out[start + j] = sh.rs.rec[i][j];
+        o += total;
+      }
+    }
+    if (lane == 0) out[0] = (uint32_t)(o - 1) | ((uint32_t)log2 << 24);
+    z += units;
   }
-  if (lane == 0) out[0] = (uint32_t)(o - 1) | ((uint32_t)log2 << 24);
 }
 
 __global__ void __launch_bounds__(32)
@@ -744,8 +751,8 @@ cudaError_t launch_pack_rows(int rows, const uint8_t *src, uint32_t row_cap, con
 
 cudaError_t launch_binarise(const FrameParams &fp, const CuInfo *cu, const int16_t *levels, uint32_t *recs, cudaStream_t s)
 {
-  const int units = fp.ctb_cols * fp.ctb_rows * 64;
-  k_binarise<<<(units + kBinWarps - 1) / kBinWarps, 32 * kBinWarps, 0, s>>>(fp, cu, levels, recs);
+  const int quads = fp.ctb_cols * fp.ctb_rows * 4;
+  k_binarise<<<(quads + kBinWarps - 1) / kBinWarps, 32 * kBinWarps, 0, s>>>(fp, cu, levels, recs);
   return cudaGetLastError();
 }
 

@@ -163,6 +163,7 @@ bool Encoder::open(const EncoderConfig &c)
   // runs at the low priority.
   int prio_lo = 0, prio_hi = 0;
   cudaDeviceGetStreamPriorityRange(&prio_lo, &prio_hi);
+  if (const char *ev = getenv("B200_FLAT_PRIO")) { if (atoi(ev)) prio_hi = prio_lo; }
   ENC_CHECK(cudaStreamCreateWithPriority(&stream, cudaStreamNonBlocking, prio_lo), "cudaStreamCreate");
   ENC_CHECK(cudaStreamCreateWithPriority(&intra_stream, cudaStreamNonBlocking, prio_hi), "cudaStreamCreate intra");
   ENC_CHECK(cudaEventCreateWithFlags(&ev_intra, cudaEventDisableTiming), "cudaEventCreate");
@@ -324,7 +325,7 @@ bool Encoder::submit(FrameSlot &s, const uint8_t *d_i420)
     // an IDR is enqueued on the intra stream as well, see input_stream()).
     cudaStream_t is = cfg.overlap_idr ? intra_stream : stream;
     if (cfg.overlap_idr && frame_idx >= kRecRing - 1) ENC_CHECK(cudaStreamWaitEvent(is, ev_ring[(frame_idx + 1) % kRecRing], 0), "stream wait");
-    ENC_CHECK(cudaMemsetAsync(s.d_levels, 0, frame_bytes * sizeof(int16_t), is), "memset levels");
+    // (no memset of the level planes: both reconstruction kernels write every level of the picture)
     PROF_BEGIN(K_INTRA, is);
     ENC_CHECK(launch_intra_frame(p, d_i420, rec, s.d_levels, s.d_cu, progress, ticket, d_order, is), "intra launch");
     PROF_END(K_INTRA, is);
@@ -335,7 +336,6 @@ bool Encoder::submit(FrameSlot &s, const uint8_t *d_i420)
     count_launch(2);
   } else {
     // prediction chain, main stream, picture order
-    ENC_CHECK(cudaMemsetAsync(s.d_levels, 0, frame_bytes * sizeof(int16_t), stream), "memset levels");
     PROF_BEGIN(K_ME, stream);
     ENC_CHECK(launch_inter_me(p, d_i420, ref, s.d_cu, stream), "me launch");
     PROF_END(K_ME, stream);
@@ -349,14 +349,16 @@ bool Encoder::submit(FrameSlot &s, const uint8_t *d_i420)
   }
   ENC_CHECK(cudaEventRecord(ev_ring[frame_idx % kRecRing], stream), "event record");   // done reading the reference
   if (cfg.debug) ENC_CHECK(cudaMemcpyAsync(d_rec_pre, rec, frame_bytes, cudaMemcpyDeviceToDevice, stream), "copy pre-deblock");
-  ENC_CHECK(cudaEventRecord(s.ev_pred, stream), "event record");
   if (cfg.deblock) {
     PROF_BEGIN(K_DEBLOCK, stream);
     ENC_CHECK(launch_deblock(p, rec, s.d_cu, stream), "deblock launch");
     PROF_END(K_DEBLOCK, stream);
     count_launch(2);
   }
-  // entropy coding, slot stream: needs the cu map and the levels, not the deblocked picture
+  // Entropy coding (slot stream) needs only the cu map and the levels, but it is released after
+  // the deblocking: started before it, the binariser's 16k CTAs share the SMs with the two short
+  // deblocking kernels and stretch them from 15 us to 75 us on the critical prediction chain.
+  ENC_CHECK(cudaEventRecord(s.ev_pred, stream), "event record");
   ENC_CHECK(cudaStreamWaitEvent(s.stream, s.ev_pred, 0), "stream wait");
   PROF_BEGIN(K_BINARISE, s.stream);
   ENC_CHECK(launch_binarise(p, s.d_cu, s.d_levels, s.d_recs, s.stream), "binarise launch");
