@@ -93,14 +93,25 @@ __device__ __forceinline__ void mc_luma_2x8(const uint32_t *s_win, int wsw, int 
     h0[r] = dp4a_us(p0, tl, dp4a_us(p1, th, 0));
     h1[r] = dp4a_us(q0, tl, dp4a_us(q1, th, 0));
   }
-  int f[8];
+  // vertical pass by DP2A: the row sums fit int16 (|sum| <= 88 * 255), so two of them and two
+  // taps go through one instruction.  Pairs (r, r+1) are packed once for even and once for odd r.
+  const unsigned t01 = pack4(c_luma_filter[fy]), t23 = t01 >> 16, t45 = pack4(c_luma_filter[fy] + 4), t67 = t45 >> 16;
+  unsigned p0[14], p1[14];                 // p[r] = (h[r] & 0xffff) | (h[r+1] << 16)
 #pragma unroll
-  for (int t = 0; t < 8; t++) f[t] = c_luma_filter[fy][t];
+  for (int r = 0; r < 14; r++) {
+    p0[r] = __byte_perm((unsigned)h0[r], (unsigned)h0[r + 1], 0x5410);
+    p1[r] = __byte_perm((unsigned)h1[r], (unsigned)h1[r + 1], 0x5410);
+  }
 #pragma unroll
   for (int r = 0; r < 8; r++) {
-    int v0 = 0, v1 = 0;
-#pragma unroll
-    for (int t = 0; t < 8; t++) { v0 += f[t] * h0[r + t]; v1 += f[t] * h1[r + t]; }
+    int v0 = __dp2a_lo((int)p0[r], (int)t01, 0);
+    v0 = __dp2a_lo((int)p0[r + 2], (int)t23, v0);
+    v0 = __dp2a_lo((int)p0[r + 4], (int)t45, v0);
+    v0 = __dp2a_lo((int)p0[r + 6], (int)t67, v0);
+    int v1 = __dp2a_lo((int)p1[r], (int)t01, 0);
+    v1 = __dp2a_lo((int)p1[r + 2], (int)t23, v1);
+    v1 = __dp2a_lo((int)p1[r + 4], (int)t45, v1);
+    v1 = __dp2a_lo((int)p1[r + 6], (int)t67, v1);
     v0 = clip8(((v0 >> 6) + 32) >> 6);
     v1 = clip8(((v1 >> 6) + 32) >> 6);
     out[r] = (unsigned)v0 | ((unsigned)v1 << 8);

@@ -32,6 +32,7 @@ struct MeShared {
   short cmx[64], cmy[64];          // per origin unit: centre of the current refinement step
   unsigned best[64];               // per origin unit: best cost so far
   unsigned acc8[64][8];            // per origin unit: SAD accumulators of the eight candidates of a step
+  unsigned short pen[65 * 65];     // mv penalty of every full-sample candidate (index = (dy+R)*side + dx+R)
 };
 
 __global__ void __launch_bounds__(kThreads)
@@ -54,6 +55,10 @@ k_me_ctu(FrameParams fp, const uint8_t *__restrict__ src, const uint8_t *__restr
     s_src[i] = (y < fp.h && x < fp.w) ? __ldg((const uint32_t *)(src + (size_t)y * fp.w + x)) : 0u;
   }
   if (t < 64) { sh.key8[t] = 0xffffffffu; for (int k = 0; k < 8; k++) sh.acc8[t][k] = 0; }
+  for (int c = t; c < (2 * R + 1) * (2 * R + 1); c += kThreads) {
+    int dy = c / (2 * R + 1) - R, dx = c - (dy + R) * (2 * R + 1) - R;
+    sh.pen[c] = (unsigned short)mv_penalty(fp.lambda_q4, dx * 4, dy * 4);
+  }
   if (t < 16) sh.key16[t] = 0xffffffffu;
   if (t < 4) sh.key32[t] = 0xffffffffu;
   __syncthreads();
@@ -107,7 +112,7 @@ k_me_ctu(FrameParams fp, const uint8_t *__restrict__ src, const uint8_t *__restr
         s32 += __shfl_xor_sync(0xffffffffu, s32, 8);
         if (!in_range) continue;
         const unsigned c = (unsigned)((dy + R) * side + dx + R);
-        const unsigned pen = mv_penalty(fp.lambda_q4, dx * 4, dy * 4);
+        const unsigned pen = sh.pen[c];
         if (v8) k8 = min(k8, ((sad + pen) << 13) | c);
         if (v16) k16 = min(k16, ((s16 + pen) << 13) | c);
         if (v32) k32 = min(k32, ((s32 + pen) << 13) | c);
