@@ -261,8 +261,12 @@ def run_b200(args):
         kernels[k] = {"launches": cnt, "avg_us": round(avg * 1e3, 2), "share": round(ms / total_ms, 4),
                       "achieved_gbs": round(ach, 2), "frac": round(ach / hbm_peak, 5)}
     top = max(kernels, key=lambda k: kernels[k]["share"])
+    traffic = ncu_traffic()
+    for k in kernels:
+        kernels[k]["ncu_dram_bytes"] = traffic.get(k)
     roofline = {"kernel": top, "bound": "hbm", "achieved": kernels[top]["achieved_gbs"], "peak": hbm_peak,
-                "peak_source": peak_src, "unit": "GB/s", "frac": kernels[top]["frac"], "traffic": None,
+                "peak_source": peak_src, "unit": "GB/s", "frac": kernels[top]["frac"], "traffic": traffic.get(top),
+                "traffic_source": "profiles/r01_ncu_launch_summary.csv (dram__bytes_read+write per launch, same command under ncu)",
                 "algorithmic_bytes_per_launch": int(alg[top]), "avg_launch_us": kernels[top]["avg_us"],
                 "note": "integer / latency bound kernels: see profiles/ for the ncu pipe utilisation; fraction of HBM "
                         "roofline is reported because the contract asks for it",
@@ -292,6 +296,24 @@ def run_b200(args):
     print(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()
+
+
+def ncu_traffic():
+    """DRAM bytes per launch of each kernel from the committed ncu launch summary (None if absent)."""
+    names = {"k_intra_frame<0>": "intra", "k_intra_modes": "intra_modes", "k_me_ctu": "me", "k_inter_recon<0>": "recon",
+             "k_inter_modes": "modes", "k_deblock": "deblock", "k_binarise": "binarise", "k_arith_rows": "arith",
+             "k_pack_rows": "pack"}
+    out = {}
+    try:
+        with open(os.path.join(ROOT, "profiles", "r01_ncu_launch_summary.csv")) as f:
+            next(f)
+            for ln in f:
+                c = ln.strip().split(",")
+                if c[0] in names:
+                    out[names[c[0]]] = int((float(c[5]) + float(c[6])) * 1e6)
+    except (OSError, ValueError, IndexError):
+        pass
+    return out
 
 
 def qp_sweep(d_frames):

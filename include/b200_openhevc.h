@@ -59,13 +59,17 @@ typedef struct OpenHevc_Frame {
   OpenHevc_FrameInfo frameInfo;
 } OpenHevc_Frame;
 
-/* thread_type: 1 frame, 2 slice, 4 frame+slice (openhevcfilter.cpp:11); accepted and ignored --
- * parallelism comes from the WPP substreams on the GPU. */
+/* thread_type: 1 frame, 2 slice, 3 frame+slice (openhevcfilter.cpp:11).  Slice threading needs no
+ * host threads here (WPP substreams are parsed in parallel on the GPU) and outputs every picture
+ * in the call that completes it.  Frame threading keeps nb_pthreads pictures in flight (their
+ * CABAC parses run concurrently on the GPU) and, like OpenHEVC's frame threads, delays output by
+ * nb_pthreads - 1 pictures. */
 OpenHevc_Handle libOpenHevcInit(int nb_pthreads, int thread_type);
 int  libOpenHevcStartDecoder(OpenHevc_Handle h);            /* -1 on failure (no CUDA device) */
 /* buff: one or more NAL units, each with a 3- or 4-byte start code (the reference passes one NAL
  * per call, openhevcfilter.cpp:145).  Returns 1 when a picture became available, 0 when not, -1 on
- * error. */
+ * error.  buff == NULL / nal_len == 0 hands over the next held-back picture (frame threading),
+ * 0 when none is left. */
 int  libOpenHevcDecode(OpenHevc_Handle h, const unsigned char *buff, int nal_len, int64_t pts);
 int  libOpenHevcGetOutput(OpenHevc_Handle h, int got_picture, OpenHevc_Frame *frame);   /* >0: frame filled */
 void libOpenHevcGetPictureInfo(OpenHevc_Handle h, OpenHevc_FrameInfo *info);

@@ -71,6 +71,12 @@ int b200_half_rgb(const uint8_t *input, uint8_t *output, uint16_t width, uint16_
 int b200_flip_rgb(const uint8_t *input, uint8_t *output, uint16_t width, uint16_t height,
                   int horizontally, int vertically);
 
+/* Self-view chain fused (Camera -> I420 -> RGB32 -> HalfRGB -> mirrored Display,
+ * filtergraph.cpp:247-325): equals b200_flip_rgb(b200_half_rgb(b200_yuv420_to_rgb32(in))) with the
+ * stages selected by the flags, written in one pass.  Output: (half ? w/2 x h/2 : w x h) RGB32. */
+int b200_selfview(const uint8_t *input, uint8_t *output, uint16_t width, uint16_t height,
+                  int half, int horizontally, int vertically);
+
 /* ---- camera conversion: any supported format -> I420 -------------------
  * C twin of libyuv::ConvertToI420 (sole call site
  * src/media/processing/libyuvconverter.cpp:120-127).  Same argument list;
@@ -97,6 +103,8 @@ int b200_i420_to_rgb32_dev(const uint8_t *d_i420, uint8_t *d_bgra, int width, in
 int b200_half_rgb_dev(const uint8_t *d_in, uint8_t *d_out, int width, int height,
                       int n_frames, void *stream);
 int b200_flip_rgb_dev(const uint8_t *d_in, uint8_t *d_out, int width, int height,
+                      int horizontally, int vertically, int n_frames, void *stream);
+int b200_selfview_dev(const uint8_t *d_i420, uint8_t *d_out, int width, int height, int half,
                       int horizontally, int vertically, int n_frames, void *stream);
 int b200_convert_to_i420_dev(const uint8_t *d_src, uint8_t *d_i420, int width, int height,
                              uint32_t fourcc, int n_frames, void *stream);

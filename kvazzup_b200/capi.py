@@ -38,6 +38,8 @@ SIGNATURES = {
     "b200_yuv420_to_rgb32": (C.c_int, [C.c_void_p, C.c_void_p, C.c_uint16, C.c_uint16]),
     "b200_half_rgb": (C.c_int, [C.c_void_p, C.c_void_p, C.c_uint16, C.c_uint16]),
     "b200_flip_rgb": (C.c_int, [C.c_void_p, C.c_void_p, C.c_uint16, C.c_uint16, C.c_int, C.c_int]),
+    "b200_selfview": (C.c_int, [C.c_void_p, C.c_void_p, C.c_uint16, C.c_uint16, C.c_int, C.c_int, C.c_int]),
+    "b200_selfview_dev": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p]),
     "b200_ConvertToI420": (C.c_int, [C.c_void_p, C.c_size_t, C.c_void_p, C.c_int, C.c_void_p, C.c_int,
                                      C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int,
                                      C.c_int, C.c_int, C.c_uint32]),

@@ -39,6 +39,14 @@ def flip_rgb(rgb: np.ndarray, w: int, h: int, horizontally: bool, vertically: bo
     return out
 
 
+def selfview(i420: np.ndarray, w: int, h: int, half: bool, horizontally: bool, vertically: bool) -> np.ndarray:
+    """Fused self-view chain: YUVtoRGB32 -> HalfRGBFilter -> mirror (filtergraph.cpp:247-325)."""
+    ow, oh = (w // 2, (h + 1) // 2) if half else (w, h)
+    out = np.empty(ow * oh * 4, np.uint8)
+    check(lib().b200_selfview(_p(i420), _p(out), w, h, int(half), int(horizontally), int(vertically)), "b200_selfview")
+    return out
+
+
 def convert_to_i420(sample: np.ndarray, w: int, h: int, fourcc: int, fill: int | None = None):
     """Returns (rc, packed I420).  rc follows libyuv: 0 ok, -1 unsupported (output untouched)."""
     out = np.empty(w * h * 3 // 2, np.uint8) if fill is None else np.full(w * h * 3 // 2, fill, np.uint8)

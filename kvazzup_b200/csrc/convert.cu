@@ -417,6 +417,43 @@ k_to_i420_generic(const uint8_t *__restrict__ in, uint8_t *__restrict__ out, int
   }
 }
 
+// ---------------------------------------------------------------------------
+// Self-view path fused: I420 -> RGB32, optional 2x point decimation
+// (HalfRGBFilter, halfrgbfilter.cpp:21-43) and optional mirroring (Filter::normalizeOrientation,
+// filter.cpp:263-294) in one pass -- the RGB32 picture is written once instead of three times.
+// Output pixel (ox,oy) takes source pixel (sx,sy) = (half ? 2 : 1) * (flip ? last - o : o).
+// One thread produces 4 output pixels (one 16-byte store).  Requires ow % 4 == 0.
+__global__ void __launch_bounds__(kThreads)
+k_selfview(const uint8_t *__restrict__ in, uint8_t *__restrict__ out, int w, int h, int half, int hor, int ver, int n_frames)
+{
+  const int ow = half ? w >> 1 : w, oh = half ? (h + 1) >> 1 : h;
+  const int gpr = ow >> 2;
+  const size_t per = (size_t)gpr * oh, total = per * n_frames;
+  const size_t ysz = (size_t)w * h, fin = ysz + (ysz >> 1);
+  const int step = half ? 2 : 1;
+  for (size_t it = (size_t)blockIdx.x * blockDim.x + threadIdx.x; it < total;
+       it += (size_t)gridDim.x * blockDim.x) {
+    int f = (int)(it / per);
+    int r = (int)(it - (size_t)f * per);
+    int oy = r / gpr, g = r - oy * gpr;
+    const uint8_t *fy = in + (size_t)f * fin;
+    const uint8_t *fu = fy + ysz, *fv = fu + (ysz >> 2);
+    const int sy = step * (ver ? oh - 1 - oy : oy);
+    unsigned px[4];
+#pragma unroll
+    for (int i = 0; i < 4; i++) {
+      int ox = 4 * g + i;
+      int sx = step * (hor ? ow - 1 - ox : ox);
+      int Y = __ldg(fy + (size_t)sy * w + sx);
+      size_t co = (size_t)(sy >> 1) * (w >> 1) + (sx >> 1);
+      ChromaOff c = chroma_offsets(__ldg(fu + co), __ldg(fv + co));
+      uint2 two = two_pixels((unsigned)Y, c);
+      px[i] = two.x;
+    }
+    __stcs((uint4 *)(out + ((size_t)f * ow * oh + (size_t)oy * ow + 4 * g) * 4), make_uint4(px[0], px[1], px[2], px[3]));
+  }
+}
+
 struct FmtInfo { int fmt, bpp, ro, go, bo; bool ok; };
 
 FmtInfo fmt_info(uint32_t fourcc)
@@ -506,6 +543,21 @@ int b200_flip_rgb_dev(const uint8_t *d_in, uint8_t *d_out, int w, int h, int hor
   }
   count_launch();
   B200_CHECK(cudaGetLastError(), "flip_rgb launch");
+  return B200_OK;
+}
+
+int b200_selfview_dev(const uint8_t *d_i420, uint8_t *d_out, int w, int h, int half, int hor, int ver, int n, void *stream)
+{
+  const int ow = half ? w >> 1 : w;
+  if (!d_i420 || !d_out || w <= 0 || h <= 0 || (w & 1) || (h & 1) || (ow & 3) || n <= 0 || !aligned16(d_out)) {
+    set_error("b200_selfview_dev: bad arguments (w=%d h=%d; output width must be a multiple of 4)", w, h);
+    return B200_ERR_ARG;
+  }
+  const int oh = half ? (h + 1) >> 1 : h;
+  size_t items = (size_t)(ow >> 2) * oh * n;
+  k_selfview<<<grid_for(items, 8), kThreads, 0, (cudaStream_t)stream>>>(d_i420, d_out, w, h, half, hor, ver, n);
+  count_launch();
+  B200_CHECK(cudaGetLastError(), "selfview launch");
   return B200_OK;
 }
 
@@ -605,6 +657,19 @@ int b200_flip_rgb(const uint8_t *input, uint8_t *output, uint16_t width, uint16_
                   [](const uint8_t *di, uint8_t *dout, void *s, void *c) {
                     WH *p = (WH *)c;
                     return b200_flip_rgb_dev(di, dout, p->w, p->h, p->a, p->b, 1, s);
+                  }, &wh);
+}
+
+int b200_selfview(const uint8_t *input, uint8_t *output, uint16_t width, uint16_t height, int half, int hor, int ver)
+{
+  if (!input || !output || !width || !height) { set_error("b200_selfview: bad arguments"); return B200_ERR_ARG; }
+  WH wh{width, height, half | (hor << 1) | (ver << 2), 0, 0};
+  size_t px = (size_t)width * height;
+  size_t opx = half ? (size_t)(width / 2) * ((height + 1) / 2) : px;
+  return run_host(input, px + px / 2, output, opx * 4,
+                  [](const uint8_t *di, uint8_t *dout, void *s, void *c) {
+                    WH *p = (WH *)c;
+                    return b200_selfview_dev(di, dout, p->w, p->h, p->a & 1, (p->a >> 1) & 1, (p->a >> 2) & 1, 1, s);
                   }, &wh);
 }
 

@@ -6,6 +6,7 @@
 #include <string.h>
 
 #include <algorithm>
+#include <deque>
 #include <vector>
 
 #include "../../include/b200_openhevc.h"
@@ -74,22 +75,37 @@ const uint8_t kChromaQpD[58] = {
 
 }  // namespace
 
+// One picture in flight: everything the CABAC parse of a picture reads and writes.  Parsing needs
+// nothing from other pictures (no TMVP), so the parses of up to `frame_delay + 1` pictures run
+// concurrently on their own streams; only reconstruction is chained from picture to picture.
+struct DecSlot {
+  cudaStream_t stream = nullptr;
+  cudaEvent_t ev_parsed = nullptr;
+  uint8_t *d_data = nullptr, *d_small = nullptr;
+  CuInfo *d_cu = nullptr;
+  int16_t *d_levels = nullptr;
+  uint8_t *h_data = nullptr, *h_out = nullptr;
+  uint32_t *h_bases = nullptr;
+  int *h_status = nullptr;
+  FrameParams fp{};
+  int64_t pts = 0;
+};
+
 struct Decoder {
   Sps sps;
   Pps pps;
   bool vps_seen = false, started = false;
   FrameParams fp{};
   size_t frame_bytes = 0;
-  cudaStream_t stream = nullptr;
-  uint8_t *d_rec[2] = {nullptr, nullptr}, *d_data = nullptr, *d_small = nullptr;
+  cudaStream_t stream = nullptr;          // reconstruction chain
+  uint8_t *d_rec[2] = {nullptr, nullptr};
   int *d_order = nullptr;
-  CuInfo *d_cu = nullptr;
-  int16_t *d_levels = nullptr;
-  uint8_t *h_out = nullptr, *h_data = nullptr;
-  uint32_t *h_bases = nullptr;
-  int *h_status = nullptr;
+  std::vector<DecSlot> slots;
+  std::deque<int> pending;                // slots whose parse was launched, oldest first
   size_t data_cap = 0, small_bytes = 0, off_flag = 0, off_prog = 0, off_ticket = 0, off_status = 0, off_bases = 0, off_ctx = 0;
-  int cur = 0, have_ref = 0, have_out = 0, pictures = 0;
+  int frame_delay = 0;                    // pictures held back (OpenHEVC frame threads - 1)
+  int next_slot = 0, out_slot = -1;
+  int cur = 0, have_ref = 0, pictures = 0;
   int64_t out_pts = 0;
   int fr_num = 0, fr_den = 0;
 
@@ -97,20 +113,26 @@ struct Decoder {
   void release()
   {
     if (stream) cudaStreamSynchronize(stream);
+    for (DecSlot &s : slots) {
+      if (s.stream) cudaStreamSynchronize(s.stream);
+      if (s.d_data) cudaFree(s.d_data);
+      if (s.d_small) cudaFree(s.d_small);
+      if (s.d_cu) cudaFree(s.d_cu);
+      if (s.d_levels) cudaFree(s.d_levels);
+      if (s.h_data) cudaFreeHost(s.h_data);
+      if (s.h_out) cudaFreeHost(s.h_out);
+      if (s.h_bases) cudaFreeHost(s.h_bases);
+      if (s.h_status) cudaFreeHost(s.h_status);
+      if (s.ev_parsed) cudaEventDestroy(s.ev_parsed);
+      if (s.stream) cudaStreamDestroy(s.stream);
+    }
+    slots.clear();
+    pending.clear();
     for (int i = 0; i < 2; i++) if (d_rec[i]) cudaFree(d_rec[i]);
     if (d_order) cudaFree(d_order);
-    d_order = nullptr;
-    if (d_data) cudaFree(d_data);
-    if (d_small) cudaFree(d_small);
-    if (d_cu) cudaFree(d_cu);
-    if (d_levels) cudaFree(d_levels);
-    if (h_out) cudaFreeHost(h_out);
-    if (h_data) cudaFreeHost(h_data);
-    if (h_bases) cudaFreeHost(h_bases);
-    if (h_status) cudaFreeHost(h_status);
     if (stream) cudaStreamDestroy(stream);
-    d_rec[0] = d_rec[1] = d_data = d_small = nullptr; d_cu = nullptr; d_levels = nullptr;
-    h_out = h_data = nullptr; h_bases = nullptr; h_status = nullptr; stream = nullptr;
+    d_rec[0] = d_rec[1] = nullptr; d_order = nullptr; stream = nullptr;
+    next_slot = 0; out_slot = -1;
   }
 
   bool alloc(int w, int h)
@@ -120,7 +142,7 @@ struct Decoder {
     fp.ctb_cols = (w + kCtb - 1) / kCtb; fp.ctb_rows = (h + kCtb - 1) / kCtb;
     fp.deblock = 1; fp.search_range = 8; fp.lambda_q4 = 0;
     frame_bytes = (size_t)w * h * 3 / 2;
-    data_cap = frame_bytes * 3 + 65536;
+    data_cap = frame_bytes * 2 + 65536;
     const int rows = fp.ctb_rows;
     off_flag = 0; off_prog = sizeof(int) * rows; off_ticket = 2 * sizeof(int) * rows;
     off_status = off_ticket + 2 * sizeof(int); off_bases = off_status + 2 * sizeof(int);
@@ -129,21 +151,26 @@ struct Decoder {
     if (!cuda_ok(cudaStreamCreateWithFlags(&stream, cudaStreamNonBlocking), "cudaStreamCreate")) return false;
     if (!cuda_ok(cudaMalloc((void **)&d_rec[0], frame_bytes), "cudaMalloc")) return false;
     if (!cuda_ok(cudaMalloc((void **)&d_rec[1], frame_bytes), "cudaMalloc")) return false;
-    if (!cuda_ok(cudaMalloc((void **)&d_data, data_cap), "cudaMalloc")) return false;
-    if (!cuda_ok(cudaMalloc((void **)&d_small, small_bytes), "cudaMalloc")) return false;
-    if (!cuda_ok(cudaMalloc((void **)&d_cu, sizeof(CuInfo) * fp.w8 * fp.h8), "cudaMalloc")) return false;
-    if (!cuda_ok(cudaMalloc((void **)&d_levels, frame_bytes * sizeof(int16_t)), "cudaMalloc")) return false;
     {
       std::vector<int> order((size_t)fp.ctb_cols * fp.ctb_rows);
       intra_wavefront_order(fp.ctb_cols, fp.ctb_rows, order.data());
       if (!cuda_ok(cudaMalloc((void **)&d_order, order.size() * sizeof(int)), "cudaMalloc")) return false;
       if (!cuda_ok(cudaMemcpy(d_order, order.data(), order.size() * sizeof(int), cudaMemcpyHostToDevice), "H2D order")) return false;
     }
-    if (!cuda_ok(cudaMallocHost((void **)&h_out, frame_bytes), "cudaMallocHost")) return false;
-    if (!cuda_ok(cudaMallocHost((void **)&h_data, data_cap), "cudaMallocHost")) return false;
-    if (!cuda_ok(cudaMallocHost((void **)&h_bases, sizeof(uint32_t) * (rows + 1)), "cudaMallocHost")) return false;
-    if (!cuda_ok(cudaMallocHost((void **)&h_status, sizeof(int) * 2), "cudaMallocHost")) return false;
-    cur = 0; have_ref = 0; have_out = 0;
+    slots.resize(frame_delay + 1);
+    for (DecSlot &s : slots) {
+      if (!cuda_ok(cudaStreamCreateWithFlags(&s.stream, cudaStreamNonBlocking), "cudaStreamCreate")) return false;
+      if (!cuda_ok(cudaEventCreateWithFlags(&s.ev_parsed, cudaEventDisableTiming), "cudaEventCreate")) return false;
+      if (!cuda_ok(cudaMalloc((void **)&s.d_data, data_cap), "cudaMalloc")) return false;
+      if (!cuda_ok(cudaMalloc((void **)&s.d_small, small_bytes), "cudaMalloc")) return false;
+      if (!cuda_ok(cudaMalloc((void **)&s.d_cu, sizeof(CuInfo) * fp.w8 * fp.h8), "cudaMalloc")) return false;
+      if (!cuda_ok(cudaMalloc((void **)&s.d_levels, frame_bytes * sizeof(int16_t)), "cudaMalloc")) return false;
+      if (!cuda_ok(cudaMallocHost((void **)&s.h_out, frame_bytes), "cudaMallocHost")) return false;
+      if (!cuda_ok(cudaMallocHost((void **)&s.h_data, data_cap), "cudaMallocHost")) return false;
+      if (!cuda_ok(cudaMallocHost((void **)&s.h_bases, sizeof(uint32_t) * (rows + 1)), "cudaMallocHost")) return false;
+      if (!cuda_ok(cudaMallocHost((void **)&s.h_status, sizeof(int) * 2), "cudaMallocHost")) return false;
+    }
+    cur = 0; have_ref = 0;
     return true;
   }
 
@@ -285,7 +312,6 @@ struct Decoder {
     b.align();
     if (b.bad || qp < 0 || qp > 51) { set_error("decoder: malformed slice header"); return -1; }
     if (n_entry != rows - 1) { set_error("decoder: %d entry points for %d CTU rows (WPP expected)", n_entry, rows); return -1; }
-    if (slice_type == 1 && !have_ref) { set_error("decoder: P slice without a reference picture"); return -1; }
     // escaped offset of the first slice-data byte
     const size_t hdr_unesc = b.pos >> 3;
     size_t hdr_esc = hdr_unesc;
@@ -295,60 +321,85 @@ struct Decoder {
       size_t k = std::lower_bound(epb_pos.begin(), epb_pos.end(), (uint32_t)esc) - epb_pos.begin();
       return esc - k;
     };
+    DecSlot &sl = slots[next_slot];
     size_t esc = hdr_esc;
     for (int r = 0; r < rows; r++) {
-      h_bases[r] = (uint32_t)(to_unesc(esc) - hdr_unesc);
+      sl.h_bases[r] = (uint32_t)(to_unesc(esc) - hdr_unesc);
       if (r < rows - 1) esc += entry[r];
     }
     const size_t data_len = rbsp.size() - hdr_unesc;
-    h_bases[rows] = (uint32_t)data_len;
+    sl.h_bases[rows] = (uint32_t)data_len;
     for (int r = 0; r < rows; r++)
-      if (h_bases[r] > h_bases[r + 1]) { set_error("decoder: entry points run past the slice data"); return -1; }
+      if (sl.h_bases[r] > sl.h_bases[r + 1]) { set_error("decoder: entry points run past the slice data"); return -1; }
     if (data_len > data_cap) { set_error("decoder: slice larger than the staging buffer"); return -1; }
-    memcpy(h_data, rbsp.data() + hdr_unesc, data_len);
+    memcpy(sl.h_data, rbsp.data() + hdr_unesc, data_len);
 
-    fp.qp = qp; fp.qp_c = kChromaQpD[qp]; fp.is_idr = slice_type == 2 ? 1 : 0; fp.deblock = deblock;
-    uint8_t *rec = d_rec[cur], *ref = d_rec[cur ^ 1];
-    int *sync_flag = (int *)(d_small + off_flag), *progress = (int *)(d_small + off_prog), *ticket = (int *)(d_small + off_ticket);
-    int *status = (int *)(d_small + off_status);
-    uint32_t *d_bases = (uint32_t *)(d_small + off_bases);
+    sl.fp = fp;
+    sl.fp.qp = qp; sl.fp.qp_c = kChromaQpD[qp]; sl.fp.is_idr = slice_type == 2 ? 1 : 0; sl.fp.deblock = deblock;
+    sl.pts = pts;
+    int *sync_flag = (int *)(sl.d_small + off_flag), *progress = (int *)(sl.d_small + off_prog);
+    int *status = (int *)(sl.d_small + off_status);
+    uint32_t *d_bases = (uint32_t *)(sl.d_small + off_bases);
 #define DEC_CHECK(expr, what) do { if (!cuda_ok((expr), (what))) return -1; } while (0)
-    DEC_CHECK(cudaMemcpyAsync(d_data, h_data, data_len, cudaMemcpyHostToDevice, stream), "H2D slice");
-    DEC_CHECK(cudaMemcpyAsync(d_bases, h_bases, sizeof(uint32_t) * (rows + 1), cudaMemcpyHostToDevice, stream), "H2D bases");
-    DEC_CHECK(cudaMemsetAsync(d_levels, 0, frame_bytes * sizeof(int16_t), stream), "memset levels");
-    DEC_CHECK(launch_parse(fp, d_data, d_bases, d_cu, d_levels, d_small + off_ctx, sync_flag, progress, status, stream), "parse launch");
+    DEC_CHECK(cudaMemcpyAsync(sl.d_data, sl.h_data, data_len, cudaMemcpyHostToDevice, sl.stream), "H2D slice");
+    DEC_CHECK(cudaMemcpyAsync(d_bases, sl.h_bases, sizeof(uint32_t) * (rows + 1), cudaMemcpyHostToDevice, sl.stream), "H2D bases");
+    DEC_CHECK(cudaMemsetAsync(sl.d_levels, 0, frame_bytes * sizeof(int16_t), sl.stream), "memset levels");
+    DEC_CHECK(launch_parse(sl.fp, sl.d_data, d_bases, sl.d_cu, sl.d_levels, sl.d_small + off_ctx, sync_flag, progress, status, sl.stream), "parse launch");
     count_launch(1);
-    DEC_CHECK(cudaMemcpyAsync(h_status, status, sizeof(int) * 2, cudaMemcpyDeviceToHost, stream), "D2H status");
-    DEC_CHECK(cudaStreamSynchronize(stream), "sync parse");
-    if (h_status[0] != 0) {
+    DEC_CHECK(cudaMemcpyAsync(sl.h_status, status, sizeof(int) * 2, cudaMemcpyDeviceToHost, sl.stream), "D2H status");
+    DEC_CHECK(cudaEventRecord(sl.ev_parsed, sl.stream), "record parse");
+    pending.push_back(next_slot);
+    next_slot = (next_slot + 1) % (int)slots.size();
+    if ((int)pending.size() <= frame_delay) return 0;
+    return finish_oldest();
+  }
+
+  // Reconstructs the oldest parsed picture (prediction + residual, deblocking) and copies it to the
+  // host.  Returns 1 with the picture in slots[out_slot].h_out, -1 on error.
+  int finish_oldest()
+  {
+    const int idx = pending.front();
+    pending.pop_front();
+    DecSlot &sl = slots[idx];
+    FrameParams &f = sl.fp;
+    int *progress = (int *)(sl.d_small + off_prog), *ticket = (int *)(sl.d_small + off_ticket);
+    if (!cuda_ok(cudaEventSynchronize(sl.ev_parsed), "sync parse")) { have_ref = 0; return -1; }
+    if (sl.h_status[0] != 0) {
       static const char *const why[] = {"", "escape code too long", "intra CU in a P slice", "partition other than 2Nx2N", "mvd too long",
         "NxN intra partition", "intra chroma mode other than derived", "64x64 CU with residual", "end_of_slice_segment_flag mismatch",
         "end_of_subset_one_bit missing", "intra CU size other than 16x16 (8x8 at the picture edge)"};
-      int c = h_status[0];
+      int c = sl.h_status[0];
       set_error("decoder: unsupported or corrupt slice data (%s)", c > 0 && c <= 10 ? why[c] : "unknown");
+      have_ref = 0;
       return -1;
     }
-    if (fp.is_idr) {
-      DEC_CHECK(launch_intra_decode(fp, rec, d_levels, d_cu, progress, ticket, d_order, stream), "intra decode launch");
+    if (!f.is_idr && !have_ref) { set_error("decoder: P slice without a reference picture"); return -1; }
+    uint8_t *rec = d_rec[cur], *ref = d_rec[cur ^ 1];
+    have_ref = 0;                          // until this picture is complete
+    if (f.is_idr) {
+      DEC_CHECK(launch_intra_decode(f, rec, sl.d_levels, sl.d_cu, progress, ticket, d_order, stream), "intra decode launch");
       count_launch(1);
     } else {
-      fp.search_range = std::max(1, (h_status[1] + 3) / 4 + 1);
-      cudaError_t e = launch_inter_decode(fp, ref, rec, d_levels, d_cu, stream);
-      if (e == cudaErrorInvalidValue) { set_error("decoder: motion vectors of +-%d samples exceed the supported window", fp.search_range); return -1; }
+      f.search_range = std::max(1, (sl.h_status[1] + 3) / 4 + 1);
+      cudaError_t e = launch_inter_decode(f, ref, rec, sl.d_levels, sl.d_cu, stream);
+      if (e == cudaErrorInvalidValue) { set_error("decoder: motion vectors of +-%d samples exceed the supported window", f.search_range); return -1; }
       DEC_CHECK(e, "inter decode launch");
       count_launch(1);
     }
-    if (deblock) {
-      DEC_CHECK(launch_deblock(fp, rec, d_cu, stream), "deblock launch");
+    if (f.deblock) {
+      DEC_CHECK(launch_deblock(f, rec, sl.d_cu, stream), "deblock launch");
       count_launch(2);
     }
-    DEC_CHECK(cudaMemcpyAsync(h_out, rec, frame_bytes, cudaMemcpyDeviceToHost, stream), "D2H picture");
+    DEC_CHECK(cudaMemcpyAsync(sl.h_out, rec, frame_bytes, cudaMemcpyDeviceToHost, stream), "D2H picture");
     DEC_CHECK(cudaStreamSynchronize(stream), "sync picture");
 #undef DEC_CHECK
     cur ^= 1;
-    have_ref = 1; have_out = 1; out_pts = pts; pictures++;
+    have_ref = 1; out_slot = idx; out_pts = sl.pts; pictures++;
     return 1;
   }
+
+  // libOpenHevcDecode(h, NULL, 0, pts): hand over the next held-back picture, 0 when none is left.
+  int drain_one() { return pending.empty() ? 0 : finish_oldest(); }
 
   int decode_nal(const uint8_t *nal, size_t n, int64_t pts)
   {
@@ -371,8 +422,12 @@ extern "C" {
 
 OpenHevc_Handle libOpenHevcInit(int nb_pthreads, int thread_type)
 {
-  (void)nb_pthreads; (void)thread_type;
-  return new Decoder();
+  // Frame threading (thread_type 1 or 3) in OpenHEVC keeps nb_pthreads pictures in flight and
+  // delays output by nb_pthreads - 1 pictures; here the pictures in flight are concurrent CABAC
+  // parses on the GPU.  Slice threading (2) has no delay: WPP substreams are always parallel.
+  Decoder *d = new Decoder();
+  if (thread_type & 1) d->frame_delay = std::min(std::max(nb_pthreads, 1), 64) - 1;
+  return d;
 }
 
 int libOpenHevcStartDecoder(OpenHevc_Handle h)
@@ -387,10 +442,11 @@ int libOpenHevcStartDecoder(OpenHevc_Handle h)
 int libOpenHevcDecode(OpenHevc_Handle h, const unsigned char *buff, int nal_len, int64_t pts)
 {
   Decoder *d = (Decoder *)h;
-  if (!d || !d->started || !buff || nal_len <= 0) { b200::set_error("libOpenHevcDecode: bad arguments or decoder not started"); return -1; }
+  if (!d || !d->started) { b200::set_error("libOpenHevcDecode: decoder not started"); return -1; }
+  if (!buff || nal_len <= 0) return d->drain_one();
   // split on start codes (00 00 01 / 00 00 00 01)
   int got = 0;
-  size_t i = 0, n = (size_t)nal_len;
+  size_t n = (size_t)nal_len;
   auto find_sc = [&](size_t from, size_t &sc_len) -> size_t {
     for (size_t k = from; k + 3 <= n; k++)
       if (buff[k] == 0 && buff[k + 1] == 0 && buff[k + 2] == 1) { sc_len = 3; return k; }
@@ -409,7 +465,6 @@ int libOpenHevcDecode(OpenHevc_Handle h, const unsigned char *buff, int nal_len,
     if (rc < 0) return -1;
     got |= rc;
     pos = next; sc_len = next_len;
-    (void)i;
   }
   return got;
 }
@@ -417,11 +472,12 @@ int libOpenHevcDecode(OpenHevc_Handle h, const unsigned char *buff, int nal_len,
 int libOpenHevcGetOutput(OpenHevc_Handle h, int got_picture, OpenHevc_Frame *frame)
 {
   Decoder *d = (Decoder *)h;
-  if (!d || !frame || !got_picture || !d->have_out) return 0;
+  if (!d || !frame || !got_picture || d->out_slot < 0) return 0;
   const size_t ysz = (size_t)d->fp.w * d->fp.h;
-  frame->pvY = d->h_out;
-  frame->pvU = d->h_out + ysz;
-  frame->pvV = d->h_out + ysz + ysz / 4;
+  uint8_t *out = d->slots[d->out_slot].h_out;
+  frame->pvY = out;
+  frame->pvU = out + ysz;
+  frame->pvV = out + ysz + ysz / 4;
   libOpenHevcGetPictureInfo(h, &frame->frameInfo);
   return 1;
 }
@@ -449,15 +505,18 @@ const char *libOpenHevcVersion(OpenHevc_Handle) { return "b200-hevc-dec 0.1 (sm_
 void libOpenHevcFlush(OpenHevc_Handle h)
 {
   Decoder *d = (Decoder *)h;
-  if (d) { d->have_ref = 0; d->have_out = 0; }
+  if (!d) return;
+  for (b200::DecSlot &s : d->slots) cudaStreamSynchronize(s.stream);
+  d->pending.clear();
+  d->have_ref = 0; d->out_slot = -1;
 }
 void libOpenHevcClose(OpenHevc_Handle h) { delete (Decoder *)h; }
 
 int b200_dec_last_picture(OpenHevc_Handle h, uint8_t *dst, int cap)
 {
   Decoder *d = (Decoder *)h;
-  if (!d || !dst || !d->have_out || (size_t)cap < d->frame_bytes) return -1;
-  memcpy(dst, d->h_out, d->frame_bytes);
+  if (!d || !dst || d->out_slot < 0 || (size_t)cap < d->frame_bytes) return -1;
+  memcpy(dst, d->slots[d->out_slot].h_out, d->frame_bytes);
   return (int)d->frame_bytes;
 }
 

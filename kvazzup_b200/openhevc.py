@@ -60,7 +60,7 @@ class OpenHEVCFilter:
         self.discarded = 0
 
     def init(self) -> bool:
-        ttype = {"Slice": 2, "Frame": 1}.get(self.mode, 4)
+        ttype = {"Slice": 2, "Frame": 1}.get(self.mode, 3)      # OHThreadType, openhevcfilter.cpp:11
         self.handle = self.l.libOpenHevcInit(self.threads, ttype)
         if self.l.libOpenHevcStartDecoder(self.handle) == -1:
             return False
@@ -90,6 +90,18 @@ class OpenHEVCFilter:
         if got == 0:
             return None
         return self._send_decoded_output(got)
+
+    def drain(self):
+        """Held-back pictures of frame threading (not in the reference filter, which never drains:
+        it flushes and closes, openhevcfilter.cpp:81-82)."""
+        out = []
+        while True:
+            got = self.l.libOpenHevcDecode(self.handle, None, 0, 0)
+            if got <= -1:
+                raise B200Error("libOpenHevcDecode failed: " + self.l.b200_last_error().decode())
+            if got == 0:
+                return out
+            out.append(self._send_decoded_output(got))
 
     def _send_decoded_output(self, got):
         fr = OpenHevcFrame()

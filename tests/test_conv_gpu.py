@@ -117,3 +117,24 @@ def test_convert_dev_batched_yuyv(oracle_lib):
     for f in range(n):
         _, exp = oracle_convert_to_i420(oracle_lib, src[f * fb:(f + 1) * fb], w, h, FOURCC["YUYV"])
         assert np.array_equal(got[f * ob:(f + 1) * ob], exp), f
+
+
+@pytest.mark.parametrize("wh", [(1280, 720), (640, 480), (72, 40)])
+def test_fused_selfview_equals_the_three_stage_chain(oracle_lib, wh):
+    """I420 -> RGB32 -> half -> mirror fused in one kernel == the oracle's (reference-pinned) stages in sequence."""
+    w, h = wh
+    i420 = synth.noise(17, w * h * 3 // 2)
+    rgb = oracle_i420_to_rgb32(oracle_lib, i420, w, h)
+    for half in (0, 1):
+        if half:
+            stage = np.zeros((w // 2) * (h // 2) * 4, np.uint8)
+            oracle_lib.oracle_half_rgb(ptr(rgb), ptr(stage), w, h)
+            ow, oh = w // 2, h // 2
+        else:
+            stage, ow, oh = rgb, w, h
+        for hor, ver in ((0, 0), (1, 0), (0, 1), (1, 1)):
+            exp = stage.copy()
+            if hor or ver:
+                oracle_lib.oracle_flip_rgb(ptr(stage), ptr(exp), ow, oh, hor, ver)
+            got = convert.selfview(i420, w, h, bool(half), bool(hor), bool(ver))
+            assert np.array_equal(got, exp), (half, hor, ver)

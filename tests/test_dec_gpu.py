@@ -76,6 +76,37 @@ def test_decoder_on_gpu_encoder_stream_1080p_and_ffmpeg_agreement():
             assert np.array_equal(dec[i][0], ff[i][0]), i
 
 
+@pytest.mark.parametrize("threads,mode", [(1, "Frame"), (4, "Frame"), (9, "Both"), (6, "Slice")])
+def test_frame_threading_delays_output_and_changes_nothing_else(threads, mode):
+    """OpenHEVC frame threads keep `threads` pictures in flight and delay output by threads - 1;
+    ours are concurrent parses on the GPU.  Same pictures, same order, IDR in the middle."""
+    w, h, n = 416, 240, 12
+    enc = OracleEncoder(w, h, qp=30, intra_period=5)
+    aus, recs = [], []
+    for f in frames_of("camera", w, h, n):
+        aus.append(enc.encode(f))
+        recs.append(enc.recon())
+    delay = threads - 1 if mode != "Slice" else 0
+    f = OpenHEVCFilter(threads, mode)
+    assert f.init()
+    out, counts = [], []
+    for i, au in enumerate(aus):
+        k = 0
+        for nal in split_nals(au):
+            got = f.process(nal, pts=1000 + i)
+            if got is not None:
+                out.append(got)
+                k += 1
+        counts.append(k)
+    assert counts == [0] * min(delay, n) + [1] * max(n - delay, 0)
+    out += f.drain()
+    assert f.drain() == []
+    f.close()
+    assert len(out) == n
+    for i in range(n):
+        assert np.array_equal(out[i][0], recs[i]), i
+
+
 def test_filter_gates_on_parameter_sets_and_reports_picture_info():
     w, h = 192, 136
     enc = OracleEncoder(w, h, qp=30, intra_period=0)
