@@ -5,7 +5,8 @@
 // (context hand-over after the second CTU, H.265 9.3.1, and the above / above-right neighbours
 // that merge / AMVP derivation reads).  Parsing cannot be split from arithmetic decoding -- what
 // to read next depends on what was just decoded -- so the warp runs the parser redundantly in all
-// lanes on private context tables; lane 0 stores the cu map entries and the non-zero levels.
+// lanes on private context tables, with no branch that depends on the lane index; stores of
+// identical values from all lanes coalesce into one transaction.
 //
 // Scope: the syntax subset the B200 encoder (and any encoder with the same parameter sets)
 // produces -- 2Nx2N CUs 8..64, one TU per CU, I and P slices, one reference picture, no SAO /
@@ -23,6 +24,7 @@ struct Reader {
   uint32_t range, value;
   int bits_needed;
   uint8_t *ctx;          // this lane's private context table, entry i at ctx[i * 32]
+  const uint2 *tab;      // per state: .x = the four rangeTabLps bytes, .y = transIdxLps | (flip mps) << 6
   int err;
 };
 
@@ -43,13 +45,14 @@ __device__ __forceinline__ int dec_bin(Reader &r, int ctx_idx)
 {
   uint32_t s = r.ctx[ctx_idx * 32];
   uint32_t st = s >> 1, mps = s & 1;
-  uint32_t lps = (c_range_lps[st] >> (((r.range >> 6) & 3) * 8)) & 0xff;
+  const uint2 e = r.tab[st];
+  uint32_t lps = (e.x >> (((r.range >> 6) & 3) * 8)) & 0xff;
   r.range -= lps;
   uint32_t scaled = r.range << 7;
   int bin;
   if (r.value < scaled) {
     bin = (int)mps;
-    if (st < 62) st++;
+    st = min(st + 1, 62u);
     if (scaled < (256u << 7)) {
       r.range = scaled >> 6;
       r.value += r.value;
@@ -60,8 +63,8 @@ __device__ __forceinline__ int dec_bin(Reader &r, int ctx_idx)
     int nb = __clz(lps) - 23;
     r.value = (r.value - scaled) << nb;
     r.range = lps << nb;
-    if (st == 0) mps ^= 1;
-    st = c_trans_lps[st];
+    mps ^= e.y >> 6;
+    st = e.y & 63;
     r.bits_needed += nb;
     if (r.bits_needed >= 0) { r.value += next_byte(r) << r.bits_needed; r.bits_needed -= 8; }
   }
@@ -133,21 +136,33 @@ __device__ __forceinline__ int scan_index_d(int scan_idx, int blk_log2, int x, i
   return 0;
 }
 
+// Everything a CU reads from its neighbours (skip / depth contexts, merge and AMVP candidates,
+// intra MPMs) lies in the current CTU, the CTU to its left, or the bottom unit line of the CTU row
+// above between x = cx - 8 and cx + 71.  Those live in shared memory: a global (L2) round trip per
+// neighbour cost more than the arithmetic decoding of the CU itself.
 struct ParseCtx {
   FrameParams fp;
-  CuInfo *cu;            // global cu map (written by lane 0, read back with ld.cg)
+  CuInfo *cu;            // global cu map (written by lane 0 for the later kernels and the row below)
   int16_t *levels;       // zeroed by the host before the launch; only non-zero levels are stored
   int lane;
   int max_mv;            // largest |mv component| seen (quarter samples)
+  uint32_t *s_ctu;       // [2][64][3]: 8x8 units of the current (cur_buf) and the previous CTU, raster order
+  uint32_t *s_above;     // [10][3]: units (cx/8 - 1 .. cx/8 + 8) of the line above the CTU row
+  int cx, cy, cur_buf;
 };
 
 __device__ __forceinline__ CuInfo load_cu(const ParseCtx &pc, int x, int y)
 {
-  const uint32_t *s = (const uint32_t *)(pc.cu + (size_t)(y >> 3) * pc.fp.w8 + (x >> 3));
-  uint32_t w0 = __ldcg(s), w1 = __ldcg(s + 1), w2 = __ldcg(s + 2);
+  const uint32_t *s;
+  if (y < pc.cy) {
+    s = pc.s_above + 3 * (((x - pc.cx) >> 3) + 1);
+  } else {
+    const int buf = x < pc.cx ? pc.cur_buf ^ 1 : pc.cur_buf;
+    s = pc.s_ctu + 3 * (buf * 64 + (((y - pc.cy) >> 3) << 3) + ((x >> 3) & 7));
+  }
   CuInfo c;
   uint32_t *d = (uint32_t *)&c;
-  d[0] = w0; d[1] = w1; d[2] = w2;
+  d[0] = s[0]; d[1] = s[1]; d[2] = s[2];
   return c;
 }
 
@@ -282,7 +297,7 @@ __device__ void parse_residual(Reader &r, const ParseCtx &pc, int16_t *plane, in
       num_sig++;
       int xp, yp;
       scan_pos_d(scan_idx, 2, p, xp, yp);
-      if (pc.lane == 0) {
+      {                                   // all lanes store the same value to the same address
         int v = min(absv, 32767);
         plane[(size_t)(y0 + ys * 4 + yp) * pw + x0 + xs * 4 + xp] = (int16_t)(((neg >> p) & 1) ? -v : v);
       }
@@ -415,17 +430,27 @@ __device__ void parse_cu(Reader &r, ParseCtx &pc, int x0, int y0, int log2)
     if (cu.pred_mode == 1 || cb || cr) lu = dec_bin(r, CTX_CBF_LUMA + 1);
     cu.cbf = (uint8_t)(lu | (cb << 1) | (cr << 2));
   }
-  // publish the cu map entry before any later CU reads it
-  if (pc.lane == 0) {
+  // publish the cu map entry: shared memory for the CUs that follow in this row, global memory for
+  // the row below and the reconstruction kernels (lane u takes unit u of the CU)
+  {
     const uint32_t *s = (const uint32_t *)&cu;
-    const int n8 = n >> 3;
-    for (int j = 0; j < n8; j++)
-      for (int i = 0; i < n8; i++) {
-        uint32_t *d = (uint32_t *)(pc.cu + (size_t)((y0 >> 3) + j) * fp.w8 + (x0 >> 3) + i);
-        __stcg(d, s[0]); __stcg(d + 1, s[1]); __stcg(d + 2, s[2]);
-      }
+    const int n8 = n >> 3, units = n8 * n8;
+    __syncwarp();
+    // Branch-free on purpose: a lane-dependent branch here left the warp split into two groups that
+    // ran the rest of the (lane-redundant) parse one after the other, doubling the time.  Lanes with
+    // no unit of their own repeat the store of unit 0 (same address, same value).
+    for (int base = 0; base < units; base += 32) {
+      int u = base + pc.lane;
+      int i = u & (n8 - 1), j = u >> (log2 - 3);
+      const bool mine = u < units && x0 + 8 * i < fp.w && y0 + 8 * j < fp.h;
+      i = mine ? i : 0; j = mine ? j : 0;
+      uint32_t *t = pc.s_ctu + 3 * (pc.cur_buf * 64 + ((((y0 - pc.cy) >> 3) + j) << 3) + ((x0 >> 3) & 7) + i);
+      t[0] = s[0]; t[1] = s[1]; t[2] = s[2];
+      uint32_t *d = (uint32_t *)(pc.cu + (size_t)((y0 >> 3) + j) * fp.w8 + (x0 >> 3) + i);
+      __stcg(d, s[0]); __stcg(d + 1, s[1]); __stcg(d + 2, s[2]);
+    }
+    __syncwarp();
   }
-  __syncwarp();
   const size_t ysz = (size_t)fp.w * fp.h;
   for (int k = 0; k < 3 && !r.err; k++) {
     if (!((cu.cbf >> k) & 1)) continue;
@@ -442,34 +467,53 @@ k_parse_rows(FrameParams fp, const uint8_t *__restrict__ data, const uint32_t *_
              int16_t *levels, uint8_t *sync_ctx, int *sync_flag, int *progress, int *status)
 {
   __shared__ uint8_t s_ctx[CTX_COUNT * 32];
+  __shared__ uint2 s_tab[64];
+  __shared__ uint32_t s_ctu[2 * 64 * 3];
+  __shared__ uint32_t s_above[10 * 3];
   const int row = blockIdx.x, lane = threadIdx.x;
+  for (int i = lane; i < 64; i += 32) s_tab[i] = make_uint2(c_range_lps[i], (uint32_t)c_trans_lps[i] | (i == 0 ? 64u : 0u));
   Reader r;
-  r.p = data + bases[row]; r.end = data + bases[row + 1]; r.ctx = s_ctx + lane; r.err = 0;
-  ParseCtx pc{fp, cu, levels, lane, 0};
+  r.p = data + bases[row]; r.end = data + bases[row + 1]; r.ctx = s_ctx + lane; r.tab = s_tab; r.err = 0;
+  ParseCtx pc{fp, cu, levels, lane, 0, s_ctu, s_above, 0, row * kCtb, 0};
   if (row == 0 || fp.ctb_cols < 2) {
     init_contexts_d(r.ctx, fp.is_idr ? 0 : 1, fp.qp);
   } else {
-    if (lane == 0) {
+    // All lanes poll (one broadcast load per iteration).  Nothing in this kernel branches on the
+    // lane index: a leader-only branch followed by __syncwarp() has left the warp split into groups
+    // that then ran the lane-redundant parser one after the other (measured: 16 instead of 32
+    // threads per instruction, twice the time).
+    {
       volatile int *f = sync_flag;
       while (f[row - 1] == 0) __nanosleep(100);
       __threadfence();
     }
-    __syncwarp();
     for (int i = 0; i < CTX_COUNT; i++) r.ctx[i * 32] = __ldcg(sync_ctx + (size_t)(row - 1) * CTX_COUNT + i);
   }
   __syncwarp();
   reader_start(r);
   for (int col = 0; col < fp.ctb_cols && !r.err; col++) {
     if (row > 0) {                       // above and above-right CTUs must be parsed (cu map reads)
-      if (lane == 0) {
+      {
         volatile int *p = progress;
-        int need = min(col + 2, fp.ctb_cols);
-        while (p[row - 1] < need && p[row - 1] >= 0) __nanosleep(64);
+        const int need = min(col + 2, fp.ctb_cols);
+        for (;;) {
+          const int have = p[row - 1];
+          if (have >= need || have < 0) break;
+          __nanosleep(64);
+        }
         __threadfence();
       }
-      __syncwarp();
+      {
+        const int slot = min(lane, 9);
+        const int ux = min(max(col * 8 - 1 + slot, 0), fp.w8 - 1);
+        const uint32_t *s = (const uint32_t *)(cu + (size_t)(row * 8 - 1) * fp.w8 + ux);
+        uint32_t *d = s_above + 3 * slot;
+        d[0] = __ldcg(s); d[1] = __ldcg(s + 1); d[2] = __ldcg(s + 2);
+      }
     }
     const int cx = col * kCtb, cy = row * kCtb;
+    pc.cx = cx; pc.cur_buf = col & 1;
+    __syncwarp();
     for (int z = 0; z < 64 && !r.err;) {
       int x0 = cx + 8 * z_to_x(z), y0 = cy + 8 * z_to_y(z);
       if (x0 >= fp.w || y0 >= fp.h) { z++; continue; }
@@ -492,20 +536,19 @@ k_parse_rows(FrameParams fp, const uint8_t *__restrict__ data, const uint32_t *_
       z += 1 << (2 * (log2 - 3));
     }
     if (col == 1 && row + 1 < fp.ctb_rows) {
-      __syncwarp();
-      if (lane == 0)
-        for (int i = 0; i < CTX_COUNT; i++) sync_ctx[(size_t)row * CTX_COUNT + i] = r.ctx[i * 32];
+      // every lane holds the same table; all store it (same addresses, same values)
+      for (int i = 0; i < CTX_COUNT; i++) sync_ctx[(size_t)row * CTX_COUNT + i] = r.ctx[i * 32];
       __threadfence();
       __syncwarp();
-      if (lane == 0) atomicExch(&sync_flag[row], 1);
+      *(volatile int *)&sync_flag[row] = 1;
     }
     const bool last = row == fp.ctb_rows - 1 && col == fp.ctb_cols - 1;
     int eos = dec_terminate(r);                                        // end_of_slice_segment_flag
     if (eos != (last ? 1 : 0)) r.err = 8;
     if (col == fp.ctb_cols - 1 && !last && !dec_terminate(r)) r.err = 9;   // end_of_subset_one_bit
     __threadfence();
-    __syncwarp();
-    if (lane == 0) atomicExch(&progress[row], r.err ? -1 : col + 1);
+    __syncwarp();                        // every lane's cu map stores are fenced before any lane publishes
+    *(volatile int *)&progress[row] = r.err ? -1 : col + 1;
   }
   if (lane == 0) {
     if (r.err) {
