@@ -84,6 +84,13 @@ void libOpenHevcClose(OpenHevc_Handle h);
 
 /* B200 extension: copy of the last decoded picture as packed I420 (w*h*3/2 bytes). */
 int  b200_dec_last_picture(OpenHevc_Handle h, uint8_t *dst, int cap);
+/* B200 extensions for an adjacent GPU filter (decode -> I420-to-RGB32 without a
+ * host bounce).  b200_dec_output_dev: DEVICE pointer to the last output picture, packed I420,
+ * complete when libOpenHevcDecode returned; read-only (it is the next picture's reference) and valid
+ * until the next libOpenHevcDecode call.  b200_dec_set_host_output(h, 0) skips the device-to-host
+ * copy; libOpenHevcGetOutput planes are then stale. */
+const uint8_t *b200_dec_output_dev(OpenHevc_Handle h);
+void b200_dec_set_host_output(OpenHevc_Handle h, int on);
 
 #ifdef __cplusplus
 }

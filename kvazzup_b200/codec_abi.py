@@ -34,6 +34,8 @@ SIGNATURES: dict = {
     "libOpenHevcFlush": (None, [v]),
     "libOpenHevcClose": (None, [v]),
     "b200_dec_last_picture": (i, [v, v, i]),
+    "b200_dec_output_dev": (v, [v]),
+    "b200_dec_set_host_output": (None, [v, i]),
 }
 
 

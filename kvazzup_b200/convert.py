@@ -63,21 +63,30 @@ def convert_to_i420(sample: np.ndarray, w: int, h: int, fourcc: int, fill: int |
 
 # ---- device-resident batched path ---------------------------------------------------------------
 
+class _Ptr:
+    """Lets the *_dev wrappers take either a torch tensor or a raw device address."""
+    def __init__(self, a):
+        self.a = a
+
+    def data_ptr(self):
+        return self.a.data_ptr() if hasattr(self.a, "data_ptr") else int(self.a)
+
+
 def i420_to_rgb32_dev(d_in, d_out, w: int, h: int, n: int, stream: int = 0):
-    check(lib().b200_i420_to_rgb32_dev(d_in.data_ptr(), d_out.data_ptr(), w, h, n, stream), "b200_i420_to_rgb32_dev")
+    check(lib().b200_i420_to_rgb32_dev(_Ptr(d_in).data_ptr(), _Ptr(d_out).data_ptr(), w, h, n, stream), "b200_i420_to_rgb32_dev")
 
 
 def half_rgb_dev(d_in, d_out, w: int, h: int, n: int, stream: int = 0):
-    check(lib().b200_half_rgb_dev(d_in.data_ptr(), d_out.data_ptr(), w, h, n, stream), "b200_half_rgb_dev")
+    check(lib().b200_half_rgb_dev(_Ptr(d_in).data_ptr(), _Ptr(d_out).data_ptr(), w, h, n, stream), "b200_half_rgb_dev")
 
 
 def flip_rgb_dev(d_in, d_out, w: int, h: int, hor: bool, ver: bool, n: int, stream: int = 0):
-    check(lib().b200_flip_rgb_dev(d_in.data_ptr(), d_out.data_ptr(), w, h, int(hor), int(ver), n, stream),
+    check(lib().b200_flip_rgb_dev(_Ptr(d_in).data_ptr(), _Ptr(d_out).data_ptr(), w, h, int(hor), int(ver), n, stream),
           "b200_flip_rgb_dev")
 
 
 def convert_to_i420_dev(d_src, d_dst, w: int, h: int, fourcc: int, n: int, stream: int = 0):
-    check(lib().b200_convert_to_i420_dev(d_src.data_ptr(), d_dst.data_ptr(), w, h, fourcc, n, stream),
+    check(lib().b200_convert_to_i420_dev(_Ptr(d_src).data_ptr(), _Ptr(d_dst).data_ptr(), w, h, fourcc, n, stream),
           "b200_convert_to_i420_dev")
 
 

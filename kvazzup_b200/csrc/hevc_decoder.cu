@@ -105,6 +105,8 @@ struct Decoder {
   size_t data_cap = 0, small_bytes = 0, off_flag = 0, off_prog = 0, off_ticket = 0, off_status = 0, off_bases = 0, off_ctx = 0;
   int frame_delay = 0;                    // pictures held back (OpenHEVC frame threads - 1)
   int next_slot = 0, out_slot = -1;
+  bool host_output = true;                // false: pictures stay on the GPU (b200_dec_output_dev)
+  const uint8_t *d_out = nullptr;         // device copy of the last output picture (the new reference)
   int cur = 0, have_ref = 0, pictures = 0;
   int64_t out_pts = 0;
   int fr_num = 0, fr_den = 0;
@@ -390,8 +392,9 @@ struct Decoder {
       DEC_CHECK(launch_deblock(f, rec, sl.d_cu, stream), "deblock launch");
       count_launch(2);
     }
-    DEC_CHECK(cudaMemcpyAsync(sl.h_out, rec, frame_bytes, cudaMemcpyDeviceToHost, stream), "D2H picture");
+    if (host_output) DEC_CHECK(cudaMemcpyAsync(sl.h_out, rec, frame_bytes, cudaMemcpyDeviceToHost, stream), "D2H picture");
     DEC_CHECK(cudaStreamSynchronize(stream), "sync picture");
+    d_out = rec;
 #undef DEC_CHECK
     cur ^= 1;
     have_ref = 1; out_slot = idx; out_pts = sl.pts; pictures++;
@@ -508,9 +511,21 @@ void libOpenHevcFlush(OpenHevc_Handle h)
   if (!d) return;
   for (b200::DecSlot &s : d->slots) cudaStreamSynchronize(s.stream);
   d->pending.clear();
-  d->have_ref = 0; d->out_slot = -1;
+  d->have_ref = 0; d->out_slot = -1; d->d_out = nullptr;
 }
 void libOpenHevcClose(OpenHevc_Handle h) { delete (Decoder *)h; }
+
+const uint8_t *b200_dec_output_dev(OpenHevc_Handle h)
+{
+  Decoder *d = (Decoder *)h;
+  return d && d->out_slot >= 0 ? d->d_out : NULL;
+}
+
+void b200_dec_set_host_output(OpenHevc_Handle h, int on)
+{
+  Decoder *d = (Decoder *)h;
+  if (d) d->host_output = on != 0;
+}
 
 int b200_dec_last_picture(OpenHevc_Handle h, uint8_t *dst, int cap)
 {

@@ -91,6 +91,22 @@ class OpenHEVCFilter:
             return None
         return self._send_decoded_output(got)
 
+    def set_host_output(self, on: bool):
+        """False: decoded pictures stay on the GPU; read them with output_dev()."""
+        self.l.b200_dec_set_host_output(self.handle, int(on))
+
+    def output_dev(self) -> int:
+        """Device pointer (packed I420) of the picture the last successful process() call completed."""
+        return self.l.b200_dec_output_dev(self.handle) or 0
+
+    def process_dev(self, nal: bytes, pts: int = 0) -> int:
+        """process() for a GPU consumer: returns the device pointer of the completed picture or 0."""
+        buf = (C.c_ubyte * len(nal)).from_buffer_copy(nal)
+        got = self.l.libOpenHevcDecode(self.handle, buf, len(nal), pts)
+        if got <= -1:
+            raise B200Error("libOpenHevcDecode failed: " + self.l.b200_last_error().decode())
+        return self.output_dev() if got > 0 else 0
+
     def drain(self):
         """Held-back pictures of frame threading (not in the reference filter, which never drains:
         it flushes and closes, openhevcfilter.cpp:81-82)."""

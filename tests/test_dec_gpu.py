@@ -152,3 +152,61 @@ def test_decoder_rejects_what_it_cannot_decode():
     except B200Error:
         pass
     g.close()
+
+
+def test_rtp_loopback_encoder_packets_decoder():
+    """Encoder -> RFC 7798 packets (uvgRTP's role) -> one NAL per buffer -> decoder, as in a call;
+    a lost slice fragment costs that picture and drifts until the next IDR, which is exact again."""
+    from kvazzup_b200 import rtp
+    w, h, n = 416, 240, 8
+    frames = frames_of("camera", w, h, n)
+    g = GpuEncoder(w, h, qp=30, intra_period=4, search_range=8)
+    snd, rcv = rtp.RtpSender(5, 96, 300), rtp.RtpReceiver(5)
+    f = OpenHEVCFilter()
+    assert f.init()
+    shown = {}
+    for i, fr in enumerate(frames):
+        au = g.encode(fr)
+        rec = g.recon()
+        pkts = snd.push_frame(au, 3000 * i)
+        assert len(pkts) > 4
+        if i == 1:
+            pkts = pkts[:-1]                     # lose the last fragment of picture 1's slice
+        for p in pkts:
+            for nal, ts, marker in rcv.receive(p):
+                assert ts == 3000 * i
+                assert rtp.is_hevc_intra(nal) == (nal[4] >> 1 == 19)
+                got = f.process(nal, pts=i)
+                if got is not None:
+                    # pictures 2 and 3 predict from the lost picture 1: like OpenHEVC the decoder
+                    # conceals with the last picture it has, so they drift until the next IDR
+                    assert np.array_equal(got[0], rec) == (i not in (2, 3)), i
+                    shown[i] = True
+    f.close()
+    assert rcv.lost == 1
+    assert sorted(shown) == [0, 2, 3, 4, 5, 6, 7]
+
+
+def test_device_resident_decode_to_rgb32_equals_the_host_chain():
+    """decoder output stays on the GPU and feeds the display conversion directly."""
+    import torch
+    from kvazzup_b200 import convert
+    w, h, n = 416, 240, 3
+    g = GpuEncoder(w, h, qp=30, intra_period=0)
+    aus = [g.encode(f) for f in frames_of("camera", w, h, n)]
+    host = [convert.yuv420_to_rgb32(p[0], w, h) for p in decode_all(aus)]
+    f = OpenHEVCFilter()
+    assert f.init()
+    f.set_host_output(False)
+    d_rgb = torch.empty(w * h * 4, dtype=torch.uint8, device="cuda")
+    k = 0
+    for au in aus:
+        for nal in split_nals(au):
+            d_pic = f.process_dev(nal)
+            if d_pic:
+                convert.i420_to_rgb32_dev(d_pic, d_rgb.data_ptr(), w, h, 1, torch.cuda.current_stream().cuda_stream)
+                torch.cuda.synchronize()
+                assert np.array_equal(d_rgb.cpu().numpy(), host[k]), k
+                k += 1
+    assert k == n
+    f.close()

@@ -242,3 +242,31 @@ def test_full_size_roundtrip_properties(kind, w, h, qp):
         ff, errs = ffhevc.decode_stream(aus)
         assert errs == 0 and all(np.array_equal(f[0], r) for f, r in zip(ff, recs))
     assert synth.psnr(frames[-1][:w * h], recs[-1][:w * h]) > 30.0
+
+
+def test_device_resident_camera_to_encoder_chain_equals_the_host_chain():
+    """YUYV camera frame -> I420 -> encoder without leaving the GPU gives the same
+    access units as the reference-shaped host chain (LibYUVConverter -> KvazaarFilter)."""
+    import torch
+    from kvazzup_b200 import convert, devmem, synth
+    from kvazzup_b200.convert import FOURCC
+    w, h, n = 416, 240, 4
+    cams = []
+    for t in range(n):
+        i420 = synth.camera_i420(w, h, t)
+        y = i420[:w * h].reshape(h, w)
+        u = i420[w * h:w * h * 5 // 4].reshape(h // 2, w // 2)
+        v = i420[w * h * 5 // 4:].reshape(h // 2, w // 2)
+        yuyv = np.empty((h, w // 2, 4), np.uint8)
+        yuyv[:, :, 0], yuyv[:, :, 2] = y[:, 0::2], y[:, 1::2]
+        yuyv[:, :, 1], yuyv[:, :, 3] = np.repeat(u, 2, axis=0), np.repeat(v, 2, axis=0)
+        cams.append(yuyv.ravel())
+    a = GpuEncoder(w, h, qp=30, intra_period=0)
+    b = GpuEncoder(w, h, qp=30, intra_period=0)
+    d_i420 = torch.empty(w * h * 3 // 2, dtype=torch.uint8, device="cuda")
+    for cam in cams:
+        rc, host_i420 = convert.convert_to_i420(cam, w, h, FOURCC["YUYV"])
+        assert rc == 0
+        convert.convert_to_i420_dev(devmem.to_device(cam), d_i420, w, h, FOURCC["YUYV"], 1, devmem.current_stream_ptr())
+        torch.cuda.synchronize()
+        assert a.encode(host_i420) == b.encode_dev(d_i420)
