@@ -25,6 +25,13 @@ extern "C" {
  * Returns NULL on error (see b200_last_error()). */
 void *b200_enc_open(int width, int height, int qp, int intra_period, int search_range, int deblock, int debug,
                     int depth);
+/* Same, with cu_qp_delta enabled in the PPS (one quantisation group per CTU): the region-of-interest
+ * path behind kvz_picture::roi (kvazaarfilter.cpp:423-431).  Without offsets every CTU codes delta 0. */
+void *b200_enc_open_roi(int width, int height, int qp, int intra_period, int search_range, int deblock, int debug,
+                        int depth);
+/* Per-CTU QP offsets (raster, one int8 per 64x64 CTU, n = CTU count) for the pictures submitted
+ * from now on; CTU QP = clip(qp + dqp, 0, 51).  NULL clears.  Needs b200_enc_open_roi. */
+int   b200_enc_set_ctu_dqp(void *enc, const int8_t *dqp, int n);
 void  b200_enc_close(void *enc);
 /* Encode one packed I420 picture from host / device memory; writes one Annex-B access unit
  * (VPS+SPS+PPS precede every IDR).  Returns its size, or <0 (-needed when cap is short). */

@@ -66,7 +66,7 @@ typedef struct kvz_config {
   int32_t rc_algorithm;                  /* "rc-algorithm" */
   int32_t lossless;                      /* must be 0 */
   enum kvz_mv_constraint mv_constraint;
-  int32_t set_qp_in_cu;
+  int32_t set_qp_in_cu;                  /* != 0 enables per-CTU QP (cu_qp_delta), see roi_enable */
   enum kvz_hash hash;
   int32_t deblock_enable;                /* "deblock" */
   int32_t sao_type;                      /* "sao": accepted; SAO is not applied */
@@ -78,6 +78,8 @@ typedef struct kvz_config {
   int32_t me_range;                      /* full-sample search range, from "preset" or "b200-me-range" */
   int32_t return_recon;                  /* "b200-recon": 1 = encoder_encode also returns the reconstruction */
   int32_t device;                        /* "b200-device": CUDA device ordinal, -1 = current */
+  int32_t roi_enable;                    /* "b200-roi" (also implied by set_qp_in_cu): cu_qp_delta in the PPS so that
+                                            kvz_picture::roi maps take effect */
   char preset[16];
 } kvz_config;
 
@@ -91,7 +93,10 @@ typedef struct kvz_picture {
   int32_t refcount;
   int64_t pts, dts;
   enum kvz_chroma_format chroma_format;
-  struct { int width; int height; int8_t *roi_array; } roi;   /* caller-owned delta-QP map (ignored: CQP) */
+  /* caller-owned delta-QP map (kvazaarfilter.cpp:423-431).  Like Kvazaar, each 64x64 CTU takes the
+   * entry at (ctu_x * width / ctus_wide, ctu_y * height / ctus_high).  Takes effect when the encoder
+   * was opened with set_qp_in_cu or "b200-roi" and target_bitrate == 0; ignored otherwise. */
+  struct { int width; int height; int8_t *roi_array; } roi;
 } kvz_picture;
 
 typedef struct kvz_frame_info {

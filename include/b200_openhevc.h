@@ -18,8 +18,9 @@
  * Decoding scope this round: streams of the B200 encoder's syntax family:
  * Main profile 8-bit 4:2:0, 64x64 CTUs, 2Nx2N CUs with one TU, I and P slices with one reference
  * picture, WPP entry points, deblocking; no SAO / PCM / AMP / scaling lists / transform skip /
- * sign hiding / cu_qp_delta / TMVP / tiles.  Anything else makes libOpenHevcDecode return -1 with
- * the reason in b200_last_error() -- never a silently wrong picture.
+ * sign hiding / TMVP / tiles; cu_qp_delta with one quantisation group per CTU.  Anything else
+ * makes libOpenHevcDecode return -1 with the reason in b200_last_error() -- never a silently wrong
+ * picture.
  */
 #ifndef B200_OPENHEVC_H_
 #define B200_OPENHEVC_H_

@@ -8,6 +8,8 @@ i = C.c_int
 
 SIGNATURES: dict = {
     "b200_enc_open": (v, [i, i, i, i, i, i, i, i]),
+    "b200_enc_open_roi": (v, [i, i, i, i, i, i, i, i]),
+    "b200_enc_set_ctu_dqp": (i, [v, v, i]),
     "b200_enc_flush": (i, [v, v, i]),
     "b200_enc_pending": (i, [v]),
     "b200_enc_set_profile": (i, [v, i]),

@@ -530,6 +530,25 @@ __device__ __forceinline__ int put_cu_header(Syn &s, const CuView &v, const CuIn
   put_ctx(s, CTX_CBF_CHROMA, cb);
   put_ctx(s, CTX_CBF_CHROMA, cr);
   if (cu.pred_mode == 1 || cb || cr) put_ctx(s, CTX_CBF_LUMA + 1, lu);
+  if (fp.ctu_qp && cu.cbf) {
+    // transform_unit (7.3.8.10): cu_qp_delta_abs / sign once per quantisation group (= CTU), in the
+    // first TU with a coded block flag (k_cu_qps found it).  Binarisation 9.3.3.10: prefix TR cMax 5
+    // (first bin ctx 0, then ctx 1), suffix EG0 bypass, sign bypass.
+    const int ctu = (y0 >> kCtbLog2) * fp.ctb_cols + (x0 >> kCtbLog2);
+    if (xy_to_z((x0 >> 3) & 7, (y0 >> 3) & 7) == fp.ctu_first[ctu]) {
+      const int d = fp.ctu_delta[ctu], a = abs(d);
+      const int pre = min(a, 5);
+      for (int i = 0; i < pre; i++) put_ctx(s, CTX_CU_QP_DELTA + (i ? 1 : 0), 1);
+      if (pre < 5) {
+        put_ctx(s, CTX_CU_QP_DELTA + (pre ? 1 : 0), 0);
+      } else {
+        int v = a - 5, k = 0, ones = 0;
+        while (v >= (1 << k)) { ones++; v -= 1 << k; k++; }
+        put_byp(s, ((((1ull << (ones + 1)) - 2) << k) | (unsigned)v), ones + 1 + k);
+      }
+      if (a) put_byp(s, d < 0, 1);
+    }
+  }
   return cu.cbf;
 }
 

@@ -33,7 +33,7 @@ struct CuInfo {
   uint8_t skip;
   uint8_t merge_idx;    // 0xff = not merged
   uint8_t mvp_idx;
-  uint8_t pad;
+  uint8_t qp;           // luma QP of the CU when cu_qp_delta is enabled (FrameParams::ctu_qp != 0), else 0
 };
 static_assert(sizeof(CuInfo) == 12, "CuInfo layout is part of the test ABI");
 
@@ -43,7 +43,7 @@ enum CtxOffset {
   CTX_PRED_MODE = 12, CTX_PREV_INTRA_LUMA = 13, CTX_INTRA_CHROMA = 14, CTX_MVD_GT0 = 15,
   CTX_MVD_GT1 = 16, CTX_MVP_IDX = 17, CTX_RQT_ROOT_CBF = 18, CTX_SPLIT_TRANSFORM = 19,
   CTX_CBF_LUMA = 22, CTX_CBF_CHROMA = 24, CTX_LAST_X = 28, CTX_LAST_Y = 46, CTX_CSBF = 64,
-  CTX_SIG = 68, CTX_GT1 = 110, CTX_GT2 = 134, CTX_COUNT = 140
+  CTX_SIG = 68, CTX_GT1 = 110, CTX_GT2 = 134, CTX_CU_QP_DELTA = 140, CTX_COUNT = 142
 };
 
 struct FrameParams {
@@ -55,6 +55,12 @@ struct FrameParams {
   int search_range;
   int is_idr;           // quantiser rounding offset and CABAC init type follow the slice type
   int deblock;
+  // cu_qp_delta (ROI) state, all null when the PPS flag is off.  ctu_qp: luma QP each CTU quantises
+  // with (encoder: slice QP + ROI offset; decoder: written by the parser).  ctu_delta / ctu_first:
+  // CuQpDeltaVal coded in the CTU and the z-index (8x8 units) of the CU that codes it (64 = none).
+  uint8_t *ctu_qp;
+  int8_t *ctu_delta;
+  uint8_t *ctu_first;
 };
 
 }  // namespace b200

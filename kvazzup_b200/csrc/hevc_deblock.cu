@@ -94,20 +94,77 @@ k_deblock(FrameParams fp, uint8_t *rec, const CuInfo *__restrict__ cu, int dir)
   int bs = edge_bs(p, q);
   if (!bs) return;
   int x = x8 * 8, y = y8 * 8;
-  if (dir == 0) luma_segment(rec + (size_t)(y + 4 * seg) * fp.w + x, 1, fp.w, bs, fp.qp);
-  else luma_segment(rec + (size_t)y * fp.w + x + 4 * seg, fp.w, 1, bs, fp.qp);
+  // QpL = (QpQ + QpP + 1) >> 1 (8.7.2.5.3); the two differ only across CTUs with different ROI offsets
+  const int qp = fp.ctu_qp ? (p.qp + q.qp + 1) >> 1 : fp.qp;
+  const int qp_c = fp.ctu_qp ? c_chroma_qp_tab[qp] : fp.qp_c;
+  if (dir == 0) luma_segment(rec + (size_t)(y + 4 * seg) * fp.w + x, 1, fp.w, bs, qp);
+  else luma_segment(rec + (size_t)y * fp.w + x + 4 * seg, fp.w, 1, bs, qp);
   if (bs == 2 && ((dir == 0 ? x : y) & 15) == 0) {
     // chroma edges lie on the 8-sample chroma grid and are filtered for bS 2 only; seg 0 -> Cb, seg 1 -> Cr
     const size_t ysz = (size_t)fp.w * fp.h;
     const int cw = fp.w >> 1;
     uint8_t *plane = rec + ysz + (seg ? ysz / 4 : 0);
     uint8_t *pc = plane + (size_t)(y / 2) * cw + x / 2;
-    if (dir == 0) chroma_segment(pc, 1, cw, fp.qp_c);
-    else chroma_segment(pc, cw, 1, fp.qp_c);
+    if (dir == 0) chroma_segment(pc, 1, cw, qp_c);
+    else chroma_segment(pc, cw, 1, qp_c);
+  }
+}
+
+// Luma QP of every CU with one quantisation group per CTU (8.6.1, diff_cu_qp_delta_depth = 0); the
+// encoder's counterpart of what the parser derives while decoding.  The left / above groups lie in
+// other CTBs, so qPY_PRED is the slice QP at the start of a CTU row (WPP) and otherwise the QP of
+// the last CU of the previous CTU.  Inside a CTU the CUs before the first coded residual keep the
+// predicted QP; that CU codes CuQpDeltaVal and it and all later CUs have the CTU's target QP.
+// One CTA per CTU row: warps find the first coded CU of their CTUs, thread 0 runs the (short)
+// prediction chain along the row, then the warps write the per-CU QPs.
+constexpr int kMaxCtbCols = 128;
+__global__ void __launch_bounds__(256)
+k_cu_qps(FrameParams fp, CuInfo *cu)
+{
+  __shared__ uint8_t s_first[kMaxCtbCols], s_pred[kMaxCtbCols];
+  const int row = blockIdx.x, warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  for (int col = warp; col < fp.ctb_cols; col += 8) {
+    unsigned first = 64;
+    for (int h = 0; h < 2; h++) {
+      const int z = 32 * h + lane;
+      const int x8 = col * 8 + z_to_x(z), y8 = row * 8 + z_to_y(z);
+      const bool coded = x8 < fp.w8 && y8 < fp.h8 && cu[(size_t)y8 * fp.w8 + x8].cbf != 0;
+      const unsigned m = __ballot_sync(0xffffffffu, coded);
+      if (m && first == 64) first = 32 * h + __ffs(m) - 1;
+    }
+    if (lane == 0) s_first[col] = (uint8_t)first;
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    int pred = fp.qp;
+    for (int col = 0; col < fp.ctb_cols; col++) {
+      const int ctu = row * fp.ctb_cols + col, target = fp.ctu_qp[ctu];
+      const bool coded = s_first[col] < 64;
+      s_pred[col] = (uint8_t)pred;
+      fp.ctu_first[ctu] = s_first[col];
+      fp.ctu_delta[ctu] = (int8_t)(coded ? ((target - pred + 26 + 52) % 52) - 26 : 0);
+      if (coded) pred = target;
+    }
+  }
+  __syncthreads();
+  for (int col = warp; col < fp.ctb_cols; col += 8) {
+    const int target = fp.ctu_qp[row * fp.ctb_cols + col];
+    for (int h = 0; h < 2; h++) {
+      const int z = 32 * h + lane;
+      const int x8 = col * 8 + z_to_x(z), y8 = row * 8 + z_to_y(z);
+      if (x8 < fp.w8 && y8 < fp.h8) cu[(size_t)y8 * fp.w8 + x8].qp = (uint8_t)(z < s_first[col] ? s_pred[col] : target);
+    }
   }
 }
 
 }  // namespace
+
+cudaError_t launch_cu_qps(const FrameParams &fp, CuInfo *cu, cudaStream_t s)
+{
+  if (!fp.ctu_qp || fp.ctb_cols > kMaxCtbCols) return cudaErrorInvalidValue;
+  k_cu_qps<<<fp.ctb_rows, 256, 0, s>>>(fp, cu);
+  return cudaGetLastError();
+}
 
 cudaError_t launch_deblock(const FrameParams &fp, uint8_t *rec, const CuInfo *cu, cudaStream_t s)
 {

@@ -66,7 +66,7 @@ struct Sps {
 };
 struct Pps {
   bool valid = false;
-  int init_qp = 26, deblock_disabled = 0, loop_across_slices = 0, deblock_ctrl = 0;
+  int init_qp = 26, deblock_disabled = 0, loop_across_slices = 0, deblock_ctrl = 0, qp_delta = 0;
 };
 
 const uint8_t kChromaQpD[58] = {
@@ -81,7 +81,7 @@ const uint8_t kChromaQpD[58] = {
 struct DecSlot {
   cudaStream_t stream = nullptr;
   cudaEvent_t ev_parsed = nullptr;
-  uint8_t *d_data = nullptr, *d_small = nullptr;
+  uint8_t *d_data = nullptr, *d_small = nullptr, *d_ctu_qp = nullptr;
   CuInfo *d_cu = nullptr;
   int16_t *d_levels = nullptr;
   uint8_t *h_data = nullptr, *h_out = nullptr;
@@ -119,6 +119,7 @@ struct Decoder {
       if (s.stream) cudaStreamSynchronize(s.stream);
       if (s.d_data) cudaFree(s.d_data);
       if (s.d_small) cudaFree(s.d_small);
+      if (s.d_ctu_qp) cudaFree(s.d_ctu_qp);
       if (s.d_cu) cudaFree(s.d_cu);
       if (s.d_levels) cudaFree(s.d_levels);
       if (s.h_data) cudaFreeHost(s.h_data);
@@ -142,7 +143,7 @@ struct Decoder {
     release();
     fp.w = w; fp.h = h; fp.w8 = w / 8; fp.h8 = h / 8;
     fp.ctb_cols = (w + kCtb - 1) / kCtb; fp.ctb_rows = (h + kCtb - 1) / kCtb;
-    fp.deblock = 1; fp.search_range = 8; fp.lambda_q4 = 0;
+    fp.deblock = 1; fp.search_range = 8; fp.lambda_q4 = 0; fp.ctu_qp = nullptr; fp.ctu_delta = nullptr; fp.ctu_first = nullptr;
     frame_bytes = (size_t)w * h * 3 / 2;
     data_cap = frame_bytes * 2 + 65536;
     const int rows = fp.ctb_rows;
@@ -165,6 +166,7 @@ struct Decoder {
       if (!cuda_ok(cudaEventCreateWithFlags(&s.ev_parsed, cudaEventDisableTiming), "cudaEventCreate")) return false;
       if (!cuda_ok(cudaMalloc((void **)&s.d_data, data_cap), "cudaMalloc")) return false;
       if (!cuda_ok(cudaMalloc((void **)&s.d_small, small_bytes), "cudaMalloc")) return false;
+      if (!cuda_ok(cudaMalloc((void **)&s.d_ctu_qp, (size_t)fp.ctb_cols * fp.ctb_rows), "cudaMalloc")) return false;
       if (!cuda_ok(cudaMalloc((void **)&s.d_cu, sizeof(CuInfo) * fp.w8 * fp.h8), "cudaMalloc")) return false;
       if (!cuda_ok(cudaMalloc((void **)&s.d_levels, frame_bytes * sizeof(int16_t)), "cudaMalloc")) return false;
       if (!cuda_ok(cudaMallocHost((void **)&s.h_out, frame_bytes), "cudaMallocHost")) return false;
@@ -237,7 +239,8 @@ struct Decoder {
     int init_qp = 26 + b.se();
     if (b.u(1)) { set_error("decoder: constrained intra prediction is not supported"); return false; }
     if (b.u(1)) { set_error("decoder: transform skip is not supported"); return false; }
-    if (b.u(1)) { set_error("decoder: cu_qp_delta is not supported"); return false; }
+    const int qp_delta = (int)b.u(1);
+    if (qp_delta && b.ue() != 0) { set_error("decoder: quantisation groups smaller than the CTU are not supported"); return false; }
     if (b.se() != 0 || b.se() != 0) { set_error("decoder: chroma QP offsets are not supported"); return false; }
     if (b.u(1)) { set_error("decoder: slice chroma QP offsets are not supported"); return false; }
     if (b.u(1) || b.u(1)) { set_error("decoder: weighted prediction is not supported"); return false; }
@@ -257,7 +260,7 @@ struct Decoder {
     if (b.ue() != 0) { set_error("decoder: parallel merge level > 2 is not supported"); return false; }
     if (b.u(1)) { set_error("decoder: slice header extensions are not supported"); return false; }
     if (b.bad) { set_error("decoder: malformed PPS"); return false; }
-    pps.valid = true; pps.init_qp = init_qp;
+    pps.valid = true; pps.init_qp = init_qp; pps.qp_delta = qp_delta;
     return true;
   }
 
@@ -338,6 +341,7 @@ struct Decoder {
 
     sl.fp = fp;
     sl.fp.qp = qp; sl.fp.qp_c = kChromaQpD[qp]; sl.fp.is_idr = slice_type == 2 ? 1 : 0; sl.fp.deblock = deblock;
+    sl.fp.ctu_qp = pps.qp_delta ? sl.d_ctu_qp : nullptr; sl.fp.ctu_delta = nullptr; sl.fp.ctu_first = nullptr;
     sl.pts = pts;
     int *sync_flag = (int *)(sl.d_small + off_flag), *progress = (int *)(sl.d_small + off_prog);
     int *status = (int *)(sl.d_small + off_status);
@@ -369,9 +373,9 @@ struct Decoder {
     if (sl.h_status[0] != 0) {
       static const char *const why[] = {"", "escape code too long", "intra CU in a P slice", "partition other than 2Nx2N", "mvd too long",
         "NxN intra partition", "intra chroma mode other than derived", "64x64 CU with residual", "end_of_slice_segment_flag mismatch",
-        "end_of_subset_one_bit missing", "intra CU size other than 16x16 (8x8 at the picture edge)"};
+        "end_of_subset_one_bit missing", "intra CU size other than 16x16 (8x8 at the picture edge)", "cu_qp_delta out of range"};
       int c = sl.h_status[0];
-      set_error("decoder: unsupported or corrupt slice data (%s)", c > 0 && c <= 10 ? why[c] : "unknown");
+      set_error("decoder: unsupported or corrupt slice data (%s)", c > 0 && c <= 11 ? why[c] : "unknown");
       have_ref = 0;
       return -1;
     }

@@ -11,6 +11,28 @@ namespace b200 {
 __device__ __forceinline__ int clip3(int lo, int hi, int v) { return min(max(v, lo), hi); }
 __device__ __forceinline__ int clip8(int v) { return min(max(v, 0), 255); }
 
+// Per-CTU quantiser (cu_qp_delta / ROI): tables the host otherwise folds into FrameParams.
+static __constant__ uint16_t c_lambda_q4_tab[52] = {   // round(16 * sqrt(0.57 * 2^((qp-12)/3)))
+  3, 3, 4, 4, 5, 5, 6, 7, 8, 9, 10, 11, 12, 14, 15, 17, 19, 22, 24, 27, 30, 34, 38, 43, 48, 54, 61, 68,
+  77, 86, 97, 108, 122, 137, 153, 172, 193, 217, 244, 273, 307, 344, 387, 434, 487, 547, 614, 689, 773,
+  868, 974, 1093};
+static __constant__ uint8_t c_chroma_qp_tab[52] = {     // Table 8-10, cQpPicOffset = 0
+  0, 1, 2, 3, 4, 5, 6, 7, 8, 9, 10, 11, 12, 13, 14, 15, 16, 17, 18, 19, 20, 21, 22, 23, 24, 25, 26, 27, 28, 29,
+  29, 30, 31, 32, 33, 33, 34, 34, 35, 35, 36, 36, 37, 37, 38, 39, 40, 41, 42, 43, 44, 45};
+// luma QP / chroma QP / SAD-domain lambda of the CTU that holds luma sample (x, y)
+__device__ __forceinline__ int qp_at(const FrameParams &fp, int x, int y)
+{
+  return fp.ctu_qp ? fp.ctu_qp[(y >> kCtbLog2) * fp.ctb_cols + (x >> kCtbLog2)] : fp.qp;
+}
+__device__ __forceinline__ int qp_c_at(const FrameParams &fp, int x, int y)
+{
+  return fp.ctu_qp ? c_chroma_qp_tab[qp_at(fp, x, y)] : fp.qp_c;
+}
+__device__ __forceinline__ int lambda_q4_at(const FrameParams &fp, int x, int y)
+{
+  return fp.ctu_qp ? c_lambda_q4_tab[qp_at(fp, x, y)] : fp.lambda_q4;
+}
+
 // sum of absolute differences of four packed bytes, accumulated (one VABSDIFF4)
 __device__ __forceinline__ unsigned sad4_acc(unsigned a, unsigned b, unsigned acc)
 {

@@ -112,6 +112,8 @@ void Encoder::release()
     if (s.d_rows) cudaFree(s.d_rows);
     if (s.d_recs) cudaFree(s.d_recs);
     if (s.d_small) cudaFree(s.d_small);
+    if (s.d_qpinfo) cudaFree(s.d_qpinfo);
+    if (s.h_ctu_qp) cudaFreeHost(s.h_ctu_qp);
     if (s.d_src) cudaFree(s.d_src);
     if (s.h_src) cudaFreeHost(s.h_src);
     if (s.h_pack) cudaFreeHost(s.h_pack);
@@ -192,6 +194,10 @@ bool Encoder::open(const EncoderConfig &c)
     ENC_CHECK(cudaMalloc((void **)&s.d_rows, (size_t)row_cap * fp.ctb_rows), "cudaMalloc rows");
     ENC_CHECK(cudaMalloc((void **)&s.d_recs, (size_t)fp.ctb_cols * fp.ctb_rows * 64 * kRecUnitCap * sizeof(uint32_t)), "cudaMalloc recs");
     ENC_CHECK(cudaMalloc((void **)&s.d_small, small_bytes), "cudaMalloc small");
+    if (c.qp_delta) {
+      ENC_CHECK(cudaMalloc((void **)&s.d_qpinfo, 3 * (size_t)fp.ctb_cols * fp.ctb_rows), "cudaMalloc qp info");
+      ENC_CHECK(cudaMallocHost((void **)&s.h_ctu_qp, (size_t)fp.ctb_cols * fp.ctb_rows), "cudaMallocHost ctu qp");
+    }
     ENC_CHECK(cudaMemset(s.d_small, 0, small_bytes), "memset small");
     ENC_CHECK(cudaMalloc((void **)&s.d_src, frame_bytes), "cudaMalloc src");
     ENC_CHECK(cudaMallocHost((void **)&s.h_src, frame_bytes), "cudaMallocHost src");
@@ -250,7 +256,9 @@ void Encoder::write_parameter_sets(std::vector<uint8_t> &out) const
     b.put(0, 1); b.put(0, 1); b.put(0, 3); b.put(0, 1); b.put(0, 1);
     b.ue(0); b.ue(0);
     b.se(0);                                 // init_qp_minus26
-    b.put(0, 1); b.put(0, 1); b.put(0, 1);   // constrained intra, transform skip, cu_qp_delta
+    b.put(0, 1); b.put(0, 1);                // constrained intra, transform skip
+    b.put(cfg.qp_delta ? 1 : 0, 1);          // cu_qp_delta_enabled_flag
+    if (cfg.qp_delta) b.ue(0);               // diff_cu_qp_delta_depth: one quantisation group per CTB
     b.se(0); b.se(0);
     b.put(0, 1); b.put(0, 1); b.put(0, 1); b.put(0, 1);
     b.put(0, 1);                             // tiles_enabled_flag
@@ -312,6 +320,14 @@ bool Encoder::submit(FrameSlot &s, const uint8_t *d_i420)
   p.is_idr = idr ? 1 : 0;
   p.qp = cur_qp; p.qp_c = kChromaQp[cur_qp]; p.lambda_q4 = kLambdaQ4[cur_qp];
   uint8_t *rec = d_rec[frame_idx % kRecRing], *ref = d_rec[(frame_idx + kRecRing - 1) % kRecRing];
+  p.ctu_qp = nullptr; p.ctu_delta = nullptr; p.ctu_first = nullptr;
+  if (cfg.qp_delta) {
+    const int ctus = fp.ctb_cols * fp.ctb_rows;
+    for (int i = 0; i < ctus; i++)
+      s.h_ctu_qp[i] = (uint8_t)std::min(std::max(cur_qp + (ctu_dqp.empty() ? 0 : ctu_dqp[i]), 0), 51);
+    p.ctu_qp = s.d_qpinfo; p.ctu_delta = (int8_t *)(s.d_qpinfo + ctus); p.ctu_first = s.d_qpinfo + 2 * ctus;
+    ENC_CHECK(cudaMemcpyAsync(s.d_qpinfo, s.h_ctu_qp, ctus, cudaMemcpyHostToDevice, (idr && cfg.overlap_idr) ? intra_stream : stream), "H2D ctu qp");
+  }
   uint32_t *row_len = (uint32_t *)s.d_small;
   int *sync_flag = (int *)(s.d_small + off_flag), *progress = (int *)(s.d_small + off_prog), *ticket = (int *)(s.d_small + off_ticket);
   unsigned long long *bins = (unsigned long long *)(s.d_small + off_bins);
@@ -346,6 +362,10 @@ bool Encoder::submit(FrameSlot &s, const uint8_t *d_i420)
     ENC_CHECK(launch_inter_modes(p, s.d_cu, stream), "modes launch");
     PROF_END(K_MODES, stream);
     count_launch(3);
+  }
+  if (cfg.qp_delta) {                    // per-CU QPs and the delta each CTU codes (deblocking and binarisation read them)
+    ENC_CHECK(launch_cu_qps(p, s.d_cu, stream), "cu qp launch");
+    count_launch(1);
   }
   ENC_CHECK(cudaEventRecord(ev_ring[frame_idx % kRecRing], stream), "event record");   // done reading the reference
   if (cfg.debug) ENC_CHECK(cudaMemcpyAsync(d_rec_pre, rec, frame_bytes, cudaMemcpyDeviceToDevice, stream), "copy pre-deblock");
@@ -408,6 +428,15 @@ bool Encoder::collect(FrameSlot &s, std::vector<uint8_t> &out)
 }
 
 void Encoder::set_qp(int qp) { cur_qp = std::min(std::max(qp, 0), 51); }
+
+bool Encoder::set_ctu_dqp(const int8_t *dqp, int n)
+{
+  if (!cfg.qp_delta) { set_error("encoder: per-CTU QP offsets need an encoder opened with qp_delta"); return false; }
+  if (!dqp) { ctu_dqp.clear(); return true; }
+  if (n != fp.ctb_cols * fp.ctb_rows) { set_error("encoder: %d QP offsets for %d CTUs", n, fp.ctb_cols * fp.ctb_rows); return false; }
+  ctu_dqp.assign(dqp, dqp + n);
+  return true;
+}
 
 // stream that consumes the next picture's input: the intra stream for an IDR, else the main stream
 cudaStream_t Encoder::input_stream() const
@@ -474,6 +503,23 @@ void *b200_enc_open(int width, int height, int qp, int intra_period, int search_
   c.deblock = deblock; c.debug = debug; c.depth = depth;
   if (!e->open(c)) { delete e; return nullptr; }
   return e;
+}
+
+void *b200_enc_open_roi(int width, int height, int qp, int intra_period, int search_range, int deblock, int debug, int depth)
+{
+  Encoder *e = new Encoder();
+  EncoderConfig c;
+  c.width = width; c.height = height; c.qp = qp; c.intra_period = intra_period; c.search_range = search_range;
+  c.deblock = deblock; c.debug = debug; c.depth = depth; c.qp_delta = 1;
+  if (!e->open(c)) { delete e; return nullptr; }
+  return e;
+}
+
+int b200_enc_set_ctu_dqp(void *h, const int8_t *dqp, int n)
+{
+  Encoder *e = (Encoder *)h;
+  if (!e) { b200::set_error("b200_enc_set_ctu_dqp: bad arguments"); return B200_ERR_ARG; }
+  return e->set_ctu_dqp(dqp, n) ? B200_OK : B200_ERR_ARG;
 }
 
 void b200_enc_close(void *h) { delete (Encoder *)h; }

@@ -19,6 +19,7 @@ struct EncoderConfig {
   int debug = 0;             // keep a copy of the reconstruction before deblocking
   int overlap_idr = 1;       // run an IDR on its own stream, concurrently with the P pictures queued before it
                              // (B200, 1080p GOP 64: 1812 -> 2200 pictures/s)
+  int qp_delta = 0;          // cu_qp_delta_enabled_flag: per-CTU QP offsets (ROI), one quantisation group per CTU
   int depth = 1;             // pictures in flight (Kvazaar's owf + 1): output of picture n is
                              // returned by the call that submits picture n + depth - 1
 };
@@ -31,6 +32,8 @@ struct FrameSlot {
   int16_t *d_levels = nullptr;
   uint8_t *d_rows = nullptr;       // per-row substreams
   uint32_t *d_recs = nullptr;      // bin records (binariser -> arithmetic coder)
+  uint8_t *d_qpinfo = nullptr;     // qp_delta: ctu_qp | ctu_delta | ctu_first, one byte per CTU each
+  uint8_t *h_ctu_qp = nullptr;     // pinned staging of ctu_qp
   uint8_t *d_small = nullptr;      // row_len | sync flags | progress | ticket | bins | sync contexts
   uint8_t *d_src = nullptr;        // device copy of a host-supplied picture
   uint8_t *h_src = nullptr;        // pinned staging of the input
@@ -61,6 +64,9 @@ class Encoder {
   int pending() const { return (int)inflight.size(); }
   // QP of the pictures submitted from now on (frame-level rate control hook)
   void set_qp(int qp);
+  // per-CTU QP offsets (raster, ctb_cols*ctb_rows) of the pictures submitted from now on; null clears
+  bool set_ctu_dqp(const int8_t *dqp, int n);
+  std::vector<int8_t> ctu_dqp;
   int qp() const { return cur_qp; }
 
   EncoderConfig cfg;

@@ -48,6 +48,7 @@ k_me_ctu(FrameParams fp, const uint8_t *__restrict__ src, const uint8_t *__restr
   const int ctb_x = blockIdx.x % fp.ctb_cols, ctb_y = blockIdx.x / fp.ctb_cols;
   const int cx = ctb_x * kCtb, cy = ctb_y * kCtb;
   const int t = threadIdx.x;
+  const int lambda_q4 = lambda_q4_at(fp, cx, cy);
 
   load_window(ref, fp.w, fp.h, cx - M, cy - M, WS, WSW, s_ref);
   for (int i = t; i < 64 * 16; i += kThreads) {
@@ -57,7 +58,7 @@ k_me_ctu(FrameParams fp, const uint8_t *__restrict__ src, const uint8_t *__restr
   if (t < 64) { sh.key8[t] = 0xffffffffu; for (int k = 0; k < 8; k++) sh.acc8[t][k] = 0; }
   for (int c = t; c < (2 * R + 1) * (2 * R + 1); c += kThreads) {
     int dy = c / (2 * R + 1) - R, dx = c - (dy + R) * (2 * R + 1) - R;
-    sh.pen[c] = (unsigned short)mv_penalty(fp.lambda_q4, dx * 4, dy * 4);
+    sh.pen[c] = (unsigned short)mv_penalty(lambda_q4, dx * 4, dy * 4);
   }
   if (t < 16) sh.key16[t] = 0xffffffffu;
   if (t < 4) sh.key32[t] = 0xffffffffu;
@@ -125,7 +126,7 @@ k_me_ctu(FrameParams fp, const uint8_t *__restrict__ src, const uint8_t *__restr
   __syncthreads();
 
   // ---- bottom-up partition decision ----
-  const unsigned ovh = (unsigned)((fp.lambda_q4 * kCuOverheadBits) >> 4);
+  const unsigned ovh = (unsigned)((lambda_q4 * kCuOverheadBits) >> 4);
   if (t < 16) {
     unsigned sum8 = 0;
     for (int i = 0; i < 4; i++) {
@@ -200,7 +201,7 @@ k_me_ctu(FrameParams fp, const uint8_t *__restrict__ src, const uint8_t *__restr
           const int ox = (k < 3 ? k - 1 : (k == 3 ? -1 : (k == 4 ? 1 : k - 6)));
           const int oy = k < 3 ? -1 : (k < 5 ? 0 : 1);
           const int mx = sh.cmx[t] + ox * step, my = sh.cmy[t] + oy * step;
-          unsigned cost = sh.acc8[t][k] + mv_penalty(fp.lambda_q4, mx, my);
+          unsigned cost = sh.acc8[t][k] + mv_penalty(lambda_q4, mx, my);
           if (cost < sh.best[t]) { sh.best[t] = cost; sh.mvx[t] = (short)mx; sh.mvy[t] = (short)my; }
           sh.acc8[t][k] = 0;
         }
@@ -219,7 +220,7 @@ k_me_ctu(FrameParams fp, const uint8_t *__restrict__ src, const uint8_t *__restr
       CuInfo ci;
       ci.mvx = sh.mvx[org]; ci.mvy = sh.mvy[org];
       ci.log2_size = sh.log2[t]; ci.pred_mode = 0; ci.intra_mode = 0; ci.cbf = 0;
-      ci.skip = 0; ci.merge_idx = 0xff; ci.mvp_idx = 0; ci.pad = 0;
+      ci.skip = 0; ci.merge_idx = 0xff; ci.mvp_idx = 0; ci.qp = 0;
       cu[(size_t)y8 * fp.w8 + x8] = ci;
     }
   }
@@ -324,7 +325,7 @@ k_inter_recon(FrameParams fp, const uint8_t *__restrict__ src, const uint8_t *__
     }
     __syncthreads();
     TileGeom g{T, c ? 5 : 6, c ? 2 : 3, cs};
-    TqParams q{c ? fp.qp_c : fp.qp, fp.is_idr};
+    TqParams q{c ? qp_c_at(fp, cx, cy) : qp_at(fp, cx, cy), fp.is_idr};
     if (!kDecode) {
       forward_tq(g, q, s_src, s_pred, sh.org, sh.log2, sh.w, s_a, s_b, sh.nz);
       // levels (s_b) -> HBM, 4 per thread; s_b then becomes the scratch tile of the inverse path

@@ -163,12 +163,12 @@ __device__ void decide_cu(ModeShared &sh, const FrameParams &fp, const uint8_t *
     int bm = 0;
     for (int mode = 0; mode < 35; mode++) {
       int bits = (mode == 0 || mode == 1 || mode == 26) ? 2 : 6;     // fixed prior: the MPM list is unknown here
-      unsigned cost = sh.sad[mode] + (unsigned)((fp.lambda_q4 * bits) >> 4);
+      unsigned cost = sh.sad[mode] + (unsigned)((lambda_q4_at(fp, x0, y0) * bits) >> 4);
       if (cost < best) { best = cost; bm = mode; }
     }
     CuInfo ci;
     ci.mvx = 0; ci.mvy = 0; ci.log2_size = (uint8_t)log2; ci.pred_mode = 1; ci.intra_mode = (uint8_t)bm;
-    ci.cbf = 0; ci.skip = 0; ci.merge_idx = 0xff; ci.mvp_idx = 0; ci.pad = 0;
+    ci.cbf = 0; ci.skip = 0; ci.merge_idx = 0xff; ci.mvp_idx = 0; ci.qp = 0;
     const int n8 = n >> 3;
     for (int j = 0; j < n8; j++)
       for (int i = 0; i < n8; i++) cu[(size_t)((y0 >> 3) + j) * fp.w8 + (x0 >> 3) + i] = ci;
@@ -225,7 +225,7 @@ __device__ void recon_cu(ReconSharedI &sh, const FrameParams &fp, const uint8_t 
   const int pw = p == 0 ? fp.w : fp.w >> 1;
   const size_t poff = p <= 0 ? 0 : ysz + (p == 2 ? ysz / 4 : 0);
   const int bx = p == 0 ? x0 : x0 >> 1, by = p == 0 ? y0 : y0 >> 1;
-  const int qp = p == 0 ? fp.qp : fp.qp_c;
+  const int qp = p == 0 ? qp_at(fp, x0, y0) : qp_c_at(fp, x0, y0);
   const int mode = __ldcg(&cu[(size_t)(y0 >> 3) * fp.w8 + (x0 >> 3)].intra_mode);
   // neighbours: groups of 128 threads gather one plane each (4n+1 <= 65 samples, +1 for the DC sum)
   {

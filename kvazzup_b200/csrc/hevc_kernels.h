@@ -29,6 +29,11 @@ cudaError_t launch_intra_decode(const FrameParams &fp, uint8_t *rec, const int16
 cudaError_t launch_parse(const FrameParams &fp, const uint8_t *data, const uint32_t *bases, CuInfo *cu, int16_t *levels,
                          uint8_t *sync_ctx, int *sync_flag, int *progress, int *status, cudaStream_t s);
 
+// cu_qp_delta (fp.ctu_qp != 0): per-CU luma QP into the cu map, per-CTU coded delta and the CU that
+// codes it into fp.ctu_delta / fp.ctu_first.  After reconstruction (needs the cbf), before
+// deblocking and binarisation.
+cudaError_t launch_cu_qps(const FrameParams &fp, CuInfo *cu, cudaStream_t s);
+
 // in-loop deblocking, in place on `rec` (vertical edges of the whole picture, then horizontal)
 cudaError_t launch_deblock(const FrameParams &fp, uint8_t *rec, const CuInfo *cu, cudaStream_t s);
 

@@ -149,6 +149,9 @@ struct ParseCtx {
   uint32_t *s_ctu;       // [2][64][3]: 8x8 units of the current (cur_buf) and the previous CTU, raster order
   uint32_t *s_above;     // [10][3]: units (cx/8 - 1 .. cx/8 + 8) of the line above the CTU row
   int cx, cy, cur_buf;
+  // cu_qp_delta with one quantisation group per CTU (8.6.1): qp_cur is QpY of the CU being parsed
+  // (the prediction until the CTU's delta is coded), reset to the slice QP at each row start (WPP)
+  int qp_cur, delta_coded;
 };
 
 __device__ __forceinline__ CuInfo load_cu(const ParseCtx &pc, int x, int y)
@@ -320,7 +323,7 @@ __device__ void parse_cu(Reader &r, ParseCtx &pc, int x0, int y0, int log2)
   const int n = 1 << log2;
   CuInfo cu;
   cu.mvx = 0; cu.mvy = 0; cu.log2_size = (uint8_t)log2; cu.pred_mode = 0; cu.intra_mode = 1; cu.cbf = 0;
-  cu.skip = 0; cu.merge_idx = 0xff; cu.mvp_idx = 0; cu.pad = 0;
+  cu.skip = 0; cu.merge_idx = 0xff; cu.mvp_idx = 0; cu.qp = 0;
   bool tu = false;
   if (!fp.is_idr) {
     int ctx = 0;
@@ -429,7 +432,23 @@ __device__ void parse_cu(Reader &r, ParseCtx &pc, int x0, int y0, int log2)
     int cb = dec_bin(r, CTX_CBF_CHROMA), cr = dec_bin(r, CTX_CBF_CHROMA), lu = 1;
     if (cu.pred_mode == 1 || cb || cr) lu = dec_bin(r, CTX_CBF_LUMA + 1);
     cu.cbf = (uint8_t)(lu | (cb << 1) | (cr << 2));
+    if (fp.ctu_qp && cu.cbf && !pc.delta_coded) {
+      // cu_qp_delta_abs (9.3.3.10: prefix TR cMax 5, ctx 0 then ctx 1; suffix EG0) and sign
+      int a = 0;
+      while (a < 5 && dec_bin(r, CTX_CU_QP_DELTA + (a ? 1 : 0))) a++;
+      if (a == 5) {
+        int k = 0, v = 0;
+        while (k < 8 && dec_bypass(r)) { v += 1 << k; k++; }
+        if (k >= 8) { r.err = 11; return; }
+        a += v + (int)dec_bypass_bits(r, k);
+      }
+      const int d = (a && dec_bypass(r)) ? -a : a;
+      if (d < -26 || d > 25) { r.err = 11; return; }
+      pc.qp_cur = (pc.qp_cur + d + 52) % 52;
+      pc.delta_coded = 1;
+    }
   }
+  if (fp.ctu_qp) cu.qp = (uint8_t)pc.qp_cur;
   // publish the cu map entry: shared memory for the CUs that follow in this row, global memory for
   // the row below and the reconstruction kernels (lane u takes unit u of the CU)
   {
@@ -474,7 +493,7 @@ k_parse_rows(FrameParams fp, const uint8_t *__restrict__ data, const uint32_t *_
   for (int i = lane; i < 64; i += 32) s_tab[i] = make_uint2(c_range_lps[i], (uint32_t)c_trans_lps[i] | (i == 0 ? 64u : 0u));
   Reader r;
   r.p = data + bases[row]; r.end = data + bases[row + 1]; r.ctx = s_ctx + lane; r.tab = s_tab; r.err = 0;
-  ParseCtx pc{fp, cu, levels, lane, 0, s_ctu, s_above, 0, row * kCtb, 0};
+  ParseCtx pc{fp, cu, levels, lane, 0, s_ctu, s_above, 0, row * kCtb, 0, fp.qp, 0};
   if (row == 0 || fp.ctb_cols < 2) {
     init_contexts_d(r.ctx, fp.is_idr ? 0 : 1, fp.qp);
   } else {
@@ -513,6 +532,7 @@ k_parse_rows(FrameParams fp, const uint8_t *__restrict__ data, const uint32_t *_
     }
     const int cx = col * kCtb, cy = row * kCtb;
     pc.cx = cx; pc.cur_buf = col & 1;
+    pc.delta_coded = 0;                  // new quantisation group; qp_cur carries over as qPY_PREV
     __syncwarp();
     for (int z = 0; z < 64 && !r.err;) {
       int x0 = cx + 8 * z_to_x(z), y0 = cy + 8 * z_to_y(z);
@@ -542,6 +562,7 @@ k_parse_rows(FrameParams fp, const uint8_t *__restrict__ data, const uint32_t *_
       __syncwarp();
       *(volatile int *)&sync_flag[row] = 1;
     }
+    if (fp.ctu_qp) fp.ctu_qp[row * fp.ctb_cols + col] = (uint8_t)pc.qp_cur;     // what the CTU's residuals are scaled with
     const bool last = row == fp.ctb_rows - 1 && col == fp.ctb_cols - 1;
     int eos = dec_terminate(r);                                        // end_of_slice_segment_flag
     if (eos != (last ? 1 : 0)) r.err = 8;

@@ -162,6 +162,7 @@ int config_parse(kvz_config *cfg, const char *name, const char *value)
   if (!strcmp(name, "set-qp-in-cu")) { if (!parse_bool(value, &v)) return 0; cfg->set_qp_in_cu = v; return 1; }
   if (!strcmp(name, "b200-me-range")) { if (!parse_int(value, &v) || v < 1 || v > 32) return 0; cfg->me_range = v; return 1; }
   if (!strcmp(name, "b200-recon")) { if (!parse_bool(value, &v)) return 0; cfg->return_recon = v; return 1; }
+  if (!strcmp(name, "b200-roi")) { if (!parse_bool(value, &v)) return 0; cfg->roi_enable = v; return 1; }
   if (!strcmp(name, "b200-device")) { if (!parse_int(value, &v)) return 0; cfg->device = v; return 1; }
   for (int i = 0; kIgnored[i]; i++)
     if (!strcmp(name, kIgnored[i])) return 1;
@@ -238,6 +239,7 @@ kvz_encoder *encoder_open(const kvz_config *cfg)
   c.width = cfg->width; c.height = cfg->height; c.qp = cfg->qp; c.intra_period = cfg->intra_period;
   c.search_range = cfg->me_range > 0 ? cfg->me_range : 12;
   c.deblock = cfg->deblock_enable; c.debug = 0; c.depth = cfg->owf + 1;
+  c.qp_delta = (cfg->roi_enable || cfg->set_qp_in_cu) ? 1 : 0;
   if (!e->eng.open(c)) { delete e; return NULL; }
   if (cfg->target_bitrate > 0 && cfg->framerate_num > 0) {
     e->bits_per_frame = (double)cfg->target_bitrate * cfg->framerate_denom / cfg->framerate_num;
@@ -286,6 +288,20 @@ int encoder_encode(kvz_encoder *e, kvz_picture *pic_in, kvz_data_chunk **data_ou
     if (pic_in->width != e->cfg.width || pic_in->height != e->cfg.height || !pic_in->y || !pic_in->u || !pic_in->v) {
       b200::set_error("encoder_encode: picture does not match the configured %dx%d", e->cfg.width, e->cfg.height);
       return 0;
+    }
+    if (e->eng.cfg.qp_delta) {
+      // ROI: Kvazaar reads the delta-QP map at the top-left corner of each LCU (the reference's
+      // overlay code compensates for exactly that, videodrawhelper.cpp:737-739)
+      const int cols = e->eng.fp.ctb_cols, rows = e->eng.fp.ctb_rows;
+      if (pic_in->roi.roi_array && pic_in->roi.width > 0 && pic_in->roi.height > 0 && e->cfg.target_bitrate == 0) {
+        std::vector<int8_t> dqp((size_t)cols * rows);
+        for (int cy = 0; cy < rows; cy++)
+          for (int cx = 0; cx < cols; cx++)
+            dqp[(size_t)cy * cols + cx] = pic_in->roi.roi_array[(size_t)(cy * pic_in->roi.height / rows) * pic_in->roi.width + cx * pic_in->roi.width / cols];
+        e->eng.set_ctu_dqp(dqp.data(), cols * rows);
+      } else {
+        e->eng.set_ctu_dqp(nullptr, 0);
+      }
     }
     const size_t ysz = (size_t)e->cfg.width * e->cfg.height;
     if (pic_in->u == pic_in->y + ysz && pic_in->v == pic_in->u + ysz / 4 && pic_in->stride == pic_in->width) {

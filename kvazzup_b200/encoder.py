@@ -13,14 +13,15 @@ from .capi import B200Error, lib
 
 CU_DTYPE = np.dtype([("mvx", "<i2"), ("mvy", "<i2"), ("log2_size", "u1"), ("pred_mode", "u1"),
                      ("intra_mode", "u1"), ("cbf", "u1"), ("skip", "u1"), ("merge_idx", "u1"),
-                     ("mvp_idx", "u1"), ("pad", "u1")])
+                     ("mvp_idx", "u1"), ("qp", "u1")])
 
 
 class GpuEncoder:
-    def __init__(self, w, h, qp=32, intra_period=64, search_range=8, deblock=1, debug=0, depth=1):
+    def __init__(self, w, h, qp=32, intra_period=64, search_range=8, deblock=1, debug=0, depth=1, qp_delta=0):
         self.l = lib()
         self.w, self.h = w, h
-        self.h_enc = self.l.b200_enc_open(w, h, qp, intra_period, search_range, deblock, debug, depth)
+        opener = self.l.b200_enc_open_roi if qp_delta else self.l.b200_enc_open
+        self.h_enc = opener(w, h, qp, intra_period, search_range, deblock, debug, depth)
         if not self.h_enc:
             raise B200Error("b200_enc_open failed: " + self.l.b200_last_error().decode())
         self.out = np.empty(w * h * 3 + 65536, np.uint8)
@@ -29,6 +30,16 @@ class GpuEncoder:
         if n < 0:
             raise B200Error(f"encode failed ({n}): " + self.l.b200_last_error().decode())
         return self.out[:n].tobytes()
+
+    def set_ctu_dqp(self, dqp):
+        """Per-CTU QP offsets (int8, raster) for the following pictures; None clears.  Needs qp_delta=1."""
+        if dqp is None:
+            rc = self.l.b200_enc_set_ctu_dqp(self.h_enc, None, 0)
+        else:
+            a = np.ascontiguousarray(dqp, dtype=np.int8)
+            rc = self.l.b200_enc_set_ctu_dqp(self.h_enc, C.c_void_p(a.ctypes.data), a.size)
+        if rc != 0:
+            raise B200Error("b200_enc_set_ctu_dqp failed: " + self.l.b200_last_error().decode())
 
     def encode(self, i420: np.ndarray) -> bytes:
         assert i420.dtype == np.uint8 and i420.size == self.w * self.h * 3 // 2

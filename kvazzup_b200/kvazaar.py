@@ -29,7 +29,7 @@ class KvzConfig(C.Structure):
         "width", "height", "framerate_num", "framerate_denom", "qp", "intra_period", "vps_period", "wpp", "owf",
         "threads", "target_bitrate", "rc_algorithm", "lossless", "mv_constraint", "set_qp_in_cu", "hash",
         "deblock_enable", "sao_type", "tiles_width_count", "tiles_height_count", "slices", "vaq", "scaling_list",
-        "gop_lowdelay", "gop_len", "me_range", "return_recon", "device")] + [("preset", C.c_char * 16)]
+        "gop_lowdelay", "gop_len", "me_range", "return_recon", "device", "roi_enable")] + [("preset", C.c_char * 16)]
 
 
 class KvzRoi(C.Structure):
@@ -199,10 +199,12 @@ class KvazaarFilter:
         return out
 
     # kvazaarfilter.cpp:374-450
-    def feed_input(self, i420: np.ndarray, drain: bool = True):
+    def feed_input(self, i420: np.ndarray, drain: bool = True, roi: np.ndarray | None = None):
         """Returns the list of access units that became available (0 or more).  drain=True is the
         reference's loop (encoder_encode(pic=NULL) after every output, kvazaarfilter.cpp:440-449);
-        drain=False is the one-line variant of INTEGRATION.md that keeps the pipeline full."""
+        drain=False is the one-line variant of INTEGRATION.md that keeps the pipeline full.
+        roi: int8 delta-QP map (rows x cols, any resolution; the ROI filters make it per pixel),
+        attached like vInfo->roi when the bitrate is 0 (:423-431)."""
         c = self.config.contents
         w, h = c.width, c.height
         assert i420.size == w * h * 3 // 2
@@ -214,6 +216,13 @@ class KvazaarFilter:
         C.memmove(pic.contents.v, src.ctypes.data + w * h + w * h // 4, w * h // 4)
         pic.contents.pts = self.pts
         self.pts += 1
+        if c.target_bitrate == 0 and roi is not None:
+            self._roi = np.ascontiguousarray(roi, dtype=np.int8)          # caller-owned until the output arrives
+            pic.contents.roi.width, pic.contents.roi.height = self._roi.shape[1], self._roi.shape[0]
+            pic.contents.roi.roi_array = self._roi.ctypes.data_as(C.POINTER(C.c_int8))
+        else:
+            pic.contents.roi.width = pic.contents.roi.height = 0
+            pic.contents.roi.roi_array = None
         return self._drain(pic, drain)
 
     def flush(self):

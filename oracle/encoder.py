@@ -10,15 +10,15 @@ from .sigs import OrcCu, OrcEncCfg
 
 CU_DTYPE = np.dtype([("mvx", "<i2"), ("mvy", "<i2"), ("log2_size", "u1"), ("pred_mode", "u1"),
                      ("intra_mode", "u1"), ("cbf", "u1"), ("skip", "u1"), ("merge_idx", "u1"),
-                     ("mvp_idx", "u1"), ("pad", "u1")])
+                     ("mvp_idx", "u1"), ("qp", "u1")])
 assert CU_DTYPE.itemsize == C.sizeof(OrcCu) == 12
 
 
 class OracleEncoder:
-    def __init__(self, w, h, qp=32, intra_period=64, search_range=8, deblock=1, hash_sei=0):
+    def __init__(self, w, h, qp=32, intra_period=64, search_range=8, deblock=1, hash_sei=0, qp_delta=0):
         self.lib = load()
         self.w, self.h = w, h
-        cfg = OrcEncCfg(w, h, qp, intra_period, search_range, deblock, hash_sei)
+        cfg = OrcEncCfg(w, h, qp, intra_period, search_range, deblock, hash_sei, qp_delta)
         self.h_enc = self.lib.orc_enc_open(C.byref(cfg))
         if not self.h_enc:
             raise ValueError("orc_enc_open rejected the configuration")
@@ -32,6 +32,17 @@ class OracleEncoder:
         if n < 0:
             raise RuntimeError(f"orc_enc_encode failed ({n})")
         return self.out[:n].tobytes()
+
+    def set_ctu_dqp(self, dqp):
+        """Per-CTU QP offsets (int8, ctb_cols*ctb_rows, raster) for the following pictures; None clears."""
+        if dqp is None:
+            rc = self.lib.orc_enc_set_ctu_dqp(self.h_enc, None)
+        else:
+            a = np.ascontiguousarray(dqp, dtype=np.int8)
+            assert a.size == ((self.w + 63) // 64) * ((self.h + 63) // 64)
+            rc = self.lib.orc_enc_set_ctu_dqp(self.h_enc, C.c_void_p(a.ctypes.data))
+        if rc != 0:
+            raise ValueError("set_ctu_dqp needs qp_delta=1")
 
     def _view(self, ptr, dtype, count):
         t = (C.c_uint8 * (count * np.dtype(dtype).itemsize)).from_address(ptr)

@@ -38,7 +38,9 @@ struct orc_encoder {
   orc_enc_cfg_t cfg;
   int w, h, cw, ch, w8, h8, ctb_cols, ctb_rows;
   int frame_idx, poc, is_idr;
-  int lambda_q4;
+  int8_t *ctu_dqp;               /* per-CTU QP offset (ROI), zeros by default */
+  int8_t *ctu_delta;             /* CuQpDeltaVal coded in each CTU (0 if none) */
+  uint8_t *ctu_first;            /* z-index (8x8 units) of the first CU with a coded residual, 64 = none */
   const uint8_t *src;
   uint8_t *rec, *rec_pre;        /* packed I420 */
   uint8_t *refpad[3];            /* padded previous reconstruction */
@@ -74,7 +76,9 @@ orc_encoder_t *orc_enc_open(const orc_enc_cfg_t *cfg)
   e->w = cfg->width; e->h = cfg->height; e->cw = e->w / 2; e->ch = e->h / 2;
   e->w8 = e->w / 8; e->h8 = e->h / 8;
   e->ctb_cols = (e->w + CTB - 1) / CTB; e->ctb_rows = (e->h + CTB - 1) / CTB;
-  e->lambda_q4 = lambda_q4_tab[cfg->qp];
+  e->ctu_dqp = (int8_t *)calloc((size_t)e->ctb_cols * e->ctb_rows, 1);
+  e->ctu_delta = (int8_t *)calloc((size_t)e->ctb_cols * e->ctb_rows, 1);
+  e->ctu_first = (uint8_t *)calloc((size_t)e->ctb_cols * e->ctb_rows, 1);
   size_t fsz = (size_t)e->w * e->h * 3 / 2;
   e->rec = (uint8_t *)calloc(fsz, 1);
   e->rec_pre = (uint8_t *)calloc(fsz, 1);
@@ -93,6 +97,7 @@ orc_encoder_t *orc_enc_open(const orc_enc_cfg_t *cfg)
 
 void orc_enc_close(orc_encoder_t *e)
 {
+  if (e) { free(e->ctu_dqp); free(e->ctu_delta); free(e->ctu_first); }
   if (!e) return;
   free(e->rec); free(e->rec_pre);
   for (int c = 0; c < 3; c++) free(e->refpad[c]);
@@ -127,6 +132,21 @@ const orc_cu_t *orc_enc_cu_map(const orc_encoder_t *e) { return e->cu; }
 const int16_t *orc_enc_levels(const orc_encoder_t *e) { return e->levels; }
 int orc_enc_last_was_idr(const orc_encoder_t *e) { return e->is_idr; }
 unsigned long long orc_enc_bins(const orc_encoder_t *e) { return e->bins; }
+/* QP of the CTU that holds luma sample (x, y): the slice QP plus the ROI offset */
+static int ctu_qp(const orc_encoder_t *e, int x, int y)
+{
+  if (!e->cfg.qp_delta) return e->cfg.qp;
+  return clip3i(0, 51, e->cfg.qp + e->ctu_dqp[(y / CTB) * e->ctb_cols + x / CTB]);
+}
+static int lambda_at(const orc_encoder_t *e, int x, int y) { return lambda_q4_tab[ctu_qp(e, x, y)]; }
+
+int orc_enc_set_ctu_dqp(orc_encoder_t *e, const int8_t *dqp)
+{
+  if (!e || !e->cfg.qp_delta) return -1;
+  if (dqp) memcpy(e->ctu_dqp, dqp, (size_t)e->ctb_cols * e->ctb_rows);
+  else memset(e->ctu_dqp, 0, (size_t)e->ctb_cols * e->ctb_rows);
+  return 0;
+}
 
 /* ------------------------------------------------------------------------------------------ */
 /* residual path shared by intra and inter: src - pred -> DCT -> Q -> (IQ -> IDCT) -> recon     */
@@ -139,7 +159,8 @@ static int recon_tb(orc_encoder_t *e, int c, int x0, int y0, int log2n, const ui
   uint8_t *rec = plane(e->rec, e->w, e->h, c);
   int16_t *lv = lplane(e->levels, e->w, e->h, c);
   int16_t resid[32 * 32], coef[32 * 32], level[32 * 32];
-  const int qp = c ? orc_chroma_qp(e->cfg.qp) : e->cfg.qp;
+  const int qpy = c ? ctu_qp(e, x0 * 2, y0 * 2) : ctu_qp(e, x0, y0);
+  const int qp = c ? orc_chroma_qp(qpy) : qpy;
   (void)ph;
   for (int y = 0; y < n; y++)
     for (int x = 0; x < n; x++)
@@ -229,7 +250,7 @@ static void intra_cu(orc_encoder_t *e, int x0, int y0, int log2)
     orc_intra_predict(refs, log2, mode, 0, pred, n);
     uint32_t sad = orc_sad(src + (size_t)y0 * e->w + x0, e->w, pred, n, n, n);
     int bits = (mode == 0 || mode == 1 || mode == 26) ? 2 : 6;
-    uint32_t cost = sad + (uint32_t)((e->lambda_q4 * bits) >> 4);
+    uint32_t cost = sad + (uint32_t)((lambda_at(e, x0, y0) * bits) >> 4);
     if (cost < best_cost) { best_cost = cost; best_mode = mode; }
   }
   gather_refs(e, 0, x0, y0, n, refs);
@@ -274,9 +295,9 @@ static int mv_comp_bits(int v)
   while (t != 1) { t >>= 1; len += 2; }
   return len;
 }
-static inline uint32_t mv_penalty(const orc_encoder_t *e, int mvx, int mvy)
+static inline uint32_t mv_penalty(int lambda_q4, int mvx, int mvy)
 {
-  return (uint32_t)((e->lambda_q4 * (mv_comp_bits(mvx) + mv_comp_bits(mvy))) >> 4);
+  return (uint32_t)((lambda_q4 * (mv_comp_bits(mvx) + mv_comp_bits(mvy))) >> 4);
 }
 
 static void pad_reference(orc_encoder_t *e)
@@ -309,6 +330,7 @@ typedef struct { uint32_t cost; int dx, dy; } me_best_t;
 static void me_ctu(orc_encoder_t *e, int cx, int cy)
 {
   const int R = e->cfg.search_range;
+  const int lam = lambda_at(e, cx, cy);
   const uint8_t *src = e->src;
   const uint8_t *ref = e->refpad[0];
   const int rs = e->refstride[0];
@@ -318,7 +340,7 @@ static void me_ctu(orc_encoder_t *e, int cx, int cy)
   for (int j = 0; j < 2; j++) for (int i = 0; i < 2; i++) b32[j][i].cost = UINT_MAX;
   for (int dy = -R; dy <= R; dy++)
     for (int dx = -R; dx <= R; dx++) {
-      uint32_t pen = mv_penalty(e, dx * 4, dy * 4);
+      uint32_t pen = mv_penalty(lam, dx * 4, dy * 4);
       uint32_t s8[8][8];
       for (int j = 0; j < 8; j++)
         for (int i = 0; i < 8; i++) {
@@ -345,7 +367,7 @@ static void me_ctu(orc_encoder_t *e, int cx, int cy)
         }
     }
   /* bottom-up partition decision */
-  const uint32_t ovh = (uint32_t)((e->lambda_q4 * CU_OVERHEAD_BITS) >> 4);
+  const uint32_t ovh = (uint32_t)((lam * CU_OVERHEAD_BITS) >> 4);
   uint32_t eff16[4][4];
   uint8_t use16[4][4];
   for (int j = 0; j < 4; j++)
@@ -398,13 +420,14 @@ static void inter_cu(orc_encoder_t *e, int x0, int y0, int log2)
   uint8_t pred[32 * 32], best_pred[32 * 32];
   int bx = cu.mvx, by = cu.mvy;
   mc_luma(e, x0, y0, n, bx, by, best_pred);
-  uint32_t best = orc_sad(src, e->w, best_pred, n, n, n) + mv_penalty(e, bx, by);
+  const int lam = lambda_at(e, x0, y0);
+  uint32_t best = orc_sad(src, e->w, best_pred, n, n, n) + mv_penalty(lam, bx, by);
   for (int step = 2; step >= 1; step--) {
     int cxm = bx, cym = by;
     for (int k = 0; k < 8; k++) {
       int mx = cxm + off[k][0] * step, my = cym + off[k][1] * step;
       mc_luma(e, x0, y0, n, mx, my, pred);
-      uint32_t cost = orc_sad(src, e->w, pred, n, n, n) + mv_penalty(e, mx, my);
+      uint32_t cost = orc_sad(src, e->w, pred, n, n, n) + mv_penalty(lam, mx, my);
       if (cost < best) { best = cost; bx = mx; by = my; memcpy(best_pred, pred, (size_t)n * n); }
     }
   }
@@ -434,6 +457,36 @@ static void inter_frame(orc_encoder_t *e)
 }
 
 /* ------------------------------------------------------------------------------------------ */
+/* luma QP derivation with one quantisation group per CTU (8.6.1, diff_cu_qp_delta_depth = 0).
+ * The left and above quantisation groups lie in other CTBs, so qPY_PRED = qPY_PREV: the slice QP
+ * at the start of every CTU row (WPP), else the QP of the last CU of the previous CTU.  Inside a
+ * CTU, CUs before the first one with a coded residual keep the predicted QP (CuQpDeltaVal is still
+ * 0 there); that CU codes the delta and it and all later CUs have the CTU's target QP. */
+static void derive_cu_qps(orc_encoder_t *e)
+{
+  for (int r = 0; r < e->ctb_rows; r++) {
+    int pred = e->cfg.qp;
+    for (int cidx = 0; cidx < e->ctb_cols; cidx++) {
+      const int ctu = r * e->ctb_cols + cidx, target = ctu_qp(e, cidx * CTB, r * CTB);
+      int first = 64;
+      for (int z = 0; z < 64 && first == 64; z++) {
+        int x8 = cidx * 8, y8 = r * 8;
+        for (int b = 0; b < 3; b++) { x8 += ((z >> (2 * b)) & 1) << b; y8 += ((z >> (2 * b + 1)) & 1) << b; }
+        if (x8 < e->w8 && y8 < e->h8 && e->cu[(size_t)y8 * e->w8 + x8].cbf) first = z;
+      }
+      for (int z = 0; z < 64; z++) {
+        int x8 = cidx * 8, y8 = r * 8;
+        for (int b = 0; b < 3; b++) { x8 += ((z >> (2 * b)) & 1) << b; y8 += ((z >> (2 * b + 1)) & 1) << b; }
+        if (x8 < e->w8 && y8 < e->h8) e->cu[(size_t)y8 * e->w8 + x8].qp = (uint8_t)(z < first ? pred : target);
+      }
+      e->ctu_first[ctu] = (uint8_t)first;
+      e->ctu_delta[ctu] = (int8_t)(first < 64 ? ((target - pred + 26 + 52) % 52) - 26 : 0);
+      if (first < 64) pred = target;
+    }
+  }
+}
+
+/* ------------------------------------------------------------------------------------------ */
 /* deblocking (8.7.2): all vertical edges of the picture, then all horizontal edges             */
 
 static int edge_bs(const orc_cu_t *p, const orc_cu_t *q)
@@ -446,7 +499,6 @@ static int edge_bs(const orc_cu_t *p, const orc_cu_t *q)
 static void deblock_frame(orc_encoder_t *e)
 {
   uint8_t *Y = e->rec, *U = plane(e->rec, e->w, e->h, 1), *V = plane(e->rec, e->w, e->h, 2);
-  const int qp = e->cfg.qp;
   for (int dir = 0; dir < 2; dir++)                    /* 0: vertical edges, 1: horizontal edges */
 #pragma omp parallel for schedule(static)
     for (int y8 = 0; y8 < e->h8; y8++)
@@ -458,6 +510,7 @@ static void deblock_frame(orc_encoder_t *e)
         int bs = edge_bs(p, q);
         if (!bs) continue;
         int x = x8 * 8, y = y8 * 8;
+        const int qp = e->cfg.qp_delta ? (p->qp + q->qp + 1) >> 1 : e->cfg.qp;     /* QpL (8.7.2.5.3) */
         for (int seg = 0; seg < 2; seg++) {
           if (dir == 0) orc_deblock_luma_segment(Y + (size_t)(y + 4 * seg) * e->w + x, 1, e->w, bs, qp);
           else          orc_deblock_luma_segment(Y + (size_t)y * e->w + x + 4 * seg, e->w, 1, bs, qp);
@@ -573,6 +626,27 @@ static void code_transform_unit(orc_encoder_t *e, orc_cabac_t *c, int x0, int y0
   orc_cabac_bin(c, CTX_CBF_CHROMA + 0, cb);
   orc_cabac_bin(c, CTX_CBF_CHROMA + 0, cr);
   if (cu->pred_mode == 1 || cb || cr) orc_cabac_bin(c, CTX_CBF_LUMA + 1, lu);
+  if (e->cfg.qp_delta && cu->cbf) {
+    /* transform_unit (7.3.8.10): cu_qp_delta_abs / sign once per quantisation group, in the first
+     * TU with a coded block flag.  Binarisation 9.3.3.10: prefix TR cMax 5 (ctx 0, then ctx 1),
+     * suffix EG0 bypass. */
+    const int ctu = (y0 / CTB) * e->ctb_cols + x0 / CTB;
+    int x8 = (x0 / 8) & 7, y8 = (y0 / 8) & 7, z = 0;
+    for (int b = 0; b < 3; b++) z |= (((x8 >> b) & 1) << (2 * b)) | (((y8 >> b) & 1) << (2 * b + 1));
+    if (z == e->ctu_first[ctu]) {
+      const int d = e->ctu_delta[ctu], a = abs(d);
+      const int pre = a < 5 ? a : 5;
+      for (int i = 0; i < pre; i++) orc_cabac_bin(c, CTX_CU_QP_DELTA + (i ? 1 : 0), 1);
+      if (pre < 5) orc_cabac_bin(c, CTX_CU_QP_DELTA + (pre ? 1 : 0), 0);
+      else {
+        int v = a - 5, k = 0;
+        while (v >= (1 << k)) { orc_cabac_bypass(c, 1); v -= 1 << k; k++; }
+        orc_cabac_bypass(c, 0);
+        if (k) orc_cabac_bypass_bits(c, (uint32_t)v, k);
+      }
+      if (a) orc_cabac_bypass(c, d < 0);
+    }
+  }
   if (lu)
     orc_code_residual(c, e->levels + (size_t)y0 * e->w + x0, e->w, log2, 0,
                       scan_idx_for(cu->pred_mode, cu->intra_mode, log2, 0));
@@ -780,7 +854,8 @@ static size_t write_parameter_sets(const orc_encoder_t *e, uint8_t *out, size_t 
   orc_bits_se(&b, 0);                 /* init_qp_minus26 */
   orc_bits_put(&b, 0, 1);             /* constrained_intra_pred_flag */
   orc_bits_put(&b, 0, 1);             /* transform_skip_enabled_flag */
-  orc_bits_put(&b, 0, 1);             /* cu_qp_delta_enabled_flag */
+  orc_bits_put(&b, e->cfg.qp_delta ? 1 : 0, 1);     /* cu_qp_delta_enabled_flag */
+  if (e->cfg.qp_delta) orc_bits_ue(&b, 0);          /* diff_cu_qp_delta_depth: one quantisation group per CTB */
   orc_bits_se(&b, 0); orc_bits_se(&b, 0);       /* pps_cb_qp_offset, pps_cr_qp_offset */
   orc_bits_put(&b, 0, 1);             /* pps_slice_chroma_qp_offsets_present_flag */
   orc_bits_put(&b, 0, 1);             /* weighted_pred_flag */
@@ -960,6 +1035,7 @@ int orc_enc_encode(orc_encoder_t *e, const uint8_t *i420, uint8_t *out, int cap)
     inter_frame(e);
   }
   memcpy(e->rec_pre, e->rec, fsz);
+  if (e->cfg.qp_delta) derive_cu_qps(e);
   if (e->cfg.deblock) deblock_frame(e);
   size_t o = 0, n = 0;
   if (e->is_idr) o += write_parameter_sets(e, out, (size_t)cap);

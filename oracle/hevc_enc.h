@@ -17,7 +17,7 @@ typedef struct {
   uint8_t skip;            /* filled by the entropy stage */
   uint8_t merge_idx;       /* 0xff = not merged */
   uint8_t mvp_idx;
-  uint8_t pad;
+  uint8_t qp;              /* luma QP of the CU when cu_qp_delta is enabled (8.6.1), else 0 */
 } orc_cu_t;
 
 typedef struct {
@@ -27,6 +27,7 @@ typedef struct {
   int search_range;        /* full-sample search range (+-), 1..32 */
   int deblock;             /* 1 = in-loop deblocking on */
   int hash_sei;            /* 1 = append MD5 decoded-picture-hash SEI (test use) */
+  int qp_delta;            /* 1 = cu_qp_delta_enabled_flag, one quantisation group per CTU (ROI) */
 } orc_enc_cfg_t;
 
 typedef struct orc_encoder orc_encoder_t;
@@ -39,6 +40,9 @@ void orc_enc_close(orc_encoder_t *e);
 /* Encode one packed I420 frame; writes one Annex-B access unit (4-byte start codes;
  * VPS+SPS+PPS precede every IDR).  Returns the AU size in bytes or <0 (-needed if cap is short). */
 int orc_enc_encode(orc_encoder_t *e, const uint8_t *i420, uint8_t *out, int cap);
+/* Per-CTU QP offsets for the pictures that follow (ctb_cols*ctb_rows entries, raster; NULL = none).
+ * Needs cfg.qp_delta; CTU QP = clip(qp + dqp, 0, 51). */
+int orc_enc_set_ctu_dqp(orc_encoder_t *e, const int8_t *dqp);
 
 const uint8_t *orc_enc_recon(const orc_encoder_t *e);            /* packed I420, after deblocking */
 const uint8_t *orc_enc_recon_predeblock(const orc_encoder_t *e); /* packed I420, before deblocking */

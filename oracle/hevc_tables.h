@@ -60,7 +60,8 @@ enum {
   CTX_SIG = 68,                 /* 42 */
   CTX_GT1 = 110,                /* 24 */
   CTX_GT2 = 134,                /* 6 */
-  CTX_COUNT = 140
+  CTX_CU_QP_DELTA = 140,        /* 2 */
+  CTX_COUNT = 142
 };
 
 /* init values, [initType 0=I,1=P,2=B][CTX_COUNT]; 154 where the element cannot occur */

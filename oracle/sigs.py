@@ -25,12 +25,12 @@ def bind(lib) -> None:
 class OrcCu(C.Structure):
     _fields_ = [("mvx", C.c_int16), ("mvy", C.c_int16), ("log2_size", C.c_uint8), ("pred_mode", C.c_uint8),
                 ("intra_mode", C.c_uint8), ("cbf", C.c_uint8), ("skip", C.c_uint8), ("merge_idx", C.c_uint8),
-                ("mvp_idx", C.c_uint8), ("pad", C.c_uint8)]
+                ("mvp_idx", C.c_uint8), ("qp", C.c_uint8)]
 
 
 class OrcEncCfg(C.Structure):
     _fields_ = [("width", i), ("height", i), ("qp", i), ("intra_period", i), ("search_range", i),
-                ("deblock", i), ("hash_sei", i)]
+                ("deblock", i), ("hash_sei", i), ("qp_delta", i)]
 
 
 SIGS.update({
@@ -39,6 +39,7 @@ SIGS.update({
     "orc_set_threads": (None, [i]),
     "orc_max_threads": (i, []),
     "orc_enc_encode": (i, [v, v, v, i]),
+    "orc_enc_set_ctu_dqp": (i, [v, v]),
     "orc_enc_recon": (v, [v]),
     "orc_enc_recon_predeblock": (v, [v]),
     "orc_enc_cu_map": (v, [v]),

@@ -65,6 +65,64 @@ def test_oracle_streams_decode_bit_exactly_in_ffmpeg(kind, w, h, n, qp, kw):
         assert np.array_equal(fr, recs[i]), f"frame {i}: decoder output differs from encoder reconstruction"
 
 
+def roi_pattern(w, h, t, kind):
+    """Per-CTU QP offsets: a moving low-QP window on a high-QP background, or extreme random values."""
+    cols, rows = (w + 63) // 64, (h + 63) // 64
+    if kind == "random":
+        rng = np.random.default_rng(7 + t)
+        return rng.integers(-30, 31, size=cols * rows).astype(np.int8)       # clipped to 0..51 by the encoder
+    d = np.full((rows, cols), 6, np.int8)
+    d[(t // 2) % rows, :] = -8
+    d[:, (t + 1) % cols] = -3
+    return d.ravel()
+
+
+@needs_ff
+@pytest.mark.parametrize("kind,w,h,n,qp,roi,kw", [
+    ("camera", 192, 136, 4, 32, "window", {}),
+    ("camera", 416, 240, 6, 27, "window", {"hash_sei": 1, "intra_period": 4}),
+    ("camera", 416, 240, 5, 30, "random", {"hash_sei": 1}),            # deltas beyond +-26 wrap modulo 52
+    ("noise", 256, 136, 3, 25, "random", {}),
+    ("screen", 416, 240, 5, 40, "random", {}),                          # many CTUs with no coded residual: QP prediction chain
+    ("camera", 128, 72, 3, 32, None, {}),                               # flag on, no offsets: delta 0 everywhere
+])
+def test_per_ctu_qp_streams_decode_bit_exactly_in_ffmpeg(kind, w, h, n, qp, roi, kw):
+    """cu_qp_delta (ROI) path: QP prediction, delta binarisation, per-CU QP in dequantisation and
+    deblocking are all normative -- FFmpeg's reconstruction must equal the oracle's."""
+    frames = frames_of(kind, w, h, n)
+    enc = OracleEncoder(w, h, qp=qp, qp_delta=1, **({"intra_period": 0} | kw))
+    aus, recs, qps = [], [], []
+    for t, f in enumerate(frames):
+        if roi:
+            enc.set_ctu_dqp(roi_pattern(w, h, t, roi))
+        aus.append(enc.encode(f))
+        recs.append(enc.recon())
+        qps.append(enc.cu_map()["qp"].copy())
+    enc.close()
+    dec, errs = ffhevc.decode_stream(aus)
+    assert errs == 0 and len(dec) == n
+    for i, (fr, fw, fh) in enumerate(dec):
+        assert np.array_equal(fr, recs[i]), f"frame {i}: decoder output differs from encoder reconstruction"
+    if roi:
+        assert len(np.unique(np.concatenate(qps))) > 2           # the offsets really reached the CUs
+    else:
+        assert all((q == qp).all() for q in qps)
+
+
+def test_per_ctu_qp_changes_rate_where_asked():
+    w, h = 416, 240
+    frames = frames_of("camera", w, h, 3)
+    sizes = {}
+    for name, d in (("flat", 0), ("fine", -10), ("coarse", 10)):
+        enc = OracleEncoder(w, h, qp=30, qp_delta=1, intra_period=0)
+        enc.set_ctu_dqp(np.full(7 * 4, d, np.int8))
+        sizes[name] = sum(len(enc.encode(f)) for f in frames)
+        enc.close()
+    assert sizes["fine"] > sizes["flat"] > sizes["coarse"]
+    with pytest.raises(ValueError):
+        OracleEncoder(w, h, qp=30).set_ctu_dqp(np.zeros(28, np.int8))
+
+
 @needs_ff
 def test_corrupted_hash_is_detected():
     """Guards the guard: the decoder really does check the MD5 SEI."""
