@@ -215,7 +215,7 @@ def run_b200(args):
         step_e2e()
     filt.flush()
     barrier()
-    e2e_steps = max(1, args.steps // 2)
+    e2e_steps = max(1, args.steps)
     t0 = time.perf_counter()
     nb = 0
     for _ in range(e2e_steps):

@@ -54,6 +54,14 @@ unsigned long long b200_enc_last_bins(void *enc);
 int   b200_enc_debug_read(void *enc, int what, void *dst, size_t bytes);
 int   b200_enc_debug_set_reference(void *enc, const uint8_t *i420);
 
+/* ---- K2: SATD primitive -------------------------------------------------------
+ * SATD of every 8x8 block between two 8-bit planes of width x height (multiples of 8), HM / Kvazaar
+ * convention: 8x8 Hadamard of the difference, (sum |h| + 2) >> 2; the SATD of a larger block is the
+ * sum of its 8x8 entries.  out: (width/8)*(height/8) values, raster.  _dev: device pointers,
+ * asynchronous on `stream` (cudaStream_t as void*). */
+int   b200_satd8x8(const uint8_t *a, const uint8_t *b, int width, int height, uint32_t *out);
+int   b200_satd8x8_dev(const uint8_t *d_a, const uint8_t *d_b, int width, int height, uint32_t *d_out, void *stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -22,6 +22,8 @@ SIGNATURES: dict = {
     "b200_enc_last_bins": (C.c_ulonglong, [v]),
     "b200_enc_debug_read": (i, [v, i, v, C.c_size_t]),
     "b200_enc_debug_set_reference": (i, [v, v]),
+    "b200_satd8x8": (i, [v, v, i, i, v]),
+    "b200_satd8x8_dev": (i, [v, v, i, i, v, v]),
     "libOpenHevcInit": (v, [i, i]),
     "libOpenHevcStartDecoder": (i, [v]),
     "libOpenHevcDecode": (i, [v, v, i, C.c_int64]),

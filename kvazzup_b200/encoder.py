@@ -114,3 +114,15 @@ class GpuEncoder:
             self.close()
         except Exception:
             pass
+
+
+def satd8x8(a: np.ndarray, b: np.ndarray, w: int, h: int) -> np.ndarray:
+    """SATD (8x8 Hadamard, HM convention) of every 8x8 block between two w x h planes -> (h/8, w/8) uint32."""
+    a = np.ascontiguousarray(a, dtype=np.uint8)
+    b = np.ascontiguousarray(b, dtype=np.uint8)
+    assert a.size == b.size == w * h
+    out = np.empty((h // 8, w // 8), np.uint32)
+    rc = lib().b200_satd8x8(C.c_void_p(a.ctypes.data), C.c_void_p(b.ctypes.data), w, h, C.c_void_p(out.ctypes.data))
+    if rc != 0:
+        raise B200Error("b200_satd8x8 failed: " + lib().b200_last_error().decode())
+    return out

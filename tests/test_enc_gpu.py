@@ -357,3 +357,27 @@ def test_roi_through_kvz_api_and_pipelining():
     assert got == want_plain
     with pytest.raises(Exception):
         plain.set_ctu_dqp(dqp.ravel())
+
+
+@pytest.mark.parametrize("w,h,kind", [(64, 64, "noise"), (416, 240, "camera"), (1920, 1080, "camera"), (8, 8, "extreme")])
+def test_satd_primitive_matches_oracle(w, h, kind):
+    """K2: 8x8 Hadamard SATD map of two planes equals the oracle's orc_satd block by block."""
+    from kvazzup_b200.encoder import satd8x8
+    from oracle.binding import load as load_oracle
+    from tests.helpers import ptr
+    if kind == "noise":
+        a, b = synth.noise(1, w * h), synth.noise(2, w * h)
+    elif kind == "extreme":
+        a, b = np.full(w * h, 255, np.uint8), np.zeros(w * h, np.uint8)
+        b[::2] = 255
+    else:
+        a, b = synth.camera_i420(w, h, 0)[:w * h].copy(), synth.camera_i420(w, h, 3)[:w * h].copy()
+    got = satd8x8(a, b, w, h)
+    orc = load_oracle()
+    step = 1 if w * h <= 416 * 240 else 7           # the oracle call is per block; sample the big picture
+    for by in range(0, h // 8, step):
+        for bx in range(0, w // 8, step):
+            off = by * 8 * w + bx * 8
+            want = orc.orc_satd(ptr(a[off:]), w, ptr(b[off:]), w, 8, 8)
+            assert got[by, bx] == want, (bx, by)
+    assert satd8x8(a, a, w, h).sum() == 0
