@@ -15,10 +15,12 @@ assert CU_DTYPE.itemsize == C.sizeof(OrcCu) == 12
 
 
 class OracleEncoder:
-    def __init__(self, w, h, qp=32, intra_period=64, search_range=8, deblock=1, hash_sei=0, qp_delta=0):
+    def __init__(self, w, h, qp=32, intra_period=64, search_range=8, deblock=1, hash_sei=0, qp_delta=0,
+                 mv_edges=0, more_tiles=0, raw_slice_data=0):
         self.lib = load()
         self.w, self.h = w, h
-        cfg = OrcEncCfg(w, h, qp, intra_period, search_range, deblock, hash_sei, qp_delta)
+        cfg = OrcEncCfg(w, h, qp, intra_period, search_range, deblock, hash_sei, qp_delta, mv_edges, more_tiles,
+                        raw_slice_data, 0, 0)
         self.h_enc = self.lib.orc_enc_open(C.byref(cfg))
         if not self.h_enc:
             raise ValueError("orc_enc_open rejected the configuration")
@@ -76,3 +78,33 @@ class OracleEncoder:
             self.close()
         except Exception:
             pass
+
+
+class OracleTiledEncoder:
+    """Tile columns coded as independent strips (oracle/hevc_enc.c: orc_tiled_*)."""
+
+    def __init__(self, w, h, tiles, qp=32, intra_period=64, search_range=8, deblock=1, hash_sei=0, wpp=0):
+        self.lib = load()
+        self.w, self.h = w, h
+        cfg = OrcEncCfg(w, h, qp, intra_period, search_range, deblock, hash_sei, 0, 0, 0, 0, 0 if wpp else 1, 0)
+        self.h_enc = self.lib.orc_tiled_open(C.byref(cfg), tiles)
+        if not self.h_enc:
+            raise ValueError("orc_tiled_open rejected the configuration")
+        self.out = np.empty(w * h * 3 + 65536, np.uint8)
+
+    def encode(self, i420: np.ndarray) -> bytes:
+        frame = np.ascontiguousarray(i420)
+        n = self.lib.orc_tiled_encode(self.h_enc, C.c_void_p(frame.ctypes.data), C.c_void_p(self.out.ctypes.data), self.out.size)
+        if n < 0:
+            raise RuntimeError(f"orc_tiled_encode failed ({n})")
+        return self.out[:n].tobytes()
+
+    def recon(self):
+        n = self.w * self.h * 3 // 2
+        t = (C.c_uint8 * n).from_address(self.lib.orc_tiled_recon(self.h_enc))
+        return np.frombuffer(t, dtype=np.uint8, count=n).copy()
+
+    def close(self):
+        if self.h_enc:
+            self.lib.orc_tiled_close(self.h_enc)
+            self.h_enc = None

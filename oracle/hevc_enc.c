@@ -300,6 +300,18 @@ static inline uint32_t mv_penalty(int lambda_q4, int mvx, int mvy)
   return (uint32_t)((lambda_q4 * (mv_comp_bits(mvx) + mv_comp_bits(mvy))) >> 4);
 }
 
+/* Tile-column mode (cfg.mv_edges): may a block at x, n wide, use horizontal motion mvx?  With a
+ * fractional luma or chroma position ((mvx & 7) != 0) the interpolation taps reach up to 4 luma
+ * samples further on either side. */
+static inline int mv_allowed(const orc_encoder_t *e, int x, int n, int mvx)
+{
+  if (!e->cfg.mv_edges) return 1;
+  const int ix = mvx >> 2, m = (mvx & 7) ? 4 : 0;
+  if ((e->cfg.mv_edges & 1) && x + ix - m < 0) return 0;
+  if ((e->cfg.mv_edges & 2) && x + n + ix + m > e->w) return 0;
+  return 1;
+}
+
 static void pad_reference(orc_encoder_t *e)
 {
   for (int c = 0; c < 3; c++) {
@@ -348,7 +360,7 @@ static void me_ctu(orc_encoder_t *e, int cx, int cy)
           if (x >= e->w || y >= e->h) { s8[j][i] = 0; continue; }
           s8[j][i] = orc_sad(src + (size_t)y * e->w + x, e->w, ref + (size_t)(y + PAD + dy) * rs + x + PAD + dx, rs, 8, 8);
           uint32_t cost = s8[j][i] + pen;
-          if (cost < b8[j][i].cost) { b8[j][i].cost = cost; b8[j][i].dx = dx; b8[j][i].dy = dy; }
+          if (cost < b8[j][i].cost && mv_allowed(e, x, 8, dx * 4)) { b8[j][i].cost = cost; b8[j][i].dx = dx; b8[j][i].dy = dy; }
         }
       uint32_t s16[4][4];
       for (int j = 0; j < 4; j++)
@@ -356,14 +368,14 @@ static void me_ctu(orc_encoder_t *e, int cx, int cy)
           s16[j][i] = s8[2 * j][2 * i] + s8[2 * j][2 * i + 1] + s8[2 * j + 1][2 * i] + s8[2 * j + 1][2 * i + 1];
           if (cx + 16 * i + 16 > e->w || cy + 16 * j + 16 > e->h) continue;
           uint32_t cost = s16[j][i] + pen;
-          if (cost < b16[j][i].cost) { b16[j][i].cost = cost; b16[j][i].dx = dx; b16[j][i].dy = dy; }
+          if (cost < b16[j][i].cost && mv_allowed(e, cx + 16 * i, 16, dx * 4)) { b16[j][i].cost = cost; b16[j][i].dx = dx; b16[j][i].dy = dy; }
         }
       for (int j = 0; j < 2; j++)
         for (int i = 0; i < 2; i++) {
           if (cx + 32 * i + 32 > e->w || cy + 32 * j + 32 > e->h) continue;
           uint32_t s = s16[2 * j][2 * i] + s16[2 * j][2 * i + 1] + s16[2 * j + 1][2 * i] + s16[2 * j + 1][2 * i + 1];
           uint32_t cost = s + pen;
-          if (cost < b32[j][i].cost) { b32[j][i].cost = cost; b32[j][i].dx = dx; b32[j][i].dy = dy; }
+          if (cost < b32[j][i].cost && mv_allowed(e, cx + 32 * i, 32, dx * 4)) { b32[j][i].cost = cost; b32[j][i].dx = dx; b32[j][i].dy = dy; }
         }
     }
   /* bottom-up partition decision */
@@ -426,6 +438,7 @@ static void inter_cu(orc_encoder_t *e, int x0, int y0, int log2)
     int cxm = bx, cym = by;
     for (int k = 0; k < 8; k++) {
       int mx = cxm + off[k][0] * step, my = cym + off[k][1] * step;
+      if (!mv_allowed(e, x0, n, mx)) continue;
       mc_luma(e, x0, y0, n, mx, my, pred);
       uint32_t cost = orc_sad(src, e->w, pred, n, n, n) + mv_penalty(lam, mx, my);
       if (cost < best) { best = cost; bx = mx; by = my; memcpy(best_pred, pred, (size_t)n * n); }
@@ -861,8 +874,14 @@ static size_t write_parameter_sets(const orc_encoder_t *e, uint8_t *out, size_t 
   orc_bits_put(&b, 0, 1);             /* weighted_pred_flag */
   orc_bits_put(&b, 0, 1);             /* weighted_bipred_flag */
   orc_bits_put(&b, 0, 1);             /* transquant_bypass_enabled_flag */
-  orc_bits_put(&b, 0, 1);             /* tiles_enabled_flag */
-  orc_bits_put(&b, 1, 1);             /* entropy_coding_sync_enabled_flag (WPP) */
+  orc_bits_put(&b, e->cfg.tile_cols > 1, 1);        /* tiles_enabled_flag */
+  orc_bits_put(&b, e->cfg.no_wpp ? 0 : 1, 1);       /* entropy_coding_sync_enabled_flag (WPP) */
+  if (e->cfg.tile_cols > 1) {
+    orc_bits_ue(&b, (uint32_t)(e->cfg.tile_cols - 1));   /* num_tile_columns_minus1 */
+    orc_bits_ue(&b, 0);                                  /* num_tile_rows_minus1 */
+    orc_bits_put(&b, 1, 1);                              /* uniform_spacing_flag */
+    orc_bits_put(&b, 0, 1);                              /* loop_filter_across_tiles_enabled_flag */
+  }
   orc_bits_put(&b, 1, 1);             /* pps_loop_filter_across_slices_enabled_flag */
   if (e->cfg.deblock) {
     orc_bits_put(&b, 0, 1);           /* deblocking_filter_control_present_flag */
@@ -951,39 +970,12 @@ static size_t write_hash_sei(const orc_encoder_t *e, uint8_t *out, size_t cap)
 
 /* ---- slice ------------------------------------------------------------------------------------ */
 
-static int encode_slice(orc_encoder_t *e, uint8_t *out, size_t cap, size_t *written)
+/* slice segment header (7.3.6.1) + slice data -> one NAL.  n_sub substreams, sub_esc[i] = size of
+ * substream i once emulation prevention bytes are in, data = the unescaped substreams back to back. */
+static int assemble_slice(const orc_encoder_t *e, int n_sub, const size_t *sub_esc, const uint8_t *data, size_t pos,
+                          uint8_t *out, size_t cap, size_t *written)
 {
-  const int rows = e->ctb_rows, cols = e->ctb_cols;
-  size_t *sub_len = (size_t *)calloc((size_t)rows, sizeof(size_t));
-  size_t *sub_esc = (size_t *)calloc((size_t)rows, sizeof(size_t));
-  orc_cabac_t cab, saved;
-  memset(&cab, 0, sizeof(cab));
-  memset(&saved, 0, sizeof(saved));
-  size_t pos = 0;
-  e->bins = 0;
-  for (int r = 0; r < rows; r++) {
-    orc_bits_t bits;
-    orc_bits_init(&bits, e->sub + pos, e->sub_cap - pos);
-    if (r == 0 || cols < 2) orc_cabac_init_contexts(&cab, e->is_idr ? 0 : 1, e->cfg.qp);
-    else memcpy(cab.ctx, saved.ctx, sizeof(cab.ctx));            /* WPP sync from CTU 1 of the row above */
-    orc_cabac_start(&cab, &bits);
-    for (int cidx = 0; cidx < cols; cidx++) {
-      code_quadtree(e, &cab, cidx * CTB, r * CTB, CTB_LOG2, 0);
-      if (cidx == 1) memcpy(saved.ctx, cab.ctx, sizeof(cab.ctx));
-      int last_in_slice = r == rows - 1 && cidx == cols - 1;
-      orc_cabac_terminate(&cab, last_in_slice);                  /* end_of_slice_segment_flag */
-      if (cidx == cols - 1 && !last_in_slice) orc_cabac_terminate(&cab, 1);   /* end_of_subset_one_bit */
-    }
-    orc_cabac_finish(&cab);
-    if (bits.overflow) { free(sub_len); free(sub_esc); return -1; }
-    sub_len[r] = orc_bits_bytes(&bits);
-    /* emulation prevention bytes this substream will receive inside the NAL */
-    sub_esc[r] = orc_nal_escape(e->sub + pos, sub_len[r], NULL, 0);
-    pos += sub_len[r];
-    e->bins += cab.bins; cab.bins = 0;
-  }
-  /* slice segment header (7.3.6.1) */
-  uint8_t hdr[4096];
+  uint8_t hdr[8192];
   orc_bits_t b;
   orc_bits_init(&b, hdr, sizeof(hdr));
   orc_bits_put(&b, 1, 1);                               /* first_slice_segment_in_pic_flag */
@@ -998,25 +990,83 @@ static int encode_slice(orc_encoder_t *e, uint8_t *out, size_t cap, size_t *writ
   }
   orc_bits_se(&b, e->cfg.qp - 26);                      /* slice_qp_delta */
   if (e->cfg.deblock) orc_bits_put(&b, 1, 1);           /* slice_loop_filter_across_slices_enabled_flag */
-  orc_bits_ue(&b, (uint32_t)(rows - 1));                /* num_entry_point_offsets */
-  if (rows > 1) {
+  orc_bits_ue(&b, (uint32_t)(n_sub - 1));               /* num_entry_point_offsets */
+  if (n_sub > 1) {
     size_t mx = 1;
-    for (int r = 0; r < rows - 1; r++) if (sub_esc[r] > mx) mx = sub_esc[r];
+    for (int r = 0; r < n_sub - 1; r++) if (sub_esc[r] > mx) mx = sub_esc[r];
     int len = 1;
     while (((mx - 1) >> len) > 0) len++;
     orc_bits_ue(&b, (uint32_t)(len - 1));               /* offset_len_minus1 */
-    for (int r = 0; r < rows - 1; r++) orc_bits_put(&b, (uint32_t)(sub_esc[r] - 1), len);
+    for (int r = 0; r < n_sub - 1; r++) orc_bits_put(&b, (uint32_t)(sub_esc[r] - 1), len);
   }
   orc_bits_trailing(&b);                                /* byte_alignment() */
+  if (b.overflow) return -1;
   size_t hl = orc_bits_bytes(&b);
   /* assemble the NAL: header + substreams, escaped as one RBSP */
   uint8_t *rbsp = (uint8_t *)malloc(hl + pos);
   memcpy(rbsp, hdr, hl);
-  memcpy(rbsp + hl, e->sub, pos);
+  memcpy(rbsp + hl, data, pos);
   size_t n = write_nal(out, cap, e->is_idr ? 19 : 1, rbsp, hl + pos);
-  free(rbsp); free(sub_len); free(sub_esc);
+  free(rbsp);
   *written = n;
   return n <= cap ? 0 : -1;
+}
+
+static int encode_slice(orc_encoder_t *e, uint8_t *out, size_t cap, size_t *written)
+{
+  const int rows = e->ctb_rows, cols = e->ctb_cols;
+  size_t *sub_len = (size_t *)calloc((size_t)rows, sizeof(size_t));
+  size_t *sub_esc = (size_t *)calloc((size_t)rows, sizeof(size_t));
+  orc_cabac_t cab, saved;
+  memset(&cab, 0, sizeof(cab));
+  memset(&saved, 0, sizeof(saved));
+  size_t pos = 0;
+  e->bins = 0;
+  const int wpp = !e->cfg.no_wpp;
+  const int n_sub = wpp ? rows : 1;
+  orc_bits_t bits;
+  for (int r = 0; r < rows; r++) {
+    if (wpp || r == 0) {
+      orc_bits_init(&bits, e->sub + pos, e->sub_cap - pos);
+      if (r == 0 || cols < 2) orc_cabac_init_contexts(&cab, e->is_idr ? 0 : 1, e->cfg.qp);
+      else memcpy(cab.ctx, saved.ctx, sizeof(cab.ctx));          /* WPP sync from CTU 1 of the row above */
+      orc_cabac_start(&cab, &bits);
+    }
+    for (int cidx = 0; cidx < cols; cidx++) {
+      code_quadtree(e, &cab, cidx * CTB, r * CTB, CTB_LOG2, 0);
+      if (cidx == 1) memcpy(saved.ctx, cab.ctx, sizeof(cab.ctx));
+      int last_in_slice = r == rows - 1 && cidx == cols - 1 && !e->cfg.more_tiles;
+      int last_in_sub = cidx == cols - 1 && (wpp || r == rows - 1);
+      orc_cabac_terminate(&cab, last_in_slice);                  /* end_of_slice_segment_flag */
+      if (last_in_sub && !last_in_slice) orc_cabac_terminate(&cab, 1);        /* end_of_subset_one_bit */
+    }
+    if (!wpp && r < rows - 1) continue;                          /* one substream: keep coding */
+    orc_cabac_finish(&cab);
+    if (bits.overflow) { free(sub_len); free(sub_esc); return -1; }
+    const int si = wpp ? r : 0;
+    sub_len[si] = orc_bits_bytes(&bits);
+    /* emulation prevention bytes this substream will receive inside the NAL */
+    sub_esc[si] = orc_nal_escape(e->sub + pos, sub_len[si], NULL, 0);
+    pos += sub_len[si];
+    e->bins += cab.bins; cab.bins = 0;
+  }
+  if (e->cfg.raw_slice_data) {
+    size_t need = pos + 4 * (size_t)n_sub, o = 0, off = 0;
+    free(sub_esc);
+    if (need > cap) { free(sub_len); return -1; }
+    for (int r = 0; r < n_sub; r++) {
+      uint32_t n = (uint32_t)sub_len[r];
+      out[o++] = (uint8_t)n; out[o++] = (uint8_t)(n >> 8); out[o++] = (uint8_t)(n >> 16); out[o++] = (uint8_t)(n >> 24);
+      memcpy(out + o, e->sub + off, n);
+      o += n; off += n;
+    }
+    free(sub_len);
+    *written = o;
+    return 0;
+  }
+  int rc = assemble_slice(e, n_sub, sub_esc, e->sub, pos, out, cap, written);
+  free(sub_len); free(sub_esc);
+  return rc;
 }
 
 int orc_enc_encode(orc_encoder_t *e, const uint8_t *i420, uint8_t *out, int cap)
@@ -1038,13 +1088,111 @@ int orc_enc_encode(orc_encoder_t *e, const uint8_t *i420, uint8_t *out, int cap)
   if (e->cfg.qp_delta) derive_cu_qps(e);
   if (e->cfg.deblock) deblock_frame(e);
   size_t o = 0, n = 0;
-  if (e->is_idr) o += write_parameter_sets(e, out, (size_t)cap);
+  if (e->is_idr && !e->cfg.raw_slice_data) o += write_parameter_sets(e, out, (size_t)cap);
   if (o > (size_t)cap) return -1;
   if (encode_slice(e, out + o, (size_t)cap - o, &n) != 0) return -1;
   o += n;
-  if (e->cfg.hash_sei) o += write_hash_sei(e, out + o, (size_t)cap - o);
+  if (e->cfg.hash_sei && !e->cfg.raw_slice_data) o += write_hash_sei(e, out + o, (size_t)cap - o);
   if (o > (size_t)cap) return -1;
   pad_reference(e);
+  e->frame_idx++;
+  e->poc++;
+  return (int)o;
+}
+
+
+/* ------------------------------------------------------------------------------------------ */
+/* tile columns as independent strips                                                            */
+
+struct orc_tiled {
+  orc_encoder_t *hdr;             /* full-size instance: parameter sets, slice header, hash SEI, composite recon */
+  int tiles, x0[64], wd[64];
+  orc_encoder_t *strip[64];
+  uint8_t *strip_src, *raw;
+  size_t raw_cap;
+};
+
+orc_tiled_t *orc_tiled_open(const orc_enc_cfg_t *cfg, int tile_cols)
+{
+  if (!cfg || tile_cols < 1 || tile_cols > 64) return NULL;
+  const int ctb_cols = (cfg->width + CTB - 1) / CTB;
+  if (tile_cols > ctb_cols / 2) return NULL;              /* every tile at least two CTUs wide (WPP sync) */
+  if (cfg->qp_delta) return NULL;                         /* the QP prediction chain of derive_cu_qps assumes WPP rows */
+  orc_tiled_t *t = (orc_tiled_t *)calloc(1, sizeof(*t));
+  orc_enc_cfg_t hc = *cfg;
+  hc.tile_cols = tile_cols; hc.mv_edges = 0; hc.more_tiles = 0; hc.raw_slice_data = 0;
+  t->hdr = orc_enc_open(&hc);
+  t->tiles = tile_cols;
+  if (!t->hdr) { free(t); return NULL; }
+  for (int i = 0; i < tile_cols; i++) {
+    const int c0 = i * ctb_cols / tile_cols, c1 = (i + 1) * ctb_cols / tile_cols;   /* colBd, 6.5.1 */
+    t->x0[i] = c0 * CTB;
+    t->wd[i] = imin(cfg->width, c1 * CTB) - t->x0[i];
+    orc_enc_cfg_t sc = *cfg;
+    sc.width = t->wd[i]; sc.hash_sei = 0; sc.tile_cols = 0; sc.raw_slice_data = 1;
+    sc.mv_edges = (i > 0 ? 1 : 0) | (i < tile_cols - 1 ? 2 : 0);
+    sc.more_tiles = i < tile_cols - 1;
+    t->strip[i] = orc_enc_open(&sc);
+    if (!t->strip[i]) { orc_tiled_close(t); return NULL; }
+  }
+  t->strip_src = (uint8_t *)malloc((size_t)cfg->width * cfg->height * 3 / 2);
+  t->raw_cap = (size_t)cfg->width * cfg->height * 3 + 65536;
+  t->raw = (uint8_t *)malloc(t->raw_cap);
+  return t;
+}
+
+void orc_tiled_close(orc_tiled_t *t)
+{
+  if (!t) return;
+  for (int i = 0; i < t->tiles; i++) if (t->strip[i]) orc_enc_close(t->strip[i]);
+  orc_enc_close(t->hdr);
+  free(t->strip_src); free(t->raw); free(t);
+}
+
+const uint8_t *orc_tiled_recon(const orc_tiled_t *t) { return t->hdr->rec; }
+
+/* copies columns [x0, x0+wd) of a packed I420 picture into / out of a packed I420 strip */
+static void strip_copy(uint8_t *pic, int w, int h, uint8_t *strip, int x0, int wd, int to_strip)
+{
+  for (int c = 0; c < 3; c++) {
+    const int pw = c ? w / 2 : w, ph = c ? h / 2 : h, sx = c ? x0 / 2 : x0, sw = c ? wd / 2 : wd;
+    uint8_t *pp = plane(pic, w, h, c), *sp = plane(strip, wd, h, c);
+    for (int y = 0; y < ph; y++) {
+      if (to_strip) memcpy(sp + (size_t)y * sw, pp + (size_t)y * pw + sx, sw);
+      else memcpy(pp + (size_t)y * pw + sx, sp + (size_t)y * sw, sw);
+    }
+  }
+}
+
+int orc_tiled_encode(orc_tiled_t *t, const uint8_t *i420, uint8_t *out, int cap)
+{
+  orc_encoder_t *e = t->hdr;
+  e->is_idr = e->frame_idx == 0 || (e->cfg.intra_period > 0 && e->frame_idx % e->cfg.intra_period == 0);
+  if (e->is_idr) e->poc = 0;
+  size_t sub_esc[64 * 64], total = 0;
+  int n_sub = 0;
+  uint8_t *data = (uint8_t *)malloc(t->raw_cap);
+  for (int i = 0; i < t->tiles; i++) {
+    strip_copy((uint8_t *)i420, e->w, e->h, t->strip_src, t->x0[i], t->wd[i], 1);
+    int n = orc_enc_encode(t->strip[i], t->strip_src, t->raw, (int)t->raw_cap);
+    if (n < 0) { free(data); return -1; }
+    for (int o = 0; o < n;) {                                /* 4-byte length + substream, repeated */
+      uint32_t len = t->raw[o] | (t->raw[o + 1] << 8) | (t->raw[o + 2] << 16) | ((uint32_t)t->raw[o + 3] << 24);
+      o += 4;
+      memcpy(data + total, t->raw + o, len);
+      sub_esc[n_sub++] = orc_nal_escape(t->raw + o, len, NULL, 0);
+      total += len; o += (int)len;
+    }
+    strip_copy(e->rec, e->w, e->h, (uint8_t *)orc_enc_recon(t->strip[i]), t->x0[i], t->wd[i], 0);
+  }
+  size_t o = 0, n = 0;
+  if (e->is_idr) o += write_parameter_sets(e, out, (size_t)cap);
+  int rc = o > (size_t)cap ? -1 : assemble_slice(e, n_sub, sub_esc, data, total, out + o, (size_t)cap - o, &n);
+  free(data);
+  if (rc != 0) return -1;
+  o += n;
+  if (e->cfg.hash_sei) o += write_hash_sei(e, out + o, (size_t)cap - o);
+  if (o > (size_t)cap) return -1;
   e->frame_idx++;
   e->poc++;
   return (int)o;

@@ -28,6 +28,15 @@ typedef struct {
   int deblock;             /* 1 = in-loop deblocking on */
   int hash_sei;            /* 1 = append MD5 decoded-picture-hash SEI (test use) */
   int qp_delta;            /* 1 = cu_qp_delta_enabled_flag, one quantisation group per CTU (ROI) */
+  /* Tile-column mode: this encoder codes one tile (a column strip) of a larger picture as if it were
+   * a picture of its own.  mv_edges: bit 0 / bit 1 = the left / right edge is an interior tile edge,
+   * so no reference sample beyond it may be touched (the neighbouring tile's samples are there, not
+   * edge padding).  more_tiles: tiles follow in the slice, so the last CTU does not end the slice
+   * segment.  raw_slice_data: orc_enc_encode returns only the substreams, each prefixed by its
+   * 4-byte little-endian length (the compositor writes parameter sets and the slice header). */
+  int mv_edges, more_tiles, raw_slice_data;
+  int no_wpp;              /* 1 = entropy_coding_sync off: one substream for the whole (strip) picture */
+  int tile_cols;           /* > 1: PPS / slice header of a picture with that many uniform tile columns (compositor only) */
 } orc_enc_cfg_t;
 
 typedef struct orc_encoder orc_encoder_t;
@@ -43,6 +52,15 @@ int orc_enc_encode(orc_encoder_t *e, const uint8_t *i420, uint8_t *out, int cap)
 /* Per-CTU QP offsets for the pictures that follow (ctb_cols*ctb_rows entries, raster; NULL = none).
  * Needs cfg.qp_delta; CTU QP = clip(qp + dqp, 0, 51). */
 int orc_enc_set_ctu_dqp(orc_encoder_t *e, const int8_t *dqp);
+
+/* Tile columns (H.265 6.5.1, uniform spacing) coded as independent strips: one encoder per tile with
+ * mv_edges / more_tiles / raw_slice_data set, loop filtering across tiles off, substreams
+ * concatenated in tile order behind one slice header.  Same call shape as the plain encoder. */
+typedef struct orc_tiled orc_tiled_t;
+orc_tiled_t *orc_tiled_open(const orc_enc_cfg_t *cfg, int tile_cols);
+void orc_tiled_close(orc_tiled_t *t);
+int orc_tiled_encode(orc_tiled_t *t, const uint8_t *i420, uint8_t *out, int cap);
+const uint8_t *orc_tiled_recon(const orc_tiled_t *t);            /* packed I420 of the whole picture */
 
 const uint8_t *orc_enc_recon(const orc_encoder_t *e);            /* packed I420, after deblocking */
 const uint8_t *orc_enc_recon_predeblock(const orc_encoder_t *e); /* packed I420, before deblocking */

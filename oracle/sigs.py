@@ -30,7 +30,8 @@ class OrcCu(C.Structure):
 
 class OrcEncCfg(C.Structure):
     _fields_ = [("width", i), ("height", i), ("qp", i), ("intra_period", i), ("search_range", i),
-                ("deblock", i), ("hash_sei", i), ("qp_delta", i)]
+                ("deblock", i), ("hash_sei", i), ("qp_delta", i),
+                ("mv_edges", i), ("more_tiles", i), ("raw_slice_data", i), ("no_wpp", i), ("tile_cols", i)]
 
 
 SIGS.update({
@@ -40,6 +41,10 @@ SIGS.update({
     "orc_max_threads": (i, []),
     "orc_enc_encode": (i, [v, v, v, i]),
     "orc_enc_set_ctu_dqp": (i, [v, v]),
+    "orc_tiled_open": (v, [C.POINTER(OrcEncCfg), i]),
+    "orc_tiled_close": (None, [v]),
+    "orc_tiled_encode": (i, [v, v, v, i]),
+    "orc_tiled_recon": (v, [v]),
     "orc_enc_recon": (v, [v]),
     "orc_enc_recon_predeblock": (v, [v]),
     "orc_enc_cu_map": (v, [v]),

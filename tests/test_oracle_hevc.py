@@ -109,6 +109,34 @@ def test_per_ctu_qp_streams_decode_bit_exactly_in_ffmpeg(kind, w, h, n, qp, roi,
         assert all((q == qp).all() for q in qps)
 
 
+@needs_ff
+@pytest.mark.parametrize("kind,w,h,n,qp,tiles,kw", [
+    ("camera", 416, 240, 5, 30, 2, {"hash_sei": 1}),                  # 7 CTU columns -> tiles of 3 and 4
+    ("camera", 416, 240, 6, 27, 3, {"hash_sei": 1, "intra_period": 4}),
+    ("noise", 512, 136, 3, 20, 4, {}),                                  # every tile exactly two CTUs wide
+    ("screen", 640, 200, 5, 35, 2, {"deblock": 0}),
+    ("camera", 1920, 1080, 2, 32, 4, {"hash_sei": 1, "search_range": 12}),
+])
+def test_tile_columns_as_independent_strips_decode_bit_exactly_in_ffmpeg(kind, w, h, n, qp, tiles, kw):
+    """Tiles (PPS tile columns, uniform spacing, no loop filter across tiles) built from strip
+    encoders whose motion never reaches across an interior tile edge: an independent decoder that
+    knows nothing about the trick must reproduce the composite reconstruction."""
+    from oracle.encoder import OracleTiledEncoder
+    frames = frames_of(kind, w, h, n)
+    enc = OracleTiledEncoder(w, h, tiles, qp=qp, **({"intra_period": 0} | kw))
+    aus, recs = [], []
+    for f in frames:
+        aus.append(enc.encode(f))
+        recs.append(enc.recon())
+    enc.close()
+    dec, errs = ffhevc.decode_stream(aus)
+    assert errs == 0 and len(dec) == n
+    for i, (fr, fw, fh) in enumerate(dec):
+        assert (fw, fh) == (w, h)
+        bad = np.flatnonzero(fr != recs[i])
+        assert bad.size == 0, f"frame {i}: {bad.size} samples differ, first at {bad[:6]}"
+
+
 def test_per_ctu_qp_changes_rate_where_asked():
     w, h = 416, 240
     frames = frames_of("camera", w, h, 3)
