@@ -54,6 +54,23 @@ unsigned long long b200_enc_last_bins(void *enc);
 int   b200_enc_debug_read(void *enc, int what, void *dst, size_t bytes);
 int   b200_enc_debug_set_reference(void *enc, const uint8_t *i420);
 
+/* ---- tile columns (BASELINE config 3: 4K call with tiles) -----------------------------------
+ * One encoder per tile column (uniform spacing), each coding its strip as a picture of its own:
+ * motion never crosses an interior tile edge (Kvazaar's mv-constraint frametilemargin) and tiles are
+ * not loop-filtered across, so the strips need nothing from each other and may run on different
+ * GPUs (`devices`: CUDA ordinals, tile i on devices[i % n_devices]; n_devices = 0 = current device).
+ * wpp = 0: one substream per tile (HEVC Main: tiles or WPP, not both -- the mode verified with an
+ * independent decoder); wpp = 1: one substream per CTU row of every tile, as Kvazaar emits with
+ * --tiles and --wpp.  Every tile must be at least two CTUs (128 samples) wide.  Same call shape as
+ * b200_enc_*: access units come back in order, `depth` pictures in flight. */
+void *b200_tiled_open(int width, int height, int qp, int intra_period, int search_range, int deblock, int depth,
+                      int tile_cols, int wpp, const int *devices, int n_devices);
+void  b200_tiled_close(void *enc);
+int   b200_tiled_encode(void *enc, const uint8_t *i420, uint8_t *out, int cap);   /* host picture */
+int   b200_tiled_flush(void *enc, uint8_t *out, int cap);
+int   b200_tiled_pending(void *enc);
+int   b200_tiled_recon(void *enc, uint8_t *dst, size_t cap);     /* last picture, depth 1 only */
+
 /* ---- K2: SATD primitive -------------------------------------------------------
  * SATD of every 8x8 block between two 8-bit planes of width x height (multiples of 8), HM / Kvazaar
  * convention: 8x8 Hadamard of the difference, (sum |h| + 2) >> 2; the SATD of a larger block is the

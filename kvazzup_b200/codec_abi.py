@@ -22,6 +22,12 @@ SIGNATURES: dict = {
     "b200_enc_last_bins": (C.c_ulonglong, [v]),
     "b200_enc_debug_read": (i, [v, i, v, C.c_size_t]),
     "b200_enc_debug_set_reference": (i, [v, v]),
+    "b200_tiled_open": (v, [i, i, i, i, i, i, i, i, i, v, i]),
+    "b200_tiled_close": (None, [v]),
+    "b200_tiled_encode": (i, [v, v, v, i]),
+    "b200_tiled_flush": (i, [v, v, i]),
+    "b200_tiled_pending": (i, [v]),
+    "b200_tiled_recon": (i, [v, v, C.c_size_t]),
     "b200_satd8x8": (i, [v, v, i, i, v]),
     "b200_satd8x8_dev": (i, [v, v, i, i, v, v]),
     "libOpenHevcInit": (v, [i, i]),

@@ -639,11 +639,16 @@ k_arith_rows(FrameParams fp, const uint32_t *__restrict__ recs, uint8_t *rows, u
   __shared__ uint8_t s_ctx[CTX_COUNT * 32];
   __shared__ uint2 s_tab[64];
   __shared__ uint32_t s_chunk[2][32];
-  const int r = blockIdx.x, lane = threadIdx.x;
+  // WPP: one substream per CTU row (r_first == r_last == blockIdx.x).  no_wpp (a tile without
+  // entropy_coding_sync): one block codes every row into a single substream.
+  const int lane = threadIdx.x;
+  const int r_first = fp.no_wpp ? 0 : blockIdx.x, r_last = fp.no_wpp ? fp.ctb_rows - 1 : blockIdx.x;
   for (int i = lane; i < 64; i += 32) s_tab[i] = make_uint2(c_range_lps[i], (uint32_t)c_trans_lps[i] | (i == 0 ? 64u : 0u));
   Coder c;
-  c.out = rows + (size_t)r * row_cap; c.pos = 0; c.cap = row_cap; c.zeros = 0; c.ctx = s_ctx + lane; c.bins = 0;
+  c.out = rows + (size_t)r_first * row_cap; c.pos = 0; c.cap = fp.no_wpp ? row_cap * fp.ctb_rows : row_cap;
+  c.zeros = 0; c.ctx = s_ctx + lane; c.bins = 0;
   c.writer = lane == 0;
+  int r = r_first;
   if (r == 0 || fp.ctb_cols < 2) {
     init_contexts(c.ctx, fp.is_idr ? 0 : 1, fp.qp);
   } else {
@@ -657,6 +662,7 @@ k_arith_rows(FrameParams fp, const uint32_t *__restrict__ recs, uint8_t *rows, u
   }
   __syncwarp();
   coder_start(c);
+  for (; r <= r_last; r++) {
   // Flat walk over the CUs of the row.  The address of the next CU's record list is known as
   // soon as the current header is read, so its header and first 32 records are fetched while the
   // current list is being coded (a lone warp has nothing else to hide the ~1 us load latency).
@@ -699,7 +705,7 @@ k_arith_rows(FrameParams fp, const uint32_t *__restrict__ recs, uint8_t *rows, u
       buf ^= 1;
     }
     if (ncol != col) {                                    // the CTU is complete
-      if (col == 1 && r + 1 < fp.ctb_rows) {
+      if (col == 1 && r + 1 < fp.ctb_rows && !fp.no_wpp) {
         __syncwarp();
         if (lane == 0)
           for (int i = 0; i < CTX_COUNT; i++) sync_ctx[(size_t)r * CTX_COUNT + i] = c.ctx[i * 32];
@@ -707,15 +713,18 @@ k_arith_rows(FrameParams fp, const uint32_t *__restrict__ recs, uint8_t *rows, u
         __syncwarp();
         if (lane == 0) atomicExch(&sync_flag[r], 1);
       }
-      const bool last = r == fp.ctb_rows - 1 && col == fp.ctb_cols - 1;
+      const bool end_sub = col == fp.ctb_cols - 1 && (!fp.no_wpp || r == fp.ctb_rows - 1);
+      const bool last = r == fp.ctb_rows - 1 && col == fp.ctb_cols - 1 && !fp.more_tiles;
       enc_terminate(c, last);                                           // end_of_slice_segment_flag
-      if (col == fp.ctb_cols - 1 && !last) enc_terminate(c, 1);         // end_of_subset_one_bit
+      if (end_sub && !last) enc_terminate(c, 1);                        // end_of_subset_one_bit
     }
     col = ncol; z = nz; reg = nreg; hdr = nhdr; first = nfirst;
   }
+  }                                                                     // rows of this substream
   coder_finish(c);
   if (lane == 0) {
-    row_len[r] = c.pos <= c.cap ? c.pos : 0xffffffffu;
+    row_len[r_first] = c.pos <= c.cap ? c.pos : 0xffffffffu;
+    for (int i = r_first + 1; i <= r_last; i++) row_len[i] = 0;
     atomicAdd(bins, c.bins);
   }
 }
@@ -782,7 +791,7 @@ cudaError_t launch_arith(const FrameParams &fp, const uint32_t *recs, uint8_t *r
   if (e != cudaSuccess) return e;
   e = cudaMemsetAsync(bins, 0, sizeof(unsigned long long), s);
   if (e != cudaSuccess) return e;
-  k_arith_rows<<<fp.ctb_rows, 32, 0, s>>>(fp, recs, rows, row_cap, row_len, sync_ctx, sync_flag, bins);
+  k_arith_rows<<<fp.no_wpp ? 1 : fp.ctb_rows, 32, 0, s>>>(fp, recs, rows, row_cap, row_len, sync_ctx, sync_flag, bins);
   return cudaGetLastError();
 }
 

@@ -28,6 +28,16 @@ __device__ __forceinline__ int qp_c_at(const FrameParams &fp, int x, int y)
 {
   return fp.ctu_qp ? c_chroma_qp_tab[qp_at(fp, x, y)] : fp.qp_c;
 }
+// Tile-column mode: may a block at x, n wide, use horizontal motion mvx (quarter samples)?  With a
+// fractional luma or chroma position ((mvx & 7) != 0) the interpolation reaches up to 4 luma samples
+// further on either side.
+__device__ __forceinline__ bool mv_allowed(const FrameParams &fp, int x, int n, int mvx)
+{
+  const int ix = mvx >> 2, m = (mvx & 7) ? 4 : 0;
+  if ((fp.mv_edges & 1) && x + ix - m < 0) return false;
+  if ((fp.mv_edges & 2) && x + n + ix + m > fp.w) return false;
+  return true;
+}
 __device__ __forceinline__ int lambda_q4_at(const FrameParams &fp, int x, int y)
 {
   return fp.ctu_qp ? c_lambda_q4_tab[qp_at(fp, x, y)] : fp.lambda_q4;

@@ -214,9 +214,9 @@ bool Encoder::open(const EncoderConfig &c)
   return true;
 }
 
-void Encoder::write_parameter_sets(std::vector<uint8_t> &out) const
+void write_parameter_sets(const StreamLayout &l, std::vector<uint8_t> &out)
 {
-  const int level = level_for(fp.w, fp.h);
+  const int level = level_for(l.w, l.h);
   {  // VPS (7.3.2.1)
     BitWriter b;
     b.put(0, 4); b.put(1, 1); b.put(1, 1); b.put(0, 6); b.put(0, 3); b.put(1, 1); b.put(0xffff, 16);
@@ -233,7 +233,7 @@ void Encoder::write_parameter_sets(std::vector<uint8_t> &out) const
     b.put(0, 4); b.put(0, 3); b.put(1, 1);
     put_profile_tier_level(b, level);
     b.ue(0); b.ue(1);                        // sps id, chroma_format_idc 4:2:0
-    b.ue((uint32_t)fp.w); b.ue((uint32_t)fp.h);
+    b.ue((uint32_t)l.w); b.ue((uint32_t)l.h);
     b.put(0, 1);                             // conformance_window_flag
     b.ue(0); b.ue(0);                        // bit depths
     b.ue(4);                                 // log2_max_pic_order_cnt_lsb_minus4
@@ -257,14 +257,20 @@ void Encoder::write_parameter_sets(std::vector<uint8_t> &out) const
     b.ue(0); b.ue(0);
     b.se(0);                                 // init_qp_minus26
     b.put(0, 1); b.put(0, 1);                // constrained intra, transform skip
-    b.put(cfg.qp_delta ? 1 : 0, 1);          // cu_qp_delta_enabled_flag
-    if (cfg.qp_delta) b.ue(0);               // diff_cu_qp_delta_depth: one quantisation group per CTB
+    b.put(l.qp_delta ? 1 : 0, 1);          // cu_qp_delta_enabled_flag
+    if (l.qp_delta) b.ue(0);               // diff_cu_qp_delta_depth: one quantisation group per CTB
     b.se(0); b.se(0);
     b.put(0, 1); b.put(0, 1); b.put(0, 1); b.put(0, 1);
-    b.put(0, 1);                             // tiles_enabled_flag
-    b.put(1, 1);                             // entropy_coding_sync_enabled_flag
+    b.put(l.tile_cols > 1 ? 1 : 0, 1);       // tiles_enabled_flag
+    b.put(l.wpp ? 1 : 0, 1);                 // entropy_coding_sync_enabled_flag
+    if (l.tile_cols > 1) {
+      b.ue((uint32_t)(l.tile_cols - 1));     // num_tile_columns_minus1
+      b.ue(0);                               // num_tile_rows_minus1
+      b.put(1, 1);                           // uniform_spacing_flag
+      b.put(0, 1);                           // loop_filter_across_tiles_enabled_flag
+    }
     b.put(1, 1);                             // pps_loop_filter_across_slices_enabled_flag
-    if (cfg.deblock) {
+    if (l.deblock) {
       b.put(0, 1);
     } else {
       b.put(1, 1); b.put(0, 1); b.put(1, 1);
@@ -278,36 +284,42 @@ void Encoder::write_parameter_sets(std::vector<uint8_t> &out) const
   }
 }
 
-void Encoder::write_slice(std::vector<uint8_t> &out, const FrameSlot &s) const
+void write_slice_nal(const StreamLayout &l, bool idr, int poc, int qp, const uint32_t *sub_len, int n_sub,
+                     const uint8_t *data, size_t data_len, std::vector<uint8_t> &out)
 {
-  const int rows = fp.ctb_rows;
-  const uint32_t *row_len = s.h_hdr + 1;
   BitWriter b;
   b.put(1, 1);
-  if (s.idr) b.put(0, 1);
+  if (idr) b.put(0, 1);
   b.ue(0);
-  b.ue(s.idr ? 2 : 1);
-  if (!s.idr) {
-    b.put((uint32_t)(s.poc & 255), 8);
+  b.ue(idr ? 2 : 1);
+  if (!idr) {
+    b.put((uint32_t)(poc & 255), 8);
     b.put(1, 1);
     b.put(0, 1);
     b.ue(5 - kMaxMerge);
   }
-  b.se(s.qp - 26);
-  if (cfg.deblock) b.put(1, 1);
-  b.ue((uint32_t)(rows - 1));
-  if (rows > 1) {
+  b.se(qp - 26);
+  if (l.deblock) b.put(1, 1);
+  b.ue((uint32_t)(n_sub - 1));
+  if (n_sub > 1) {
     uint32_t mx = 1;
-    for (int r = 0; r < rows - 1; r++) mx = std::max(mx, row_len[r]);
+    for (int r = 0; r < n_sub - 1; r++) mx = std::max(mx, sub_len[r]);
     int len = 1;
     while (((mx - 1) >> len) > 0) len++;
     b.ue((uint32_t)(len - 1));
-    for (int r = 0; r < rows - 1; r++) b.put(row_len[r] - 1, len);
+    for (int r = 0; r < n_sub - 1; r++) b.put(sub_len[r] - 1, len);
   }
   b.trailing();
-  start_nal(out, s.idr ? 19 : 1);
+  start_nal(out, idr ? 19 : 1);
   append_escaped(out, b.bytes.data(), b.bytes.size());
-  out.insert(out.end(), s.h_pack, s.h_pack + s.h_hdr[0]);      // substreams are already escaped
+  out.insert(out.end(), data, data + data_len);               // substreams are already escaped
+}
+
+StreamLayout Encoder::layout() const
+{
+  StreamLayout l;
+  l.w = fp.w; l.h = fp.h; l.deblock = cfg.deblock; l.qp_delta = cfg.qp_delta; l.tile_cols = 1; l.wpp = cfg.no_wpp ? 0 : 1;
+  return l;
 }
 
 // Enqueue everything for one picture; returns without waiting for the GPU.
@@ -321,6 +333,7 @@ bool Encoder::submit(FrameSlot &s, const uint8_t *d_i420)
   p.qp = cur_qp; p.qp_c = kChromaQp[cur_qp]; p.lambda_q4 = kLambdaQ4[cur_qp];
   uint8_t *rec = d_rec[frame_idx % kRecRing], *ref = d_rec[(frame_idx + kRecRing - 1) % kRecRing];
   p.ctu_qp = nullptr; p.ctu_delta = nullptr; p.ctu_first = nullptr;
+  p.mv_edges = cfg.mv_edges; p.more_tiles = cfg.more_tiles; p.no_wpp = cfg.no_wpp;
   if (cfg.qp_delta) {
     const int ctus = fp.ctb_cols * fp.ctb_rows;
     for (int i = 0; i < ctus; i++)
@@ -421,9 +434,16 @@ bool Encoder::collect(FrameSlot &s, std::vector<uint8_t> &out)
     return false;
   }
   out.clear();
-  if (s.idr) write_parameter_sets(out);
-  write_slice(out, s);
+  const int n_sub = cfg.no_wpp ? 1 : fp.ctb_rows;
   last_idr = s.idr; last_qp = s.qp; last_poc = s.poc;
+  if (cfg.raw) {                         // tile-column mode: the compositor writes the headers
+    last_sub_len.assign(s.h_hdr + 1, s.h_hdr + 1 + n_sub);
+    last_data = s.h_pack; last_data_len = s.h_hdr[0];
+    out.push_back(0);                    // "a picture is ready"
+    return true;
+  }
+  if (s.idr) write_parameter_sets(layout(), out);
+  write_slice_nal(layout(), s.idr, s.poc, s.qp, s.h_hdr + 1, n_sub, s.h_pack, s.h_hdr[0], out);
   return true;
 }
 
@@ -472,6 +492,20 @@ bool Encoder::encode_host(const uint8_t *i420, std::vector<uint8_t> &out, bool p
   // the upload runs on its own stream so that the copy engine works while the previous picture's
   // kernels execute; the consuming stream waits for it
   ENC_CHECK(cudaMemcpyAsync(s.d_src, from, frame_bytes, cudaMemcpyHostToDevice, upload_stream), "H2D frame");
+  ENC_CHECK(cudaEventRecord(ev_upload, upload_stream), "event record");
+  ENC_CHECK(cudaStreamWaitEvent(input_stream(), ev_upload, 0), "stream wait");
+  return encode_device(s.d_src, out);
+}
+
+bool Encoder::encode_host_strip(const uint8_t *pic, int pic_w, int x0, std::vector<uint8_t> &out)
+{
+  FrameSlot &s = slots[frame_idx % cfg.depth];
+  const int w = fp.w, h = fp.h;
+  const size_t pic_y = (size_t)pic_w * h, ysz = (size_t)w * h;
+  // the three planes of the strip, straight from the caller's picture into device memory
+  ENC_CHECK(cudaMemcpy2DAsync(s.d_src, w, pic + x0, pic_w, w, h, cudaMemcpyHostToDevice, upload_stream), "H2D strip Y");
+  ENC_CHECK(cudaMemcpy2DAsync(s.d_src + ysz, w / 2, pic + pic_y + x0 / 2, pic_w / 2, w / 2, h / 2, cudaMemcpyHostToDevice, upload_stream), "H2D strip U");
+  ENC_CHECK(cudaMemcpy2DAsync(s.d_src + ysz + ysz / 4, w / 2, pic + pic_y + pic_y / 4 + x0 / 2, pic_w / 2, w / 2, h / 2, cudaMemcpyHostToDevice, upload_stream), "H2D strip V");
   ENC_CHECK(cudaEventRecord(ev_upload, upload_stream), "event record");
   ENC_CHECK(cudaStreamWaitEvent(input_stream(), ev_upload, 0), "stream wait");
   return encode_device(s.d_src, out);

@@ -20,6 +20,11 @@ struct EncoderConfig {
   int overlap_idr = 1;       // run an IDR on its own stream, concurrently with the P pictures queued before it
                              // (B200, 1080p GOP 64: 1812 -> 2200 pictures/s)
   int qp_delta = 0;          // cu_qp_delta_enabled_flag: per-CTU QP offsets (ROI), one quantisation group per CTU
+  // Tile-column mode (hevc_tiles.cu): this encoder codes one tile of a larger picture as a picture of
+  // its own.  mv_edges bit 0 / 1 = left / right edge is an interior tile edge; more_tiles = tiles
+  // follow in the slice; no_wpp = one substream per tile (Main profile: tiles or WPP, not both);
+  // raw = collect() hands back the substreams instead of an access unit.
+  int mv_edges = 0, more_tiles = 0, no_wpp = 0, raw = 0;
   int depth = 1;             // pictures in flight (Kvazaar's owf + 1): output of picture n is
                              // returned by the call that submits picture n + depth - 1
 };
@@ -48,6 +53,18 @@ struct FrameSlot {
   long long seq = 0;
 };
 
+// What the parameter sets and the slice header describe (shared by Encoder and TiledEncoder).
+struct StreamLayout {
+  int w = 0, h = 0, deblock = 1, qp_delta = 0;
+  int tile_cols = 1;         // > 1: uniform tile columns, no loop filtering across tiles
+  int wpp = 1;               // entropy_coding_sync_enabled_flag
+};
+void write_parameter_sets(const StreamLayout &l, std::vector<uint8_t> &out);
+// Slice segment header with the entry points of `sub_len` (escaped sizes) followed by `data_len`
+// bytes of already escaped slice data.
+void write_slice_nal(const StreamLayout &l, bool idr, int poc, int qp, const uint32_t *sub_len, int n_sub,
+                     const uint8_t *data, size_t data_len, std::vector<uint8_t> &out);
+
 class Encoder {
  public:
   ~Encoder();
@@ -59,6 +76,13 @@ class Encoder {
   // unit has been returned (kvz_api pictures from picture_alloc): it is then uploaded in place.
   bool encode_host(const uint8_t *i420, std::vector<uint8_t> &au, bool pinned = false);
   bool encode_device(const uint8_t *d_i420, std::vector<uint8_t> &au);
+  // Columns [x0, x0 + width) of a packed I420 host picture that is pic_w wide (tile-column mode).
+  bool encode_host_strip(const uint8_t *pic, int pic_w, int x0, std::vector<uint8_t> &au);
+  // raw mode: substreams of the picture the last collect() returned (valid until its slot is reused)
+  std::vector<uint32_t> last_sub_len;
+  const uint8_t *last_data = nullptr;
+  size_t last_data_len = 0;
+  StreamLayout layout() const;
   // Drain: returns the next pending access unit (empty when none is left).
   bool flush(std::vector<uint8_t> &au);
   int pending() const { return (int)inflight.size(); }
@@ -107,8 +131,6 @@ class Encoder {
   cudaStream_t input_stream() const;
   bool submit(FrameSlot &s, const uint8_t *d_i420);
   bool collect(FrameSlot &s, std::vector<uint8_t> &au);
-  void write_parameter_sets(std::vector<uint8_t> &out) const;
-  void write_slice(std::vector<uint8_t> &out, const FrameSlot &s) const;
 };
 
 }  // namespace b200

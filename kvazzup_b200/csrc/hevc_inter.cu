@@ -114,9 +114,15 @@ k_me_ctu(FrameParams fp, const uint8_t *__restrict__ src, const uint8_t *__restr
         if (!in_range) continue;
         const unsigned c = (unsigned)((dy + R) * side + dx + R);
         const unsigned pen = sh.pen[c];
-        if (v8) k8 = min(k8, ((sad + pen) << 13) | c);
-        if (v16) k16 = min(k16, ((s16 + pen) << 13) | c);
-        if (v32) k32 = min(k32, ((s32 + pen) << 13) | c);
+        bool a8 = v8, a16 = v16, a32 = v32;
+        if (fp.mv_edges) {                                   // tile-column mode only (uniform branch)
+          a8 = a8 && mv_allowed(fp, cx + 8 * bx, 8, 4 * dx);
+          a16 = a16 && mv_allowed(fp, cx + 16 * (bx >> 1), 16, 4 * dx);
+          a32 = a32 && mv_allowed(fp, cx + 32 * (bx >> 2), 32, 4 * dx);
+        }
+        if (a8) k8 = min(k8, ((sad + pen) << 13) | c);
+        if (a16) k16 = min(k16, ((s16 + pen) << 13) | c);
+        if (a32) k32 = min(k32, ((s32 + pen) << 13) | c);
       }
     }
     atomicMin(&sh.key8[z], k8);
@@ -202,7 +208,8 @@ k_me_ctu(FrameParams fp, const uint8_t *__restrict__ src, const uint8_t *__restr
           const int oy = k < 3 ? -1 : (k < 5 ? 0 : 1);
           const int mx = sh.cmx[t] + ox * step, my = sh.cmy[t] + oy * step;
           unsigned cost = sh.acc8[t][k] + mv_penalty(lambda_q4, mx, my);
-          if (cost < sh.best[t]) { sh.best[t] = cost; sh.mvx[t] = (short)mx; sh.mvy[t] = (short)my; }
+          const bool ok = !fp.mv_edges || mv_allowed(fp, cx + 8 * z_to_x(t), 1 << sh.log2[t], mx);
+          if (ok && cost < sh.best[t]) { sh.best[t] = cost; sh.mvx[t] = (short)mx; sh.mvy[t] = (short)my; }
           sh.acc8[t][k] = 0;
         }
         sh.cmx[t] = sh.mvx[t]; sh.cmy[t] = sh.mvy[t];

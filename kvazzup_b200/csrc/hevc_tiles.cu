@@ -1,0 +1,173 @@
+// HEVC tile columns as independent strip encoders ("4K call, tiles").
+//
+// A tile column whose motion vectors never reach across its interior edges (Kvazaar's
+// mv-constraint=frametilemargin, which the reference exposes, kvazaarfilter.cpp:246-276) and that is
+// not loop-filtered across those edges is coded exactly like a picture of its own: neighbours in
+// another tile are unavailable just as they are beyond a picture edge, CABAC restarts at the tile, and
+// the slice data is the tiles' substreams back to back behind one slice header.  So the tiled encoder
+// is T ordinary encoders -- each may sit on its own GPU, and nothing is exchanged between them
+// (option A of SURVEY 8e) -- plus this compositor, which writes the parameter sets (PPS with uniform
+// tile columns, loop_filter_across_tiles off) and the slice header with all entry points.
+//
+// HEVC Main allows tiles or WPP in a picture, not both, and FFmpeg's decoder (the independent pin
+// of this repository) follows that; `wpp = 0` (one substream per tile) is therefore the mode whose
+// streams are verified externally.  `wpp = 1` keeps one substream per CTU row inside every tile --
+// what Kvazaar emits with --tiles and --wpp and what keeps the entropy coder parallel -- and is
+// checked against the oracle only.
+#include <string.h>
+
+#include <algorithm>
+#include <memory>
+
+#include "../../include/b200_hevc.h"
+#include "hevc_encoder.h"
+#include "runtime.h"
+
+namespace b200 {
+
+struct TiledEncoder {
+  struct Strip { std::unique_ptr<Encoder> enc; int x0 = 0, wd = 0, device = 0; };
+  std::vector<Strip> strips;
+  StreamLayout layout;
+  int width = 0, height = 0, pending_pics = 0;
+  std::vector<uint8_t> au, tmp, data;
+  std::vector<uint32_t> sub_len;
+
+  bool open(const EncoderConfig &c, int tiles, int wpp, const int *devices, int n_devices)
+  {
+    const int ctb_cols = (c.width + kCtb - 1) / kCtb;
+    if (tiles < 1 || tiles > ctb_cols / 2) { set_error("tiled encoder: %d tile columns for %d CTU columns (each tile must be at least two CTUs wide)", tiles, ctb_cols); return false; }
+    if (c.qp_delta) { set_error("tiled encoder: per-CTU QP is not available together with tiles"); return false; }
+    width = c.width; height = c.height;
+    layout.w = c.width; layout.h = c.height; layout.deblock = c.deblock; layout.qp_delta = 0;
+    layout.tile_cols = tiles; layout.wpp = wpp ? 1 : 0;
+    int prev = 0;
+    cudaGetDevice(&prev);
+    strips.resize(tiles);
+    for (int i = 0; i < tiles; i++) {
+      Strip &s = strips[i];
+      const int c0 = i * ctb_cols / tiles, c1 = (i + 1) * ctb_cols / tiles;        // colBd of uniform spacing (6.5.1)
+      s.x0 = c0 * kCtb;
+      s.wd = std::min(c.width, c1 * kCtb) - s.x0;
+      s.device = n_devices > 0 ? devices[i % n_devices] : prev;
+      EncoderConfig sc = c;
+      sc.width = s.wd;
+      sc.mv_edges = (i > 0 ? 1 : 0) | (i < tiles - 1 ? 2 : 0);
+      sc.more_tiles = i < tiles - 1 ? 1 : 0;
+      sc.no_wpp = wpp ? 0 : 1;
+      sc.raw = 1;
+      if (cudaSetDevice(s.device) != cudaSuccess) { set_error("tiled encoder: cannot select CUDA device %d", s.device); cudaSetDevice(prev); return false; }
+      s.enc.reset(new Encoder());
+      if (!s.enc->open(sc)) { cudaSetDevice(prev); return false; }
+    }
+    cudaSetDevice(prev);
+    return true;
+  }
+
+  // Assemble the access unit of the picture every strip has just handed back.
+  void compose()
+  {
+    sub_len.clear();
+    data.clear();
+    for (Strip &s : strips) {
+      sub_len.insert(sub_len.end(), s.enc->last_sub_len.begin(), s.enc->last_sub_len.end());
+      data.insert(data.end(), s.enc->last_data, s.enc->last_data + s.enc->last_data_len);
+    }
+    const Encoder &e0 = *strips[0].enc;
+    au.clear();
+    if (e0.last_idr) write_parameter_sets(layout, au);
+    write_slice_nal(layout, e0.last_idr != 0, e0.last_poc, e0.last_qp, sub_len.data(), (int)sub_len.size(), data.data(), data.size(), au);
+  }
+
+  // pic == nullptr drains.  au is empty while the strips' pipelines fill.
+  bool step(const uint8_t *pic)
+  {
+    int prev = 0, ready = 0;
+    cudaGetDevice(&prev);
+    bool ok = true;
+    for (Strip &s : strips) {            // enqueue on every GPU first ...
+      cudaSetDevice(s.device);
+      ok = ok && (pic ? s.enc->encode_host_strip(pic, width, s.x0, tmp) : s.enc->flush(tmp));
+      if (!ok) break;
+      ready += tmp.empty() ? 0 : 1;      // ... the strips run in lock step, so all or none return a picture
+    }
+    cudaSetDevice(prev);
+    au.clear();
+    if (!ok) return false;
+    if (ready == 0) return true;
+    if (ready != (int)strips.size()) { set_error("tiled encoder: strips out of step"); return false; }
+    compose();
+    return true;
+  }
+
+  int pending() const { return strips.empty() ? 0 : strips[0].enc->pending(); }
+};
+
+}  // namespace b200
+
+using b200::TiledEncoder;
+
+extern "C" {
+
+void *b200_tiled_open(int width, int height, int qp, int intra_period, int search_range, int deblock, int depth,
+                      int tile_cols, int wpp, const int *devices, int n_devices)
+{
+  b200::EncoderConfig c;
+  c.width = width; c.height = height; c.qp = qp; c.intra_period = intra_period; c.search_range = search_range;
+  c.deblock = deblock; c.depth = depth; c.debug = 0;
+  TiledEncoder *t = new TiledEncoder();
+  if (!t->open(c, tile_cols, wpp, devices, n_devices)) { delete t; return nullptr; }
+  return t;
+}
+
+void b200_tiled_close(void *h) { delete (TiledEncoder *)h; }
+
+static int tiled_finish(TiledEncoder *t, uint8_t *out, int cap)
+{
+  if (t->au.empty()) return 0;
+  if ((size_t)cap < t->au.size()) { b200::set_error("tiled encoder: output buffer too small (%zu needed)", t->au.size()); return -(int)t->au.size(); }
+  memcpy(out, t->au.data(), t->au.size());
+  return (int)t->au.size();
+}
+
+int b200_tiled_encode(void *h, const uint8_t *i420, uint8_t *out, int cap)
+{
+  TiledEncoder *t = (TiledEncoder *)h;
+  if (!t || !i420 || !out) { b200::set_error("b200_tiled_encode: bad arguments"); return B200_ERR_ARG; }
+  if (!t->step(i420)) return B200_ERR_CUDA;
+  return tiled_finish(t, out, cap);
+}
+
+int b200_tiled_flush(void *h, uint8_t *out, int cap)
+{
+  TiledEncoder *t = (TiledEncoder *)h;
+  if (!t || !out) { b200::set_error("b200_tiled_flush: bad arguments"); return B200_ERR_ARG; }
+  if (!t->step(nullptr)) return B200_ERR_CUDA;
+  return tiled_finish(t, out, cap);
+}
+
+int b200_tiled_pending(void *h) { return h ? ((TiledEncoder *)h)->pending() : 0; }
+
+// Reconstruction of the last submitted picture (depth 1 only), packed I420 of the whole picture.
+int b200_tiled_recon(void *h, uint8_t *dst, size_t cap)
+{
+  TiledEncoder *t = (TiledEncoder *)h;
+  const size_t ysz = t ? (size_t)t->width * t->height : 0;
+  if (!t || !dst || cap < ysz * 3 / 2) { b200::set_error("b200_tiled_recon: bad arguments"); return B200_ERR_ARG; }
+  int prev = 0;
+  cudaGetDevice(&prev);
+  for (TiledEncoder::Strip &s : t->strips) {
+    cudaSetDevice(s.device);
+    b200::Encoder &e = *s.enc;
+    cudaStreamSynchronize(e.stream);
+    const uint8_t *rec = e.last_rec();
+    const size_t sy = (size_t)s.wd * t->height;
+    cudaMemcpy2D(dst + s.x0, t->width, rec, s.wd, s.wd, t->height, cudaMemcpyDeviceToHost);
+    cudaMemcpy2D(dst + ysz + s.x0 / 2, t->width / 2, rec + sy, s.wd / 2, s.wd / 2, t->height / 2, cudaMemcpyDeviceToHost);
+    cudaMemcpy2D(dst + ysz + ysz / 4 + s.x0 / 2, t->width / 2, rec + sy + sy / 4, s.wd / 2, s.wd / 2, t->height / 2, cudaMemcpyDeviceToHost);
+  }
+  cudaSetDevice(prev);
+  return B200_OK;
+}
+
+}  // extern "C"

@@ -116,6 +116,46 @@ class GpuEncoder:
             pass
 
 
+class GpuTiledEncoder:
+    """Tile columns as independent strip encoders, optionally one GPU per strip (include/b200_hevc.h)."""
+
+    def __init__(self, w, h, tiles, qp=32, intra_period=64, search_range=8, deblock=1, depth=1, wpp=0, devices=()):
+        self.l = lib()
+        self.w, self.h = w, h
+        devs = (C.c_int * max(len(devices), 1))(*devices)
+        self.h_enc = self.l.b200_tiled_open(w, h, qp, intra_period, search_range, deblock, depth, tiles, wpp, devs, len(devices))
+        if not self.h_enc:
+            raise B200Error("b200_tiled_open failed: " + self.l.b200_last_error().decode())
+        self.out = np.empty(w * h * 3 + 65536, np.uint8)
+
+    def _ret(self, n):
+        if n < 0:
+            raise B200Error(f"tiled encode failed ({n}): " + self.l.b200_last_error().decode())
+        return self.out[:n].tobytes()
+
+    def encode(self, i420: np.ndarray) -> bytes:
+        f = np.ascontiguousarray(i420)
+        assert f.size == self.w * self.h * 3 // 2
+        return self._ret(self.l.b200_tiled_encode(self.h_enc, C.c_void_p(f.ctypes.data), C.c_void_p(self.out.ctypes.data), self.out.size))
+
+    def flush(self) -> bytes:
+        return self._ret(self.l.b200_tiled_flush(self.h_enc, C.c_void_p(self.out.ctypes.data), self.out.size))
+
+    def pending(self) -> int:
+        return self.l.b200_tiled_pending(self.h_enc)
+
+    def recon(self) -> np.ndarray:
+        out = np.empty(self.w * self.h * 3 // 2, np.uint8)
+        if self.l.b200_tiled_recon(self.h_enc, C.c_void_p(out.ctypes.data), out.size) != 0:
+            raise B200Error("b200_tiled_recon failed: " + self.l.b200_last_error().decode())
+        return out
+
+    def close(self):
+        if self.h_enc:
+            self.l.b200_tiled_close(self.h_enc)
+            self.h_enc = None
+
+
 def satd8x8(a: np.ndarray, b: np.ndarray, w: int, h: int) -> np.ndarray:
     """SATD (8x8 Hadamard, HM convention) of every 8x8 block between two w x h planes -> (h/8, w/8) uint32."""
     a = np.ascontiguousarray(a, dtype=np.uint8)

@@ -381,3 +381,62 @@ def test_satd_primitive_matches_oracle(w, h, kind):
             want = orc.orc_satd(ptr(a[off:]), w, ptr(b[off:]), w, 8, 8)
             assert got[by, bx] == want, (bx, by)
     assert satd8x8(a, a, w, h).sum() == 0
+
+
+# ---- tile columns (independent strips) -------------------------------------------------------------
+
+TILE_CASES = [
+    ("camera", 416, 240, 5, 30, 2, 0, {}),
+    ("camera", 416, 240, 6, 27, 3, 0, {"intra_period": 4}),
+    ("noise", 512, 136, 3, 20, 4, 0, {}),
+    ("screen", 640, 200, 5, 35, 2, 0, {"deblock": 0}),
+    ("camera", 416, 240, 5, 30, 2, 1, {}),                       # tiles + WPP substreams (oracle only, see hevc_tiles.cu)
+    ("camera", 1920, 1080, 3, 32, 4, 0, {"search_range": 12}),
+    ("camera", 1920, 1080, 3, 32, 4, 1, {"search_range": 12}),
+]
+
+
+@pytest.mark.parametrize("kind,w,h,n,qp,tiles,wpp,kw", TILE_CASES)
+def test_tiled_encoder_matches_oracle_and_decodes_in_ffmpeg(kind, w, h, n, qp, tiles, wpp, kw):
+    """Tile columns coded as independent strips: access units and reconstruction equal the oracle's
+    compositor; without WPP inside the tiles (HEVC Main) FFmpeg decodes the stream to the same picture."""
+    from kvazzup_b200.encoder import GpuTiledEncoder
+    from oracle.encoder import OracleTiledEncoder
+    frames = frames_of(kind, w, h, n)
+    args = {"intra_period": 0} | kw
+    g = GpuTiledEncoder(w, h, tiles, qp=qp, wpp=wpp, **args)
+    o = OracleTiledEncoder(w, h, tiles, qp=qp, wpp=wpp, **args)
+    aus = []
+    for i, f in enumerate(frames):
+        ga, oa = g.encode(f), o.encode(f)
+        bad = np.flatnonzero(g.recon() != o.recon())
+        assert bad.size == 0, f"frame {i}: reconstruction differs at {bad[:8]} (of {bad.size})"
+        assert ga == oa, f"frame {i}: access unit differs (gpu {len(ga)} B, oracle {len(oa)} B)"
+        aus.append(ga)
+    if ffhevc.available() and not wpp:
+        dec, errs = ffhevc.decode_stream(aus)
+        assert errs == 0 and len(dec) == n
+        assert np.array_equal(dec[-1][0], g.recon())
+    g.close()
+    o.close()
+
+
+def test_tiled_encoder_pipelined_output_is_identical():
+    from kvazzup_b200.encoder import GpuTiledEncoder
+    w, h, n, tiles = 640, 256, 9, 3
+    frames = frames_of("camera", w, h, n)
+    a = GpuTiledEncoder(w, h, tiles, qp=30, intra_period=4, depth=1)
+    want = [a.encode(f) for f in frames]
+    a.close()
+    b = GpuTiledEncoder(w, h, tiles, qp=30, intra_period=4, depth=4)
+    got = []
+    for f in frames:
+        au = b.encode(f)
+        if au:
+            got.append(au)
+    while b.pending():
+        got.append(b.flush())
+    b.close()
+    assert got == want
+    with pytest.raises(Exception):
+        GpuTiledEncoder(256, 128, 3)            # 4 CTU columns cannot hold three tiles of two CTUs
