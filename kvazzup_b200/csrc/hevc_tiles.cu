@@ -18,8 +18,11 @@
 
 #include <algorithm>
 #include <memory>
+#include <string>
+#include <thread>
 
 #include "../../include/b200_hevc.h"
+#include "../../include/b200media.h"
 #include "hevc_encoder.h"
 #include "runtime.h"
 
@@ -79,23 +82,42 @@ struct TiledEncoder {
     write_slice_nal(layout, e0.last_idr != 0, e0.last_poc, e0.last_qp, sub_len.data(), (int)sub_len.size(), data.data(), data.size(), au);
   }
 
-  // pic == nullptr drains.  au is empty while the strips' pipelines fill.
+  // pic == nullptr drains.  au is empty while the strips' pipelines fill.  Every strip is driven by
+  // its own host thread for the duration of the call: the per-picture host work (three strided
+  // uploads, a dozen launches, one event wait) then overlaps across strips and GPUs instead of
+  // adding up on the caller's thread.
   bool step(const uint8_t *pic)
   {
-    int prev = 0, ready = 0;
-    cudaGetDevice(&prev);
-    bool ok = true;
-    for (Strip &s : strips) {            // enqueue on every GPU first ...
-      cudaSetDevice(s.device);
-      ok = ok && (pic ? s.enc->encode_host_strip(pic, width, s.x0, tmp) : s.enc->flush(tmp));
-      if (!ok) break;
-      ready += tmp.empty() ? 0 : 1;      // ... the strips run in lock step, so all or none return a picture
+    const int n = (int)strips.size();
+    std::vector<int> ok(n, 0), ready(n, 0);
+    std::vector<std::string> err(n);
+    auto work = [&](int i) {
+      Strip &s = strips[i];
+      std::vector<uint8_t> got;
+      if (cudaSetDevice(s.device) != cudaSuccess) { err[i] = "cannot select the strip's CUDA device"; return; }
+      ok[i] = pic ? s.enc->encode_host_strip(pic, width, s.x0, got) : s.enc->flush(got);
+      if (!ok[i]) err[i] = b200_last_error();
+      ready[i] = got.empty() ? 0 : 1;
+    };
+    if (n == 1) {
+      int prev = 0;
+      cudaGetDevice(&prev);
+      work(0);
+      cudaSetDevice(prev);
+    } else {
+      std::vector<std::thread> th;
+      th.reserve(n);
+      for (int i = 0; i < n; i++) th.emplace_back(work, i);
+      for (std::thread &t : th) t.join();
     }
-    cudaSetDevice(prev);
     au.clear();
-    if (!ok) return false;
-    if (ready == 0) return true;
-    if (ready != (int)strips.size()) { set_error("tiled encoder: strips out of step"); return false; }
+    int n_ready = 0;
+    for (int i = 0; i < n; i++) {
+      if (!ok[i]) { set_error("tiled encoder, strip %d: %s", i, err[i].c_str()); return false; }
+      n_ready += ready[i];
+    }
+    if (n_ready == 0) return true;
+    if (n_ready != n) { set_error("tiled encoder: strips out of step"); return false; }   // they run in lock step
     compose();
     return true;
   }

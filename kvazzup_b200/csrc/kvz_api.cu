@@ -9,6 +9,7 @@
 #include <new>
 
 #include "../../include/b200_kvazaar.h"
+#include "../../include/b200_hevc.h"
 #include "hevc_encoder.h"
 #include "runtime.h"
 
@@ -17,6 +18,9 @@ using b200::EncoderConfig;
 
 struct kvz_encoder {
   Encoder eng;
+  void *tiled = nullptr;                // b200_tiled_* handle when cfg.tiles_width_count > 1 (eng stays closed)
+  std::vector<uint8_t> tiled_out;
+  ~kvz_encoder() { if (tiled) b200_tiled_close(tiled); }
   kvz_config cfg;
   std::deque<int64_t> pts;              // presentation timestamps of the pictures in flight
   // frame-level rate control (target_bitrate != 0): leaky bucket on the produced bits
@@ -113,7 +117,7 @@ int config_parse(kvz_config *cfg, const char *name, const char *value)
   if (!strcmp(name, "tiles")) {
     int c = 0, r = 0;
     if (!value || sscanf(value, "%dx%d", &c, &r) != 2) return 0;
-    if (c != 1 || r != 1) return 0;            // tile columns are a planned multi-GPU split, not built yet
+    if (c < 1 || c > 32 || r != 1) return 0;   // tile columns only ("WxH" with H = 1), see hevc_tiles.cu
     cfg->tiles_width_count = c; cfg->tiles_height_count = r;
     return 1;
   }
@@ -230,7 +234,7 @@ kvz_encoder *encoder_open(const kvz_config *cfg)
 {
   if (!cfg) { b200::set_error("encoder_open: NULL config"); return NULL; }
   if (cfg->lossless) { b200::set_error("encoder_open: lossless coding is not supported"); return NULL; }
-  if (cfg->tiles_width_count != 1 || cfg->tiles_height_count != 1) { b200::set_error("encoder_open: tiles are not supported yet"); return NULL; }
+  if (cfg->tiles_height_count != 1) { b200::set_error("encoder_open: tile rows are not supported (tile columns are)"); return NULL; }
   if (cfg->device >= 0 && cudaSetDevice(cfg->device) != cudaSuccess) { b200::set_error("encoder_open: cannot select CUDA device %d", cfg->device); return NULL; }
   kvz_encoder *e = new (std::nothrow) kvz_encoder();
   if (!e) return NULL;
@@ -240,6 +244,16 @@ kvz_encoder *encoder_open(const kvz_config *cfg)
   c.search_range = cfg->me_range > 0 ? cfg->me_range : 12;
   c.deblock = cfg->deblock_enable; c.debug = 0; c.depth = cfg->owf + 1;
   c.qp_delta = (cfg->roi_enable || cfg->set_qp_in_cu) ? 1 : 0;
+  if (cfg->tiles_width_count > 1) {
+    // tile columns: independent strip encoders on this GPU; motion is confined to the tile, like
+    // Kvazaar's mv-constraint frametilemargin (the reference exposes it, kvazaarfilter.cpp:246-276);
+    // constant QP only (no ROI, no rate control)
+    e->tiled = b200_tiled_open(c.width, c.height, c.qp, c.intra_period, c.search_range, c.deblock, c.depth,
+                               cfg->tiles_width_count, cfg->wpp ? 1 : 0, nullptr, 0);
+    if (!e->tiled) { delete e; return NULL; }
+    e->tiled_out.resize((size_t)c.width * c.height * 3 + 65536);
+    return e;
+  }
   if (!e->eng.open(c)) { delete e; return NULL; }
   if (cfg->target_bitrate > 0 && cfg->framerate_num > 0) {
     e->bits_per_frame = (double)cfg->target_bitrate * cfg->framerate_denom / cfg->framerate_num;
@@ -283,6 +297,30 @@ int encoder_encode(kvz_encoder *e, kvz_picture *pic_in, kvz_data_chunk **data_ou
   if (pic_recon) *pic_recon = NULL;
   if (pic_src) *pic_src = NULL;
   if (!e) { b200::set_error("encoder_encode: NULL encoder"); return 0; }
+  if (e->tiled) {
+    int n;
+    if (pic_in) {
+      const size_t ysz = (size_t)e->cfg.width * e->cfg.height;
+      if (pic_in->width != e->cfg.width || pic_in->height != e->cfg.height || !pic_in->y || pic_in->u != pic_in->y + ysz ||
+          pic_in->v != pic_in->u + ysz / 4 || pic_in->stride != pic_in->width) {
+        b200::set_error("encoder_encode: tiled encoding needs a contiguous picture from picture_alloc of the configured size");
+        return 0;
+      }
+      n = b200_tiled_encode(e->tiled, pic_in->y, e->tiled_out.data(), (int)e->tiled_out.size());
+    } else {
+      n = b200_tiled_flush(e->tiled, e->tiled_out.data(), (int)e->tiled_out.size());
+    }
+    if (n < 0) return 0;
+    if (n == 0) return 1;
+    e->au.assign(e->tiled_out.begin(), e->tiled_out.begin() + n);
+    if (data_out) {
+      *data_out = to_chunks(e->au);
+      if (!*data_out) { b200::set_error("encoder_encode: out of memory"); return 0; }
+    }
+    if (len_out) *len_out = (uint32_t)n;
+    if (info_out) memset(info_out, 0, sizeof(*info_out));
+    return 1;
+  }
   bool ok;
   if (pic_in) {
     if (pic_in->width != e->cfg.width || pic_in->height != e->cfg.height || !pic_in->y || !pic_in->u || !pic_in->v) {

@@ -440,3 +440,34 @@ def test_tiled_encoder_pipelined_output_is_identical():
     assert got == want
     with pytest.raises(Exception):
         GpuTiledEncoder(256, 128, 3)            # 4 CTU columns cannot hold three tiles of two CTUs
+
+
+def test_tiles_through_kvz_api():
+    """video/Tiles + video/tileDimensions (kvazaarfilter.cpp:196-202): "Cx1" selects the tiled encoder;
+    the reference's default "2x2" has tile rows, which config_parse refuses (the filter logs a warning
+    and encodes untiled)."""
+    from kvazzup_b200.encoder import GpuTiledEncoder
+    from kvazzup_b200.kvazaar import KvazaarFilter
+    w, h, n = 640, 256, 5
+    frames = frames_of("camera", w, h, n)
+    base = {"video/ResolutionWidth": w, "video/ResolutionHeight": h, "video/QP": 30, "video/Intra": 0, "video/Preset": "ultrafast"}
+    for wpp in (1, 0):
+        eng = GpuTiledEncoder(w, h, 3, qp=30, intra_period=0, search_range=8, wpp=wpp)
+        want = [eng.encode(f) for f in frames]
+        eng.close()
+        f = KvazaarFilter(base | {"video/Tiles": 1, "video/tileDimensions": "3x1", "video/WPP": wpp})
+        assert f.init()
+        got = []
+        for fr in frames:
+            got += f.feed_input(fr)
+        f.close()
+        assert got == want, wpp
+    plain = GpuEncoder(w, h, qp=30, intra_period=0, search_range=8)
+    want = [plain.encode(f) for f in frames]
+    f = KvazaarFilter(base | {"video/Tiles": 1, "video/tileDimensions": "2x2"})
+    assert f.init() and any("tiles" in str(x) for x in f.warnings)
+    got = []
+    for fr in frames:
+        got += f.feed_input(fr)
+    f.close()
+    assert got == want
