@@ -18,7 +18,9 @@
  * Decoding scope this round: streams of the B200 encoder's syntax family:
  * Main profile 8-bit 4:2:0, 64x64 CTUs, 2Nx2N CUs with one TU, I and P slices with one reference
  * picture, WPP entry points, deblocking; no SAO / PCM / AMP / scaling lists / transform skip /
- * sign hiding / TMVP / tiles; cu_qp_delta with one quantisation group per CTU.  Anything else
+ * sign hiding / TMVP; cu_qp_delta with one quantisation group per CTU; uniformly spaced tile
+ * columns without loop filtering across tiles whose motion stays inside the tile (what
+ * b200_tiled_* and kvz_api "tiles" emit), with or without WPP inside the tiles.  Anything else
  * makes libOpenHevcDecode return -1 with the reason in b200_last_error() -- never a silently wrong
  * picture.
  */

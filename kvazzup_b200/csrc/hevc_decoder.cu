@@ -67,6 +67,7 @@ struct Sps {
 struct Pps {
   bool valid = false;
   int init_qp = 26, deblock_disabled = 0, loop_across_slices = 0, deblock_ctrl = 0, qp_delta = 0;
+  int tile_cols = 1, wpp = 1;
 };
 
 const uint8_t kChromaQpD[58] = {
@@ -75,19 +76,40 @@ const uint8_t kChromaQpD[58] = {
 
 }  // namespace
 
-// One picture in flight: everything the CABAC parse of a picture reads and writes.  Parsing needs
-// nothing from other pictures (no TMVP), so the parses of up to `frame_delay + 1` pictures run
-// concurrently on their own streams; only reconstruction is chained from picture to picture.
-struct DecSlot {
+// A tile column is decoded as a picture of its own ("strip", see hevc_tiles.cu for why that is exact
+// when motion stays inside the tile and tiles are not loop-filtered across); a picture without
+// tiles is a single strip covering everything.  Per decoder: the strip's geometry, reconstruction
+// ping-pong and reconstruction stream.
+struct StripGeom {
+  int x0 = 0, wd = 0;
+  FrameParams fp{};                       // strip-sized
+  size_t bytes = 0;                       // packed I420 of the strip
+  uint8_t *d_rec[2] = {nullptr, nullptr};
+  int *d_order = nullptr;
+  cudaStream_t stream = nullptr;          // reconstruction chain of this strip
+  cudaEvent_t ev_done = nullptr;
+};
+
+// Per picture in flight and strip: what the CABAC parse of the strip reads and writes.
+struct StripBufs {
   cudaStream_t stream = nullptr;
   cudaEvent_t ev_parsed = nullptr;
-  uint8_t *d_data = nullptr, *d_small = nullptr, *d_ctu_qp = nullptr;
+  uint8_t *d_small = nullptr, *d_ctu_qp = nullptr;
   CuInfo *d_cu = nullptr;
   int16_t *d_levels = nullptr;
-  uint8_t *h_data = nullptr, *h_out = nullptr;
   uint32_t *h_bases = nullptr;
   int *h_status = nullptr;
   FrameParams fp{};
+};
+
+// One picture in flight.  Parsing needs nothing from other pictures (no TMVP), so the parses of up
+// to `frame_delay + 1` pictures run concurrently on their own streams; only reconstruction is
+// chained from picture to picture.
+struct DecSlot {
+  cudaStream_t stream = nullptr;          // slice data upload
+  cudaEvent_t ev_uploaded = nullptr;
+  uint8_t *d_data = nullptr, *h_data = nullptr, *h_out = nullptr;
+  std::vector<StripBufs> strips;
   int64_t pts = 0;
 };
 
@@ -95,18 +117,19 @@ struct Decoder {
   Sps sps;
   Pps pps;
   bool vps_seen = false, started = false;
-  FrameParams fp{};
+  FrameParams fp{};                       // whole picture
   size_t frame_bytes = 0;
-  cudaStream_t stream = nullptr;          // reconstruction chain
-  uint8_t *d_rec[2] = {nullptr, nullptr};
-  int *d_order = nullptr;
+  cudaStream_t stream = nullptr;          // output assembly / copy
+  std::vector<StripGeom> geom;
+  uint8_t *d_full = nullptr;              // whole picture on the device when there are several strips
+  int conf_w = 0, conf_h = 0, conf_tiles = 0;
   std::vector<DecSlot> slots;
   std::deque<int> pending;                // slots whose parse was launched, oldest first
   size_t data_cap = 0, small_bytes = 0, off_flag = 0, off_prog = 0, off_ticket = 0, off_status = 0, off_bases = 0, off_ctx = 0;
   int frame_delay = 0;                    // pictures held back (OpenHEVC frame threads - 1)
   int next_slot = 0, out_slot = -1;
   bool host_output = true;                // false: pictures stay on the GPU (b200_dec_output_dev)
-  const uint8_t *d_out = nullptr;         // device copy of the last output picture (the new reference)
+  const uint8_t *d_out = nullptr;         // device copy of the last output picture
   int cur = 0, have_ref = 0, pictures = 0;
   int64_t out_pts = 0;
   int fr_num = 0, fr_den = 0;
@@ -115,35 +138,47 @@ struct Decoder {
   void release()
   {
     if (stream) cudaStreamSynchronize(stream);
+    for (StripGeom &g : geom) {
+      if (g.stream) { cudaStreamSynchronize(g.stream); cudaStreamDestroy(g.stream); }
+      if (g.ev_done) cudaEventDestroy(g.ev_done);
+      for (int i = 0; i < 2; i++) if (g.d_rec[i]) cudaFree(g.d_rec[i]);
+      if (g.d_order) cudaFree(g.d_order);
+    }
+    geom.clear();
     for (DecSlot &s : slots) {
       if (s.stream) cudaStreamSynchronize(s.stream);
+      for (StripBufs &t : s.strips) {
+        if (t.stream) { cudaStreamSynchronize(t.stream); cudaStreamDestroy(t.stream); }
+        if (t.ev_parsed) cudaEventDestroy(t.ev_parsed);
+        if (t.d_small) cudaFree(t.d_small);
+        if (t.d_ctu_qp) cudaFree(t.d_ctu_qp);
+        if (t.d_cu) cudaFree(t.d_cu);
+        if (t.d_levels) cudaFree(t.d_levels);
+        if (t.h_bases) cudaFreeHost(t.h_bases);
+        if (t.h_status) cudaFreeHost(t.h_status);
+      }
       if (s.d_data) cudaFree(s.d_data);
-      if (s.d_small) cudaFree(s.d_small);
-      if (s.d_ctu_qp) cudaFree(s.d_ctu_qp);
-      if (s.d_cu) cudaFree(s.d_cu);
-      if (s.d_levels) cudaFree(s.d_levels);
       if (s.h_data) cudaFreeHost(s.h_data);
       if (s.h_out) cudaFreeHost(s.h_out);
-      if (s.h_bases) cudaFreeHost(s.h_bases);
-      if (s.h_status) cudaFreeHost(s.h_status);
-      if (s.ev_parsed) cudaEventDestroy(s.ev_parsed);
+      if (s.ev_uploaded) cudaEventDestroy(s.ev_uploaded);
       if (s.stream) cudaStreamDestroy(s.stream);
     }
     slots.clear();
     pending.clear();
-    for (int i = 0; i < 2; i++) if (d_rec[i]) cudaFree(d_rec[i]);
-    if (d_order) cudaFree(d_order);
+    if (d_full) cudaFree(d_full);
     if (stream) cudaStreamDestroy(stream);
-    d_rec[0] = d_rec[1] = nullptr; d_order = nullptr; stream = nullptr;
-    next_slot = 0; out_slot = -1;
+    d_full = nullptr; stream = nullptr;
+    next_slot = 0; out_slot = -1; conf_tiles = 0;
   }
 
-  bool alloc(int w, int h)
+  // (Re)allocate for a picture size and tile-column count; pictures in flight are dropped.
+  bool configure(int w, int h, int tiles)
   {
     release();
+    fp = FrameParams{};
     fp.w = w; fp.h = h; fp.w8 = w / 8; fp.h8 = h / 8;
     fp.ctb_cols = (w + kCtb - 1) / kCtb; fp.ctb_rows = (h + kCtb - 1) / kCtb;
-    fp.deblock = 1; fp.search_range = 8; fp.lambda_q4 = 0; fp.ctu_qp = nullptr; fp.ctu_delta = nullptr; fp.ctu_first = nullptr;
+    fp.deblock = 1; fp.search_range = 8;
     frame_bytes = (size_t)w * h * 3 / 2;
     data_cap = frame_bytes * 2 + 65536;
     const int rows = fp.ctb_rows;
@@ -152,29 +187,50 @@ struct Decoder {
     off_ctx = off_bases + sizeof(uint32_t) * (rows + 1);
     small_bytes = off_ctx + (size_t)rows * CTX_COUNT;
     if (!cuda_ok(cudaStreamCreateWithFlags(&stream, cudaStreamNonBlocking), "cudaStreamCreate")) return false;
-    if (!cuda_ok(cudaMalloc((void **)&d_rec[0], frame_bytes), "cudaMalloc")) return false;
-    if (!cuda_ok(cudaMalloc((void **)&d_rec[1], frame_bytes), "cudaMalloc")) return false;
-    {
-      std::vector<int> order((size_t)fp.ctb_cols * fp.ctb_rows);
-      intra_wavefront_order(fp.ctb_cols, fp.ctb_rows, order.data());
-      if (!cuda_ok(cudaMalloc((void **)&d_order, order.size() * sizeof(int)), "cudaMalloc")) return false;
-      if (!cuda_ok(cudaMemcpy(d_order, order.data(), order.size() * sizeof(int), cudaMemcpyHostToDevice), "H2D order")) return false;
+    geom.resize(tiles);
+    for (int i = 0; i < tiles; i++) {
+      StripGeom &g = geom[i];
+      const int c0 = i * fp.ctb_cols / tiles, c1 = (i + 1) * fp.ctb_cols / tiles;      // colBd, uniform spacing (6.5.1)
+      g.x0 = c0 * kCtb;
+      g.wd = std::min(w, c1 * kCtb) - g.x0;
+      g.fp = fp;
+      g.fp.w = g.wd; g.fp.w8 = g.wd / 8; g.fp.ctb_cols = c1 - c0;
+      g.fp.mv_edges = tiles > 1 ? ((i > 0 ? 1 : 0) | (i < tiles - 1 ? 2 : 0)) : 0;
+      g.fp.more_tiles = i < tiles - 1 ? 1 : 0;
+      g.bytes = (size_t)g.wd * h * 3 / 2;
+      if (!cuda_ok(cudaStreamCreateWithFlags(&g.stream, cudaStreamNonBlocking), "cudaStreamCreate")) return false;
+      if (!cuda_ok(cudaEventCreateWithFlags(&g.ev_done, cudaEventDisableTiming), "cudaEventCreate")) return false;
+      if (!cuda_ok(cudaMalloc((void **)&g.d_rec[0], g.bytes), "cudaMalloc")) return false;
+      if (!cuda_ok(cudaMalloc((void **)&g.d_rec[1], g.bytes), "cudaMalloc")) return false;
+      std::vector<int> order((size_t)g.fp.ctb_cols * rows);
+      intra_wavefront_order(g.fp.ctb_cols, rows, order.data());
+      if (!cuda_ok(cudaMalloc((void **)&g.d_order, order.size() * sizeof(int)), "cudaMalloc")) return false;
+      if (!cuda_ok(cudaMemcpy(g.d_order, order.data(), order.size() * sizeof(int), cudaMemcpyHostToDevice), "H2D order")) return false;
     }
+    if (tiles > 1 && !cuda_ok(cudaMalloc((void **)&d_full, frame_bytes), "cudaMalloc")) return false;
     slots.resize(frame_delay + 1);
     for (DecSlot &s : slots) {
       if (!cuda_ok(cudaStreamCreateWithFlags(&s.stream, cudaStreamNonBlocking), "cudaStreamCreate")) return false;
-      if (!cuda_ok(cudaEventCreateWithFlags(&s.ev_parsed, cudaEventDisableTiming), "cudaEventCreate")) return false;
+      if (!cuda_ok(cudaEventCreateWithFlags(&s.ev_uploaded, cudaEventDisableTiming), "cudaEventCreate")) return false;
       if (!cuda_ok(cudaMalloc((void **)&s.d_data, data_cap), "cudaMalloc")) return false;
-      if (!cuda_ok(cudaMalloc((void **)&s.d_small, small_bytes), "cudaMalloc")) return false;
-      if (!cuda_ok(cudaMalloc((void **)&s.d_ctu_qp, (size_t)fp.ctb_cols * fp.ctb_rows), "cudaMalloc")) return false;
-      if (!cuda_ok(cudaMalloc((void **)&s.d_cu, sizeof(CuInfo) * fp.w8 * fp.h8), "cudaMalloc")) return false;
-      if (!cuda_ok(cudaMalloc((void **)&s.d_levels, frame_bytes * sizeof(int16_t)), "cudaMalloc")) return false;
       if (!cuda_ok(cudaMallocHost((void **)&s.h_out, frame_bytes), "cudaMallocHost")) return false;
       if (!cuda_ok(cudaMallocHost((void **)&s.h_data, data_cap), "cudaMallocHost")) return false;
-      if (!cuda_ok(cudaMallocHost((void **)&s.h_bases, sizeof(uint32_t) * (rows + 1)), "cudaMallocHost")) return false;
-      if (!cuda_ok(cudaMallocHost((void **)&s.h_status, sizeof(int) * 2), "cudaMallocHost")) return false;
+      s.strips.resize(tiles);
+      for (int i = 0; i < tiles; i++) {
+        StripBufs &t = s.strips[i];
+        const StripGeom &g = geom[i];
+        if (!cuda_ok(cudaStreamCreateWithFlags(&t.stream, cudaStreamNonBlocking), "cudaStreamCreate")) return false;
+        if (!cuda_ok(cudaEventCreateWithFlags(&t.ev_parsed, cudaEventDisableTiming), "cudaEventCreate")) return false;
+        if (!cuda_ok(cudaMalloc((void **)&t.d_small, small_bytes), "cudaMalloc")) return false;
+        if (!cuda_ok(cudaMalloc((void **)&t.d_ctu_qp, (size_t)g.fp.ctb_cols * rows), "cudaMalloc")) return false;
+        if (!cuda_ok(cudaMalloc((void **)&t.d_cu, sizeof(CuInfo) * g.fp.w8 * g.fp.h8), "cudaMalloc")) return false;
+        if (!cuda_ok(cudaMalloc((void **)&t.d_levels, g.bytes * sizeof(int16_t)), "cudaMalloc")) return false;
+        if (!cuda_ok(cudaMallocHost((void **)&t.h_bases, sizeof(uint32_t) * (rows + 1)), "cudaMallocHost")) return false;
+        if (!cuda_ok(cudaMallocHost((void **)&t.h_status, sizeof(int) * 2), "cudaMallocHost")) return false;
+      }
     }
     cur = 0; have_ref = 0;
+    conf_w = w; conf_h = h; conf_tiles = tiles;
     return true;
   }
 
@@ -218,9 +274,6 @@ struct Decoder {
     if (b.u(1)) { set_error("decoder: temporal MVP is not supported"); return false; }
     b.u(1);      // strong_intra_smoothing: irrelevant, no 32x32 intra blocks are accepted
     if (b.bad || w <= 0 || h <= 0 || (w & 7) || (h & 7)) { set_error("decoder: malformed SPS"); return false; }
-    if (!sps.valid || sps.width != w || sps.height != h) {
-      if (!alloc(w, h)) return false;
-    }
     sps.valid = true; sps.width = w; sps.height = h; sps.log2_max_poc = log2_max_poc; sps.num_rps = num_rps;
     return true;
   }
@@ -245,8 +298,16 @@ struct Decoder {
     if (b.u(1)) { set_error("decoder: slice chroma QP offsets are not supported"); return false; }
     if (b.u(1) || b.u(1)) { set_error("decoder: weighted prediction is not supported"); return false; }
     if (b.u(1)) { set_error("decoder: transquant bypass is not supported"); return false; }
-    if (b.u(1)) { set_error("decoder: tiles are not supported"); return false; }
-    if (!b.u(1)) { set_error("decoder: streams without WPP entry points are not supported"); return false; }
+    const int tiles_on = (int)b.u(1), wpp = (int)b.u(1);
+    int tile_cols = 1;
+    if (tiles_on) {
+      tile_cols = (int)b.ue() + 1;
+      if (b.ue() != 0) { set_error("decoder: tile rows are not supported (tile columns are)"); return false; }
+      if (!b.u(1)) { set_error("decoder: only uniformly spaced tile columns are supported"); return false; }
+      if (b.u(1)) { set_error("decoder: loop filtering across tiles is not supported"); return false; }
+      if (tile_cols > 32) { set_error("decoder: too many tile columns"); return false; }
+    }
+    if (!tiles_on && !wpp) { set_error("decoder: streams with neither WPP nor tiles are not supported"); return false; }
     pps.loop_across_slices = (int)b.u(1);
     pps.deblock_ctrl = (int)b.u(1);
     pps.deblock_disabled = 0;
@@ -260,7 +321,7 @@ struct Decoder {
     if (b.ue() != 0) { set_error("decoder: parallel merge level > 2 is not supported"); return false; }
     if (b.u(1)) { set_error("decoder: slice header extensions are not supported"); return false; }
     if (b.bad) { set_error("decoder: malformed PPS"); return false; }
-    pps.valid = true; pps.init_qp = init_qp; pps.qp_delta = qp_delta;
+    pps.valid = true; pps.init_qp = init_qp; pps.qp_delta = qp_delta; pps.tile_cols = tile_cols; pps.wpp = wpp;
     return true;
   }
 
@@ -306,8 +367,17 @@ struct Decoder {
     int qp = pps.init_qp + b.se();
     const int deblock = !pps.deblock_disabled;
     if (pps.loop_across_slices && deblock) b.u(1);
-    const int rows = fp.ctb_rows;
+    // geometry: picture size from the SPS, tile columns from the PPS (pictures in flight are dropped
+    // when either changes)
+    if (conf_w != sps.width || conf_h != sps.height || conf_tiles != pps.tile_cols) {
+      const int ctb_cols = (sps.width + kCtb - 1) / kCtb;
+      if (pps.tile_cols > 1 && pps.tile_cols > ctb_cols / 2) { set_error("decoder: tile columns narrower than two CTUs are not supported"); return -1; }
+      if (!configure(sps.width, sps.height, pps.tile_cols)) return -1;
+    }
+    const int rows = fp.ctb_rows, tiles = conf_tiles;
+    const int per_tile = pps.wpp ? rows : 1;                  // substreams per tile
     int n_entry = (int)b.ue();
+    if (n_entry < 0 || n_entry > 4096) { set_error("decoder: implausible number of entry points"); return -1; }
     std::vector<uint32_t> entry(n_entry);
     if (n_entry > 0) {
       int len = (int)b.ue() + 1;
@@ -316,7 +386,10 @@ struct Decoder {
     if (!b.u(1)) { set_error("decoder: malformed slice header (alignment bit)"); return -1; }
     b.align();
     if (b.bad || qp < 0 || qp > 51) { set_error("decoder: malformed slice header"); return -1; }
-    if (n_entry != rows - 1) { set_error("decoder: %d entry points for %d CTU rows (WPP expected)", n_entry, rows); return -1; }
+    if (n_entry != tiles * per_tile - 1) {
+      set_error("decoder: %d entry points for %d tile column(s) x %d substream(s)", n_entry, tiles, per_tile);
+      return -1;
+    }
     // escaped offset of the first slice-data byte
     const size_t hdr_unesc = b.pos >> 3;
     size_t hdr_esc = hdr_unesc;
@@ -327,78 +400,109 @@ struct Decoder {
       return esc - k;
     };
     DecSlot &sl = slots[next_slot];
-    size_t esc = hdr_esc;
-    for (int r = 0; r < rows; r++) {
-      sl.h_bases[r] = (uint32_t)(to_unesc(esc) - hdr_unesc);
-      if (r < rows - 1) esc += entry[r];
-    }
     const size_t data_len = rbsp.size() - hdr_unesc;
-    sl.h_bases[rows] = (uint32_t)data_len;
-    for (int r = 0; r < rows; r++)
-      if (sl.h_bases[r] > sl.h_bases[r + 1]) { set_error("decoder: entry points run past the slice data"); return -1; }
     if (data_len > data_cap) { set_error("decoder: slice larger than the staging buffer"); return -1; }
+    {
+      size_t esc = hdr_esc;
+      uint32_t prev = 0;
+      for (int k = 0; k < tiles * per_tile; k++) {
+        const uint32_t base = (uint32_t)(to_unesc(esc) - hdr_unesc);
+        if (base < prev || base > data_len) { set_error("decoder: entry points run past the slice data"); return -1; }
+        prev = base;
+        StripBufs &t = sl.strips[k / per_tile];
+        t.h_bases[k % per_tile] = base;
+        if (k % per_tile == 0 && k > 0) sl.strips[k / per_tile - 1].h_bases[per_tile] = base;
+        if (k < tiles * per_tile - 1) esc += entry[k];
+      }
+      sl.strips[tiles - 1].h_bases[per_tile] = (uint32_t)data_len;
+    }
     memcpy(sl.h_data, rbsp.data() + hdr_unesc, data_len);
-
-    sl.fp = fp;
-    sl.fp.qp = qp; sl.fp.qp_c = kChromaQpD[qp]; sl.fp.is_idr = slice_type == 2 ? 1 : 0; sl.fp.deblock = deblock;
-    sl.fp.ctu_qp = pps.qp_delta ? sl.d_ctu_qp : nullptr; sl.fp.ctu_delta = nullptr; sl.fp.ctu_first = nullptr;
     sl.pts = pts;
-    int *sync_flag = (int *)(sl.d_small + off_flag), *progress = (int *)(sl.d_small + off_prog);
-    int *status = (int *)(sl.d_small + off_status);
-    uint32_t *d_bases = (uint32_t *)(sl.d_small + off_bases);
 #define DEC_CHECK(expr, what) do { if (!cuda_ok((expr), (what))) return -1; } while (0)
     DEC_CHECK(cudaMemcpyAsync(sl.d_data, sl.h_data, data_len, cudaMemcpyHostToDevice, sl.stream), "H2D slice");
-    DEC_CHECK(cudaMemcpyAsync(d_bases, sl.h_bases, sizeof(uint32_t) * (rows + 1), cudaMemcpyHostToDevice, sl.stream), "H2D bases");
-    DEC_CHECK(cudaMemsetAsync(sl.d_levels, 0, frame_bytes * sizeof(int16_t), sl.stream), "memset levels");
-    DEC_CHECK(launch_parse(sl.fp, sl.d_data, d_bases, sl.d_cu, sl.d_levels, sl.d_small + off_ctx, sync_flag, progress, status, sl.stream), "parse launch");
-    count_launch(1);
-    DEC_CHECK(cudaMemcpyAsync(sl.h_status, status, sizeof(int) * 2, cudaMemcpyDeviceToHost, sl.stream), "D2H status");
-    DEC_CHECK(cudaEventRecord(sl.ev_parsed, sl.stream), "record parse");
+    DEC_CHECK(cudaEventRecord(sl.ev_uploaded, sl.stream), "record upload");
+    for (int i = 0; i < tiles; i++) {
+      StripBufs &t = sl.strips[i];
+      const StripGeom &g = geom[i];
+      t.fp = g.fp;
+      t.fp.qp = qp; t.fp.qp_c = kChromaQpD[qp]; t.fp.is_idr = slice_type == 2 ? 1 : 0; t.fp.deblock = deblock;
+      t.fp.no_wpp = pps.wpp ? 0 : 1;
+      t.fp.ctu_qp = pps.qp_delta ? t.d_ctu_qp : nullptr; t.fp.ctu_delta = nullptr; t.fp.ctu_first = nullptr;
+      int *sync_flag = (int *)(t.d_small + off_flag), *progress = (int *)(t.d_small + off_prog);
+      int *status = (int *)(t.d_small + off_status);
+      uint32_t *d_bases = (uint32_t *)(t.d_small + off_bases);
+      DEC_CHECK(cudaStreamWaitEvent(t.stream, sl.ev_uploaded, 0), "stream wait");
+      DEC_CHECK(cudaMemcpyAsync(d_bases, t.h_bases, sizeof(uint32_t) * (per_tile + 1), cudaMemcpyHostToDevice, t.stream), "H2D bases");
+      DEC_CHECK(cudaMemsetAsync(t.d_levels, 0, g.bytes * sizeof(int16_t), t.stream), "memset levels");
+      DEC_CHECK(launch_parse(t.fp, sl.d_data, d_bases, t.d_cu, t.d_levels, t.d_small + off_ctx, sync_flag, progress, status, t.stream), "parse launch");
+      count_launch(1);
+      DEC_CHECK(cudaMemcpyAsync(t.h_status, status, sizeof(int) * 2, cudaMemcpyDeviceToHost, t.stream), "D2H status");
+      DEC_CHECK(cudaEventRecord(t.ev_parsed, t.stream), "record parse");
+    }
     pending.push_back(next_slot);
     next_slot = (next_slot + 1) % (int)slots.size();
     if ((int)pending.size() <= frame_delay) return 0;
     return finish_oldest();
   }
 
-  // Reconstructs the oldest parsed picture (prediction + residual, deblocking) and copies it to the
-  // host.  Returns 1 with the picture in slots[out_slot].h_out, -1 on error.
+  // Reconstructs the oldest parsed picture (prediction + residual, deblocking, strip by strip) and
+  // copies it to the host.  Returns 1 with the picture in slots[out_slot].h_out, -1 on error.
   int finish_oldest()
   {
     const int idx = pending.front();
     pending.pop_front();
     DecSlot &sl = slots[idx];
-    FrameParams &f = sl.fp;
-    int *progress = (int *)(sl.d_small + off_prog), *ticket = (int *)(sl.d_small + off_ticket);
-    if (!cuda_ok(cudaEventSynchronize(sl.ev_parsed), "sync parse")) { have_ref = 0; return -1; }
-    if (sl.h_status[0] != 0) {
-      static const char *const why[] = {"", "escape code too long", "intra CU in a P slice", "partition other than 2Nx2N", "mvd too long",
-        "NxN intra partition", "intra chroma mode other than derived", "64x64 CU with residual", "end_of_slice_segment_flag mismatch",
-        "end_of_subset_one_bit missing", "intra CU size other than 16x16 (8x8 at the picture edge)", "cu_qp_delta out of range"};
-      int c = sl.h_status[0];
-      set_error("decoder: unsupported or corrupt slice data (%s)", c > 0 && c <= 11 ? why[c] : "unknown");
-      have_ref = 0;
-      return -1;
+    const int tiles = (int)sl.strips.size();
+    for (int i = 0; i < tiles; i++) {
+      StripBufs &t = sl.strips[i];
+      if (!cuda_ok(cudaEventSynchronize(t.ev_parsed), "sync parse")) { have_ref = 0; return -1; }
+      if (t.h_status[0] != 0) {
+        static const char *const why[] = {"", "escape code too long", "intra CU in a P slice", "partition other than 2Nx2N", "mvd too long",
+          "NxN intra partition", "intra chroma mode other than derived", "64x64 CU with residual", "end_of_slice_segment_flag mismatch",
+          "end_of_subset_one_bit missing", "intra CU size other than 16x16 (8x8 at the picture edge)", "cu_qp_delta out of range",
+          "motion vector reaches across a tile boundary"};
+        int c = t.h_status[0];
+        set_error("decoder: unsupported or corrupt slice data (%s)", c > 0 && c <= 12 ? why[c] : "unknown");
+        have_ref = 0;
+        return -1;
+      }
     }
-    if (!f.is_idr && !have_ref) { set_error("decoder: P slice without a reference picture"); return -1; }
-    uint8_t *rec = d_rec[cur], *ref = d_rec[cur ^ 1];
+    const bool is_idr = sl.strips[0].fp.is_idr != 0;
+    if (!is_idr && !have_ref) { set_error("decoder: P slice without a reference picture"); return -1; }
     have_ref = 0;                          // until this picture is complete
-    if (f.is_idr) {
-      DEC_CHECK(launch_intra_decode(f, rec, sl.d_levels, sl.d_cu, progress, ticket, d_order, stream), "intra decode launch");
-      count_launch(1);
-    } else {
-      f.search_range = std::max(1, (sl.h_status[1] + 3) / 4 + 1);
-      cudaError_t e = launch_inter_decode(f, ref, rec, sl.d_levels, sl.d_cu, stream);
-      if (e == cudaErrorInvalidValue) { set_error("decoder: motion vectors of +-%d samples exceed the supported window", f.search_range); return -1; }
-      DEC_CHECK(e, "inter decode launch");
-      count_launch(1);
+    const size_t ysz = (size_t)fp.w * fp.h;
+    for (int i = 0; i < tiles; i++) {      // the strips reconstruct concurrently, each on its own stream
+      StripBufs &t = sl.strips[i];
+      StripGeom &g = geom[i];
+      FrameParams &f = t.fp;
+      int *progress = (int *)(t.d_small + off_prog), *ticket = (int *)(t.d_small + off_ticket);
+      uint8_t *rec = g.d_rec[cur], *ref = g.d_rec[cur ^ 1];
+      if (f.is_idr) {
+        DEC_CHECK(launch_intra_decode(f, rec, t.d_levels, t.d_cu, progress, ticket, g.d_order, g.stream), "intra decode launch");
+        count_launch(1);
+      } else {
+        f.search_range = std::max(1, (t.h_status[1] + 3) / 4 + 1);
+        cudaError_t e = launch_inter_decode(f, ref, rec, t.d_levels, t.d_cu, g.stream);
+        if (e == cudaErrorInvalidValue) { set_error("decoder: motion vectors of +-%d samples exceed the supported window", f.search_range); return -1; }
+        DEC_CHECK(e, "inter decode launch");
+        count_launch(1);
+      }
+      if (f.deblock) {
+        DEC_CHECK(launch_deblock(f, rec, t.d_cu, g.stream), "deblock launch");
+        count_launch(2);
+      }
+      if (tiles > 1) {                     // place the strip in the whole picture
+        const size_t sy = (size_t)g.wd * fp.h;
+        DEC_CHECK(cudaMemcpy2DAsync(d_full + g.x0, fp.w, rec, g.wd, g.wd, fp.h, cudaMemcpyDeviceToDevice, g.stream), "assemble Y");
+        DEC_CHECK(cudaMemcpy2DAsync(d_full + ysz + g.x0 / 2, fp.w / 2, rec + sy, g.wd / 2, g.wd / 2, fp.h / 2, cudaMemcpyDeviceToDevice, g.stream), "assemble U");
+        DEC_CHECK(cudaMemcpy2DAsync(d_full + ysz + ysz / 4 + g.x0 / 2, fp.w / 2, rec + sy + sy / 4, g.wd / 2, g.wd / 2, fp.h / 2, cudaMemcpyDeviceToDevice, g.stream), "assemble V");
+      }
+      DEC_CHECK(cudaEventRecord(g.ev_done, g.stream), "record strip");
+      DEC_CHECK(cudaStreamWaitEvent(stream, g.ev_done, 0), "stream wait");
     }
-    if (f.deblock) {
-      DEC_CHECK(launch_deblock(f, rec, sl.d_cu, stream), "deblock launch");
-      count_launch(2);
-    }
-    if (host_output) DEC_CHECK(cudaMemcpyAsync(sl.h_out, rec, frame_bytes, cudaMemcpyDeviceToHost, stream), "D2H picture");
+    d_out = tiles > 1 ? d_full : geom[0].d_rec[cur];
+    if (host_output) DEC_CHECK(cudaMemcpyAsync(sl.h_out, d_out, frame_bytes, cudaMemcpyDeviceToHost, stream), "D2H picture");
     DEC_CHECK(cudaStreamSynchronize(stream), "sync picture");
-    d_out = rec;
 #undef DEC_CHECK
     cur ^= 1;
     have_ref = 1; out_slot = idx; out_pts = sl.pts; pictures++;
@@ -513,7 +617,10 @@ void libOpenHevcFlush(OpenHevc_Handle h)
 {
   Decoder *d = (Decoder *)h;
   if (!d) return;
-  for (b200::DecSlot &s : d->slots) cudaStreamSynchronize(s.stream);
+  for (b200::DecSlot &s : d->slots) {
+    cudaStreamSynchronize(s.stream);
+    for (b200::StripBufs &t : s.strips) cudaStreamSynchronize(t.stream);
+  }
   d->pending.clear();
   d->have_ref = 0; d->out_slot = -1; d->d_out = nullptr;
 }

@@ -148,7 +148,7 @@ struct ParseCtx {
   int max_mv;            // largest |mv component| seen (quarter samples)
   uint32_t *s_ctu;       // [2][64][3]: 8x8 units of the current (cur_buf) and the previous CTU, raster order
   uint32_t *s_above;     // [10][3]: units (cx/8 - 1 .. cx/8 + 8) of the line above the CTU row
-  int cx, cy, cur_buf;
+  int cx, cy, cur_buf;           // cy: top of the CTU row being parsed
   // cu_qp_delta with one quantisation group per CTU (8.6.1): qp_cur is QpY of the CU being parsed
   // (the prediction until the CTU's delta is coded), reset to the slice QP at each row start (WPP)
   int qp_cur, delta_coded;
@@ -390,6 +390,7 @@ __device__ void parse_cu(Reader &r, ParseCtx &pc, int x0, int y0, int log2)
       tu = dec_bin(r, CTX_RQT_ROOT_CBF) != 0;
     }
     pc.max_mv = max(pc.max_mv, max(abs((int)cu.mvx), abs((int)cu.mvy)));
+    if (fp.mv_edges && !mv_allowed(fp, x0, n, cu.mvx)) { r.err = 12; return; }   // motion across an interior tile edge
   } else {
     cu.pred_mode = 1;
     {
@@ -489,10 +490,14 @@ k_parse_rows(FrameParams fp, const uint8_t *__restrict__ data, const uint32_t *_
   __shared__ uint2 s_tab[64];
   __shared__ uint32_t s_ctu[2 * 64 * 3];
   __shared__ uint32_t s_above[10 * 3];
-  const int row = blockIdx.x, lane = threadIdx.x;
+  // WPP: one substream per CTU row (row_first == row_last == blockIdx.x).  no_wpp (a tile without
+  // entropy_coding_sync): one warp reads every row from a single substream; bases[0..1] bound it.
+  const int lane = threadIdx.x;
+  const int row_first = fp.no_wpp ? 0 : blockIdx.x, row_last = fp.no_wpp ? fp.ctb_rows - 1 : blockIdx.x;
+  int row = row_first;
   for (int i = lane; i < 64; i += 32) s_tab[i] = make_uint2(c_range_lps[i], (uint32_t)c_trans_lps[i] | (i == 0 ? 64u : 0u));
   Reader r;
-  r.p = data + bases[row]; r.end = data + bases[row + 1]; r.ctx = s_ctx + lane; r.tab = s_tab; r.err = 0;
+  r.p = data + bases[fp.no_wpp ? 0 : row]; r.end = data + bases[fp.no_wpp ? 1 : row + 1]; r.ctx = s_ctx + lane; r.tab = s_tab; r.err = 0;
   ParseCtx pc{fp, cu, levels, lane, 0, s_ctu, s_above, 0, row * kCtb, 0, fp.qp, 0};
   if (row == 0 || fp.ctb_cols < 2) {
     init_contexts_d(r.ctx, fp.is_idr ? 0 : 1, fp.qp);
@@ -510,9 +515,11 @@ k_parse_rows(FrameParams fp, const uint8_t *__restrict__ data, const uint32_t *_
   }
   __syncwarp();
   reader_start(r);
+  for (; row <= row_last && !r.err; row++) {
+  pc.cy = row * kCtb;
   for (int col = 0; col < fp.ctb_cols && !r.err; col++) {
     if (row > 0) {                       // above and above-right CTUs must be parsed (cu map reads)
-      {
+      if (!fp.no_wpp) {                  // (one warp does all rows without WPP: nothing to wait for)
         volatile int *p = progress;
         const int need = min(col + 2, fp.ctb_cols);
         for (;;) {
@@ -555,7 +562,7 @@ k_parse_rows(FrameParams fp, const uint8_t *__restrict__ data, const uint32_t *_
       parse_cu(r, pc, x0, y0, log2);
       z += 1 << (2 * (log2 - 3));
     }
-    if (col == 1 && row + 1 < fp.ctb_rows) {
+    if (col == 1 && row + 1 < fp.ctb_rows && !fp.no_wpp) {
       // every lane holds the same table; all store it (same addresses, same values)
       for (int i = 0; i < CTX_COUNT; i++) sync_ctx[(size_t)row * CTX_COUNT + i] = r.ctx[i * 32];
       __threadfence();
@@ -563,19 +570,23 @@ k_parse_rows(FrameParams fp, const uint8_t *__restrict__ data, const uint32_t *_
       *(volatile int *)&sync_flag[row] = 1;
     }
     if (fp.ctu_qp) fp.ctu_qp[row * fp.ctb_cols + col] = (uint8_t)pc.qp_cur;     // what the CTU's residuals are scaled with
-    const bool last = row == fp.ctb_rows - 1 && col == fp.ctb_cols - 1;
+    const bool last = row == fp.ctb_rows - 1 && col == fp.ctb_cols - 1 && !fp.more_tiles;
+    const bool end_sub = col == fp.ctb_cols - 1 && (!fp.no_wpp || row == fp.ctb_rows - 1);
     int eos = dec_terminate(r);                                        // end_of_slice_segment_flag
     if (eos != (last ? 1 : 0)) r.err = 8;
-    if (col == fp.ctb_cols - 1 && !last && !dec_terminate(r)) r.err = 9;   // end_of_subset_one_bit
+    if (end_sub && !last && !dec_terminate(r)) r.err = 9;              // end_of_subset_one_bit
     __threadfence();
     __syncwarp();                        // every lane's cu map stores are fenced before any lane publishes
     *(volatile int *)&progress[row] = r.err ? -1 : col + 1;
   }
+  }                                      // rows of this substream
   if (lane == 0) {
     if (r.err) {
       atomicCAS(&status[0], 0, r.err);
-      atomicExch(&progress[row], -1);          // release the rows below
-      atomicExch(&sync_flag[row], 1);
+      for (int i = row_first; i <= row_last; i++) {
+        atomicExch(&progress[i], -1);          // release the rows below
+        atomicExch(&sync_flag[i], 1);
+      }
     }
     atomicMax(&status[1], pc.max_mv);
   }
@@ -592,7 +603,7 @@ cudaError_t launch_parse(const FrameParams &fp, const uint8_t *data, const uint3
   if (e != cudaSuccess) return e;
   e = cudaMemsetAsync(status, 0, sizeof(int) * 2, s);
   if (e != cudaSuccess) return e;
-  k_parse_rows<<<fp.ctb_rows, 32, 0, s>>>(fp, data, bases, cu, levels, sync_ctx, sync_flag, progress, status);
+  k_parse_rows<<<fp.no_wpp ? 1 : fp.ctb_rows, 32, 0, s>>>(fp, data, bases, cu, levels, sync_ctx, sync_flag, progress, status);
   return cudaGetLastError();
 }
 

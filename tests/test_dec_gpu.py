@@ -210,3 +210,61 @@ def test_device_resident_decode_to_rgb32_equals_the_host_chain():
                 k += 1
     assert k == n
     f.close()
+
+
+@pytest.mark.parametrize("kind,w,h,n,qp,tiles,wpp,threads,kw", [
+    ("camera", 416, 240, 5, 30, 2, 0, 1, {}),
+    ("camera", 416, 240, 6, 27, 3, 1, 1, {"intra_period": 4}),
+    ("noise", 512, 136, 3, 20, 4, 0, 1, {}),
+    ("screen", 640, 200, 5, 35, 2, 1, 1, {"deblock": 0}),
+    ("camera", 640, 256, 9, 30, 3, 1, 4, {"intra_period": 4}),          # tiles + decoder frame threading
+    ("camera", 1920, 1080, 3, 32, 4, 1, 1, {"search_range": 12}),
+    ("camera", 1920, 1080, 3, 32, 4, 0, 1, {"search_range": 12}),
+])
+def test_decoder_reads_tile_columns_as_strips(kind, w, h, n, qp, tiles, wpp, threads, kw):
+    """Tiled streams (tile columns, no loop filter across tiles, motion inside the tile; with or
+    without WPP inside the tiles) decode strip by strip to the encoder's reconstruction; for the
+    WPP-less mode that reconstruction is also what FFmpeg produces (tests/test_enc_gpu.py)."""
+    from kvazzup_b200.encoder import GpuTiledEncoder
+    frames = frames_of(kind, w, h, n)
+    g = GpuTiledEncoder(w, h, tiles, qp=qp, wpp=wpp, **({"intra_period": 0} | kw))
+    aus, recs = [], []
+    for f in frames:
+        aus.append(g.encode(f))
+        recs.append(g.recon())
+    g.close()
+    f = OpenHEVCFilter(threads, "Frame" if threads > 1 else "Slice")
+    assert f.init()
+    out = []
+    for i, au in enumerate(aus):
+        for nal in split_nals(au):
+            got = f.process(nal, pts=i)
+            if got is not None:
+                out.append(got)
+    out += f.drain()
+    f.close()
+    assert len(out) == n
+    for i, (pic, pw, ph) in enumerate(out):
+        assert (pw, ph) == (w, h)
+        bad = np.flatnonzero(pic != recs[i])
+        assert bad.size == 0, f"picture {i}: {bad.size} samples differ, first at {bad[:6]}"
+
+
+def test_decoder_switches_between_tiled_and_untiled_streams():
+    from kvazzup_b200.encoder import GpuTiledEncoder
+    w, h = 416, 240
+    frames = frames_of("camera", w, h, 3)
+    f = OpenHEVCFilter()
+    assert f.init()
+    for tiles in (1, 3, 1, 2):
+        if tiles == 1:
+            e = GpuEncoder(w, h, qp=30, intra_period=0)
+        else:
+            e = GpuTiledEncoder(w, h, tiles, qp=30, intra_period=0, wpp=1)
+        for fr in frames:
+            au = e.encode(fr)
+            rec = e.recon()
+            pics = [p for nal in split_nals(au) if (p := f.process(nal)) is not None]
+            assert len(pics) == 1 and np.array_equal(pics[0][0], rec), tiles
+        e.close()
+    f.close()
