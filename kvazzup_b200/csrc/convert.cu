@@ -45,6 +45,13 @@ inline int grid_for(size_t items, int per_sm = 8)
 // "add luma, clamp to [0,255]" for two horizontally adjacent pixels in one
 // instruction, and two PRMTs per pixel assemble the B,G,R,0 word.
 
+// Item index -> frame / position: 64-bit division costs about as much as the rest of an item, and
+// every realistic batch fits 32 bits, so take the short division whenever both operands allow it.
+__device__ __forceinline__ size_t div_idx(size_t a, size_t b)
+{
+  return ((a | b) >> 32) == 0 ? (size_t)((unsigned)a / (unsigned)b) : a / b;
+}
+
 struct ChromaOff { unsigned r2, g2, b2; };  // offsets duplicated in both s16 lanes
 
 __device__ __forceinline__ ChromaOff chroma_offsets(int U, int V)
@@ -84,6 +91,25 @@ __device__ __forceinline__ uint4 four_pixels(unsigned y4, const ChromaOff &c0, c
 }
 
 // One item = 2 rows x 4 pixels.  Requires w % 4 == 0 and h % 2 == 0.
+__device__ __forceinline__ void i420_to_rgb32_item(const uint8_t *__restrict__ in, uint8_t *__restrict__ out,
+                                                   int w, size_t ysz, int gpr, int f, int rp, int g)
+{
+  const uint8_t *fy = in + (size_t)f * (ysz + (ysz >> 1));
+  const uint8_t *fu = fy + ysz;
+  const uint8_t *fv = fu + (ysz >> 2);
+  size_t yoff = (size_t)(2 * rp) * w + 4 * g;
+  unsigned ya = __ldg((const unsigned *)(fy + yoff));
+  unsigned yb = __ldg((const unsigned *)(fy + yoff + w));
+  size_t coff = (size_t)rp * (w >> 1) + 2 * g;
+  unsigned uu = __ldg((const unsigned short *)(fu + coff));
+  unsigned vv = __ldg((const unsigned short *)(fv + coff));
+  ChromaOff c0 = chroma_offsets(uu & 0xFF, vv & 0xFF);
+  ChromaOff c1 = chroma_offsets(uu >> 8, vv >> 8);
+  uint4 *o = (uint4 *)(out + ((size_t)f * ysz + yoff) * 4);
+  __stcs(o, four_pixels(ya, c0, c1));
+  __stcs(o + gpr, four_pixels(yb, c0, c1));    // next row: + w*4 bytes = gpr uint4
+}
+
 __global__ void __launch_bounds__(kThreads)
 k_i420_to_rgb32_v4(const uint8_t *__restrict__ in, uint8_t *__restrict__ out,
                    int w, int h, int n_frames)
@@ -92,27 +118,23 @@ k_i420_to_rgb32_v4(const uint8_t *__restrict__ in, uint8_t *__restrict__ out,
   const size_t items_per_frame = (size_t)gpr * (h >> 1);
   const size_t total = items_per_frame * n_frames;
   const size_t ysz = (size_t)w * h;
-  const size_t fin = ysz + (ysz >> 1);
+  if (total < 0x80000000ull) {
+    // 32-bit index arithmetic: the two divisions below are a fifth of the work of an item when
+    // done in 64 bits
+    const unsigned ipf = (unsigned)items_per_frame, tot = (unsigned)total, stride = gridDim.x * blockDim.x;
+    for (unsigned it = blockIdx.x * blockDim.x + threadIdx.x; it < tot; it += stride) {
+      const unsigned f = it / ipf, r = it - f * ipf;
+      const unsigned rp = r / (unsigned)gpr;
+      i420_to_rgb32_item(in, out, w, ysz, gpr, (int)f, (int)rp, (int)(r - rp * gpr));
+    }
+    return;
+  }
   for (size_t it = (size_t)blockIdx.x * blockDim.x + threadIdx.x; it < total;
        it += (size_t)gridDim.x * blockDim.x) {
     int f = (int)(it / items_per_frame);
     int r = (int)(it - (size_t)f * items_per_frame);
     int rp = r / gpr;                           // row pair
-    int g = r - rp * gpr;
-    const uint8_t *fy = in + (size_t)f * fin;
-    const uint8_t *fu = fy + ysz;
-    const uint8_t *fv = fu + (ysz >> 2);
-    size_t yoff = (size_t)(2 * rp) * w + 4 * g;
-    unsigned ya = __ldg((const unsigned *)(fy + yoff));
-    unsigned yb = __ldg((const unsigned *)(fy + yoff + w));
-    size_t coff = (size_t)rp * (w >> 1) + 2 * g;
-    unsigned uu = __ldg((const unsigned short *)(fu + coff));
-    unsigned vv = __ldg((const unsigned short *)(fv + coff));
-    ChromaOff c0 = chroma_offsets(uu & 0xFF, vv & 0xFF);
-    ChromaOff c1 = chroma_offsets(uu >> 8, vv >> 8);
-    uint4 *o = (uint4 *)(out + ((size_t)f * ysz + yoff) * 4);
-    __stcs(o, four_pixels(ya, c0, c1));
-    __stcs(o + gpr, four_pixels(yb, c0, c1));    // next row: + w*4 bytes = gpr uint4
+    i420_to_rgb32_item(in, out, w, ysz, gpr, f, rp, r - rp * gpr);
   }
 }
 
@@ -126,7 +148,7 @@ k_i420_to_rgb32_generic(const uint8_t *__restrict__ in, uint8_t *__restrict__ ou
   const size_t ysz = (size_t)w * h, fin = ysz + (ysz >> 1);
   for (size_t it = (size_t)blockIdx.x * blockDim.x + threadIdx.x; it < total;
        it += (size_t)gridDim.x * blockDim.x) {
-    int f = (int)(it / per);
+    int f = (int)div_idx(it, per);
     int r = (int)(it - (size_t)f * per);
     int cy = r / cw, cx = r - cy * cw;
     const uint8_t *fy = in + (size_t)f * fin;
@@ -153,7 +175,7 @@ k_half_rgb(const uint32_t *__restrict__ in, uint32_t *__restrict__ out, int w, i
   const size_t per = (size_t)gpr * oh, total = per * n_frames;
   for (size_t it = (size_t)blockIdx.x * blockDim.x + threadIdx.x; it < total;
        it += (size_t)gridDim.x * blockDim.x) {
-    int f = (int)(it / per);
+    int f = (int)div_idx(it, per);
     int r = (int)(it - (size_t)f * per);
     int y = r / gpr, g = r - y * gpr;
     uint4 v = __ldcs((const uint4 *)(in + (size_t)f * w * h + (size_t)(2 * y) * w + 4 * g));
@@ -168,7 +190,7 @@ k_half_rgb_generic(const uint32_t *__restrict__ in, uint32_t *__restrict__ out, 
   const size_t per = (size_t)ow * oh, total = per * n_frames;
   for (size_t it = (size_t)blockIdx.x * blockDim.x + threadIdx.x; it < total;
        it += (size_t)gridDim.x * blockDim.x) {
-    int f = (int)(it / per);
+    int f = (int)div_idx(it, per);
     int r = (int)(it - (size_t)f * per);
     int y = r / ow, x = r - y * ow;
     out[(size_t)f * per + r] = in[(size_t)f * w * h + (size_t)(2 * y) * w + 2 * x];
@@ -184,7 +206,7 @@ k_flip_rgb_v4(const uint32_t *__restrict__ in, uint32_t *__restrict__ out, int w
   const size_t per = (size_t)gpr * h, total = per * n_frames;
   for (size_t it = (size_t)blockIdx.x * blockDim.x + threadIdx.x; it < total;
        it += (size_t)gridDim.x * blockDim.x) {
-    int f = (int)(it / per);
+    int f = (int)div_idx(it, per);
     int r = (int)(it - (size_t)f * per);
     int y = r / gpr, g = r - y * gpr;
     int sy = ver ? h - 1 - y : y;
@@ -202,7 +224,7 @@ k_flip_rgb_generic(const uint32_t *__restrict__ in, uint32_t *__restrict__ out, 
   const size_t per = (size_t)w * h, total = per * n_frames;
   for (size_t it = (size_t)blockIdx.x * blockDim.x + threadIdx.x; it < total;
        it += (size_t)gridDim.x * blockDim.x) {
-    int f = (int)(it / per);
+    int f = (int)div_idx(it, per);
     int r = (int)(it - (size_t)f * per);
     int y = r / w, x = r - y * w;
     int sy = ver ? h - 1 - y : y, sx = hor ? w - 1 - x : x;
@@ -213,6 +235,13 @@ k_flip_rgb_generic(const uint32_t *__restrict__ in, uint32_t *__restrict__ out, 
 // ---------------------------------------------------------------------------
 // Camera formats -> I420.
 
+// dot product of four unsigned bytes (a) with four signed bytes (b), accumulated
+__device__ __forceinline__ int dp4a_u8s8(unsigned a, unsigned b, int c)
+{
+  int d;
+  asm("dp4a.u32.s32 %0, %1, %2, %3;" : "=r"(d) : "r"(a), "r"(b), "r"(c));
+  return d;
+}
 __device__ __forceinline__ unsigned rgb_y(int r, int g, int b) { return (unsigned)(66 * r + 129 * g + 25 * b + 0x1080) >> 8; }
 __device__ __forceinline__ unsigned rgb_u(int r, int g, int b) { return ((unsigned)(112 * b - 74 * g - 38 * r + 0x8080) >> 8) & 0xFF; }
 __device__ __forceinline__ unsigned rgb_v(int r, int g, int b) { return ((unsigned)(112 * r - 94 * g - 18 * b + 0x8080) >> 8) & 0xFF; }
@@ -229,7 +258,7 @@ k_packed422_to_i420_v8(const uint8_t *__restrict__ in, uint8_t *__restrict__ out
   const size_t ysz = (size_t)w * h, fout = ysz + (ysz >> 1), fin = ysz * 2;
   for (size_t it = (size_t)blockIdx.x * blockDim.x + threadIdx.x; it < total;
        it += (size_t)gridDim.x * blockDim.x) {
-    int f = (int)(it / per);
+    int f = (int)div_idx(it, per);
     int r = (int)(it - (size_t)f * per);
     int rp = r / gpr, g = r - rp * gpr;
     const uint8_t *src = in + (size_t)f * fin + (size_t)(2 * rp) * w * 2 + (size_t)g * 16;
@@ -272,7 +301,7 @@ k_planar_to_i420_v16(const uint8_t *__restrict__ in, uint8_t *__restrict__ out, 
   const size_t per = yitems + citems, total = per * n_frames;
   for (size_t it = (size_t)blockIdx.x * blockDim.x + threadIdx.x; it < total;
        it += (size_t)gridDim.x * blockDim.x) {
-    int f = (int)(it / per);
+    int f = (int)div_idx(it, per);
     size_t r = it - (size_t)f * per;
     const uint8_t *src = in + (size_t)f * fin;
     uint8_t *dst = out + (size_t)f * fout;
@@ -281,7 +310,7 @@ k_planar_to_i420_v16(const uint8_t *__restrict__ in, uint8_t *__restrict__ out, 
       continue;
     }
     r -= yitems;
-    int cy = (int)(r / cgpr), g = (int)(r - (size_t)cy * cgpr);
+    int cy = (int)div_idx(r, (size_t)cgpr), g = (int)(r - (size_t)cy * cgpr);
     size_t coff = (size_t)cy * (w >> 1) + 8 * g;
     uint2 u8, v8;
     if (kMode == 2) {
@@ -315,7 +344,7 @@ k_rgb_to_i420_v4(const uint8_t *__restrict__ in, uint8_t *__restrict__ out, int 
   const size_t ysz = (size_t)w * h, fout = ysz + (ysz >> 1), fin = ysz * kBpp;
   for (size_t it = (size_t)blockIdx.x * blockDim.x + threadIdx.x; it < total;
        it += (size_t)gridDim.x * blockDim.x) {
-    int f = (int)(it / per);
+    int f = (int)div_idx(it, per);
     int r = (int)(it - (size_t)f * per);
     int rp = r / gpr, g = r - rp * gpr;
     const uint8_t *src = in + (size_t)f * fin + ((size_t)(2 * rp) * w + 4 * g) * kBpp;
@@ -332,23 +361,29 @@ k_rgb_to_i420_v4(const uint8_t *__restrict__ in, uint8_t *__restrict__ out, int 
       wa[0] = a0; wa[1] = __byte_perm(a0, a1, 0x0543); wa[2] = __byte_perm(a1, a2, 0x0432); wa[3] = a2 >> 8;
       wb[0] = b0; wb[1] = __byte_perm(b0, b1, 0x0543); wb[2] = __byte_perm(b1, b2, 0x0432); wb[3] = b2 >> 8;
     }
+    // One DP4A per output sample: the pixel word (bytes in memory order) times a coefficient word
+    // with 66 / 129 / 25 (unsigned) or the signed chroma weights at the R, G, B byte positions; the
+    // unused byte of a pixel (alpha, or the next pixel's first byte for 24-bit input) meets a 0.
     const int rs = ro * 8, gs = go * 8, bs = bo * 8;
+    const unsigned cy = (66u << rs) | (129u << gs) | (25u << bs);
+    const unsigned cu = ((unsigned)(uint8_t)(-38) << rs) | ((unsigned)(uint8_t)(-74) << gs) | (112u << bs);
+    const unsigned cv = (112u << rs) | ((unsigned)(uint8_t)(-94) << gs) | ((unsigned)(uint8_t)(-18) << bs);
     unsigned ya = 0, yb = 0, u2 = 0, v2 = 0;
 #pragma unroll
     for (int i = 0; i < 4; i++) {
-      int r0 = (wa[i] >> rs) & 0xFF, g0 = (wa[i] >> gs) & 0xFF, b0 = (wa[i] >> bs) & 0xFF;
-      int r1 = (wb[i] >> rs) & 0xFF, g1 = (wb[i] >> gs) & 0xFF, b1 = (wb[i] >> bs) & 0xFF;
-      ya |= rgb_y(r0, g0, b0) << (8 * i);
-      yb |= rgb_y(r1, g1, b1) << (8 * i);
+      ya |= (__dp4a(wa[i], cy, 0x1080u) >> 8) << (8 * i);
+      yb |= (__dp4a(wb[i], cy, 0x1080u) >> 8) << (8 * i);
     }
 #pragma unroll
     for (int i = 0; i < 2; i++) {
-      unsigned p00 = wa[2 * i], p01 = wa[2 * i + 1], p10 = wb[2 * i], p11 = wb[2 * i + 1];
-      int r = (int)(((p00 >> rs) & 0xFF) + ((p01 >> rs) & 0xFF) + ((p10 >> rs) & 0xFF) + ((p11 >> rs) & 0xFF) + 2) >> 2;
-      int g = (int)(((p00 >> gs) & 0xFF) + ((p01 >> gs) & 0xFF) + ((p10 >> gs) & 0xFF) + ((p11 >> gs) & 0xFF) + 2) >> 2;
-      int b = (int)(((p00 >> bs) & 0xFF) + ((p01 >> bs) & 0xFF) + ((p10 >> bs) & 0xFF) + ((p11 >> bs) & 0xFF) + 2) >> 2;
-      u2 |= rgb_u(r, g, b) << (8 * i);
-      v2 |= rgb_v(r, g, b) << (8 * i);
+      // rounded 2x2 box average of every byte lane, two 16-bit lanes at a time
+      const unsigned k = 0x00FF00FFu;
+      const unsigned p00 = wa[2 * i], p01 = wa[2 * i + 1], p10 = wb[2 * i], p11 = wb[2 * i + 1];
+      const unsigned ev = (p00 & k) + (p01 & k) + (p10 & k) + (p11 & k) + 0x00020002u;
+      const unsigned od = ((p00 >> 8) & k) + ((p01 >> 8) & k) + ((p10 >> 8) & k) + ((p11 >> 8) & k) + 0x00020002u;
+      const unsigned avg = ((ev >> 2) & k) | (((od >> 2) & k) << 8);
+      u2 |= (((unsigned)dp4a_u8s8(avg, cu, 0x8080) >> 8) & 0xFF) << (8 * i);
+      v2 |= (((unsigned)dp4a_u8s8(avg, cv, 0x8080) >> 8) & 0xFF) << (8 * i);
     }
     uint8_t *fy = out + (size_t)f * fout;
     size_t yoff = (size_t)(2 * rp) * w + 4 * g;
@@ -371,7 +406,7 @@ k_to_i420_generic(const uint8_t *__restrict__ in, uint8_t *__restrict__ out, int
   const size_t ysz = (size_t)w * h, fout = ysz + (ysz >> 1);
   for (size_t it = (size_t)blockIdx.x * blockDim.x + threadIdx.x; it < total;
        it += (size_t)gridDim.x * blockDim.x) {
-    int f = (int)(it / per);
+    int f = (int)div_idx(it, per);
     int r = (int)(it - (size_t)f * per);
     int cy = r / cw, cx = r - cy * cw;
     const uint8_t *src = in + (size_t)f * fin;
@@ -433,7 +468,7 @@ k_selfview(const uint8_t *__restrict__ in, uint8_t *__restrict__ out, int w, int
   const int step = half ? 2 : 1;
   for (size_t it = (size_t)blockIdx.x * blockDim.x + threadIdx.x; it < total;
        it += (size_t)gridDim.x * blockDim.x) {
-    int f = (int)(it / per);
+    int f = (int)div_idx(it, per);
     int r = (int)(it - (size_t)f * per);
     int oy = r / gpr, g = r - oy * gpr;
     const uint8_t *fy = in + (size_t)f * fin;
