@@ -632,95 +632,210 @@ k_binarise(FrameParams fp, const CuInfo *__restrict__ cu, const int16_t *__restr
   }
 }
 
+// ---- entropy coding in two phases ---------------------------------------------------------------
+// The state of a CABAC context evolves with the bins coded in it (MPS / LPS outcomes) and with
+// nothing else -- not with range or low.  So the arithmetic coder is split:
+//
+//   k_ctx_rows   (phase A) walks the bin records of a CTU row 32 at a time and replaces every
+//                context-coded record (context index, bin) by (pStateIdx, is-LPS).  Records of one
+//                batch that share a context are ordered with __match_any_sync and resolved in as
+//                many rounds as the most frequent context occurs; everything else is parallel.  The
+//                WPP hand-over (contexts after the second CTU of the row above) lives here, so the
+//                two-CTU stagger between rows costs two CTUs of this cheap pass only.
+//   k_arith_rows (phase B) is the serial range coder over the resolved records: no context table,
+//                no dependency between rows at all, and the rangeTabLps row of the next record is
+//                fetched while the current one is coded.
+//
+// Before the split one kernel did both and every row waited for the row above to arithmetic-code
+// two CTUs: 3.4 ms per 1080p P picture, 26 ms per IDR (profiles/r01_summary.md).
+
+__global__ void __launch_bounds__(32)
+k_ctx_rows(FrameParams fp, const CuInfo *__restrict__ cu, uint32_t *recs, uint8_t *sync_ctx, int *sync_flag)
+{
+  __shared__ uint8_t s_ctx[CTX_COUNT + 2];
+  __shared__ uint8_t s_trans[64];
+  const int lane = threadIdx.x;
+  const int r_first = fp.no_wpp ? 0 : blockIdx.x, r_last = fp.no_wpp ? fp.ctb_rows - 1 : blockIdx.x;
+  for (int i = lane; i < 64; i += 32) s_trans[i] = c_trans_lps[i];
+  if (r_first == 0 || fp.ctb_cols < 2) {
+    const int qp = clip3(0, 51, fp.qp), init_type = fp.is_idr ? 0 : 1;
+    for (int i = lane; i < CTX_COUNT; i += 32) {
+      int iv = c_ctx_init[init_type][i];
+      int m = (iv >> 4) * 5 - 45, n = ((iv & 15) << 3) - 16;
+      int pre = clip3(1, 126, ((m * qp) >> 4) + n);
+      int mps = pre <= 63 ? 0 : 1;
+      int st = mps ? pre - 64 : 63 - pre;
+      s_ctx[i] = (uint8_t)((st << 1) | mps);
+    }
+  } else {
+    volatile int *f = sync_flag;
+    while (f[r_first - 1] == 0) __nanosleep(100);
+    __threadfence();
+    for (int i = lane; i < CTX_COUNT; i += 32) s_ctx[i] = __ldcg(sync_ctx + (size_t)(r_first - 1) * CTX_COUNT + i);
+  }
+  __syncwarp();
+  for (int r = r_first; r <= r_last; r++) {
+    for (int col = 0; col < fp.ctb_cols; col++) {
+      // the CUs of this CTU from the cu map: unit z starts a CU when z is a multiple of the CU's unit count
+      unsigned starts[2];
+      for (int h = 0; h < 2; h++) {
+        const int z = 32 * h + lane;
+        const int x8 = col * 8 + z_to_x(z), y8 = r * 8 + z_to_y(z);
+        bool st = false;
+        if (x8 < fp.w8 && y8 < fp.h8) {
+          const int l2 = cu[(size_t)y8 * fp.w8 + x8].log2_size;
+          st = l2 >= 3 && (z & ((1 << (2 * (l2 - 3))) - 1)) == 0;
+        }
+        starts[h] = __ballot_sync(0xffffffffu, st);
+      }
+      const int n0 = __popc(starts[0]), n_cu = n0 + __popc(starts[1]);
+      uint32_t *const ctu_recs = recs + (size_t)(r * fp.ctb_cols + col) * 64 * kRecUnitCap;
+      // record counts of up to 64 CUs, fetched in parallel (lane j: CUs j and j + 32 of the CTU)
+      int zs[2] = {64, 64}, cnts[2] = {0, 0};
+      for (int h = 0; h < 2; h++) {
+        const int j = 32 * h + lane;
+        if (j < n_cu) {
+          zs[h] = j < n0 ? (int)__fns(starts[0], 0, j + 1) : 32 + (int)__fns(starts[1], 0, j - n0 + 1);
+          cnts[h] = (int)(__ldg(ctu_recs + (size_t)zs[h] * kRecUnitCap) & 0xffffffu);
+        }
+      }
+      // first chunk of the first CU
+      int z = __shfl_sync(0xffffffffu, zs[0], 0), cnt = __shfl_sync(0xffffffffu, cnts[0], 0);
+      uint32_t *reg = ctu_recs + (size_t)z * kRecUnitCap;
+      uint32_t v = (n_cu > 0 && lane < cnt) ? __ldcg(reg + 1 + lane) : 0x80000000u;
+      for (int k = 0; k < n_cu; k++) {
+        // cursor of the next CU, whose first chunk is fetched while this CU is resolved
+        const int kn = k + 1;
+        const int zn = __shfl_sync(0xffffffffu, zs[kn >> 5 & 1], kn & 31), cntn = __shfl_sync(0xffffffffu, cnts[kn >> 5 & 1], kn & 31);
+        uint32_t *regn = ctu_recs + (size_t)zn * kRecUnitCap;
+        uint32_t vnext_cu = (kn < n_cu && lane < cntn) ? __ldcg(regn + 1 + lane) : 0x80000000u;
+        for (int base = 0; base < cnt; base += 32) {
+          const int nb = base + 32;
+          const uint32_t vnext = nb + lane < cnt ? __ldcg(reg + 1 + nb + lane) : 0x80000000u;
+          const bool in = base + lane < cnt;
+          const bool active = in && !(v & 0x80000000u);
+          const unsigned ctx = v >> 1, bin = v & 1;
+          const unsigned grp = __match_any_sync(0xffffffffu, active ? ctx : 0x10000u + lane);
+          const int rank = __popc(grp & ((1u << lane) - 1));
+          const int rounds = __reduce_max_sync(0xffffffffu, active ? __popc(grp) : 0);
+          uint32_t out = v;
+          for (int round = 0; round < rounds; round++) {
+            if (active && rank == round) {
+              const unsigned s = s_ctx[ctx];
+              unsigned st = s >> 1, mps = s & 1;
+              const unsigned is_lps = bin != mps;
+              out = (st << 1) | is_lps;
+              if (is_lps) { mps ^= (st == 0); st = s_trans[st]; }
+              else st = min(st + 1, 62u);
+              s_ctx[ctx] = (uint8_t)((st << 1) | mps);
+            }
+            __syncwarp();
+          }
+          if (active) reg[1 + base + lane] = out;
+          v = vnext;
+        }
+        z = zn; cnt = cntn; reg = regn; v = vnext_cu;
+      }
+      if (col == 1 && r + 1 < fp.ctb_rows && !fp.no_wpp) {       // WPP: hand the contexts to the row below
+        __syncwarp();
+        for (int i = lane; i < CTX_COUNT; i += 32) sync_ctx[(size_t)r * CTX_COUNT + i] = s_ctx[i];
+        __threadfence();
+        __syncwarp();
+        if (lane == 0) atomicExch(&sync_flag[r], 1);
+      }
+    }
+  }
+}
+
+// phase B: context-coded records are (pStateIdx << 1) | is-LPS here
+__device__ __forceinline__ void enc_bin_resolved(Coder &c, const uint2 e, unsigned is_lps)
+{
+  const uint32_t lps = (e.x >> (((c.range >> 6) & 3) * 8)) & 0xff;
+  c.bins++;
+  c.range -= lps;
+  if (is_lps) {
+    const int nb = __clz(lps) - 23;
+    c.low = (c.low + c.range) << nb;
+    c.range = lps << nb;
+    c.bits_left -= nb;
+  } else if (c.range < 256) {
+    c.low <<= 1; c.range <<= 1; c.bits_left--;
+  }
+  if (c.bits_left < 12) write_out(c);
+}
+
 __global__ void __launch_bounds__(32)
 k_arith_rows(FrameParams fp, const uint32_t *__restrict__ recs, uint8_t *rows, uint32_t row_cap, uint32_t *row_len,
-             uint8_t *sync_ctx, int *sync_flag, unsigned long long *bins)
+             unsigned long long *bins)
 {
-  __shared__ uint8_t s_ctx[CTX_COUNT * 32];
   __shared__ uint2 s_tab[64];
   __shared__ uint32_t s_chunk[2][32];
   // WPP: one substream per CTU row (r_first == r_last == blockIdx.x).  no_wpp (a tile without
   // entropy_coding_sync): one block codes every row into a single substream.
   const int lane = threadIdx.x;
   const int r_first = fp.no_wpp ? 0 : blockIdx.x, r_last = fp.no_wpp ? fp.ctb_rows - 1 : blockIdx.x;
-  for (int i = lane; i < 64; i += 32) s_tab[i] = make_uint2(c_range_lps[i], (uint32_t)c_trans_lps[i] | (i == 0 ? 64u : 0u));
+  for (int i = lane; i < 64; i += 32) s_tab[i] = make_uint2(c_range_lps[i], 0u);
   Coder c;
   c.out = rows + (size_t)r_first * row_cap; c.pos = 0; c.cap = fp.no_wpp ? row_cap * fp.ctb_rows : row_cap;
-  c.zeros = 0; c.ctx = s_ctx + lane; c.bins = 0;
+  c.zeros = 0; c.ctx = nullptr; c.bins = 0;
   c.writer = lane == 0;
-  int r = r_first;
-  if (r == 0 || fp.ctb_cols < 2) {
-    init_contexts(c.ctx, fp.is_idr ? 0 : 1, fp.qp);
-  } else {
-    if (lane == 0) {
-      volatile int *f = sync_flag;
-      while (f[r - 1] == 0) __nanosleep(100);
-      __threadfence();
-    }
-    __syncwarp();
-    for (int i = 0; i < CTX_COUNT; i++) c.ctx[i * 32] = __ldcg(sync_ctx + (size_t)(r - 1) * CTX_COUNT + i);
-  }
   __syncwarp();
   coder_start(c);
-  for (; r <= r_last; r++) {
-  // Flat walk over the CUs of the row.  The address of the next CU's record list is known as
-  // soon as the current header is read, so its header and first 32 records are fetched while the
-  // current list is being coded (a lone warp has nothing else to hide the ~1 us load latency).
-  const int cy = r * kCtb;
-  auto first_unit = [&](int col, int z) -> int {          // first z >= given whose unit lies inside the picture, 64 if none
-    while (z < 64 && (col * kCtb + 8 * z_to_x(z) >= fp.w || cy + 8 * z_to_y(z) >= fp.h)) z++;
-    return z;
-  };
-  int col = 0, z = first_unit(0, 0);
-  const uint32_t *reg = recs + ((size_t)(r * fp.ctb_cols) * 64 + z) * kRecUnitCap;
-  uint32_t hdr = __ldg(reg);
-  uint32_t first = __ldg(reg + 1 + lane);
-  while (col < fp.ctb_cols) {
-    const int cnt = (int)(hdr & 0xffffffu), log2 = (int)(hdr >> 24);
-    // cursor of the CU after this one
-    int ncol = col, nz = first_unit(col, z + (1 << (2 * (log2 - 3))));
-    if (nz >= 64) { ncol = col + 1; nz = ncol < fp.ctb_cols ? first_unit(ncol, 0) : 64; }
-    const uint32_t *nreg = recs + ((size_t)(r * fp.ctb_cols + ncol) * 64 + nz) * kRecUnitCap;
-    uint32_t nhdr = 0, nfirst = 0;
-    if (ncol < fp.ctb_cols) { nhdr = __ldg(nreg); nfirst = __ldg(nreg + 1 + lane); }
-    // code this CU: each 32-record chunk is staged in shared memory (double buffered) so that the
-    // next record's load is independent of the coder state and can be issued early
-    uint32_t curv = first;
-    int buf = 0;
-    for (int base = 0; base < cnt; base += 32) {
-      const int nb = base + 32;
-      uint32_t nxt = nb + lane < cnt ? __ldg(reg + 1 + nb + lane) : 0;
-      s_chunk[buf][lane] = curv;
-      __syncwarp();
-      const int m = min(32, cnt - base);
-      const uint32_t *ch = s_chunk[buf];
-      uint32_t vn = ch[0];
-      for (int k = 0; k < m; k++) {
-        const uint32_t v = vn;
-        vn = ch[min(k + 1, 31)];
-        if (v & 0x80000000u) enc_bypass_group(c, v & 0xffffu, (int)((v >> 24) & 31));
-        else enc_bin(c, s_tab, (int)(v >> 1), (int)(v & 1));
-      }
-      curv = nxt;
-      buf ^= 1;
-    }
-    if (ncol != col) {                                    // the CTU is complete
-      if (col == 1 && r + 1 < fp.ctb_rows && !fp.no_wpp) {
+  for (int r = r_first; r <= r_last; r++) {
+    // Flat walk over the CUs of the row.  The address of the next CU's record list is known as
+    // soon as the current header is read, so its header and first 32 records are fetched while the
+    // current list is being coded (a lone warp has nothing else to hide the ~1 us load latency).
+    const int cy = r * kCtb;
+    auto first_unit = [&](int col, int z) -> int {          // first z >= given whose unit lies inside the picture, 64 if none
+      while (z < 64 && (col * kCtb + 8 * z_to_x(z) >= fp.w || cy + 8 * z_to_y(z) >= fp.h)) z++;
+      return z;
+    };
+    int col = 0, z = first_unit(0, 0);
+    const uint32_t *reg = recs + ((size_t)(r * fp.ctb_cols) * 64 + z) * kRecUnitCap;
+    uint32_t hdr = __ldcg(reg);
+    uint32_t first = __ldcg(reg + 1 + lane);
+    while (col < fp.ctb_cols) {
+      const int cnt = (int)(hdr & 0xffffffu), log2 = (int)(hdr >> 24);
+      // cursor of the CU after this one
+      int ncol = col, nz = first_unit(col, z + (1 << (2 * (log2 - 3))));
+      if (nz >= 64) { ncol = col + 1; nz = ncol < fp.ctb_cols ? first_unit(ncol, 0) : 64; }
+      const uint32_t *nreg = recs + ((size_t)(r * fp.ctb_cols + ncol) * 64 + nz) * kRecUnitCap;
+      uint32_t nhdr = 0, nfirst = 0;
+      if (ncol < fp.ctb_cols) { nhdr = __ldcg(nreg); nfirst = __ldcg(nreg + 1 + lane); }
+      // code this CU: each 32-record chunk is staged in shared memory (double buffered); the
+      // rangeTabLps row of record k + 1 is fetched while record k is coded -- neither load depends
+      // on the coder state
+      uint32_t curv = first;
+      int buf = 0;
+      for (int base = 0; base < cnt; base += 32) {
+        const int nb = base + 32;
+        uint32_t nxt = nb + lane < cnt ? __ldcg(reg + 1 + nb + lane) : 0;
+        s_chunk[buf][lane] = curv;
         __syncwarp();
-        if (lane == 0)
-          for (int i = 0; i < CTX_COUNT; i++) sync_ctx[(size_t)r * CTX_COUNT + i] = c.ctx[i * 32];
-        __threadfence();
-        __syncwarp();
-        if (lane == 0) atomicExch(&sync_flag[r], 1);
+        const int m = min(32, cnt - base);
+        const uint32_t *ch = s_chunk[buf];
+        uint32_t vn = ch[0];
+        uint2 en = s_tab[(vn >> 1) & 63];
+        for (int k = 0; k < m; k++) {
+          const uint32_t v = vn;
+          const uint2 e = en;
+          vn = ch[min(k + 1, 31)];
+          en = s_tab[(vn >> 1) & 63];
+          if (v & 0x80000000u) enc_bypass_group(c, v & 0xffffu, (int)((v >> 24) & 31));
+          else enc_bin_resolved(c, e, v & 1);
+        }
+        curv = nxt;
+        buf ^= 1;
       }
-      const bool end_sub = col == fp.ctb_cols - 1 && (!fp.no_wpp || r == fp.ctb_rows - 1);
-      const bool last = r == fp.ctb_rows - 1 && col == fp.ctb_cols - 1 && !fp.more_tiles;
-      enc_terminate(c, last);                                           // end_of_slice_segment_flag
-      if (end_sub && !last) enc_terminate(c, 1);                        // end_of_subset_one_bit
+      if (ncol != col) {                                    // the CTU is complete
+        const bool end_sub = col == fp.ctb_cols - 1 && (!fp.no_wpp || r == fp.ctb_rows - 1);
+        const bool last = r == fp.ctb_rows - 1 && col == fp.ctb_cols - 1 && !fp.more_tiles;
+        enc_terminate(c, last);                                           // end_of_slice_segment_flag
+        if (end_sub && !last) enc_terminate(c, 1);                        // end_of_subset_one_bit
+      }
+      col = ncol; z = nz; reg = nreg; hdr = nhdr; first = nfirst;
     }
-    col = ncol; z = nz; reg = nreg; hdr = nhdr; first = nfirst;
-  }
-  }                                                                     // rows of this substream
+  }                                                                       // rows of this substream
   coder_finish(c);
   if (lane == 0) {
     row_len[r_first] = c.pos <= c.cap ? c.pos : 0xffffffffu;
@@ -784,14 +899,16 @@ cudaError_t launch_binarise(const FrameParams &fp, const CuInfo *cu, const int16
   return cudaGetLastError();
 }
 
-cudaError_t launch_arith(const FrameParams &fp, const uint32_t *recs, uint8_t *rows, uint32_t row_cap, uint32_t *row_len,
-                         uint8_t *sync_ctx, int *sync_flag, unsigned long long *bins, cudaStream_t s)
+cudaError_t launch_arith(const FrameParams &fp, const CuInfo *cu, uint32_t *recs, uint8_t *rows, uint32_t row_cap,
+                         uint32_t *row_len, uint8_t *sync_ctx, int *sync_flag, unsigned long long *bins, cudaStream_t s)
 {
   cudaError_t e = cudaMemsetAsync(sync_flag, 0, sizeof(int) * fp.ctb_rows, s);
   if (e != cudaSuccess) return e;
   e = cudaMemsetAsync(bins, 0, sizeof(unsigned long long), s);
   if (e != cudaSuccess) return e;
-  k_arith_rows<<<fp.no_wpp ? 1 : fp.ctb_rows, 32, 0, s>>>(fp, recs, rows, row_cap, row_len, sync_ctx, sync_flag, bins);
+  const int subs = fp.no_wpp ? 1 : fp.ctb_rows;
+  k_ctx_rows<<<subs, 32, 0, s>>>(fp, cu, recs, sync_ctx, sync_flag);
+  k_arith_rows<<<subs, 32, 0, s>>>(fp, recs, rows, row_cap, row_len, bins);
   return cudaGetLastError();
 }
 

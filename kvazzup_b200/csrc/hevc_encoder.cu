@@ -397,7 +397,7 @@ bool Encoder::submit(FrameSlot &s, const uint8_t *d_i420)
   ENC_CHECK(launch_binarise(p, s.d_cu, s.d_levels, s.d_recs, s.stream), "binarise launch");
   PROF_END(K_BINARISE, s.stream);
   PROF_BEGIN(K_ARITH, s.stream);
-  ENC_CHECK(launch_arith(p, s.d_recs, s.d_rows, row_cap, row_len, s.d_small + off_ctx, sync_flag, bins, s.stream), "arith launch");
+  ENC_CHECK(launch_arith(p, s.d_cu, s.d_recs, s.d_rows, row_cap, row_len, s.d_small + off_ctx, sync_flag, bins, s.stream), "arith launch");
   PROF_END(K_ARITH, s.stream);
   PROF_BEGIN(K_PACK, s.stream);
   ENC_CHECK(launch_pack_rows(p.ctb_rows, s.d_rows, row_cap, row_len, s.h_pack, pack_cap, s.h_hdr, s.stream), "pack launch");

@@ -42,8 +42,8 @@ cudaError_t launch_deblock(const FrameParams &fp, uint8_t *rec, const CuInfo *cu
 // and k_arith_rows (one warp per CTU row / WPP substream).  rows[r*row_cap ..] receives the escaped
 // bytes of row r, row_len[r] its length (0xffffffff on overflow).
 cudaError_t launch_binarise(const FrameParams &fp, const CuInfo *cu, const int16_t *levels, uint32_t *recs, cudaStream_t s);
-cudaError_t launch_arith(const FrameParams &fp, const uint32_t *recs, uint8_t *rows, uint32_t row_cap, uint32_t *row_len,
-                         uint8_t *sync_ctx, int *sync_flag, unsigned long long *bins, cudaStream_t s);
+cudaError_t launch_arith(const FrameParams &fp, const CuInfo *cu, uint32_t *recs, uint8_t *rows, uint32_t row_cap,
+                         uint32_t *row_len, uint8_t *sync_ctx, int *sync_flag, unsigned long long *bins, cudaStream_t s);
 
 // substreams -> one contiguous buffer + header {total, row_len[rows]} (dst/hdr may be mapped host memory)
 cudaError_t launch_pack_rows(int rows, const uint8_t *src, uint32_t row_cap, const uint32_t *row_len, uint8_t *dst,
