@@ -699,42 +699,56 @@ k_ctx_rows(FrameParams fp, const CuInfo *__restrict__ cu, uint32_t *recs, uint8_
           cnts[h] = (int)(__ldg(ctu_recs + (size_t)zs[h] * kRecUnitCap) & 0xffffffu);
         }
       }
-      // first chunk of the first CU
+      // Records are fetched four chunks (128 records) at a time and one such group ahead: a chunk
+      // resolves in a few hundred cycles, far less than a round trip to L2, and this warp has
+      // nothing else to run meanwhile.
+      auto load4 = [&](const uint32_t *rg, int count, int base, uint32_t v4[4]) {
+#pragma unroll
+        for (int j = 0; j < 4; j++) v4[j] = base + 32 * j + lane < count ? __ldcg(rg + 1 + base + 32 * j + lane) : 0x80000000u;
+      };
       int z = __shfl_sync(0xffffffffu, zs[0], 0), cnt = __shfl_sync(0xffffffffu, cnts[0], 0);
       uint32_t *reg = ctu_recs + (size_t)z * kRecUnitCap;
-      uint32_t v = (n_cu > 0 && lane < cnt) ? __ldcg(reg + 1 + lane) : 0x80000000u;
+      uint32_t v4[4];
+      load4(reg, n_cu > 0 ? cnt : 0, 0, v4);
       for (int k = 0; k < n_cu; k++) {
-        // cursor of the next CU, whose first chunk is fetched while this CU is resolved
+        // cursor of the next CU, whose first group is fetched while this CU's last group is resolved
         const int kn = k + 1;
         const int zn = __shfl_sync(0xffffffffu, zs[kn >> 5 & 1], kn & 31), cntn = __shfl_sync(0xffffffffu, cnts[kn >> 5 & 1], kn & 31);
         uint32_t *regn = ctu_recs + (size_t)zn * kRecUnitCap;
-        uint32_t vnext_cu = (kn < n_cu && lane < cntn) ? __ldcg(regn + 1 + lane) : 0x80000000u;
-        for (int base = 0; base < cnt; base += 32) {
-          const int nb = base + 32;
-          const uint32_t vnext = nb + lane < cnt ? __ldcg(reg + 1 + nb + lane) : 0x80000000u;
-          const bool in = base + lane < cnt;
-          const bool active = in && !(v & 0x80000000u);
-          const unsigned ctx = v >> 1, bin = v & 1;
-          const unsigned grp = __match_any_sync(0xffffffffu, active ? ctx : 0x10000u + lane);
-          const int rank = __popc(grp & ((1u << lane) - 1));
-          const int rounds = __reduce_max_sync(0xffffffffu, active ? __popc(grp) : 0);
-          uint32_t out = v;
-          for (int round = 0; round < rounds; round++) {
-            if (active && rank == round) {
-              const unsigned s = s_ctx[ctx];
-              unsigned st = s >> 1, mps = s & 1;
-              const unsigned is_lps = bin != mps;
-              out = (st << 1) | is_lps;
-              if (is_lps) { mps ^= (st == 0); st = s_trans[st]; }
-              else st = min(st + 1, 62u);
-              s_ctx[ctx] = (uint8_t)((st << 1) | mps);
+        for (int base = 0; base < cnt; base += 128) {
+          uint32_t n4[4];
+          if (base + 128 < cnt) load4(reg, cnt, base + 128, n4);
+          else load4(regn, kn < n_cu ? cntn : 0, 0, n4);
+#pragma unroll
+          for (int j = 0; j < 4; j++) {
+            const int off = base + 32 * j;
+            if (off >= cnt) break;
+            const uint32_t v = v4[j];
+            const bool active = off + lane < cnt && !(v & 0x80000000u);
+            const unsigned ctx = v >> 1, bin = v & 1;
+            const unsigned grp = __match_any_sync(0xffffffffu, active ? ctx : 0x10000u + lane);
+            const int rank = __popc(grp & ((1u << lane) - 1));
+            const int rounds = __reduce_max_sync(0xffffffffu, active ? __popc(grp) : 0);
+            uint32_t out = v;
+            for (int round = 0; round < rounds; round++) {
+              if (active && rank == round) {
+                const unsigned s = s_ctx[ctx];
+                unsigned st = s >> 1, mps = s & 1;
+                const unsigned is_lps = bin != mps;
+                out = (st << 1) | is_lps;
+                if (is_lps) { mps ^= (st == 0); st = s_trans[st]; }
+                else st = min(st + 1, 62u);
+                s_ctx[ctx] = (uint8_t)((st << 1) | mps);
+              }
+              __syncwarp();
             }
-            __syncwarp();
+            if (active) reg[1 + off + lane] = out;
           }
-          if (active) reg[1 + base + lane] = out;
-          v = vnext;
+#pragma unroll
+          for (int j = 0; j < 4; j++) v4[j] = n4[j];
         }
-        z = zn; cnt = cntn; reg = regn; v = vnext_cu;
+        if (cnt == 0) load4(regn, kn < n_cu ? cntn : 0, 0, v4);     // (a CU always has records; keep the cursor sound anyway)
+        z = zn; cnt = cntn; reg = regn;
       }
       if (col == 1 && r + 1 < fp.ctb_rows && !fp.no_wpp) {       // WPP: hand the contexts to the row below
         __syncwarp();
