@@ -247,7 +247,7 @@ def run_b200(args):
         "modes": (px / 64) * 12 * 2,
         "deblock": 2 * (px * 1.0 * 2),                        # two passes, luma read + written
         "binarise": px * 3.0 + (px / 64) * 12 + 4.0 * 8 * out_bytes[0] / GOP,   # levels + cu map read, ~1 record (4 B) per bin written
-        "arith": 4.0 * 8 * out_bytes[0] / GOP + out_bytes[0] / GOP,              # records read, bitstream written
+        "arith": 12.0 * 8 * out_bytes[0] / GOP + out_bytes[0] / GOP,             # records: phase A reads + rewrites, phase B reads; bitstream written
         "pack": 2.0 * out_bytes[0] / GOP,
     }
     total_ms = sum(v[0] for v in prof.values()) or 1.0

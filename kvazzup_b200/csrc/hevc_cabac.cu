@@ -1,22 +1,20 @@
 // CABAC entropy coding of the B200 HEVC encoder (sm_100a); SURVEY.md 8a-K row K8.
 //
-// Arithmetic coding is serial per substream, binarisation is not, so the work is split in two
-// kernels that meet in a record buffer in HBM (hevc_common.h kRecUnitCap):
+// Only the range-coder update (low, range) is inherently serial per substream; binarisation and
+// even the evolution of the context states are not.  So entropy coding is three kernels that meet in
+// a record buffer in HBM (hevc_common.h kRecUnitCap):
 //
-//   k_binarise     one warp per CU, every CU of the picture at once.  Writes the CU's complete
-//                  syntax as a list of bin RECORDS (context index + value, a group of <= 16 bypass
-//                  bins, or a terminate bin).  All context indices of HEVC's coding_unit /
-//                  residual_coding syntax are functions of the cu map and the levels only -- never
-//                  of the arithmetic coder's state -- so the whole picture binarises in parallel;
-//                  inside a transform block every lane binarises whole 4x4 sub-blocks.
-//   k_arith_rows   one warp per WPP substream (CTU row), all rows in flight.  Streams the record
-//                  lists of its CUs with coalesced 32-record loads (one per lane, broadcast by
-//                  shuffle, next chunk prefetched) and runs the range coder; every lane runs it
-//                  redundantly on a private context table, lane 0 stores the bytes, escaped on the
-//                  fly (exact: each substream starts after a non-zero byte).  Row r starts from
-//                  the tables row r-1 published after its second CTU (H.265 9.3.1).
-//
-// The only serial work left per bin is the range coder update itself.
+//   k_binarise     one warp per CTU quadrant, every CU of the picture at once.  Writes each CU's
+//                  complete syntax as a list of bin RECORDS (context index + value, a group of
+//                  <= 16 bypass bins).  All context indices of HEVC's coding_unit / residual_coding
+//                  syntax are functions of the cu map and the levels only -- never of the coder's
+//                  state -- so the whole picture binarises in parallel; inside a transform block
+//                  every lane binarises whole 4x4 sub-blocks.
+//   k_ctx_rows     one warp per WPP substream (CTU row): context-state resolution, 32 records at a
+//                  time (see the comment above the kernel); owns the WPP context hand-over.
+//   k_arith_rows   one warp per substream: the range coder over resolved records, no dependency
+//                  between rows; every lane runs it redundantly, lane 0 stores the bytes, escaped
+//                  on the fly (exact: each substream starts after a non-zero byte).
 #include "hevc_device.cuh"
 #include "hevc_kernels.h"
 
@@ -30,7 +28,6 @@ struct Coder {
   uint8_t *out;
   uint32_t pos, cap;
   int zeros;
-  uint8_t *ctx;               // shared memory, this lane's private table: entry i at ctx[i * 32]
   unsigned long long bins;
   bool writer;                // lane 0
 };
@@ -71,31 +68,6 @@ __device__ __forceinline__ void write_out(Coder &c)
     c.num_buffered = 1;
     c.buffered_byte = (int)lead;
   }
-}
-
-// One 64-bit shared-memory entry per pStateIdx: .x = rangeTabLps row (4 bytes), .y = state after
-// an LPS (transIdxLps) | (valMps flips) << 6 -- a single load feeds the whole update.
-__device__ __forceinline__ void enc_bin(Coder &c, const uint2 *tab, int ctx_idx, int bin)
-{
-  uint32_t s = c.ctx[ctx_idx * 32];
-  uint32_t st = s >> 1, mps = s & 1;
-  const uint2 e = tab[st];
-  uint32_t lps = (e.x >> (((c.range >> 6) & 3) * 8)) & 0xff;
-  c.bins++;
-  c.range -= lps;
-  if ((uint32_t)bin != mps) {
-    int nb = __clz(lps) - 23;                     // shifts until lps >= 256
-    c.low = (c.low + c.range) << nb;
-    c.range = lps << nb;
-    mps ^= e.y >> 6;
-    st = e.y & 63;
-    c.bits_left -= nb;
-  } else {
-    st = min(st + 1, 62u);
-    if (c.range < 256) { c.low <<= 1; c.range <<= 1; c.bits_left--; }
-  }
-  c.ctx[ctx_idx * 32] = (uint8_t)((st << 1) | mps);
-  if (c.bits_left < 12) write_out(c);
 }
 
 // n <= 16 bypass bins at once (HM encodeBinsEP): low = low * 2^n + range * value, eight at a time
@@ -156,19 +128,6 @@ __device__ __forceinline__ void coder_finish(Coder &c)
 // Every lane keeps a private copy of the context table (entry i of lane l at s_ctx[i*32 + l]):
 // the lanes run the same coder redundantly, and private tables make that independent of warp
 // reconvergence timing.
-__device__ __forceinline__ void init_contexts(uint8_t *ctx, int init_type, int qp)
-{
-  qp = clip3(0, 51, qp);
-  for (int i = 0; i < CTX_COUNT; i++) {
-    int iv = c_ctx_init[init_type][i];
-    int m = (iv >> 4) * 5 - 45, n = ((iv & 15) << 3) - 16;
-    int pre = clip3(1, 126, ((m * qp) >> 4) + n);
-    int mps = pre <= 63 ? 0 : 1;
-    int st = mps ? pre - 64 : 63 - pre;
-    ctx[i * 32] = (uint8_t)((st << 1) | mps);
-  }
-}
-
 // ---- bin records ------------------------------------------------------------------------------------
 //   bit31 = 0, bit30 = 0 : context-coded bin,  bits 15..1 context index, bit 0 value
 //   bit31 = 1            : bypass group,       bits 28..24 count (1..16), bits 15..0 value
@@ -791,7 +750,7 @@ k_arith_rows(FrameParams fp, const uint32_t *__restrict__ recs, uint8_t *rows, u
   for (int i = lane; i < 64; i += 32) s_tab[i] = make_uint2(c_range_lps[i], 0u);
   Coder c;
   c.out = rows + (size_t)r_first * row_cap; c.pos = 0; c.cap = fp.no_wpp ? row_cap * fp.ctb_rows : row_cap;
-  c.zeros = 0; c.ctx = nullptr; c.bins = 0;
+  c.zeros = 0; c.bins = 0;
   c.writer = lane == 0;
   __syncwarp();
   coder_start(c);

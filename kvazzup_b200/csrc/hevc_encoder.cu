@@ -402,10 +402,10 @@ bool Encoder::submit(FrameSlot &s, const uint8_t *d_i420)
   PROF_BEGIN(K_PACK, s.stream);
   ENC_CHECK(launch_pack_rows(p.ctb_rows, s.d_rows, row_cap, row_len, s.h_pack, pack_cap, s.h_hdr, s.stream), "pack launch");
   PROF_END(K_PACK, s.stream);
-  count_launch(1);                                 // launch_cabac is two kernels
+  count_launch(2);                                 // entropy coding: k_binarise, k_ctx_rows ...
 #undef PROF_BEGIN
 #undef PROF_END
-  count_launch(2);
+  count_launch(2);                                 // ... k_arith_rows, k_pack_rows
   ENC_CHECK(cudaEventRecord(s.ev_done, s.stream), "event record");
   frame_idx++;
   poc++;
