@@ -28,7 +28,7 @@ struct Coder {
   uint8_t *out;
   uint32_t pos, cap;
   int zeros;
-  unsigned long long bins;
+  unsigned bins;              // of this substream (added to the picture's 64-bit total at the end)
   bool writer;                // lane 0
 };
 
@@ -723,17 +723,15 @@ k_ctx_rows(FrameParams fp, const CuInfo *__restrict__ cu, uint32_t *recs, uint8_
 // phase B: context-coded records are (pStateIdx << 1) | is-LPS here
 __device__ __forceinline__ void enc_bin_resolved(Coder &c, const uint2 e, unsigned is_lps)
 {
+  // Branch-free: a lone warp pays a pipeline refill for every taken branch, and LPS / MPS /
+  // renormalise-by-one are only selects on the same three registers.
   const uint32_t lps = (e.x >> (((c.range >> 6) & 3) * 8)) & 0xff;
+  const uint32_t rmps = c.range - lps;
+  const int nb = is_lps ? __clz(lps) - 23 : (rmps < 256 ? 1 : 0);
+  c.low = (c.low + (is_lps ? rmps : 0u)) << nb;
+  c.range = (is_lps ? lps : rmps) << nb;
+  c.bits_left -= nb;
   c.bins++;
-  c.range -= lps;
-  if (is_lps) {
-    const int nb = __clz(lps) - 23;
-    c.low = (c.low + c.range) << nb;
-    c.range = lps << nb;
-    c.bits_left -= nb;
-  } else if (c.range < 256) {
-    c.low <<= 1; c.range <<= 1; c.bits_left--;
-  }
   if (c.bits_left < 12) write_out(c);
 }
 
