@@ -74,6 +74,10 @@ class ClockSampler(threading.Thread):
         self.proc = None
 
     def run(self):
+        # NVML first: a query takes microseconds and the first sample lands at once (the timed region
+        # of a default run is well under a second); nvidia-smi -lms as the fallback of the recipe.
+        if self._run_nvml():
+            return
         q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
              "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
         try:
@@ -94,6 +98,30 @@ class ClockSampler(threading.Thread):
                         self.reasons.add(n)
             except Exception:
                 continue
+
+    def _run_nvml(self) -> bool:
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            vis = os.environ.get("CUDA_VISIBLE_DEVICES")
+            idx = self.gpu
+            if vis:
+                ids = [v.strip() for v in vis.split(",") if v.strip()]
+                if self.gpu < len(ids) and ids[self.gpu].isdigit():
+                    idx = int(ids[self.gpu])
+            h = pynvml.nvmlDeviceGetHandleByIndex(idx)
+            self.max_mhz = float(pynvml.nvmlDeviceGetMaxClockInfo(h, pynvml.NVML_CLOCK_SM))
+            bits = {0x8: "hw_slowdown", 0x40: "hw_thermal_slowdown", 0x20: "sw_thermal_slowdown", 0x4: "sw_power_cap"}
+            while not self.stop_flag.is_set():
+                self.samples.append(float(pynvml.nvmlDeviceGetClockInfo(h, pynvml.NVML_CLOCK_SM)))
+                r = pynvml.nvmlDeviceGetCurrentClocksThrottleReasons(h)
+                for b, n in bits.items():
+                    if r & b:
+                        self.reasons.add(n)
+                time.sleep(0.02)
+            return True
+        except Exception:
+            return bool(self.samples)
 
     def finish(self):
         self.stop_flag.set()
@@ -417,7 +445,7 @@ def run_reference(args):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--steps", type=int, default=32)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--sweep", action="store_true", help="also report the QP 22/27/32/37 sweep")
