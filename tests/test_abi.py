@@ -62,3 +62,43 @@ def test_compute_fails_loudly_without_gpu():
     o = np.zeros(16, np.uint8)
     rc = l.b200_yuv420_to_rgb32(C.c_void_p(a.ctypes.data), C.c_void_p(o.ctypes.data), 2, 2)
     assert rc < 0 and b"no CPU fallback" in l.b200_last_error()
+
+
+def test_headers_are_plain_c_and_self_contained(tmp_path):
+    """The drop-in boundary is a C ABI: every header must compile as C99 on its own (no C++ / CUDA /
+    torch types in the signatures), and a C program must link against the library."""
+    import shutil
+    import subprocess
+    gcc = "/usr/bin/gcc" if Path("/usr/bin/gcc").exists() else shutil.which("gcc")
+    assert gcc
+    for hdr in sorted((ROOT / "include").glob("*.h")):
+        src = tmp_path / f"only_{hdr.stem}.c"
+        src.write_text(f'#include "{hdr.name}"\nint main(void) {{ return 0; }}\n')
+        r = subprocess.run([gcc, "-std=c99", "-Wall", "-Werror", "-pedantic", "-fsyntax-only", "-I", str(ROOT / "include"), str(src)],
+                           capture_output=True, text=True)
+        assert r.returncode == 0, f"{hdr.name}: {r.stderr}"
+    prog = tmp_path / "link.c"
+    prog.write_text('''
+#include <stdio.h>
+#include "b200media.h"
+#include "b200_kvazaar.h"
+#include "b200_openhevc.h"
+#include "b200_rtp.h"
+#include "b200_hevc.h"
+int main(void) {
+  const kvz_api *api = kvz_api_get(8);
+  b200_nal_span span[4];
+  const unsigned char au[] = {0, 0, 0, 1, 0x40, 1, 0xaa, 0, 0, 1, 0x42, 1, 0xbb};
+  int n = b200_annexb_split(au, sizeof au, span, 4);
+  printf("%s %d %d %d\\n", b200_version(), api != NULL, kvz_api_get(10) == NULL, n);
+  return (api && n == 2) ? 0 : 1;
+}
+''')
+    exe = tmp_path / "link_test"
+    libdir = ROOT / "kvazzup_b200"
+    kvazzup_b200.load()
+    r = subprocess.run([gcc, "-std=c99", "-I", str(ROOT / "include"), str(prog), "-o", str(exe), "-L", str(libdir), "-lb200media",
+                        f"-Wl,-rpath,{libdir}"], capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
+    r = subprocess.run([str(exe)], capture_output=True, text=True)
+    assert r.returncode == 0 and "b200media" in r.stdout, r.stdout + r.stderr
