@@ -597,8 +597,8 @@ k_binarise(FrameParams fp, const CuInfo *__restrict__ cu, const int16_t *__restr
 //
 //   k_ctx_rows   (phase A) walks the bin records of a CTU row 32 at a time and replaces every
 //                context-coded record (context index, bin) by (pStateIdx, is-LPS).  Records of one
-//                batch that share a context are ordered with __match_any_sync and resolved in as
-//                many rounds as the most frequent context occurs; everything else is parallel.  The
+//                batch that share a context are grouped with __match_any_sync and walked in order
+//                by the group's first lane; the groups run side by side.  The
 //                WPP hand-over (contexts after the second CTU of the row above) lives here, so the
 //                two-CTU stagger between rows costs two CTUs of this cheap pass only.
 //   k_arith_rows (phase B) is the serial range coder over the resolved records: no context table,
@@ -613,6 +613,7 @@ k_ctx_rows(FrameParams fp, const CuInfo *__restrict__ cu, uint32_t *recs, uint8_
 {
   __shared__ uint8_t s_ctx[CTX_COUNT + 2];
   __shared__ uint8_t s_trans[64];
+  __shared__ uint8_t s_out[32];
   const int lane = threadIdx.x;
   const int r_first = fp.no_wpp ? 0 : blockIdx.x, r_last = fp.no_wpp ? fp.ctb_rows - 1 : blockIdx.x;
   for (int i = lane; i < 64; i += 32) s_trans[i] = c_trans_lps[i];
@@ -685,23 +686,25 @@ k_ctx_rows(FrameParams fp, const CuInfo *__restrict__ cu, uint32_t *recs, uint8_
             const uint32_t v = v4[j];
             const bool active = off + lane < cnt && !(v & 0x80000000u);
             const unsigned ctx = v >> 1, bin = v & 1;
+            // records of this chunk that share a context form a group; the first lane of each group
+            // walks its members in order, entirely in registers, and leaves their results in s_out
             const unsigned grp = __match_any_sync(0xffffffffu, active ? ctx : 0x10000u + lane);
-            const int rank = __popc(grp & ((1u << lane) - 1));
-            const int rounds = __reduce_max_sync(0xffffffffu, active ? __popc(grp) : 0);
-            uint32_t out = v;
-            for (int round = 0; round < rounds; round++) {
-              if (active && rank == round) {
-                const unsigned s = s_ctx[ctx];
-                unsigned st = s >> 1, mps = s & 1;
-                const unsigned is_lps = bin != mps;
-                out = (st << 1) | is_lps;
+            const unsigned bins32 = __ballot_sync(0xffffffffu, active && bin);
+            if (active && (grp & ((1u << lane) - 1)) == 0) {
+              const unsigned s = s_ctx[ctx];
+              unsigned st = s >> 1, mps = s & 1;
+              for (unsigned m = grp; m; m &= m - 1) {
+                const int j = __ffs(m) - 1;
+                const unsigned is_lps = ((bins32 >> j) & 1) != mps;
+                s_out[j] = (uint8_t)((st << 1) | is_lps);
                 if (is_lps) { mps ^= (st == 0); st = s_trans[st]; }
                 else st = min(st + 1, 62u);
-                s_ctx[ctx] = (uint8_t)((st << 1) | mps);
               }
-              __syncwarp();
+              s_ctx[ctx] = (uint8_t)((st << 1) | mps);
             }
-            if (active) reg[1 + off + lane] = out;
+            __syncwarp();
+            if (active) reg[1 + off + lane] = s_out[lane];
+            __syncwarp();
           }
 #pragma unroll
           for (int j = 0; j < 4; j++) v4[j] = n4[j];

@@ -19,6 +19,11 @@ namespace b200 {
 
 namespace {
 
+// sig_coeff_flag context increments (9.3.4.2.5) by scan position, two bits per position:
+// c_sig_pat[scan_idx][prevCsbf]; for 4x4 blocks four bits per position from ctxIdxMap.
+static __constant__ uint32_t c_sig_pat[3][4] = {{0x00000556u, 0x01090926u, 0x0010619au, 0xaaaaaaaau}, {0x00010516u, 0x000055aau, 0x06060606u, 0xaaaaaaaau}, {0x00010516u, 0x06060606u, 0x000055aau, 0xaaaaaaaau}};
+static __constant__ unsigned long long c_sig_pat4[3] = {0x8885875467436120ull, 0x8877886654325410ull, 0x8855884476317620ull};
+
 struct Reader {
   const uint8_t *p, *end;
   uint32_t range, value;
@@ -235,26 +240,20 @@ __device__ void parse_residual(Reader &r, const ParseCtx &pc, int16_t *plane, in
     unsigned sig = 0;
     int start = 15;
     if (i == last_sb) { sig = 1u << last_pos; start = last_pos - 1; }
+    // context of every sig_coeff_flag of this sub-block: base + a pattern looked up by scan position
+    const int sig_base = CTX_SIG + (cidx ? 27 : 0);
+    int sub_base;
+    if (cidx == 0) sub_base = ((xs || ys) ? 3 : 0) + (log2n == 3 ? (scan_idx == 0 ? 9 : 15) : 21);
+    else sub_base = log2n == 3 ? 9 : 12;
+    const uint32_t pat = c_sig_pat[scan_idx][prev_csbf];
+    const unsigned long long pat4 = c_sig_pat4[scan_idx];
     for (int p = start; p >= 0; p--) {
       if (p == 0 && infer_dc) { sig |= 1u; break; }
-      int xp, yp;
-      scan_pos_d(scan_idx, 2, p, xp, yp);
-      int xc = xs * 4 + xp, yc = ys * 4 + yp, sctx;
-      if (log2n == 2) sctx = c_sig_ctx_4x4[(yc << 2) + xc];
-      else if (xc + yc == 0) sctx = 0;
-      else {
-        if (prev_csbf == 0) sctx = (xp + yp == 0) ? 2 : (xp + yp < 3) ? 1 : 0;
-        else if (prev_csbf == 1) sctx = yp == 0 ? 2 : (yp == 1 ? 1 : 0);
-        else if (prev_csbf == 2) sctx = xp == 0 ? 2 : (xp == 1 ? 1 : 0);
-        else sctx = 2;
-        if (cidx == 0) {
-          if (xs || ys) sctx += 3;
-          sctx += log2n == 3 ? (scan_idx == 0 ? 9 : 15) : 21;
-        } else {
-          sctx += log2n == 3 ? 9 : 12;
-        }
-      }
-      if (dec_bin(r, CTX_SIG + (cidx == 0 ? sctx : 27 + sctx))) { sig |= 1u << p; infer_dc = 0; }
+      int sctx;
+      if (log2n == 2) sctx = (int)((pat4 >> (4 * p)) & 15);
+      else if (p == 0 && i == 0) sctx = 0;                               // the DC coefficient
+      else sctx = sub_base + (int)((pat >> (2 * p)) & 3);
+      if (dec_bin(r, sig_base + sctx)) { sig |= 1u << p; infer_dc = 0; }
     }
     if (!sig) continue;
     int ctx_set = (i > 0 && cidx == 0) ? 2 : 0;
