@@ -22,6 +22,10 @@ namespace {
 // sig_coeff_flag context increments (9.3.4.2.5) by scan position, two bits per position:
 // c_sig_pat[scan_idx][prevCsbf]; for 4x4 blocks four bits per position from ctxIdxMap.
 static __constant__ uint32_t c_sig_pat[3][4] = {{0x00000556u, 0x01090926u, 0x0010619au, 0xaaaaaaaau}, {0x00010516u, 0x000055aau, 0x06060606u, 0xaaaaaaaau}, {0x00010516u, 0x06060606u, 0x000055aau, 0xaaaaaaaau}};
+// inverse up-right diagonal scans: scan index of position (x, y), row-major
+static __constant__ uint8_t c_inv_diag2[4] = {0, 2, 1, 3};
+static __constant__ uint8_t c_inv_diag4[16] = {0, 2, 5, 9, 1, 4, 8, 12, 3, 7, 11, 14, 6, 10, 13, 15};
+static __constant__ uint8_t c_inv_diag8[64] = {0, 2, 5, 9, 14, 20, 27, 35, 1, 4, 8, 13, 19, 26, 34, 42, 3, 7, 12, 18, 25, 33, 41, 48, 6, 11, 17, 24, 32, 40, 47, 53, 10, 16, 23, 31, 39, 46, 52, 57, 15, 22, 30, 38, 45, 51, 56, 60, 21, 29, 37, 44, 50, 55, 59, 62, 28, 36, 43, 49, 54, 58, 61, 63};
 static __constant__ unsigned long long c_sig_pat4[3] = {0x8885875467436120ull, 0x8877886654325410ull, 0x8855884476317620ull};
 
 struct Reader {
@@ -133,11 +137,9 @@ __device__ __forceinline__ int scan_index_d(int scan_idx, int blk_log2, int x, i
   int n = 1 << blk_log2;
   if (scan_idx == 1) return y * n + x;
   if (scan_idx == 2) return x * n + y;
-  for (int i = 0; i < n * n; i++) {
-    int xx, yy;
-    scan_pos_d(0, blk_log2, i, xx, yy);
-    if (xx == x && yy == y) return i;
-  }
+  if (blk_log2 == 2) return c_inv_diag4[y * 4 + x];
+  if (blk_log2 == 3) return c_inv_diag8[y * 8 + x];
+  if (blk_log2 == 1) return c_inv_diag2[y * 2 + x];
   return 0;
 }
 
@@ -259,23 +261,30 @@ __device__ void parse_residual(Reader &r, const ParseCtx &pc, int16_t *plane, in
     int ctx_set = (i > 0 && cidx == 0) ? 2 : 0;
     if (c1 == 0) ctx_set++;
     c1 = 1;
+    // The three passes below visit the significant positions only, from the highest scan position
+    // down (sparse sub-blocks are the common case: looping over all 16 positions cost more than
+    // the bins themselves).
     int num_g1 = 0, first_g1 = -1;
     unsigned g1 = 0;
-    for (int p = 15; p >= 0; p--) {
-      if (!((sig >> p) & 1) || num_g1 >= 8) continue;
+    for (unsigned t = sig; t && num_g1 < 8; num_g1++) {
+      const int p = 31 - __clz(t);
+      t &= ~(1u << p);
       int f = dec_bin(r, CTX_GT1 + (cidx ? 16 : 0) + 4 * ctx_set + c1);
       if (f) { g1 |= 1u << p; c1 = 0; if (first_g1 < 0) first_g1 = p; }
       else if (c1 < 3 && c1 > 0) c1++;
-      num_g1++;
     }
     int g2 = 0;
     if (first_g1 >= 0) g2 = dec_bin(r, CTX_GT2 + (cidx ? 4 : 0) + ctx_set);
     unsigned neg = 0;
-    for (int p = 15; p >= 0; p--)
-      if ((sig >> p) & 1) neg |= (unsigned)dec_bypass(r) << p;
+    for (unsigned t = sig; t;) {
+      const int p = 31 - __clz(t);
+      t &= ~(1u << p);
+      neg |= (unsigned)dec_bypass(r) << p;
+    }
     int num_sig = 0, rice = 0;
-    for (int p = 15; p >= 0; p--) {
-      if (!((sig >> p) & 1)) continue;
+    for (unsigned t = sig; t;) {
+      const int p = 31 - __clz(t);
+      t &= ~(1u << p);
       int base = 1 + (num_sig < 8 ? (int)((g1 >> p) & 1) : 0) + (p == first_g1 ? g2 : 0);
       int thresh = num_sig < 8 ? (p == first_g1 ? 3 : 2) : 1;
       int absv = base;
