@@ -524,69 +524,69 @@ k_parse_rows(FrameParams fp, const uint8_t *__restrict__ data, const uint32_t *_
   __syncwarp();
   reader_start(r);
   for (; row <= row_last && !r.err; row++) {
-  pc.cy = row * kCtb;
-  for (int col = 0; col < fp.ctb_cols && !r.err; col++) {
-    if (row > 0) {                       // above and above-right CTUs must be parsed (cu map reads)
-      if (!fp.no_wpp) {                  // (one warp does all rows without WPP: nothing to wait for)
-        volatile int *p = progress;
-        const int need = min(col + 2, fp.ctb_cols);
-        for (;;) {
-          const int have = p[row - 1];
-          if (have >= need || have < 0) break;
-          __nanosleep(64);
+    pc.cy = row * kCtb;
+    for (int col = 0; col < fp.ctb_cols && !r.err; col++) {
+      if (row > 0) {                       // above and above-right CTUs must be parsed (cu map reads)
+        if (!fp.no_wpp) {                  // (one warp does all rows without WPP: nothing to wait for)
+          volatile int *p = progress;
+          const int need = min(col + 2, fp.ctb_cols);
+          for (;;) {
+            const int have = p[row - 1];
+            if (have >= need || have < 0) break;
+            __nanosleep(64);
+          }
+          __threadfence();
         }
-        __threadfence();
-      }
-      {
-        const int slot = min(lane, 9);
-        const int ux = min(max(col * 8 - 1 + slot, 0), fp.w8 - 1);
-        const uint32_t *s = (const uint32_t *)(cu + (size_t)(row * 8 - 1) * fp.w8 + ux);
-        uint32_t *d = s_above + 3 * slot;
-        d[0] = __ldcg(s); d[1] = __ldcg(s + 1); d[2] = __ldcg(s + 2);
-      }
-    }
-    const int cx = col * kCtb, cy = row * kCtb;
-    pc.cx = cx; pc.cur_buf = col & 1;
-    pc.delta_coded = 0;                  // new quantisation group; qp_cur carries over as qPY_PREV
-    __syncwarp();
-    for (int z = 0; z < 64 && !r.err;) {
-      int x0 = cx + 8 * z_to_x(z), y0 = cy + 8 * z_to_y(z);
-      if (x0 >= fp.w || y0 >= fp.h) { z++; continue; }
-      int log2 = 3;
-      for (int L = 6; L > 3; L--) {
-        if (z & ((1 << (2 * (L - 3))) - 1)) continue;
-        const int nn = 1 << L;
-        int split;
-        if (x0 + nn <= fp.w && y0 + nn <= fp.h) {
-          int ctx = 0, depth = 6 - L;
-          if (x0 > 0) ctx += (kCtbLog2 - load_cu(pc, x0 - 1, y0).log2_size) > depth;
-          if (y0 > 0) ctx += (kCtbLog2 - load_cu(pc, x0, y0 - 1).log2_size) > depth;
-          split = dec_bin(r, CTX_SPLIT_CU + ctx);
-        } else {
-          split = 1;
+        {
+          const int slot = min(lane, 9);
+          const int ux = min(max(col * 8 - 1 + slot, 0), fp.w8 - 1);
+          const uint32_t *s = (const uint32_t *)(cu + (size_t)(row * 8 - 1) * fp.w8 + ux);
+          uint32_t *d = s_above + 3 * slot;
+          d[0] = __ldcg(s); d[1] = __ldcg(s + 1); d[2] = __ldcg(s + 2);
         }
-        if (!split) { log2 = L; break; }
       }
-      parse_cu(r, pc, x0, y0, log2);
-      z += 1 << (2 * (log2 - 3));
-    }
-    if (col == 1 && row + 1 < fp.ctb_rows && !fp.no_wpp) {
-      // every lane holds the same table; all store it (same addresses, same values)
-      for (int i = 0; i < CTX_COUNT; i++) sync_ctx[(size_t)row * CTX_COUNT + i] = r.ctx[i * 32];
-      __threadfence();
+      const int cx = col * kCtb, cy = row * kCtb;
+      pc.cx = cx; pc.cur_buf = col & 1;
+      pc.delta_coded = 0;                  // new quantisation group; qp_cur carries over as qPY_PREV
       __syncwarp();
-      *(volatile int *)&sync_flag[row] = 1;
+      for (int z = 0; z < 64 && !r.err;) {
+        int x0 = cx + 8 * z_to_x(z), y0 = cy + 8 * z_to_y(z);
+        if (x0 >= fp.w || y0 >= fp.h) { z++; continue; }
+        int log2 = 3;
+        for (int L = 6; L > 3; L--) {
+          if (z & ((1 << (2 * (L - 3))) - 1)) continue;
+          const int nn = 1 << L;
+          int split;
+          if (x0 + nn <= fp.w && y0 + nn <= fp.h) {
+            int ctx = 0, depth = 6 - L;
+            if (x0 > 0) ctx += (kCtbLog2 - load_cu(pc, x0 - 1, y0).log2_size) > depth;
+            if (y0 > 0) ctx += (kCtbLog2 - load_cu(pc, x0, y0 - 1).log2_size) > depth;
+            split = dec_bin(r, CTX_SPLIT_CU + ctx);
+          } else {
+            split = 1;
+          }
+          if (!split) { log2 = L; break; }
+        }
+        parse_cu(r, pc, x0, y0, log2);
+        z += 1 << (2 * (log2 - 3));
+      }
+      if (col == 1 && row + 1 < fp.ctb_rows && !fp.no_wpp) {
+        // every lane holds the same table; all store it (same addresses, same values)
+        for (int i = 0; i < CTX_COUNT; i++) sync_ctx[(size_t)row * CTX_COUNT + i] = r.ctx[i * 32];
+        __threadfence();
+        __syncwarp();
+        *(volatile int *)&sync_flag[row] = 1;
+      }
+      if (fp.ctu_qp) fp.ctu_qp[row * fp.ctb_cols + col] = (uint8_t)pc.qp_cur;     // what the CTU's residuals are scaled with
+      const bool last = row == fp.ctb_rows - 1 && col == fp.ctb_cols - 1 && !fp.more_tiles;
+      const bool end_sub = col == fp.ctb_cols - 1 && (!fp.no_wpp || row == fp.ctb_rows - 1);
+      int eos = dec_terminate(r);                                        // end_of_slice_segment_flag
+      if (eos != (last ? 1 : 0)) r.err = 8;
+      if (end_sub && !last && !dec_terminate(r)) r.err = 9;              // end_of_subset_one_bit
+      __threadfence();
+      __syncwarp();                        // every lane's cu map stores are fenced before any lane publishes
+      *(volatile int *)&progress[row] = r.err ? -1 : col + 1;
     }
-    if (fp.ctu_qp) fp.ctu_qp[row * fp.ctb_cols + col] = (uint8_t)pc.qp_cur;     // what the CTU's residuals are scaled with
-    const bool last = row == fp.ctb_rows - 1 && col == fp.ctb_cols - 1 && !fp.more_tiles;
-    const bool end_sub = col == fp.ctb_cols - 1 && (!fp.no_wpp || row == fp.ctb_rows - 1);
-    int eos = dec_terminate(r);                                        // end_of_slice_segment_flag
-    if (eos != (last ? 1 : 0)) r.err = 8;
-    if (end_sub && !last && !dec_terminate(r)) r.err = 9;              // end_of_subset_one_bit
-    __threadfence();
-    __syncwarp();                        // every lane's cu map stores are fenced before any lane publishes
-    *(volatile int *)&progress[row] = r.err ? -1 : col + 1;
-  }
   }                                      // rows of this substream
   if (lane == 0) {
     if (r.err) {

@@ -102,3 +102,31 @@ int main(void) {
     assert r.returncode == 0, r.stderr
     r = subprocess.run([str(exe)], capture_output=True, text=True)
     assert r.returncode == 0 and "b200media" in r.stdout, r.stdout + r.stderr
+
+
+def test_kvz_config_parse_follows_the_reference_contract():
+    """config_parse returns 1 on success and the reference only warns otherwise
+    (kvazaarfilter.cpp:363-369): known Kvazaar options are applied or knowingly ignored, unknown names
+    and unsupported values return 0.  No GPU needed: the encoder is not opened."""
+    from kvazzup_b200.kvazaar import kvz_api_get
+    api = kvz_api_get(8)
+    assert api is not None
+    cfg = api.config_alloc()
+    assert api.config_init(cfg) == 1
+    ok = lambda n, v: api.config_parse(cfg, n.encode(), v.encode() if v is not None else None)
+    for preset, rng in (("ultrafast", 8), ("veryfast", 12), ("medium", 16), ("placebo", 32)):
+        assert ok("preset", preset) == 1 and cfg.contents.me_range == rng
+    assert ok("preset", "warp-speed") == 0
+    assert ok("qp", "27") == 1 and cfg.contents.qp == 27
+    assert ok("qp", "52") == 0 and ok("qp", "abc") == 0
+    assert ok("period", "64") == 1 and ok("vps-period", "1") == 1 and ok("owf", "3") == 1 and cfg.contents.owf == 3
+    assert ok("gop", "lp-g4d3t1") == 1 and ok("intra-bits", "") == 1 and ok("rd", "0") == 1 and ok("sao", "off") == 1
+    assert ok("tiles", "3x1") == 1 and cfg.contents.tiles_width_count == 3
+    assert ok("tiles", "2x2") == 0 and cfg.contents.tiles_width_count == 3      # tile rows: refused, state unchanged
+    assert ok("tiles", "banana") == 0 and ok("slices", "tiles") == 0
+    assert ok("b200-roi", "1") == 1 and cfg.contents.roi_enable == 1
+    assert ok("set-qp-in-cu", "1") == 1 and cfg.contents.set_qp_in_cu == 1
+    assert ok("bitrate", "1500000") == 1 and cfg.contents.target_bitrate == 1500000
+    assert ok("no-such-option", "1") == 0
+    api.config_destroy(cfg)
+    assert kvz_api_get(10) is None                      # only 8-bit, like the reference's kvz_api_get(8) (:145)
