@@ -125,3 +125,29 @@ def test_small_output_buffer_is_reported_and_consumes_nothing():
     n = l.b200_rtp_push_frame(h, au, len(au), 0, big, 4096, lens, 64)
     assert n == 6 and bytes(big[2:4]) == b"\0\0"                           # first sequence number is still 0
     l.b200_rtp_sender_free(h)
+
+
+def test_receiver_survives_garbage_and_truncations():
+    """Packets come from the network: random bytes, truncated and bit-flipped packets must be
+    rejected or parsed, never crash, and a clean packet afterwards still comes through."""
+    rng = np.random.default_rng(2024)
+    s, r = rtp.RtpSender(3, 96, 120), rtp.RtpReceiver(3)
+    good = s.push_frame(fake_au([20, 30, 10, 700]), 0)
+    for k in range(3000):
+        kind = k % 3
+        if kind == 0:
+            pkt = rng.integers(0, 256, size=int(rng.integers(0, 200)), dtype=np.uint8).tobytes()
+        elif kind == 1:
+            p = good[int(rng.integers(0, len(good)))]
+            pkt = p[:int(rng.integers(0, len(p) + 1))]
+        else:
+            p = bytearray(good[int(rng.integers(0, len(good)))])
+            for _ in range(3):
+                p[int(rng.integers(0, len(p)))] ^= 1 << int(rng.integers(0, 8))
+            pkt = bytes(p)
+        out = r.receive(pkt)
+        assert out is None or all(n[0][:4] == b"\0\0\0\1" and len(n[0]) >= 6 for n in out)
+    au = fake_au([900], seed=9, idr=False)
+    out = [x for p in s.push_frame(au, 9000) for x in (r.receive(p) or [])]
+    assert [o[0] for o in out][-1:] == split_nals(au)
+    assert rtp.annexb_split(bytes(rng.integers(0, 2, size=5000, dtype=np.uint8))) is not None     # dense start codes
