@@ -52,32 +52,23 @@ __device__ __forceinline__ void reader_start(Reader &r)
 
 __device__ __forceinline__ int dec_bin(Reader &r, int ctx_idx)
 {
-  uint32_t s = r.ctx[ctx_idx * 32];
+  // 9.3.4.3.2, written without branches up to the byte refill: a lone warp pays a pipeline refill
+  // for every taken branch, and the MPS / LPS / renormalise cases are selects on the same registers.
+  const uint32_t s = r.ctx[ctx_idx * 32];
   uint32_t st = s >> 1, mps = s & 1;
   const uint2 e = r.tab[st];
-  uint32_t lps = (e.x >> (((r.range >> 6) & 3) * 8)) & 0xff;
-  r.range -= lps;
-  uint32_t scaled = r.range << 7;
-  int bin;
-  if (r.value < scaled) {
-    bin = (int)mps;
-    st = min(st + 1, 62u);
-    if (scaled < (256u << 7)) {
-      r.range = scaled >> 6;
-      r.value += r.value;
-      if (++r.bits_needed == 0) { r.bits_needed = -8; r.value += next_byte(r); }
-    }
-  } else {
-    bin = (int)(mps ^ 1);
-    int nb = __clz(lps) - 23;
-    r.value = (r.value - scaled) << nb;
-    r.range = lps << nb;
-    mps ^= e.y >> 6;
-    st = e.y & 63;
-    r.bits_needed += nb;
-    if (r.bits_needed >= 0) { r.value += next_byte(r) << r.bits_needed; r.bits_needed -= 8; }
-  }
+  const uint32_t lps = (e.x >> (((r.range >> 6) & 3) * 8)) & 0xff;
+  const uint32_t rmps = r.range - lps, scaled = rmps << 7;
+  const bool is_lps = r.value >= scaled;
+  const int nb = is_lps ? __clz(lps) - 23 : (rmps < 256 ? 1 : 0);
+  r.value = (r.value - (is_lps ? scaled : 0u)) << nb;
+  r.range = (is_lps ? lps : rmps) << nb;
+  const int bin = (int)(mps ^ (is_lps ? 1u : 0u));
+  mps ^= is_lps ? (e.y >> 6) : 0u;
+  st = is_lps ? (e.y & 63) : min(st + 1, 62u);
   r.ctx[ctx_idx * 32] = (uint8_t)((st << 1) | mps);
+  r.bits_needed += nb;
+  if (r.bits_needed >= 0) { r.value += next_byte(r) << r.bits_needed; r.bits_needed -= 8; }
   return bin;
 }
 
