@@ -4,13 +4,19 @@
 // OpenHEVCFilter::process / sendDecodedOutput (openhevcfilter.cpp:103-239) do -- in C++ over the
 // C ABI of libb200media.so, no Python in the loop.
 //
-//   conference_bench <frames.yuv> <w> <h> <frames_in_file> <streams> <frames_per_stream> <encode_only> <decoder_frame_threads>
+//   conference_bench <frames.yuv> <w> <h> <frames_in_file> <streams> <frames_per_stream> <encode_only> <decoder_frame_threads> [pace_fps]
+//
+// pace_fps > 0: every stream delivers its pictures at that rate (a live call) with nothing in flight
+// (owf 0) and the time from handing a picture to the encoder until its decoded copy is back in host
+// memory is recorded per picture: the glass-to-glass share of the media path under N-stream load.
 #include <pthread.h>
 #include <stdio.h>
 #include <stdlib.h>
 #include <string.h>
 
+#include <algorithm>
 #include <chrono>
+#include <thread>
 #include <vector>
 
 #include "b200_kvazaar.h"
@@ -19,6 +25,8 @@
 #include "b200media.h"
 
 static int W, H, NFILE, STREAMS, FRAMES, ENC_ONLY, DEC_THREADS;
+static double PACE_FPS = 0;
+static std::vector<std::vector<float>> g_lat;      // per stream: latency of every picture, ms
 static std::vector<uint8_t> g_yuv;
 static pthread_barrier_t g_bar;
 static std::vector<int> g_decoded, g_ok;
@@ -97,7 +105,7 @@ static void *worker(void *arg)
   s.cfg->width = W; s.cfg->height = H; s.cfg->framerate_num = 30; s.cfg->framerate_denom = 1;
   s.api->config_parse(s.cfg, "qp", "32");
   s.api->config_parse(s.cfg, "period", "64");
-  s.api->config_parse(s.cfg, "owf", "3");
+  s.api->config_parse(s.cfg, "owf", PACE_FPS > 0 ? "0" : "3");
   s.enc = s.api->encoder_open(s.cfg);
   bool ok = s.enc != nullptr;
   for (int i = 0; ok && i < s.cfg->owf + 1; i++) s.pics.push_back(s.api->picture_alloc(W, H));
@@ -109,7 +117,19 @@ static void *worker(void *arg)
   for (int t = 0; ok && t < 6; t++) ok = feed(s, &g_yuv[(size_t)((t + sid) % NFILE) * fb]);
   pthread_barrier_wait(&g_bar);
   s.decoded = 0;
-  for (int t = 0; ok && t < FRAMES; t++) ok = feed(s, &g_yuv[(size_t)((t + 6 + sid) % NFILE) * fb]);
+  const auto t_start = std::chrono::steady_clock::now();
+  for (int t = 0; ok && t < FRAMES; t++) {
+    if (PACE_FPS > 0) {
+      // streams are phase-shifted across the frame interval like independent cameras
+      const double due = (t + (double)sid / STREAMS) / PACE_FPS;
+      std::this_thread::sleep_until(t_start + std::chrono::duration_cast<std::chrono::steady_clock::duration>(std::chrono::duration<double>(due)));
+    }
+    const auto t0 = std::chrono::steady_clock::now();
+    const int before = s.decoded;
+    ok = feed(s, &g_yuv[(size_t)((t + 6 + sid) % NFILE) * fb]);
+    if (PACE_FPS > 0 && (ENC_ONLY || s.decoded > before))
+      g_lat[sid].push_back(std::chrono::duration<float, std::milli>(std::chrono::steady_clock::now() - t0).count());
+  }
   for (int i = 0; ok && i < s.cfg->owf; i++) ok = feed(s, nullptr);          // drain the encoder pipeline
   if (ok && s.dec) {
     int got;
@@ -130,12 +150,14 @@ int main(int argc, char **argv)
   if (argc < 9) { fprintf(stderr, "usage: %s frames.yuv w h frames_in_file streams frames_per_stream encode_only decoder_frame_threads\n", argv[0]); return 2; }
   W = atoi(argv[2]); H = atoi(argv[3]); NFILE = atoi(argv[4]); STREAMS = atoi(argv[5]); FRAMES = atoi(argv[6]);
   ENC_ONLY = atoi(argv[7]); DEC_THREADS = atoi(argv[8]);
+  if (argc > 9) PACE_FPS = atof(argv[9]);
   const size_t fb = (size_t)W * H * 3 / 2;
   g_yuv.resize(fb * NFILE);
   FILE *f = fopen(argv[1], "rb");
   if (!f || fread(g_yuv.data(), 1, g_yuv.size(), f) != g_yuv.size()) { fprintf(stderr, "cannot read %s\n", argv[1]); return 2; }
   fclose(f);
   g_decoded.assign(STREAMS, 0); g_ok.assign(STREAMS, 0);
+  g_lat.assign(STREAMS, {});
   pthread_barrier_init(&g_bar, nullptr, STREAMS + 1);
   std::vector<pthread_t> th(STREAMS);
   for (int i = 0; i < STREAMS; i++) pthread_create(&th[i], nullptr, worker, (void *)(intptr_t)i);
@@ -147,6 +169,18 @@ int main(int argc, char **argv)
   bool all = true;
   for (int i = 0; i < STREAMS; i++) all = all && g_ok[i] && (ENC_ONLY || g_decoded[i] >= FRAMES);
   double fps = (double)STREAMS * FRAMES / dt;
+  if (PACE_FPS > 0) {
+    std::vector<float> lat;
+    for (auto &v : g_lat) lat.insert(lat.end(), v.begin(), v.end());
+    std::sort(lat.begin(), lat.end());
+    auto pct = [&](double q) { return lat.empty() ? 0.f : lat[std::min(lat.size() - 1, (size_t)(q * lat.size()))]; };
+    printf("{\"workload\": \"conference %dx%d QP32 veryfast paced at %.0f fps, nothing in flight, encode%s per stream\", \"streams\": %d, "
+           "\"frames_per_stream\": %d, \"achieved_fps_per_stream\": %.2f, \"latency_ms\": {\"p50\": %.2f, \"p95\": %.2f, \"p99\": %.2f, \"max\": %.2f}, "
+           "\"pictures_timed\": %zu, \"all_pictures_decoded\": %s}\n",
+           W, H, PACE_FPS, ENC_ONLY ? "" : "+decode", STREAMS, FRAMES, fps / STREAMS, pct(0.50), pct(0.95), pct(0.99), lat.empty() ? 0.f : lat.back(),
+           lat.size(), all ? "true" : "false");
+    return lat.empty() || !all ? 1 : 0;
+  }
   printf("{\"workload\": \"conference %dx%d QP32 veryfast, encode%s per stream, C++ harness over the C ABI\", \"streams\": %d, "
          "\"frames_per_stream\": %d, \"decoder_frame_threads\": %d, \"seconds\": %.3f, \"aggregate_fps\": %.1f, "
          "\"fps_per_stream\": %.1f, \"streams_sustained_at_30fps\": %d, \"all_pictures_decoded\": %s}\n",
