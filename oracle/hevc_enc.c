@@ -34,6 +34,14 @@ static const uint16_t lambda_q4_tab[52] = {   /* round(16*sqrt(0.57*2^((qp-12)/3
   77, 86, 97, 108, 122, 137, 153, 172, 193, 217, 244, 273, 307, 344, 387, 434, 487, 547, 614, 689, 773,
   868, 974, 1093};
 
+/* SAO parameters of one CTU (7.4.9.3): [0] luma, [1] chroma (type and class shared by Cb / Cr) */
+struct orc_sao {
+  uint8_t type[2];               /* 0 off, 1 band offset, 2 edge offset */
+  uint8_t eo_class[2];
+  uint8_t band_pos[3];
+  int8_t offset[3][4];
+};
+
 struct orc_encoder {
   orc_enc_cfg_t cfg;
   int w, h, cw, ch, w8, h8, ctb_cols, ctb_rows;
@@ -41,6 +49,8 @@ struct orc_encoder {
   int8_t *ctu_dqp;               /* per-CTU QP offset (ROI), zeros by default */
   int8_t *ctu_delta;             /* CuQpDeltaVal coded in each CTU (0 if none) */
   uint8_t *ctu_first;            /* z-index (8x8 units) of the first CU with a coded residual, 64 = none */
+  struct orc_sao *sao;           /* per CTU, when cfg.sao */
+  uint8_t *dbk;                  /* copy of the deblocked picture: SAO reads it, writes rec */
   const uint8_t *src;
   uint8_t *rec, *rec_pre;        /* packed I420 */
   uint8_t *refpad[3];            /* padded previous reconstruction */
@@ -79,6 +89,10 @@ orc_encoder_t *orc_enc_open(const orc_enc_cfg_t *cfg)
   e->ctu_dqp = (int8_t *)calloc((size_t)e->ctb_cols * e->ctb_rows, 1);
   e->ctu_delta = (int8_t *)calloc((size_t)e->ctb_cols * e->ctb_rows, 1);
   e->ctu_first = (uint8_t *)calloc((size_t)e->ctb_cols * e->ctb_rows, 1);
+  if (cfg->sao) {
+    e->sao = (struct orc_sao *)calloc((size_t)e->ctb_cols * e->ctb_rows, sizeof(struct orc_sao));
+    e->dbk = (uint8_t *)malloc((size_t)e->w * e->h * 3 / 2);
+  }
   size_t fsz = (size_t)e->w * e->h * 3 / 2;
   e->rec = (uint8_t *)calloc(fsz, 1);
   e->rec_pre = (uint8_t *)calloc(fsz, 1);
@@ -97,7 +111,7 @@ orc_encoder_t *orc_enc_open(const orc_enc_cfg_t *cfg)
 
 void orc_enc_close(orc_encoder_t *e)
 {
-  if (e) { free(e->ctu_dqp); free(e->ctu_delta); free(e->ctu_first); }
+  if (e) { free(e->ctu_dqp); free(e->ctu_delta); free(e->ctu_first); free(e->sao); free(e->dbk); }
   if (!e) return;
   free(e->rec); free(e->rec_pre);
   for (int c = 0; c < 3; c++) free(e->refpad[c]);
@@ -541,6 +555,188 @@ static void deblock_frame(orc_encoder_t *e)
       }
 }
 
+
+/* ------------------------------------------------------------------------------------------ */
+/* sample adaptive offset (8.7.3): decision per CTU on source vs deblocked samples, then applied   */
+/* from the deblocked copy into rec.  Never merged with a neighbour (the flags are coded as 0).    */
+
+static inline int sgn(int v) { return (v > 0) - (v < 0); }
+
+static const int8_t sao_dir[4][2][2] = {          /* class: {a, b} as (dx, dy) */
+  {{-1, 0}, {1, 0}}, {{0, -1}, {0, 1}}, {{-1, -1}, {1, 1}}, {{1, -1}, {-1, 1}}};
+
+/* category 1..4 of a sample for an edge class, 0 = none (also when a neighbour is outside the picture) */
+static int sao_category(const uint8_t *p, int stride, int x, int y, int pw, int ph, int cls)
+{
+  const int ax = x + sao_dir[cls][0][0], ay = y + sao_dir[cls][0][1];
+  const int bx = x + sao_dir[cls][1][0], by = y + sao_dir[cls][1][1];
+  if (ax < 0 || ay < 0 || bx < 0 || by < 0 || ax >= pw || ay >= ph || bx >= pw || by >= ph) return 0;
+  const int c = p[(size_t)y * stride + x];
+  const int e = 2 + sgn(c - p[(size_t)ay * stride + ax]) + sgn(c - p[(size_t)by * stride + bx]);
+  return e == 2 ? 0 : (e < 2 ? e + 1 : e);          /* 0 -> 1 (local minimum), 1 -> 2, 3 -> 3, 4 -> 4 (local maximum) */
+}
+
+typedef struct { long long gain_cost; int type, cls, band; int8_t off[4]; } sao_choice_t;
+
+/* best offset of a category given count and sum of (source - deblocked); returns the change in SSE */
+static long long sao_best_offset(long long count, long long sum, int lo, int hi, int *off)
+{
+  if (count == 0) { *off = 0; return 0; }
+  int o = (int)((sum >= 0 ? sum + count / 2 : sum - count / 2) / count);
+  o = clip3i(lo, hi, o);
+  long long best = 0;
+  int best_o = 0;
+  for (int k = o; k != 0; k += (k > 0 ? -1 : 1)) {          /* smaller magnitudes cost fewer bits: check them all */
+    long long d = count * k * k - 2 * k * sum;
+    if (d < best) { best = d; best_o = k; }
+  }
+  *off = best_o;
+  return best;
+}
+
+/* statistics and decision of one component group of one CTU: comps = {0} or {1, 2} */
+static void sao_decide_group(orc_encoder_t *e, int cx, int cy, int group, struct orc_sao *out)
+{
+  const int lq = lambda_at(e, cx, cy);
+  const int lam = (lq * lq + 128) >> 8;                                /* lambda, SSE domain */
+  const int c_first = group ? 1 : 0, c_last = group ? 2 : 0;
+  long long best_cost = 0;                                             /* "off": no change, one bin */
+  int best_type = 0, best_cls = 0, best_band[3] = {0, 0, 0};
+  int8_t best_off[3][4];
+  memset(best_off, 0, sizeof(best_off));
+  /* edge offset, classes 0..3 */
+  for (int cls = 0; cls < 4; cls++) {
+    long long cost = (long long)lam * 4;                               /* type + class */
+    int8_t off[3][4];
+    for (int c = c_first; c <= c_last; c++) {
+      const int pw = c ? e->cw : e->w, ph = c ? e->ch : e->h, sh = c ? 1 : 0;
+      const uint8_t *src = plane((uint8_t *)e->src, e->w, e->h, c), *dbk = plane(e->dbk, e->w, e->h, c);
+      const int x0 = cx >> sh, y0 = cy >> sh, x1 = imin(pw, (cx + CTB) >> sh), y1 = imin(ph, (cy + CTB) >> sh);
+      long long cnt[5] = {0}, sum[5] = {0};
+      for (int y = y0; y < y1; y++)
+        for (int x = x0; x < x1; x++) {
+          int k = sao_category(dbk, pw, x, y, pw, ph, cls);
+          cnt[k]++; sum[k] += (int)src[(size_t)y * pw + x] - (int)dbk[(size_t)y * pw + x];
+        }
+      for (int k = 1; k <= 4; k++) {
+        int o;
+        cost += sao_best_offset(cnt[k], sum[k], k <= 2 ? 0 : -7, k <= 2 ? 7 : 0, &o);
+        cost += (long long)lam * (abs(o) + 1);
+        off[c][k - 1] = (int8_t)o;
+      }
+    }
+    if (cost < best_cost) {
+      best_cost = cost; best_type = 2; best_cls = cls;
+      for (int c = c_first; c <= c_last; c++) memcpy(best_off[c], off[c], 4);
+    }
+  }
+  /* band offset: four consecutive bands of 8 levels */
+  {
+    long long cost = (long long)lam * 2;
+    int8_t off[3][4];
+    int band[3] = {0, 0, 0};
+    for (int c = c_first; c <= c_last; c++) {
+      const int pw = c ? e->cw : e->w, ph = c ? e->ch : e->h, sh = c ? 1 : 0;
+      const uint8_t *src = plane((uint8_t *)e->src, e->w, e->h, c), *dbk = plane(e->dbk, e->w, e->h, c);
+      const int x0 = cx >> sh, y0 = cy >> sh, x1 = imin(pw, (cx + CTB) >> sh), y1 = imin(ph, (cy + CTB) >> sh);
+      long long cnt[32] = {0}, sum[32] = {0}, gain[32];
+      int bo[32];
+      for (int y = y0; y < y1; y++)
+        for (int x = x0; x < x1; x++) {
+          int k = dbk[(size_t)y * pw + x] >> 3;
+          cnt[k]++; sum[k] += (int)src[(size_t)y * pw + x] - (int)dbk[(size_t)y * pw + x];
+        }
+      for (int k = 0; k < 32; k++) {
+        gain[k] = sao_best_offset(cnt[k], sum[k], -7, 7, &bo[k]);
+        gain[k] += (long long)lam * (abs(bo[k]) + 1 + (bo[k] != 0));
+      }
+      long long bg = 0;
+      int bs = 0;
+      for (int st = 0; st <= 28; st++) {
+        long long g = gain[st] + gain[st + 1] + gain[st + 2] + gain[st + 3];
+        if (st == 0 || g < bg) { bg = g; bs = st; }
+      }
+      cost += bg + (long long)lam * 5;
+      band[c] = bs;
+      for (int k = 0; k < 4; k++) off[c][k] = (int8_t)bo[bs + k];
+    }
+    if (cost < best_cost) {
+      best_cost = cost; best_type = 1;
+      for (int c = c_first; c <= c_last; c++) { memcpy(best_off[c], off[c], 4); best_band[c] = band[c]; }
+    }
+  }
+  out->type[group] = (uint8_t)best_type;
+  out->eo_class[group] = (uint8_t)best_cls;
+  for (int c = c_first; c <= c_last; c++) {
+    out->band_pos[c] = (uint8_t)best_band[c];
+    memcpy(out->offset[c], best_off[c], 4);
+  }
+}
+
+static void sao_frame(orc_encoder_t *e)
+{
+  const size_t fsz = (size_t)e->w * e->h * 3 / 2;
+  memcpy(e->dbk, e->rec, fsz);
+  const int nctb = e->ctb_cols * e->ctb_rows;
+#pragma omp parallel for schedule(dynamic, 1)
+  for (int i = 0; i < nctb; i++) {
+    const int cx = (i % e->ctb_cols) * CTB, cy = (i / e->ctb_cols) * CTB;
+    struct orc_sao *p = &e->sao[i];
+    memset(p, 0, sizeof(*p));
+    sao_decide_group(e, cx, cy, 0, p);
+    sao_decide_group(e, cx, cy, 1, p);
+    for (int c = 0; c < 3; c++) {
+      const int g = c ? 1 : 0;
+      if (!p->type[g]) continue;
+      const int pw = c ? e->cw : e->w, ph = c ? e->ch : e->h, sh = c ? 1 : 0;
+      const uint8_t *dbk = plane(e->dbk, e->w, e->h, c);
+      uint8_t *rec = plane(e->rec, e->w, e->h, c);
+      const int x0 = cx >> sh, y0 = cy >> sh, x1 = imin(pw, (cx + CTB) >> sh), y1 = imin(ph, (cy + CTB) >> sh);
+      for (int y = y0; y < y1; y++)
+        for (int x = x0; x < x1; x++) {
+          const int v = dbk[(size_t)y * pw + x];
+          int o = 0;
+          if (p->type[g] == 2) {
+            int k = sao_category(dbk, pw, x, y, pw, ph, p->eo_class[g]);
+            if (k) o = p->offset[c][k - 1];
+          } else {
+            int k = (v >> 3) - p->band_pos[c];
+            if (k >= 0 && k < 4) o = p->offset[c][k];
+          }
+          rec[(size_t)y * pw + x] = (uint8_t)clip3i(0, 255, v + o);
+        }
+    }
+  }
+}
+
+/* sao() syntax of one CTU (7.3.8.3); merge candidates are never used */
+static void code_sao(const orc_encoder_t *e, orc_cabac_t *c, int rx, int ry)
+{
+  const struct orc_sao *p = &e->sao[ry * e->ctb_cols + rx];
+  if (rx > 0) orc_cabac_bin(c, CTX_SAO_MERGE, 0);                 /* sao_merge_left_flag */
+  if (ry > 0) orc_cabac_bin(c, CTX_SAO_MERGE, 0);                 /* sao_merge_up_flag */
+  for (int comp = 0; comp < 3; comp++) {
+    const int g = comp ? 1 : 0;
+    if (comp < 2) {                                               /* sao_type_idx_luma / _chroma: TR cMax 2, first bin coded */
+      orc_cabac_bin(c, CTX_SAO_TYPE, p->type[g] != 0);
+      if (p->type[g]) orc_cabac_bypass(c, p->type[g] == 2);
+    }
+    if (!p->type[g]) continue;
+    for (int k = 0; k < 4; k++) {                                 /* sao_offset_abs: TR cMax 7, bypass */
+      const int a = abs(p->offset[comp][k]);
+      for (int i = 0; i < a; i++) orc_cabac_bypass(c, 1);
+      if (a < 7) orc_cabac_bypass(c, 0);
+    }
+    if (p->type[g] == 1) {
+      for (int k = 0; k < 4; k++)
+        if (p->offset[comp][k]) orc_cabac_bypass(c, p->offset[comp][k] < 0);     /* sao_offset_sign */
+      orc_cabac_bypass_bits(c, p->band_pos[comp], 5);             /* sao_band_position */
+    } else if (comp < 2) {
+      orc_cabac_bypass_bits(c, p->eo_class[g], 2);                /* sao_eo_class_luma / _chroma */
+    }
+  }
+}
+
 /* ------------------------------------------------------------------------------------------ */
 /* entropy coding                                                                                 */
 
@@ -843,7 +1039,7 @@ static size_t write_parameter_sets(const orc_encoder_t *e, uint8_t *out, size_t 
   orc_bits_ue(&b, 0); orc_bits_ue(&b, 0);       /* max_transform_hierarchy_depth_inter / intra */
   orc_bits_put(&b, 0, 1);             /* scaling_list_enabled_flag */
   orc_bits_put(&b, 0, 1);             /* amp_enabled_flag */
-  orc_bits_put(&b, 0, 1);             /* sample_adaptive_offset_enabled_flag */
+  orc_bits_put(&b, e->cfg.sao ? 1 : 0, 1);          /* sample_adaptive_offset_enabled_flag */
   orc_bits_put(&b, 0, 1);             /* pcm_enabled_flag */
   orc_bits_ue(&b, 1);                 /* num_short_term_ref_pic_sets */
   orc_bits_ue(&b, 1); orc_bits_ue(&b, 0);       /* num_negative_pics = 1, num_positive_pics = 0 */
@@ -985,11 +1181,14 @@ static int assemble_slice(const orc_encoder_t *e, int n_sub, const size_t *sub_e
   if (!e->is_idr) {
     orc_bits_put(&b, (uint32_t)(e->poc & 255), 8);      /* slice_pic_order_cnt_lsb */
     orc_bits_put(&b, 1, 1);                             /* short_term_ref_pic_set_sps_flag */
+  }
+  if (e->cfg.sao) orc_bits_put(&b, 3, 2);               /* slice_sao_luma_flag, slice_sao_chroma_flag */
+  if (!e->is_idr) {
     orc_bits_put(&b, 0, 1);                             /* num_ref_idx_active_override_flag */
     orc_bits_ue(&b, 5 - MAX_MERGE);                     /* five_minus_max_num_merge_cand */
   }
   orc_bits_se(&b, e->cfg.qp - 26);                      /* slice_qp_delta */
-  if (e->cfg.deblock) orc_bits_put(&b, 1, 1);           /* slice_loop_filter_across_slices_enabled_flag */
+  if (e->cfg.deblock || e->cfg.sao) orc_bits_put(&b, 1, 1);   /* slice_loop_filter_across_slices_enabled_flag */
   orc_bits_ue(&b, (uint32_t)(n_sub - 1));               /* num_entry_point_offsets */
   if (n_sub > 1) {
     size_t mx = 1;
@@ -1033,6 +1232,7 @@ static int encode_slice(orc_encoder_t *e, uint8_t *out, size_t cap, size_t *writ
       orc_cabac_start(&cab, &bits);
     }
     for (int cidx = 0; cidx < cols; cidx++) {
+      if (e->cfg.sao) code_sao(e, &cab, cidx, r);
       code_quadtree(e, &cab, cidx * CTB, r * CTB, CTB_LOG2, 0);
       if (cidx == 1) memcpy(saved.ctx, cab.ctx, sizeof(cab.ctx));
       int last_in_slice = r == rows - 1 && cidx == cols - 1 && !e->cfg.more_tiles;
@@ -1087,6 +1287,7 @@ int orc_enc_encode(orc_encoder_t *e, const uint8_t *i420, uint8_t *out, int cap)
   memcpy(e->rec_pre, e->rec, fsz);
   if (e->cfg.qp_delta) derive_cu_qps(e);
   if (e->cfg.deblock) deblock_frame(e);
+  if (e->cfg.sao) sao_frame(e);
   size_t o = 0, n = 0;
   if (e->is_idr && !e->cfg.raw_slice_data) o += write_parameter_sets(e, out, (size_t)cap);
   if (o > (size_t)cap) return -1;

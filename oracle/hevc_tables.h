@@ -61,7 +61,9 @@ enum {
   CTX_GT1 = 110,                /* 24 */
   CTX_GT2 = 134,                /* 6 */
   CTX_CU_QP_DELTA = 140,        /* 2 */
-  CTX_COUNT = 142
+  CTX_SAO_MERGE = 142,          /* 1 */
+  CTX_SAO_TYPE = 143,           /* 1 */
+  CTX_COUNT = 144
 };
 
 /* init values, [initType 0=I,1=P,2=B][CTX_COUNT]; 154 where the element cannot occur */

@@ -137,6 +137,37 @@ def test_tile_columns_as_independent_strips_decode_bit_exactly_in_ffmpeg(kind, w
         assert bad.size == 0, f"frame {i}: {bad.size} samples differ, first at {bad[:6]}"
 
 
+@needs_ff
+@pytest.mark.parametrize("kind,w,h,n,qp,kw", [
+    ("camera", 192, 136, 4, 32, {}),
+    ("camera", 416, 240, 6, 37, {"hash_sei": 1, "intra_period": 4}),
+    ("noise", 256, 136, 3, 30, {"hash_sei": 1}),                       # band offsets on noise, large offsets
+    ("screen", 416, 240, 5, 40, {}),                                    # sharp edges: edge offsets
+    ("camera", 200, 72, 3, 45, {"deblock": 0}),                         # SAO without deblocking, partial CTUs
+    ("camera", 1280, 720, 2, 35, {"hash_sei": 1, "search_range": 12}),
+])
+def test_sao_streams_decode_bit_exactly_in_ffmpeg(kind, w, h, n, qp, kw):
+    """Sample adaptive offset (oracle only so far): per-CTU edge / band offsets after deblocking.  The
+    syntax (slice flags, sao() per CTU), the categories at picture and CTU borders and the clipping
+    are normative -- FFmpeg must reproduce the oracle's picture -- and it must actually help."""
+    frames = frames_of(kind, w, h, n)
+    enc = OracleEncoder(w, h, qp=qp, sao=1, **({"intra_period": 0} | kw))
+    plain = OracleEncoder(w, h, qp=qp, **({"intra_period": 0} | {k: v for k, v in kw.items() if k != "hash_sei"}))
+    aus, recs, gain = [], [], 0.0
+    for f in frames:
+        aus.append(enc.encode(f))
+        recs.append(enc.recon())
+        plain.encode(f)
+        gain += synth.psnr(f[:w * h], recs[-1][:w * h]) - synth.psnr(f[:w * h], plain.recon()[:w * h])
+    enc.close(); plain.close()
+    dec, errs = ffhevc.decode_stream(aus)
+    assert errs == 0 and len(dec) == n
+    for i, (fr, fw, fh) in enumerate(dec):
+        bad = np.flatnonzero(fr != recs[i])
+        assert bad.size == 0, f"frame {i}: {bad.size} samples differ, first at {bad[:6]}"
+    assert gain / n > -0.05                                              # never worse than without (it may choose "off")
+
+
 def test_per_ctu_qp_changes_rate_where_asked():
     w, h = 416, 240
     frames = frames_of("camera", w, h, 3)
