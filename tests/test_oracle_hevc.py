@@ -168,6 +168,24 @@ def test_sao_streams_decode_bit_exactly_in_ffmpeg(kind, w, h, n, qp, kw):
     assert gain / n > -0.05                                              # never worse than without (it may choose "off")
 
 
+@needs_ff
+def test_sao_with_per_ctu_qp_and_periodic_idr_decodes_in_ffmpeg():
+    """The two per-CTU syntax additions together: sao() precedes the coding quadtree, cu_qp_delta sits
+    in the first coded transform unit; both follow the WPP context hand-over."""
+    w, h, n = 416, 240, 6
+    enc = OracleEncoder(w, h, qp=33, sao=1, qp_delta=1, hash_sei=1, intra_period=3)
+    aus, recs = [], []
+    for t, f in enumerate(frames_of("camera", w, h, n)):
+        enc.set_ctu_dqp(roi_pattern(w, h, t, "random" if t % 2 else "window"))
+        aus.append(enc.encode(f))
+        recs.append(enc.recon())
+    enc.close()
+    dec, errs = ffhevc.decode_stream(aus)
+    assert errs == 0 and len(dec) == n
+    for i in range(n):
+        assert np.array_equal(dec[i][0], recs[i]), i
+
+
 def test_per_ctu_qp_changes_rate_where_asked():
     w, h = 416, 240
     frames = frames_of("camera", w, h, 3)
