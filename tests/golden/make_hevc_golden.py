@@ -1,0 +1,66 @@
+"""Writes tests/golden/hevc_golden.json: SHA-256 of the oracle encoder's access units and
+reconstructions for small fixed inputs.  The streams behind these hashes were decoded bit-exactly by
+FFmpeg's HEVC decoder when the file was generated (tests/test_oracle_hevc.py does that live wherever
+the cv2 wheel is present); the hashes keep the oracle pinned on machines without it and catch
+unintended changes of the oracle, which every GPU parity test leans on.
+
+  python tests/golden/make_hevc_golden.py
+"""
+import hashlib
+import json
+import sys
+from pathlib import Path
+
+ROOT = Path(__file__).resolve().parents[2]
+sys.path.insert(0, str(ROOT))
+
+import numpy as np  # noqa: E402
+
+from oracle.encoder import OracleEncoder, OracleTiledEncoder  # noqa: E402
+from tests import ffhevc  # noqa: E402
+from tests.test_oracle_hevc import frames_of, roi_pattern  # noqa: E402
+
+CASES = [
+    {"name": "camera_192x136_qp32", "kind": "camera", "w": 192, "h": 136, "n": 4, "kw": {"qp": 32, "intra_period": 0}},
+    {"name": "noise_128x72_qp10", "kind": "noise", "w": 128, "h": 72, "n": 3, "kw": {"qp": 10, "intra_period": 0}},
+    {"name": "screen_416x240_qp32", "kind": "screen", "w": 416, "h": 240, "n": 5, "kw": {"qp": 32, "intra_period": 0}},
+    {"name": "camera_200x200_idr3", "kind": "camera", "w": 200, "h": 200, "n": 7, "kw": {"qp": 30, "intra_period": 3}},
+    {"name": "camera_416x240_roi", "kind": "camera", "w": 416, "h": 240, "n": 5, "kw": {"qp": 30, "intra_period": 0, "qp_delta": 1}, "roi": "random"},
+    {"name": "camera_416x240_sao", "kind": "camera", "w": 416, "h": 240, "n": 4, "kw": {"qp": 37, "intra_period": 0, "sao": 1}},
+    {"name": "camera_416x240_tiles3", "kind": "camera", "w": 416, "h": 240, "n": 4, "kw": {"qp": 30, "intra_period": 0}, "tiles": 3},
+]
+
+
+def run_case(c):
+    frames = frames_of(c["kind"], c["w"], c["h"], c["n"])
+    if c.get("tiles"):
+        enc = OracleTiledEncoder(c["w"], c["h"], c["tiles"], **c["kw"])
+    else:
+        enc = OracleEncoder(c["w"], c["h"], **c["kw"])
+    aus, recs = [], []
+    for t, f in enumerate(frames):
+        if c.get("roi"):
+            enc.set_ctu_dqp(roi_pattern(c["w"], c["h"], t, c["roi"]))
+        aus.append(enc.encode(f))
+        recs.append(enc.recon())
+    enc.close()
+    return aus, recs
+
+
+def digest(aus, recs):
+    return {"au_sha256": hashlib.sha256(b"".join(aus)).hexdigest(), "au_bytes": [len(a) for a in aus],
+            "recon_sha256": hashlib.sha256(b"".join(r.tobytes() for r in recs)).hexdigest()}
+
+
+if __name__ == "__main__":
+    out = {}
+    for c in CASES:
+        aus, recs = run_case(c)
+        ok = None
+        if ffhevc.available():
+            dec, errs = ffhevc.decode_stream(aus)
+            ok = errs == 0 and len(dec) == len(recs) and all(np.array_equal(d[0], r) for d, r in zip(dec, recs))
+            assert ok, c["name"]
+        out[c["name"]] = digest(aus, recs) | {"ffmpeg_verified_when_generated": ok}
+    (ROOT / "tests" / "golden" / "hevc_golden.json").write_text(json.dumps(out, indent=1) + "\n")
+    print("wrote", len(out), "cases")

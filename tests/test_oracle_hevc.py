@@ -366,3 +366,19 @@ def test_deblock_known_answers(oracle_lib):
     buf = img.ravel().copy()
     oracle_lib.orc_deblock_luma_segment(C.c_void_p(buf.ctypes.data + 8), 1, 16, 2, 37)
     assert np.array_equal(buf.reshape(4, 16), img)
+
+
+def test_oracle_streams_match_the_committed_golden_hashes():
+    """tests/golden/hevc_golden.json (generator: make_hevc_golden.py) pins the oracle's streams and
+    reconstructions; every stream behind a hash was decoded bit-exactly by FFmpeg when generated."""
+    import json
+    from pathlib import Path
+    from tests.golden.make_hevc_golden import CASES, digest, run_case
+    gold = json.loads((Path(__file__).parent / "golden" / "hevc_golden.json").read_text())
+    assert set(gold) == {c["name"] for c in CASES}
+    for c in CASES:
+        got = digest(*run_case(c))
+        want = gold[c["name"]]
+        assert want["ffmpeg_verified_when_generated"] is True
+        assert got["au_bytes"] == want["au_bytes"], c["name"]
+        assert got["au_sha256"] == want["au_sha256"] and got["recon_sha256"] == want["recon_sha256"], c["name"]
