@@ -447,14 +447,15 @@ static void inter_cu(orc_encoder_t *e, int x0, int y0, int log2)
   int bx = cu.mvx, by = cu.mvy;
   mc_luma(e, x0, y0, n, bx, by, best_pred);
   const int lam = lambda_at(e, x0, y0);
-  uint32_t best = orc_sad(src, e->w, best_pred, n, n, n) + mv_penalty(lam, bx, by);
+  const int satd = e->cfg.subme_satd;
+  uint32_t best = (satd ? orc_satd(src, e->w, best_pred, n, n, n) : orc_sad(src, e->w, best_pred, n, n, n)) + mv_penalty(lam, bx, by);
   for (int step = 2; step >= 1; step--) {
     int cxm = bx, cym = by;
     for (int k = 0; k < 8; k++) {
       int mx = cxm + off[k][0] * step, my = cym + off[k][1] * step;
       if (!mv_allowed(e, x0, n, mx)) continue;
       mc_luma(e, x0, y0, n, mx, my, pred);
-      uint32_t cost = orc_sad(src, e->w, pred, n, n, n) + mv_penalty(lam, mx, my);
+      uint32_t cost = (satd ? orc_satd(src, e->w, pred, n, n, n) : orc_sad(src, e->w, pred, n, n, n)) + mv_penalty(lam, mx, my);
       if (cost < best) { best = cost; bx = mx; by = my; memcpy(best_pred, pred, (size_t)n * n); }
     }
   }

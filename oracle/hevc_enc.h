@@ -36,6 +36,7 @@ typedef struct {
    * 4-byte little-endian length (the compositor writes parameter sets and the slice header). */
   int mv_edges, more_tiles, raw_slice_data;
   int no_wpp;              /* 1 = entropy_coding_sync off: one substream for the whole (strip) picture */
+  int subme_satd;          /* 1 = fractional motion refinement by SATD (Kvazaar / HM style) instead of SAD; oracle only */
   int sao;                 /* 1 = sample adaptive offset (8.7.3) after deblocking; oracle only so far */
   int tile_cols;           /* > 1: PPS / slice header of a picture with that many uniform tile columns (compositor only) */
 } orc_enc_cfg_t;
