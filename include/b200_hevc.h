@@ -29,6 +29,17 @@ void *b200_enc_open(int width, int height, int qp, int intra_period, int search_
  * path behind kvz_picture::roi (kvazaarfilter.cpp:423-431).  Without offsets every CTU codes delta 0. */
 void *b200_enc_open_roi(int width, int height, int qp, int intra_period, int search_range, int deblock, int debug,
                         int depth);
+/* The same engine with every option by name.  Fill with b200_enc_params_default(), change what is
+ * needed, open.  struct_size lets the structure grow: fields beyond it keep their defaults. */
+typedef struct b200_enc_params {
+  int struct_size;               /* sizeof(b200_enc_params) of the caller */
+  int width, height, qp, intra_period, search_range, deblock, debug, depth;
+  int qp_delta;                  /* cu_qp_delta_enabled_flag (what b200_enc_open_roi sets) */
+  int fps_num, fps_den;          /* both > 0: VUI timing info in the SPS */
+  int sao;                       /* sample adaptive offset (edge / band offsets per CTU) after deblocking */
+} b200_enc_params;
+void  b200_enc_params_default(b200_enc_params *p);
+void *b200_enc_open_params(const b200_enc_params *p);
 /* Per-CTU QP offsets (raster, one int8 per 64x64 CTU, n = CTU count) for the pictures submitted
  * from now on; CTU QP = clip(qp + dqp, 0, 51).  NULL clears.  Needs b200_enc_open_roi. */
 int   b200_enc_set_ctu_dqp(void *enc, const int8_t *dqp, int n);
@@ -66,6 +77,7 @@ int   b200_enc_debug_set_reference(void *enc, const uint8_t *i420);
 void *b200_tiled_open(int width, int height, int qp, int intra_period, int search_range, int deblock, int depth,
                       int tile_cols, int wpp, const int *devices, int n_devices);
 void  b200_tiled_close(void *enc);
+void  b200_tiled_set_fps(void *enc, int fps_num, int fps_den);   /* VUI timing info of the parameter sets (both > 0) */
 int   b200_tiled_encode(void *enc, const uint8_t *i420, uint8_t *out, int cap);   /* host picture */
 int   b200_tiled_flush(void *enc, uint8_t *out, int cap);
 int   b200_tiled_pending(void *enc);

@@ -69,8 +69,8 @@ typedef struct kvz_config {
   int32_t set_qp_in_cu;                  /* != 0 enables per-CTU QP (cu_qp_delta), see roi_enable */
   enum kvz_hash hash;
   int32_t deblock_enable;                /* "deblock" */
-  int32_t sao_type;                      /* "sao": accepted; SAO is not applied */
-  int32_t tiles_width_count, tiles_height_count;   /* "tiles": accepted only as 1x1 */
+  int32_t sao_type;                      /* "sao": 0 off, != 0 edge + band offsets per CTU (hevc_sao.cu) */
+  int32_t tiles_width_count, tiles_height_count;   /* "tiles": "Cx1" tile columns (hevc_tiles.cu); tile rows are refused */
   int32_t slices;                        /* "slices" */
   int32_t vaq;                           /* "vaq": accepted, ignored */
   int32_t scaling_list;                  /* "scaling-list": only off (0) */
@@ -123,7 +123,12 @@ typedef struct kvz_api {
   void (*encoder_close)(kvz_encoder *encoder);
   int (*encoder_headers)(kvz_encoder *encoder, kvz_data_chunk **data_out, uint32_t *len_out);
   /* pic_in may be NULL to drain.  *data_out == NULL means "no access unit ready".  Outputs come
-   * back in input order.  pic_in stays caller-owned and may be reused as soon as the call returns.
+   * back in input order.  pic_in stays caller-owned.  As with Kvazaar (which keeps a reference to the
+   * input picture until it is coded), a picture from picture_alloc must stay UNTOUCHED until its own
+   * access unit has been returned: it is page-locked and uploaded asynchronously in place.  With
+   * owf = n that means a ring of n + 1 pictures, exactly what the reference keeps
+   * (kvazaarfilter.cpp:76-88, 299).  A picture whose planes were not allocated by picture_alloc is
+   * copied before the call returns and may be reused at once.
    * Returns 1 on success, 0 on failure. */
   int (*encoder_encode)(kvz_encoder *encoder, kvz_picture *pic_in, kvz_data_chunk **data_out, uint32_t *len_out,
                         kvz_picture **pic_recon, kvz_picture **pic_src, kvz_frame_info *info_out);

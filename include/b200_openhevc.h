@@ -94,6 +94,11 @@ int  b200_dec_last_picture(OpenHevc_Handle h, uint8_t *dst, int cap);
  * copy; libOpenHevcGetOutput planes are then stale. */
 const uint8_t *b200_dec_output_dev(OpenHevc_Handle h);
 void b200_dec_set_host_output(OpenHevc_Handle h, int on);
+/* Number of P pictures decoded although the picture they reference (POC - 1) was not the previously
+ * decoded one -- a picture was lost on the way.  Like OpenHEVC the decoder conceals with the last
+ * picture it has and the error drifts until the next IDR; an application that watches this counter
+ * can ask the sender for a key frame instead. */
+int  b200_dec_missing_refs(OpenHevc_Handle h);
 
 #ifdef __cplusplus
 }

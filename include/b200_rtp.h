@@ -67,7 +67,10 @@ void b200_rtp_receiver_free(b200_rtp_receiver *r);
  * uvgRTP does; b200_rtp_receiver_lost() counts the NAL units dropped that way. */
 int b200_rtp_receive(b200_rtp_receiver *r, const uint8_t *pkt, size_t len);
 /* Pops the oldest queued NAL as the receiver filter sees it: 4-byte start code + NAL.  Returns its
- * size, 0 when the queue is empty, -2 when `cap` is too small (the NAL stays queued). */
+ * size, 0 when the queue is empty, -2 when `cap` is too small (the NAL stays queued and
+ * *rtp_timestamp receives the size needed, so the caller can grow its buffer and call again).
+ * Memory is bounded: a fragmented NAL growing beyond 16 MB and NALs arriving while 1024 are queued
+ * are dropped and counted by b200_rtp_receiver_lost(). */
 int b200_rtp_next_nal(b200_rtp_receiver *r, uint8_t *out, size_t cap, uint32_t *rtp_timestamp, int *marker);
 unsigned b200_rtp_receiver_lost(const b200_rtp_receiver *r);
 

@@ -34,6 +34,11 @@ const char *b200_last_error(void);            /* thread-local, never NULL */
 const char *b200_version(void);
 /* Number of kernels this library has launched in the calling process. */
 unsigned long long b200_launch_count(void);
+/* Measured peak of one integer instruction on the current device, thread-level instructions per
+ * second (register-only microbenchmark, csrc/int_peaks.cu): the roofline denominator of the
+ * integer-pipe-bound encoder kernels.  kind: 0 vabsdiff4.add, 1 dp4a, 2 dp2a,
+ * 3 mad.lo.s32, 4 shf, 5 add.u32.  < 0 on error. */
+double      b200_int_peak(int kind);
 
 /* ---- FOURCC codes (values identical to libyuv's video_common.h) -------- */
 #define B200_FOURCC(a, b, c, d) \

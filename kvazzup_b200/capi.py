@@ -35,6 +35,7 @@ SIGNATURES = {
     "b200_last_error": (C.c_char_p, []),
     "b200_version": (C.c_char_p, []),
     "b200_launch_count": (C.c_ulonglong, []),
+    "b200_int_peak": (C.c_double, [C.c_int]),
     "b200_yuv420_to_rgb32": (C.c_int, [C.c_void_p, C.c_void_p, C.c_uint16, C.c_uint16]),
     "b200_half_rgb": (C.c_int, [C.c_void_p, C.c_void_p, C.c_uint16, C.c_uint16]),
     "b200_flip_rgb": (C.c_int, [C.c_void_p, C.c_void_p, C.c_uint16, C.c_uint16, C.c_int, C.c_int]),

@@ -9,6 +9,8 @@ i = C.c_int
 SIGNATURES: dict = {
     "b200_enc_open": (v, [i, i, i, i, i, i, i, i]),
     "b200_enc_open_roi": (v, [i, i, i, i, i, i, i, i]),
+    "b200_enc_params_default": (None, [v]),
+    "b200_enc_open_params": (v, [v]),
     "b200_enc_set_ctu_dqp": (i, [v, v, i]),
     "b200_enc_flush": (i, [v, v, i]),
     "b200_enc_pending": (i, [v]),
@@ -24,6 +26,7 @@ SIGNATURES: dict = {
     "b200_enc_debug_set_reference": (i, [v, v]),
     "b200_tiled_open": (v, [i, i, i, i, i, i, i, i, i, v, i]),
     "b200_tiled_close": (None, [v]),
+    "b200_tiled_set_fps": (None, [v, i, i]),
     "b200_tiled_encode": (i, [v, v, v, i]),
     "b200_tiled_flush": (i, [v, v, i]),
     "b200_tiled_pending": (i, [v]),
@@ -45,6 +48,7 @@ SIGNATURES: dict = {
     "libOpenHevcClose": (None, [v]),
     "b200_dec_last_picture": (i, [v, v, i]),
     "b200_dec_output_dev": (v, [v]),
+    "b200_dec_missing_refs": (i, [v]),
     "b200_dec_set_host_output": (None, [v, i]),
 }
 

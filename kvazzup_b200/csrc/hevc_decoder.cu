@@ -10,42 +10,13 @@
 #include <vector>
 
 #include "../../include/b200_openhevc.h"
+#include "hevc_headers.h"
 #include "hevc_kernels.h"
 #include "runtime.h"
 
 namespace b200 {
 
 namespace {
-
-struct BitReader {
-  const uint8_t *p;
-  size_t n, pos = 0;       // pos in bits
-  bool bad = false;
-  BitReader(const uint8_t *d, size_t len) : p(d), n(len) {}
-  uint32_t u(int bits)
-  {
-    uint32_t v = 0;
-    for (int i = 0; i < bits; i++) {
-      if (pos >= n * 8) { bad = true; return 0; }
-      v = (v << 1) | ((p[pos >> 3] >> (7 - (pos & 7))) & 1);
-      pos++;
-    }
-    return v;
-  }
-  uint32_t ue()
-  {
-    int z = 0;
-    while (!bad && u(1) == 0 && z < 32) z++;
-    if (z >= 32) { bad = true; return 0; }
-    return z ? ((1u << z) - 1 + u(z)) : 0;
-  }
-  int32_t se()
-  {
-    uint32_t k = ue();
-    return (k & 1) ? (int32_t)((k + 1) >> 1) : -(int32_t)(k >> 1);
-  }
-  void align() { pos = (pos + 7) & ~(size_t)7; }
-};
 
 std::vector<uint8_t> unescape(const uint8_t *p, size_t n)
 {
@@ -59,16 +30,6 @@ std::vector<uint8_t> unescape(const uint8_t *p, size_t n)
   }
   return out;
 }
-
-struct Sps {
-  bool valid = false;
-  int width = 0, height = 0, log2_max_poc = 8, num_rps = 0;
-};
-struct Pps {
-  bool valid = false;
-  int init_qp = 26, deblock_disabled = 0, loop_across_slices = 0, deblock_ctrl = 0, qp_delta = 0;
-  int tile_cols = 1, wpp = 1;
-};
 
 const uint8_t kChromaQpD[58] = {
   0, 1, 2, 3, 4, 5, 6, 7, 8, 9, 10, 11, 12, 13, 14, 15, 16, 17, 18, 19, 20, 21, 22, 23, 24, 25, 26, 27, 28, 29,
@@ -114,9 +75,12 @@ struct DecSlot {
 };
 
 struct Decoder {
-  Sps sps;
+  Sps sps_tab[16];                        // parameter sets by id (7.4.2.4.2: a slice activates its PPS, the PPS its SPS)
+  Pps pps_tab[64];
+  Sps sps;                                // the active ones
   Pps pps;
   bool vps_seen = false, started = false;
+  int prev_poc = 0, prev_poc_lsb = 0, prev_poc_msb = 0;   // POC of the last decoded picture (8.3.1)
   FrameParams fp{};                       // whole picture
   size_t frame_bytes = 0;
   cudaStream_t stream = nullptr;          // output assembly / copy
@@ -131,6 +95,8 @@ struct Decoder {
   bool host_output = true;                // false: pictures stay on the GPU (b200_dec_output_dev)
   const uint8_t *d_out = nullptr;         // device copy of the last output picture
   int cur = 0, have_ref = 0, pictures = 0;
+  bool have_submitted = false;            // a picture whose POC is prev_poc went into the pipeline
+  int missing_refs = 0;                   // P pictures whose reference (POC - 1) was not the previous decoded picture
   int64_t out_pts = 0;
   int fr_num = 0, fr_den = 0;
 
@@ -229,110 +195,81 @@ struct Decoder {
         if (!cuda_ok(cudaMallocHost((void **)&t.h_status, sizeof(int) * 2), "cudaMallocHost")) return false;
       }
     }
-    cur = 0; have_ref = 0;
+    cur = 0; have_ref = 0; have_submitted = false;
     conf_w = w; conf_h = h; conf_tiles = tiles;
     return true;
   }
 
   bool parse_sps(const std::vector<uint8_t> &rbsp)
   {
-    BitReader b(rbsp.data(), rbsp.size());
-    b.u(4);
-    int max_sub = (int)b.u(3);
-    b.u(1);
-    if (max_sub != 0) { set_error("decoder: SPS with sub-layers is not supported"); return false; }
-    b.u(2); b.u(1);
-    int profile = (int)b.u(5);
-    b.u(32); b.u(4); b.u(32); b.u(11); b.u(1); b.u(8);
-    (void)profile;
-    b.ue();
-    if (b.ue() != 1) { set_error("decoder: only 4:2:0 is supported"); return false; }
-    int w = (int)b.ue(), h = (int)b.ue();
-    if (b.u(1)) {
-      uint32_t l = b.ue(), r = b.ue(), t = b.ue(), bo = b.ue();
-      if (l | r | t | bo) { set_error("decoder: conformance window cropping is not supported"); return false; }
-    }
-    if (b.ue() != 0 || b.ue() != 0) { set_error("decoder: only 8-bit video is supported"); return false; }
-    int log2_max_poc = (int)b.ue() + 4;
-    b.u(1);
-    b.ue(); b.ue(); b.ue();
-    uint32_t min_cb = b.ue(), diff_cb = b.ue(), min_tb = b.ue(), diff_tb = b.ue(), depth_inter = b.ue(), depth_intra = b.ue();
-    if (min_cb != 0 || diff_cb != 3) { set_error("decoder: coding block sizes other than 8..64 are not supported"); return false; }
-    if (min_tb != 0 || diff_tb != 3) { set_error("decoder: transform block sizes other than 4..32 are not supported"); return false; }
-    if (depth_inter != 0 || depth_intra != 0) { set_error("decoder: transform hierarchy depth > 0 is not supported"); return false; }
-    if (b.u(1)) { set_error("decoder: scaling lists are not supported"); return false; }
-    if (b.u(1)) { set_error("decoder: AMP is not supported"); return false; }
-    if (b.u(1)) { set_error("decoder: SAO is not supported"); return false; }
-    if (b.u(1)) { set_error("decoder: PCM is not supported"); return false; }
-    int num_rps = (int)b.ue();
-    if (num_rps > 1) { set_error("decoder: more than one short-term RPS in the SPS is not supported"); return false; }
-    if (num_rps == 1) {
-      uint32_t neg = b.ue(), pos = b.ue();
-      if (neg != 1 || pos != 0 || b.ue() != 0 || b.u(1) != 1) { set_error("decoder: only the previous picture as reference is supported"); return false; }
-    }
-    if (b.u(1)) { set_error("decoder: long-term reference pictures are not supported"); return false; }
-    if (b.u(1)) { set_error("decoder: temporal MVP is not supported"); return false; }
-    b.u(1);      // strong_intra_smoothing: irrelevant, no 32x32 intra blocks are accepted
-    if (b.bad || w <= 0 || h <= 0 || (w & 7) || (h & 7)) { set_error("decoder: malformed SPS"); return false; }
-    sps.valid = true; sps.width = w; sps.height = h; sps.log2_max_poc = log2_max_poc; sps.num_rps = num_rps;
+    Sps t;
+    std::string err;
+    if (!parse_sps_rbsp(rbsp.data(), rbsp.size(), t, err)) { set_error("decoder: %s", err.c_str()); return false; }
+    if (t.id > 15) { set_error("decoder: SPS id out of range"); return false; }
+    sps_tab[t.id] = t;
     return true;
   }
 
   bool parse_pps(const std::vector<uint8_t> &rbsp)
   {
-    BitReader b(rbsp.data(), rbsp.size());
-    b.ue(); b.ue();
-    if (b.u(1)) { set_error("decoder: dependent slice segments are not supported"); return false; }
-    if (b.u(1)) { set_error("decoder: output_flag_present is not supported"); return false; }
-    if (b.u(3)) { set_error("decoder: extra slice header bits are not supported"); return false; }
-    if (b.u(1)) { set_error("decoder: sign data hiding is not supported"); return false; }
-    if (b.u(1)) { set_error("decoder: cabac_init_present is not supported"); return false; }
-    if (b.ue() != 0) { set_error("decoder: more than one reference picture is not supported"); return false; }
-    b.ue();
-    int init_qp = 26 + b.se();
-    if (b.u(1)) { set_error("decoder: constrained intra prediction is not supported"); return false; }
-    if (b.u(1)) { set_error("decoder: transform skip is not supported"); return false; }
-    const int qp_delta = (int)b.u(1);
-    if (qp_delta && b.ue() != 0) { set_error("decoder: quantisation groups smaller than the CTU are not supported"); return false; }
-    if (b.se() != 0 || b.se() != 0) { set_error("decoder: chroma QP offsets are not supported"); return false; }
-    if (b.u(1)) { set_error("decoder: slice chroma QP offsets are not supported"); return false; }
-    if (b.u(1) || b.u(1)) { set_error("decoder: weighted prediction is not supported"); return false; }
-    if (b.u(1)) { set_error("decoder: transquant bypass is not supported"); return false; }
-    const int tiles_on = (int)b.u(1), wpp = (int)b.u(1);
-    int tile_cols = 1;
-    if (tiles_on) {
-      tile_cols = (int)b.ue() + 1;
-      if (b.ue() != 0) { set_error("decoder: tile rows are not supported (tile columns are)"); return false; }
-      if (!b.u(1)) { set_error("decoder: only uniformly spaced tile columns are supported"); return false; }
-      if (b.u(1)) { set_error("decoder: loop filtering across tiles is not supported"); return false; }
-      if (tile_cols > 32) { set_error("decoder: too many tile columns"); return false; }
-    }
-    if (!tiles_on && !wpp) { set_error("decoder: streams with neither WPP nor tiles are not supported"); return false; }
-    pps.loop_across_slices = (int)b.u(1);
-    pps.deblock_ctrl = (int)b.u(1);
-    pps.deblock_disabled = 0;
-    if (pps.deblock_ctrl) {
-      if (b.u(1)) { set_error("decoder: deblocking override is not supported"); return false; }
-      pps.deblock_disabled = (int)b.u(1);
-      if (!pps.deblock_disabled && (b.se() != 0 || b.se() != 0)) { set_error("decoder: deblocking offsets are not supported"); return false; }
-    }
-    if (b.u(1)) { set_error("decoder: scaling lists are not supported"); return false; }
-    if (b.u(1)) { set_error("decoder: reference list modification is not supported"); return false; }
-    if (b.ue() != 0) { set_error("decoder: parallel merge level > 2 is not supported"); return false; }
-    if (b.u(1)) { set_error("decoder: slice header extensions are not supported"); return false; }
-    if (b.bad) { set_error("decoder: malformed PPS"); return false; }
-    pps.valid = true; pps.init_qp = init_qp; pps.qp_delta = qp_delta; pps.tile_cols = tile_cols; pps.wpp = wpp;
+    Pps t;
+    std::string err;
+    if (!parse_pps_rbsp(rbsp.data(), rbsp.size(), t, err)) { set_error("decoder: %s", err.c_str()); return false; }
+    pps_tab[t.id] = t;
     return true;
+  }
+
+  // What the CUDA kernels can reconstruct, checked once per slice against the active parameter sets
+  // and the slice header.  Returns nullptr when everything is supported.
+  const char *unsupported(const Sps &s, const Pps &p, const SliceHeader &sh) const
+  {
+    if (s.chroma_format_idc != 1) return "only 4:2:0 is supported";
+    if (s.bit_depth_luma != 8 || s.bit_depth_chroma != 8) return "only 8-bit video is supported";
+    if ((s.width & 7) || (s.height & 7)) return "picture sizes that are not multiples of 8 are not supported";
+    if (s.conf_left | s.conf_right | s.conf_top | s.conf_bottom) return "conformance window cropping is not supported";
+    if (s.log2_min_cb != 3 || s.log2_ctb != 6) return "coding block sizes other than 8..64 are not supported";
+    if (s.log2_min_tb != 2 || s.log2_max_tb != 5) return "transform block sizes other than 4..32 are not supported";
+    if (s.max_tr_depth_inter != 0 || s.max_tr_depth_intra != 0) return "transform hierarchy depth > 0 is not supported";
+    if (s.scaling_list) return "scaling lists are not supported";
+    if (s.amp) return "AMP is not supported";
+    if (s.sao) return "SAO is not supported";
+    if (s.pcm) return "PCM is not supported";
+    if (s.long_term_refs) return "long-term reference pictures are not supported";
+    if (s.tmvp && sh.tmvp) return "temporal MVP is not supported";
+    if (p.dependent_slices) return "dependent slice segments are not supported";
+    if (p.sign_hiding) return "sign data hiding is not supported";
+    if (p.cabac_init_present && sh.cabac_init_flag) return "cabac_init_flag is not supported";
+    if (p.constrained_intra) return "constrained intra prediction is not supported";
+    if (p.transform_skip) return "transform skip is not supported";
+    if (p.qp_delta && p.diff_cu_qp_delta_depth != 0) return "quantisation groups smaller than the CTU are not supported";
+    if (p.cb_qp_offset || p.cr_qp_offset || sh.cb_qp_offset || sh.cr_qp_offset) return "chroma QP offsets are not supported";
+    if (p.transquant_bypass) return "transquant bypass is not supported";
+    if (p.tiles) {
+      if (p.tile_rows != 1) return "tile rows are not supported (tile columns are)";
+      if (!p.uniform_spacing) return "only uniformly spaced tile columns are supported";
+      if (p.loop_filter_across_tiles) return "loop filtering across tiles is not supported";
+      if (p.tile_cols > 32) return "too many tile columns";
+    }
+    if (!p.tiles && !p.wpp) return "streams with neither WPP nor tiles are not supported";
+    if (!sh.deblock_disabled && (sh.beta_offset_div2 || sh.tc_offset_div2)) return "deblocking offsets are not supported";
+    if (p.log2_parallel_merge_level != 2) return "parallel merge level > 2 is not supported";
+    if (!sh.first_slice_in_pic) return "multiple slice segments per picture are not supported";
+    if (sh.slice_type == 0) return "B slices are not supported";
+    if (sh.slice_type == 1) {
+      if (sh.num_ref_idx_l0 != 1) return "more than one reference picture is not supported";
+      if (sh.max_merge_cand != 5) return "MaxNumMergeCand other than 5 is not supported";
+      if (sh.rps.num_neg < 1 || sh.rps.delta_poc[0] != -1 || !sh.rps.used[0]) return "only the previous picture as reference is supported";
+      for (int i = 1; i < sh.rps.num_delta(); i++) if (sh.rps.used[i]) return "only the previous picture as reference is supported";
+    }
+    return nullptr;
   }
 
   // returns 1 picture decoded, 0 nothing, -1 error
   int decode_slice(int nal_type, const uint8_t *payload, size_t n, int64_t pts)
   {
-    if (!sps.valid || !pps.valid) { set_error("decoder: slice before parameter sets"); return -1; }
     // The slice header sits in the first bytes; unescape the whole NAL payload once and keep a map
     // from escaped to unescaped offsets for the entry points (which count escaped bytes).
     std::vector<uint8_t> rbsp;
-    std::vector<uint32_t> removed_before;     // number of 0x03 bytes removed before escaped offset i (sampled at removals)
     rbsp.reserve(n);
     std::vector<uint32_t> epb_pos;            // escaped offsets of removed bytes
     int zeros = 0;
@@ -341,32 +278,45 @@ struct Decoder {
       rbsp.push_back(payload[i]);
       zeros = payload[i] == 0 ? zeros + 1 : 0;
     }
-    BitReader b(rbsp.data(), rbsp.size());
-    const bool irap = nal_type >= 16 && nal_type <= 23;
+    // activate the parameter sets the slice names (slice_pic_parameter_set_id is the second or third
+    // syntax element; parse it ahead of the full header, which needs the sets)
+    {
+      BitReader pb(rbsp.data(), rbsp.size());
+      pb.u(1);
+      if (nal_type >= 16 && nal_type <= 23) pb.u(1);
+      const uint32_t pid = pb.ue();
+      if (pb.bad || pid > 63 || !pps_tab[pid].valid || !sps_tab[pps_tab[pid].sps_id].valid) { set_error("decoder: slice before parameter sets"); return -1; }
+      pps = pps_tab[pid];
+      sps = sps_tab[pps.sps_id];
+    }
+    SliceHeader sh;
+    {
+      std::string err;
+      if (!parse_slice_header_rbsp(rbsp.data(), rbsp.size(), nal_type, sps, pps, sh, err)) { set_error("decoder: %s", err.c_str()); return -1; }
+    }
+    if (const char *why = unsupported(sps, pps, sh)) { set_error("decoder: %s", why); return -1; }
     const bool idr = nal_type == 19 || nal_type == 20;
-    if (!b.u(1)) { set_error("decoder: multiple slice segments per picture are not supported"); return -1; }
-    if (irap) b.u(1);
-    b.ue();
-    int slice_type = (int)b.ue();
-    if (slice_type == 0) { set_error("decoder: B slices are not supported"); return -1; }
+    const int slice_type = sh.slice_type, qp = sh.qp;
+    const int deblock = !sh.deblock_disabled;
+    // picture order count (8.3.1) and the reference it names: this decoder keeps one reference, the
+    // previously decoded picture, so the picture with POC - 1 must be exactly that one.  A gap (a P
+    // picture lost on the way) is reported so that the application can wait for / request an IDR
+    // instead of silently predicting from the wrong picture.
+    int poc = 0, poc_msb = 0;
     if (!idr) {
-      b.u(sps.log2_max_poc);
-      if (!b.u(1)) {
-        uint32_t neg = b.ue(), pos = b.ue();
-        if (neg != 1 || pos != 0 || b.ue() != 0 || b.u(1) != 1) { set_error("decoder: only the previous picture as reference is supported"); return -1; }
-      } else if (sps.num_rps < 1) {
-        set_error("decoder: slice refers to a missing RPS"); return -1;
-      }
+      const int max_lsb = 1 << sps.log2_max_poc;
+      if (sh.poc_lsb < prev_poc_lsb && prev_poc_lsb - sh.poc_lsb >= max_lsb / 2) poc_msb = prev_poc_msb + max_lsb;
+      else if (sh.poc_lsb > prev_poc_lsb && sh.poc_lsb - prev_poc_lsb > max_lsb / 2) poc_msb = prev_poc_msb - max_lsb;
+      else poc_msb = prev_poc_msb;
+      if (nal_type >= 16 && nal_type <= 18) poc_msb = 0;       // BLA
+      poc = poc_msb + sh.poc_lsb;
+      // A gap (a P picture lost on the way): like OpenHEVC the decoder conceals with the last picture
+      // it has -- the reference application just keeps feeding NALs (openhevcfilter.cpp:145-152) --
+      // but the event is counted so that an application can ask the sender for an IDR
+      // (b200_dec_missing_refs) instead of drifting unknowingly until the next one.
+      if (slice_type != 2 && have_submitted && poc - 1 != prev_poc) missing_refs++;
     }
-    if (slice_type == 1) {
-      if (b.u(1)) {
-        if (b.ue() != 0) { set_error("decoder: more than one reference picture is not supported"); return -1; }
-      }
-      if (b.ue() != 0) { set_error("decoder: MaxNumMergeCand other than 5 is not supported"); return -1; }
-    }
-    int qp = pps.init_qp + b.se();
-    const int deblock = !pps.deblock_disabled;
-    if (pps.loop_across_slices && deblock) b.u(1);
+    fr_num = sps.fps_num; fr_den = sps.fps_den;
     // geometry: picture size from the SPS, tile columns from the PPS (pictures in flight are dropped
     // when either changes)
     if (conf_w != sps.width || conf_h != sps.height || conf_tiles != pps.tile_cols) {
@@ -376,22 +326,16 @@ struct Decoder {
     }
     const int rows = fp.ctb_rows, tiles = conf_tiles;
     const int per_tile = pps.wpp ? rows : 1;                  // substreams per tile
-    int n_entry = (int)b.ue();
-    if (n_entry < 0 || n_entry > 4096) { set_error("decoder: implausible number of entry points"); return -1; }
-    std::vector<uint32_t> entry(n_entry);
-    if (n_entry > 0) {
-      int len = (int)b.ue() + 1;
-      for (int i = 0; i < n_entry; i++) entry[i] = b.u(len) + 1;
-    }
-    if (!b.u(1)) { set_error("decoder: malformed slice header (alignment bit)"); return -1; }
-    b.align();
-    if (b.bad || qp < 0 || qp > 51) { set_error("decoder: malformed slice header"); return -1; }
+    const int n_entry = (int)sh.entry.size();
+    const std::vector<uint32_t> &entry = sh.entry;
     if (n_entry != tiles * per_tile - 1) {
       set_error("decoder: %d entry points for %d tile column(s) x %d substream(s)", n_entry, tiles, per_tile);
       return -1;
     }
+    prev_poc = poc; prev_poc_lsb = idr ? 0 : sh.poc_lsb; prev_poc_msb = poc_msb; have_submitted = true;
+    const size_t hdr_unesc_pos = sh.data_offset;
     // escaped offset of the first slice-data byte
-    const size_t hdr_unesc = b.pos >> 3;
+    const size_t hdr_unesc = hdr_unesc_pos;
     size_t hdr_esc = hdr_unesc;
     for (uint32_t e : epb_pos) { if (e < hdr_esc + 1) hdr_esc++; else break; }
     // substream boundaries in escaped bytes -> unescaped offsets
@@ -463,7 +407,7 @@ struct Decoder {
           "motion vector reaches across a tile boundary"};
         int c = t.h_status[0];
         set_error("decoder: unsupported or corrupt slice data (%s)", c > 0 && c <= 12 ? why[c] : "unknown");
-        have_ref = 0;
+        have_ref = 0; have_submitted = false;
         return -1;
       }
     }
@@ -602,7 +546,10 @@ void libOpenHevcGetPictureInfo(OpenHevc_Handle h, OpenHevc_FrameInfo *info)
   info->nYPitch = d->fp.w; info->nUPitch = d->fp.w / 2; info->nVPitch = d->fp.w / 2;
   info->nBitDepth = 8; info->chromat_format = 1;
   info->sample_aspect_ratio.num = 1; info->sample_aspect_ratio.den = 1;
-  info->frameRate.num = d->fr_num; info->frameRate.den = d->fr_den;     // 0/0: the stream carries no VUI timing
+  // VUI timing when the stream carries it; never 0/0 -- the reference copies this into vInfo
+  // (openhevcfilter.cpp:232-233) and DisplayFilter divides by it (displayfilter.cpp:153)
+  info->frameRate.num = d->fr_num > 0 && d->fr_den > 0 ? d->fr_num : 30;
+  info->frameRate.den = d->fr_num > 0 && d->fr_den > 0 ? d->fr_den : 1;
   info->display_picture_number = d->pictures - 1;
   info->nTimeStamp = d->out_pts;
 }
@@ -622,7 +569,7 @@ void libOpenHevcFlush(OpenHevc_Handle h)
     for (b200::StripBufs &t : s.strips) cudaStreamSynchronize(t.stream);
   }
   d->pending.clear();
-  d->have_ref = 0; d->out_slot = -1; d->d_out = nullptr;
+  d->have_ref = 0; d->have_submitted = false; d->out_slot = -1; d->d_out = nullptr;
 }
 void libOpenHevcClose(OpenHevc_Handle h) { delete (Decoder *)h; }
 
@@ -630,6 +577,12 @@ const uint8_t *b200_dec_output_dev(OpenHevc_Handle h)
 {
   Decoder *d = (Decoder *)h;
   return d && d->out_slot >= 0 ? d->d_out : NULL;
+}
+
+int b200_dec_missing_refs(OpenHevc_Handle h)
+{
+  Decoder *d = (Decoder *)h;
+  return d ? d->missing_refs : 0;
 }
 
 void b200_dec_set_host_output(OpenHevc_Handle h, int on)

@@ -12,6 +12,7 @@
 
 #include <algorithm>
 
+#include "../../include/b200_hevc.h"
 #include "hevc_kernels.h"
 #include "runtime.h"
 
@@ -241,11 +242,23 @@ void write_parameter_sets(const StreamLayout &l, std::vector<uint8_t> &out)
     b.ue(0); b.ue(3);                        // CB 8..64
     b.ue(0); b.ue(3);                        // TB 4..32
     b.ue(0); b.ue(0);                        // max_transform_hierarchy_depth inter / intra
-    b.put(0, 1); b.put(0, 1); b.put(0, 1); b.put(0, 1);   // scaling lists, AMP, SAO, PCM off
+    b.put(0, 1); b.put(0, 1); b.put(l.sao ? 1 : 0, 1); b.put(0, 1);   // scaling lists, AMP off; SAO; PCM off
     b.ue(1);                                 // one short-term RPS: the previous picture
     b.ue(1); b.ue(0); b.ue(0); b.put(1, 1);
     b.put(0, 1); b.put(0, 1); b.put(0, 1);   // long-term refs, TMVP, strong intra smoothing off
-    b.put(0, 1); b.put(0, 1);                // VUI, extension
+    if (l.fps_num > 0 && l.fps_den > 0) {    // VUI (E.2.1) with nothing but the timing info
+      b.put(1, 1);
+      b.put(0, 1); b.put(0, 1); b.put(0, 1); b.put(0, 1);   // aspect ratio, overscan, video signal type, chroma loc
+      b.put(0, 3); b.put(0, 1);              // neutral chroma / field seq / frame-field info, default display window
+      b.put(1, 1);                           // vui_timing_info_present_flag
+      b.put((uint32_t)l.fps_den, 32);        // vui_num_units_in_tick
+      b.put((uint32_t)l.fps_num, 32);        // vui_time_scale
+      b.put(0, 1); b.put(0, 1);              // poc proportional to timing, HRD
+      b.put(0, 1);                           // bitstream_restriction_flag
+    } else {
+      b.put(0, 1);
+    }
+    b.put(0, 1);                             // sps_extension_present_flag
     b.trailing();
     start_nal(out, 33);
     append_escaped(out, b.bytes.data(), b.bytes.size());
@@ -295,11 +308,14 @@ void write_slice_nal(const StreamLayout &l, bool idr, int poc, int qp, const uin
   if (!idr) {
     b.put((uint32_t)(poc & 255), 8);
     b.put(1, 1);
+  }
+  if (l.sao) b.put(3, 2);                    // slice_sao_luma_flag, slice_sao_chroma_flag
+  if (!idr) {
     b.put(0, 1);
     b.ue(5 - kMaxMerge);
   }
   b.se(qp - 26);
-  if (l.deblock) b.put(1, 1);
+  if (l.deblock || l.sao) b.put(1, 1);       // slice_loop_filter_across_slices_enabled_flag
   b.ue((uint32_t)(n_sub - 1));
   if (n_sub > 1) {
     uint32_t mx = 1;
@@ -319,6 +335,7 @@ StreamLayout Encoder::layout() const
 {
   StreamLayout l;
   l.w = fp.w; l.h = fp.h; l.deblock = cfg.deblock; l.qp_delta = cfg.qp_delta; l.tile_cols = 1; l.wpp = cfg.no_wpp ? 0 : 1;
+  l.fps_num = cfg.fps_num; l.fps_den = cfg.fps_den; l.sao = cfg.sao;
   return l;
 }
 
@@ -545,6 +562,29 @@ void *b200_enc_open_roi(int width, int height, int qp, int intra_period, int sea
   EncoderConfig c;
   c.width = width; c.height = height; c.qp = qp; c.intra_period = intra_period; c.search_range = search_range;
   c.deblock = deblock; c.debug = debug; c.depth = depth; c.qp_delta = 1;
+  if (!e->open(c)) { delete e; return nullptr; }
+  return e;
+}
+
+void b200_enc_params_default(b200_enc_params *p)
+{
+  if (!p) return;
+  memset(p, 0, sizeof(*p));
+  p->struct_size = (int)sizeof(*p);
+  p->qp = 32; p->intra_period = 64; p->search_range = 8; p->deblock = 1; p->depth = 1;
+}
+
+void *b200_enc_open_params(const b200_enc_params *up)
+{
+  if (!up || up->struct_size < (int)(9 * sizeof(int))) { b200::set_error("b200_enc_open_params: bad arguments"); return nullptr; }
+  b200_enc_params p;
+  b200_enc_params_default(&p);
+  memcpy(&p, up, std::min<size_t>((size_t)up->struct_size, sizeof(p)));
+  Encoder *e = new Encoder();
+  EncoderConfig c;
+  c.width = p.width; c.height = p.height; c.qp = p.qp; c.intra_period = p.intra_period; c.search_range = p.search_range;
+  c.deblock = p.deblock; c.debug = p.debug; c.depth = p.depth; c.qp_delta = p.qp_delta;
+  c.fps_num = p.fps_num; c.fps_den = p.fps_den; c.sao = p.sao;
   if (!e->open(c)) { delete e; return nullptr; }
   return e;
 }

@@ -25,6 +25,9 @@ struct EncoderConfig {
   // follow in the slice; no_wpp = one substream per tile (Main profile: tiles or WPP, not both);
   // raw = collect() hands back the substreams instead of an access unit.
   int mv_edges = 0, more_tiles = 0, no_wpp = 0, raw = 0;
+  int fps_num = 0, fps_den = 0;   // both > 0: VUI timing info in the SPS (the reference's DisplayFilter divides by
+                             // the frame rate the decoder reports, displayfilter.cpp:153)
+  int sao = 0;               // sample adaptive offset after deblocking (hevc_sao.cu)
   int depth = 1;             // pictures in flight (Kvazaar's owf + 1): output of picture n is
                              // returned by the call that submits picture n + depth - 1
 };
@@ -56,6 +59,8 @@ struct FrameSlot {
 // What the parameter sets and the slice header describe (shared by Encoder and TiledEncoder).
 struct StreamLayout {
   int w = 0, h = 0, deblock = 1, qp_delta = 0;
+  int fps_num = 0, fps_den = 0;   // VUI timing info when both > 0
+  int sao = 0;               // sample_adaptive_offset_enabled_flag; slices switch luma and chroma SAO on
   int tile_cols = 1;         // > 1: uniform tile columns, no loop filtering across tiles
   int wpp = 1;               // entropy_coding_sync_enabled_flag
 };

@@ -44,6 +44,7 @@ struct TiledEncoder {
     width = c.width; height = c.height;
     layout.w = c.width; layout.h = c.height; layout.deblock = c.deblock; layout.qp_delta = 0;
     layout.tile_cols = tiles; layout.wpp = wpp ? 1 : 0;
+    layout.fps_num = c.fps_num; layout.fps_den = c.fps_den;
     int prev = 0;
     cudaGetDevice(&prev);
     strips.resize(tiles);
@@ -143,6 +144,13 @@ void *b200_tiled_open(int width, int height, int qp, int intra_period, int searc
 }
 
 void b200_tiled_close(void *h) { delete (TiledEncoder *)h; }
+
+// VUI timing info of the parameter sets written from now on (kvz_api: "input-fps")
+void b200_tiled_set_fps(void *h, int fps_num, int fps_den)
+{
+  TiledEncoder *t = (TiledEncoder *)h;
+  if (t) { t->layout.fps_num = fps_num; t->layout.fps_den = fps_den; }
+}
 
 static int tiled_finish(TiledEncoder *t, uint8_t *out, int cap)
 {

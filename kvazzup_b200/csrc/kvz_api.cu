@@ -244,6 +244,7 @@ kvz_encoder *encoder_open(const kvz_config *cfg)
   c.search_range = cfg->me_range > 0 ? cfg->me_range : 12;
   c.deblock = cfg->deblock_enable; c.debug = 0; c.depth = cfg->owf + 1;
   c.qp_delta = (cfg->roi_enable || cfg->set_qp_in_cu) ? 1 : 0;
+  c.fps_num = cfg->framerate_num; c.fps_den = cfg->framerate_denom;     // VUI timing: the decoder side reports it
   if (cfg->tiles_width_count > 1) {
     // tile columns: independent strip encoders on this GPU; motion is confined to the tile, like
     // Kvazaar's mv-constraint frametilemargin (the reference exposes it, kvazaarfilter.cpp:246-276);
@@ -251,6 +252,7 @@ kvz_encoder *encoder_open(const kvz_config *cfg)
     e->tiled = b200_tiled_open(c.width, c.height, c.qp, c.intra_period, c.search_range, c.deblock, c.depth,
                                cfg->tiles_width_count, cfg->wpp ? 1 : 0, nullptr, 0);
     if (!e->tiled) { delete e; return NULL; }
+    b200_tiled_set_fps(e->tiled, c.fps_num, c.fps_den);
     e->tiled_out.resize((size_t)c.width * c.height * 3 + 65536);
     return e;
   }

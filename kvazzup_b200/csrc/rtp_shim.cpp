@@ -55,6 +55,11 @@ struct b200_rtp_sender {
   uint16_t seq;
 };
 
+// Limits of the receiver: a NAL of a level-6.2 picture stays far below 16 MB; 1024 queued NALs are
+// more than 30 access units of a 4K tiled picture.
+constexpr size_t kMaxNalBytes = 16u << 20;
+constexpr size_t kMaxReadyNals = 1024;
+
 struct b200_rtp_receiver {
   struct Nal { std::vector<uint8_t> bytes; uint32_t ts; int marker; };
   uint32_t ssrc;
@@ -191,15 +196,19 @@ int b200_rtp_receive(b200_rtp_receiver *r, const uint8_t *pkt, size_t len)
   const int marker = pkt[1] >> 7;
   const uint16_t seq = (uint16_t)((pkt[2] << 8) | pkt[3]);
   const uint32_t ts = ((uint32_t)pkt[4] << 24) | ((uint32_t)pkt[5] << 16) | ((uint32_t)pkt[6] << 8) | pkt[7];
-  const bool gap = r->have_seq && seq != (uint16_t)(r->last_seq + 1);
-  r->have_seq = true; r->last_seq = seq;
-  if (gap && r->fu_open) { r->fu_open = false; r->fu_skipping = true; r->fu.clear(); r->lost++; }
   const uint8_t *p = pkt + hdr;
   const size_t n = end - hdr;
   const int type = (p[0] >> 1) & 63;
+  if (type >= 50 || (type == kTypeFu && n < 4)) return -1;   // PACI / reserved / truncated FU: sequence state untouched
+  const bool gap = r->have_seq && seq != (uint16_t)(r->last_seq + 1);
+  r->have_seq = true; r->last_seq = seq;
+  // Bounded memory: a sender that never sets the E bit, or a consumer that never pops, must not
+  // grow this receiver without limit.  Oversized NALs and NALs arriving at a full queue are dropped
+  // and counted as lost.
+  if (r->ready.size() >= kMaxReadyNals) { r->ready.pop_front(); r->lost++; }
+  if (gap && r->fu_open) { r->fu_open = false; r->fu_skipping = true; r->fu.clear(); r->lost++; }
   static const uint8_t sc[4] = {0, 0, 0, 1};
   if (type == kTypeFu) {
-    if (n < 4) return -1;
     const bool s_bit = p[2] & 0x80, e_bit = p[2] & 0x40;
     if (s_bit) {
       if (r->fu_open) r->lost++;                             // previous NAL never saw its end fragment
@@ -210,6 +219,10 @@ int b200_rtp_receive(b200_rtp_receiver *r, const uint8_t *pkt, size_t len)
     } else if (!r->fu_open) {
       if (!r->fu_skipping) { r->lost++; r->fu_skipping = true; }   // fragment of a NAL whose start was lost
       if (e_bit) r->fu_skipping = false;
+      return (int)r->ready.size();
+    }
+    if (r->fu.size() + (n - 3) > kMaxNalBytes) {             // runaway fragment train: drop the NAL, skip to its end
+      r->fu.clear(); r->fu.shrink_to_fit(); r->fu_open = false; r->fu_skipping = !e_bit; r->lost++;
       return (int)r->ready.size();
     }
     r->fu.insert(r->fu.end(), p + 3, p + n);
@@ -238,7 +251,6 @@ int b200_rtp_receive(b200_rtp_receiver *r, const uint8_t *pkt, size_t len)
     for (auto &g : got) r->ready.push_back(std::move(g));
     return (int)r->ready.size();
   }
-  if (type >= 50) return -1;                                 // PACI / reserved
   b200_rtp_receiver::Nal nal{std::vector<uint8_t>(sc, sc + 4), ts, marker};
   nal.bytes.insert(nal.bytes.end(), p, p + n);
   r->ready.push_back(std::move(nal));
@@ -250,7 +262,10 @@ int b200_rtp_next_nal(b200_rtp_receiver *r, uint8_t *out, size_t cap, uint32_t *
   if (!r || !out) return -1;
   if (r->ready.empty()) return 0;
   const b200_rtp_receiver::Nal &n = r->ready.front();
-  if (n.bytes.size() > cap) return -2;
+  if (n.bytes.size() > cap) {                                // caller's buffer too small: report the size needed, keep the NAL
+    if (ts) *ts = (uint32_t)n.bytes.size();
+    return -2;
+  }
   memcpy(out, n.bytes.data(), n.bytes.size());
   if (ts) *ts = n.ts;
   if (marker) *marker = n.marker;

@@ -16,12 +16,28 @@ CU_DTYPE = np.dtype([("mvx", "<i2"), ("mvy", "<i2"), ("log2_size", "u1"), ("pred
                      ("mvp_idx", "u1"), ("qp", "u1")])
 
 
+class EncParams(C.Structure):
+    """b200_enc_params (include/b200_hevc.h)."""
+    _fields_ = [(n, C.c_int) for n in ("struct_size", "width", "height", "qp", "intra_period", "search_range", "deblock",
+                                       "debug", "depth", "qp_delta", "fps_num", "fps_den", "sao")]
+
+
 class GpuEncoder:
-    def __init__(self, w, h, qp=32, intra_period=64, search_range=8, deblock=1, debug=0, depth=1, qp_delta=0):
+    def __init__(self, w, h, qp=32, intra_period=64, search_range=8, deblock=1, debug=0, depth=1, **options):
+        """`options`: further fields of b200_enc_params by name (qp_delta, fps_num, fps_den, sao, ...)."""
         self.l = lib()
         self.w, self.h = w, h
-        opener = self.l.b200_enc_open_roi if qp_delta else self.l.b200_enc_open
-        self.h_enc = opener(w, h, qp, intra_period, search_range, deblock, debug, depth)
+        p = EncParams()
+        self.l.b200_enc_params_default(C.byref(p))
+        assert p.struct_size == C.sizeof(EncParams), "EncParams out of step with include/b200_hevc.h"
+        p.width, p.height, p.qp, p.intra_period, p.search_range = w, h, qp, intra_period, search_range
+        p.deblock, p.debug, p.depth = deblock, debug, depth
+        known = {f[0] for f in EncParams._fields_}
+        for k, val in options.items():
+            if k not in known:
+                raise TypeError(f"unknown encoder option {k!r}")
+            setattr(p, k, int(val))
+        self.h_enc = self.l.b200_enc_open_params(C.byref(p))
         if not self.h_enc:
             raise B200Error("b200_enc_open failed: " + self.l.b200_last_error().decode())
         self.out = np.empty(w * h * 3 + 65536, np.uint8)
@@ -137,6 +153,9 @@ class GpuTiledEncoder:
         f = np.ascontiguousarray(i420)
         assert f.size == self.w * self.h * 3 // 2
         return self._ret(self.l.b200_tiled_encode(self.h_enc, C.c_void_p(f.ctypes.data), C.c_void_p(self.out.ctypes.data), self.out.size))
+
+    def set_fps(self, num: int, den: int):
+        self.l.b200_tiled_set_fps(self.h_enc, num, den)
 
     def flush(self) -> bytes:
         return self._ret(self.l.b200_tiled_flush(self.h_enc, C.c_void_p(self.out.ctypes.data), self.out.size))

@@ -91,6 +91,16 @@ class OpenHEVCFilter:
             return None
         return self._send_decoded_output(got)
 
+    def frame_rate(self):
+        """(num, den) the decoder reports for the stream (OpenHevc_FrameInfo::frameRate)."""
+        info = OpenHevcFrameInfo()
+        self.l.libOpenHevcGetPictureInfo(self.handle, C.byref(info))
+        return info.frameRate.num, info.frameRate.den
+
+    def missing_refs(self) -> int:
+        """P pictures decoded although their reference picture had been lost (concealed, drifting)."""
+        return int(self.l.b200_dec_missing_refs(self.handle))
+
     def set_host_output(self, on: bool):
         """False: decoded pictures stay on the GPU; read them with output_dev()."""
         self.l.b200_dec_set_host_output(self.handle, int(on))

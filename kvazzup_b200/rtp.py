@@ -106,6 +106,9 @@ class RtpReceiver:
         ts, mk = u32(), i()
         while True:
             n = self.l.b200_rtp_next_nal(self.h, self.buf, len(self.buf), C.byref(ts), C.byref(mk))
+            if n == -2:                      # NAL larger than the buffer: ts holds the size needed
+                self.buf = (C.c_ubyte * max(ts.value, 2 * len(self.buf)))()
+                continue
             if n <= 0:
                 break
             out.append((bytes(self.buf[:n]), ts.value, mk.value))

@@ -15,12 +15,16 @@ assert CU_DTYPE.itemsize == C.sizeof(OrcCu) == 12
 
 
 class OracleEncoder:
-    def __init__(self, w, h, qp=32, intra_period=64, search_range=8, deblock=1, hash_sei=0, qp_delta=0,
-                 mv_edges=0, more_tiles=0, raw_slice_data=0, sao=0, subme_satd=0):
+    def __init__(self, w, h, qp=32, intra_period=64, search_range=8, deblock=1, **options):
+        """`options`: any further field of orc_enc_cfg_t (oracle/hevc_enc.h) by name, e.g. sao=1, fps_num=30."""
         self.lib = load()
         self.w, self.h = w, h
-        cfg = OrcEncCfg(w, h, qp, intra_period, search_range, deblock, hash_sei, qp_delta, mv_edges, more_tiles,
-                        raw_slice_data, 0, subme_satd, sao, 0)
+        cfg = OrcEncCfg(width=w, height=h, qp=qp, intra_period=intra_period, search_range=search_range, deblock=deblock)
+        known = {f[0] for f in OrcEncCfg._fields_}
+        for k, val in options.items():
+            if k not in known:
+                raise TypeError(f"unknown oracle encoder option {k!r}")
+            setattr(cfg, k, int(val))
         self.h_enc = self.lib.orc_enc_open(C.byref(cfg))
         if not self.h_enc:
             raise ValueError("orc_enc_open rejected the configuration")
@@ -86,7 +90,8 @@ class OracleTiledEncoder:
     def __init__(self, w, h, tiles, qp=32, intra_period=64, search_range=8, deblock=1, hash_sei=0, wpp=0):
         self.lib = load()
         self.w, self.h = w, h
-        cfg = OrcEncCfg(w, h, qp, intra_period, search_range, deblock, hash_sei, 0, 0, 0, 0, 0 if wpp else 1, 0, 0, 0)
+        cfg = OrcEncCfg(width=w, height=h, qp=qp, intra_period=intra_period, search_range=search_range, deblock=deblock,
+                        hash_sei=hash_sei, no_wpp=0 if wpp else 1)
         self.h_enc = self.lib.orc_tiled_open(C.byref(cfg), tiles)
         if not self.h_enc:
             raise ValueError("orc_tiled_open rejected the configuration")

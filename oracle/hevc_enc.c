@@ -1048,7 +1048,25 @@ static size_t write_parameter_sets(const orc_encoder_t *e, uint8_t *out, size_t 
   orc_bits_put(&b, 0, 1);             /* long_term_ref_pics_present_flag */
   orc_bits_put(&b, 0, 1);             /* sps_temporal_mvp_enabled_flag */
   orc_bits_put(&b, 0, 1);             /* strong_intra_smoothing_enabled_flag */
-  orc_bits_put(&b, 0, 1);             /* vui_parameters_present_flag */
+  if (e->cfg.fps_num > 0 && e->cfg.fps_den > 0) {
+    /* VUI (E.2.1) carrying only the timing: the reference copies the decoder's frame rate into
+     * vInfo (openhevcfilter.cpp:232-233) and DisplayFilter divides by it (displayfilter.cpp:153) */
+    orc_bits_put(&b, 1, 1);           /* vui_parameters_present_flag */
+    orc_bits_put(&b, 0, 1);           /* aspect_ratio_info_present_flag */
+    orc_bits_put(&b, 0, 1);           /* overscan_info_present_flag */
+    orc_bits_put(&b, 0, 1);           /* video_signal_type_present_flag */
+    orc_bits_put(&b, 0, 1);           /* chroma_loc_info_present_flag */
+    orc_bits_put(&b, 0, 3);           /* neutral_chroma_indication, field_seq, frame_field_info_present */
+    orc_bits_put(&b, 0, 1);           /* default_display_window_flag */
+    orc_bits_put(&b, 1, 1);           /* vui_timing_info_present_flag */
+    orc_bits_put(&b, (uint32_t)e->cfg.fps_den, 32);   /* vui_num_units_in_tick */
+    orc_bits_put(&b, (uint32_t)e->cfg.fps_num, 32);   /* vui_time_scale */
+    orc_bits_put(&b, 0, 1);           /* vui_poc_proportional_to_timing_flag */
+    orc_bits_put(&b, 0, 1);           /* vui_hrd_parameters_present_flag */
+    orc_bits_put(&b, 0, 1);           /* bitstream_restriction_flag */
+  } else {
+    orc_bits_put(&b, 0, 1);           /* vui_parameters_present_flag */
+  }
   orc_bits_put(&b, 0, 1);             /* sps_extension_present_flag */
   orc_bits_trailing(&b);
   o += write_nal(out + o, cap - o, 33, tmp, orc_bits_bytes(&b));

@@ -39,6 +39,7 @@ typedef struct {
   int subme_satd;          /* 1 = fractional motion refinement by SATD (Kvazaar / HM style) instead of SAD; oracle only */
   int sao;                 /* 1 = sample adaptive offset (8.7.3) after deblocking; oracle only so far */
   int tile_cols;           /* > 1: PPS / slice header of a picture with that many uniform tile columns (compositor only) */
+  int fps_num, fps_den;    /* both > 0: VUI timing info in the SPS (vui_time_scale / vui_num_units_in_tick); 0 = no VUI */
 } orc_enc_cfg_t;
 
 typedef struct orc_encoder orc_encoder_t;

@@ -29,6 +29,20 @@ def available() -> bool:
     return _find("avcodec") is not None and _find("avutil") is not None
 
 
+def required() -> bool:
+    """For the `-m gpu` tests: the independent decoder must take part.  A missing cv2 wheel FAILS the
+    test (it would otherwise silently skip the one check that does not come from this repository)
+    unless B200_ALLOW_NO_FFMPEG=1 says the box is known not to have it."""
+    if available():
+        return True
+    if os.environ.get("B200_ALLOW_NO_FFMPEG") == "1":
+        import warnings
+        warnings.warn("FFmpeg (cv2 wheel) absent: independent-decoder check SKIPPED by B200_ALLOW_NO_FFMPEG=1")
+        return False
+    raise AssertionError("FFmpeg libavcodec (cv2 wheel) not found: the independent-decoder check cannot run "
+                         "(set B200_ALLOW_NO_FFMPEG=1 to skip it knowingly)")
+
+
 def _libs():
     if _state:
         return _state["avc"], _state["avu"]

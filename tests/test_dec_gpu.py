@@ -69,7 +69,7 @@ def test_decoder_on_gpu_encoder_stream_1080p_and_ffmpeg_agreement():
     assert len(dec) == n
     for i in range(n):
         assert np.array_equal(dec[i][0], recs[i]), i
-    if ffhevc.available():
+    if ffhevc.required():
         ff, errs = ffhevc.decode_stream(aus)
         assert errs == 0
         for i in range(n):
@@ -120,6 +120,16 @@ def test_filter_gates_on_parameter_sets_and_reports_picture_info():
         assert f.process(nal) is None
     pic = f.process(nals[3])
     assert pic is not None and pic[1:] == (w, h)
+    # the reference copies the frame rate into vInfo (openhevcfilter.cpp:232-233) and DisplayFilter
+    # divides by it (displayfilter.cpp:153): never 0/0, the VUI timing when the stream has one
+    assert f.frame_rate() == (30, 1)
+    f.close()
+    enc = OracleEncoder(w, h, qp=30, intra_period=0, fps_num=30000, fps_den=1001)
+    f = OpenHEVCFilter()
+    assert f.init()
+    for nal in split_nals(enc.encode(frames_of("camera", w, h, 1)[0])):
+        pic = f.process(nal)
+    assert pic is not None and f.frame_rate() == (30000, 1001)
     f.close()
 
 
@@ -182,6 +192,7 @@ def test_rtp_loopback_encoder_packets_decoder():
                     # conceals with the last picture it has, so they drift until the next IDR
                     assert np.array_equal(got[0], rec) == (i not in (2, 3)), i
                     shown[i] = True
+    assert f.missing_refs() == 1               # picture 2 named POC 1, which never arrived: the application can ask for an IDR
     f.close()
     assert rcv.lost == 1
     assert sorted(shown) == [0, 2, 3, 4, 5, 6, 7]

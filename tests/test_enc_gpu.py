@@ -65,7 +65,7 @@ def test_gpu_encoder_matches_oracle_stage_by_stage(kind, w, h, n, qp, kw):
         assert ga == oa, f"frame {i}: access unit differs (gpu {len(ga)} B, oracle {len(oa)} B)"
         assert g.bins() == o.bins()
         aus.append(ga)
-    if ffhevc.available():
+    if ffhevc.required():
         dec, errs = ffhevc.decode_stream(aus)
         assert errs == 0 and len(dec) == n
         assert np.array_equal(dec[-1][0], g.recon())
@@ -141,9 +141,9 @@ def test_kvazaar_filter_default_settings_stream_equals_engine_and_decodes():
         assert len(got) == 1
         aus += got
     f.close()
-    o = OracleEncoder(w, h, qp=32, intra_period=64, search_range=8)
+    o = OracleEncoder(w, h, qp=32, intra_period=64, search_range=8, fps_num=30, fps_den=1)    # "input-fps" -> VUI timing
     assert aus == [o.encode(fr) for fr in frames]
-    if ffhevc.available():
+    if ffhevc.required():
         dec, errs = ffhevc.decode_stream(aus)
         assert errs == 0 and len(dec) == n and np.array_equal(dec[-1][0], o.recon())
 
@@ -200,7 +200,7 @@ def test_rate_control_tracks_the_target_bitrate():
         aus = [f.feed_input(fr)[0] for fr in frames]
         f.close()
         sizes[kbps] = sum(len(a) for a in aus[8:]) * 8 / (n - 8) * 30 / 1000      # kbit/s after the intra picture
-        if ffhevc.available():
+        if ffhevc.required():
             dec, errs = ffhevc.decode_stream(aus)
             assert errs == 0 and len(dec) == n
     assert sizes[300] < sizes[1500]
@@ -238,7 +238,7 @@ def test_full_size_roundtrip_properties(kind, w, h, qp):
                 got.append(pic[0])
     dec.close()
     assert len(got) == n and all(np.array_equal(g, r) for g, r in zip(got, recs))
-    if ffhevc.available():
+    if ffhevc.required():
         ff, errs = ffhevc.decode_stream(aus)
         assert errs == 0 and all(np.array_equal(f[0], r) for f, r in zip(ff, recs))
     assert synth.psnr(frames[-1][:w * h], recs[-1][:w * h]) > 30.0
@@ -314,7 +314,7 @@ def test_per_ctu_qp_matches_oracle_stage_by_stage(kind, w, h, n, qp, roi, kw):
     assert len(dec) == n
     for i in range(n):
         assert np.array_equal(dec[i][0], recs[i]), f"GPU decoder, picture {i}"
-    if ffhevc.available():
+    if ffhevc.required():
         ff, errs = ffhevc.decode_stream(aus)
         assert errs == 0 and np.array_equal(ff[-1][0], recs[-1])
     g.close()
@@ -333,7 +333,7 @@ def test_roi_through_kvz_api_and_pipelining():
     cols, rows = (w + 63) // 64, (h + 63) // 64
     dqp = np.array([[roi_px[cy * h // rows, cx * w // cols] for cx in range(cols)] for cy in range(rows)], np.int8)
     base = {"video/ResolutionWidth": w, "video/ResolutionHeight": h, "video/QP": 30, "video/Intra": 0, "video/Preset": "ultrafast"}
-    eng = GpuEncoder(w, h, qp=30, intra_period=0, search_range=8, qp_delta=1)
+    eng = GpuEncoder(w, h, qp=30, intra_period=0, search_range=8, qp_delta=1, fps_num=30, fps_den=1)
     eng.set_ctu_dqp(dqp.ravel())
     want = [eng.encode(f) for f in frames]
     for owf in (0, 3):
@@ -346,7 +346,7 @@ def test_roi_through_kvz_api_and_pipelining():
         f.close()
         assert got == want, owf
     # not enabled: the map is accepted and ignored, as before
-    plain = GpuEncoder(w, h, qp=30, intra_period=0, search_range=8)
+    plain = GpuEncoder(w, h, qp=30, intra_period=0, search_range=8, fps_num=30, fps_den=1)
     want_plain = [plain.encode(f) for f in frames]
     f = KvazaarFilter(base)
     assert f.init()
@@ -413,7 +413,7 @@ def test_tiled_encoder_matches_oracle_and_decodes_in_ffmpeg(kind, w, h, n, qp, t
         assert bad.size == 0, f"frame {i}: reconstruction differs at {bad[:8]} (of {bad.size})"
         assert ga == oa, f"frame {i}: access unit differs (gpu {len(ga)} B, oracle {len(oa)} B)"
         aus.append(ga)
-    if ffhevc.available() and not wpp:
+    if not wpp and ffhevc.required():
         dec, errs = ffhevc.decode_stream(aus)
         assert errs == 0 and len(dec) == n
         assert np.array_equal(dec[-1][0], g.recon())
@@ -453,6 +453,7 @@ def test_tiles_through_kvz_api():
     base = {"video/ResolutionWidth": w, "video/ResolutionHeight": h, "video/QP": 30, "video/Intra": 0, "video/Preset": "ultrafast"}
     for wpp in (1, 0):
         eng = GpuTiledEncoder(w, h, 3, qp=30, intra_period=0, search_range=8, wpp=wpp)
+        eng.set_fps(30, 1)
         want = [eng.encode(f) for f in frames]
         eng.close()
         f = KvazaarFilter(base | {"video/Tiles": 1, "video/tileDimensions": "3x1", "video/WPP": wpp})
@@ -462,7 +463,7 @@ def test_tiles_through_kvz_api():
             got += f.feed_input(fr)
         f.close()
         assert got == want, wpp
-    plain = GpuEncoder(w, h, qp=30, intra_period=0, search_range=8)
+    plain = GpuEncoder(w, h, qp=30, intra_period=0, search_range=8, fps_num=30, fps_den=1)
     want = [plain.encode(f) for f in frames]
     f = KvazaarFilter(base | {"video/Tiles": 1, "video/tileDimensions": "2x2"})
     assert f.init() and any("tiles" in str(x) for x in f.warnings)
