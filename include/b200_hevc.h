@@ -76,6 +76,15 @@ int   b200_enc_debug_set_reference(void *enc, const uint8_t *i420);
  * b200_enc_*: access units come back in order, `depth` pictures in flight. */
 void *b200_tiled_open(int width, int height, int qp, int intra_period, int search_range, int deblock, int depth,
                       int tile_cols, int wpp, const int *devices, int n_devices);
+/* The same with every option by name (see b200_enc_params). */
+typedef struct b200_tiled_params {
+  int struct_size;
+  int width, height, qp, intra_period, search_range, deblock, depth, tile_cols, wpp;
+  int fps_num, fps_den;          /* both > 0: VUI timing info in the SPS */
+  int sao;                       /* SAO inside every tile (never across tile edges) */
+} b200_tiled_params;
+void  b200_tiled_params_default(b200_tiled_params *p);
+void *b200_tiled_open_params(const b200_tiled_params *p, const int *devices, int n_devices);
 void  b200_tiled_close(void *enc);
 void  b200_tiled_set_fps(void *enc, int fps_num, int fps_den);   /* VUI timing info of the parameter sets (both > 0) */
 int   b200_tiled_encode(void *enc, const uint8_t *i420, uint8_t *out, int cap);   /* host picture */

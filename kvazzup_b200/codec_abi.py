@@ -25,6 +25,8 @@ SIGNATURES: dict = {
     "b200_enc_debug_read": (i, [v, i, v, C.c_size_t]),
     "b200_enc_debug_set_reference": (i, [v, v]),
     "b200_tiled_open": (v, [i, i, i, i, i, i, i, i, i, v, i]),
+    "b200_tiled_params_default": (None, [v]),
+    "b200_tiled_open_params": (v, [v, v, i]),
     "b200_tiled_close": (None, [v]),
     "b200_tiled_set_fps": (None, [v, i, i]),
     "b200_tiled_encode": (i, [v, v, v, i]),

@@ -511,6 +511,51 @@ __device__ __forceinline__ int put_cu_header(Syn &s, const CuView &v, const CuIn
   return cu.cbf;
 }
 
+// sao() of one CTU (7.3.8.3), both slice flags on.  fp.sao_flags bit 2: a CTU whose parameters equal
+// its left (else its upper) neighbour's codes the merge flag instead of repeating them.
+// sao_type_idx: TR cMax 2, first bin context-coded; sao_offset_abs: TR cMax 7, bypass; signs, band
+// position (5 bits) and edge class (2 bits) bypass.
+__device__ __forceinline__ void put_sao(Syn &s, const FrameParams &fp, int ctu)
+{
+  const SaoCtu p = fp.sao[ctu];
+  const int rx = ctu % fp.ctb_cols, ry = ctu / fp.ctb_cols;
+  auto same = [&](int other) {
+    const uint32_t *a = (const uint32_t *)&p, *b = (const uint32_t *)(fp.sao + other);
+    return a[0] == b[0] && a[1] == b[1] && a[2] == b[2] && a[3] == b[3] && ((a[4] ^ b[4]) & 0xffffffu) == 0;
+  };
+  const bool try_merge = (fp.sao_flags & 4) != 0;
+  if (rx > 0) {
+    const bool m = try_merge && same(ctu - 1);
+    put_ctx(s, CTX_SAO_MERGE, m);
+    if (m) return;
+  }
+  if (ry > 0) {
+    const bool m = try_merge && same(ctu - fp.ctb_cols);
+    put_ctx(s, CTX_SAO_MERGE, m);
+    if (m) return;
+  }
+  for (int comp = 0; comp < 3; comp++) {
+    const int g = comp ? 1 : 0, type = p.type[g];
+    if (comp < 2) {
+      put_ctx(s, CTX_SAO_TYPE, type != 0);
+      if (type) put_byp(s, type == 2, 1);
+    }
+    if (!type) continue;
+    for (int k = 0; k < 4; k++) {
+      const int a = abs((int)p.offset[comp][k]);
+      if (a < 7) put_byp(s, ((1ull << a) - 1) << 1, a + 1);
+      else put_byp(s, 0x7f, 7);
+    }
+    if (type == 1) {
+      for (int k = 0; k < 4; k++)
+        if (p.offset[comp][k]) put_byp(s, p.offset[comp][k] < 0, 1);
+      put_byp(s, p.band_pos[comp], 5);
+    } else if (comp < 2) {
+      put_byp(s, p.eo_class[g], 2);
+    }
+  }
+}
+
 // Record region of the CU whose first unit is (ctu, z): fixed address, no prefix sums needed.
 // Word 0 = record count | log2 CU size << 24; records follow.
 __device__ __forceinline__ uint32_t *cu_region(uint32_t *recs, int ctu, int z) { return recs + ((size_t)ctu * 64 + z) * kRecUnitCap; }
@@ -520,7 +565,7 @@ constexpr int kBinWarps = 2;           // warps (CUs) per CTA of the binariser
 struct BinWarpShared {
   int16_t lv[32 * 32];
   ResidualShared rs;
-  uint32_t syn[128];
+  uint32_t syn[192];
 };
 
 // One warp per 32x32 quadrant of a CTU; the warp walks the (1..16) CUs that start inside it.
@@ -548,6 +593,7 @@ k_binarise(FrameParams fp, const CuInfo *__restrict__ cu, const int16_t *__restr
     Syn syn{sh.syn, 0};
     uint32_t *out = cu_region(recs, ctu, z);
     int o = 1;                                                // word 0 is the header
+    if (z == 0 && fp.sao) put_sao(syn, fp, ctu);              // the CTU's sao() syntax precedes its first CU
     // split flags of every ancestor block that starts at this unit, top down, then this CU's own
     for (int L = 6; L > 3; L--) {
       if (L < log2) break;

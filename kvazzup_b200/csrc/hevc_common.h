@@ -37,13 +37,24 @@ struct CuInfo {
 };
 static_assert(sizeof(CuInfo) == 12, "CuInfo layout is part of the test ABI");
 
+// SAO parameters of one CTU (7.4.9.3): [0] luma, [1] chroma (type and class shared by Cb and Cr)
+struct SaoCtu {
+  uint8_t type[2];        // 0 off, 1 band offset, 2 edge offset
+  uint8_t eo_class[2];
+  uint8_t band_pos[3];
+  int8_t offset[3][4];    // signed SaoOffsetVal of categories 1..4 / the four bands
+  uint8_t pad;
+};
+static_assert(sizeof(SaoCtu) == 20, "SaoCtu layout");
+
 // CABAC context layout (one flat table per substream)
 enum CtxOffset {
   CTX_SPLIT_CU = 0, CTX_SKIP = 3, CTX_MERGE_FLAG = 6, CTX_MERGE_IDX = 7, CTX_PART_MODE = 8,
   CTX_PRED_MODE = 12, CTX_PREV_INTRA_LUMA = 13, CTX_INTRA_CHROMA = 14, CTX_MVD_GT0 = 15,
   CTX_MVD_GT1 = 16, CTX_MVP_IDX = 17, CTX_RQT_ROOT_CBF = 18, CTX_SPLIT_TRANSFORM = 19,
   CTX_CBF_LUMA = 22, CTX_CBF_CHROMA = 24, CTX_LAST_X = 28, CTX_LAST_Y = 46, CTX_CSBF = 64,
-  CTX_SIG = 68, CTX_GT1 = 110, CTX_GT2 = 134, CTX_CU_QP_DELTA = 140, CTX_COUNT = 142
+  CTX_SIG = 68, CTX_GT1 = 110, CTX_GT2 = 134, CTX_CU_QP_DELTA = 140, CTX_SAO_MERGE = 142, CTX_SAO_TYPE = 143,
+  CTX_COUNT = 144
 };
 
 struct FrameParams {
@@ -67,6 +78,11 @@ struct FrameParams {
   // tiles follow in the slice, the last CTU does not end the slice segment.  no_wpp: one substream
   // for the whole picture (entropy_coding_sync off; HEVC Main allows tiles or WPP, not both).
   int mv_edges, more_tiles, no_wpp;
+  // SAO: per-CTU parameters (raster) -- written by k_sao_ctu (encoder) or the parser (decoder), read by
+  // the binariser / the decoder's apply pass; null when SAO is off.  sao_flags: bit 0 slice_sao_luma_flag,
+  // bit 1 slice_sao_chroma_flag, bit 2 (encoder) use the merge flags where parameters repeat.
+  SaoCtu *sao;
+  int sao_flags;
 };
 
 }  // namespace b200

@@ -46,6 +46,7 @@ struct StripGeom {
   FrameParams fp{};                       // strip-sized
   size_t bytes = 0;                       // packed I420 of the strip
   uint8_t *d_rec[2] = {nullptr, nullptr};
+  uint8_t *d_dbk = nullptr;               // deblocked picture of a slice with SAO (SAO reads it, writes d_rec)
   int *d_order = nullptr;
   cudaStream_t stream = nullptr;          // reconstruction chain of this strip
   cudaEvent_t ev_done = nullptr;
@@ -56,6 +57,7 @@ struct StripBufs {
   cudaStream_t stream = nullptr;
   cudaEvent_t ev_parsed = nullptr;
   uint8_t *d_small = nullptr, *d_ctu_qp = nullptr;
+  SaoCtu *d_sao = nullptr;                // per-CTU SAO parameters from the parser
   CuInfo *d_cu = nullptr;
   int16_t *d_levels = nullptr;
   uint32_t *h_bases = nullptr;
@@ -108,6 +110,7 @@ struct Decoder {
       if (g.stream) { cudaStreamSynchronize(g.stream); cudaStreamDestroy(g.stream); }
       if (g.ev_done) cudaEventDestroy(g.ev_done);
       for (int i = 0; i < 2; i++) if (g.d_rec[i]) cudaFree(g.d_rec[i]);
+      if (g.d_dbk) cudaFree(g.d_dbk);
       if (g.d_order) cudaFree(g.d_order);
     }
     geom.clear();
@@ -118,6 +121,7 @@ struct Decoder {
         if (t.ev_parsed) cudaEventDestroy(t.ev_parsed);
         if (t.d_small) cudaFree(t.d_small);
         if (t.d_ctu_qp) cudaFree(t.d_ctu_qp);
+        if (t.d_sao) cudaFree(t.d_sao);
         if (t.d_cu) cudaFree(t.d_cu);
         if (t.d_levels) cudaFree(t.d_levels);
         if (t.h_bases) cudaFreeHost(t.h_bases);
@@ -168,6 +172,7 @@ struct Decoder {
       if (!cuda_ok(cudaEventCreateWithFlags(&g.ev_done, cudaEventDisableTiming), "cudaEventCreate")) return false;
       if (!cuda_ok(cudaMalloc((void **)&g.d_rec[0], g.bytes), "cudaMalloc")) return false;
       if (!cuda_ok(cudaMalloc((void **)&g.d_rec[1], g.bytes), "cudaMalloc")) return false;
+      if (!cuda_ok(cudaMalloc((void **)&g.d_dbk, g.bytes), "cudaMalloc")) return false;
       std::vector<int> order((size_t)g.fp.ctb_cols * rows);
       intra_wavefront_order(g.fp.ctb_cols, rows, order.data());
       if (!cuda_ok(cudaMalloc((void **)&g.d_order, order.size() * sizeof(int)), "cudaMalloc")) return false;
@@ -189,6 +194,7 @@ struct Decoder {
         if (!cuda_ok(cudaEventCreateWithFlags(&t.ev_parsed, cudaEventDisableTiming), "cudaEventCreate")) return false;
         if (!cuda_ok(cudaMalloc((void **)&t.d_small, small_bytes), "cudaMalloc")) return false;
         if (!cuda_ok(cudaMalloc((void **)&t.d_ctu_qp, (size_t)g.fp.ctb_cols * rows), "cudaMalloc")) return false;
+        if (!cuda_ok(cudaMalloc((void **)&t.d_sao, sizeof(SaoCtu) * g.fp.ctb_cols * rows), "cudaMalloc")) return false;
         if (!cuda_ok(cudaMalloc((void **)&t.d_cu, sizeof(CuInfo) * g.fp.w8 * g.fp.h8), "cudaMalloc")) return false;
         if (!cuda_ok(cudaMalloc((void **)&t.d_levels, g.bytes * sizeof(int16_t)), "cudaMalloc")) return false;
         if (!cuda_ok(cudaMallocHost((void **)&t.h_bases, sizeof(uint32_t) * (rows + 1)), "cudaMallocHost")) return false;
@@ -232,7 +238,6 @@ struct Decoder {
     if (s.max_tr_depth_inter != 0 || s.max_tr_depth_intra != 0) return "transform hierarchy depth > 0 is not supported";
     if (s.scaling_list) return "scaling lists are not supported";
     if (s.amp) return "AMP is not supported";
-    if (s.sao) return "SAO is not supported";
     if (s.pcm) return "PCM is not supported";
     if (s.long_term_refs) return "long-term reference pictures are not supported";
     if (s.tmvp && sh.tmvp) return "temporal MVP is not supported";
@@ -372,6 +377,8 @@ struct Decoder {
       t.fp.qp = qp; t.fp.qp_c = kChromaQpD[qp]; t.fp.is_idr = slice_type == 2 ? 1 : 0; t.fp.deblock = deblock;
       t.fp.no_wpp = pps.wpp ? 0 : 1;
       t.fp.ctu_qp = pps.qp_delta ? t.d_ctu_qp : nullptr; t.fp.ctu_delta = nullptr; t.fp.ctu_first = nullptr;
+      t.fp.sao_flags = (sh.sao_luma ? 1 : 0) | (sh.sao_chroma ? 2 : 0);
+      t.fp.sao = t.fp.sao_flags ? t.d_sao : nullptr;
       int *sync_flag = (int *)(t.d_small + off_flag), *progress = (int *)(t.d_small + off_prog);
       int *status = (int *)(t.d_small + off_status);
       uint32_t *d_bases = (uint32_t *)(t.d_small + off_bases);
@@ -420,7 +427,9 @@ struct Decoder {
       StripGeom &g = geom[i];
       FrameParams &f = t.fp;
       int *progress = (int *)(t.d_small + off_prog), *ticket = (int *)(t.d_small + off_ticket);
-      uint8_t *rec = g.d_rec[cur], *ref = g.d_rec[cur ^ 1];
+      // with SAO the picture is reconstructed and deblocked in g.d_dbk; SAO writes the output picture
+      uint8_t *const out_rec = g.d_rec[cur], *ref = g.d_rec[cur ^ 1];
+      uint8_t *rec = f.sao_flags ? g.d_dbk : out_rec;
       if (f.is_idr) {
         DEC_CHECK(launch_intra_decode(f, rec, t.d_levels, t.d_cu, progress, ticket, g.d_order, g.stream), "intra decode launch");
         count_launch(1);
@@ -434,6 +443,11 @@ struct Decoder {
       if (f.deblock) {
         DEC_CHECK(launch_deblock(f, rec, t.d_cu, g.stream), "deblock launch");
         count_launch(2);
+      }
+      if (f.sao_flags) {
+        DEC_CHECK(launch_sao_decode(f, rec, out_rec, t.d_sao, g.stream), "sao launch");
+        count_launch(1);
+        rec = out_rec;
       }
       if (tiles > 1) {                     // place the strip in the whole picture
         const size_t sy = (size_t)g.wd * fp.h;

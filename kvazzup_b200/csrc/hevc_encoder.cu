@@ -114,6 +114,8 @@ void Encoder::release()
     if (s.d_recs) cudaFree(s.d_recs);
     if (s.d_small) cudaFree(s.d_small);
     if (s.d_qpinfo) cudaFree(s.d_qpinfo);
+    if (s.d_dbk) cudaFree(s.d_dbk);
+    if (s.d_sao) cudaFree(s.d_sao);
     if (s.h_ctu_qp) cudaFreeHost(s.h_ctu_qp);
     if (s.d_src) cudaFree(s.d_src);
     if (s.h_src) cudaFreeHost(s.h_src);
@@ -200,6 +202,10 @@ bool Encoder::open(const EncoderConfig &c)
       ENC_CHECK(cudaMallocHost((void **)&s.h_ctu_qp, (size_t)fp.ctb_cols * fp.ctb_rows), "cudaMallocHost ctu qp");
     }
     ENC_CHECK(cudaMemset(s.d_small, 0, small_bytes), "memset small");
+    if (c.sao) {
+      ENC_CHECK(cudaMalloc((void **)&s.d_dbk, frame_bytes), "cudaMalloc dbk");
+      ENC_CHECK(cudaMalloc((void **)&s.d_sao, sizeof(SaoCtu) * fp.ctb_cols * fp.ctb_rows), "cudaMalloc sao");
+    }
     ENC_CHECK(cudaMalloc((void **)&s.d_src, frame_bytes), "cudaMalloc src");
     ENC_CHECK(cudaMallocHost((void **)&s.h_src, frame_bytes), "cudaMallocHost src");
     ENC_CHECK(cudaHostAlloc((void **)&s.h_pack, pack_cap, cudaHostAllocMapped), "cudaHostAlloc pack");
@@ -348,7 +354,11 @@ bool Encoder::submit(FrameSlot &s, const uint8_t *d_i420)
   FrameParams p = fp;
   p.is_idr = idr ? 1 : 0;
   p.qp = cur_qp; p.qp_c = kChromaQp[cur_qp]; p.lambda_q4 = kLambdaQ4[cur_qp];
-  uint8_t *rec = d_rec[frame_idx % kRecRing], *ref = d_rec[(frame_idx + kRecRing - 1) % kRecRing];
+  uint8_t *const out_rec = d_rec[frame_idx % kRecRing], *ref = d_rec[(frame_idx + kRecRing - 1) % kRecRing];
+  // with SAO the prediction chain reconstructs and deblocks into the slot's own picture; SAO reads it
+  // (a CTU needs its neighbours' DEBLOCKED samples) and writes the reconstruction ring
+  uint8_t *rec = cfg.sao ? s.d_dbk : out_rec;
+  p.sao = cfg.sao ? s.d_sao : nullptr; p.sao_flags = cfg.sao ? (cfg.sao == 2 ? 7 : 3) : 0;
   p.ctu_qp = nullptr; p.ctu_delta = nullptr; p.ctu_first = nullptr;
   p.mv_edges = cfg.mv_edges; p.more_tiles = cfg.more_tiles; p.no_wpp = cfg.no_wpp;
   if (cfg.qp_delta) {
@@ -405,6 +415,12 @@ bool Encoder::submit(FrameSlot &s, const uint8_t *d_i420)
     PROF_END(K_DEBLOCK, stream);
     count_launch(2);
   }
+  if (cfg.sao) {
+    PROF_BEGIN(K_SAO, stream);
+    ENC_CHECK(launch_sao_encode(p, d_i420, rec, out_rec, s.d_sao, stream), "sao launch");
+    PROF_END(K_SAO, stream);
+    count_launch(1);
+  }
   // Entropy coding (slot stream) needs only the cu map and the levels, but it is released after
   // the deblocking: started before it, the binariser's 16k CTAs share the SMs with the two short
   // deblocking kernels and stretch them from 15 us to 75 us on the critical prediction chain.
@@ -437,6 +453,7 @@ bool Encoder::collect(FrameSlot &s, std::vector<uint8_t> &out)
     // the deblocking of this picture (main stream) may still be running: wait for ITS end event
     // only -- synchronising the whole main stream would drain the pictures submitted after it
     if (s.prof_mask & (1u << K_DEBLOCK)) cudaEventSynchronize(s.pev[2 * K_DEBLOCK + 1]);
+    if (s.prof_mask & (1u << K_SAO)) cudaEventSynchronize(s.pev[2 * K_SAO + 1]);
     for (int k = 0; k < K_COUNT; k++) {
       if (!(s.prof_mask & (1u << k))) continue;
       float ms = 0;

@@ -43,13 +43,15 @@ struct FrameSlot {
   uint8_t *d_qpinfo = nullptr;     // qp_delta: ctu_qp | ctu_delta | ctu_first, one byte per CTU each
   uint8_t *h_ctu_qp = nullptr;     // pinned staging of ctu_qp
   uint8_t *d_small = nullptr;      // row_len | sync flags | progress | ticket | bins | sync contexts
+  uint8_t *d_dbk = nullptr;        // sao: the deblocked picture (SAO reads it and writes the reconstruction ring)
+  SaoCtu *d_sao = nullptr;         // sao: per-CTU parameters (k_sao_ctu -> k_binarise)
   uint8_t *d_src = nullptr;        // device copy of a host-supplied picture
   uint8_t *h_src = nullptr;        // pinned staging of the input
   uint8_t *h_pack = nullptr;       // mapped pinned: packed substreams
   uint32_t *h_hdr = nullptr;       // mapped pinned: {total, row_len[rows]}
   cudaStream_t stream = nullptr;
   cudaEvent_t ev_pred = nullptr, ev_done = nullptr;
-  cudaEvent_t pev[16] = {};        // profiling: begin/end event per kernel slot (kernel ids below)
+  cudaEvent_t pev[18] = {};        // profiling: begin/end event per kernel slot (kernel ids below)
   unsigned prof_mask = 0;          // which kernel ids were recorded for the picture in this slot
   bool idr = false;
   int poc = 0, qp = 0;
@@ -124,7 +126,7 @@ class Encoder {
   cudaStream_t stream = nullptr;     // main (prediction chain) stream
 
   // per-kernel device time, measured with CUDA events on the launching stream (profile != 0)
-  enum { K_INTRA = 0, K_ME, K_RECON, K_MODES, K_DEBLOCK, K_BINARISE, K_ARITH, K_PACK, K_COUNT };
+  enum { K_INTRA = 0, K_ME, K_RECON, K_MODES, K_DEBLOCK, K_BINARISE, K_ARITH, K_PACK, K_SAO, K_COUNT };
   int profile = 0;
   cudaEvent_t ev_base = nullptr;      // time origin of the timeline below
   float timeline[2 * K_COUNT] = {};  // begin/end (ms since ev_base) of each kernel of the last collected picture

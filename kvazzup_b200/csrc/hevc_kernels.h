@@ -37,6 +37,12 @@ cudaError_t launch_cu_qps(const FrameParams &fp, CuInfo *cu, cudaStream_t s);
 // in-loop deblocking, in place on `rec` (vertical edges of the whole picture, then horizontal)
 cudaError_t launch_deblock(const FrameParams &fp, uint8_t *rec, const CuInfo *cu, cudaStream_t s);
 
+// sample adaptive offset (hevc_sao.cu), one launch: deblocked picture `dbk` -> output picture `out`.
+// encode: statistics against `src`, per-CTU decision into `params`, apply.  decode: apply `params`.
+cudaError_t launch_sao_encode(const FrameParams &fp, const uint8_t *src, const uint8_t *dbk, uint8_t *out, SaoCtu *params,
+                              cudaStream_t s);
+cudaError_t launch_sao_decode(const FrameParams &fp, const uint8_t *dbk, uint8_t *out, const SaoCtu *params, cudaStream_t s);
+
 // CABAC, two kernels meeting in the bin-record buffer `recs`
 // (ctb_cols*ctb_rows*64*kRecUnitCap words): k_binarise (one warp per CU, whole picture in parallel)
 // and k_arith_rows (one warp per CTU row / WPP substream).  rows[r*row_cap ..] receives the escaped

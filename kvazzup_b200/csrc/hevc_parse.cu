@@ -8,10 +8,9 @@
 // lanes on private context tables, with no branch that depends on the lane index; stores of
 // identical values from all lanes coalesce into one transaction.
 //
-// Scope: the syntax subset the B200 encoder (and any encoder with the same parameter sets)
-// produces -- 2Nx2N CUs 8..64, one TU per CU, I and P slices, one reference picture, no SAO /
-// PCM / AMP / scaling lists / transform skip / sign hiding / cu_qp_delta / TMVP.  Anything else is
-// reported through `status` and the picture is rejected by the host.
+// Scope: 2Nx2N CUs 8..64, one TU per CU, I and P slices, one reference picture, SAO (with merge
+// candidates), cu_qp_delta per CTU; no PCM / AMP / scaling lists / transform skip / sign hiding /
+// TMVP.  Anything else is reported through `status` and the picture is rejected by the host.
 #include "hevc_device.cuh"
 #include "hevc_kernels.h"
 
@@ -479,6 +478,58 @@ __device__ void parse_cu(Reader &r, ParseCtx &pc, int x0, int y0, int log2)
   }
 }
 
+// sao() of one CTU (7.3.8.3) -> fp.sao[ctu].  `left`: the previous CTU's parameters (sao_merge_left_flag).
+__device__ void parse_sao(Reader &r, const FrameParams &fp, int row, int col, SaoCtu &left)
+{
+  SaoCtu p;
+  bool merged = false;
+  if (col > 0 && dec_bin(r, CTX_SAO_MERGE)) { p = left; merged = true; }
+  if (!merged && row > 0 && dec_bin(r, CTX_SAO_MERGE)) {
+    // the CTU above was completed at least two CTUs ago (WPP progress wait) or by this warp (no_wpp)
+    const uint32_t *s = (const uint32_t *)(fp.sao + (size_t)(row - 1) * fp.ctb_cols + col);
+    uint32_t *d = (uint32_t *)&p;
+    for (int i = 0; i < 5; i++) d[i] = __ldcg(s + i);
+    merged = true;
+  }
+  if (!merged) {
+    uint32_t *z = (uint32_t *)&p;
+    for (int i = 0; i < 5; i++) z[i] = 0;
+    for (int comp = 0; comp < 3; comp++) {
+      const int g = comp ? 1 : 0;
+      if (!((fp.sao_flags >> g) & 1)) continue;
+      if (comp < 2) {
+        int type = 0;
+        if (dec_bin(r, CTX_SAO_TYPE)) type = dec_bypass(r) ? 2 : 1;
+        p.type[g] = (uint8_t)type;
+      }
+      const int type = p.type[g];
+      if (!type) continue;
+      int a[4];
+      for (int k = 0; k < 4; k++) {
+        int v = 0;
+        while (v < 7 && dec_bypass(r)) v++;
+        a[k] = v;
+      }
+      if (type == 1) {
+        for (int k = 0; k < 4; k++)
+          if (a[k] && dec_bypass(r)) a[k] = -a[k];
+        p.band_pos[comp] = (uint8_t)dec_bypass_bits(r, 5);
+      } else {
+        if (comp == 0) p.eo_class[0] = (uint8_t)dec_bypass_bits(r, 2);
+        if (comp == 1) p.eo_class[1] = (uint8_t)dec_bypass_bits(r, 2);
+        a[2] = -a[2]; a[3] = -a[3];                    // categories 3 and 4 (local maxima) take negative offsets
+      }
+      for (int k = 0; k < 4; k++) p.offset[comp][k] = (int8_t)a[k];
+    }
+  }
+  left = p;
+  {                                                    // every lane stores the same five words
+    const uint32_t *s = (const uint32_t *)&p;
+    uint32_t *d = (uint32_t *)(fp.sao + (size_t)row * fp.ctb_cols + col);
+    for (int i = 0; i < 5; i++) __stcg(d + i, s[i]);
+  }
+}
+
 // bases[r] = byte offset of substream r inside `data`, bases[rows] = end.  status[0] receives the
 // first error code (0 = ok), status[1] the largest |mv| component.
 __global__ void __launch_bounds__(32)
@@ -498,6 +549,8 @@ k_parse_rows(FrameParams fp, const uint8_t *__restrict__ data, const uint32_t *_
   Reader r;
   r.p = data + bases[fp.no_wpp ? 0 : row]; r.end = data + bases[fp.no_wpp ? 1 : row + 1]; r.ctx = s_ctx + lane; r.tab = s_tab; r.err = 0;
   ParseCtx pc{fp, cu, levels, lane, 0, s_ctu, s_above, 0, row * kCtb, 0, fp.qp, 0};
+  SaoCtu sao_left;
+  { uint32_t *z = (uint32_t *)&sao_left; for (int i = 0; i < 5; i++) z[i] = 0; }
   if (row == 0 || fp.ctb_cols < 2) {
     init_contexts_d(r.ctx, fp.is_idr ? 0 : 1, fp.qp);
   } else {
@@ -540,6 +593,7 @@ k_parse_rows(FrameParams fp, const uint8_t *__restrict__ data, const uint32_t *_
       pc.cx = cx; pc.cur_buf = col & 1;
       pc.delta_coded = 0;                  // new quantisation group; qp_cur carries over as qPY_PREV
       __syncwarp();
+      if (fp.sao_flags) parse_sao(r, fp, row, col, sao_left);
       for (int z = 0; z < 64 && !r.err;) {
         int x0 = cx + 8 * z_to_x(z), y0 = cy + 8 * z_to_y(z);
         if (x0 >= fp.w || y0 >= fp.h) { z++; continue; }

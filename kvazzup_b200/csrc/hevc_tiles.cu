@@ -44,7 +44,7 @@ struct TiledEncoder {
     width = c.width; height = c.height;
     layout.w = c.width; layout.h = c.height; layout.deblock = c.deblock; layout.qp_delta = 0;
     layout.tile_cols = tiles; layout.wpp = wpp ? 1 : 0;
-    layout.fps_num = c.fps_num; layout.fps_den = c.fps_den;
+    layout.fps_num = c.fps_num; layout.fps_den = c.fps_den; layout.sao = c.sao;
     int prev = 0;
     cudaGetDevice(&prev);
     strips.resize(tiles);
@@ -140,6 +140,28 @@ void *b200_tiled_open(int width, int height, int qp, int intra_period, int searc
   c.deblock = deblock; c.depth = depth; c.debug = 0;
   TiledEncoder *t = new TiledEncoder();
   if (!t->open(c, tile_cols, wpp, devices, n_devices)) { delete t; return nullptr; }
+  return t;
+}
+
+void b200_tiled_params_default(b200_tiled_params *p)
+{
+  if (!p) return;
+  memset(p, 0, sizeof(*p));
+  p->struct_size = (int)sizeof(*p);
+  p->qp = 32; p->intra_period = 64; p->search_range = 8; p->deblock = 1; p->depth = 1; p->tile_cols = 1;
+}
+
+void *b200_tiled_open_params(const b200_tiled_params *up, const int *devices, int n_devices)
+{
+  if (!up || up->struct_size < (int)(11 * sizeof(int))) { b200::set_error("b200_tiled_open_params: bad arguments"); return nullptr; }
+  b200_tiled_params p;
+  b200_tiled_params_default(&p);
+  memcpy(&p, up, std::min<size_t>((size_t)up->struct_size, sizeof(p)));
+  b200::EncoderConfig c;
+  c.width = p.width; c.height = p.height; c.qp = p.qp; c.intra_period = p.intra_period; c.search_range = p.search_range;
+  c.deblock = p.deblock; c.depth = p.depth; c.debug = 0; c.fps_num = p.fps_num; c.fps_den = p.fps_den; c.sao = p.sao;
+  TiledEncoder *t = new TiledEncoder();
+  if (!t->open(c, p.tile_cols, p.wpp, devices, n_devices)) { delete t; return nullptr; }
   return t;
 }
 

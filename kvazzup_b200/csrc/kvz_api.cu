@@ -31,9 +31,11 @@ struct kvz_encoder {
 
 namespace {
 
-struct Preset { const char *name; int me_range; };
-const Preset kPresets[] = {{"ultrafast", 8}, {"superfast", 8}, {"veryfast", 12}, {"faster", 12}, {"fast", 16},
-                           {"medium", 16}, {"slow", 24}, {"slower", 24}, {"veryslow", 32}, {"placebo", 32}};
+// What a preset selects.  Restated from Kvazaar's preset table (cfg.c; not verified against 2.3.1,
+// which is absent from this image): SAO is off in ultrafast and on ("full") from superfast up.
+struct Preset { const char *name; int me_range; int sao; };
+const Preset kPresets[] = {{"ultrafast", 8, 0}, {"superfast", 8, 3}, {"veryfast", 12, 3}, {"faster", 12, 3}, {"fast", 16, 3},
+                           {"medium", 16, 3}, {"slow", 24, 3}, {"slower", 24, 3}, {"veryslow", 32, 3}, {"placebo", 32, 3}};
 
 int parse_int(const char *v, int *out)
 {
@@ -65,7 +67,7 @@ int config_init(kvz_config *cfg)
   cfg->qp = 22;                    // Kvazaar's default; the reference always overrides it (:219)
   cfg->intra_period = 64; cfg->vps_period = 0;
   cfg->wpp = 1; cfg->owf = 0; cfg->threads = 0;
-  cfg->deblock_enable = 1; cfg->sao_type = 0;
+  cfg->deblock_enable = 1; cfg->sao_type = 3;    // preset veryfast
   cfg->tiles_width_count = 1; cfg->tiles_height_count = 1;
   cfg->gop_lowdelay = 1; cfg->gop_len = 4;
   cfg->me_range = 12; cfg->device = -1;
@@ -89,7 +91,7 @@ int config_parse(kvz_config *cfg, const char *name, const char *value)
   if (!strncmp(name, "--", 2)) name += 2;
   if (!strcmp(name, "preset")) {
     for (const Preset &p : kPresets)
-      if (value && !strcmp(value, p.name)) { cfg->me_range = p.me_range; snprintf(cfg->preset, sizeof(cfg->preset), "%s", p.name); return 1; }
+      if (value && !strcmp(value, p.name)) { cfg->me_range = p.me_range; cfg->sao_type = p.sao; snprintf(cfg->preset, sizeof(cfg->preset), "%s", p.name); return 1; }
     return 0;
   }
   if (!strcmp(name, "input-res")) {
@@ -155,7 +157,16 @@ int config_parse(kvz_config *cfg, const char *name, const char *value)
     return 0;
   }
   if (!strcmp(name, "no-deblock")) { cfg->deblock_enable = 0; return 1; }
-  if (!strcmp(name, "sao")) { cfg->sao_type = 0; return value != NULL; }
+  if (!strcmp(name, "sao")) {
+    // Kvazaar: off / edge / band / full.  Edge and band offsets are always decided together here, so
+    // any value but "off" switches both on.
+    if (!value || !*value) { cfg->sao_type = 3; return 1; }
+    if (!strcmp(value, "off") || !strcmp(value, "0")) { cfg->sao_type = 0; return 1; }
+    if (!strcmp(value, "edge")) { cfg->sao_type = 1; return 1; }
+    if (!strcmp(value, "band")) { cfg->sao_type = 2; return 1; }
+    if (!strcmp(value, "full") || !strcmp(value, "1")) { cfg->sao_type = 3; return 1; }
+    return 0;
+  }
   if (!strcmp(name, "no-sao")) { cfg->sao_type = 0; return 1; }
   if (!strcmp(name, "lossless")) { if (!parse_bool(value, &v)) return 0; cfg->lossless = v; return 1; }
   if (!strcmp(name, "hash")) {
@@ -245,14 +256,18 @@ kvz_encoder *encoder_open(const kvz_config *cfg)
   c.deblock = cfg->deblock_enable; c.debug = 0; c.depth = cfg->owf + 1;
   c.qp_delta = (cfg->roi_enable || cfg->set_qp_in_cu) ? 1 : 0;
   c.fps_num = cfg->framerate_num; c.fps_den = cfg->framerate_denom;     // VUI timing: the decoder side reports it
+  c.sao = cfg->sao_type != 0 ? 2 : 0;             // with sao_merge_left / _up flags
   if (cfg->tiles_width_count > 1) {
     // tile columns: independent strip encoders on this GPU; motion is confined to the tile, like
     // Kvazaar's mv-constraint frametilemargin (the reference exposes it, kvazaarfilter.cpp:246-276);
     // constant QP only (no ROI, no rate control)
-    e->tiled = b200_tiled_open(c.width, c.height, c.qp, c.intra_period, c.search_range, c.deblock, c.depth,
-                               cfg->tiles_width_count, cfg->wpp ? 1 : 0, nullptr, 0);
+    b200_tiled_params tp;
+    b200_tiled_params_default(&tp);
+    tp.width = c.width; tp.height = c.height; tp.qp = c.qp; tp.intra_period = c.intra_period; tp.search_range = c.search_range;
+    tp.deblock = c.deblock; tp.depth = c.depth; tp.tile_cols = cfg->tiles_width_count; tp.wpp = cfg->wpp ? 1 : 0;
+    tp.fps_num = c.fps_num; tp.fps_den = c.fps_den; tp.sao = c.sao;
+    e->tiled = b200_tiled_open_params(&tp, nullptr, 0);
     if (!e->tiled) { delete e; return NULL; }
-    b200_tiled_set_fps(e->tiled, c.fps_num, c.fps_den);
     e->tiled_out.resize((size_t)c.width * c.height * 3 + 65536);
     return e;
   }

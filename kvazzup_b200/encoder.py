@@ -72,22 +72,22 @@ class GpuEncoder:
     def pending(self) -> int:
         return int(self.l.b200_enc_pending(self.h_enc))
 
-    KERNELS = ("intra", "me", "recon", "modes", "deblock", "binarise", "arith", "pack")
+    KERNELS = ("intra", "me", "recon", "modes", "deblock", "binarise", "arith", "pack", "sao")
 
     def set_profile(self, on: bool):
         self.l.b200_enc_set_profile(self.h_enc, int(on))
 
     def profile(self) -> dict:
         """{kernel: (total_ms, launches)} measured with CUDA events on the launching streams."""
-        ms = (C.c_double * 8)()
-        cnt = (C.c_ulonglong * 8)()
-        self.l.b200_enc_get_profile(self.h_enc, ms, cnt, 8)
+        ms = (C.c_double * 9)()
+        cnt = (C.c_ulonglong * 9)()
+        self.l.b200_enc_get_profile(self.h_enc, ms, cnt, 9)
         return {k: (ms[i], int(cnt[i])) for i, k in enumerate(self.KERNELS)}
 
     def timeline(self) -> dict:
         """{kernel: (begin_ms, end_ms)} of the last returned picture, since the encoder was opened."""
-        t = (C.c_float * 16)()
-        self.l.b200_enc_get_timeline(self.h_enc, t, 16)
+        t = (C.c_float * 18)()
+        self.l.b200_enc_get_timeline(self.h_enc, t, 18)
         return {k: (t[2 * i], t[2 * i + 1]) for i, k in enumerate(self.KERNELS)}
 
     def _read(self, what, dtype, count):
@@ -132,14 +132,30 @@ class GpuEncoder:
             pass
 
 
+class TiledParams(C.Structure):
+    """b200_tiled_params (include/b200_hevc.h)."""
+    _fields_ = [(n, C.c_int) for n in ("struct_size", "width", "height", "qp", "intra_period", "search_range", "deblock",
+                                       "depth", "tile_cols", "wpp", "fps_num", "fps_den", "sao")]
+
+
 class GpuTiledEncoder:
     """Tile columns as independent strip encoders, optionally one GPU per strip (include/b200_hevc.h)."""
 
-    def __init__(self, w, h, tiles, qp=32, intra_period=64, search_range=8, deblock=1, depth=1, wpp=0, devices=()):
+    def __init__(self, w, h, tiles, qp=32, intra_period=64, search_range=8, deblock=1, depth=1, wpp=0, devices=(), **options):
         self.l = lib()
         self.w, self.h = w, h
         devs = (C.c_int * max(len(devices), 1))(*devices)
-        self.h_enc = self.l.b200_tiled_open(w, h, qp, intra_period, search_range, deblock, depth, tiles, wpp, devs, len(devices))
+        p = TiledParams()
+        self.l.b200_tiled_params_default(C.byref(p))
+        assert p.struct_size == C.sizeof(TiledParams), "TiledParams out of step with include/b200_hevc.h"
+        p.width, p.height, p.qp, p.intra_period, p.search_range = w, h, qp, intra_period, search_range
+        p.deblock, p.depth, p.tile_cols, p.wpp = deblock, depth, tiles, wpp
+        known = {f[0] for f in TiledParams._fields_}
+        for k, val in options.items():
+            if k not in known:
+                raise TypeError(f"unknown tiled encoder option {k!r}")
+            setattr(p, k, int(val))
+        self.h_enc = self.l.b200_tiled_open_params(C.byref(p), devs, len(devices))
         if not self.h_enc:
             raise B200Error("b200_tiled_open failed: " + self.l.b200_last_error().decode())
         self.out = np.empty(w * h * 3 + 65536, np.uint8)

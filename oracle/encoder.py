@@ -87,11 +87,16 @@ class OracleEncoder:
 class OracleTiledEncoder:
     """Tile columns coded as independent strips (oracle/hevc_enc.c: orc_tiled_*)."""
 
-    def __init__(self, w, h, tiles, qp=32, intra_period=64, search_range=8, deblock=1, hash_sei=0, wpp=0):
+    def __init__(self, w, h, tiles, qp=32, intra_period=64, search_range=8, deblock=1, hash_sei=0, wpp=0, **options):
         self.lib = load()
         self.w, self.h = w, h
         cfg = OrcEncCfg(width=w, height=h, qp=qp, intra_period=intra_period, search_range=search_range, deblock=deblock,
                         hash_sei=hash_sei, no_wpp=0 if wpp else 1)
+        known = {f[0] for f in OrcEncCfg._fields_}
+        for k, val in options.items():
+            if k not in known:
+                raise TypeError(f"unknown oracle encoder option {k!r}")
+            setattr(cfg, k, int(val))
         self.h_enc = self.lib.orc_tiled_open(C.byref(cfg), tiles)
         if not self.h_enc:
             raise ValueError("orc_tiled_open rejected the configuration")

@@ -667,7 +667,7 @@ static void sao_decide_group(orc_encoder_t *e, int cx, int cy, int group, struct
     }
   }
   out->type[group] = (uint8_t)best_type;
-  out->eo_class[group] = (uint8_t)best_cls;
+  out->eo_class[group] = (uint8_t)(best_type == 2 ? best_cls : 0);
   for (int c = c_first; c <= c_last; c++) {
     out->band_pos[c] = (uint8_t)best_band[c];
     memcpy(out->offset[c], best_off[c], 4);
@@ -710,12 +710,24 @@ static void sao_frame(orc_encoder_t *e)
   }
 }
 
-/* sao() syntax of one CTU (7.3.8.3); merge candidates are never used */
+/* sao() syntax of one CTU (7.3.8.3).  cfg.sao == 1: merge candidates are never used; cfg.sao == 2: a
+ * CTU whose parameters equal those of the CTU to its left (else of the one above) says so with the
+ * merge flag instead of repeating them (the parameters themselves are decided independently, so this
+ * changes the rate only). */
 static void code_sao(const orc_encoder_t *e, orc_cabac_t *c, int rx, int ry)
 {
   const struct orc_sao *p = &e->sao[ry * e->ctb_cols + rx];
-  if (rx > 0) orc_cabac_bin(c, CTX_SAO_MERGE, 0);                 /* sao_merge_left_flag */
-  if (ry > 0) orc_cabac_bin(c, CTX_SAO_MERGE, 0);                 /* sao_merge_up_flag */
+  const int try_merge = e->cfg.sao == 2;
+  if (rx > 0) {
+    const int m = try_merge && memcmp(p, p - 1, sizeof(*p)) == 0;
+    orc_cabac_bin(c, CTX_SAO_MERGE, m);                           /* sao_merge_left_flag */
+    if (m) return;
+  }
+  if (ry > 0) {
+    const int m = try_merge && memcmp(p, p - e->ctb_cols, sizeof(*p)) == 0;
+    orc_cabac_bin(c, CTX_SAO_MERGE, m);                           /* sao_merge_up_flag */
+    if (m) return;
+  }
   for (int comp = 0; comp < 3; comp++) {
     const int g = comp ? 1 : 0;
     if (comp < 2) {                                               /* sao_type_idx_luma / _chroma: TR cMax 2, first bin coded */

@@ -37,7 +37,8 @@ typedef struct {
   int mv_edges, more_tiles, raw_slice_data;
   int no_wpp;              /* 1 = entropy_coding_sync off: one substream for the whole (strip) picture */
   int subme_satd;          /* 1 = fractional motion refinement by SATD (Kvazaar / HM style) instead of SAD; oracle only */
-  int sao;                 /* 1 = sample adaptive offset (8.7.3) after deblocking; oracle only so far */
+  int sao;                 /* sample adaptive offset (8.7.3) after deblocking: 1 = on, 2 = on and sao_merge_left / _up
+                            * flags are used where a CTU's parameters repeat its neighbour's */
   int tile_cols;           /* > 1: PPS / slice header of a picture with that many uniform tile columns (compositor only) */
   int fps_num, fps_den;    /* both > 0: VUI timing info in the SPS (vui_time_scale / vui_num_units_in_tick); 0 = no VUI */
 } orc_enc_cfg_t;

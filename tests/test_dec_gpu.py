@@ -41,6 +41,14 @@ def decode_all(aus):
     ("camera", 256, 128, 4, 22, {"search_range": 16}),
     ("camera", 64, 8, 3, 37, {}),
     ("camera", 640, 480, 3, 32, {}),
+    ("camera", 192, 136, 4, 32, {"sao": 1}),
+    ("noise", 128, 72, 3, 10, {"sao": 1}),
+    ("screen", 416, 240, 5, 32, {"sao": 1}),
+    ("camera", 200, 200, 7, 30, {"sao": 1, "intra_period": 3}),
+    ("camera", 72, 200, 3, 27, {"sao": 1, "deblock": 0}),
+    ("camera", 640, 480, 3, 22, {"sao": 1, "qp_delta": 1}),
+    ("camera", 416, 240, 6, 37, {"sao": 2, "intra_period": 4}),          # sao_merge_left / _up
+    ("screen", 640, 256, 5, 40, {"sao": 2}),
 ])
 def test_decoder_reproduces_oracle_reconstruction(kind, w, h, n, qp, kw):
     frames = frames_of(kind, w, h, n)

@@ -49,6 +49,19 @@ CASES = [
     ("camera", 256, 128, 4, 22, {"search_range": 16}),
     ("camera", 64, 8, 3, 37, {}),
     ("camera", 640, 480, 3, 32, {}),
+    # sample adaptive offset (hevc_sao.cu): per-CTU statistics, decision and sao() syntax
+    ("camera", 64, 64, 2, 32, {"sao": 1}),
+    ("camera", 192, 136, 4, 32, {"sao": 1}),
+    ("camera", 72, 200, 3, 27, {"sao": 1, "deblock": 0}),
+    ("noise", 128, 72, 3, 10, {"sao": 1}),
+    ("noise", 128, 72, 3, 45, {"sao": 1}),
+    ("camera", 128, 72, 3, 51, {"sao": 1}),
+    ("screen", 416, 240, 5, 32, {"sao": 1}),
+    ("camera", 200, 200, 7, 30, {"sao": 1, "intra_period": 3}),
+    ("camera", 64, 8, 3, 37, {"sao": 1}),
+    ("camera", 640, 480, 3, 22, {"sao": 1}),
+    ("camera", 416, 240, 5, 37, {"sao": 2}),                     # with sao_merge_left / _up flags
+    ("screen", 640, 256, 4, 40, {"sao": 2, "intra_period": 2}),
 ]
 
 
@@ -105,15 +118,17 @@ def test_pipelined_encoder_returns_the_same_access_units_in_order():
         assert got == ref
 
 
-def test_full_hd_two_frames_match_oracle():
-    """BASELINE config 2 size (1080p, partial bottom CTU row): I + P picture, bit-identical stream."""
+@pytest.mark.parametrize("qp,kw", [(27, {}), (22, {"sao": 1}), (32, {"sao": 1, "search_range": 12}), (37, {"sao": 1})])
+def test_full_hd_two_frames_match_oracle(qp, kw):
+    """BASELINE config 2 size (1080p, partial bottom CTU row) at the four QPs of the sweep: I + P picture,
+    bit-identical stream."""
     w, h = 1920, 1080
     frames = frames_of("camera", w, h, 2)
-    g = GpuEncoder(w, h, qp=27, intra_period=0, debug=1)
-    o = OracleEncoder(w, h, qp=27, intra_period=0)
+    g = GpuEncoder(w, h, qp=qp, intra_period=0, debug=1, **kw)
+    o = OracleEncoder(w, h, qp=qp, intra_period=0, **kw)
     for i, f in enumerate(frames):
         ga, oa = g.encode(f), o.encode(f)
-        compare_frame(f"1080p frame {i}", g, o, w, h)
+        compare_frame(f"1080p qp {qp} frame {i}", g, o, w, h)
         assert ga == oa
 
 
@@ -393,6 +408,8 @@ TILE_CASES = [
     ("camera", 416, 240, 5, 30, 2, 1, {}),                       # tiles + WPP substreams (oracle only, see hevc_tiles.cu)
     ("camera", 1920, 1080, 3, 32, 4, 0, {"search_range": 12}),
     ("camera", 1920, 1080, 3, 32, 4, 1, {"search_range": 12}),
+    ("camera", 416, 240, 5, 30, 2, 0, {"sao": 1}),               # SAO stays inside each tile
+    ("screen", 640, 200, 4, 35, 3, 1, {"sao": 1}),
 ]
 
 

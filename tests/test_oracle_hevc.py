@@ -145,14 +145,17 @@ def test_tile_columns_as_independent_strips_decode_bit_exactly_in_ffmpeg(kind, w
     ("screen", 416, 240, 5, 40, {}),                                    # sharp edges: edge offsets
     ("camera", 200, 72, 3, 45, {"deblock": 0}),                         # SAO without deblocking, partial CTUs
     ("camera", 1280, 720, 2, 35, {"hash_sei": 1, "search_range": 12}),
+    ("camera", 416, 240, 6, 37, {"sao": 2, "hash_sei": 1, "intra_period": 4}),    # sao_merge_left / _up flags in use
+    ("screen", 640, 256, 5, 40, {"sao": 2}),
+    ("noise", 256, 136, 3, 51, {"sao": 2, "hash_sei": 1}),
 ])
 def test_sao_streams_decode_bit_exactly_in_ffmpeg(kind, w, h, n, qp, kw):
-    """Sample adaptive offset (oracle only so far): per-CTU edge / band offsets after deblocking.  The
+    """Sample adaptive offset: per-CTU edge / band offsets after deblocking.  The
     syntax (slice flags, sao() per CTU), the categories at picture and CTU borders and the clipping
     are normative -- FFmpeg must reproduce the oracle's picture -- and it must actually help."""
     frames = frames_of(kind, w, h, n)
-    enc = OracleEncoder(w, h, qp=qp, sao=1, **({"intra_period": 0} | kw))
-    plain = OracleEncoder(w, h, qp=qp, **({"intra_period": 0} | {k: v for k, v in kw.items() if k != "hash_sei"}))
+    enc = OracleEncoder(w, h, qp=qp, **({"intra_period": 0, "sao": 1} | kw))
+    plain = OracleEncoder(w, h, qp=qp, **({"intra_period": 0} | {k: v for k, v in kw.items() if k not in ("hash_sei", "sao")}))
     aus, recs, gain = [], [], 0.0
     for f in frames:
         aus.append(enc.encode(f))
@@ -166,6 +169,10 @@ def test_sao_streams_decode_bit_exactly_in_ffmpeg(kind, w, h, n, qp, kw):
         bad = np.flatnonzero(fr != recs[i])
         assert bad.size == 0, f"frame {i}: {bad.size} samples differ, first at {bad[:6]}"
     assert gain / n > -0.05                                              # never worse than without (it may choose "off")
+    if kw.get("sao") == 2:                                               # merging changes the rate only, never the picture
+        nomerge = OracleEncoder(w, h, qp=qp, **({"intra_period": 0} | kw | {"sao": 1}))
+        sizes = [len(nomerge.encode(f)) for f in frames]
+        assert np.array_equal(nomerge.recon(), recs[-1]) and sum(len(a) for a in aus) <= sum(sizes)
 
 
 @needs_ff
