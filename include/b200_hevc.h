@@ -36,7 +36,12 @@ typedef struct b200_enc_params {
   int width, height, qp, intra_period, search_range, deblock, debug, depth;
   int qp_delta;                  /* cu_qp_delta_enabled_flag (what b200_enc_open_roi sets) */
   int fps_num, fps_den;          /* both > 0: VUI timing info in the SPS */
-  int sao;                       /* sample adaptive offset (edge / band offsets per CTU) after deblocking */
+  int sao;                       /* sample adaptive offset (edge / band offsets per CTU) after deblocking;
+                                    2 = also use sao_merge_left / _up where parameters repeat */
+  int intra_in_p;                /* 16x16 intra CUs in P pictures where inter prediction is poor */
+  int me_coarse;                 /* two-level motion search: range of the coarse level in 4x4-mean samples (multiple
+                                    of 4, <= 32; 16 = +-64 luma samples); search_range (<= 16) is then the window
+                                    searched around the zero vector and around each 32x32 block's coarse vector */
 } b200_enc_params;
 void  b200_enc_params_default(b200_enc_params *p);
 void *b200_enc_open_params(const b200_enc_params *p);
@@ -82,6 +87,8 @@ typedef struct b200_tiled_params {
   int width, height, qp, intra_period, search_range, deblock, depth, tile_cols, wpp;
   int fps_num, fps_den;          /* both > 0: VUI timing info in the SPS */
   int sao;                       /* SAO inside every tile (never across tile edges) */
+  int intra_in_p;                /* intra CUs in P pictures */
+  int me_coarse;                 /* two-level motion search (see b200_enc_params) */
 } b200_tiled_params;
 void  b200_tiled_params_default(b200_tiled_params *p);
 void *b200_tiled_open_params(const b200_tiled_params *p, const int *devices, int n_devices);

@@ -417,12 +417,15 @@ __device__ __forceinline__ int put_cu_header(Syn &s, const CuView &v, const CuIn
   const FrameParams &fp = *v.fp;
   const int n = 1 << log2;
   bool tu = false;
+  const bool intra = cu.pred_mode == 1;
   if (!fp.is_idr) {
     int ctx = 0;
     if (x0 > 0) ctx += cu_at(v, x0 - 1, y0).skip;
     if (y0 > 0) ctx += cu_at(v, x0, y0 - 1).skip;
     put_ctx(s, CTX_SKIP + ctx, cu.skip);
-    if (cu.merge_idx != 0xff) {
+    if (intra) {
+      put_ctx(s, CTX_PRED_MODE, 1);                 // intra CU in a P slice
+    } else if (cu.merge_idx != 0xff) {
       int midx = cu.merge_idx;
       if (!cu.skip) {
         put_ctx(s, CTX_PRED_MODE, 0);
@@ -453,12 +456,14 @@ __device__ __forceinline__ int put_cu_header(Syn &s, const CuView &v, const CuIn
       put_ctx(s, CTX_RQT_ROOT_CBF, cu.cbf != 0);
       tu = cu.cbf != 0;
     }
-  } else {
+  }
+  if (intra) {
     if (log2 == 3) put_ctx(s, CTX_PART_MODE, 1);
+    // candidate modes (8.4.2): a neighbour that is not intra-coded, or lies in the CTB row above, counts as DC
     int cand[3];
     int a = 1, b = 1;
-    if (x0 > 0) a = cu_at(v, x0 - 1, y0).intra_mode;
-    if (y0 > 0 && (y0 & (kCtb - 1))) b = cu_at(v, x0, y0 - 1).intra_mode;
+    if (x0 > 0) { const CuInfo &l = cu_at(v, x0 - 1, y0); if (l.pred_mode == 1) a = l.intra_mode; }
+    if (y0 > 0 && (y0 & (kCtb - 1))) { const CuInfo &u = cu_at(v, x0, y0 - 1); if (u.pred_mode == 1) b = u.intra_mode; }
     if (a == b) {
       if (a < 2) { cand[0] = 0; cand[1] = 1; cand[2] = 26; }
       else { cand[0] = a; cand[1] = 2 + ((a + 29) % 32); cand[2] = 2 + ((a - 2 + 1) % 32); }

@@ -83,6 +83,20 @@ struct FrameParams {
   // bit 1 slice_sao_chroma_flag, bit 2 (encoder) use the merge flags where parameters repeat.
   SaoCtu *sao;
   int sao_flags;
+  // Intra CUs in P pictures.  intra_in_p (encoder): the motion search also tries 16x16 intra CUs.
+  // any_intra: set to 1 by whoever finds an intra CU in a P picture (motion search / parser), so that
+  // the intra pass over a P picture without any returns at once; ctu_done: one flag per CTU for the
+  // intra pass's wavefront (hevc_intra.cu).
+  int intra_in_p;
+  int *any_intra;
+  int *ctu_done;
+  // Two-level motion search (encoder): me_coarse > 0 = range of the coarse level in coarse samples (a
+  // multiple of 4); src_q / ref_q = quarter-resolution luma of the source and of the reference.
+  // mc_range: largest |mv| component in full samples that motion compensation must reach
+  // (encoder: 4 * me_coarse + search_range; decoder: from the parsed vectors).
+  int me_coarse;
+  const uint8_t *src_q, *ref_q;
+  int mc_range;
 };
 
 }  // namespace b200

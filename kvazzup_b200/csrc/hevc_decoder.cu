@@ -58,6 +58,7 @@ struct StripBufs {
   cudaEvent_t ev_parsed = nullptr;
   uint8_t *d_small = nullptr, *d_ctu_qp = nullptr;
   SaoCtu *d_sao = nullptr;                // per-CTU SAO parameters from the parser
+  int *d_ctu_done = nullptr;              // intra wavefront: one flag per CTU, then "the P picture has intra CUs"
   CuInfo *d_cu = nullptr;
   int16_t *d_levels = nullptr;
   uint32_t *h_bases = nullptr;
@@ -122,6 +123,7 @@ struct Decoder {
         if (t.d_small) cudaFree(t.d_small);
         if (t.d_ctu_qp) cudaFree(t.d_ctu_qp);
         if (t.d_sao) cudaFree(t.d_sao);
+        if (t.d_ctu_done) cudaFree(t.d_ctu_done);
         if (t.d_cu) cudaFree(t.d_cu);
         if (t.d_levels) cudaFree(t.d_levels);
         if (t.h_bases) cudaFreeHost(t.h_bases);
@@ -195,6 +197,7 @@ struct Decoder {
         if (!cuda_ok(cudaMalloc((void **)&t.d_small, small_bytes), "cudaMalloc")) return false;
         if (!cuda_ok(cudaMalloc((void **)&t.d_ctu_qp, (size_t)g.fp.ctb_cols * rows), "cudaMalloc")) return false;
         if (!cuda_ok(cudaMalloc((void **)&t.d_sao, sizeof(SaoCtu) * g.fp.ctb_cols * rows), "cudaMalloc")) return false;
+        if (!cuda_ok(cudaMalloc((void **)&t.d_ctu_done, sizeof(int) * (g.fp.ctb_cols * rows + 1)), "cudaMalloc")) return false;
         if (!cuda_ok(cudaMalloc((void **)&t.d_cu, sizeof(CuInfo) * g.fp.w8 * g.fp.h8), "cudaMalloc")) return false;
         if (!cuda_ok(cudaMalloc((void **)&t.d_levels, g.bytes * sizeof(int16_t)), "cudaMalloc")) return false;
         if (!cuda_ok(cudaMallocHost((void **)&t.h_bases, sizeof(uint32_t) * (rows + 1)), "cudaMallocHost")) return false;
@@ -379,6 +382,8 @@ struct Decoder {
       t.fp.ctu_qp = pps.qp_delta ? t.d_ctu_qp : nullptr; t.fp.ctu_delta = nullptr; t.fp.ctu_first = nullptr;
       t.fp.sao_flags = (sh.sao_luma ? 1 : 0) | (sh.sao_chroma ? 2 : 0);
       t.fp.sao = t.fp.sao_flags ? t.d_sao : nullptr;
+      t.fp.ctu_done = t.d_ctu_done; t.fp.any_intra = t.d_ctu_done + g.fp.ctb_cols * rows; t.fp.intra_in_p = 0;
+      DEC_CHECK(cudaMemsetAsync(t.fp.any_intra, 0, sizeof(int), t.stream), "memset any_intra");
       int *sync_flag = (int *)(t.d_small + off_flag), *progress = (int *)(t.d_small + off_prog);
       int *status = (int *)(t.d_small + off_status);
       uint32_t *d_bases = (uint32_t *)(t.d_small + off_bases);
@@ -408,9 +413,9 @@ struct Decoder {
       StripBufs &t = sl.strips[i];
       if (!cuda_ok(cudaEventSynchronize(t.ev_parsed), "sync parse")) { have_ref = 0; return -1; }
       if (t.h_status[0] != 0) {
-        static const char *const why[] = {"", "escape code too long", "intra CU in a P slice", "partition other than 2Nx2N", "mvd too long",
+        static const char *const why[] = {"", "escape code too long", "(unused)", "partition other than 2Nx2N", "mvd too long",
           "NxN intra partition", "intra chroma mode other than derived", "64x64 CU with residual", "end_of_slice_segment_flag mismatch",
-          "end_of_subset_one_bit missing", "intra CU size other than 16x16 (8x8 at the picture edge)", "cu_qp_delta out of range",
+          "end_of_subset_one_bit missing", "intra CU larger than 16x16", "cu_qp_delta out of range",
           "motion vector reaches across a tile boundary"};
         int c = t.h_status[0];
         set_error("decoder: unsupported or corrupt slice data (%s)", c > 0 && c <= 12 ? why[c] : "unknown");
@@ -426,19 +431,22 @@ struct Decoder {
       StripBufs &t = sl.strips[i];
       StripGeom &g = geom[i];
       FrameParams &f = t.fp;
-      int *progress = (int *)(t.d_small + off_prog), *ticket = (int *)(t.d_small + off_ticket);
+      int *ticket = (int *)(t.d_small + off_ticket);
       // with SAO the picture is reconstructed and deblocked in g.d_dbk; SAO writes the output picture
       uint8_t *const out_rec = g.d_rec[cur], *ref = g.d_rec[cur ^ 1];
       uint8_t *rec = f.sao_flags ? g.d_dbk : out_rec;
       if (f.is_idr) {
-        DEC_CHECK(launch_intra_decode(f, rec, t.d_levels, t.d_cu, progress, ticket, g.d_order, g.stream), "intra decode launch");
+        DEC_CHECK(launch_intra_decode(f, rec, t.d_levels, t.d_cu, ticket, g.d_order, g.stream), "intra decode launch");
         count_launch(1);
       } else {
-        f.search_range = std::max(1, (t.h_status[1] + 3) / 4 + 1);
+        f.mc_range = std::max(1, (t.h_status[1] + 3) / 4 + 1);
         cudaError_t e = launch_inter_decode(f, ref, rec, t.d_levels, t.d_cu, g.stream);
-        if (e == cudaErrorInvalidValue) { set_error("decoder: motion vectors of +-%d samples exceed the supported window", f.search_range); return -1; }
+        if (e == cudaErrorInvalidValue) { set_error("decoder: motion vectors of +-%d samples exceed the supported window", f.mc_range); return -1; }
         DEC_CHECK(e, "inter decode launch");
-        count_launch(1);
+        // intra CUs of the P picture predict from the reconstructed inter CUs (the kernel returns at
+        // once when the parser met none)
+        DEC_CHECK(launch_intra_decode(f, rec, t.d_levels, t.d_cu, ticket, g.d_order, g.stream), "intra decode launch");
+        count_launch(2);
       }
       if (f.deblock) {
         DEC_CHECK(launch_deblock(f, rec, t.d_cu, g.stream), "deblock launch");

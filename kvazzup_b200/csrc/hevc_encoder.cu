@@ -114,6 +114,7 @@ void Encoder::release()
     if (s.d_recs) cudaFree(s.d_recs);
     if (s.d_small) cudaFree(s.d_small);
     if (s.d_qpinfo) cudaFree(s.d_qpinfo);
+    if (s.d_ctu_done) cudaFree(s.d_ctu_done);
     if (s.d_dbk) cudaFree(s.d_dbk);
     if (s.d_sao) cudaFree(s.d_sao);
     if (s.h_ctu_qp) cudaFreeHost(s.h_ctu_qp);
@@ -139,6 +140,9 @@ void Encoder::release()
   upload_stream = nullptr; ev_upload = nullptr;
   ev_intra = nullptr; intra_stream = nullptr;
   if (d_rec_pre) cudaFree(d_rec_pre);
+  if (d_src_q) cudaFree(d_src_q);
+  if (d_ref_q) cudaFree(d_ref_q);
+  d_src_q = d_ref_q = nullptr;
   if (ev_base) cudaEventDestroy(ev_base);
   if (stream) cudaStreamDestroy(stream);
   d_rec_pre = nullptr; stream = nullptr; ev_base = nullptr;
@@ -149,6 +153,7 @@ bool Encoder::open(const EncoderConfig &c)
   if (c.width <= 0 || c.height <= 0 || (c.width & 7) || (c.height & 7)) { set_error("encoder: width/height must be positive multiples of 8 (got %dx%d)", c.width, c.height); return false; }
   if (c.qp < 0 || c.qp > 51) { set_error("encoder: qp %d out of range 0..51", c.qp); return false; }
   if (c.search_range < 1 || c.search_range > 32) { set_error("encoder: search range %d out of range 1..32", c.search_range); return false; }
+  if (c.me_coarse < 0 || c.me_coarse > 32 || (c.me_coarse & 3) || (c.me_coarse > 0 && c.search_range > 16)) { set_error("encoder: me_coarse %d must be a multiple of 4 in 0..32 (and search_range <= 16 with it)", c.me_coarse); return false; }
   if (c.depth < 1 || c.depth > 128) { set_error("encoder: depth %d out of range 1..128", c.depth); return false; }
   if (b200_device_count() <= 0) { set_error("no CUDA device: the B200 encoder has no CPU fallback"); return false; }
   cfg = c;
@@ -185,6 +190,10 @@ bool Encoder::open(const EncoderConfig &c)
     ENC_CHECK(cudaEventCreateWithFlags(&ev_ring[i], cudaEventDisableTiming), "cudaEventCreate");
   }
   if (c.debug) ENC_CHECK(cudaMalloc((void **)&d_rec_pre, frame_bytes), "cudaMalloc rec_pre");
+  if (c.me_coarse > 0) {
+    ENC_CHECK(cudaMalloc((void **)&d_src_q, (size_t)(fp.w / 4) * (fp.h / 4)), "cudaMalloc src_q");
+    ENC_CHECK(cudaMalloc((void **)&d_ref_q, (size_t)(fp.w / 4) * (fp.h / 4)), "cudaMalloc ref_q");
+  }
   // small state: row_len[rows] | sync_flag[rows] | progress[rows] | ticket | bins(8) | sync_ctx[rows*CTX_COUNT]
   off_flag = sizeof(int) * fp.ctb_rows; off_prog = 2 * off_flag; off_ticket = 3 * off_flag;
   off_bins = (off_ticket + sizeof(int) + 7) & ~(size_t)7; off_ctx = off_bins + 8;
@@ -202,6 +211,7 @@ bool Encoder::open(const EncoderConfig &c)
       ENC_CHECK(cudaMallocHost((void **)&s.h_ctu_qp, (size_t)fp.ctb_cols * fp.ctb_rows), "cudaMallocHost ctu qp");
     }
     ENC_CHECK(cudaMemset(s.d_small, 0, small_bytes), "memset small");
+    ENC_CHECK(cudaMalloc((void **)&s.d_ctu_done, sizeof(int) * (fp.ctb_cols * fp.ctb_rows + 1)), "cudaMalloc ctu done");
     if (c.sao) {
       ENC_CHECK(cudaMalloc((void **)&s.d_dbk, frame_bytes), "cudaMalloc dbk");
       ENC_CHECK(cudaMalloc((void **)&s.d_sao, sizeof(SaoCtu) * fp.ctb_cols * fp.ctb_rows), "cudaMalloc sao");
@@ -358,6 +368,8 @@ bool Encoder::submit(FrameSlot &s, const uint8_t *d_i420)
   // with SAO the prediction chain reconstructs and deblocks into the slot's own picture; SAO reads it
   // (a CTU needs its neighbours' DEBLOCKED samples) and writes the reconstruction ring
   uint8_t *rec = cfg.sao ? s.d_dbk : out_rec;
+  p.ctu_done = s.d_ctu_done; p.any_intra = s.d_ctu_done + fp.ctb_cols * fp.ctb_rows; p.intra_in_p = cfg.intra_in_p;
+  p.me_coarse = cfg.me_coarse; p.src_q = d_src_q; p.ref_q = d_ref_q; p.mc_range = 4 * cfg.me_coarse + cfg.search_range;
   p.sao = cfg.sao ? s.d_sao : nullptr; p.sao_flags = cfg.sao ? (cfg.sao == 2 ? 7 : 3) : 0;
   p.ctu_qp = nullptr; p.ctu_delta = nullptr; p.ctu_first = nullptr;
   p.mv_edges = cfg.mv_edges; p.more_tiles = cfg.more_tiles; p.no_wpp = cfg.no_wpp;
@@ -369,7 +381,7 @@ bool Encoder::submit(FrameSlot &s, const uint8_t *d_i420)
     ENC_CHECK(cudaMemcpyAsync(s.d_qpinfo, s.h_ctu_qp, ctus, cudaMemcpyHostToDevice, (idr && cfg.overlap_idr) ? intra_stream : stream), "H2D ctu qp");
   }
   uint32_t *row_len = (uint32_t *)s.d_small;
-  int *sync_flag = (int *)(s.d_small + off_flag), *progress = (int *)(s.d_small + off_prog), *ticket = (int *)(s.d_small + off_ticket);
+  int *sync_flag = (int *)(s.d_small + off_flag), *ticket = (int *)(s.d_small + off_ticket);
   unsigned long long *bins = (unsigned long long *)(s.d_small + off_bins);
   s.prof_mask = 0;
 #define PROF_BEGIN(id, st) do { if (profile) { ENC_CHECK(cudaEventRecord(s.pev[2 * (id)], st), "prof event"); s.prof_mask |= 1u << (id); } } while (0)
@@ -383,7 +395,7 @@ bool Encoder::submit(FrameSlot &s, const uint8_t *d_i420)
     if (cfg.overlap_idr && frame_idx >= kRecRing - 1) ENC_CHECK(cudaStreamWaitEvent(is, ev_ring[(frame_idx + 1) % kRecRing], 0), "stream wait");
     // (no memset of the level planes: both reconstruction kernels write every level of the picture)
     PROF_BEGIN(K_INTRA, is);
-    ENC_CHECK(launch_intra_frame(p, d_i420, rec, s.d_levels, s.d_cu, progress, ticket, d_order, is), "intra launch");
+    ENC_CHECK(launch_intra_frame(p, d_i420, rec, s.d_levels, s.d_cu, ticket, d_order, is), "intra launch");
     PROF_END(K_INTRA, is);
     if (cfg.overlap_idr) {
       ENC_CHECK(cudaEventRecord(ev_intra, is), "event record");
@@ -392,11 +404,17 @@ bool Encoder::submit(FrameSlot &s, const uint8_t *d_i420)
     count_launch(2);
   } else {
     // prediction chain, main stream, picture order
+    if (cfg.intra_in_p) ENC_CHECK(cudaMemsetAsync(p.any_intra, 0, sizeof(int), stream), "memset any_intra");
     PROF_BEGIN(K_ME, stream);
+    if (cfg.me_coarse > 0) { ENC_CHECK(launch_down4(d_i420, fp.w, fp.h, d_src_q, stream), "down4 launch"); count_launch(1); }
     ENC_CHECK(launch_inter_me(p, d_i420, ref, s.d_cu, stream), "me launch");
     PROF_END(K_ME, stream);
     PROF_BEGIN(K_RECON, stream);
     ENC_CHECK(launch_inter_recon(p, d_i420, ref, rec, s.d_levels, s.d_cu, stream), "recon launch");
+    if (cfg.intra_in_p) {                // the intra CUs the search chose predict from the reconstructed inter CUs
+      ENC_CHECK(launch_intra_in_p(p, d_i420, rec, s.d_levels, s.d_cu, ticket, d_order, stream), "intra-in-P launch");
+      count_launch(1);
+    }
     PROF_END(K_RECON, stream);
     PROF_BEGIN(K_MODES, stream);
     ENC_CHECK(launch_inter_modes(p, s.d_cu, stream), "modes launch");
@@ -421,6 +439,8 @@ bool Encoder::submit(FrameSlot &s, const uint8_t *d_i420)
     PROF_END(K_SAO, stream);
     count_launch(1);
   }
+  // the finished picture at quarter resolution: the coarse search level of the next picture reads it
+  if (cfg.me_coarse > 0) { ENC_CHECK(launch_down4(out_rec, fp.w, fp.h, d_ref_q, stream), "down4 launch"); count_launch(1); }
   // Entropy coding (slot stream) needs only the cu map and the levels, but it is released after
   // the deblocking: started before it, the binariser's 16k CTAs share the SMs with the two short
   // deblocking kernels and stretch them from 15 us to 75 us on the critical prediction chain.
@@ -601,7 +621,7 @@ void *b200_enc_open_params(const b200_enc_params *up)
   EncoderConfig c;
   c.width = p.width; c.height = p.height; c.qp = p.qp; c.intra_period = p.intra_period; c.search_range = p.search_range;
   c.deblock = p.deblock; c.debug = p.debug; c.depth = p.depth; c.qp_delta = p.qp_delta;
-  c.fps_num = p.fps_num; c.fps_den = p.fps_den; c.sao = p.sao;
+  c.fps_num = p.fps_num; c.fps_den = p.fps_den; c.sao = p.sao; c.intra_in_p = p.intra_in_p; c.me_coarse = p.me_coarse;
   if (!e->open(c)) { delete e; return nullptr; }
   return e;
 }

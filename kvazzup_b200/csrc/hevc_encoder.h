@@ -27,7 +27,10 @@ struct EncoderConfig {
   int mv_edges = 0, more_tiles = 0, no_wpp = 0, raw = 0;
   int fps_num = 0, fps_den = 0;   // both > 0: VUI timing info in the SPS (the reference's DisplayFilter divides by
                              // the frame rate the decoder reports, displayfilter.cpp:153)
-  int sao = 0;               // sample adaptive offset after deblocking (hevc_sao.cu)
+  int sao = 0;               // sample adaptive offset after deblocking (hevc_sao.cu); 2 = with merge flags
+  int intra_in_p = 0;        // 16x16 intra CUs in P pictures where inter prediction is poor
+  int me_coarse = 0;         // two-level motion search: range of the coarse level in coarse (4x4-mean) samples,
+                             // a multiple of 4; search_range (<= 16) is then the window around each centre
   int depth = 1;             // pictures in flight (Kvazaar's owf + 1): output of picture n is
                              // returned by the call that submits picture n + depth - 1
 };
@@ -43,6 +46,7 @@ struct FrameSlot {
   uint8_t *d_qpinfo = nullptr;     // qp_delta: ctu_qp | ctu_delta | ctu_first, one byte per CTU each
   uint8_t *h_ctu_qp = nullptr;     // pinned staging of ctu_qp
   uint8_t *d_small = nullptr;      // row_len | sync flags | progress | ticket | bins | sync contexts
+  int *d_ctu_done = nullptr;       // intra wavefront: one flag per CTU, then the picture's "any intra CU" flag
   uint8_t *d_dbk = nullptr;        // sao: the deblocked picture (SAO reads it and writes the reconstruction ring)
   SaoCtu *d_sao = nullptr;         // sao: per-CTU parameters (k_sao_ctu -> k_binarise)
   uint8_t *d_src = nullptr;        // device copy of a host-supplied picture
@@ -113,6 +117,7 @@ class Encoder {
   // its own stream concurrently with the P pictures queued before it.
   static constexpr int kRecRing = 32;
   uint8_t *d_rec[kRecRing] = {}, *d_rec_pre = nullptr;
+  uint8_t *d_src_q = nullptr, *d_ref_q = nullptr;   // me_coarse: quarter-resolution source / previous reconstruction (main stream order)
   cudaEvent_t ev_ring[kRecRing] = {};    // "picture n finished reading its reference" (main stream)
   cudaStream_t intra_stream = nullptr, upload_stream = nullptr;
   cudaEvent_t ev_upload = nullptr;

@@ -12,7 +12,9 @@
 //   k_inter_modes   one thread per 8x8 unit: merge candidates, skip decision, AMVP predictor
 //                   choice from the final motion field (row K10) -- keeps the entropy coder
 //                   free of any decision logic.
-#include "hevc_device.cuh"
+#include <algorithm>
+
+#include "hevc_intra.cuh"
 #include "hevc_kernels.h"
 
 namespace b200 {
@@ -33,22 +35,65 @@ struct MeShared {
   unsigned best[64];               // per origin unit: best cost so far
   unsigned acc8[64][8];            // per origin unit: SAD accumulators of the eight candidates of a step
   unsigned short pen[65 * 65];     // mv penalty of every full-sample candidate (index = (dy+R)*side + dx+R)
+  // intra candidates of a P picture (fp.intra_in_p): per 16x16 block (z-order) "try it" / chosen mode
+  // (-1 = stays inter); per 8x8 unit: intra mode + 1 of the intra CU covering it (0 = inter)
+  uint8_t try_intra[16];
+  int8_t intra_mode16[16];
+  uint8_t intra_unit[64];
+  // two-level search (fp.me_coarse): best key and resulting centre (full samples) of the coarse level
+  // per 32x32 quadrant; per origin unit, the set whose window the CU's vector came from
+  unsigned ckey[4];
+  short ctr_x[4], ctr_y[4];
+  uint8_t wset[64];
 };
 
+// Intra CUs in P pictures: a 16x16 block whose best inter cost exceeds kIntraTryCost gets the 35-mode
+// source-based intra search; intra wins when 1.5 x its cost (prediction from reconstructed neighbours
+// is worse than from the source ones the search uses) plus kIntraOverheadBits of signalling is smaller.
+constexpr unsigned kIntraTryCost = 1024;
+constexpr int kIntraOverheadBits = 24;
+
+// quarter-resolution picture for the coarse level of the motion search: every sample the rounded mean
+// of a 4x4 block of the luma plane.  One thread per coarse sample.
+__global__ void __launch_bounds__(256)
+k_down4(const uint8_t *__restrict__ plane, int w, int h, uint8_t *__restrict__ out)
+{
+  const int wq = w >> 2, hq = h >> 2;
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= wq * hq) return;
+  const int y = i / wq, x = i - y * wq;
+  unsigned s = 8;
+#pragma unroll
+  for (int j = 0; j < 4; j++) {
+    const unsigned v = __ldg((const uint32_t *)(plane + (size_t)(4 * y + j) * w + 4 * x));
+    s += (v & 0xff) + ((v >> 8) & 0xff) + ((v >> 16) & 0xff) + (v >> 24);
+  }
+  out[i] = (uint8_t)(s >> 4);
+}
+
+// Search centres of the full-sample level.  Set 0: the zero vector, searched on the CTU-wide window.
+// Set 1 (fp.me_coarse > 0): per 32x32 quadrant, the vector the coarse level found on the
+// quarter-resolution pictures (+-me_coarse coarse samples = 4 * me_coarse luma samples), searched on
+// a window of the quadrant's own; skipped where it is the zero vector again.  Around every centre
+// the same +-R window is searched and the mv penalty counts from the centre.
 __global__ void __launch_bounds__(kThreads)
 k_me_ctu(FrameParams fp, const uint8_t *__restrict__ src, const uint8_t *__restrict__ ref, CuInfo *__restrict__ cu)
 {
   extern __shared__ uint32_t s_dyn[];
   __shared__ MeShared sh;
+  __shared__ ModeShared shm;
   const int R = fp.search_range;
   const int M = window_margin(R);
   const int WS = kCtb + 2 * M, WSW = (WS >> 2) + 1;
+  const int WSq = 32 + 2 * M, WSWq = (WSq >> 2) + 1;          // quadrant windows (set 1)
   uint32_t *s_ref = s_dyn;                     // WS rows x WSW words
   uint32_t *s_src = s_dyn + WS * WSW;          // 64 rows x 16 words
+  uint32_t *s_qwin = s_src + 64 * 16;          // 4 x (WSq rows x WSWq words), only with me_coarse
   const int ctb_x = blockIdx.x % fp.ctb_cols, ctb_y = blockIdx.x / fp.ctb_cols;
   const int cx = ctb_x * kCtb, cy = ctb_y * kCtb;
   const int t = threadIdx.x;
   const int lambda_q4 = lambda_q4_at(fp, cx, cy);
+  const int side = 2 * R + 1;
 
   load_window(ref, fp.w, fp.h, cx - M, cy - M, WS, WSW, s_ref);
   for (int i = t; i < 64 * 16; i += kThreads) {
@@ -56,13 +101,89 @@ k_me_ctu(FrameParams fp, const uint8_t *__restrict__ src, const uint8_t *__restr
     s_src[i] = (y < fp.h && x < fp.w) ? __ldg((const uint32_t *)(src + (size_t)y * fp.w + x)) : 0u;
   }
   if (t < 64) { sh.key8[t] = 0xffffffffu; for (int k = 0; k < 8; k++) sh.acc8[t][k] = 0; }
-  for (int c = t; c < (2 * R + 1) * (2 * R + 1); c += kThreads) {
-    int dy = c / (2 * R + 1) - R, dx = c - (dy + R) * (2 * R + 1) - R;
+  for (int c = t; c < side * side; c += kThreads) {
+    int dy = c / side - R, dx = c - (dy + R) * side - R;
     sh.pen[c] = (unsigned short)mv_penalty(lambda_q4, dx * 4, dy * 4);
   }
   if (t < 16) sh.key16[t] = 0xffffffffu;
-  if (t < 4) sh.key32[t] = 0xffffffffu;
+  if (t < 4) { sh.key32[t] = 0xffffffffu; sh.ckey[t] = 0xffffffffu; sh.ctr_x[t] = 0; sh.ctr_y[t] = 0; }
   __syncthreads();
+
+  // ---- coarse level: one displacement per 32x32 quadrant (8x8 coarse samples, cut at the picture edge) ----
+  if (fp.me_coarse > 0) {
+    const int Rc = fp.me_coarse, wq = fp.w >> 2, hq = fp.h >> 2;
+    const int CW = 16 + 2 * Rc, CWW = (CW >> 2) + 1;           // coarse reference window, Rc is a multiple of 4
+    uint32_t *s_cref = s_qwin;                                 // the quadrant windows are loaded afterwards
+    uint32_t *s_csrc = s_cref + CW * CWW;                      // 16 rows x 4 words
+    // (byte loads: the quarter-resolution plane's row pitch is a multiple of 2 only)
+    for (int i = t; i < CW * CWW; i += kThreads) {
+      const int wy = i / CWW, wi = i - wy * CWW;
+      const uint8_t *rowp = fp.ref_q + (size_t)clip3(0, hq - 1, (cy >> 2) - Rc + wy) * wq;
+      const int x = (cx >> 2) - Rc + 4 * wi;
+      s_cref[i] = (uint32_t)__ldg(rowp + clip3(0, wq - 1, x)) | ((uint32_t)__ldg(rowp + clip3(0, wq - 1, x + 1)) << 8) |
+                  ((uint32_t)__ldg(rowp + clip3(0, wq - 1, x + 2)) << 16) | ((uint32_t)__ldg(rowp + clip3(0, wq - 1, x + 3)) << 24);
+    }
+    if (t < 64) {
+      const int y = (cy >> 2) + (t >> 2), x = (cx >> 2) + 4 * (t & 3);
+      // widths are multiples of 8, so a coarse row is a whole number of 2-sample pairs: assemble bytes
+      uint32_t v = 0;
+      for (int j = 0; j < 4; j++)
+        if (y < hq && x + j < wq) v |= (uint32_t)__ldg(fp.src_q + (size_t)y * wq + x + j) << (8 * j);
+      s_csrc[t] = v;
+    }
+    __syncthreads();
+    const int cside = 2 * Rc + 1;
+    // per quadrant: extent inside the picture, as byte masks of its two words and a row count
+    unsigned m0[4], m1[4];
+    int rows[4];
+    for (int q = 0; q < 4; q++) {
+      const int bw = min(8, wq - ((cx >> 2) + 8 * (q & 1))), bh = min(8, hq - ((cy >> 2) + 8 * (q >> 1)));
+      rows[q] = max(bh, 0);
+      m0[q] = bw >= 4 ? 0xffffffffu : (bw > 0 ? (1u << (8 * bw)) - 1 : 0u);
+      m1[q] = bw >= 8 ? 0xffffffffu : (bw > 4 ? (1u << (8 * (bw - 4))) - 1 : 0u);
+      if (bw <= 0) rows[q] = 0;
+    }
+    unsigned best[4] = {0xffffffffu, 0xffffffffu, 0xffffffffu, 0xffffffffu};
+    for (int c = t; c < cside * cside; c += kThreads) {
+      const int dy = c / cside - Rc, dx = c - (dy + Rc) * cside - Rc;
+      const unsigned pen = mv_penalty(lambda_q4, dx * 16, dy * 16);
+      const int xo = Rc + dx, sft = (xo & 3) * 8;
+#pragma unroll
+      for (int q = 0; q < 4; q++) {
+        if (rows[q] == 0) continue;
+        if (fp.mv_edges && !mv_allowed(fp, cx + 32 * (q & 1), min(32, fp.w - (cx + 32 * (q & 1))), dx * 16)) continue;
+        unsigned sad = 0;
+        for (int r = 0; r < rows[q]; r++) {
+          const uint32_t *rw = s_cref + (Rc + dy + 8 * (q >> 1) + r) * CWW + ((xo + 8 * (q & 1)) >> 2);
+          const unsigned a = rw[0], b = rw[1], cc = rw[2];
+          const unsigned r0 = __funnelshift_r(a, b, sft), r1 = __funnelshift_r(b, cc, sft);
+          const uint32_t *sw = s_csrc + (8 * (q >> 1) + r) * 4 + 2 * (q & 1);
+          sad = sad4_acc(sw[0] & m0[q], r0 & m0[q], sad);
+          sad = sad4_acc(sw[1] & m1[q], r1 & m1[q], sad);
+        }
+        best[q] = min(best[q], ((16 * sad + pen) << 13) | (unsigned)c);
+      }
+    }
+#pragma unroll
+    for (int q = 0; q < 4; q++) {
+      const unsigned b = __reduce_min_sync(0xffffffffu, best[q]);
+      if ((t & 31) == 0 && b != 0xffffffffu) atomicMin(&sh.ckey[q], b);
+    }
+    __syncthreads();
+    if (t < 4 && sh.ckey[t] != 0xffffffffu) {
+      const int c = (int)(sh.ckey[t] & 8191u);
+      const int dy = c / cside - Rc, dx = c - (dy + Rc) * cside - Rc;
+      sh.ctr_x[t] = (short)(4 * dx); sh.ctr_y[t] = (short)(4 * dy);
+    }
+    __syncthreads();
+    // windows of set 1, centred on each quadrant's coarse vector (a multiple of 4: aligned loads)
+    for (int q = 0; q < 4; q++) {
+      if (sh.ctr_x[q] == 0 && sh.ctr_y[q] == 0) continue;      // uniform: shared memory
+      load_window(ref, fp.w, fp.h, cx + 32 * (q & 1) + sh.ctr_x[q] - M, cy + 32 * (q >> 1) + sh.ctr_y[q] - M, WSq, WSWq,
+                  s_qwin + q * WSq * WSWq);
+    }
+    __syncthreads();
+  }
 
   // ---- full-sample search: lane <-> 8x8 block (z-order), warp pair <-> candidate subset ----
   {
@@ -80,49 +201,62 @@ k_me_ctu(FrameParams fp, const uint8_t *__restrict__ src, const uint8_t *__restr
     // the three words loaded per row then serve all four (byte shifts 0..3 are compile-time), so a
     // row costs 3 LDS + 6 SHF + 8 VABSDIFF4 for four candidates.  dx runs from -Rr (R rounded up to
     // a multiple of 4); candidates beyond +R are masked out.
-    const int side = 2 * R + 1, Rr = (R + 3) & ~3, groups = (Rr + R) / 4 + 1, items = side * groups;
+    const int Rr = (R + 3) & ~3, groups = (Rr + R) / 4 + 1, items = side * groups;
     unsigned k8 = 0xffffffffu, k16 = 0xffffffffu, k32 = 0xffffffffu;
-    for (int it = q; it < items; it += 4) {
-      const int dyi = it / groups, g = it - dyi * groups;
-      const int dy = dyi - R, dx0 = 4 * g - Rr;
-      const uint32_t *row = s_ref + (M + by * 8 + dy) * WSW + ((M + bx * 8 + dx0) >> 2);
-      unsigned sad0 = 0, sad1 = 0, sad2 = 0, sad3 = 0;
+    const int nsets = fp.me_coarse > 0 ? 2 : 1;
+    for (int set = 0; set < nsets; set++) {
+      // where this lane's block sits in the window of the set, and the set's centre for it
+      const int qd = z >> 4;                               // quadrant of the block (lanes 0-15 / 16-31 differ)
+      const int mcx = set ? sh.ctr_x[qd] : 0, mcy = set ? sh.ctr_y[qd] : 0;
+      const bool live = set == 0 || mcx != 0 || mcy != 0;
+      if (set && __all_sync(0xffffffffu, !live)) continue;  // both quadrants of this warp skip set 1
+      const uint32_t *wbase = set ? s_qwin + qd * WSq * WSWq : s_ref;
+      const int wp = set ? WSWq : WSW;
+      const int lx = M + (set ? (bx & 3) : bx) * 8, ly = M + (set ? (by & 3) : by) * 8;
+      const unsigned cbase = (unsigned)(set * side * side);
+      for (int it = q; it < items; it += 4) {
+        const int dyi = it / groups, g = it - dyi * groups;
+        const int dy = dyi - R, dx0 = 4 * g - Rr;
+        const uint32_t *row = wbase + (ly + dy) * wp + ((lx + dx0) >> 2);
+        unsigned sad0 = 0, sad1 = 0, sad2 = 0, sad3 = 0;
 #pragma unroll
-      for (int r = 0; r < 8; r++) {
-        const unsigned a = row[0], b = row[1], cc = row[2];
-        const unsigned s0 = s[2 * r], s1 = s[2 * r + 1];
-        sad0 = sad4_acc(s0, a, sad0);
-        sad0 = sad4_acc(s1, b, sad0);
-        sad1 = sad4_acc(s0, __funnelshift_r(a, b, 8), sad1);
-        sad1 = sad4_acc(s1, __funnelshift_r(b, cc, 8), sad1);
-        sad2 = sad4_acc(s0, __funnelshift_r(a, b, 16), sad2);
-        sad2 = sad4_acc(s1, __funnelshift_r(b, cc, 16), sad2);
-        sad3 = sad4_acc(s0, __funnelshift_r(a, b, 24), sad3);
-        sad3 = sad4_acc(s1, __funnelshift_r(b, cc, 24), sad3);
-        row += WSW;
-      }
-      const unsigned sads[4] = {sad0, sad1, sad2, sad3};
-#pragma unroll
-      for (int j = 0; j < 4; j++) {
-        const int dx = dx0 + j;
-        const bool in_range = dx >= -R && dx <= R;          // uniform across the warp
-        unsigned sad = v8 ? sads[j] : 0;
-        unsigned s16 = sad + __shfl_xor_sync(0xffffffffu, sad, 1);
-        s16 += __shfl_xor_sync(0xffffffffu, s16, 2);
-        unsigned s32 = s16 + __shfl_xor_sync(0xffffffffu, s16, 4);
-        s32 += __shfl_xor_sync(0xffffffffu, s32, 8);
-        if (!in_range) continue;
-        const unsigned c = (unsigned)((dy + R) * side + dx + R);
-        const unsigned pen = sh.pen[c];
-        bool a8 = v8, a16 = v16, a32 = v32;
-        if (fp.mv_edges) {                                   // tile-column mode only (uniform branch)
-          a8 = a8 && mv_allowed(fp, cx + 8 * bx, 8, 4 * dx);
-          a16 = a16 && mv_allowed(fp, cx + 16 * (bx >> 1), 16, 4 * dx);
-          a32 = a32 && mv_allowed(fp, cx + 32 * (bx >> 2), 32, 4 * dx);
+        for (int r = 0; r < 8; r++) {
+          const unsigned a = row[0], b = row[1], cc = row[2];
+          const unsigned s0 = s[2 * r], s1 = s[2 * r + 1];
+          sad0 = sad4_acc(s0, a, sad0);
+          sad0 = sad4_acc(s1, b, sad0);
+          sad1 = sad4_acc(s0, __funnelshift_r(a, b, 8), sad1);
+          sad1 = sad4_acc(s1, __funnelshift_r(b, cc, 8), sad1);
+          sad2 = sad4_acc(s0, __funnelshift_r(a, b, 16), sad2);
+          sad2 = sad4_acc(s1, __funnelshift_r(b, cc, 16), sad2);
+          sad3 = sad4_acc(s0, __funnelshift_r(a, b, 24), sad3);
+          sad3 = sad4_acc(s1, __funnelshift_r(b, cc, 24), sad3);
+          row += wp;
         }
-        if (a8) k8 = min(k8, ((sad + pen) << 13) | c);
-        if (a16) k16 = min(k16, ((s16 + pen) << 13) | c);
-        if (a32) k32 = min(k32, ((s32 + pen) << 13) | c);
+        const unsigned sads[4] = {sad0, sad1, sad2, sad3};
+#pragma unroll
+        for (int j = 0; j < 4; j++) {
+          const int dx = dx0 + j;
+          const bool in_range = dx >= -R && dx <= R;          // uniform across the warp
+          unsigned sad = v8 ? sads[j] : 0;
+          unsigned s16 = sad + __shfl_xor_sync(0xffffffffu, sad, 1);
+          s16 += __shfl_xor_sync(0xffffffffu, s16, 2);
+          unsigned s32 = s16 + __shfl_xor_sync(0xffffffffu, s16, 4);
+          s32 += __shfl_xor_sync(0xffffffffu, s32, 8);
+          if (!in_range) continue;
+          const unsigned c = (unsigned)((dy + R) * side + dx + R);
+          const unsigned pen = sh.pen[c];
+          bool a8 = v8 && live, a16 = v16 && live, a32 = v32 && live;
+          if (fp.mv_edges) {                                   // tile-column mode only (uniform branch)
+            const int mvx = 4 * (mcx + dx);
+            a8 = a8 && mv_allowed(fp, cx + 8 * bx, 8, mvx);
+            a16 = a16 && mv_allowed(fp, cx + 16 * (bx >> 1), 16, mvx);
+            a32 = a32 && mv_allowed(fp, cx + 32 * (bx >> 2), 32, mvx);
+          }
+          if (a8) k8 = min(k8, ((sad + pen) << 13) | (cbase + c));
+          if (a16) k16 = min(k16, ((s16 + pen) << 13) | (cbase + c));
+          if (a32) k32 = min(k32, ((s32 + pen) << 13) | (cbase + c));
+        }
       }
     }
     atomicMin(&sh.key8[z], k8);
@@ -143,8 +277,22 @@ k_me_ctu(FrameParams fp, const uint8_t *__restrict__ src, const uint8_t *__restr
     bool use = k16 != 0xffffffffu && (k16 >> 13) + ovh <= sum8;
     sh.use16[t] = use;
     sh.eff16[t] = use ? (k16 >> 13) + ovh : sum8;
+    sh.intra_mode16[t] = -1;
+    // intra candidate: blocks that lie wholly inside the picture and predict badly
+    sh.try_intra[t] = fp.intra_in_p && k16 != 0xffffffffu && sh.eff16[t] > kIntraTryCost;
   }
   __syncthreads();
+  if (fp.intra_in_p) {
+    for (int b = 0; b < 16; b++) {
+      if (!sh.try_intra[b]) continue;                          // uniform: shared memory
+      intra_search_cu(shm, fp, src, cx + 8 * z_to_x(4 * b), cy + 8 * z_to_y(4 * b), 4);
+      if (t == 0) {
+        const unsigned ic = shm.best_cost + shm.best_cost / 2 + (unsigned)((lambda_q4 * kIntraOverheadBits) >> 4) + ovh;
+        if (ic < sh.eff16[b]) { sh.eff16[b] = ic; sh.intra_mode16[b] = (int8_t)shm.best_mode; }
+      }
+      __syncthreads();
+    }
+  }
   if (t < 4) {
     unsigned sum16 = sh.eff16[4 * t] + sh.eff16[4 * t + 1] + sh.eff16[4 * t + 2] + sh.eff16[4 * t + 3];
     unsigned k32 = sh.key32[t];
@@ -154,16 +302,22 @@ k_me_ctu(FrameParams fp, const uint8_t *__restrict__ src, const uint8_t *__restr
   if (t < 64) {
     unsigned key;
     int org, l2;
+    int imode = 0;
     if (sh.use32[t >> 4]) { key = sh.key32[t >> 4]; org = t & ~15; l2 = 5; }
+    else if (sh.intra_mode16[t >> 2] >= 0) { key = 0; org = 0xff; l2 = 4; imode = sh.intra_mode16[t >> 2] + 1; }
     else if (sh.use16[t >> 2]) { key = sh.key16[t >> 2]; org = t & ~3; l2 = 4; }
     else { key = sh.key8[t]; org = t; l2 = 3; }
     if (key == 0xffffffffu) { org = 0xff; l2 = 0; }
+    sh.intra_unit[t] = (uint8_t)imode;                       // intra units take no part in the refinement (org = 0xff)
     sh.org[t] = (uint8_t)org;
     sh.log2[t] = (uint8_t)l2;
     if (org == t) {
-      const int side = 2 * R + 1;
       int c = (int)(key & 8191u);
+      const int set = c >= side * side ? 1 : 0;
+      c -= set * side * side;
       int dy = c / side - R, dx = c - (dy + R) * side - R;
+      if (set) { dx += sh.ctr_x[t >> 4]; dy += sh.ctr_y[t >> 4]; }
+      sh.wset[t] = (uint8_t)set;
       sh.mvx[t] = (short)(dx * 4); sh.mvy[t] = (short)(dy * 4);
       sh.cmx[t] = (short)(dx * 4); sh.cmy[t] = (short)(dy * 4);
       sh.best[t] = key >> 13;                    // SAD at the full-sample mv + its mv penalty
@@ -174,7 +328,8 @@ k_me_ctu(FrameParams fp, const uint8_t *__restrict__ src, const uint8_t *__restr
   // ---- half- then quarter-sample refinement: 4 threads per 8x8 unit, 2 columns x 8 rows each.
   // The eight candidates of a step share one centre, so they are evaluated back to back into
   // eight accumulators per CU and compared once per step (same result as comparing one by one:
-  // the first strictly smaller cost in candidate order wins).
+  // the first strictly smaller cost in candidate order wins).  Samples come from the window of the
+  // set that won the CU; the mv penalty keeps counting from that set's centre.
   {
     const int z = t >> 2, qc = t & 3;
     const int ux = z_to_x(z), uy = z_to_y(z);
@@ -186,6 +341,11 @@ k_me_ctu(FrameParams fp, const uint8_t *__restrict__ src, const uint8_t *__restr
       const uint8_t *sp = srcb + (uy * 8 + r) * 64 + ux * 8 + 2 * qc;
       sv[r] = (unsigned)sp[0] | ((unsigned)sp[1] << 8);
     }
+    const int set = org != 0xff ? sh.wset[org] : 0, qd = z >> 4;
+    const uint32_t *wbase = set ? s_qwin + qd * WSq * WSWq : s_ref;
+    const int wp = set ? WSWq : WSW;
+    // window coordinates of the unit for a zero vector
+    const int wx0 = M + (set ? (ux & 3) * 8 - sh.ctr_x[qd] : ux * 8) + 2 * qc, wy0 = M + (set ? (uy & 3) * 8 - sh.ctr_y[qd] : uy * 8);
     for (int step = 2; step >= 1; step--) {
       if (org != 0xff) {
         const int cmx = sh.cmx[org], cmy = sh.cmy[org];
@@ -194,7 +354,7 @@ k_me_ctu(FrameParams fp, const uint8_t *__restrict__ src, const uint8_t *__restr
           const int oy = k < 3 ? -1 : (k < 5 ? 0 : 1);
           const int mx = cmx + ox * step, my = cmy + oy * step;
           unsigned pr[8];
-          mc_luma_2x8(s_ref, WSW, M + ux * 8 + 2 * qc + (mx >> 2), M + uy * 8 + (my >> 2), mx & 3, my & 3, pr);
+          mc_luma_2x8(wbase, wp, wx0 + (mx >> 2), wy0 + (my >> 2), mx & 3, my & 3, pr);
           unsigned sad = 0;
 #pragma unroll
           for (int r = 0; r < 8; r++) sad = sad4_acc(sv[r], pr[r], sad);
@@ -203,11 +363,12 @@ k_me_ctu(FrameParams fp, const uint8_t *__restrict__ src, const uint8_t *__restr
       }
       __syncthreads();
       if (t < 64 && sh.org[t] == t) {
+        const int pcx = sh.wset[t] ? 4 * sh.ctr_x[t >> 4] : 0, pcy = sh.wset[t] ? 4 * sh.ctr_y[t >> 4] : 0;
         for (int k = 0; k < 8; k++) {
           const int ox = (k < 3 ? k - 1 : (k == 3 ? -1 : (k == 4 ? 1 : k - 6)));
           const int oy = k < 3 ? -1 : (k < 5 ? 0 : 1);
           const int mx = sh.cmx[t] + ox * step, my = sh.cmy[t] + oy * step;
-          unsigned cost = sh.acc8[t][k] + mv_penalty(lambda_q4, mx, my);
+          unsigned cost = sh.acc8[t][k] + mv_penalty(lambda_q4, mx - pcx, my - pcy);
           const bool ok = !fp.mv_edges || mv_allowed(fp, cx + 8 * z_to_x(t), 1 << sh.log2[t], mx);
           if (ok && cost < sh.best[t]) { sh.best[t] = cost; sh.mvx[t] = (short)mx; sh.mvy[t] = (short)my; }
           sh.acc8[t][k] = 0;
@@ -223,7 +384,14 @@ k_me_ctu(FrameParams fp, const uint8_t *__restrict__ src, const uint8_t *__restr
     int ux = z_to_x(t), uy = z_to_y(t);
     int x8 = (cx >> 3) + ux, y8 = (cy >> 3) + uy;
     int org = sh.org[t];
-    if (org != 0xff && x8 < fp.w8 && y8 < fp.h8) {
+    if (sh.intra_unit[t] && x8 < fp.w8 && y8 < fp.h8) {
+      // reconstructed by the intra pass that follows the inter reconstruction (k_intra_frame)
+      CuInfo ci;
+      ci.mvx = 0; ci.mvy = 0; ci.log2_size = 4; ci.pred_mode = 1; ci.intra_mode = (uint8_t)(sh.intra_unit[t] - 1); ci.cbf = 0;
+      ci.skip = 0; ci.merge_idx = 0xff; ci.mvp_idx = 0; ci.qp = 0;
+      cu[(size_t)y8 * fp.w8 + x8] = ci;
+      if (fp.any_intra) *fp.any_intra = 1;
+    } else if (org != 0xff && x8 < fp.w8 && y8 < fp.h8) {
       CuInfo ci;
       ci.mvx = sh.mvx[org]; ci.mvy = sh.mvy[org];
       ci.log2_size = sh.log2[t]; ci.pred_mode = 0; ci.intra_mode = 0; ci.cbf = 0;
@@ -254,7 +422,7 @@ k_inter_recon(FrameParams fp, const uint8_t *__restrict__ src, const uint8_t *__
 {
   extern __shared__ uint32_t s_dyn[];
   __shared__ ReconShared sh;
-  const int R = fp.search_range;
+  const int R = fp.mc_range;
   const int M = window_margin(R), WS = kCtb + 2 * M, WSW = (WS >> 2) + 1;
   uint32_t *s_ref = s_dyn;                                   // luma window; reused for chroma windows
   uint8_t *s_src = (uint8_t *)(s_dyn + WS * WSW);            // 64 x 64
@@ -279,7 +447,7 @@ k_inter_recon(FrameParams fp, const uint8_t *__restrict__ src, const uint8_t *__
       org = xy_to_z(ux & ~(n8 - 1), uy & ~(n8 - 1));
       sh.mvx[t] = ci.mvx; sh.mvy[t] = ci.mvy;
       sh.cbf[t] = kDecode ? ci.cbf : 0;
-      if (kDecode && ci.pred_mode != 0) org = 0xff;        // not an inter CU: left to the intra path
+      if (ci.pred_mode != 0) org = 0xff;                   // not an inter CU: left to the intra pass (k_intra_frame)
     } else {
       sh.cbf[t] = 0;
     }
@@ -458,10 +626,15 @@ k_inter_modes(FrameParams fp, CuInfo *__restrict__ cu)
 
 }  // namespace
 
-static size_t me_smem(int range)
+static size_t me_smem(int range, int coarse)
 {
   int M = (range + 4 + 3) & ~3, WS = kCtb + 2 * M, WSW = (WS >> 2) + 1;
-  return (size_t)(WS * WSW + 64 * 16) * 4;
+  size_t words = (size_t)WS * WSW + 64 * 16;
+  if (coarse > 0) {
+    const int WSq = 32 + 2 * M, WSWq = (WSq >> 2) + 1, CW = 16 + 2 * coarse, CWW = (CW >> 2) + 1;
+    words += std::max<size_t>((size_t)4 * WSq * WSWq, (size_t)CW * CWW + 64);    // the coarse window lives where the quadrant windows go
+  }
+  return words * 4;
 }
 static size_t recon_smem(int range)
 {
@@ -486,7 +659,8 @@ static void allow_big_smem()
 
 cudaError_t launch_inter_me(const FrameParams &fp, const uint8_t *src, const uint8_t *ref, CuInfo *cu, cudaStream_t s)
 {
-  size_t sm = me_smem(fp.search_range);
+  if (fp.me_coarse < 0 || (fp.me_coarse & 3) || fp.me_coarse > 32 || (fp.me_coarse > 0 && fp.search_range > 16)) return cudaErrorInvalidValue;
+  size_t sm = me_smem(fp.search_range, fp.me_coarse);
   allow_big_smem();
   k_me_ctu<<<fp.ctb_cols * fp.ctb_rows, kThreads, sm, s>>>(fp, src, ref, cu);
   return cudaGetLastError();
@@ -495,21 +669,29 @@ cudaError_t launch_inter_me(const FrameParams &fp, const uint8_t *src, const uin
 cudaError_t launch_inter_recon(const FrameParams &fp, const uint8_t *src, const uint8_t *ref, uint8_t *rec,
                                int16_t *levels, CuInfo *cu, cudaStream_t s)
 {
-  size_t sm = recon_smem(fp.search_range);
+  size_t sm = recon_smem(fp.mc_range);
+  if (sm > (size_t)kMaxDynSmem) return cudaErrorInvalidValue;
   allow_big_smem();
   k_inter_recon<false><<<fp.ctb_cols * fp.ctb_rows, kThreads, sm, s>>>(fp, src, ref, rec, levels, cu);
   return cudaGetLastError();
 }
 
 // Decoder reconstruction of a P picture: motion compensation + dequantisation + inverse transform.
-// fp.search_range must cover the largest motion vector of the picture (in full samples).
+// fp.mc_range must cover the largest motion vector of the picture (in full samples).
 cudaError_t launch_inter_decode(const FrameParams &fp, const uint8_t *ref, uint8_t *rec, const int16_t *levels,
                                 const CuInfo *cu, cudaStream_t s)
 {
-  size_t sm = recon_smem(fp.search_range);
+  size_t sm = recon_smem(fp.mc_range);
   if (sm > (size_t)kMaxDynSmem) return cudaErrorInvalidValue;
   allow_big_smem();
   k_inter_recon<true><<<fp.ctb_cols * fp.ctb_rows, kThreads, sm, s>>>(fp, nullptr, ref, rec, (int16_t *)levels, (CuInfo *)cu);
+  return cudaGetLastError();
+}
+
+cudaError_t launch_down4(const uint8_t *plane, int w, int h, uint8_t *out, cudaStream_t s)
+{
+  const int n = (w >> 2) * (h >> 2);
+  k_down4<<<(n + 255) / 256, 256, 0, s>>>(plane, w, h, out);
   return cudaGetLastError();
 }
 

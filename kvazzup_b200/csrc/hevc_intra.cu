@@ -14,7 +14,7 @@
 //                   reconstruction (rows K5, K6) concurrently: 256 + 64 + 64 threads.
 #include <algorithm>
 
-#include "hevc_device.cuh"
+#include "hevc_intra.cuh"
 #include "hevc_kernels.h"
 
 namespace b200 {
@@ -24,150 +24,15 @@ namespace {
 constexpr int kModeThreads = 256;     // k_intra_modes: one thread per luma sample of a 16x16 CU
 constexpr int kReconThreads = 384;    // k_intra_frame: 256 luma + 64 Cb + 64 Cr samples of a 16x16 CU
 
-// neighbour samples of one block: raw gather, substituted, [1 2 1]-filtered, availability
-struct RefSet { uint8_t raw[68], sub[68], filt[68], av[68]; int dc; };
-
-__device__ __forceinline__ unsigned coding_order_i(const FrameParams &fp, int x, int y)
-{
-  return (unsigned)((y >> kCtbLog2) * fp.ctb_cols + (x >> kCtbLog2)) * 64u + (unsigned)xy_to_z((x >> 3) & 7, (y >> 3) & 7);
-}
-
-// prediction of sample (x,y) of an n x n block, H.265 8.4.4.2.4-6.  `u` = substituted
-// neighbours, `f` = their [1 2 1]-filtered version; layout: [0..2n-1] left column from the
-// bottom up, [2n] corner, [2n+1..4n] top row.
-__device__ __forceinline__ int intra_pixel(const uint8_t *u, const uint8_t *f, int n, int log2n, int mode, int cidx,
-                                           int dc, int x, int y)
-{
-  const uint8_t *r = u;
-  if (cidx == 0 && mode != 1 && n != 4) {
-    int d = min(abs(mode - 26), abs(mode - 10));
-    int thres = n == 8 ? 7 : (n == 16 ? 1 : 0);
-    if (d > thres) r = f;
-  }
-#define LEFT(yy) r[2 * n - 1 - (yy)]
-#define TOP(xx) r[2 * n + 1 + (xx)]
-  if (mode == 0)
-    return ((n - 1 - x) * LEFT(y) + (x + 1) * TOP(n) + (n - 1 - y) * TOP(x) + (y + 1) * LEFT(n) + n) >> (log2n + 1);
-  if (mode == 1) {
-    if (cidx == 0 && n < 32) {
-      if (x == 0 && y == 0) return (LEFT(0) + 2 * dc + TOP(0) + 2) >> 2;
-      if (y == 0) return (TOP(x) + 3 * dc + 2) >> 2;
-      if (x == 0) return (LEFT(y) + 3 * dc + 2) >> 2;
-    }
-    return dc;
-  }
-  const int angle = c_intra_angle[mode], inv = c_inv_angle[mode];
-  const bool vert = mode >= 18;
-  const int a = vert ? x : y, b = vert ? y : x;          // a runs along the reference, b away from it
-  const int idx = ((b + 1) * angle) >> 5, fact = ((b + 1) * angle) & 31;
-  int i0 = a + idx + 1;
-  // ref[i]: i >= 0 -> main side sample i-1 (i = 0 is the corner); i < 0 -> projected side sample
-  auto ref_at = [&](int i) -> int {
-    if (i >= 0) return vert ? TOP(i - 1) : LEFT(i - 1);
-    int s = -1 + ((i * inv + 128) >> 8);
-    return vert ? LEFT(s) : TOP(s);
-  };
-  int v = fact ? ((32 - fact) * ref_at(i0) + fact * ref_at(i0 + 1) + 16) >> 5 : ref_at(i0);
-  if (cidx == 0 && n < 32 && a == 0 && angle == 0) {       // modes 26 / 10: first column / row smoothing
-    if (vert) v = clip8(TOP(0) + ((LEFT(b) - LEFT(-1)) >> 1));
-    else v = clip8(LEFT(0) + ((TOP(b) - TOP(-1)) >> 1));
-  }
-  return v;
-#undef LEFT
-#undef TOP
-}
-
-// Gather (8.4.4.2.2) the 4n+1 neighbours of the n x n block at (x0,y0) of `plane` (plane c of the
-// picture; c > 0 is 4:2:0 chroma) into rs.raw / rs.av.  `first` = index of the first thread of
-// the group of >= 4n+1 threads doing this block.  Caller synchronises, then calls finish_refs.
-// `tile` (may be NULL): the current CTU's reconstruction of this plane in shared memory, T x T
-// samples whose top-left is plane sample (tx0,ty0); neighbours inside it are read from there
-// (no L2 round trip on the wavefront's critical path), the others from HBM / L2.
-__device__ __forceinline__ void gather_refs(RefSet &rs, const FrameParams &fp, const uint8_t *plane, int pw, int c,
-                                            int x0, int y0, int n, unsigned cur_order, int t,
-                                            const uint8_t *tile = nullptr, int T = 0, int tx0 = 0, int ty0 = 0)
-{
-  const int cnt = 4 * n + 1, sft = c ? 1 : 0;
-  if (t >= 0 && t < cnt) {
-    int x, y;
-    if (t < 2 * n) { x = x0 - 1; y = y0 + 2 * n - 1 - t; }
-    else if (t == 2 * n) { x = x0 - 1; y = y0 - 1; }
-    else { x = x0 + (t - 2 * n - 1); y = y0 - 1; }
-    int lx = x << sft, ly = y << sft;
-    bool ok = lx >= 0 && ly >= 0 && lx < fp.w && ly < fp.h && coding_order_i(fp, lx, ly) < cur_order;
-    rs.av[t] = ok;
-    uint8_t v = 0;
-    if (ok) {
-      const int lx2 = x - tx0, ly2 = y - ty0;
-      if (tile && lx2 >= 0 && ly2 >= 0 && lx2 < T && ly2 < T) v = tile[ly2 * T + lx2];
-      else v = __ldcg(plane + (size_t)y * pw + x);
-    }
-    rs.raw[t] = v;
-  }
-}
-// substitution (8.4.4.2.2) by thread t of the group; caller synchronises afterwards
-__device__ __forceinline__ void substitute_refs(RefSet &rs, int n, int t)
-{
-  const int cnt = 4 * n + 1;
-  if (t >= 0 && t < cnt) {
-    int j = t;
-    while (j >= 0 && !rs.av[j]) j--;
-    if (j < 0) { j = t + 1; while (j < cnt && !rs.av[j]) j++; }
-    rs.sub[t] = j < cnt ? rs.raw[j] : 128;
-  }
-}
-// [1 2 1] smoothing (8.4.4.2.3) and the DC value; caller synchronises afterwards
-__device__ __forceinline__ void filter_refs(RefSet &rs, int n, int t)
-{
-  const int cnt = 4 * n + 1;
-  if (t >= 0 && t < cnt)
-    rs.filt[t] = (t == 0 || t == cnt - 1) ? rs.sub[t] : (uint8_t)((rs.sub[t - 1] + 2 * rs.sub[t] + rs.sub[t + 1] + 2) >> 2);
-  if (t == cnt) {                      // one spare thread of the group sums the DC value
-    int s = n;
-    for (int i = 0; i < n; i++) s += rs.sub[2 * n + 1 + i] + rs.sub[2 * n - 1 - i];
-    rs.dc = s >> (31 - __clz(n) + 1);
-  }
-}
-
 // ---- mode decision, whole picture in parallel ----------------------------------------------------
-
-struct ModeShared {
-  RefSet rs;
-  unsigned sad[36];
-  uint8_t src[256];
-};
 
 __device__ void decide_cu(ModeShared &sh, const FrameParams &fp, const uint8_t *src, CuInfo *cu, int x0, int y0, int log2)
 {
   const int n = 1 << log2, t = threadIdx.x;
-  const unsigned cur = coding_order_i(fp, x0, y0);
-  const int y = t >> log2, x = t & (n - 1);
-  const bool act = t < n * n;
-  if (t < 36) sh.sad[t] = 0;
-  if (act) sh.src[t] = __ldg(src + (size_t)(y0 + y) * fp.w + x0 + x);
-  gather_refs(sh.rs, fp, src, fp.w, 0, x0, y0, n, cur, t);
-  __syncthreads();
-  substitute_refs(sh.rs, n, t);
-  __syncthreads();
-  filter_refs(sh.rs, n, t);
-  __syncthreads();
-  for (int mode = 0; mode < 35; mode++) {
-    unsigned d = 0;
-    if (act) d = (unsigned)abs((int)sh.src[t] - intra_pixel(sh.rs.sub, sh.rs.filt, n, log2, mode, 0, sh.rs.dc, x, y));
-    d = __reduce_add_sync(0xffffffffu, d);
-    if ((t & 31) == 0 && d) atomicAdd(&sh.sad[mode], d);
-  }
-  __syncthreads();
+  intra_search_cu(sh, fp, src, x0, y0, log2);
   if (t == 0) {
-    unsigned best = 0xffffffffu;
-    int bm = 0;
-    for (int mode = 0; mode < 35; mode++) {
-      int bits = (mode == 0 || mode == 1 || mode == 26) ? 2 : 6;     // fixed prior: the MPM list is unknown here
-      unsigned cost = sh.sad[mode] + (unsigned)((lambda_q4_at(fp, x0, y0) * bits) >> 4);
-      if (cost < best) { best = cost; bm = mode; }
-    }
     CuInfo ci;
-    ci.mvx = 0; ci.mvy = 0; ci.log2_size = (uint8_t)log2; ci.pred_mode = 1; ci.intra_mode = (uint8_t)bm;
+    ci.mvx = 0; ci.mvy = 0; ci.log2_size = (uint8_t)log2; ci.pred_mode = 1; ci.intra_mode = (uint8_t)sh.best_mode;
     ci.cbf = 0; ci.skip = 0; ci.merge_idx = 0xff; ci.mvp_idx = 0; ci.qp = 0;
     const int n8 = n >> 3;
     for (int j = 0; j < n8; j++)
@@ -321,10 +186,12 @@ __device__ void recon_cu(ReconSharedI &sh, const FrameParams &fp, const uint8_t 
 template <bool kDecode>
 __global__ void __launch_bounds__(kReconThreads, 2)     // <= 85 registers: a CTA then fits beside two motion-search CTAs
 k_intra_frame(FrameParams fp, const uint8_t *__restrict__ src, uint8_t *rec, int16_t *levels, CuInfo *cu,
-              int *progress, int *ticket, const int *__restrict__ order)
+              int *ticket, const int *__restrict__ order)
 {
   __shared__ ReconSharedI sh;
   const int t = threadIdx.x;
+  // P picture: the intra CUs (if any) follow the inter reconstruction; a picture without any is done
+  if (!fp.is_idr && *(volatile int *)fp.any_intra == 0) return;
   for (int i = t; i < 1024; i += kReconThreads) {
     ((int8_t *)sh.dct)[i] = c_dct32[i >> 5][i & 31];
     ((int8_t *)sh.dctT)[i] = c_dct32[i & 31][i >> 5];
@@ -333,6 +200,7 @@ k_intra_frame(FrameParams fp, const uint8_t *__restrict__ src, uint8_t *rec, int
   // that keeps taking tickets does the same work as one CTA per CTU without parking hundreds of
   // waiting CTAs (384 threads x ~150 registers each) on SMs that other streams' kernels could use.
   const int nctu = fp.ctb_cols * fp.ctb_rows;
+  const size_t ysz = (size_t)fp.w * fp.h;
   for (;;) {
     __syncthreads();
     if (t == 0) sh.ctu = atomicAdd(ticket, 1);
@@ -340,51 +208,84 @@ k_intra_frame(FrameParams fp, const uint8_t *__restrict__ src, uint8_t *rec, int
     if (sh.ctu >= nctu) break;
     // tickets follow the wavefront (anti-diagonals c + 2r), not raster order, so that the CTUs a
     // small resident grid holds at any time are the ones that can actually run concurrently;
-    // every dependency (left, above-right) still has a smaller ticket
+    // every dependency (left, above-left, above, above-right) still has a smaller ticket
     const int ctu = order[sh.ctu];
     const int row = ctu / fp.ctb_cols, col = ctu - row * fp.ctb_cols;
-    if (t == 0) {
-      // left CTU of this row, and the above-right CTU of the row above
-      volatile int *p = progress;
-      while (col > 0 && p[row] < col) __nanosleep(32);
-      if (row > 0) {
-        int need = min(col + 2, fp.ctb_cols);
-        while (p[row - 1] < need) __nanosleep(32);
+    const int cx = col * kCtb, cy = row * kCtb;
+    // does this CTU hold intra CUs at all?  (always in an I picture)
+    int has = 1;
+    if (!fp.is_idr) {
+      int mine = 0;
+      if (t < 64) {
+        const int x8 = (cx >> 3) + z_to_x(t), y8 = (cy >> 3) + z_to_y(t);
+        if (x8 < fp.w8 && y8 < fp.h8) mine = cu[(size_t)y8 * fp.w8 + x8].pred_mode == 1;
+      }
+      has = __syncthreads_or(mine);
+    }
+    if (has) {
+      if (t == 0) {
+        // One flag per CTU (a CTU without intra CUs completes at once, so "everything before column c
+        // of this row" no longer follows from its left neighbour): wait for the four CTUs whose
+        // samples intra prediction can read.
+        volatile int *d = fp.ctu_done;
+        if (col > 0) while (d[ctu - 1] == 0) __nanosleep(32);
+        if (row > 0) {
+          if (col > 0) while (d[ctu - fp.ctb_cols - 1] == 0) __nanosleep(32);
+          while (d[ctu - fp.ctb_cols] == 0) __nanosleep(32);
+          if (col + 1 < fp.ctb_cols) while (d[ctu - fp.ctb_cols + 1] == 0) __nanosleep(32);
+        }
+        __threadfence();
+      }
+      __syncthreads();
+      if (!fp.is_idr) {
+        // the inter CUs of this CTU were reconstructed by the kernel before: bring the CTU's samples
+        // into the tile that neighbour gathering reads
+        for (int i = t; i < 64 * 16; i += kReconThreads) {
+          int y = cy + (i >> 4), x = cx + 4 * (i & 15);
+          ((uint32_t *)sh.rec_y)[i] = (y < fp.h && x < fp.w) ? __ldcg((const uint32_t *)(rec + (size_t)y * fp.w + x)) : 0u;
+        }
+        for (int i = t; i < 2 * 32 * 8; i += kReconThreads) {
+          int c = i >> 8, j = i & 255;
+          int y = (cy >> 1) + (j >> 3), x = (cx >> 1) + 4 * (j & 7);
+          const uint8_t *pl = rec + ysz + (c ? ysz / 4 : 0);
+          ((uint32_t *)sh.rec_c[c])[j] = (y < (fp.h >> 1) && x < (fp.w >> 1)) ? __ldcg((const uint32_t *)(pl + (size_t)y * (fp.w >> 1) + x)) : 0u;
+        }
+      }
+      if (!kDecode) {
+        for (int i = t; i < 64 * 16; i += kReconThreads) {
+          int y = cy + (i >> 4), x = cx + 4 * (i & 15);
+          ((uint32_t *)sh.src_y)[i] = (y < fp.h && x < fp.w) ? __ldg((const uint32_t *)(src + (size_t)y * fp.w + x)) : 0u;
+        }
+        for (int i = t; i < 2 * 32 * 8; i += kReconThreads) {
+          int c = i >> 8, j = i & 255;
+          int y = (cy >> 1) + (j >> 3), x = (cx >> 1) + 4 * (j & 7);
+          const uint8_t *pl = src + ysz + (c ? ysz / 4 : 0);
+          ((uint32_t *)sh.src_c[c])[j] = (y < (fp.h >> 1) && x < (fp.w >> 1)) ? __ldg((const uint32_t *)(pl + (size_t)y * (fp.w >> 1) + x)) : 0u;
+        }
+      }
+      __syncthreads();
+      // z-order walk over the sixteen 16x16 positions of the CTU: an intra CU of 16x16, or the 8x8
+      // intra CUs among its four quarters (picture edges of an I picture; anywhere in a foreign stream)
+      for (int z16 = 0; z16 < 16; z16++) {
+        int x0 = cx + 16 * ((z16 & 1) | ((z16 >> 1) & 2)), y0 = cy + 16 * (((z16 >> 1) & 1) | ((z16 >> 2) & 2));
+        if (x0 >= fp.w || y0 >= fp.h) continue;
+        const CuInfo *u = &cu[(size_t)(y0 >> 3) * fp.w8 + (x0 >> 3)];
+        const int l2 = u->log2_size;
+        if (l2 == 4) {
+          if (u->pred_mode == 1) recon_cu<kDecode>(sh, fp, src, rec, levels, cu, cx, cy, x0, y0, 4);
+        } else if (l2 == 3) {
+          for (int q = 0; q < 4; q++) {
+            int x1 = x0 + 8 * (q & 1), y1 = y0 + 8 * (q >> 1);
+            if (x1 >= fp.w || y1 >= fp.h) continue;
+            const CuInfo *v = &cu[(size_t)(y1 >> 3) * fp.w8 + (x1 >> 3)];
+            if (v->pred_mode == 1 && v->log2_size == 3) recon_cu<kDecode>(sh, fp, src, rec, levels, cu, cx, cy, x1, y1, 3);
+          }
+        }
       }
       __threadfence();
     }
     __syncthreads();
-    const int cx = col * kCtb, cy = row * kCtb;
-    if (!kDecode) {
-      const size_t ysz = (size_t)fp.w * fp.h;
-      for (int i = t; i < 64 * 16; i += kReconThreads) {
-        int y = cy + (i >> 4), x = cx + 4 * (i & 15);
-        ((uint32_t *)sh.src_y)[i] = (y < fp.h && x < fp.w) ? __ldg((const uint32_t *)(src + (size_t)y * fp.w + x)) : 0u;
-      }
-      for (int i = t; i < 2 * 32 * 8; i += kReconThreads) {
-        int c = i >> 8, j = i & 255;
-        int y = (cy >> 1) + (j >> 3), x = (cx >> 1) + 4 * (j & 7);
-        const uint8_t *pl = src + ysz + (c ? ysz / 4 : 0);
-        ((uint32_t *)sh.src_c[c])[j] = (y < (fp.h >> 1) && x < (fp.w >> 1)) ? __ldg((const uint32_t *)(pl + (size_t)y * (fp.w >> 1) + x)) : 0u;
-      }
-      __syncthreads();
-    }
-    // z-order walk over the sixteen 16x16 positions of the CTU; 16x16 that cross the picture edge fall to 8x8
-    for (int z16 = 0; z16 < 16; z16++) {
-      int x0 = cx + 16 * ((z16 & 1) | ((z16 >> 1) & 2)), y0 = cy + 16 * (((z16 >> 1) & 1) | ((z16 >> 2) & 2));
-      if (x0 >= fp.w || y0 >= fp.h) continue;
-      if (x0 + 16 <= fp.w && y0 + 16 <= fp.h) {
-        recon_cu<kDecode>(sh, fp, src, rec, levels, cu, cx, cy, x0, y0, 4);
-      } else {
-        for (int q = 0; q < 4; q++) {
-          int x1 = x0 + 8 * (q & 1), y1 = y0 + 8 * (q >> 1);
-          if (x1 < fp.w && y1 < fp.h) recon_cu<kDecode>(sh, fp, src, rec, levels, cu, cx, cy, x1, y1, 3);
-        }
-      }
-    }
-    __threadfence();
-    __syncthreads();
-    if (t == 0) atomicExch(&progress[row], col + 1);
+    if (t == 0) atomicExch(&fp.ctu_done[ctu], 1);
   }
 }
 
@@ -401,36 +302,54 @@ void intra_wavefront_order(int cols, int rows, int *out)
     }
 }
 
-// wavefront width + slack, never more CTAs than CTUs
+// I picture: wavefront width + slack, never more CTAs than CTUs.  P picture: most CTUs hold no intra
+// CU and finish at once, and those that do wait for their four neighbours only, so a wider grid pays.
 static int intra_grid(const FrameParams &fp)
 {
   int width = std::min(fp.ctb_rows, (fp.ctb_cols + 1) / 2) + 3;
+  if (!fp.is_idr) width = std::max(width, 148);
   return std::max(1, std::min(width, fp.ctb_cols * fp.ctb_rows));
 }
 
+// `ticket` = 1 int; fp.ctu_done = one int per CTU; both zeroed here.  I pictures: mode decision for the
+// whole picture, then the reconstruction wavefront.
 cudaError_t launch_intra_frame(const FrameParams &fp, const uint8_t *src, uint8_t *rec, int16_t *levels, CuInfo *cu,
-                               int *progress, int *ticket, const int *order, cudaStream_t s)
+                               int *ticket, const int *order, cudaStream_t s)
 {
-  cudaError_t e = cudaMemsetAsync(progress, 0, sizeof(int) * fp.ctb_rows, s);
+  cudaError_t e = cudaMemsetAsync(fp.ctu_done, 0, sizeof(int) * fp.ctb_cols * fp.ctb_rows, s);
   if (e != cudaSuccess) return e;
   e = cudaMemsetAsync(ticket, 0, sizeof(int), s);
   if (e != cudaSuccess) return e;
   const int blocks16 = ((fp.w + 15) >> 4) * ((fp.h + 15) >> 4);
   k_intra_modes<<<blocks16, kModeThreads, 0, s>>>(fp, src, cu);
-  k_intra_frame<false><<<intra_grid(fp), kReconThreads, 0, s>>>(fp, src, rec, levels, cu, progress, ticket, order);
+  k_intra_frame<false><<<intra_grid(fp), kReconThreads, 0, s>>>(fp, src, rec, levels, cu, ticket, order);
   return cudaGetLastError();
 }
 
-// Decoder reconstruction of an I picture (modes, cbf and levels from the parser).  Intra CUs must
-// be 16x16 or 8x8 (what the parser accepts for I slices produced by this encoder family).
-cudaError_t launch_intra_decode(const FrameParams &fp, uint8_t *rec, const int16_t *levels, const CuInfo *cu,
-                                int *progress, int *ticket, const int *order, cudaStream_t s)
+// P pictures: the intra CUs the motion search chose (cu map), after the inter reconstruction.  The
+// kernel returns at once when *fp.any_intra is 0.
+cudaError_t launch_intra_in_p(const FrameParams &fp, const uint8_t *src, uint8_t *rec, int16_t *levels, CuInfo *cu,
+                              int *ticket, const int *order, cudaStream_t s)
 {
-  cudaError_t e = cudaMemsetAsync(progress, 0, sizeof(int) * fp.ctb_rows, s);
+  cudaError_t e = cudaMemsetAsync(fp.ctu_done, 0, sizeof(int) * fp.ctb_cols * fp.ctb_rows, s);
   if (e != cudaSuccess) return e;
   e = cudaMemsetAsync(ticket, 0, sizeof(int), s);
   if (e != cudaSuccess) return e;
-  k_intra_frame<true><<<intra_grid(fp), kReconThreads, 0, s>>>(fp, nullptr, rec, (int16_t *)levels, (CuInfo *)cu, progress, ticket, order);
+  k_intra_frame<false><<<intra_grid(fp), kReconThreads, 0, s>>>(fp, src, rec, levels, cu, ticket, order);
+  return cudaGetLastError();
+}
+
+// Decoder reconstruction of the intra CUs of a picture (modes, cbf and levels from the parser): all
+// CUs of an I picture; in a P picture the intra CUs, after launch_inter_decode.  Intra CUs must be
+// 16x16 or 8x8 (what the parser accepts).
+cudaError_t launch_intra_decode(const FrameParams &fp, uint8_t *rec, const int16_t *levels, const CuInfo *cu,
+                                int *ticket, const int *order, cudaStream_t s)
+{
+  cudaError_t e = cudaMemsetAsync(fp.ctu_done, 0, sizeof(int) * fp.ctb_cols * fp.ctb_rows, s);
+  if (e != cudaSuccess) return e;
+  e = cudaMemsetAsync(ticket, 0, sizeof(int), s);
+  if (e != cudaSuccess) return e;
+  k_intra_frame<true><<<intra_grid(fp), kReconThreads, 0, s>>>(fp, nullptr, rec, (int16_t *)levels, (CuInfo *)cu, ticket, order);
   return cudaGetLastError();
 }
 

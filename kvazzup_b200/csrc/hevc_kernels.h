@@ -13,17 +13,24 @@ cudaError_t launch_inter_me(const FrameParams &fp, const uint8_t *src, const uin
 cudaError_t launch_inter_recon(const FrameParams &fp, const uint8_t *src, const uint8_t *ref, uint8_t *rec,
                                int16_t *levels, CuInfo *cu, cudaStream_t s);
 cudaError_t launch_inter_modes(const FrameParams &fp, CuInfo *cu, cudaStream_t s);
+// quarter-resolution luma (rounded 4x4 means) for the coarse level of the motion search
+cudaError_t launch_down4(const uint8_t *plane, int w, int h, uint8_t *out, cudaStream_t s);
 
-// I pictures: wavefront over CTUs. `progress` = ctb_rows ints, `ticket` = 1 int, both zeroed by the launcher.
+// Intra CUs: wavefront over CTUs in ticket order.  `ticket` = 1 int and fp.ctu_done = one int per CTU,
+// both zeroed by the launcher.  launch_intra_frame: I picture (mode decision + reconstruction of every
+// CU).  launch_intra_in_p: the intra CUs the motion search put into the cu map of a P picture, after
+// launch_inter_recon (returns at once when *fp.any_intra == 0).
 void intra_wavefront_order(int cols, int rows, int *out);      // host: CTU indices sorted by (col + 2*row, row)
 cudaError_t launch_intra_frame(const FrameParams &fp, const uint8_t *src, uint8_t *rec, int16_t *levels, CuInfo *cu,
-                               int *progress, int *ticket, const int *order, cudaStream_t s);
+                               int *ticket, const int *order, cudaStream_t s);
+cudaError_t launch_intra_in_p(const FrameParams &fp, const uint8_t *src, uint8_t *rec, int16_t *levels, CuInfo *cu,
+                              int *ticket, const int *order, cudaStream_t s);
 
 // decoder-side reconstruction (levels / modes / motion from the parser)
 cudaError_t launch_inter_decode(const FrameParams &fp, const uint8_t *ref, uint8_t *rec, const int16_t *levels,
                                 const CuInfo *cu, cudaStream_t s);
 cudaError_t launch_intra_decode(const FrameParams &fp, uint8_t *rec, const int16_t *levels, const CuInfo *cu,
-                                int *progress, int *ticket, const int *order, cudaStream_t s);
+                                int *ticket, const int *order, cudaStream_t s);
 // CABAC parse: one warp per substream.  data = unescaped slice data, bases[r] = offset of row r
 // (bases[rows] = end).  status[0] = first error (0 ok), status[1] = largest |mv| component.
 cudaError_t launch_parse(const FrameParams &fp, const uint8_t *data, const uint32_t *bases, CuInfo *cu, int16_t *levels,

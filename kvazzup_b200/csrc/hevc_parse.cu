@@ -149,6 +149,7 @@ struct ParseCtx {
   // cu_qp_delta with one quantisation group per CTU (8.6.1): qp_cur is QpY of the CU being parsed
   // (the prediction until the CTU's delta is coded), reset to the slice QP at each row start (WPP)
   int qp_cur, delta_coded;
+  int any_intra;                 // an intra CU was met in a P slice
 };
 
 __device__ __forceinline__ CuInfo load_cu(const ParseCtx &pc, int x, int y)
@@ -323,6 +324,7 @@ __device__ void parse_cu(Reader &r, ParseCtx &pc, int x0, int y0, int log2)
   cu.mvx = 0; cu.mvy = 0; cu.log2_size = (uint8_t)log2; cu.pred_mode = 0; cu.intra_mode = 1; cu.cbf = 0;
   cu.skip = 0; cu.merge_idx = 0xff; cu.mvp_idx = 0; cu.qp = 0;
   bool tu = false;
+  bool intra = fp.is_idr != 0;
   if (!fp.is_idr) {
     int ctx = 0;
     if (x0 > 0) ctx += load_cu(pc, x0 - 1, y0).skip;
@@ -330,10 +332,13 @@ __device__ void parse_cu(Reader &r, ParseCtx &pc, int x0, int y0, int log2)
     cu.skip = (uint8_t)dec_bin(r, CTX_SKIP + ctx);
     int merge = cu.skip;
     if (!cu.skip) {
-      if (dec_bin(r, CTX_PRED_MODE)) { r.err = 2; return; }            // intra CU in a P slice: not supported
-      if (!dec_bin(r, CTX_PART_MODE)) { r.err = 3; return; }           // only PART_2Nx2N
-      merge = dec_bin(r, CTX_MERGE_FLAG);
+      intra = dec_bin(r, CTX_PRED_MODE) != 0;                          // intra CU in a P slice
+      if (!intra) {
+        if (!dec_bin(r, CTX_PART_MODE)) { r.err = 3; return; }         // only PART_2Nx2N
+        merge = dec_bin(r, CTX_MERGE_FLAG);
+      }
     }
+    if (!intra) {
     const unsigned cur = coding_order_p(fp, x0, y0);
     NbP a1 = nb_p(pc, cur, x0 - 1, y0 + n - 1), b1 = nb_p(pc, cur, x0 + n - 1, y0 - 1);
     NbP b0 = nb_p(pc, cur, x0 + n, y0 - 1), a0 = nb_p(pc, cur, x0 - 1, y0 + n), b2 = nb_p(pc, cur, x0 - 1, y0 - 1);
@@ -389,16 +394,14 @@ __device__ void parse_cu(Reader &r, ParseCtx &pc, int x0, int y0, int log2)
     }
     pc.max_mv = max(pc.max_mv, max(abs((int)cu.mvx), abs((int)cu.mvy)));
     if (fp.mv_edges && !mv_allowed(fp, x0, n, cu.mvx)) { r.err = 12; return; }   // motion across an interior tile edge
-  } else {
-    cu.pred_mode = 1;
-    {
-      // the intra reconstruction kernel handles 16x16 CUs, and 8x8 only where 16x16 crosses the picture edge
-      const int bx = x0 & ~15, by = y0 & ~15;
-      const bool fits16 = bx + 16 <= fp.w && by + 16 <= fp.h;
-      if (!((log2 == 4 && fits16) || (log2 == 3 && !fits16))) { r.err = 10; return; }
     }
+  }
+  if (intra) {
+    cu.pred_mode = 1;
+    if (log2 > 4) { r.err = 10; return; }                                // the intra pass reconstructs 16x16 and 8x8 CUs
     if (log2 == 3 && !dec_bin(r, CTX_PART_MODE)) { r.err = 5; return; }   // PART_NxN: not supported
     int prev = dec_bin(r, CTX_PREV_INTRA_LUMA);
+    // candidate modes (8.4.2): inter neighbours carry intra_mode 1 (DC) in the cu map, as the rule asks
     int a = 1, b = 1;
     if (x0 > 0) a = load_cu(pc, x0 - 1, y0).intra_mode;
     if (y0 > 0 && (y0 & (kCtb - 1))) b = load_cu(pc, x0, y0 - 1).intra_mode;
@@ -424,6 +427,7 @@ __device__ void parse_cu(Reader &r, ParseCtx &pc, int x0, int y0, int log2)
     }
     cu.intra_mode = (uint8_t)mode;
     if (dec_bin(r, CTX_INTRA_CHROMA)) { r.err = 6; return; }              // only intra_chroma_pred_mode 4 (derived)
+    if (!fp.is_idr) pc.any_intra = 1;
     tu = true;
   }
   if (tu) {
@@ -548,7 +552,7 @@ k_parse_rows(FrameParams fp, const uint8_t *__restrict__ data, const uint32_t *_
   for (int i = lane; i < 64; i += 32) s_tab[i] = make_uint2(c_range_lps[i], (uint32_t)c_trans_lps[i] | (i == 0 ? 64u : 0u));
   Reader r;
   r.p = data + bases[fp.no_wpp ? 0 : row]; r.end = data + bases[fp.no_wpp ? 1 : row + 1]; r.ctx = s_ctx + lane; r.tab = s_tab; r.err = 0;
-  ParseCtx pc{fp, cu, levels, lane, 0, s_ctu, s_above, 0, row * kCtb, 0, fp.qp, 0};
+  ParseCtx pc{fp, cu, levels, lane, 0, s_ctu, s_above, 0, row * kCtb, 0, fp.qp, 0, 0};
   SaoCtu sao_left;
   { uint32_t *z = (uint32_t *)&sao_left; for (int i = 0; i < 5; i++) z[i] = 0; }
   if (row == 0 || fp.ctb_cols < 2) {
@@ -642,6 +646,7 @@ k_parse_rows(FrameParams fp, const uint8_t *__restrict__ data, const uint32_t *_
       }
     }
     atomicMax(&status[1], pc.max_mv);
+    if (pc.any_intra && fp.any_intra) *fp.any_intra = 1;
   }
 }
 

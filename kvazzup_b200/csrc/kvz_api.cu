@@ -257,6 +257,7 @@ kvz_encoder *encoder_open(const kvz_config *cfg)
   c.qp_delta = (cfg->roi_enable || cfg->set_qp_in_cu) ? 1 : 0;
   c.fps_num = cfg->framerate_num; c.fps_den = cfg->framerate_denom;     // VUI timing: the decoder side reports it
   c.sao = cfg->sao_type != 0 ? 2 : 0;             // with sao_merge_left / _up flags
+  c.intra_in_p = 1;                               // every Kvazaar preset may code intra CUs in P pictures
   if (cfg->tiles_width_count > 1) {
     // tile columns: independent strip encoders on this GPU; motion is confined to the tile, like
     // Kvazaar's mv-constraint frametilemargin (the reference exposes it, kvazaarfilter.cpp:246-276);
@@ -265,7 +266,7 @@ kvz_encoder *encoder_open(const kvz_config *cfg)
     b200_tiled_params_default(&tp);
     tp.width = c.width; tp.height = c.height; tp.qp = c.qp; tp.intra_period = c.intra_period; tp.search_range = c.search_range;
     tp.deblock = c.deblock; tp.depth = c.depth; tp.tile_cols = cfg->tiles_width_count; tp.wpp = cfg->wpp ? 1 : 0;
-    tp.fps_num = c.fps_num; tp.fps_den = c.fps_den; tp.sao = c.sao;
+    tp.fps_num = c.fps_num; tp.fps_den = c.fps_den; tp.sao = c.sao; tp.intra_in_p = c.intra_in_p;
     e->tiled = b200_tiled_open_params(&tp, nullptr, 0);
     if (!e->tiled) { delete e; return NULL; }
     e->tiled_out.resize((size_t)c.width * c.height * 3 + 65536);

@@ -19,7 +19,7 @@ CU_DTYPE = np.dtype([("mvx", "<i2"), ("mvy", "<i2"), ("log2_size", "u1"), ("pred
 class EncParams(C.Structure):
     """b200_enc_params (include/b200_hevc.h)."""
     _fields_ = [(n, C.c_int) for n in ("struct_size", "width", "height", "qp", "intra_period", "search_range", "deblock",
-                                       "debug", "depth", "qp_delta", "fps_num", "fps_den", "sao")]
+                                       "debug", "depth", "qp_delta", "fps_num", "fps_den", "sao", "intra_in_p", "me_coarse")]
 
 
 class GpuEncoder:
@@ -135,7 +135,7 @@ class GpuEncoder:
 class TiledParams(C.Structure):
     """b200_tiled_params (include/b200_hevc.h)."""
     _fields_ = [(n, C.c_int) for n in ("struct_size", "width", "height", "qp", "intra_period", "search_range", "deblock",
-                                       "depth", "tile_cols", "wpp", "fps_num", "fps_den", "sao")]
+                                       "depth", "tile_cols", "wpp", "fps_num", "fps_den", "sao", "intra_in_p", "me_coarse")]
 
 
 class GpuTiledEncoder:

@@ -4,6 +4,7 @@ noise(seed)  every byte from the 64-bit LCG  s = s*6364136223846793005 + 1442695
              byte = s >> 56
 camera(t)    moving gradients + four moving textured squares (I420, or YUYV for config 1)
 screen(t)    static black-on-white glyph cells with a scrolling band (screen-share content)
+sports(t)    fast pan (37 samples per picture), a fast foreground object and a scene cut at t = 3
 """
 from __future__ import annotations
 
@@ -87,6 +88,37 @@ def screen_i420(w: int, h: int, t: int) -> np.ndarray:
         Y[r * 16:(r + 1) * 16] = np.where(mask, blockrow, 255)
     out = np.full(i420_size(w, h), 128, np.uint8)
     out[: w * h] = Y[:h, :w].ravel()
+    return out
+
+
+def _world(seed: int, w: int, h: int) -> np.ndarray:
+    """Textured plane: 8x8-blocky random base (strong structure a block matcher can lock onto) plus
+    fine-grained detail, integer only."""
+    bw, bh = (w + 7) // 8 + 1, (h + 7) // 8 + 1
+    base = lcg_bytes(seed, bw * bh).reshape(bh, bw).astype(np.int64)
+    big = np.kron(base, np.ones((8, 8), np.int64))[:h, :w]
+    fine = lcg_bytes(seed + 1, w * h).reshape(h, w).astype(np.int64)
+    return 32 + (3 * big + fine) // 5
+
+
+def sports_i420(w: int, h: int, t: int) -> np.ndarray:
+    """Fast motion and a scene cut (what a zero-centred +-12 search cannot follow): the background
+    pans by (+37, -11) samples per picture, a 96x96 foreground object crosses it by (-45, +19) per
+    picture, and at t = 3 the scene changes to other content altogether."""
+    scene = 0 if t < 3 else 1
+    ww, wh = w + 37 * 8, h + 11 * 8
+    world = _world(300 + 10 * scene, ww, wh)
+    ox, oy = (37 * t) % (ww - w + 1), (11 * (7 - t % 8)) % (wh - h + 1)
+    Y = world[oy:oy + h, ox:ox + w].copy()
+    obj = _world(900 + scene, 96, 96)
+    px, py = (w - 96 - 45 * t) % max(w - 96, 1), (19 * t) % max(h - 96, 1)
+    hh, ow = min(96, h - py), min(96, w - px)
+    Y[py:py + hh, px:px + ow] = 255 - obj[:hh, :ow] // 2
+    out = np.empty(i420_size(w, h), np.uint8)
+    out[: w * h] = np.clip(Y, 0, 255).astype(np.uint8).ravel()
+    c = Y[0::2, 0::2]
+    out[w * h: w * h + w * h // 4] = (128 + (c % 32) - 16).astype(np.uint8).ravel()
+    out[w * h + w * h // 4:] = (128 - (c % 24) + 12).astype(np.uint8).ravel()
     return out
 
 

@@ -40,6 +40,10 @@ typedef struct {
   int sao;                 /* sample adaptive offset (8.7.3) after deblocking: 1 = on, 2 = on and sao_merge_left / _up
                             * flags are used where a CTU's parameters repeat its neighbour's */
   int tile_cols;           /* > 1: PPS / slice header of a picture with that many uniform tile columns (compositor only) */
+  int me_coarse;           /* > 0: two-level motion search -- a coarse level on quarter-resolution pictures (+- me_coarse
+                            * coarse samples = 4 * me_coarse luma samples) gives every 32x32 block a second search
+                            * centre besides the zero vector; search_range (<= 16) is the window around each centre */
+  int intra_in_p;          /* 1 = 16x16 intra CUs in P pictures where inter prediction is poor (scene cuts, uncovered areas) */
   int fps_num, fps_den;    /* both > 0: VUI timing info in the SPS (vui_time_scale / vui_num_units_in_tick); 0 = no VUI */
 } orc_enc_cfg_t;
 

@@ -49,6 +49,12 @@ def decode_all(aus):
     ("camera", 640, 480, 3, 22, {"sao": 1, "qp_delta": 1}),
     ("camera", 416, 240, 6, 37, {"sao": 2, "intra_period": 4}),          # sao_merge_left / _up
     ("screen", 640, 256, 5, 40, {"sao": 2}),
+    ("sports", 416, 240, 6, 32, {"intra_in_p": 1}),                       # intra CUs in P pictures
+    ("sports", 200, 136, 5, 22, {"intra_in_p": 1}),
+    ("noise", 128, 72, 3, 30, {"intra_in_p": 1}),
+    ("sports", 640, 480, 5, 35, {"intra_in_p": 1, "sao": 2, "intra_period": 4, "search_range": 12, "qp_delta": 1}),
+    ("sports", 416, 240, 6, 32, {"me_coarse": 16, "search_range": 4}),   # vectors of +-70 samples, also beyond the picture edge
+    ("sports", 640, 256, 4, 30, {"me_coarse": 32, "search_range": 6, "intra_in_p": 1}),
 ])
 def test_decoder_reproduces_oracle_reconstruction(kind, w, h, n, qp, kw):
     frames = frames_of(kind, w, h, n)

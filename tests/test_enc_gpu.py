@@ -62,6 +62,21 @@ CASES = [
     ("camera", 640, 480, 3, 22, {"sao": 1}),
     ("camera", 416, 240, 5, 37, {"sao": 2}),                     # with sao_merge_left / _up flags
     ("screen", 640, 256, 4, 40, {"sao": 2, "intra_period": 2}),
+    # intra CUs in P pictures (fast pan + scene cut; noise): decision in k_me_ctu, intra pass after the inter reconstruction
+    ("sports", 416, 240, 6, 32, {"intra_in_p": 1}),
+    ("sports", 200, 136, 5, 22, {"intra_in_p": 1}),
+    ("noise", 128, 72, 3, 30, {"intra_in_p": 1}),
+    ("camera", 416, 240, 5, 37, {"intra_in_p": 1, "sao": 2}),
+    ("sports", 640, 256, 4, 30, {"intra_in_p": 1, "deblock": 0}),
+    ("sports", 640, 480, 5, 35, {"intra_in_p": 1, "sao": 2, "intra_period": 4, "search_range": 12}),
+    # two-level motion search: coarse level on quarter-resolution pictures + windows around two centres
+    ("sports", 416, 240, 6, 32, {"me_coarse": 16, "search_range": 4}),
+    ("sports", 200, 136, 5, 27, {"me_coarse": 16, "search_range": 8}),
+    ("camera", 416, 240, 5, 37, {"me_coarse": 8, "search_range": 4, "sao": 2, "intra_in_p": 1}),
+    ("sports", 640, 256, 4, 30, {"me_coarse": 32, "search_range": 6, "intra_in_p": 1}),
+    ("noise", 128, 72, 3, 30, {"me_coarse": 16, "search_range": 4}),
+    ("camera", 64, 8, 3, 37, {"me_coarse": 16, "search_range": 4}),
+    ("screen", 640, 480, 4, 32, {"me_coarse": 16, "search_range": 6, "sao": 2, "intra_in_p": 1}),
 ]
 
 
@@ -118,7 +133,8 @@ def test_pipelined_encoder_returns_the_same_access_units_in_order():
         assert got == ref
 
 
-@pytest.mark.parametrize("qp,kw", [(27, {}), (22, {"sao": 1}), (32, {"sao": 1, "search_range": 12}), (37, {"sao": 1})])
+@pytest.mark.parametrize("qp,kw", [(27, {}), (22, {"sao": 1}), (32, {"sao": 1, "search_range": 12}), (37, {"sao": 1}),
+                                   (27, {"sao": 2, "intra_in_p": 1, "me_coarse": 16, "search_range": 6})])
 def test_full_hd_two_frames_match_oracle(qp, kw):
     """BASELINE config 2 size (1080p, partial bottom CTU row) at the four QPs of the sweep: I + P picture,
     bit-identical stream."""
@@ -156,7 +172,7 @@ def test_kvazaar_filter_default_settings_stream_equals_engine_and_decodes():
         assert len(got) == 1
         aus += got
     f.close()
-    o = OracleEncoder(w, h, qp=32, intra_period=64, search_range=8, fps_num=30, fps_den=1)    # "input-fps" -> VUI timing
+    o = OracleEncoder(w, h, qp=32, intra_period=64, search_range=8, fps_num=30, fps_den=1, intra_in_p=1)    # "input-fps" -> VUI timing
     assert aus == [o.encode(fr) for fr in frames]
     if ffhevc.required():
         dec, errs = ffhevc.decode_stream(aus)
@@ -348,7 +364,7 @@ def test_roi_through_kvz_api_and_pipelining():
     cols, rows = (w + 63) // 64, (h + 63) // 64
     dqp = np.array([[roi_px[cy * h // rows, cx * w // cols] for cx in range(cols)] for cy in range(rows)], np.int8)
     base = {"video/ResolutionWidth": w, "video/ResolutionHeight": h, "video/QP": 30, "video/Intra": 0, "video/Preset": "ultrafast"}
-    eng = GpuEncoder(w, h, qp=30, intra_period=0, search_range=8, qp_delta=1, fps_num=30, fps_den=1)
+    eng = GpuEncoder(w, h, qp=30, intra_period=0, search_range=8, qp_delta=1, fps_num=30, fps_den=1, intra_in_p=1)
     eng.set_ctu_dqp(dqp.ravel())
     want = [eng.encode(f) for f in frames]
     for owf in (0, 3):
@@ -361,7 +377,7 @@ def test_roi_through_kvz_api_and_pipelining():
         f.close()
         assert got == want, owf
     # not enabled: the map is accepted and ignored, as before
-    plain = GpuEncoder(w, h, qp=30, intra_period=0, search_range=8, fps_num=30, fps_den=1)
+    plain = GpuEncoder(w, h, qp=30, intra_period=0, search_range=8, fps_num=30, fps_den=1, intra_in_p=1)
     want_plain = [plain.encode(f) for f in frames]
     f = KvazaarFilter(base)
     assert f.init()
@@ -410,6 +426,8 @@ TILE_CASES = [
     ("camera", 1920, 1080, 3, 32, 4, 1, {"search_range": 12}),
     ("camera", 416, 240, 5, 30, 2, 0, {"sao": 1}),               # SAO stays inside each tile
     ("screen", 640, 200, 4, 35, 3, 1, {"sao": 1}),
+    ("sports", 640, 256, 5, 30, 2, 0, {"sao": 2, "intra_in_p": 1}),
+    ("sports", 640, 256, 5, 30, 2, 0, {"me_coarse": 16, "search_range": 4}),     # coarse vectors stay inside the tile too
 ]
 
 
@@ -469,8 +487,7 @@ def test_tiles_through_kvz_api():
     frames = frames_of("camera", w, h, n)
     base = {"video/ResolutionWidth": w, "video/ResolutionHeight": h, "video/QP": 30, "video/Intra": 0, "video/Preset": "ultrafast"}
     for wpp in (1, 0):
-        eng = GpuTiledEncoder(w, h, 3, qp=30, intra_period=0, search_range=8, wpp=wpp)
-        eng.set_fps(30, 1)
+        eng = GpuTiledEncoder(w, h, 3, qp=30, intra_period=0, search_range=8, wpp=wpp, fps_num=30, fps_den=1, intra_in_p=1)
         want = [eng.encode(f) for f in frames]
         eng.close()
         f = KvazaarFilter(base | {"video/Tiles": 1, "video/tileDimensions": "3x1", "video/WPP": wpp})
@@ -480,7 +497,7 @@ def test_tiles_through_kvz_api():
             got += f.feed_input(fr)
         f.close()
         assert got == want, wpp
-    plain = GpuEncoder(w, h, qp=30, intra_period=0, search_range=8, fps_num=30, fps_den=1)
+    plain = GpuEncoder(w, h, qp=30, intra_period=0, search_range=8, fps_num=30, fps_den=1, intra_in_p=1)
     want = [plain.encode(f) for f in frames]
     f = KvazaarFilter(base | {"video/Tiles": 1, "video/tileDimensions": "2x2"})
     assert f.init() and any("tiles" in str(x) for x in f.warnings)

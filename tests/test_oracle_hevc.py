@@ -25,6 +25,8 @@ def frames_of(kind, w, h, n):
             out.append(synth.noise(100 + t, w * h * 3 // 2))
         elif kind == "screen":
             out.append(synth.screen_i420(w, h, t * 5))
+        elif kind == "sports":
+            out.append(synth.sports_i420(w, h, t))
         else:
             out.append(synth.camera_i420(w, h, t))
     return out
@@ -173,6 +175,61 @@ def test_sao_streams_decode_bit_exactly_in_ffmpeg(kind, w, h, n, qp, kw):
         nomerge = OracleEncoder(w, h, qp=qp, **({"intra_period": 0} | kw | {"sao": 1}))
         sizes = [len(nomerge.encode(f)) for f in frames]
         assert np.array_equal(nomerge.recon(), recs[-1]) and sum(len(a) for a in aus) <= sum(sizes)
+
+
+@needs_ff
+@pytest.mark.parametrize("kind,w,h,n,qp,kw", [
+    ("sports", 416, 240, 6, 32, {}),                                     # fast pan + scene cut: many intra CUs
+    ("sports", 200, 136, 5, 22, {"hash_sei": 1}),                        # partial CTUs: intra only where 16x16 fits
+    ("noise", 128, 72, 3, 30, {}),
+    ("camera", 416, 240, 5, 37, {"sao": 2, "hash_sei": 1}),
+    ("sports", 416, 240, 6, 35, {"sao": 1, "qp_delta": 1, "intra_period": 4}),
+    ("sports", 640, 256, 4, 30, {"deblock": 0}),
+])
+def test_intra_cus_in_p_pictures_decode_bit_exactly_in_ffmpeg(kind, w, h, n, qp, kw):
+    """cfg.intra_in_p: 16x16 intra CUs inside P pictures where inter prediction is poor.  Normative
+    side: pred_mode_flag, the MPM derivation next to inter neighbours (they count as DC), intra
+    prediction from reconstructed INTER samples, bS 2 deblocking -- FFmpeg must agree bit for bit."""
+    frames = frames_of(kind, w, h, n)
+    enc = OracleEncoder(w, h, qp=qp, intra_in_p=1, **({"intra_period": 0} | kw))
+    if kw.get("qp_delta"):
+        enc.set_ctu_dqp(roi_pattern(w, h, 1, "random"))
+    aus, recs, n_intra = [], [], 0
+    for f in frames:
+        aus.append(enc.encode(f))
+        recs.append(enc.recon())
+        if not enc.last_was_idr():
+            n_intra += int((enc.cu_map()["pred_mode"] == 1).sum())
+    enc.close()
+    if kind == "sports":
+        assert n_intra > 0                                                # the option is actually exercised
+    dec, errs = ffhevc.decode_stream(aus)
+    assert errs == 0 and len(dec) == n
+    for i in range(n):
+        bad = np.flatnonzero(dec[i][0] != recs[i])
+        assert bad.size == 0, f"frame {i}: {bad.size} samples differ, first at {bad[:6]}"
+
+
+@needs_ff
+@pytest.mark.parametrize("kind,w,h,n,qp,kw", [
+    ("sports", 416, 240, 6, 32, {"me_coarse": 16, "search_range": 4}),
+    ("sports", 200, 136, 5, 27, {"me_coarse": 16, "search_range": 8, "hash_sei": 1}),     # partial CTUs and quadrants
+    ("camera", 416, 240, 5, 37, {"me_coarse": 8, "search_range": 4, "sao": 2, "intra_in_p": 1}),
+    ("sports", 640, 256, 4, 30, {"me_coarse": 32, "search_range": 6, "intra_in_p": 1, "hash_sei": 1}),
+])
+def test_two_level_motion_search_streams_decode_in_ffmpeg(kind, w, h, n, qp, kw):
+    """cfg.me_coarse: vectors far beyond search_range (up to 4 * me_coarse + search_range samples, also
+    pointing outside the picture); the search is not normative, the motion compensation at those
+    vectors is -- FFmpeg must agree -- and on fast motion it must beat the zero-centred window."""
+    frames = frames_of(kind, w, h, n)
+    aus, recs = encode_all(frames, w, h, qp=qp, **({"intra_period": 0} | kw))
+    dec, errs = ffhevc.decode_stream(aus)
+    assert errs == 0 and len(dec) == n
+    for i in range(n):
+        assert np.array_equal(dec[i][0], recs[i]), i
+    if kind == "sports":
+        plain, _ = encode_all(frames, w, h, qp=qp, intra_period=0, search_range=12)
+        assert sum(map(len, aus)) < 0.9 * sum(map(len, plain))
 
 
 @needs_ff
