@@ -45,6 +45,9 @@ typedef struct b200_enc_params {
 } b200_enc_params;
 void  b200_enc_params_default(b200_enc_params *p);
 void *b200_enc_open_params(const b200_enc_params *p);
+/* Fills search_range, me_coarse, sao and intra_in_p with what the kvz_api preset of that name selects
+ * ("ultrafast" ... "placebo"); the other fields are left alone.  0 on success. */
+int   b200_enc_params_from_preset(const char *preset, b200_enc_params *p);
 /* Per-CTU QP offsets (raster, one int8 per 64x64 CTU, n = CTU count) for the pictures submitted
  * from now on; CTU QP = clip(qp + dqp, 0, 51).  NULL clears.  Needs b200_enc_open_roi. */
 int   b200_enc_set_ctu_dqp(void *enc, const int8_t *dqp, int n);
@@ -57,16 +60,19 @@ int   b200_enc_flush(void *enc, uint8_t *out, int cap);   /* next pending access
 int   b200_enc_pending(void *enc);
 /* Per-kernel device time measured with CUDA events on the launching stream.  Kernel ids:
  * 0 intra, 1 motion search, 2 inter reconstruction, 3 merge/skip modes, 4 deblocking, 5 binarisation,
- * 6 arithmetic coding, 7 pack. */
+ * 6 arithmetic coding (both phases), 7 pack, 8 SAO. */
 int   b200_enc_set_profile(void *enc, int on);
 int   b200_enc_get_profile(void *enc, double *ms, unsigned long long *count, int n);
+/* Work counters of the motion search since b200_enc_set_profile(enc, 1): out[0] CTUs, [1] 32x32 quadrants
+ * whose second centre set was searched, [2] 16x16 intra mode searches, [3] intra CUs chosen.  n >= 4. */
+int   b200_enc_get_me_stats(void *enc, unsigned long long *out, int n);
 /* begin/end (ms since open) of each kernel id of the last returned picture: out[2*id], out[2*id+1] */
 int   b200_enc_get_timeline(void *enc, float *out, int n);
 int   b200_enc_last_was_idr(void *enc);
 unsigned long long b200_enc_last_bins(void *enc);
 
 /* Test hooks.  what: 0 reconstruction after deblocking, 1 before deblocking (debug=1),
- * 2 cu map (12 bytes per 8x8 unit), 3 quantised levels (int16, I420-shaped). */
+ * 2 cu map (16 bytes per 8x8 unit), 3 quantised levels (int16, I420-shaped). */
 int   b200_enc_debug_read(void *enc, int what, void *dst, size_t bytes);
 int   b200_enc_debug_set_reference(void *enc, const uint8_t *i420);
 

@@ -11,11 +11,13 @@ SIGNATURES: dict = {
     "b200_enc_open_roi": (v, [i, i, i, i, i, i, i, i]),
     "b200_enc_params_default": (None, [v]),
     "b200_enc_open_params": (v, [v]),
+    "b200_enc_params_from_preset": (i, [C.c_char_p, v]),
     "b200_enc_set_ctu_dqp": (i, [v, v, i]),
     "b200_enc_flush": (i, [v, v, i]),
     "b200_enc_pending": (i, [v]),
     "b200_enc_set_profile": (i, [v, i]),
     "b200_enc_get_profile": (i, [v, v, v, i]),
+    "b200_enc_get_me_stats": (i, [v, v, i]),
     "b200_enc_get_timeline": (i, [v, v, i]),
     "b200_enc_close": (None, [v]),
     "b200_enc_encode": (i, [v, v, v, i]),

@@ -6,7 +6,7 @@
 //   levels         quantised transform levels, int16, same I420 geometry: the level of the
 //                  coefficient (u,v) of the TU whose top-left sample is (x0,y0) lives at
 //                  plane[(y0+v)*stride + x0+u]
-//   cu map         one 12-byte CuInfo per 8x8 luma unit, raster order, every unit of a CU
+//   cu map         one 16-byte CuInfo per 8x8 luma unit, raster order, every unit of a CU
 //                  carries the CU's values (what the entropy coder, the deblocking filter
 //                  and the decoder's reconstruction all index by sample position)
 //   substreams     one byte buffer per CTU row (WPP substream), already escaped
@@ -25,17 +25,29 @@ constexpr int kCuOverheadBits = 3;
 constexpr int kRecUnitCap = 640;
 
 struct CuInfo {
-  int16_t mvx, mvy;     // quarter-sample motion vector
+  int16_t mvx, mvy;     // quarter-sample motion vector (inter).  Intra NxN CUs keep the modes of parts 1..3 here:
+                        // mvx & 0xff, mvx >> 8, mvy & 0xff
   uint8_t log2_size;    // CU size 3..6 (0 = outside the picture / not yet decided)
   uint8_t pred_mode;    // 0 inter, 1 intra
-  uint8_t intra_mode;   // 0..34
-  uint8_t cbf;          // bit0 Y, bit1 Cb, bit2 Cr
+  uint8_t intra_mode;   // 0..34 (part 0 of an NxN CU)
+  uint8_t cbf;          // bit0 Y, bit1 Cb, bit2 Cr of the transform unit covering this 8x8 unit; bits 4-7: luma cbf
+                        // of its four 4x4 transform blocks when tu_log2 == 2
   uint8_t skip;
   uint8_t merge_idx;    // 0xff = not merged
   uint8_t mvp_idx;
   uint8_t qp;           // luma QP of the CU when cu_qp_delta is enabled (FrameParams::ctu_qp != 0), else 0
+  uint8_t ref_idx;      // index into reference picture list 0 (inter)
+  uint8_t chroma_mode;  // intra: resolved chroma prediction mode 0..34 (mode 4 "derived" already replaced)
+  uint8_t tu_log2;      // luma size of the transform unit covering this 8x8 unit: 2 (four 4x4 blocks) .. 5
+  uint8_t flags;        // bit 0: intra NxN partition (8x8 CU, four 4x4 prediction blocks)
 };
-static_assert(sizeof(CuInfo) == 12, "CuInfo layout is part of the test ABI");
+static_assert(sizeof(CuInfo) == 16, "CuInfo layout is part of the test ABI");
+
+// Reference picture list 0 of a picture (packed I420 pictures in HBM); the encoder has one entry.
+struct RefList {
+  const uint8_t *pic[16];
+  int n;
+};
 
 // SAO parameters of one CTU (7.4.9.3): [0] luma, [1] chroma (type and class shared by Cb and Cr)
 struct SaoCtu {
@@ -92,11 +104,11 @@ struct FrameParams {
   int *ctu_done;
   // Two-level motion search (encoder): me_coarse > 0 = range of the coarse level in coarse samples (a
   // multiple of 4); src_q / ref_q = quarter-resolution luma of the source and of the reference.
-  // mc_range: largest |mv| component in full samples that motion compensation must reach
-  // (encoder: 4 * me_coarse + search_range; decoder: from the parsed vectors).
   int me_coarse;
   const uint8_t *src_q, *ref_q;
-  int mc_range;
+  // optional work counters of the motion search (profiling): [0] CTUs, [1] 32x32 quadrants whose second
+  // centre set was searched, [2] 16x16 intra mode searches, [3] intra CUs chosen (16x16)
+  unsigned long long *me_stats;
 };
 
 }  // namespace b200

@@ -439,9 +439,9 @@ struct Decoder {
         DEC_CHECK(launch_intra_decode(f, rec, t.d_levels, t.d_cu, ticket, g.d_order, g.stream), "intra decode launch");
         count_launch(1);
       } else {
-        f.mc_range = std::max(1, (t.h_status[1] + 3) / 4 + 1);
-        cudaError_t e = launch_inter_decode(f, ref, rec, t.d_levels, t.d_cu, g.stream);
-        if (e == cudaErrorInvalidValue) { set_error("decoder: motion vectors of +-%d samples exceed the supported window", f.mc_range); return -1; }
+        RefList refs{};
+        refs.pic[0] = ref; refs.n = 1;
+        cudaError_t e = launch_inter_decode(f, refs, rec, t.d_levels, t.d_cu, g.stream);
         DEC_CHECK(e, "inter decode launch");
         // intra CUs of the P picture predict from the reconstructed inter CUs (the kernel returns at
         // once when the parser met none)

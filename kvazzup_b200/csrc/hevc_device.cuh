@@ -106,6 +106,31 @@ __device__ __forceinline__ void load_window(const uint8_t *__restrict__ plane, i
   }
 }
 
+// One row of a reference patch: `nwords` words holding plane bytes x .. x + 4 * nwords - 1 of row y,
+// coordinates clamped to the picture (8.5.3.3.3.1), for any byte alignment of x.  Rows of the plane
+// are word aligned (pw is a multiple of 4).
+__device__ __forceinline__ void load_patch_row(const uint8_t *__restrict__ plane, int pw, int ph, int x, int y, int nwords,
+                                               uint32_t *dst)
+{
+  const uint8_t *row = plane + (size_t)clip3(0, ph - 1, y) * pw;
+  if (x >= 0 && (x & ~3) + 4 * (nwords + 1) <= pw) {
+    const uint32_t *w = (const uint32_t *)(row + (x & ~3));
+    const int sh = (x & 3) * 8;
+    uint32_t a = __ldg(w);
+    for (int i = 0; i < nwords; i++) {
+      const uint32_t b = __ldg(w + i + 1);
+      dst[i] = __funnelshift_r(a, b, sh);
+      a = b;
+    }
+  } else {
+    for (int i = 0; i < nwords; i++) {
+      const int xx = x + 4 * i;
+      dst[i] = (uint32_t)row[clip3(0, pw - 1, xx)] | ((uint32_t)row[clip3(0, pw - 1, xx + 1)] << 8) |
+               ((uint32_t)row[clip3(0, pw - 1, xx + 2)] << 16) | ((uint32_t)row[clip3(0, pw - 1, xx + 3)] << 24);
+    }
+  }
+}
+
 // ---- luma motion compensation: 2 columns x 8 rows at window position (xi,yi), fractional
 // phase (fx,fy).  Separable 8-tap, rows first (8.5.3.3.3); exact for zero phases as well
 // because the zero-phase filter is {0,0,0,64,0,0,0,0}.  out[r] = pixel(col0) | pixel(col1) << 8.

@@ -140,6 +140,8 @@ void Encoder::release()
   upload_stream = nullptr; ev_upload = nullptr;
   ev_intra = nullptr; intra_stream = nullptr;
   if (d_rec_pre) cudaFree(d_rec_pre);
+  if (d_me_stats) cudaFree(d_me_stats);
+  d_me_stats = nullptr;
   if (d_src_q) cudaFree(d_src_q);
   if (d_ref_q) cudaFree(d_ref_q);
   d_src_q = d_ref_q = nullptr;
@@ -225,6 +227,8 @@ bool Encoder::open(const EncoderConfig &c)
     ENC_CHECK(cudaEventCreateWithFlags(&s.ev_done, cudaEventDisableTiming), "cudaEventCreate");
     for (cudaEvent_t &e : s.pev) ENC_CHECK(cudaEventCreate(&e), "cudaEventCreate");
   }
+  ENC_CHECK(cudaMalloc((void **)&d_me_stats, 4 * sizeof(unsigned long long)), "cudaMalloc me stats");
+  ENC_CHECK(cudaMemset(d_me_stats, 0, 4 * sizeof(unsigned long long)), "memset me stats");
   ENC_CHECK(cudaEventCreate(&ev_base), "cudaEventCreate");
   ENC_CHECK(cudaEventRecord(ev_base, stream), "event record");
   frame_idx = 0; poc = 0; cur = 0; cur_qp = c.qp;
@@ -369,7 +373,8 @@ bool Encoder::submit(FrameSlot &s, const uint8_t *d_i420)
   // (a CTU needs its neighbours' DEBLOCKED samples) and writes the reconstruction ring
   uint8_t *rec = cfg.sao ? s.d_dbk : out_rec;
   p.ctu_done = s.d_ctu_done; p.any_intra = s.d_ctu_done + fp.ctb_cols * fp.ctb_rows; p.intra_in_p = cfg.intra_in_p;
-  p.me_coarse = cfg.me_coarse; p.src_q = d_src_q; p.ref_q = d_ref_q; p.mc_range = 4 * cfg.me_coarse + cfg.search_range;
+  p.me_stats = profile ? d_me_stats : nullptr;
+  p.me_coarse = cfg.me_coarse; p.src_q = d_src_q; p.ref_q = d_ref_q;
   p.sao = cfg.sao ? s.d_sao : nullptr; p.sao_flags = cfg.sao ? (cfg.sao == 2 ? 7 : 3) : 0;
   p.ctu_qp = nullptr; p.ctu_delta = nullptr; p.ctu_first = nullptr;
   p.mv_edges = cfg.mv_edges; p.more_tiles = cfg.more_tiles; p.no_wpp = cfg.no_wpp;
@@ -678,7 +683,19 @@ int b200_enc_set_profile(void *h, int on)
   if (!e) return B200_ERR_ARG;
   e->profile = on;
   for (int k = 0; k < Encoder::K_COUNT; k++) { e->prof_ms[k] = 0; e->prof_cnt[k] = 0; }
+  if (on) { cudaStreamSynchronize(e->stream); cudaMemset(e->d_me_stats, 0, 4 * sizeof(unsigned long long)); }
   return B200_OK;
+}
+
+// Work counters of the motion search since b200_enc_set_profile(enc, 1): out[0] CTUs, [1] 32x32
+// quadrants whose second centre set was searched, [2] 16x16 intra mode searches, [3] intra CUs chosen.
+int b200_enc_get_me_stats(void *h, unsigned long long *out, int n)
+{
+  Encoder *e = (Encoder *)h;
+  if (!e || !out || n < 4) return B200_ERR_ARG;
+  B200_CHECK(cudaStreamSynchronize(e->stream), "me stats sync");
+  B200_CHECK(cudaMemcpy(out, e->d_me_stats, 4 * sizeof(unsigned long long), cudaMemcpyDeviceToHost), "me stats read");
+  return 4;
 }
 
 // begin/end times (ms since the encoder was opened) of each kernel of the last collected picture

@@ -117,6 +117,7 @@ class Encoder {
   // its own stream concurrently with the P pictures queued before it.
   static constexpr int kRecRing = 32;
   uint8_t *d_rec[kRecRing] = {}, *d_rec_pre = nullptr;
+  unsigned long long *d_me_stats = nullptr;         // profiling: work counters of k_me_ctu (FrameParams::me_stats)
   uint8_t *d_src_q = nullptr, *d_ref_q = nullptr;   // me_coarse: quarter-resolution source / previous reconstruction (main stream order)
   cudaEvent_t ev_ring[kRecRing] = {};    // "picture n finished reading its reference" (main stream)
   cudaStream_t intra_stream = nullptr, upload_stream = nullptr;

@@ -42,7 +42,7 @@ struct MeShared {
   uint8_t intra_unit[64];
   // two-level search (fp.me_coarse): best key and resulting centre (full samples) of the coarse level
   // per 32x32 quadrant; per origin unit, the set whose window the CU's vector came from
-  unsigned ckey[4];
+  unsigned ckey[4], czero[4];
   short ctr_x[4], ctr_y[4];
   uint8_t wset[64];
 };
@@ -50,7 +50,7 @@ struct MeShared {
 // Intra CUs in P pictures: a 16x16 block whose best inter cost exceeds kIntraTryCost gets the 35-mode
 // source-based intra search; intra wins when 1.5 x its cost (prediction from reconstructed neighbours
 // is worse than from the source ones the search uses) plus kIntraOverheadBits of signalling is smaller.
-constexpr unsigned kIntraTryCost = 1024;
+constexpr unsigned kIntraTryCost = 4096;
 constexpr int kIntraOverheadBits = 24;
 
 // quarter-resolution picture for the coarse level of the motion search: every sample the rounded mean
@@ -76,7 +76,7 @@ k_down4(const uint8_t *__restrict__ plane, int w, int h, uint8_t *__restrict__ o
 // quarter-resolution pictures (+-me_coarse coarse samples = 4 * me_coarse luma samples), searched on
 // a window of the quadrant's own; skipped where it is the zero vector again.  Around every centre
 // the same +-R window is searched and the mv penalty counts from the centre.
-__global__ void __launch_bounds__(kThreads)
+__global__ void __launch_bounds__(kThreads, 4)     // <= 64 registers: four CTAs per SM hold the 510 CTUs of a 1080p picture in one wave
 k_me_ctu(FrameParams fp, const uint8_t *__restrict__ src, const uint8_t *__restrict__ ref, CuInfo *__restrict__ cu)
 {
   extern __shared__ uint32_t s_dyn[];
@@ -106,7 +106,7 @@ k_me_ctu(FrameParams fp, const uint8_t *__restrict__ src, const uint8_t *__restr
     sh.pen[c] = (unsigned short)mv_penalty(lambda_q4, dx * 4, dy * 4);
   }
   if (t < 16) sh.key16[t] = 0xffffffffu;
-  if (t < 4) { sh.key32[t] = 0xffffffffu; sh.ckey[t] = 0xffffffffu; sh.ctr_x[t] = 0; sh.ctr_y[t] = 0; }
+  if (t < 4) { sh.key32[t] = 0xffffffffu; sh.ckey[t] = 0xffffffffu; sh.czero[t] = 0xffffffffu; sh.ctr_x[t] = 0; sh.ctr_y[t] = 0; }
   __syncthreads();
 
   // ---- coarse level: one displacement per 32x32 quadrant (8x8 coarse samples, cut at the picture edge) ----
@@ -162,6 +162,7 @@ k_me_ctu(FrameParams fp, const uint8_t *__restrict__ src, const uint8_t *__restr
           sad = sad4_acc(sw[1] & m1[q], r1 & m1[q], sad);
         }
         best[q] = min(best[q], ((16 * sad + pen) << 13) | (unsigned)c);
+        if (dx == 0 && dy == 0) sh.czero[q] = 16 * sad + pen;
       }
     }
 #pragma unroll
@@ -170,10 +171,14 @@ k_me_ctu(FrameParams fp, const uint8_t *__restrict__ src, const uint8_t *__restr
       if ((t & 31) == 0 && b != 0xffffffffu) atomicMin(&sh.ckey[q], b);
     }
     __syncthreads();
-    if (t < 4 && sh.ckey[t] != 0xffffffffu) {
+    // a second centre only where it clearly beats staying put (below 3/4 of the zero displacement's
+    // cost): smooth content matches equally well at many coarse displacements
+    if (t < 4 && sh.ckey[t] != 0xffffffffu && (sh.ckey[t] >> 13) < sh.czero[t] - (sh.czero[t] >> 2)) {
       const int c = (int)(sh.ckey[t] & 8191u);
       const int dy = c / cside - Rc, dx = c - (dy + Rc) * cside - Rc;
-      sh.ctr_x[t] = (short)(4 * dx); sh.ctr_y[t] = (short)(4 * dy);
+      // ... and only where the zero-centred window does not cover it anyway (the vector behind a
+      // coarse displacement lies within half a coarse step, 2 samples, of it)
+      if (max(abs(4 * dx), abs(4 * dy)) + 2 > R) { sh.ctr_x[t] = (short)(4 * dx); sh.ctr_y[t] = (short)(4 * dy); }
     }
     __syncthreads();
     // windows of set 1, centred on each quadrant's coarse vector (a multiple of 4: aligned loads)
@@ -379,6 +384,16 @@ k_me_ctu(FrameParams fp, const uint8_t *__restrict__ src, const uint8_t *__restr
     }
   }
 
+  if (fp.me_stats && t == 0) {
+    int live = 0, tries = 0, chosen = 0;
+    for (int q = 0; q < 4; q++) live += sh.ctr_x[q] != 0 || sh.ctr_y[q] != 0;
+    for (int b = 0; b < 16; b++) { tries += sh.try_intra[b]; chosen += sh.intra_mode16[b] >= 0; }
+    atomicAdd(&fp.me_stats[0], 1ull);
+    if (live) atomicAdd(&fp.me_stats[1], (unsigned long long)live);
+    if (tries) atomicAdd(&fp.me_stats[2], (unsigned long long)tries);
+    if (chosen) atomicAdd(&fp.me_stats[3], (unsigned long long)chosen);
+  }
+
   // ---- cu map ----
   if (t < 64) {
     int ux = z_to_x(t), uy = z_to_y(t);
@@ -389,6 +404,7 @@ k_me_ctu(FrameParams fp, const uint8_t *__restrict__ src, const uint8_t *__restr
       CuInfo ci;
       ci.mvx = 0; ci.mvy = 0; ci.log2_size = 4; ci.pred_mode = 1; ci.intra_mode = (uint8_t)(sh.intra_unit[t] - 1); ci.cbf = 0;
       ci.skip = 0; ci.merge_idx = 0xff; ci.mvp_idx = 0; ci.qp = 0;
+      ci.ref_idx = 0; ci.chroma_mode = ci.intra_mode; ci.tu_log2 = ci.log2_size < 5 ? ci.log2_size : 5; ci.flags = 0;
       cu[(size_t)y8 * fp.w8 + x8] = ci;
       if (fp.any_intra) *fp.any_intra = 1;
     } else if (org != 0xff && x8 < fp.w8 && y8 < fp.h8) {
@@ -396,6 +412,7 @@ k_me_ctu(FrameParams fp, const uint8_t *__restrict__ src, const uint8_t *__restr
       ci.mvx = sh.mvx[org]; ci.mvy = sh.mvy[org];
       ci.log2_size = sh.log2[t]; ci.pred_mode = 0; ci.intra_mode = 0; ci.cbf = 0;
       ci.skip = 0; ci.merge_idx = 0xff; ci.mvp_idx = 0; ci.qp = 0;
+      ci.ref_idx = 0; ci.chroma_mode = ci.intra_mode; ci.tu_log2 = ci.log2_size < 5 ? ci.log2_size : 5; ci.flags = 0;
       cu[(size_t)y8 * fp.w8 + x8] = ci;
     }
   }
@@ -406,26 +423,28 @@ k_me_ctu(FrameParams fp, const uint8_t *__restrict__ src, const uint8_t *__restr
 struct ReconShared {
   uint8_t org[64], log2[64];
   short mvx[64], mvy[64];
+  uint8_t ref[64];                 // per unit: reference index of its CU
   int nz[64];
   uint8_t cbf[64];
   DctWords w;
 };
 
-__device__ __forceinline__ int chroma_margin(int range) { return (((range + 1) >> 1) + 2 + 3) & ~3; }
+// Reference samples are staged per 8x8 unit (luma: 15 rows x 16 bytes around the unit at its own
+// vector; chroma: 7 rows x 8 bytes), straight from the unit's reference picture -- so any vector and
+// any reference index work, whatever the search range was (a decoder meets arbitrary vectors).
+constexpr int kPatchWordsY = 15 * 4, kPatchWordsC = 7 * 2;
 
 // kDecode = false: encoder (source given, levels and cbf produced).
 // kDecode = true : decoder (levels and cbf given by the parser; `src` unused).
 template <bool kDecode>
 __global__ void __launch_bounds__(kThreads)
-k_inter_recon(FrameParams fp, const uint8_t *__restrict__ src, const uint8_t *__restrict__ ref,
+k_inter_recon(FrameParams fp, const uint8_t *__restrict__ src, const RefList refs,
               uint8_t *__restrict__ rec, int16_t *__restrict__ levels, CuInfo *__restrict__ cu)
 {
   extern __shared__ uint32_t s_dyn[];
   __shared__ ReconShared sh;
-  const int R = fp.mc_range;
-  const int M = window_margin(R), WS = kCtb + 2 * M, WSW = (WS >> 2) + 1;
-  uint32_t *s_ref = s_dyn;                                   // luma window; reused for chroma windows
-  uint8_t *s_src = (uint8_t *)(s_dyn + WS * WSW);            // 64 x 64
+  uint32_t *s_ref = s_dyn;                                   // 64 unit patches (luma size; reused for chroma)
+  uint8_t *s_src = (uint8_t *)(s_dyn + 64 * kPatchWordsY);   // 64 x 64
   uint8_t *s_pred = s_src + 4096;                            // 64 x 64
   uint8_t *s_rec = s_pred + 4096;                            // 64 x 64
   int16_t *s_a = (int16_t *)(s_rec + 4096);                  // 64 rows, pitch 66
@@ -446,6 +465,7 @@ k_inter_recon(FrameParams fp, const uint8_t *__restrict__ src, const uint8_t *__
       int n8 = 1 << (l2 - 3);
       org = xy_to_z(ux & ~(n8 - 1), uy & ~(n8 - 1));
       sh.mvx[t] = ci.mvx; sh.mvy[t] = ci.mvy;
+      sh.ref[t] = ci.ref_idx < refs.n ? ci.ref_idx : 0;
       sh.cbf[t] = kDecode ? ci.cbf : 0;
       if (ci.pred_mode != 0) org = 0xff;                   // not an inter CU: left to the intra pass (k_intra_frame)
     } else {
@@ -459,13 +479,22 @@ k_inter_recon(FrameParams fp, const uint8_t *__restrict__ src, const uint8_t *__
     const int cs = c ? 1 : 0;                                // chroma shift
     const int T = kCtb >> cs, pw = fp.w >> cs, ph = fp.h >> cs;
     const uint8_t *psrc = src + (c == 0 ? 0 : ysz + (c == 2 ? ysz / 4 : 0));
-    const uint8_t *pref = ref + (c == 0 ? 0 : ysz + (c == 2 ? ysz / 4 : 0));
-    uint8_t *prec = rec + (c == 0 ? 0 : ysz + (c == 2 ? ysz / 4 : 0));
-    int16_t *plev = levels + (c == 0 ? 0 : ysz + (c == 2 ? ysz / 4 : 0));
-    const int Mc = c ? chroma_margin(R) : M;
-    const int ws = T + 2 * Mc, wsw = (ws >> 2) + 1;
+    const size_t poff = c == 0 ? 0 : ysz + (c == 2 ? ysz / 4 : 0);
+    uint8_t *prec = rec + poff;
+    int16_t *plev = levels + poff;
     const int px0 = cx >> cs, py0 = cy >> cs;
-    load_window(pref, pw, ph, px0 - Mc, py0 - Mc, ws, wsw, s_ref);
+    // reference patches: one (unit, row) task per thread and pass
+    {
+      const int prow = c ? 7 : 15, pw4 = c ? 2 : 4, us = c ? 4 : 8;
+      for (int i = t; i < 64 * prow; i += kThreads) {
+        const int z = i / prow, r = i - z * prow;
+        if (sh.org[z] == 0xff) continue;
+        const int mx = sh.mvx[z], my = sh.mvy[z];
+        const int x = px0 + z_to_x(z) * us + (c ? (mx >> 3) - 1 : (mx >> 2) - 3);
+        const int y = py0 + z_to_y(z) * us + (c ? (my >> 3) - 1 : (my >> 2) - 3) + r;
+        load_patch_row(refs.pic[sh.ref[z]] + poff, pw, ph, x, y, pw4, s_ref + z * (c ? kPatchWordsC : kPatchWordsY) + r * pw4);
+      }
+    }
     if (!kDecode) {
       for (int i = t; i < T * T / 4; i += kThreads) {
         int y = i / (T / 4), xw = i - y * (T / 4);
@@ -475,7 +504,7 @@ k_inter_recon(FrameParams fp, const uint8_t *__restrict__ src, const uint8_t *__
     }
     if (t < 64) sh.nz[t] = kDecode ? ((sh.cbf[t] >> c) & 1) : 0;
     __syncthreads();
-    // motion compensation: 4 threads per unit
+    // motion compensation: 4 threads per unit, each from its unit's own patch
     {
       const int z = t >> 2, qc = t & 3;
       const int ux = z_to_x(z), uy = z_to_y(z);
@@ -484,7 +513,7 @@ k_inter_recon(FrameParams fp, const uint8_t *__restrict__ src, const uint8_t *__
         int mx = sh.mvx[z], my = sh.mvy[z];
         if (c == 0) {
           unsigned pr[8];
-          mc_luma_2x8(s_ref, wsw, Mc + ux * 8 + 2 * qc + (mx >> 2), Mc + uy * 8 + (my >> 2), mx & 3, my & 3, pr);
+          mc_luma_2x8(s_ref + z * kPatchWordsY, 4, 3 + 2 * qc, 3, mx & 3, my & 3, pr);
 #pragma unroll
           for (int r = 0; r < 8; r++) {
             uint8_t *d = s_pred + (uy * 8 + r) * 64 + ux * 8 + 2 * qc;
@@ -492,7 +521,7 @@ k_inter_recon(FrameParams fp, const uint8_t *__restrict__ src, const uint8_t *__
           }
         } else {
           unsigned pr[4];
-          mc_chroma_1x4(s_ref, wsw, Mc + ux * 4 + qc + (mx >> 3), Mc + uy * 4 + (my >> 3), mx & 7, my & 7, pr);
+          mc_chroma_1x4(s_ref + z * kPatchWordsC, 2, 1 + qc, 1, mx & 7, my & 7, pr);
 #pragma unroll
           for (int r = 0; r < 4; r++) s_pred[(uy * 4 + r) * 32 + ux * 4 + qc] = (uint8_t)pr[r];
         }
@@ -636,10 +665,9 @@ static size_t me_smem(int range, int coarse)
   }
   return words * 4;
 }
-static size_t recon_smem(int range)
+static size_t recon_smem()
 {
-  int M = (range + 4 + 3) & ~3, WS = kCtb + 2 * M, WSW = (WS >> 2) + 1;
-  return (size_t)WS * WSW * 4 + 3 * 4096 + 2 * 64 * 66 * 2;
+  return (size_t)64 * kPatchWordsY * 4 + 3 * 4096 + 2 * 64 * 66 * 2;
 }
 
 // The opt-in limit of dynamic shared memory is a per-function, process-wide attribute: set it once
@@ -669,22 +697,22 @@ cudaError_t launch_inter_me(const FrameParams &fp, const uint8_t *src, const uin
 cudaError_t launch_inter_recon(const FrameParams &fp, const uint8_t *src, const uint8_t *ref, uint8_t *rec,
                                int16_t *levels, CuInfo *cu, cudaStream_t s)
 {
-  size_t sm = recon_smem(fp.mc_range);
-  if (sm > (size_t)kMaxDynSmem) return cudaErrorInvalidValue;
   allow_big_smem();
-  k_inter_recon<false><<<fp.ctb_cols * fp.ctb_rows, kThreads, sm, s>>>(fp, src, ref, rec, levels, cu);
+  RefList refs{};
+  refs.pic[0] = ref; refs.n = 1;
+  k_inter_recon<false><<<fp.ctb_cols * fp.ctb_rows, kThreads, recon_smem(), s>>>(fp, src, refs, rec, levels, cu);
   return cudaGetLastError();
 }
 
-// Decoder reconstruction of a P picture: motion compensation + dequantisation + inverse transform.
-// fp.mc_range must cover the largest motion vector of the picture (in full samples).
-cudaError_t launch_inter_decode(const FrameParams &fp, const uint8_t *ref, uint8_t *rec, const int16_t *levels,
+// Decoder reconstruction of the inter CUs of a P picture: motion compensation from the reference
+// picture each CU names (any vector: reference samples are fetched per 8x8 unit with clamped
+// coordinates) + dequantisation + inverse transform.
+cudaError_t launch_inter_decode(const FrameParams &fp, const RefList &refs, uint8_t *rec, const int16_t *levels,
                                 const CuInfo *cu, cudaStream_t s)
 {
-  size_t sm = recon_smem(fp.mc_range);
-  if (sm > (size_t)kMaxDynSmem) return cudaErrorInvalidValue;
+  if (refs.n < 1 || refs.n > 16) return cudaErrorInvalidValue;
   allow_big_smem();
-  k_inter_recon<true><<<fp.ctb_cols * fp.ctb_rows, kThreads, sm, s>>>(fp, nullptr, ref, rec, (int16_t *)levels, (CuInfo *)cu);
+  k_inter_recon<true><<<fp.ctb_cols * fp.ctb_rows, kThreads, recon_smem(), s>>>(fp, nullptr, refs, rec, (int16_t *)levels, (CuInfo *)cu);
   return cudaGetLastError();
 }
 

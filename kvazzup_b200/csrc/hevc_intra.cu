@@ -34,6 +34,7 @@ __device__ void decide_cu(ModeShared &sh, const FrameParams &fp, const uint8_t *
     CuInfo ci;
     ci.mvx = 0; ci.mvy = 0; ci.log2_size = (uint8_t)log2; ci.pred_mode = 1; ci.intra_mode = (uint8_t)sh.best_mode;
     ci.cbf = 0; ci.skip = 0; ci.merge_idx = 0xff; ci.mvp_idx = 0; ci.qp = 0;
+      ci.ref_idx = 0; ci.chroma_mode = ci.intra_mode; ci.tu_log2 = ci.log2_size < 5 ? ci.log2_size : 5; ci.flags = 0;
     const int n8 = n >> 3;
     for (int j = 0; j < n8; j++)
       for (int i = 0; i < n8; i++) cu[(size_t)((y0 >> 3) + j) * fp.w8 + (x0 >> 3) + i] = ci;

@@ -27,7 +27,7 @@ cudaError_t launch_intra_in_p(const FrameParams &fp, const uint8_t *src, uint8_t
                               int *ticket, const int *order, cudaStream_t s);
 
 // decoder-side reconstruction (levels / modes / motion from the parser)
-cudaError_t launch_inter_decode(const FrameParams &fp, const uint8_t *ref, uint8_t *rec, const int16_t *levels,
+cudaError_t launch_inter_decode(const FrameParams &fp, const RefList &refs, uint8_t *rec, const int16_t *levels,
                                 const CuInfo *cu, cudaStream_t s);
 cudaError_t launch_intra_decode(const FrameParams &fp, uint8_t *rec, const int16_t *levels, const CuInfo *cu,
                                 int *ticket, const int *order, cudaStream_t s);

@@ -143,8 +143,8 @@ struct ParseCtx {
   int16_t *levels;       // zeroed by the host before the launch; only non-zero levels are stored
   int lane;
   int max_mv;            // largest |mv component| seen (quarter samples)
-  uint32_t *s_ctu;       // [2][64][3]: 8x8 units of the current (cur_buf) and the previous CTU, raster order
-  uint32_t *s_above;     // [10][3]: units (cx/8 - 1 .. cx/8 + 8) of the line above the CTU row
+  uint32_t *s_ctu;       // [2][64][4]: 8x8 units of the current (cur_buf) and the previous CTU, raster order
+  uint32_t *s_above;     // [10][4]: units (cx/8 - 1 .. cx/8 + 8) of the line above the CTU row
   int cx, cy, cur_buf;           // cy: top of the CTU row being parsed
   // cu_qp_delta with one quantisation group per CTU (8.6.1): qp_cur is QpY of the CU being parsed
   // (the prediction until the CTU's delta is coded), reset to the slice QP at each row start (WPP)
@@ -156,14 +156,14 @@ __device__ __forceinline__ CuInfo load_cu(const ParseCtx &pc, int x, int y)
 {
   const uint32_t *s;
   if (y < pc.cy) {
-    s = pc.s_above + 3 * (((x - pc.cx) >> 3) + 1);
+    s = pc.s_above + 4 * (((x - pc.cx) >> 3) + 1);
   } else {
     const int buf = x < pc.cx ? pc.cur_buf ^ 1 : pc.cur_buf;
-    s = pc.s_ctu + 3 * (buf * 64 + (((y - pc.cy) >> 3) << 3) + ((x >> 3) & 7));
+    s = pc.s_ctu + 4 * (buf * 64 + (((y - pc.cy) >> 3) << 3) + ((x >> 3) & 7));
   }
   CuInfo c;
   uint32_t *d = (uint32_t *)&c;
-  d[0] = s[0]; d[1] = s[1]; d[2] = s[2];
+  d[0] = s[0]; d[1] = s[1]; d[2] = s[2]; d[3] = s[3];
   return c;
 }
 
@@ -323,6 +323,7 @@ __device__ void parse_cu(Reader &r, ParseCtx &pc, int x0, int y0, int log2)
   CuInfo cu;
   cu.mvx = 0; cu.mvy = 0; cu.log2_size = (uint8_t)log2; cu.pred_mode = 0; cu.intra_mode = 1; cu.cbf = 0;
   cu.skip = 0; cu.merge_idx = 0xff; cu.mvp_idx = 0; cu.qp = 0;
+  cu.ref_idx = 0; cu.chroma_mode = 1; cu.tu_log2 = (uint8_t)min(log2, 5); cu.flags = 0;
   bool tu = false;
   bool intra = fp.is_idr != 0;
   if (!fp.is_idr) {
@@ -425,7 +426,7 @@ __device__ void parse_cu(Reader &r, ParseCtx &pc, int x0, int y0, int log2)
       mode = (int)dec_bypass_bits(r, 5);
       for (int i = 0; i < 3; i++) if (mode >= cand[i]) mode++;
     }
-    cu.intra_mode = (uint8_t)mode;
+    cu.intra_mode = (uint8_t)mode; cu.chroma_mode = (uint8_t)mode;
     if (dec_bin(r, CTX_INTRA_CHROMA)) { r.err = 6; return; }              // only intra_chroma_pred_mode 4 (derived)
     if (!fp.is_idr) pc.any_intra = 1;
     tu = true;
@@ -466,10 +467,10 @@ __device__ void parse_cu(Reader &r, ParseCtx &pc, int x0, int y0, int log2)
       int i = u & (n8 - 1), j = u >> (log2 - 3);
       const bool mine = u < units && x0 + 8 * i < fp.w && y0 + 8 * j < fp.h;
       i = mine ? i : 0; j = mine ? j : 0;
-      uint32_t *t = pc.s_ctu + 3 * (pc.cur_buf * 64 + ((((y0 - pc.cy) >> 3) + j) << 3) + ((x0 >> 3) & 7) + i);
-      t[0] = s[0]; t[1] = s[1]; t[2] = s[2];
+      uint32_t *t = pc.s_ctu + 4 * (pc.cur_buf * 64 + ((((y0 - pc.cy) >> 3) + j) << 3) + ((x0 >> 3) & 7) + i);
+      t[0] = s[0]; t[1] = s[1]; t[2] = s[2]; t[3] = s[3];
       uint32_t *d = (uint32_t *)(pc.cu + (size_t)((y0 >> 3) + j) * fp.w8 + (x0 >> 3) + i);
-      __stcg(d, s[0]); __stcg(d + 1, s[1]); __stcg(d + 2, s[2]);
+      __stcg(d, s[0]); __stcg(d + 1, s[1]); __stcg(d + 2, s[2]); __stcg(d + 3, s[3]);
     }
     __syncwarp();
   }
@@ -542,8 +543,8 @@ k_parse_rows(FrameParams fp, const uint8_t *__restrict__ data, const uint32_t *_
 {
   __shared__ uint8_t s_ctx[CTX_COUNT * 32];
   __shared__ uint2 s_tab[64];
-  __shared__ uint32_t s_ctu[2 * 64 * 3];
-  __shared__ uint32_t s_above[10 * 3];
+  __shared__ uint32_t s_ctu[2 * 64 * 4];
+  __shared__ uint32_t s_above[10 * 4];
   // WPP: one substream per CTU row (row_first == row_last == blockIdx.x).  no_wpp (a tile without
   // entropy_coding_sync): one warp reads every row from a single substream; bases[0..1] bound it.
   const int lane = threadIdx.x;
@@ -589,8 +590,8 @@ k_parse_rows(FrameParams fp, const uint8_t *__restrict__ data, const uint32_t *_
           const int slot = min(lane, 9);
           const int ux = min(max(col * 8 - 1 + slot, 0), fp.w8 - 1);
           const uint32_t *s = (const uint32_t *)(cu + (size_t)(row * 8 - 1) * fp.w8 + ux);
-          uint32_t *d = s_above + 3 * slot;
-          d[0] = __ldcg(s); d[1] = __ldcg(s + 1); d[2] = __ldcg(s + 2);
+          uint32_t *d = s_above + 4 * slot;
+          d[0] = __ldcg(s); d[1] = __ldcg(s + 1); d[2] = __ldcg(s + 2); d[3] = __ldcg(s + 3);
         }
       }
       const int cx = col * kCtb, cy = row * kCtb;

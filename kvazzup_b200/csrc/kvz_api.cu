@@ -31,11 +31,15 @@ struct kvz_encoder {
 
 namespace {
 
-// What a preset selects.  Restated from Kvazaar's preset table (cfg.c; not verified against 2.3.1,
-// which is absent from this image): SAO is off in ultrafast and on ("full") from superfast up.
-struct Preset { const char *name; int me_range; int sao; };
-const Preset kPresets[] = {{"ultrafast", 8, 0}, {"superfast", 8, 3}, {"veryfast", 12, 3}, {"faster", 12, 3}, {"fast", 16, 3},
-                           {"medium", 16, 3}, {"slow", 24, 3}, {"slower", 24, 3}, {"veryslow", 32, 3}, {"placebo", 32, 3}};
+// What a preset selects.  Restated from the intent of Kvazaar's preset table (cfg.c; not verified against
+// 2.3.1, which is absent from this image): SAO is off in ultrafast and on ("full") from superfast up;
+// faster presets search less.  Here "search" is the two-level motion search of k_me_ctu: me_coarse =
+// range of the coarse level in 4x4-mean samples (16 = +-64 luma samples), me_range = window searched
+// around the zero vector and around each 32x32 block's coarse vector.
+struct Preset { const char *name; int me_range; int sao; int me_coarse; };
+const Preset kPresets[] = {{"ultrafast", 4, 0, 16}, {"superfast", 4, 3, 16}, {"veryfast", 6, 3, 16}, {"faster", 8, 3, 16},
+                           {"fast", 8, 3, 32},      {"medium", 12, 3, 32},   {"slow", 16, 3, 32},    {"slower", 16, 3, 32},
+                           {"veryslow", 16, 3, 32}, {"placebo", 16, 3, 32}};
 
 int parse_int(const char *v, int *out)
 {
@@ -70,7 +74,7 @@ int config_init(kvz_config *cfg)
   cfg->deblock_enable = 1; cfg->sao_type = 3;    // preset veryfast
   cfg->tiles_width_count = 1; cfg->tiles_height_count = 1;
   cfg->gop_lowdelay = 1; cfg->gop_len = 4;
-  cfg->me_range = 12; cfg->device = -1;
+  cfg->me_range = 6; cfg->me_coarse = 16; cfg->device = -1;     // preset veryfast
   snprintf(cfg->preset, sizeof(cfg->preset), "veryfast");
   return 1;
 }
@@ -91,7 +95,7 @@ int config_parse(kvz_config *cfg, const char *name, const char *value)
   if (!strncmp(name, "--", 2)) name += 2;
   if (!strcmp(name, "preset")) {
     for (const Preset &p : kPresets)
-      if (value && !strcmp(value, p.name)) { cfg->me_range = p.me_range; cfg->sao_type = p.sao; snprintf(cfg->preset, sizeof(cfg->preset), "%s", p.name); return 1; }
+      if (value && !strcmp(value, p.name)) { cfg->me_range = p.me_range; cfg->sao_type = p.sao; cfg->me_coarse = p.me_coarse; snprintf(cfg->preset, sizeof(cfg->preset), "%s", p.name); return 1; }
     return 0;
   }
   if (!strcmp(name, "input-res")) {
@@ -176,6 +180,7 @@ int config_parse(kvz_config *cfg, const char *name, const char *value)
   }
   if (!strcmp(name, "set-qp-in-cu")) { if (!parse_bool(value, &v)) return 0; cfg->set_qp_in_cu = v; return 1; }
   if (!strcmp(name, "b200-me-range")) { if (!parse_int(value, &v) || v < 1 || v > 32) return 0; cfg->me_range = v; return 1; }
+  if (!strcmp(name, "b200-me-coarse")) { if (!parse_int(value, &v) || v < 0 || v > 32 || (v & 3)) return 0; cfg->me_coarse = v; return 1; }
   if (!strcmp(name, "b200-recon")) { if (!parse_bool(value, &v)) return 0; cfg->return_recon = v; return 1; }
   if (!strcmp(name, "b200-roi")) { if (!parse_bool(value, &v)) return 0; cfg->roi_enable = v; return 1; }
   if (!strcmp(name, "b200-device")) { if (!parse_int(value, &v)) return 0; cfg->device = v; return 1; }
@@ -252,7 +257,9 @@ kvz_encoder *encoder_open(const kvz_config *cfg)
   e->cfg = *cfg;
   EncoderConfig c;
   c.width = cfg->width; c.height = cfg->height; c.qp = cfg->qp; c.intra_period = cfg->intra_period;
-  c.search_range = cfg->me_range > 0 ? cfg->me_range : 12;
+  c.search_range = cfg->me_range > 0 ? cfg->me_range : 6;
+  c.me_coarse = cfg->me_coarse;
+  if (c.me_coarse > 0 && c.search_range > 16) c.search_range = 16;
   c.deblock = cfg->deblock_enable; c.debug = 0; c.depth = cfg->owf + 1;
   c.qp_delta = (cfg->roi_enable || cfg->set_qp_in_cu) ? 1 : 0;
   c.fps_num = cfg->framerate_num; c.fps_den = cfg->framerate_denom;     // VUI timing: the decoder side reports it
@@ -266,7 +273,7 @@ kvz_encoder *encoder_open(const kvz_config *cfg)
     b200_tiled_params_default(&tp);
     tp.width = c.width; tp.height = c.height; tp.qp = c.qp; tp.intra_period = c.intra_period; tp.search_range = c.search_range;
     tp.deblock = c.deblock; tp.depth = c.depth; tp.tile_cols = cfg->tiles_width_count; tp.wpp = cfg->wpp ? 1 : 0;
-    tp.fps_num = c.fps_num; tp.fps_den = c.fps_den; tp.sao = c.sao; tp.intra_in_p = c.intra_in_p;
+    tp.fps_num = c.fps_num; tp.fps_den = c.fps_den; tp.sao = c.sao; tp.intra_in_p = c.intra_in_p; tp.me_coarse = c.me_coarse;
     e->tiled = b200_tiled_open_params(&tp, nullptr, 0);
     if (!e->tiled) { delete e; return NULL; }
     e->tiled_out.resize((size_t)c.width * c.height * 3 + 65536);
@@ -407,6 +414,20 @@ const kvz_api kApi = {config_alloc, config_destroy, config_init, config_parse, p
                       chunk_free, encoder_open, encoder_close, encoder_headers, encoder_encode, picture_alloc_csp};
 
 }  // namespace
+
+// The engine parameters a preset stands for (what encoder_open derives from "preset"): lets the
+// benchmark and the tests run the bare engine in exactly the configuration kvz_api would.
+extern "C" int b200_enc_params_from_preset(const char *preset, b200_enc_params *p)
+{
+  if (!preset || !p) return B200_ERR_ARG;
+  for (const Preset &pr : kPresets)
+    if (!strcmp(preset, pr.name)) {
+      p->search_range = pr.me_range; p->me_coarse = pr.me_coarse; p->sao = pr.sao ? 2 : 0; p->intra_in_p = 1;
+      return B200_OK;
+    }
+  b200::set_error("unknown preset '%s'", preset);
+  return B200_ERR_ARG;
+}
 
 extern "C" const kvz_api *kvz_api_get(int bit_depth)
 {

@@ -13,13 +13,24 @@ from .capi import B200Error, lib
 
 CU_DTYPE = np.dtype([("mvx", "<i2"), ("mvy", "<i2"), ("log2_size", "u1"), ("pred_mode", "u1"),
                      ("intra_mode", "u1"), ("cbf", "u1"), ("skip", "u1"), ("merge_idx", "u1"),
-                     ("mvp_idx", "u1"), ("qp", "u1")])
+                     ("mvp_idx", "u1"), ("qp", "u1"), ("ref_idx", "u1"), ("chroma_mode", "u1"), ("tu_log2", "u1"),
+                     ("flags", "u1")])
+assert CU_DTYPE.itemsize == 16
 
 
 class EncParams(C.Structure):
     """b200_enc_params (include/b200_hevc.h)."""
     _fields_ = [(n, C.c_int) for n in ("struct_size", "width", "height", "qp", "intra_period", "search_range", "deblock",
                                        "debug", "depth", "qp_delta", "fps_num", "fps_den", "sao", "intra_in_p", "me_coarse")]
+
+
+def preset_options(preset: str) -> dict:
+    """Engine options (search_range, me_coarse, sao, intra_in_p) the kvz_api preset of that name selects."""
+    p = EncParams()
+    lib().b200_enc_params_default(C.byref(p))
+    if lib().b200_enc_params_from_preset(preset.encode(), C.byref(p)) != 0:
+        raise B200Error("unknown preset " + preset)
+    return {"search_range": p.search_range, "me_coarse": p.me_coarse, "sao": p.sao, "intra_in_p": p.intra_in_p}
 
 
 class GpuEncoder:
@@ -83,6 +94,12 @@ class GpuEncoder:
         cnt = (C.c_ulonglong * 9)()
         self.l.b200_enc_get_profile(self.h_enc, ms, cnt, 9)
         return {k: (ms[i], int(cnt[i])) for i, k in enumerate(self.KERNELS)}
+
+    def me_stats(self) -> dict:
+        """Work counters of the motion search since set_profile(True)."""
+        a = (C.c_ulonglong * 4)()
+        self.l.b200_enc_get_me_stats(self.h_enc, a, 4)
+        return {"ctus": int(a[0]), "second_set_quadrants": int(a[1]), "intra_searches": int(a[2]), "intra_cus": int(a[3])}
 
     def timeline(self) -> dict:
         """{kernel: (begin_ms, end_ms)} of the last returned picture, since the encoder was opened."""

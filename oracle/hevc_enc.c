@@ -32,8 +32,9 @@
  * exceeds INTRA_TRY_COST gets the 35-mode source-based intra search; intra wins when 1.5 x its cost
  * (the search predicts from source neighbours; the real prediction, from reconstructed ones, is worse
  * and its residual dearer) plus INTRA_OVERHEAD_BITS of signalling is smaller.  Tuned on the synthetic
- * sequences: never worse than +0.8 % bits on `camera`, -0.7 ... -1.6 % on `sports` (scene cut). */
-#define INTRA_TRY_COST 1024
+ * sequences: never worse than +0.8 % bits on `camera`, -0.7 ... -1.6 % on `sports` (scene cut); the
+ * same CUs end up intra with INTRA_TRY_COST anywhere in 1024 ... 4096, at a fifth of the searches. */
+#define INTRA_TRY_COST 4096
 #define INTRA_OVERHEAD_BITS 24
 
 static const uint16_t lambda_q4_tab[52] = {   /* round(16*sqrt(0.57*2^((qp-12)/3))) */
@@ -404,14 +405,15 @@ static void down4(const uint8_t *p, int w, int h, uint8_t *out)
 /* Coarse level of the motion search: best displacement of the 32x32 block at (qx, qy) on the
  * quarter-resolution pictures (an 8x8 block of coarse samples, cut at the picture edge), within
  * +-me_coarse coarse samples, reference coordinates clamped to the picture.  Cost = 16 * SAD + lambda *
- * bits of the vector; raster order, the first strictly smaller cost wins.  out = full samples. */
+ * bits of the vector; raster order, the first strictly smaller cost wins; kept only when below 3/4 of
+ * the cost of the zero displacement.  out = full samples. */
 static void coarse_search(const orc_encoder_t *e, int qx, int qy, int lam, int out[2])
 {
   out[0] = out[1] = 0;
   if (qx >= e->w || qy >= e->h) return;
   const int wq = e->w / 4, hq = e->h / 4, Rc = e->cfg.me_coarse;
   const int x0 = qx / 4, y0 = qy / 4, bw = imin(8, wq - x0), bh = imin(8, hq - y0);
-  uint32_t best = UINT_MAX;
+  uint32_t best = UINT_MAX, zero = UINT_MAX;
   for (int dy = -Rc; dy <= Rc; dy++)
     for (int dx = -Rc; dx <= Rc; dx++) {
       if (!mv_allowed(e, qx, imin(32, e->w - qx), dx * 16)) continue;
@@ -421,8 +423,15 @@ static void coarse_search(const orc_encoder_t *e, int qx, int qy, int lam, int o
           sad += (uint32_t)abs((int)e->src_q[(size_t)(y0 + y) * wq + x0 + x] -
                                (int)e->ref_q[(size_t)clip3i(0, hq - 1, y0 + y + dy) * wq + clip3i(0, wq - 1, x0 + x + dx)]);
       const uint32_t cost = 16 * sad + mv_penalty(lam, dx * 16, dy * 16);
+      if (dx == 0 && dy == 0) zero = cost;
       if (cost < best) { best = cost; out[0] = 4 * dx; out[1] = 4 * dy; }
     }
+  /* a second centre only where it clearly beats staying put: smooth content matches equally well at
+   * many coarse displacements (aperture problem) and would otherwise buy a second window for nothing */
+  if (best >= zero - (zero >> 2)) out[0] = out[1] = 0;
+  /* ... and only where the zero-centred window does not cover it anyway (the vector behind a coarse
+   * displacement lies within half a coarse step, 2 samples, of it) */
+  if (imax(abs(out[0]), abs(out[1])) + 2 <= e->cfg.search_range) out[0] = out[1] = 0;
 }
 
 /* the centre the mv penalty of a CU counts from (quarter samples), kept for the fractional refinement */

@@ -114,8 +114,12 @@ def test_kvz_config_parse_follows_the_reference_contract():
     cfg = api.config_alloc()
     assert api.config_init(cfg) == 1
     ok = lambda n, v: api.config_parse(cfg, n.encode(), v.encode() if v is not None else None)
-    for preset, rng in (("ultrafast", 8), ("veryfast", 12), ("medium", 16), ("placebo", 32)):
-        assert ok("preset", preset) == 1 and cfg.contents.me_range == rng
+    # a preset selects the search (window around each centre, coarse-level range) and SAO
+    for preset, rng, coarse, sao in (("ultrafast", 4, 16, 0), ("veryfast", 6, 16, 3), ("medium", 12, 32, 3), ("placebo", 16, 32, 3)):
+        assert ok("preset", preset) == 1
+        assert (cfg.contents.me_range, cfg.contents.me_coarse, cfg.contents.sao_type) == (rng, coarse, sao)
+    assert ok("sao", "band") == 1 and cfg.contents.sao_type == 2 and ok("sao", "full") == 1 and ok("sao", "purple") == 0
+    assert ok("b200-me-coarse", "8") == 1 and cfg.contents.me_coarse == 8 and ok("b200-me-coarse", "7") == 0
     assert ok("preset", "warp-speed") == 0
     assert ok("qp", "27") == 1 and cfg.contents.qp == 27
     assert ok("qp", "52") == 0 and ok("qp", "abc") == 0

@@ -172,7 +172,9 @@ def test_kvazaar_filter_default_settings_stream_equals_engine_and_decodes():
         assert len(got) == 1
         aus += got
     f.close()
-    o = OracleEncoder(w, h, qp=32, intra_period=64, search_range=8, fps_num=30, fps_den=1, intra_in_p=1)    # "input-fps" -> VUI timing
+    from kvazzup_b200.encoder import preset_options
+    assert preset_options("ultrafast") == {"search_range": 4, "me_coarse": 16, "sao": 0, "intra_in_p": 1}
+    o = OracleEncoder(w, h, qp=32, intra_period=64, fps_num=30, fps_den=1, **preset_options("ultrafast"))    # "input-fps" -> VUI timing
     assert aus == [o.encode(fr) for fr in frames]
     if ffhevc.required():
         dec, errs = ffhevc.decode_stream(aus)
@@ -364,7 +366,9 @@ def test_roi_through_kvz_api_and_pipelining():
     cols, rows = (w + 63) // 64, (h + 63) // 64
     dqp = np.array([[roi_px[cy * h // rows, cx * w // cols] for cx in range(cols)] for cy in range(rows)], np.int8)
     base = {"video/ResolutionWidth": w, "video/ResolutionHeight": h, "video/QP": 30, "video/Intra": 0, "video/Preset": "ultrafast"}
-    eng = GpuEncoder(w, h, qp=30, intra_period=0, search_range=8, qp_delta=1, fps_num=30, fps_den=1, intra_in_p=1)
+    from kvazzup_b200.encoder import preset_options
+    uf = preset_options("ultrafast")
+    eng = GpuEncoder(w, h, qp=30, intra_period=0, qp_delta=1, fps_num=30, fps_den=1, **uf)
     eng.set_ctu_dqp(dqp.ravel())
     want = [eng.encode(f) for f in frames]
     for owf in (0, 3):
@@ -377,7 +381,7 @@ def test_roi_through_kvz_api_and_pipelining():
         f.close()
         assert got == want, owf
     # not enabled: the map is accepted and ignored, as before
-    plain = GpuEncoder(w, h, qp=30, intra_period=0, search_range=8, fps_num=30, fps_den=1, intra_in_p=1)
+    plain = GpuEncoder(w, h, qp=30, intra_period=0, fps_num=30, fps_den=1, **uf)
     want_plain = [plain.encode(f) for f in frames]
     f = KvazaarFilter(base)
     assert f.init()
@@ -481,13 +485,14 @@ def test_tiles_through_kvz_api():
     """video/Tiles + video/tileDimensions (kvazaarfilter.cpp:196-202): "Cx1" selects the tiled encoder;
     the reference's default "2x2" has tile rows, which config_parse refuses (the filter logs a warning
     and encodes untiled)."""
-    from kvazzup_b200.encoder import GpuTiledEncoder
+    from kvazzup_b200.encoder import GpuTiledEncoder, preset_options
     from kvazzup_b200.kvazaar import KvazaarFilter
+    uf = preset_options("ultrafast")
     w, h, n = 640, 256, 5
     frames = frames_of("camera", w, h, n)
     base = {"video/ResolutionWidth": w, "video/ResolutionHeight": h, "video/QP": 30, "video/Intra": 0, "video/Preset": "ultrafast"}
     for wpp in (1, 0):
-        eng = GpuTiledEncoder(w, h, 3, qp=30, intra_period=0, search_range=8, wpp=wpp, fps_num=30, fps_den=1, intra_in_p=1)
+        eng = GpuTiledEncoder(w, h, 3, qp=30, intra_period=0, wpp=wpp, fps_num=30, fps_den=1, **uf)
         want = [eng.encode(f) for f in frames]
         eng.close()
         f = KvazaarFilter(base | {"video/Tiles": 1, "video/tileDimensions": "3x1", "video/WPP": wpp})
@@ -497,7 +502,7 @@ def test_tiles_through_kvz_api():
             got += f.feed_input(fr)
         f.close()
         assert got == want, wpp
-    plain = GpuEncoder(w, h, qp=30, intra_period=0, search_range=8, fps_num=30, fps_den=1, intra_in_p=1)
+    plain = GpuEncoder(w, h, qp=30, intra_period=0, fps_num=30, fps_den=1, **uf)
     want = [plain.encode(f) for f in frames]
     f = KvazaarFilter(base | {"video/Tiles": 1, "video/tileDimensions": "2x2"})
     assert f.init() and any("tiles" in str(x) for x in f.warnings)
