@@ -10,8 +10,9 @@ from .sigs import OrcCu, OrcEncCfg
 
 CU_DTYPE = np.dtype([("mvx", "<i2"), ("mvy", "<i2"), ("log2_size", "u1"), ("pred_mode", "u1"),
                      ("intra_mode", "u1"), ("cbf", "u1"), ("skip", "u1"), ("merge_idx", "u1"),
-                     ("mvp_idx", "u1"), ("qp", "u1")])
-assert CU_DTYPE.itemsize == C.sizeof(OrcCu) == 12
+                     ("mvp_idx", "u1"), ("qp", "u1"), ("ref_idx", "u1"), ("chroma_mode", "u1"), ("tu_log2", "u1"),
+                     ("flags", "u1")])
+assert CU_DTYPE.itemsize == C.sizeof(OrcCu) == 16
 
 
 class OracleEncoder:

@@ -28,6 +28,7 @@
 #define PAD 160                /* luma padding of the reference planes: covers 4 * me_coarse + search_range + interpolation taps */
 #define CU_OVERHEAD_BITS 3
 #define MAX_MERGE 5
+#define MAX_REFS 4
 /* intra CUs in P pictures (cfg.intra_in_p): a 16x16 block whose best inter cost (SAD + lambda * bits)
  * exceeds INTRA_TRY_COST gets the 35-mode source-based intra search; intra wins when 1.5 x its cost
  * (the search predicts from source neighbours; the real prediction, from reconstructed ones, is worse
@@ -41,6 +42,9 @@ static const uint16_t lambda_q4_tab[52] = {   /* round(16*sqrt(0.57*2^((qp-12)/3
   3, 3, 4, 4, 5, 5, 6, 7, 8, 9, 10, 11, 12, 14, 15, 17, 19, 22, 24, 27, 30, 34, 38, 43, 48, 54, 61, 68,
   77, 86, 97, 108, 122, 137, 153, 172, 193, 217, 244, 273, 307, 344, 387, 434, 487, 547, 614, 689, 773,
   868, 974, 1093};
+
+/* motion of one 8x8 unit of a reference picture, for temporal motion vector prediction */
+struct orc_mvf { int16_t mvx, mvy; int16_t ref_poc; uint8_t inter; };
 
 /* SAO parameters of one CTU (7.4.9.3): [0] luma, [1] chroma (type and class shared by Cb / Cr) */
 struct orc_sao {
@@ -61,9 +65,17 @@ struct orc_encoder {
   uint8_t *dbk;                  /* copy of the deblocked picture: SAO reads it, writes rec */
   const uint8_t *src;
   uint8_t *rec, *rec_pre;        /* packed I420 */
-  uint8_t *refpad[3];            /* padded previous reconstruction */
+  /* decoded picture buffer: dpb[0] is the previous picture (reference index 0), dpb[1] the one before ... */
+  struct orc_ref {
+    uint8_t *pad[3];             /* padded reconstruction */
+    uint8_t *q;                  /* me_coarse: quarter-resolution luma */
+    struct orc_mvf *mvf;         /* tmvp: motion field, one entry per 8x8 unit */
+    int poc;
+  } dpb[MAX_REFS];
+  int n_dpb;                     /* pictures in the buffer (reset by an IDR) */
+  int n_refs;                    /* of the picture being coded: min(cfg.refs, n_dpb) */
   int16_t *pen_ctr;              /* per 8x8 unit (origin unit of a CU): centre of its mv penalty, quarter samples */
-  uint8_t *src_q, *ref_q;        /* me_coarse: quarter-resolution luma of the source / the previous reconstruction */
+  uint8_t *src_q;                /* me_coarse: quarter-resolution luma of the source */
   int refstride[3];
   orc_cu_t *cu;
   int16_t *levels;               /* I420-shaped */
@@ -89,6 +101,7 @@ orc_encoder_t *orc_enc_open(const orc_enc_cfg_t *cfg)
 {
   if (!cfg || cfg->width <= 0 || cfg->height <= 0 || (cfg->width & 7) || (cfg->height & 7)) return NULL;
   if (cfg->qp < 0 || cfg->qp > 51 || cfg->search_range < 1 || cfg->search_range > 32) return NULL;
+  if (cfg->refs < 0 || cfg->refs > MAX_REFS) return NULL;
   if (cfg->me_coarse < 0 || cfg->me_coarse > 32 || (cfg->me_coarse > 0 && cfg->search_range > 16)) return NULL;
   orc_encoder_t *e = (orc_encoder_t *)calloc(1, sizeof(*e));
   if (!e) return NULL;
@@ -106,14 +119,18 @@ orc_encoder_t *orc_enc_open(const orc_enc_cfg_t *cfg)
   size_t fsz = (size_t)e->w * e->h * 3 / 2;
   e->rec = (uint8_t *)calloc(fsz, 1);
   e->rec_pre = (uint8_t *)calloc(fsz, 1);
-  for (int c = 0; c < 3; c++) {
-    int pw = c ? e->cw : e->w, ph = c ? e->ch : e->h, pad = c ? PAD / 2 : PAD;
-    e->refstride[c] = pw + 2 * pad;
-    e->refpad[c] = (uint8_t *)calloc((size_t)e->refstride[c] * (ph + 2 * pad), 1);
+  if (e->cfg.refs < 1) e->cfg.refs = 1;
+  for (int r = 0; r < e->cfg.refs; r++) {
+    for (int c = 0; c < 3; c++) {
+      int pw = c ? e->cw : e->w, ph = c ? e->ch : e->h, pad = c ? PAD / 2 : PAD;
+      e->refstride[c] = pw + 2 * pad;
+      e->dpb[r].pad[c] = (uint8_t *)calloc((size_t)e->refstride[c] * (ph + 2 * pad), 1);
+    }
+    e->dpb[r].q = (uint8_t *)calloc((size_t)(e->w / 4) * (e->h / 4), 1);
+    e->dpb[r].mvf = (struct orc_mvf *)calloc((size_t)e->w8 * e->h8, sizeof(struct orc_mvf));
   }
   e->pen_ctr = (int16_t *)calloc((size_t)e->w8 * e->h8 * 2, sizeof(int16_t));
   e->src_q = (uint8_t *)calloc((size_t)(e->w / 4) * (e->h / 4), 1);
-  e->ref_q = (uint8_t *)calloc((size_t)(e->w / 4) * (e->h / 4), 1);
   e->cu = (orc_cu_t *)calloc((size_t)e->w8 * e->h8, sizeof(orc_cu_t));
   e->levels = (int16_t *)calloc(fsz, sizeof(int16_t));
   e->sub_cap = fsz * 2 + 65536;
@@ -126,8 +143,11 @@ void orc_enc_close(orc_encoder_t *e)
   if (e) { free(e->ctu_dqp); free(e->ctu_delta); free(e->ctu_first); free(e->sao); free(e->dbk); }
   if (!e) return;
   free(e->rec); free(e->rec_pre);
-  for (int c = 0; c < 3; c++) free(e->refpad[c]);
-  free(e->cu); free(e->levels); free(e->sub); free(e->src_q); free(e->ref_q); free(e->pen_ctr);
+  for (int r = 0; r < MAX_REFS; r++) {
+    for (int c = 0; c < 3; c++) free(e->dpb[r].pad[c]);
+    free(e->dpb[r].q); free(e->dpb[r].mvf);
+  }
+  free(e->cu); free(e->levels); free(e->sub); free(e->src_q); free(e->pen_ctr);
   free(e);
 }
 
@@ -363,31 +383,48 @@ static inline int mv_allowed(const orc_encoder_t *e, int x, int n, int mvx)
   return 1;
 }
 
-static void pad_reference(orc_encoder_t *e)
+/* The finished picture enters the decoded picture buffer as reference index 0; the oldest one leaves. */
+static void down4(const uint8_t *p, int w, int h, uint8_t *out);
+static void dpb_insert(orc_encoder_t *e)
 {
+  struct orc_ref last = e->dpb[e->cfg.refs - 1];
+  for (int r = e->cfg.refs - 1; r > 0; r--) e->dpb[r] = e->dpb[r - 1];
+  e->dpb[0] = last;
+  struct orc_ref *d = &e->dpb[0];
   for (int c = 0; c < 3; c++) {
     int pw = c ? e->cw : e->w, ph = c ? e->ch : e->h, pad = c ? PAD / 2 : PAD, st = e->refstride[c];
     const uint8_t *s = plane(e->rec, e->w, e->h, c);
     for (int y = -pad; y < ph + pad; y++) {
       const uint8_t *row = s + (size_t)clip3i(0, ph - 1, y) * pw;
-      uint8_t *d = e->refpad[c] + (size_t)(y + pad) * st;
-      memset(d, row[0], pad);
-      memcpy(d + pad, row, pw);
-      memset(d + pad + pw, row[pw - 1], pad);
+      uint8_t *o = d->pad[c] + (size_t)(y + pad) * st;
+      memset(o, row[0], pad);
+      memcpy(o + pad, row, pw);
+      memset(o + pad + pw, row[pw - 1], pad);
     }
   }
+  if (e->cfg.me_coarse > 0) down4(e->rec, e->w, e->h, d->q);
+  d->poc = e->poc;
+  if (e->cfg.tmvp)
+    for (size_t i = 0; i < (size_t)e->w8 * e->h8; i++) {
+      const orc_cu_t *cu = &e->cu[i];
+      struct orc_mvf *m = &d->mvf[i];
+      m->inter = cu->pred_mode == 0 && cu->log2_size >= 3;
+      m->mvx = cu->mvx; m->mvy = cu->mvy;
+      m->ref_poc = (int16_t)(e->poc - 1 - cu->ref_idx);            /* list 0 of a picture: POC - 1, POC - 2, ... */
+    }
+  if (e->n_dpb < e->cfg.refs) e->n_dpb++;
 }
 
-static void mc_luma(const orc_encoder_t *e, int x0, int y0, int n, int mvx, int mvy, uint8_t *dst)
+static void mc_luma(const orc_encoder_t *e, int ref, int x0, int y0, int n, int mvx, int mvy, uint8_t *dst)
 {
-  orc_mc_luma(e->refpad[0], e->refstride[0], e->w + 2 * PAD, e->h + 2 * PAD, x0 + PAD, y0 + PAD, n, n, mvx, mvy, dst, n);
+  orc_mc_luma(e->dpb[ref].pad[0], e->refstride[0], e->w + 2 * PAD, e->h + 2 * PAD, x0 + PAD, y0 + PAD, n, n, mvx, mvy, dst, n);
 }
-static void mc_chroma(const orc_encoder_t *e, int c, int x0, int y0, int n, int mvx, int mvy, uint8_t *dst)
+static void mc_chroma(const orc_encoder_t *e, int ref, int c, int x0, int y0, int n, int mvx, int mvy, uint8_t *dst)
 {
-  orc_mc_chroma(e->refpad[c], e->refstride[c], e->cw + PAD, e->ch + PAD, x0 + PAD / 2, y0 + PAD / 2, n, n, mvx, mvy, dst, n);
+  orc_mc_chroma(e->dpb[ref].pad[c], e->refstride[c], e->cw + PAD, e->ch + PAD, x0 + PAD / 2, y0 + PAD / 2, n, n, mvx, mvy, dst, n);
 }
 
-typedef struct { uint32_t cost; int dx, dy, cx, cy; } me_best_t;     /* vector and the centre it was found around, full samples */
+typedef struct { uint32_t cost; int dx, dy, cx, cy, ref; } me_best_t;     /* vector, the centre it was found around (full samples), reference index */
 
 /* quarter-resolution picture: every sample the rounded mean of a 4x4 block of the luma plane */
 static void down4(const uint8_t *p, int w, int h, uint8_t *out)
@@ -407,7 +444,7 @@ static void down4(const uint8_t *p, int w, int h, uint8_t *out)
  * +-me_coarse coarse samples, reference coordinates clamped to the picture.  Cost = 16 * SAD + lambda *
  * bits of the vector; raster order, the first strictly smaller cost wins; kept only when below 3/4 of
  * the cost of the zero displacement.  out = full samples. */
-static void coarse_search(const orc_encoder_t *e, int qx, int qy, int lam, int out[2])
+static void coarse_search(const orc_encoder_t *e, int ref, int qx, int qy, int lam, int out[2])
 {
   out[0] = out[1] = 0;
   if (qx >= e->w || qy >= e->h) return;
@@ -421,7 +458,7 @@ static void coarse_search(const orc_encoder_t *e, int qx, int qy, int lam, int o
       for (int y = 0; y < bh; y++)
         for (int x = 0; x < bw; x++)
           sad += (uint32_t)abs((int)e->src_q[(size_t)(y0 + y) * wq + x0 + x] -
-                               (int)e->ref_q[(size_t)clip3i(0, hq - 1, y0 + y + dy) * wq + clip3i(0, wq - 1, x0 + x + dx)]);
+                               (int)e->dpb[ref].q[(size_t)clip3i(0, hq - 1, y0 + y + dy) * wq + clip3i(0, wq - 1, x0 + x + dx)]);
       const uint32_t cost = 16 * sad + mv_penalty(lam, dx * 16, dy * 16);
       if (dx == 0 && dy == 0) zero = cost;
       if (cost < best) { best = cost; out[0] = 4 * dx; out[1] = 4 * dy; }
@@ -433,6 +470,9 @@ static void coarse_search(const orc_encoder_t *e, int qx, int qy, int lam, int o
    * displacement lies within half a coarse step, 2 samples, of it) */
   if (imax(abs(out[0]), abs(out[1])) + 2 <= e->cfg.search_range) out[0] = out[1] = 0;
 }
+
+/* bins of ref_idx_l0 = r (TR, cMax = n - 1) */
+static int ref_idx_bits(int r, int n) { return n <= 1 ? 0 : (r < n - 1 ? r + 1 : r); }
 
 /* the centre the mv penalty of a CU counts from (quarter samples), kept for the fractional refinement */
 static void set_pen_centre(orc_encoder_t *e, int x0, int y0, const me_best_t *b)
@@ -447,7 +487,6 @@ static void me_ctu(orc_encoder_t *e, int cx, int cy)
   const int R = e->cfg.search_range;
   const int lam = lambda_at(e, cx, cy);
   const uint8_t *src = e->src;
-  const uint8_t *ref = e->refpad[0];
   const int rs = e->refstride[0];
   me_best_t b8[8][8], b16[4][4], b32[2][2];
   for (int j = 0; j < 8; j++) for (int i = 0; i < 8; i++) b8[j][i].cost = UINT_MAX;
@@ -458,11 +497,16 @@ static void me_ctu(orc_encoder_t *e, int cx, int cy)
    * is the zero vector again.  Around every centre the same +-R full-sample window is searched; the
    * mv penalty counts from the centre (the predictor of the real coder is expected near it).
    * Candidates are ordered set 0 (raster), then set 1 (raster); the first strictly smaller cost wins. */
+  /* With several reference pictures (cfg.refs) everything is repeated per reference; a candidate of
+   * reference index r pays lambda * bits(ref_idx = r) on top.  Order: reference 0 first. */
+  for (int r = 0; r < e->n_refs; r++) {
+  const uint8_t *ref = e->dpb[r].pad[0];
+  const uint32_t refpen = (uint32_t)((lam * ref_idx_bits(r, e->n_refs)) >> 4);
   int ctr[2][4][2], nsets = 1;
   memset(ctr, 0, sizeof(ctr));
   if (e->cfg.me_coarse > 0) {
     nsets = 2;
-    for (int q = 0; q < 4; q++) coarse_search(e, cx + 32 * (q & 1), cy + 32 * (q >> 1), lam, ctr[1][q]);
+    for (int q = 0; q < 4; q++) coarse_search(e, r, cx + 32 * (q & 1), cy + 32 * (q >> 1), lam, ctr[1][q]);
   }
   for (int set = 0; set < nsets; set++)
     for (int q = 0; q < 4; q++) {
@@ -472,7 +516,7 @@ static void me_ctu(orc_encoder_t *e, int cx, int cy)
       if (set == 1 && mx0 == 0 && my0 == 0) continue;
       for (int dy = -R; dy <= R; dy++)
         for (int dx = -R; dx <= R; dx++) {
-          const uint32_t pen = mv_penalty(lam, dx * 4, dy * 4);
+          const uint32_t pen = mv_penalty(lam, dx * 4, dy * 4) + refpen;
           const int mx = mx0 + dx, my = my0 + dy;                    /* full-sample vector of this candidate */
           uint32_t s8[4][4], s16[2][2];
           for (int j = 0; j < 4; j++)
@@ -481,7 +525,7 @@ static void me_ctu(orc_encoder_t *e, int cx, int cy)
               if (x >= e->w || y >= e->h) { s8[j][i] = 0; continue; }
               s8[j][i] = orc_sad(src + (size_t)y * e->w + x, e->w, ref + (size_t)(y + PAD + my) * rs + x + PAD + mx, rs, 8, 8);
               uint32_t cost = s8[j][i] + pen;
-              if (cost < b8[jj][ii].cost && mv_allowed(e, x, 8, mx * 4)) { b8[jj][ii].cost = cost; b8[jj][ii].dx = mx; b8[jj][ii].dy = my; b8[jj][ii].cx = mx0; b8[jj][ii].cy = my0; }
+              if (cost < b8[jj][ii].cost && mv_allowed(e, x, 8, mx * 4)) { b8[jj][ii].cost = cost; b8[jj][ii].dx = mx; b8[jj][ii].dy = my; b8[jj][ii].cx = mx0; b8[jj][ii].cy = my0; b8[jj][ii].ref = r; }
             }
           for (int j = 0; j < 2; j++)
             for (int i = 0; i < 2; i++) {
@@ -489,15 +533,16 @@ static void me_ctu(orc_encoder_t *e, int cx, int cy)
               s16[j][i] = s8[2 * j][2 * i] + s8[2 * j][2 * i + 1] + s8[2 * j + 1][2 * i] + s8[2 * j + 1][2 * i + 1];
               if (x + 16 > e->w || y + 16 > e->h) continue;
               uint32_t cost = s16[j][i] + pen;
-              if (cost < b16[jj][ii].cost && mv_allowed(e, x, 16, mx * 4)) { b16[jj][ii].cost = cost; b16[jj][ii].dx = mx; b16[jj][ii].dy = my; b16[jj][ii].cx = mx0; b16[jj][ii].cy = my0; }
+              if (cost < b16[jj][ii].cost && mv_allowed(e, x, 16, mx * 4)) { b16[jj][ii].cost = cost; b16[jj][ii].dx = mx; b16[jj][ii].dy = my; b16[jj][ii].cx = mx0; b16[jj][ii].cy = my0; b16[jj][ii].ref = r; }
             }
           if (qx + 32 <= e->w && qy + 32 <= e->h) {
             uint32_t cost = s16[0][0] + s16[0][1] + s16[1][0] + s16[1][1] + pen;
             me_best_t *b = &b32[q >> 1][q & 1];
-            if (cost < b->cost && mv_allowed(e, qx, 32, mx * 4)) { b->cost = cost; b->dx = mx; b->dy = my; b->cx = mx0; b->cy = my0; }
+            if (cost < b->cost && mv_allowed(e, qx, 32, mx * 4)) { b->cost = cost; b->dx = mx; b->dy = my; b->cx = mx0; b->cy = my0; b->ref = r; }
           }
         }
     }
+  }
   /* bottom-up partition decision */
   const uint32_t ovh = (uint32_t)((lam * CU_OVERHEAD_BITS) >> 4);
   uint32_t eff16[4][4];
@@ -530,7 +575,7 @@ static void me_ctu(orc_encoder_t *e, int cx, int cy)
       memset(&cu, 0, sizeof(cu));
       cu.merge_idx = 0xff;
       if (use32) {
-        cu.log2_size = 5; cu.mvx = (int16_t)(b32[j][i].dx * 4); cu.mvy = (int16_t)(b32[j][i].dy * 4);
+        cu.log2_size = 5; cu.mvx = (int16_t)(b32[j][i].dx * 4); cu.mvy = (int16_t)(b32[j][i].dy * 4); cu.ref_idx = (uint8_t)b32[j][i].ref;
         set_cu(e, cx + 32 * i, cy + 32 * j, 5, &cu);
         set_pen_centre(e, cx + 32 * i, cy + 32 * j, &b32[j][i]);
         continue;
@@ -545,7 +590,7 @@ static void me_ctu(orc_encoder_t *e, int cx, int cy)
           continue;
         }
         if (use16[jj][ii]) {
-          cu.log2_size = 4; cu.mvx = (int16_t)(b16[jj][ii].dx * 4); cu.mvy = (int16_t)(b16[jj][ii].dy * 4);
+          cu.log2_size = 4; cu.mvx = (int16_t)(b16[jj][ii].dx * 4); cu.mvy = (int16_t)(b16[jj][ii].dy * 4); cu.ref_idx = (uint8_t)b16[jj][ii].ref;
           set_cu(e, cx + 16 * ii, cy + 16 * jj, 4, &cu);
           set_pen_centre(e, cx + 16 * ii, cy + 16 * jj, &b16[jj][ii]);
           continue;
@@ -553,7 +598,7 @@ static void me_ctu(orc_encoder_t *e, int cx, int cy)
         for (int r = 0; r < 4; r++) {
           int j8 = 2 * jj + (r >> 1), i8 = 2 * ii + (r & 1);
           if (b8[j8][i8].cost == UINT_MAX) continue;
-          cu.log2_size = 3; cu.mvx = (int16_t)(b8[j8][i8].dx * 4); cu.mvy = (int16_t)(b8[j8][i8].dy * 4);
+          cu.log2_size = 3; cu.mvx = (int16_t)(b8[j8][i8].dx * 4); cu.mvy = (int16_t)(b8[j8][i8].dy * 4); cu.ref_idx = (uint8_t)b8[j8][i8].ref;
           set_cu(e, cx + 8 * i8, cy + 8 * j8, 3, &cu);
           set_pen_centre(e, cx + 8 * i8, cy + 8 * j8, &b8[j8][i8]);
         }
@@ -570,7 +615,8 @@ static void inter_cu(orc_encoder_t *e, int x0, int y0, int log2)
   const uint8_t *src = e->src + (size_t)y0 * e->w + x0;
   uint8_t pred[32 * 32], best_pred[32 * 32];
   int bx = cu.mvx, by = cu.mvy;
-  mc_luma(e, x0, y0, n, bx, by, best_pred);
+  const int rf = cu.ref_idx;
+  mc_luma(e, rf, x0, y0, n, bx, by, best_pred);
   const int lam = lambda_at(e, x0, y0);
   const int satd = e->cfg.subme_satd;
   const int16_t *pc = e->pen_ctr + 2 * ((size_t)(y0 / 8) * e->w8 + x0 / 8);     /* the mv penalty counts from the search centre */
@@ -580,7 +626,7 @@ static void inter_cu(orc_encoder_t *e, int x0, int y0, int log2)
     for (int k = 0; k < 8; k++) {
       int mx = cxm + off[k][0] * step, my = cym + off[k][1] * step;
       if (!mv_allowed(e, x0, n, mx)) continue;
-      mc_luma(e, x0, y0, n, mx, my, pred);
+      mc_luma(e, rf, x0, y0, n, mx, my, pred);
       uint32_t cost = (satd ? orc_satd(src, e->w, pred, n, n, n) : orc_sad(src, e->w, pred, n, n, n)) + mv_penalty(lam, mx - pc[0], my - pc[1]);
       if (cost < best) { best = cost; bx = mx; by = my; memcpy(best_pred, pred, (size_t)n * n); }
     }
@@ -588,7 +634,7 @@ static void inter_cu(orc_encoder_t *e, int x0, int y0, int log2)
   cu.mvx = (int16_t)bx; cu.mvy = (int16_t)by;
   cu.cbf = (uint8_t)recon_tb(e, 0, x0, y0, log2, best_pred);
   for (int c = 1; c < 3; c++) {
-    mc_chroma(e, c, x0 / 2, y0 / 2, n / 2, bx, by, pred);
+    mc_chroma(e, rf, c, x0 / 2, y0 / 2, n / 2, bx, by, pred);
     cu.cbf |= (uint8_t)(recon_tb(e, c, x0 / 2, y0 / 2, log2 - 1, pred) << c);
   }
   set_cu(e, x0, y0, log2, &cu);
@@ -660,6 +706,7 @@ static int edge_bs(const orc_cu_t *p, const orc_cu_t *q)
 {
   if (p->pred_mode == 1 || q->pred_mode == 1) return 2;
   if ((p->cbf & 1) || (q->cbf & 1)) return 1;          /* TU edge == CU edge (TU = CU) */
+  if (p->ref_idx != q->ref_idx) return 1;              /* different reference pictures (list 0 has no duplicates here) */
   return abs(p->mvx - q->mvx) >= 4 || abs(p->mvy - q->mvy) >= 4;
 }
 
@@ -892,7 +939,7 @@ static void code_sao(const orc_encoder_t *e, orc_cabac_t *c, int rx, int ry)
 /* ------------------------------------------------------------------------------------------ */
 /* entropy coding                                                                                 */
 
-typedef struct { int16_t x, y; } mv_t;
+typedef struct { int16_t x, y; int8_t ref; } mv_t;
 
 /* 6.4.2: neighbouring prediction block available for inter candidates */
 static const orc_cu_t *inter_nb(const orc_encoder_t *e, int xc, int yc, int xn, int yn)
@@ -902,9 +949,42 @@ static const orc_cu_t *inter_nb(const orc_encoder_t *e, int xc, int yc, int xn, 
   const orc_cu_t *n = &e->cu[(size_t)(yn >> 3) * e->w8 + (xn >> 3)];
   return n->pred_mode == 0 ? n : NULL;
 }
-static inline int same_mv(const orc_cu_t *a, const orc_cu_t *b) { return a->mvx == b->mvx && a->mvy == b->mvy; }
+static inline int same_mv(const orc_cu_t *a, const orc_cu_t *b) { return a->mvx == b->mvx && a->mvy == b->mvy && a->ref_idx == b->ref_idx; }
 
-/* 8.5.3.2.2-8.5.3.2.4 merge candidate list, P slice, one reference picture, no TMVP */
+/* 8.5.3.2.7 / 8.5.3.2.8: a vector that spans td pictures rescaled to span tb pictures */
+static int scale_mv(int mv, int td, int tb)
+{
+  td = clip3i(-128, 127, td); tb = clip3i(-128, 127, tb);
+  const int tx = (16384 + (abs(td) >> 1)) / td;
+  const int dsf = clip3i(-4096, 4095, (tb * tx + 32) >> 6);
+  const int p = dsf * mv;
+  return clip3i(-32768, 32767, (p < 0 ? -1 : 1) * ((abs(p) + 127) >> 8));
+}
+
+/* 8.5.3.2.8 temporal luma motion vector prediction for a block whose target is reference index
+ * `ref`: the collocated picture is reference index 0 (collocated_ref_idx = 0), bottom-right
+ * candidate first (same CTB row, inside the picture), then the centre; motion is read from the
+ * 16x16-compressed motion field. */
+static int temporal_mv(const orc_encoder_t *e, int x0, int y0, int n, int ref, mv_t *out)
+{
+  if (!e->cfg.tmvp || e->n_refs < 1) return 0;
+  const struct orc_ref *col = &e->dpb[0];
+  const int cand[2][2] = {{x0 + n, y0 + n}, {x0 + n / 2, y0 + n / 2}};
+  for (int k = 0; k < 2; k++) {
+    const int x = cand[k][0], y = cand[k][1];
+    if (k == 0 && ((y0 >> CTB_LOG2) != (y >> CTB_LOG2) || y >= e->h || x >= e->w)) continue;
+    const struct orc_mvf *m = &col->mvf[(size_t)(((y >> 4) << 4) >> 3) * e->w8 + ((((x >> 4) << 4)) >> 3)];
+    if (!m->inter) continue;
+    const int col_diff = col->poc - m->ref_poc, cur_diff = 1 + ref;      /* POC distances: the collocated block's, ours */
+    out->ref = (int8_t)ref;
+    if (col_diff == cur_diff) { out->x = m->mvx; out->y = m->mvy; }
+    else { out->x = (int16_t)scale_mv(m->mvx, col_diff, cur_diff); out->y = (int16_t)scale_mv(m->mvy, col_diff, cur_diff); }
+    return 1;
+  }
+  return 0;
+}
+
+/* 8.5.3.2.2-8.5.3.2.5 merge candidate list of a P slice: spatial, temporal, zero candidates */
 static int merge_candidates(const orc_encoder_t *e, int x0, int y0, int n, mv_t out[MAX_MERGE])
 {
   const orc_cu_t *a1 = inter_nb(e, x0, y0, x0 - 1, y0 + n - 1);
@@ -918,27 +998,55 @@ static int merge_candidates(const orc_encoder_t *e, int x0, int y0, int n, mv_t 
   if (b0 && b1o && same_mv(b0, b1o)) b0 = NULL;
   if (a0 && a1 && same_mv(a0, a1)) a0 = NULL;
   if (b2 && ((a1 && same_mv(b2, a1)) || (b1o && same_mv(b2, b1o)))) b2 = NULL;
-  if (a1) { out[cnt].x = a1->mvx; out[cnt++].y = a1->mvy; }
-  if (b1) { out[cnt].x = b1->mvx; out[cnt++].y = b1->mvy; }
-  if (b0) { out[cnt].x = b0->mvx; out[cnt++].y = b0->mvy; }
-  if (a0) { out[cnt].x = a0->mvx; out[cnt++].y = a0->mvy; }
-  if (b2 && cnt < 4) { out[cnt].x = b2->mvx; out[cnt++].y = b2->mvy; }
-  while (cnt < MAX_MERGE) { out[cnt].x = 0; out[cnt++].y = 0; }
+#define PUSH(c) do { out[cnt].x = (c)->mvx; out[cnt].y = (c)->mvy; out[cnt++].ref = (int8_t)(c)->ref_idx; } while (0)
+  if (a1) PUSH(a1);
+  if (b1) PUSH(b1);
+  if (b0) PUSH(b0);
+  if (a0) PUSH(a0);
+  if (b2 && cnt < 4) PUSH(b2);
+#undef PUSH
+  if (cnt < MAX_MERGE && temporal_mv(e, x0, y0, n, 0, &out[cnt])) cnt++;
+  for (int zero_idx = 0; cnt < MAX_MERGE; zero_idx++) {              /* zero candidates walk the reference indices */
+    out[cnt].x = 0; out[cnt].y = 0; out[cnt++].ref = (int8_t)(zero_idx < e->n_refs ? zero_idx : 0);
+  }
   return cnt;
 }
 
-/* 8.5.3.2.6-7 AMVP list for one reference picture, no TMVP */
-static void amvp_candidates(const orc_encoder_t *e, int x0, int y0, int n, mv_t out[2])
+/* 8.5.3.2.6-8.5.3.2.8 AMVP list for reference index `ref`: spatial candidates A (A0, A1) and B (B0, B1,
+ * B2) -- first the neighbours that point to the same reference picture, then any, rescaled by the
+ * ratio of POC distances -- then the temporal candidate, then zero vectors */
+static void amvp_candidates(const orc_encoder_t *e, int x0, int y0, int n, int ref, mv_t out[2])
 {
-  const orc_cu_t *a = inter_nb(e, x0, y0, x0 - 1, y0 + n);          /* A0 */
-  if (!a) a = inter_nb(e, x0, y0, x0 - 1, y0 + n - 1);             /* A1 */
-  const orc_cu_t *b = inter_nb(e, x0, y0, x0 + n, y0 - 1);          /* B0 */
-  if (!b) b = inter_nb(e, x0, y0, x0 + n - 1, y0 - 1);             /* B1 */
-  if (!b) b = inter_nb(e, x0, y0, x0 - 1, y0 - 1);                 /* B2 */
+  const orc_cu_t *ak[2] = {inter_nb(e, x0, y0, x0 - 1, y0 + n), inter_nb(e, x0, y0, x0 - 1, y0 + n - 1)};
+  const orc_cu_t *bk[3] = {inter_nb(e, x0, y0, x0 + n, y0 - 1), inter_nb(e, x0, y0, x0 + n - 1, y0 - 1), inter_nb(e, x0, y0, x0 - 1, y0 - 1)};
+  const int is_scaled = ak[0] || ak[1];
+  int fa = 0, fb = 0;
+  mv_t a = {0, 0, 0}, b = {0, 0, 0};
+  for (int k = 0; k < 2 && !fa; k++)
+    if (ak[k] && ak[k]->ref_idx == ref) { a.x = ak[k]->mvx; a.y = ak[k]->mvy; fa = 1; }
+  for (int k = 0; k < 2 && !fa; k++)
+    if (ak[k]) {
+      a.x = (int16_t)scale_mv(ak[k]->mvx, 1 + ak[k]->ref_idx, 1 + ref); a.y = (int16_t)scale_mv(ak[k]->mvy, 1 + ak[k]->ref_idx, 1 + ref);
+      fa = 1;
+    }
+  for (int k = 0; k < 3 && !fb; k++)
+    if (bk[k] && bk[k]->ref_idx == ref) { b.x = bk[k]->mvx; b.y = bk[k]->mvy; fb = 1; }
+  if (!is_scaled && fb) { a = b; fa = 1; }
+  if (!is_scaled) {
+    fb = 0;
+    for (int k = 0; k < 3 && !fb; k++)
+      if (bk[k]) {
+        if (bk[k]->ref_idx == ref) { b.x = bk[k]->mvx; b.y = bk[k]->mvy; }
+        else { b.x = (int16_t)scale_mv(bk[k]->mvx, 1 + bk[k]->ref_idx, 1 + ref); b.y = (int16_t)scale_mv(bk[k]->mvy, 1 + bk[k]->ref_idx, 1 + ref); }
+        fb = 1;
+      }
+  }
   int cnt = 0;
-  if (a) { out[cnt].x = a->mvx; out[cnt++].y = a->mvy; }
-  if (b && !(a && same_mv(a, b))) { out[cnt].x = b->mvx; out[cnt++].y = b->mvy; }
+  if (fa) out[cnt++] = a;
+  if (fb && !(fa && a.x == b.x && a.y == b.y)) out[cnt++] = b;
+  if (cnt < 2 && temporal_mv(e, x0, y0, n, ref, &out[cnt])) cnt++;
   while (cnt < 2) { out[cnt].x = 0; out[cnt++].y = 0; }
+  out[0].ref = out[1].ref = (int8_t)ref;
 }
 
 static void code_mvd(orc_cabac_t *c, int dx, int dy)
@@ -1068,7 +1176,7 @@ static void code_cu(orc_encoder_t *e, orc_cabac_t *c, int x0, int y0, int log2)
     merge_candidates(e, x0, y0, n, mc);
     int midx = -1;
     for (int i = 0; i < MAX_MERGE && midx < 0; i++)
-      if (mc[i].x == cu->mvx && mc[i].y == cu->mvy) midx = i;
+      if (mc[i].x == cu->mvx && mc[i].y == cu->mvy && mc[i].ref == cu->ref_idx) midx = i;
     int skip = midx >= 0 && cu->cbf == 0;
     orc_cabac_bin(c, CTX_SKIP + ctx, skip);
     upd.skip = (uint8_t)skip;
@@ -1086,7 +1194,12 @@ static void code_cu(orc_encoder_t *e, orc_cabac_t *c, int x0, int y0, int log2)
       orc_cabac_bin(c, CTX_PRED_MODE, 0);
       orc_cabac_bin(c, CTX_PART_MODE, 1);
       orc_cabac_bin(c, CTX_MERGE_FLAG, 0);
-      amvp_candidates(e, x0, y0, n, ac);
+      if (e->n_refs > 1) {                                       /* ref_idx_l0: TR cMax n_refs - 1, two context-coded bins, then bypass */
+        const int r = cu->ref_idx, cmax = e->n_refs - 1;
+        for (int i = 0; i < r; i++) { if (i < 2) orc_cabac_bin(c, CTX_REF_IDX + i, 1); else orc_cabac_bypass(c, 1); }
+        if (r < cmax) { if (r < 2) orc_cabac_bin(c, CTX_REF_IDX + r, 0); else orc_cabac_bypass(c, 0); }
+      }
+      amvp_candidates(e, x0, y0, n, cu->ref_idx, ac);
       int b0 = mv_comp_bits(cu->mvx - ac[0].x) + mv_comp_bits(cu->mvy - ac[0].y);
       int b1 = mv_comp_bits(cu->mvx - ac[1].x) + mv_comp_bits(cu->mvy - ac[1].y);
       int pi = b1 < b0;
@@ -1173,7 +1286,7 @@ static size_t write_parameter_sets(const orc_encoder_t *e, uint8_t *out, size_t 
   orc_bits_put(&b, 0xffff, 16);
   put_ptl(&b, level);
   orc_bits_put(&b, 0, 1);             /* vps_sub_layer_ordering_info_present_flag */
-  orc_bits_ue(&b, 1); orc_bits_ue(&b, 0); orc_bits_ue(&b, 0);
+  orc_bits_ue(&b, (uint32_t)imax(1, e->cfg.refs)); orc_bits_ue(&b, 0); orc_bits_ue(&b, 0);   /* max_dec_pic_buffering_minus1, ... */
   orc_bits_put(&b, 0, 6);             /* vps_max_layer_id */
   orc_bits_ue(&b, 0);                 /* vps_num_layer_sets_minus1 */
   orc_bits_put(&b, 0, 1);             /* vps_timing_info_present_flag */
@@ -1191,7 +1304,7 @@ static size_t write_parameter_sets(const orc_encoder_t *e, uint8_t *out, size_t 
   orc_bits_ue(&b, 0); orc_bits_ue(&b, 0);       /* bit depths - 8 */
   orc_bits_ue(&b, 4);                 /* log2_max_pic_order_cnt_lsb_minus4 -> 8 bits */
   orc_bits_put(&b, 0, 1);             /* sps_sub_layer_ordering_info_present_flag */
-  orc_bits_ue(&b, 1); orc_bits_ue(&b, 0); orc_bits_ue(&b, 0);
+  orc_bits_ue(&b, (uint32_t)imax(1, e->cfg.refs)); orc_bits_ue(&b, 0); orc_bits_ue(&b, 0);
   orc_bits_ue(&b, 0);                 /* log2_min_luma_coding_block_size_minus3 -> 8 */
   orc_bits_ue(&b, 3);                 /* log2_diff_max_min -> 64 */
   orc_bits_ue(&b, 0);                 /* log2_min_luma_transform_block_size_minus2 -> 4 */
@@ -1202,10 +1315,10 @@ static size_t write_parameter_sets(const orc_encoder_t *e, uint8_t *out, size_t 
   orc_bits_put(&b, e->cfg.sao ? 1 : 0, 1);          /* sample_adaptive_offset_enabled_flag */
   orc_bits_put(&b, 0, 1);             /* pcm_enabled_flag */
   orc_bits_ue(&b, 1);                 /* num_short_term_ref_pic_sets */
-  orc_bits_ue(&b, 1); orc_bits_ue(&b, 0);       /* num_negative_pics = 1, num_positive_pics = 0 */
-  orc_bits_ue(&b, 0); orc_bits_put(&b, 1, 1);   /* delta_poc_s0_minus1 = 0, used_by_curr_pic_s0 */
+  orc_bits_ue(&b, (uint32_t)imax(1, e->cfg.refs)); orc_bits_ue(&b, 0);      /* num_negative_pics, num_positive_pics = 0 */
+  for (int r = 0; r < imax(1, e->cfg.refs); r++) { orc_bits_ue(&b, 0); orc_bits_put(&b, 1, 1); }   /* delta_poc_s0_minus1 = 0, used_by_curr_pic_s0 */
   orc_bits_put(&b, 0, 1);             /* long_term_ref_pics_present_flag */
-  orc_bits_put(&b, 0, 1);             /* sps_temporal_mvp_enabled_flag */
+  orc_bits_put(&b, e->cfg.tmvp ? 1 : 0, 1);     /* sps_temporal_mvp_enabled_flag */
   orc_bits_put(&b, 0, 1);             /* strong_intra_smoothing_enabled_flag */
   if (e->cfg.fps_num > 0 && e->cfg.fps_den > 0) {
     /* VUI (E.2.1) carrying only the timing: the reference copies the decoder's frame rate into
@@ -1358,11 +1471,21 @@ static int assemble_slice(const orc_encoder_t *e, int n_sub, const size_t *sub_e
   orc_bits_ue(&b, e->is_idr ? 2 : 1);                   /* slice_type */
   if (!e->is_idr) {
     orc_bits_put(&b, (uint32_t)(e->poc & 255), 8);      /* slice_pic_order_cnt_lsb */
-    orc_bits_put(&b, 1, 1);                             /* short_term_ref_pic_set_sps_flag */
+    if (e->n_refs == imax(1, e->cfg.refs)) {
+      orc_bits_put(&b, 1, 1);                           /* short_term_ref_pic_set_sps_flag */
+    } else {                                            /* fewer pictures exist yet: the set is written here */
+      orc_bits_put(&b, 0, 1);
+      orc_bits_put(&b, 0, 1);                           /* inter_ref_pic_set_prediction_flag (stRpsIdx = 1) */
+      orc_bits_ue(&b, (uint32_t)e->n_refs); orc_bits_ue(&b, 0);
+      for (int r = 0; r < e->n_refs; r++) { orc_bits_ue(&b, 0); orc_bits_put(&b, 1, 1); }
+    }
+    if (e->cfg.tmvp) orc_bits_put(&b, 1, 1);            /* slice_temporal_mvp_enabled_flag */
   }
   if (e->cfg.sao) orc_bits_put(&b, 3, 2);               /* slice_sao_luma_flag, slice_sao_chroma_flag */
   if (!e->is_idr) {
-    orc_bits_put(&b, 0, 1);                             /* num_ref_idx_active_override_flag */
+    orc_bits_put(&b, e->n_refs != 1, 1);                /* num_ref_idx_active_override_flag */
+    if (e->n_refs != 1) orc_bits_ue(&b, (uint32_t)(e->n_refs - 1));
+    if (e->cfg.tmvp && e->n_refs > 1) orc_bits_ue(&b, 0);   /* collocated_ref_idx */
     orc_bits_ue(&b, 5 - MAX_MERGE);                     /* five_minus_max_num_merge_cand */
   }
   orc_bits_se(&b, e->cfg.qp - 26);                      /* slice_qp_delta */
@@ -1454,6 +1577,7 @@ int orc_enc_encode(orc_encoder_t *e, const uint8_t *i420, uint8_t *out, int cap)
   e->src = i420;
   e->is_idr = e->frame_idx == 0 || (e->cfg.intra_period > 0 && e->frame_idx % e->cfg.intra_period == 0);
   if (e->is_idr) e->poc = 0;
+  e->n_refs = e->is_idr ? 0 : imin(imax(1, e->cfg.refs), e->n_dpb);
   memset(e->levels, 0, fsz * sizeof(int16_t));
   if (e->is_idr) {
     for (int cy = 0; cy < e->h; cy += CTB)
@@ -1472,8 +1596,8 @@ int orc_enc_encode(orc_encoder_t *e, const uint8_t *i420, uint8_t *out, int cap)
   o += n;
   if (e->cfg.hash_sei && !e->cfg.raw_slice_data) o += write_hash_sei(e, out + o, (size_t)cap - o);
   if (o > (size_t)cap) return -1;
-  pad_reference(e);
-  if (e->cfg.me_coarse > 0) down4(e->rec, e->w, e->h, e->ref_q);
+  if (e->is_idr) e->n_dpb = 0;                  /* an IDR empties the decoded picture buffer */
+  dpb_insert(e);
   e->frame_idx++;
   e->poc++;
   return (int)o;
@@ -1565,6 +1689,7 @@ int orc_tiled_encode(orc_tiled_t *t, const uint8_t *i420, uint8_t *out, int cap)
     strip_copy(e->rec, e->w, e->h, (uint8_t *)orc_enc_recon(t->strip[i]), t->x0[i], t->wd[i], 0);
   }
   size_t o = 0, n = 0;
+  e->n_refs = t->strip[0]->n_refs;                        /* what the slice header says about the reference list */
   if (e->is_idr) o += write_parameter_sets(e, out, (size_t)cap);
   int rc = o > (size_t)cap ? -1 : assemble_slice(e, n_sub, sub_esc, data, total, out + o, (size_t)cap - o, &n);
   free(data);

@@ -18,6 +18,10 @@ typedef struct {
   uint8_t merge_idx;       /* 0xff = not merged */
   uint8_t mvp_idx;
   uint8_t qp;              /* luma QP of the CU when cu_qp_delta is enabled (8.6.1), else 0 */
+  uint8_t ref_idx;         /* index into reference picture list 0 (inter) */
+  uint8_t chroma_mode;     /* intra: resolved chroma prediction mode */
+  uint8_t tu_log2;         /* luma size of the transform unit covering this unit */
+  uint8_t flags;           /* bit 0: intra NxN */
 } orc_cu_t;
 
 typedef struct {
@@ -40,6 +44,11 @@ typedef struct {
   int sao;                 /* sample adaptive offset (8.7.3) after deblocking: 1 = on, 2 = on and sao_merge_left / _up
                             * flags are used where a CTU's parameters repeat its neighbour's */
   int tile_cols;           /* > 1: PPS / slice header of a picture with that many uniform tile columns (compositor only) */
+  int refs;                /* reference pictures (0 or 1 = the previous picture only, up to 4): every CU picks the
+                            * reference with the smallest cost; ref_idx_l0, the short-term RPS in the slice header
+                            * while fewer pictures exist, AMVP with vector scaling, bS from reference pictures */
+  int tmvp;                /* 1 = temporal motion vector prediction (8.5.3.2.8): collocated candidates in the merge and
+                            * AMVP lists, from the previous picture's motion field */
   int me_coarse;           /* > 0: two-level motion search -- a coarse level on quarter-resolution pictures (+- me_coarse
                             * coarse samples = 4 * me_coarse luma samples) gives every 32x32 block a second search
                             * centre besides the zero vector; search_range (<= 16) is the window around each centre */

@@ -63,7 +63,8 @@ enum {
   CTX_CU_QP_DELTA = 140,        /* 2 */
   CTX_SAO_MERGE = 142,          /* 1 */
   CTX_SAO_TYPE = 143,           /* 1 */
-  CTX_COUNT = 144
+  CTX_REF_IDX = 144,            /* 2 */
+  CTX_COUNT = 146
 };
 
 /* init values, [initType 0=I,1=P,2=B][CTX_COUNT]; 154 where the element cannot occur */

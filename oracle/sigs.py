@@ -25,14 +25,15 @@ def bind(lib) -> None:
 class OrcCu(C.Structure):
     _fields_ = [("mvx", C.c_int16), ("mvy", C.c_int16), ("log2_size", C.c_uint8), ("pred_mode", C.c_uint8),
                 ("intra_mode", C.c_uint8), ("cbf", C.c_uint8), ("skip", C.c_uint8), ("merge_idx", C.c_uint8),
-                ("mvp_idx", C.c_uint8), ("qp", C.c_uint8)]
+                ("mvp_idx", C.c_uint8), ("qp", C.c_uint8), ("ref_idx", C.c_uint8), ("chroma_mode", C.c_uint8),
+                ("tu_log2", C.c_uint8), ("flags", C.c_uint8)]
 
 
 class OrcEncCfg(C.Structure):
     _fields_ = [("width", i), ("height", i), ("qp", i), ("intra_period", i), ("search_range", i),
                 ("deblock", i), ("hash_sei", i), ("qp_delta", i),
                 ("mv_edges", i), ("more_tiles", i), ("raw_slice_data", i), ("no_wpp", i), ("subme_satd", i), ("sao", i), ("tile_cols", i),
-                ("me_coarse", i), ("intra_in_p", i), ("fps_num", i), ("fps_den", i)]
+                ("refs", i), ("tmvp", i), ("me_coarse", i), ("intra_in_p", i), ("fps_num", i), ("fps_den", i)]
 
 
 SIGS.update({
