@@ -43,6 +43,15 @@ struct CuInfo {
 };
 static_assert(sizeof(CuInfo) == 16, "CuInfo layout is part of the test ABI");
 
+// Motion of one 16x16 block of a decoded picture (the 8x8 unit at its top-left corner), kept for the
+// temporal motion vector prediction of later pictures (8.5.3.2.8; the standard compresses to 16x16).
+struct MvField {
+  int16_t mvx, mvy;
+  int16_t poc_diff;     // POC(picture) - POC(the reference picture the vector points to)
+  uint8_t inter, pad;
+};
+static_assert(sizeof(MvField) == 8, "MvField layout");
+
 // Reference picture list 0 of a picture (packed I420 pictures in HBM); the encoder has one entry.
 struct RefList {
   const uint8_t *pic[16];
@@ -66,7 +75,7 @@ enum CtxOffset {
   CTX_MVD_GT1 = 16, CTX_MVP_IDX = 17, CTX_RQT_ROOT_CBF = 18, CTX_SPLIT_TRANSFORM = 19,
   CTX_CBF_LUMA = 22, CTX_CBF_CHROMA = 24, CTX_LAST_X = 28, CTX_LAST_Y = 46, CTX_CSBF = 64,
   CTX_SIG = 68, CTX_GT1 = 110, CTX_GT2 = 134, CTX_CU_QP_DELTA = 140, CTX_SAO_MERGE = 142, CTX_SAO_TYPE = 143,
-  CTX_COUNT = 144
+  CTX_REF_IDX = 144, CTX_COUNT = 146
 };
 
 struct FrameParams {
@@ -106,6 +115,14 @@ struct FrameParams {
   // multiple of 4); src_q / ref_q = quarter-resolution luma of the source and of the reference.
   int me_coarse;
   const uint8_t *src_q, *ref_q;
+  // Reference picture list 0 as the entropy stage and the deblocking filter see it.  n_refs =
+  // num_ref_idx_l0_active (1 in the encoder); ref_dist[i] = POC(current) - POC(RefPicList0[i]): two
+  // indices name the same picture iff their distances are equal, and vector scaling uses the ratio.
+  // max_merge = MaxNumMergeCand.  col_mvf (decoder, slice_temporal_mvp_enabled_flag): motion field of
+  // the collocated picture, ((w + 15) / 16) entries per row; null = no temporal candidates.
+  int n_refs, max_merge;
+  int16_t ref_dist[16];
+  const MvField *col_mvf;
   // optional work counters of the motion search (profiling): [0] CTUs, [1] 32x32 quadrants whose second
   // centre set was searched, [2] 16x16 intra mode searches, [3] intra CUs chosen (16x16)
   unsigned long long *me_stats;

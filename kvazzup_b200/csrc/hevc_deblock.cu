@@ -15,10 +15,12 @@ namespace {
 
 constexpr int kThreads = 256;
 
-__device__ __forceinline__ int edge_bs(const CuInfo &p, const CuInfo &q)
+__device__ __forceinline__ int edge_bs(const FrameParams &fp, const CuInfo &p, const CuInfo &q)
 {
   if (p.pred_mode == 1 || q.pred_mode == 1) return 2;
   if ((p.cbf & 1) || (q.cbf & 1)) return 1;
+  // different reference PICTURES (8.7.2.4): compared by POC distance, two list entries may name one picture
+  if (fp.n_refs > 1 && fp.ref_dist[p.ref_idx & 15] != fp.ref_dist[q.ref_idx & 15]) return 1;
   return (abs(p.mvx - q.mvx) >= 4 || abs(p.mvy - q.mvy) >= 4) ? 1 : 0;
 }
 
@@ -91,7 +93,7 @@ k_deblock(FrameParams fp, uint8_t *rec, const CuInfo *__restrict__ cu, int dir)
   int n8 = 1 << (q.log2_size - 3);
   if (dir == 0 ? (x8 == 0 || (x8 & (n8 - 1))) : (y8 == 0 || (y8 & (n8 - 1)))) return;
   CuInfo p = cu[dir == 0 ? u - 1 : u - fp.w8];
-  int bs = edge_bs(p, q);
+  int bs = edge_bs(fp, p, q);
   if (!bs) return;
   int x = x8 * 8, y = y8 * 8;
   // QpL = (QpQ + QpP + 1) >> 1 (8.7.2.5.3); the two differ only across CTUs with different ROI offsets

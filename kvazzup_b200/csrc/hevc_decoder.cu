@@ -45,7 +45,11 @@ struct StripGeom {
   int x0 = 0, wd = 0;
   FrameParams fp{};                       // strip-sized
   size_t bytes = 0;                       // packed I420 of the strip
-  uint8_t *d_rec[2] = {nullptr, nullptr};
+  // decoded picture buffer of the strip: kPool pictures (index shared by all strips of a picture), each
+  // with its 16x16 motion field for temporal MV prediction and the event that says the field is written
+  uint8_t *d_pic[8] = {};
+  MvField *d_mvf[8] = {};
+  cudaEvent_t ev_mvf[8] = {};
   uint8_t *d_dbk = nullptr;               // deblocked picture of a slice with SAO (SAO reads it, writes d_rec)
   int *d_order = nullptr;
   cudaStream_t stream = nullptr;          // reconstruction chain of this strip
@@ -75,6 +79,8 @@ struct DecSlot {
   uint8_t *d_data = nullptr, *h_data = nullptr, *h_out = nullptr;
   std::vector<StripBufs> strips;
   int64_t pts = 0;
+  int cur_idx = 0;                        // pool entry this picture is reconstructed into
+  int n_refs = 0, ref_pool[16] = {};      // reference picture list 0 as pool entries
 };
 
 struct Decoder {
@@ -97,7 +103,11 @@ struct Decoder {
   int next_slot = 0, out_slot = -1;
   bool host_output = true;                // false: pictures stay on the GPU (b200_dec_output_dev)
   const uint8_t *d_out = nullptr;         // device copy of the last output picture
-  int cur = 0, have_ref = 0, pictures = 0;
+  // Decoded picture buffer bookkeeping (8.3.2): which pool entries hold a picture that may still be
+  // referenced, and its POC.  Managed in decoding order when a slice is submitted.
+  static constexpr int kPool = 8;
+  struct DpbEntry { int poc = 0; bool valid = false; } dpb[kPool];
+  int pictures = 0;
   bool have_submitted = false;            // a picture whose POC is prev_poc went into the pipeline
   int missing_refs = 0;                   // P pictures whose reference (POC - 1) was not the previous decoded picture
   int64_t out_pts = 0;
@@ -110,7 +120,11 @@ struct Decoder {
     for (StripGeom &g : geom) {
       if (g.stream) { cudaStreamSynchronize(g.stream); cudaStreamDestroy(g.stream); }
       if (g.ev_done) cudaEventDestroy(g.ev_done);
-      for (int i = 0; i < 2; i++) if (g.d_rec[i]) cudaFree(g.d_rec[i]);
+      for (int i = 0; i < kPool; i++) {
+        if (g.d_pic[i]) cudaFree(g.d_pic[i]);
+        if (g.d_mvf[i]) cudaFree(g.d_mvf[i]);
+        if (g.ev_mvf[i]) cudaEventDestroy(g.ev_mvf[i]);
+      }
       if (g.d_dbk) cudaFree(g.d_dbk);
       if (g.d_order) cudaFree(g.d_order);
     }
@@ -172,8 +186,13 @@ struct Decoder {
       g.bytes = (size_t)g.wd * h * 3 / 2;
       if (!cuda_ok(cudaStreamCreateWithFlags(&g.stream, cudaStreamNonBlocking), "cudaStreamCreate")) return false;
       if (!cuda_ok(cudaEventCreateWithFlags(&g.ev_done, cudaEventDisableTiming), "cudaEventCreate")) return false;
-      if (!cuda_ok(cudaMalloc((void **)&g.d_rec[0], g.bytes), "cudaMalloc")) return false;
-      if (!cuda_ok(cudaMalloc((void **)&g.d_rec[1], g.bytes), "cudaMalloc")) return false;
+      for (int k = 0; k < kPool; k++) {
+        const size_t n16 = (size_t)((g.wd + 15) / 16) * ((h + 15) / 16);
+        if (!cuda_ok(cudaMalloc((void **)&g.d_pic[k], g.bytes), "cudaMalloc")) return false;
+        if (!cuda_ok(cudaMalloc((void **)&g.d_mvf[k], n16 * sizeof(MvField)), "cudaMalloc")) return false;
+        if (!cuda_ok(cudaMemset(g.d_mvf[k], 0, n16 * sizeof(MvField)), "memset")) return false;
+        if (!cuda_ok(cudaEventCreateWithFlags(&g.ev_mvf[k], cudaEventDisableTiming), "cudaEventCreate")) return false;
+      }
       if (!cuda_ok(cudaMalloc((void **)&g.d_dbk, g.bytes), "cudaMalloc")) return false;
       std::vector<int> order((size_t)g.fp.ctb_cols * rows);
       intra_wavefront_order(g.fp.ctb_cols, rows, order.data());
@@ -204,7 +223,8 @@ struct Decoder {
         if (!cuda_ok(cudaMallocHost((void **)&t.h_status, sizeof(int) * 2), "cudaMallocHost")) return false;
       }
     }
-    cur = 0; have_ref = 0; have_submitted = false;
+    for (DpbEntry &d : dpb) d = DpbEntry();
+    have_submitted = false;
     conf_w = w; conf_h = h; conf_tiles = tiles;
     return true;
   }
@@ -243,7 +263,6 @@ struct Decoder {
     if (s.amp) return "AMP is not supported";
     if (s.pcm) return "PCM is not supported";
     if (s.long_term_refs) return "long-term reference pictures are not supported";
-    if (s.tmvp && sh.tmvp) return "temporal MVP is not supported";
     if (p.dependent_slices) return "dependent slice segments are not supported";
     if (p.sign_hiding) return "sign data hiding is not supported";
     if (p.cabac_init_present && sh.cabac_init_flag) return "cabac_init_flag is not supported";
@@ -263,12 +282,12 @@ struct Decoder {
     if (p.log2_parallel_merge_level != 2) return "parallel merge level > 2 is not supported";
     if (!sh.first_slice_in_pic) return "multiple slice segments per picture are not supported";
     if (sh.slice_type == 0) return "B slices are not supported";
-    if (sh.slice_type == 1) {
-      if (sh.num_ref_idx_l0 != 1) return "more than one reference picture is not supported";
-      if (sh.max_merge_cand != 5) return "MaxNumMergeCand other than 5 is not supported";
-      if (sh.rps.num_neg < 1 || sh.rps.delta_poc[0] != -1 || !sh.rps.used[0]) return "only the previous picture as reference is supported";
-      for (int i = 1; i < sh.rps.num_delta(); i++) if (sh.rps.used[i]) return "only the previous picture as reference is supported";
-    }
+    // reference pictures: any short-term set of earlier pictures; pictures that FOLLOW in output order
+    // would need output reordering, which a low-delay call never uses
+    if (sh.rps.num_pos > 0) return "reference picture sets with pictures that follow in output order are not supported";
+    if (sh.rps.num_delta() > kPool - 1) return "too many pictures in the reference picture set";
+    if (sh.slice_type == 1 && (sh.num_ref_idx_l0 < 1 || sh.num_ref_idx_l0 > 16)) return "bad number of reference indices";
+    if (sh.slice_type == 1 && sh.collocated_ref_idx >= sh.num_ref_idx_l0) return "collocated_ref_idx out of range";
     return nullptr;
   }
 
@@ -318,11 +337,47 @@ struct Decoder {
       else poc_msb = prev_poc_msb;
       if (nal_type >= 16 && nal_type <= 18) poc_msb = 0;       // BLA
       poc = poc_msb + sh.poc_lsb;
-      // A gap (a P picture lost on the way): like OpenHEVC the decoder conceals with the last picture
-      // it has -- the reference application just keeps feeding NALs (openhevcfilter.cpp:145-152) --
-      // but the event is counted so that an application can ask the sender for an IDR
-      // (b200_dec_missing_refs) instead of drifting unknowingly until the next one.
-      if (slice_type != 2 && have_submitted && poc - 1 != prev_poc) missing_refs++;
+    }
+    // Reference picture set (8.3.2): pictures it does not name leave the buffer; the pictures it marks
+    // "used by the current picture" form list 0 (closest first, repeated cyclically up to
+    // num_ref_idx_l0_active).  A named picture that is not there was lost on the way: like OpenHEVC the
+    // decoder conceals with the nearest picture it has -- the reference application just keeps feeding
+    // NALs (openhevcfilter.cpp:145-152) -- and counts the event (b200_dec_missing_refs) so that an
+    // application can ask the sender for an IDR instead of drifting unknowingly until the next one.
+    int n_refs = 0, ref_pool[16], ref_poc[16], cur_idx = -1;
+    {
+      if (idr) for (DpbEntry &d : dpb) d.valid = false;
+      std::vector<int> curr;
+      for (int i = 0; i < sh.rps.num_delta(); i++) if (sh.rps.used[i]) curr.push_back(poc + sh.rps.delta_poc[i]);
+      bool concealing[kPool] = {};
+      if (slice_type != 2) {
+        if (curr.empty()) { set_error("decoder: P slice with an empty reference picture set"); return -1; }
+        bool counted = false;
+        for (int i = 0; i < sh.num_ref_idx_l0; i++) {
+          const int want = curr[i % curr.size()];
+          int found = -1, best = -1;
+          for (int k = 0; k < kPool; k++) {
+            if (!dpb[k].valid) continue;
+            if (dpb[k].poc == want) found = k;
+            if (best < 0 || std::abs(dpb[k].poc - want) < std::abs(dpb[best].poc - want)) best = k;
+          }
+          if (found < 0) {
+            if (best < 0) { set_error("decoder: P slice without a reference picture (waiting for an IDR)"); return -1; }
+            if (!counted) { missing_refs++; counted = true; }
+            found = best;
+            concealing[best] = true;
+          }
+          ref_pool[n_refs] = found; ref_poc[n_refs++] = want;
+        }
+      }
+      if (!idr)
+        for (int k = 0; k < kPool; k++) {
+          bool keep = concealing[k];               // a stand-in for a lost picture stays until it is not needed
+          for (int i = 0; i < sh.rps.num_delta(); i++) keep |= dpb[k].poc == poc + sh.rps.delta_poc[i];
+          if (!keep) dpb[k].valid = false;
+        }
+      for (int k = 0; k < kPool && cur_idx < 0; k++) if (!dpb[k].valid) cur_idx = k;
+      if (cur_idx < 0) { set_error("decoder: decoded picture buffer full"); return -1; }
     }
     fr_num = sps.fps_num; fr_den = sps.fps_den;
     // geometry: picture size from the SPS, tile columns from the PPS (pictures in flight are dropped
@@ -341,6 +396,7 @@ struct Decoder {
       return -1;
     }
     prev_poc = poc; prev_poc_lsb = idr ? 0 : sh.poc_lsb; prev_poc_msb = poc_msb; have_submitted = true;
+    dpb[cur_idx].valid = true; dpb[cur_idx].poc = poc;
     const size_t hdr_unesc_pos = sh.data_offset;
     // escaped offset of the first slice-data byte
     const size_t hdr_unesc = hdr_unesc_pos;
@@ -382,6 +438,10 @@ struct Decoder {
       t.fp.ctu_qp = pps.qp_delta ? t.d_ctu_qp : nullptr; t.fp.ctu_delta = nullptr; t.fp.ctu_first = nullptr;
       t.fp.sao_flags = (sh.sao_luma ? 1 : 0) | (sh.sao_chroma ? 2 : 0);
       t.fp.sao = t.fp.sao_flags ? t.d_sao : nullptr;
+      t.fp.n_refs = std::max(n_refs, 1); t.fp.max_merge = sh.max_merge_cand;
+      for (int k = 0; k < 16; k++) t.fp.ref_dist[k] = (int16_t)(k < n_refs ? poc - ref_poc[k] : 1);
+      t.fp.col_mvf = (slice_type != 2 && sh.tmvp) ? g.d_mvf[ref_pool[sh.collocated_ref_idx]] : nullptr;
+      if (t.fp.col_mvf) DEC_CHECK(cudaStreamWaitEvent(t.stream, g.ev_mvf[ref_pool[sh.collocated_ref_idx]], 0), "stream wait");
       t.fp.ctu_done = t.d_ctu_done; t.fp.any_intra = t.d_ctu_done + g.fp.ctb_cols * rows; t.fp.intra_in_p = 0;
       DEC_CHECK(cudaMemsetAsync(t.fp.any_intra, 0, sizeof(int), t.stream), "memset any_intra");
       int *sync_flag = (int *)(t.d_small + off_flag), *progress = (int *)(t.d_small + off_prog);
@@ -392,9 +452,16 @@ struct Decoder {
       DEC_CHECK(cudaMemsetAsync(t.d_levels, 0, g.bytes * sizeof(int16_t), t.stream), "memset levels");
       DEC_CHECK(launch_parse(t.fp, sl.d_data, d_bases, t.d_cu, t.d_levels, t.d_small + off_ctx, sync_flag, progress, status, t.stream), "parse launch");
       count_launch(1);
+      if (sps.tmvp) {                      // the motion field later pictures' temporal candidates read
+        DEC_CHECK(launch_store_mvf(t.fp, t.d_cu, g.d_mvf[cur_idx], t.stream), "mvf launch");
+        DEC_CHECK(cudaEventRecord(g.ev_mvf[cur_idx], t.stream), "record mvf");
+        count_launch(1);
+      }
       DEC_CHECK(cudaMemcpyAsync(t.h_status, status, sizeof(int) * 2, cudaMemcpyDeviceToHost, t.stream), "D2H status");
       DEC_CHECK(cudaEventRecord(t.ev_parsed, t.stream), "record parse");
     }
+    sl.cur_idx = cur_idx; sl.n_refs = n_refs;
+    for (int k = 0; k < n_refs; k++) sl.ref_pool[k] = ref_pool[k];
     pending.push_back(next_slot);
     next_slot = (next_slot + 1) % (int)slots.size();
     if ((int)pending.size() <= frame_delay) return 0;
@@ -411,7 +478,7 @@ struct Decoder {
     const int tiles = (int)sl.strips.size();
     for (int i = 0; i < tiles; i++) {
       StripBufs &t = sl.strips[i];
-      if (!cuda_ok(cudaEventSynchronize(t.ev_parsed), "sync parse")) { have_ref = 0; return -1; }
+      if (!cuda_ok(cudaEventSynchronize(t.ev_parsed), "sync parse")) { dpb[sl.cur_idx].valid = false; return -1; }
       if (t.h_status[0] != 0) {
         static const char *const why[] = {"", "escape code too long", "(unused)", "partition other than 2Nx2N", "mvd too long",
           "NxN intra partition", "intra chroma mode other than derived", "64x64 CU with residual", "end_of_slice_segment_flag mismatch",
@@ -419,13 +486,10 @@ struct Decoder {
           "motion vector reaches across a tile boundary"};
         int c = t.h_status[0];
         set_error("decoder: unsupported or corrupt slice data (%s)", c > 0 && c <= 12 ? why[c] : "unknown");
-        have_ref = 0; have_submitted = false;
+        dpb[sl.cur_idx].valid = false;     // never a reference: what follows it conceals and counts
         return -1;
       }
     }
-    const bool is_idr = sl.strips[0].fp.is_idr != 0;
-    if (!is_idr && !have_ref) { set_error("decoder: P slice without a reference picture"); return -1; }
-    have_ref = 0;                          // until this picture is complete
     const size_t ysz = (size_t)fp.w * fp.h;
     for (int i = 0; i < tiles; i++) {      // the strips reconstruct concurrently, each on its own stream
       StripBufs &t = sl.strips[i];
@@ -433,14 +497,15 @@ struct Decoder {
       FrameParams &f = t.fp;
       int *ticket = (int *)(t.d_small + off_ticket);
       // with SAO the picture is reconstructed and deblocked in g.d_dbk; SAO writes the output picture
-      uint8_t *const out_rec = g.d_rec[cur], *ref = g.d_rec[cur ^ 1];
+      uint8_t *const out_rec = g.d_pic[sl.cur_idx];
       uint8_t *rec = f.sao_flags ? g.d_dbk : out_rec;
       if (f.is_idr) {
         DEC_CHECK(launch_intra_decode(f, rec, t.d_levels, t.d_cu, ticket, g.d_order, g.stream), "intra decode launch");
         count_launch(1);
       } else {
         RefList refs{};
-        refs.pic[0] = ref; refs.n = 1;
+        refs.n = sl.n_refs;
+        for (int k = 0; k < sl.n_refs; k++) refs.pic[k] = g.d_pic[sl.ref_pool[k]];
         cudaError_t e = launch_inter_decode(f, refs, rec, t.d_levels, t.d_cu, g.stream);
         DEC_CHECK(e, "inter decode launch");
         // intra CUs of the P picture predict from the reconstructed inter CUs (the kernel returns at
@@ -466,12 +531,11 @@ struct Decoder {
       DEC_CHECK(cudaEventRecord(g.ev_done, g.stream), "record strip");
       DEC_CHECK(cudaStreamWaitEvent(stream, g.ev_done, 0), "stream wait");
     }
-    d_out = tiles > 1 ? d_full : geom[0].d_rec[cur];
+    d_out = tiles > 1 ? d_full : geom[0].d_pic[sl.cur_idx];
     if (host_output) DEC_CHECK(cudaMemcpyAsync(sl.h_out, d_out, frame_bytes, cudaMemcpyDeviceToHost, stream), "D2H picture");
     DEC_CHECK(cudaStreamSynchronize(stream), "sync picture");
 #undef DEC_CHECK
-    cur ^= 1;
-    have_ref = 1; out_slot = idx; out_pts = sl.pts; pictures++;
+    out_slot = idx; out_pts = sl.pts; pictures++;
     return 1;
   }
 
@@ -591,7 +655,8 @@ void libOpenHevcFlush(OpenHevc_Handle h)
     for (b200::StripBufs &t : s.strips) cudaStreamSynchronize(t.stream);
   }
   d->pending.clear();
-  d->have_ref = 0; d->have_submitted = false; d->out_slot = -1; d->d_out = nullptr;
+  for (Decoder::DpbEntry &e : d->dpb) e.valid = false;
+  d->have_submitted = false; d->out_slot = -1; d->d_out = nullptr;
 }
 void libOpenHevcClose(OpenHevc_Handle h) { delete (Decoder *)h; }
 

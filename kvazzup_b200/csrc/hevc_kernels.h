@@ -36,6 +36,10 @@ cudaError_t launch_intra_decode(const FrameParams &fp, uint8_t *rec, const int16
 cudaError_t launch_parse(const FrameParams &fp, const uint8_t *data, const uint32_t *bases, CuInfo *cu, int16_t *levels,
                          uint8_t *sync_ctx, int *sync_flag, int *progress, int *status, cudaStream_t s);
 
+// motion field of a parsed picture at 16x16 granularity ((w+15)/16 x (h+15)/16 entries), what later
+// pictures' temporal motion vector candidates read (FrameParams::col_mvf)
+cudaError_t launch_store_mvf(const FrameParams &fp, const CuInfo *cu, MvField *out, cudaStream_t s);
+
 // cu_qp_delta (fp.ctu_qp != 0): per-CU luma QP into the cu map, per-CTU coded delta and the CU that
 // codes it into fp.ctu_delta / fp.ctu_first.  After reconstruction (needs the cbf), before
 // deblocking and binarisation.

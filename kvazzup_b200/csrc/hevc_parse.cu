@@ -172,19 +172,58 @@ __device__ __forceinline__ unsigned coding_order_p(const FrameParams &fp, int x,
   return (unsigned)((y >> kCtbLog2) * fp.ctb_cols + (x >> kCtbLog2)) * 64u + (unsigned)xy_to_z((x >> 3) & 7, (y >> 3) & 7);
 }
 
-struct NbP { bool ok; int mvx, mvy; };
+struct NbP { bool ok; int mvx, mvy, ref; };
 __device__ __forceinline__ NbP nb_p(const ParseCtx &pc, unsigned cur, int xn, int yn)
 {
-  NbP n{false, 0, 0};
+  NbP n{false, 0, 0, 0};
   const FrameParams &fp = pc.fp;
   if (xn < 0 || yn < 0 || xn >= fp.w || yn >= fp.h) return n;
   if (coding_order_p(fp, xn, yn) >= cur) return n;
   CuInfo c = load_cu(pc, xn, yn);
   if (c.pred_mode != 0) return n;
-  n.ok = true; n.mvx = c.mvx; n.mvy = c.mvy;
+  n.ok = true; n.mvx = c.mvx; n.mvy = c.mvy; n.ref = c.ref_idx;
   return n;
 }
-__device__ __forceinline__ bool same_p(const NbP &a, const NbP &b) { return a.mvx == b.mvx && a.mvy == b.mvy; }
+__device__ __forceinline__ bool same_p(const NbP &a, const NbP &b) { return a.mvx == b.mvx && a.mvy == b.mvy && a.ref == b.ref; }
+
+// 8.5.3.2.7 / 8.5.3.2.8: a vector that spans td pictures rescaled to span tb pictures
+__device__ __forceinline__ int scale_mv_d(int mv, int td, int tb)
+{
+  td = clip3(-128, 127, td); tb = clip3(-128, 127, tb);
+  if (td == 0) return mv;                              // (a stream cannot name the current picture; keeps the division safe)
+  const int tx = (16384 + (abs(td) >> 1)) / td;
+  const int dsf = clip3(-4096, 4095, (tb * tx + 32) >> 6);
+  const int p = dsf * mv;
+  return clip3(-32768, 32767, (p < 0 ? -1 : 1) * ((abs(p) + 127) >> 8));
+}
+// a neighbour's vector as a predictor for reference index `ref`: as it is when it points to the same
+// picture, else rescaled by the ratio of the POC distances
+__device__ __forceinline__ void nb_for_ref(const FrameParams &fp, const NbP &n, int ref, int &mx, int &my)
+{
+  const int td = fp.ref_dist[n.ref & 15], tb = fp.ref_dist[ref & 15];
+  mx = n.mvx; my = n.mvy;
+  if (td != tb) { mx = scale_mv_d(mx, td, tb); my = scale_mv_d(my, td, tb); }
+}
+
+// 8.5.3.2.8 temporal luma motion vector prediction for reference index `ref`: bottom-right candidate
+// (same CTB row, inside the picture), then the centre, from the collocated picture's 16x16 motion field
+__device__ __forceinline__ bool temporal_mv_d(const FrameParams &fp, int x0, int y0, int n, int ref, int &mx, int &my)
+{
+  if (!fp.col_mvf) return false;
+  const int w16 = (fp.w + 15) >> 4;
+  for (int k = 0; k < 2; k++) {
+    const int x = k ? x0 + (n >> 1) : x0 + n, y = k ? y0 + (n >> 1) : y0 + n;
+    if (k == 0 && ((y0 >> kCtbLog2) != (y >> kCtbLog2) || y >= fp.h || x >= fp.w)) continue;
+    const uint2 raw = __ldg((const uint2 *)(fp.col_mvf + (size_t)(y >> 4) * w16 + (x >> 4)));
+    if (!((raw.y >> 16) & 0xff)) continue;             // intra or outside
+    const int cmx = (int16_t)(raw.x & 0xffff), cmy = (int16_t)(raw.x >> 16), col_diff = (int16_t)(raw.y & 0xffff);
+    const int cur_diff = fp.ref_dist[ref & 15];
+    mx = cmx; my = cmy;
+    if (col_diff != cur_diff) { mx = scale_mv_d(cmx, col_diff, cur_diff); my = scale_mv_d(cmy, col_diff, cur_diff); }
+    return true;
+  }
+  return false;
+}
 
 // residual_coding (7.3.8.11): decoded levels go straight to the picture-shaped level plane
 __device__ void parse_residual(Reader &r, const ParseCtx &pc, int16_t *plane, int pw, int x0, int y0, int log2n, int cidx,
@@ -345,25 +384,35 @@ __device__ void parse_cu(Reader &r, ParseCtx &pc, int x0, int y0, int log2)
     NbP b0 = nb_p(pc, cur, x0 + n, y0 - 1), a0 = nb_p(pc, cur, x0 - 1, y0 + n), b2 = nb_p(pc, cur, x0 - 1, y0 - 1);
     if (merge) {
       int midx = 0;
-      if (dec_bin(r, CTX_MERGE_IDX)) {
+      if (fp.max_merge > 1 && dec_bin(r, CTX_MERGE_IDX)) {
         midx = 1;
-        while (midx < kMaxMerge - 1 && dec_bypass(r)) midx++;
+        while (midx < fp.max_merge - 1 && dec_bypass(r)) midx++;
       }
-      int mvx[kMaxMerge], mvy[kMaxMerge], cnt = 0;
+      // merge candidates (8.5.3.2.2-5): spatial, temporal (reference index 0), zero candidates that
+      // walk the reference indices
+      int mvx[kMaxMerge], mvy[kMaxMerge], mref[kMaxMerge], cnt = 0;
       bool use_b1 = b1.ok && !(a1.ok && same_p(b1, a1));
       bool use_b0 = b0.ok && !(b1.ok && same_p(b0, b1));
       bool use_a0 = a0.ok && !(a1.ok && same_p(a0, a1));
       bool use_b2 = b2.ok && !(a1.ok && same_p(b2, a1)) && !(b1.ok && same_p(b2, b1));
-      if (a1.ok) { mvx[cnt] = a1.mvx; mvy[cnt++] = a1.mvy; }
-      if (use_b1) { mvx[cnt] = b1.mvx; mvy[cnt++] = b1.mvy; }
-      if (use_b0) { mvx[cnt] = b0.mvx; mvy[cnt++] = b0.mvy; }
-      if (use_a0) { mvx[cnt] = a0.mvx; mvy[cnt++] = a0.mvy; }
-      if (use_b2 && cnt < 4) { mvx[cnt] = b2.mvx; mvy[cnt++] = b2.mvy; }
-      while (cnt < kMaxMerge) { mvx[cnt] = 0; mvy[cnt++] = 0; }
-      cu.mvx = (int16_t)mvx[midx]; cu.mvy = (int16_t)mvy[midx];
+      if (a1.ok) { mvx[cnt] = a1.mvx; mvy[cnt] = a1.mvy; mref[cnt++] = a1.ref; }
+      if (use_b1) { mvx[cnt] = b1.mvx; mvy[cnt] = b1.mvy; mref[cnt++] = b1.ref; }
+      if (use_b0) { mvx[cnt] = b0.mvx; mvy[cnt] = b0.mvy; mref[cnt++] = b0.ref; }
+      if (use_a0) { mvx[cnt] = a0.mvx; mvy[cnt] = a0.mvy; mref[cnt++] = a0.ref; }
+      if (use_b2 && cnt < 4) { mvx[cnt] = b2.mvx; mvy[cnt] = b2.mvy; mref[cnt++] = b2.ref; }
+      if (cnt < kMaxMerge && temporal_mv_d(fp, x0, y0, n, 0, mvx[cnt], mvy[cnt])) mref[cnt++] = 0;
+      for (int zero_idx = 0; cnt < kMaxMerge; zero_idx++) { mvx[cnt] = 0; mvy[cnt] = 0; mref[cnt++] = zero_idx < fp.n_refs ? zero_idx : 0; }
+      cu.mvx = (int16_t)mvx[midx]; cu.mvy = (int16_t)mvy[midx]; cu.ref_idx = (uint8_t)mref[midx];
       cu.merge_idx = (uint8_t)midx;
       tu = !cu.skip;
     } else {
+      // ref_idx_l0 (TR, cMax n_refs - 1: two context-coded bins, then bypass)
+      int ref = 0;
+      if (fp.n_refs > 1) {
+        const int cmax = fp.n_refs - 1;
+        while (ref < cmax && (ref < 2 ? dec_bin(r, CTX_REF_IDX + ref) : dec_bypass(r))) ref++;
+      }
+      cu.ref_idx = (uint8_t)ref;
       // mvd_coding (7.3.8.9)
       int gt0[2], gt1[2] = {0, 0}, mvd[2] = {0, 0};
       gt0[0] = dec_bin(r, CTX_MVD_GT0);
@@ -383,11 +432,30 @@ __device__ void parse_cu(Reader &r, ParseCtx &pc, int x0, int y0, int log2)
         mvd[k] = dec_bypass(r) ? -a : a;
       }
       int pi = dec_bin(r, CTX_MVP_IDX);
-      NbP a = a0.ok ? a0 : a1;
-      NbP b = b0.ok ? b0 : (b1.ok ? b1 : b2);
-      int px[2], py[2], k = 0;
-      if (a.ok) { px[k] = a.mvx; py[k++] = a.mvy; }
-      if (b.ok && !(a.ok && same_p(a, b))) { px[k] = b.mvx; py[k++] = b.mvy; }
+      // AMVP (8.5.3.2.6-8): candidate A from (A0, A1), B from (B0, B1, B2) -- first a neighbour that
+      // points to the same reference picture, then any neighbour, rescaled -- then temporal, then zero
+      const int tdist = fp.ref_dist[ref & 15];
+      const bool is_scaled = a0.ok || a1.ok;
+      bool fa = false, fb = false;
+      int ax = 0, ay = 0, bx = 0, by = 0;
+      if (a0.ok && fp.ref_dist[a0.ref & 15] == tdist) { ax = a0.mvx; ay = a0.mvy; fa = true; }
+      else if (a1.ok && fp.ref_dist[a1.ref & 15] == tdist) { ax = a1.mvx; ay = a1.mvy; fa = true; }
+      else if (a0.ok) { nb_for_ref(fp, a0, ref, ax, ay); fa = true; }
+      else if (a1.ok) { nb_for_ref(fp, a1, ref, ax, ay); fa = true; }
+      if (b0.ok && fp.ref_dist[b0.ref & 15] == tdist) { bx = b0.mvx; by = b0.mvy; fb = true; }
+      else if (b1.ok && fp.ref_dist[b1.ref & 15] == tdist) { bx = b1.mvx; by = b1.mvy; fb = true; }
+      else if (b2.ok && fp.ref_dist[b2.ref & 15] == tdist) { bx = b2.mvx; by = b2.mvy; fb = true; }
+      if (!is_scaled && fb) { ax = bx; ay = by; fa = true; }
+      if (!is_scaled) {
+        fb = false;
+        if (b0.ok) { nb_for_ref(fp, b0, ref, bx, by); fb = true; }
+        else if (b1.ok) { nb_for_ref(fp, b1, ref, bx, by); fb = true; }
+        else if (b2.ok) { nb_for_ref(fp, b2, ref, bx, by); fb = true; }
+      }
+      int px[3], py[3], k = 0;
+      if (fa) { px[k] = ax; py[k++] = ay; }
+      if (fb && !(fa && ax == bx && ay == by)) { px[k] = bx; py[k++] = by; }
+      if (k < 2 && temporal_mv_d(fp, x0, y0, n, ref, px[k], py[k])) k++;
       while (k < 2) { px[k] = 0; py[k++] = 0; }
       cu.mvx = (int16_t)(px[pi] + mvd[0]); cu.mvy = (int16_t)(py[pi] + mvd[1]);
       cu.mvp_idx = (uint8_t)pi;
@@ -652,6 +720,28 @@ k_parse_rows(FrameParams fp, const uint8_t *__restrict__ data, const uint32_t *_
 }
 
 }  // namespace
+
+// Motion field of the parsed picture at 16x16 granularity, for the temporal candidates of later pictures
+__global__ void __launch_bounds__(256)
+k_store_mvf(FrameParams fp, const CuInfo *__restrict__ cu, MvField *__restrict__ out)
+{
+  const int w16 = (fp.w + 15) >> 4, h16 = (fp.h + 15) >> 4;
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= w16 * h16) return;
+  const int y16 = i / w16, x16 = i - y16 * w16;
+  const CuInfo c = cu[(size_t)(2 * y16) * fp.w8 + 2 * x16];
+  MvField m;
+  m.inter = !fp.is_idr && c.pred_mode == 0 && c.log2_size >= 3;
+  m.mvx = c.mvx; m.mvy = c.mvy; m.poc_diff = m.inter ? fp.ref_dist[c.ref_idx & 15] : 0; m.pad = 0;
+  out[i] = m;
+}
+
+cudaError_t launch_store_mvf(const FrameParams &fp, const CuInfo *cu, MvField *out, cudaStream_t s)
+{
+  const int n = ((fp.w + 15) >> 4) * ((fp.h + 15) >> 4);
+  k_store_mvf<<<(n + 255) / 256, 256, 0, s>>>(fp, cu, out);
+  return cudaGetLastError();
+}
 
 cudaError_t launch_parse(const FrameParams &fp, const uint8_t *data, const uint32_t *bases, CuInfo *cu, int16_t *levels,
                          uint8_t *sync_ctx, int *sync_flag, int *progress, int *status, cudaStream_t s)

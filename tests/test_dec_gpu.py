@@ -55,6 +55,14 @@ def decode_all(aus):
     ("sports", 640, 480, 5, 35, {"intra_in_p": 1, "sao": 2, "intra_period": 4, "search_range": 12, "qp_delta": 1}),
     ("sports", 416, 240, 6, 32, {"me_coarse": 16, "search_range": 4}),   # vectors of +-70 samples, also beyond the picture edge
     ("sports", 640, 256, 4, 30, {"me_coarse": 32, "search_range": 6, "intra_in_p": 1}),
+    # several reference pictures and temporal MV prediction (what a Kvazaar peer sends)
+    ("sports", 416, 240, 7, 32, {"tmvp": 1}),
+    ("sports", 416, 240, 7, 32, {"refs": 2}),
+    ("camera", 192, 136, 6, 30, {"refs": 3, "tmvp": 1}),
+    ("noise", 128, 72, 5, 32, {"refs": 4, "tmvp": 1}),
+    ("sports", 416, 240, 8, 32, {"refs": 4, "tmvp": 1, "me_coarse": 16, "search_range": 4, "sao": 2, "intra_in_p": 1, "intra_period": 5}),
+    ("sports", 640, 256, 5, 27, {"refs": 3, "tmvp": 1, "qp_delta": 1}),
+    ("camera", 1280, 720, 4, 32, {"refs": 3, "tmvp": 1, "sao": 2, "intra_in_p": 1, "me_coarse": 16, "search_range": 6}),
 ])
 def test_decoder_reproduces_oracle_reconstruction(kind, w, h, n, qp, kw):
     frames = frames_of(kind, w, h, n)

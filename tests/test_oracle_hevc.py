@@ -233,6 +233,39 @@ def test_two_level_motion_search_streams_decode_in_ffmpeg(kind, w, h, n, qp, kw)
 
 
 @needs_ff
+@pytest.mark.parametrize("kind,w,h,n,qp,kw", [
+    ("sports", 416, 240, 7, 32, {"tmvp": 1}),
+    ("sports", 416, 240, 7, 32, {"refs": 2}),
+    ("camera", 192, 136, 6, 30, {"refs": 3, "tmvp": 1, "hash_sei": 1}),
+    ("noise", 128, 72, 5, 32, {"refs": 4, "tmvp": 1}),
+    ("sports", 416, 240, 8, 32, {"refs": 4, "tmvp": 1, "me_coarse": 16, "search_range": 4, "sao": 2, "intra_in_p": 1,
+                                 "hash_sei": 1, "intra_period": 5}),
+    ("sports", 640, 256, 5, 27, {"refs": 3, "tmvp": 1, "qp_delta": 1}),
+])
+def test_several_references_and_temporal_mv_prediction_decode_in_ffmpeg(kind, w, h, n, qp, kw):
+    """cfg.refs / cfg.tmvp: what a Kvazaar peer's streams use (its `lp-g4d3t1` structure keeps several
+    references; TMVP is on by default).  Normative: the reference picture set in the slice header while
+    the buffer fills, list construction, ref_idx_l0, merge / AMVP candidates across different
+    reference pictures (vector scaling by POC distance), collocated candidates from the compressed
+    motion field, boundary strength across different references -- FFmpeg must agree bit for bit."""
+    frames = frames_of(kind, w, h, n)
+    enc = OracleEncoder(w, h, qp=qp, **({"intra_period": 0} | kw))
+    if kw.get("qp_delta"):
+        enc.set_ctu_dqp(roi_pattern(w, h, 1, "random"))
+    aus, recs, max_ref = [], [], 0
+    for f in frames:
+        aus.append(enc.encode(f))
+        recs.append(enc.recon())
+        max_ref = max(max_ref, int(enc.cu_map()["ref_idx"].max()))
+    enc.close()
+    assert max_ref == min(kw.get("refs", 1), n - 1, (kw.get("intra_period") or n) - 1) - 1 or kw.get("refs", 1) == 1
+    dec, errs = ffhevc.decode_stream(aus)
+    assert errs == 0 and len(dec) == n
+    for i in range(n):
+        assert np.array_equal(dec[i][0], recs[i]), i
+
+
+@needs_ff
 def test_sao_with_per_ctu_qp_and_periodic_idr_decodes_in_ffmpeg():
     """The two per-CTU syntax additions together: sao() precedes the coding quadtree, cu_qp_delta sits
     in the first coded transform unit; both follow the WPP context hand-over."""
