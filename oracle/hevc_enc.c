@@ -74,6 +74,7 @@ struct orc_encoder {
   } dpb[MAX_REFS];
   int n_dpb;                     /* pictures in the buffer (reset by an IDR) */
   int n_refs;                    /* of the picture being coded: min(cfg.refs, n_dpb) */
+  int delta_coded;               /* entropy stage: the current CTU's cu_qp_delta has been coded */
   int16_t *pen_ctr;              /* per 8x8 unit (origin unit of a CU): centre of its mv penalty, quarter samples */
   uint8_t *src_q;                /* me_coarse: quarter-resolution luma of the source */
   int refstride[3];
@@ -102,6 +103,7 @@ orc_encoder_t *orc_enc_open(const orc_enc_cfg_t *cfg)
   if (!cfg || cfg->width <= 0 || cfg->height <= 0 || (cfg->width & 7) || (cfg->height & 7)) return NULL;
   if (cfg->qp < 0 || cfg->qp > 51 || cfg->search_range < 1 || cfg->search_range > 32) return NULL;
   if (cfg->refs < 0 || cfg->refs > MAX_REFS) return NULL;
+  if (cfg->tr_depth < 0 || cfg->tr_depth > 2) return NULL;
   if (cfg->me_coarse < 0 || cfg->me_coarse > 32 || (cfg->me_coarse > 0 && cfg->search_range > 16)) return NULL;
   orc_encoder_t *e = (orc_encoder_t *)calloc(1, sizeof(*e));
   if (!e) return NULL;
@@ -197,20 +199,23 @@ int orc_enc_set_ctu_dqp(orc_encoder_t *e, const int8_t *dqp)
 /* ------------------------------------------------------------------------------------------ */
 /* residual path shared by intra and inter: src - pred -> DCT -> Q -> (IQ -> IDCT) -> recon     */
 
-static int recon_tb(orc_encoder_t *e, int c, int x0, int y0, int log2n, const uint8_t *pred)
+/* `pred`: prediction samples with row pitch `ps`.  rd (may be NULL): adds the squared error of the
+ * reconstruction and a bit estimate of the levels (what the transform-tree decision compares). */
+typedef struct { long long sse; int bits; } tb_rd_t;
+
+static int recon_tb_s(orc_encoder_t *e, int c, int x0, int y0, int log2n, const uint8_t *pred, int ps, tb_rd_t *rd)
 {
   const int n = 1 << log2n;
-  const int pw = c ? e->cw : e->w, ph = c ? e->ch : e->h;
+  const int pw = c ? e->cw : e->w;
   const uint8_t *src = plane((uint8_t *)e->src, e->w, e->h, c);
   uint8_t *rec = plane(e->rec, e->w, e->h, c);
   int16_t *lv = lplane(e->levels, e->w, e->h, c);
   int16_t resid[32 * 32], coef[32 * 32], level[32 * 32];
   const int qpy = c ? ctu_qp(e, x0 * 2, y0 * 2) : ctu_qp(e, x0, y0);
   const int qp = c ? orc_chroma_qp(qpy) : qpy;
-  (void)ph;
   for (int y = 0; y < n; y++)
     for (int x = 0; x < n; x++)
-      resid[y * n + x] = (int16_t)((int)src[(size_t)(y0 + y) * pw + x0 + x] - (int)pred[y * n + x]);
+      resid[y * n + x] = (int16_t)((int)src[(size_t)(y0 + y) * pw + x0 + x] - (int)pred[y * ps + x]);
   orc_fdct(resid, coef, log2n);
   int nz = orc_quant(coef, level, log2n, qp, e->is_idr);
   for (int y = 0; y < n; y++) memcpy(lv + (size_t)(y0 + y) * pw + x0, level + y * n, n * sizeof(int16_t));
@@ -219,11 +224,105 @@ static int recon_tb(orc_encoder_t *e, int c, int x0, int y0, int log2n, const ui
     orc_idct(coef, resid, log2n);
     for (int y = 0; y < n; y++)
       for (int x = 0; x < n; x++)
-        rec[(size_t)(y0 + y) * pw + x0 + x] = (uint8_t)clip3i(0, 255, pred[y * n + x] + resid[y * n + x]);
+        rec[(size_t)(y0 + y) * pw + x0 + x] = (uint8_t)clip3i(0, 255, pred[y * ps + x] + resid[y * n + x]);
   } else {
-    for (int y = 0; y < n; y++) memcpy(rec + (size_t)(y0 + y) * pw + x0, pred + y * n, n);
+    for (int y = 0; y < n; y++) memcpy(rec + (size_t)(y0 + y) * pw + x0, pred + y * ps, n);
+  }
+  if (rd) {
+    for (int y = 0; y < n; y++)
+      for (int x = 0; x < n; x++) {
+        const int d = (int)src[(size_t)(y0 + y) * pw + x0 + x] - (int)rec[(size_t)(y0 + y) * pw + x0 + x];
+        rd->sse += d * d;
+      }
+    rd->bits += 1;                                               /* the coded block flag */
+    for (int i = 0; i < n * n; i++)
+      if (level[i]) { int a = abs(level[i]), l = 0; while (a >> (l + 1)) l++; rd->bits += 2 * l + 3; }
   }
   return nz != 0;
+}
+
+/* ---- transform tree (7.3.8.8) ------------------------------------------------------------------
+ * cfg.tr_depth = max_transform_hierarchy_depth_inter = _intra.  A transform unit of a CU may be
+ * split into four (down to 8x8 luma); the decision compares squared error + lambda * estimated bits
+ * of both alternatives, bottom-up.  The tree is kept in the cu map: every 8x8 unit records the size of
+ * the transform unit that covers it and that unit's coded block flags. */
+
+typedef struct { const uint8_t *pred[3]; int ps[3]; int x0, y0; } cu_pred_t;   /* inter: the CU's prediction, origin (x0, y0) luma */
+
+static void gather_refs(const orc_encoder_t *e, int c, int x0, int y0, int n, uint8_t *refs);
+
+/* one transform unit, not split: luma block of 1 << log2tu, chroma blocks of half that.  ip == NULL:
+ * intra, predicted here from the reconstructed neighbours with `mode`.  Returns the cbf bits. */
+static int tu_leaf(orc_encoder_t *e, int x0, int y0, int log2tu, const cu_pred_t *ip, int mode, tb_rd_t *rd)
+{
+  uint8_t refs[4 * 32 + 1], pred[32 * 32];
+  int cbf = 0;
+  for (int c = 0; c < 3; c++) {
+    const int sh = c ? 1 : 0, l2 = log2tu - sh, n = 1 << l2, px = x0 >> sh, py = y0 >> sh;
+    if (ip) {
+      cbf |= recon_tb_s(e, c, px, py, l2, ip->pred[c] + (size_t)((y0 - ip->y0) >> sh) * ip->ps[c] + ((x0 - ip->x0) >> sh), ip->ps[c], rd) << c;
+    } else {
+      gather_refs(e, c, px, py, n, refs);
+      orc_intra_predict(refs, l2, mode, c, pred, n);
+      cbf |= recon_tb_s(e, c, px, py, l2, pred, n, rd) << c;
+    }
+  }
+  const int n8 = 1 << (log2tu - 3);
+  for (int j = 0; j < n8; j++)
+    for (int i = 0; i < n8; i++) {
+      orc_cu_t *u = &e->cu[(size_t)(y0 / 8 + j) * e->w8 + x0 / 8 + i];
+      u->tu_log2 = (uint8_t)log2tu; u->cbf = (uint8_t)cbf;
+    }
+  return cbf;
+}
+
+static long long tu_node(orc_encoder_t *e, int x0, int y0, int log2tu, int depth, const cu_pred_t *ip, int mode)
+{
+  const int lq = lambda_at(e, x0, y0);
+  const long long lam = (lq * lq + 128) >> 8;                             /* lambda, SSE domain */
+  tb_rd_t rd = {0, 0};
+  tu_leaf(e, x0, y0, log2tu, ip, mode, &rd);
+  long long cost0 = rd.sse + lam * (rd.bits + 1);
+  if (depth >= e->cfg.tr_depth || log2tu <= 3) return cost0;
+  /* keep the unsplit result, try the split, take the cheaper */
+  const int n = 1 << log2tu, n8 = n / 8;
+  uint8_t save_rec[32 * 32 * 3 / 2];
+  int16_t save_lv[32 * 32 * 3 / 2];
+  orc_cu_t save_cu[16];
+  size_t o = 0;
+  for (int c = 0; c < 3; c++) {
+    const int sh = c ? 1 : 0, pw = c ? e->cw : e->w, m = n >> sh;
+    uint8_t *rec = plane(e->rec, e->w, e->h, c) + (size_t)(y0 >> sh) * pw + (x0 >> sh);
+    int16_t *lv = lplane(e->levels, e->w, e->h, c) + (size_t)(y0 >> sh) * pw + (x0 >> sh);
+    for (int y = 0; y < m; y++) { memcpy(save_rec + o, rec + (size_t)y * pw, m); memcpy(save_lv + o, lv + (size_t)y * pw, m * sizeof(int16_t)); o += m; }
+  }
+  for (int j = 0; j < n8; j++) for (int i = 0; i < n8; i++) save_cu[j * n8 + i] = e->cu[(size_t)(y0 / 8 + j) * e->w8 + x0 / 8 + i];
+  long long cost1 = lam;
+  for (int q = 0; q < 4; q++) cost1 += tu_node(e, x0 + (q & 1) * n / 2, y0 + (q >> 1) * n / 2, log2tu - 1, depth + 1, ip, mode);
+  if (cost1 < cost0) return cost1;
+  o = 0;
+  for (int c = 0; c < 3; c++) {
+    const int sh = c ? 1 : 0, pw = c ? e->cw : e->w, m = n >> sh;
+    uint8_t *rec = plane(e->rec, e->w, e->h, c) + (size_t)(y0 >> sh) * pw + (x0 >> sh);
+    int16_t *lv = lplane(e->levels, e->w, e->h, c) + (size_t)(y0 >> sh) * pw + (x0 >> sh);
+    for (int y = 0; y < m; y++) { memcpy(rec + (size_t)y * pw, save_rec + o, m); memcpy(lv + (size_t)y * pw, save_lv + o, m * sizeof(int16_t)); o += m; }
+  }
+  for (int j = 0; j < n8; j++) for (int i = 0; i < n8; i++) e->cu[(size_t)(y0 / 8 + j) * e->w8 + x0 / 8 + i] = save_cu[j * n8 + i];
+  return cost0;
+}
+
+/* after the tree of a CU: bit 1 of `flags` on all its units = the CU has a coded residual (rqt_root_cbf) */
+static int cu_root_cbf(orc_encoder_t *e, int x0, int y0, int log2)
+{
+  const int n8 = 1 << (log2 - 3);
+  int any = 0;
+  for (int j = 0; j < n8; j++) for (int i = 0; i < n8; i++) any |= e->cu[(size_t)(y0 / 8 + j) * e->w8 + x0 / 8 + i].cbf;
+  for (int j = 0; j < n8; j++)
+    for (int i = 0; i < n8; i++) {
+      orc_cu_t *u = &e->cu[(size_t)(y0 / 8 + j) * e->w8 + x0 / 8 + i];
+      u->flags = (uint8_t)((u->flags & ~2) | (any ? 2 : 0));
+    }
+  return any;
 }
 
 static void set_cu(orc_encoder_t *e, int x0, int y0, int log2, const orc_cu_t *v)
@@ -314,23 +413,17 @@ static uint32_t intra_mode_search(const orc_encoder_t *e, int x0, int y0, int lo
   return best_cost;
 }
 
-/* prediction of the given mode from RECONSTRUCTED neighbours, residual, reconstruction, cu map */
+/* prediction of the given mode from RECONSTRUCTED neighbours, residual, reconstruction, cu map;
+ * prediction and reconstruction go transform unit by transform unit (8.4.4.1) */
 static void intra_cu_recon(orc_encoder_t *e, int x0, int y0, int log2, int best_mode)
 {
-  const int n = 1 << log2;
-  uint8_t refs[4 * 32 + 1], pred[32 * 32], best_pred[32 * 32];
-  gather_refs(e, 0, x0, y0, n, refs);
-  orc_intra_predict(refs, log2, best_mode, 0, best_pred, n);
   orc_cu_t cu;
   memset(&cu, 0, sizeof(cu));
-  cu.log2_size = (uint8_t)log2; cu.pred_mode = 1; cu.intra_mode = (uint8_t)best_mode; cu.merge_idx = 0xff;
-  cu.cbf = (uint8_t)recon_tb(e, 0, x0, y0, log2, best_pred);
-  for (int c = 1; c < 3; c++) {
-    gather_refs(e, c, x0 / 2, y0 / 2, n / 2, refs);
-    orc_intra_predict(refs, log2 - 1, best_mode, c, pred, n / 2);     /* intra_chroma_pred_mode 4 (DM) */
-    cu.cbf |= (uint8_t)(recon_tb(e, c, x0 / 2, y0 / 2, log2 - 1, pred) << c);
-  }
+  cu.log2_size = (uint8_t)log2; cu.pred_mode = 1; cu.intra_mode = (uint8_t)best_mode; cu.chroma_mode = (uint8_t)best_mode;
+  cu.merge_idx = 0xff; cu.tu_log2 = (uint8_t)log2;
   set_cu(e, x0, y0, log2, &cu);
+  tu_node(e, x0, y0, log2, 0, NULL, best_mode);             /* intra_chroma_pred_mode 4 (DM): chroma uses the luma mode */
+  cu_root_cbf(e, x0, y0, log2);
 }
 
 static void intra_cu(orc_encoder_t *e, int x0, int y0, int log2)
@@ -631,13 +724,13 @@ static void inter_cu(orc_encoder_t *e, int x0, int y0, int log2)
       if (cost < best) { best = cost; bx = mx; by = my; memcpy(best_pred, pred, (size_t)n * n); }
     }
   }
-  cu.mvx = (int16_t)bx; cu.mvy = (int16_t)by;
-  cu.cbf = (uint8_t)recon_tb(e, 0, x0, y0, log2, best_pred);
-  for (int c = 1; c < 3; c++) {
-    mc_chroma(e, rf, c, x0 / 2, y0 / 2, n / 2, bx, by, pred);
-    cu.cbf |= (uint8_t)(recon_tb(e, c, x0 / 2, y0 / 2, log2 - 1, pred) << c);
-  }
+  cu.mvx = (int16_t)bx; cu.mvy = (int16_t)by; cu.tu_log2 = (uint8_t)log2;
   set_cu(e, x0, y0, log2, &cu);
+  uint8_t pred_c[2][16 * 16];
+  for (int c = 1; c < 3; c++) mc_chroma(e, rf, c, x0 / 2, y0 / 2, n / 2, bx, by, pred_c[c - 1]);
+  cu_pred_t ip = {{best_pred, pred_c[0], pred_c[1]}, {n, n / 2, n / 2}, x0, y0};
+  tu_node(e, x0, y0, log2, 0, &ip, 0);
+  cu_root_cbf(e, x0, y0, log2);
 }
 
 /* P pictures have no intra-picture dependency before the entropy stage, so both loops are
@@ -685,7 +778,7 @@ static void derive_cu_qps(orc_encoder_t *e)
       for (int z = 0; z < 64 && first == 64; z++) {
         int x8 = cidx * 8, y8 = r * 8;
         for (int b = 0; b < 3; b++) { x8 += ((z >> (2 * b)) & 1) << b; y8 += ((z >> (2 * b + 1)) & 1) << b; }
-        if (x8 < e->w8 && y8 < e->h8 && e->cu[(size_t)y8 * e->w8 + x8].cbf) first = z;
+        if (x8 < e->w8 && y8 < e->h8 && (e->cu[(size_t)y8 * e->w8 + x8].flags & 2)) first = z;
       }
       for (int z = 0; z < 64; z++) {
         int x8 = cidx * 8, y8 = r * 8;
@@ -705,7 +798,7 @@ static void derive_cu_qps(orc_encoder_t *e)
 static int edge_bs(const orc_cu_t *p, const orc_cu_t *q)
 {
   if (p->pred_mode == 1 || q->pred_mode == 1) return 2;
-  if ((p->cbf & 1) || (q->cbf & 1)) return 1;          /* TU edge == CU edge (TU = CU) */
+  if ((p->cbf & 1) || (q->cbf & 1)) return 1;          /* either transform block has coefficients */
   if (p->ref_idx != q->ref_idx) return 1;              /* different reference pictures (list 0 has no duplicates here) */
   return abs(p->mvx - q->mvx) >= 4 || abs(p->mvy - q->mvy) >= 4;
 }
@@ -718,7 +811,7 @@ static void deblock_frame(orc_encoder_t *e)
     for (int y8 = 0; y8 < e->h8; y8++)
       for (int x8 = 0; x8 < e->w8; x8++) {
         const orc_cu_t *q = &e->cu[(size_t)y8 * e->w8 + x8];
-        int n8 = 1 << (q->log2_size - 3);
+        int n8 = q->tu_log2 > 3 ? 1 << (q->tu_log2 - 3) : 1;     /* transform unit edges (they include the CU edges) */
         if (dir == 0 ? (x8 == 0 || (x8 & (n8 - 1))) : (y8 == 0 || (y8 & (n8 - 1)))) continue;
         const orc_cu_t *p = dir == 0 ? q - 1 : q - e->w8;
         int bs = edge_bs(p, q);
@@ -1078,41 +1171,63 @@ static int scan_idx_for(int pred_mode, int intra_mode, int log2n, int cidx)
   return 0;
 }
 
-static void code_transform_unit(orc_encoder_t *e, orc_cabac_t *c, int x0, int y0, int log2, const orc_cu_t *cu)
+/* cu_qp_delta_abs / sign (7.3.8.10, 9.3.3.10): prefix TR cMax 5 (ctx 0, then ctx 1), suffix EG0 bypass */
+static void code_cu_qp_delta(orc_cabac_t *c, int d)
 {
-  /* transform_tree at depth 0 with no split (7.3.8.8): cbf_cb, cbf_cr, cbf_luma */
-  int cb = (cu->cbf >> 1) & 1, cr = (cu->cbf >> 2) & 1, lu = cu->cbf & 1;
-  orc_cabac_bin(c, CTX_CBF_CHROMA + 0, cb);
-  orc_cabac_bin(c, CTX_CBF_CHROMA + 0, cr);
-  if (cu->pred_mode == 1 || cb || cr) orc_cabac_bin(c, CTX_CBF_LUMA + 1, lu);
-  if (e->cfg.qp_delta && cu->cbf) {
-    /* transform_unit (7.3.8.10): cu_qp_delta_abs / sign once per quantisation group, in the first
-     * TU with a coded block flag.  Binarisation 9.3.3.10: prefix TR cMax 5 (ctx 0, then ctx 1),
-     * suffix EG0 bypass. */
-    const int ctu = (y0 / CTB) * e->ctb_cols + x0 / CTB;
-    int x8 = (x0 / 8) & 7, y8 = (y0 / 8) & 7, z = 0;
-    for (int b = 0; b < 3; b++) z |= (((x8 >> b) & 1) << (2 * b)) | (((y8 >> b) & 1) << (2 * b + 1));
-    if (z == e->ctu_first[ctu]) {
-      const int d = e->ctu_delta[ctu], a = abs(d);
-      const int pre = a < 5 ? a : 5;
-      for (int i = 0; i < pre; i++) orc_cabac_bin(c, CTX_CU_QP_DELTA + (i ? 1 : 0), 1);
-      if (pre < 5) orc_cabac_bin(c, CTX_CU_QP_DELTA + (pre ? 1 : 0), 0);
-      else {
-        int v = a - 5, k = 0;
-        while (v >= (1 << k)) { orc_cabac_bypass(c, 1); v -= 1 << k; k++; }
-        orc_cabac_bypass(c, 0);
-        if (k) orc_cabac_bypass_bits(c, (uint32_t)v, k);
-      }
-      if (a) orc_cabac_bypass(c, d < 0);
+  const int a = abs(d), pre = a < 5 ? a : 5;
+  for (int i = 0; i < pre; i++) orc_cabac_bin(c, CTX_CU_QP_DELTA + (i ? 1 : 0), 1);
+  if (pre < 5) orc_cabac_bin(c, CTX_CU_QP_DELTA + (pre ? 1 : 0), 0);
+  else {
+    int v = a - 5, k = 0;
+    while (v >= (1 << k)) { orc_cabac_bypass(c, 1); v -= 1 << k; k++; }
+    orc_cabac_bypass(c, 0);
+    if (k) orc_cabac_bypass_bits(c, (uint32_t)v, k);
+  }
+  if (a) orc_cabac_bypass(c, d < 0);
+}
+
+/* transform_tree (7.3.8.8) of the node (x0, y0, log2) at trafoDepth `depth`; the tree itself is read
+ * from the cu map (size of the transform unit covering each 8x8 unit).  par_cb / par_cr: the parent's
+ * chroma flags (1 at depth 0). */
+static void code_transform_tree(orc_encoder_t *e, orc_cabac_t *c, int x0, int y0, int log2, int depth, int par_cb, int par_cr,
+                                const orc_cu_t *cu)
+{
+  const int n8 = 1 << (log2 - 3);
+  const orc_cu_t *u0 = &e->cu[(size_t)(y0 >> 3) * e->w8 + (x0 >> 3)];
+  const int split = u0->tu_log2 < log2;
+  if (log2 <= 5 && log2 > 2 && depth < e->cfg.tr_depth) orc_cabac_bin(c, CTX_SPLIT_TRANSFORM + 5 - log2, split);
+  int cb = 0, cr = 0;                                    /* of the node: set when any transform unit below has them */
+  for (int j = 0; j < n8; j++)
+    for (int i = 0; i < n8; i++) {
+      const orc_cu_t *u = &e->cu[(size_t)((y0 >> 3) + j) * e->w8 + (x0 >> 3) + i];
+      cb |= (u->cbf >> 1) & 1; cr |= (u->cbf >> 2) & 1;
     }
+  if (par_cb) orc_cabac_bin(c, CTX_CBF_CHROMA + depth, cb);
+  if (par_cr) orc_cabac_bin(c, CTX_CBF_CHROMA + depth, cr);
+  if (split) {
+    const int h = 1 << (log2 - 1);
+    for (int q = 0; q < 4; q++) code_transform_tree(e, c, x0 + (q & 1) * h, y0 + (q >> 1) * h, log2 - 1, depth + 1, cb, cr, cu);
+    return;
+  }
+  const int lu = u0->cbf & 1;
+  if (cu->pred_mode == 1 || depth != 0 || cb || cr) orc_cabac_bin(c, CTX_CBF_LUMA + (depth == 0 ? 1 : 0), lu);
+  if (e->cfg.qp_delta && (lu || cb || cr) && !e->delta_coded) {
+    /* once per quantisation group (= CTU), in its first transform unit with a coded block flag */
+    code_cu_qp_delta(c, e->ctu_delta[(y0 / CTB) * e->ctb_cols + x0 / CTB]);
+    e->delta_coded = 1;
   }
   if (lu)
     orc_code_residual(c, e->levels + (size_t)y0 * e->w + x0, e->w, log2, 0,
                       scan_idx_for(cu->pred_mode, cu->intra_mode, log2, 0));
   for (int k = 1; k < 3; k++)
-    if ((cu->cbf >> k) & 1)
+    if ((u0->cbf >> k) & 1)
       orc_code_residual(c, lplane(e->levels, e->w, e->h, k) + (size_t)(y0 / 2) * e->cw + x0 / 2, e->cw, log2 - 1, k,
-                        scan_idx_for(cu->pred_mode, cu->intra_mode, log2 - 1, k));
+                        scan_idx_for(cu->pred_mode, cu->chroma_mode, log2 - 1, k));
+}
+
+static void code_transform_unit(orc_encoder_t *e, orc_cabac_t *c, int x0, int y0, int log2, const orc_cu_t *cu)
+{
+  code_transform_tree(e, c, x0, y0, log2, 0, 1, 1, cu);
 }
 
 /* prev_intra_luma_pred_flag / mpm_idx / rem_intra_luma_pred_mode (8.4.2) and intra_chroma_pred_mode */
@@ -1177,7 +1292,8 @@ static void code_cu(orc_encoder_t *e, orc_cabac_t *c, int x0, int y0, int log2)
     int midx = -1;
     for (int i = 0; i < MAX_MERGE && midx < 0; i++)
       if (mc[i].x == cu->mvx && mc[i].y == cu->mvy && mc[i].ref == cu->ref_idx) midx = i;
-    int skip = midx >= 0 && cu->cbf == 0;
+    const int root_cbf = (cu->flags & 2) != 0;
+    int skip = midx >= 0 && !root_cbf;
     orc_cabac_bin(c, CTX_SKIP + ctx, skip);
     upd.skip = (uint8_t)skip;
     upd.merge_idx = (uint8_t)(midx >= 0 ? midx : 0xff);
@@ -1206,8 +1322,8 @@ static void code_cu(orc_encoder_t *e, orc_cabac_t *c, int x0, int y0, int log2)
       upd.mvp_idx = (uint8_t)pi;
       code_mvd(c, cu->mvx - ac[pi].x, cu->mvy - ac[pi].y);
       orc_cabac_bin(c, CTX_MVP_IDX, pi);
-      orc_cabac_bin(c, CTX_RQT_ROOT_CBF, cu->cbf != 0);
-      if (cu->cbf) code_transform_unit(e, c, x0, y0, log2, cu);
+      orc_cabac_bin(c, CTX_RQT_ROOT_CBF, root_cbf);
+      if (root_cbf) code_transform_unit(e, c, x0, y0, log2, cu);
     }
   } else {
     code_intra_modes(e, c, x0, y0, log2, cu);
@@ -1309,7 +1425,7 @@ static size_t write_parameter_sets(const orc_encoder_t *e, uint8_t *out, size_t 
   orc_bits_ue(&b, 3);                 /* log2_diff_max_min -> 64 */
   orc_bits_ue(&b, 0);                 /* log2_min_luma_transform_block_size_minus2 -> 4 */
   orc_bits_ue(&b, 3);                 /* log2_diff_max_min transform -> 32 */
-  orc_bits_ue(&b, 0); orc_bits_ue(&b, 0);       /* max_transform_hierarchy_depth_inter / intra */
+  orc_bits_ue(&b, (uint32_t)e->cfg.tr_depth); orc_bits_ue(&b, (uint32_t)e->cfg.tr_depth);   /* max_transform_hierarchy_depth_inter / intra */
   orc_bits_put(&b, 0, 1);             /* scaling_list_enabled_flag */
   orc_bits_put(&b, 0, 1);             /* amp_enabled_flag */
   orc_bits_put(&b, e->cfg.sao ? 1 : 0, 1);          /* sample_adaptive_offset_enabled_flag */
@@ -1349,7 +1465,7 @@ static size_t write_parameter_sets(const orc_encoder_t *e, uint8_t *out, size_t 
   orc_bits_put(&b, 0, 1);             /* output_flag_present_flag */
   orc_bits_put(&b, 0, 3);             /* num_extra_slice_header_bits */
   orc_bits_put(&b, 0, 1);             /* sign_data_hiding_enabled_flag */
-  orc_bits_put(&b, 0, 1);             /* cabac_init_present_flag */
+  orc_bits_put(&b, e->cfg.cabac_init ? 1 : 0, 1);   /* cabac_init_present_flag */
   orc_bits_ue(&b, 0); orc_bits_ue(&b, 0);       /* num_ref_idx_l0/l1_default_active_minus1 */
   orc_bits_se(&b, 0);                 /* init_qp_minus26 */
   orc_bits_put(&b, 0, 1);             /* constrained_intra_pred_flag */
@@ -1485,6 +1601,7 @@ static int assemble_slice(const orc_encoder_t *e, int n_sub, const size_t *sub_e
   if (!e->is_idr) {
     orc_bits_put(&b, e->n_refs != 1, 1);                /* num_ref_idx_active_override_flag */
     if (e->n_refs != 1) orc_bits_ue(&b, (uint32_t)(e->n_refs - 1));
+    if (e->cfg.cabac_init) orc_bits_put(&b, 1, 1);      /* cabac_init_flag: P slices start from the B-slice tables */
     if (e->cfg.tmvp && e->n_refs > 1) orc_bits_ue(&b, 0);   /* collocated_ref_idx */
     orc_bits_ue(&b, 5 - MAX_MERGE);                     /* five_minus_max_num_merge_cand */
   }
@@ -1528,12 +1645,13 @@ static int encode_slice(orc_encoder_t *e, uint8_t *out, size_t cap, size_t *writ
   for (int r = 0; r < rows; r++) {
     if (wpp || r == 0) {
       orc_bits_init(&bits, e->sub + pos, e->sub_cap - pos);
-      if (r == 0 || cols < 2) orc_cabac_init_contexts(&cab, e->is_idr ? 0 : 1, e->cfg.qp);
+      if (r == 0 || cols < 2) orc_cabac_init_contexts(&cab, e->is_idr ? 0 : (e->cfg.cabac_init ? 2 : 1), e->cfg.qp);
       else memcpy(cab.ctx, saved.ctx, sizeof(cab.ctx));          /* WPP sync from CTU 1 of the row above */
       orc_cabac_start(&cab, &bits);
     }
     for (int cidx = 0; cidx < cols; cidx++) {
       if (e->cfg.sao) code_sao(e, &cab, cidx, r);
+      e->delta_coded = 0;
       code_quadtree(e, &cab, cidx * CTB, r * CTB, CTB_LOG2, 0);
       if (cidx == 1) memcpy(saved.ctx, cab.ctx, sizeof(cab.ctx));
       int last_in_slice = r == rows - 1 && cidx == cols - 1 && !e->cfg.more_tiles;

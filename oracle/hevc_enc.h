@@ -44,6 +44,9 @@ typedef struct {
   int sao;                 /* sample adaptive offset (8.7.3) after deblocking: 1 = on, 2 = on and sao_merge_left / _up
                             * flags are used where a CTU's parameters repeat its neighbour's */
   int tile_cols;           /* > 1: PPS / slice header of a picture with that many uniform tile columns (compositor only) */
+  int tr_depth;            /* max_transform_hierarchy_depth_inter = _intra (0..2): transform units may be split into four,
+                            * down to 8x8 luma; decided by squared error + lambda * estimated bits */
+  int cabac_init;          /* 1 = cabac_init_present_flag, P slices signal cabac_init_flag = 1 (initialisation type 2) */
   int refs;                /* reference pictures (0 or 1 = the previous picture only, up to 4): every CU picks the
                             * reference with the smallest cost; ref_idx_l0, the short-term RPS in the slice header
                             * while fewer pictures exist, AMVP with vector scaling, bS from reference pictures */

@@ -33,7 +33,7 @@ class OrcEncCfg(C.Structure):
     _fields_ = [("width", i), ("height", i), ("qp", i), ("intra_period", i), ("search_range", i),
                 ("deblock", i), ("hash_sei", i), ("qp_delta", i),
                 ("mv_edges", i), ("more_tiles", i), ("raw_slice_data", i), ("no_wpp", i), ("subme_satd", i), ("sao", i), ("tile_cols", i),
-                ("refs", i), ("tmvp", i), ("me_coarse", i), ("intra_in_p", i), ("fps_num", i), ("fps_den", i)]
+                ("tr_depth", i), ("cabac_init", i), ("refs", i), ("tmvp", i), ("me_coarse", i), ("intra_in_p", i), ("fps_num", i), ("fps_den", i)]
 
 
 SIGS.update({

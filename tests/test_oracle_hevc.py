@@ -266,6 +266,38 @@ def test_several_references_and_temporal_mv_prediction_decode_in_ffmpeg(kind, w,
 
 
 @needs_ff
+@pytest.mark.parametrize("kind,w,h,n,qp,kw", [
+    ("camera", 192, 136, 4, 30, {"tr_depth": 1}),
+    ("sports", 416, 240, 5, 30, {"tr_depth": 2}),
+    ("screen", 416, 240, 4, 30, {"tr_depth": 2, "hash_sei": 1}),
+    ("noise", 128, 72, 3, 22, {"tr_depth": 1, "cabac_init": 1}),
+    ("camera", 416, 240, 5, 32, {"tr_depth": 2, "cabac_init": 1, "sao": 2, "intra_in_p": 1, "refs": 2, "tmvp": 1, "qp_delta": 1,
+                                 "hash_sei": 1, "intra_period": 3}),
+])
+def test_transform_tree_streams_decode_in_ffmpeg(kind, w, h, n, qp, kw):
+    """cfg.tr_depth: split transform units (split_transform_flag, the cbf_cb / cbf_cr hierarchy, cbf_luma
+    contexts by depth), intra prediction transform unit by transform unit, deblocking of transform
+    edges inside CUs, cu_qp_delta in the first coded transform unit; cfg.cabac_init: initialisation
+    type 2 for P slices.  All normative: FFmpeg must agree."""
+    frames = frames_of(kind, w, h, n)
+    enc = OracleEncoder(w, h, qp=qp, **({"intra_period": 0} | kw))
+    if kw.get("qp_delta"):
+        enc.set_ctu_dqp(roi_pattern(w, h, 1, "random"))
+    aus, recs, split = [], [], 0
+    for f in frames:
+        aus.append(enc.encode(f))
+        recs.append(enc.recon())
+        m = enc.cu_map()
+        split += int((m["tu_log2"] < m["log2_size"]).sum())
+    enc.close()
+    assert split > 0
+    dec, errs = ffhevc.decode_stream(aus)
+    assert errs == 0 and len(dec) == n
+    for i in range(n):
+        assert np.array_equal(dec[i][0], recs[i]), i
+
+
+@needs_ff
 def test_sao_with_per_ctu_qp_and_periodic_idr_decodes_in_ffmpeg():
     """The two per-CTU syntax additions together: sao() precedes the coding quadtree, cu_qp_delta sits
     in the first coded transform unit; both follow the WPP context hand-over."""
