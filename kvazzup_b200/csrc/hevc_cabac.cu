@@ -669,7 +669,7 @@ k_ctx_rows(FrameParams fp, const CuInfo *__restrict__ cu, uint32_t *recs, uint8_
   const int r_first = fp.no_wpp ? 0 : blockIdx.x, r_last = fp.no_wpp ? fp.ctb_rows - 1 : blockIdx.x;
   for (int i = lane; i < 64; i += 32) s_trans[i] = c_trans_lps[i];
   if (r_first == 0 || fp.ctb_cols < 2) {
-    const int qp = clip3(0, 51, fp.qp), init_type = fp.is_idr ? 0 : 1;
+    const int qp = clip3(0, 51, fp.qp), init_type = fp.init_type;
     for (int i = lane; i < CTX_COUNT; i += 32) {
       int iv = c_ctx_init[init_type][i];
       int m = (iv >> 4) * 5 - 45, n = ((iv & 15) << 3) - 16;

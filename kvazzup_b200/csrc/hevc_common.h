@@ -121,6 +121,9 @@ struct FrameParams {
   // max_merge = MaxNumMergeCand.  col_mvf (decoder, slice_temporal_mvp_enabled_flag): motion field of
   // the collocated picture, ((w + 15) / 16) entries per row; null = no temporal candidates.
   int n_refs, max_merge;
+  // CABAC initialisation type (9.3.2.2): 0 I slices, 1 P slices, 2 P slices with cabac_init_flag; decoder:
+  // max_transform_hierarchy_depth_inter / _intra of the SPS
+  int init_type, tr_depth_inter, tr_depth_intra;
   int16_t ref_dist[16];
   const MvField *col_mvf;
   // optional work counters of the motion search (profiling): [0] CTUs, [1] 32x32 quadrants whose second

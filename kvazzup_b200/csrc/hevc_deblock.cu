@@ -4,8 +4,8 @@
 // the vertically filtered samples -- the order the standard prescribes.  One thread per 4-line
 // edge segment: edges lie on the 8x8 grid, a segment reads 8 samples across the edge for 4
 // lines and rewrites at most 3 on each side, so segments of one pass never overlap and the
-// filter runs in place.  Transform-block and prediction-block edges coincide with CU edges
-// because every CU is one 2Nx2N PU with one TU.
+// filter runs in place.  Edges are the transform unit edges on the 8x8 grid (every CU is one 2Nx2N PU, so
+// prediction edges are CU edges, which transform edges include).
 #include "hevc_device.cuh"
 #include "hevc_kernels.h"
 
@@ -90,7 +90,7 @@ k_deblock(FrameParams fp, uint8_t *rec, const CuInfo *__restrict__ cu, int dir)
   if (u >= fp.w8 * fp.h8) return;
   int x8 = u % fp.w8, y8 = u / fp.w8;
   CuInfo q = cu[u];
-  int n8 = 1 << (q.log2_size - 3);
+  int n8 = q.tu_log2 > 3 ? 1 << (q.tu_log2 - 3) : 1;          // transform unit edges (they include the CU edges)
   if (dir == 0 ? (x8 == 0 || (x8 & (n8 - 1))) : (y8 == 0 || (y8 & (n8 - 1)))) return;
   CuInfo p = cu[dir == 0 ? u - 1 : u - fp.w8];
   int bs = edge_bs(fp, p, q);

@@ -258,14 +258,13 @@ struct Decoder {
     if (s.conf_left | s.conf_right | s.conf_top | s.conf_bottom) return "conformance window cropping is not supported";
     if (s.log2_min_cb != 3 || s.log2_ctb != 6) return "coding block sizes other than 8..64 are not supported";
     if (s.log2_min_tb != 2 || s.log2_max_tb != 5) return "transform block sizes other than 4..32 are not supported";
-    if (s.max_tr_depth_inter != 0 || s.max_tr_depth_intra != 0) return "transform hierarchy depth > 0 is not supported";
+    if (s.max_tr_depth_inter > 3 || s.max_tr_depth_intra > 3) return "transform hierarchy depth > 3 is not supported";
     if (s.scaling_list) return "scaling lists are not supported";
     if (s.amp) return "AMP is not supported";
     if (s.pcm) return "PCM is not supported";
     if (s.long_term_refs) return "long-term reference pictures are not supported";
     if (p.dependent_slices) return "dependent slice segments are not supported";
     if (p.sign_hiding) return "sign data hiding is not supported";
-    if (p.cabac_init_present && sh.cabac_init_flag) return "cabac_init_flag is not supported";
     if (p.constrained_intra) return "constrained intra prediction is not supported";
     if (p.transform_skip) return "transform skip is not supported";
     if (p.qp_delta && p.diff_cu_qp_delta_depth != 0) return "quantisation groups smaller than the CTU are not supported";
@@ -277,7 +276,6 @@ struct Decoder {
       if (p.loop_filter_across_tiles) return "loop filtering across tiles is not supported";
       if (p.tile_cols > 32) return "too many tile columns";
     }
-    if (!p.tiles && !p.wpp) return "streams with neither WPP nor tiles are not supported";
     if (!sh.deblock_disabled && (sh.beta_offset_div2 || sh.tc_offset_div2)) return "deblocking offsets are not supported";
     if (p.log2_parallel_merge_level != 2) return "parallel merge level > 2 is not supported";
     if (!sh.first_slice_in_pic) return "multiple slice segments per picture are not supported";
@@ -438,6 +436,8 @@ struct Decoder {
       t.fp.ctu_qp = pps.qp_delta ? t.d_ctu_qp : nullptr; t.fp.ctu_delta = nullptr; t.fp.ctu_first = nullptr;
       t.fp.sao_flags = (sh.sao_luma ? 1 : 0) | (sh.sao_chroma ? 2 : 0);
       t.fp.sao = t.fp.sao_flags ? t.d_sao : nullptr;
+      t.fp.init_type = slice_type == 2 ? 0 : (sh.cabac_init_flag ? 2 : 1);
+      t.fp.tr_depth_inter = sps.max_tr_depth_inter; t.fp.tr_depth_intra = sps.max_tr_depth_intra;
       t.fp.n_refs = std::max(n_refs, 1); t.fp.max_merge = sh.max_merge_cand;
       for (int k = 0; k < 16; k++) t.fp.ref_dist[k] = (int16_t)(k < n_refs ? poc - ref_poc[k] : 1);
       t.fp.col_mvf = (slice_type != 2 && sh.tmvp) ? g.d_mvf[ref_pool[sh.collocated_ref_idx]] : nullptr;
@@ -483,9 +483,9 @@ struct Decoder {
         static const char *const why[] = {"", "escape code too long", "(unused)", "partition other than 2Nx2N", "mvd too long",
           "NxN intra partition", "intra chroma mode other than derived", "64x64 CU with residual", "end_of_slice_segment_flag mismatch",
           "end_of_subset_one_bit missing", "intra CU larger than 16x16", "cu_qp_delta out of range",
-          "motion vector reaches across a tile boundary"};
+          "motion vector reaches across a tile boundary", "4x4 luma transform blocks"};
         int c = t.h_status[0];
-        set_error("decoder: unsupported or corrupt slice data (%s)", c > 0 && c <= 12 ? why[c] : "unknown");
+        set_error("decoder: unsupported or corrupt slice data (%s)", c > 0 && c <= 13 ? why[c] : "unknown");
         dpb[sl.cur_idx].valid = false;     // never a reference: what follows it conceals and counts
         return -1;
       }

@@ -373,6 +373,7 @@ bool Encoder::submit(FrameSlot &s, const uint8_t *d_i420)
   // (a CTU needs its neighbours' DEBLOCKED samples) and writes the reconstruction ring
   uint8_t *rec = cfg.sao ? s.d_dbk : out_rec;
   p.ctu_done = s.d_ctu_done; p.any_intra = s.d_ctu_done + fp.ctb_cols * fp.ctb_rows; p.intra_in_p = cfg.intra_in_p;
+  p.init_type = idr ? 0 : 1; p.tr_depth_inter = 0; p.tr_depth_intra = 0;
   p.n_refs = 1; p.max_merge = kMaxMerge; p.ref_dist[0] = 1; p.col_mvf = nullptr;
   p.me_stats = profile ? d_me_stats : nullptr;
   p.me_coarse = cfg.me_coarse; p.src_q = d_src_q; p.ref_q = d_ref_q;

@@ -461,7 +461,9 @@ k_inter_recon(FrameParams fp, const uint8_t *__restrict__ src, const RefList ref
     int org = 0xff, l2 = 0;
     if (x8 < fp.w8 && y8 < fp.h8) {
       CuInfo ci = cu[(size_t)y8 * fp.w8 + x8];
-      l2 = ci.log2_size;
+      // the transform blocks are what the residual pipeline works on: the CU itself in the encoder, the
+      // transform unit covering the 8x8 unit in the decoder (cbf and size per unit from the parser)
+      l2 = kDecode ? ci.tu_log2 : ci.log2_size;
       int n8 = 1 << (l2 - 3);
       org = xy_to_z(ux & ~(n8 - 1), uy & ~(n8 - 1));
       sh.mvx[t] = ci.mvx; sh.mvy[t] = ci.mvy;

@@ -270,16 +270,17 @@ k_intra_frame(FrameParams fp, const uint8_t *__restrict__ src, uint8_t *rec, int
       for (int z16 = 0; z16 < 16; z16++) {
         int x0 = cx + 16 * ((z16 & 1) | ((z16 >> 1) & 2)), y0 = cy + 16 * (((z16 >> 1) & 1) | ((z16 >> 2) & 2));
         if (x0 >= fp.w || y0 >= fp.h) continue;
+        // prediction and reconstruction go transform unit by transform unit (8.4.4.1): 16x16 units
+        // here, else the 8x8 units among the four quarters
         const CuInfo *u = &cu[(size_t)(y0 >> 3) * fp.w8 + (x0 >> 3)];
-        const int l2 = u->log2_size;
-        if (l2 == 4) {
+        if (u->tu_log2 == 4) {
           if (u->pred_mode == 1) recon_cu<kDecode>(sh, fp, src, rec, levels, cu, cx, cy, x0, y0, 4);
-        } else if (l2 == 3) {
+        } else if (u->tu_log2 <= 3) {
           for (int q = 0; q < 4; q++) {
             int x1 = x0 + 8 * (q & 1), y1 = y0 + 8 * (q >> 1);
             if (x1 >= fp.w || y1 >= fp.h) continue;
             const CuInfo *v = &cu[(size_t)(y1 >> 3) * fp.w8 + (x1 >> 3)];
-            if (v->pred_mode == 1 && v->log2_size == 3) recon_cu<kDecode>(sh, fp, src, rec, levels, cu, cx, cy, x1, y1, 3);
+            if (v->pred_mode == 1 && v->tu_log2 == 3) recon_cu<kDecode>(sh, fp, src, rec, levels, cu, cx, cy, x1, y1, 3);
           }
         }
       }

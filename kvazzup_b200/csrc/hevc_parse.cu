@@ -150,6 +150,7 @@ struct ParseCtx {
   // (the prediction until the CTU's delta is coded), reset to the slice QP at each row start (WPP)
   int qp_cur, delta_coded;
   int any_intra;                 // an intra CU was met in a P slice
+  uint16_t *s_tu;                // [64] transform-tree scratch of the CU being parsed (see parse_cu)
 };
 
 __device__ __forceinline__ CuInfo load_cu(const ParseCtx &pc, int x, int y)
@@ -499,33 +500,97 @@ __device__ void parse_cu(Reader &r, ParseCtx &pc, int x0, int y0, int log2)
     if (!fp.is_idr) pc.any_intra = 1;
     tu = true;
   }
+  // ---- transform tree (7.3.8.8), depth first with a small explicit stack.  Per 8x8 unit of the CU the
+  // size of the transform unit covering it and that unit's coded block flags go to pc.s_tu (raster
+  // inside the CU, 8 units per row): cbf | tu_log2 << 8.
+  const int n8 = n >> 3, units = n8 * n8;
+  const size_t ysz = (size_t)fp.w * fp.h;
+  for (int base = 0; base < units; base += 32) {               // branch-free: surplus lanes repeat the last unit
+    const int u = min(base + pc.lane, units - 1);
+    pc.s_tu[((u >> (log2 - 3)) << 3) + (u & (n8 - 1))] = (uint16_t)(min(log2, 5) << 8);
+  }
+  __syncwarp();
+  int root = 0;
   if (tu) {
-    if (log2 > 5) { r.err = 7; return; }                                   // a 64x64 CU with residual needs a split transform tree
-    int cb = dec_bin(r, CTX_CBF_CHROMA), cr = dec_bin(r, CTX_CBF_CHROMA), lu = 1;
-    if (cu.pred_mode == 1 || cb || cr) lu = dec_bin(r, CTX_CBF_LUMA + 1);
-    cu.cbf = (uint8_t)(lu | (cb << 1) | (cr << 2));
-    if (fp.ctu_qp && cu.cbf && !pc.delta_coded) {
-      // cu_qp_delta_abs (9.3.3.10: prefix TR cMax 5, ctx 0 then ctx 1; suffix EG0) and sign
-      int a = 0;
-      while (a < 5 && dec_bin(r, CTX_CU_QP_DELTA + (a ? 1 : 0))) a++;
-      if (a == 5) {
-        int k = 0, v = 0;
-        while (k < 8 && dec_bypass(r)) { v += 1 << k; k++; }
-        if (k >= 8) { r.err = 11; return; }
-        a += v + (int)dec_bypass_bits(r, k);
+    const int max_depth = cu.pred_mode == 1 ? fp.tr_depth_intra : fp.tr_depth_inter;
+    struct Node { short x, y; signed char l2, depth, child, cb, cr; } st[5];
+    int sp = 0;
+    st[0] = {(short)x0, (short)y0, (signed char)log2, 0, -1, 1, 1};
+    while (sp >= 0 && !r.err) {
+      Node &nd = st[sp];
+      if (nd.child < 0) {
+        // node header: split_transform_flag (parsed or inferred), then the chroma flags of the node
+        int split;
+        if (nd.l2 <= 5 && nd.l2 > 2 && nd.depth < max_depth) split = dec_bin(r, CTX_SPLIT_TRANSFORM + 5 - nd.l2);
+        else split = nd.l2 > 5;                                // larger than the largest transform block: inferred
+        if (split && nd.l2 == 3) { r.err = 13; return; }       // 4x4 luma transform blocks: not supported yet
+        const int par_cb = nd.cb, par_cr = nd.cr;
+        const int cb = par_cb ? dec_bin(r, CTX_CBF_CHROMA + nd.depth) : 0;
+        const int cr = par_cr ? dec_bin(r, CTX_CBF_CHROMA + nd.depth) : 0;
+        nd.cb = (signed char)cb; nd.cr = (signed char)cr;
+        if (split) { nd.child = 0; continue; }
+        // leaf: transform_unit
+        int lu = 1;
+        if (cu.pred_mode == 1 || nd.depth != 0 || cb || cr) lu = dec_bin(r, CTX_CBF_LUMA + (nd.depth == 0 ? 1 : 0));
+        const int cbf = lu | (cb << 1) | (cr << 2);
+        root |= cbf;
+        if (fp.ctu_qp && cbf && !pc.delta_coded) {
+          // cu_qp_delta_abs (9.3.3.10: prefix TR cMax 5, ctx 0 then ctx 1; suffix EG0) and sign
+          int a = 0;
+          while (a < 5 && dec_bin(r, CTX_CU_QP_DELTA + (a ? 1 : 0))) a++;
+          if (a == 5) {
+            int k = 0, v = 0;
+            while (k < 8 && dec_bypass(r)) { v += 1 << k; k++; }
+            if (k >= 8) { r.err = 11; return; }
+            a += v + (int)dec_bypass_bits(r, k);
+          }
+          const int d = (a && dec_bypass(r)) ? -a : a;
+          if (d < -26 || d > 25) { r.err = 11; return; }
+          pc.qp_cur = (pc.qp_cur + d + 52) % 52;
+          pc.delta_coded = 1;
+        }
+        {
+          const int t8 = 1 << (nd.l2 - 3), tunits = t8 * t8;
+          const int bx = (nd.x - x0) >> 3, by = (nd.y - y0) >> 3;
+          for (int base = 0; base < tunits; base += 32) {
+            const int u = min(base + pc.lane, tunits - 1);
+            pc.s_tu[((by + (u >> (nd.l2 - 3))) << 3) + bx + (u & (t8 - 1))] = (uint16_t)(cbf | (nd.l2 << 8));
+          }
+          __syncwarp();
+        }
+        for (int k = 0; k < 3 && !r.err; k++) {
+          if (!((cbf >> k) & 1)) continue;
+          const int sft = k ? 1 : 0;
+          int16_t *plane = pc.levels + (k == 0 ? 0 : ysz + (k == 2 ? ysz / 4 : 0));
+          parse_residual(r, pc, plane, fp.w >> sft, nd.x >> sft, nd.y >> sft, nd.l2 - sft, k,
+                         scan_idx_for_d(cu.pred_mode, k ? cu.chroma_mode : cu.intra_mode, nd.l2 - sft, k));
+        }
+        sp--;
+        continue;
       }
-      const int d = (a && dec_bypass(r)) ? -a : a;
-      if (d < -26 || d > 25) { r.err = 11; return; }
-      pc.qp_cur = (pc.qp_cur + d + 52) % 52;
-      pc.delta_coded = 1;
+      if (nd.child < 4) {
+        const int q = nd.child++, h = 1 << (nd.l2 - 1);
+        const short cx2 = (short)(nd.x + (q & 1) * h), cy2 = (short)(nd.y + (q >> 1) * h);
+        const signed char l2 = (signed char)(nd.l2 - 1), dp = (signed char)(nd.depth + 1), pcb = nd.cb, pcr = nd.cr;
+        sp++;
+        st[sp] = {cx2, cy2, l2, dp, -1, pcb, pcr};
+      } else {
+        sp--;
+      }
     }
+    if (r.err) return;
   }
   if (fp.ctu_qp) cu.qp = (uint8_t)pc.qp_cur;
-  // publish the cu map entry: shared memory for the CUs that follow in this row, global memory for
-  // the row below and the reconstruction kernels (lane u takes unit u of the CU)
+  cu.flags = (uint8_t)(root ? 2 : 0);                        // bit 1: the CU has a coded residual
+  // publish the cu map entries: shared memory for the CUs that follow in this row, global memory for
+  // the row below and the reconstruction kernels (lane u takes unit u of the CU); cbf and the
+  // transform unit size are per unit
   {
-    const uint32_t *s = (const uint32_t *)&cu;
-    const int n8 = n >> 3, units = n8 * n8;
+    uint32_t s[4];
+    {
+      const uint32_t *c32 = (const uint32_t *)&cu;
+      s[0] = c32[0]; s[1] = c32[1]; s[2] = c32[2]; s[3] = c32[3];
+    }
     __syncwarp();
     // Branch-free on purpose: a lane-dependent branch here left the warp split into two groups that
     // ran the rest of the (lane-redundant) parse one after the other, doubling the time.  Lanes with
@@ -535,19 +600,16 @@ __device__ void parse_cu(Reader &r, ParseCtx &pc, int x0, int y0, int log2)
       int i = u & (n8 - 1), j = u >> (log2 - 3);
       const bool mine = u < units && x0 + 8 * i < fp.w && y0 + 8 * j < fp.h;
       i = mine ? i : 0; j = mine ? j : 0;
+      const unsigned tuv = pc.s_tu[(j << 3) + i];
+      // CuInfo bytes: word 1 = log2_size | pred_mode << 8 | intra_mode << 16 | cbf << 24; word 3 = ref_idx | chroma_mode << 8 | tu_log2 << 16 | flags << 24
+      const uint32_t w1 = (s[1] & 0x00ffffffu) | ((tuv & 0xffu) << 24);
+      const uint32_t w3 = (s[3] & 0xff00ffffu) | ((tuv >> 8) << 16);
       uint32_t *t = pc.s_ctu + 4 * (pc.cur_buf * 64 + ((((y0 - pc.cy) >> 3) + j) << 3) + ((x0 >> 3) & 7) + i);
-      t[0] = s[0]; t[1] = s[1]; t[2] = s[2]; t[3] = s[3];
+      t[0] = s[0]; t[1] = w1; t[2] = s[2]; t[3] = w3;
       uint32_t *d = (uint32_t *)(pc.cu + (size_t)((y0 >> 3) + j) * fp.w8 + (x0 >> 3) + i);
-      __stcg(d, s[0]); __stcg(d + 1, s[1]); __stcg(d + 2, s[2]); __stcg(d + 3, s[3]);
+      __stcg(d, s[0]); __stcg(d + 1, w1); __stcg(d + 2, s[2]); __stcg(d + 3, w3);
     }
     __syncwarp();
-  }
-  const size_t ysz = (size_t)fp.w * fp.h;
-  for (int k = 0; k < 3 && !r.err; k++) {
-    if (!((cu.cbf >> k) & 1)) continue;
-    const int sft = k ? 1 : 0;
-    int16_t *plane = pc.levels + (k == 0 ? 0 : ysz + (k == 2 ? ysz / 4 : 0));
-    parse_residual(r, pc, plane, fp.w >> sft, x0 >> sft, y0 >> sft, log2 - sft, k, scan_idx_for_d(cu.pred_mode, cu.intra_mode, log2 - sft, k));
   }
 }
 
@@ -621,11 +683,12 @@ k_parse_rows(FrameParams fp, const uint8_t *__restrict__ data, const uint32_t *_
   for (int i = lane; i < 64; i += 32) s_tab[i] = make_uint2(c_range_lps[i], (uint32_t)c_trans_lps[i] | (i == 0 ? 64u : 0u));
   Reader r;
   r.p = data + bases[fp.no_wpp ? 0 : row]; r.end = data + bases[fp.no_wpp ? 1 : row + 1]; r.ctx = s_ctx + lane; r.tab = s_tab; r.err = 0;
-  ParseCtx pc{fp, cu, levels, lane, 0, s_ctu, s_above, 0, row * kCtb, 0, fp.qp, 0, 0};
+  __shared__ uint16_t s_tu[64];
+  ParseCtx pc{fp, cu, levels, lane, 0, s_ctu, s_above, 0, row * kCtb, 0, fp.qp, 0, 0, s_tu};
   SaoCtu sao_left;
   { uint32_t *z = (uint32_t *)&sao_left; for (int i = 0; i < 5; i++) z[i] = 0; }
   if (row == 0 || fp.ctb_cols < 2) {
-    init_contexts_d(r.ctx, fp.is_idr ? 0 : 1, fp.qp);
+    init_contexts_d(r.ctx, fp.init_type, fp.qp);
   } else {
     // All lanes poll (one broadcast load per iteration).  Nothing in this kernel branches on the
     // lane index: a leader-only branch followed by __syncwarp() has left the warp split into groups

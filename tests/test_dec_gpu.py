@@ -63,6 +63,15 @@ def decode_all(aus):
     ("sports", 416, 240, 8, 32, {"refs": 4, "tmvp": 1, "me_coarse": 16, "search_range": 4, "sao": 2, "intra_in_p": 1, "intra_period": 5}),
     ("sports", 640, 256, 5, 27, {"refs": 3, "tmvp": 1, "qp_delta": 1}),
     ("camera", 1280, 720, 4, 32, {"refs": 3, "tmvp": 1, "sao": 2, "intra_in_p": 1, "me_coarse": 16, "search_range": 6}),
+    # transform tree (split transform units, TU-level intra prediction, TU-edge deblocking), cabac_init_flag,
+    # one substream per picture (neither WPP nor tiles)
+    ("camera", 192, 136, 4, 30, {"tr_depth": 1}),
+    ("sports", 416, 240, 5, 30, {"tr_depth": 2}),
+    ("screen", 416, 240, 4, 30, {"tr_depth": 2}),
+    ("noise", 128, 72, 3, 22, {"tr_depth": 1, "cabac_init": 1}),
+    ("camera", 416, 240, 5, 32, {"tr_depth": 2, "cabac_init": 1, "sao": 2, "intra_in_p": 1, "refs": 2, "tmvp": 1, "qp_delta": 1, "intra_period": 3}),
+    ("camera", 416, 240, 4, 32, {"no_wpp": 1, "tr_depth": 1, "sao": 1}),
+    ("camera", 1920, 1080, 3, 27, {"tr_depth": 2, "refs": 2, "tmvp": 1, "sao": 2, "me_coarse": 16, "search_range": 6}),
 ])
 def test_decoder_reproduces_oracle_reconstruction(kind, w, h, n, qp, kw):
     frames = frames_of(kind, w, h, n)
