@@ -93,6 +93,7 @@ struct Decoder {
   FrameParams fp{};                       // whole picture
   size_t frame_bytes = 0;
   cudaStream_t stream = nullptr;          // output assembly / copy
+  cudaEvent_t ev_out = nullptr;           // the picture is in host memory (what libOpenHevcDecode waits for)
   std::vector<StripGeom> geom;
   uint8_t *d_full = nullptr;              // whole picture on the device when there are several strips
   int conf_w = 0, conf_h = 0, conf_tiles = 0;
@@ -152,8 +153,9 @@ struct Decoder {
     slots.clear();
     pending.clear();
     if (d_full) cudaFree(d_full);
+    if (ev_out) cudaEventDestroy(ev_out);
     if (stream) cudaStreamDestroy(stream);
-    d_full = nullptr; stream = nullptr;
+    d_full = nullptr; stream = nullptr; ev_out = nullptr;
     next_slot = 0; out_slot = -1; conf_tiles = 0;
   }
 
@@ -173,6 +175,7 @@ struct Decoder {
     off_ctx = off_bases + sizeof(uint32_t) * (rows + 1);
     small_bytes = off_ctx + (size_t)rows * CTX_COUNT;
     if (!cuda_ok(cudaStreamCreateWithFlags(&stream, cudaStreamNonBlocking), "cudaStreamCreate")) return false;
+    if (!cuda_ok(cudaEventCreateWithFlags(&ev_out, wait_event_flags(frame_delay > 0)), "cudaEventCreate")) return false;
     geom.resize(tiles);
     for (int i = 0; i < tiles; i++) {
       StripGeom &g = geom[i];
@@ -212,7 +215,7 @@ struct Decoder {
         StripBufs &t = s.strips[i];
         const StripGeom &g = geom[i];
         if (!cuda_ok(cudaStreamCreateWithFlags(&t.stream, cudaStreamNonBlocking), "cudaStreamCreate")) return false;
-        if (!cuda_ok(cudaEventCreateWithFlags(&t.ev_parsed, cudaEventDisableTiming), "cudaEventCreate")) return false;
+        if (!cuda_ok(cudaEventCreateWithFlags(&t.ev_parsed, wait_event_flags(frame_delay > 0)), "cudaEventCreate")) return false;
         if (!cuda_ok(cudaMalloc((void **)&t.d_small, small_bytes), "cudaMalloc")) return false;
         if (!cuda_ok(cudaMalloc((void **)&t.d_ctu_qp, (size_t)g.fp.ctb_cols * rows), "cudaMalloc")) return false;
         if (!cuda_ok(cudaMalloc((void **)&t.d_sao, sizeof(SaoCtu) * g.fp.ctb_cols * rows), "cudaMalloc")) return false;
@@ -533,7 +536,8 @@ struct Decoder {
     }
     d_out = tiles > 1 ? d_full : geom[0].d_pic[sl.cur_idx];
     if (host_output) DEC_CHECK(cudaMemcpyAsync(sl.h_out, d_out, frame_bytes, cudaMemcpyDeviceToHost, stream), "D2H picture");
-    DEC_CHECK(cudaStreamSynchronize(stream), "sync picture");
+    DEC_CHECK(cudaEventRecord(ev_out, stream), "record picture");
+    DEC_CHECK(cudaEventSynchronize(ev_out), "sync picture");
 #undef DEC_CHECK
     out_slot = idx; out_pts = sl.pts; pictures++;
     return 1;

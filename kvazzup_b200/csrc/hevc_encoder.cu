@@ -224,7 +224,7 @@ bool Encoder::open(const EncoderConfig &c)
     ENC_CHECK(cudaHostAlloc((void **)&s.h_hdr, sizeof(uint32_t) * (fp.ctb_rows + 2), cudaHostAllocMapped), "cudaHostAlloc hdr");
     ENC_CHECK(cudaStreamCreateWithPriority(&s.stream, cudaStreamNonBlocking, prio_hi), "cudaStreamCreate slot");
     ENC_CHECK(cudaEventCreateWithFlags(&s.ev_pred, cudaEventDisableTiming), "cudaEventCreate");
-    ENC_CHECK(cudaEventCreateWithFlags(&s.ev_done, cudaEventDisableTiming), "cudaEventCreate");
+    ENC_CHECK(cudaEventCreateWithFlags(&s.ev_done, wait_event_flags(c.depth > 1)), "cudaEventCreate");
     for (cudaEvent_t &e : s.pev) ENC_CHECK(cudaEventCreate(&e), "cudaEventCreate");
   }
   ENC_CHECK(cudaMalloc((void **)&d_me_stats, 4 * sizeof(unsigned long long)), "cudaMalloc me stats");

@@ -25,6 +25,16 @@ struct ConnectionsInit {
 static thread_local char t_err[512] = "";
 std::atomic<unsigned long long> g_launches{0};
 
+unsigned wait_event_flags(bool pipelined)
+{
+  bool block = !pipelined;
+  if (const char *ev = getenv("B200_SYNC")) {
+    if (!strcmp(ev, "spin")) block = false;
+    else if (!strcmp(ev, "block")) block = true;
+  }
+  return cudaEventDisableTiming | (block ? cudaEventBlockingSync : 0u);
+}
+
 void set_error(const char *fmt, ...)
 {
   va_list ap;

@@ -12,6 +12,12 @@ namespace b200 {
 void set_error(const char *fmt, ...);
 bool cuda_ok(cudaError_t e, const char *what);
 
+// Flags for an event a host thread waits on.  A pipelined stream (pictures in flight) wants the lowest
+// wake-up latency and spins; a call-shaped stream (one picture at a time, dozens of streams per GPU, one
+// host thread each) must not burn a core while its picture is on the GPU: the thread sleeps on the
+// event instead (cudaEventBlockingSync).  B200_SYNC=spin|block overrides the choice.
+unsigned wait_event_flags(bool pipelined);
+
 extern std::atomic<unsigned long long> g_launches;
 inline void count_launch(unsigned n = 1) { g_launches.fetch_add(n, std::memory_order_relaxed); }
 

@@ -4,7 +4,12 @@
 // OpenHEVCFilter::process / sendDecodedOutput (openhevcfilter.cpp:103-239) do -- in C++ over the
 // C ABI of libb200media.so, no Python in the loop.
 //
-//   conference_bench <frames.yuv> <w> <h> <frames_in_file> <streams> <frames_per_stream> <encode_only> <decoder_frame_threads> [pace_fps]
+//   conference_bench <frames.yuv> <w> <h> <frames_in_file> <streams> <frames_per_stream> <encode_only> <decoder_frame_threads> [pace_fps] [n_devices]
+//
+// n_devices > 1: participant stream s lives on GPU s mod n_devices (encoder via "b200-device",
+// decoder via the thread's current device) -- the streams share no data, so nothing crosses GPUs
+// (SURVEY.md 8e).  The FNV-1a hash of every stream's access units is printed: it must not depend on
+// n_devices (determinism check).
 //
 // pace_fps > 0: every stream delivers its pictures at that rate (a live call) with nothing in flight
 // (owf 0) and the time from handing a picture to the encoder until its decoded copy is back in host
@@ -24,7 +29,8 @@
 #include "b200_rtp.h"
 #include "b200media.h"
 
-static int W, H, NFILE, STREAMS, FRAMES, ENC_ONLY, DEC_THREADS;
+static int W, H, NFILE, STREAMS, FRAMES, ENC_ONLY, DEC_THREADS, NDEV = 1;
+static std::vector<uint64_t> g_hash;               // per stream: FNV-1a over all access units of the timed pictures
 static double PACE_FPS = 0;
 static std::vector<std::vector<float>> g_lat;      // per stream: latency of every picture, ms
 static std::vector<uint8_t> g_yuv;
@@ -40,6 +46,7 @@ struct Stream {
   OpenHevc_Handle dec = nullptr;
   std::vector<uint8_t> au, nal, out;
   int decoded = 0;
+  uint64_t hash = 1469598103934665603ull;
 };
 
 static bool decode_au(Stream &s)
@@ -90,6 +97,7 @@ static bool feed(Stream &s, const uint8_t *frame)
   for (kvz_data_chunk *c = chunks; c; c = c->next) s.au.insert(s.au.end(), c->data, c->data + c->len);   // :465-474
   s.api->chunk_free(chunks);
   s.api->picture_free(recon);
+  for (uint8_t b : s.au) { s.hash ^= b; s.hash *= 1099511628211ull; }
   if (!ENC_ONLY) return decode_au(s);
   return true;
 }
@@ -106,6 +114,11 @@ static void *worker(void *arg)
   s.api->config_parse(s.cfg, "qp", "32");
   s.api->config_parse(s.cfg, "period", "64");
   s.api->config_parse(s.cfg, "owf", PACE_FPS > 0 ? "0" : "3");
+  const int dev = sid % NDEV;
+  char devs[16];
+  snprintf(devs, sizeof(devs), "%d", dev);
+  s.api->config_parse(s.cfg, "b200-device", devs);
+  b200_set_device(dev);                                                     // the decoder lives on the thread's current device
   s.enc = s.api->encoder_open(s.cfg);
   bool ok = s.enc != nullptr;
   for (int i = 0; ok && i < s.cfg->owf + 1; i++) s.pics.push_back(s.api->picture_alloc(W, H));
@@ -117,6 +130,7 @@ static void *worker(void *arg)
   for (int t = 0; ok && t < 6; t++) ok = feed(s, &g_yuv[(size_t)((t + sid) % NFILE) * fb]);
   pthread_barrier_wait(&g_bar);
   s.decoded = 0;
+  s.hash = 1469598103934665603ull;
   const auto t_start = std::chrono::steady_clock::now();
   for (int t = 0; ok && t < FRAMES; t++) {
     if (PACE_FPS > 0) {
@@ -138,6 +152,7 @@ static void *worker(void *arg)
   pthread_barrier_wait(&g_bar);
   g_decoded[sid] = s.decoded;
   g_ok[sid] = ok;
+  g_hash[sid] = s.hash;
   if (s.dec) libOpenHevcClose(s.dec);
   for (kvz_picture *p : s.pics) s.api->picture_free(p);
   if (s.enc) s.api->encoder_close(s.enc);
@@ -151,6 +166,7 @@ int main(int argc, char **argv)
   W = atoi(argv[2]); H = atoi(argv[3]); NFILE = atoi(argv[4]); STREAMS = atoi(argv[5]); FRAMES = atoi(argv[6]);
   ENC_ONLY = atoi(argv[7]); DEC_THREADS = atoi(argv[8]);
   if (argc > 9) PACE_FPS = atof(argv[9]);
+  if (argc > 10) NDEV = std::max(1, atoi(argv[10]));
   const size_t fb = (size_t)W * H * 3 / 2;
   g_yuv.resize(fb * NFILE);
   FILE *f = fopen(argv[1], "rb");
@@ -158,6 +174,7 @@ int main(int argc, char **argv)
   fclose(f);
   g_decoded.assign(STREAMS, 0); g_ok.assign(STREAMS, 0);
   g_lat.assign(STREAMS, {});
+  g_hash.assign(STREAMS, 0);
   pthread_barrier_init(&g_bar, nullptr, STREAMS + 1);
   std::vector<pthread_t> th(STREAMS);
   for (int i = 0; i < STREAMS; i++) pthread_create(&th[i], nullptr, worker, (void *)(intptr_t)i);
@@ -169,6 +186,8 @@ int main(int argc, char **argv)
   bool all = true;
   for (int i = 0; i < STREAMS; i++) all = all && g_ok[i] && (ENC_ONLY || g_decoded[i] >= FRAMES);
   double fps = (double)STREAMS * FRAMES / dt;
+  uint64_t all_hash = 1469598103934665603ull;                               // over the per-stream hashes, in stream order
+  for (int i = 0; i < STREAMS; i++) for (int b = 0; b < 8; b++) { all_hash ^= (g_hash[i] >> (8 * b)) & 0xff; all_hash *= 1099511628211ull; }
   if (PACE_FPS > 0) {
     std::vector<float> lat;
     for (auto &v : g_lat) lat.insert(lat.end(), v.begin(), v.end());
@@ -176,14 +195,15 @@ int main(int argc, char **argv)
     auto pct = [&](double q) { return lat.empty() ? 0.f : lat[std::min(lat.size() - 1, (size_t)(q * lat.size()))]; };
     printf("{\"workload\": \"conference %dx%d QP32 veryfast paced at %.0f fps, nothing in flight, encode%s per stream\", \"streams\": %d, "
            "\"frames_per_stream\": %d, \"achieved_fps_per_stream\": %.2f, \"latency_ms\": {\"p50\": %.2f, \"p95\": %.2f, \"p99\": %.2f, \"max\": %.2f}, "
-           "\"pictures_timed\": %zu, \"all_pictures_decoded\": %s}\n",
+           "\"pictures_timed\": %zu, \"all_pictures_decoded\": %s, \"gpus\": %d, \"streams_hash\": \"%016llx\"}\n",
            W, H, PACE_FPS, ENC_ONLY ? "" : "+decode", STREAMS, FRAMES, fps / STREAMS, pct(0.50), pct(0.95), pct(0.99), lat.empty() ? 0.f : lat.back(),
-           lat.size(), all ? "true" : "false");
+           lat.size(), all ? "true" : "false", NDEV, (unsigned long long)all_hash);
     return lat.empty() || !all ? 1 : 0;
   }
   printf("{\"workload\": \"conference %dx%d QP32 veryfast, encode%s per stream, C++ harness over the C ABI\", \"streams\": %d, "
          "\"frames_per_stream\": %d, \"decoder_frame_threads\": %d, \"seconds\": %.3f, \"aggregate_fps\": %.1f, "
-         "\"fps_per_stream\": %.1f, \"streams_sustained_at_30fps\": %d, \"all_pictures_decoded\": %s}\n",
-         W, H, ENC_ONLY ? "" : "+decode", STREAMS, FRAMES, DEC_THREADS, dt, fps, fps / STREAMS, (int)(fps / 30), all ? "true" : "false");
+         "\"fps_per_stream\": %.1f, \"streams_sustained_at_30fps\": %d, \"all_pictures_decoded\": %s, \"gpus\": %d, \"streams_hash\": \"%016llx\"}\n",
+         W, H, ENC_ONLY ? "" : "+decode", STREAMS, FRAMES, DEC_THREADS, dt, fps, fps / STREAMS, (int)(fps / 30), all ? "true" : "false", NDEV,
+         (unsigned long long)all_hash);
   return all ? 0 : 1;
 }
