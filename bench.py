@@ -243,20 +243,30 @@ def run_b200(args):
     last_gop = last_gop[-GOP:]                     # the access units of the last timed step (its GOP starts with an IDR)
 
     # ---- e2e: kvz_api with host buffers ----
-    def kvz_run(owf, stock_drain, steps, warm):
+    def kvz_run(owf, stock_drain, steps, warm, pinned_ring=False):
         """pictures/s through kvz_api.  stock_drain: the reference's own loop, which after every access
         unit keeps calling encoder_encode(NULL) until nothing comes back (kvazaarfilter.cpp:440-449) and
-        so empties the pipeline; else the one-line patch of INTEGRATION.md section 1 (poll once)."""
+        so empties the pipeline; else the one-line patch of INTEGRATION.md section 1 (poll once).
+        pinned_ring: the source pictures already sit in picture_alloc (page-locked) pictures -- a producer
+        writing straight into the encoder's ring -- instead of being copied there plane by plane per
+        picture as the reference's filter does (kvazaarfilter.cpp:410-418)."""
         f = KvazaarFilter({"video/ResolutionWidth": W, "video/ResolutionHeight": H, "video/Preset": PRESET, "video/QP": QP,
                            "video/Intra": GOP, "video/OWF": owf, "video/FramerateNumerator": 30})
         if not f.init():
             raise SystemExit("KvazaarFilter.init failed: " + lib.b200_last_error().decode())
 
+        pics = f.alloc_pictures(frames) if pinned_ring else None
+
         def step():
             n = 0
-            for fr in frames:
-                for au in f.feed_input(fr, drain=stock_drain):
-                    n += len(au)
+            if pinned_ring:
+                for pic in pics:
+                    for au in f.feed_picture(pic, drain=stock_drain):
+                        n += len(au)
+            else:
+                for fr in frames:
+                    for au in f.feed_input(fr, drain=stock_drain):
+                        n += len(au)
             return n
 
         for _ in range(warm):
@@ -274,6 +284,8 @@ def run_b200(args):
             t = torch.tensor([dt], device="cuda")
             dist.all_reduce(t, op=dist.ReduceOp.MAX)
             dt = float(t.item())
+        if pics:
+            f.free_pictures(pics)
         f.close()
         return GOP * steps * world / dt, nb // steps
 
@@ -282,6 +294,7 @@ def run_b200(args):
     short = max(1, min(args.steps, 4))
     e2e_stock_owf2, _ = kvz_run(2, True, short, 1)          # the reference's own loop at its largest default owf
     e2e_stock_deep, _ = kvz_run(DEPTH - 1, True, short, 1)  # the reference's own loop, deep pipeline
+    e2e_pinned, _ = kvz_run(DEPTH - 1, False, e2e_steps, 1, pinned_ring=True)
 
     if rank != 0:
         if world > 1:
@@ -372,8 +385,12 @@ def run_b200(args):
                    "bitrate_kbps_at_30fps": round(bitrate_kbps, 1)},
         "e2e": {"value": round(e2e_value, 2), "unit": "frames/s", "h2d_bytes_per_step": frame_bytes * GOP,
                 "d2h_bytes_per_step": d2h,
-                "api": "kvz_api (picture_alloc/encoder_encode/chunk_free), host I420 buffers, owf 95, feedInput polling once per "
+                "api": "kvz_api (picture_alloc/encoder_encode/chunk_free), host I420 buffers copied plane by plane into the ring "
+                       "picture as the reference's filter does (kvazaarfilter.cpp:410-418), owf 95, feedInput polling once per "
                        "picture (INTEGRATION.md section 1)",
+                "from_pinned_ring": {"value": round(e2e_pinned, 2), "unit": "frames/s",
+                                     "note": "same call, source pictures already in picture_alloc (page-locked) pictures: no "
+                                             "frame-sized host copy per picture, H2D straight from the ring"},
                 "stock_drain_loop": {"owf_2": round(e2e_stock_owf2, 2), "owf_95": round(e2e_stock_deep, 2), "unit": "frames/s",
                                      "note": "the reference's unmodified feedInput loop (kvazaarfilter.cpp:440-449), which empties "
                                              "the pipeline after every access unit; owf 2 is the largest value the reference's "

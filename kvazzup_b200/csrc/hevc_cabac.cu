@@ -816,6 +816,7 @@ k_arith_rows(FrameParams fp, const uint32_t *__restrict__ recs, uint8_t *rows, u
       return z;
     };
     int col = 0, z = first_unit(0, 0);
+    int buf = 0;
     const uint32_t *reg = recs + ((size_t)(r * fp.ctb_cols) * 64 + z) * kRecUnitCap;
     uint32_t hdr = __ldcg(reg);
     uint32_t first = __ldcg(reg + 1 + lane);
@@ -830,8 +831,9 @@ k_arith_rows(FrameParams fp, const uint32_t *__restrict__ recs, uint8_t *rows, u
       // code this CU: each 32-record chunk is staged in shared memory (double buffered); the
       // rangeTabLps row of record k + 1 is fetched while record k is coded -- neither load depends
       // on the coder state
+      // (`buf` keeps alternating across CUs: a chunk buffer is rewritten only after the __syncwarp of the
+      // chunk in between, which every lane reaches after its last read -- found by racecheck)
       uint32_t curv = first;
-      int buf = 0;
       for (int base = 0; base < cnt; base += 32) {
         const int nb = base + 32;
         uint32_t nxt = nb + lane < cnt ? __ldcg(reg + 1 + nb + lane) : 0;

@@ -225,6 +225,34 @@ class KvazaarFilter:
             pic.contents.roi.roi_array = None
         return self._drain(pic, drain)
 
+    def alloc_pictures(self, frames):
+        """Page-locked pictures from picture_alloc holding `frames` (what a producer that writes its
+        output straight into the encoder's input ring leaves behind): feed them with feed_picture()."""
+        c = self.config.contents
+        w, h = c.width, c.height
+        pics = []
+        for f in frames:
+            pic = self.api.picture_alloc(w, h)
+            if not pic:
+                raise B200Error("picture_alloc failed")
+            src = np.ascontiguousarray(f)
+            C.memmove(pic.contents.y, src.ctypes.data, w * h * 3 // 2)       # planes are contiguous (b200_kvazaar.h)
+            pics.append(pic)
+        return pics
+
+    def free_pictures(self, pics):
+        for p in pics:
+            self.api.picture_free(p)
+
+    def feed_picture(self, pic, drain: bool = True):
+        """encoder_encode on a picture that already sits in picture_alloc memory: no copy on the way in.
+        The picture must stay untouched until its access unit has been returned (b200_kvazaar.h)."""
+        pic.contents.pts = self.pts
+        self.pts += 1
+        pic.contents.roi.width = pic.contents.roi.height = 0
+        pic.contents.roi.roi_array = None
+        return self._drain(pic, drain)
+
     def flush(self):
         """Drain the frames still in flight (owf > 0): encoder_encode(pic = NULL) until empty."""
         out = []
