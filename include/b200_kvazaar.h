@@ -63,7 +63,7 @@ typedef struct kvz_config {
   int32_t owf;                           /* "owf": pictures in flight - 1 */
   int32_t threads;                       /* "threads": accepted, meaningless on a GPU */
   int32_t target_bitrate;                /* bits/s; 0 = constant QP */
-  int32_t rc_algorithm;                  /* "rc-algorithm" */
+  int32_t rc_algorithm;                  /* "rc-algorithm": no-rc / lambda (frame-level lambda-domain control); oba is refused */
   int32_t lossless;                      /* must be 0 */
   enum kvz_mv_constraint mv_constraint;
   int32_t set_qp_in_cu;                  /* != 0 enables per-CTU QP (cu_qp_delta), see roi_enable */
@@ -135,6 +135,12 @@ typedef struct kvz_api {
                         kvz_picture **pic_recon, kvz_picture **pic_src, kvz_frame_info *info_out);
   kvz_picture *(*picture_alloc_csp)(enum kvz_chroma_format chroma_format, int32_t width, int32_t height);
 } kvz_api;
+
+/* B200 extensions for bitrate adaptation during a call: a new target for a running encoder (0 = back to
+ * constant QP), and the reference's reaction to an RTCP receiver report (resourceallocator.cpp:67-90) as
+ * a function. */
+int b200_kvz_set_bitrate(kvz_encoder *encoder, int bits_per_second);
+int b200_rtcp_bitrate_update(int bitrate, int lost_increased, int jitter_increased);
 
 /* bit_depth must be 8; any other value returns NULL (kvazaarfilter.cpp:145-150 treats NULL as failure). */
 const kvz_api *kvz_api_get(int bit_depth);

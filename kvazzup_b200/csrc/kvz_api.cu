@@ -1,10 +1,12 @@
 // kvz_api boundary (include/b200_kvazaar.h): the C ABI KvazaarFilter binds
 // (reference src/media/processing/kvazaarfilter.cpp:145-318, 374-484), implemented on the B200
 // encoder engine.  Option names follow Kvazaar's config_parse; presets map to the search range.
+#include <math.h>
 #include <stdio.h>
 #include <stdlib.h>
 #include <string.h>
 
+#include <algorithm>
 #include <deque>
 #include <new>
 
@@ -23,9 +25,18 @@ struct kvz_encoder {
   ~kvz_encoder() { if (tiled) b200_tiled_close(tiled); }
   kvz_config cfg;
   std::deque<int64_t> pts;              // presentation timestamps of the pictures in flight
-  // frame-level rate control (target_bitrate != 0): leaky bucket on the produced bits
-  double bits_per_frame = 0, bucket = 0;
-  int rc_window = 0;
+  // Frame-level rate control in the lambda domain (target_bitrate != 0, rc-algorithm lambda; K9 of
+  // SURVEY.md 8a): bits per pixel of a picture <-> lambda through R = (lambda / alpha)^(1 / beta), the
+  // model Kvazaar's (and HM's, JCTVC-K0103) lambda-domain control uses, one (alpha, beta) pair per
+  // picture type, updated from every coded picture; the target of a picture comes from a sliding
+  // window over the bits spent so far.
+  struct RcModel { double alpha = 3.2003, beta = -1.367; };
+  RcModel rc_model[2];                  // [0] P pictures, [1] IDR pictures
+  double bits_per_frame = 0;            // target_bitrate / frame rate
+  double rc_spent = 0;                  // bits of the pictures returned so far
+  long long rc_returned = 0, rc_submitted = 0;
+  std::deque<std::pair<int, bool>> rc_pending;   // (QP, IDR) of the pictures in flight, oldest first
+  int rc_last_qp[2] = {-1, -1};
   std::vector<uint8_t> au;
 };
 
@@ -133,7 +144,8 @@ int config_parse(kvz_config *cfg, const char *name, const char *value)
     if (!value) return 0;
     if (!strcmp(value, "no-rc")) { cfg->rc_algorithm = KVZ_NO_RC; return 1; }
     if (!strcmp(value, "lambda")) { cfg->rc_algorithm = KVZ_LAMBDA; return 1; }
-    if (!strcmp(value, "oba")) { cfg->rc_algorithm = KVZ_OBA; return 1; }
+    // "oba" (Kvazaar's optimal bit allocation) is not built: refused, the reference then logs a warning
+    // and the lambda-domain control stays in force (kvazaarfilter.cpp:363-369)
     return 0;
   }
   if (!strcmp(name, "gop")) {
@@ -297,21 +309,60 @@ int encoder_headers(kvz_encoder *e, kvz_data_chunk **data_out, uint32_t *len_out
   return 1;
 }
 
-// frame-level rate control: nudge the QP of future pictures so that the produced bits track the
-// target (a restatement of the intent of Kvazaar's rate control, not of its lambda / OBA models)
+// ---- lambda-domain rate control ----------------------------------------------------------------
+// QP <-> lambda: QP = 4.2005 ln(lambda) + 13.7122 (JCTVC-K0103, the relation HM and Kvazaar use)
+double rc_lambda_of_qp(int qp) { return exp((qp - 13.7122) / 4.2005); }
+
+constexpr int kRcWindow = 40;           // pictures over which a surplus / deficit is worked off
+constexpr double kRcIntraShare = 6.0;   // an IDR picture may take this many average pictures' worth of bits
+
+// QP of the picture about to be submitted.
+int rate_control_pick_qp(kvz_encoder *e, bool idr)
+{
+  const double px = (double)e->cfg.width * e->cfg.height;
+  // bits spent by pictures still in flight are not known yet: count them at the average
+  const double spent = e->rc_spent + (double)(e->rc_submitted - e->rc_returned) * e->bits_per_frame;
+  const double n = (double)e->rc_submitted;
+  double target = (e->bits_per_frame * (n + kRcWindow) - spent) / kRcWindow;         // sliding-window allocation
+  target = std::min(std::max(target, 0.25 * e->bits_per_frame), 4.0 * e->bits_per_frame);
+  // an intra period of P pictures holds one IDR worth kRcIntraShare average pictures: the P pictures share the rest
+  const double period = (double)e->cfg.intra_period;
+  if (idr) target *= kRcIntraShare;
+  else if (period > kRcIntraShare + 1) target *= (period - kRcIntraShare) / (period - 1.0);
+  if (target < 64) target = 64;
+  const kvz_encoder::RcModel &m = e->rc_model[idr ? 1 : 0];
+  const double bpp = target / px;
+  double lambda = m.alpha * pow(bpp, m.beta);
+  lambda = std::min(std::max(lambda, 0.1), 10000.0);
+  int qp = (int)floor(4.2005 * log(lambda) + 13.7122 + 0.5);
+  const int last = e->rc_last_qp[idr ? 1 : 0];
+  if (last >= 0) qp = std::min(std::max(qp, last - 3), last + 3);                      // no jumps between pictures of a kind
+  else if (idr && e->rc_last_qp[0] >= 0) qp = std::min(std::max(qp, e->rc_last_qp[0] - 6), e->rc_last_qp[0] + 2);
+  qp = std::min(std::max(qp, 10), 51);
+  e->rc_last_qp[idr ? 1 : 0] = qp;
+  return qp;
+}
+
+// A coded picture came back: account its bits and move (alpha, beta) of its kind towards what it showed.
 void rate_control_update(kvz_encoder *e, size_t au_bytes, bool idr)
 {
-  if (e->bits_per_frame <= 0) return;
-  double bits = 8.0 * au_bytes;
-  e->bucket += bits - e->bits_per_frame;
-  if (idr) return;                                // let the bucket absorb the intra picture over the GOP
-  if (++e->rc_window < 2) return;
-  e->rc_window = 0;
-  int qp = e->eng.qp();
-  const double hi = 4.0 * e->bits_per_frame, lo = -4.0 * e->bits_per_frame;
-  if (e->bucket > hi || bits > 1.5 * e->bits_per_frame) qp++;
-  else if (e->bucket < lo || bits < 0.6 * e->bits_per_frame) qp--;
-  e->eng.set_qp(std::min(std::max(qp, 10), 51));
+  if (e->bits_per_frame <= 0 || e->rc_pending.empty()) return;
+  const int qp = e->rc_pending.front().first;
+  e->rc_pending.pop_front();
+  const double bits = 8.0 * au_bytes, px = (double)e->cfg.width * e->cfg.height;
+  e->rc_spent += bits;
+  e->rc_returned++;
+  kvz_encoder::RcModel &m = e->rc_model[idr ? 1 : 0];
+  const double bpp = std::max(bits / px, 1e-5);
+  const double ln_real = log(rc_lambda_of_qp(qp)), ln_comp = log(m.alpha) + m.beta * log(bpp);
+  // Only alpha follows the content, and fast (half of the log error per picture): with K0103's step
+  // sizes (0.1 / 0.05 for alpha / beta) content far from the model's natural-video starting point drives
+  // beta into its clip within ten pictures and the model goes flat -- the loop then has no authority
+  // over the rate.  The exponent stays at its starting value; the sliding window absorbs what a fixed
+  // exponent misses.
+  const double err = std::min(std::max(ln_real - ln_comp, -2.0), 2.0);
+  m.alpha *= exp(0.5 * err);
+  m.alpha = std::min(std::max(m.alpha, 0.001), 200.0);
 }
 
 int encoder_encode(kvz_encoder *e, kvz_picture *pic_in, kvz_data_chunk **data_out, uint32_t *len_out,
@@ -366,6 +417,13 @@ int encoder_encode(kvz_encoder *e, kvz_picture *pic_in, kvz_data_chunk **data_ou
         e->eng.set_ctu_dqp(nullptr, 0);
       }
     }
+    if (e->bits_per_frame > 0) {
+      const bool idr = e->eng.frame_idx == 0 || (e->cfg.intra_period > 0 && e->eng.frame_idx % e->cfg.intra_period == 0);
+      const int qp = rate_control_pick_qp(e, idr);
+      e->eng.set_qp(qp);
+      e->rc_pending.emplace_back(qp, idr);
+      e->rc_submitted++;
+    }
     const size_t ysz = (size_t)e->cfg.width * e->cfg.height;
     if (pic_in->u == pic_in->y + ysz && pic_in->v == pic_in->u + ysz / 4 && pic_in->stride == pic_in->width) {
       ok = e->eng.encode_host(pic_in->y, e->au, pic_in->base_image == pic_in);
@@ -414,6 +472,28 @@ const kvz_api kApi = {config_alloc, config_destroy, config_init, config_parse, p
                       chunk_free, encoder_open, encoder_close, encoder_headers, encoder_encode, picture_alloc_csp};
 
 }  // namespace
+
+// Changes the target bitrate of a running encoder (what an RTCP-driven allocation such as the
+// reference's ResourceAllocator::addRTCPReport, resourceallocator.cpp:67-104, would feed back); 0
+// switches rate control off.  The (alpha, beta) models are kept.
+extern "C" int b200_kvz_set_bitrate(kvz_encoder *e, int bits_per_second)
+{
+  if (!e || bits_per_second < 0 || e->tiled) { b200::set_error("b200_kvz_set_bitrate: bad arguments"); return B200_ERR_ARG; }
+  e->cfg.target_bitrate = bits_per_second;
+  e->bits_per_frame = bits_per_second > 0 && e->cfg.framerate_num > 0 ? (double)bits_per_second * e->cfg.framerate_denom / e->cfg.framerate_num : 0;
+  // restart the window so that the old rate's surplus / deficit does not leak into the new target
+  e->rc_spent = (double)e->rc_returned * e->bits_per_frame;
+  return B200_OK;
+}
+
+// The reference's reaction to an RTCP receiver report (resourceallocator.cpp:67-90): halve the bitrate
+// when more packets were lost, take 10 % off when only the jitter grew, add 10 % otherwise.
+extern "C" int b200_rtcp_bitrate_update(int bitrate, int lost_increased, int jitter_increased)
+{
+  if (lost_increased) return bitrate / 2;
+  if (jitter_increased) return (int)(bitrate * 0.9);
+  return (int)(bitrate * 1.1);
+}
 
 // The engine parameters a preset stands for (what encoder_open derives from "preset"): lets the
 // benchmark and the tests run the bare engine in exactly the configuration kvz_api would.

@@ -131,6 +131,7 @@ def test_kvz_config_parse_follows_the_reference_contract():
     assert ok("b200-roi", "1") == 1 and cfg.contents.roi_enable == 1
     assert ok("set-qp-in-cu", "1") == 1 and cfg.contents.set_qp_in_cu == 1
     assert ok("bitrate", "1500000") == 1 and cfg.contents.target_bitrate == 1500000
+    assert ok("rc-algorithm", "lambda") == 1 and ok("rc-algorithm", "no-rc") == 1 and ok("rc-algorithm", "oba") == 0   # oba is not built
     assert ok("no-such-option", "1") == 0
     api.config_destroy(cfg)
     assert kvz_api_get(10) is None                      # only 8-bit, like the reference's kvz_api_get(8) (:145)
