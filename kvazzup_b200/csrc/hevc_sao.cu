@@ -20,18 +20,19 @@ namespace {
 
 constexpr int kSaoThreads = 256, kSaoWarps = kSaoThreads / 32;
 
+// Tiles hold the deblocked samples of a plane of the CTU with a one-sample ring; the interior starts
+// at byte column 4 so that every group of four samples is one aligned word (ring: column 3 and
+// column T + 4).  Row pitch T + 8.
 struct SaoShared {
-  uint8_t tile_y[66 * 68];                     // deblocked samples with a one-sample ring, row pitch 68
-  uint8_t tile_c[2][34 * 36];                  // pitch 36
-  unsigned hist[kSaoWarps][48];                // per warp: 16 edge bins (class * 4 + category - 1) + 32 bands;
-                                               // packed count << 20 | sum (20-bit two's complement)
+  uint32_t tile_y[66 * 18];                    // 66 rows x 72 bytes
+  uint32_t tile_c[2][34 * 10];                 // 34 rows x 40 bytes
+  unsigned hist[kSaoWarps][32];                // per warp: the 32 bands; packed count << 20 | sum (20-bit two's complement)
+  int eo_cnt[16], eo_sum[16];                  // edge bins (class * 4 + category index 0..3) of the plane in work
   long long eo_term[3][16];                    // per plane: SSE change + lambda * bits of the bin's best offset
   long long band_term[3][32];
   int8_t eo_off[3][16], band_off[3][32];
   SaoCtu prm;
 };
-
-__device__ __forceinline__ int sgn(int v) { return (v > 0) - (v < 0); }
 
 // best offset of a bin given count and sum of (source - deblocked); returns the change in SSE
 __device__ __forceinline__ long long best_offset(int count, int sum, int lo, int hi, int &off)
@@ -48,7 +49,7 @@ __device__ __forceinline__ long long best_offset(int count, int sum, int lo, int
   return best;
 }
 
-struct PlaneGeom { int pw, ph, x0, y0, x1, y1, T, pitch; };
+struct PlaneGeom { int pw, ph, x0, y0, x1, y1, T, pitchw; };
 
 __device__ __forceinline__ PlaneGeom plane_geom(const FrameParams &fp, int cx, int cy, int c)
 {
@@ -57,28 +58,49 @@ __device__ __forceinline__ PlaneGeom plane_geom(const FrameParams &fp, int cx, i
   g.pw = fp.w >> sh; g.ph = fp.h >> sh;
   g.x0 = cx >> sh; g.y0 = cy >> sh;
   g.x1 = min(g.pw, (cx + kCtb) >> sh); g.y1 = min(g.ph, (cy + kCtb) >> sh);
-  g.T = kCtb >> sh; g.pitch = g.T + 4;
+  g.T = kCtb >> sh; g.pitchw = (g.T + 8) >> 2;
   return g;
 }
 
-// edge category 1..4 (0 = none) of the sample at tile position (tx, ty) (ring offset included)
-// (`inside`: both neighbours of the class lie in the picture -- otherwise the category is 0, 8.7.3.2)
-__device__ __forceinline__ int edge_category(const uint8_t *tile, int pitch, int tx, int ty, int cls, bool inside)
+// The four samples of word `xw` of tile row `row` (0 = first row of the CTU) and their two neighbours
+// of edge class `cls`, as packed bytes.  class 0: a = left, b = right; 1: above, below; 2: above-left,
+// below-right; 3: above-right, below-left (8.7.3.2, Table 8-13).
+__device__ __forceinline__ void edge_neighbours(const uint32_t *tile, int pitchw, int row, int xw, int cls, uint32_t &c, uint32_t &a, uint32_t &b)
 {
-  if (!inside) return 0;
-  // class 0: a = (-1, 0), b = (1, 0); 1: (0,-1),(0,1); 2: (-1,-1),(1,1); 3: (1,-1),(-1,1)
-  const int ax = cls == 0 ? -1 : (cls == 1 ? 0 : (cls == 2 ? -1 : 1)), ay = cls == 0 ? 0 : -1;
-  const int v = tile[ty * pitch + tx];
-  const int e = 2 + sgn(v - tile[(ty + ay) * pitch + tx + ax]) + sgn(v - tile[(ty - ay) * pitch + tx - ax]);
-  return e == 2 ? 0 : (e < 2 ? e + 1 : e);
+  const uint32_t *r1 = tile + (row + 1) * pitchw + xw + 1;      // centre word (interior starts at word 1)
+  c = r1[0];
+  if (cls == 0) { a = __funnelshift_r(r1[-1], r1[0], 24); b = __funnelshift_r(r1[0], r1[1], 8); return; }
+  const uint32_t *r0 = r1 - pitchw, *r2 = r1 + pitchw;
+  if (cls == 1) { a = r0[0]; b = r2[0]; }
+  else if (cls == 2) { a = __funnelshift_r(r0[-1], r0[0], 24); b = __funnelshift_r(r2[0], r2[1], 8); }
+  else { a = __funnelshift_r(r0[0], r0[1], 8); b = __funnelshift_r(r2[-1], r2[0], 24); }
 }
 
-// are the two neighbours of class `cls` of plane sample (x, y) inside the picture?
-__device__ __forceinline__ bool nb_inside(int x, int y, int pw, int ph, int cls)
+// edgeIdx of four samples at once: 2 + sign(c - a) + sign(c - b) per byte (0..4; 2 = no offset)
+__device__ __forceinline__ uint32_t edge_index4(uint32_t c, uint32_t a, uint32_t b)
 {
-  const int ax = cls == 0 ? -1 : (cls == 1 ? 0 : (cls == 2 ? -1 : 1)), ay = cls == 0 ? 0 : -1;
-  const int x_a = x + ax, y_a = y + ay, x_b = x - ax, y_b = y - ay;
-  return x_a >= 0 && x_a < pw && y_a >= 0 && y_a < ph && x_b >= 0 && x_b < pw && y_b >= 0 && y_b < ph;
+  const uint32_t one = 0x01010101u;
+  return 0x02020202u + (__vcmpgtu4(c, a) & one) + (__vcmpgtu4(c, b) & one) - (__vcmpltu4(c, a) & one) - (__vcmpltu4(c, b) & one);
+}
+
+// Byte mask (0xff per sample) of the samples of a word whose class-`cls` neighbours both lie inside the
+// picture; x = plane column of the word's first sample, y = plane row.
+__device__ __forceinline__ uint32_t inside_mask4(int x, int y, int pw, int ph, int cls)
+{
+  if (cls != 0 && (y == 0 || y == ph - 1)) return 0u;
+  uint32_t m = 0xffffffffu;
+  if (cls != 1) {
+    if (x == 0) m &= 0xffffff00u;
+    if (x + 4 == pw) m &= 0x00ffffffu;
+  }
+  return m;
+}
+
+// four byte values 0..7 -> a PRMT selector (nibble per byte)
+__device__ __forceinline__ uint32_t nibbles_of(uint32_t e)
+{
+  const uint32_t t = e | (e >> 4);
+  return (t & 0xffu) | ((t >> 8) & 0xff00u);
 }
 
 template <bool kDecide>
@@ -92,16 +114,22 @@ k_sao_ctu(FrameParams fp, const uint8_t *__restrict__ src, const uint8_t *__rest
   const int cx = (ctu % fp.ctb_cols) * kCtb, cy = (ctu / fp.ctb_cols) * kCtb;
   const size_t ysz = (size_t)fp.w * fp.h;
 
-  // ---- deblocked samples of the three planes, with their ring, into shared memory ----
+  // ---- deblocked samples of the three planes, with their ring, into shared memory (coordinates
+  // clamped to the picture: what lies outside is never used, inside_mask4 sees to that) ----
   for (int c = 0; c < 3; c++) {
     const PlaneGeom g = plane_geom(fp, cx, cy, c);
     const uint8_t *pl = dbk + (c == 0 ? 0 : ysz + (c == 2 ? ysz / 4 : 0));
-    uint8_t *tile = c == 0 ? sh.tile_y : sh.tile_c[c - 1];
-    const int side = g.T + 2;
-    for (int i = t; i < side * side; i += kSaoThreads) {
-      const int ty = i / side, tx = i - ty * side;
-      const int x = min(max(g.x0 - 1 + tx, 0), g.pw - 1), y = min(max(g.y0 - 1 + ty, 0), g.ph - 1);
-      tile[ty * g.pitch + tx] = __ldg(pl + (size_t)y * g.pw + x);
+    uint32_t *tile = c == 0 ? sh.tile_y : sh.tile_c[c - 1];
+    const int rows = g.T + 2;
+    for (int i = t; i < rows * g.pitchw; i += kSaoThreads) {
+      const int ty = i / g.pitchw, wi = i - ty * g.pitchw;
+      const int y = min(max(g.y0 - 1 + ty, 0), g.ph - 1), x = g.x0 - 4 + 4 * wi;
+      const uint8_t *rowp = pl + (size_t)y * g.pw;
+      uint32_t v;
+      if (x >= 0 && x + 4 <= g.pw) v = __ldg((const uint32_t *)(rowp + x));
+      else v = (uint32_t)rowp[min(max(x, 0), g.pw - 1)] | ((uint32_t)rowp[min(max(x + 1, 0), g.pw - 1)] << 8) |
+               ((uint32_t)rowp[min(max(x + 2, 0), g.pw - 1)] << 16) | ((uint32_t)rowp[min(max(x + 3, 0), g.pw - 1)] << 24);
+      tile[i] = v;
     }
   }
   if (!kDecide && t == 0) sh.prm = params[ctu];
@@ -113,43 +141,65 @@ k_sao_ctu(FrameParams fp, const uint8_t *__restrict__ src, const uint8_t *__rest
     for (int c = 0; c < 3; c++) {
       const PlaneGeom g = plane_geom(fp, cx, cy, c);
       const uint8_t *ps = src + (c == 0 ? 0 : ysz + (c == 2 ? ysz / 4 : 0));
-      const uint8_t *tile = c == 0 ? sh.tile_y : sh.tile_c[c - 1];
-      for (int i = t; i < kSaoWarps * 48; i += kSaoThreads) (&sh.hist[0][0])[i] = 0;
+      const uint32_t *tile = c == 0 ? sh.tile_y : sh.tile_c[c - 1];
+      for (int i = t; i < kSaoWarps * 32; i += kSaoThreads) (&sh.hist[0][0])[i] = 0;
+      if (t < 16) { sh.eo_cnt[t] = 0; sh.eo_sum[t] = 0; }
       __syncthreads();
-      // a warp takes whole rows (32 consecutive samples per pass): <= 512 samples per warp and
-      // plane, so count (<= 512) and |sum| (<= 130560) fit the packed 12 + 20 bit accumulators
-      const int wd = g.x1 - g.x0, ht = g.y1 - g.y0;
-      for (int row = warp; row < ht; row += kSaoWarps) {
-        for (int xx = lane; xx < wd; xx += 32) {
-          const int x = g.x0 + xx, y = g.y0 + row;
-          const int v = tile[(row + 1) * g.pitch + xx + 1];
-          const int diff = (int)__ldg(ps + (size_t)y * g.pw + x) - v;
-          const unsigned add = (1u << 20) + (unsigned)diff;
-          atomicAdd(&sh.hist[warp][16 + (v >> 3)], add);
+      // Statistics, four samples per step.  Edge bins: per class the edgeIdx of the four samples as
+      // packed bytes, then per category a byte mask, the count from its population and the sum of
+      // (source - deblocked) as two masked byte sums -- accumulated in registers, reduced at the end.
+      // Bands: one packed shared-memory atomic per sample into the warp's own histogram (a warp sees
+      // <= 512 samples per plane, so count and |sum| fit 12 + 20 bits).
+      const int wd4 = (g.x1 - g.x0) >> 2, ht = g.y1 - g.y0;
+      int cnt[16], sum[16];
 #pragma unroll
-          for (int cls = 0; cls < 4; cls++) {
-            const int k = edge_category(tile, g.pitch, xx + 1, row + 1, cls, nb_inside(x, y, g.pw, g.ph, cls));
-            if (k) atomicAdd(&sh.hist[warp][cls * 4 + k - 1], add);
+      for (int k = 0; k < 16; k++) { cnt[k] = 0; sum[k] = 0; }
+      for (int i = t; i < wd4 * ht; i += kSaoThreads) {
+        const int row = i / wd4, xw = i - row * wd4;
+        const int x = g.x0 + 4 * xw, y = g.y0 + row;
+        const uint32_t sw = __ldg((const uint32_t *)(ps + (size_t)y * g.pw + x));
+        uint32_t cw = 0;
+#pragma unroll
+        for (int cls = 0; cls < 4; cls++) {
+          uint32_t a, b;
+          edge_neighbours(tile, g.pitchw, row, xw, cls, cw, a, b);
+          const uint32_t in = inside_mask4(x, y, g.pw, g.ph, cls);
+          const uint32_t e = (edge_index4(cw, a, b) & in) | (0x02020202u & ~in);
+#pragma unroll
+          for (int k = 0; k < 4; k++) {
+            const uint32_t m = __vcmpeq4(e, 0x01010101u * (uint32_t)(k < 2 ? k : k + 1));     // categories 1, 2, 3, 4 = edgeIdx 0, 1, 3, 4
+            cnt[cls * 4 + k] += __popc(m) >> 3;
+            sum[cls * 4 + k] += (int)__vsadu4(sw & m, 0u) - (int)__vsadu4(cw & m, 0u);
           }
         }
+#pragma unroll
+        for (int j = 0; j < 4; j++) {
+          const int v = (cw >> (8 * j)) & 0xff, d = (int)((sw >> (8 * j)) & 0xff) - v;
+          atomicAdd(&sh.hist[warp][v >> 3], (1u << 20) + (unsigned)d);
+        }
+      }
+#pragma unroll
+      for (int k = 0; k < 16; k++) {
+        const int cs = __reduce_add_sync(0xffffffffu, cnt[k]), ss = __reduce_add_sync(0xffffffffu, sum[k]);
+        if (lane == 0 && cs) { atomicAdd(&sh.eo_cnt[k], cs); atomicAdd(&sh.eo_sum[k], ss); }
       }
       __syncthreads();
       if (t < 48) {
-        int cnt = 0, sum = 0;
-        for (int w = 0; w < kSaoWarps; w++) {
-          const unsigned h = sh.hist[w][t];
-          const int s = ((int)(h << 12)) >> 12;
-          sum += s;
-          cnt += (int)((h - (unsigned)s) >> 20);
-        }
         int o;
         if (t < 16) {
           const int k = (t & 3) + 1;
-          const long long d = best_offset(cnt, sum, k <= 2 ? 0 : -7, k <= 2 ? 7 : 0, o);
+          const long long d = best_offset(sh.eo_cnt[t], sh.eo_sum[t], k <= 2 ? 0 : -7, k <= 2 ? 7 : 0, o);
           sh.eo_term[c][t] = d + lam * (abs(o) + 1);
           sh.eo_off[c][t] = (int8_t)o;
         } else {
-          const long long d = best_offset(cnt, sum, -7, 7, o);
+          int bc = 0, bs = 0;
+          for (int w = 0; w < kSaoWarps; w++) {
+            const unsigned h = sh.hist[w][t - 16];
+            const int s2 = ((int)(h << 12)) >> 12;
+            bs += s2;
+            bc += (int)((h - (unsigned)s2) >> 20);
+          }
+          const long long d = best_offset(bc, bs, -7, 7, o);
           sh.band_term[c][t - 16] = d + lam * (abs(o) + 1 + (o != 0));
           sh.band_off[c][t - 16] = (int8_t)o;
         }
@@ -195,32 +245,46 @@ k_sao_ctu(FrameParams fp, const uint8_t *__restrict__ src, const uint8_t *__rest
     if (t == 0) params[ctu] = sh.prm;
   }
 
-  // ---- apply ----
+  // ---- apply: four samples per step.  The offsets of a plane sit in two byte tables (positive and
+  // negative parts) that PRMT indexes with the four edgeIdx / band indices at once; saturating byte
+  // add and subtract clip to 0..255. ----
   for (int c = 0; c < 3; c++) {
     const PlaneGeom g = plane_geom(fp, cx, cy, c);
     uint8_t *po = out + (c == 0 ? 0 : ysz + (c == 2 ? ysz / 4 : 0));
-    const uint8_t *tile = c == 0 ? sh.tile_y : sh.tile_c[c - 1];
+    const uint32_t *tile = c == 0 ? sh.tile_y : sh.tile_c[c - 1];
     const int grp = c ? 1 : 0;
     const int type = sh.prm.type[grp], cls = sh.prm.eo_class[grp], bpos = sh.prm.band_pos[c];
+    // table index: edge offset -> edgeIdx (0, 1: categories 1, 2; 2: none; 3, 4: categories 3, 4); band
+    // offset -> band index 0..3, 4 = none
+    uint32_t pos_lo = 0, pos_hi = 0, neg_lo = 0, neg_hi = 0;
+    for (int k = 0; k < 4; k++) {
+      const int o = sh.prm.offset[c][k], idx = type == 2 ? (k < 2 ? k : k + 1) : k;
+      const uint32_t p = (uint32_t)max(o, 0), n = (uint32_t)max(-o, 0);
+      if (idx < 4) { pos_lo |= p << (8 * idx); neg_lo |= n << (8 * idx); }
+      else { pos_hi |= p; neg_hi |= n; }
+    }
     const int wd4 = (g.x1 - g.x0) >> 2, ht = g.y1 - g.y0;
     for (int i = t; i < wd4 * ht; i += kSaoThreads) {
       const int row = i / wd4, xw = i - row * wd4;
-      uint32_t word = 0;
-#pragma unroll
-      for (int j = 0; j < 4; j++) {
-        const int xx = 4 * xw + j;
-        const int v = tile[(row + 1) * g.pitch + xx + 1];
-        int o = 0;
-        if (type == 2) {
-          const int k = edge_category(tile, g.pitch, xx + 1, row + 1, cls, nb_inside(g.x0 + xx, g.y0 + row, g.pw, g.ph, cls));
-          if (k) o = sh.prm.offset[c][k - 1];
-        } else if (type == 1) {
-          const int k = ((v >> 3) - bpos) & 31;
-          if (k < 4) o = sh.prm.offset[c][k];
-        }
-        word |= (uint32_t)clip8(v + o) << (8 * j);
+      const int x = g.x0 + 4 * xw, y = g.y0 + row;
+      uint32_t cw, idx4;
+      if (type == 2) {
+        uint32_t a, b;
+        edge_neighbours(tile, g.pitchw, row, xw, cls, cw, a, b);
+        const uint32_t in = inside_mask4(x, y, g.pw, g.ph, cls);
+        idx4 = (edge_index4(cw, a, b) & in) | (0x02020202u & ~in);
+      } else {
+        cw = tile[(row + 1) * g.pitchw + xw + 1];
+        const uint32_t d = __vsub4((cw >> 3) & 0x1f1f1f1fu, 0x01010101u * (uint32_t)bpos) & 0x1f1f1f1fu;
+        const uint32_t lt = __vcmpltu4(d, 0x04040404u);
+        idx4 = (d & lt) | (0x04040404u & ~lt);
       }
-      *(uint32_t *)(po + (size_t)(g.y0 + row) * g.pw + g.x0 + 4 * xw) = word;
+      uint32_t word = cw;
+      if (type) {
+        const uint32_t sel = nibbles_of(idx4);
+        word = __vsubus4(__vaddus4(cw, __byte_perm(pos_lo, pos_hi, sel)), __byte_perm(neg_lo, neg_hi, sel));
+      }
+      *(uint32_t *)(po + (size_t)y * g.pw + x) = word;
     }
   }
 }
