@@ -224,6 +224,11 @@ static void code_remaining(orc_cabac_t *c, int value, int rice)
 
 void orc_code_residual(orc_cabac_t *c, const int16_t *lv, int stride, int log2n, int cidx, int scan_idx)
 {
+  orc_code_residual2(c, lv, stride, log2n, cidx, scan_idx, 0);
+}
+
+void orc_code_residual2(orc_cabac_t *c, const int16_t *lv, int stride, int log2n, int cidx, int scan_idx, int sign_hiding)
+{
   const int n = 1 << log2n;
   const int sb_log2 = log2n - 2;           /* grid of 4x4 sub-blocks */
   const int nsb = 1 << (2 * sb_log2);
@@ -323,9 +328,13 @@ void orc_code_residual(orc_cabac_t *c, const int16_t *lv, int stride, int log2n,
       g2flag = abs_lv[first_g1_pos] > 2;
       orc_cabac_bin(c, CTX_GT2 + (cidx ? 4 : 0) + ctx_set, g2flag);
     }
-    /* signs (no sign data hiding) */
+    /* signs; with sign data hiding the sign of the first coefficient in scan order is not coded when
+     * the significant coefficients of the group span more than three scan positions (7.3.8.11) */
+    int first_sig = -1, last_sig = -1;
+    for (int p = 0; p < 16; p++) if (sig[p]) { if (first_sig < 0) first_sig = p; last_sig = p; }
+    const int hidden = sign_hiding && last_sig - first_sig > 3;
     for (int p = 15; p >= 0; p--)
-      if (sig[p]) orc_cabac_bypass(c, sign[p]);
+      if (sig[p] && !(hidden && p == first_sig)) orc_cabac_bypass(c, sign[p]);
     /* remaining levels */
     int num_sig = 0, rice = 0;
     for (int p = 15; p >= 0; p--) {

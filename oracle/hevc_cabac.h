@@ -43,5 +43,7 @@ void orc_cabac_finish(orc_cabac_t *c);      /* flush + the stop/alignment bit + 
 /* residual_coding( ) for one transform block.  levels: row-major N x N with the given stride.
  * scan_idx: 0 diagonal, 1 horizontal, 2 vertical (7.4.9.11). */
 void orc_code_residual(orc_cabac_t *c, const int16_t *levels, int stride, int log2n, int cidx, int scan_idx);
+/* ... with sign_data_hiding_enabled_flag = `sign_hiding` (the levels must already obey the parity rule) */
+void orc_code_residual2(orc_cabac_t *c, const int16_t *levels, int stride, int log2n, int cidx, int scan_idx, int sign_hiding);
 
 #endif

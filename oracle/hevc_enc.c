@@ -103,7 +103,9 @@ orc_encoder_t *orc_enc_open(const orc_enc_cfg_t *cfg)
   if (!cfg || cfg->width <= 0 || cfg->height <= 0 || (cfg->width & 7) || (cfg->height & 7)) return NULL;
   if (cfg->qp < 0 || cfg->qp > 51 || cfg->search_range < 1 || cfg->search_range > 32) return NULL;
   if (cfg->refs < 0 || cfg->refs > MAX_REFS) return NULL;
-  if (cfg->tr_depth < 0 || cfg->tr_depth > 2) return NULL;
+  if (cfg->tr_depth < 0 || cfg->tr_depth > 3) return NULL;
+  if (cfg->cb_qp_offset < -12 || cfg->cb_qp_offset > 12 || cfg->cr_qp_offset < -12 || cfg->cr_qp_offset > 12) return NULL;
+  if (cfg->beta_offset_div2 < -6 || cfg->beta_offset_div2 > 6 || cfg->tc_offset_div2 < -6 || cfg->tc_offset_div2 > 6) return NULL;
   if (cfg->me_coarse < 0 || cfg->me_coarse > 32 || (cfg->me_coarse > 0 && cfg->search_range > 16)) return NULL;
   orc_encoder_t *e = (orc_encoder_t *)calloc(1, sizeof(*e));
   if (!e) return NULL;
@@ -199,11 +201,61 @@ int orc_enc_set_ctu_dqp(orc_encoder_t *e, const int8_t *dqp)
 /* ------------------------------------------------------------------------------------------ */
 /* residual path shared by intra and inter: src - pred -> DCT -> Q -> (IQ -> IDCT) -> recon     */
 
+/* QP of plane c at luma position (x, y): Table 8-10 with the PPS chroma offsets */
+static int plane_qp(const orc_encoder_t *e, int c, int x, int y)
+{
+  const int qpy = ctu_qp(e, x, y);
+  return c == 0 ? qpy : orc_chroma_qp(qpy + (c == 1 ? e->cfg.cb_qp_offset : e->cfg.cr_qp_offset));
+}
+
+/* Sign data hiding, encoder side: in every 4x4 group whose significant levels span more than three
+ * scan positions the decoder takes the sign of the first one (lowest scan position) from the parity of
+ * the sum of magnitudes (odd = negative).  Where the parity is wrong one magnitude between the first
+ * and the last significant position changes by one -- the change with the smallest increase of the
+ * quantisation error; the first and the last position never become zero, so the span is unchanged. */
+static int sign_hide(const int16_t *coef, int16_t *level, int log2n, int qp, int scan_idx)
+{
+  const int n = 1 << log2n, nsb = 1 << (log2n - 2);
+  const int qbits = 14 + qp / 6 + (15 - 8 - log2n);
+  const int64_t scale = orc_quant_scales[qp % 6];
+  int nz = 0;
+  for (int ys = 0; ys < nsb; ys++)
+    for (int xs = 0; xs < nsb; xs++) {
+      int idx[16], first = -1, last = -1, sum = 0;
+      for (int p = 0; p < 16; p++) {
+        int xp, yp;
+        orc_scan_pos(scan_idx, 2, p, &xp, &yp);
+        idx[p] = (ys * 4 + yp) * n + xs * 4 + xp;
+        if (level[idx[p]]) { if (first < 0) first = p; last = p; sum += abs(level[idx[p]]); }
+      }
+      if (first >= 0 && last - first > 3 && (sum & 1) != (level[idx[first]] < 0)) {
+        int64_t best = INT64_MAX;
+        int bp = last, bd = 1;
+        for (int p = last; p >= first; p--) {
+          const int l = abs(level[idx[p]]);
+          const int64_t t = (int64_t)abs(coef[idx[p]]) * scale, d0 = llabs(t - ((int64_t)l << qbits));
+          for (int d = 1; d >= -1; d -= 2) {
+            if (l + d < 0 || l + d > 32767) continue;
+            if (l + d == 0 && (p == first || p == last)) continue;
+            const int64_t cost = llabs(t - ((int64_t)(l + d) << qbits)) - d0;
+            if (cost < best) { best = cost; bp = p; bd = d; }
+          }
+        }
+        const int l = abs(level[idx[bp]]) + bd;
+        const int neg = level[idx[bp]] ? level[idx[bp]] < 0 : coef[idx[bp]] < 0;
+        level[idx[bp]] = (int16_t)(neg ? -l : l);
+      }
+    }
+  for (int i = 0; i < n * n; i++) nz += level[i] != 0;
+  return nz;
+}
+
 /* `pred`: prediction samples with row pitch `ps`.  rd (may be NULL): adds the squared error of the
- * reconstruction and a bit estimate of the levels (what the transform-tree decision compares). */
+ * reconstruction and a bit estimate of the levels (what the transform-tree decision compares).
+ * dst: DST-VII (4x4 intra luma) instead of the DCT.  scan_idx: coefficient scan of the block (sign hiding). */
 typedef struct { long long sse; int bits; } tb_rd_t;
 
-static int recon_tb_s(orc_encoder_t *e, int c, int x0, int y0, int log2n, const uint8_t *pred, int ps, tb_rd_t *rd)
+static int recon_tb_x(orc_encoder_t *e, int c, int x0, int y0, int log2n, const uint8_t *pred, int ps, tb_rd_t *rd, int dst, int scan_idx)
 {
   const int n = 1 << log2n;
   const int pw = c ? e->cw : e->w;
@@ -211,17 +263,17 @@ static int recon_tb_s(orc_encoder_t *e, int c, int x0, int y0, int log2n, const 
   uint8_t *rec = plane(e->rec, e->w, e->h, c);
   int16_t *lv = lplane(e->levels, e->w, e->h, c);
   int16_t resid[32 * 32], coef[32 * 32], level[32 * 32];
-  const int qpy = c ? ctu_qp(e, x0 * 2, y0 * 2) : ctu_qp(e, x0, y0);
-  const int qp = c ? orc_chroma_qp(qpy) : qpy;
+  const int qp = c ? plane_qp(e, c, x0 * 2, y0 * 2) : plane_qp(e, 0, x0, y0);
   for (int y = 0; y < n; y++)
     for (int x = 0; x < n; x++)
       resid[y * n + x] = (int16_t)((int)src[(size_t)(y0 + y) * pw + x0 + x] - (int)pred[y * ps + x]);
-  orc_fdct(resid, coef, log2n);
+  if (dst) orc_fdst4(resid, coef); else orc_fdct(resid, coef, log2n);
   int nz = orc_quant(coef, level, log2n, qp, e->is_idr);
+  if (nz && e->cfg.sign_hiding) nz = sign_hide(coef, level, log2n, qp, scan_idx);
   for (int y = 0; y < n; y++) memcpy(lv + (size_t)(y0 + y) * pw + x0, level + y * n, n * sizeof(int16_t));
   if (nz) {
     orc_dequant(level, coef, log2n, qp);
-    orc_idct(coef, resid, log2n);
+    if (dst) orc_idst4(coef, resid); else orc_idct(coef, resid, log2n);
     for (int y = 0; y < n; y++)
       for (int x = 0; x < n; x++)
         rec[(size_t)(y0 + y) * pw + x0 + x] = (uint8_t)clip3i(0, 255, pred[y * ps + x] + resid[y * n + x]);
@@ -243,29 +295,37 @@ static int recon_tb_s(orc_encoder_t *e, int c, int x0, int y0, int log2n, const 
 
 /* ---- transform tree (7.3.8.8) ------------------------------------------------------------------
  * cfg.tr_depth = max_transform_hierarchy_depth_inter = _intra.  A transform unit of a CU may be
- * split into four (down to 8x8 luma); the decision compares squared error + lambda * estimated bits
- * of both alternatives, bottom-up.  The tree is kept in the cu map: every 8x8 unit records the size of
- * the transform unit that covers it and that unit's coded block flags. */
+ * split into four (down to 8x8 luma, with cfg.tu4 down to four 4x4 luma blocks + one 4x4 block per
+ * chroma plane); the decision compares squared error + lambda * estimated bits of both alternatives,
+ * bottom-up.  The tree is kept in the cu map: every 8x8 unit records the size of the transform unit
+ * that covers it and that unit's coded block flags (tu_log2 = 2: bits 4..7 = the four luma blocks). */
 
-typedef struct { const uint8_t *pred[3]; int ps[3]; int x0, y0; } cu_pred_t;   /* inter: the CU's prediction, origin (x0, y0) luma */
+/* what a transform unit predicts with.  pred[0] != NULL: inter, the CU's prediction with origin (x0, y0)
+ * luma.  Else intra: luma mode(s) (four when the CU is NxN, else all equal) and the chroma mode. */
+typedef struct { const uint8_t *pred[3]; int ps[3]; int x0, y0; int mode[4], chroma_mode; } cu_pred_t;
 
 static void gather_refs(const orc_encoder_t *e, int c, int x0, int y0, int n, uint8_t *refs);
+static int scan_idx_for(int pred_mode, int intra_mode, int log2n, int cidx);
 
-/* one transform unit, not split: luma block of 1 << log2tu, chroma blocks of half that.  ip == NULL:
- * intra, predicted here from the reconstructed neighbours with `mode`.  Returns the cbf bits. */
-static int tu_leaf(orc_encoder_t *e, int x0, int y0, int log2tu, const cu_pred_t *ip, int mode, tb_rd_t *rd)
+/* one transform block of plane c at plane position (px, py) */
+static int tu_block(orc_encoder_t *e, int c, int px, int py, int l2, const cu_pred_t *ip, int mode, tb_rd_t *rd)
 {
+  const int sh = c ? 1 : 0, n = 1 << l2;
+  if (ip->pred[0])
+    return recon_tb_x(e, c, px, py, l2, ip->pred[c] + (size_t)(py - (ip->y0 >> sh)) * ip->ps[c] + (px - (ip->x0 >> sh)), ip->ps[c], rd, 0, 0);
   uint8_t refs[4 * 32 + 1], pred[32 * 32];
+  gather_refs(e, c, px, py, n, refs);
+  orc_intra_predict2(refs, l2, mode, c, e->cfg.strong_intra, pred, n);
+  return recon_tb_x(e, c, px, py, l2, pred, n, rd, c == 0 && l2 == 2, scan_idx_for(1, mode, l2, c));
+}
+
+/* one transform unit, not split: luma block of 1 << log2tu, chroma blocks of half that.  Returns the cbf bits. */
+static int tu_leaf(orc_encoder_t *e, int x0, int y0, int log2tu, const cu_pred_t *ip, tb_rd_t *rd)
+{
   int cbf = 0;
   for (int c = 0; c < 3; c++) {
-    const int sh = c ? 1 : 0, l2 = log2tu - sh, n = 1 << l2, px = x0 >> sh, py = y0 >> sh;
-    if (ip) {
-      cbf |= recon_tb_s(e, c, px, py, l2, ip->pred[c] + (size_t)((y0 - ip->y0) >> sh) * ip->ps[c] + ((x0 - ip->x0) >> sh), ip->ps[c], rd) << c;
-    } else {
-      gather_refs(e, c, px, py, n, refs);
-      orc_intra_predict(refs, l2, mode, c, pred, n);
-      cbf |= recon_tb_s(e, c, px, py, l2, pred, n, rd) << c;
-    }
+    const int sh = c ? 1 : 0;
+    cbf |= tu_block(e, c, x0 >> sh, y0 >> sh, log2tu - sh, ip, c ? ip->chroma_mode : ip->mode[0], rd) << c;
   }
   const int n8 = 1 << (log2tu - 3);
   for (int j = 0; j < n8; j++)
@@ -276,14 +336,27 @@ static int tu_leaf(orc_encoder_t *e, int x0, int y0, int log2tu, const cu_pred_t
   return cbf;
 }
 
-static long long tu_node(orc_encoder_t *e, int x0, int y0, int log2tu, int depth, const cu_pred_t *ip, int mode)
+/* an 8x8 transform unit split into four 4x4 luma blocks (in z order, each predicted from the
+ * reconstruction of the ones before it) and, after the fourth, one 4x4 block per chroma plane */
+static int tu_leaf4(orc_encoder_t *e, int x0, int y0, const cu_pred_t *ip, tb_rd_t *rd)
+{
+  int cbf = 0;
+  for (int b = 0; b < 4; b++)
+    if (tu_block(e, 0, x0 + 4 * (b & 1), y0 + 4 * (b >> 1), 2, ip, ip->mode[b], rd)) cbf |= 1 | (16 << b);
+  for (int c = 1; c < 3; c++) cbf |= tu_block(e, c, x0 >> 1, y0 >> 1, 2, ip, ip->chroma_mode, rd) << c;
+  orc_cu_t *u = &e->cu[(size_t)(y0 / 8) * e->w8 + x0 / 8];
+  u->tu_log2 = 2; u->cbf = (uint8_t)cbf;
+  return cbf;
+}
+
+static long long tu_node(orc_encoder_t *e, int x0, int y0, int log2tu, int depth, const cu_pred_t *ip)
 {
   const int lq = lambda_at(e, x0, y0);
   const long long lam = (lq * lq + 128) >> 8;                             /* lambda, SSE domain */
   tb_rd_t rd = {0, 0};
-  tu_leaf(e, x0, y0, log2tu, ip, mode, &rd);
+  tu_leaf(e, x0, y0, log2tu, ip, &rd);
   long long cost0 = rd.sse + lam * (rd.bits + 1);
-  if (depth >= e->cfg.tr_depth || log2tu <= 3) return cost0;
+  if (depth >= e->cfg.tr_depth || log2tu < 3 + !e->cfg.tu4) return cost0;
   /* keep the unsplit result, try the split, take the cheaper */
   const int n = 1 << log2tu, n8 = n / 8;
   uint8_t save_rec[32 * 32 * 3 / 2];
@@ -298,7 +371,13 @@ static long long tu_node(orc_encoder_t *e, int x0, int y0, int log2tu, int depth
   }
   for (int j = 0; j < n8; j++) for (int i = 0; i < n8; i++) save_cu[j * n8 + i] = e->cu[(size_t)(y0 / 8 + j) * e->w8 + x0 / 8 + i];
   long long cost1 = lam;
-  for (int q = 0; q < 4; q++) cost1 += tu_node(e, x0 + (q & 1) * n / 2, y0 + (q >> 1) * n / 2, log2tu - 1, depth + 1, ip, mode);
+  if (log2tu == 3) {
+    tb_rd_t rd4 = {0, 0};
+    tu_leaf4(e, x0, y0, ip, &rd4);
+    cost1 += rd4.sse + lam * (rd4.bits + 1);
+  } else {
+    for (int q = 0; q < 4; q++) cost1 += tu_node(e, x0 + (q & 1) * n / 2, y0 + (q >> 1) * n / 2, log2tu - 1, depth + 1, ip);
+  }
   if (cost1 < cost0) return cost1;
   o = 0;
   for (int c = 0; c < 3; c++) {
@@ -348,10 +427,14 @@ static unsigned coding_order(const orc_encoder_t *e, int x, int y)
 /* 6.4.1 availability of luma location (x, y) for the block at (xc, yc): inside the picture and
  * earlier in coding order.  (In a P picture the inter CUs are all reconstructed before the intra
  * CUs are visited, but a later CU is still unavailable -- the decoder has not seen it yet.) */
+static unsigned coding_order4(const orc_encoder_t *e, int x, int y)      /* ... at 4x4 granularity (blocks of an NxN CU / a split 8x8 unit) */
+{
+  return coding_order(e, x, y) * 4 + (unsigned)(((y >> 2) & 1) << 1 | ((x >> 2) & 1));
+}
 static int avail_luma(const orc_encoder_t *e, int xc, int yc, int x, int y)
 {
   if (x < 0 || y < 0 || x >= e->w || y >= e->h) return 0;
-  return coding_order(e, x, y) < coding_order(e, xc, yc);
+  return coding_order4(e, x, y) < coding_order4(e, xc, yc);
 }
 
 /* 8.4.4.2.2: gather the 4N+1 neighbours (layout of orc_intra_predict) with substitution */
@@ -403,7 +486,7 @@ static uint32_t intra_mode_search(const orc_encoder_t *e, int x0, int y0, int lo
   uint32_t best_cost = UINT_MAX;
   int best_mode = 0;
   for (int mode = 0; mode < 35; mode++) {
-    orc_intra_predict(refs, log2, mode, 0, pred, n);
+    orc_intra_predict2(refs, log2, mode, 0, e->cfg.strong_intra, pred, n);
     uint32_t sad = orc_sad(e->src + (size_t)y0 * e->w + x0, e->w, pred, n, n, n);
     int bits = (mode == 0 || mode == 1 || mode == 26) ? 2 : 6;
     uint32_t cost = sad + (uint32_t)((lambda_at(e, x0, y0) * bits) >> 4);
@@ -413,39 +496,119 @@ static uint32_t intra_mode_search(const orc_encoder_t *e, int x0, int y0, int lo
   return best_cost;
 }
 
-/* prediction of the given mode from RECONSTRUCTED neighbours, residual, reconstruction, cu map;
- * prediction and reconstruction go transform unit by transform unit (8.4.4.1) */
-static void intra_cu_recon(orc_encoder_t *e, int x0, int y0, int log2, int best_mode)
+/* cfg.chroma_modes: intra_chroma_pred_mode of a CU by SAD on source neighbours of both chroma planes --
+ * planar, vertical, horizontal, DC (each replaced by mode 34 where it equals the luma mode, 8.4.3) or
+ * the luma mode itself (derived, one bin instead of three) */
+static int intra_chroma_search(const orc_encoder_t *e, int x0, int y0, int log2, int luma_mode)
+{
+  static const uint8_t base[4] = {0, 26, 10, 1};
+  const int l2 = log2 - 1, n = 1 << l2;
+  uint8_t refs[2][4 * 32 + 1], pred[16 * 16];
+  for (int c = 1; c < 3; c++) gather_refs_from(e, e->src, c, x0 / 2, y0 / 2, n, refs[c - 1]);
+  uint32_t best = UINT_MAX;
+  int best_mode = luma_mode;
+  for (int k = 4; k >= 0; k--) {                      /* derived first: it wins ties */
+    const int mode = k == 4 ? luma_mode : (base[k] == luma_mode ? 34 : base[k]);
+    uint32_t cost = (uint32_t)((lambda_at(e, x0, y0) * (k == 4 ? 1 : 3)) >> 4);
+    for (int c = 1; c < 3; c++) {
+      orc_intra_predict2(refs[c - 1], l2, mode, c, 0, pred, n);
+      cost += orc_sad(plane((uint8_t *)e->src, e->w, e->h, c) + (size_t)(y0 / 2) * e->cw + x0 / 2, e->cw, pred, n, n, n);
+    }
+    if (cost < best) { best = cost; best_mode = mode; }
+  }
+  return best_mode;
+}
+
+/* prediction of the given mode(s) from RECONSTRUCTED neighbours, residual, reconstruction, cu map;
+ * prediction and reconstruction go transform block by transform block (8.4.4.1).  nxn: four 4x4
+ * prediction blocks with modes[0..3] (8x8 CUs only), else modes[0] for the whole CU. */
+static void intra_cu_recon_x(orc_encoder_t *e, int x0, int y0, int log2, const int *modes, int nxn)
 {
   orc_cu_t cu;
   memset(&cu, 0, sizeof(cu));
-  cu.log2_size = (uint8_t)log2; cu.pred_mode = 1; cu.intra_mode = (uint8_t)best_mode; cu.chroma_mode = (uint8_t)best_mode;
+  cu.log2_size = (uint8_t)log2; cu.pred_mode = 1; cu.intra_mode = (uint8_t)modes[0];
   cu.merge_idx = 0xff; cu.tu_log2 = (uint8_t)log2;
+  cu_pred_t ip;
+  memset(&ip, 0, sizeof(ip));
+  for (int b = 0; b < 4; b++) ip.mode[b] = nxn ? modes[b] : modes[0];
+  ip.chroma_mode = e->cfg.chroma_modes ? intra_chroma_search(e, x0, y0, log2, modes[0]) : modes[0];
+  cu.chroma_mode = (uint8_t)ip.chroma_mode;
+  if (nxn) {
+    cu.flags = 1;
+    cu.mvx = (int16_t)(modes[1] | (modes[2] << 8)); cu.mvy = (int16_t)modes[3];
+  }
   set_cu(e, x0, y0, log2, &cu);
-  tu_node(e, x0, y0, log2, 0, NULL, best_mode);             /* intra_chroma_pred_mode 4 (DM): chroma uses the luma mode */
+  if (nxn) tu_leaf4(e, x0, y0, &ip, NULL);                /* IntraSplitFlag: the split is inferred */
+  else tu_node(e, x0, y0, log2, 0, &ip);
   cu_root_cbf(e, x0, y0, log2);
 }
 
-static void intra_cu(orc_encoder_t *e, int x0, int y0, int log2)
+static void intra_cu_recon(orc_encoder_t *e, int x0, int y0, int log2, int best_mode)
 {
-  int mode;
-  intra_mode_search(e, x0, y0, log2, &mode);
-  intra_cu_recon(e, x0, y0, log2, mode);
+  intra_cu_recon_x(e, x0, y0, log2, &best_mode, 0);
+}
+
+/* I pictures.  Default: 16x16 CUs (8x8 where 16 does not fit the picture).  cfg.intra_sizes widens the
+ * choice bottom-up by the search costs (source neighbours): NxN vs 2Nx2N in 8x8 CUs, four 8x8 CUs vs
+ * one 16x16, four 16x16 vs one 32x32; every CU pays CU_OVERHEAD_BITS.  The tree is decided first, then
+ * coded in z order. */
+typedef struct { uint32_t cost; int8_t log2, nxn; uint8_t mode[4]; } intra_plan_t;
+
+static uint32_t intra_plan(orc_encoder_t *e, int x0, int y0, int log2, intra_plan_t *plan /* per 8x8 unit of the CTU */)
+{
+  if (x0 >= e->w || y0 >= e->h) return 0;
+  const int n = 1 << log2, fits = x0 + n <= e->w && y0 + n <= e->h;
+  const uint32_t ovh = (uint32_t)((lambda_at(e, x0, y0) * CU_OVERHEAD_BITS) >> 4);
+  intra_plan_t *me = &plan[((y0 & (CTB - 1)) >> 3) * 8 + ((x0 & (CTB - 1)) >> 3)];
+  if (log2 == 3) {
+    int mode;
+    me->cost = intra_mode_search(e, x0, y0, 3, &mode) + ovh;
+    me->log2 = 3; me->nxn = 0; me->mode[0] = (uint8_t)mode;
+    if (e->cfg.intra_sizes & 4) {
+      uint32_t c4 = ovh + (uint32_t)((lambda_at(e, x0, y0) * 2) >> 4);
+      int m4[4];
+      for (int b = 0; b < 4; b++) c4 += intra_mode_search(e, x0 + 4 * (b & 1), y0 + 4 * (b >> 1), 2, &m4[b]);
+      if (c4 < me->cost) { me->cost = c4; me->nxn = 1; for (int b = 0; b < 4; b++) me->mode[b] = (uint8_t)m4[b]; }
+    }
+    return me->cost;
+  }
+  const int can_split = log2 > 4 || (e->cfg.intra_sizes & 1) || !fits;
+  const int can_whole = fits && (log2 == 4 || (log2 == 5 && (e->cfg.intra_sizes & 2)));
+  uint32_t split_cost = UINT_MAX;
+  if (can_split) {
+    split_cost = 0;
+    for (int q = 0; q < 4; q++) split_cost += intra_plan(e, x0 + (q & 1) * n / 2, y0 + (q >> 1) * n / 2, log2 - 1, plan);
+  }
+  if (can_whole) {
+    int mode;
+    const uint32_t whole = intra_mode_search(e, x0, y0, log2, &mode) + ovh;
+    if (whole <= split_cost) {
+      me->cost = whole; me->log2 = (int8_t)log2; me->nxn = 0; me->mode[0] = (uint8_t)mode;
+      return whole;
+    }
+  }
+  return split_cost;                                     /* split: the entry keeps the plan of the first sub-block */
+}
+
+static void intra_emit(orc_encoder_t *e, int x0, int y0, int log2, const intra_plan_t *plan)
+{
+  if (x0 >= e->w || y0 >= e->h) return;
+  const intra_plan_t *me = &plan[((y0 & (CTB - 1)) >> 3) * 8 + ((x0 & (CTB - 1)) >> 3)];
+  if (me->log2 == log2) {
+    int modes[4] = {me->mode[0], me->mode[1], me->mode[2], me->mode[3]};
+    intra_cu_recon_x(e, x0, y0, log2, modes, me->nxn);
+    return;
+  }
+  const int hn = 1 << (log2 - 1);
+  for (int q = 0; q < 4; q++) intra_emit(e, x0 + (q & 1) * hn, y0 + (q >> 1) * hn, log2 - 1, plan);
 }
 
 static void intra_quadtree(orc_encoder_t *e, int x0, int y0, int log2)
 {
-  if (x0 >= e->w || y0 >= e->h) return;
-  int n = 1 << log2;
-  if (x0 + n > e->w || y0 + n > e->h || log2 > 4) {
-    int hn = n / 2;
-    intra_quadtree(e, x0, y0, log2 - 1);
-    intra_quadtree(e, x0 + hn, y0, log2 - 1);
-    intra_quadtree(e, x0, y0 + hn, log2 - 1);
-    intra_quadtree(e, x0 + hn, y0 + hn, log2 - 1);
-  } else {
-    intra_cu(e, x0, y0, log2);
-  }
+  intra_plan_t plan[64];
+  memset(plan, 0, sizeof(plan));
+  intra_plan(e, x0, y0, log2, plan);
+  intra_emit(e, x0, y0, log2, plan);
 }
 
 /* ------------------------------------------------------------------------------------------ */
@@ -728,8 +891,8 @@ static void inter_cu(orc_encoder_t *e, int x0, int y0, int log2)
   set_cu(e, x0, y0, log2, &cu);
   uint8_t pred_c[2][16 * 16];
   for (int c = 1; c < 3; c++) mc_chroma(e, rf, c, x0 / 2, y0 / 2, n / 2, bx, by, pred_c[c - 1]);
-  cu_pred_t ip = {{best_pred, pred_c[0], pred_c[1]}, {n, n / 2, n / 2}, x0, y0};
-  tu_node(e, x0, y0, log2, 0, &ip, 0);
+  cu_pred_t ip = {{best_pred, pred_c[0], pred_c[1]}, {n, n / 2, n / 2}, x0, y0, {0, 0, 0, 0}, 0};
+  tu_node(e, x0, y0, log2, 0, &ip);
   cu_root_cbf(e, x0, y0, log2);
 }
 
@@ -795,10 +958,19 @@ static void derive_cu_qps(orc_encoder_t *e)
 /* ------------------------------------------------------------------------------------------ */
 /* deblocking (8.7.2): all vertical edges of the picture, then all horizontal edges             */
 
-static int edge_bs(const orc_cu_t *p, const orc_cu_t *q)
+/* luma coded block flag of the transform block of unit u that touches edge segment `seg` (0 / 1: first /
+ * second four samples along the edge); side 0: u lies before the edge (P), 1: after it (Q) */
+static int edge_cbf(const orc_cu_t *u, int dir, int side, int seg)
+{
+  if (u->tu_log2 != 2) return u->cbf & 1;
+  const int b = dir == 0 ? (side ? 0 : 1) + 2 * seg : (side ? 0 : 2) + seg;
+  return (u->cbf >> (4 + b)) & 1;
+}
+
+static int edge_bs(const orc_cu_t *p, const orc_cu_t *q, int dir, int seg)
 {
   if (p->pred_mode == 1 || q->pred_mode == 1) return 2;
-  if ((p->cbf & 1) || (q->cbf & 1)) return 1;          /* either transform block has coefficients */
+  if (edge_cbf(p, dir, 0, seg) || edge_cbf(q, dir, 1, seg)) return 1;      /* either transform block has coefficients */
   if (p->ref_idx != q->ref_idx) return 1;              /* different reference pictures (list 0 has no duplicates here) */
   return abs(p->mvx - q->mvx) >= 4 || abs(p->mvy - q->mvy) >= 4;
 }
@@ -814,22 +986,23 @@ static void deblock_frame(orc_encoder_t *e)
         int n8 = q->tu_log2 > 3 ? 1 << (q->tu_log2 - 3) : 1;     /* transform unit edges (they include the CU edges) */
         if (dir == 0 ? (x8 == 0 || (x8 & (n8 - 1))) : (y8 == 0 || (y8 & (n8 - 1)))) continue;
         const orc_cu_t *p = dir == 0 ? q - 1 : q - e->w8;
-        int bs = edge_bs(p, q);
-        if (!bs) continue;
-        int x = x8 * 8, y = y8 * 8;
+        int x = x8 * 8, y = y8 * 8, bs = 0;
         const int qp = e->cfg.qp_delta ? (p->qp + q->qp + 1) >> 1 : e->cfg.qp;     /* QpL (8.7.2.5.3) */
+        const int bo = e->cfg.beta_offset_div2, to = e->cfg.tc_offset_div2;
         for (int seg = 0; seg < 2; seg++) {
-          if (dir == 0) orc_deblock_luma_segment(Y + (size_t)(y + 4 * seg) * e->w + x, 1, e->w, bs, qp);
-          else          orc_deblock_luma_segment(Y + (size_t)y * e->w + x + 4 * seg, e->w, 1, bs, qp);
+          bs = edge_bs(p, q, dir, seg);
+          if (!bs) continue;
+          if (dir == 0) orc_deblock_luma_segment2(Y + (size_t)(y + 4 * seg) * e->w + x, 1, e->w, bs, qp, bo, to);
+          else          orc_deblock_luma_segment2(Y + (size_t)y * e->w + x + 4 * seg, e->w, 1, bs, qp, bo, to);
         }
         if (bs == 2 && (dir == 0 ? (x & 15) == 0 : (y & 15) == 0)) {
           int xc = x / 2, yc = y / 2;
           if (dir == 0) {
-            orc_deblock_chroma_segment(U + (size_t)yc * e->cw + xc, 1, e->cw, qp, 4);
-            orc_deblock_chroma_segment(V + (size_t)yc * e->cw + xc, 1, e->cw, qp, 4);
+            orc_deblock_chroma_segment2(U + (size_t)yc * e->cw + xc, 1, e->cw, qp, 4, e->cfg.cb_qp_offset, to);
+            orc_deblock_chroma_segment2(V + (size_t)yc * e->cw + xc, 1, e->cw, qp, 4, e->cfg.cr_qp_offset, to);
           } else {
-            orc_deblock_chroma_segment(U + (size_t)yc * e->cw + xc, e->cw, 1, qp, 4);
-            orc_deblock_chroma_segment(V + (size_t)yc * e->cw + xc, e->cw, 1, qp, 4);
+            orc_deblock_chroma_segment2(U + (size_t)yc * e->cw + xc, e->cw, 1, qp, 4, e->cfg.cb_qp_offset, to);
+            orc_deblock_chroma_segment2(V + (size_t)yc * e->cw + xc, e->cw, 1, qp, 4, e->cfg.cr_qp_offset, to);
           }
         }
       }
@@ -1186,6 +1359,30 @@ static void code_cu_qp_delta(orc_cabac_t *c, int d)
   if (a) orc_cabac_bypass(c, d < 0);
 }
 
+/* luma intra prediction mode of the 4x4 block that covers luma sample (x, y) of an intra CU */
+static int intra_mode_at(const orc_cu_t *u, int x, int y)
+{
+  if (!(u->flags & 1)) return u->intra_mode;
+  const int part = (((y >> 2) & 1) << 1) | ((x >> 2) & 1);
+  return part == 0 ? u->intra_mode : part == 1 ? (u->mvx & 0xff) : part == 2 ? ((u->mvx >> 8) & 0xff) : (u->mvy & 0xff);
+}
+
+static void code_tu_residuals(orc_encoder_t *e, orc_cabac_t *c, int x0, int y0, int log2, int cidx, const orc_cu_t *cu)
+{
+  const int sh = cidx ? 1 : 0, pw = cidx ? e->cw : e->w;
+  const int mode = cidx ? cu->chroma_mode : intra_mode_at(cu, x0, y0);
+  orc_code_residual2(c, lplane(e->levels, e->w, e->h, cidx) + (size_t)(y0 >> sh) * pw + (x0 >> sh), pw, log2, cidx,
+                     scan_idx_for(cu->pred_mode, mode, log2, cidx), e->cfg.sign_hiding);
+}
+
+static void code_delta_qp_once(orc_encoder_t *e, orc_cabac_t *c, int x0, int y0)
+{
+  if (!e->cfg.qp_delta || e->delta_coded) return;
+  /* once per quantisation group (= CTU), in its first transform unit with a coded block flag */
+  code_cu_qp_delta(c, e->ctu_delta[(y0 / CTB) * e->ctb_cols + x0 / CTB]);
+  e->delta_coded = 1;
+}
+
 /* transform_tree (7.3.8.8) of the node (x0, y0, log2) at trafoDepth `depth`; the tree itself is read
  * from the cu map (size of the transform unit covering each 8x8 unit).  par_cb / par_cr: the parent's
  * chroma flags (1 at depth 0). */
@@ -1195,7 +1392,9 @@ static void code_transform_tree(orc_encoder_t *e, orc_cabac_t *c, int x0, int y0
   const int n8 = 1 << (log2 - 3);
   const orc_cu_t *u0 = &e->cu[(size_t)(y0 >> 3) * e->w8 + (x0 >> 3)];
   const int split = u0->tu_log2 < log2;
-  if (log2 <= 5 && log2 > 2 && depth < e->cfg.tr_depth) orc_cabac_bin(c, CTX_SPLIT_TRANSFORM + 5 - log2, split);
+  const int nxn = cu->pred_mode == 1 && (cu->flags & 1);             /* IntraSplitFlag */
+  if (log2 <= 5 && log2 > 2 && depth < e->cfg.tr_depth + nxn && !(nxn && depth == 0))
+    orc_cabac_bin(c, CTX_SPLIT_TRANSFORM + 5 - log2, split);
   int cb = 0, cr = 0;                                    /* of the node: set when any transform unit below has them */
   for (int j = 0; j < n8; j++)
     for (int i = 0; i < n8; i++) {
@@ -1204,6 +1403,18 @@ static void code_transform_tree(orc_encoder_t *e, orc_cabac_t *c, int x0, int y0
     }
   if (par_cb) orc_cabac_bin(c, CTX_CBF_CHROMA + depth, cb);
   if (par_cr) orc_cabac_bin(c, CTX_CBF_CHROMA + depth, cr);
+  if (split && log2 == 3) {
+    /* four 4x4 luma transform units; the chroma blocks of the 8x8 node follow the fourth */
+    for (int b = 0; b < 4; b++) {
+      const int lu = (u0->cbf >> (4 + b)) & 1, xb = x0 + 4 * (b & 1), yb = y0 + 4 * (b >> 1);
+      orc_cabac_bin(c, CTX_CBF_LUMA, lu);                /* trafoDepth > 0 */
+      if (lu || cb || cr) code_delta_qp_once(e, c, x0, y0);
+      if (lu) code_tu_residuals(e, c, xb, yb, 2, 0, cu);
+    }
+    if (cb) code_tu_residuals(e, c, x0, y0, 2, 1, cu);
+    if (cr) code_tu_residuals(e, c, x0, y0, 2, 2, cu);
+    return;
+  }
   if (split) {
     const int h = 1 << (log2 - 1);
     for (int q = 0; q < 4; q++) code_transform_tree(e, c, x0 + (q & 1) * h, y0 + (q >> 1) * h, log2 - 1, depth + 1, cb, cr, cu);
@@ -1211,18 +1422,10 @@ static void code_transform_tree(orc_encoder_t *e, orc_cabac_t *c, int x0, int y0
   }
   const int lu = u0->cbf & 1;
   if (cu->pred_mode == 1 || depth != 0 || cb || cr) orc_cabac_bin(c, CTX_CBF_LUMA + (depth == 0 ? 1 : 0), lu);
-  if (e->cfg.qp_delta && (lu || cb || cr) && !e->delta_coded) {
-    /* once per quantisation group (= CTU), in its first transform unit with a coded block flag */
-    code_cu_qp_delta(c, e->ctu_delta[(y0 / CTB) * e->ctb_cols + x0 / CTB]);
-    e->delta_coded = 1;
-  }
-  if (lu)
-    orc_code_residual(c, e->levels + (size_t)y0 * e->w + x0, e->w, log2, 0,
-                      scan_idx_for(cu->pred_mode, cu->intra_mode, log2, 0));
-  for (int k = 1; k < 3; k++)
-    if ((u0->cbf >> k) & 1)
-      orc_code_residual(c, lplane(e->levels, e->w, e->h, k) + (size_t)(y0 / 2) * e->cw + x0 / 2, e->cw, log2 - 1, k,
-                        scan_idx_for(cu->pred_mode, cu->chroma_mode, log2 - 1, k));
+  if (lu || cb || cr) code_delta_qp_once(e, c, x0, y0);
+  if (lu) code_tu_residuals(e, c, x0, y0, log2, 0, cu);
+  if (cb) code_tu_residuals(e, c, x0, y0, log2 - 1, 1, cu);
+  if (cr) code_tu_residuals(e, c, x0, y0, log2 - 1, 2, cu);
 }
 
 static void code_transform_unit(orc_encoder_t *e, orc_cabac_t *c, int x0, int y0, int log2, const orc_cu_t *cu)
@@ -1230,45 +1433,66 @@ static void code_transform_unit(orc_encoder_t *e, orc_cabac_t *c, int x0, int y0
   code_transform_tree(e, c, x0, y0, log2, 0, 1, 1, cu);
 }
 
-/* prev_intra_luma_pred_flag / mpm_idx / rem_intra_luma_pred_mode (8.4.2) and intra_chroma_pred_mode */
+/* the three most probable modes (8.4.2) of the luma prediction block at (x, y) */
+static void intra_mpm(const orc_encoder_t *e, int x, int y, int cand[3])
+{
+  /* a neighbour that is not intra-coded, or lies in the CTB row above, counts as DC */
+  int a = 1, b = 1;
+  if (x > 0) {
+    const orc_cu_t *l = &e->cu[(size_t)(y >> 3) * e->w8 + ((x - 1) >> 3)];
+    if (l->pred_mode == 1) a = intra_mode_at(l, x - 1, y);
+  }
+  if (y > 0 && (y & (CTB - 1))) {
+    const orc_cu_t *u = &e->cu[(size_t)((y - 1) >> 3) * e->w8 + (x >> 3)];
+    if (u->pred_mode == 1) b = intra_mode_at(u, x, y - 1);
+  }
+  if (a == b) {
+    if (a < 2) { cand[0] = 0; cand[1] = 1; cand[2] = 26; }
+    else { cand[0] = a; cand[1] = 2 + ((a + 29) % 32); cand[2] = 2 + ((a - 2 + 1) % 32); }
+  } else {
+    cand[0] = a; cand[1] = b;
+    cand[2] = (a != 0 && b != 0) ? 0 : ((a != 1 && b != 1) ? 1 : 26);
+  }
+}
+
+/* part_mode, prev_intra_luma_pred_flag / mpm_idx / rem_intra_luma_pred_mode (8.4.2) of every prediction
+ * block (the flags of all blocks first, 7.3.8.5) and intra_chroma_pred_mode */
 static void code_intra_modes(orc_encoder_t *e, orc_cabac_t *c, int x0, int y0, int log2, const orc_cu_t *cu)
 {
-  if (log2 == 3) orc_cabac_bin(c, CTX_PART_MODE, 1);             /* PART_2Nx2N */
-  /* a neighbour that is not intra-coded, or lies in the CTB row above, counts as DC */
-  int cand[3];
-  {
-    int a = 1, b = 1;
-    if (x0 > 0) {
-      const orc_cu_t *l = &e->cu[(size_t)(y0 >> 3) * e->w8 + ((x0 - 1) >> 3)];
-      if (l->pred_mode == 1) a = l->intra_mode;
-    }
-    if (y0 > 0 && (y0 & (CTB - 1))) {
-      const orc_cu_t *u = &e->cu[(size_t)((y0 - 1) >> 3) * e->w8 + (x0 >> 3)];
-      if (u->pred_mode == 1) b = u->intra_mode;
-    }
-    if (a == b) {
-      if (a < 2) { cand[0] = 0; cand[1] = 1; cand[2] = 26; }
-      else { cand[0] = a; cand[1] = 2 + ((a + 29) % 32); cand[2] = 2 + ((a - 2 + 1) % 32); }
+  const int nxn = cu->flags & 1, parts = nxn ? 4 : 1;
+  if (log2 == 3) orc_cabac_bin(c, CTX_PART_MODE, !nxn);          /* PART_2Nx2N / PART_NxN */
+  int mpm[4], cand[4][3], mode[4];
+  for (int b = 0; b < parts; b++) {
+    const int xb = x0 + 4 * (b & 1), yb = y0 + 4 * (b >> 1);
+    intra_mpm(e, xb, yb, cand[b]);
+    mode[b] = intra_mode_at(cu, xb, yb);
+    mpm[b] = -1;
+    for (int i = 0; i < 3; i++) if (cand[b][i] == mode[b]) mpm[b] = i;
+    orc_cabac_bin(c, CTX_PREV_INTRA_LUMA, mpm[b] >= 0);
+  }
+  for (int b = 0; b < parts; b++) {
+    if (mpm[b] >= 0) {
+      orc_cabac_bypass(c, mpm[b] > 0);
+      if (mpm[b] > 0) orc_cabac_bypass(c, mpm[b] > 1);
     } else {
-      cand[0] = a; cand[1] = b;
-      cand[2] = (a != 0 && b != 0) ? 0 : ((a != 1 && b != 1) ? 1 : 26);
+      int *cd = cand[b];
+      if (cd[0] > cd[1]) { int t = cd[0]; cd[0] = cd[1]; cd[1] = t; }
+      if (cd[0] > cd[2]) { int t = cd[0]; cd[0] = cd[2]; cd[2] = t; }
+      if (cd[1] > cd[2]) { int t = cd[1]; cd[1] = cd[2]; cd[2] = t; }
+      int rem = mode[b];
+      for (int i = 2; i >= 0; i--) if (rem > cd[i]) rem--;
+      orc_cabac_bypass_bits(c, (uint32_t)rem, 5);
     }
   }
-  int mode = cu->intra_mode, mpm = -1;
-  for (int i = 0; i < 3; i++) if (cand[i] == mode) mpm = i;
-  orc_cabac_bin(c, CTX_PREV_INTRA_LUMA, mpm >= 0);
-  if (mpm >= 0) {
-    orc_cabac_bypass(c, mpm > 0);
-    if (mpm > 0) orc_cabac_bypass(c, mpm > 1);
-  } else {
-    if (cand[0] > cand[1]) { int t = cand[0]; cand[0] = cand[1]; cand[1] = t; }
-    if (cand[0] > cand[2]) { int t = cand[0]; cand[0] = cand[2]; cand[2] = t; }
-    if (cand[1] > cand[2]) { int t = cand[1]; cand[1] = cand[2]; cand[2] = t; }
-    int rem = mode;
-    for (int i = 2; i >= 0; i--) if (rem > cand[i]) rem--;
-    orc_cabac_bypass_bits(c, (uint32_t)rem, 5);
-  }
-  orc_cabac_bin(c, CTX_INTRA_CHROMA, 0);                          /* intra_chroma_pred_mode = 4 */
+  /* intra_chroma_pred_mode: 4 = derived from the luma mode (of the first block); 0..3 = planar, vertical,
+   * horizontal, DC, where the one that equals the luma mode stands for mode 34 */
+  static const uint8_t base[4] = {0, 26, 10, 1};
+  int cidx = 4;
+  if (cu->chroma_mode != cu->intra_mode)
+    for (int k = 0; k < 4; k++)
+      if (cu->chroma_mode == (base[k] == cu->intra_mode ? 34 : base[k])) cidx = k;
+  orc_cabac_bin(c, CTX_INTRA_CHROMA, cidx != 4);
+  if (cidx != 4) orc_cabac_bypass_bits(c, (uint32_t)cidx, 2);
 }
 
 static void code_cu(orc_encoder_t *e, orc_cabac_t *c, int x0, int y0, int log2)
@@ -1435,7 +1659,7 @@ static size_t write_parameter_sets(const orc_encoder_t *e, uint8_t *out, size_t 
   for (int r = 0; r < imax(1, e->cfg.refs); r++) { orc_bits_ue(&b, 0); orc_bits_put(&b, 1, 1); }   /* delta_poc_s0_minus1 = 0, used_by_curr_pic_s0 */
   orc_bits_put(&b, 0, 1);             /* long_term_ref_pics_present_flag */
   orc_bits_put(&b, e->cfg.tmvp ? 1 : 0, 1);     /* sps_temporal_mvp_enabled_flag */
-  orc_bits_put(&b, 0, 1);             /* strong_intra_smoothing_enabled_flag */
+  orc_bits_put(&b, e->cfg.strong_intra ? 1 : 0, 1);   /* strong_intra_smoothing_enabled_flag */
   if (e->cfg.fps_num > 0 && e->cfg.fps_den > 0) {
     /* VUI (E.2.1) carrying only the timing: the reference copies the decoder's frame rate into
      * vInfo (openhevcfilter.cpp:232-233) and DisplayFilter divides by it (displayfilter.cpp:153) */
@@ -1464,7 +1688,7 @@ static size_t write_parameter_sets(const orc_encoder_t *e, uint8_t *out, size_t 
   orc_bits_put(&b, 0, 1);             /* dependent_slice_segments_enabled_flag */
   orc_bits_put(&b, 0, 1);             /* output_flag_present_flag */
   orc_bits_put(&b, 0, 3);             /* num_extra_slice_header_bits */
-  orc_bits_put(&b, 0, 1);             /* sign_data_hiding_enabled_flag */
+  orc_bits_put(&b, e->cfg.sign_hiding ? 1 : 0, 1);    /* sign_data_hiding_enabled_flag */
   orc_bits_put(&b, e->cfg.cabac_init ? 1 : 0, 1);   /* cabac_init_present_flag */
   orc_bits_ue(&b, 0); orc_bits_ue(&b, 0);       /* num_ref_idx_l0/l1_default_active_minus1 */
   orc_bits_se(&b, 0);                 /* init_qp_minus26 */
@@ -1472,7 +1696,7 @@ static size_t write_parameter_sets(const orc_encoder_t *e, uint8_t *out, size_t 
   orc_bits_put(&b, 0, 1);             /* transform_skip_enabled_flag */
   orc_bits_put(&b, e->cfg.qp_delta ? 1 : 0, 1);     /* cu_qp_delta_enabled_flag */
   if (e->cfg.qp_delta) orc_bits_ue(&b, 0);          /* diff_cu_qp_delta_depth: one quantisation group per CTB */
-  orc_bits_se(&b, 0); orc_bits_se(&b, 0);       /* pps_cb_qp_offset, pps_cr_qp_offset */
+  orc_bits_se(&b, e->cfg.cb_qp_offset); orc_bits_se(&b, e->cfg.cr_qp_offset);       /* pps_cb_qp_offset, pps_cr_qp_offset */
   orc_bits_put(&b, 0, 1);             /* pps_slice_chroma_qp_offsets_present_flag */
   orc_bits_put(&b, 0, 1);             /* weighted_pred_flag */
   orc_bits_put(&b, 0, 1);             /* weighted_bipred_flag */
@@ -1486,12 +1710,13 @@ static size_t write_parameter_sets(const orc_encoder_t *e, uint8_t *out, size_t 
     orc_bits_put(&b, 0, 1);                              /* loop_filter_across_tiles_enabled_flag */
   }
   orc_bits_put(&b, 1, 1);             /* pps_loop_filter_across_slices_enabled_flag */
-  if (e->cfg.deblock) {
+  if (e->cfg.deblock && !e->cfg.beta_offset_div2 && !e->cfg.tc_offset_div2) {
     orc_bits_put(&b, 0, 1);           /* deblocking_filter_control_present_flag */
   } else {
     orc_bits_put(&b, 1, 1);
     orc_bits_put(&b, 0, 1);           /* deblocking_filter_override_enabled_flag */
-    orc_bits_put(&b, 1, 1);           /* pps_deblocking_filter_disabled_flag */
+    orc_bits_put(&b, e->cfg.deblock ? 0 : 1, 1);      /* pps_deblocking_filter_disabled_flag */
+    if (e->cfg.deblock) { orc_bits_se(&b, e->cfg.beta_offset_div2); orc_bits_se(&b, e->cfg.tc_offset_div2); }
   }
   orc_bits_put(&b, 0, 1);             /* pps_scaling_list_data_present_flag */
   orc_bits_put(&b, 0, 1);             /* lists_modification_present_flag */

@@ -21,7 +21,7 @@ typedef struct {
   uint8_t ref_idx;         /* index into reference picture list 0 (inter) */
   uint8_t chroma_mode;     /* intra: resolved chroma prediction mode */
   uint8_t tu_log2;         /* luma size of the transform unit covering this unit */
-  uint8_t flags;           /* bit 0: intra NxN */
+  uint8_t flags;           /* bit 0: intra NxN (modes of parts 1..3: mvx & 0xff, mvx >> 8, mvy & 0xff); bit 1: coded residual */
 } orc_cu_t;
 
 typedef struct {
@@ -57,6 +57,18 @@ typedef struct {
                             * centre besides the zero vector; search_range (<= 16) is the window around each centre */
   int intra_in_p;          /* 1 = 16x16 intra CUs in P pictures where inter prediction is poor (scene cuts, uncovered areas) */
   int fps_num, fps_den;    /* both > 0: VUI timing info in the SPS (vui_time_scale / vui_num_units_in_tick); 0 = no VUI */
+  /* Syntax the GPU encoder does not produce but a Kvazaar-family peer may: streams for the decoder tests. */
+  int tu4;                 /* 1 = an 8x8 transform unit may split into four 4x4 luma blocks (and one 4x4 block per chroma
+                            * plane, coded after the fourth luma block): DST-VII for intra luma, DCT otherwise; needs
+                            * tr_depth >= 1 (NxN CUs split by inference) */
+  int intra_sizes;         /* I pictures, each where its search cost is smaller: bit 0 = 8x8 CUs, bit 1 = 32x32 CUs,
+                            * bit 2 = NxN partition of 8x8 CUs (four 4x4 prediction blocks) */
+  int chroma_modes;        /* 1 = intra_chroma_pred_mode chosen among planar / vertical / horizontal / DC / derived */
+  int sign_hiding;         /* 1 = sign_data_hiding_enabled_flag: the sign of the first coefficient of a 4x4 group whose
+                            * significant coefficients span more than three scan positions is the parity of the sum */
+  int strong_intra;        /* 1 = strong_intra_smoothing_enabled_flag */
+  int cb_qp_offset, cr_qp_offset;         /* pps_cb_qp_offset / pps_cr_qp_offset (-12..12) */
+  int beta_offset_div2, tc_offset_div2;   /* pps_beta_offset_div2 / pps_tc_offset_div2 (-6..6) */
 } orc_enc_cfg_t;
 
 typedef struct orc_encoder orc_encoder_t;

@@ -164,6 +164,11 @@ void orc_dequant(const int16_t *level, int16_t *coeff, int log2n, int qp)
 
 void orc_intra_predict(const uint8_t *refs_in, int log2n, int mode, int cidx, uint8_t *dst, int ds)
 {
+  orc_intra_predict2(refs_in, log2n, mode, cidx, 0, dst, ds);
+}
+
+void orc_intra_predict2(const uint8_t *refs_in, int log2n, int mode, int cidx, int strong, uint8_t *dst, int ds)
+{
   const int n = 1 << log2n;
   uint8_t filt[4 * 32 + 1];
   const uint8_t *refs = refs_in;
@@ -175,7 +180,18 @@ void orc_intra_predict(const uint8_t *refs_in, int log2n, int mode, int cidx, ui
     if (min_dist > thres) {
       filt[0] = refs_in[0];
       filt[4 * n] = refs_in[4 * n];
-      for (int i = 1; i < 4 * n; i++) filt[i] = (uint8_t)((refs_in[i - 1] + 2 * refs_in[i] + refs_in[i + 1] + 2) >> 2);
+      /* strong (bi-linear) smoothing of 32x32 blocks whose neighbours are nearly linear */
+      const int corner = refs_in[2 * n];
+      if (strong && n == 32 && abs(corner + refs_in[4 * n] - 2 * refs_in[3 * n]) < 8 &&
+          abs(corner + refs_in[0] - 2 * refs_in[n]) < 8) {
+        filt[2 * n] = (uint8_t)corner;
+        for (int i = 0; i < 63; i++) {
+          filt[2 * n - 1 - i] = (uint8_t)(((63 - i) * corner + (i + 1) * refs_in[0] + 32) >> 6);          /* left, downwards */
+          filt[2 * n + 1 + i] = (uint8_t)(((63 - i) * corner + (i + 1) * refs_in[4 * n] + 32) >> 6);      /* top, rightwards */
+        }
+      } else {
+        for (int i = 1; i < 4 * n; i++) filt[i] = (uint8_t)((refs_in[i - 1] + 2 * refs_in[i] + refs_in[i + 1] + 2) >> 2);
+      }
       refs = filt;
     }
   }
@@ -317,8 +333,14 @@ void orc_mc_chroma(const uint8_t *ref, int stride, int pw, int ph, int x0, int y
 
 void orc_deblock_luma_segment(uint8_t *pix, int xs, int ys, int bs, int qp)
 {
-  int beta = orc_beta_table[clip3(0, 51, qp)];
-  int tc = orc_tc_table[clip3(0, 53, qp + 2 * (bs - 1))];
+  orc_deblock_luma_segment2(pix, xs, ys, bs, qp, 0, 0);
+}
+
+/* beta_off / tc_off: slice_beta_offset_div2 / slice_tc_offset_div2 (8.7.2.5.3) */
+void orc_deblock_luma_segment2(uint8_t *pix, int xs, int ys, int bs, int qp, int beta_off, int tc_off)
+{
+  int beta = orc_beta_table[clip3(0, 51, qp + 2 * beta_off)];
+  int tc = orc_tc_table[clip3(0, 53, qp + 2 * (bs - 1) + 2 * tc_off)];
 #define P(i, l) pix[-(i + 1) * xs + (l) * ys]
 #define Q(i, l) pix[(i) * xs + (l) * ys]
   int dp0 = abs(P(2, 0) - 2 * P(1, 0) + P(0, 0)), dp3 = abs(P(2, 3) - 2 * P(1, 3) + P(0, 3));
@@ -358,8 +380,14 @@ void orc_deblock_luma_segment(uint8_t *pix, int xs, int ys, int bs, int qp)
 /* chroma edges are filtered only for bS == 2; cQpPicOffset = 0 */
 void orc_deblock_chroma_segment(uint8_t *pix, int xs, int ys, int qp_y, int lines)
 {
-  int qpc = orc_chroma_qp(qp_y);
-  int tc = orc_tc_table[clip3(0, 53, qpc + 2)];
+  orc_deblock_chroma_segment2(pix, xs, ys, qp_y, lines, 0, 0);
+}
+
+/* c_off: cQpPicOffset = pps_cb_qp_offset / pps_cr_qp_offset; tc_off: slice_tc_offset_div2 (8.7.2.5.5) */
+void orc_deblock_chroma_segment2(uint8_t *pix, int xs, int ys, int qp_y, int lines, int c_off, int tc_off)
+{
+  int qpc = orc_chroma_qp(qp_y + c_off);
+  int tc = orc_tc_table[clip3(0, 53, qpc + 2 + 2 * tc_off)];
   for (int l = 0; l < lines; l++) {
     uint8_t *p = pix + l * ys;
     int p0 = p[-xs], p1 = p[-2 * xs], q0 = p[0], q1 = p[xs];

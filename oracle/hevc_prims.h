@@ -28,6 +28,8 @@ int  orc_chroma_qp(int qp_y);
  * Applies 8.4.4.2.3 neighbour filtering when cidx==0 (strong_intra_smoothing off) and the
  * DC / horizontal / vertical edge filters of 8.4.4.2.5-6. */
 void orc_intra_predict(const uint8_t *refs, int log2n, int mode, int cidx, uint8_t *dst, int dstride);
+/* ... with strong_intra_smoothing_enabled_flag = `strong` (bi-linear smoothing of 32x32 luma neighbours, 8.4.4.2.3) */
+void orc_intra_predict2(const uint8_t *refs, int log2n, int mode, int cidx, int strong, uint8_t *dst, int dstride);
 /* K3: motion compensated prediction, uni-directional, 8-bit; mv in quarter luma samples.
  * Reference samples outside the picture are edge-clamped (8.5.3.3.3.1). */
 void orc_mc_luma(const uint8_t *ref, int stride, int pic_w, int pic_h, int x0, int y0, int w, int h,
@@ -41,5 +43,8 @@ void orc_mc_chroma(const uint8_t *ref, int stride, int pic_w, int pic_h, int x0,
  * `pix` points at q0 of the first line; xstride moves across the edge, ystride along it. */
 void orc_deblock_luma_segment(uint8_t *pix, int xstride, int ystride, int bs, int qp);
 void orc_deblock_chroma_segment(uint8_t *pix, int xstride, int ystride, int qp_y, int lines);
+/* ... with slice_beta_offset_div2 / slice_tc_offset_div2 and the chroma QP offset of the PPS (cQpPicOffset) */
+void orc_deblock_luma_segment2(uint8_t *pix, int xstride, int ystride, int bs, int qp, int beta_off, int tc_off);
+void orc_deblock_chroma_segment2(uint8_t *pix, int xstride, int ystride, int qp_y, int lines, int c_off, int tc_off);
 
 #endif

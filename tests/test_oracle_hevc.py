@@ -297,6 +297,63 @@ def test_transform_tree_streams_decode_in_ffmpeg(kind, w, h, n, qp, kw):
         assert np.array_equal(dec[i][0], recs[i]), i
 
 
+PEER_SYNTAX_CASES = [
+    ("camera", 192, 136, 3, 30, {"tr_depth": 1, "tu4": 1}),                       # 4x4 luma blocks: DST (intra) / DCT (inter)
+    ("noise", 128, 72, 3, 22, {"tr_depth": 2, "tu4": 1}),
+    ("camera", 192, 136, 3, 30, {"intra_sizes": 1}),                              # 8x8 intra CUs by decision
+    ("camera", 192, 136, 3, 30, {"intra_sizes": 2}),                              # 32x32 intra CUs
+    ("camera", 192, 136, 3, 30, {"intra_sizes": 5}),                              # NxN partitions
+    ("noise", 128, 72, 2, 27, {"intra_sizes": 7, "tr_depth": 2, "tu4": 1}),
+    ("camera", 192, 136, 3, 30, {"chroma_modes": 1}),                             # explicit intra_chroma_pred_mode
+    ("camera", 192, 136, 3, 27, {"sign_hiding": 1}),
+    ("noise", 128, 72, 3, 22, {"sign_hiding": 1, "tr_depth": 2, "tu4": 1, "intra_sizes": 7, "chroma_modes": 1}),
+    ("camera", 256, 256, 2, 30, {"intra_sizes": 2, "strong_intra": 1}),
+    ("camera", 192, 136, 3, 30, {"cb_qp_offset": 3, "cr_qp_offset": -4}),
+    ("camera", 192, 136, 3, 30, {"beta_offset_div2": 2, "tc_offset_div2": -3}),
+    ("sports", 416, 240, 5, 30, {"tr_depth": 2, "tu4": 1, "intra_sizes": 7, "chroma_modes": 1, "sign_hiding": 1, "strong_intra": 1,
+                                 "cb_qp_offset": 2, "cr_qp_offset": -2, "beta_offset_div2": 1, "tc_offset_div2": 1, "sao": 2,
+                                 "intra_in_p": 1, "refs": 2, "tmvp": 1, "qp_delta": 1, "hash_sei": 1, "intra_period": 3, "cabac_init": 1}),
+]
+
+
+@needs_ff
+@pytest.mark.parametrize("kind,w,h,n,qp,kw", PEER_SYNTAX_CASES)
+def test_peer_syntax_streams_decode_in_ffmpeg(kind, w, h, n, qp, kw):
+    """Syntax the GPU encoder does not produce but a Kvazaar-family peer may (streams for the decoder
+    tests): 4x4 luma transform blocks with the DST, NxN / 8x8 / 32x32 intra CUs, explicit chroma
+    modes, sign data hiding, strong intra smoothing, chroma QP and deblocking offsets.  All
+    normative: FFmpeg must reproduce the oracle's reconstruction."""
+    frames = frames_of(kind, w, h, n)
+    enc = OracleEncoder(w, h, qp=qp, **({"intra_period": 0} | kw))
+    if kw.get("qp_delta"):
+        enc.set_ctu_dqp(roi_pattern(w, h, 1, "random"))
+    aus, recs = [], []
+    seen = {"tu4": 0, "nxn": 0, "cu8": 0, "cu32": 0, "chroma": 0}
+    for f in frames:
+        aus.append(enc.encode(f))
+        recs.append(enc.recon())
+        m = enc.cu_map()
+        intra = m["pred_mode"] == 1
+        seen["tu4"] += int((m["tu_log2"] == 2).sum())
+        seen["nxn"] += int(((m["flags"] & 1) == 1).sum())
+        seen["cu8"] += int(((m["log2_size"] == 3) & intra).sum())
+        seen["cu32"] += int(((m["log2_size"] == 5) & intra).sum())
+        seen["chroma"] += int(((m["chroma_mode"] != m["intra_mode"]) & intra).sum())
+    enc.close()
+    if kw.get("tu4"):
+        assert seen["tu4"] > 0
+    if kw.get("intra_sizes", 0) & 4:
+        assert seen["nxn"] > 0
+    if kw.get("intra_sizes", 0) & 2 and w >= 256:
+        assert seen["cu32"] > 0
+    if kw.get("chroma_modes"):
+        assert seen["chroma"] > 0
+    dec, errs = ffhevc.decode_stream(aus)
+    assert errs == 0 and len(dec) == n
+    for i in range(n):
+        assert np.array_equal(dec[i][0], recs[i]), i
+
+
 @needs_ff
 def test_sao_with_per_ctu_qp_and_periodic_idr_decodes_in_ffmpeg():
     """The two per-CTU syntax additions together: sao() precedes the coding quadtree, cu_qp_delta sits
