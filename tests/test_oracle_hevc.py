@@ -344,7 +344,7 @@ def test_peer_syntax_streams_decode_in_ffmpeg(kind, w, h, n, qp, kw):
         assert seen["tu4"] > 0
     if kw.get("intra_sizes", 0) & 4:
         assert seen["nxn"] > 0
-    if kw.get("intra_sizes", 0) & 2 and w >= 256:
+    if kw.get("intra_sizes", 0) == 2:
         assert seen["cu32"] > 0
     if kw.get("chroma_modes"):
         assert seen["chroma"] > 0
