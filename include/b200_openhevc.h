@@ -15,14 +15,18 @@
  * Struct members read by the reference: OpenHevc_Frame::{pvY,pvU,pvV,frameInfo},
  * frameInfo.{nWidth,nHeight,nYPitch,nUPitch,frameRate.num,frameRate.den}   :201-233
  *
- * Decoding scope this round: streams of the B200 encoder's syntax family:
- * Main profile 8-bit 4:2:0, 64x64 CTUs, 2Nx2N CUs with one TU, I and P slices with one reference
- * picture, WPP entry points, deblocking; no SAO / PCM / AMP / scaling lists / transform skip /
- * sign hiding / TMVP; cu_qp_delta with one quantisation group per CTU; uniformly spaced tile
- * columns without loop filtering across tiles whose motion stays inside the tile (what
- * b200_tiled_* and kvz_api "tiles" emit), with or without WPP inside the tiles.  Anything else
- * makes libOpenHevcDecode return -1 with the reason in b200_last_error() -- never a silently wrong
- * picture.
+ * Decoding scope: Main profile 8-bit 4:2:0 low-delay streams as a Kvazaar-family
+ * peer sends them -- 64x64 CTUs with CUs of 8..64; inter CUs 2Nx2N (merge / skip / AMVP, several
+ * reference pictures from any short-term RPS of earlier pictures, temporal motion vector candidates);
+ * intra CUs 2Nx2N and NxN of every size with explicit chroma modes and strong intra smoothing;
+ * transform trees down to 4x4 luma blocks (DST-VII for intra); sign data hiding; cu_qp_delta with one
+ * quantisation group per CTU; chroma QP and deblocking offsets; deblocking and SAO; WPP entry points;
+ * cabac_init_flag; uniformly spaced tile columns without loop filtering across tiles whose motion stays
+ * inside the tile (what b200_tiled_* and kvz_api "tiles" emit), with or without WPP inside the tiles.
+ * Not decoded: B slices, AMP / 2NxN / Nx2N inter partitions, PCM, scaling lists, transform skip,
+ * transquant bypass, long-term references, several slices per picture, quantisation groups below the
+ * CTU, tile rows, a conformance window.  Those make libOpenHevcDecode return -1 with the reason in
+ * b200_last_error() -- never a silently wrong picture.
  */
 #ifndef B200_OPENHEVC_H_
 #define B200_OPENHEVC_H_

@@ -126,6 +126,13 @@ struct FrameParams {
   int init_type, tr_depth_inter, tr_depth_intra;
   int16_t ref_dist[16];
   const MvField *col_mvf;
+  // Decoder: syntax of foreign (Kvazaar-family) streams that this encoder does not produce -- all zero in
+  // the encoder.  sign_hiding / strong_intra: the PPS / SPS flags.  cb / cr_qp_offset: PPS + slice chroma QP
+  // offsets (8.6.1); *_pps: the PPS part alone, what chroma deblocking uses (cQpPicOffset, 8.7.2.5.5).
+  // beta / tc_offset_div2: deblocking offsets in force for the slice.
+  int sign_hiding, strong_intra;
+  int cb_qp_offset, cr_qp_offset, cb_qp_offset_pps, cr_qp_offset_pps;
+  int beta_offset_div2, tc_offset_div2;
   // optional work counters of the motion search (profiling): [0] CTUs, [1] 32x32 quadrants whose second
   // centre set was searched, [2] 16x16 intra mode searches, [3] intra CUs chosen (16x16)
   unsigned long long *me_stats;

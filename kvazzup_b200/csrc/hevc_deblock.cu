@@ -15,20 +15,30 @@ namespace {
 
 constexpr int kThreads = 256;
 
-__device__ __forceinline__ int edge_bs(const FrameParams &fp, const CuInfo &p, const CuInfo &q)
+// luma coded block flag of the transform block of unit u that touches segment `seg` of the edge; side 0:
+// u lies before the edge (P), 1: after it (Q).  A unit split into four 4x4 luma blocks (tu_log2 == 2, a
+// foreign stream) keeps one flag per block in cbf bits 4..7.
+__device__ __forceinline__ int edge_cbf(const CuInfo &u, int dir, int side, int seg)
+{
+  if (u.tu_log2 != 2) return u.cbf & 1;
+  const int b = dir == 0 ? (side ? 0 : 1) + 2 * seg : (side ? 0 : 2) + seg;
+  return (u.cbf >> (4 + b)) & 1;
+}
+
+__device__ __forceinline__ int edge_bs(const FrameParams &fp, const CuInfo &p, const CuInfo &q, int dir, int seg)
 {
   if (p.pred_mode == 1 || q.pred_mode == 1) return 2;
-  if ((p.cbf & 1) || (q.cbf & 1)) return 1;
+  if (edge_cbf(p, dir, 0, seg) || edge_cbf(q, dir, 1, seg)) return 1;
   // different reference PICTURES (8.7.2.4): compared by POC distance, two list entries may name one picture
   if (fp.n_refs > 1 && fp.ref_dist[p.ref_idx & 15] != fp.ref_dist[q.ref_idx & 15]) return 1;
   return (abs(p.mvx - q.mvx) >= 4 || abs(p.mvy - q.mvy) >= 4) ? 1 : 0;
 }
 
 // pix -> q0 of line 0; xs steps across the edge, ys along it
-__device__ __forceinline__ void luma_segment(uint8_t *pix, int xs, int ys, int bs, int qp)
+__device__ __forceinline__ void luma_segment(uint8_t *pix, int xs, int ys, int bs, int qp, int beta_off, int tc_off)
 {
-  const int beta = c_beta[clip3(0, 51, qp)];
-  const int tc = c_tc[clip3(0, 53, qp + 2 * (bs - 1))];
+  const int beta = c_beta[clip3(0, 51, qp + 2 * beta_off)];
+  const int tc = c_tc[clip3(0, 53, qp + 2 * (bs - 1) + 2 * tc_off)];
   int p[4][4], q[4][4];
 #pragma unroll
   for (int l = 0; l < 4; l++)
@@ -68,9 +78,9 @@ __device__ __forceinline__ void luma_segment(uint8_t *pix, int xs, int ys, int b
   }
 }
 
-__device__ __forceinline__ void chroma_segment(uint8_t *pix, int xs, int ys, int qp_c)
+__device__ __forceinline__ void chroma_segment(uint8_t *pix, int xs, int ys, int qp_c, int tc_off)
 {
-  const int tc = c_tc[clip3(0, 53, qp_c + 2)];
+  const int tc = c_tc[clip3(0, 53, qp_c + 2 + 2 * tc_off)];
 #pragma unroll
   for (int l = 0; l < 4; l++) {
     uint8_t *c = pix + l * ys;
@@ -93,22 +103,23 @@ k_deblock(FrameParams fp, uint8_t *rec, const CuInfo *__restrict__ cu, int dir)
   int n8 = q.tu_log2 > 3 ? 1 << (q.tu_log2 - 3) : 1;          // transform unit edges (they include the CU edges)
   if (dir == 0 ? (x8 == 0 || (x8 & (n8 - 1))) : (y8 == 0 || (y8 & (n8 - 1)))) return;
   CuInfo p = cu[dir == 0 ? u - 1 : u - fp.w8];
-  int bs = edge_bs(fp, p, q);
+  int bs = edge_bs(fp, p, q, dir, seg);
   if (!bs) return;
   int x = x8 * 8, y = y8 * 8;
   // QpL = (QpQ + QpP + 1) >> 1 (8.7.2.5.3); the two differ only across CTUs with different ROI offsets
   const int qp = fp.ctu_qp ? (p.qp + q.qp + 1) >> 1 : fp.qp;
-  const int qp_c = fp.ctu_qp ? c_chroma_qp_tab[qp] : fp.qp_c;
-  if (dir == 0) luma_segment(rec + (size_t)(y + 4 * seg) * fp.w + x, 1, fp.w, bs, qp);
-  else luma_segment(rec + (size_t)y * fp.w + x + 4 * seg, fp.w, 1, bs, qp);
+  const int c_off = seg ? fp.cr_qp_offset_pps : fp.cb_qp_offset_pps;         // cQpPicOffset (8.7.2.5.5)
+  const int qp_c = (fp.ctu_qp || c_off) ? c_chroma_qp_tab[clip3(0, 57, qp + c_off)] : fp.qp_c;
+  if (dir == 0) luma_segment(rec + (size_t)(y + 4 * seg) * fp.w + x, 1, fp.w, bs, qp, fp.beta_offset_div2, fp.tc_offset_div2);
+  else luma_segment(rec + (size_t)y * fp.w + x + 4 * seg, fp.w, 1, bs, qp, fp.beta_offset_div2, fp.tc_offset_div2);
   if (bs == 2 && ((dir == 0 ? x : y) & 15) == 0) {
     // chroma edges lie on the 8-sample chroma grid and are filtered for bS 2 only; seg 0 -> Cb, seg 1 -> Cr
     const size_t ysz = (size_t)fp.w * fp.h;
     const int cw = fp.w >> 1;
     uint8_t *plane = rec + ysz + (seg ? ysz / 4 : 0);
     uint8_t *pc = plane + (size_t)(y / 2) * cw + x / 2;
-    if (dir == 0) chroma_segment(pc, 1, cw, qp_c);
-    else chroma_segment(pc, cw, 1, qp_c);
+    if (dir == 0) chroma_segment(pc, 1, cw, qp_c, fp.tc_offset_div2);
+    else chroma_segment(pc, cw, 1, qp_c, fp.tc_offset_div2);
   }
 }
 

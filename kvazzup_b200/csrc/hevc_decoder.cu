@@ -267,11 +267,10 @@ struct Decoder {
     if (s.pcm) return "PCM is not supported";
     if (s.long_term_refs) return "long-term reference pictures are not supported";
     if (p.dependent_slices) return "dependent slice segments are not supported";
-    if (p.sign_hiding) return "sign data hiding is not supported";
     if (p.constrained_intra) return "constrained intra prediction is not supported";
     if (p.transform_skip) return "transform skip is not supported";
     if (p.qp_delta && p.diff_cu_qp_delta_depth != 0) return "quantisation groups smaller than the CTU are not supported";
-    if (p.cb_qp_offset || p.cr_qp_offset || sh.cb_qp_offset || sh.cr_qp_offset) return "chroma QP offsets are not supported";
+    if (abs(p.cb_qp_offset + sh.cb_qp_offset) > 12 || abs(p.cr_qp_offset + sh.cr_qp_offset) > 12) return "chroma QP offsets out of range";
     if (p.transquant_bypass) return "transquant bypass is not supported";
     if (p.tiles) {
       if (p.tile_rows != 1) return "tile rows are not supported (tile columns are)";
@@ -279,7 +278,7 @@ struct Decoder {
       if (p.loop_filter_across_tiles) return "loop filtering across tiles is not supported";
       if (p.tile_cols > 32) return "too many tile columns";
     }
-    if (!sh.deblock_disabled && (sh.beta_offset_div2 || sh.tc_offset_div2)) return "deblocking offsets are not supported";
+    if (abs(sh.beta_offset_div2) > 6 || abs(sh.tc_offset_div2) > 6) return "deblocking offsets out of range";
     if (p.log2_parallel_merge_level != 2) return "parallel merge level > 2 is not supported";
     if (!sh.first_slice_in_pic) return "multiple slice segments per picture are not supported";
     if (sh.slice_type == 0) return "B slices are not supported";
@@ -441,6 +440,10 @@ struct Decoder {
       t.fp.sao = t.fp.sao_flags ? t.d_sao : nullptr;
       t.fp.init_type = slice_type == 2 ? 0 : (sh.cabac_init_flag ? 2 : 1);
       t.fp.tr_depth_inter = sps.max_tr_depth_inter; t.fp.tr_depth_intra = sps.max_tr_depth_intra;
+      t.fp.sign_hiding = pps.sign_hiding; t.fp.strong_intra = sps.strong_intra_smoothing;
+      t.fp.cb_qp_offset = pps.cb_qp_offset + sh.cb_qp_offset; t.fp.cr_qp_offset = pps.cr_qp_offset + sh.cr_qp_offset;
+      t.fp.cb_qp_offset_pps = pps.cb_qp_offset; t.fp.cr_qp_offset_pps = pps.cr_qp_offset;
+      t.fp.beta_offset_div2 = sh.beta_offset_div2; t.fp.tc_offset_div2 = sh.tc_offset_div2;
       t.fp.n_refs = std::max(n_refs, 1); t.fp.max_merge = sh.max_merge_cand;
       for (int k = 0; k < 16; k++) t.fp.ref_dist[k] = (int16_t)(k < n_refs ? poc - ref_poc[k] : 1);
       t.fp.col_mvf = (slice_type != 2 && sh.tmvp) ? g.d_mvf[ref_pool[sh.collocated_ref_idx]] : nullptr;
@@ -483,10 +486,10 @@ struct Decoder {
       StripBufs &t = sl.strips[i];
       if (!cuda_ok(cudaEventSynchronize(t.ev_parsed), "sync parse")) { dpb[sl.cur_idx].valid = false; return -1; }
       if (t.h_status[0] != 0) {
-        static const char *const why[] = {"", "escape code too long", "(unused)", "partition other than 2Nx2N", "mvd too long",
-          "NxN intra partition", "intra chroma mode other than derived", "64x64 CU with residual", "end_of_slice_segment_flag mismatch",
-          "end_of_subset_one_bit missing", "intra CU larger than 16x16", "cu_qp_delta out of range",
-          "motion vector reaches across a tile boundary", "4x4 luma transform blocks"};
+        static const char *const why[] = {"", "escape code too long", "(unused)", "inter partition other than 2Nx2N", "mvd too long",
+          "(unused)", "(unused)", "(unused)", "end_of_slice_segment_flag mismatch",
+          "end_of_subset_one_bit missing", "(unused)", "cu_qp_delta out of range",
+          "motion vector reaches across a tile boundary", "(unused)"};
         int c = t.h_status[0];
         set_error("decoder: unsupported or corrupt slice data (%s)", c > 0 && c <= 13 ? why[c] : "unknown");
         dpb[sl.cur_idx].valid = false;     // never a reference: what follows it conceals and counts

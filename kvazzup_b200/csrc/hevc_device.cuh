@@ -16,9 +16,9 @@ static __constant__ uint16_t c_lambda_q4_tab[52] = {   // round(16 * sqrt(0.57 *
   3, 3, 4, 4, 5, 5, 6, 7, 8, 9, 10, 11, 12, 14, 15, 17, 19, 22, 24, 27, 30, 34, 38, 43, 48, 54, 61, 68,
   77, 86, 97, 108, 122, 137, 153, 172, 193, 217, 244, 273, 307, 344, 387, 434, 487, 547, 614, 689, 773,
   868, 974, 1093};
-static __constant__ uint8_t c_chroma_qp_tab[52] = {     // Table 8-10, cQpPicOffset = 0
+static __constant__ uint8_t c_chroma_qp_tab[58] = {     // Table 8-10: qPi (0..57) -> QpC
   0, 1, 2, 3, 4, 5, 6, 7, 8, 9, 10, 11, 12, 13, 14, 15, 16, 17, 18, 19, 20, 21, 22, 23, 24, 25, 26, 27, 28, 29,
-  29, 30, 31, 32, 33, 33, 34, 34, 35, 35, 36, 36, 37, 37, 38, 39, 40, 41, 42, 43, 44, 45};
+  29, 30, 31, 32, 33, 33, 34, 34, 35, 35, 36, 36, 37, 37, 38, 39, 40, 41, 42, 43, 44, 45, 46, 47, 48, 49, 50, 51};
 // luma QP / chroma QP / SAD-domain lambda of the CTU that holds luma sample (x, y)
 __device__ __forceinline__ int qp_at(const FrameParams &fp, int x, int y)
 {
@@ -27,6 +27,13 @@ __device__ __forceinline__ int qp_at(const FrameParams &fp, int x, int y)
 __device__ __forceinline__ int qp_c_at(const FrameParams &fp, int x, int y)
 {
   return fp.ctu_qp ? c_chroma_qp_tab[qp_at(fp, x, y)] : fp.qp_c;
+}
+// ... of chroma plane c (1 Cb, 2 Cr) with the chroma QP offsets a foreign stream may carry (8.6.1)
+__device__ __forceinline__ int qp_c_at(const FrameParams &fp, int x, int y, int c)
+{
+  const int off = c == 1 ? fp.cb_qp_offset : fp.cr_qp_offset;
+  if (!fp.ctu_qp && off == 0) return fp.qp_c;
+  return c_chroma_qp_tab[clip3(0, 57, qp_at(fp, x, y) + off)];
 }
 // Tile-column mode: may a block at x, n wide, use horizontal motion mvx (quarter samples)?  With a
 // fractional luma or chroma position ((mvx & 7) != 0) the interpolation reaches up to 4 luma samples
@@ -263,17 +270,26 @@ __device__ __forceinline__ int dot_dp2a(const uint32_t *data, const uint32_t *cw
 }
 
 // One sample position (x,y) of the tile -> its transform block; returns false outside the picture.
-struct TbPos { int ox, oy, n, log2n, org; };
+// `sub`: bit of s_nz[org] that says whether the block has levels -- 0, except for the four 4x4 luma
+// blocks of an 8x8 unit whose transform unit is split once more (s_log2 == 2; decoder only), which
+// share the unit's entry (their chroma is one 4x4 block per plane, as for any 8x8 unit).
+struct TbPos { int ox, oy, n, log2n, org, sub; };
 __device__ __forceinline__ bool tb_at(const TileGeom &g, const uint8_t *s_org, const uint8_t *s_log2, int x, int y, TbPos &tb)
 {
   int z = xy_to_z(x >> g.unit_log2, y >> g.unit_log2);
   int o = s_org[z];
   if (o == 0xff) return false;
   tb.org = o;
-  tb.log2n = s_log2[o] - g.chroma;
+  const int l2 = s_log2[o];
+  tb.log2n = max(l2 - g.chroma, 2);
   tb.n = 1 << tb.log2n;
   tb.ox = z_to_x(o) << g.unit_log2;
   tb.oy = z_to_y(o) << g.unit_log2;
+  tb.sub = 0;
+  if (l2 == 2 && !g.chroma) {
+    tb.ox += x & 4; tb.oy += y & 4;
+    tb.sub = ((y >> 1) & 2) | ((x >> 2) & 1);
+  }
   return true;
 }
 
@@ -356,7 +372,7 @@ __device__ __forceinline__ void inverse_recon(const TileGeom g, const uint8_t *s
   for (int p = threadIdx.x; p < total; p += blockDim.x) {
     int x = p >> g.tlog2, y = p & (T - 1);
     TbPos tb;
-    if (!tb_at(g, s_org, s_log2, x, y, tb) || !s_nz[tb.org]) continue;
+    if (!tb_at(g, s_org, s_log2, x, y, tb) || !((s_nz[tb.org] >> tb.sub) & 1)) continue;
     const int yy = y - tb.oy, xx = x - tb.ox;
     const uint32_t *row = (const uint32_t *)(s_a + (tb.oy + xx) * P + tb.ox);
     int acc = dot_dp2a(row, &w.wct[wct_offset(tb.log2n) + yy], tb.n, tb.n);
@@ -369,7 +385,7 @@ __device__ __forceinline__ void inverse_recon(const TileGeom g, const uint8_t *s
     TbPos tb;
     if (!tb_at(g, s_org, s_log2, x, y, tb)) continue;
     int pr = s_pred[p];
-    if (s_nz[tb.org]) {
+    if ((s_nz[tb.org] >> tb.sub) & 1) {
       const int xx = x - tb.ox;
       const uint32_t *row = (const uint32_t *)(s_t + y * P + tb.ox);
       int acc = dot_dp2a(row, &w.wct[wct_offset(tb.log2n) + xx], tb.n, tb.n);

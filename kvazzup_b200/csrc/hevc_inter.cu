@@ -464,7 +464,7 @@ k_inter_recon(FrameParams fp, const uint8_t *__restrict__ src, const RefList ref
       // the transform blocks are what the residual pipeline works on: the CU itself in the encoder, the
       // transform unit covering the 8x8 unit in the decoder (cbf and size per unit from the parser)
       l2 = kDecode ? ci.tu_log2 : ci.log2_size;
-      int n8 = 1 << (l2 - 3);
+      int n8 = l2 > 3 ? 1 << (l2 - 3) : 1;
       org = xy_to_z(ux & ~(n8 - 1), uy & ~(n8 - 1));
       sh.mvx[t] = ci.mvx; sh.mvy[t] = ci.mvy;
       sh.ref[t] = ci.ref_idx < refs.n ? ci.ref_idx : 0;
@@ -504,7 +504,8 @@ k_inter_recon(FrameParams fp, const uint8_t *__restrict__ src, const RefList ref
         ((uint32_t *)s_src)[i] = (gy < ph && gx < pw) ? __ldg((const uint32_t *)(psrc + (size_t)gy * pw + gx)) : 0u;
       }
     }
-    if (t < 64) sh.nz[t] = kDecode ? ((sh.cbf[t] >> c) & 1) : 0;
+    // decoder: bit 0 = the block has levels; a unit split into four 4x4 luma blocks has one bit per block
+    if (t < 64) sh.nz[t] = kDecode ? ((c == 0 && sh.log2[t] == 2) ? (sh.cbf[t] >> 4) : ((sh.cbf[t] >> c) & 1)) : 0;
     __syncthreads();
     // motion compensation: 4 threads per unit, each from its unit's own patch
     {
@@ -531,7 +532,7 @@ k_inter_recon(FrameParams fp, const uint8_t *__restrict__ src, const RefList ref
     }
     __syncthreads();
     TileGeom g{T, c ? 5 : 6, c ? 2 : 3, cs};
-    TqParams q{c ? qp_c_at(fp, cx, cy) : qp_at(fp, cx, cy), fp.is_idr};
+    TqParams q{c ? qp_c_at(fp, cx, cy, c) : qp_at(fp, cx, cy), fp.is_idr};
     if (!kDecode) {
       forward_tq(g, q, s_src, s_pred, sh.org, sh.log2, sh.w, s_a, s_b, sh.nz);
       // levels (s_b) -> HBM, 4 per thread; s_b then becomes the scratch tile of the inverse path
@@ -550,7 +551,7 @@ k_inter_recon(FrameParams fp, const uint8_t *__restrict__ src, const RefList ref
       for (int p = t; p < T * T; p += kThreads) {
         int y = p >> g.tlog2, x = p & (T - 1);
         TbPos tb;
-        if (tb_at(g, sh.org, sh.log2, x, y, tb) && sh.nz[tb.org]) {
+        if (tb_at(g, sh.org, sh.log2, x, y, tb) && ((sh.nz[tb.org] >> tb.sub) & 1)) {
           int lvl = plev[(size_t)(py0 + y) * pw + px0 + x];
           s_a[(tb.oy + (x - tb.ox)) * (T + 2) + tb.ox + (y - tb.oy)] = dequant_level(lvl, tb.log2n, qper, dscale);
         }

@@ -72,10 +72,10 @@ struct ReconSharedI {
 
 // One CU: the three planes side by side.  Thread t: plane p (0: t < 256, 1: 256..319, 2: 320..383
 // for a 16x16 CU), sample (x,y) of that plane's n_p x n_p block.
-template <bool kDecode>
 __device__ void recon_cu(ReconSharedI &sh, const FrameParams &fp, const uint8_t *src, uint8_t *rec, int16_t *levels,
                          CuInfo *cu, int cx, int cy, int x0, int y0, int log2)
 {
+  constexpr bool kDecode = false;          // the decoder has its own walk (k_intra_decode below)
   const int t = threadIdx.x;
   const size_t ysz = (size_t)fp.w * fp.h;
   const unsigned cur = coding_order_i(fp, x0, y0);
@@ -184,11 +184,11 @@ __device__ void recon_cu(ReconSharedI &sh, const FrameParams &fp, const uint8_t 
   __syncthreads();
 }
 
-template <bool kDecode>
 __global__ void __launch_bounds__(kReconThreads, 2)     // <= 85 registers: a CTA then fits beside two motion-search CTAs
 k_intra_frame(FrameParams fp, const uint8_t *__restrict__ src, uint8_t *rec, int16_t *levels, CuInfo *cu,
               int *ticket, const int *__restrict__ order)
 {
+  constexpr bool kDecode = false;
   __shared__ ReconSharedI sh;
   const int t = threadIdx.x;
   // P picture: the intra CUs (if any) follow the inter reconstruction; a picture without any is done
@@ -274,13 +274,238 @@ k_intra_frame(FrameParams fp, const uint8_t *__restrict__ src, uint8_t *rec, int
         // here, else the 8x8 units among the four quarters
         const CuInfo *u = &cu[(size_t)(y0 >> 3) * fp.w8 + (x0 >> 3)];
         if (u->tu_log2 == 4) {
-          if (u->pred_mode == 1) recon_cu<kDecode>(sh, fp, src, rec, levels, cu, cx, cy, x0, y0, 4);
+          if (u->pred_mode == 1) recon_cu(sh, fp, src, rec, levels, cu, cx, cy, x0, y0, 4);
         } else if (u->tu_log2 <= 3) {
           for (int q = 0; q < 4; q++) {
             int x1 = x0 + 8 * (q & 1), y1 = y0 + 8 * (q >> 1);
             if (x1 >= fp.w || y1 >= fp.h) continue;
             const CuInfo *v = &cu[(size_t)(y1 >> 3) * fp.w8 + (x1 >> 3)];
-            if (v->pred_mode == 1 && v->tu_log2 == 3) recon_cu<kDecode>(sh, fp, src, rec, levels, cu, cx, cy, x1, y1, 3);
+            if (v->pred_mode == 1 && v->tu_log2 == 3) recon_cu(sh, fp, src, rec, levels, cu, cx, cy, x1, y1, 3);
+          }
+        }
+      }
+      __threadfence();
+    }
+    __syncthreads();
+    if (t == 0) atomicExch(&fp.ctu_done[ctu], 1);
+  }
+}
+
+
+// ---- decoder: intra CUs of any conforming stream -------------------------------------------------
+// Same wavefront over CTUs as k_intra_frame; inside a CTU the walk follows the cu map the parser
+// wrote: transform units in z order, each predicted from the reconstruction before it (8.4.4.1) --
+// luma blocks of 4x4 (DST-VII, four per 8x8 unit, NxN CUs with a mode per block) up to 32x32 (with
+// strong smoothing when the SPS says so), chroma blocks of half the size with their own mode.  The
+// three planes of a unit go side by side: threads 0..255 luma, 256..319 Cb, 320..383 Cr, up to four
+// samples per thread.
+
+struct RefSetD { uint8_t raw[132], sub[132], filt[132], av[132]; int dc; };     // 4 * 32 + 1 neighbours
+
+struct DecSharedI {
+  uint8_t rec_y[64 * 64], rec_c[2][32 * 32];      // reconstruction of the current CTU
+  uint32_t cu[64][4];                             // its cu map entries, z order (log2_size 0 = outside the picture)
+  RefSetD rs[3];
+  int ctu;
+  int8_t dct[32][32];
+  int16_t a[1024 + 2 * 256], b[1024 + 2 * 256];   // a 32x32 luma block and two 16x16 chroma blocks
+};
+
+static __constant__ int8_t c_dst4[4][4] = {{29, 55, 74, 84}, {74, 74, 0, -74}, {84, -29, -74, 55}, {55, -84, 74, -29}};
+
+__device__ __forceinline__ unsigned coding_order4(const FrameParams &fp, int x, int y)
+{
+  return coding_order_i(fp, x, y) * 4u + (unsigned)((((y >> 2) & 1) << 1) | ((x >> 2) & 1));
+}
+
+// One transform unit.  Luma block of 1 << l2y at luma (lx, ly) with mode_y; when with_c, the chroma blocks
+// of 1 << l2c at chroma (lx >> 1 & ~3.., see caller) = (ccx, ccy) with mode_c.  cbf: bit 0 luma, 1 Cb, 2 Cr.
+__device__ void dec_tu(DecSharedI &sh, const FrameParams &fp, uint8_t *rec, const int16_t *levels, int cx, int cy,
+                       int lx, int ly, int l2y, int mode_y, bool with_c, int ccx, int ccy, int l2c, int mode_c, int cbf)
+{
+  const int t = threadIdx.x;
+  const size_t ysz = (size_t)fp.w * fp.h;
+  const int p = t < 256 ? 0 : (t < 320 ? 1 : 2);
+  const int gi = p == 0 ? t : (p == 1 ? t - 256 : t - 320), gs = p == 0 ? 256 : 64;
+  const bool act = p == 0 || with_c;
+  const int l2 = p == 0 ? l2y : l2c, n = 1 << l2, cnt = 4 * n + 1;
+  const int bx = p == 0 ? lx : ccx, by = p == 0 ? ly : ccy, sft = p ? 1 : 0;
+  const int pw = fp.w >> sft;
+  const size_t poff = p == 0 ? 0 : ysz + (p == 2 ? ysz / 4 : 0);
+  const int T = p == 0 ? 64 : 32, tx0 = cx >> sft, ty0 = cy >> sft;
+  uint8_t *tile = p == 0 ? sh.rec_y : sh.rec_c[p - 1];
+  RefSetD &rs = sh.rs[p];
+  const int mode = p == 0 ? mode_y : mode_c;
+  const bool nz = (cbf >> p) & 1;
+  const bool dst = p == 0 && l2 == 2;
+  if (act) {
+    // neighbours (8.4.4.2.2): available = inside the picture and earlier in decoding order, at 4x4 granularity
+    const unsigned cur = coding_order4(fp, bx << sft, by << sft);
+    for (int k = gi; k < cnt; k += gs) {
+      int x, y;
+      if (k < 2 * n) { x = bx - 1; y = by + 2 * n - 1 - k; }
+      else if (k == 2 * n) { x = bx - 1; y = by - 1; }
+      else { x = bx + (k - 2 * n - 1); y = by - 1; }
+      const int ax = x << sft, ay = y << sft;
+      const bool ok = ax >= 0 && ay >= 0 && ax < fp.w && ay < fp.h && coding_order4(fp, ax, ay) < cur;
+      uint8_t v = 0;
+      if (ok) {
+        const int ux = x - tx0, uy = y - ty0;
+        v = (ux >= 0 && uy >= 0 && ux < T && uy < T) ? tile[uy * T + ux] : __ldcg(rec + poff + (size_t)y * pw + x);
+      }
+      rs.av[k] = ok; rs.raw[k] = v;
+    }
+  }
+  __syncthreads();
+  if (act)
+    for (int k = gi; k < cnt; k += gs) {
+      int j = k;
+      while (j >= 0 && !rs.av[j]) j--;
+      if (j < 0) { j = k + 1; while (j < cnt && !rs.av[j]) j++; }
+      rs.sub[k] = j < cnt ? rs.raw[j] : 128;
+    }
+  __syncthreads();
+  if (act) {
+    // [1 2 1] smoothing, or the bi-linear one for nearly flat 32x32 luma neighbourhoods (8.4.4.2.3)
+    const int corner = rs.sub[2 * n];
+    const bool strong = p == 0 && n == 32 && fp.strong_intra && abs(corner + rs.sub[4 * n] - 2 * rs.sub[3 * n]) < 8 &&
+                        abs(corner + rs.sub[0] - 2 * rs.sub[n]) < 8;
+    for (int k = gi; k < cnt; k += gs) {
+      int v;
+      if (k == 0 || k == cnt - 1 || (strong && k == 2 * n)) v = rs.sub[k];
+      else if (strong) {
+        const int i = k < 2 * n ? 2 * n - 1 - k : k - 2 * n - 1;
+        v = ((63 - i) * corner + (i + 1) * rs.sub[k < 2 * n ? 0 : 4 * n] + 32) >> 6;
+      } else v = (rs.sub[k - 1] + 2 * rs.sub[k] + rs.sub[k + 1] + 2) >> 2;
+      rs.filt[k] = (uint8_t)v;
+    }
+    if (gi == gs - 1) {
+      int sum = n;
+      for (int i = 0; i < n; i++) sum += rs.sub[2 * n + 1 + i] + rs.sub[2 * n - 1 - i];
+      rs.dc = sum >> (l2 + 1);
+    }
+  }
+  __syncthreads();
+  int16_t *a = sh.a + (p == 0 ? 0 : (p == 1 ? 1024 : 1280));
+  int16_t *b = sh.b + (p == 0 ? 0 : (p == 1 ? 1024 : 1280));
+  const int nshift = 5 - l2;
+  int pr[4] = {0, 0, 0, 0};
+  if (act) {
+    const int qp = p == 0 ? qp_at(fp, lx, ly) : qp_c_at(fp, lx, ly, p);
+    const int qper = qp / 6, dscale = 16 * c_level_scale[qp % 6], bd = l2 + 3;
+    int s = 0;
+    for (int i = gi; i < n * n; i += gs, s++) {
+      const int y = i >> l2, x = i & (n - 1);
+      pr[s] = intra_pixel(rs.sub, rs.filt, n, l2, mode, p, rs.dc, x, y);
+      if (nz) {
+        const int lvl = levels[poff + (size_t)(by + y) * pw + bx + x];
+        long long d = ((long long)lvl * dscale) << qper;
+        d = (d + (1LL << (bd - 1))) >> bd;
+        a[i] = (int16_t)max(-32768LL, min(32767LL, d));
+      }
+    }
+  }
+  __syncthreads();
+  if (act && nz)
+    for (int i = gi; i < n * n; i += gs) {
+      const int y = i >> l2, x = i & (n - 1);
+      int acc = 0;
+      for (int k = 0; k < n; k++) acc += (dst ? c_dst4[k][y] : sh.dct[k << nshift][y]) * a[k * n + x];
+      b[i] = (int16_t)clip3(-32768, 32767, (acc + 64) >> 7);
+    }
+  __syncthreads();
+  if (act) {
+    int s = 0;
+    for (int i = gi; i < n * n; i += gs, s++) {
+      const int y = i >> l2, x = i & (n - 1);
+      int v = pr[s];
+      if (nz) {
+        int acc = 0;
+        for (int k = 0; k < n; k++) acc += (dst ? c_dst4[k][x] : sh.dct[k << nshift][x]) * b[y * n + k];
+        v = clip8(v + clip3(-32768, 32767, (acc + 2048) >> 12));
+      }
+      __stcg(rec + poff + (size_t)(by + y) * pw + bx + x, (uint8_t)v);
+      tile[(by + y - ty0) * T + bx + x - tx0] = (uint8_t)v;
+    }
+  }
+  __syncthreads();
+}
+
+__global__ void __launch_bounds__(kReconThreads)
+k_intra_decode(FrameParams fp, uint8_t *rec, const int16_t *__restrict__ levels, const CuInfo *cu, int *ticket,
+               const int *__restrict__ order)
+{
+  __shared__ DecSharedI sh;
+  const int t = threadIdx.x;
+  if (!fp.is_idr && *(volatile int *)fp.any_intra == 0) return;
+  for (int i = t; i < 1024; i += kReconThreads) ((int8_t *)sh.dct)[i] = c_dct32[i >> 5][i & 31];
+  const int nctu = fp.ctb_cols * fp.ctb_rows;
+  const size_t ysz = (size_t)fp.w * fp.h;
+  for (;;) {
+    __syncthreads();
+    if (t == 0) sh.ctu = atomicAdd(ticket, 1);
+    __syncthreads();
+    if (sh.ctu >= nctu) break;
+    const int ctu = order[sh.ctu];
+    const int row = ctu / fp.ctb_cols, col = ctu - row * fp.ctb_cols;
+    const int cx = col * kCtb, cy = row * kCtb;
+    int mine = 0;
+    if (t < 64) {
+      const int x8 = (cx >> 3) + z_to_x(t), y8 = (cy >> 3) + z_to_y(t);
+      uint32_t w0 = 0, w1 = 0, w2 = 0, w3 = 0;
+      if (x8 < fp.w8 && y8 < fp.h8) {
+        const uint32_t *s = (const uint32_t *)(cu + (size_t)y8 * fp.w8 + x8);
+        w0 = __ldcg(s); w1 = __ldcg(s + 1); w2 = __ldcg(s + 2); w3 = __ldcg(s + 3);
+        mine = ((w1 >> 8) & 0xff) == 1 && (w1 & 0xff) != 0;
+      } else {
+        w1 = 0;
+      }
+      sh.cu[t][0] = w0; sh.cu[t][1] = w1; sh.cu[t][2] = w2; sh.cu[t][3] = w3;
+    }
+    const int has = __syncthreads_or(mine);
+    if (has) {
+      if (t == 0) {
+        volatile int *d = fp.ctu_done;
+        if (col > 0) while (d[ctu - 1] == 0) __nanosleep(32);
+        if (row > 0) {
+          if (col > 0) while (d[ctu - fp.ctb_cols - 1] == 0) __nanosleep(32);
+          while (d[ctu - fp.ctb_cols] == 0) __nanosleep(32);
+          if (col + 1 < fp.ctb_cols) while (d[ctu - fp.ctb_cols + 1] == 0) __nanosleep(32);
+        }
+        __threadfence();
+      }
+      __syncthreads();
+      if (!fp.is_idr) {
+        // the inter CUs of this CTU were reconstructed by the kernel before
+        for (int i = t; i < 64 * 16; i += kReconThreads) {
+          int y = cy + (i >> 4), x = cx + 4 * (i & 15);
+          ((uint32_t *)sh.rec_y)[i] = (y < fp.h && x < fp.w) ? __ldcg((const uint32_t *)(rec + (size_t)y * fp.w + x)) : 0u;
+        }
+        for (int i = t; i < 2 * 32 * 8; i += kReconThreads) {
+          int c = i >> 8, j = i & 255;
+          int y = (cy >> 1) + (j >> 3), x = (cx >> 1) + 4 * (j & 7);
+          const uint8_t *pl = rec + ysz + (c ? ysz / 4 : 0);
+          ((uint32_t *)sh.rec_c[c])[j] = (y < (fp.h >> 1) && x < (fp.w >> 1)) ? __ldcg((const uint32_t *)(pl + (size_t)y * (fp.w >> 1) + x)) : 0u;
+        }
+        __syncthreads();
+      }
+      for (int z = 0; z < 64; z++) {
+        const CuInfo u = *(const CuInfo *)sh.cu[z];
+        if (u.log2_size == 0 || u.pred_mode != 1) continue;
+        const int ux = z_to_x(z), uy = z_to_y(z);
+        const int x0 = cx + 8 * ux, y0 = cy + 8 * uy;
+        if (u.tu_log2 >= 3) {
+          const int n8 = 1 << (u.tu_log2 - 3);
+          if ((ux & (n8 - 1)) || (uy & (n8 - 1))) continue;              // not the first unit of its transform unit
+          dec_tu(sh, fp, rec, levels, cx, cy, x0, y0, u.tu_log2, u.intra_mode, true, x0 >> 1, y0 >> 1, u.tu_log2 - 1,
+                 u.chroma_mode, u.cbf & 7);
+        } else {
+          // four 4x4 luma blocks (each with its own mode in an NxN CU), chroma alongside the first
+          const bool nxn = u.flags & 1;
+          for (int b = 0; b < 4; b++) {
+            const int m = !nxn || b == 0 ? u.intra_mode : (b == 1 ? (u.mvx & 0xff) : (b == 2 ? ((u.mvx >> 8) & 0xff) : (u.mvy & 0xff)));
+            dec_tu(sh, fp, rec, levels, cx, cy, x0 + 4 * (b & 1), y0 + 4 * (b >> 1), 2, m, b == 0, x0 >> 1, y0 >> 1, 2,
+                   u.chroma_mode, ((u.cbf >> (4 + b)) & 1) | (u.cbf & 6));
           }
         }
       }
@@ -324,7 +549,7 @@ cudaError_t launch_intra_frame(const FrameParams &fp, const uint8_t *src, uint8_
   if (e != cudaSuccess) return e;
   const int blocks16 = ((fp.w + 15) >> 4) * ((fp.h + 15) >> 4);
   k_intra_modes<<<blocks16, kModeThreads, 0, s>>>(fp, src, cu);
-  k_intra_frame<false><<<intra_grid(fp), kReconThreads, 0, s>>>(fp, src, rec, levels, cu, ticket, order);
+  k_intra_frame<<<intra_grid(fp), kReconThreads, 0, s>>>(fp, src, rec, levels, cu, ticket, order);
   return cudaGetLastError();
 }
 
@@ -337,13 +562,12 @@ cudaError_t launch_intra_in_p(const FrameParams &fp, const uint8_t *src, uint8_t
   if (e != cudaSuccess) return e;
   e = cudaMemsetAsync(ticket, 0, sizeof(int), s);
   if (e != cudaSuccess) return e;
-  k_intra_frame<false><<<intra_grid(fp), kReconThreads, 0, s>>>(fp, src, rec, levels, cu, ticket, order);
+  k_intra_frame<<<intra_grid(fp), kReconThreads, 0, s>>>(fp, src, rec, levels, cu, ticket, order);
   return cudaGetLastError();
 }
 
 // Decoder reconstruction of the intra CUs of a picture (modes, cbf and levels from the parser): all
-// CUs of an I picture; in a P picture the intra CUs, after launch_inter_decode.  Intra CUs must be
-// 16x16 or 8x8 (what the parser accepts).
+// CUs of an I picture; in a P picture the intra CUs, after launch_inter_decode.
 cudaError_t launch_intra_decode(const FrameParams &fp, uint8_t *rec, const int16_t *levels, const CuInfo *cu,
                                 int *ticket, const int *order, cudaStream_t s)
 {
@@ -351,7 +575,7 @@ cudaError_t launch_intra_decode(const FrameParams &fp, uint8_t *rec, const int16
   if (e != cudaSuccess) return e;
   e = cudaMemsetAsync(ticket, 0, sizeof(int), s);
   if (e != cudaSuccess) return e;
-  k_intra_frame<true><<<intra_grid(fp), kReconThreads, 0, s>>>(fp, nullptr, rec, (int16_t *)levels, (CuInfo *)cu, ticket, order);
+  k_intra_decode<<<intra_grid(fp), kReconThreads, 0, s>>>(fp, rec, levels, cu, ticket, order);
   return cudaGetLastError();
 }
 

@@ -8,9 +8,10 @@
 // lanes on private context tables, with no branch that depends on the lane index; stores of
 // identical values from all lanes coalesce into one transaction.
 //
-// Scope: 2Nx2N CUs 8..64, one TU per CU, I and P slices, one reference picture, SAO (with merge
-// candidates), cu_qp_delta per CTU; no PCM / AMP / scaling lists / transform skip / sign hiding /
-// TMVP.  Anything else is reported through `status` and the picture is rejected by the host.
+// Scope: CUs 8..64 (inter 2Nx2N; intra 2Nx2N and NxN with explicit chroma modes), transform trees down
+// to 4x4 luma blocks, I and P slices, several reference pictures with temporal candidates, SAO (with
+// merge candidates), cu_qp_delta per CTU, sign data hiding; no PCM / AMP / scaling lists / transform
+// skip.  Anything else is reported through `status` and the picture is rejected by the host.
 #include "hevc_device.cuh"
 #include "hevc_kernels.h"
 
@@ -306,13 +307,17 @@ __device__ void parse_residual(Reader &r, const ParseCtx &pc, int16_t *plane, in
     }
     int g2 = 0;
     if (first_g1 >= 0) g2 = dec_bin(r, CTX_GT2 + (cidx ? 4 : 0) + ctx_set);
+    // sign data hiding (7.3.8.11): the sign of the first coefficient in scan order is not coded when the
+    // significant coefficients of the group span more than three positions; it is the parity of the sum
+    const int first_sig = __ffs(sig) - 1;
+    const bool hidden = pc.fp.sign_hiding && (31 - __clz(sig)) - first_sig > 3;
     unsigned neg = 0;
-    for (unsigned t = sig; t;) {
+    for (unsigned t = hidden ? sig & (sig - 1) : sig; t;) {
       const int p = 31 - __clz(t);
       t &= ~(1u << p);
       neg |= (unsigned)dec_bypass(r) << p;
     }
-    int num_sig = 0, rice = 0;
+    int num_sig = 0, rice = 0, sum_abs = 0;
     for (unsigned t = sig; t;) {
       const int p = 31 - __clz(t);
       t &= ~(1u << p);
@@ -337,11 +342,13 @@ __device__ void parse_residual(Reader &r, const ParseCtx &pc, int16_t *plane, in
         if (absv > (3 << rice)) rice = min(rice + 1, 4);
       }
       num_sig++;
+      sum_abs += absv;
       int xp, yp;
       scan_pos_d(scan_idx, 2, p, xp, yp);
       {                                   // all lanes store the same value to the same address
         int v = min(absv, 32767);
-        plane[(size_t)(y0 + ys * 4 + yp) * pw + x0 + xs * 4 + xp] = (int16_t)(((neg >> p) & 1) ? -v : v);
+        const bool negative = (hidden && p == first_sig) ? (sum_abs & 1) != 0 : ((neg >> p) & 1) != 0;
+        plane[(size_t)(y0 + ys * 4 + yp) * pw + x0 + xs * 4 + xp] = (int16_t)(negative ? -v : v);
       }
     }
   }
@@ -354,6 +361,32 @@ __device__ __forceinline__ int scan_idx_for_d(int pred_mode, int intra_mode, int
   if (intra_mode >= 6 && intra_mode <= 14) return 2;
   if (intra_mode >= 22 && intra_mode <= 30) return 1;
   return 0;
+}
+
+// luma intra prediction mode of the 4x4 block that covers luma sample (x, y) of a CU of the cu map
+// (inter CUs carry mode 1, DC, as the candidate derivation of 8.4.2 asks)
+__device__ __forceinline__ int intra_mode_of(const CuInfo &c, int x, int y)
+{
+  if (!(c.flags & 1) || c.pred_mode != 1) return c.intra_mode;
+  const int part = (((y >> 2) & 1) << 1) | ((x >> 2) & 1);
+  return part == 0 ? c.intra_mode : (part == 1 ? (c.mvx & 0xff) : (part == 2 ? ((c.mvx >> 8) & 0xff) : (c.mvy & 0xff)));
+}
+
+// cu_qp_delta_abs (9.3.3.10: prefix TR cMax 5, ctx 0 then ctx 1; suffix EG0) and sign, once per quantisation group
+__device__ __forceinline__ void parse_cu_qp_delta(Reader &r, ParseCtx &pc)
+{
+  int a = 0;
+  while (a < 5 && dec_bin(r, CTX_CU_QP_DELTA + (a ? 1 : 0))) a++;
+  if (a == 5) {
+    int k = 0, v = 0;
+    while (k < 8 && dec_bypass(r)) { v += 1 << k; k++; }
+    if (k >= 8) { r.err = 11; return; }
+    a += v + (int)dec_bypass_bits(r, k);
+  }
+  const int d = (a && dec_bypass(r)) ? -a : a;
+  if (d < -26 || d > 25) { r.err = 11; return; }
+  pc.qp_cur = (pc.qp_cur + d + 52) % 52;
+  pc.delta_coded = 1;
 }
 
 __device__ void parse_cu(Reader &r, ParseCtx &pc, int x0, int y0, int log2)
@@ -466,37 +499,60 @@ __device__ void parse_cu(Reader &r, ParseCtx &pc, int x0, int y0, int log2)
     if (fp.mv_edges && !mv_allowed(fp, x0, n, cu.mvx)) { r.err = 12; return; }   // motion across an interior tile edge
     }
   }
+  int part_mode_v[4] = {1, 1, 1, 1};                                     // luma modes of the prediction blocks
   if (intra) {
     cu.pred_mode = 1;
-    if (log2 > 4) { r.err = 10; return; }                                // the intra pass reconstructs 16x16 and 8x8 CUs
-    if (log2 == 3 && !dec_bin(r, CTX_PART_MODE)) { r.err = 5; return; }   // PART_NxN: not supported
-    int prev = dec_bin(r, CTX_PREV_INTRA_LUMA);
-    // candidate modes (8.4.2): inter neighbours carry intra_mode 1 (DC) in the cu map, as the rule asks
-    int a = 1, b = 1;
-    if (x0 > 0) a = load_cu(pc, x0 - 1, y0).intra_mode;
-    if (y0 > 0 && (y0 & (kCtb - 1))) b = load_cu(pc, x0, y0 - 1).intra_mode;
-    int cand[3];
-    if (a == b) {
-      if (a < 2) { cand[0] = 0; cand[1] = 1; cand[2] = 26; }
-      else { cand[0] = a; cand[1] = 2 + ((a + 29) % 32); cand[2] = 2 + ((a - 2 + 1) % 32); }
-    } else {
-      cand[0] = a; cand[1] = b;
-      cand[2] = (a != 0 && b != 0) ? 0 : ((a != 1 && b != 1) ? 1 : 26);
+    // part_mode: only the smallest CUs choose between PART_2Nx2N and PART_NxN (four 4x4 prediction blocks)
+    const bool nxn = log2 == 3 && !dec_bin(r, CTX_PART_MODE);
+    const int parts = nxn ? 4 : 1;
+    int prev[4];
+    for (int b = 0; b < parts; b++) prev[b] = dec_bin(r, CTX_PREV_INTRA_LUMA);
+    for (int b = 0; b < parts; b++) {
+      const int xb = x0 + 4 * (b & 1), yb = y0 + 4 * (b >> 1);
+      // candidate modes (8.4.2): inter neighbours carry intra_mode 1 (DC) in the cu map, as the rule asks;
+      // the blocks of this CU itself are not in the map yet
+      int ca = 1, cb = 1;
+      if (b & 1) ca = part_mode_v[b - 1];
+      else if (xb > 0) ca = intra_mode_of(load_cu(pc, xb - 1, yb), xb - 1, yb);
+      if (b & 2) cb = part_mode_v[b - 2];
+      else if (yb > 0 && (yb & (kCtb - 1))) cb = intra_mode_of(load_cu(pc, xb, yb - 1), xb, yb - 1);
+      int cand[3];
+      if (ca == cb) {
+        if (ca < 2) { cand[0] = 0; cand[1] = 1; cand[2] = 26; }
+        else { cand[0] = ca; cand[1] = 2 + ((ca + 29) % 32); cand[2] = 2 + ((ca - 2 + 1) % 32); }
+      } else {
+        cand[0] = ca; cand[1] = cb;
+        cand[2] = (ca != 0 && cb != 0) ? 0 : ((ca != 1 && cb != 1) ? 1 : 26);
+      }
+      int mode;
+      if (prev[b]) {
+        int idx = 0;
+        if (dec_bypass(r)) idx = dec_bypass(r) ? 2 : 1;
+        mode = cand[idx];
+      } else {
+        if (cand[0] > cand[1]) { int t = cand[0]; cand[0] = cand[1]; cand[1] = t; }
+        if (cand[0] > cand[2]) { int t = cand[0]; cand[0] = cand[2]; cand[2] = t; }
+        if (cand[1] > cand[2]) { int t = cand[1]; cand[1] = cand[2]; cand[2] = t; }
+        mode = (int)dec_bypass_bits(r, 5);
+        for (int i = 0; i < 3; i++) if (mode >= cand[i]) mode++;
+      }
+      part_mode_v[b] = mode;
     }
-    int mode;
-    if (prev) {
-      int idx = 0;
-      if (dec_bypass(r)) idx = dec_bypass(r) ? 2 : 1;
-      mode = cand[idx];
-    } else {
-      if (cand[0] > cand[1]) { int t = cand[0]; cand[0] = cand[1]; cand[1] = t; }
-      if (cand[0] > cand[2]) { int t = cand[0]; cand[0] = cand[2]; cand[2] = t; }
-      if (cand[1] > cand[2]) { int t = cand[1]; cand[1] = cand[2]; cand[2] = t; }
-      mode = (int)dec_bypass_bits(r, 5);
-      for (int i = 0; i < 3; i++) if (mode >= cand[i]) mode++;
+    if (!nxn) part_mode_v[1] = part_mode_v[2] = part_mode_v[3] = part_mode_v[0];
+    cu.intra_mode = (uint8_t)part_mode_v[0];
+    if (nxn) {
+      cu.flags = 1;
+      cu.mvx = (int16_t)(part_mode_v[1] | (part_mode_v[2] << 8)); cu.mvy = (int16_t)part_mode_v[3];
     }
-    cu.intra_mode = (uint8_t)mode; cu.chroma_mode = (uint8_t)mode;
-    if (dec_bin(r, CTX_INTRA_CHROMA)) { r.err = 6; return; }              // only intra_chroma_pred_mode 4 (derived)
+    // intra_chroma_pred_mode (8.4.3): derived from the luma mode (of the first block), or planar / vertical /
+    // horizontal / DC, where the one that equals the luma mode stands for mode 34
+    int cmode = part_mode_v[0];
+    if (dec_bin(r, CTX_INTRA_CHROMA)) {
+      const int k = (int)dec_bypass_bits(r, 2);
+      const int m = k == 0 ? 0 : (k == 1 ? 26 : (k == 2 ? 10 : 1));
+      cmode = m == part_mode_v[0] ? 34 : m;
+    }
+    cu.chroma_mode = (uint8_t)cmode;
     if (!fp.is_idr) pc.any_intra = 1;
     tu = true;
   }
@@ -512,7 +568,8 @@ __device__ void parse_cu(Reader &r, ParseCtx &pc, int x0, int y0, int log2)
   __syncwarp();
   int root = 0;
   if (tu) {
-    const int max_depth = cu.pred_mode == 1 ? fp.tr_depth_intra : fp.tr_depth_inter;
+    const int nxn = cu.flags & 1;                                // IntraSplitFlag: the first split is inferred
+    const int max_depth = (cu.pred_mode == 1 ? fp.tr_depth_intra : fp.tr_depth_inter) + nxn;
     struct Node { short x, y; signed char l2, depth, child, cb, cr; } st[5];
     int sp = 0;
     st[0] = {(short)x0, (short)y0, (signed char)log2, 0, -1, 1, 1};
@@ -521,34 +578,41 @@ __device__ void parse_cu(Reader &r, ParseCtx &pc, int x0, int y0, int log2)
       if (nd.child < 0) {
         // node header: split_transform_flag (parsed or inferred), then the chroma flags of the node
         int split;
-        if (nd.l2 <= 5 && nd.l2 > 2 && nd.depth < max_depth) split = dec_bin(r, CTX_SPLIT_TRANSFORM + 5 - nd.l2);
-        else split = nd.l2 > 5;                                // larger than the largest transform block: inferred
-        if (split && nd.l2 == 3) { r.err = 13; return; }       // 4x4 luma transform blocks: not supported yet
+        if (nd.l2 <= 5 && nd.l2 > 2 && nd.depth < max_depth && !(nxn && nd.depth == 0)) split = dec_bin(r, CTX_SPLIT_TRANSFORM + 5 - nd.l2);
+        else split = nd.l2 > 5 || (nxn && nd.depth == 0);      // larger than the largest transform block / NxN: inferred
         const int par_cb = nd.cb, par_cr = nd.cr;
         const int cb = par_cb ? dec_bin(r, CTX_CBF_CHROMA + nd.depth) : 0;
         const int cr = par_cr ? dec_bin(r, CTX_CBF_CHROMA + nd.depth) : 0;
         nd.cb = (signed char)cb; nd.cr = (signed char)cr;
+        if (split && nd.l2 == 3) {
+          // four 4x4 luma transform units (7.3.8.10 with log2TrafoSize 2); the two 4x4 chroma blocks of the
+          // 8x8 node follow the fourth.  The unit keeps cbf bit 0 = any luma block, bits 4..7 = the blocks.
+          int cbf = (cb << 1) | (cr << 2);
+          for (int b = 0; b < 4 && !r.err; b++) {
+            const int lu = dec_bin(r, CTX_CBF_LUMA);           // trafoDepth > 0
+            if (fp.ctu_qp && (lu | cb | cr) && !pc.delta_coded) parse_cu_qp_delta(r, pc);
+            if (!lu || r.err) continue;
+            cbf |= 1 | (16 << b);
+            parse_residual(r, pc, pc.levels, fp.w, nd.x + 4 * (b & 1), nd.y + 4 * (b >> 1), 2, 0,
+                           scan_idx_for_d(cu.pred_mode, part_mode_v[b], 2, 0));
+          }
+          for (int k = 1; k < 3 && !r.err; k++)
+            if ((cbf >> k) & 1)
+              parse_residual(r, pc, pc.levels + ysz + (k == 2 ? ysz / 4 : 0), fp.w >> 1, nd.x >> 1, nd.y >> 1, 2, k,
+                             scan_idx_for_d(cu.pred_mode, cu.chroma_mode, 2, k));
+          root |= cbf;
+          pc.s_tu[(((nd.y - y0) >> 3) << 3) + ((nd.x - x0) >> 3)] = (uint16_t)(cbf | (2 << 8));   // every lane: same value
+          __syncwarp();
+          sp--;
+          continue;
+        }
         if (split) { nd.child = 0; continue; }
         // leaf: transform_unit
         int lu = 1;
         if (cu.pred_mode == 1 || nd.depth != 0 || cb || cr) lu = dec_bin(r, CTX_CBF_LUMA + (nd.depth == 0 ? 1 : 0));
         const int cbf = lu | (cb << 1) | (cr << 2);
         root |= cbf;
-        if (fp.ctu_qp && cbf && !pc.delta_coded) {
-          // cu_qp_delta_abs (9.3.3.10: prefix TR cMax 5, ctx 0 then ctx 1; suffix EG0) and sign
-          int a = 0;
-          while (a < 5 && dec_bin(r, CTX_CU_QP_DELTA + (a ? 1 : 0))) a++;
-          if (a == 5) {
-            int k = 0, v = 0;
-            while (k < 8 && dec_bypass(r)) { v += 1 << k; k++; }
-            if (k >= 8) { r.err = 11; return; }
-            a += v + (int)dec_bypass_bits(r, k);
-          }
-          const int d = (a && dec_bypass(r)) ? -a : a;
-          if (d < -26 || d > 25) { r.err = 11; return; }
-          pc.qp_cur = (pc.qp_cur + d + 52) % 52;
-          pc.delta_coded = 1;
-        }
+        if (fp.ctu_qp && cbf && !pc.delta_coded) { parse_cu_qp_delta(r, pc); if (r.err) return; }
         {
           const int t8 = 1 << (nd.l2 - 3), tunits = t8 * t8;
           const int bx = (nd.x - x0) >> 3, by = (nd.y - y0) >> 3;
@@ -563,7 +627,7 @@ __device__ void parse_cu(Reader &r, ParseCtx &pc, int x0, int y0, int log2)
           const int sft = k ? 1 : 0;
           int16_t *plane = pc.levels + (k == 0 ? 0 : ysz + (k == 2 ? ysz / 4 : 0));
           parse_residual(r, pc, plane, fp.w >> sft, nd.x >> sft, nd.y >> sft, nd.l2 - sft, k,
-                         scan_idx_for_d(cu.pred_mode, k ? cu.chroma_mode : cu.intra_mode, nd.l2 - sft, k));
+                         scan_idx_for_d(cu.pred_mode, k ? cu.chroma_mode : part_mode_v[0], nd.l2 - sft, k));
         }
         sp--;
         continue;
@@ -581,7 +645,7 @@ __device__ void parse_cu(Reader &r, ParseCtx &pc, int x0, int y0, int log2)
     if (r.err) return;
   }
   if (fp.ctu_qp) cu.qp = (uint8_t)pc.qp_cur;
-  cu.flags = (uint8_t)(root ? 2 : 0);                        // bit 1: the CU has a coded residual
+  cu.flags |= (uint8_t)(root ? 2 : 0);                       // bit 1: the CU has a coded residual
   // publish the cu map entries: shared memory for the CUs that follow in this row, global memory for
   // the row below and the reconstruction kernels (lane u takes unit u of the CU); cbf and the
   // transform unit size are per unit

@@ -72,10 +72,32 @@ def decode_all(aus):
     ("camera", 416, 240, 5, 32, {"tr_depth": 2, "cabac_init": 1, "sao": 2, "intra_in_p": 1, "refs": 2, "tmvp": 1, "qp_delta": 1, "intra_period": 3}),
     ("camera", 416, 240, 4, 32, {"no_wpp": 1, "tr_depth": 1, "sao": 1}),
     ("camera", 1920, 1080, 3, 27, {"tr_depth": 2, "refs": 2, "tmvp": 1, "sao": 2, "me_coarse": 16, "search_range": 6}),
+    # syntax of a Kvazaar-family peer (oracle/hevc_enc.h: tu4, intra_sizes, chroma_modes, sign_hiding, ...)
+    ("camera", 192, 136, 3, 30, {"tr_depth": 1, "tu4": 1}),                       # 4x4 luma blocks: DST (intra) / DCT (inter)
+    ("noise", 128, 72, 3, 22, {"tr_depth": 2, "tu4": 1}),
+    ("camera", 192, 136, 3, 30, {"intra_sizes": 1}),                              # 8x8 intra CUs by decision
+    ("camera", 192, 136, 3, 30, {"intra_sizes": 2}),                              # 32x32 intra CUs
+    ("camera", 192, 136, 3, 30, {"intra_sizes": 5}),                              # NxN partitions
+    ("noise", 128, 72, 2, 27, {"intra_sizes": 7, "tr_depth": 2, "tu4": 1}),
+    ("camera", 192, 136, 3, 30, {"chroma_modes": 1}),                             # explicit intra_chroma_pred_mode
+    ("camera", 192, 136, 3, 27, {"sign_hiding": 1}),
+    ("noise", 128, 72, 3, 22, {"sign_hiding": 1, "tr_depth": 2, "tu4": 1, "intra_sizes": 7, "chroma_modes": 1}),
+    ("camera", 256, 256, 2, 30, {"intra_sizes": 2, "strong_intra": 1}),
+    ("camera", 192, 136, 3, 30, {"cb_qp_offset": 3, "cr_qp_offset": -4}),
+    ("camera", 192, 136, 3, 30, {"beta_offset_div2": 2, "tc_offset_div2": -3}),
+    ("camera", 640, 480, 3, 24, {"cb_qp_offset": -5, "cr_qp_offset": 6, "qp_delta": 1, "sao": 2, "beta_offset_div2": -2, "tc_offset_div2": 3}),
+    ("sports", 416, 240, 5, 30, {"tr_depth": 2, "tu4": 1, "intra_sizes": 7, "chroma_modes": 1, "sign_hiding": 1, "strong_intra": 1,
+                                 "cb_qp_offset": 2, "cr_qp_offset": -2, "beta_offset_div2": 1, "tc_offset_div2": 1, "sao": 2,
+                                 "intra_in_p": 1, "refs": 2, "tmvp": 1, "qp_delta": 1, "intra_period": 3, "cabac_init": 1}),
+    ("camera", 1920, 1080, 3, 27, {"tr_depth": 3, "tu4": 1, "intra_sizes": 7, "chroma_modes": 1, "sign_hiding": 1, "refs": 2, "tmvp": 1,
+                                   "sao": 2, "me_coarse": 16, "search_range": 6, "intra_in_p": 1}),
 ])
 def test_decoder_reproduces_oracle_reconstruction(kind, w, h, n, qp, kw):
     frames = frames_of(kind, w, h, n)
     enc = OracleEncoder(w, h, qp=qp, **({"intra_period": 0} | kw))
+    if kw.get("qp_delta"):
+        from tests.test_oracle_hevc import roi_pattern
+        enc.set_ctu_dqp(roi_pattern(w, h, 1, "random"))
     aus, recs = [], []
     for f in frames:
         aus.append(enc.encode(f))
