@@ -42,10 +42,12 @@ typedef struct b200_enc_params {
   int me_coarse;                 /* two-level motion search: range of the coarse level in 4x4-mean samples (multiple
                                     of 4, <= 32; 16 = +-64 luma samples); search_range (<= 16) is then the window
                                     searched around the zero vector and around each 32x32 block's coarse vector */
+  int intra_satd;                /* I pictures: the 35-mode intra search compares the Hadamard SATD of the residual
+                                    (8x8 tiles) instead of its SAD */
 } b200_enc_params;
 void  b200_enc_params_default(b200_enc_params *p);
 void *b200_enc_open_params(const b200_enc_params *p);
-/* Fills search_range, me_coarse, sao and intra_in_p with what the kvz_api preset of that name selects
+/* Fills search_range, me_coarse, sao, intra_in_p and intra_satd with what the kvz_api preset of that name selects
  * ("ultrafast" ... "placebo"); the other fields are left alone.  0 on success. */
 int   b200_enc_params_from_preset(const char *preset, b200_enc_params *p);
 /* Per-CTU QP offsets (raster, one int8 per 64x64 CTU, n = CTU count) for the pictures submitted
@@ -95,6 +97,7 @@ typedef struct b200_tiled_params {
   int sao;                       /* SAO inside every tile (never across tile edges) */
   int intra_in_p;                /* intra CUs in P pictures */
   int me_coarse;                 /* two-level motion search (see b200_enc_params) */
+  int intra_satd;                /* SATD-based intra mode search in I pictures (see b200_enc_params) */
 } b200_tiled_params;
 void  b200_tiled_params_default(b200_tiled_params *p);
 void *b200_tiled_open_params(const b200_tiled_params *p, const int *devices, int n_devices);

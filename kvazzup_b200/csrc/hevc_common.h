@@ -109,6 +109,7 @@ struct FrameParams {
   // the intra pass over a P picture without any returns at once; ctu_done: one flag per CTU for the
   // intra pass's wavefront (hevc_intra.cu).
   int intra_in_p;
+  int intra_satd;       // encoder, I pictures: the 35-mode search compares Hadamard SATD instead of SAD (row K2)
   int *any_intra;
   int *ctu_done;
   // Two-level motion search (encoder): me_coarse > 0 = range of the coarse level in coarse samples (a

@@ -26,10 +26,10 @@ constexpr int kReconThreads = 384;    // k_intra_frame: 256 luma + 64 Cb + 64 Cr
 
 // ---- mode decision, whole picture in parallel ----------------------------------------------------
 
-__device__ void decide_cu(ModeShared &sh, const FrameParams &fp, const uint8_t *src, CuInfo *cu, int x0, int y0, int log2)
+__device__ void decide_cu(ModeShared &sh, int16_t (*resid)[256], const FrameParams &fp, const uint8_t *src, CuInfo *cu, int x0, int y0, int log2)
 {
   const int n = 1 << log2, t = threadIdx.x;
-  intra_search_cu(sh, fp, src, x0, y0, log2);
+  intra_search_cu(sh, fp, src, x0, y0, log2, fp.intra_satd ? resid : nullptr);
   if (t == 0) {
     CuInfo ci;
     ci.mvx = 0; ci.mvy = 0; ci.log2_size = (uint8_t)log2; ci.pred_mode = 1; ci.intra_mode = (uint8_t)sh.best_mode;
@@ -46,14 +46,15 @@ __global__ void __launch_bounds__(kModeThreads)
 k_intra_modes(FrameParams fp, const uint8_t *__restrict__ src, CuInfo *__restrict__ cu)
 {
   __shared__ ModeShared sh;
+  __shared__ int16_t resid[2][256];
   const int bw = (fp.w + 15) >> 4;
   const int x0 = (blockIdx.x % bw) * 16, y0 = (blockIdx.x / bw) * 16;
   if (x0 + 16 <= fp.w && y0 + 16 <= fp.h) {
-    decide_cu(sh, fp, src, cu, x0, y0, 4);
+    decide_cu(sh, resid, fp, src, cu, x0, y0, 4);
   } else {
     for (int q = 0; q < 4; q++) {
       int x1 = x0 + 8 * (q & 1), y1 = y0 + 8 * (q >> 1);
-      if (x1 < fp.w && y1 < fp.h) decide_cu(sh, fp, src, cu, x1, y1, 3);
+      if (x1 < fp.w && y1 < fp.h) decide_cu(sh, resid, fp, src, cu, x1, y1, 3);
     }
   }
 }

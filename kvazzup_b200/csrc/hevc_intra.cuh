@@ -121,7 +121,13 @@ struct ModeShared {
   int best_mode;
 };
 
-__device__ __forceinline__ void intra_search_cu(ModeShared &sh, const FrameParams &fp, const uint8_t *src, int x0, int y0, int log2)
+// `resid` (may be null): two buffers of 256 residuals.  Given, the modes are compared by the Hadamard SATD
+// of the residual over 8x8 tiles, (sum |h| + 2) >> 2 per tile as oracle/hevc_prims.c orc_satd (SURVEY.md
+// 8a-K row K2), instead of the SAD: the residuals of a mode go through shared memory to one warp per tile,
+// two rows of the tile per lane (rows r and r + 4), so that the first vertical butterfly is in registers
+// and the other five stages are warp shuffles.
+__device__ __forceinline__ void intra_search_cu(ModeShared &sh, const FrameParams &fp, const uint8_t *src, int x0, int y0, int log2,
+                                                int16_t (*resid)[256] = nullptr)
 {
   const int n = 1 << log2, t = threadIdx.x;
   const unsigned cur = coding_order_i(fp, x0, y0);
@@ -135,11 +141,39 @@ __device__ __forceinline__ void intra_search_cu(ModeShared &sh, const FrameParam
   __syncthreads();
   filter_refs(sh.rs, n, t);
   __syncthreads();
-  for (int mode = 0; mode < 35; mode++) {
-    unsigned d = 0;
-    if (act) d = (unsigned)abs((int)sh.src[t] - intra_pixel(sh.rs.sub, sh.rs.filt, n, log2, mode, 0, sh.rs.dc, x, y));
-    d = __reduce_add_sync(0xffffffffu, d);
-    if ((t & 31) == 0 && d) atomicAdd(&sh.sad[mode], d);
+  if (resid) {
+    const int tiles_log2 = log2 - 3, ntile = 1 << (2 * tiles_log2);
+    const int lane = t & 31, tile = t >> 5;
+    const int tx = (tile & ((1 << tiles_log2) - 1)) * 8 + (lane & 7), ty = (tile >> tiles_log2) * 8 + (lane >> 3);
+    for (int mode = 0; mode < 35; mode++) {
+      int16_t *d = resid[mode & 1];
+      if (act) d[t] = (int16_t)((int)sh.src[t] - intra_pixel(sh.rs.sub, sh.rs.filt, n, log2, mode, 0, sh.rs.dc, x, y));
+      __syncthreads();                                   // (the buffer of mode - 1 is still being read: two buffers)
+      if (tile < ntile) {
+        const int v0 = d[(ty << log2) + tx], v1 = d[((ty + 4) << log2) + tx];
+        int a = v0 + v1, b = v0 - v1;
+#pragma unroll
+        for (int m = 8; m != 4; m = m == 16 ? 1 : m << 1) {          // lane bits 3, 4 (rows), then 0, 1, 2 (columns)
+          const int oa = __shfl_xor_sync(0xffffffffu, a, m), ob = __shfl_xor_sync(0xffffffffu, b, m);
+          a = (lane & m) ? oa - a : a + oa;
+          b = (lane & m) ? ob - b : b + ob;
+        }
+        {
+          const int oa = __shfl_xor_sync(0xffffffffu, a, 4), ob = __shfl_xor_sync(0xffffffffu, b, 4);
+          a = (lane & 4) ? oa - a : a + oa;
+          b = (lane & 4) ? ob - b : b + ob;
+        }
+        const unsigned sum = __reduce_add_sync(0xffffffffu, (unsigned)(abs(a) + abs(b)));
+        if (lane == 0) atomicAdd(&sh.sad[mode], (sum + 2) >> 2);
+      }
+    }
+  } else {
+    for (int mode = 0; mode < 35; mode++) {
+      unsigned d = 0;
+      if (act) d = (unsigned)abs((int)sh.src[t] - intra_pixel(sh.rs.sub, sh.rs.filt, n, log2, mode, 0, sh.rs.dc, x, y));
+      d = __reduce_add_sync(0xffffffffu, d);
+      if ((t & 31) == 0 && d) atomicAdd(&sh.sad[mode], d);
+    }
   }
   __syncthreads();
   if (t == 0) {

@@ -21,16 +21,18 @@ assert CU_DTYPE.itemsize == 16
 class EncParams(C.Structure):
     """b200_enc_params (include/b200_hevc.h)."""
     _fields_ = [(n, C.c_int) for n in ("struct_size", "width", "height", "qp", "intra_period", "search_range", "deblock",
-                                       "debug", "depth", "qp_delta", "fps_num", "fps_den", "sao", "intra_in_p", "me_coarse")]
+                                       "debug", "depth", "qp_delta", "fps_num", "fps_den", "sao", "intra_in_p", "me_coarse",
+                                       "intra_satd")]
 
 
 def preset_options(preset: str) -> dict:
-    """Engine options (search_range, me_coarse, sao, intra_in_p) the kvz_api preset of that name selects."""
+    """Engine options (search_range, me_coarse, sao, intra_in_p, intra_satd) the kvz_api preset of that name selects."""
     p = EncParams()
     lib().b200_enc_params_default(C.byref(p))
     if lib().b200_enc_params_from_preset(preset.encode(), C.byref(p)) != 0:
         raise B200Error("unknown preset " + preset)
-    return {"search_range": p.search_range, "me_coarse": p.me_coarse, "sao": p.sao, "intra_in_p": p.intra_in_p}
+    return {"search_range": p.search_range, "me_coarse": p.me_coarse, "sao": p.sao, "intra_in_p": p.intra_in_p,
+            "intra_satd": p.intra_satd}
 
 
 class GpuEncoder:
@@ -152,7 +154,8 @@ class GpuEncoder:
 class TiledParams(C.Structure):
     """b200_tiled_params (include/b200_hevc.h)."""
     _fields_ = [(n, C.c_int) for n in ("struct_size", "width", "height", "qp", "intra_period", "search_range", "deblock",
-                                       "depth", "tile_cols", "wpp", "fps_num", "fps_den", "sao", "intra_in_p", "me_coarse")]
+                                       "depth", "tile_cols", "wpp", "fps_num", "fps_den", "sao", "intra_in_p", "me_coarse",
+                                       "intra_satd")]
 
 
 class GpuTiledEncoder:

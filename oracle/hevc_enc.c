@@ -478,7 +478,7 @@ static void gather_refs(const orc_encoder_t *e, int c, int x0, int y0, int n, ui
  * picture in one parallel pass and the reconstruction wavefront only predicts the chosen mode.
  * Cost = SAD + lambda * bits with a fixed prior (planar / DC / vertical cheap) because the
  * neighbours' modes -- hence the MPM list -- are not known in a parallel pass. */
-static uint32_t intra_mode_search(const orc_encoder_t *e, int x0, int y0, int log2, int *mode_out)
+static uint32_t intra_mode_search_x(const orc_encoder_t *e, int x0, int y0, int log2, int *mode_out, int satd)
 {
   const int n = 1 << log2;
   uint8_t refs[4 * 32 + 1], pred[32 * 32];
@@ -487,13 +487,21 @@ static uint32_t intra_mode_search(const orc_encoder_t *e, int x0, int y0, int lo
   int best_mode = 0;
   for (int mode = 0; mode < 35; mode++) {
     orc_intra_predict2(refs, log2, mode, 0, e->cfg.strong_intra, pred, n);
-    uint32_t sad = orc_sad(e->src + (size_t)y0 * e->w + x0, e->w, pred, n, n, n);
+    /* cfg.intra_satd (I pictures, blocks of 8x8 and larger): Hadamard SATD of the residual, the measure
+     * Kvazaar / HM use in the rough mode search, instead of the SAD */
+    uint32_t sad = satd ? orc_satd(e->src + (size_t)y0 * e->w + x0, e->w, pred, n, n, n)
+                        : orc_sad(e->src + (size_t)y0 * e->w + x0, e->w, pred, n, n, n);
     int bits = (mode == 0 || mode == 1 || mode == 26) ? 2 : 6;
     uint32_t cost = sad + (uint32_t)((lambda_at(e, x0, y0) * bits) >> 4);
     if (cost < best_cost) { best_cost = cost; best_mode = mode; }
   }
   *mode_out = best_mode;
   return best_cost;
+}
+
+static uint32_t intra_mode_search(const orc_encoder_t *e, int x0, int y0, int log2, int *mode_out)
+{
+  return intra_mode_search_x(e, x0, y0, log2, mode_out, 0);
 }
 
 /* cfg.chroma_modes: intra_chroma_pred_mode of a CU by SAD on source neighbours of both chroma planes --
@@ -562,7 +570,7 @@ static uint32_t intra_plan(orc_encoder_t *e, int x0, int y0, int log2, intra_pla
   intra_plan_t *me = &plan[((y0 & (CTB - 1)) >> 3) * 8 + ((x0 & (CTB - 1)) >> 3)];
   if (log2 == 3) {
     int mode;
-    me->cost = intra_mode_search(e, x0, y0, 3, &mode) + ovh;
+    me->cost = intra_mode_search_x(e, x0, y0, 3, &mode, e->cfg.intra_satd) + ovh;
     me->log2 = 3; me->nxn = 0; me->mode[0] = (uint8_t)mode;
     if (e->cfg.intra_sizes & 4) {
       uint32_t c4 = ovh + (uint32_t)((lambda_at(e, x0, y0) * 2) >> 4);
@@ -581,7 +589,7 @@ static uint32_t intra_plan(orc_encoder_t *e, int x0, int y0, int log2, intra_pla
   }
   if (can_whole) {
     int mode;
-    const uint32_t whole = intra_mode_search(e, x0, y0, log2, &mode) + ovh;
+    const uint32_t whole = intra_mode_search_x(e, x0, y0, log2, &mode, e->cfg.intra_satd) + ovh;
     if (whole <= split_cost) {
       me->cost = whole; me->log2 = (int8_t)log2; me->nxn = 0; me->mode[0] = (uint8_t)mode;
       return whole;

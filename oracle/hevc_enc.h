@@ -57,6 +57,7 @@ typedef struct {
                             * centre besides the zero vector; search_range (<= 16) is the window around each centre */
   int intra_in_p;          /* 1 = 16x16 intra CUs in P pictures where inter prediction is poor (scene cuts, uncovered areas) */
   int fps_num, fps_den;    /* both > 0: VUI timing info in the SPS (vui_time_scale / vui_num_units_in_tick); 0 = no VUI */
+  int intra_satd;          /* 1 = I pictures: the 35-mode search of blocks >= 8x8 compares Hadamard SATD (8x8 tiles) instead of SAD */
   /* Syntax the GPU encoder does not produce but a Kvazaar-family peer may: streams for the decoder tests. */
   int tu4;                 /* 1 = an 8x8 transform unit may split into four 4x4 luma blocks (and one 4x4 block per chroma
                             * plane, coded after the fourth luma block): DST-VII for intra luma, DCT otherwise; needs

@@ -77,6 +77,12 @@ CASES = [
     ("noise", 128, 72, 3, 30, {"me_coarse": 16, "search_range": 4}),
     ("camera", 64, 8, 3, 37, {"me_coarse": 16, "search_range": 4}),
     ("screen", 640, 480, 4, 32, {"me_coarse": 16, "search_range": 6, "sao": 2, "intra_in_p": 1}),
+    # SATD-based intra mode search in I pictures (row K2): 16x16 CUs, and the 8x8 CUs of partial CTUs
+    ("camera", 192, 136, 3, 30, {"intra_satd": 1, "intra_period": 1}),
+    ("noise", 128, 72, 2, 27, {"intra_satd": 1}),
+    ("screen", 640, 480, 3, 32, {"intra_satd": 1, "intra_period": 2, "sao": 2}),
+    ("sports", 416, 240, 5, 32, {"intra_satd": 1, "intra_in_p": 1, "me_coarse": 16, "search_range": 4, "intra_period": 3}),
+    ("camera", 64, 8, 2, 37, {"intra_satd": 1}),
 ]
 
 
@@ -173,7 +179,8 @@ def test_kvazaar_filter_default_settings_stream_equals_engine_and_decodes():
         aus += got
     f.close()
     from kvazzup_b200.encoder import preset_options
-    assert preset_options("ultrafast") == {"search_range": 4, "me_coarse": 16, "sao": 0, "intra_in_p": 1}
+    assert preset_options("ultrafast") == {"search_range": 4, "me_coarse": 16, "sao": 0, "intra_in_p": 1, "intra_satd": 0}
+    assert preset_options("veryfast") == {"search_range": 6, "me_coarse": 16, "sao": 2, "intra_in_p": 1, "intra_satd": 1}
     o = OracleEncoder(w, h, qp=32, intra_period=64, fps_num=30, fps_den=1, **preset_options("ultrafast"))    # "input-fps" -> VUI timing
     assert aus == [o.encode(fr) for fr in frames]
     if ffhevc.required():
