@@ -332,6 +332,47 @@ k_planar_to_i420_v16(const uint8_t *__restrict__ in, uint8_t *__restrict__ out, 
   }
 }
 
+// Four pixels of two rows, one word per pixel (bytes in memory order; the byte that is not R, G or B meets
+// a zero coefficient) -> four luma samples per row and two chroma pairs.
+__device__ __forceinline__ void rgb_quads_to_i420(const unsigned (&wa)[4], const unsigned (&wb)[4], int ro, int go, int bo,
+                                                  uint8_t *fy, size_t ysz, int w, int rp, int g)
+{
+    // One DP4A per output sample: the pixel word (bytes in memory order) times a coefficient word
+    // with 66 / 129 / 25 (unsigned) or the signed chroma weights at the R, G, B byte positions; the
+    // unused byte of a pixel (alpha, or the next pixel's first byte for 24-bit input) meets a 0.
+    const int rs = ro * 8, gs = go * 8, bs = bo * 8;
+    const unsigned cy = (66u << rs) | (129u << gs) | (25u << bs);
+    const unsigned cu = ((unsigned)(uint8_t)(-38) << rs) | ((unsigned)(uint8_t)(-74) << gs) | (112u << bs);
+    const unsigned cv = (112u << rs) | ((unsigned)(uint8_t)(-94) << gs) | ((unsigned)(uint8_t)(-18) << bs);
+    // the sample is byte 1 of each sum (>> 8): PRMT gathers four of them into a word (the sums stay
+    // below 2^16, so nothing else has to be masked)
+    const unsigned ya = __byte_perm(__byte_perm(__dp4a(wa[0], cy, 0x1080u), __dp4a(wa[1], cy, 0x1080u), 0x0051),
+                                    __byte_perm(__dp4a(wa[2], cy, 0x1080u), __dp4a(wa[3], cy, 0x1080u), 0x0051), 0x5410);
+    const unsigned yb = __byte_perm(__byte_perm(__dp4a(wb[0], cy, 0x1080u), __dp4a(wb[1], cy, 0x1080u), 0x0051),
+                                    __byte_perm(__dp4a(wb[2], cy, 0x1080u), __dp4a(wb[3], cy, 0x1080u), 0x0051), 0x5410);
+    unsigned us[2], vs[2];
+#pragma unroll
+    for (int i = 0; i < 2; i++) {
+      // rounded 2x2 box average of every byte lane, two 16-bit lanes at a time
+      const unsigned k = 0x00FF00FFu;
+      const unsigned p00 = wa[2 * i], p01 = wa[2 * i + 1], p10 = wb[2 * i], p11 = wb[2 * i + 1];
+      const unsigned ev = (p00 & k) + (p01 & k) + (p10 & k) + (p11 & k) + 0x00020002u;
+      const unsigned od = __byte_perm(p00, 0, 0x4341) + __byte_perm(p01, 0, 0x4341) + __byte_perm(p10, 0, 0x4341) +
+                          __byte_perm(p11, 0, 0x4341) + 0x00020002u;
+      // (sum >> 2) of the four 16-bit lanes back into byte order: even lanes to bytes 0, 2, odd lanes to 1, 3
+      const unsigned avg = __byte_perm((ev >> 2) & k, (od >> 2) & k, 0x6240);
+      us[i] = (unsigned)dp4a_u8s8(avg, cu, 0x8080);
+      vs[i] = (unsigned)dp4a_u8s8(avg, cv, 0x8080);
+    }
+    const unsigned u2 = __byte_perm(us[0], us[1], 0x0051), v2 = __byte_perm(vs[0], vs[1], 0x0051);
+    size_t yoff = (size_t)(2 * rp) * w + 4 * g;
+    *(unsigned *)(fy + yoff) = ya;
+    *(unsigned *)(fy + yoff + w) = yb;
+    size_t coff = (size_t)rp * (w >> 1) + 2 * g;
+    *(unsigned short *)(fy + ysz + coff) = (unsigned short)u2;
+    *(unsigned short *)(fy + ysz + (ysz >> 2) + coff) = (unsigned short)v2;
+}
+
 // Packed RGB (3 or 4 bytes per pixel), one item = 2 rows x 4 pixels.
 // ro/go/bo are byte offsets of R,G,B inside a pixel.  Requires w % 4 == 0.
 template <int kBpp>
@@ -342,11 +383,18 @@ k_rgb_to_i420_v4(const uint8_t *__restrict__ in, uint8_t *__restrict__ out, int 
   const int gpr = w >> 2;
   const size_t per = (size_t)gpr * (h >> 1), total = per * n_frames;
   const size_t ysz = (size_t)w * h, fout = ysz + (ysz >> 1), fin = ysz * kBpp;
+  const bool small = total < 0x80000000ull;      // 32-bit index arithmetic when it fits (the divisions are a good part of an item)
   for (size_t it = (size_t)blockIdx.x * blockDim.x + threadIdx.x; it < total;
        it += (size_t)gridDim.x * blockDim.x) {
-    int f = (int)div_idx(it, per);
-    int r = (int)(it - (size_t)f * per);
-    int rp = r / gpr, g = r - rp * gpr;
+    int f, rp, g;
+    if (small) {
+      const unsigned i32 = (unsigned)it, uf = i32 / (unsigned)per, r = i32 - uf * (unsigned)per, urp = r / (unsigned)gpr;
+      f = (int)uf; rp = (int)urp; g = (int)(r - urp * (unsigned)gpr);
+    } else {
+      f = (int)div_idx(it, per);
+      const int r = (int)(it - (size_t)f * per);
+      rp = r / gpr; g = r - rp * gpr;
+    }
     const uint8_t *src = in + (size_t)f * fin + ((size_t)(2 * rp) * w + 4 * g) * kBpp;
     unsigned wa[4], wb[4];
     if (kBpp == 4) {
@@ -361,37 +409,46 @@ k_rgb_to_i420_v4(const uint8_t *__restrict__ in, uint8_t *__restrict__ out, int 
       wa[0] = a0; wa[1] = __byte_perm(a0, a1, 0x0543); wa[2] = __byte_perm(a1, a2, 0x0432); wa[3] = a2 >> 8;
       wb[0] = b0; wb[1] = __byte_perm(b0, b1, 0x0543); wb[2] = __byte_perm(b1, b2, 0x0432); wb[3] = b2 >> 8;
     }
-    // One DP4A per output sample: the pixel word (bytes in memory order) times a coefficient word
-    // with 66 / 129 / 25 (unsigned) or the signed chroma weights at the R, G, B byte positions; the
-    // unused byte of a pixel (alpha, or the next pixel's first byte for 24-bit input) meets a 0.
-    const int rs = ro * 8, gs = go * 8, bs = bo * 8;
-    const unsigned cy = (66u << rs) | (129u << gs) | (25u << bs);
-    const unsigned cu = ((unsigned)(uint8_t)(-38) << rs) | ((unsigned)(uint8_t)(-74) << gs) | (112u << bs);
-    const unsigned cv = (112u << rs) | ((unsigned)(uint8_t)(-94) << gs) | ((unsigned)(uint8_t)(-18) << bs);
-    unsigned ya = 0, yb = 0, u2 = 0, v2 = 0;
-#pragma unroll
-    for (int i = 0; i < 4; i++) {
-      ya |= (__dp4a(wa[i], cy, 0x1080u) >> 8) << (8 * i);
-      yb |= (__dp4a(wb[i], cy, 0x1080u) >> 8) << (8 * i);
+    rgb_quads_to_i420(wa, wb, ro, go, bo, out + (size_t)f * fout, ysz, w, rp, g);
+  }
+}
+
+// 24-bit RGB with w % 16 == 0: a thread's four pixels are 12 bytes, so direct loads are 4-byte words at a
+// 12-byte stride (every warp-wide load touches three times the sectors it uses).  Here every warp stages
+// two rows x 128 pixels (2 x 384 bytes) through its own slice of shared memory with coalesced 16-byte
+// loads -- no CTA-wide barrier, warps run independently -- and the 12-byte reads that follow are
+// conflict-free (word stride 3 is coprime with the 32 banks).
+constexpr int kRgb24TilePx = 128;
+__global__ void __launch_bounds__(kThreads)
+k_rgb24_to_i420_staged(const uint8_t *__restrict__ in, uint8_t *__restrict__ out, int w, int h, int n_frames,
+                       int ro, int go, int bo)
+{
+  __shared__ uint4 s_rows[kThreads / 32][2][kRgb24TilePx * 3 / 16];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int tpr = (w + kRgb24TilePx - 1) / kRgb24TilePx;            // tiles per row pair
+  const unsigned per = (unsigned)tpr * (unsigned)(h >> 1), total = per * (unsigned)n_frames;
+  const size_t ysz = (size_t)w * h, fout = ysz + (ysz >> 1), fin = ysz * 3;
+  const unsigned wstride = gridDim.x * (kThreads / 32);
+  uint4 (*sr)[kRgb24TilePx * 3 / 16] = s_rows[warp];
+  for (unsigned it = blockIdx.x * (kThreads / 32) + warp; it < total; it += wstride) {
+    const unsigned f = it / per, r = it - f * per;
+    const int rp = (int)(r / (unsigned)tpr), tile = (int)(r - (unsigned)rp * tpr);
+    const int x0 = tile * kRgb24TilePx, tw = min(kRgb24TilePx, w - x0), nvec = tw * 3 / 16;     // nvec <= 24
+    const uint8_t *src = in + (size_t)f * fin + ((size_t)(2 * rp) * w + x0) * 3;
+    __syncwarp();                                         // the previous tile has been read
+    if (lane < nvec) {
+      sr[0][lane] = __ldg((const uint4 *)src + lane);
+      sr[1][lane] = __ldg((const uint4 *)(src + (size_t)w * 3) + lane);
     }
-#pragma unroll
-    for (int i = 0; i < 2; i++) {
-      // rounded 2x2 box average of every byte lane, two 16-bit lanes at a time
-      const unsigned k = 0x00FF00FFu;
-      const unsigned p00 = wa[2 * i], p01 = wa[2 * i + 1], p10 = wb[2 * i], p11 = wb[2 * i + 1];
-      const unsigned ev = (p00 & k) + (p01 & k) + (p10 & k) + (p11 & k) + 0x00020002u;
-      const unsigned od = ((p00 >> 8) & k) + ((p01 >> 8) & k) + ((p10 >> 8) & k) + ((p11 >> 8) & k) + 0x00020002u;
-      const unsigned avg = ((ev >> 2) & k) | (((od >> 2) & k) << 8);
-      u2 |= (((unsigned)dp4a_u8s8(avg, cu, 0x8080) >> 8) & 0xFF) << (8 * i);
-      v2 |= (((unsigned)dp4a_u8s8(avg, cv, 0x8080) >> 8) & 0xFF) << (8 * i);
+    __syncwarp();
+    if (4 * lane < tw) {
+      const unsigned *pa = (const unsigned *)sr[0] + 3 * lane, *pb = (const unsigned *)sr[1] + 3 * lane;
+      const unsigned a0 = pa[0], a1 = pa[1], a2 = pa[2], b0 = pb[0], b1 = pb[1], b2 = pb[2];
+      unsigned wa[4], wb[4];
+      wa[0] = a0; wa[1] = __byte_perm(a0, a1, 0x0543); wa[2] = __byte_perm(a1, a2, 0x0432); wa[3] = a2 >> 8;
+      wb[0] = b0; wb[1] = __byte_perm(b0, b1, 0x0543); wb[2] = __byte_perm(b1, b2, 0x0432); wb[3] = b2 >> 8;
+      rgb_quads_to_i420(wa, wb, ro, go, bo, out + (size_t)f * fout, ysz, w, rp, (x0 >> 2) + lane);
     }
-    uint8_t *fy = out + (size_t)f * fout;
-    size_t yoff = (size_t)(2 * rp) * w + 4 * g;
-    *(unsigned *)(fy + yoff) = ya;
-    *(unsigned *)(fy + yoff + w) = yb;
-    size_t coff = (size_t)rp * (w >> 1) + 2 * g;
-    *(unsigned short *)(fy + ysz + coff) = (unsigned short)u2;
-    *(unsigned short *)(fy + ysz + (ysz >> 2) + coff) = (unsigned short)v2;
   }
 }
 
@@ -622,7 +679,10 @@ int b200_convert_to_i420_dev(const uint8_t *d_src, uint8_t *d_dst, int w, int h,
     else                  k_planar_to_i420_v16<2><<<grid_for(items), kThreads, 0, s>>>(d_src, d_dst, w, h, n);
   } else if (fi.fmt == 5 && (w & 3) == 0 && al) {
     size_t items = (size_t)(w >> 2) * (h >> 1) * n;
+    const size_t tiles24 = (size_t)((w + kRgb24TilePx - 1) / kRgb24TilePx) * (h >> 1) * n;
     if (fi.bpp == 4) k_rgb_to_i420_v4<4><<<grid_for(items), kThreads, 0, s>>>(d_src, d_dst, w, h, n, fi.ro, fi.go, fi.bo);
+    else if ((w & 15) == 0 && tiles24 < 0x7fffffffull)
+      k_rgb24_to_i420_staged<<<grid_for(tiles24 * 32), kThreads, 0, s>>>(d_src, d_dst, w, h, n, fi.ro, fi.go, fi.bo);
     else             k_rgb_to_i420_v4<3><<<grid_for(items), kThreads, 0, s>>>(d_src, d_dst, w, h, n, fi.ro, fi.go, fi.bo);
   } else {
     size_t items = (size_t)(w >> 1) * (h >> 1) * n;
