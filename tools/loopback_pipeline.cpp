@@ -22,6 +22,7 @@ struct Sink {
   std::mutex m;
   uint64_t hash = 1469598103934665603ull;
   int pictures = 0;
+  std::chrono::steady_clock::time_point last;          // when the newest picture arrived
   FILE *dump = nullptr;                                // B200_LOOPBACK_DUMP: the pictures themselves, for the parity test
   void take(std::unique_ptr<Data> d)
   {
@@ -29,6 +30,7 @@ struct Sink {
     for (uint32_t i = 0; i < d->data_size; i++) { hash ^= d->data[i]; hash *= 1099511628211ull; }
     if (dump) fwrite(d->data.get(), 1, d->data_size, dump);
     pictures++;
+    last = std::chrono::steady_clock::now();
   }
 };
 
@@ -83,12 +85,14 @@ int main(int argc, char **argv)
     d->vInfo.reset(new VideoInfo);
     d->vInfo->width = (int16_t)w; d->vInfo->height = (int16_t)h; d->vInfo->framerateNumerator = 30; d->vInfo->framerateDenominator = 1;
     // unpaced: do not outrun the bounded queues (a camera never does), or the drop policy kicks in
-    while (pace <= 0 && (conv->buffered() > 4 || enc->buffered() > 4)) std::this_thread::sleep_for(std::chrono::microseconds(50));
+    while (pace <= 0 && (conv->buffered() > 4 || enc->buffered() > 4 || rtp->buffered() > 4 || dec->buffered() > 4 ||
+                         disp->buffered() > 4 || self->buffered() > 4))
+      std::this_thread::sleep_for(std::chrono::microseconds(50));
     conv->putInput(std::move(d));
   }
   for (int spin = 0; spin < 20000 && (display.pictures < frames || selfview.pictures < frames); spin++)
     std::this_thread::sleep_for(std::chrono::milliseconds(1));
-  const double dt = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
+  const double dt = std::chrono::duration<double>(std::max(display.last, selfview.last) - t0).count();
   const uint32_t dropped = conv->inputDiscarded() + enc->inputDiscarded() + dec->inputDiscarded() + disp->inputDiscarded() + self->inputDiscarded();
   for (auto &flt : std::vector<std::shared_ptr<Filter>>{conv, enc, rtp, dec, disp, self}) flt->stop();
   if (display.dump) fclose(display.dump);
