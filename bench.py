@@ -506,7 +506,8 @@ def qp_sweep(d_frames, opts):
 def oracle_options(opts):
     """The oracle port runs the same algorithm as the engine options of the preset."""
     return {"search_range": opts["search_range"], "me_coarse": opts["me_coarse"], "sao": opts["sao"],
-            "intra_in_p": opts["intra_in_p"], "intra_satd": opts.get("intra_satd", 0), "fps_num": 30, "fps_den": 1}
+            "intra_in_p": opts["intra_in_p"], "intra_satd": opts.get("intra_satd", 0),
+            "subme_satd": opts.get("subme_satd", 0), "fps_num": 30, "fps_den": 1}
 
 
 def cpu_baseline_sample(frames, opts, max_seconds, threads):

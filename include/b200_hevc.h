@@ -44,10 +44,11 @@ typedef struct b200_enc_params {
                                     searched around the zero vector and around each 32x32 block's coarse vector */
   int intra_satd;                /* I pictures: the 35-mode intra search compares the Hadamard SATD of the residual
                                     (8x8 tiles) instead of its SAD */
+  int subme_satd;                /* P pictures: the half- / quarter-sample motion refinement compares SATD instead of SAD */
 } b200_enc_params;
 void  b200_enc_params_default(b200_enc_params *p);
 void *b200_enc_open_params(const b200_enc_params *p);
-/* Fills search_range, me_coarse, sao, intra_in_p and intra_satd with what the kvz_api preset of that name selects
+/* Fills search_range, me_coarse, sao, intra_in_p, intra_satd and subme_satd with what the kvz_api preset of that name selects
  * ("ultrafast" ... "placebo"); the other fields are left alone.  0 on success. */
 int   b200_enc_params_from_preset(const char *preset, b200_enc_params *p);
 /* Per-CTU QP offsets (raster, one int8 per 64x64 CTU, n = CTU count) for the pictures submitted
@@ -98,6 +99,7 @@ typedef struct b200_tiled_params {
   int intra_in_p;                /* intra CUs in P pictures */
   int me_coarse;                 /* two-level motion search (see b200_enc_params) */
   int intra_satd;                /* SATD-based intra mode search in I pictures (see b200_enc_params) */
+  int subme_satd;                /* SATD-based fractional motion refinement (see b200_enc_params) */
 } b200_tiled_params;
 void  b200_tiled_params_default(b200_tiled_params *p);
 void *b200_tiled_open_params(const b200_tiled_params *p, const int *devices, int n_devices);

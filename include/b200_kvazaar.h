@@ -77,6 +77,7 @@ typedef struct kvz_config {
   int32_t gop_lowdelay, gop_len;         /* "gop lp-g4d3t1": low-delay P is the only structure */
   int32_t me_range;                      /* full-sample search window around each centre, from "preset" or "b200-me-range" */
   int32_t me_coarse;                     /* range of the coarse search level (4x4-mean samples), "preset" or "b200-me-coarse" */
+  int32_t subme_satd;                    /* SATD instead of SAD in the fractional motion refinement, from "preset" or "b200-subme-satd" */
   int32_t intra_satd;                    /* SATD instead of SAD in the intra mode search of I pictures, from "preset" or "b200-intra-satd" */
   int32_t return_recon;                  /* "b200-recon": 1 = encoder_encode also returns the reconstruction */
   int32_t device;                        /* "b200-device": CUDA device ordinal, -1 = current */

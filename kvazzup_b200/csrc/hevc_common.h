@@ -109,6 +109,7 @@ struct FrameParams {
   // the intra pass over a P picture without any returns at once; ctu_done: one flag per CTU for the
   // intra pass's wavefront (hevc_intra.cu).
   int intra_in_p;
+  int subme_satd;       // encoder, P pictures: the fractional motion refinement compares SATD instead of SAD (row K2)
   int intra_satd;       // encoder, I pictures: the 35-mode search compares Hadamard SATD instead of SAD (row K2)
   int *any_intra;
   int *ctu_done;

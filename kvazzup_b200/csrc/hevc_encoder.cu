@@ -372,7 +372,7 @@ bool Encoder::submit(FrameSlot &s, const uint8_t *d_i420)
   // with SAO the prediction chain reconstructs and deblocks into the slot's own picture; SAO reads it
   // (a CTU needs its neighbours' DEBLOCKED samples) and writes the reconstruction ring
   uint8_t *rec = cfg.sao ? s.d_dbk : out_rec;
-  p.ctu_done = s.d_ctu_done; p.any_intra = s.d_ctu_done + fp.ctb_cols * fp.ctb_rows; p.intra_in_p = cfg.intra_in_p; p.intra_satd = cfg.intra_satd;
+  p.ctu_done = s.d_ctu_done; p.any_intra = s.d_ctu_done + fp.ctb_cols * fp.ctb_rows; p.intra_in_p = cfg.intra_in_p; p.intra_satd = cfg.intra_satd; p.subme_satd = cfg.subme_satd;
   p.init_type = idr ? 0 : 1; p.tr_depth_inter = 0; p.tr_depth_intra = 0;
   p.n_refs = 1; p.max_merge = kMaxMerge; p.ref_dist[0] = 1; p.col_mvf = nullptr;
   p.me_stats = profile ? d_me_stats : nullptr;
@@ -629,7 +629,7 @@ void *b200_enc_open_params(const b200_enc_params *up)
   c.width = p.width; c.height = p.height; c.qp = p.qp; c.intra_period = p.intra_period; c.search_range = p.search_range;
   c.deblock = p.deblock; c.debug = p.debug; c.depth = p.depth; c.qp_delta = p.qp_delta;
   c.fps_num = p.fps_num; c.fps_den = p.fps_den; c.sao = p.sao; c.intra_in_p = p.intra_in_p; c.me_coarse = p.me_coarse;
-  c.intra_satd = p.intra_satd;
+  c.intra_satd = p.intra_satd; c.subme_satd = p.subme_satd;
   if (!e->open(c)) { delete e; return nullptr; }
   return e;
 }

@@ -30,6 +30,7 @@ struct EncoderConfig {
   int sao = 0;               // sample adaptive offset after deblocking (hevc_sao.cu); 2 = with merge flags
   int intra_in_p = 0;        // 16x16 intra CUs in P pictures where inter prediction is poor
   int intra_satd = 0;        // I pictures: SATD instead of SAD in the intra mode search
+  int subme_satd = 0;        // P pictures: SATD instead of SAD in the fractional motion refinement
   int me_coarse = 0;         // two-level motion search: range of the coarse level in coarse (4x4-mean) samples,
                              // a multiple of 4; search_range (<= 16) is then the window around each centre
   int depth = 1;             // pictures in flight (Kvazaar's owf + 1): output of picture n is

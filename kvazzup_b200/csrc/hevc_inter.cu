@@ -33,7 +33,8 @@ struct MeShared {
   short mvx[64], mvy[64];          // per origin unit: best mv so far (quarter samples)
   short cmx[64], cmy[64];          // per origin unit: centre of the current refinement step
   unsigned best[64];               // per origin unit: best cost so far
-  unsigned acc8[64][8];            // per origin unit: SAD accumulators of the eight candidates of a step
+  unsigned acc8[64][8];            // per origin unit: SAD (or SATD) accumulators of the eight candidates of a step
+  unsigned acc_c[64];              // kSatd: SATD at the centre of the first step (the full-sample vector)
   unsigned short pen[65 * 65];     // mv penalty of every full-sample candidate (index = (dy+R)*side + dx+R)
   // intra candidates of a P picture (fp.intra_in_p): per 16x16 block (z-order) "try it" / chosen mode
   // (-1 = stays inter); per 8x8 unit: intra mode + 1 of the intra CU covering it (0 = inter)
@@ -76,7 +77,13 @@ k_down4(const uint8_t *__restrict__ plane, int w, int h, uint8_t *__restrict__ o
 // quarter-resolution pictures (+-me_coarse coarse samples = 4 * me_coarse luma samples), searched on
 // a window of the quadrant's own; skipped where it is the zero vector again.  Around every centre
 // the same +-R window is searched and the mv penalty counts from the centre.
-__global__ void __launch_bounds__(kThreads, 4)     // <= 64 registers: four CTAs per SM hold the 510 CTUs of a 1080p picture in one wave
+//
+// kSatd (fp.subme_satd): the fractional refinement compares the Hadamard SATD of the
+// residual, 8x8 tiles with (sum |h| + 2) >> 2 each as oracle/hevc_prims.c orc_satd, instead of the SAD.  The
+// four threads of a unit hold two columns x eight rows each: the first horizontal butterfly and the eight-point
+// vertical transform are in registers, the other two horizontal stages are shuffles among the four lanes.
+template <bool kSatd>
+__global__ void __launch_bounds__(kThreads, kSatd ? 3 : 4)     // SAD: <= 64 registers, four CTAs per SM hold the 510 CTUs of a 1080p picture in one wave
 k_me_ctu(FrameParams fp, const uint8_t *__restrict__ src, const uint8_t *__restrict__ ref, CuInfo *__restrict__ cu)
 {
   extern __shared__ uint32_t s_dyn[];
@@ -100,7 +107,7 @@ k_me_ctu(FrameParams fp, const uint8_t *__restrict__ src, const uint8_t *__restr
     int y = cy + (i >> 4), x = cx + 4 * (i & 15);
     s_src[i] = (y < fp.h && x < fp.w) ? __ldg((const uint32_t *)(src + (size_t)y * fp.w + x)) : 0u;
   }
-  if (t < 64) { sh.key8[t] = 0xffffffffu; for (int k = 0; k < 8; k++) sh.acc8[t][k] = 0; }
+  if (t < 64) { sh.key8[t] = 0xffffffffu; sh.acc_c[t] = 0; for (int k = 0; k < 8; k++) sh.acc8[t][k] = 0; }
   for (int c = t; c < side * side; c += kThreads) {
     int dy = c / side - R, dx = c - (dy + R) * side - R;
     sh.pen[c] = (unsigned short)mv_penalty(lambda_q4, dx * 4, dy * 4);
@@ -351,24 +358,58 @@ k_me_ctu(FrameParams fp, const uint8_t *__restrict__ src, const uint8_t *__restr
     const int wp = set ? WSWq : WSW;
     // window coordinates of the unit for a zero vector
     const int wx0 = M + (set ? (ux & 3) * 8 - sh.ctr_x[qd] : ux * 8) + 2 * qc, wy0 = M + (set ? (uy & 3) * 8 - sh.ctr_y[qd] : uy * 8);
+    const unsigned live = __ballot_sync(0xffffffffu, org != 0xff);      // the four lanes of a unit are in or out together
     for (int step = 2; step >= 1; step--) {
       if (org != 0xff) {
         const int cmx = sh.cmx[org], cmy = sh.cmy[org];
-        for (int k = 0; k < 8; k++) {
-          const int ox = (k < 3 ? k - 1 : (k == 3 ? -1 : (k == 4 ? 1 : k - 6)));
-          const int oy = k < 3 ? -1 : (k < 5 ? 0 : 1);
+        for (int k = 0; k < ((kSatd && step == 2) ? 9 : 8); k++) {          // kSatd: candidate 8 of the first step = the centre itself
+          const int ox = k == 8 ? 0 : (k < 3 ? k - 1 : (k == 3 ? -1 : (k == 4 ? 1 : k - 6)));
+          const int oy = k == 8 ? 0 : (k < 3 ? -1 : (k < 5 ? 0 : 1));
           const int mx = cmx + ox * step, my = cmy + oy * step;
           unsigned pr[8];
           mc_luma_2x8(wbase, wp, wx0 + (mx >> 2), wy0 + (my >> 2), mx & 3, my & 3, pr);
-          unsigned sad = 0;
+          if (!kSatd) {
+            unsigned sad = 0;
 #pragma unroll
-          for (int r = 0; r < 8; r++) sad = sad4_acc(sv[r], pr[r], sad);
-          atomicAdd(&sh.acc8[org][k], sad);
+            for (int r = 0; r < 8; r++) sad = sad4_acc(sv[r], pr[r], sad);
+            atomicAdd(&sh.acc8[org][k], sad);
+          } else {
+            int a[8], b[8];
+#pragma unroll
+            for (int r = 0; r < 8; r++) {
+              const int d0 = (int)(sv[r] & 0xff) - (int)(pr[r] & 0xff), d1 = (int)(sv[r] >> 8) - (int)(pr[r] >> 8);
+              a[r] = d0 + d1; b[r] = d0 - d1;
+            }
+#pragma unroll
+            for (int len = 1; len < 8; len <<= 1)
+#pragma unroll
+              for (int i = 0; i < 8; i += 2 * len)
+#pragma unroll
+                for (int j = i; j < i + len; j++) {
+                  const int ua = a[j], va = a[j + len], ub = b[j], vb = b[j + len];
+                  a[j] = ua + va; a[j + len] = ua - va; b[j] = ub + vb; b[j + len] = ub - vb;
+                }
+            unsigned sum = 0;
+#pragma unroll
+            for (int r = 0; r < 8; r++) {
+#pragma unroll
+              for (int m = 1; m <= 2; m <<= 1) {
+                const int oa = __shfl_xor_sync(live, a[r], m), ob = __shfl_xor_sync(live, b[r], m);
+                a[r] = (qc & m) ? oa - a[r] : a[r] + oa;
+                b[r] = (qc & m) ? ob - b[r] : b[r] + ob;
+              }
+              sum += (unsigned)(abs(a[r]) + abs(b[r]));
+            }
+            sum += __shfl_xor_sync(live, sum, 1);
+            sum += __shfl_xor_sync(live, sum, 2);
+            if (qc == 0) atomicAdd(k == 8 ? &sh.acc_c[org] : &sh.acc8[org][k], (sum + 2) >> 2);
+          }
         }
       }
       __syncthreads();
       if (t < 64 && sh.org[t] == t) {
         const int pcx = sh.wset[t] ? 4 * sh.ctr_x[t >> 4] : 0, pcy = sh.wset[t] ? 4 * sh.ctr_y[t >> 4] : 0;
+        if (kSatd && step == 2) sh.best[t] = sh.acc_c[t] + mv_penalty(lambda_q4, sh.cmx[t] - pcx, sh.cmy[t] - pcy);
         for (int k = 0; k < 8; k++) {
           const int ox = (k < 3 ? k - 1 : (k == 3 ? -1 : (k == 4 ? 1 : k - 6)));
           const int oy = k < 3 ? -1 : (k < 5 ? 0 : 1);
@@ -680,7 +721,8 @@ constexpr int kMaxDynSmem = 200 * 1024;
 static void allow_big_smem()
 {
   static const bool once = [] {
-    cudaFuncSetAttribute(k_me_ctu, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxDynSmem);
+    cudaFuncSetAttribute(k_me_ctu<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxDynSmem);
+    cudaFuncSetAttribute(k_me_ctu<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxDynSmem);
     cudaFuncSetAttribute(k_inter_recon<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxDynSmem);
     cudaFuncSetAttribute(k_inter_recon<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxDynSmem);
     return true;
@@ -693,7 +735,8 @@ cudaError_t launch_inter_me(const FrameParams &fp, const uint8_t *src, const uin
   if (fp.me_coarse < 0 || (fp.me_coarse & 3) || fp.me_coarse > 32 || (fp.me_coarse > 0 && fp.search_range > 16)) return cudaErrorInvalidValue;
   size_t sm = me_smem(fp.search_range, fp.me_coarse);
   allow_big_smem();
-  k_me_ctu<<<fp.ctb_cols * fp.ctb_rows, kThreads, sm, s>>>(fp, src, ref, cu);
+  if (fp.subme_satd) k_me_ctu<true><<<fp.ctb_cols * fp.ctb_rows, kThreads, sm, s>>>(fp, src, ref, cu);
+  else k_me_ctu<false><<<fp.ctb_cols * fp.ctb_rows, kThreads, sm, s>>>(fp, src, ref, cu);
   return cudaGetLastError();
 }
 

@@ -22,17 +22,17 @@ class EncParams(C.Structure):
     """b200_enc_params (include/b200_hevc.h)."""
     _fields_ = [(n, C.c_int) for n in ("struct_size", "width", "height", "qp", "intra_period", "search_range", "deblock",
                                        "debug", "depth", "qp_delta", "fps_num", "fps_den", "sao", "intra_in_p", "me_coarse",
-                                       "intra_satd")]
+                                       "intra_satd", "subme_satd")]
 
 
 def preset_options(preset: str) -> dict:
-    """Engine options (search_range, me_coarse, sao, intra_in_p, intra_satd) the kvz_api preset of that name selects."""
+    """Engine options (search_range, me_coarse, sao, intra_in_p, intra_satd, subme_satd) the kvz_api preset of that name selects."""
     p = EncParams()
     lib().b200_enc_params_default(C.byref(p))
     if lib().b200_enc_params_from_preset(preset.encode(), C.byref(p)) != 0:
         raise B200Error("unknown preset " + preset)
     return {"search_range": p.search_range, "me_coarse": p.me_coarse, "sao": p.sao, "intra_in_p": p.intra_in_p,
-            "intra_satd": p.intra_satd}
+            "intra_satd": p.intra_satd, "subme_satd": p.subme_satd}
 
 
 class GpuEncoder:
@@ -155,7 +155,7 @@ class TiledParams(C.Structure):
     """b200_tiled_params (include/b200_hevc.h)."""
     _fields_ = [(n, C.c_int) for n in ("struct_size", "width", "height", "qp", "intra_period", "search_range", "deblock",
                                        "depth", "tile_cols", "wpp", "fps_num", "fps_den", "sao", "intra_in_p", "me_coarse",
-                                       "intra_satd")]
+                                       "intra_satd", "subme_satd")]
 
 
 class GpuTiledEncoder:

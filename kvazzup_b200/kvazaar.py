@@ -29,7 +29,7 @@ class KvzConfig(C.Structure):
         "width", "height", "framerate_num", "framerate_denom", "qp", "intra_period", "vps_period", "wpp", "owf",
         "threads", "target_bitrate", "rc_algorithm", "lossless", "mv_constraint", "set_qp_in_cu", "hash",
         "deblock_enable", "sao_type", "tiles_width_count", "tiles_height_count", "slices", "vaq", "scaling_list",
-        "gop_lowdelay", "gop_len", "me_range", "me_coarse", "intra_satd", "return_recon", "device", "roi_enable")] + [("preset", C.c_char * 16)]
+        "gop_lowdelay", "gop_len", "me_range", "me_coarse", "subme_satd", "intra_satd", "return_recon", "device", "roi_enable")] + [("preset", C.c_char * 16)]
 
 
 class KvzRoi(C.Structure):

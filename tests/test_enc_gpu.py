@@ -83,6 +83,13 @@ CASES = [
     ("screen", 640, 480, 3, 32, {"intra_satd": 1, "intra_period": 2, "sao": 2}),
     ("sports", 416, 240, 5, 32, {"intra_satd": 1, "intra_in_p": 1, "me_coarse": 16, "search_range": 4, "intra_period": 3}),
     ("camera", 64, 8, 2, 37, {"intra_satd": 1}),
+    # SATD in the fractional motion refinement (row K2)
+    ("camera", 192, 136, 4, 30, {"subme_satd": 1}),
+    ("sports", 416, 240, 5, 32, {"subme_satd": 1, "intra_in_p": 1, "me_coarse": 16, "search_range": 4}),
+    ("noise", 128, 72, 3, 27, {"subme_satd": 1}),
+    ("screen", 640, 480, 4, 32, {"subme_satd": 1, "intra_satd": 1, "sao": 2, "me_coarse": 16, "search_range": 6, "intra_in_p": 1}),
+    ("camera", 64, 8, 3, 37, {"subme_satd": 1}),
+    ("camera", 1280, 720, 3, 27, {"subme_satd": 1, "intra_satd": 1, "sao": 2, "me_coarse": 32, "search_range": 12, "intra_in_p": 1}),
 ]
 
 
@@ -179,8 +186,9 @@ def test_kvazaar_filter_default_settings_stream_equals_engine_and_decodes():
         aus += got
     f.close()
     from kvazzup_b200.encoder import preset_options
-    assert preset_options("ultrafast") == {"search_range": 4, "me_coarse": 16, "sao": 0, "intra_in_p": 1, "intra_satd": 0}
-    assert preset_options("veryfast") == {"search_range": 6, "me_coarse": 16, "sao": 2, "intra_in_p": 1, "intra_satd": 1}
+    assert preset_options("ultrafast") == {"search_range": 4, "me_coarse": 16, "sao": 0, "intra_in_p": 1, "intra_satd": 0, "subme_satd": 0}
+    assert preset_options("veryfast") == {"search_range": 6, "me_coarse": 16, "sao": 2, "intra_in_p": 1, "intra_satd": 1, "subme_satd": 0}
+    assert preset_options("medium") == {"search_range": 12, "me_coarse": 32, "sao": 2, "intra_in_p": 1, "intra_satd": 1, "subme_satd": 1}
     o = OracleEncoder(w, h, qp=32, intra_period=64, fps_num=30, fps_den=1, **preset_options("ultrafast"))    # "input-fps" -> VUI timing
     assert aus == [o.encode(fr) for fr in frames]
     if ffhevc.required():
