@@ -41,7 +41,7 @@ import numpy as np  # noqa: E402
 W, H = 1920, 1080
 GOP = 64
 QP = 27
-PRESET = "veryfast"
+PRESET = os.environ.get("B200_BENCH_PRESET", "veryfast")      # the headline is veryfast (BASELINE configs[1]); others for comparison
 DEPTH = 96                         # pictures in flight (owf = 95): an IDR's serial entropy coding overlaps the next GOP's prediction chain
 KERNELS = ("intra", "me", "recon", "modes", "deblock", "sao", "binarise", "arith", "pack")
 CHAIN = ("me", "recon", "modes", "deblock", "sao")     # the P-picture prediction chain: what one picture must wait for
@@ -378,7 +378,7 @@ def run_b200(args):
         "metric": "1080p HEVC encode fps", "value": round(value, 2), "unit": "frames/s", "n_gpus": world,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": round(elapsed / args.steps * 1e3, 3),
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u8", "data": "synthetic",
-        "config": {"workload": "1080p30 veryfast low-delay-P QP27, GOP 64, one stream per GPU (BASELINE configs[1])",
+        "config": {"workload": f"1080p30 {PRESET} low-delay-P QP27, GOP 64, one stream per GPU (BASELINE configs[1])",
                    "width": W, "height": H, "qp": QP, "preset": PRESET, "gop": GOP, **opts,
                    "frames_per_step": GOP, "pictures_in_flight": DEPTH, "streams": world,
                    "l2_policy": "inputs larger than L2: 64 distinct 3.1 MB pictures (199 MB) cycled per step",
