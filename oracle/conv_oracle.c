@@ -158,11 +158,12 @@ static void packed422_to_i420(const uint8_t *s, int yoff, int uoff, int voff,
  * rotation 0 (the only way the reference calls it,
  * /root/reference/src/media/processing/libyuvconverter.cpp:120-127).
  * Returns 0 on success, -1 for an unsupported fourcc (output untouched). */
+int oracle_mjpg_to_i420(const uint8_t *sample, size_t sample_size, uint8_t *y, int sy, uint8_t *u, int su, uint8_t *v, int sv, int w, int h);
+
 int oracle_convert_to_i420(const uint8_t *sample, size_t sample_size,
                            uint8_t *y, int sy, uint8_t *u, int su, uint8_t *v, int sv,
                            int w, int h, uint32_t fourcc)
 {
-  (void)sample_size;
   int hw = (w + 1) / 2, hh = (h + 1) / 2;
   if (!sample || !y || !u || !v || w <= 0 || h <= 0) return -1;
   switch (fourcc) {
@@ -214,9 +215,9 @@ int oracle_convert_to_i420(const uint8_t *sample, size_t sample_size,
   case ORC_FOURCC_RGBA: rgb_to_i420(sample, 4, 3, 2, 1, y, sy, u, su, v, sv, w, h); return 0; /* mem A,B,G,R */
   case ORC_FOURCC_24BG: rgb_to_i420(sample, 3, 2, 1, 0, y, sy, u, su, v, sv, w, h); return 0; /* mem B,G,R */
   case ORC_FOURCC_RAW:  rgb_to_i420(sample, 3, 0, 1, 2, y, sy, u, su, v, sv, w, h); return 0; /* mem R,G,B */
+  case ORC_FOURCC_MJPG: return oracle_mjpg_to_i420(sample, sample_size, y, sy, u, su, v, sv, w, h);   /* mjpg_oracle.c */
   default:
-    /* includes the literal `2` the reference passes for DT_RGB24VIDEO
-     * (libyuvconverter.cpp:84) and MJPG (no JPEG decoder in this build). */
+    /* includes the literal `2` the reference passes for DT_RGB24VIDEO (libyuvconverter.cpp:84) */
     return -1;
   }
 }

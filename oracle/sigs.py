@@ -9,6 +9,8 @@ SIGS = {
     "oracle_half_rgb": (None, [v, v, i, i]),
     "oracle_flip_rgb": (None, [v, v, i, i, i, i]),
     "oracle_convert_to_i420": (i, [v, C.c_size_t, v, i, v, i, v, i, i, i, C.c_uint32]),
+    "oracle_mjpg_to_i420": (i, [v, C.c_size_t, v, i, v, i, v, i, i, i]),
+    "oracle_mjpg_planes": (i, [v, C.c_size_t, v, v, v, v, v]),
 }
 
 
