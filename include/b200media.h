@@ -113,6 +113,13 @@ int b200_selfview_dev(const uint8_t *d_i420, uint8_t *d_out, int width, int heig
                       int horizontally, int vertically, int n_frames, void *stream);
 int b200_convert_to_i420_dev(const uint8_t *d_src, uint8_t *d_i420, int width, int height,
                              uint32_t fourcc, int n_frames, void *stream);
+/* MJPG (the thirteenth format of LibYUVConverter, libyuvconverter.cpp:94): one baseline JPEG frame in HOST
+ * memory -> packed I420 in DEVICE memory (for b200_enc_encode_dev).  The Huffman-coded scan is read on the
+ * host (one serial bit stream per frame); dequantisation, libjpeg's accurate integer IDCT and the conversion
+ * of 4:2:2 / 4:4:4 / 4:0:0 to 4:2:0 (libyuv's rules) run on the GPU.  8-bit baseline frames with one
+ * interleaved scan, restart intervals, frames without DHT (the tables of T.81 Annex K).  The frame must be
+ * width x height (libyuv::MJPGToI420 fails otherwise).  One stream per calling thread.  B200_OK or < 0. */
+int b200_mjpg_to_i420_dev(const uint8_t *jpeg, size_t jpeg_bytes, uint8_t *d_i420, int width, int height, void *stream);
 
 #ifdef __cplusplus
 }

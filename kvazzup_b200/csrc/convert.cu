@@ -774,22 +774,31 @@ int b200_ConvertToI420(const uint8_t *sample, size_t sample_size,
                        int rotation, uint32_t fourcc)
 {
   FmtInfo fi = fmt_info(fourcc);
-  if (!fi.ok) { set_error("b200_ConvertToI420: unsupported fourcc 0x%08x", fourcc); return -1; }
+  const bool mjpg = fourcc == B200_FOURCC_MJPG;
+  if (!fi.ok && !mjpg) { set_error("b200_ConvertToI420: unsupported fourcc 0x%08x", fourcc); return -1; }
   if (!sample || !dst_y || !dst_u || !dst_v || src_w <= 0 || src_h <= 0) { set_error("b200_ConvertToI420: bad arguments"); return -1; }
   if (crop_x || crop_y || crop_w != src_w || crop_h != src_h || rotation != 0) {
     set_error("b200_ConvertToI420: crop/rotation not supported (the reference never uses them)");
     return -1;
   }
   if ((src_w & 1) || (src_h & 1)) { set_error("b200_ConvertToI420: odd dimensions not supported"); return -1; }
-  size_t need = b200_frame_bytes(fourcc, src_w, src_h);
+  size_t need = mjpg ? sample_size : b200_frame_bytes(fourcc, src_w, src_h);
+  if (mjpg && !sample_size) { set_error("b200_ConvertToI420: an MJPG sample needs its size"); return -1; }
   if (sample_size && sample_size < need) { set_error("b200_ConvertToI420: sample_size %zu < %zu", sample_size, need); return -1; }
   if (b200_device_count() <= 0) { set_error("no CUDA device: libb200media has no CPU fallback"); return B200_ERR_CUDA; }
   size_t ysz = (size_t)src_w * src_h, out_bytes = ysz + ysz / 2;
   Scratch &sc = scratch();
-  if (!sc.ensure(need, out_bytes)) return B200_ERR_CUDA;
-  memcpy(sc.h_in, sample, need);
-  B200_CHECK(cudaMemcpyAsync(sc.d_in, sc.h_in, need, cudaMemcpyHostToDevice, sc.stream), "H2D");
-  int rc = b200_convert_to_i420_dev(sc.d_in, sc.d_out, src_w, src_h, fourcc, 1, sc.stream);
+  if (!sc.ensure(mjpg ? 16 : need, out_bytes)) return B200_ERR_CUDA;
+  int rc;
+  if (mjpg) {
+    // the scan is read on the host straight from the caller's buffer; the GPU gets coefficients (mjpg.cu)
+    rc = b200_mjpg_to_i420_dev(sample, sample_size, sc.d_out, src_w, src_h, sc.stream);
+    if (rc != B200_OK) return -1;                       // libyuv::MJPGToI420 fails likewise: the output stays untouched
+  } else {
+    memcpy(sc.h_in, sample, need);
+    B200_CHECK(cudaMemcpyAsync(sc.d_in, sc.h_in, need, cudaMemcpyHostToDevice, sc.stream), "H2D");
+    rc = b200_convert_to_i420_dev(sc.d_in, sc.d_out, src_w, src_h, fourcc, 1, sc.stream);
+  }
   if (rc != B200_OK) return rc;
   B200_CHECK(cudaMemcpyAsync(sc.h_out, sc.d_out, out_bytes, cudaMemcpyDeviceToHost, sc.stream), "D2H");
   B200_CHECK(cudaStreamSynchronize(sc.stream), "sync");

@@ -138,3 +138,68 @@ def test_fused_selfview_equals_the_three_stage_chain(oracle_lib, wh):
                 oracle_lib.oracle_flip_rgb(ptr(stage), ptr(exp), ow, oh, hor, ver)
             got = convert.selfview(i420, w, h, bool(half), bool(hor), bool(ver))
             assert np.array_equal(got, exp), (half, hor, ver)
+
+
+# ---- MJPG, the thirteenth camera format (libyuvconverter.cpp:94) ---------------------------------
+
+def test_mjpg_committed_frames_equal_the_oracle_and_their_golden_hashes(oracle_lib):
+    from tests import mjpg_util
+    gold = json.loads((Path(__file__).parent / "golden" / "mjpg_golden.json").read_text())
+    for name, e in gold["frames"].items():
+        jpeg = np.frombuffer((Path(__file__).parent / "golden" / name).read_bytes(), np.uint8)
+        rc, got = convert.convert_to_i420(jpeg, e["w"], e["h"], FOURCC["MJPG"])
+        assert rc == 0, name
+        assert np.array_equal(got, mjpg_util.oracle_mjpg_to_i420(oracle_lib, jpeg.tobytes(), e["w"], e["h"])[1]), name
+        assert hashlib.sha256(got.tobytes()).hexdigest() == e["i420_sha256"], name
+
+
+@pytest.mark.parametrize("w,h,q,sampling,restart,kind", [
+    (640, 480, 75, "422", 0, "camera"), (640, 480, 50, "420", 0, "camera"), (200, 136, 95, "444", 0, "camera"),
+    (640, 480, 30, "422", 4, "camera"), (72, 40, 100, "422", 0, "noise"), (1280, 720, 85, "422", 0, "camera"),
+    (1920, 1080, 90, "420", 0, "camera"), (1920, 1080, 60, "422", 16, "noise"), (8, 8, 90, "444", 0, "noise"),
+    (24, 16, 80, "420", 0, "noise"), (416, 240, 100, "444", 5, "noise"),
+])
+def test_mjpg_to_i420_bit_exact(oracle_lib, w, h, q, sampling, restart, kind):
+    from tests import mjpg_util
+    if not mjpg_util.have_cv2():
+        pytest.skip("cv2 (JPEG encoder for the test frames) not present")
+    jpeg = mjpg_util.make_jpeg(w, h, q, sampling, restart, kind)
+    rc_o, exp = mjpg_util.oracle_mjpg_to_i420(oracle_lib, jpeg, w, h)
+    rc, got = convert.convert_to_i420(np.frombuffer(jpeg, np.uint8), w, h, FOURCC["MJPG"])
+    assert rc == rc_o == 0
+    bad = np.flatnonzero(got != exp)
+    assert bad.size == 0, f"{bad.size} samples differ, first at {bad[:8]}"
+
+
+def test_mjpg_grey_no_dht_and_rejections(oracle_lib):
+    from tests import mjpg_util
+    if not mjpg_util.have_cv2():
+        pytest.skip("cv2 not present")
+    w, h = 160, 120
+    for jpeg in (mjpg_util.make_jpeg(w, h, 80, grey=True), mjpg_util.strip_dht(mjpg_util.make_jpeg(w, h, 70, "422"))):
+        rc, got = convert.convert_to_i420(np.frombuffer(jpeg, np.uint8), w, h, FOURCC["MJPG"])
+        assert rc == 0 and np.array_equal(got, mjpg_util.oracle_mjpg_to_i420(oracle_lib, jpeg, w, h)[1])
+    jpeg = mjpg_util.make_jpeg(w, h, 80, "422")
+    for bad, bw in ((jpeg, 2 * w), (b"\xff\xd8\xff\xd9", w), (jpeg[:200], w)):       # wrong size, no scan, cut inside the headers
+        rc, out = convert.convert_to_i420(np.frombuffer(bad, np.uint8), bw, h, FOURCC["MJPG"], fill=0xAA)
+        assert rc == -1 and (out == 0xAA).all()
+    # a frame cut inside the scan decodes (the rest is grey), as it does in the oracle: never a crash
+    cut = jpeg[:len(jpeg) // 2]
+    rc, got = convert.convert_to_i420(np.frombuffer(cut, np.uint8), w, h, FOURCC["MJPG"])
+    rc_o, exp = mjpg_util.oracle_mjpg_to_i420(oracle_lib, cut, w, h)
+    assert rc == rc_o and (rc != 0 or np.array_equal(got, exp))
+
+
+def test_mjpg_device_resident_output_feeds_the_encoder(oracle_lib):
+    from tests import mjpg_util
+    if not mjpg_util.have_cv2():
+        pytest.skip("cv2 not present")
+    from kvazzup_b200.capi import lib
+    import ctypes as C
+    w, h = 640, 480
+    jpeg = np.frombuffer(mjpg_util.make_jpeg(w, h, 85, "422"), np.uint8)
+    d_out = devmem.empty_u8(w * h * 3 // 2)
+    lib().b200_mjpg_to_i420_dev.argtypes = [C.c_void_p, C.c_size_t, C.c_void_p, C.c_int, C.c_int, C.c_void_p]
+    rc = lib().b200_mjpg_to_i420_dev(jpeg.ctypes.data, jpeg.size, d_out.data_ptr(), w, h, devmem.current_stream_ptr())
+    assert rc == 0
+    assert np.array_equal(d_out.cpu().numpy(), mjpg_util.oracle_mjpg_to_i420(oracle_lib, jpeg.tobytes(), w, h)[1])

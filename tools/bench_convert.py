@@ -63,6 +63,42 @@ def main():
     b = torch.empty(1 << 30, dtype=torch.uint8, device="cuda")
     t = time_it(lambda: b.copy_(a))
     rows.append(dict(kernel="torch_copy_1GiB", gbs=2 * (1 << 30) / t / 1e9, frac=2 * (1 << 30) / t / 1e9 / peak))
+    # MJPG: one frame per call (host JPEG -> device I420): Huffman decoding on the host, IDCT + resampling on the GPU
+    try:
+        import ctypes as C
+        import time as _t
+
+        import numpy as np
+
+        import oracle
+        from kvazzup_b200.capi import lib
+        from tests import mjpg_util
+        fn = lib().b200_mjpg_to_i420_dev
+        fn.argtypes = [C.c_void_p, C.c_size_t, C.c_void_p, C.c_int, C.c_int, C.c_void_p]
+        for (mw, mh, q) in ((640, 480, 80), (1280, 720, 80), (1920, 1080, 80)):
+            jpeg = np.frombuffer(mjpg_util.make_jpeg(mw, mh, q, "422"), np.uint8)
+            dst = torch.empty(mw * mh * 3 // 2, dtype=torch.uint8, device="cuda")
+            for _ in range(5):
+                fn(jpeg.ctypes.data, jpeg.size, dst.data_ptr(), mw, mh, s)
+            torch.cuda.synchronize()
+            t0 = _t.perf_counter()
+            iters = 100
+            for _ in range(iters):
+                fn(jpeg.ctypes.data, jpeg.size, dst.data_ptr(), mw, mh, s)
+            torch.cuda.synchronize()
+            dt = (_t.perf_counter() - t0) / iters
+            ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            fn(jpeg.ctypes.data, jpeg.size, dst.data_ptr(), mw, mh, s)
+            torch.cuda.synchronize()
+            # the oracle (one host core) on the same frame
+            t1 = _t.perf_counter()
+            for _ in range(5):
+                mjpg_util.oracle_mjpg_to_i420(oracle.load(), jpeg.tobytes(), mw, mh)
+            cpu = (_t.perf_counter() - t1) / 5
+            rows.append(dict(kernel="MJPG_to_i420 (4:2:2, quality %d, %d kB)" % (q, jpeg.size // 1000), w=mw, h=mh,
+                             us_per_frame=dt * 1e6, frames_per_s=1 / dt, cpu_oracle_us_per_frame=cpu * 1e6))
+    except Exception as e:                                  # cv2 (the test frames' encoder) missing
+        rows.append(dict(kernel="MJPG_to_i420", skipped=str(e)))
     for r in rows:
         print(json.dumps(r))
 
