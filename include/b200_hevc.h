@@ -100,6 +100,8 @@ typedef struct b200_tiled_params {
   int me_coarse;                 /* two-level motion search (see b200_enc_params) */
   int intra_satd;                /* SATD-based intra mode search in I pictures (see b200_enc_params) */
   int subme_satd;                /* SATD-based fractional motion refinement (see b200_enc_params) */
+  int tile_rows;                 /* uniform tile rows (default 1): tile_cols x tile_rows tiles in raster order; a tile
+                                    row may be a single CTU row high */
 } b200_tiled_params;
 void  b200_tiled_params_default(b200_tiled_params *p);
 void *b200_tiled_open_params(const b200_tiled_params *p, const int *devices, int n_devices);

@@ -70,7 +70,7 @@ typedef struct kvz_config {
   enum kvz_hash hash;
   int32_t deblock_enable;                /* "deblock" */
   int32_t sao_type;                      /* "sao": 0 off, != 0 edge + band offsets per CTU (hevc_sao.cu) */
-  int32_t tiles_width_count, tiles_height_count;   /* "tiles": "Cx1" tile columns (hevc_tiles.cu); tile rows are refused */
+  int32_t tiles_width_count, tiles_height_count;   /* "tiles": "CxR" uniform tile grid (hevc_tiles.cu) */
   int32_t slices;                        /* "slices" */
   int32_t vaq;                           /* "vaq": accepted, ignored */
   int32_t scaling_list;                  /* "scaling-list": only off (0) */

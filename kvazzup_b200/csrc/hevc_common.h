@@ -93,8 +93,8 @@ struct FrameParams {
   uint8_t *ctu_qp;
   int8_t *ctu_delta;
   uint8_t *ctu_first;
-  // Tile-column mode: this picture is one tile (a column strip) of a larger one, coded as a picture of
-  // its own.  mv_edges bit 0 / 1: the left / right edge is an interior tile edge, so no reference
+  // Tile mode: this picture is one tile of a larger one, coded as a picture of its own.  mv_edges bit
+  // 0 / 1 / 2 / 3: the left / right / top / bottom edge is an interior tile edge, so no reference
   // sample beyond it may be used (the neighbouring tile is there, not edge padding).  more_tiles:
   // tiles follow in the slice, the last CTU does not end the slice segment.  no_wpp: one substream
   // for the whole picture (entropy_coding_sync off; HEVC Main allows tiles or WPP, not both).

@@ -37,12 +37,12 @@ const uint8_t kChromaQpD[58] = {
 
 }  // namespace
 
-// A tile column is decoded as a picture of its own ("strip", see hevc_tiles.cu for why that is exact
-// when motion stays inside the tile and tiles are not loop-filtered across); a picture without
-// tiles is a single strip covering everything.  Per decoder: the strip's geometry, reconstruction
+// A tile (of a uniform grid of tile columns x tile rows) is decoded as a picture of its own ("strip", see
+// hevc_tiles.cu for why that is exact when motion stays inside the tile and tiles are not loop-filtered
+// across); a picture without tiles is a single strip covering everything.  Per decoder: the strip's geometry, reconstruction
 // ping-pong and reconstruction stream.
 struct StripGeom {
-  int x0 = 0, wd = 0;
+  int x0 = 0, y0 = 0, wd = 0, ht = 0;
   FrameParams fp{};                       // strip-sized
   size_t bytes = 0;                       // packed I420 of the strip
   // decoded picture buffer of the strip: kPool pictures (index shared by all strips of a picture), each
@@ -96,7 +96,7 @@ struct Decoder {
   cudaEvent_t ev_out = nullptr;           // the picture is in host memory (what libOpenHevcDecode waits for)
   std::vector<StripGeom> geom;
   uint8_t *d_full = nullptr;              // whole picture on the device when there are several strips
-  int conf_w = 0, conf_h = 0, conf_tiles = 0;
+  int conf_w = 0, conf_h = 0, conf_tiles = 0, conf_tile_cols = 0, conf_tile_rows = 0;
   std::vector<DecSlot> slots;
   std::deque<int> pending;                // slots whose parse was launched, oldest first
   size_t data_cap = 0, small_bytes = 0, off_flag = 0, off_prog = 0, off_ticket = 0, off_status = 0, off_bases = 0, off_ctx = 0;
@@ -156,13 +156,14 @@ struct Decoder {
     if (ev_out) cudaEventDestroy(ev_out);
     if (stream) cudaStreamDestroy(stream);
     d_full = nullptr; stream = nullptr; ev_out = nullptr;
-    next_slot = 0; out_slot = -1; conf_tiles = 0;
+    next_slot = 0; out_slot = -1; conf_tiles = 0; conf_tile_cols = 0; conf_tile_rows = 0;
   }
 
-  // (Re)allocate for a picture size and tile-column count; pictures in flight are dropped.
-  bool configure(int w, int h, int tiles)
+  // (Re)allocate for a picture size and tile grid; pictures in flight are dropped.
+  bool configure(int w, int h, int tile_cols, int tile_rows)
   {
     release();
+    const int tiles = tile_cols * tile_rows;
     fp = FrameParams{};
     fp.w = w; fp.h = h; fp.w8 = w / 8; fp.h8 = h / 8;
     fp.ctb_cols = (w + kCtb - 1) / kCtb; fp.ctb_rows = (h + kCtb - 1) / kCtb;
@@ -179,26 +180,31 @@ struct Decoder {
     geom.resize(tiles);
     for (int i = 0; i < tiles; i++) {
       StripGeom &g = geom[i];
-      const int c0 = i * fp.ctb_cols / tiles, c1 = (i + 1) * fp.ctb_cols / tiles;      // colBd, uniform spacing (6.5.1)
+      const int tc = i % tile_cols, tr = i / tile_cols;                                 // tiles in raster order
+      const int c0 = tc * fp.ctb_cols / tile_cols, c1 = (tc + 1) * fp.ctb_cols / tile_cols;   // colBd, uniform spacing (6.5.1)
+      const int r0 = tr * fp.ctb_rows / tile_rows, r1 = (tr + 1) * fp.ctb_rows / tile_rows;   // rowBd
       g.x0 = c0 * kCtb;
       g.wd = std::min(w, c1 * kCtb) - g.x0;
+      g.y0 = r0 * kCtb;
+      g.ht = std::min(h, r1 * kCtb) - g.y0;
       g.fp = fp;
       g.fp.w = g.wd; g.fp.w8 = g.wd / 8; g.fp.ctb_cols = c1 - c0;
-      g.fp.mv_edges = tiles > 1 ? ((i > 0 ? 1 : 0) | (i < tiles - 1 ? 2 : 0)) : 0;
+      g.fp.h = g.ht; g.fp.h8 = g.ht / 8; g.fp.ctb_rows = r1 - r0;
+      g.fp.mv_edges = (tc > 0 ? 1 : 0) | (tc < tile_cols - 1 ? 2 : 0) | (tr > 0 ? 4 : 0) | (tr < tile_rows - 1 ? 8 : 0);
       g.fp.more_tiles = i < tiles - 1 ? 1 : 0;
-      g.bytes = (size_t)g.wd * h * 3 / 2;
+      g.bytes = (size_t)g.wd * g.ht * 3 / 2;
       if (!cuda_ok(cudaStreamCreateWithFlags(&g.stream, cudaStreamNonBlocking), "cudaStreamCreate")) return false;
       if (!cuda_ok(cudaEventCreateWithFlags(&g.ev_done, cudaEventDisableTiming), "cudaEventCreate")) return false;
       for (int k = 0; k < kPool; k++) {
-        const size_t n16 = (size_t)((g.wd + 15) / 16) * ((h + 15) / 16);
+        const size_t n16 = (size_t)((g.wd + 15) / 16) * ((g.ht + 15) / 16);
         if (!cuda_ok(cudaMalloc((void **)&g.d_pic[k], g.bytes), "cudaMalloc")) return false;
         if (!cuda_ok(cudaMalloc((void **)&g.d_mvf[k], n16 * sizeof(MvField)), "cudaMalloc")) return false;
         if (!cuda_ok(cudaMemset(g.d_mvf[k], 0, n16 * sizeof(MvField)), "memset")) return false;
         if (!cuda_ok(cudaEventCreateWithFlags(&g.ev_mvf[k], cudaEventDisableTiming), "cudaEventCreate")) return false;
       }
       if (!cuda_ok(cudaMalloc((void **)&g.d_dbk, g.bytes), "cudaMalloc")) return false;
-      std::vector<int> order((size_t)g.fp.ctb_cols * rows);
-      intra_wavefront_order(g.fp.ctb_cols, rows, order.data());
+      std::vector<int> order((size_t)g.fp.ctb_cols * g.fp.ctb_rows);
+      intra_wavefront_order(g.fp.ctb_cols, g.fp.ctb_rows, order.data());
       if (!cuda_ok(cudaMalloc((void **)&g.d_order, order.size() * sizeof(int)), "cudaMalloc")) return false;
       if (!cuda_ok(cudaMemcpy(g.d_order, order.data(), order.size() * sizeof(int), cudaMemcpyHostToDevice), "H2D order")) return false;
     }
@@ -228,7 +234,7 @@ struct Decoder {
     }
     for (DpbEntry &d : dpb) d = DpbEntry();
     have_submitted = false;
-    conf_w = w; conf_h = h; conf_tiles = tiles;
+    conf_w = w; conf_h = h; conf_tiles = tiles; conf_tile_cols = tile_cols; conf_tile_rows = tile_rows;
     return true;
   }
 
@@ -273,10 +279,9 @@ struct Decoder {
     if (abs(p.cb_qp_offset + sh.cb_qp_offset) > 12 || abs(p.cr_qp_offset + sh.cr_qp_offset) > 12) return "chroma QP offsets out of range";
     if (p.transquant_bypass) return "transquant bypass is not supported";
     if (p.tiles) {
-      if (p.tile_rows != 1) return "tile rows are not supported (tile columns are)";
-      if (!p.uniform_spacing) return "only uniformly spaced tile columns are supported";
+      if (!p.uniform_spacing) return "only uniformly spaced tiles are supported";
       if (p.loop_filter_across_tiles) return "loop filtering across tiles is not supported";
-      if (p.tile_cols > 32) return "too many tile columns";
+      if (p.tile_cols > 32 || p.tile_rows > 32 || p.tile_cols * p.tile_rows > 64) return "too many tiles";
     }
     if (abs(sh.beta_offset_div2) > 6 || abs(sh.tc_offset_div2) > 6) return "deblocking offsets out of range";
     if (p.log2_parallel_merge_level != 2) return "parallel merge level > 2 is not supported";
@@ -382,17 +387,22 @@ struct Decoder {
     fr_num = sps.fps_num; fr_den = sps.fps_den;
     // geometry: picture size from the SPS, tile columns from the PPS (pictures in flight are dropped
     // when either changes)
-    if (conf_w != sps.width || conf_h != sps.height || conf_tiles != pps.tile_cols) {
-      const int ctb_cols = (sps.width + kCtb - 1) / kCtb;
+    if (conf_w != sps.width || conf_h != sps.height || conf_tile_cols != pps.tile_cols || conf_tile_rows != pps.tile_rows) {
+      const int ctb_cols = (sps.width + kCtb - 1) / kCtb, ctb_rows = (sps.height + kCtb - 1) / kCtb;
       if (pps.tile_cols > 1 && pps.tile_cols > ctb_cols / 2) { set_error("decoder: tile columns narrower than two CTUs are not supported"); return -1; }
-      if (!configure(sps.width, sps.height, pps.tile_cols)) return -1;
+      if (pps.tile_rows > ctb_rows) { set_error("decoder: more tile rows than CTU rows"); return -1; }
+      if (!configure(sps.width, sps.height, pps.tile_cols, pps.tile_rows)) return -1;
     }
     const int rows = fp.ctb_rows, tiles = conf_tiles;
-    const int per_tile = pps.wpp ? rows : 1;                  // substreams per tile
+    // substreams: one per CTU row of every tile with WPP, else one per tile
+    int n_sub = 0;
+    std::vector<int> first_sub(tiles + 1, 0);
+    for (int i = 0; i < tiles; i++) { first_sub[i] = n_sub; n_sub += pps.wpp ? geom[i].fp.ctb_rows : 1; }
+    first_sub[tiles] = n_sub;
     const int n_entry = (int)sh.entry.size();
     const std::vector<uint32_t> &entry = sh.entry;
-    if (n_entry != tiles * per_tile - 1) {
-      set_error("decoder: %d entry points for %d tile column(s) x %d substream(s)", n_entry, tiles, per_tile);
+    if (n_entry != n_sub - 1) {
+      set_error("decoder: %d entry points for %d tile(s) with %d substream(s)", n_entry, tiles, n_sub);
       return -1;
     }
     prev_poc = poc; prev_poc_lsb = idr ? 0 : sh.poc_lsb; prev_poc_msb = poc_msb; have_submitted = true;
@@ -413,16 +423,18 @@ struct Decoder {
     {
       size_t esc = hdr_esc;
       uint32_t prev = 0;
-      for (int k = 0; k < tiles * per_tile; k++) {
-        const uint32_t base = (uint32_t)(to_unesc(esc) - hdr_unesc);
-        if (base < prev || base > data_len) { set_error("decoder: entry points run past the slice data"); return -1; }
-        prev = base;
-        StripBufs &t = sl.strips[k / per_tile];
-        t.h_bases[k % per_tile] = base;
-        if (k % per_tile == 0 && k > 0) sl.strips[k / per_tile - 1].h_bases[per_tile] = base;
-        if (k < tiles * per_tile - 1) esc += entry[k];
+      for (int i = 0, k = 0; i < tiles; i++) {
+        const int per_tile = first_sub[i + 1] - first_sub[i];
+        for (int j = 0; j < per_tile; j++, k++) {
+          const uint32_t base = (uint32_t)(to_unesc(esc) - hdr_unesc);
+          if (base < prev || base > data_len) { set_error("decoder: entry points run past the slice data"); return -1; }
+          prev = base;
+          sl.strips[i].h_bases[j] = base;
+          if (j == 0 && i > 0) sl.strips[i - 1].h_bases[first_sub[i] - first_sub[i - 1]] = base;
+          if (k < n_sub - 1) esc += entry[k];
+        }
       }
-      sl.strips[tiles - 1].h_bases[per_tile] = (uint32_t)data_len;
+      sl.strips[tiles - 1].h_bases[first_sub[tiles] - first_sub[tiles - 1]] = (uint32_t)data_len;
     }
     memcpy(sl.h_data, rbsp.data() + hdr_unesc, data_len);
     sl.pts = pts;
@@ -454,7 +466,7 @@ struct Decoder {
       int *status = (int *)(t.d_small + off_status);
       uint32_t *d_bases = (uint32_t *)(t.d_small + off_bases);
       DEC_CHECK(cudaStreamWaitEvent(t.stream, sl.ev_uploaded, 0), "stream wait");
-      DEC_CHECK(cudaMemcpyAsync(d_bases, t.h_bases, sizeof(uint32_t) * (per_tile + 1), cudaMemcpyHostToDevice, t.stream), "H2D bases");
+      DEC_CHECK(cudaMemcpyAsync(d_bases, t.h_bases, sizeof(uint32_t) * (first_sub[i + 1] - first_sub[i] + 1), cudaMemcpyHostToDevice, t.stream), "H2D bases");
       DEC_CHECK(cudaMemsetAsync(t.d_levels, 0, g.bytes * sizeof(int16_t), t.stream), "memset levels");
       DEC_CHECK(launch_parse(t.fp, sl.d_data, d_bases, t.d_cu, t.d_levels, t.d_small + off_ctx, sync_flag, progress, status, t.stream), "parse launch");
       count_launch(1);
@@ -528,11 +540,11 @@ struct Decoder {
         count_launch(1);
         rec = out_rec;
       }
-      if (tiles > 1) {                     // place the strip in the whole picture
-        const size_t sy = (size_t)g.wd * fp.h;
-        DEC_CHECK(cudaMemcpy2DAsync(d_full + g.x0, fp.w, rec, g.wd, g.wd, fp.h, cudaMemcpyDeviceToDevice, g.stream), "assemble Y");
-        DEC_CHECK(cudaMemcpy2DAsync(d_full + ysz + g.x0 / 2, fp.w / 2, rec + sy, g.wd / 2, g.wd / 2, fp.h / 2, cudaMemcpyDeviceToDevice, g.stream), "assemble U");
-        DEC_CHECK(cudaMemcpy2DAsync(d_full + ysz + ysz / 4 + g.x0 / 2, fp.w / 2, rec + sy + sy / 4, g.wd / 2, g.wd / 2, fp.h / 2, cudaMemcpyDeviceToDevice, g.stream), "assemble V");
+      if (tiles > 1) {                     // place the tile in the whole picture
+        const size_t sy = (size_t)g.wd * g.ht, cw = fp.w / 2;
+        DEC_CHECK(cudaMemcpy2DAsync(d_full + (size_t)g.y0 * fp.w + g.x0, fp.w, rec, g.wd, g.wd, g.ht, cudaMemcpyDeviceToDevice, g.stream), "assemble Y");
+        DEC_CHECK(cudaMemcpy2DAsync(d_full + ysz + (size_t)(g.y0 / 2) * cw + g.x0 / 2, cw, rec + sy, g.wd / 2, g.wd / 2, g.ht / 2, cudaMemcpyDeviceToDevice, g.stream), "assemble U");
+        DEC_CHECK(cudaMemcpy2DAsync(d_full + ysz + ysz / 4 + (size_t)(g.y0 / 2) * cw + g.x0 / 2, cw, rec + sy + sy / 4, g.wd / 2, g.wd / 2, g.ht / 2, cudaMemcpyDeviceToDevice, g.stream), "assemble V");
       }
       DEC_CHECK(cudaEventRecord(g.ev_done, g.stream), "record strip");
       DEC_CHECK(cudaStreamWaitEvent(stream, g.ev_done, 0), "stream wait");

@@ -45,6 +45,15 @@ __device__ __forceinline__ bool mv_allowed(const FrameParams &fp, int x, int n, 
   if ((fp.mv_edges & 2) && x + n + ix + m > fp.w) return false;
   return true;
 }
+// ... and vertical motion mvy for a block at y, n high (mv_edges bit 2 / 3: the top / bottom edge is an
+// interior tile edge -- tile rows)
+__device__ __forceinline__ bool mv_allowed_v(const FrameParams &fp, int y, int n, int mvy)
+{
+  const int iy = mvy >> 2, m = (mvy & 7) ? 4 : 0;
+  if ((fp.mv_edges & 4) && y + iy - m < 0) return false;
+  if ((fp.mv_edges & 8) && y + n + iy + m > fp.h) return false;
+  return true;
+}
 __device__ __forceinline__ int lambda_q4_at(const FrameParams &fp, int x, int y)
 {
   return fp.ctu_qp ? c_lambda_q4_tab[qp_at(fp, x, y)] : fp.lambda_q4;

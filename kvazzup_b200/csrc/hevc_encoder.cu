@@ -294,11 +294,11 @@ void write_parameter_sets(const StreamLayout &l, std::vector<uint8_t> &out)
     if (l.qp_delta) b.ue(0);               // diff_cu_qp_delta_depth: one quantisation group per CTB
     b.se(0); b.se(0);
     b.put(0, 1); b.put(0, 1); b.put(0, 1); b.put(0, 1);
-    b.put(l.tile_cols > 1 ? 1 : 0, 1);       // tiles_enabled_flag
+    b.put(l.tile_cols > 1 || l.tile_rows > 1 ? 1 : 0, 1);       // tiles_enabled_flag
     b.put(l.wpp ? 1 : 0, 1);                 // entropy_coding_sync_enabled_flag
-    if (l.tile_cols > 1) {
+    if (l.tile_cols > 1 || l.tile_rows > 1) {
       b.ue((uint32_t)(l.tile_cols - 1));     // num_tile_columns_minus1
-      b.ue(0);                               // num_tile_rows_minus1
+      b.ue((uint32_t)(l.tile_rows - 1));     // num_tile_rows_minus1
       b.put(1, 1);                           // uniform_spacing_flag
       b.put(0, 1);                           // loop_filter_across_tiles_enabled_flag
     }
@@ -558,15 +558,16 @@ bool Encoder::encode_host(const uint8_t *i420, std::vector<uint8_t> &out, bool p
   return encode_device(s.d_src, out);
 }
 
-bool Encoder::encode_host_strip(const uint8_t *pic, int pic_w, int x0, std::vector<uint8_t> &out)
+bool Encoder::encode_host_strip(const uint8_t *pic, int pic_w, int pic_h, int x0, int y0, std::vector<uint8_t> &out)
 {
   FrameSlot &s = slots[frame_idx % cfg.depth];
   const int w = fp.w, h = fp.h;
-  const size_t pic_y = (size_t)pic_w * h, ysz = (size_t)w * h;
-  // the three planes of the strip, straight from the caller's picture into device memory
-  ENC_CHECK(cudaMemcpy2DAsync(s.d_src, w, pic + x0, pic_w, w, h, cudaMemcpyHostToDevice, upload_stream), "H2D strip Y");
-  ENC_CHECK(cudaMemcpy2DAsync(s.d_src + ysz, w / 2, pic + pic_y + x0 / 2, pic_w / 2, w / 2, h / 2, cudaMemcpyHostToDevice, upload_stream), "H2D strip U");
-  ENC_CHECK(cudaMemcpy2DAsync(s.d_src + ysz + ysz / 4, w / 2, pic + pic_y + pic_y / 4 + x0 / 2, pic_w / 2, w / 2, h / 2, cudaMemcpyHostToDevice, upload_stream), "H2D strip V");
+  const size_t pic_y = (size_t)pic_w * pic_h, ysz = (size_t)w * h;
+  // the three planes of the tile, straight from the caller's picture into device memory
+  const uint8_t *py = pic + (size_t)y0 * pic_w + x0, *pu = pic + pic_y + (size_t)(y0 / 2) * (pic_w / 2) + x0 / 2, *pv = pu + pic_y / 4;
+  ENC_CHECK(cudaMemcpy2DAsync(s.d_src, w, py, pic_w, w, h, cudaMemcpyHostToDevice, upload_stream), "H2D strip Y");
+  ENC_CHECK(cudaMemcpy2DAsync(s.d_src + ysz, w / 2, pu, pic_w / 2, w / 2, h / 2, cudaMemcpyHostToDevice, upload_stream), "H2D strip U");
+  ENC_CHECK(cudaMemcpy2DAsync(s.d_src + ysz + ysz / 4, w / 2, pv, pic_w / 2, w / 2, h / 2, cudaMemcpyHostToDevice, upload_stream), "H2D strip V");
   ENC_CHECK(cudaEventRecord(ev_upload, upload_stream), "event record");
   ENC_CHECK(cudaStreamWaitEvent(input_stream(), ev_upload, 0), "stream wait");
   return encode_device(s.d_src, out);

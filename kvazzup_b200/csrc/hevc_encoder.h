@@ -21,7 +21,7 @@ struct EncoderConfig {
                              // (B200, 1080p GOP 64: 1812 -> 2200 pictures/s)
   int qp_delta = 0;          // cu_qp_delta_enabled_flag: per-CTU QP offsets (ROI), one quantisation group per CTU
   // Tile-column mode (hevc_tiles.cu): this encoder codes one tile of a larger picture as a picture of
-  // its own.  mv_edges bit 0 / 1 = left / right edge is an interior tile edge; more_tiles = tiles
+  // its own.  mv_edges bit 0 / 1 / 2 / 3 = left / right / top / bottom edge is an interior tile edge; more_tiles = tiles
   // follow in the slice; no_wpp = one substream per tile (Main profile: tiles or WPP, not both);
   // raw = collect() hands back the substreams instead of an access unit.
   int mv_edges = 0, more_tiles = 0, no_wpp = 0, raw = 0;
@@ -70,6 +70,7 @@ struct StreamLayout {
   int fps_num = 0, fps_den = 0;   // VUI timing info when both > 0
   int sao = 0;               // sample_adaptive_offset_enabled_flag; slices switch luma and chroma SAO on
   int tile_cols = 1;         // > 1: uniform tile columns, no loop filtering across tiles
+  int tile_rows = 1;         // > 1: uniform tile rows
   int wpp = 1;               // entropy_coding_sync_enabled_flag
 };
 void write_parameter_sets(const StreamLayout &l, std::vector<uint8_t> &out);
@@ -90,7 +91,7 @@ class Encoder {
   bool encode_host(const uint8_t *i420, std::vector<uint8_t> &au, bool pinned = false);
   bool encode_device(const uint8_t *d_i420, std::vector<uint8_t> &au);
   // Columns [x0, x0 + width) of a packed I420 host picture that is pic_w wide (tile-column mode).
-  bool encode_host_strip(const uint8_t *pic, int pic_w, int x0, std::vector<uint8_t> &au);
+  bool encode_host_strip(const uint8_t *pic, int pic_w, int pic_h, int x0, int y0, std::vector<uint8_t> &au);
   // raw mode: substreams of the picture the last collect() returned (valid until its slot is reused)
   std::vector<uint32_t> last_sub_len;
   const uint8_t *last_data = nullptr;

@@ -158,7 +158,8 @@ k_me_ctu(FrameParams fp, const uint8_t *__restrict__ src, const uint8_t *__restr
 #pragma unroll
       for (int q = 0; q < 4; q++) {
         if (rows[q] == 0) continue;
-        if (fp.mv_edges && !mv_allowed(fp, cx + 32 * (q & 1), min(32, fp.w - (cx + 32 * (q & 1))), dx * 16)) continue;
+        if (fp.mv_edges && !(mv_allowed(fp, cx + 32 * (q & 1), min(32, fp.w - (cx + 32 * (q & 1))), dx * 16) &&
+                             mv_allowed_v(fp, cy + 32 * (q >> 1), min(32, fp.h - (cy + 32 * (q >> 1))), dy * 16))) continue;
         unsigned sad = 0;
         for (int r = 0; r < rows[q]; r++) {
           const uint32_t *rw = s_cref + (Rc + dy + 8 * (q >> 1) + r) * CWW + ((xo + 8 * (q & 1)) >> 2);
@@ -259,11 +260,11 @@ k_me_ctu(FrameParams fp, const uint8_t *__restrict__ src, const uint8_t *__restr
           const unsigned c = (unsigned)((dy + R) * side + dx + R);
           const unsigned pen = sh.pen[c];
           bool a8 = v8 && live, a16 = v16 && live, a32 = v32 && live;
-          if (fp.mv_edges) {                                   // tile-column mode only (uniform branch)
-            const int mvx = 4 * (mcx + dx);
-            a8 = a8 && mv_allowed(fp, cx + 8 * bx, 8, mvx);
-            a16 = a16 && mv_allowed(fp, cx + 16 * (bx >> 1), 16, mvx);
-            a32 = a32 && mv_allowed(fp, cx + 32 * (bx >> 2), 32, mvx);
+          if (fp.mv_edges) {                                   // tile mode only (uniform branch)
+            const int mvx = 4 * (mcx + dx), mvy = 4 * (mcy + dy);
+            a8 = a8 && mv_allowed(fp, cx + 8 * bx, 8, mvx) && mv_allowed_v(fp, cy + 8 * by, 8, mvy);
+            a16 = a16 && mv_allowed(fp, cx + 16 * (bx >> 1), 16, mvx) && mv_allowed_v(fp, cy + 16 * (by >> 1), 16, mvy);
+            a32 = a32 && mv_allowed(fp, cx + 32 * (bx >> 2), 32, mvx) && mv_allowed_v(fp, cy + 32 * (by >> 2), 32, mvy);
           }
           if (a8) k8 = min(k8, ((sad + pen) << 13) | (cbase + c));
           if (a16) k16 = min(k16, ((s16 + pen) << 13) | (cbase + c));
@@ -415,7 +416,8 @@ k_me_ctu(FrameParams fp, const uint8_t *__restrict__ src, const uint8_t *__restr
           const int oy = k < 3 ? -1 : (k < 5 ? 0 : 1);
           const int mx = sh.cmx[t] + ox * step, my = sh.cmy[t] + oy * step;
           unsigned cost = sh.acc8[t][k] + mv_penalty(lambda_q4, mx - pcx, my - pcy);
-          const bool ok = !fp.mv_edges || mv_allowed(fp, cx + 8 * z_to_x(t), 1 << sh.log2[t], mx);
+          const bool ok = !fp.mv_edges || (mv_allowed(fp, cx + 8 * z_to_x(t), 1 << sh.log2[t], mx) &&
+                                           mv_allowed_v(fp, cy + 8 * z_to_y(t), 1 << sh.log2[t], my));
           if (ok && cost < sh.best[t]) { sh.best[t] = cost; sh.mvx[t] = (short)mx; sh.mvy[t] = (short)my; }
           sh.acc8[t][k] = 0;
         }

@@ -496,7 +496,7 @@ __device__ void parse_cu(Reader &r, ParseCtx &pc, int x0, int y0, int log2)
       tu = dec_bin(r, CTX_RQT_ROOT_CBF) != 0;
     }
     pc.max_mv = max(pc.max_mv, max(abs((int)cu.mvx), abs((int)cu.mvy)));
-    if (fp.mv_edges && !mv_allowed(fp, x0, n, cu.mvx)) { r.err = 12; return; }   // motion across an interior tile edge
+    if (fp.mv_edges && !(mv_allowed(fp, x0, n, cu.mvx) && mv_allowed_v(fp, y0, n, cu.mvy))) { r.err = 12; return; }   // motion across an interior tile edge
     }
   }
   int part_mode_v[4] = {1, 1, 1, 1};                                     // luma modes of the prediction blocks

@@ -1,6 +1,6 @@
-// HEVC tile columns as independent strip encoders ("4K call, tiles").
+// HEVC tiles (uniform columns x rows) as independent encoders ("4K call, tiles").
 //
-// A tile column whose motion vectors never reach across its interior edges (Kvazaar's
+// A tile whose motion vectors never reach across its interior edges (Kvazaar's
 // mv-constraint=frametilemargin, which the reference exposes, kvazaarfilter.cpp:246-276) and that is
 // not loop-filtered across those edges is coded exactly like a picture of its own: neighbours in
 // another tile are unavailable just as they are beyond a picture edge, CABAC restarts at the tile, and
@@ -29,34 +29,40 @@
 namespace b200 {
 
 struct TiledEncoder {
-  struct Strip { std::unique_ptr<Encoder> enc; int x0 = 0, wd = 0, device = 0; };
+  struct Strip { std::unique_ptr<Encoder> enc; int x0 = 0, y0 = 0, wd = 0, ht = 0, device = 0; };
   std::vector<Strip> strips;
   StreamLayout layout;
   int width = 0, height = 0, pending_pics = 0;
   std::vector<uint8_t> au, tmp, data;
   std::vector<uint32_t> sub_len;
 
-  bool open(const EncoderConfig &c, int tiles, int wpp, const int *devices, int n_devices)
+  bool open(const EncoderConfig &c, int tile_cols, int tile_rows, int wpp, const int *devices, int n_devices)
   {
-    const int ctb_cols = (c.width + kCtb - 1) / kCtb;
-    if (tiles < 1 || tiles > ctb_cols / 2) { set_error("tiled encoder: %d tile columns for %d CTU columns (each tile must be at least two CTUs wide)", tiles, ctb_cols); return false; }
+    const int ctb_cols = (c.width + kCtb - 1) / kCtb, ctb_rows = (c.height + kCtb - 1) / kCtb;
+    if (tile_cols < 1 || (tile_cols > 1 && tile_cols > ctb_cols / 2)) { set_error("tiled encoder: %d tile columns for %d CTU columns (each tile must be at least two CTUs wide)", tile_cols, ctb_cols); return false; }
+    if (tile_rows < 1 || tile_rows > ctb_rows || tile_cols * tile_rows > 64) { set_error("tiled encoder: %d tile rows for %d CTU rows", tile_rows, ctb_rows); return false; }
+    const int tiles = tile_cols * tile_rows;
     if (c.qp_delta) { set_error("tiled encoder: per-CTU QP is not available together with tiles"); return false; }
     width = c.width; height = c.height;
     layout.w = c.width; layout.h = c.height; layout.deblock = c.deblock; layout.qp_delta = 0;
-    layout.tile_cols = tiles; layout.wpp = wpp ? 1 : 0;
+    layout.tile_cols = tile_cols; layout.tile_rows = tile_rows; layout.wpp = wpp ? 1 : 0;
     layout.fps_num = c.fps_num; layout.fps_den = c.fps_den; layout.sao = c.sao;
     int prev = 0;
     cudaGetDevice(&prev);
     strips.resize(tiles);
-    for (int i = 0; i < tiles; i++) {
+    for (int i = 0; i < tiles; i++) {                                              // tiles in raster order (6.5.1)
       Strip &s = strips[i];
-      const int c0 = i * ctb_cols / tiles, c1 = (i + 1) * ctb_cols / tiles;        // colBd of uniform spacing (6.5.1)
+      const int tc = i % tile_cols, tr = i / tile_cols;
+      const int c0 = tc * ctb_cols / tile_cols, c1 = (tc + 1) * ctb_cols / tile_cols;   // colBd of uniform spacing
+      const int r0 = tr * ctb_rows / tile_rows, r1 = (tr + 1) * ctb_rows / tile_rows;   // rowBd
       s.x0 = c0 * kCtb;
       s.wd = std::min(c.width, c1 * kCtb) - s.x0;
+      s.y0 = r0 * kCtb;
+      s.ht = std::min(c.height, r1 * kCtb) - s.y0;
       s.device = n_devices > 0 ? devices[i % n_devices] : prev;
       EncoderConfig sc = c;
-      sc.width = s.wd;
-      sc.mv_edges = (i > 0 ? 1 : 0) | (i < tiles - 1 ? 2 : 0);
+      sc.width = s.wd; sc.height = s.ht;
+      sc.mv_edges = (tc > 0 ? 1 : 0) | (tc < tile_cols - 1 ? 2 : 0) | (tr > 0 ? 4 : 0) | (tr < tile_rows - 1 ? 8 : 0);
       sc.more_tiles = i < tiles - 1 ? 1 : 0;
       sc.no_wpp = wpp ? 0 : 1;
       sc.raw = 1;
@@ -96,7 +102,7 @@ struct TiledEncoder {
       Strip &s = strips[i];
       std::vector<uint8_t> got;
       if (cudaSetDevice(s.device) != cudaSuccess) { err[i] = "cannot select the strip's CUDA device"; return; }
-      ok[i] = pic ? s.enc->encode_host_strip(pic, width, s.x0, got) : s.enc->flush(got);
+      ok[i] = pic ? s.enc->encode_host_strip(pic, width, height, s.x0, s.y0, got) : s.enc->flush(got);
       if (!ok[i]) err[i] = b200_last_error();
       ready[i] = got.empty() ? 0 : 1;
     };
@@ -139,7 +145,7 @@ void *b200_tiled_open(int width, int height, int qp, int intra_period, int searc
   c.width = width; c.height = height; c.qp = qp; c.intra_period = intra_period; c.search_range = search_range;
   c.deblock = deblock; c.depth = depth; c.debug = 0;
   TiledEncoder *t = new TiledEncoder();
-  if (!t->open(c, tile_cols, wpp, devices, n_devices)) { delete t; return nullptr; }
+  if (!t->open(c, tile_cols, 1, wpp, devices, n_devices)) { delete t; return nullptr; }
   return t;
 }
 
@@ -148,7 +154,7 @@ void b200_tiled_params_default(b200_tiled_params *p)
   if (!p) return;
   memset(p, 0, sizeof(*p));
   p->struct_size = (int)sizeof(*p);
-  p->qp = 32; p->intra_period = 64; p->search_range = 8; p->deblock = 1; p->depth = 1; p->tile_cols = 1;
+  p->qp = 32; p->intra_period = 64; p->search_range = 8; p->deblock = 1; p->depth = 1; p->tile_cols = 1; p->tile_rows = 1;
 }
 
 void *b200_tiled_open_params(const b200_tiled_params *up, const int *devices, int n_devices)
@@ -161,7 +167,7 @@ void *b200_tiled_open_params(const b200_tiled_params *up, const int *devices, in
   c.width = p.width; c.height = p.height; c.qp = p.qp; c.intra_period = p.intra_period; c.search_range = p.search_range;
   c.deblock = p.deblock; c.depth = p.depth; c.debug = 0; c.fps_num = p.fps_num; c.fps_den = p.fps_den; c.sao = p.sao; c.intra_in_p = p.intra_in_p; c.me_coarse = p.me_coarse; c.intra_satd = p.intra_satd; c.subme_satd = p.subme_satd;
   TiledEncoder *t = new TiledEncoder();
-  if (!t->open(c, p.tile_cols, p.wpp, devices, n_devices)) { delete t; return nullptr; }
+  if (!t->open(c, p.tile_cols, p.tile_rows < 1 ? 1 : p.tile_rows, p.wpp, devices, n_devices)) { delete t; return nullptr; }
   return t;
 }
 
@@ -213,10 +219,10 @@ int b200_tiled_recon(void *h, uint8_t *dst, size_t cap)
     b200::Encoder &e = *s.enc;
     cudaStreamSynchronize(e.stream);
     const uint8_t *rec = e.last_rec();
-    const size_t sy = (size_t)s.wd * t->height;
-    cudaMemcpy2D(dst + s.x0, t->width, rec, s.wd, s.wd, t->height, cudaMemcpyDeviceToHost);
-    cudaMemcpy2D(dst + ysz + s.x0 / 2, t->width / 2, rec + sy, s.wd / 2, s.wd / 2, t->height / 2, cudaMemcpyDeviceToHost);
-    cudaMemcpy2D(dst + ysz + ysz / 4 + s.x0 / 2, t->width / 2, rec + sy + sy / 4, s.wd / 2, s.wd / 2, t->height / 2, cudaMemcpyDeviceToHost);
+    const size_t sy = (size_t)s.wd * s.ht, cw = t->width / 2;
+    cudaMemcpy2D(dst + (size_t)s.y0 * t->width + s.x0, t->width, rec, s.wd, s.wd, s.ht, cudaMemcpyDeviceToHost);
+    cudaMemcpy2D(dst + ysz + (size_t)(s.y0 / 2) * cw + s.x0 / 2, cw, rec + sy, s.wd / 2, s.wd / 2, s.ht / 2, cudaMemcpyDeviceToHost);
+    cudaMemcpy2D(dst + ysz + ysz / 4 + (size_t)(s.y0 / 2) * cw + s.x0 / 2, cw, rec + sy + sy / 4, s.wd / 2, s.wd / 2, s.ht / 2, cudaMemcpyDeviceToHost);
   }
   cudaSetDevice(prev);
   return B200_OK;

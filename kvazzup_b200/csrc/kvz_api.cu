@@ -137,7 +137,7 @@ int config_parse(kvz_config *cfg, const char *name, const char *value)
   if (!strcmp(name, "tiles")) {
     int c = 0, r = 0;
     if (!value || sscanf(value, "%dx%d", &c, &r) != 2) return 0;
-    if (c < 1 || c > 32 || r != 1) return 0;   // tile columns only ("WxH" with H = 1), see hevc_tiles.cu
+    if (c < 1 || c > 32 || r < 1 || r > 32 || c * r > 64) return 0;   // uniform tile grid, see hevc_tiles.cu
     cfg->tiles_width_count = c; cfg->tiles_height_count = r;
     return 1;
   }
@@ -267,7 +267,6 @@ kvz_encoder *encoder_open(const kvz_config *cfg)
 {
   if (!cfg) { b200::set_error("encoder_open: NULL config"); return NULL; }
   if (cfg->lossless) { b200::set_error("encoder_open: lossless coding is not supported"); return NULL; }
-  if (cfg->tiles_height_count != 1) { b200::set_error("encoder_open: tile rows are not supported (tile columns are)"); return NULL; }
   if (cfg->device >= 0 && cudaSetDevice(cfg->device) != cudaSuccess) { b200::set_error("encoder_open: cannot select CUDA device %d", cfg->device); return NULL; }
   kvz_encoder *e = new (std::nothrow) kvz_encoder();
   if (!e) return NULL;
@@ -283,14 +282,14 @@ kvz_encoder *encoder_open(const kvz_config *cfg)
   c.fps_num = cfg->framerate_num; c.fps_den = cfg->framerate_denom;     // VUI timing: the decoder side reports it
   c.sao = cfg->sao_type != 0 ? 2 : 0;             // with sao_merge_left / _up flags
   c.intra_in_p = 1;                               // every Kvazaar preset may code intra CUs in P pictures
-  if (cfg->tiles_width_count > 1) {
-    // tile columns: independent strip encoders on this GPU; motion is confined to the tile, like
+  if (cfg->tiles_width_count > 1 || cfg->tiles_height_count > 1) {
+    // tiles: independent tile encoders on this GPU; motion is confined to the tile, like
     // Kvazaar's mv-constraint frametilemargin (the reference exposes it, kvazaarfilter.cpp:246-276);
     // constant QP only (no ROI, no rate control)
     b200_tiled_params tp;
     b200_tiled_params_default(&tp);
     tp.width = c.width; tp.height = c.height; tp.qp = c.qp; tp.intra_period = c.intra_period; tp.search_range = c.search_range;
-    tp.deblock = c.deblock; tp.depth = c.depth; tp.tile_cols = cfg->tiles_width_count; tp.wpp = cfg->wpp ? 1 : 0;
+    tp.deblock = c.deblock; tp.depth = c.depth; tp.tile_cols = cfg->tiles_width_count; tp.tile_rows = cfg->tiles_height_count; tp.wpp = cfg->wpp ? 1 : 0;
     tp.fps_num = c.fps_num; tp.fps_den = c.fps_den; tp.sao = c.sao; tp.intra_in_p = c.intra_in_p; tp.me_coarse = c.me_coarse; tp.intra_satd = c.intra_satd; tp.subme_satd = c.subme_satd;
     e->tiled = b200_tiled_open_params(&tp, nullptr, 0);
     if (!e->tiled) { delete e; return NULL; }

@@ -88,7 +88,7 @@ class OracleEncoder:
 class OracleTiledEncoder:
     """Tile columns coded as independent strips (oracle/hevc_enc.c: orc_tiled_*)."""
 
-    def __init__(self, w, h, tiles, qp=32, intra_period=64, search_range=8, deblock=1, hash_sei=0, wpp=0, **options):
+    def __init__(self, w, h, tiles, qp=32, intra_period=64, search_range=8, deblock=1, hash_sei=0, wpp=0, tile_rows=1, **options):
         self.lib = load()
         self.w, self.h = w, h
         cfg = OrcEncCfg(width=w, height=h, qp=qp, intra_period=intra_period, search_range=search_range, deblock=deblock,
@@ -98,7 +98,7 @@ class OracleTiledEncoder:
             if k not in known:
                 raise TypeError(f"unknown oracle encoder option {k!r}")
             setattr(cfg, k, int(val))
-        self.h_enc = self.lib.orc_tiled_open(C.byref(cfg), tiles)
+        self.h_enc = self.lib.orc_tiled_open2(C.byref(cfg), tiles, tile_rows)
         if not self.h_enc:
             raise ValueError("orc_tiled_open rejected the configuration")
         self.out = np.empty(w * h * 3 + 65536, np.uint8)

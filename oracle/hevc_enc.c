@@ -646,6 +646,15 @@ static inline int mv_allowed(const orc_encoder_t *e, int x, int n, int mvx)
   if ((e->cfg.mv_edges & 2) && x + n + ix + m > e->w) return 0;
   return 1;
 }
+/* ... and vertical motion mvy for a block at y, n high (tile rows: mv_edges bit 2 / 3 = top / bottom edge) */
+static inline int mv_allowed_v(const orc_encoder_t *e, int y, int n, int mvy)
+{
+  if (!e->cfg.mv_edges) return 1;
+  const int iy = mvy >> 2, m = (mvy & 7) ? 4 : 0;
+  if ((e->cfg.mv_edges & 4) && y + iy - m < 0) return 0;
+  if ((e->cfg.mv_edges & 8) && y + n + iy + m > e->h) return 0;
+  return 1;
+}
 
 /* The finished picture enters the decoded picture buffer as reference index 0; the oldest one leaves. */
 static void down4(const uint8_t *p, int w, int h, uint8_t *out);
@@ -717,7 +726,7 @@ static void coarse_search(const orc_encoder_t *e, int ref, int qx, int qy, int l
   uint32_t best = UINT_MAX, zero = UINT_MAX;
   for (int dy = -Rc; dy <= Rc; dy++)
     for (int dx = -Rc; dx <= Rc; dx++) {
-      if (!mv_allowed(e, qx, imin(32, e->w - qx), dx * 16)) continue;
+      if (!mv_allowed(e, qx, imin(32, e->w - qx), dx * 16) || !mv_allowed_v(e, qy, imin(32, e->h - qy), dy * 16)) continue;
       uint32_t sad = 0;
       for (int y = 0; y < bh; y++)
         for (int x = 0; x < bw; x++)
@@ -789,7 +798,7 @@ static void me_ctu(orc_encoder_t *e, int cx, int cy)
               if (x >= e->w || y >= e->h) { s8[j][i] = 0; continue; }
               s8[j][i] = orc_sad(src + (size_t)y * e->w + x, e->w, ref + (size_t)(y + PAD + my) * rs + x + PAD + mx, rs, 8, 8);
               uint32_t cost = s8[j][i] + pen;
-              if (cost < b8[jj][ii].cost && mv_allowed(e, x, 8, mx * 4)) { b8[jj][ii].cost = cost; b8[jj][ii].dx = mx; b8[jj][ii].dy = my; b8[jj][ii].cx = mx0; b8[jj][ii].cy = my0; b8[jj][ii].ref = r; }
+              if (cost < b8[jj][ii].cost && mv_allowed(e, x, 8, mx * 4) && mv_allowed_v(e, y, 8, my * 4)) { b8[jj][ii].cost = cost; b8[jj][ii].dx = mx; b8[jj][ii].dy = my; b8[jj][ii].cx = mx0; b8[jj][ii].cy = my0; b8[jj][ii].ref = r; }
             }
           for (int j = 0; j < 2; j++)
             for (int i = 0; i < 2; i++) {
@@ -797,12 +806,12 @@ static void me_ctu(orc_encoder_t *e, int cx, int cy)
               s16[j][i] = s8[2 * j][2 * i] + s8[2 * j][2 * i + 1] + s8[2 * j + 1][2 * i] + s8[2 * j + 1][2 * i + 1];
               if (x + 16 > e->w || y + 16 > e->h) continue;
               uint32_t cost = s16[j][i] + pen;
-              if (cost < b16[jj][ii].cost && mv_allowed(e, x, 16, mx * 4)) { b16[jj][ii].cost = cost; b16[jj][ii].dx = mx; b16[jj][ii].dy = my; b16[jj][ii].cx = mx0; b16[jj][ii].cy = my0; b16[jj][ii].ref = r; }
+              if (cost < b16[jj][ii].cost && mv_allowed(e, x, 16, mx * 4) && mv_allowed_v(e, y, 16, my * 4)) { b16[jj][ii].cost = cost; b16[jj][ii].dx = mx; b16[jj][ii].dy = my; b16[jj][ii].cx = mx0; b16[jj][ii].cy = my0; b16[jj][ii].ref = r; }
             }
           if (qx + 32 <= e->w && qy + 32 <= e->h) {
             uint32_t cost = s16[0][0] + s16[0][1] + s16[1][0] + s16[1][1] + pen;
             me_best_t *b = &b32[q >> 1][q & 1];
-            if (cost < b->cost && mv_allowed(e, qx, 32, mx * 4)) { b->cost = cost; b->dx = mx; b->dy = my; b->cx = mx0; b->cy = my0; b->ref = r; }
+            if (cost < b->cost && mv_allowed(e, qx, 32, mx * 4) && mv_allowed_v(e, qy, 32, my * 4)) { b->cost = cost; b->dx = mx; b->dy = my; b->cx = mx0; b->cy = my0; b->ref = r; }
           }
         }
     }
@@ -889,7 +898,7 @@ static void inter_cu(orc_encoder_t *e, int x0, int y0, int log2)
     int cxm = bx, cym = by;
     for (int k = 0; k < 8; k++) {
       int mx = cxm + off[k][0] * step, my = cym + off[k][1] * step;
-      if (!mv_allowed(e, x0, n, mx)) continue;
+      if (!mv_allowed(e, x0, n, mx) || !mv_allowed_v(e, y0, n, my)) continue;
       mc_luma(e, rf, x0, y0, n, mx, my, pred);
       uint32_t cost = (satd ? orc_satd(src, e->w, pred, n, n, n) : orc_sad(src, e->w, pred, n, n, n)) + mv_penalty(lam, mx - pc[0], my - pc[1]);
       if (cost < best) { best = cost; bx = mx; by = my; memcpy(best_pred, pred, (size_t)n * n); }
@@ -1709,11 +1718,11 @@ static size_t write_parameter_sets(const orc_encoder_t *e, uint8_t *out, size_t 
   orc_bits_put(&b, 0, 1);             /* weighted_pred_flag */
   orc_bits_put(&b, 0, 1);             /* weighted_bipred_flag */
   orc_bits_put(&b, 0, 1);             /* transquant_bypass_enabled_flag */
-  orc_bits_put(&b, e->cfg.tile_cols > 1, 1);        /* tiles_enabled_flag */
+  orc_bits_put(&b, e->cfg.tile_cols > 1 || e->cfg.tile_rows > 1, 1);        /* tiles_enabled_flag */
   orc_bits_put(&b, e->cfg.no_wpp ? 0 : 1, 1);       /* entropy_coding_sync_enabled_flag (WPP) */
-  if (e->cfg.tile_cols > 1) {
-    orc_bits_ue(&b, (uint32_t)(e->cfg.tile_cols - 1));   /* num_tile_columns_minus1 */
-    orc_bits_ue(&b, 0);                                  /* num_tile_rows_minus1 */
+  if (e->cfg.tile_cols > 1 || e->cfg.tile_rows > 1) {
+    orc_bits_ue(&b, (uint32_t)(imax(e->cfg.tile_cols, 1) - 1));   /* num_tile_columns_minus1 */
+    orc_bits_ue(&b, (uint32_t)(imax(e->cfg.tile_rows, 1) - 1));   /* num_tile_rows_minus1 */
     orc_bits_put(&b, 1, 1);                              /* uniform_spacing_flag */
     orc_bits_put(&b, 0, 1);                              /* loop_filter_across_tiles_enabled_flag */
   }
@@ -1956,36 +1965,40 @@ int orc_enc_encode(orc_encoder_t *e, const uint8_t *i420, uint8_t *out, int cap)
 
 
 /* ------------------------------------------------------------------------------------------ */
-/* tile columns as independent strips                                                            */
+/* tiles (uniform columns x rows) as independent pictures                                        */
 
+#define MAX_TILES 64
 struct orc_tiled {
   orc_encoder_t *hdr;             /* full-size instance: parameter sets, slice header, hash SEI, composite recon */
-  int tiles, x0[64], wd[64];
-  orc_encoder_t *strip[64];
+  int tiles, x0[MAX_TILES], y0[MAX_TILES], wd[MAX_TILES], ht[MAX_TILES];
+  orc_encoder_t *strip[MAX_TILES];
   uint8_t *strip_src, *raw;
   size_t raw_cap;
 };
 
-orc_tiled_t *orc_tiled_open(const orc_enc_cfg_t *cfg, int tile_cols)
+orc_tiled_t *orc_tiled_open2(const orc_enc_cfg_t *cfg, int tile_cols, int tile_rows)
 {
-  if (!cfg || tile_cols < 1 || tile_cols > 64) return NULL;
-  const int ctb_cols = (cfg->width + CTB - 1) / CTB;
-  if (tile_cols > ctb_cols / 2) return NULL;              /* every tile at least two CTUs wide (WPP sync) */
+  if (!cfg || tile_cols < 1 || tile_rows < 1 || tile_cols * tile_rows > MAX_TILES) return NULL;
+  const int ctb_cols = (cfg->width + CTB - 1) / CTB, ctb_rows = (cfg->height + CTB - 1) / CTB;
+  if (tile_cols > 1 && tile_cols > ctb_cols / 2) return NULL;   /* every tile at least two CTUs wide (WPP sync) */
+  if (tile_rows > ctb_rows) return NULL;
   if (cfg->qp_delta) return NULL;                         /* the QP prediction chain of derive_cu_qps assumes WPP rows */
   orc_tiled_t *t = (orc_tiled_t *)calloc(1, sizeof(*t));
   orc_enc_cfg_t hc = *cfg;
-  hc.tile_cols = tile_cols; hc.mv_edges = 0; hc.more_tiles = 0; hc.raw_slice_data = 0;
+  hc.tile_cols = tile_cols; hc.tile_rows = tile_rows; hc.mv_edges = 0; hc.more_tiles = 0; hc.raw_slice_data = 0;
   t->hdr = orc_enc_open(&hc);
-  t->tiles = tile_cols;
+  t->tiles = tile_cols * tile_rows;
   if (!t->hdr) { free(t); return NULL; }
-  for (int i = 0; i < tile_cols; i++) {
-    const int c0 = i * ctb_cols / tile_cols, c1 = (i + 1) * ctb_cols / tile_cols;   /* colBd, 6.5.1 */
-    t->x0[i] = c0 * CTB;
-    t->wd[i] = imin(cfg->width, c1 * CTB) - t->x0[i];
+  for (int i = 0; i < t->tiles; i++) {                    /* tiles in raster order (6.5.1) */
+    const int tc = i % tile_cols, tr = i / tile_cols;
+    const int c0 = tc * ctb_cols / tile_cols, c1 = (tc + 1) * ctb_cols / tile_cols;   /* colBd, uniform spacing */
+    const int r0 = tr * ctb_rows / tile_rows, r1 = (tr + 1) * ctb_rows / tile_rows;   /* rowBd */
+    t->x0[i] = c0 * CTB; t->wd[i] = imin(cfg->width, c1 * CTB) - t->x0[i];
+    t->y0[i] = r0 * CTB; t->ht[i] = imin(cfg->height, r1 * CTB) - t->y0[i];
     orc_enc_cfg_t sc = *cfg;
-    sc.width = t->wd[i]; sc.hash_sei = 0; sc.tile_cols = 0; sc.raw_slice_data = 1;
-    sc.mv_edges = (i > 0 ? 1 : 0) | (i < tile_cols - 1 ? 2 : 0);
-    sc.more_tiles = i < tile_cols - 1;
+    sc.width = t->wd[i]; sc.height = t->ht[i]; sc.hash_sei = 0; sc.tile_cols = 0; sc.tile_rows = 0; sc.raw_slice_data = 1;
+    sc.mv_edges = (tc > 0 ? 1 : 0) | (tc < tile_cols - 1 ? 2 : 0) | (tr > 0 ? 4 : 0) | (tr < tile_rows - 1 ? 8 : 0);
+    sc.more_tiles = i < t->tiles - 1;
     t->strip[i] = orc_enc_open(&sc);
     if (!t->strip[i]) { orc_tiled_close(t); return NULL; }
   }
@@ -1994,6 +2007,8 @@ orc_tiled_t *orc_tiled_open(const orc_enc_cfg_t *cfg, int tile_cols)
   t->raw = (uint8_t *)malloc(t->raw_cap);
   return t;
 }
+
+orc_tiled_t *orc_tiled_open(const orc_enc_cfg_t *cfg, int tile_cols) { return orc_tiled_open2(cfg, tile_cols, 1); }
 
 void orc_tiled_close(orc_tiled_t *t)
 {
@@ -2005,15 +2020,15 @@ void orc_tiled_close(orc_tiled_t *t)
 
 const uint8_t *orc_tiled_recon(const orc_tiled_t *t) { return t->hdr->rec; }
 
-/* copies columns [x0, x0+wd) of a packed I420 picture into / out of a packed I420 strip */
-static void strip_copy(uint8_t *pic, int w, int h, uint8_t *strip, int x0, int wd, int to_strip)
+/* copies the rectangle (x0, y0, wd, ht) of a packed I420 picture into / out of a packed I420 tile */
+static void strip_copy(uint8_t *pic, int w, int h, uint8_t *strip, int x0, int y0, int wd, int ht, int to_strip)
 {
   for (int c = 0; c < 3; c++) {
-    const int pw = c ? w / 2 : w, ph = c ? h / 2 : h, sx = c ? x0 / 2 : x0, sw = c ? wd / 2 : wd;
-    uint8_t *pp = plane(pic, w, h, c), *sp = plane(strip, wd, h, c);
-    for (int y = 0; y < ph; y++) {
-      if (to_strip) memcpy(sp + (size_t)y * sw, pp + (size_t)y * pw + sx, sw);
-      else memcpy(pp + (size_t)y * pw + sx, sp + (size_t)y * sw, sw);
+    const int pw = c ? w / 2 : w, sx = c ? x0 / 2 : x0, sy = c ? y0 / 2 : y0, sw = c ? wd / 2 : wd, sh = c ? ht / 2 : ht;
+    uint8_t *pp = plane(pic, w, h, c), *sp = plane(strip, wd, ht, c);
+    for (int y = 0; y < sh; y++) {
+      if (to_strip) memcpy(sp + (size_t)y * sw, pp + (size_t)(sy + y) * pw + sx, sw);
+      else memcpy(pp + (size_t)(sy + y) * pw + sx, sp + (size_t)y * sw, sw);
     }
   }
 }
@@ -2023,13 +2038,13 @@ int orc_tiled_encode(orc_tiled_t *t, const uint8_t *i420, uint8_t *out, int cap)
   orc_encoder_t *e = t->hdr;
   e->is_idr = e->frame_idx == 0 || (e->cfg.intra_period > 0 && e->frame_idx % e->cfg.intra_period == 0);
   if (e->is_idr) e->poc = 0;
-  size_t sub_esc[64 * 64], total = 0;
+  size_t *sub_esc = (size_t *)calloc((size_t)MAX_TILES * 64, sizeof(size_t)), total = 0;
   int n_sub = 0;
   uint8_t *data = (uint8_t *)malloc(t->raw_cap);
   for (int i = 0; i < t->tiles; i++) {
-    strip_copy((uint8_t *)i420, e->w, e->h, t->strip_src, t->x0[i], t->wd[i], 1);
+    strip_copy((uint8_t *)i420, e->w, e->h, t->strip_src, t->x0[i], t->y0[i], t->wd[i], t->ht[i], 1);
     int n = orc_enc_encode(t->strip[i], t->strip_src, t->raw, (int)t->raw_cap);
-    if (n < 0) { free(data); return -1; }
+    if (n < 0) { free(data); free(sub_esc); return -1; }
     for (int o = 0; o < n;) {                                /* 4-byte length + substream, repeated */
       uint32_t len = t->raw[o] | (t->raw[o + 1] << 8) | (t->raw[o + 2] << 16) | ((uint32_t)t->raw[o + 3] << 24);
       o += 4;
@@ -2037,13 +2052,13 @@ int orc_tiled_encode(orc_tiled_t *t, const uint8_t *i420, uint8_t *out, int cap)
       sub_esc[n_sub++] = orc_nal_escape(t->raw + o, len, NULL, 0);
       total += len; o += (int)len;
     }
-    strip_copy(e->rec, e->w, e->h, (uint8_t *)orc_enc_recon(t->strip[i]), t->x0[i], t->wd[i], 0);
+    strip_copy(e->rec, e->w, e->h, (uint8_t *)orc_enc_recon(t->strip[i]), t->x0[i], t->y0[i], t->wd[i], t->ht[i], 0);
   }
   size_t o = 0, n = 0;
   e->n_refs = t->strip[0]->n_refs;                        /* what the slice header says about the reference list */
   if (e->is_idr) o += write_parameter_sets(e, out, (size_t)cap);
   int rc = o > (size_t)cap ? -1 : assemble_slice(e, n_sub, sub_esc, data, total, out + o, (size_t)cap - o, &n);
-  free(data);
+  free(data); free(sub_esc);
   if (rc != 0) return -1;
   o += n;
   if (e->cfg.hash_sei) o += write_hash_sei(e, out + o, (size_t)cap - o);

@@ -70,6 +70,8 @@ typedef struct {
   int strong_intra;        /* 1 = strong_intra_smoothing_enabled_flag */
   int cb_qp_offset, cr_qp_offset;         /* pps_cb_qp_offset / pps_cr_qp_offset (-12..12) */
   int beta_offset_div2, tc_offset_div2;   /* pps_beta_offset_div2 / pps_tc_offset_div2 (-6..6) */
+  int tile_rows;           /* > 1 (or tile_cols > 1): PPS of a picture with that many uniform tile rows (compositor only);
+                            * mv_edges bits 2 / 3 then mark the top / bottom edge of a tile as interior */
 } orc_enc_cfg_t;
 
 typedef struct orc_encoder orc_encoder_t;
@@ -91,6 +93,7 @@ int orc_enc_set_ctu_dqp(orc_encoder_t *e, const int8_t *dqp);
  * concatenated in tile order behind one slice header.  Same call shape as the plain encoder. */
 typedef struct orc_tiled orc_tiled_t;
 orc_tiled_t *orc_tiled_open(const orc_enc_cfg_t *cfg, int tile_cols);
+orc_tiled_t *orc_tiled_open2(const orc_enc_cfg_t *cfg, int tile_cols, int tile_rows);   /* uniform tile grid, tiles in raster order */
 void orc_tiled_close(orc_tiled_t *t);
 int orc_tiled_encode(orc_tiled_t *t, const uint8_t *i420, uint8_t *out, int cap);
 const uint8_t *orc_tiled_recon(const orc_tiled_t *t);            /* packed I420 of the whole picture */

@@ -126,7 +126,8 @@ def test_kvz_config_parse_follows_the_reference_contract():
     assert ok("period", "64") == 1 and ok("vps-period", "1") == 1 and ok("owf", "3") == 1 and cfg.contents.owf == 3
     assert ok("gop", "lp-g4d3t1") == 1 and ok("intra-bits", "") == 1 and ok("rd", "0") == 1 and ok("sao", "off") == 1
     assert ok("tiles", "3x1") == 1 and cfg.contents.tiles_width_count == 3
-    assert ok("tiles", "2x2") == 0 and cfg.contents.tiles_width_count == 3      # tile rows: refused, state unchanged
+    assert ok("tiles", "2x2") == 1 and (cfg.contents.tiles_width_count, cfg.contents.tiles_height_count) == (2, 2)   # the reference's default
+    assert ok("tiles", "9x9") == 0 and cfg.contents.tiles_width_count == 2      # more than 64 tiles: refused, state unchanged
     assert ok("tiles", "banana") == 0 and ok("slices", "tiles") == 0
     assert ok("b200-roi", "1") == 1 and cfg.contents.roi_enable == 1
     assert ok("set-qp-in-cu", "1") == 1 and cfg.contents.set_qp_in_cu == 1

@@ -284,6 +284,10 @@ def test_device_resident_decode_to_rgb32_equals_the_host_chain():
     ("camera", 640, 256, 9, 30, 3, 1, 4, {"intra_period": 4}),          # tiles + decoder frame threading
     ("camera", 1920, 1080, 3, 32, 4, 1, 1, {"search_range": 12}),
     ("camera", 1920, 1080, 3, 32, 4, 0, 1, {"search_range": 12}),
+    ("camera", 416, 240, 5, 30, 2, 0, 1, {"tile_rows": 2}),                       # tile grids
+    ("camera", 640, 256, 6, 27, 3, 1, 1, {"tile_rows": 2, "intra_period": 4}),
+    ("sports", 640, 480, 5, 32, 2, 0, 4, {"tile_rows": 3, "me_coarse": 16, "search_range": 4, "sao": 2, "intra_in_p": 1}),
+    ("camera", 1920, 1080, 3, 32, 2, 1, 1, {"tile_rows": 2, "search_range": 12}),
 ])
 def test_decoder_reads_tile_columns_as_strips(kind, w, h, n, qp, tiles, wpp, threads, kw):
     """Tiled streams (tile columns, no loop filter across tiles, motion inside the tile; with or

@@ -472,6 +472,13 @@ TILE_CASES = [
     ("screen", 640, 200, 4, 35, 3, 1, {"sao": 1}),
     ("sports", 640, 256, 5, 30, 2, 0, {"sao": 2, "intra_in_p": 1}),
     ("sports", 640, 256, 5, 30, 2, 0, {"me_coarse": 16, "search_range": 4}),     # coarse vectors stay inside the tile too
+    # tile rows: a uniform grid of tiles, motion confined vertically as well
+    ("camera", 416, 240, 5, 30, 2, 0, {"tile_rows": 2}),                          # the reference's default "2x2"
+    ("camera", 640, 256, 5, 27, 3, 0, {"tile_rows": 2, "intra_period": 3}),
+    ("noise", 512, 136, 3, 22, 1, 0, {"tile_rows": 2}),
+    ("sports", 640, 480, 5, 32, 2, 0, {"tile_rows": 3, "me_coarse": 16, "search_range": 4, "sao": 2, "intra_in_p": 1}),
+    ("camera", 640, 480, 4, 30, 2, 1, {"tile_rows": 2, "sao": 2}),                # grid + WPP rows inside every tile
+    ("camera", 1920, 1080, 3, 32, 2, 0, {"tile_rows": 2, "search_range": 12}),
 ]
 
 
@@ -522,9 +529,8 @@ def test_tiled_encoder_pipelined_output_is_identical():
 
 
 def test_tiles_through_kvz_api():
-    """video/Tiles + video/tileDimensions (kvazaarfilter.cpp:196-202): "Cx1" selects the tiled encoder;
-    the reference's default "2x2" has tile rows, which config_parse refuses (the filter logs a warning
-    and encodes untiled)."""
+    """video/Tiles + video/tileDimensions (kvazaarfilter.cpp:196-202): "CxR" selects the tiled encoder,
+    the reference's default "2x2" included."""
     from kvazzup_b200.encoder import GpuTiledEncoder, preset_options
     from kvazzup_b200.kvazaar import KvazaarFilter
     uf = preset_options("ultrafast")
@@ -542,10 +548,11 @@ def test_tiles_through_kvz_api():
             got += f.feed_input(fr)
         f.close()
         assert got == want, wpp
-    plain = GpuEncoder(w, h, qp=30, intra_period=0, fps_num=30, fps_den=1, **uf)
-    want = [plain.encode(f) for f in frames]
-    f = KvazaarFilter(base | {"video/Tiles": 1, "video/tileDimensions": "2x2"})
-    assert f.init() and any("tiles" in str(x) for x in f.warnings)
+    eng = GpuTiledEncoder(w, h, 2, qp=30, intra_period=0, wpp=1, tile_rows=2, fps_num=30, fps_den=1, **uf)
+    want = [eng.encode(f) for f in frames]
+    eng.close()
+    f = KvazaarFilter(base | {"video/Tiles": 1, "video/tileDimensions": "2x2", "video/WPP": 1})
+    assert f.init() and not any("tiles" in str(x) for x in f.warnings)
     got = []
     for fr in frames:
         got += f.feed_input(fr)

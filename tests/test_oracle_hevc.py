@@ -118,6 +118,10 @@ def test_per_ctu_qp_streams_decode_bit_exactly_in_ffmpeg(kind, w, h, n, qp, roi,
     ("noise", 512, 136, 3, 20, 4, {}),                                  # every tile exactly two CTUs wide
     ("screen", 640, 200, 5, 35, 2, {"deblock": 0}),
     ("camera", 1920, 1080, 2, 32, 4, {"hash_sei": 1, "search_range": 12}),
+    ("camera", 416, 240, 4, 30, 2, {"hash_sei": 1, "tile_rows": 2}),  # tile grids: motion confined vertically as well
+    ("camera", 640, 256, 5, 27, 3, {"hash_sei": 1, "tile_rows": 2, "intra_period": 3}),
+    ("noise", 512, 136, 3, 22, 1, {"tile_rows": 2}),
+    ("sports", 640, 480, 5, 32, 2, {"hash_sei": 1, "tile_rows": 3, "me_coarse": 16, "search_range": 4, "sao": 2, "intra_in_p": 1}),
 ])
 def test_tile_columns_as_independent_strips_decode_bit_exactly_in_ffmpeg(kind, w, h, n, qp, tiles, kw):
     """Tiles (PPS tile columns, uniform spacing, no loop filter across tiles) built from strip
