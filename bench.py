@@ -449,7 +449,7 @@ def ncu_traffic():
     """DRAM bytes per launch of each kernel from the newest committed ncu launch summary, and its name."""
     names = {"k_intra_frame<0>": "intra", "k_intra_modes": "intra_modes", "k_me_ctu": "me", "k_inter_recon<0>": "recon",
              "k_inter_modes": "modes", "k_deblock": "deblock", "k_sao_ctu<1>": "sao", "k_binarise": "binarise",
-             "k_ctx_rows": "ctx", "k_arith_rows": "arith", "k_pack_rows": "pack"}
+             "k_ctx_rows": "ctx", "k_arith_rows": "arith", "k_entropy_rows": "arith", "k_pack_rows": "pack"}
     out = {}
     for name in ("r02_ncu_launch_summary.csv", "r01_ncu_launch_summary.csv"):
         path = os.path.join(ROOT, "profiles", name)

@@ -10,9 +10,10 @@
 //                  syntax are functions of the cu map and the levels only -- never of the coder's
 //                  state -- so the whole picture binarises in parallel; inside a transform block
 //                  every lane binarises whole 4x4 sub-blocks.
-//   k_ctx_rows     one warp per WPP substream (CTU row): context-state resolution, 32 records at a
-//                  time (see the comment above the kernel); owns the WPP context hand-over.
-//   k_arith_rows   one warp per substream: the range coder over resolved records, no dependency
+//   k_entropy_rows two warps per WPP substream (CTU row), one launch:
+//     ctx_rows     context-state resolution, 32 records at a time (see the comment above it); owns the
+//                  WPP context hand-over; publishes the number of CTUs it has resolved.
+//     arith_rows   the range coder over resolved records, one CTU behind ctx_rows, no dependency
 //                  between rows; every lane runs it redundantly, lane 0 stores the bytes, escaped
 //                  on the fly (exact: each substream starts after a non-zero byte).
 #include "hevc_device.cuh"
@@ -646,27 +647,30 @@ k_binarise(FrameParams fp, const CuInfo *__restrict__ cu, const int16_t *__restr
 // The state of a CABAC context evolves with the bins coded in it (MPS / LPS outcomes) and with
 // nothing else -- not with range or low.  So the arithmetic coder is split:
 //
-//   k_ctx_rows   (phase A) walks the bin records of a CTU row 32 at a time and replaces every
+//   ctx_rows     (phase A) walks the bin records of a CTU row 32 at a time and replaces every
 //                context-coded record (context index, bin) by (pStateIdx, is-LPS).  Records of one
 //                batch that share a context are grouped with __match_any_sync and walked in order
 //                by the group's first lane; the groups run side by side.  The
 //                WPP hand-over (contexts after the second CTU of the row above) lives here, so the
 //                two-CTU stagger between rows costs two CTUs of this cheap pass only.
-//   k_arith_rows (phase B) is the serial range coder over the resolved records: no context table,
+//   arith_rows   (phase B) is the serial range coder over the resolved records: no context table,
 //                no dependency between rows at all, and the rangeTabLps row of the next record is
 //                fetched while the current one is coded.
 //
 // Before the split one kernel did both and every row waited for the row above to arithmetic-code
-// two CTUs: 3.4 ms per 1080p P picture, 26 ms per IDR (profiles/r01_summary.md).
+// two CTUs: 3.4 ms per 1080p P picture, 26 ms per IDR (profiles/r01_summary.md).  The two phases run
+// as the two halves of one launch (k_entropy_rows): phase B follows phase A of its substream CTU by CTU
+// instead of waiting for the whole picture.
 
-__global__ void __launch_bounds__(32)
-k_ctx_rows(FrameParams fp, const CuInfo *__restrict__ cu, uint32_t *recs, uint8_t *sync_ctx, int *sync_flag)
+__device__ void
+ctx_rows(const FrameParams &fp, const int sub, const CuInfo *__restrict__ cu, uint32_t *recs, uint8_t *sync_ctx, int *sync_flag,
+         int *row_prog)
 {
   __shared__ uint8_t s_ctx[CTX_COUNT + 2];
   __shared__ uint8_t s_trans[64];
   __shared__ uint8_t s_out[32];
   const int lane = threadIdx.x;
-  const int r_first = fp.no_wpp ? 0 : blockIdx.x, r_last = fp.no_wpp ? fp.ctb_rows - 1 : blockIdx.x;
+  const int r_first = fp.no_wpp ? 0 : sub, r_last = fp.no_wpp ? fp.ctb_rows - 1 : sub;
   for (int i = lane; i < 64; i += 32) s_trans[i] = c_trans_lps[i];
   if (r_first == 0 || fp.ctb_cols < 2) {
     const int qp = clip3(0, 51, fp.qp), init_type = fp.init_type;
@@ -770,6 +774,10 @@ k_ctx_rows(FrameParams fp, const CuInfo *__restrict__ cu, uint32_t *recs, uint8_
         __syncwarp();
         if (lane == 0) atomicExch(&sync_flag[r], 1);
       }
+      // the CTU's records are resolved: the range coder of this substream (the other role of the launch) may take it
+      __threadfence();
+      __syncwarp();
+      if (row_prog && lane == 0) atomicExch(&row_prog[r_first], (r - r_first) * fp.ctb_cols + col + 1);
     }
   }
 }
@@ -789,16 +797,25 @@ __device__ __forceinline__ void enc_bin_resolved(Coder &c, const uint2 e, unsign
   if (c.bits_left < 12) write_out(c);
 }
 
-__global__ void __launch_bounds__(32)
-k_arith_rows(FrameParams fp, const uint32_t *__restrict__ recs, uint8_t *rows, uint32_t row_cap, uint32_t *row_len,
-             unsigned long long *bins)
+__device__ void
+arith_rows(const FrameParams &fp, const int sub, const uint32_t *__restrict__ recs, uint8_t *rows, uint32_t row_cap, uint32_t *row_len,
+           unsigned long long *bins, const int *row_prog)
 {
   __shared__ uint2 s_tab[64];
   __shared__ uint32_t s_chunk[2][32];
-  // WPP: one substream per CTU row (r_first == r_last == blockIdx.x).  no_wpp (a tile without
+  // WPP: one substream per CTU row (r_first == r_last == sub).  no_wpp (a tile without
   // entropy_coding_sync): one block codes every row into a single substream.
   const int lane = threadIdx.x;
-  const int r_first = fp.no_wpp ? 0 : blockIdx.x, r_last = fp.no_wpp ? fp.ctb_rows - 1 : blockIdx.x;
+  const int r_first = fp.no_wpp ? 0 : sub, r_last = fp.no_wpp ? fp.ctb_rows - 1 : sub;
+  // Phase A of this substream runs concurrently (the other role of the launch) and publishes how many
+  // CTUs it has resolved; a CTU's records are read only after that (all lanes poll: no lane-dependent branch).
+  auto wait_ctu = [&](int r, int col) {
+    if (!row_prog) return;                                  // phase A ran to completion in a launch of its own
+    const int need = (r - r_first) * fp.ctb_cols + col + 1;
+    volatile const int *p = row_prog + r_first;
+    while (*p < need) __nanosleep(64);
+    __threadfence();
+  };
   for (int i = lane; i < 64; i += 32) s_tab[i] = make_uint2(c_range_lps[i], 0u);
   Coder c;
   c.out = rows + (size_t)r_first * row_cap; c.pos = 0; c.cap = fp.no_wpp ? row_cap * fp.ctb_rows : row_cap;
@@ -818,6 +835,7 @@ k_arith_rows(FrameParams fp, const uint32_t *__restrict__ recs, uint8_t *rows, u
     int col = 0, z = first_unit(0, 0);
     int buf = 0;
     const uint32_t *reg = recs + ((size_t)(r * fp.ctb_cols) * 64 + z) * kRecUnitCap;
+    wait_ctu(r, 0);
     uint32_t hdr = __ldcg(reg);
     uint32_t first = __ldcg(reg + 1 + lane);
     while (col < fp.ctb_cols) {
@@ -827,7 +845,10 @@ k_arith_rows(FrameParams fp, const uint32_t *__restrict__ recs, uint8_t *rows, u
       if (nz >= 64) { ncol = col + 1; nz = ncol < fp.ctb_cols ? first_unit(ncol, 0) : 64; }
       const uint32_t *nreg = recs + ((size_t)(r * fp.ctb_cols + ncol) * 64 + nz) * kRecUnitCap;
       uint32_t nhdr = 0, nfirst = 0;
-      if (ncol < fp.ctb_cols) { nhdr = __ldcg(nreg); nfirst = __ldcg(nreg + 1 + lane); }
+      if (ncol < fp.ctb_cols) {
+        if (ncol != col) wait_ctu(r, ncol);                 // the fetch ahead crosses into the next CTU
+        nhdr = __ldcg(nreg); nfirst = __ldcg(nreg + 1 + lane);
+      }
       // code this CU: each 32-record chunk is staged in shared memory (double buffered); the
       // rangeTabLps row of record k + 1 is fetched while record k is coded -- neither load depends
       // on the coder state
@@ -869,6 +890,34 @@ k_arith_rows(FrameParams fp, const uint32_t *__restrict__ recs, uint8_t *rows, u
     for (int i = r_first + 1; i <= r_last; i++) row_len[i] = 0;
     atomicAdd(bins, c.bins);
   }
+}
+
+// Both phases of the entropy coder in one launch: CTAs [0, subs) resolve the context states of their
+// substream (phase A), CTAs [subs, 2 * subs) run its range coder (phase B) one CTU behind.  Every wait is
+// on a CTA with a smaller index (phase A of row r on phase A of row r - 1, phase B on phase A), which the
+// hardware has placed before it, so the waits cannot starve what they wait for.
+__global__ void __launch_bounds__(32)
+k_entropy_rows(FrameParams fp, const CuInfo *__restrict__ cu, uint32_t *recs, uint8_t *sync_ctx, int *sync_flag, int *row_prog,
+               uint8_t *rows, uint32_t row_cap, uint32_t *row_len, unsigned long long *bins)
+{
+  const int subs = fp.no_wpp ? 1 : fp.ctb_rows;
+  if ((int)blockIdx.x < subs) ctx_rows(fp, (int)blockIdx.x, cu, recs, sync_ctx, sync_flag, row_prog);
+  else arith_rows(fp, (int)blockIdx.x - subs, recs, rows, row_cap, row_len, bins, row_prog);
+}
+
+// ... or as two launches, phase B after phase A: no warp ever waits for another launch's progress, which
+// is what a deep pipeline wants (dozens of pictures' entropy coders share the SMs with the prediction
+// chain; the polling of the fused form costs the chain a few per cent).
+__global__ void __launch_bounds__(32)
+k_ctx_rows(FrameParams fp, const CuInfo *__restrict__ cu, uint32_t *recs, uint8_t *sync_ctx, int *sync_flag)
+{
+  ctx_rows(fp, (int)blockIdx.x, cu, recs, sync_ctx, sync_flag, nullptr);
+}
+__global__ void __launch_bounds__(32)
+k_arith_rows(FrameParams fp, const uint32_t *__restrict__ recs, uint8_t *rows, uint32_t row_cap, uint32_t *row_len,
+             unsigned long long *bins)
+{
+  arith_rows(fp, (int)blockIdx.x, recs, rows, row_cap, row_len, bins, nullptr);
 }
 
 // Gather the substreams into one contiguous buffer (normally mapped pinned host memory, so the
@@ -927,15 +976,20 @@ cudaError_t launch_binarise(const FrameParams &fp, const CuInfo *cu, const int16
 }
 
 cudaError_t launch_arith(const FrameParams &fp, const CuInfo *cu, uint32_t *recs, uint8_t *rows, uint32_t row_cap,
-                         uint32_t *row_len, uint8_t *sync_ctx, int *sync_flag, unsigned long long *bins, cudaStream_t s)
+                         uint32_t *row_len, uint8_t *sync_ctx, int *sync_flag, unsigned long long *bins, bool fused, cudaStream_t s)
 {
-  cudaError_t e = cudaMemsetAsync(sync_flag, 0, sizeof(int) * fp.ctb_rows, s);
+  // sync_flag[rows] is followed by progress[rows] in the encoder's small state: phase A's per-substream CTU count
+  cudaError_t e = cudaMemsetAsync(sync_flag, 0, 2 * sizeof(int) * fp.ctb_rows, s);
   if (e != cudaSuccess) return e;
   e = cudaMemsetAsync(bins, 0, sizeof(unsigned long long), s);
   if (e != cudaSuccess) return e;
   const int subs = fp.no_wpp ? 1 : fp.ctb_rows;
-  k_ctx_rows<<<subs, 32, 0, s>>>(fp, cu, recs, sync_ctx, sync_flag);
-  k_arith_rows<<<subs, 32, 0, s>>>(fp, recs, rows, row_cap, row_len, bins);
+  if (fused) {
+    k_entropy_rows<<<2 * subs, 32, 0, s>>>(fp, cu, recs, sync_ctx, sync_flag, sync_flag + fp.ctb_rows, rows, row_cap, row_len, bins);
+  } else {
+    k_ctx_rows<<<subs, 32, 0, s>>>(fp, cu, recs, sync_ctx, sync_flag);
+    k_arith_rows<<<subs, 32, 0, s>>>(fp, recs, rows, row_cap, row_len, bins);
+  }
   return cudaGetLastError();
 }
 

@@ -457,15 +457,15 @@ bool Encoder::submit(FrameSlot &s, const uint8_t *d_i420)
   ENC_CHECK(launch_binarise(p, s.d_cu, s.d_levels, s.d_recs, s.stream), "binarise launch");
   PROF_END(K_BINARISE, s.stream);
   PROF_BEGIN(K_ARITH, s.stream);
-  ENC_CHECK(launch_arith(p, s.d_cu, s.d_recs, s.d_rows, row_cap, row_len, s.d_small + off_ctx, sync_flag, bins, s.stream), "arith launch");
+  ENC_CHECK(launch_arith(p, s.d_cu, s.d_recs, s.d_rows, row_cap, row_len, s.d_small + off_ctx, sync_flag, bins, cfg.depth <= 2, s.stream), "arith launch");
   PROF_END(K_ARITH, s.stream);
   PROF_BEGIN(K_PACK, s.stream);
   ENC_CHECK(launch_pack_rows(p.ctb_rows, s.d_rows, row_cap, row_len, s.h_pack, pack_cap, s.h_hdr, s.stream), "pack launch");
   PROF_END(K_PACK, s.stream);
-  count_launch(2);                                 // entropy coding: k_binarise, k_ctx_rows ...
+  count_launch(2);                                 // entropy coding: k_binarise, k_entropy_rows ...
 #undef PROF_BEGIN
 #undef PROF_END
-  count_launch(2);                                 // ... k_arith_rows, k_pack_rows
+  count_launch(cfg.depth <= 2 ? 1 : 2);            // ... (k_arith_rows when the phases are two launches,) k_pack_rows
   ENC_CHECK(cudaEventRecord(s.ev_done, s.stream), "event record");
   frame_idx++;
   poc++;

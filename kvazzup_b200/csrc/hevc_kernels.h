@@ -56,11 +56,13 @@ cudaError_t launch_sao_decode(const FrameParams &fp, const uint8_t *dbk, uint8_t
 
 // CABAC, two kernels meeting in the bin-record buffer `recs`
 // (ctb_cols*ctb_rows*64*kRecUnitCap words): k_binarise (one warp per CU, whole picture in parallel)
-// and k_arith_rows (one warp per CTU row / WPP substream).  rows[r*row_cap ..] receives the escaped
-// bytes of row r, row_len[r] its length (0xffffffff on overflow).
+// and the two entropy phases per CTU row / WPP substream (context resolution, then the range coder): as the
+// two halves of one launch, the range coder one CTU behind (`fused`: lowest latency, what a stream with
+// nothing in flight wants), or as two launches (a deep pipeline: no polling next to the prediction chain).
+// rows[r*row_cap ..] receives the escaped bytes of row r, row_len[r] its length (0xffffffff on overflow).
 cudaError_t launch_binarise(const FrameParams &fp, const CuInfo *cu, const int16_t *levels, uint32_t *recs, cudaStream_t s);
 cudaError_t launch_arith(const FrameParams &fp, const CuInfo *cu, uint32_t *recs, uint8_t *rows, uint32_t row_cap,
-                         uint32_t *row_len, uint8_t *sync_ctx, int *sync_flag, unsigned long long *bins, cudaStream_t s);
+                         uint32_t *row_len, uint8_t *sync_ctx, int *sync_flag, unsigned long long *bins, bool fused, cudaStream_t s);
 
 // substreams -> one contiguous buffer + header {total, row_len[rows]} (dst/hdr may be mapped host memory)
 cudaError_t launch_pack_rows(int rows, const uint8_t *src, uint32_t row_cap, const uint32_t *row_len, uint8_t *dst,
