@@ -65,6 +65,8 @@ struct ReconSharedI {
   uint8_t rec_y[64 * 64], rec_c[2][32 * 32];      // reconstruction of the current CTU
   uint8_t src_y[64 * 64], src_c[2][32 * 32];      // source samples of the current CTU
   RefSet rs[3];
+  CtuBorder bd;                                   // row above / column left of the CTU (gather_refs)
+  uint32_t cuw[64][2];                            // words 1 and 3 of the CTU's cu map entries, raster order of 8x8 units
   int nz[3], ctu;
   int8_t dct[32][32], dctT[32][32];
   uint8_t pred[384];
@@ -93,7 +95,7 @@ __device__ void recon_cu(ReconSharedI &sh, const FrameParams &fp, const uint8_t 
   const size_t poff = p <= 0 ? 0 : ysz + (p == 2 ? ysz / 4 : 0);
   const int bx = p == 0 ? x0 : x0 >> 1, by = p == 0 ? y0 : y0 >> 1;
   const int qp = p == 0 ? qp_at(fp, x0, y0) : qp_c_at(fp, x0, y0);
-  const int mode = __ldcg(&cu[(size_t)(y0 >> 3) * fp.w8 + (x0 >> 3)].intra_mode);
+  const int mode = (sh.cuw[(((y0 - cy) >> 3) << 3) + ((x0 - cx) >> 3)][0] >> 16) & 0xff;
   // neighbours: groups of 128 threads gather one plane each (4n+1 <= 65 samples, +1 for the DC sum)
   {
     const int g = t >> 7, gt = t & 127;                    // g = plane whose neighbours this thread helps with
@@ -103,7 +105,8 @@ __device__ void recon_cu(ReconSharedI &sh, const FrameParams &fp, const uint8_t 
     const int gx = g == 0 ? x0 : x0 >> 1, gy = g == 0 ? y0 : y0 >> 1;
     if (t < 3) sh.nz[t] = kDecode ? ((__ldcg(&cu[(size_t)(y0 >> 3) * fp.w8 + (x0 >> 3)].cbf) >> t) & 1) : 0;
     const uint8_t *tile = g == 0 ? sh.rec_y : sh.rec_c[g - 1];
-    gather_refs(sh.rs[g], fp, rec + goff, gpw, g, gx, gy, gn, cur, gt, tile, g == 0 ? 64 : 32, g == 0 ? cx : cx >> 1, g == 0 ? cy : cy >> 1);
+    gather_refs(sh.rs[g], fp, rec + goff, gpw, g, gx, gy, gn, cur, gt, tile, g == 0 ? 64 : 32, g == 0 ? cx : cx >> 1, g == 0 ? cy : cy >> 1,
+                g == 0 ? sh.bd.top_y : sh.bd.top_c[g - 1], g == 0 ? sh.bd.left_y : sh.bd.left_c[g - 1]);
     __syncthreads();
     substitute_refs(sh.rs[g], gn, gt);
     __syncthreads();
@@ -253,6 +256,16 @@ k_intra_frame(FrameParams fp, const uint8_t *__restrict__ src, uint8_t *rec, int
           ((uint32_t *)sh.rec_c[c])[j] = (y < (fp.h >> 1) && x < (fp.w >> 1)) ? __ldcg((const uint32_t *)(pl + (size_t)y * (fp.w >> 1) + x)) : 0u;
         }
       }
+      load_ctu_border(sh.bd, fp, rec, cx, cy, t, kReconThreads);
+      if (t < 64) {
+        const int x8 = (cx >> 3) + (t & 7), y8 = (cy >> 3) + (t >> 3);
+        uint32_t w1 = 0, w3 = 0;
+        if (x8 < fp.w8 && y8 < fp.h8) {
+          const uint32_t *e = (const uint32_t *)(cu + (size_t)y8 * fp.w8 + x8);
+          w1 = __ldcg(e + 1); w3 = __ldcg(e + 3);
+        }
+        sh.cuw[t][0] = w1; sh.cuw[t][1] = w3;
+      }
       if (!kDecode) {
         for (int i = t; i < 64 * 16; i += kReconThreads) {
           int y = cy + (i >> 4), x = cx + 4 * (i & 15);
@@ -273,15 +286,16 @@ k_intra_frame(FrameParams fp, const uint8_t *__restrict__ src, uint8_t *rec, int
         if (x0 >= fp.w || y0 >= fp.h) continue;
         // prediction and reconstruction go transform unit by transform unit (8.4.4.1): 16x16 units
         // here, else the 8x8 units among the four quarters
-        const CuInfo *u = &cu[(size_t)(y0 >> 3) * fp.w8 + (x0 >> 3)];
-        if (u->tu_log2 == 4) {
-          if (u->pred_mode == 1) recon_cu(sh, fp, src, rec, levels, cu, cx, cy, x0, y0, 4);
-        } else if (u->tu_log2 <= 3) {
+        const uint32_t *u = sh.cuw[(((y0 - cy) >> 3) << 3) + ((x0 - cx) >> 3)];     // [0]: log2_size | pred_mode << 8 | ...; [1]: ... | tu_log2 << 16
+        const int u_tu = (u[1] >> 16) & 0xff;
+        if (u_tu == 4) {
+          if (((u[0] >> 8) & 0xff) == 1) recon_cu(sh, fp, src, rec, levels, cu, cx, cy, x0, y0, 4);
+        } else if (u_tu <= 3) {
           for (int q = 0; q < 4; q++) {
             int x1 = x0 + 8 * (q & 1), y1 = y0 + 8 * (q >> 1);
             if (x1 >= fp.w || y1 >= fp.h) continue;
-            const CuInfo *v = &cu[(size_t)(y1 >> 3) * fp.w8 + (x1 >> 3)];
-            if (v->pred_mode == 1 && v->tu_log2 == 3) recon_cu(sh, fp, src, rec, levels, cu, cx, cy, x1, y1, 3);
+            const uint32_t *v = sh.cuw[(((y1 - cy) >> 3) << 3) + ((x1 - cx) >> 3)];
+            if (((v[0] >> 8) & 0xff) == 1 && ((v[1] >> 16) & 0xff) == 3) recon_cu(sh, fp, src, rec, levels, cu, cx, cy, x1, y1, 3);
           }
         }
       }
@@ -301,12 +315,13 @@ k_intra_frame(FrameParams fp, const uint8_t *__restrict__ src, uint8_t *rec, int
 // three planes of a unit go side by side: threads 0..255 luma, 256..319 Cb, 320..383 Cr, up to four
 // samples per thread.
 
-struct RefSetD { uint8_t raw[132], sub[132], filt[132], av[132]; int dc; };     // 4 * 32 + 1 neighbours
+struct RefSetD { uint8_t raw[132], sub[132], filt[132], av[132]; unsigned avm[5]; int dc; };     // 4 * 32 + 1 neighbours; avm = availability bits
 
 struct DecSharedI {
   uint8_t rec_y[64 * 64], rec_c[2][32 * 32];      // reconstruction of the current CTU
   uint32_t cu[64][4];                             // its cu map entries, z order (log2_size 0 = outside the picture)
   RefSetD rs[3];
+  CtuBorder bd;                                   // row above / column left of the CTU
   int ctu;
   int8_t dct[32][32];
   int16_t a[1024 + 2 * 256], b[1024 + 2 * 256];   // a 32x32 luma block and two 16x16 chroma blocks
@@ -339,31 +354,42 @@ __device__ void dec_tu(DecSharedI &sh, const FrameParams &fp, uint8_t *rec, cons
   const int mode = p == 0 ? mode_y : mode_c;
   const bool nz = (cbf >> p) & 1;
   const bool dst = p == 0 && l2 == 2;
-  if (act) {
-    // neighbours (8.4.4.2.2): available = inside the picture and earlier in decoding order, at 4x4 granularity
+  {
+    // neighbours (8.4.4.2.2): available = inside the picture and earlier in decoding order, at 4x4 granularity.
+    // The availability bits go to rs.avm by warp ballot (a warp belongs to one plane group and the loop
+    // bound is the group's: every lane reaches the ballot).
     const unsigned cur = coding_order4(fp, bx << sft, by << sft);
-    for (int k = gi; k < cnt; k += gs) {
+    for (int base = 0; base < cnt; base += gs) {
+      const int k = base + gi;
+      bool ok = false;
+      if (act && k < cnt) {
       int x, y;
       if (k < 2 * n) { x = bx - 1; y = by + 2 * n - 1 - k; }
       else if (k == 2 * n) { x = bx - 1; y = by - 1; }
       else { x = bx + (k - 2 * n - 1); y = by - 1; }
       const int ax = x << sft, ay = y << sft;
-      const bool ok = ax >= 0 && ay >= 0 && ax < fp.w && ay < fp.h && coding_order4(fp, ax, ay) < cur;
+      ok = ax >= 0 && ay >= 0 && ax < fp.w && ay < fp.h && coding_order4(fp, ax, ay) < cur;
       uint8_t v = 0;
       if (ok) {
+        // inside the CTU: its tile; else the border fetched once per CTU (every available neighbour lies there)
         const int ux = x - tx0, uy = y - ty0;
-        v = (ux >= 0 && uy >= 0 && ux < T && uy < T) ? tile[uy * T + ux] : __ldcg(rec + poff + (size_t)y * pw + x);
+        const uint8_t *top = p == 0 ? sh.bd.top_y : sh.bd.top_c[p - 1], *left = p == 0 ? sh.bd.left_y : sh.bd.left_c[p - 1];
+        if (ux >= 0 && uy >= 0 && ux < T && uy < T) v = tile[uy * T + ux];
+        else if (uy == -1 && ux >= -1 && ux < 2 * T) v = top[ux + 1];
+        else if (ux == -1 && uy >= 0 && uy < T) v = left[uy];
+        else v = __ldcg(rec + poff + (size_t)y * pw + x);
       }
       rs.av[k] = ok; rs.raw[k] = v;
+      }
+      const unsigned bal = __ballot_sync(0xffffffffu, ok);
+      if (act && (gi & 31) == 0 && k < 160) rs.avm[k >> 5] = bal;
     }
   }
   __syncthreads();
   if (act)
     for (int k = gi; k < cnt; k += gs) {
-      int j = k;
-      while (j >= 0 && !rs.av[j]) j--;
-      if (j < 0) { j = k + 1; while (j < cnt && !rs.av[j]) j++; }
-      rs.sub[k] = j < cnt ? rs.raw[j] : 128;
+      const int j = substitute_from(rs.avm, (cnt + 31) >> 5, k);
+      rs.sub[k] = j >= 0 ? rs.raw[j] : 128;
     }
   __syncthreads();
   if (act) {
@@ -488,8 +514,9 @@ k_intra_decode(FrameParams fp, uint8_t *rec, const int16_t *__restrict__ levels,
           const uint8_t *pl = rec + ysz + (c ? ysz / 4 : 0);
           ((uint32_t *)sh.rec_c[c])[j] = (y < (fp.h >> 1) && x < (fp.w >> 1)) ? __ldcg((const uint32_t *)(pl + (size_t)y * (fp.w >> 1) + x)) : 0u;
         }
-        __syncthreads();
       }
+      load_ctu_border(sh.bd, fp, rec, cx, cy, t, kReconThreads);
+      __syncthreads();
       for (int z = 0; z < 64; z++) {
         const CuInfo u = *(const CuInfo *)sh.cu[z];
         if (u.log2_size == 0 || u.pred_mode != 1) continue;

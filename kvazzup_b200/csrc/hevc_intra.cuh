@@ -6,7 +6,24 @@
 namespace b200 {
 
 // neighbour samples of one block: raw gather, substituted, [1 2 1]-filtered, availability
-struct RefSet { uint8_t raw[68], sub[68], filt[68], av[68]; int dc; };
+struct RefSet { uint8_t raw[68], sub[68], filt[68], av[68]; unsigned avm[4]; int dc; };      // avm: availability as bit masks (32 entries per word)
+
+// 8.4.4.2.2 in constant time: index of the entry that entry t takes its value from -- the nearest
+// available one at or below t, else the lowest available one (the search "from the bottom-left up");
+// -1 when nothing is available.  `avm` = availability bits, `words` of them.
+__device__ __forceinline__ int substitute_from(const unsigned *avm, int words, int t)
+{
+  const int w = t >> 5;
+  unsigned m = avm[w] & (0xffffffffu >> (31 - (t & 31)));
+  for (int k = w; ; ) {
+    if (m) return 32 * k + 31 - __clz(m);
+    if (--k < 0) break;
+    m = avm[k];
+  }
+  for (int k = 0; k < words; k++)
+    if (avm[k]) return 32 * k + __ffs(avm[k]) - 1;
+  return -1;
+}
 
 __device__ __forceinline__ unsigned coding_order_i(const FrameParams &fp, int x, int y)
 {
@@ -63,12 +80,16 @@ __device__ __forceinline__ int intra_pixel(const uint8_t *u, const uint8_t *f, i
 // the group of >= 4n+1 threads doing this block.  Caller synchronises, then calls finish_refs.
 // `tile` (may be NULL): the current CTU's reconstruction of this plane in shared memory, T x T
 // samples whose top-left is plane sample (tx0,ty0); neighbours inside it are read from there
-// (no L2 round trip on the wavefront's critical path), the others from HBM / L2.
+// (no L2 round trip on the wavefront's critical path).  `top` / `left` (with `tile`): the row above the
+// CTU from x = tx0 - 1 (1 + 2T samples) and the column left of it (T samples), fetched once per CTU --
+// every available neighbour outside the tile lies there, so nothing is read from HBM / L2 per CU.
 __device__ __forceinline__ void gather_refs(RefSet &rs, const FrameParams &fp, const uint8_t *plane, int pw, int c,
                                             int x0, int y0, int n, unsigned cur_order, int t,
-                                            const uint8_t *tile = nullptr, int T = 0, int tx0 = 0, int ty0 = 0)
+                                            const uint8_t *tile = nullptr, int T = 0, int tx0 = 0, int ty0 = 0,
+                                            const uint8_t *top = nullptr, const uint8_t *left = nullptr)
 {
   const int cnt = 4 * n + 1, sft = c ? 1 : 0;
+  bool avail = false;
   if (t >= 0 && t < cnt) {
     int x, y;
     if (t < 2 * n) { x = x0 - 1; y = y0 + 2 * n - 1 - t; }
@@ -77,24 +98,28 @@ __device__ __forceinline__ void gather_refs(RefSet &rs, const FrameParams &fp, c
     int lx = x << sft, ly = y << sft;
     bool ok = lx >= 0 && ly >= 0 && lx < fp.w && ly < fp.h && coding_order_i(fp, lx, ly) < cur_order;
     rs.av[t] = ok;
+    avail = ok;
     uint8_t v = 0;
     if (ok) {
       const int lx2 = x - tx0, ly2 = y - ty0;
       if (tile && lx2 >= 0 && ly2 >= 0 && lx2 < T && ly2 < T) v = tile[ly2 * T + lx2];
+      else if (top && ly2 == -1 && lx2 >= -1 && lx2 < 2 * T) v = top[lx2 + 1];
+      else if (left && lx2 == -1 && ly2 >= 0 && ly2 < T) v = left[ly2];
       else v = __ldcg(plane + (size_t)y * pw + x);
     }
     rs.raw[t] = v;
   }
+  // availability bits, one word per warp of the group (whole warps call this: t runs over a multiple of 32)
+  const unsigned bal = __ballot_sync(0xffffffffu, avail);
+  if (t >= 0 && t < 128 && (t & 31) == 0) rs.avm[t >> 5] = bal;
 }
 // substitution (8.4.4.2.2) by thread t of the group; caller synchronises afterwards
 __device__ __forceinline__ void substitute_refs(RefSet &rs, int n, int t)
 {
   const int cnt = 4 * n + 1;
   if (t >= 0 && t < cnt) {
-    int j = t;
-    while (j >= 0 && !rs.av[j]) j--;
-    if (j < 0) { j = t + 1; while (j < cnt && !rs.av[j]) j++; }
-    rs.sub[t] = j < cnt ? rs.raw[j] : 128;
+    const int j = substitute_from(rs.avm, (cnt + 31) >> 5, t);
+    rs.sub[t] = j >= 0 ? rs.raw[j] : 128;
   }
 }
 // [1 2 1] smoothing (8.4.4.2.3) and the DC value; caller synchronises afterwards
@@ -113,6 +138,36 @@ __device__ __forceinline__ void filter_refs(RefSet &rs, int n, int t)
 // ---- 35-mode search of one CU from SOURCE neighbours, by a group of 256 threads (thread t <->
 // sample t of the CU).  Result: sh.best_mode / sh.best_cost = SAD + lambda * mode bits (fixed prior:
 // the MPM list is unknown in a parallel pass).  All threads of the CTA must call it (barriers).
+// The border of a CTU for gather_refs: the row above it (from x = tx0 - 1, 1 + 2T samples) and the column
+// left of it (T samples) of the three planes.  Loaded by all threads of the CTA after the CTU's dependencies
+// are complete; samples outside the picture are not touched (they are never available).
+struct CtuBorder { uint8_t top_y[132], left_y[64], top_c[2][68], left_c[2][32]; };
+
+__device__ __forceinline__ void load_ctu_border(CtuBorder &b, const FrameParams &fp, const uint8_t *rec, int cx, int cy, int t, int nthreads)
+{
+  const size_t ysz = (size_t)fp.w * fp.h;
+  const int cw = fp.w >> 1, chh = fp.h >> 1, ccx = cx >> 1, ccy = cy >> 1;
+  for (int i = t; i < 129 + 64 + 2 * (65 + 32); i += nthreads) {
+    if (i < 129) {                                      // luma, row above
+      const int x = cx - 1 + i;
+      if (cy > 0 && x >= 0 && x < fp.w) b.top_y[i] = __ldcg(rec + (size_t)(cy - 1) * fp.w + x);
+    } else if (i < 193) {                               // luma, column to the left
+      const int y = cy + i - 129;
+      if (cx > 0 && y < fp.h) b.left_y[i - 129] = __ldcg(rec + (size_t)y * fp.w + cx - 1);
+    } else {
+      const int j = i - 193, c = j / 97, k = j - c * 97;
+      const uint8_t *pl = rec + ysz + (c ? ysz / 4 : 0);
+      if (k < 65) {
+        const int x = ccx - 1 + k;
+        if (ccy > 0 && x >= 0 && x < cw) b.top_c[c][k] = __ldcg(pl + (size_t)(ccy - 1) * cw + x);
+      } else {
+        const int y = ccy + k - 65;
+        if (ccx > 0 && y < chh) b.left_c[c][k - 65] = __ldcg(pl + (size_t)y * cw + ccx - 1);
+      }
+    }
+  }
+}
+
 struct ModeShared {
   RefSet rs;
   unsigned sad[36];
