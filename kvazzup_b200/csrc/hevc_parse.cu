@@ -28,22 +28,56 @@ static __constant__ uint8_t c_inv_diag4[16] = {0, 2, 5, 9, 1, 4, 8, 12, 3, 7, 11
 static __constant__ uint8_t c_inv_diag8[64] = {0, 2, 5, 9, 14, 20, 27, 35, 1, 4, 8, 13, 19, 26, 34, 42, 3, 7, 12, 18, 25, 33, 41, 48, 6, 11, 17, 24, 32, 40, 47, 53, 10, 16, 23, 31, 39, 46, 52, 57, 15, 22, 30, 38, 45, 51, 56, 60, 21, 29, 37, 44, 50, 55, 59, 62, 28, 36, 43, 49, 54, 58, 61, 63};
 static __constant__ unsigned long long c_sig_pat4[3] = {0x8885875467436120ull, 0x8877886654325410ull, 0x8855884476317620ull};
 
+// Context table: one entry per context, shared by the lanes (they all run the same decoder: loads are
+// broadcasts, stores write the same value).  An entry carries what a bin needs in ONE load -- .x = the four
+// rangeTabLps bytes of its state, .y = (pStateIdx << 1) | valMps -- and the entry a context moves to comes
+// from `next` (indexed by .y * 2 + is-LPS), fetched while the bin's result is already in use.  The updated
+// entry is written back at the start of the next decodeDecision, behind that bin's own table load, so that
+// neither the transition lookup nor the store sits on the value / range dependency chain; a bin in the same
+// context takes it from the registers.  (A lone warp pays the full latency of every dependent load.)
 struct Reader {
-  const uint8_t *p, *end;
+  const uint8_t *p, *end;   // next byte to fetch INTO the window / end of the substream
+  // The next 64 bytes of the substream sit in two registers per lane, one byte per lane each: a byte is
+  // handed out by a shuffle, and a fresh half is fetched (one coalesced 32-byte load) a whole half ahead of
+  // its first use -- instead of one dependent global load per byte.
+  uint32_t win, win_next;
+  int widx, lane;
   uint32_t range, value;
   int bits_needed;
-  uint8_t *ctx;          // this lane's private context table, entry i at ctx[i * 32]
-  const uint2 *tab;      // per state: .x = the four rangeTabLps bytes, .y = transIdxLps | (flip mps) << 6
+  uint2 *ctx;            // [CTX_COUNT + 1]; entry CTX_COUNT takes the write-back while nothing is pending
+  const uint2 *next;     // [128 * 2]
+  uint2 pend;            // the update of context pend_idx, not yet in the table
+  uint32_t pend_idx;
   int err;
 };
 
+__device__ __forceinline__ uint2 ctx_entry(uint32_t state_mps) { return make_uint2(c_range_lps[state_mps >> 1], state_mps); }
+// all pending updates into the table (before it is read as a whole: WPP hand-over)
+__device__ __forceinline__ void ctx_flush(Reader &r) { r.ctx[r.pend_idx] = r.pend; __syncwarp(); }
+
+__device__ __forceinline__ uint32_t window_load(const Reader &r)
+{
+  const uint8_t *q = r.p + r.lane;
+  return q < r.end ? (uint32_t)__ldg(q) : 0u;      // past the end: zeros (a truncated substream decodes to an error, not a fault)
+}
+
 __device__ __forceinline__ uint32_t next_byte(Reader &r)
 {
-  return r.p < r.end ? *r.p++ : 0u;
+  const uint32_t b = __shfl_sync(0xffffffffu, r.win, r.widx);
+  if (++r.widx == 32) {
+    r.widx = 0;
+    r.win = r.win_next;
+    r.win_next = window_load(r);
+    r.p += 32;
+  }
+  return b;
 }
 
 __device__ __forceinline__ void reader_start(Reader &r)
 {
+  r.widx = 0;
+  r.win = window_load(r); r.p += 32;
+  r.win_next = window_load(r); r.p += 32;
   r.range = 510;
   r.bits_needed = -8;
   r.value = next_byte(r) << 8;
@@ -54,19 +88,18 @@ __device__ __forceinline__ int dec_bin(Reader &r, int ctx_idx)
 {
   // 9.3.4.3.2, written without branches up to the byte refill: a lone warp pays a pipeline refill
   // for every taken branch, and the MPS / LPS / renormalise cases are selects on the same registers.
-  const uint32_t s = r.ctx[ctx_idx * 32];
-  uint32_t st = s >> 1, mps = s & 1;
-  const uint2 e = r.tab[st];
+  const uint2 loaded = r.ctx[ctx_idx];
+  r.ctx[r.pend_idx] = r.pend;                                  // the previous bin's update, behind this bin's load
+  const uint2 e = (uint32_t)ctx_idx == r.pend_idx ? r.pend : loaded;
   const uint32_t lps = (e.x >> (((r.range >> 6) & 3) * 8)) & 0xff;
   const uint32_t rmps = r.range - lps, scaled = rmps << 7;
   const bool is_lps = r.value >= scaled;
   const int nb = is_lps ? __clz(lps) - 23 : (rmps < 256 ? 1 : 0);
   r.value = (r.value - (is_lps ? scaled : 0u)) << nb;
   r.range = (is_lps ? lps : rmps) << nb;
-  const int bin = (int)(mps ^ (is_lps ? 1u : 0u));
-  mps ^= is_lps ? (e.y >> 6) : 0u;
-  st = is_lps ? (e.y & 63) : min(st + 1, 62u);
-  r.ctx[ctx_idx * 32] = (uint8_t)((st << 1) | mps);
+  const int bin = (int)((e.y & 1u) ^ (is_lps ? 1u : 0u));
+  r.pend = r.next[e.y * 2 + (is_lps ? 1u : 0u)];
+  r.pend_idx = (uint32_t)ctx_idx;
   r.bits_needed += nb;
   if (r.bits_needed >= 0) { r.value += next_byte(r) << r.bits_needed; r.bits_needed -= 8; }
   return bin;
@@ -101,16 +134,16 @@ __device__ __forceinline__ int dec_terminate(Reader &r)
   return 0;
 }
 
-__device__ __forceinline__ void init_contexts_d(uint8_t *ctx, int init_type, int qp)
+__device__ __forceinline__ void init_contexts_d(uint2 *ctx, int init_type, int qp, int lane)
 {
   qp = clip3(0, 51, qp);
-  for (int i = 0; i < CTX_COUNT; i++) {
+  for (int i = lane; i < CTX_COUNT; i += 32) {
     int iv = c_ctx_init[init_type][i];
     int m = (iv >> 4) * 5 - 45, n = ((iv & 15) << 3) - 16;
     int pre = clip3(1, 126, ((m * qp) >> 4) + n);
     int mps = pre <= 63 ? 0 : 1;
     int st = mps ? pre - 64 : 63 - pre;
-    ctx[i * 32] = (uint8_t)((st << 1) | mps);
+    ctx[i] = ctx_entry((uint32_t)((st << 1) | mps));
   }
 }
 
@@ -139,7 +172,7 @@ __device__ __forceinline__ int scan_index_d(int scan_idx, int blk_log2, int x, i
 // above between x = cx - 8 and cx + 71.  Those live in shared memory: a global (L2) round trip per
 // neighbour cost more than the arithmetic decoding of the CU itself.
 struct ParseCtx {
-  FrameParams fp;
+  const FrameParams &fp;  // the kernel's __grid_constant__ parameter: fields (ref_dist[] by index too) come from the constant bank, no local copy
   CuInfo *cu;            // global cu map (written by lane 0 for the later kernels and the row below)
   int16_t *levels;       // zeroed by the host before the launch; only non-zero levels are stored
   int lane;
@@ -163,9 +196,13 @@ __device__ __forceinline__ CuInfo load_cu(const ParseCtx &pc, int x, int y)
     const int buf = x < pc.cx ? pc.cur_buf ^ 1 : pc.cur_buf;
     s = pc.s_ctu + 4 * (buf * 64 + (((y - pc.cy) >> 3) << 3) + ((x >> 3) & 7));
   }
+  // fields unpacked with shifts: punning the words into the struct would send it through local memory
+  const uint32_t w0 = s[0], w1 = s[1], w2 = s[2], w3 = s[3];
   CuInfo c;
-  uint32_t *d = (uint32_t *)&c;
-  d[0] = s[0]; d[1] = s[1]; d[2] = s[2]; d[3] = s[3];
+  c.mvx = (int16_t)(w0 & 0xffff); c.mvy = (int16_t)(w0 >> 16);
+  c.log2_size = (uint8_t)w1; c.pred_mode = (uint8_t)(w1 >> 8); c.intra_mode = (uint8_t)(w1 >> 16); c.cbf = (uint8_t)(w1 >> 24);
+  c.skip = (uint8_t)w2; c.merge_idx = (uint8_t)(w2 >> 8); c.mvp_idx = (uint8_t)(w2 >> 16); c.qp = (uint8_t)(w2 >> 24);
+  c.ref_idx = (uint8_t)w3; c.chroma_mode = (uint8_t)(w3 >> 8); c.tu_log2 = (uint8_t)(w3 >> 16); c.flags = (uint8_t)(w3 >> 24);
   return c;
 }
 
@@ -424,19 +461,26 @@ __device__ void parse_cu(Reader &r, ParseCtx &pc, int x0, int y0, int log2)
       }
       // merge candidates (8.5.3.2.2-5): spatial, temporal (reference index 0), zero candidates that
       // walk the reference indices
-      int mvx[kMaxMerge], mvy[kMaxMerge], mref[kMaxMerge], cnt = 0;
+      // (the list is not stored: the candidate whose position equals merge_idx is kept as it goes by --
+      // an array indexed by merge_idx would live in local memory)
+      int cnt = 0, sel_x = 0, sel_y = 0, sel_ref = 0;
       bool use_b1 = b1.ok && !(a1.ok && same_p(b1, a1));
       bool use_b0 = b0.ok && !(b1.ok && same_p(b0, b1));
       bool use_a0 = a0.ok && !(a1.ok && same_p(a0, a1));
       bool use_b2 = b2.ok && !(a1.ok && same_p(b2, a1)) && !(b1.ok && same_p(b2, b1));
-      if (a1.ok) { mvx[cnt] = a1.mvx; mvy[cnt] = a1.mvy; mref[cnt++] = a1.ref; }
-      if (use_b1) { mvx[cnt] = b1.mvx; mvy[cnt] = b1.mvy; mref[cnt++] = b1.ref; }
-      if (use_b0) { mvx[cnt] = b0.mvx; mvy[cnt] = b0.mvy; mref[cnt++] = b0.ref; }
-      if (use_a0) { mvx[cnt] = a0.mvx; mvy[cnt] = a0.mvy; mref[cnt++] = a0.ref; }
-      if (use_b2 && cnt < 4) { mvx[cnt] = b2.mvx; mvy[cnt] = b2.mvy; mref[cnt++] = b2.ref; }
-      if (cnt < kMaxMerge && temporal_mv_d(fp, x0, y0, n, 0, mvx[cnt], mvy[cnt])) mref[cnt++] = 0;
-      for (int zero_idx = 0; cnt < kMaxMerge; zero_idx++) { mvx[cnt] = 0; mvy[cnt] = 0; mref[cnt++] = zero_idx < fp.n_refs ? zero_idx : 0; }
-      cu.mvx = (int16_t)mvx[midx]; cu.mvy = (int16_t)mvy[midx]; cu.ref_idx = (uint8_t)mref[midx];
+#define MERGE_PUSH(X, Y, R) do { if (cnt == midx) { sel_x = (X); sel_y = (Y); sel_ref = (R); } cnt++; } while (0)
+      if (a1.ok) MERGE_PUSH(a1.mvx, a1.mvy, a1.ref);
+      if (use_b1) MERGE_PUSH(b1.mvx, b1.mvy, b1.ref);
+      if (use_b0) MERGE_PUSH(b0.mvx, b0.mvy, b0.ref);
+      if (use_a0) MERGE_PUSH(a0.mvx, a0.mvy, a0.ref);
+      if (use_b2 && cnt < 4) MERGE_PUSH(b2.mvx, b2.mvy, b2.ref);
+      if (cnt <= midx) {                                  // not among the spatial candidates: temporal, then zero candidates
+        int tx = 0, ty = 0;
+        if (cnt < kMaxMerge && temporal_mv_d(fp, x0, y0, n, 0, tx, ty)) MERGE_PUSH(tx, ty, 0);
+        for (int zero_idx = 0; cnt <= midx; zero_idx++) MERGE_PUSH(0, 0, zero_idx < fp.n_refs ? zero_idx : 0);
+      }
+#undef MERGE_PUSH
+      cu.mvx = (int16_t)sel_x; cu.mvy = (int16_t)sel_y; cu.ref_idx = (uint8_t)sel_ref;
       cu.merge_idx = (uint8_t)midx;
       tu = !cu.skip;
     } else {
@@ -486,12 +530,14 @@ __device__ void parse_cu(Reader &r, ParseCtx &pc, int x0, int y0, int log2)
         else if (b1.ok) { nb_for_ref(fp, b1, ref, bx, by); fb = true; }
         else if (b2.ok) { nb_for_ref(fp, b2, ref, bx, by); fb = true; }
       }
-      int px[3], py[3], k = 0;
-      if (fa) { px[k] = ax; py[k++] = ay; }
-      if (fb && !(fa && ax == bx && ay == by)) { px[k] = bx; py[k++] = by; }
-      if (k < 2 && temporal_mv_d(fp, x0, y0, n, ref, px[k], py[k])) k++;
-      while (k < 2) { px[k] = 0; py[k++] = 0; }
-      cu.mvx = (int16_t)(px[pi] + mvd[0]); cu.mvy = (int16_t)(py[pi] + mvd[1]);
+      int k = 0, pvx = 0, pvy = 0;                          // the predictor at position mvp_l0_flag, kept as it goes by
+      if (fa) { if (k == pi) { pvx = ax; pvy = ay; } k++; }
+      if (fb && !(fa && ax == bx && ay == by)) { if (k == pi) { pvx = bx; pvy = by; } k++; }
+      if (k <= pi) {
+        int tx = 0, ty = 0;
+        if (temporal_mv_d(fp, x0, y0, n, ref, tx, ty)) { if (k == pi) { pvx = tx; pvy = ty; } k++; }
+      }
+      cu.mvx = (int16_t)(pvx + mvd[0]); cu.mvy = (int16_t)(pvy + mvd[1]);
       cu.mvp_idx = (uint8_t)pi;
       tu = dec_bin(r, CTX_RQT_ROOT_CBF) != 0;
     }
@@ -650,11 +696,12 @@ __device__ void parse_cu(Reader &r, ParseCtx &pc, int x0, int y0, int log2)
   // the row below and the reconstruction kernels (lane u takes unit u of the CU); cbf and the
   // transform unit size are per unit
   {
+    // the entry's four words, packed with shifts (no pointer punning: the struct stays in registers)
     uint32_t s[4];
-    {
-      const uint32_t *c32 = (const uint32_t *)&cu;
-      s[0] = c32[0]; s[1] = c32[1]; s[2] = c32[2]; s[3] = c32[3];
-    }
+    s[0] = (uint32_t)(uint16_t)cu.mvx | ((uint32_t)(uint16_t)cu.mvy << 16);
+    s[1] = (uint32_t)cu.log2_size | ((uint32_t)cu.pred_mode << 8) | ((uint32_t)cu.intra_mode << 16) | ((uint32_t)cu.cbf << 24);
+    s[2] = (uint32_t)cu.skip | ((uint32_t)cu.merge_idx << 8) | ((uint32_t)cu.mvp_idx << 16) | ((uint32_t)cu.qp << 24);
+    s[3] = (uint32_t)cu.ref_idx | ((uint32_t)cu.chroma_mode << 8) | ((uint32_t)cu.tu_log2 << 16) | ((uint32_t)cu.flags << 24);
     __syncwarp();
     // Branch-free on purpose: a lane-dependent branch here left the warp split into two groups that
     // ran the rest of the (lane-redundant) parse one after the other, doubling the time.  Lanes with
@@ -732,11 +779,11 @@ __device__ void parse_sao(Reader &r, const FrameParams &fp, int row, int col, Sa
 // bases[r] = byte offset of substream r inside `data`, bases[rows] = end.  status[0] receives the
 // first error code (0 = ok), status[1] the largest |mv| component.
 __global__ void __launch_bounds__(32)
-k_parse_rows(FrameParams fp, const uint8_t *__restrict__ data, const uint32_t *__restrict__ bases, CuInfo *cu,
+k_parse_rows(const __grid_constant__ FrameParams fp, const uint8_t *__restrict__ data, const uint32_t *__restrict__ bases, CuInfo *cu,
              int16_t *levels, uint8_t *sync_ctx, int *sync_flag, int *progress, int *status)
 {
-  __shared__ uint8_t s_ctx[CTX_COUNT * 32];
-  __shared__ uint2 s_tab[64];
+  __shared__ uint2 s_ctx[CTX_COUNT + 1];
+  __shared__ uint2 s_next[128 * 2];
   __shared__ uint32_t s_ctu[2 * 64 * 4];
   __shared__ uint32_t s_above[10 * 4];
   // WPP: one substream per CTU row (row_first == row_last == blockIdx.x).  no_wpp (a tile without
@@ -744,15 +791,21 @@ k_parse_rows(FrameParams fp, const uint8_t *__restrict__ data, const uint32_t *_
   const int lane = threadIdx.x;
   const int row_first = fp.no_wpp ? 0 : blockIdx.x, row_last = fp.no_wpp ? fp.ctb_rows - 1 : blockIdx.x;
   int row = row_first;
-  for (int i = lane; i < 64; i += 32) s_tab[i] = make_uint2(c_range_lps[i], (uint32_t)c_trans_lps[i] | (i == 0 ? 64u : 0u));
+  for (int i = lane; i < 128; i += 32) {                  // i = (pStateIdx << 1) | valMps
+    const uint32_t st = (uint32_t)i >> 1, mps = (uint32_t)i & 1;
+    s_next[2 * i] = ctx_entry((min(st + 1, 62u) << 1) | mps);                                  // after an MPS
+    s_next[2 * i + 1] = ctx_entry(((uint32_t)c_trans_lps[min(st, 63u)] << 1) | (mps ^ (st == 0 ? 1u : 0u)));   // after an LPS
+  }
+  if (lane == 0) s_ctx[CTX_COUNT] = make_uint2(0, 0);
   Reader r;
-  r.p = data + bases[fp.no_wpp ? 0 : row]; r.end = data + bases[fp.no_wpp ? 1 : row + 1]; r.ctx = s_ctx + lane; r.tab = s_tab; r.err = 0;
+  r.p = data + bases[fp.no_wpp ? 0 : row]; r.end = data + bases[fp.no_wpp ? 1 : row + 1]; r.ctx = s_ctx; r.next = s_next; r.err = 0; r.lane = lane;
+  r.pend = make_uint2(0, 0); r.pend_idx = CTX_COUNT;
   __shared__ uint16_t s_tu[64];
   ParseCtx pc{fp, cu, levels, lane, 0, s_ctu, s_above, 0, row * kCtb, 0, fp.qp, 0, 0, s_tu};
   SaoCtu sao_left;
   { uint32_t *z = (uint32_t *)&sao_left; for (int i = 0; i < 5; i++) z[i] = 0; }
   if (row == 0 || fp.ctb_cols < 2) {
-    init_contexts_d(r.ctx, fp.init_type, fp.qp);
+    init_contexts_d(r.ctx, fp.init_type, fp.qp, lane);
   } else {
     // All lanes poll (one broadcast load per iteration).  Nothing in this kernel branches on the
     // lane index: a leader-only branch followed by __syncwarp() has left the warp split into groups
@@ -763,7 +816,7 @@ k_parse_rows(FrameParams fp, const uint8_t *__restrict__ data, const uint32_t *_
       while (f[row - 1] == 0) __nanosleep(100);
       __threadfence();
     }
-    for (int i = 0; i < CTX_COUNT; i++) r.ctx[i * 32] = __ldcg(sync_ctx + (size_t)(row - 1) * CTX_COUNT + i);
+    for (int i = lane; i < CTX_COUNT; i += 32) r.ctx[i] = ctx_entry(__ldcg(sync_ctx + (size_t)(row - 1) * CTX_COUNT + i));
   }
   __syncwarp();
   reader_start(r);
@@ -817,7 +870,8 @@ k_parse_rows(FrameParams fp, const uint8_t *__restrict__ data, const uint32_t *_
       }
       if (col == 1 && row + 1 < fp.ctb_rows && !fp.no_wpp) {
         // every lane holds the same table; all store it (same addresses, same values)
-        for (int i = 0; i < CTX_COUNT; i++) sync_ctx[(size_t)row * CTX_COUNT + i] = r.ctx[i * 32];
+        ctx_flush(r);
+        for (int i = lane; i < CTX_COUNT; i += 32) sync_ctx[(size_t)row * CTX_COUNT + i] = (uint8_t)r.ctx[i].y;
         __threadfence();
         __syncwarp();
         *(volatile int *)&sync_flag[row] = 1;
