@@ -447,7 +447,8 @@ def parity_check(frames, timed_aus, opts):
 
 def ncu_traffic():
     """DRAM bytes per launch of each kernel from the newest committed ncu launch summary, and its name."""
-    names = {"k_intra_frame<0>": "intra", "k_intra_modes": "intra_modes", "k_me_ctu": "me", "k_inter_recon<0>": "recon",
+    names = {"k_intra_frame<0>": "intra", "k_intra_frame": "intra", "k_intra_modes": "intra_modes", "k_me_ctu": "me",
+             "k_me_ctu<0>": "me", "k_me_ctu<1>": "me", "k_inter_recon<0>": "recon",
              "k_inter_modes": "modes", "k_deblock": "deblock", "k_sao_ctu<1>": "sao", "k_binarise": "binarise",
              "k_ctx_rows": "ctx", "k_arith_rows": "arith", "k_entropy_rows": "arith", "k_pack_rows": "pack"}
     out = {}
