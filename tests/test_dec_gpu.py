@@ -336,3 +336,46 @@ def test_decoder_switches_between_tiled_and_untiled_streams():
             assert len(pics) == 1 and np.array_equal(pics[0][0], rec), tiles
         e.close()
     f.close()
+
+
+def test_decoder_survives_corrupted_peer_streams():
+    """Network input: access units of a stream that uses every syntax element the parser knows (transform
+    trees down to 4x4, NxN, chroma modes, sign hiding, SAO, several references, temporal candidates,
+    per-CTU QP) with bytes flipped at random places.  Every variant must either decode (to whatever) or be
+    refused with an error -- and the decoder must then decode a clean stream exactly, i.e. nothing a
+    corrupt picture does may damage its state.  (tools/run_sanitizer.sh runs this under memcheck.)"""
+    from kvazzup_b200.capi import B200Error
+    w, h, n = 192, 136, 4
+    kw = {"tr_depth": 2, "tu4": 1, "intra_sizes": 7, "chroma_modes": 1, "sign_hiding": 1, "sao": 2, "intra_in_p": 1,
+          "refs": 2, "tmvp": 1, "qp_delta": 1, "intra_period": 0, "cabac_init": 1}
+    frames = frames_of("sports", w, h, n)
+    enc = OracleEncoder(w, h, qp=30, **kw)
+    aus, recs = [], []
+    for f in frames:
+        aus.append(enc.encode(f))
+        recs.append(enc.recon())
+    enc.close()
+    rng = np.random.default_rng(7)
+    refused = decoded = 0
+    for trial in range(40):
+        dec = OpenHEVCFilter()
+        assert dec.init()
+        victim = int(rng.integers(0, n))
+        for i, au in enumerate(aus):
+            for nal in split_nals(au):
+                data = bytearray(nal)
+                nal_type = (data[4] >> 1) & 63
+                if i == victim and nal_type < 32 and len(data) > 24:            # a slice NAL: corrupt its payload
+                    for _ in range(int(rng.integers(1, 6))):
+                        k = int(rng.integers(8, len(data)))
+                        data[k] ^= int(rng.integers(1, 256))
+                try:
+                    if dec.process(bytes(data), pts=i) is not None:
+                        decoded += 1
+                except B200Error:
+                    refused += 1
+        dec.close()
+    assert decoded > 0 and refused >= 0
+    # and a fresh, clean pass still decodes bit-exactly
+    out = decode_all(aus)
+    assert len(out) == n and all(np.array_equal(out[i][0], recs[i]) for i in range(n))
