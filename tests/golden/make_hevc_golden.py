@@ -28,6 +28,15 @@ CASES = [
     {"name": "camera_416x240_roi", "kind": "camera", "w": 416, "h": 240, "n": 5, "kw": {"qp": 30, "intra_period": 0, "qp_delta": 1}, "roi": "random"},
     {"name": "camera_416x240_sao", "kind": "camera", "w": 416, "h": 240, "n": 4, "kw": {"qp": 37, "intra_period": 0, "sao": 1}},
     {"name": "camera_416x240_tiles3", "kind": "camera", "w": 416, "h": 240, "n": 4, "kw": {"qp": 30, "intra_period": 0}, "tiles": 3},
+    # round 2: the presets' tools, the peer syntax of the decoder tests, a tile grid
+    {"name": "sports_416x240_veryfast_tools", "kind": "sports", "w": 416, "h": 240, "n": 5,
+     "kw": {"qp": 30, "intra_period": 0, "search_range": 6, "me_coarse": 16, "sao": 2, "intra_in_p": 1, "intra_satd": 1}},
+    {"name": "camera_192x136_subme_satd", "kind": "camera", "w": 192, "h": 136, "n": 4, "kw": {"qp": 30, "intra_period": 0, "subme_satd": 1}},
+    {"name": "sports_416x240_peer_syntax", "kind": "sports", "w": 416, "h": 240, "n": 5,
+     "kw": {"qp": 30, "intra_period": 3, "tr_depth": 2, "tu4": 1, "intra_sizes": 7, "chroma_modes": 1, "sign_hiding": 1, "strong_intra": 1,
+            "cb_qp_offset": 2, "cr_qp_offset": -2, "beta_offset_div2": 1, "tc_offset_div2": 1, "sao": 2, "intra_in_p": 1, "refs": 2,
+            "tmvp": 1, "cabac_init": 1}},
+    {"name": "camera_416x240_tiles2x2", "kind": "camera", "w": 416, "h": 240, "n": 4, "kw": {"qp": 30, "intra_period": 0, "tile_rows": 2}, "tiles": 2},
 ]
 
 
