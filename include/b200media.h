@@ -120,6 +120,9 @@ int b200_convert_to_i420_dev(const uint8_t *d_src, uint8_t *d_i420, int width, i
  * interleaved scan, restart intervals, frames without DHT (the tables of T.81 Annex K).  The frame must be
  * width x height (libyuv::MJPGToI420 fails otherwise).  One stream per calling thread.  B200_OK or < 0. */
 int b200_mjpg_to_i420_dev(const uint8_t *jpeg, size_t jpeg_bytes, uint8_t *d_i420, int width, int height, void *stream);
+/* Host only (no GPU needed): B200_OK when the frame is one b200_mjpg_to_i420_dev converts -- headers parsed, the
+ * whole scan read -- with its size and subsampling (420, 422, 444 or 400); < 0 with b200_last_error() otherwise. */
+int b200_mjpg_probe(const uint8_t *jpeg, size_t jpeg_bytes, int *width, int *height, int *subsampling);
 
 #ifdef __cplusplus
 }

@@ -38,8 +38,10 @@ struct HuffLut {
     memcpy(vals, symbols, (size_t)n);
     memset(fast, 0, sizeof(fast));
     int code = 0, k = 0;
+    ok = false;
     for (int len = 1; len <= 16; len++) {
       delta[len] = k - code;
+      if (code + counts[len - 1] > (1 << len) || k + counts[len - 1] > n) return;      // over-subscribed (corrupt DHT): the table stays unusable
       for (int i = 0; i < counts[len - 1]; i++, code++, k++)
         if (len <= kFast) {
           const int lo = code << (kFast - len);
@@ -424,6 +426,36 @@ struct MjpgScratch {
 }  // namespace b200
 
 using namespace b200;
+
+// Host only (no CUDA call): is this a frame b200_mjpg_to_i420_dev can convert?  Parses the headers and reads
+// the whole entropy-coded scan, as the conversion does.
+extern "C" int b200_mjpg_probe(const uint8_t *jpeg, size_t jpeg_bytes, int *width, int *height, int *subsampling)
+{
+  if (!jpeg) { set_error("b200_mjpg_probe: bad arguments"); return B200_ERR_ARG; }
+  static thread_local HuffLut dc[4], ac[4];
+  for (int i = 0; i < 4; i++) dc[i].ok = ac[i].ok = false;
+  FrameHeader f;
+  if (!parse_headers(jpeg, jpeg_bytes, f, dc, ac)) return B200_ERR_ARG;
+  if (!dc[0].ok && !ac[0].ok) {
+    dc[0].build(kStdDcLumCounts, kStdDcSymbols, 12); dc[1].build(kStdDcChrCounts, kStdDcSymbols, 12);
+    ac[0].build(kStdAcLumCounts, kStdAcLumSymbols, 162); ac[1].build(kStdAcChrCounts, kStdAcChrSymbols, 162);
+  }
+  int mode;
+  if (f.nc == 1) mode = 400;
+  else if (f.c[1].hs != 1 || f.c[1].vs != 1 || f.c[2].hs != 1 || f.c[2].vs != 1) { set_error("mjpg: unsupported chroma sampling"); return B200_ERR_ARG; }
+  else if (f.c[0].hs == 2 && f.c[0].vs == 2) mode = 420;
+  else if (f.c[0].hs == 2 && f.c[0].vs == 1) mode = 422;
+  else if (f.c[0].hs == 1 && f.c[0].vs == 1) mode = 444;
+  else { set_error("mjpg: unsupported luma sampling %dx%d", f.c[0].hs, f.c[0].vs); return B200_ERR_ARG; }
+  for (int i = 0; i < f.nc; i++)
+    if (!f.have_q[f.c[i].tq] || !dc[f.c[i].td].ok || !ac[f.c[i].ta].ok) { set_error("mjpg: a table the scan names is missing"); return B200_ERR_ARG; }
+  std::vector<int16_t> coef(f.blocks * 64);
+  if (!read_scan(jpeg, jpeg_bytes, f, dc, ac, coef.data())) return B200_ERR_ARG;
+  if (width) *width = f.w;
+  if (height) *height = f.h;
+  if (subsampling) *subsampling = mode;
+  return B200_OK;
+}
 
 extern "C" int b200_mjpg_to_i420_dev(const uint8_t *jpeg, size_t jpeg_bytes, uint8_t *d_i420, int w, int h, void *stream)
 {
