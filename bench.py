@@ -363,7 +363,8 @@ def run_b200(args):
                              "peak_source": "b200_int_peak, measured live (vabsdiff4 / dp4a / dp2a: %s Ginstr/s)"
                                             % "/".join(str(round(v / 1e9)) for v in int_peak.values()),
                              "me_work": {k: round(v / n_me, 1) for k, v in me_stats.items()},
-                             "note": "useful SAD / interpolation instructions only; address arithmetic, shifts and shuffles excluded"},
+                             "note": "useful SAD / interpolation instructions only; address arithmetic, shifts and shuffles excluded",
+                             "ncu_pipe_utilisation": ncu_pipes("k_me_ctu")},
                 "critical_path": {"kernels": list(CHAIN), "us_per_picture": round(chain_us, 1),
                                   "us_per_wavefront_step": round(chain_us / WAVEFRONT_STEPS, 2), "floor_us_per_step_at_1000fps": 16.1,
                                   "note": "sum of the average launch times of the P-picture chain; per-picture kernels cover all "
@@ -443,6 +444,25 @@ def parity_check(frames, timed_aus, opts):
         out["ffmpeg_error"] = repr(ex)
     out["ok"] = bool(out["depth96_equals_depth1"] and out.get("ffmpeg_equals_recon", out.get("ffmpeg_decodes") is None))
     return out
+
+
+def ncu_pipes(kernel):
+    """ALU pipe / issue utilisation of a kernel from the committed --set full capture (tools/summarise_ncu.py full):
+    what the hardware counters say about the integer pipe, next to the counted-instruction fraction."""
+    path = os.path.join(ROOT, "profiles", "r02_ncu_full_chain.csv")
+    try:
+        with open(path) as f:
+            hdr = next(f).strip().split(",")
+            col = {h.split("[")[0]: i for i, h in enumerate(hdr)}
+            rows = [ln.strip().split(",") for ln in f if ln.startswith(kernel)]
+        rows = [r for r in rows if float(r[col["time"]]) > 0.05]          # the launches that did a picture's work
+        if not rows:
+            return None
+        mean = lambda k: round(sum(float(r[col[k]]) for r in rows) / len(rows), 1)
+        return {"alu_pipe_pct": mean("alu_%"), "issue_slots_pct": mean("issue_%"), "occupancy_pct": mean("occ_%"),
+                "launches": len(rows), "source": "profiles/r02_ncu_full_chain.csv (ncu --set full, cold cache, serialised)"}
+    except (OSError, ValueError, KeyError, StopIteration):
+        return None
 
 
 def ncu_traffic():
