@@ -45,6 +45,9 @@ typedef struct b200_enc_params {
   int intra_satd;                /* I pictures: the 35-mode intra search compares the Hadamard SATD of the residual
                                     (8x8 tiles) instead of its SAD */
   int subme_satd;                /* P pictures: the half- / quarter-sample motion refinement compares SATD instead of SAD */
+  int vaq;                       /* variance adaptive quantisation strength (Kvazaar --vaq, kvazaarfilter.cpp:280-284), 0 = off,
+                                    1..20: every picture each CTU's QP moves by strength * 0.1 * ln(CTU variance / picture
+                                    variance), on top of the offsets of b200_enc_set_ctu_dqp; needs qp_delta */
 } b200_enc_params;
 void  b200_enc_params_default(b200_enc_params *p);
 void *b200_enc_open_params(const b200_enc_params *p);

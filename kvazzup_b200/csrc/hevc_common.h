@@ -23,6 +23,9 @@ constexpr int kCuOverheadBits = 3;
 // CTU), so the record list of a CU starts at a fixed address and owns the capacity of all its
 // units.  Worst case of an 8x8 CU: 6 sub-blocks x 75 records + CU header + 3 last positions < 640.
 constexpr int kRecUnitCap = 640;
+// Variance adaptive quantisation: the host stages picture QP + ROI offset of every CTU biased by
+// kVaqBias (unclipped), k_vaq_qp adds its offset and clips to 0..51.
+constexpr int kVaqBias = 76;
 
 struct CuInfo {
   int16_t mvx, mvy;     // quarter-sample motion vector (inter).  Intra NxN CUs keep the modes of parts 1..3 here:

@@ -118,6 +118,7 @@ void Encoder::release()
     if (s.d_dbk) cudaFree(s.d_dbk);
     if (s.d_sao) cudaFree(s.d_sao);
     if (s.h_ctu_qp) cudaFreeHost(s.h_ctu_qp);
+    if (s.d_vaq) cudaFree(s.d_vaq);
     if (s.d_src) cudaFree(s.d_src);
     if (s.h_src) cudaFreeHost(s.h_src);
     if (s.h_pack) cudaFreeHost(s.h_pack);
@@ -156,6 +157,7 @@ bool Encoder::open(const EncoderConfig &c)
   if (c.qp < 0 || c.qp > 51) { set_error("encoder: qp %d out of range 0..51", c.qp); return false; }
   if (c.search_range < 1 || c.search_range > 32) { set_error("encoder: search range %d out of range 1..32", c.search_range); return false; }
   if (c.me_coarse < 0 || c.me_coarse > 32 || (c.me_coarse & 3) || (c.me_coarse > 0 && c.search_range > 16)) { set_error("encoder: me_coarse %d must be a multiple of 4 in 0..32 (and search_range <= 16 with it)", c.me_coarse); return false; }
+  if (c.vaq < 0 || c.vaq > 20 || (c.vaq && !c.qp_delta)) { set_error("encoder: vaq %d must be 0..20 and needs qp_delta", c.vaq); return false; }
   if (c.depth < 1 || c.depth > 128) { set_error("encoder: depth %d out of range 1..128", c.depth); return false; }
   if (b200_device_count() <= 0) { set_error("no CUDA device: the B200 encoder has no CPU fallback"); return false; }
   cfg = c;
@@ -211,6 +213,7 @@ bool Encoder::open(const EncoderConfig &c)
     if (c.qp_delta) {
       ENC_CHECK(cudaMalloc((void **)&s.d_qpinfo, 3 * (size_t)fp.ctb_cols * fp.ctb_rows), "cudaMalloc qp info");
       ENC_CHECK(cudaMallocHost((void **)&s.h_ctu_qp, (size_t)fp.ctb_cols * fp.ctb_rows), "cudaMallocHost ctu qp");
+      if (c.vaq) ENC_CHECK(cudaMalloc((void **)&s.d_vaq, 6 * sizeof(uint32_t) * fp.ctb_cols * fp.ctb_rows), "cudaMalloc vaq");
     }
     ENC_CHECK(cudaMemset(s.d_small, 0, small_bytes), "memset small");
     ENC_CHECK(cudaMalloc((void **)&s.d_ctu_done, sizeof(int) * (fp.ctb_cols * fp.ctb_rows + 1)), "cudaMalloc ctu done");
@@ -382,10 +385,17 @@ bool Encoder::submit(FrameSlot &s, const uint8_t *d_i420)
   p.mv_edges = cfg.mv_edges; p.more_tiles = cfg.more_tiles; p.no_wpp = cfg.no_wpp;
   if (cfg.qp_delta) {
     const int ctus = fp.ctb_cols * fp.ctb_rows;
-    for (int i = 0; i < ctus; i++)
-      s.h_ctu_qp[i] = (uint8_t)std::min(std::max(cur_qp + (ctu_dqp.empty() ? 0 : ctu_dqp[i]), 0), 51);
+    cudaStream_t qs = (idr && cfg.overlap_idr) ? intra_stream : stream;       // the stream that consumes the input picture
+    for (int i = 0; i < ctus; i++) {
+      const int q = cur_qp + (ctu_dqp.empty() ? 0 : ctu_dqp[i]);
+      s.h_ctu_qp[i] = cfg.vaq ? (uint8_t)(std::min(std::max(q, -kVaqBias), 127) + kVaqBias) : (uint8_t)std::min(std::max(q, 0), 51);
+    }
     p.ctu_qp = s.d_qpinfo; p.ctu_delta = (int8_t *)(s.d_qpinfo + ctus); p.ctu_first = s.d_qpinfo + 2 * ctus;
-    ENC_CHECK(cudaMemcpyAsync(s.d_qpinfo, s.h_ctu_qp, ctus, cudaMemcpyHostToDevice, (idr && cfg.overlap_idr) ? intra_stream : stream), "H2D ctu qp");
+    ENC_CHECK(cudaMemcpyAsync(s.d_qpinfo, s.h_ctu_qp, ctus, cudaMemcpyHostToDevice, qs), "H2D ctu qp");
+    if (cfg.vaq) {                       // every CTU's QP moves with its sample variance against the picture's
+      ENC_CHECK(launch_vaq(p, d_i420, cfg.vaq, s.d_vaq, s.d_qpinfo, qs), "vaq launch");
+      count_launch(2);
+    }
   }
   uint32_t *row_len = (uint32_t *)s.d_small;
   int *sync_flag = (int *)(s.d_small + off_flag), *ticket = (int *)(s.d_small + off_ticket);
@@ -630,7 +640,7 @@ void *b200_enc_open_params(const b200_enc_params *up)
   c.width = p.width; c.height = p.height; c.qp = p.qp; c.intra_period = p.intra_period; c.search_range = p.search_range;
   c.deblock = p.deblock; c.debug = p.debug; c.depth = p.depth; c.qp_delta = p.qp_delta;
   c.fps_num = p.fps_num; c.fps_den = p.fps_den; c.sao = p.sao; c.intra_in_p = p.intra_in_p; c.me_coarse = p.me_coarse;
-  c.intra_satd = p.intra_satd; c.subme_satd = p.subme_satd;
+  c.intra_satd = p.intra_satd; c.subme_satd = p.subme_satd; c.vaq = p.vaq;
   if (!e->open(c)) { delete e; return nullptr; }
   return e;
 }

@@ -31,6 +31,7 @@ struct EncoderConfig {
   int intra_in_p = 0;        // 16x16 intra CUs in P pictures where inter prediction is poor
   int intra_satd = 0;        // I pictures: SATD instead of SAD in the intra mode search
   int subme_satd = 0;        // P pictures: SATD instead of SAD in the fractional motion refinement
+  int vaq = 0;               // variance adaptive quantisation strength (Kvazaar --vaq), 1..20; needs qp_delta
   int me_coarse = 0;         // two-level motion search: range of the coarse level in coarse (4x4-mean) samples,
                              // a multiple of 4; search_range (<= 16) is then the window around each centre
   int depth = 1;             // pictures in flight (Kvazaar's owf + 1): output of picture n is
@@ -47,6 +48,7 @@ struct FrameSlot {
   uint32_t *d_recs = nullptr;      // bin records (binariser -> arithmetic coder)
   uint8_t *d_qpinfo = nullptr;     // qp_delta: ctu_qp | ctu_delta | ctu_first, one byte per CTU each
   uint8_t *h_ctu_qp = nullptr;     // pinned staging of ctu_qp
+  uint32_t *d_vaq = nullptr;       // vaq: per-CTU sample statistics (6 words each)
   uint8_t *d_small = nullptr;      // row_len | sync flags | progress | ticket | bins | sync contexts
   int *d_ctu_done = nullptr;       // intra wavefront: one flag per CTU, then the picture's "any intra CU" flag
   uint8_t *d_dbk = nullptr;        // sao: the deblocked picture (SAO reads it and writes the reconstruction ring)

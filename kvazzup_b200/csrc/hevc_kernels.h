@@ -45,6 +45,10 @@ cudaError_t launch_store_mvf(const FrameParams &fp, const CuInfo *cu, MvField *o
 // deblocking and binarisation.
 cudaError_t launch_cu_qps(const FrameParams &fp, CuInfo *cu, cudaStream_t s);
 
+// variance adaptive quantisation (hevc_vaq.cu), two launches: per-CTU sample statistics of the source picture
+// into `stats` (6 words per CTU), then ctu_qp[i] (staged as QP + kVaqBias) += the CTU's offset, clipped to 0..51
+cudaError_t launch_vaq(const FrameParams &fp, const uint8_t *src, int strength, uint32_t *stats, uint8_t *ctu_qp, cudaStream_t s);
+
 // in-loop deblocking, in place on `rec` (vertical edges of the whole picture, then horizontal)
 cudaError_t launch_deblock(const FrameParams &fp, uint8_t *rec, const CuInfo *cu, cudaStream_t s);
 

@@ -278,11 +278,13 @@ kvz_encoder *encoder_open(const kvz_config *cfg)
   c.intra_satd = cfg->intra_satd; c.subme_satd = cfg->subme_satd;
   if (c.me_coarse > 0 && c.search_range > 16) c.search_range = 16;
   c.deblock = cfg->deblock_enable; c.debug = 0; c.depth = cfg->owf + 1;
-  c.qp_delta = (cfg->roi_enable || cfg->set_qp_in_cu) ? 1 : 0;
+  const bool tiled = cfg->tiles_width_count > 1 || cfg->tiles_height_count > 1;
+  c.vaq = tiled ? 0 : cfg->vaq;                   // per-CTU QP is not available together with tiles
+  c.qp_delta = (cfg->roi_enable || cfg->set_qp_in_cu || c.vaq) ? 1 : 0;
   c.fps_num = cfg->framerate_num; c.fps_den = cfg->framerate_denom;     // VUI timing: the decoder side reports it
   c.sao = cfg->sao_type != 0 ? 2 : 0;             // with sao_merge_left / _up flags
   c.intra_in_p = 1;                               // every Kvazaar preset may code intra CUs in P pictures
-  if (cfg->tiles_width_count > 1 || cfg->tiles_height_count > 1) {
+  if (tiled) {
     // tiles: independent tile encoders on this GPU; motion is confined to the tile, like
     // Kvazaar's mv-constraint frametilemargin (the reference exposes it, kvazaarfilter.cpp:246-276);
     // constant QP only (no ROI, no rate control)

@@ -59,6 +59,7 @@ struct orc_encoder {
   int w, h, cw, ch, w8, h8, ctb_cols, ctb_rows;
   int frame_idx, poc, is_idr;
   int8_t *ctu_dqp;               /* per-CTU QP offset (ROI), zeros by default */
+  int8_t *vaq_dqp;               /* per-CTU QP offset of variance adaptive quantisation (cfg.vaq), per picture */
   int8_t *ctu_delta;             /* CuQpDeltaVal coded in each CTU (0 if none) */
   uint8_t *ctu_first;            /* z-index (8x8 units) of the first CU with a coded residual, 64 = none */
   struct orc_sao *sao;           /* per CTU, when cfg.sao */
@@ -107,6 +108,7 @@ orc_encoder_t *orc_enc_open(const orc_enc_cfg_t *cfg)
   if (cfg->cb_qp_offset < -12 || cfg->cb_qp_offset > 12 || cfg->cr_qp_offset < -12 || cfg->cr_qp_offset > 12) return NULL;
   if (cfg->beta_offset_div2 < -6 || cfg->beta_offset_div2 > 6 || cfg->tc_offset_div2 < -6 || cfg->tc_offset_div2 > 6) return NULL;
   if (cfg->me_coarse < 0 || cfg->me_coarse > 32 || (cfg->me_coarse > 0 && cfg->search_range > 16)) return NULL;
+  if (cfg->vaq < 0 || cfg->vaq > 20 || (cfg->vaq && !cfg->qp_delta)) return NULL;
   orc_encoder_t *e = (orc_encoder_t *)calloc(1, sizeof(*e));
   if (!e) return NULL;
   e->cfg = *cfg;
@@ -114,6 +116,7 @@ orc_encoder_t *orc_enc_open(const orc_enc_cfg_t *cfg)
   e->w8 = e->w / 8; e->h8 = e->h / 8;
   e->ctb_cols = (e->w + CTB - 1) / CTB; e->ctb_rows = (e->h + CTB - 1) / CTB;
   e->ctu_dqp = (int8_t *)calloc((size_t)e->ctb_cols * e->ctb_rows, 1);
+  e->vaq_dqp = (int8_t *)calloc((size_t)e->ctb_cols * e->ctb_rows, 1);
   e->ctu_delta = (int8_t *)calloc((size_t)e->ctb_cols * e->ctb_rows, 1);
   e->ctu_first = (uint8_t *)calloc((size_t)e->ctb_cols * e->ctb_rows, 1);
   if (cfg->sao) {
@@ -144,7 +147,7 @@ orc_encoder_t *orc_enc_open(const orc_enc_cfg_t *cfg)
 
 void orc_enc_close(orc_encoder_t *e)
 {
-  if (e) { free(e->ctu_dqp); free(e->ctu_delta); free(e->ctu_first); free(e->sao); free(e->dbk); }
+  if (e) { free(e->ctu_dqp); free(e->vaq_dqp); free(e->ctu_delta); free(e->ctu_first); free(e->sao); free(e->dbk); }
   if (!e) return;
   free(e->rec); free(e->rec_pre);
   for (int r = 0; r < MAX_REFS; r++) {
@@ -182,11 +185,95 @@ const orc_cu_t *orc_enc_cu_map(const orc_encoder_t *e) { return e->cu; }
 const int16_t *orc_enc_levels(const orc_encoder_t *e) { return e->levels; }
 int orc_enc_last_was_idr(const orc_encoder_t *e) { return e->is_idr; }
 unsigned long long orc_enc_bins(const orc_encoder_t *e) { return e->bins; }
-/* QP of the CTU that holds luma sample (x, y): the slice QP plus the ROI offset */
+/* QP of the CTU that holds luma sample (x, y): the slice QP plus the ROI offset plus the offset of
+ * variance adaptive quantisation */
 static int ctu_qp(const orc_encoder_t *e, int x, int y)
 {
   if (!e->cfg.qp_delta) return e->cfg.qp;
-  return clip3i(0, 51, e->cfg.qp + e->ctu_dqp[(y / CTB) * e->ctb_cols + x / CTB]);
+  const int i = (y / CTB) * e->ctb_cols + x / CTB;
+  return clip3i(0, 51, e->cfg.qp + e->ctu_dqp[i] + e->vaq_dqp[i]);
+}
+
+/* ---- variance adaptive quantisation ("vaq", Kvazaar's --vaq <strength>, set by the reference at
+ * kvazaarfilter.cpp:280-284 when the user setting is 1..20) ----
+ * Kvazaar (encoderstate.c, the "Variance adaptive quantization" block of encoder_state_init_new_frame;
+ * third-party, not under /root/reference) gives every CTU the offset
+ *     dqp = strength * 0.1 * (ln(max(var_ctu, 4)) - ln(var_picture))
+ * (here the picture's variance has the same floor of 4, so that a flat picture moves nothing),
+ * var = luma variance + the two chroma variances of the CTU / the picture, and quantises the CTU at
+ * the picture QP + round(dqp).  Restated here in integer arithmetic so that the CPU and the GPU agree
+ * bit for bit: variances as exact fractions (n * sum x^2 - (sum x)^2) / n^2 over a common
+ * denominator, log2 in Q8 fixed point by repeated squaring of a 32-bit mantissa (truncating), and
+ *     dqp = clip(round_half_away(strength * 71 * (L_ctu - L_picture) / 2^18), -12, 12)
+ * (0.1 * ln 2 / 256 = 71 / 2^18 to four digits; the clip bounds the swing of a CTU that is flat
+ * inside a busy picture). */
+typedef unsigned __int128 u128;
+
+/* floor(256 * log2(v)), v > 0 */
+static int log2_q8(u128 v)
+{
+  int msb = 127;
+  while (!(v >> msb)) msb--;
+  uint64_t m = msb >= 31 ? (uint64_t)(v >> (msb - 31)) : (uint64_t)(v << (31 - msb));    /* [2^31, 2^32) */
+  int frac = 0;
+  for (int i = 0; i < 8; i++) {
+    m = (m * m) >> 31;                               /* [2^31, 2^33) */
+    frac <<= 1;
+    if (m >> 32) { frac |= 1; m >>= 1; }
+  }
+  return msb * 256 + frac;
+}
+
+/* n^2 * (var Y + var U + var V) of a region of n luma and n / 4 samples per chroma plane */
+static u128 var_numer(uint64_t n, const uint64_t s[3], const uint64_t ss[3])
+{
+  const uint64_t nc = n / 4;
+  u128 y = (u128)n * ss[0] - (u128)s[0] * s[0];
+  u128 u = (u128)nc * ss[1] - (u128)s[1] * s[1];
+  u128 v = (u128)nc * ss[2] - (u128)s[2] * s[2];
+  return y + 16 * (u + v);
+}
+
+static void region_sums(const uint8_t *i420, int w, int h, int x0, int y0, int bw, int bh, uint64_t s[3], uint64_t ss[3])
+{
+  for (int c = 0; c < 3; c++) {
+    const uint8_t *pl = c == 0 ? i420 : i420 + (size_t)w * h + (size_t)(c - 1) * (w / 2) * (h / 2);
+    const int st = c ? w / 2 : w, sh = c ? 1 : 0;
+    uint64_t a = 0, b = 0;
+    for (int y = y0 >> sh; y < (y0 + bh) >> sh; y++)
+      for (int x = x0 >> sh; x < (x0 + bw) >> sh; x++) { const unsigned v = pl[(size_t)y * st + x]; a += v; b += v * v; }
+    s[c] = a; ss[c] = b;
+  }
+}
+
+/* per-CTU QP offsets (raster, (w+63)/64 x (h+63)/64) of one I420 picture; w and h even */
+void orc_vaq_offsets(const uint8_t *i420, int w, int h, int strength, int8_t *out)
+{
+  const int cols = (w + CTB - 1) / CTB, rows = (h + CTB - 1) / CTB;
+  uint64_t fs[3] = {0, 0, 0}, fss[3] = {0, 0, 0};
+  uint64_t *cs = (uint64_t *)malloc(sizeof(uint64_t) * 6 * (size_t)cols * rows);
+  for (int r = 0; r < rows; r++)
+    for (int c = 0; c < cols; c++) {
+      uint64_t *q = cs + 6 * ((size_t)r * cols + c);
+      region_sums(i420, w, h, c * CTB, r * CTB, imin(CTB, w - c * CTB), imin(CTB, h - r * CTB), q, q + 3);
+      for (int k = 0; k < 3; k++) { fs[k] += q[k]; fss[k] += q[3 + k]; }
+    }
+  const uint64_t fn = (uint64_t)w * h;
+  u128 fnum = var_numer(fn, fs, fss);
+  if (fnum < (u128)4 * fn * fn) fnum = (u128)4 * fn * fn;      /* the floor of the CTUs: a flat picture moves nothing */
+  const int lf = log2_q8(fnum) - 2 * log2_q8(fn);
+  for (int r = 0; r < rows; r++)
+    for (int c = 0; c < cols; c++) {
+      const uint64_t *q = cs + 6 * ((size_t)r * cols + c);
+      const uint64_t n = (uint64_t)imin(CTB, w - c * CTB) * imin(CTB, h - r * CTB);
+      u128 num = var_numer(n, q, q + 3);
+      if (num < (u128)4 * n * n) num = (u128)4 * n * n;
+      const int lc = log2_q8(num) - 2 * log2_q8(n);
+      const int t = strength * 71 * (lc - lf);
+      const int d = t >= 0 ? (t + (1 << 17)) >> 18 : -((-t + (1 << 17)) >> 18);
+      out[r * cols + c] = (int8_t)clip3i(-12, 12, d);
+    }
+  free(cs);
 }
 static int lambda_at(const orc_encoder_t *e, int x, int y) { return lambda_q4_tab[ctu_qp(e, x, y)]; }
 
@@ -1939,6 +2026,7 @@ int orc_enc_encode(orc_encoder_t *e, const uint8_t *i420, uint8_t *out, int cap)
   if (e->is_idr) e->poc = 0;
   e->n_refs = e->is_idr ? 0 : imin(imax(1, e->cfg.refs), e->n_dpb);
   memset(e->levels, 0, fsz * sizeof(int16_t));
+  if (e->cfg.vaq) orc_vaq_offsets(i420, e->w, e->h, e->cfg.vaq, e->vaq_dqp);
   if (e->is_idr) {
     for (int cy = 0; cy < e->h; cy += CTB)
       for (int cx = 0; cx < e->w; cx += CTB) intra_quadtree(e, cx, cy, CTB_LOG2);

@@ -72,6 +72,8 @@ typedef struct {
   int beta_offset_div2, tc_offset_div2;   /* pps_beta_offset_div2 / pps_tc_offset_div2 (-6..6) */
   int tile_rows;           /* > 1 (or tile_cols > 1): PPS of a picture with that many uniform tile rows (compositor only);
                             * mv_edges bits 2 / 3 then mark the top / bottom edge of a tile as interior */
+  int vaq;                 /* variance adaptive quantisation strength (Kvazaar --vaq), 0 = off, 1..20; needs qp_delta:
+                            * every picture, each CTU's QP moves by orc_vaq_offsets() on top of the ROI offsets */
 } orc_enc_cfg_t;
 
 typedef struct orc_encoder orc_encoder_t;
@@ -87,6 +89,9 @@ int orc_enc_encode(orc_encoder_t *e, const uint8_t *i420, uint8_t *out, int cap)
 /* Per-CTU QP offsets for the pictures that follow (ctb_cols*ctb_rows entries, raster; NULL = none).
  * Needs cfg.qp_delta; CTU QP = clip(qp + dqp, 0, 51). */
 int orc_enc_set_ctu_dqp(orc_encoder_t *e, const int8_t *dqp);
+/* Variance adaptive quantisation: the QP offset (-12..12) of every CTU (raster) of one I420 picture
+ * (even w, h) at `strength` (1..20), from the CTU's and the picture's sample variance. */
+void orc_vaq_offsets(const uint8_t *i420, int w, int h, int strength, int8_t *out);
 
 /* Tile columns (H.265 6.5.1, uniform spacing) coded as independent strips: one encoder per tile with
  * mv_edges / more_tiles / raw_slice_data set, loop filtering across tiles off, substreams

@@ -37,7 +37,7 @@ class OrcEncCfg(C.Structure):
                 ("mv_edges", i), ("more_tiles", i), ("raw_slice_data", i), ("no_wpp", i), ("subme_satd", i), ("sao", i), ("tile_cols", i),
                 ("tr_depth", i), ("cabac_init", i), ("refs", i), ("tmvp", i), ("me_coarse", i), ("intra_in_p", i), ("fps_num", i), ("fps_den", i),
                 ("intra_satd", i), ("tu4", i), ("intra_sizes", i), ("chroma_modes", i), ("sign_hiding", i), ("strong_intra", i),
-                ("cb_qp_offset", i), ("cr_qp_offset", i), ("beta_offset_div2", i), ("tc_offset_div2", i), ("tile_rows", i)]
+                ("cb_qp_offset", i), ("cr_qp_offset", i), ("beta_offset_div2", i), ("tc_offset_div2", i), ("tile_rows", i), ("vaq", i)]
 
 
 SIGS.update({
@@ -47,6 +47,7 @@ SIGS.update({
     "orc_max_threads": (i, []),
     "orc_enc_encode": (i, [v, v, v, i]),
     "orc_enc_set_ctu_dqp": (i, [v, v]),
+    "orc_vaq_offsets": (None, [v, i, i, i, v]),
     "orc_tiled_open": (v, [C.POINTER(OrcEncCfg), i]),
     "orc_tiled_open2": (v, [C.POINTER(OrcEncCfg), i, i]),
     "orc_tiled_close": (None, [v]),

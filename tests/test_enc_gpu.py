@@ -394,6 +394,81 @@ def test_per_ctu_qp_matches_oracle_stage_by_stage(kind, w, h, n, qp, roi, kw):
     o.close()
 
 
+VAQ_CASES = [
+    ("camera", 416, 240, 5, 30, None, {"vaq": 10}),
+    ("screen", 640, 200, 4, 35, None, {"vaq": 20, "sao": 2, "intra_period": 3}),
+    ("sports", 416, 240, 4, 27, "window", {"vaq": 5, "me_coarse": 16, "search_range": 4, "intra_in_p": 1}),
+    ("camera", 416, 240, 3, 2, None, {"vaq": 20}),
+    ("camera", 200, 136, 3, 49, "random", {"vaq": 20}),
+    ("noise", 72, 64, 2, 30, None, {"vaq": 10}),
+    ("camera", 1920, 1080, 2, 32, None, {"vaq": 8, "me_coarse": 16, "search_range": 6, "sao": 2, "intra_in_p": 1, "intra_satd": 1}),
+]
+
+
+@pytest.mark.parametrize("kind,w,h,n,qp,roi,kw", VAQ_CASES)
+def test_vaq_matches_oracle_stage_by_stage(kind, w, h, n, qp, roi, kw):
+    """Variance adaptive quantisation (Kvazaar --vaq): the per-CTU statistics kernels give every CTU
+    the QP the oracle's orc_vaq_offsets gives it, on top of ROI offsets, and everything downstream
+    (cu map, levels, reconstruction, bytes) equals the oracle's."""
+    from tests.test_oracle_hevc import roi_pattern, vaq_frames
+    frames = vaq_frames(kind, w, h, n)
+    args = {"intra_period": 0} | kw
+    g = GpuEncoder(w, h, qp=qp, debug=1, qp_delta=1, **args)
+    o = OracleEncoder(w, h, qp=qp, qp_delta=1, **args)
+    aus = []
+    for i, f in enumerate(frames):
+        if roi:
+            d = roi_pattern(w, h, i, roi)
+            g.set_ctu_dqp(d)
+            o.set_ctu_dqp(d)
+        ga, oa = g.encode(f), o.encode(f)
+        tag = f"vaq {kind} {w}x{h} qp{qp} frame {i}"
+        bad = np.flatnonzero(g.cu_map()["qp"] != o.cu_map()["qp"])
+        assert bad.size == 0, f"{tag}: per-CU QP differs at units {bad[:8]}"
+        compare_frame(tag, g, o, w, h)
+        assert ga == oa, f"{tag}: access unit differs (gpu {len(ga)} B, oracle {len(oa)} B)"
+        aus.append(ga)
+    assert len(np.unique(o.cu_map()["qp"])) > 1 or kind == "noise"
+    rec = g.recon()
+    g.close()
+    o.close()
+    if ffhevc.required():
+        ff, errs = ffhevc.decode_stream(aus)
+        assert errs == 0 and np.array_equal(ff[-1][0], rec)
+
+
+def test_vaq_through_kvz_api_and_pipelining():
+    """"vaq" (kvazaarfilter.cpp:280-284 sets it when the setting is 1..20) turns cu_qp_delta on and gives
+    the stream of the engine opened with that strength, at any pipeline depth; with a rate-control
+    target it still runs; refused out of range."""
+    from kvazzup_b200.kvazaar import KvazaarFilter
+    from kvazzup_b200.encoder import preset_options
+    from tests.test_oracle_hevc import vaq_frames
+    w, h, n = 416, 240, 6
+    frames = vaq_frames("camera", w, h, n)
+    base = {"video/ResolutionWidth": w, "video/ResolutionHeight": h, "video/QP": 30, "video/Intra": 4, "video/Preset": "ultrafast"}
+    uf = preset_options("ultrafast")
+    eng = GpuEncoder(w, h, qp=30, intra_period=4, qp_delta=1, vaq=10, fps_num=30, fps_den=1, **uf)
+    want = [eng.encode(f) for f in frames]
+    eng.close()
+    plain = GpuEncoder(w, h, qp=30, intra_period=4, fps_num=30, fps_den=1, **uf)
+    assert [plain.encode(f) for f in frames] != want
+    plain.close()
+    for owf in (0, 3):
+        f = KvazaarFilter(base | {"video/vaq": 10, "video/OWF": owf})
+        assert f.init()
+        got = []
+        for fr in frames:
+            got += f.feed_input(fr, drain=False)
+        got += f.flush()
+        f.close()
+        assert got == want, owf
+    with pytest.raises(Exception):
+        GpuEncoder(w, h, qp=30, vaq=10)              # needs qp_delta
+    with pytest.raises(Exception):
+        GpuEncoder(w, h, qp=30, qp_delta=1, vaq=21)
+
+
 def test_roi_through_kvz_api_and_pipelining():
     """kvz_picture::roi (per-pixel delta-QP map, kvazaarfilter.cpp:423-431) -> same stream as the engine
     given the per-CTU offsets Kvazaar would sample; ignored unless enabled or when a bitrate is set."""

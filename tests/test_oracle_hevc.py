@@ -111,6 +111,102 @@ def test_per_ctu_qp_streams_decode_bit_exactly_in_ffmpeg(kind, w, h, n, qp, roi,
         assert all((q == qp).all() for q in qps)
 
 
+def vaq_float_model(i420, w, h, strength):
+    """Kvazaar's formula in floating point: strength * 0.1 * (ln(max(var_ctu, 4)) - ln(var_picture)),
+    var = luma variance + the two chroma variances."""
+    y = i420[:w * h].reshape(h, w).astype(np.float64)
+    u = i420[w * h:w * h * 5 // 4].reshape(h // 2, w // 2).astype(np.float64)
+    v = i420[w * h * 5 // 4:].reshape(h // 2, w // 2).astype(np.float64)
+    fv = max(y.var() + u.var() + v.var(), 4.0)
+    cols, rows = (w + 63) // 64, (h + 63) // 64
+    out = np.zeros((rows, cols))
+    for r in range(rows):
+        for c in range(cols):
+            lv = (y[r * 64:(r + 1) * 64, c * 64:(c + 1) * 64].var() + u[r * 32:(r + 1) * 32, c * 32:(c + 1) * 32].var() +
+                  v[r * 32:(r + 1) * 32, c * 32:(c + 1) * 32].var())
+            out[r, c] = strength * 0.1 * (np.log(max(lv, 4.0)) - np.log(fv))
+    return np.clip(out, -12, 12).ravel()
+
+
+def vaq_frames(kind, w, h, n):
+    """Synthetic pictures whose CTUs differ in variance (the generators' texture is even): the left
+    third loses 7/8 of its contrast, the right third gains noise."""
+    rng = np.random.default_rng(w * 31 + h)
+    out = []
+    for f in frames_of(kind, w, h, n):
+        y = f[:w * h].reshape(h, w).astype(np.int32)
+        y[:, :w // 3] = (y[:, :w // 3] - 128) // 8 + 128
+        y[:, 2 * w // 3:] += rng.integers(-40, 41, (h, w - 2 * w // 3))
+        g = f.copy()
+        g[:w * h] = np.clip(y, 0, 255).astype(np.uint8).ravel()
+        out.append(g)
+    return out
+
+
+def oracle_vaq_offsets(i420, w, h, strength):
+    import ctypes as C
+    from oracle.binding import load
+    out = np.zeros(((w + 63) // 64) * ((h + 63) // 64), np.int8)
+    pic = np.ascontiguousarray(i420)
+    load().orc_vaq_offsets(C.c_void_p(pic.ctypes.data), w, h, strength, C.c_void_p(out.ctypes.data))
+    return out
+
+
+@pytest.mark.parametrize("kind,w,h,strength", [
+    ("camera", 416, 240, 10), ("screen", 640, 200, 5), ("noise", 256, 136, 20), ("sports", 1920, 1080, 7),
+    ("camera", 72, 64, 1), ("flat", 128, 72, 10),
+])
+def test_vaq_offsets_follow_the_published_formula(kind, w, h, strength):
+    """The integer restatement (exact variance fractions, Q8 log2) stays within rounding of Kvazaar's
+    floating-point formula; a flat picture gives offset 0 everywhere."""
+    if kind == "flat":
+        pic = np.full(w * h * 3 // 2, 97, np.uint8)
+        assert not oracle_vaq_offsets(pic, w, h, strength).any()
+        return
+    pic = vaq_frames(kind, w, h, 2)[1]
+    got = oracle_vaq_offsets(pic, w, h, strength)
+    want = vaq_float_model(pic, w, h, strength)
+    assert np.abs(got - want).max() <= 0.5 + 0.02 * strength, (got, want)
+    if strength >= 5:
+        assert got.min() < got.max()                # flat and busy CTUs really move apart
+
+
+@needs_ff
+@pytest.mark.parametrize("kind,w,h,n,qp,kw", [
+    ("camera", 416, 240, 5, 30, {"vaq": 10, "hash_sei": 1}),
+    ("screen", 640, 200, 4, 35, {"vaq": 20, "sao": 2, "intra_period": 3}),
+    ("sports", 416, 240, 4, 27, {"vaq": 5, "me_coarse": 16, "search_range": 4, "intra_in_p": 1, "roi": "window"}),
+    ("camera", 416, 240, 3, 2, {"vaq": 20}),                             # QP - offset clips at 0
+])
+def test_vaq_streams_decode_bit_exactly_in_ffmpeg(kind, w, h, n, qp, kw):
+    """Variance adaptive quantisation rides the cu_qp_delta path: the per-CTU QPs are those of
+    orc_vaq_offsets (plus the ROI offsets), and FFmpeg reconstructs the same pictures."""
+    kw = dict(kw)
+    roi = kw.pop("roi", None)
+    frames = vaq_frames(kind, w, h, n)
+    enc = OracleEncoder(w, h, qp=qp, qp_delta=1, **({"intra_period": 0} | kw))
+    cols = (w + 63) // 64
+    aus, recs = [], []
+    for t, f in enumerate(frames):
+        d = roi_pattern(w, h, t, roi) if roi else np.zeros(cols * ((h + 63) // 64), np.int8)
+        if roi:
+            enc.set_ctu_dqp(d)
+        aus.append(enc.encode(f))
+        recs.append(enc.recon())
+        want = np.clip(qp + d.astype(int) + oracle_vaq_offsets(f, w, h, kw["vaq"]), 0, 51)
+        cu = enc.cu_map().reshape(h // 8, w // 8)
+        coded = (cu["flags"] & 2) != 0                    # CUs with a residual carry their CTU's target QP
+        ctu_of = (np.arange(h // 8)[:, None] // 8) * cols + np.arange(w // 8)[None, :] // 8
+        assert np.array_equal(cu["qp"][coded], want[ctu_of][coded]), f"frame {t}"
+    enc.close()
+    dec, errs = ffhevc.decode_stream(aus)
+    assert errs == 0 and len(dec) == n
+    for i, (fr, fw, fh) in enumerate(dec):
+        assert np.array_equal(fr, recs[i]), f"frame {i}: decoder output differs from encoder reconstruction"
+    with pytest.raises(ValueError):
+        OracleEncoder(w, h, qp=qp, vaq=5)                 # needs qp_delta
+
+
 @needs_ff
 @pytest.mark.parametrize("kind,w,h,n,qp,tiles,kw", [
     ("camera", 416, 240, 5, 30, 2, {"hash_sei": 1}),                  # 7 CTU columns -> tiles of 3 and 4
