@@ -48,6 +48,8 @@ typedef struct b200_enc_params {
   int vaq;                       /* variance adaptive quantisation strength (Kvazaar --vaq, kvazaarfilter.cpp:280-284), 0 = off,
                                     1..20: every picture each CTU's QP moves by strength * 0.1 * ln(CTU variance / picture
                                     variance), on top of the offsets of b200_enc_set_ctu_dqp; needs qp_delta */
+  int scaling_list;              /* 1 = scaling_list_enabled_flag with the default lists of the standard (Kvazaar
+                                    --scaling-list default, kvazaarfilter.cpp:236-243): quantisation steps grow with frequency */
 } b200_enc_params;
 void  b200_enc_params_default(b200_enc_params *p);
 void *b200_enc_open_params(const b200_enc_params *p);
@@ -105,6 +107,7 @@ typedef struct b200_tiled_params {
   int subme_satd;                /* SATD-based fractional motion refinement (see b200_enc_params) */
   int tile_rows;                 /* uniform tile rows (default 1): tile_cols x tile_rows tiles in raster order; a tile
                                     row may be a single CTU row high */
+  int scaling_list;              /* default scaling lists (see b200_enc_params) */
 } b200_tiled_params;
 void  b200_tiled_params_default(b200_tiled_params *p);
 void *b200_tiled_open_params(const b200_tiled_params *p, const int *devices, int n_devices);

@@ -73,7 +73,7 @@ typedef struct kvz_config {
   int32_t tiles_width_count, tiles_height_count;   /* "tiles": "CxR" uniform tile grid (hevc_tiles.cu) */
   int32_t slices;                        /* "slices" */
   int32_t vaq;                           /* "vaq" 0..20: variance adaptive quantisation strength (enables cu_qp_delta; ignored with tiles) */
-  int32_t scaling_list;                  /* "scaling-list": only off (0) */
+  int32_t scaling_list;                  /* "scaling-list": off (0) or default (1: the default lists of the standard) */
   int32_t gop_lowdelay, gop_len;         /* "gop lp-g4d3t1": low-delay P is the only structure */
   int32_t me_range;                      /* full-sample search window around each centre, from "preset" or "b200-me-range" */
   int32_t me_coarse;                     /* range of the coarse search level (4x4-mean samples), "preset" or "b200-me-coarse" */

@@ -20,10 +20,11 @@
  * reference pictures from any short-term RPS of earlier pictures, temporal motion vector candidates);
  * intra CUs 2Nx2N and NxN of every size with explicit chroma modes and strong intra smoothing;
  * transform trees down to 4x4 luma blocks (DST-VII for intra); sign data hiding; cu_qp_delta with one
- * quantisation group per CTU; chroma QP and deblocking offsets; deblocking and SAO; WPP entry points;
+ * quantisation group per CTU; chroma QP and deblocking offsets; scaling lists (the default ones or lists
+ * carried in the SPS / PPS); deblocking and SAO; WPP entry points;
  * cabac_init_flag; uniformly spaced tile grids without loop filtering across tiles whose motion stays
  * inside the tile (what b200_tiled_* and kvz_api "tiles" emit), with or without WPP inside the tiles.
- * Not decoded: B slices, AMP / 2NxN / Nx2N inter partitions, PCM, scaling lists, transform skip,
+ * Not decoded: B slices, AMP / 2NxN / Nx2N inter partitions, PCM, transform skip,
  * transquant bypass, long-term references, several slices per picture, quantisation groups below the
  * CTU, a conformance window.  Those make libOpenHevcDecode return -1 with the reason in
  * b200_last_error() -- never a silently wrong picture.

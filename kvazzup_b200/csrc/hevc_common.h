@@ -138,6 +138,9 @@ struct FrameParams {
   int sign_hiding, strong_intra;
   int cb_qp_offset, cr_qp_offset, cb_qp_offset_pps, cr_qp_offset_pps;
   int beta_offset_div2, tc_offset_div2;
+  // Scaling lists (scaling_list_enabled_flag): the ScalingTable (hevc_headers.h) in force, in device memory;
+  // null = flat (every factor 16).  Encoder: the default lists ("scaling-list default").
+  const uint8_t *scaling;
   // optional work counters of the motion search (profiling): [0] CTUs, [1] 32x32 quadrants whose second
   // centre set was searched, [2] 16x16 intra mode searches, [3] intra CUs chosen (16x16)
   unsigned long long *me_stats;

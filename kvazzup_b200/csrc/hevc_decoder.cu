@@ -77,6 +77,7 @@ struct DecSlot {
   cudaStream_t stream = nullptr;          // slice data upload
   cudaEvent_t ev_uploaded = nullptr;
   uint8_t *d_data = nullptr, *h_data = nullptr, *h_out = nullptr;
+  uint8_t *d_scaling = nullptr, *h_scaling = nullptr;   // the ScalingTable this picture dequantises with (scaling lists on)
   std::vector<StripBufs> strips;
   int64_t pts = 0;
   int cur_idx = 0;                        // pool entry this picture is reconstructed into
@@ -147,6 +148,8 @@ struct Decoder {
       if (s.d_data) cudaFree(s.d_data);
       if (s.h_data) cudaFreeHost(s.h_data);
       if (s.h_out) cudaFreeHost(s.h_out);
+      if (s.d_scaling) cudaFree(s.d_scaling);
+      if (s.h_scaling) cudaFreeHost(s.h_scaling);
       if (s.ev_uploaded) cudaEventDestroy(s.ev_uploaded);
       if (s.stream) cudaStreamDestroy(s.stream);
     }
@@ -216,6 +219,8 @@ struct Decoder {
       if (!cuda_ok(cudaMalloc((void **)&s.d_data, data_cap), "cudaMalloc")) return false;
       if (!cuda_ok(cudaMallocHost((void **)&s.h_out, frame_bytes), "cudaMallocHost")) return false;
       if (!cuda_ok(cudaMallocHost((void **)&s.h_data, data_cap), "cudaMallocHost")) return false;
+      if (!cuda_ok(cudaMalloc((void **)&s.d_scaling, sizeof(ScalingTable)), "cudaMalloc")) return false;
+      if (!cuda_ok(cudaMallocHost((void **)&s.h_scaling, sizeof(ScalingTable)), "cudaMallocHost")) return false;
       s.strips.resize(tiles);
       for (int i = 0; i < tiles; i++) {
         StripBufs &t = s.strips[i];
@@ -268,7 +273,6 @@ struct Decoder {
     if (s.log2_min_cb != 3 || s.log2_ctb != 6) return "coding block sizes other than 8..64 are not supported";
     if (s.log2_min_tb != 2 || s.log2_max_tb != 5) return "transform block sizes other than 4..32 are not supported";
     if (s.max_tr_depth_inter > 3 || s.max_tr_depth_intra > 3) return "transform hierarchy depth > 3 is not supported";
-    if (s.scaling_list) return "scaling lists are not supported";
     if (s.amp) return "AMP is not supported";
     if (s.pcm) return "PCM is not supported";
     if (s.long_term_refs) return "long-term reference pictures are not supported";
@@ -440,6 +444,13 @@ struct Decoder {
     sl.pts = pts;
 #define DEC_CHECK(expr, what) do { if (!cuda_ok((expr), (what))) return -1; } while (0)
     DEC_CHECK(cudaMemcpyAsync(sl.d_data, sl.h_data, data_len, cudaMemcpyHostToDevice, sl.stream), "H2D slice");
+    if (sps.scaling_list) {              // 7.4.5: lists of the PPS, else of the SPS, else the default ones
+      ScalingTable def;
+      if (!pps.scaling_list && !sps.scaling_list_data) def.set_default();
+      const ScalingTable &lists = pps.scaling_list ? pps.lists : (sps.scaling_list_data ? sps.lists : def);
+      memcpy(sl.h_scaling, &lists, sizeof(ScalingTable));
+      DEC_CHECK(cudaMemcpyAsync(sl.d_scaling, sl.h_scaling, sizeof(ScalingTable), cudaMemcpyHostToDevice, sl.stream), "H2D scaling lists");
+    }
     DEC_CHECK(cudaEventRecord(sl.ev_uploaded, sl.stream), "record upload");
     for (int i = 0; i < tiles; i++) {
       StripBufs &t = sl.strips[i];
@@ -456,6 +467,7 @@ struct Decoder {
       t.fp.cb_qp_offset = pps.cb_qp_offset + sh.cb_qp_offset; t.fp.cr_qp_offset = pps.cr_qp_offset + sh.cr_qp_offset;
       t.fp.cb_qp_offset_pps = pps.cb_qp_offset; t.fp.cr_qp_offset_pps = pps.cr_qp_offset;
       t.fp.beta_offset_div2 = sh.beta_offset_div2; t.fp.tc_offset_div2 = sh.tc_offset_div2;
+      t.fp.scaling = sps.scaling_list ? sl.d_scaling : nullptr;
       t.fp.n_refs = std::max(n_refs, 1); t.fp.max_merge = sh.max_merge_cand;
       for (int k = 0; k < 16; k++) t.fp.ref_dist[k] = (int16_t)(k < n_refs ? poc - ref_poc[k] : 1);
       t.fp.col_mvf = (slice_type != 2 && sh.tmvp) ? g.d_mvf[ref_pool[sh.collocated_ref_idx]] : nullptr;

@@ -239,6 +239,8 @@ struct TileGeom {
 struct TqParams {
   int qp;           // QP of this plane
   int is_idr;       // quantiser offset 171 (I slices) / 85
+  const uint8_t *sl;   // FrameParams::scaling
+  int matrix;       // scaling matrix of the plane (3 + plane: inter)
 };
 
 // Coefficient words.  wc[q][r] = { c32[r][4q .. 4q+3] }: row r of the 32-point matrix; the N-point
@@ -302,6 +304,24 @@ __device__ __forceinline__ bool tb_at(const TileGeom &g, const uint8_t *s_org, c
   return true;
 }
 
+// Scaling factor m[x][y] (8.6.4.2) of the coefficient at column x, row y of a (1 << log2n)-sized block of
+// matrix 0..2 (intra Y / Cb / Cr) or 3..5 (inter); `sl` = FrameParams::scaling (ScalingTable layout), null = flat
+__device__ __forceinline__ int sl_factor(const uint8_t *sl, int log2n, int matrix, int x, int y)
+{
+  if (!sl) return 16;
+  const int sid = log2n - 2;
+  if (sid >= 2 && (x | y) == 0) return sl[1536 + (sid - 2) * 6 + matrix];
+  const int s = max(sid - 1, 0);
+  return sl[(sid * 6 + matrix) * 64 + ((y >> s) << (sid ? 3 : 2)) + (x >> s)];
+}
+// forward quantiser scale of that coefficient (HM: quantCoef = (quantScale << 4) / m)
+__device__ __forceinline__ unsigned sl_quant_scale(const uint8_t *sl, int qrem, int log2n, int matrix, int x, int y)
+{
+  const unsigned s = (unsigned)c_quant_scale[qrem];
+  return sl ? (s << 4) / (unsigned)sl_factor(sl, log2n, matrix, x, y) : s;
+}
+
+// dscale = m * levelScale[qp % 6] (m = 16 without scaling lists)
 __device__ __forceinline__ int16_t dequant_level(int lvl, int log2n, int qper, int dscale)
 {
   const int bd = log2n + 3;
@@ -338,7 +358,7 @@ __device__ __forceinline__ void forward_tq(const TileGeom g, const TqParams q, c
   __syncthreads();
   // vertical pass, lanes along v: coef[v][k] = (sum_j C[v][j] * tmpT[k][j] + rnd) >> (log2n + 6), then Q and IQ
   const int qper = q.qp / 6, qrem = q.qp % 6;
-  const int scale = c_quant_scale[qrem], dscale = 16 * c_level_scale[qrem];
+  const int lscale = c_level_scale[qrem];
   int16_t vals[16];
   int cnt = 0;
   for (int p = threadIdx.x; p < total; p += blockDim.x, cnt++) {
@@ -353,12 +373,13 @@ __device__ __forceinline__ void forward_tq(const TileGeom g, const TqParams q, c
     const int coef = (acc + (1 << (s2 - 1))) >> s2;
     const int qbits = 14 + qper + (7 - tb.log2n);
     const unsigned add = (unsigned)(q.is_idr ? 171 : 85) << (qbits - 9);
-    const unsigned a = ((unsigned)abs(coef) * (unsigned)scale + add) >> qbits;    // < 2^32: |coef| <= 2^15, scale < 2^15
+    const unsigned scale = sl_quant_scale(q.sl, qrem, tb.log2n, q.matrix, k, v);
+    const unsigned a = ((unsigned)abs(coef) * scale + add) >> qbits;    // < 2^32: |coef| <= 2^15, scale < 2^15
     int lvl = (int)min(a, 32767u);
     if (coef < 0) lvl = -lvl;
     vals[cnt] = (int16_t)lvl;
     if (lvl) s_nz[tb.org] = 1;
-    s_a[(tb.oy + k) * P + tb.ox + v] = dequant_level(lvl, tb.log2n, qper, dscale);   // deqT[k][v]
+    s_a[(tb.oy + k) * P + tb.ox + v] = dequant_level(lvl, tb.log2n, qper, sl_factor(q.sl, tb.log2n, q.matrix, k, v) * lscale);   // deqT[k][v]
   }
   __syncthreads();     // all reads of s_b (tmpT) are done; the levels may now overwrite it
   cnt = 0;

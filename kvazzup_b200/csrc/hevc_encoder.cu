@@ -13,6 +13,7 @@
 #include <algorithm>
 
 #include "../../include/b200_hevc.h"
+#include "hevc_headers.h"
 #include "hevc_kernels.h"
 #include "runtime.h"
 
@@ -142,7 +143,8 @@ void Encoder::release()
   ev_intra = nullptr; intra_stream = nullptr;
   if (d_rec_pre) cudaFree(d_rec_pre);
   if (d_me_stats) cudaFree(d_me_stats);
-  d_me_stats = nullptr;
+  if (d_scaling) cudaFree(d_scaling);
+  d_me_stats = nullptr; d_scaling = nullptr;
   if (d_src_q) cudaFree(d_src_q);
   if (d_ref_q) cudaFree(d_ref_q);
   d_src_q = d_ref_q = nullptr;
@@ -230,6 +232,13 @@ bool Encoder::open(const EncoderConfig &c)
     ENC_CHECK(cudaEventCreateWithFlags(&s.ev_done, wait_event_flags(c.depth > 1)), "cudaEventCreate");
     for (cudaEvent_t &e : s.pev) ENC_CHECK(cudaEventCreate(&e), "cudaEventCreate");
   }
+  if (c.scaling_list) {
+    ScalingTable t;
+    t.set_default();
+    ENC_CHECK(cudaMalloc((void **)&d_scaling, sizeof(t)), "cudaMalloc scaling lists");
+    ENC_CHECK(cudaMemcpy(d_scaling, &t, sizeof(t), cudaMemcpyHostToDevice), "H2D scaling lists");
+  }
+  fp.scaling = d_scaling;
   ENC_CHECK(cudaMalloc((void **)&d_me_stats, 4 * sizeof(unsigned long long)), "cudaMalloc me stats");
   ENC_CHECK(cudaMemset(d_me_stats, 0, 4 * sizeof(unsigned long long)), "memset me stats");
   ENC_CHECK(cudaEventCreate(&ev_base), "cudaEventCreate");
@@ -265,7 +274,9 @@ void write_parameter_sets(const StreamLayout &l, std::vector<uint8_t> &out)
     b.ue(0); b.ue(3);                        // CB 8..64
     b.ue(0); b.ue(3);                        // TB 4..32
     b.ue(0); b.ue(0);                        // max_transform_hierarchy_depth inter / intra
-    b.put(0, 1); b.put(0, 1); b.put(l.sao ? 1 : 0, 1); b.put(0, 1);   // scaling lists, AMP off; SAO; PCM off
+    b.put(l.scaling_list ? 1 : 0, 1);        // scaling_list_enabled_flag
+    if (l.scaling_list) b.put(0, 1);         // sps_scaling_list_data_present_flag = 0: the default lists
+    b.put(0, 1); b.put(l.sao ? 1 : 0, 1); b.put(0, 1);   // AMP off; SAO; PCM off
     b.ue(1);                                 // one short-term RPS: the previous picture
     b.ue(1); b.ue(0); b.ue(0); b.put(1, 1);
     b.put(0, 1); b.put(0, 1); b.put(0, 1);   // long-term refs, TMVP, strong intra smoothing off
@@ -358,7 +369,7 @@ StreamLayout Encoder::layout() const
 {
   StreamLayout l;
   l.w = fp.w; l.h = fp.h; l.deblock = cfg.deblock; l.qp_delta = cfg.qp_delta; l.tile_cols = 1; l.wpp = cfg.no_wpp ? 0 : 1;
-  l.fps_num = cfg.fps_num; l.fps_den = cfg.fps_den; l.sao = cfg.sao;
+  l.fps_num = cfg.fps_num; l.fps_den = cfg.fps_den; l.sao = cfg.sao; l.scaling_list = cfg.scaling_list;
   return l;
 }
 
@@ -640,7 +651,7 @@ void *b200_enc_open_params(const b200_enc_params *up)
   c.width = p.width; c.height = p.height; c.qp = p.qp; c.intra_period = p.intra_period; c.search_range = p.search_range;
   c.deblock = p.deblock; c.debug = p.debug; c.depth = p.depth; c.qp_delta = p.qp_delta;
   c.fps_num = p.fps_num; c.fps_den = p.fps_den; c.sao = p.sao; c.intra_in_p = p.intra_in_p; c.me_coarse = p.me_coarse;
-  c.intra_satd = p.intra_satd; c.subme_satd = p.subme_satd; c.vaq = p.vaq;
+  c.intra_satd = p.intra_satd; c.subme_satd = p.subme_satd; c.vaq = p.vaq; c.scaling_list = p.scaling_list ? 1 : 0;
   if (!e->open(c)) { delete e; return nullptr; }
   return e;
 }

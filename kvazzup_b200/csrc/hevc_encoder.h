@@ -32,6 +32,7 @@ struct EncoderConfig {
   int intra_satd = 0;        // I pictures: SATD instead of SAD in the intra mode search
   int subme_satd = 0;        // P pictures: SATD instead of SAD in the fractional motion refinement
   int vaq = 0;               // variance adaptive quantisation strength (Kvazaar --vaq), 1..20; needs qp_delta
+  int scaling_list = 0;      // 1 = scaling_list_enabled_flag with the default lists (Kvazaar --scaling-list default)
   int me_coarse = 0;         // two-level motion search: range of the coarse level in coarse (4x4-mean) samples,
                              // a multiple of 4; search_range (<= 16) is then the window around each centre
   int depth = 1;             // pictures in flight (Kvazaar's owf + 1): output of picture n is
@@ -74,6 +75,7 @@ struct StreamLayout {
   int tile_cols = 1;         // > 1: uniform tile columns, no loop filtering across tiles
   int tile_rows = 1;         // > 1: uniform tile rows
   int wpp = 1;               // entropy_coding_sync_enabled_flag
+  int scaling_list = 0;      // scaling_list_enabled_flag, default lists (no list data in the SPS / PPS)
 };
 void write_parameter_sets(const StreamLayout &l, std::vector<uint8_t> &out);
 // Slice segment header with the entry points of `sub_len` (escaped sizes) followed by `data_len`
@@ -122,6 +124,7 @@ class Encoder {
   // its own stream concurrently with the P pictures queued before it.
   static constexpr int kRecRing = 32;
   uint8_t *d_rec[kRecRing] = {}, *d_rec_pre = nullptr;
+  uint8_t *d_scaling = nullptr;                     // scaling_list: the ScalingTable the kernels read (FrameParams::scaling)
   unsigned long long *d_me_stats = nullptr;         // profiling: work counters of k_me_ctu (FrameParams::me_stats)
   uint8_t *d_src_q = nullptr, *d_ref_q = nullptr;   // me_coarse: quarter-resolution source / previous reconstruction (main stream order)
   cudaEvent_t ev_ring[kRecRing] = {};    // "picture n finished reading its reference" (main stream)

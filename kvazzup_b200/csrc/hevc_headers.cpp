@@ -2,6 +2,8 @@
 // Host code of the B200 decoder; see hevc_headers.h.
 #include "hevc_headers.h"
 
+#include <string.h>
+
 #include <algorithm>
 
 namespace b200 {
@@ -105,6 +107,89 @@ void parse_vui(BitReader &b, Sps &sps)
 
 }  // namespace
 
+namespace {
+
+// Table 7-6 in up-right diagonal order (shared by the colour components and by every size from 8x8 up)
+const uint8_t kDefaultIntra[64] = {
+    16, 16, 16, 16, 16, 16, 16, 16, 16, 16, 17, 16, 17, 16, 17, 18, 17, 18, 18, 17, 18, 21, 19, 20, 21, 20, 19, 21, 24, 22, 22, 24,
+    24, 22, 22, 24, 25, 25, 27, 30, 27, 25, 25, 29, 31, 35, 35, 31, 29, 36, 41, 44, 41, 36, 47, 54, 54, 47, 65, 70, 65, 88, 88, 115};
+const uint8_t kDefaultInter[64] = {
+    16, 16, 16, 16, 16, 16, 16, 16, 16, 16, 17, 17, 17, 17, 17, 18, 18, 18, 18, 18, 18, 20, 20, 20, 20, 20, 20, 20, 24, 24, 24, 24,
+    24, 24, 24, 24, 25, 25, 25, 25, 25, 25, 25, 28, 28, 28, 28, 28, 28, 33, 33, 33, 33, 33, 41, 41, 41, 41, 54, 54, 54, 71, 71, 91};
+
+// raster position of entry i of the up-right diagonal scan (6.5.3) of an n x n array
+void diag_order(int n, uint8_t *pos)
+{
+  int i = 0, x = 0, y = 0;
+  while (i < n * n) {
+    while (y >= 0) {
+      if (x < n && y < n) pos[i++] = (uint8_t)(y * n + x);
+      y--; x++;
+    }
+    y = x; x = 0;
+  }
+}
+
+void store_list(ScalingTable &t, int sid, int mid, const uint8_t *list, int dc)
+{
+  uint8_t pos[64];
+  const int n = sid == 0 ? 4 : 8;
+  diag_order(n, pos);
+  memset(t.m[sid][mid], 16, 64);
+  for (int i = 0; i < n * n; i++) t.m[sid][mid][pos[i]] = list[i];
+  if (sid >= 2) t.dc[sid - 2][mid] = (uint8_t)dc;
+}
+
+void store_default(ScalingTable &t, int sid, int mid)
+{
+  uint8_t flat[16];
+  memset(flat, 16, sizeof(flat));
+  store_list(t, sid, mid, sid == 0 ? flat : (mid < 3 ? kDefaultIntra : kDefaultInter), 16);
+}
+
+// scaling_list_data() (7.3.4).  32x32 lists exist for luma only in 4:2:0 (matrixId 0 and 3).
+bool parse_scaling_list_data(BitReader &b, ScalingTable &t)
+{
+  t.set_default();
+  for (int sid = 0; sid < 4; sid++)
+    for (int mid = 0; mid < 6; mid += sid == 3 ? 3 : 1) {
+      if (!b.u(1)) {                                  // scaling_list_pred_mode_flag = 0: copy
+        const uint32_t delta = b.ue() * (sid == 3 ? 3 : 1);
+        if (delta > (uint32_t)mid) return false;
+        if (delta == 0) { store_default(t, sid, mid); continue; }
+        memcpy(t.m[sid][mid], t.m[sid][mid - delta], 64);
+        if (sid >= 2) t.dc[sid - 2][mid] = t.dc[sid - 2][mid - delta];
+        continue;
+      }
+      uint8_t list[64];
+      const int cnt = sid == 0 ? 16 : 64;
+      int next = 8, dc = 16;
+      if (sid > 1) {
+        const int d = b.se();
+        if (d < -7 || d > 247) return false;
+        next = dc = d + 8;
+      }
+      for (int i = 0; i < cnt; i++) {
+        const int d = b.se();
+        if (d < -128 || d > 127) return false;
+        next = (next + d + 256) & 255;
+        if (next == 0) return false;                  // scaling factors are 1..255
+        list[i] = (uint8_t)next;
+      }
+      store_list(t, sid, mid, list, dc);
+    }
+  return !b.bad;
+}
+
+}  // namespace
+
+void ScalingTable::set_default()
+{
+  memset(this, 0, sizeof(*this));
+  for (int sid = 0; sid < 4; sid++)
+    for (int mid = 0; mid < 6; mid++) store_default(*this, sid, mid);
+}
+
 bool parse_sps_rbsp(const uint8_t *rbsp, size_t n, Sps &sps, std::string &err)
 {
   BitReader b(rbsp, n);
@@ -134,7 +219,10 @@ bool parse_sps_rbsp(const uint8_t *rbsp, size_t n, Sps &sps, std::string &err)
   sps.log2_max_tb = sps.log2_min_tb + (int)b.ue();
   sps.max_tr_depth_inter = (int)b.ue(); sps.max_tr_depth_intra = (int)b.ue();
   sps.scaling_list = (int)b.u(1);
-  if (sps.scaling_list && b.u(1)) { err = "SPS carries scaling list data"; return false; }
+  if (sps.scaling_list) {
+    sps.scaling_list_data = (int)b.u(1);
+    if (sps.scaling_list_data && !parse_scaling_list_data(b, sps.lists)) { err = "malformed SPS (scaling list data)"; return false; }
+  }
   sps.amp = (int)b.u(1); sps.sao = (int)b.u(1); sps.pcm = (int)b.u(1);
   if (sps.pcm) { b.skip(8); b.ue(); b.ue(); b.skip(1); }
   const uint32_t num_rps = b.ue();
@@ -200,7 +288,7 @@ bool parse_pps_rbsp(const uint8_t *rbsp, size_t n, Pps &pps, std::string &err)
     if (!pps.deblock_disabled) { pps.beta_offset_div2 = b.se(); pps.tc_offset_div2 = b.se(); }
   }
   pps.scaling_list = (int)b.u(1);
-  if (pps.scaling_list) { err = "PPS carries scaling list data"; return false; }
+  if (pps.scaling_list && !parse_scaling_list_data(b, pps.lists)) { err = "malformed PPS (scaling list data)"; return false; }
   pps.lists_modification = (int)b.u(1);
   pps.log2_parallel_merge_level = 2 + (int)b.ue();
   pps.slice_header_extension = (int)b.u(1);

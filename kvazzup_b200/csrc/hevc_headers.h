@@ -54,6 +54,18 @@ struct ShortTermRps {
   int num_delta() const { return num_neg + num_pos; }
 };
 
+// Scaling factors (7.3.4 scaling_list_data, 7.4.5, 8.6.4.2) the way the kernels read them: the factor of a
+// coefficient at (x, y) of a 4 << sizeId block is m[sizeId][matrixId][y * 4 + x] for 4x4 blocks and
+// m[sizeId][matrixId][(y >> (sizeId - 1)) * 8 + (x >> (sizeId - 1))] above, except the DC coefficient
+// of 16x16 / 32x32 blocks, dc[sizeId - 2][matrixId].  matrixId: 0..2 intra Y / Cb / Cr, 3..5 inter.
+struct ScalingTable {
+  uint8_t m[4][6][64];
+  uint8_t dc[2][6];
+  uint8_t pad[4];
+  void set_default();                               // Tables 7-5 / 7-6
+};
+static_assert(sizeof(ScalingTable) == 1552, "the kernels index this layout");
+
 struct Sps {
   bool valid = false;
   int id = 0, chroma_format_idc = 1;
@@ -65,6 +77,8 @@ struct Sps {
   int log2_min_cb = 3, log2_ctb = 6, log2_min_tb = 2, log2_max_tb = 5;
   int max_tr_depth_inter = 0, max_tr_depth_intra = 0;
   int scaling_list = 0, amp = 0, sao = 0, pcm = 0;
+  int scaling_list_data = 0;                        // sps_scaling_list_data_present_flag: `lists` holds them (else the defaults apply)
+  ScalingTable lists;
   std::vector<ShortTermRps> rps;
   int long_term_refs = 0, num_lt_sps = 0, tmvp = 0, strong_intra_smoothing = 0;
   int fps_num = 0, fps_den = 0;                     // from the VUI timing info (0 = absent)
@@ -87,6 +101,7 @@ struct Pps {
   int loop_across_slices = 0;
   int deblock_ctrl = 0, deblock_override_enabled = 0, deblock_disabled = 0, beta_offset_div2 = 0, tc_offset_div2 = 0;
   int scaling_list = 0, lists_modification = 0, log2_parallel_merge_level = 2, slice_header_extension = 0;
+  ScalingTable lists;                               // scaling_list != 0 (pps_scaling_list_data_present_flag): these replace the SPS's
 };
 
 struct SliceHeader {
@@ -104,7 +119,7 @@ struct SliceHeader {
 };
 
 // All return false with `err` set when the syntax is malformed (or uses what cannot even be
-// skipped, e.g. scaling list data); they do not judge decodability.
+// skipped); they do not judge decodability.
 bool parse_sps_rbsp(const uint8_t *rbsp, size_t n, Sps &sps, std::string &err);
 bool parse_pps_rbsp(const uint8_t *rbsp, size_t n, Pps &pps, std::string &err);
 bool parse_slice_header_rbsp(const uint8_t *rbsp, size_t n, int nal_type, const Sps &sps, const Pps &pps,

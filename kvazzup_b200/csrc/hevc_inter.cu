@@ -575,7 +575,7 @@ k_inter_recon(FrameParams fp, const uint8_t *__restrict__ src, const RefList ref
     }
     __syncthreads();
     TileGeom g{T, c ? 5 : 6, c ? 2 : 3, cs};
-    TqParams q{c ? qp_c_at(fp, cx, cy, c) : qp_at(fp, cx, cy), fp.is_idr};
+    TqParams q{c ? qp_c_at(fp, cx, cy, c) : qp_at(fp, cx, cy), fp.is_idr, fp.scaling, 3 + c};
     if (!kDecode) {
       forward_tq(g, q, s_src, s_pred, sh.org, sh.log2, sh.w, s_a, s_b, sh.nz);
       // levels (s_b) -> HBM, 4 per thread; s_b then becomes the scratch tile of the inverse path
@@ -590,13 +590,14 @@ k_inter_recon(FrameParams fp, const uint8_t *__restrict__ src, const RefList ref
     } else {
       // dequantise the parsed levels (H.265 8.6.3) straight into the coefficient tile, transposed
       // inside each block (what the inverse vertical pass contracts over)
-      const int qper = q.qp / 6, dscale = 16 * c_level_scale[q.qp % 6];
+      const int qper = q.qp / 6, lscale = c_level_scale[q.qp % 6];
       for (int p = t; p < T * T; p += kThreads) {
         int y = p >> g.tlog2, x = p & (T - 1);
         TbPos tb;
         if (tb_at(g, sh.org, sh.log2, x, y, tb) && ((sh.nz[tb.org] >> tb.sub) & 1)) {
           int lvl = plev[(size_t)(py0 + y) * pw + px0 + x];
-          s_a[(tb.oy + (x - tb.ox)) * (T + 2) + tb.ox + (y - tb.oy)] = dequant_level(lvl, tb.log2n, qper, dscale);
+          s_a[(tb.oy + (x - tb.ox)) * (T + 2) + tb.ox + (y - tb.oy)] =
+              dequant_level(lvl, tb.log2n, qper, sl_factor(q.sl, tb.log2n, q.matrix, x - tb.ox, y - tb.oy) * lscale);
         }
       }
     }

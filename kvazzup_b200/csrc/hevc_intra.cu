@@ -145,7 +145,7 @@ __device__ void recon_cu(ReconSharedI &sh, const FrameParams &fp, const uint8_t 
       int coef = (acc + (1 << (s2 - 1))) >> s2;
       int qbits = 14 + qper + (7 - l2);
       unsigned add = (unsigned)(fp.is_idr ? 171 : 85) << (qbits - 9);
-      unsigned av = ((unsigned)abs(coef) * (unsigned)c_quant_scale[qrem] + add) >> qbits;
+      unsigned av = ((unsigned)abs(coef) * sl_quant_scale(fp.scaling, qrem, l2, p, x, y) + add) >> qbits;
       lvl = (int)min(av, 32767u);
       if (coef < 0) lvl = -lvl;
       levels[poff + (size_t)(by + y) * pw + bx + x] = (int16_t)lvl;
@@ -154,7 +154,7 @@ __device__ void recon_cu(ReconSharedI &sh, const FrameParams &fp, const uint8_t 
       lvl = sh.nz[p] ? levels[poff + (size_t)(by + y) * pw + bx + x] : 0;
     }
     int bd = l2 + 3;
-    long long d = ((long long)lvl * (16 * c_level_scale[qrem])) << qper;
+    long long d = ((long long)lvl * (sl_factor(fp.scaling, l2, p, x, y) * c_level_scale[qrem])) << qper;
     d = (d + (1LL << (bd - 1))) >> bd;
     a[li] = (int16_t)max(-32768LL, min(32767LL, d));
   }
@@ -419,14 +419,14 @@ __device__ void dec_tu(DecSharedI &sh, const FrameParams &fp, uint8_t *rec, cons
   int pr[4] = {0, 0, 0, 0};
   if (act) {
     const int qp = p == 0 ? qp_at(fp, lx, ly) : qp_c_at(fp, lx, ly, p);
-    const int qper = qp / 6, dscale = 16 * c_level_scale[qp % 6], bd = l2 + 3;
+    const int qper = qp / 6, lscale = c_level_scale[qp % 6], bd = l2 + 3;
     int s = 0;
     for (int i = gi; i < n * n; i += gs, s++) {
       const int y = i >> l2, x = i & (n - 1);
       pr[s] = intra_pixel(rs.sub, rs.filt, n, l2, mode, p, rs.dc, x, y);
       if (nz) {
         const int lvl = levels[poff + (size_t)(by + y) * pw + bx + x];
-        long long d = ((long long)lvl * dscale) << qper;
+        long long d = ((long long)lvl * (sl_factor(fp.scaling, l2, p, x, y) * lscale)) << qper;
         d = (d + (1LL << (bd - 1))) >> bd;
         a[i] = (int16_t)max(-32768LL, min(32767LL, d));
       }

@@ -46,7 +46,7 @@ struct TiledEncoder {
     width = c.width; height = c.height;
     layout.w = c.width; layout.h = c.height; layout.deblock = c.deblock; layout.qp_delta = 0;
     layout.tile_cols = tile_cols; layout.tile_rows = tile_rows; layout.wpp = wpp ? 1 : 0;
-    layout.fps_num = c.fps_num; layout.fps_den = c.fps_den; layout.sao = c.sao;
+    layout.fps_num = c.fps_num; layout.fps_den = c.fps_den; layout.sao = c.sao; layout.scaling_list = c.scaling_list;
     int prev = 0;
     cudaGetDevice(&prev);
     strips.resize(tiles);
@@ -165,7 +165,7 @@ void *b200_tiled_open_params(const b200_tiled_params *up, const int *devices, in
   memcpy(&p, up, std::min<size_t>((size_t)up->struct_size, sizeof(p)));
   b200::EncoderConfig c;
   c.width = p.width; c.height = p.height; c.qp = p.qp; c.intra_period = p.intra_period; c.search_range = p.search_range;
-  c.deblock = p.deblock; c.depth = p.depth; c.debug = 0; c.fps_num = p.fps_num; c.fps_den = p.fps_den; c.sao = p.sao; c.intra_in_p = p.intra_in_p; c.me_coarse = p.me_coarse; c.intra_satd = p.intra_satd; c.subme_satd = p.subme_satd;
+  c.deblock = p.deblock; c.depth = p.depth; c.debug = 0; c.fps_num = p.fps_num; c.fps_den = p.fps_den; c.sao = p.sao; c.intra_in_p = p.intra_in_p; c.me_coarse = p.me_coarse; c.intra_satd = p.intra_satd; c.subme_satd = p.subme_satd; c.scaling_list = p.scaling_list ? 1 : 0;
   TiledEncoder *t = new TiledEncoder();
   if (!t->open(c, p.tile_cols, p.tile_rows < 1 ? 1 : p.tile_rows, p.wpp, devices, n_devices)) { delete t; return nullptr; }
   return t;

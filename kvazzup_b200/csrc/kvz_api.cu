@@ -158,7 +158,11 @@ int config_parse(kvz_config *cfg, const char *name, const char *value)
     if (!strncmp(value, "lp-", 3)) { cfg->gop_lowdelay = 1; int g = 4; sscanf(value, "lp-g%d", &g); cfg->gop_len = g; return 1; }
     return 0;
   }
-  if (!strcmp(name, "scaling-list")) { if (value && !strcmp(value, "off")) { cfg->scaling_list = 0; return 1; } return 0; }
+  if (!strcmp(name, "scaling-list")) {        // off / default (the standard's default lists); custom list files are not read
+    if (value && !strcmp(value, "off")) { cfg->scaling_list = 0; return 1; }
+    if (value && !strcmp(value, "default")) { cfg->scaling_list = 1; return 1; }
+    return 0;
+  }
   if (!strcmp(name, "mv-constraint")) {
     if (!value || !*value || !strcmp(value, "none")) { cfg->mv_constraint = KVZ_MV_CONSTRAIN_NONE; return 1; }
     if (!strcmp(value, "frame")) { cfg->mv_constraint = KVZ_MV_CONSTRAIN_FRAME; return 1; }
@@ -280,6 +284,7 @@ kvz_encoder *encoder_open(const kvz_config *cfg)
   c.deblock = cfg->deblock_enable; c.debug = 0; c.depth = cfg->owf + 1;
   const bool tiled = cfg->tiles_width_count > 1 || cfg->tiles_height_count > 1;
   c.vaq = tiled ? 0 : cfg->vaq;                   // per-CTU QP is not available together with tiles
+  c.scaling_list = cfg->scaling_list ? 1 : 0;
   c.qp_delta = (cfg->roi_enable || cfg->set_qp_in_cu || c.vaq) ? 1 : 0;
   c.fps_num = cfg->framerate_num; c.fps_den = cfg->framerate_denom;     // VUI timing: the decoder side reports it
   c.sao = cfg->sao_type != 0 ? 2 : 0;             // with sao_merge_left / _up flags
@@ -292,7 +297,7 @@ kvz_encoder *encoder_open(const kvz_config *cfg)
     b200_tiled_params_default(&tp);
     tp.width = c.width; tp.height = c.height; tp.qp = c.qp; tp.intra_period = c.intra_period; tp.search_range = c.search_range;
     tp.deblock = c.deblock; tp.depth = c.depth; tp.tile_cols = cfg->tiles_width_count; tp.tile_rows = cfg->tiles_height_count; tp.wpp = cfg->wpp ? 1 : 0;
-    tp.fps_num = c.fps_num; tp.fps_den = c.fps_den; tp.sao = c.sao; tp.intra_in_p = c.intra_in_p; tp.me_coarse = c.me_coarse; tp.intra_satd = c.intra_satd; tp.subme_satd = c.subme_satd;
+    tp.fps_num = c.fps_num; tp.fps_den = c.fps_den; tp.sao = c.sao; tp.intra_in_p = c.intra_in_p; tp.me_coarse = c.me_coarse; tp.intra_satd = c.intra_satd; tp.subme_satd = c.subme_satd; tp.scaling_list = c.scaling_list;
     e->tiled = b200_tiled_open_params(&tp, nullptr, 0);
     if (!e->tiled) { delete e; return NULL; }
     e->tiled_out.resize((size_t)c.width * c.height * 3 + 65536);

@@ -17,6 +17,7 @@
 #include "hevc_enc.h"
 #include "hevc_cabac.h"
 #include "hevc_prims.h"
+#include "hevc_scaling.h"
 #include "hevc_tables.h"
 
 #include <limits.h>
@@ -59,6 +60,7 @@ struct orc_encoder {
   int w, h, cw, ch, w8, h8, ctb_cols, ctb_rows;
   int frame_idx, poc, is_idr;
   int8_t *ctu_dqp;               /* per-CTU QP offset (ROI), zeros by default */
+  orc_scaling_t sl;              /* cfg.scaling_list: the lists in force */
   int8_t *vaq_dqp;               /* per-CTU QP offset of variance adaptive quantisation (cfg.vaq), per picture */
   int8_t *ctu_delta;             /* CuQpDeltaVal coded in each CTU (0 if none) */
   uint8_t *ctu_first;            /* z-index (8x8 units) of the first CU with a coded residual, 64 = none */
@@ -109,9 +111,11 @@ orc_encoder_t *orc_enc_open(const orc_enc_cfg_t *cfg)
   if (cfg->beta_offset_div2 < -6 || cfg->beta_offset_div2 > 6 || cfg->tc_offset_div2 < -6 || cfg->tc_offset_div2 > 6) return NULL;
   if (cfg->me_coarse < 0 || cfg->me_coarse > 32 || (cfg->me_coarse > 0 && cfg->search_range > 16)) return NULL;
   if (cfg->vaq < 0 || cfg->vaq > 20 || (cfg->vaq && !cfg->qp_delta)) return NULL;
+  if (cfg->scaling_list < 0 || cfg->scaling_list > 3) return NULL;
   orc_encoder_t *e = (orc_encoder_t *)calloc(1, sizeof(*e));
   if (!e) return NULL;
   e->cfg = *cfg;
+  if (cfg->scaling_list >= 2) orc_scaling_test_lists(&e->sl); else orc_scaling_default(&e->sl);
   e->w = cfg->width; e->h = cfg->height; e->cw = e->w / 2; e->ch = e->h / 2;
   e->w8 = e->w / 8; e->h8 = e->h / 8;
   e->ctb_cols = (e->w + CTB - 1) / CTB; e->ctb_rows = (e->h + CTB - 1) / CTB;
@@ -300,11 +304,10 @@ static int plane_qp(const orc_encoder_t *e, int c, int x, int y)
  * the sum of magnitudes (odd = negative).  Where the parity is wrong one magnitude between the first
  * and the last significant position changes by one -- the change with the smallest increase of the
  * quantisation error; the first and the last position never become zero, so the span is unchanged. */
-static int sign_hide(const int16_t *coef, int16_t *level, int log2n, int qp, int scan_idx)
+static int sign_hide(const int16_t *coef, int16_t *level, int log2n, int qp, int scan_idx, const orc_scaling_t *sl, int matrix)
 {
   const int n = 1 << log2n, nsb = 1 << (log2n - 2);
   const int qbits = 14 + qp / 6 + (15 - 8 - log2n);
-  const int64_t scale = orc_quant_scales[qp % 6];
   int nz = 0;
   for (int ys = 0; ys < nsb; ys++)
     for (int xs = 0; xs < nsb; xs++) {
@@ -320,6 +323,8 @@ static int sign_hide(const int16_t *coef, int16_t *level, int log2n, int qp, int
         int bp = last, bd = 1;
         for (int p = last; p >= first; p--) {
           const int l = abs(level[idx[p]]);
+          const int64_t scale = sl ? (orc_quant_scales[qp % 6] << 4) / orc_scaling_factor(sl, log2n, matrix, idx[p] & (n - 1), idx[p] >> log2n)
+                                   : orc_quant_scales[qp % 6];
           const int64_t t = (int64_t)abs(coef[idx[p]]) * scale, d0 = llabs(t - ((int64_t)l << qbits));
           for (int d = 1; d >= -1; d -= 2) {
             if (l + d < 0 || l + d > 32767) continue;
@@ -342,8 +347,10 @@ static int sign_hide(const int16_t *coef, int16_t *level, int log2n, int qp, int
  * dst: DST-VII (4x4 intra luma) instead of the DCT.  scan_idx: coefficient scan of the block (sign hiding). */
 typedef struct { long long sse; int bits; } tb_rd_t;
 
-static int recon_tb_x(orc_encoder_t *e, int c, int x0, int y0, int log2n, const uint8_t *pred, int ps, tb_rd_t *rd, int dst, int scan_idx)
+static int recon_tb_x(orc_encoder_t *e, int c, int x0, int y0, int log2n, const uint8_t *pred, int ps, tb_rd_t *rd, int dst, int scan_idx, int intra)
 {
+  const orc_scaling_t *sl = e->cfg.scaling_list ? &e->sl : NULL;
+  const int matrix = (intra ? 0 : 3) + c;
   const int n = 1 << log2n;
   const int pw = c ? e->cw : e->w;
   const uint8_t *src = plane((uint8_t *)e->src, e->w, e->h, c);
@@ -355,11 +362,11 @@ static int recon_tb_x(orc_encoder_t *e, int c, int x0, int y0, int log2n, const 
     for (int x = 0; x < n; x++)
       resid[y * n + x] = (int16_t)((int)src[(size_t)(y0 + y) * pw + x0 + x] - (int)pred[y * ps + x]);
   if (dst) orc_fdst4(resid, coef); else orc_fdct(resid, coef, log2n);
-  int nz = orc_quant(coef, level, log2n, qp, e->is_idr);
-  if (nz && e->cfg.sign_hiding) nz = sign_hide(coef, level, log2n, qp, scan_idx);
+  int nz = sl ? orc_quant_sl(coef, level, log2n, qp, e->is_idr, sl, matrix) : orc_quant(coef, level, log2n, qp, e->is_idr);
+  if (nz && e->cfg.sign_hiding) nz = sign_hide(coef, level, log2n, qp, scan_idx, sl, matrix);
   for (int y = 0; y < n; y++) memcpy(lv + (size_t)(y0 + y) * pw + x0, level + y * n, n * sizeof(int16_t));
   if (nz) {
-    orc_dequant(level, coef, log2n, qp);
+    if (sl) orc_dequant_sl(level, coef, log2n, qp, sl, matrix); else orc_dequant(level, coef, log2n, qp);
     if (dst) orc_idst4(coef, resid); else orc_idct(coef, resid, log2n);
     for (int y = 0; y < n; y++)
       for (int x = 0; x < n; x++)
@@ -399,11 +406,11 @@ static int tu_block(orc_encoder_t *e, int c, int px, int py, int l2, const cu_pr
 {
   const int sh = c ? 1 : 0, n = 1 << l2;
   if (ip->pred[0])
-    return recon_tb_x(e, c, px, py, l2, ip->pred[c] + (size_t)(py - (ip->y0 >> sh)) * ip->ps[c] + (px - (ip->x0 >> sh)), ip->ps[c], rd, 0, 0);
+    return recon_tb_x(e, c, px, py, l2, ip->pred[c] + (size_t)(py - (ip->y0 >> sh)) * ip->ps[c] + (px - (ip->x0 >> sh)), ip->ps[c], rd, 0, 0, 0);
   uint8_t refs[4 * 32 + 1], pred[32 * 32];
   gather_refs(e, c, px, py, n, refs);
   orc_intra_predict2(refs, l2, mode, c, e->cfg.strong_intra, pred, n);
-  return recon_tb_x(e, c, px, py, l2, pred, n, rd, c == 0 && l2 == 2, scan_idx_for(1, mode, l2, c));
+  return recon_tb_x(e, c, px, py, l2, pred, n, rd, c == 0 && l2 == 2, scan_idx_for(1, mode, l2, c), 1);
 }
 
 /* one transform unit, not split: luma block of 1 << log2tu, chroma blocks of half that.  Returns the cbf bits. */
@@ -1719,7 +1726,7 @@ static size_t write_nal(uint8_t *out, size_t cap, int type, const uint8_t *rbsp,
 
 static size_t write_parameter_sets(const orc_encoder_t *e, uint8_t *out, size_t cap)
 {
-  uint8_t tmp[256];
+  uint8_t tmp[2048];                  /* scaling list data may run to a few hundred bytes */
   orc_bits_t b;
   size_t o = 0;
   int level = level_for(e->w, e->h);
@@ -1754,7 +1761,11 @@ static size_t write_parameter_sets(const orc_encoder_t *e, uint8_t *out, size_t 
   orc_bits_ue(&b, 0);                 /* log2_min_luma_transform_block_size_minus2 -> 4 */
   orc_bits_ue(&b, 3);                 /* log2_diff_max_min transform -> 32 */
   orc_bits_ue(&b, (uint32_t)e->cfg.tr_depth); orc_bits_ue(&b, (uint32_t)e->cfg.tr_depth);   /* max_transform_hierarchy_depth_inter / intra */
-  orc_bits_put(&b, 0, 1);             /* scaling_list_enabled_flag */
+  orc_bits_put(&b, e->cfg.scaling_list ? 1 : 0, 1);       /* scaling_list_enabled_flag */
+  if (e->cfg.scaling_list) {
+    orc_bits_put(&b, e->cfg.scaling_list == 2 ? 1 : 0, 1);  /* sps_scaling_list_data_present_flag (else the default lists) */
+    if (e->cfg.scaling_list == 2) orc_scaling_write(&b, &e->sl);
+  }
   orc_bits_put(&b, 0, 1);             /* amp_enabled_flag */
   orc_bits_put(&b, e->cfg.sao ? 1 : 0, 1);          /* sample_adaptive_offset_enabled_flag */
   orc_bits_put(&b, 0, 1);             /* pcm_enabled_flag */
@@ -1822,7 +1833,8 @@ static size_t write_parameter_sets(const orc_encoder_t *e, uint8_t *out, size_t 
     orc_bits_put(&b, e->cfg.deblock ? 0 : 1, 1);      /* pps_deblocking_filter_disabled_flag */
     if (e->cfg.deblock) { orc_bits_se(&b, e->cfg.beta_offset_div2); orc_bits_se(&b, e->cfg.tc_offset_div2); }
   }
-  orc_bits_put(&b, 0, 1);             /* pps_scaling_list_data_present_flag */
+  orc_bits_put(&b, e->cfg.scaling_list == 3 ? 1 : 0, 1);  /* pps_scaling_list_data_present_flag */
+  if (e->cfg.scaling_list == 3) orc_scaling_write(&b, &e->sl);
   orc_bits_put(&b, 0, 1);             /* lists_modification_present_flag */
   orc_bits_ue(&b, 0);                 /* log2_parallel_merge_level_minus2 */
   orc_bits_put(&b, 0, 1);             /* slice_segment_header_extension_present_flag */

@@ -74,6 +74,8 @@ typedef struct {
                             * mv_edges bits 2 / 3 then mark the top / bottom edge of a tile as interior */
   int vaq;                 /* variance adaptive quantisation strength (Kvazaar --vaq), 0 = off, 1..20; needs qp_delta:
                             * every picture, each CTU's QP moves by orc_vaq_offsets() on top of the ROI offsets */
+  int scaling_list;        /* scaling_list_enabled_flag: 1 = the default lists (Kvazaar --scaling-list default; Tables 7-5 / 7-6),
+                            * 2 = test lists carried in the SPS, 3 = test lists carried in the PPS (the SPS then says "default") */
 } orc_enc_cfg_t;
 
 typedef struct orc_encoder orc_encoder_t;

@@ -91,6 +91,16 @@ def decode_all(aus):
                                  "intra_in_p": 1, "refs": 2, "tmvp": 1, "qp_delta": 1, "intra_period": 3, "cabac_init": 1}),
     ("camera", 1920, 1080, 3, 27, {"tr_depth": 3, "tu4": 1, "intra_sizes": 7, "chroma_modes": 1, "sign_hiding": 1, "refs": 2, "tmvp": 1,
                                    "sao": 2, "me_coarse": 16, "search_range": 6, "intra_in_p": 1}),
+    # scaling lists: the default ones (Kvazaar --scaling-list default), lists carried in the SPS / in the PPS
+    # (coded, copied, inferred default; DC coefficients of 16x16 / 32x32 blocks)
+    ("camera", 416, 240, 4, 22, {"scaling_list": 1, "intra_period": 3}),
+    ("noise", 256, 136, 3, 12, {"scaling_list": 1, "tr_depth": 2, "tu4": 1, "intra_sizes": 7}),
+    ("sports", 640, 480, 4, 30, {"scaling_list": 1, "sao": 2, "intra_in_p": 1, "sign_hiding": 1, "tr_depth": 1, "me_coarse": 16, "search_range": 4}),
+    ("camera", 416, 240, 4, 27, {"scaling_list": 2, "intra_period": 3, "intra_sizes": 3}),
+    ("noise", 256, 136, 3, 17, {"scaling_list": 2, "tr_depth": 2, "tu4": 1, "intra_sizes": 7, "qp_delta": 1}),
+    ("screen", 640, 200, 4, 32, {"scaling_list": 3, "tr_depth": 1, "intra_period": 2}),
+    ("noise", 512, 136, 3, 22, {"scaling_list": 3, "tr_depth": 2, "tu4": 1, "intra_sizes": 7, "cb_qp_offset": 3, "cr_qp_offset": -4}),
+    ("camera", 1920, 1080, 2, 27, {"scaling_list": 2, "tr_depth": 2, "intra_sizes": 3, "sao": 2, "me_coarse": 16, "search_range": 6}),
 ])
 def test_decoder_reproduces_oracle_reconstruction(kind, w, h, n, qp, kw):
     frames = frames_of(kind, w, h, n)

@@ -469,6 +469,82 @@ def test_vaq_through_kvz_api_and_pipelining():
         GpuEncoder(w, h, qp=30, qp_delta=1, vaq=21)
 
 
+SCALING_CASES = [
+    ("camera", 416, 240, 5, 27, {"intra_period": 3}),
+    ("noise", 256, 136, 3, 12, {}),
+    ("sports", 640, 480, 4, 32, {"sao": 2, "intra_in_p": 1, "me_coarse": 16, "search_range": 4, "intra_satd": 1}),
+    ("screen", 640, 200, 4, 37, {"qp_delta": 1, "vaq": 10}),
+    ("camera", 1920, 1080, 2, 30, {"me_coarse": 16, "search_range": 6, "sao": 2, "intra_in_p": 1, "intra_satd": 1}),
+]
+
+
+@pytest.mark.parametrize("kind,w,h,n,qp,kw", SCALING_CASES)
+def test_default_scaling_lists_match_oracle_stage_by_stage(kind, w, h, n, qp, kw):
+    """"scaling-list default": per-coefficient quantiser and dequantiser scales in the inter, the intra and
+    the intra-in-P reconstruction equal the oracle's (whose streams FFmpeg decodes bit-exactly); the GPU
+    decoder reproduces the reconstruction."""
+    from tests.test_dec_gpu import decode_all
+    frames = frames_of(kind, w, h, n)
+    args = {"intra_period": 0} | kw
+    g = GpuEncoder(w, h, qp=qp, debug=1, scaling_list=1, **args)
+    o = OracleEncoder(w, h, qp=qp, scaling_list=1, **args)
+    aus, recs = [], []
+    for i, f in enumerate(frames):
+        ga, oa = g.encode(f), o.encode(f)
+        tag = f"scaling list {kind} {w}x{h} qp{qp} frame {i}"
+        compare_frame(tag, g, o, w, h)
+        assert ga == oa, f"{tag}: access unit differs (gpu {len(ga)} B, oracle {len(oa)} B)"
+        aus.append(ga)
+        recs.append(g.recon())
+    g.close()
+    o.close()
+    dec = decode_all(aus)
+    assert len(dec) == n
+    for i in range(n):
+        assert np.array_equal(dec[i][0], recs[i]), f"GPU decoder, picture {i}"
+    if ffhevc.required():
+        ff, errs = ffhevc.decode_stream(aus)
+        assert errs == 0 and np.array_equal(ff[-1][0], recs[-1])
+
+
+def test_scaling_list_through_kvz_api_untiled_and_tiled():
+    """video/scalingList = 1 -> config_parse("scaling-list", "default") (kvazaarfilter.cpp:236-243): the stream of the
+    engine opened with scaling_list = 1; with tiles the compositor's SPS carries the flag as well and both
+    decoders reconstruct the same pictures."""
+    from kvazzup_b200.kvazaar import KvazaarFilter
+    from kvazzup_b200.encoder import preset_options
+    from tests.test_dec_gpu import decode_all
+    w, h, n = 416, 240, 5
+    frames = frames_of("camera", w, h, n)
+    base = {"video/ResolutionWidth": w, "video/ResolutionHeight": h, "video/QP": 30, "video/Intra": 4, "video/Preset": "ultrafast",
+            "video/scalingList": 1}
+    uf = preset_options("ultrafast")
+    eng = GpuEncoder(w, h, qp=30, intra_period=4, scaling_list=1, fps_num=30, fps_den=1, **uf)
+    want = [eng.encode(f) for f in frames]
+    eng.close()
+    f = KvazaarFilter(base)
+    assert f.init()
+    got = []
+    for fr in frames:
+        got += f.feed_input(fr)
+    f.close()
+    assert got == want
+    t = KvazaarFilter(base | {"video/Tiles": 1, "video/tileDimensions": "2x2", "video/WPP": 0})
+    assert t.init()
+    aus = []
+    for fr in frames:
+        aus += t.feed_input(fr)
+    t.close()
+    assert len(aus) == n and aus != want
+    dec = decode_all(aus)
+    assert len(dec) == n
+    if ffhevc.required():
+        ff, errs = ffhevc.decode_stream(aus)
+        assert errs == 0 and len(ff) == n
+        for i in range(n):
+            assert np.array_equal(ff[i][0], dec[i][0]), f"picture {i}"
+
+
 def test_roi_through_kvz_api_and_pipelining():
     """kvz_picture::roi (per-pixel delta-QP map, kvazaarfilter.cpp:423-431) -> same stream as the engine
     given the per-CTU offsets Kvazaar would sample; ignored unless enabled or when a bitrate is set."""

@@ -111,6 +111,38 @@ def test_per_ctu_qp_streams_decode_bit_exactly_in_ffmpeg(kind, w, h, n, qp, roi,
         assert all((q == qp).all() for q in qps)
 
 
+@needs_ff
+@pytest.mark.parametrize("kind,w,h,n,qp,kw", [
+    ("camera", 416, 240, 4, 22, {"scaling_list": 1, "hash_sei": 1, "intra_period": 3}),
+    ("noise", 256, 136, 3, 12, {"scaling_list": 1, "tr_depth": 2, "tu4": 1, "intra_sizes": 7}),       # every block size 4..32
+    ("sports", 640, 480, 4, 30, {"scaling_list": 1, "sao": 2, "intra_in_p": 1, "sign_hiding": 1, "tr_depth": 1, "me_coarse": 16, "search_range": 4}),
+    ("camera", 416, 240, 4, 27, {"scaling_list": 2, "hash_sei": 1, "intra_period": 3, "intra_sizes": 3}),     # lists coded in the SPS
+    ("noise", 256, 136, 3, 17, {"scaling_list": 2, "tr_depth": 2, "tu4": 1, "intra_sizes": 7, "qp_delta": 1}),
+    ("screen", 640, 200, 4, 32, {"scaling_list": 3, "tr_depth": 1, "intra_period": 2}),                       # ... in the PPS
+    ("noise", 512, 136, 3, 22, {"scaling_list": 3, "tr_depth": 2, "tu4": 1, "intra_sizes": 7, "cb_qp_offset": 3, "cr_qp_offset": -4}),
+])
+def test_scaling_list_streams_decode_bit_exactly_in_ffmpeg(kind, w, h, n, qp, kw):
+    """Scaling lists (7.3.4, 8.6.4.2): the default lists (Kvazaar --scaling-list default) and lists carried in
+    the SPS / PPS (coded, copied from another list, inferred default; DC coefficients of 16x16 / 32x32) --
+    FFmpeg's reconstruction equals the oracle's, which pins the tables, the list expansion and the
+    per-coefficient dequantisation; the lists really change the stream."""
+    frames = frames_of(kind, w, h, n)
+    enc = OracleEncoder(w, h, qp=qp, **({"intra_period": 0} | kw))
+    flat = OracleEncoder(w, h, qp=qp, **({"intra_period": 0} | kw | {"scaling_list": 0}))
+    aus, recs = [], []
+    for f in frames:
+        aus.append(enc.encode(f))
+        recs.append(enc.recon())
+        flat.encode(f)
+    assert not np.array_equal(flat.recon(), recs[-1])
+    enc.close()
+    flat.close()
+    dec, errs = ffhevc.decode_stream(aus)
+    assert errs == 0 and len(dec) == n
+    for i, (fr, fw, fh) in enumerate(dec):
+        assert np.array_equal(fr, recs[i]), f"frame {i}: decoder output differs from encoder reconstruction"
+
+
 def vaq_float_model(i420, w, h, strength):
     """Kvazaar's formula in floating point: strength * 0.1 * (ln(max(var_ctu, 4)) - ln(var_picture)),
     var = luma variance + the two chroma variances."""
