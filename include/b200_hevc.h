@@ -50,6 +50,10 @@ typedef struct b200_enc_params {
                                     variance), on top of the offsets of b200_enc_set_ctu_dqp; needs qp_delta */
   int scaling_list;              /* 1 = scaling_list_enabled_flag with the default lists of the standard (Kvazaar
                                     --scaling-list default, kvazaarfilter.cpp:236-243): quantisation steps grow with frequency */
+  int src_width, src_height;     /* size of the pictures passed to b200_enc_encode[_dev] when it is not a multiple of 8
+                                    (even, at most 6 samples short of width / height; 0 = width / height): the margins
+                                    are filled by edge repetition on the GPU and the SPS carries a conformance window, so
+                                    decoders output src_width x src_height.  b200_enc_fetch returns coded-size planes */
 } b200_enc_params;
 void  b200_enc_params_default(b200_enc_params *p);
 void *b200_enc_open_params(const b200_enc_params *p);

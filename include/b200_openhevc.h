@@ -24,9 +24,11 @@
  * carried in the SPS / PPS); deblocking and SAO; WPP entry points;
  * cabac_init_flag; uniformly spaced tile grids without loop filtering across tiles whose motion stays
  * inside the tile (what b200_tiled_* and kvz_api "tiles" emit), with or without WPP inside the tiles.
+ * A conformance window is honoured: nWidth / nHeight are the window, pvY / pvU / pvV point at its origin
+ * inside the coded picture and nYPitch / nUPitch / nVPitch are the coded pitches (always even).
  * Not decoded: B slices, AMP / 2NxN / Nx2N inter partitions, PCM, transform skip,
  * transquant bypass, long-term references, several slices per picture, quantisation groups below the
- * CTU, a conformance window.  Those make libOpenHevcDecode return -1 with the reason in
+ * CTU.  Those make libOpenHevcDecode return -1 with the reason in
  * b200_last_error() -- never a silently wrong picture.
  */
 #ifndef B200_OPENHEVC_H_

@@ -97,6 +97,11 @@ struct Decoder {
   cudaEvent_t ev_out = nullptr;           // the picture is in host memory (what libOpenHevcDecode waits for)
   std::vector<StripGeom> geom;
   uint8_t *d_full = nullptr;              // whole picture on the device when there are several strips
+  // Conformance window (7.4.3.2.1): the decoder works on the coded size and hands out the window.
+  int crop_l = 0, crop_t = 0, out_w = 0, out_h = 0;   // window origin and size, luma samples
+  size_t out_bytes = 0;
+  uint8_t *d_crop = nullptr;              // the window as a packed picture (only when it differs from the coded size)
+  bool cropped() const { return out_w != fp.w || out_h != fp.h; }
   int conf_w = 0, conf_h = 0, conf_tiles = 0, conf_tile_cols = 0, conf_tile_rows = 0;
   std::vector<DecSlot> slots;
   std::deque<int> pending;                // slots whose parse was launched, oldest first
@@ -156,6 +161,8 @@ struct Decoder {
     slots.clear();
     pending.clear();
     if (d_full) cudaFree(d_full);
+    if (d_crop) cudaFree(d_crop);
+    d_crop = nullptr;
     if (ev_out) cudaEventDestroy(ev_out);
     if (stream) cudaStreamDestroy(stream);
     d_full = nullptr; stream = nullptr; ev_out = nullptr;
@@ -163,9 +170,11 @@ struct Decoder {
   }
 
   // (Re)allocate for a picture size and tile grid; pictures in flight are dropped.
-  bool configure(int w, int h, int tile_cols, int tile_rows)
+  bool configure(int w, int h, int tile_cols, int tile_rows, int cl = 0, int cr = 0, int ct = 0, int cb = 0)
   {
     release();
+    crop_l = cl; crop_t = ct; out_w = w - cl - cr; out_h = h - ct - cb;
+    out_bytes = (size_t)out_w * out_h * 3 / 2;
     const int tiles = tile_cols * tile_rows;
     fp = FrameParams{};
     fp.w = w; fp.h = h; fp.w8 = w / 8; fp.h8 = h / 8;
@@ -212,6 +221,7 @@ struct Decoder {
       if (!cuda_ok(cudaMemcpy(g.d_order, order.data(), order.size() * sizeof(int), cudaMemcpyHostToDevice), "H2D order")) return false;
     }
     if (tiles > 1 && !cuda_ok(cudaMalloc((void **)&d_full, frame_bytes), "cudaMalloc")) return false;
+    if ((out_w != w || out_h != h) && !cuda_ok(cudaMalloc((void **)&d_crop, out_bytes), "cudaMalloc")) return false;
     slots.resize(frame_delay + 1);
     for (DecSlot &s : slots) {
       if (!cuda_ok(cudaStreamCreateWithFlags(&s.stream, cudaStreamNonBlocking), "cudaStreamCreate")) return false;
@@ -269,7 +279,8 @@ struct Decoder {
     if (s.chroma_format_idc != 1) return "only 4:2:0 is supported";
     if (s.bit_depth_luma != 8 || s.bit_depth_chroma != 8) return "only 8-bit video is supported";
     if ((s.width & 7) || (s.height & 7)) return "picture sizes that are not multiples of 8 are not supported";
-    if (s.conf_left | s.conf_right | s.conf_top | s.conf_bottom) return "conformance window cropping is not supported";
+    if (s.conf_left < 0 || s.conf_right < 0 || s.conf_top < 0 || s.conf_bottom < 0 || s.conf_left + s.conf_right >= s.width ||
+        s.conf_top + s.conf_bottom >= s.height) return "conformance window larger than the picture";
     if (s.log2_min_cb != 3 || s.log2_ctb != 6) return "coding block sizes other than 8..64 are not supported";
     if (s.log2_min_tb != 2 || s.log2_max_tb != 5) return "transform block sizes other than 4..32 are not supported";
     if (s.max_tr_depth_inter > 3 || s.max_tr_depth_intra > 3) return "transform hierarchy depth > 3 is not supported";
@@ -391,11 +402,13 @@ struct Decoder {
     fr_num = sps.fps_num; fr_den = sps.fps_den;
     // geometry: picture size from the SPS, tile columns from the PPS (pictures in flight are dropped
     // when either changes)
-    if (conf_w != sps.width || conf_h != sps.height || conf_tile_cols != pps.tile_cols || conf_tile_rows != pps.tile_rows) {
+    if (conf_w != sps.width || conf_h != sps.height || conf_tile_cols != pps.tile_cols || conf_tile_rows != pps.tile_rows ||
+        crop_l != sps.conf_left || crop_t != sps.conf_top || out_w != sps.width - sps.conf_left - sps.conf_right ||
+        out_h != sps.height - sps.conf_top - sps.conf_bottom) {
       const int ctb_cols = (sps.width + kCtb - 1) / kCtb, ctb_rows = (sps.height + kCtb - 1) / kCtb;
       if (pps.tile_cols > 1 && pps.tile_cols > ctb_cols / 2) { set_error("decoder: tile columns narrower than two CTUs are not supported"); return -1; }
       if (pps.tile_rows > ctb_rows) { set_error("decoder: more tile rows than CTU rows"); return -1; }
-      if (!configure(sps.width, sps.height, pps.tile_cols, pps.tile_rows)) return -1;
+      if (!configure(sps.width, sps.height, pps.tile_cols, pps.tile_rows, sps.conf_left, sps.conf_right, sps.conf_top, sps.conf_bottom)) return -1;
     }
     const int rows = fp.ctb_rows, tiles = conf_tiles;
     // substreams: one per CTU row of every tile with WPP, else one per tile
@@ -562,7 +575,18 @@ struct Decoder {
       DEC_CHECK(cudaStreamWaitEvent(stream, g.ev_done, 0), "stream wait");
     }
     d_out = tiles > 1 ? d_full : geom[0].d_pic[sl.cur_idx];
+    // host output: the coded picture; libOpenHevcGetOutput points into it at the window origin with the coded
+    // pitches (OpenHEVC does the same: linesize > width), which keeps the chroma pitch even -- the reference
+    // reads chroma rows at i * (nUPitch / 2) for even i (openhevcfilter.cpp:213-227)
     if (host_output) DEC_CHECK(cudaMemcpyAsync(sl.h_out, d_out, frame_bytes, cudaMemcpyDeviceToHost, stream), "D2H picture");
+    if (cropped()) {                       // device-resident hand-over: the conformance window as a packed picture
+      const size_t oy = (size_t)out_w * out_h;
+      const int cw = fp.w / 2, ow = out_w / 2;
+      DEC_CHECK(cudaMemcpy2DAsync(d_crop, out_w, d_out + (size_t)crop_t * fp.w + crop_l, fp.w, out_w, out_h, cudaMemcpyDeviceToDevice, stream), "crop Y");
+      DEC_CHECK(cudaMemcpy2DAsync(d_crop + oy, ow, d_out + ysz + (size_t)(crop_t / 2) * cw + crop_l / 2, cw, ow, out_h / 2, cudaMemcpyDeviceToDevice, stream), "crop U");
+      DEC_CHECK(cudaMemcpy2DAsync(d_crop + oy + oy / 4, ow, d_out + ysz + ysz / 4 + (size_t)(crop_t / 2) * cw + crop_l / 2, cw, ow, out_h / 2, cudaMemcpyDeviceToDevice, stream), "crop V");
+      d_out = d_crop;
+    }
     DEC_CHECK(cudaEventRecord(ev_out, stream), "record picture");
     DEC_CHECK(cudaEventSynchronize(ev_out), "sync picture");
 #undef DEC_CHECK
@@ -646,10 +670,11 @@ int libOpenHevcGetOutput(OpenHevc_Handle h, int got_picture, OpenHevc_Frame *fra
   Decoder *d = (Decoder *)h;
   if (!d || !frame || !got_picture || d->out_slot < 0) return 0;
   const size_t ysz = (size_t)d->fp.w * d->fp.h;
+  const int cw = d->fp.w / 2;
   uint8_t *out = d->slots[d->out_slot].h_out;
-  frame->pvY = out;
-  frame->pvU = out + ysz;
-  frame->pvV = out + ysz + ysz / 4;
+  frame->pvY = out + (size_t)d->crop_t * d->fp.w + d->crop_l;
+  frame->pvU = out + ysz + (size_t)(d->crop_t / 2) * cw + d->crop_l / 2;
+  frame->pvV = out + ysz + ysz / 4 + (size_t)(d->crop_t / 2) * cw + d->crop_l / 2;
   libOpenHevcGetPictureInfo(h, &frame->frameInfo);
   return 1;
 }
@@ -659,8 +684,8 @@ void libOpenHevcGetPictureInfo(OpenHevc_Handle h, OpenHevc_FrameInfo *info)
   Decoder *d = (Decoder *)h;
   if (!d || !info) return;
   memset(info, 0, sizeof(*info));
-  info->nWidth = d->fp.w; info->nHeight = d->fp.h;
-  info->nYPitch = d->fp.w; info->nUPitch = d->fp.w / 2; info->nVPitch = d->fp.w / 2;
+  info->nWidth = d->out_w; info->nHeight = d->out_h;       // the conformance window (= the coded size without one)
+  info->nYPitch = d->fp.w; info->nUPitch = d->fp.w / 2; info->nVPitch = d->fp.w / 2;       // pitches of the coded picture
   info->nBitDepth = 8; info->chromat_format = 1;
   info->sample_aspect_ratio.num = 1; info->sample_aspect_ratio.den = 1;
   // VUI timing when the stream carries it; never 0/0 -- the reference copies this into vInfo
@@ -712,9 +737,16 @@ void b200_dec_set_host_output(OpenHevc_Handle h, int on)
 int b200_dec_last_picture(OpenHevc_Handle h, uint8_t *dst, int cap)
 {
   Decoder *d = (Decoder *)h;
-  if (!d || !dst || d->out_slot < 0 || (size_t)cap < d->frame_bytes) return -1;
-  memcpy(dst, d->slots[d->out_slot].h_out, d->frame_bytes);
-  return (int)d->frame_bytes;
+  if (!d || !dst || d->out_slot < 0 || (size_t)cap < d->out_bytes) return -1;
+  OpenHevc_Frame fr;
+  libOpenHevcGetOutput(h, 1, &fr);                           // the window, packed
+  const int w = d->out_w, hh = d->out_h;
+  for (int r = 0; r < hh; r++) memcpy(dst + (size_t)r * w, (const uint8_t *)fr.pvY + (size_t)r * d->fp.w, w);
+  for (int r = 0; r < hh / 2; r++) {
+    memcpy(dst + (size_t)w * hh + (size_t)r * (w / 2), (const uint8_t *)fr.pvU + (size_t)r * (d->fp.w / 2), w / 2);
+    memcpy(dst + (size_t)w * hh * 5 / 4 + (size_t)r * (w / 2), (const uint8_t *)fr.pvV + (size_t)r * (d->fp.w / 2), w / 2);
+  }
+  return (int)d->out_bytes;
 }
 
 }  // extern "C"

@@ -159,6 +159,13 @@ bool Encoder::open(const EncoderConfig &c)
   if (c.qp < 0 || c.qp > 51) { set_error("encoder: qp %d out of range 0..51", c.qp); return false; }
   if (c.search_range < 1 || c.search_range > 32) { set_error("encoder: search range %d out of range 1..32", c.search_range); return false; }
   if (c.me_coarse < 0 || c.me_coarse > 32 || (c.me_coarse & 3) || (c.me_coarse > 0 && c.search_range > 16)) { set_error("encoder: me_coarse %d must be a multiple of 4 in 0..32 (and search_range <= 16 with it)", c.me_coarse); return false; }
+  if (c.src_width || c.src_height) {
+    const int sw = c.src_width ? c.src_width : c.width, sh = c.src_height ? c.src_height : c.height;
+    if (sw <= 0 || sh <= 0 || (sw & 1) || (sh & 1) || sw > c.width || sh > c.height || c.width - sw > 6 || c.height - sh > 6) {
+      set_error("encoder: source size %dx%d must be even and at most 6 samples short of the coded size %dx%d", sw, sh, c.width, c.height);
+      return false;
+    }
+  }
   if (c.vaq < 0 || c.vaq > 20 || (c.vaq && !c.qp_delta)) { set_error("encoder: vaq %d must be 0..20 and needs qp_delta", c.vaq); return false; }
   if (c.depth < 1 || c.depth > 128) { set_error("encoder: depth %d out of range 1..128", c.depth); return false; }
   if (b200_device_count() <= 0) { set_error("no CUDA device: the B200 encoder has no CPU fallback"); return false; }
@@ -170,6 +177,8 @@ bool Encoder::open(const EncoderConfig &c)
   fp.lambda_q4 = kLambdaQ4[c.qp];
   fp.search_range = c.search_range; fp.is_idr = 1; fp.deblock = c.deblock;
   frame_bytes = (size_t)fp.w * fp.h * 3 / 2;
+  src_w = c.src_width ? c.src_width : c.width; src_h = c.src_height ? c.src_height : c.height;
+  src_bytes = (size_t)src_w * src_h * 3 / 2;
   row_cap = (uint32_t)fp.w * kCtb * 4 + 4096;
   pack_cap = (uint32_t)std::min<size_t>((size_t)row_cap * fp.ctb_rows, frame_bytes * 3 + 65536);
   // Stream priorities: the entropy-coding kernels are tiny (one warp per CTU row) but long-running
@@ -267,7 +276,12 @@ void write_parameter_sets(const StreamLayout &l, std::vector<uint8_t> &out)
     put_profile_tier_level(b, level);
     b.ue(0); b.ue(1);                        // sps id, chroma_format_idc 4:2:0
     b.ue((uint32_t)l.w); b.ue((uint32_t)l.h);
-    b.put(0, 1);                             // conformance_window_flag
+    if (l.conf_right || l.conf_bottom) {     // conformance window, offsets in chroma samples (4:2:0)
+      b.put(1, 1);
+      b.ue(0); b.ue((uint32_t)l.conf_right / 2); b.ue(0); b.ue((uint32_t)l.conf_bottom / 2);
+    } else {
+      b.put(0, 1);
+    }
     b.ue(0); b.ue(0);                        // bit depths
     b.ue(4);                                 // log2_max_pic_order_cnt_lsb_minus4
     b.put(0, 1); b.ue(1); b.ue(0); b.ue(0);  // sub-layer ordering info
@@ -370,6 +384,7 @@ StreamLayout Encoder::layout() const
   StreamLayout l;
   l.w = fp.w; l.h = fp.h; l.deblock = cfg.deblock; l.qp_delta = cfg.qp_delta; l.tile_cols = 1; l.wpp = cfg.no_wpp ? 0 : 1;
   l.fps_num = cfg.fps_num; l.fps_den = cfg.fps_den; l.sao = cfg.sao; l.scaling_list = cfg.scaling_list;
+  l.conf_right = fp.w - src_w; l.conf_bottom = fp.h - src_h;
   return l;
 }
 
@@ -555,11 +570,25 @@ bool Encoder::encode_device(const uint8_t *d_i420, std::vector<uint8_t> &out)
   // the slot is free: its previous picture was collected when the pipeline was full.
   // Take a private copy so that the caller may reuse its buffer as soon as this call returns
   // (the caller orders its producer before this call; the copy is ~1 us of HBM time).
-  if (d_i420 != s.d_src) ENC_CHECK(cudaMemcpyAsync(s.d_src, d_i420, frame_bytes, cudaMemcpyDeviceToDevice, input_stream()), "D2D frame");
+  if (d_i420 != s.d_src) {
+    if (padded()) { if (!stage_source(s, d_i420, cudaMemcpyDeviceToDevice, input_stream())) return false; }
+    else ENC_CHECK(cudaMemcpyAsync(s.d_src, d_i420, frame_bytes, cudaMemcpyDeviceToDevice, input_stream()), "D2D frame");
+  }
+  if (padded()) { ENC_CHECK(launch_pad_edges(s.d_src, fp.w, fp.h, src_w, src_h, input_stream()), "pad launch"); count_launch(1); }
   if (!submit(s, s.d_src)) return false;
   inflight.push_back(slot);
   last_slot = slot;
   if ((int)inflight.size() >= cfg.depth) return flush(out);
+  return true;
+}
+
+// The three planes of a src_w x src_h picture into the top-left corner of the coded picture
+bool Encoder::stage_source(FrameSlot &s, const uint8_t *pic, cudaMemcpyKind kind, cudaStream_t st)
+{
+  const size_t sy = (size_t)src_w * src_h, ysz = (size_t)fp.w * fp.h;
+  ENC_CHECK(cudaMemcpy2DAsync(s.d_src, fp.w, pic, src_w, src_w, src_h, kind, st), "copy source Y");
+  ENC_CHECK(cudaMemcpy2DAsync(s.d_src + ysz, fp.w / 2, pic + sy, src_w / 2, src_w / 2, src_h / 2, kind, st), "copy source U");
+  ENC_CHECK(cudaMemcpy2DAsync(s.d_src + ysz + ysz / 4, fp.w / 2, pic + sy + sy / 4, src_w / 2, src_w / 2, src_h / 2, kind, st), "copy source V");
   return true;
 }
 
@@ -568,12 +597,13 @@ bool Encoder::encode_host(const uint8_t *i420, std::vector<uint8_t> &out, bool p
   FrameSlot &s = slots[frame_idx % cfg.depth];
   const uint8_t *from = i420;
   if (!pinned) {
-    memcpy(s.h_src, i420, frame_bytes);
+    memcpy(s.h_src, i420, src_bytes);
     from = s.h_src;
   }
   // the upload runs on its own stream so that the copy engine works while the previous picture's
   // kernels execute; the consuming stream waits for it
-  ENC_CHECK(cudaMemcpyAsync(s.d_src, from, frame_bytes, cudaMemcpyHostToDevice, upload_stream), "H2D frame");
+  if (padded()) { if (!stage_source(s, from, cudaMemcpyHostToDevice, upload_stream)) return false; }
+  else ENC_CHECK(cudaMemcpyAsync(s.d_src, from, frame_bytes, cudaMemcpyHostToDevice, upload_stream), "H2D frame");
   ENC_CHECK(cudaEventRecord(ev_upload, upload_stream), "event record");
   ENC_CHECK(cudaStreamWaitEvent(input_stream(), ev_upload, 0), "stream wait");
   return encode_device(s.d_src, out);
@@ -652,6 +682,7 @@ void *b200_enc_open_params(const b200_enc_params *up)
   c.deblock = p.deblock; c.debug = p.debug; c.depth = p.depth; c.qp_delta = p.qp_delta;
   c.fps_num = p.fps_num; c.fps_den = p.fps_den; c.sao = p.sao; c.intra_in_p = p.intra_in_p; c.me_coarse = p.me_coarse;
   c.intra_satd = p.intra_satd; c.subme_satd = p.subme_satd; c.vaq = p.vaq; c.scaling_list = p.scaling_list ? 1 : 0;
+  c.src_width = p.src_width; c.src_height = p.src_height;
   if (!e->open(c)) { delete e; return nullptr; }
   return e;
 }

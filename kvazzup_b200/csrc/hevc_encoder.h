@@ -33,6 +33,9 @@ struct EncoderConfig {
   int subme_satd = 0;        // P pictures: SATD instead of SAD in the fractional motion refinement
   int vaq = 0;               // variance adaptive quantisation strength (Kvazaar --vaq), 1..20; needs qp_delta
   int scaling_list = 0;      // 1 = scaling_list_enabled_flag with the default lists (Kvazaar --scaling-list default)
+  int src_width = 0, src_height = 0;   // size of the pictures passed in when it is not a multiple of 8 (even, at most 6
+                             // samples short of width / height; 0 = width / height): the encoder pads by edge
+                             // repetition and the SPS carries a conformance window
   int me_coarse = 0;         // two-level motion search: range of the coarse level in coarse (4x4-mean) samples,
                              // a multiple of 4; search_range (<= 16) is then the window around each centre
   int depth = 1;             // pictures in flight (Kvazaar's owf + 1): output of picture n is
@@ -76,6 +79,7 @@ struct StreamLayout {
   int tile_rows = 1;         // > 1: uniform tile rows
   int wpp = 1;               // entropy_coding_sync_enabled_flag
   int scaling_list = 0;      // scaling_list_enabled_flag, default lists (no list data in the SPS / PPS)
+  int conf_right = 0, conf_bottom = 0;   // conformance window: luma samples cropped at the right / bottom
 };
 void write_parameter_sets(const StreamLayout &l, std::vector<uint8_t> &out);
 // Slice segment header with the entry points of `sub_len` (escaped sizes) followed by `data_len`
@@ -114,6 +118,10 @@ class Encoder {
   EncoderConfig cfg;
   FrameParams fp{};
   size_t frame_bytes = 0;
+  int src_w = 0, src_h = 0;       // source picture size (= fp.w x fp.h unless a conformance window is in use)
+  size_t src_bytes = 0;
+  bool padded() const { return src_w != fp.w || src_h != fp.h; }
+  bool stage_source(FrameSlot &s, const uint8_t *pic, cudaMemcpyKind kind, cudaStream_t st);
   uint32_t row_cap = 0, pack_cap = 0;
   int frame_idx = 0, poc = 0, cur = 0, last_idr = 0, last_qp = 0, last_poc = 0, cur_qp = 32;
   unsigned long long last_bins = 0;

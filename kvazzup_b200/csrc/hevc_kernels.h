@@ -45,6 +45,10 @@ cudaError_t launch_store_mvf(const FrameParams &fp, const CuInfo *cu, MvField *o
 // deblocking and binarisation.
 cudaError_t launch_cu_qps(const FrameParams &fp, CuInfo *cu, cudaStream_t s);
 
+// margins of a coded picture (w x h) whose source is src_w x src_h (even, within 7 samples of w x h): every plane's
+// last source column / row repeated to the right / below (hevc_pad.cu).  No launch when the sizes are equal.
+cudaError_t launch_pad_edges(uint8_t *pic, int w, int h, int src_w, int src_h, cudaStream_t s);
+
 // variance adaptive quantisation (hevc_vaq.cu), two launches: per-CTU sample statistics of the source picture
 // into `stats` (6 words per CTU), then ctu_qp[i] (staged as QP + kVaqBias) += the CTU's offset, clipped to 0..51
 cudaError_t launch_vaq(const FrameParams &fp, const uint8_t *src, int strength, uint32_t *stats, uint8_t *ctu_qp, cudaStream_t s);

@@ -276,7 +276,15 @@ kvz_encoder *encoder_open(const kvz_config *cfg)
   if (!e) return NULL;
   e->cfg = *cfg;
   EncoderConfig c;
-  c.width = cfg->width; c.height = cfg->height; c.qp = cfg->qp; c.intra_period = cfg->intra_period;
+  // sizes that are not multiples of 8 are coded padded, with a conformance window (what Kvazaar does)
+  if (cfg->width <= 0 || cfg->height <= 0 || (cfg->width & 1) || (cfg->height & 1)) {
+    b200::set_error("encoder_open: width and height must be positive and even (got %dx%d)", cfg->width, cfg->height);
+    delete e;
+    return NULL;
+  }
+  c.width = (cfg->width + 7) & ~7; c.height = (cfg->height + 7) & ~7;
+  if (c.width != cfg->width || c.height != cfg->height) { c.src_width = cfg->width; c.src_height = cfg->height; }
+  c.qp = cfg->qp; c.intra_period = cfg->intra_period;
   c.search_range = cfg->me_range > 0 ? cfg->me_range : 6;
   c.me_coarse = cfg->me_coarse;
   c.intra_satd = cfg->intra_satd; c.subme_satd = cfg->subme_satd;
@@ -289,6 +297,11 @@ kvz_encoder *encoder_open(const kvz_config *cfg)
   c.fps_num = cfg->framerate_num; c.fps_den = cfg->framerate_denom;     // VUI timing: the decoder side reports it
   c.sao = cfg->sao_type != 0 ? 2 : 0;             // with sao_merge_left / _up flags
   c.intra_in_p = 1;                               // every Kvazaar preset may code intra CUs in P pictures
+  if (tiled && (c.src_width || c.src_height)) {
+    b200::set_error("encoder_open: tiles need a picture size that is a multiple of 8 (got %dx%d)", cfg->width, cfg->height);
+    delete e;
+    return NULL;
+  }
   if (tiled) {
     // tiles: independent tile encoders on this GPU; motion is confined to the tile, like
     // Kvazaar's mv-constraint frametilemargin (the reference exposes it, kvazaarfilter.cpp:246-276);
@@ -473,7 +486,11 @@ int encoder_encode(kvz_encoder *e, kvz_picture *pic_in, kvz_data_chunk **data_ou
     kvz_picture *r = picture_alloc(e->cfg.width, e->cfg.height);
     if (r) {
       cudaStreamSynchronize(e->eng.stream);
-      cudaMemcpy(r->y, e->eng.last_rec(), e->eng.frame_bytes, cudaMemcpyDeviceToHost);
+      const uint8_t *rec = e->eng.last_rec();              // coded size: crop to the conformance window
+      const int cw = e->eng.fp.w, ch = e->eng.fp.h, w = e->cfg.width, h = e->cfg.height;
+      cudaMemcpy2D(r->y, w, rec, cw, w, h, cudaMemcpyDeviceToHost);
+      cudaMemcpy2D(r->u, w / 2, rec + (size_t)cw * ch, cw / 2, w / 2, h / 2, cudaMemcpyDeviceToHost);
+      cudaMemcpy2D(r->v, w / 2, rec + (size_t)cw * ch * 5 / 4, cw / 2, w / 2, h / 2, cudaMemcpyDeviceToHost);
       *pic_recon = r;
     }
   }

@@ -22,7 +22,7 @@ class EncParams(C.Structure):
     """b200_enc_params (include/b200_hevc.h)."""
     _fields_ = [(n, C.c_int) for n in ("struct_size", "width", "height", "qp", "intra_period", "search_range", "deblock",
                                        "debug", "depth", "qp_delta", "fps_num", "fps_den", "sao", "intra_in_p", "me_coarse",
-                                       "intra_satd", "subme_satd", "vaq", "scaling_list")]
+                                       "intra_satd", "subme_satd", "vaq", "scaling_list", "src_width", "src_height")]
 
 
 def preset_options(preset: str) -> dict:
@@ -53,6 +53,8 @@ class GpuEncoder:
         self.h_enc = self.l.b200_enc_open_params(C.byref(p))
         if not self.h_enc:
             raise B200Error("b200_enc_open failed: " + self.l.b200_last_error().decode())
+        # pictures passed in are src_w x src_h (= w x h unless a conformance window is in use)
+        self.src_w, self.src_h = p.src_width or w, p.src_height or h
         self.out = np.empty(w * h * 3 + 65536, np.uint8)
 
     def _ret(self, n):
@@ -71,7 +73,7 @@ class GpuEncoder:
             raise B200Error("b200_enc_set_ctu_dqp failed: " + self.l.b200_last_error().decode())
 
     def encode(self, i420: np.ndarray) -> bytes:
-        assert i420.dtype == np.uint8 and i420.size == self.w * self.h * 3 // 2
+        assert i420.dtype == np.uint8 and i420.size == self.src_w * self.src_h * 3 // 2
         f = np.ascontiguousarray(i420)
         return self._ret(self.l.b200_enc_encode(self.h_enc, C.c_void_p(f.ctypes.data), C.c_void_p(self.out.ctypes.data), self.out.size))
 

@@ -112,6 +112,7 @@ orc_encoder_t *orc_enc_open(const orc_enc_cfg_t *cfg)
   if (cfg->me_coarse < 0 || cfg->me_coarse > 32 || (cfg->me_coarse > 0 && cfg->search_range > 16)) return NULL;
   if (cfg->vaq < 0 || cfg->vaq > 20 || (cfg->vaq && !cfg->qp_delta)) return NULL;
   if (cfg->scaling_list < 0 || cfg->scaling_list > 3) return NULL;
+  if (cfg->conf_right < 0 || cfg->conf_right > 6 || (cfg->conf_right & 1) || cfg->conf_bottom < 0 || cfg->conf_bottom > 6 || (cfg->conf_bottom & 1)) return NULL;
   orc_encoder_t *e = (orc_encoder_t *)calloc(1, sizeof(*e));
   if (!e) return NULL;
   e->cfg = *cfg;
@@ -1751,7 +1752,13 @@ static size_t write_parameter_sets(const orc_encoder_t *e, uint8_t *out, size_t 
   orc_bits_ue(&b, 0);                 /* sps_seq_parameter_set_id */
   orc_bits_ue(&b, 1);                 /* chroma_format_idc 4:2:0 */
   orc_bits_ue(&b, (uint32_t)e->w); orc_bits_ue(&b, (uint32_t)e->h);
-  orc_bits_put(&b, 0, 1);             /* conformance_window_flag */
+  if (e->cfg.conf_right || e->cfg.conf_bottom) {
+    orc_bits_put(&b, 1, 1);           /* conformance_window_flag: offsets in chroma samples (SubWidthC = SubHeightC = 2) */
+    orc_bits_ue(&b, 0); orc_bits_ue(&b, (uint32_t)e->cfg.conf_right / 2);
+    orc_bits_ue(&b, 0); orc_bits_ue(&b, (uint32_t)e->cfg.conf_bottom / 2);
+  } else {
+    orc_bits_put(&b, 0, 1);
+  }
   orc_bits_ue(&b, 0); orc_bits_ue(&b, 0);       /* bit depths - 8 */
   orc_bits_ue(&b, 4);                 /* log2_max_pic_order_cnt_lsb_minus4 -> 8 bits */
   orc_bits_put(&b, 0, 1);             /* sps_sub_layer_ordering_info_present_flag */

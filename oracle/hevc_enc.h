@@ -76,6 +76,8 @@ typedef struct {
                             * every picture, each CTU's QP moves by orc_vaq_offsets() on top of the ROI offsets */
   int scaling_list;        /* scaling_list_enabled_flag: 1 = the default lists (Kvazaar --scaling-list default; Tables 7-5 / 7-6),
                             * 2 = test lists carried in the SPS, 3 = test lists carried in the PPS (the SPS then says "default") */
+  int conf_right, conf_bottom;   /* conformance window (7.4.3.2.1): that many luma samples (0, 2, 4, 6) at the right / bottom of the
+                                  * coded picture are padding and are cropped on output -- a source size that is not a multiple of 8 */
 } orc_enc_cfg_t;
 
 typedef struct orc_encoder orc_encoder_t;

@@ -37,7 +37,7 @@ class OrcEncCfg(C.Structure):
                 ("mv_edges", i), ("more_tiles", i), ("raw_slice_data", i), ("no_wpp", i), ("subme_satd", i), ("sao", i), ("tile_cols", i),
                 ("tr_depth", i), ("cabac_init", i), ("refs", i), ("tmvp", i), ("me_coarse", i), ("intra_in_p", i), ("fps_num", i), ("fps_den", i),
                 ("intra_satd", i), ("tu4", i), ("intra_sizes", i), ("chroma_modes", i), ("sign_hiding", i), ("strong_intra", i),
-                ("cb_qp_offset", i), ("cr_qp_offset", i), ("beta_offset_div2", i), ("tc_offset_div2", i), ("tile_rows", i), ("vaq", i), ("scaling_list", i)]
+                ("cb_qp_offset", i), ("cr_qp_offset", i), ("beta_offset_div2", i), ("tc_offset_div2", i), ("tile_rows", i), ("vaq", i), ("scaling_list", i), ("conf_right", i), ("conf_bottom", i)]
 
 
 SIGS.update({

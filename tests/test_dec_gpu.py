@@ -328,6 +328,57 @@ def test_decoder_reads_tile_columns_as_strips(kind, w, h, n, qp, tiles, wpp, thr
         assert bad.size == 0, f"picture {i}: {bad.size} samples differ, first at {bad[:6]}"
 
 
+@pytest.mark.parametrize("kind,w,h,n,qp,tiles,kw", [
+    ("camera", 410, 234, 3, 30, 1, {}),
+    ("screen", 638, 200, 3, 32, 1, {"sao": 2, "tr_depth": 1}),
+    ("camera", 1366, 768, 2, 32, 1, {"search_range": 6, "refs": 2, "tmvp": 1}),
+    ("camera", 634, 250, 3, 30, 2, {"tile_rows": 2}),                      # window over an assembled tile grid
+])
+def test_decoder_crops_to_the_conformance_window(kind, w, h, n, qp, tiles, kw):
+    """Streams whose source size is not a multiple of 8 (a Kvazaar peer pads and signals a conformance window):
+    libOpenHevcGetPictureInfo reports the window, the output is the cropped reconstruction (host and device)."""
+    import torch
+    from kvazzup_b200 import convert
+    from tests.test_oracle_hevc import odd_size_frames, pad_i420, crop_i420
+    from oracle.encoder import OracleTiledEncoder
+    W, H = (w + 7) & ~7, (h + 7) & ~7
+    frames = [pad_i420(f, w, h, W, H) for f in odd_size_frames(kind, w, h, n)]
+    args = {"intra_period": 0, "conf_right": W - w, "conf_bottom": H - h} | kw
+    if tiles > 1:
+        rows = args.pop("tile_rows", 1)
+        enc = OracleTiledEncoder(W, H, tiles, qp=qp, tile_rows=rows, **args)
+    else:
+        enc = OracleEncoder(W, H, qp=qp, **args)
+    aus, recs = [], []
+    for f in frames:
+        aus.append(enc.encode(f))
+        recs.append(crop_i420(enc.recon(), W, H, w, h))
+    dec = decode_all(aus)
+    assert len(dec) == n
+    for i, (pic, pw, ph) in enumerate(dec):
+        assert (pw, ph) == (w, h)
+        assert np.array_equal(pic, recs[i]), f"picture {i}"
+    if ffhevc.required():
+        ff, errs = ffhevc.decode_stream(aus)
+        assert errs == 0 and np.array_equal(ff[-1][0], recs[-1])
+    # device-resident hand-over: the window as a packed picture
+    f = OpenHEVCFilter()
+    assert f.init()
+    f.set_host_output(False)
+    k = 0
+    for au in aus:
+        for nal in split_nals(au):
+            d_pic = f.process_dev(nal)
+            if d_pic:
+                d_rgb = torch.empty(w * h * 4, dtype=torch.uint8, device="cuda")
+                convert.i420_to_rgb32_dev(d_pic, d_rgb.data_ptr(), w, h, 1, torch.cuda.current_stream().cuda_stream)
+                torch.cuda.synchronize()
+                assert np.array_equal(d_rgb.cpu().numpy(), convert.yuv420_to_rgb32(recs[k], w, h)), k
+                k += 1
+    assert k == n
+    f.close()
+
+
 def test_decoder_switches_between_tiled_and_untiled_streams():
     from kvazzup_b200.encoder import GpuTiledEncoder
     w, h = 416, 240

@@ -545,6 +545,79 @@ def test_scaling_list_through_kvz_api_untiled_and_tiled():
             assert np.array_equal(ff[i][0], dec[i][0]), f"picture {i}"
 
 
+ODD_SIZE_CASES = [
+    ("camera", 410, 234, 4, 30, {"intra_period": 3}),
+    ("screen", 638, 200, 3, 32, {"sao": 2}),
+    ("sports", 416, 238, 4, 27, {"me_coarse": 16, "search_range": 4, "intra_in_p": 1}),
+    ("noise", 66, 58, 2, 22, {}),
+    ("camera", 1366, 768, 2, 32, {"search_range": 6, "sao": 2, "qp_delta": 1, "vaq": 8}),
+]
+
+
+@pytest.mark.parametrize("kind,w,h,n,qp,kw", ODD_SIZE_CASES)
+def test_sizes_that_are_not_multiples_of_8_are_padded_and_cropped(kind, w, h, n, qp, kw):
+    """src_width / src_height: the GPU pads the source by edge repetition (k_pad_edges) and codes the padded
+    picture exactly like the oracle given the padded picture; the SPS carries a conformance window; the GPU
+    decoder and FFmpeg output w x h pictures equal to the cropped reconstruction; device-resident input too."""
+    import torch
+    from tests.test_oracle_hevc import odd_size_frames, pad_i420, crop_i420
+    from tests.test_dec_gpu import decode_all
+    W, H = (w + 7) & ~7, (h + 7) & ~7
+    frames = odd_size_frames(kind, w, h, n)
+    args = {"intra_period": 0} | kw
+    g = GpuEncoder(W, H, qp=qp, debug=1, src_width=w, src_height=h, **args)
+    gd = GpuEncoder(W, H, qp=qp, src_width=w, src_height=h, **args)
+    o = OracleEncoder(W, H, qp=qp, conf_right=W - w, conf_bottom=H - h, **args)
+    aus, recs = [], []
+    for i, f in enumerate(frames):
+        ga, oa = g.encode(f), o.encode(pad_i420(f, w, h, W, H))
+        tag = f"odd size {kind} {w}x{h} frame {i}"
+        compare_frame(tag, g, o, W, H)
+        assert ga == oa, f"{tag}: access unit differs (gpu {len(ga)} B, oracle {len(oa)} B)"
+        assert gd.encode_dev(torch.from_numpy(f).cuda()) == ga, f"{tag}: device-resident input"
+        aus.append(ga)
+        recs.append(crop_i420(g.recon(), W, H, w, h))
+    g.close()
+    gd.close()
+    o.close()
+    dec = decode_all(aus)
+    assert len(dec) == n
+    for i in range(n):
+        assert (dec[i][1], dec[i][2]) == (w, h)
+        assert np.array_equal(dec[i][0], recs[i]), f"GPU decoder, picture {i}"
+    if ffhevc.required():
+        ff, errs = ffhevc.decode_stream(aus)
+        assert errs == 0 and (ff[-1][1], ff[-1][2]) == (w, h) and np.array_equal(ff[-1][0], recs[-1])
+    with pytest.raises(Exception):
+        GpuEncoder(W, H, qp=qp, src_width=w - 8, src_height=h)
+
+
+def test_odd_sizes_through_kvz_api():
+    """A 1366x768 screen through the KvazaarFilter mirror: same stream as the engine opened with the coded size
+    and src_width / src_height; pipelined as well; odd (not even) sizes and tiles with such sizes are refused."""
+    from kvazzup_b200.kvazaar import KvazaarFilter
+    from kvazzup_b200.encoder import preset_options
+    from tests.test_oracle_hevc import odd_size_frames
+    w, h, n = 1366, 768, 4
+    frames = odd_size_frames("screen", w, h, n)
+    base = {"video/ResolutionWidth": w, "video/ResolutionHeight": h, "video/QP": 32, "video/Intra": 0, "video/Preset": "veryfast"}
+    vf = preset_options("veryfast")
+    eng = GpuEncoder(1368, 768, qp=32, intra_period=0, src_width=w, src_height=h, fps_num=30, fps_den=1, **vf)
+    want = [eng.encode(f) for f in frames]
+    eng.close()
+    for owf in (0, 2):
+        f = KvazaarFilter(base | {"video/OWF": owf})
+        assert f.init()
+        got = []
+        for fr in frames:
+            got += f.feed_input(fr, drain=False)
+        got += f.flush()
+        f.close()
+        assert got == want, owf
+    assert not KvazaarFilter(base | {"video/ResolutionWidth": 1365}).init()
+    assert not KvazaarFilter(base | {"video/Tiles": 1, "video/tileDimensions": "2x2", "video/WPP": 0}).init()
+
+
 def test_roi_through_kvz_api_and_pipelining():
     """kvz_picture::roi (per-pixel delta-QP map, kvazaarfilter.cpp:423-431) -> same stream as the engine
     given the per-CTU offsets Kvazaar would sample; ignored unless enabled or when a bitrate is set."""

@@ -143,6 +143,51 @@ def test_scaling_list_streams_decode_bit_exactly_in_ffmpeg(kind, w, h, n, qp, kw
         assert np.array_equal(fr, recs[i]), f"frame {i}: decoder output differs from encoder reconstruction"
 
 
+def pad_i420(f, w, h, W, H):
+    """w x h I420 picture -> W x H by repeating the last column / row of every plane."""
+    planes = [f[:w * h].reshape(h, w), f[w * h:w * h * 5 // 4].reshape(h // 2, w // 2), f[w * h * 5 // 4:].reshape(h // 2, w // 2)]
+    out = [np.pad(p, ((0, (H >> (i > 0)) - p.shape[0]), (0, (W >> (i > 0)) - p.shape[1])), mode="edge") for i, p in enumerate(planes)]
+    return np.concatenate([p.ravel() for p in out])
+
+
+def crop_i420(f, W, H, w, h):
+    """top-left w x h window of a W x H I420 picture"""
+    planes = [f[:W * H].reshape(H, W)[:h, :w], f[W * H:W * H * 5 // 4].reshape(H // 2, W // 2)[:h // 2, :w // 2],
+              f[W * H * 5 // 4:].reshape(H // 2, W // 2)[:h // 2, :w // 2]]
+    return np.concatenate([p.ravel() for p in planes])
+
+
+def odd_size_frames(kind, w, h, n):
+    """n pictures of w x h (even, not multiples of 8) cut out of the generator's next multiple-of-8 size"""
+    W, H = (w + 7) & ~7, (h + 7) & ~7
+    return [crop_i420(f, W, H, w, h) for f in frames_of(kind, W, H, n)]
+
+
+@needs_ff
+@pytest.mark.parametrize("kind,w,h,n,qp,kw", [
+    ("camera", 410, 234, 3, 30, {"hash_sei": 1}),
+    ("screen", 638, 200, 3, 32, {"sao": 2}),
+    ("sports", 416, 238, 4, 27, {"me_coarse": 16, "search_range": 4, "intra_in_p": 1, "intra_period": 3}),
+    ("camera", 1366, 768, 2, 32, {"hash_sei": 1, "search_range": 6}),          # a laptop screen
+])
+def test_conformance_window_streams_decode_cropped_in_ffmpeg(kind, w, h, n, qp, kw):
+    """Source sizes that are not multiples of 8: the encoder codes the picture padded by edge replication and
+    the SPS carries a conformance window; FFmpeg returns w x h pictures equal to the cropped reconstruction."""
+    W, H = (w + 7) & ~7, (h + 7) & ~7
+    frames = odd_size_frames(kind, w, h, n)
+    enc = OracleEncoder(W, H, qp=qp, conf_right=W - w, conf_bottom=H - h, **({"intra_period": 0} | kw))
+    aus, recs = [], []
+    for f in frames:
+        aus.append(enc.encode(pad_i420(f, w, h, W, H)))
+        recs.append(crop_i420(enc.recon(), W, H, w, h))
+    enc.close()
+    dec, errs = ffhevc.decode_stream(aus)
+    assert errs == 0 and len(dec) == n
+    for i, (fr, fw, fh) in enumerate(dec):
+        assert (fw, fh) == (w, h)
+        assert np.array_equal(fr, recs[i]), f"frame {i}"
+
+
 def vaq_float_model(i420, w, h, strength):
     """Kvazaar's formula in floating point: strength * 0.1 * (ln(max(var_ctu, 4)) - ln(var_picture)),
     var = luma variance + the two chroma variances."""
