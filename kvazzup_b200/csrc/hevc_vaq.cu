@@ -27,7 +27,7 @@ __device__ int log2_q8(u128 v)
   const unsigned long long hi = (unsigned long long)(v >> 64), lo = (unsigned long long)v;
   const int msb = hi ? 127 - __clzll((long long)hi) : 63 - __clzll((long long)lo);
   unsigned long long m = msb >= 31 ? (unsigned long long)(v >> (msb - 31)) : (unsigned long long)(v << (31 - msb));
-  m &= 0xffffffffull;                       // [2^31, 2^32)
+  // m in [2^31, 2^32)
   int frac = 0;
 #pragma unroll
   for (int i = 0; i < 8; i++) {

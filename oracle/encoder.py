@@ -40,6 +40,11 @@ class OracleEncoder:
             raise RuntimeError(f"orc_enc_encode failed ({n})")
         return self.out[:n].tobytes()
 
+    def set_qp(self, qp):
+        """Slice QP of the following pictures."""
+        if self.lib.orc_enc_set_qp(self.h_enc, int(qp)) != 0:
+            raise ValueError("qp out of range")
+
     def set_ctu_dqp(self, dqp):
         """Per-CTU QP offsets (int8, ctb_cols*ctb_rows, raster) for the following pictures; None clears."""
         if dqp is None:

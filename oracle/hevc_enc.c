@@ -282,6 +282,14 @@ void orc_vaq_offsets(const uint8_t *i420, int w, int h, int strength, int8_t *ou
 }
 static int lambda_at(const orc_encoder_t *e, int x, int y) { return lambda_q4_tab[ctu_qp(e, x, y)]; }
 
+/* slice QP of the following pictures (what a rate controller or a GOP structure with QP offsets sets per picture) */
+int orc_enc_set_qp(orc_encoder_t *e, int qp)
+{
+  if (!e || qp < 0 || qp > 51) return -1;
+  e->cfg.qp = qp;
+  return 0;
+}
+
 int orc_enc_set_ctu_dqp(orc_encoder_t *e, const int8_t *dqp)
 {
   if (!e || !e->cfg.qp_delta) return -1;

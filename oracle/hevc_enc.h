@@ -93,6 +93,8 @@ int orc_enc_encode(orc_encoder_t *e, const uint8_t *i420, uint8_t *out, int cap)
 /* Per-CTU QP offsets for the pictures that follow (ctb_cols*ctb_rows entries, raster; NULL = none).
  * Needs cfg.qp_delta; CTU QP = clip(qp + dqp, 0, 51). */
 int orc_enc_set_ctu_dqp(orc_encoder_t *e, const int8_t *dqp);
+/* Slice QP (0..51) of the following pictures. */
+int orc_enc_set_qp(orc_encoder_t *e, int qp);
 /* Variance adaptive quantisation: the QP offset (-12..12) of every CTU (raster) of one I420 picture
  * (even w, h) at `strength` (1..20), from the CTU's and the picture's sample variance. */
 void orc_vaq_offsets(const uint8_t *i420, int w, int h, int strength, int8_t *out);

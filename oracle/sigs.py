@@ -47,6 +47,7 @@ SIGS.update({
     "orc_max_threads": (i, []),
     "orc_enc_encode": (i, [v, v, v, i]),
     "orc_enc_set_ctu_dqp": (i, [v, v]),
+    "orc_enc_set_qp": (i, [v, i]),
     "orc_vaq_offsets": (None, [v, i, i, i, v]),
     "orc_tiled_open": (v, [C.POINTER(OrcEncCfg), i]),
     "orc_tiled_open2": (v, [C.POINTER(OrcEncCfg), i, i]),
