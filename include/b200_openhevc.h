@@ -34,6 +34,7 @@
 #ifndef B200_OPENHEVC_H_
 #define B200_OPENHEVC_H_
 
+#include <stddef.h>
 #include <stdint.h>
 
 #ifdef __cplusplus
@@ -106,6 +107,28 @@ void b200_dec_set_host_output(OpenHevc_Handle h, int on);
  * picture it has and the error drifts until the next IDR; an application that watches this counter
  * can ask the sender for a key frame instead. */
 int  b200_dec_missing_refs(OpenHevc_Handle h);
+
+/* Host-only look at the parameter sets of a stream (no GPU needed, e.g. when the sprop parameter sets of a
+ * peer arrive): parses the VPS / SPS / PPS NAL units of an Annex-B buffer and says whether this decoder
+ * takes streams coded with them.  struct_size lets the structure grow. */
+typedef struct b200_stream_info {
+  int struct_size;
+  int width, height;               /* what libOpenHevcGetPictureInfo will report (the conformance window) */
+  int coded_width, coded_height;   /* multiples of 8 */
+  int crop_left, crop_top;         /* window origin inside the coded picture, luma samples */
+  int fps_num, fps_den;            /* VUI timing info, 0 / 0 when absent */
+  int tile_cols, tile_rows, wpp;
+  int sao, sign_hiding, qp_delta, tmvp, strong_intra, cabac_init_present;
+  int scaling_list;                /* 0 off, 1 default lists, 2 lists carried in the SPS, 3 in the PPS */
+  int max_tr_depth_inter, max_tr_depth_intra;
+  int max_dec_pic_buffering;
+  int decodable;                   /* 1 = within the decoding scope stated at the top of this header */
+  char reason[96];                 /* why not, when decodable == 0 */
+} b200_stream_info;
+/* Returns 0 when an SPS and the PPS that refers to it were found and parsed (the last pair in the buffer counts),
+ * B200_ERR_ARG otherwise (b200_last_error() says why).  scaling_table: NULL, or 1552 bytes that receive the scaling
+ * factors in force (layout: DESIGN.md, the ScalingTable of hevc_headers.h) when scaling_list != 0. */
+int  b200_dec_probe(const uint8_t *annexb, size_t n, b200_stream_info *info, uint8_t *scaling_table);
 
 #ifdef __cplusplus
 }

@@ -56,6 +56,7 @@ SIGNATURES: dict = {
     "b200_dec_output_dev": (v, [v]),
     "b200_dec_missing_refs": (i, [v]),
     "b200_dec_set_host_output": (None, [v, i]),
+    "b200_dec_probe": (i, [v, C.c_size_t, v, v]),
 }
 
 

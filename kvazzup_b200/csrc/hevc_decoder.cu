@@ -7,6 +7,8 @@
 
 #include <algorithm>
 #include <deque>
+#include <memory>
+#include <string>
 #include <vector>
 
 #include "../../include/b200_openhevc.h"
@@ -720,6 +722,66 @@ const uint8_t *b200_dec_output_dev(OpenHevc_Handle h)
 {
   Decoder *d = (Decoder *)h;
   return d && d->out_slot >= 0 ? d->d_out : NULL;
+}
+
+int b200_dec_probe(const uint8_t *buf, size_t n, b200_stream_info *info, uint8_t *scaling_table)
+{
+  if (!buf || !info || info->struct_size < (int)(3 * sizeof(int))) { b200::set_error("b200_dec_probe: bad arguments"); return B200_ERR_ARG; }
+  std::unique_ptr<Decoder> d(new Decoder());
+  int last_pps = -1;
+  size_t pos = 0;
+  auto next_sc = [&](size_t from) { for (size_t k = from; k + 3 <= n; k++) if (buf[k] == 0 && buf[k + 1] == 0 && buf[k + 2] == 1) return k; return n; };
+  for (pos = next_sc(0); pos < n;) {
+    const size_t start = pos + 3, next = next_sc(start);
+    size_t end = next;
+    while (end > start && next < n && buf[end - 1] == 0) end--;
+    if (end - start >= 2) {
+      const int type = (buf[start] >> 1) & 63;
+      if (type == 33 && !d->parse_sps(b200::unescape(buf + start + 2, end - start - 2))) return B200_ERR_ARG;
+      if (type == 34) {
+        b200::Pps t;
+        std::string err;
+        const std::vector<uint8_t> r = b200::unescape(buf + start + 2, end - start - 2);
+        if (!b200::parse_pps_rbsp(r.data(), r.size(), t, err)) { b200::set_error("b200_dec_probe: %s", err.c_str()); return B200_ERR_ARG; }
+        d->pps_tab[t.id] = t;
+        last_pps = t.id;
+      }
+    }
+    pos = next;
+  }
+  if (last_pps < 0 || !d->pps_tab[last_pps].valid || !d->sps_tab[d->pps_tab[last_pps].sps_id].valid) {
+    b200::set_error("b200_dec_probe: no SPS / PPS pair in the buffer");
+    return B200_ERR_ARG;
+  }
+  const b200::Pps &p = d->pps_tab[last_pps];
+  const b200::Sps &s = d->sps_tab[p.sps_id];
+  b200_stream_info o;
+  memset(&o, 0, sizeof(o));
+  o.coded_width = s.width; o.coded_height = s.height;
+  o.width = s.width - s.conf_left - s.conf_right; o.height = s.height - s.conf_top - s.conf_bottom;
+  o.crop_left = s.conf_left; o.crop_top = s.conf_top;
+  o.fps_num = s.fps_num; o.fps_den = s.fps_den;
+  o.tile_cols = p.tile_cols; o.tile_rows = p.tile_rows; o.wpp = p.wpp;
+  o.sao = s.sao; o.sign_hiding = p.sign_hiding; o.qp_delta = p.qp_delta; o.tmvp = s.tmvp; o.strong_intra = s.strong_intra_smoothing;
+  o.cabac_init_present = p.cabac_init_present;
+  o.scaling_list = !s.scaling_list ? 0 : (p.scaling_list ? 3 : (s.scaling_list_data ? 2 : 1));
+  o.max_tr_depth_inter = s.max_tr_depth_inter; o.max_tr_depth_intra = s.max_tr_depth_intra;
+  o.max_dec_pic_buffering = s.max_dec_pic_buffering;
+  b200::SliceHeader sh;                              // a slice that uses nothing beyond the parameter sets
+  sh.slice_type = 1; sh.num_ref_idx_l0 = 1;
+  const char *why = d->unsupported(s, p, sh);
+  o.decodable = why ? 0 : 1;
+  if (why) snprintf(o.reason, sizeof(o.reason), "%s", why);
+  if (scaling_table && o.scaling_list) {
+    b200::ScalingTable def;
+    if (o.scaling_list == 1) def.set_default();
+    const b200::ScalingTable &t = o.scaling_list == 3 ? p.lists : (o.scaling_list == 2 ? s.lists : def);
+    memcpy(scaling_table, &t, sizeof(t));
+  }
+  const int keep = info->struct_size;
+  memcpy(info, &o, std::min<size_t>((size_t)keep, sizeof(o)));
+  info->struct_size = keep;
+  return B200_OK;
 }
 
 int b200_dec_missing_refs(OpenHevc_Handle h)

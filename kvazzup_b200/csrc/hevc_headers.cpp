@@ -154,7 +154,9 @@ bool parse_scaling_list_data(BitReader &b, ScalingTable &t)
   for (int sid = 0; sid < 4; sid++)
     for (int mid = 0; mid < 6; mid += sid == 3 ? 3 : 1) {
       if (!b.u(1)) {                                  // scaling_list_pred_mode_flag = 0: copy
-        const uint32_t delta = b.ue() * (sid == 3 ? 3 : 1);
+        uint32_t delta = b.ue();
+        if (delta > 5) return false;
+        delta *= sid == 3 ? 3 : 1;
         if (delta > (uint32_t)mid) return false;
         if (delta == 0) { store_default(t, sid, mid); continue; }
         memcpy(t.m[sid][mid], t.m[sid][mid - delta], 64);

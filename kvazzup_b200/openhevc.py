@@ -51,6 +51,31 @@ def split_nals(au: bytes):
     return out
 
 
+class StreamInfo(C.Structure):
+    """b200_stream_info (include/b200_openhevc.h)."""
+    _fields_ = [(n, C.c_int) for n in ("struct_size", "width", "height", "coded_width", "coded_height", "crop_left", "crop_top",
+                                       "fps_num", "fps_den", "tile_cols", "tile_rows", "wpp", "sao", "sign_hiding", "qp_delta",
+                                       "tmvp", "strong_intra", "cabac_init_present", "scaling_list", "max_tr_depth_inter",
+                                       "max_tr_depth_intra", "max_dec_pic_buffering", "decodable")] + [("reason", C.c_char * 96)]
+
+
+def probe(annexb: bytes, with_scaling_table: bool = False):
+    """Host-only look at the parameter sets of a stream (b200_dec_probe): dict of the b200_stream_info fields, plus
+    "scaling_table" (1552 bytes: 4 x 6 x 64 factors in raster order, 2 x 6 DC factors, padding) on request."""
+    info = StreamInfo()
+    info.struct_size = C.sizeof(StreamInfo)
+    table = np.zeros(1552, np.uint8)
+    buf = np.frombuffer(annexb, np.uint8)
+    rc = lib().b200_dec_probe(C.c_void_p(buf.ctypes.data), buf.size, C.byref(info), C.c_void_p(table.ctypes.data) if with_scaling_table else None)
+    if rc != 0:
+        raise B200Error("b200_dec_probe failed: " + lib().b200_last_error().decode())
+    out = {n: getattr(info, n) for n, _ in StreamInfo._fields_ if n not in ("struct_size", "reason")}
+    out["reason"] = info.reason.decode()
+    if with_scaling_table:
+        out["scaling_table"] = table
+    return out
+
+
 class OpenHEVCFilter:
     def __init__(self, threads: int = 1, parallelization: str = "Slice"):
         self.l = lib()

@@ -81,6 +81,15 @@ int orc_scaling_factor(const orc_scaling_t *s, int log2n, int matrix, int x, int
   return s->m[sid][matrix][((y >> (sid - 1)) << 3) + (x >> (sid - 1))];
 }
 
+void orc_scaling_table(int mode, uint8_t *out)
+{
+  orc_scaling_t s;
+  if (mode >= 2) orc_scaling_test_lists(&s); else orc_scaling_default(&s);
+  memcpy(out, s.m, sizeof(s.m));
+  memcpy(out + sizeof(s.m), s.dc[2], 6);
+  memcpy(out + sizeof(s.m) + 6, s.dc[3], 6);
+}
+
 void orc_scaling_write(orc_bits_t *b, const orc_scaling_t *s)
 {
   for (int sid = 0; sid < 4; sid++)

@@ -24,6 +24,9 @@ void orc_scaling_default(orc_scaling_t *s);           /* Tables 7-5 / 7-6 */
 void orc_scaling_test_lists(orc_scaling_t *s);        /* a mix of coded, copied and default lists (decoder tests) */
 int  orc_scaling_factor(const orc_scaling_t *s, int log2n, int matrix, int x, int y);
 void orc_scaling_write(orc_bits_t *b, const orc_scaling_t *s);          /* scaling_list_data() */
+/* the factors of the default (mode 1) / the test lists (mode 2, 3) as 4 x 6 x 64 raster-order bytes followed by the
+ * DC factors of sizeId 2 and 3 (2 x 6 bytes): 1548 bytes */
+void orc_scaling_table(int mode, uint8_t *out);
 
 /* quantisation with per-coefficient scale (HM: quantCoef = (quantScale << 4) / m), dequantisation 8.6.4.2 */
 int  orc_quant_sl(const int16_t *coeff, int16_t *level, int log2n, int qp, int intra_slice, const orc_scaling_t *s, int matrix);

@@ -48,6 +48,7 @@ SIGS.update({
     "orc_enc_encode": (i, [v, v, v, i]),
     "orc_enc_set_ctu_dqp": (i, [v, v]),
     "orc_enc_set_qp": (i, [v, i]),
+    "orc_scaling_table": (None, [i, v]),
     "orc_vaq_offsets": (None, [v, i, i, i, v]),
     "orc_tiled_open": (v, [C.POINTER(OrcEncCfg), i]),
     "orc_tiled_open2": (v, [C.POINTER(OrcEncCfg), i, i]),
