@@ -229,8 +229,12 @@ def test_kvz_api_error_behaviour():
     api.config_init(cfg)
     assert api.config_parse(cfg, b"qp", b"99") == 0
     assert api.config_parse(cfg, b"preset", b"warp9") == 0
+    assert api.config_parse(cfg, b"input-res", b"101x64") == 1
+    assert not api.encoder_open(cfg)                          # odd width (I420 needs even sizes) -> NULL, like a failed open
     assert api.config_parse(cfg, b"input-res", b"100x64") == 1
-    assert not api.encoder_open(cfg)                          # width not a multiple of 8 -> NULL, like a failed open
+    enc = api.encoder_open(cfg)                               # not a multiple of 8: padded, conformance window
+    assert enc
+    api.encoder_close(enc)
     api.picture_free(None)                                    # must accept NULL (:476)
     api.chunk_free(None)
     api.config_destroy(cfg)
