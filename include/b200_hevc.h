@@ -18,7 +18,8 @@ extern "C" {
 
 /* Encoder: constant QP, low-delay P (each picture references the previous reconstruction),
  * IDR every intra_period pictures (0 = first only), one slice, WPP substreams.
- * width/height multiples of 8 (reference requirement: camerafilter.cpp:330-331).
+ * width/height multiples of 8 (the reference's camera filter truncates to that, camerafilter.cpp:329-331); other even
+ * sizes through b200_enc_params::src_width / src_height (padding + conformance window).
  * depth = pictures in flight (Kvazaar's owf + 1): with depth > 1 the access unit of picture n is
  * returned by the call that submits picture n + depth - 1 (0 = nothing ready yet) and the tail is
  * drained with b200_enc_flush(), exactly like kvz_api's encoder_encode(pic = NULL).
