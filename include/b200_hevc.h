@@ -55,6 +55,9 @@ typedef struct b200_enc_params {
                                     (even, at most 6 samples short of width / height; 0 = width / height): the margins
                                     are filled by edge repetition on the GPU and the SPS carries a conformance window, so
                                     decoders output src_width x src_height.  b200_enc_fetch returns coded-size planes */
+  int mv_edges;                  /* bit 0 / 1 / 2 / 3: motion vectors must not reach beyond the left / right / top / bottom
+                                    picture edge (no sample outside, interpolation taps included) -- 15 = Kvazaar's
+                                    mv-constraint "frame" (kvazaarfilter.cpp:246-276) */
 } b200_enc_params;
 void  b200_enc_params_default(b200_enc_params *p);
 void *b200_enc_open_params(const b200_enc_params *p);
@@ -113,6 +116,7 @@ typedef struct b200_tiled_params {
   int tile_rows;                 /* uniform tile rows (default 1): tile_cols x tile_rows tiles in raster order; a tile
                                     row may be a single CTU row high */
   int scaling_list;              /* default scaling lists (see b200_enc_params) */
+  int mv_edges;                  /* picture edges motion must not cross (see b200_enc_params); tile edges never are */
 } b200_tiled_params;
 void  b200_tiled_params_default(b200_tiled_params *p);
 void *b200_tiled_open_params(const b200_tiled_params *p, const int *devices, int n_devices);

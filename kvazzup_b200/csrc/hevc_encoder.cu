@@ -682,7 +682,7 @@ void *b200_enc_open_params(const b200_enc_params *up)
   c.deblock = p.deblock; c.debug = p.debug; c.depth = p.depth; c.qp_delta = p.qp_delta;
   c.fps_num = p.fps_num; c.fps_den = p.fps_den; c.sao = p.sao; c.intra_in_p = p.intra_in_p; c.me_coarse = p.me_coarse;
   c.intra_satd = p.intra_satd; c.subme_satd = p.subme_satd; c.vaq = p.vaq; c.scaling_list = p.scaling_list ? 1 : 0;
-  c.src_width = p.src_width; c.src_height = p.src_height;
+  c.src_width = p.src_width; c.src_height = p.src_height; c.mv_edges = p.mv_edges & 15;
   if (!e->open(c)) { delete e; return nullptr; }
   return e;
 }

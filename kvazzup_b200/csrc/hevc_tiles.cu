@@ -62,7 +62,7 @@ struct TiledEncoder {
       s.device = n_devices > 0 ? devices[i % n_devices] : prev;
       EncoderConfig sc = c;
       sc.width = s.wd; sc.height = s.ht;
-      sc.mv_edges = (tc > 0 ? 1 : 0) | (tc < tile_cols - 1 ? 2 : 0) | (tr > 0 ? 4 : 0) | (tr < tile_rows - 1 ? 8 : 0);
+      sc.mv_edges = (tc > 0 ? 1 : 0) | (tc < tile_cols - 1 ? 2 : 0) | (tr > 0 ? 4 : 0) | (tr < tile_rows - 1 ? 8 : 0) | (c.mv_edges & 15);   // interior tile edges + the constrained picture edges
       sc.more_tiles = i < tiles - 1 ? 1 : 0;
       sc.no_wpp = wpp ? 0 : 1;
       sc.raw = 1;
@@ -165,7 +165,7 @@ void *b200_tiled_open_params(const b200_tiled_params *up, const int *devices, in
   memcpy(&p, up, std::min<size_t>((size_t)up->struct_size, sizeof(p)));
   b200::EncoderConfig c;
   c.width = p.width; c.height = p.height; c.qp = p.qp; c.intra_period = p.intra_period; c.search_range = p.search_range;
-  c.deblock = p.deblock; c.depth = p.depth; c.debug = 0; c.fps_num = p.fps_num; c.fps_den = p.fps_den; c.sao = p.sao; c.intra_in_p = p.intra_in_p; c.me_coarse = p.me_coarse; c.intra_satd = p.intra_satd; c.subme_satd = p.subme_satd; c.scaling_list = p.scaling_list ? 1 : 0;
+  c.deblock = p.deblock; c.depth = p.depth; c.debug = 0; c.fps_num = p.fps_num; c.fps_den = p.fps_den; c.sao = p.sao; c.intra_in_p = p.intra_in_p; c.me_coarse = p.me_coarse; c.intra_satd = p.intra_satd; c.subme_satd = p.subme_satd; c.scaling_list = p.scaling_list ? 1 : 0; c.mv_edges = p.mv_edges & 15;
   TiledEncoder *t = new TiledEncoder();
   if (!t->open(c, p.tile_cols, p.tile_rows < 1 ? 1 : p.tile_rows, p.wpp, devices, n_devices)) { delete t; return nullptr; }
   return t;

@@ -293,6 +293,11 @@ kvz_encoder *encoder_open(const kvz_config *cfg)
   const bool tiled = cfg->tiles_width_count > 1 || cfg->tiles_height_count > 1;
   c.vaq = tiled ? 0 : cfg->vaq;                   // per-CTU QP is not available together with tiles
   c.scaling_list = cfg->scaling_list ? 1 : 0;
+  // mv-constraint frame / frametile / frametilemargin: no motion vector leaves the picture (tiles confine motion to the
+  // tile in any case, see below)
+  const bool mv_frame = cfg->mv_constraint == KVZ_MV_CONSTRAIN_FRAME || cfg->mv_constraint == KVZ_MV_CONSTRAIN_FRAME_AND_TILE ||
+                        cfg->mv_constraint == KVZ_MV_CONSTRAIN_FRAME_AND_TILE_MARGIN;
+  if (mv_frame) c.mv_edges = 15;
   c.qp_delta = (cfg->roi_enable || cfg->set_qp_in_cu || c.vaq) ? 1 : 0;
   c.fps_num = cfg->framerate_num; c.fps_den = cfg->framerate_denom;     // VUI timing: the decoder side reports it
   c.sao = cfg->sao_type != 0 ? 2 : 0;             // with sao_merge_left / _up flags
@@ -310,7 +315,7 @@ kvz_encoder *encoder_open(const kvz_config *cfg)
     b200_tiled_params_default(&tp);
     tp.width = c.width; tp.height = c.height; tp.qp = c.qp; tp.intra_period = c.intra_period; tp.search_range = c.search_range;
     tp.deblock = c.deblock; tp.depth = c.depth; tp.tile_cols = cfg->tiles_width_count; tp.tile_rows = cfg->tiles_height_count; tp.wpp = cfg->wpp ? 1 : 0;
-    tp.fps_num = c.fps_num; tp.fps_den = c.fps_den; tp.sao = c.sao; tp.intra_in_p = c.intra_in_p; tp.me_coarse = c.me_coarse; tp.intra_satd = c.intra_satd; tp.subme_satd = c.subme_satd; tp.scaling_list = c.scaling_list;
+    tp.fps_num = c.fps_num; tp.fps_den = c.fps_den; tp.sao = c.sao; tp.intra_in_p = c.intra_in_p; tp.me_coarse = c.me_coarse; tp.intra_satd = c.intra_satd; tp.subme_satd = c.subme_satd; tp.scaling_list = c.scaling_list; tp.mv_edges = c.mv_edges;
     e->tiled = b200_tiled_open_params(&tp, nullptr, 0);
     if (!e->tiled) { delete e; return NULL; }
     e->tiled_out.resize((size_t)c.width * c.height * 3 + 65536);

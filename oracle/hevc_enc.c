@@ -2112,7 +2112,7 @@ orc_tiled_t *orc_tiled_open2(const orc_enc_cfg_t *cfg, int tile_cols, int tile_r
     t->y0[i] = r0 * CTB; t->ht[i] = imin(cfg->height, r1 * CTB) - t->y0[i];
     orc_enc_cfg_t sc = *cfg;
     sc.width = t->wd[i]; sc.height = t->ht[i]; sc.hash_sei = 0; sc.tile_cols = 0; sc.tile_rows = 0; sc.raw_slice_data = 1;
-    sc.mv_edges = (tc > 0 ? 1 : 0) | (tc < tile_cols - 1 ? 2 : 0) | (tr > 0 ? 4 : 0) | (tr < tile_rows - 1 ? 8 : 0);
+    sc.mv_edges = (tc > 0 ? 1 : 0) | (tc < tile_cols - 1 ? 2 : 0) | (tr > 0 ? 4 : 0) | (tr < tile_rows - 1 ? 8 : 0) | (cfg->mv_edges & 15);
     sc.more_tiles = i < t->tiles - 1;
     t->strip[i] = orc_enc_open(&sc);
     if (!t->strip[i]) { orc_tiled_close(t); return NULL; }

@@ -622,6 +622,54 @@ def test_odd_sizes_through_kvz_api():
     assert not KvazaarFilter(base | {"video/Tiles": 1, "video/tileDimensions": "2x2", "video/WPP": 0}).init()
 
 
+@pytest.mark.parametrize("kind,w,h,n,qp,kw", [
+    ("sports", 416, 240, 5, 30, {"me_coarse": 16, "search_range": 4, "intra_in_p": 1}),
+    ("sports", 640, 256, 4, 27, {"search_range": 12, "sao": 2}),
+    ("camera", 200, 136, 4, 32, {"subme_satd": 1}),
+])
+def test_frame_motion_constraint_matches_oracle(kind, w, h, n, qp, kw):
+    """mv_edges = 15 (Kvazaar's mv-constraint frame): the same cu map, levels and bytes as the oracle, and no vector
+    that reads a sample outside the picture; through kvz_api ("mv-constraint", cfg->mv_constraint) the same stream."""
+    from tests.test_oracle_hevc import vectors_leaving_the_picture
+    frames = frames_of(kind, w, h, n)
+    args = {"intra_period": 0} | kw
+    g = GpuEncoder(w, h, qp=qp, debug=1, mv_edges=15, **args)
+    o = OracleEncoder(w, h, qp=qp, mv_edges=15, **args)
+    free = GpuEncoder(w, h, qp=qp, **args)
+    differs = False
+    for i, f in enumerate(frames):
+        ga, oa = g.encode(f), o.encode(f)
+        tag = f"mv frame {kind} {w}x{h} frame {i}"
+        compare_frame(tag, g, o, w, h)
+        assert ga == oa, f"{tag}: access unit differs"
+        assert vectors_leaving_the_picture(g.cu_map(), w, h)[0] == 0, tag
+        differs |= free.encode(f) != ga
+    assert differs or kind != "sports"          # the constraint binds on the sequence with motion across the edges
+    g.close()
+    o.close()
+    free.close()
+
+
+def test_mv_constraint_through_kvz_api():
+    from kvazzup_b200.kvazaar import KvazaarFilter
+    from kvazzup_b200.encoder import preset_options
+    w, h, n = 416, 240, 5
+    frames = frames_of("sports", w, h, n)
+    base = {"video/ResolutionWidth": w, "video/ResolutionHeight": h, "video/QP": 30, "video/Intra": 0, "video/Preset": "veryfast"}
+    vf = preset_options("veryfast")
+    for constraint, edges in (("frame", 15), ("frametilemargin", 15), ("none", 0), ("tile", 0)):
+        eng = GpuEncoder(w, h, qp=30, intra_period=0, mv_edges=edges, fps_num=30, fps_den=1, **vf)
+        want = [eng.encode(f) for f in frames]
+        eng.close()
+        f = KvazaarFilter(base | {"video/mvConstraint": constraint})
+        assert f.init()
+        got = []
+        for fr in frames:
+            got += f.feed_input(fr)
+        f.close()
+        assert got == want, constraint
+
+
 def test_roi_through_kvz_api_and_pipelining():
     """kvz_picture::roi (per-pixel delta-QP map, kvazaarfilter.cpp:423-431) -> same stream as the engine
     given the per-CTU offsets Kvazaar would sample; ignored unless enabled or when a bitrate is set."""

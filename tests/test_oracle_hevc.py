@@ -188,6 +188,37 @@ def test_conformance_window_streams_decode_cropped_in_ffmpeg(kind, w, h, n, qp, 
         assert np.array_equal(fr, recs[i]), f"frame {i}"
 
 
+def vectors_leaving_the_picture(cu, w, h):
+    """Number of inter 8x8 units whose motion vector reads a sample outside the picture (interpolation taps included)."""
+    cu = cu.reshape(h // 8, w // 8)
+    y8, x8 = np.nonzero(cu["pred_mode"] == 0)
+    n = 1 << cu["log2_size"][y8, x8].astype(int)
+    x0, y0 = (x8 * 8) & ~(n - 1), (y8 * 8) & ~(n - 1)
+    mx, my = cu["mvx"][y8, x8].astype(int), cu["mvy"][y8, x8].astype(int)
+    fx, fy = np.where(mx & 7, 4, 0), np.where(my & 7, 4, 0)
+    bad = (x0 + (mx >> 2) - fx < 0) | (x0 + n + (mx >> 2) + fx > w) | (y0 + (my >> 2) - fy < 0) | (y0 + n + (my >> 2) + fy > h)
+    return int(bad.sum()), int(bad.size)
+
+
+@needs_ff
+def test_frame_motion_constraint_keeps_every_vector_inside_the_picture():
+    """mv_edges = 15 (Kvazaar's mv-constraint frame): without it the sports sequence has vectors that leave the
+    picture, with it none does; the stream still decodes bit-exactly."""
+    w, h, n = 416, 240, 5
+    frames = frames_of("sports", w, h, n)
+    for edges in (0, 15):
+        enc = OracleEncoder(w, h, qp=30, intra_period=0, me_coarse=16, search_range=4, intra_in_p=1, mv_edges=edges, hash_sei=1)
+        aus, out = [], 0
+        for f in frames:
+            aus.append(enc.encode(f))
+            out += vectors_leaving_the_picture(enc.cu_map(), w, h)[0]
+        rec = enc.recon()
+        enc.close()
+        assert (out == 0) == (edges == 15), (edges, out)
+        dec, errs = ffhevc.decode_stream(aus)
+        assert errs == 0 and np.array_equal(dec[-1][0], rec)
+
+
 def vaq_float_model(i420, w, h, strength):
     """Kvazaar's formula in floating point: strength * 0.1 * (ln(max(var_ctu, 4)) - ln(var_picture)),
     var = luma variance + the two chroma variances."""
