@@ -58,6 +58,8 @@ typedef struct b200_enc_params {
   int mv_edges;                  /* bit 0 / 1 / 2 / 3: motion vectors must not reach beyond the left / right / top / bottom
                                     picture edge (no sample outside, interpolation taps included) -- 15 = Kvazaar's
                                     mv-constraint "frame" (kvazaarfilter.cpp:246-276) */
+  int vps_period;                /* Kvazaar's vps-period (kvazaarfilter.cpp:221): VPS / SPS / PPS before every n-th IDR picture,
+                                    the first always; 0 = before the first picture only; default 1 */
 } b200_enc_params;
 void  b200_enc_params_default(b200_enc_params *p);
 void *b200_enc_open_params(const b200_enc_params *p);
@@ -117,6 +119,7 @@ typedef struct b200_tiled_params {
                                     row may be a single CTU row high */
   int scaling_list;              /* default scaling lists (see b200_enc_params) */
   int mv_edges;                  /* picture edges motion must not cross (see b200_enc_params); tile edges never are */
+  int vps_period;                /* parameter sets before every n-th IDR picture (see b200_enc_params) */
 } b200_tiled_params;
 void  b200_tiled_params_default(b200_tiled_params *p);
 void *b200_tiled_open_params(const b200_tiled_params *p, const int *devices, int n_devices);

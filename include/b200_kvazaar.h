@@ -58,7 +58,7 @@ typedef struct kvz_config {
   int32_t framerate_num, framerate_denom;/* "input-fps" */
   int32_t qp;                            /* "qp" 0..51 */
   int32_t intra_period;                  /* "period"; 0 = only the first picture is intra */
-  int32_t vps_period;                    /* "vps-period"; parameter sets precede every IDR */
+  int32_t vps_period;                    /* "vps-period": VPS / SPS / PPS before every n-th IDR picture (the first always), 0 = first only */
   int32_t wpp;                           /* "wpp"; substreams are always one per CTU row */
   int32_t owf;                           /* "owf": pictures in flight - 1 */
   int32_t threads;                       /* "threads": accepted, meaningless on a GPU */

@@ -252,7 +252,7 @@ bool Encoder::open(const EncoderConfig &c)
   ENC_CHECK(cudaMemset(d_me_stats, 0, 4 * sizeof(unsigned long long)), "memset me stats");
   ENC_CHECK(cudaEventCreate(&ev_base), "cudaEventCreate");
   ENC_CHECK(cudaEventRecord(ev_base, stream), "event record");
-  frame_idx = 0; poc = 0; cur = 0; cur_qp = c.qp;
+  frame_idx = 0; poc = 0; cur = 0; cur_qp = c.qp; idr_count = 0;
   return true;
 }
 
@@ -394,6 +394,8 @@ bool Encoder::submit(FrameSlot &s, const uint8_t *d_i420)
   const bool idr = frame_idx == 0 || (cfg.intra_period > 0 && frame_idx % cfg.intra_period == 0);
   if (idr) poc = 0;
   s.idr = idr; s.poc = poc; s.qp = cur_qp; s.seq = frame_idx;
+  s.headers = idr && (idr_count == 0 || (cfg.vps_period > 0 && idr_count % cfg.vps_period == 0));
+  if (idr) idr_count++;
   FrameParams p = fp;
   p.is_idr = idr ? 1 : 0;
   p.qp = cur_qp; p.qp_c = kChromaQp[cur_qp]; p.lambda_q4 = kLambdaQ4[cur_qp];
@@ -532,14 +534,14 @@ bool Encoder::collect(FrameSlot &s, std::vector<uint8_t> &out)
   }
   out.clear();
   const int n_sub = cfg.no_wpp ? 1 : fp.ctb_rows;
-  last_idr = s.idr; last_qp = s.qp; last_poc = s.poc;
+  last_idr = s.idr; last_qp = s.qp; last_poc = s.poc; last_headers = s.headers;
   if (cfg.raw) {                         // tile-column mode: the compositor writes the headers
     last_sub_len.assign(s.h_hdr + 1, s.h_hdr + 1 + n_sub);
     last_data = s.h_pack; last_data_len = s.h_hdr[0];
     out.push_back(0);                    // "a picture is ready"
     return true;
   }
-  if (s.idr) write_parameter_sets(layout(), out);
+  if (s.headers) write_parameter_sets(layout(), out);
   write_slice_nal(layout(), s.idr, s.poc, s.qp, s.h_hdr + 1, n_sub, s.h_pack, s.h_hdr[0], out);
   return true;
 }
@@ -667,7 +669,7 @@ void b200_enc_params_default(b200_enc_params *p)
   if (!p) return;
   memset(p, 0, sizeof(*p));
   p->struct_size = (int)sizeof(*p);
-  p->qp = 32; p->intra_period = 64; p->search_range = 8; p->deblock = 1; p->depth = 1;
+  p->qp = 32; p->intra_period = 64; p->search_range = 8; p->deblock = 1; p->depth = 1; p->vps_period = 1;
 }
 
 void *b200_enc_open_params(const b200_enc_params *up)
@@ -682,7 +684,7 @@ void *b200_enc_open_params(const b200_enc_params *up)
   c.deblock = p.deblock; c.debug = p.debug; c.depth = p.depth; c.qp_delta = p.qp_delta;
   c.fps_num = p.fps_num; c.fps_den = p.fps_den; c.sao = p.sao; c.intra_in_p = p.intra_in_p; c.me_coarse = p.me_coarse;
   c.intra_satd = p.intra_satd; c.subme_satd = p.subme_satd; c.vaq = p.vaq; c.scaling_list = p.scaling_list ? 1 : 0;
-  c.src_width = p.src_width; c.src_height = p.src_height; c.mv_edges = p.mv_edges & 15;
+  c.src_width = p.src_width; c.src_height = p.src_height; c.mv_edges = p.mv_edges & 15; c.vps_period = p.vps_period;
   if (!e->open(c)) { delete e; return nullptr; }
   return e;
 }

@@ -33,6 +33,8 @@ struct EncoderConfig {
   int subme_satd = 0;        // P pictures: SATD instead of SAD in the fractional motion refinement
   int vaq = 0;               // variance adaptive quantisation strength (Kvazaar --vaq), 1..20; needs qp_delta
   int scaling_list = 0;      // 1 = scaling_list_enabled_flag with the default lists (Kvazaar --scaling-list default)
+  int vps_period = 1;        // Kvazaar's vps-period: VPS / SPS / PPS before every n-th IDR picture (the first always); 0 =
+                             // before the first picture only
   int src_width = 0, src_height = 0;   // size of the pictures passed in when it is not a multiple of 8 (even, at most 6
                              // samples short of width / height; 0 = width / height): the encoder pads by edge
                              // repetition and the SPS carries a conformance window
@@ -66,6 +68,7 @@ struct FrameSlot {
   cudaEvent_t pev[18] = {};        // profiling: begin/end event per kernel slot (kernel ids below)
   unsigned prof_mask = 0;          // which kernel ids were recorded for the picture in this slot
   bool idr = false;
+  bool headers = false;            // the access unit starts with the parameter sets
   int poc = 0, qp = 0;
   long long seq = 0;
 };
@@ -82,6 +85,8 @@ struct StreamLayout {
   int conf_right = 0, conf_bottom = 0;   // conformance window: luma samples cropped at the right / bottom
 };
 void write_parameter_sets(const StreamLayout &l, std::vector<uint8_t> &out);
+// layout of the stream a tiled encoder (b200_tiled_open*) writes
+const StreamLayout &tiled_layout(void *tiled_encoder);
 // Slice segment header with the entry points of `sub_len` (escaped sizes) followed by `data_len`
 // bytes of already escaped slice data.
 void write_slice_nal(const StreamLayout &l, bool idr, int poc, int qp, const uint32_t *sub_len, int n_sub,
@@ -124,6 +129,8 @@ class Encoder {
   bool stage_source(FrameSlot &s, const uint8_t *pic, cudaMemcpyKind kind, cudaStream_t st);
   uint32_t row_cap = 0, pack_cap = 0;
   int frame_idx = 0, poc = 0, cur = 0, last_idr = 0, last_qp = 0, last_poc = 0, cur_qp = 32;
+  int idr_count = 0;              // IDR pictures submitted so far (vps_period)
+  bool last_headers = false;      // the last returned access unit carries (tile mode: needs) the parameter sets
   unsigned long long last_bins = 0;
   std::vector<uint8_t> au;
 

@@ -85,7 +85,7 @@ struct TiledEncoder {
     }
     const Encoder &e0 = *strips[0].enc;
     au.clear();
-    if (e0.last_idr) write_parameter_sets(layout, au);
+    if (e0.last_headers) write_parameter_sets(layout, au);
     write_slice_nal(layout, e0.last_idr != 0, e0.last_poc, e0.last_qp, sub_len.data(), (int)sub_len.size(), data.data(), data.size(), au);
   }
 
@@ -136,6 +136,10 @@ struct TiledEncoder {
 
 using b200::TiledEncoder;
 
+namespace b200 {
+const StreamLayout &tiled_layout(void *tiled_encoder) { return ((TiledEncoder *)tiled_encoder)->layout; }
+}  // namespace b200
+
 extern "C" {
 
 void *b200_tiled_open(int width, int height, int qp, int intra_period, int search_range, int deblock, int depth,
@@ -154,7 +158,7 @@ void b200_tiled_params_default(b200_tiled_params *p)
   if (!p) return;
   memset(p, 0, sizeof(*p));
   p->struct_size = (int)sizeof(*p);
-  p->qp = 32; p->intra_period = 64; p->search_range = 8; p->deblock = 1; p->depth = 1; p->tile_cols = 1; p->tile_rows = 1;
+  p->qp = 32; p->intra_period = 64; p->search_range = 8; p->deblock = 1; p->depth = 1; p->tile_cols = 1; p->tile_rows = 1; p->vps_period = 1;
 }
 
 void *b200_tiled_open_params(const b200_tiled_params *up, const int *devices, int n_devices)
@@ -165,7 +169,7 @@ void *b200_tiled_open_params(const b200_tiled_params *up, const int *devices, in
   memcpy(&p, up, std::min<size_t>((size_t)up->struct_size, sizeof(p)));
   b200::EncoderConfig c;
   c.width = p.width; c.height = p.height; c.qp = p.qp; c.intra_period = p.intra_period; c.search_range = p.search_range;
-  c.deblock = p.deblock; c.depth = p.depth; c.debug = 0; c.fps_num = p.fps_num; c.fps_den = p.fps_den; c.sao = p.sao; c.intra_in_p = p.intra_in_p; c.me_coarse = p.me_coarse; c.intra_satd = p.intra_satd; c.subme_satd = p.subme_satd; c.scaling_list = p.scaling_list ? 1 : 0; c.mv_edges = p.mv_edges & 15;
+  c.deblock = p.deblock; c.depth = p.depth; c.debug = 0; c.fps_num = p.fps_num; c.fps_den = p.fps_den; c.sao = p.sao; c.intra_in_p = p.intra_in_p; c.me_coarse = p.me_coarse; c.intra_satd = p.intra_satd; c.subme_satd = p.subme_satd; c.scaling_list = p.scaling_list ? 1 : 0; c.mv_edges = p.mv_edges & 15; c.vps_period = p.vps_period;
   TiledEncoder *t = new TiledEncoder();
   if (!t->open(c, p.tile_cols, p.tile_rows < 1 ? 1 : p.tile_rows, p.wpp, devices, n_devices)) { delete t; return nullptr; }
   return t;

@@ -293,6 +293,7 @@ kvz_encoder *encoder_open(const kvz_config *cfg)
   const bool tiled = cfg->tiles_width_count > 1 || cfg->tiles_height_count > 1;
   c.vaq = tiled ? 0 : cfg->vaq;                   // per-CTU QP is not available together with tiles
   c.scaling_list = cfg->scaling_list ? 1 : 0;
+  c.vps_period = cfg->vps_period;
   // mv-constraint frame / frametile / frametilemargin: no motion vector leaves the picture (tiles confine motion to the
   // tile in any case, see below)
   const bool mv_frame = cfg->mv_constraint == KVZ_MV_CONSTRAIN_FRAME || cfg->mv_constraint == KVZ_MV_CONSTRAIN_FRAME_AND_TILE ||
@@ -315,7 +316,7 @@ kvz_encoder *encoder_open(const kvz_config *cfg)
     b200_tiled_params_default(&tp);
     tp.width = c.width; tp.height = c.height; tp.qp = c.qp; tp.intra_period = c.intra_period; tp.search_range = c.search_range;
     tp.deblock = c.deblock; tp.depth = c.depth; tp.tile_cols = cfg->tiles_width_count; tp.tile_rows = cfg->tiles_height_count; tp.wpp = cfg->wpp ? 1 : 0;
-    tp.fps_num = c.fps_num; tp.fps_den = c.fps_den; tp.sao = c.sao; tp.intra_in_p = c.intra_in_p; tp.me_coarse = c.me_coarse; tp.intra_satd = c.intra_satd; tp.subme_satd = c.subme_satd; tp.scaling_list = c.scaling_list; tp.mv_edges = c.mv_edges;
+    tp.fps_num = c.fps_num; tp.fps_den = c.fps_den; tp.sao = c.sao; tp.intra_in_p = c.intra_in_p; tp.me_coarse = c.me_coarse; tp.intra_satd = c.intra_satd; tp.subme_satd = c.subme_satd; tp.scaling_list = c.scaling_list; tp.mv_edges = c.mv_edges; tp.vps_period = c.vps_period;
     e->tiled = b200_tiled_open_params(&tp, nullptr, 0);
     if (!e->tiled) { delete e; return NULL; }
     e->tiled_out.resize((size_t)c.width * c.height * 3 + 65536);
@@ -332,10 +333,16 @@ void encoder_close(kvz_encoder *e) { delete e; }
 
 int encoder_headers(kvz_encoder *e, kvz_data_chunk **data_out, uint32_t *len_out)
 {
-  // parameter sets travel in-band before every IDR (vps-period 1 in the reference, :221)
-  (void)e;
-  if (data_out) *data_out = NULL;
-  if (len_out) *len_out = 0;
+  // VPS, SPS and PPS as one chunk list.  They also travel in-band: before the first picture and before every
+  // vps-period-th IDR picture after it (vps-period 1 in the reference, :221)
+  if (!e) { b200::set_error("encoder_headers: NULL encoder"); return 0; }
+  std::vector<uint8_t> ps;
+  b200::write_parameter_sets(e->tiled ? b200::tiled_layout(e->tiled) : e->eng.layout(), ps);
+  if (data_out) {
+    *data_out = to_chunks(ps);
+    if (!*data_out) { b200::set_error("encoder_headers: out of memory"); return 0; }
+  }
+  if (len_out) *len_out = (uint32_t)ps.size();
   return 1;
 }
 

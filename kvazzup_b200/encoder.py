@@ -22,7 +22,7 @@ class EncParams(C.Structure):
     """b200_enc_params (include/b200_hevc.h)."""
     _fields_ = [(n, C.c_int) for n in ("struct_size", "width", "height", "qp", "intra_period", "search_range", "deblock",
                                        "debug", "depth", "qp_delta", "fps_num", "fps_den", "sao", "intra_in_p", "me_coarse",
-                                       "intra_satd", "subme_satd", "vaq", "scaling_list", "src_width", "src_height", "mv_edges")]
+                                       "intra_satd", "subme_satd", "vaq", "scaling_list", "src_width", "src_height", "mv_edges", "vps_period")]
 
 
 def preset_options(preset: str) -> dict:
@@ -157,7 +157,7 @@ class TiledParams(C.Structure):
     """b200_tiled_params (include/b200_hevc.h)."""
     _fields_ = [(n, C.c_int) for n in ("struct_size", "width", "height", "qp", "intra_period", "search_range", "deblock",
                                        "depth", "tile_cols", "wpp", "fps_num", "fps_den", "sao", "intra_in_p", "me_coarse",
-                                       "intra_satd", "subme_satd", "tile_rows", "scaling_list", "mv_edges")]
+                                       "intra_satd", "subme_satd", "tile_rows", "scaling_list", "mv_edges", "vps_period")]
 
 
 class GpuTiledEncoder:

@@ -670,6 +670,48 @@ def test_mv_constraint_through_kvz_api():
         assert got == want, constraint
 
 
+def test_vps_period_and_encoder_headers():
+    """vps-period (kvazaarfilter.cpp:221): parameter sets before the first picture and before every n-th IDR picture after
+    it (0: the first only); nothing else in the stream changes and it still decodes.  encoder_headers returns the same
+    parameter sets as a chunk list."""
+    import ctypes as C
+    from kvazzup_b200 import kvazaar as kz
+    from kvazzup_b200.kvazaar import KvazaarFilter
+    from tests.test_dec_gpu import decode_all, split_nals
+    w, h, n = 192, 136, 7
+    frames = frames_of("camera", w, h, n)
+    streams = {}
+    for period, want in ((1, [0, 2, 4, 6]), (2, [0, 4]), (3, [0, 6]), (0, [0])):
+        g = GpuEncoder(w, h, qp=30, intra_period=2, vps_period=period)
+        aus = [g.encode(f) for f in frames]
+        g.close()
+        with_sps = [i for i, au in enumerate(aus) if any(((nal[4] >> 1) & 63) == 33 for nal in split_nals(au))]
+        assert with_sps == want, period
+        streams[period] = [[nal for nal in split_nals(au) if ((nal[4] >> 1) & 63) < 32] for au in aus]
+        dec = decode_all(aus)
+        assert len(dec) == n
+    assert streams[0] == streams[1] == streams[2]                # the slices do not depend on it
+    base = {"video/ResolutionWidth": w, "video/ResolutionHeight": h, "video/QP": 30, "video/Intra": 2, "video/Preset": "ultrafast",
+            "video/VPS": 2}
+    f = KvazaarFilter(base)
+    assert f.init()
+    aus = []
+    for fr in frames:
+        aus += f.feed_input(fr)
+    assert [i for i, au in enumerate(aus) if any(((nal[4] >> 1) & 63) == 33 for nal in split_nals(au))] == [0, 4]
+    chunks, ln = C.POINTER(kz.KvzDataChunk)(), C.c_uint32(0)
+    assert f.api.encoder_headers(f.enc, C.byref(chunks), C.byref(ln)) == 1 and ln.value > 0
+    data, c = b"", chunks
+    while c:
+        data += bytes(c.contents.data[:c.contents.len])
+        c = c.contents.next
+    f.api.chunk_free(chunks)
+    assert len(data) == ln.value
+    first = aus[0]
+    assert first.startswith(data) and ((first[len(data) + 4] >> 1) & 63) == 19      # VPS + SPS + PPS, then the IDR slice
+    f.close()
+
+
 def test_roi_through_kvz_api_and_pipelining():
     """kvz_picture::roi (per-pixel delta-QP map, kvazaarfilter.cpp:423-431) -> same stream as the engine
     given the per-CTU offsets Kvazaar would sample; ignored unless enabled or when a bitrate is set."""
