@@ -18,7 +18,7 @@ import numpy as np  # noqa: E402
 
 from oracle.encoder import OracleEncoder, OracleTiledEncoder  # noqa: E402
 from tests import ffhevc  # noqa: E402
-from tests.test_oracle_hevc import frames_of, roi_pattern  # noqa: E402
+from tests.test_oracle_hevc import crop_i420, frames_of, odd_size_frames, pad_i420, roi_pattern, vaq_frames  # noqa: E402
 
 CASES = [
     {"name": "camera_192x136_qp32", "kind": "camera", "w": 192, "h": 136, "n": 4, "kw": {"qp": 32, "intra_period": 0}},
@@ -37,11 +37,29 @@ CASES = [
             "cb_qp_offset": 2, "cr_qp_offset": -2, "beta_offset_div2": 1, "tc_offset_div2": 1, "sao": 2, "intra_in_p": 1, "refs": 2,
             "tmvp": 1, "cabac_init": 1}},
     {"name": "camera_416x240_tiles2x2", "kind": "camera", "w": 416, "h": 240, "n": 4, "kw": {"qp": 30, "intra_period": 0, "tile_rows": 2}, "tiles": 2},
+    # late round 2: variance adaptive quantisation, scaling lists (default / coded in the SPS / in the PPS), a source
+    # size that is not a multiple of 8 ("src": the pictures are padded, the hashed reconstruction is the window), the
+    # frame motion constraint
+    {"name": "camera_416x240_vaq10", "kind": "camera", "w": 416, "h": 240, "n": 4, "kw": {"qp": 30, "intra_period": 0, "qp_delta": 1, "vaq": 10},
+     "frames": "vaq"},
+    {"name": "camera_416x240_scaling_default", "kind": "camera", "w": 416, "h": 240, "n": 4, "kw": {"qp": 22, "intra_period": 3, "scaling_list": 1}},
+    {"name": "noise_256x136_scaling_sps", "kind": "noise", "w": 256, "h": 136, "n": 3,
+     "kw": {"qp": 17, "intra_period": 0, "scaling_list": 2, "tr_depth": 2, "tu4": 1, "intra_sizes": 7}},
+    {"name": "screen_640x200_scaling_pps", "kind": "screen", "w": 640, "h": 200, "n": 3, "kw": {"qp": 32, "intra_period": 2, "scaling_list": 3, "tr_depth": 1}},
+    {"name": "camera_410x234_conformance_window", "kind": "camera", "w": 416, "h": 240, "n": 3,
+     "kw": {"qp": 30, "intra_period": 0, "conf_right": 6, "conf_bottom": 6}, "src": [410, 234]},
+    {"name": "sports_416x240_mv_frame", "kind": "sports", "w": 416, "h": 240, "n": 4,
+     "kw": {"qp": 30, "intra_period": 0, "me_coarse": 16, "search_range": 4, "mv_edges": 15}},
 ]
 
 
 def run_case(c):
-    frames = frames_of(c["kind"], c["w"], c["h"], c["n"])
+    if c.get("src"):
+        frames = [pad_i420(f, c["src"][0], c["src"][1], c["w"], c["h"]) for f in odd_size_frames(c["kind"], c["src"][0], c["src"][1], c["n"])]
+    elif c.get("frames") == "vaq":
+        frames = vaq_frames(c["kind"], c["w"], c["h"], c["n"])
+    else:
+        frames = frames_of(c["kind"], c["w"], c["h"], c["n"])
     if c.get("tiles"):
         enc = OracleTiledEncoder(c["w"], c["h"], c["tiles"], **c["kw"])
     else:
@@ -51,7 +69,7 @@ def run_case(c):
         if c.get("roi"):
             enc.set_ctu_dqp(roi_pattern(c["w"], c["h"], t, c["roi"]))
         aus.append(enc.encode(f))
-        recs.append(enc.recon())
+        recs.append(crop_i420(enc.recon(), c["w"], c["h"], c["src"][0], c["src"][1]) if c.get("src") else enc.recon())
     enc.close()
     return aus, recs
 
