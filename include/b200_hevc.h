@@ -54,7 +54,7 @@ typedef struct b200_enc_params {
   int src_width, src_height;     /* size of the pictures passed to b200_enc_encode[_dev] when it is not a multiple of 8
                                     (even, at most 6 samples short of width / height; 0 = width / height): the margins
                                     are filled by edge repetition on the GPU and the SPS carries a conformance window, so
-                                    decoders output src_width x src_height.  b200_enc_fetch returns coded-size planes */
+                                    decoders output src_width x src_height.  b200_enc_debug_read returns coded-size planes */
   int mv_edges;                  /* bit 0 / 1 / 2 / 3: motion vectors must not reach beyond the left / right / top / bottom
                                     picture edge (no sample outside, interpolation taps included) -- 15 = Kvazaar's
                                     mv-constraint "frame" (kvazaarfilter.cpp:246-276) */
