@@ -88,8 +88,13 @@ __device__ __forceinline__ int dec_bin(Reader &r, int ctx_idx)
 {
   // 9.3.4.3.2, written without branches up to the byte refill: a lone warp pays a pipeline refill
   // for every taken branch, and the MPS / LPS / renormalise cases are selects on the same registers.
+  // The table is shared by the lanes of the warp, which all hold the same values and all do the same accesses;
+  // the two barriers order one lane's write-back against the other lanes' loads (before and after it), which the
+  // lockstep of a converged warp gives in practice and the memory model only with them (compute-sanitizer racecheck).
   const uint2 loaded = r.ctx[ctx_idx];
+  __syncwarp();
   r.ctx[r.pend_idx] = r.pend;                                  // the previous bin's update, behind this bin's load
+  __syncwarp();
   const uint2 e = (uint32_t)ctx_idx == r.pend_idx ? r.pend : loaded;
   const uint32_t lps = (e.x >> (((r.range >> 6) & 3) * 8)) & 0xff;
   const uint32_t rmps = r.range - lps, scaled = rmps << 7;
