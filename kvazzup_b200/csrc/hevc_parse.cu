@@ -5,13 +5,13 @@
 // (context hand-over after the second CTU, H.265 9.3.1, and the above / above-right neighbours
 // that merge / AMVP derivation reads).  Parsing cannot be split from arithmetic decoding -- what
 // to read next depends on what was just decoded -- so the warp runs the parser redundantly in all
-// lanes on private context tables, with no branch that depends on the lane index; stores of
-// identical values from all lanes coalesce into one transaction.
+// lanes on one shared context table (loads are broadcasts), with no branch that depends on the lane
+// index; stores of identical values from all lanes coalesce into one transaction.
 //
 // Scope: CUs 8..64 (inter 2Nx2N; intra 2Nx2N and NxN with explicit chroma modes), transform trees down
 // to 4x4 luma blocks, I and P slices, several reference pictures with temporal candidates, SAO (with
-// merge candidates), cu_qp_delta per CTU, sign data hiding; no PCM / AMP / scaling lists / transform
-// skip.  Anything else is reported through `status` and the picture is rejected by the host.
+// merge candidates), cu_qp_delta per CTU, sign data hiding (scaling lists act on the dequantiser, not here);
+// no PCM / AMP / transform skip.  Anything else is reported through `status` and the picture is rejected by the host.
 #include "hevc_device.cuh"
 #include "hevc_kernels.h"
 
