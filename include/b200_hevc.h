@@ -62,6 +62,11 @@ typedef struct b200_enc_params {
                                     the first always; 0 = before the first picture only; default 1 */
 } b200_enc_params;
 void  b200_enc_params_default(b200_enc_params *p);
+/* Host only (no GPU needed): the VPS, SPS and PPS (Annex B, 4-byte start codes) an encoder opened with these
+ * parameters writes -- for out-of-band signalling (sprop-vps / -sps / -pps) before an encoder exists, and what
+ * kvz_api's encoder_headers returns.  tile_cols / tile_rows / wpp as in b200_tiled_params (1, 1, 1 for
+ * b200_enc_open*).  Returns the number of bytes, or -(bytes needed) when cap is too small. */
+int   b200_enc_parameter_sets(const b200_enc_params *p, int tile_cols, int tile_rows, int wpp, uint8_t *out, int cap);
 void *b200_enc_open_params(const b200_enc_params *p);
 /* Fills search_range, me_coarse, sao, intra_in_p, intra_satd and subme_satd with what the kvz_api preset of that name selects
  * ("ultrafast" ... "placebo"); the other fields are left alone.  0 on success. */

@@ -11,6 +11,7 @@ SIGNATURES: dict = {
     "b200_enc_open_roi": (v, [i, i, i, i, i, i, i, i]),
     "b200_enc_params_default": (None, [v]),
     "b200_enc_open_params": (v, [v]),
+    "b200_enc_parameter_sets": (i, [v, i, i, i, v, i]),
     "b200_kvz_set_bitrate": (i, [v, i]),
     "b200_rtcp_bitrate_update": (i, [i, i, i]),
     "b200_enc_params_from_preset": (i, [C.c_char_p, v]),

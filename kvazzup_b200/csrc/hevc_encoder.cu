@@ -672,6 +672,31 @@ void b200_enc_params_default(b200_enc_params *p)
   p->qp = 32; p->intra_period = 64; p->search_range = 8; p->deblock = 1; p->depth = 1; p->vps_period = 1;
 }
 
+int b200_enc_parameter_sets(const b200_enc_params *up, int tile_cols, int tile_rows, int wpp, uint8_t *out, int cap)
+{
+  if (!up || up->struct_size < (int)(9 * sizeof(int)) || !out || cap < 0 || tile_cols < 1 || tile_rows < 1) {
+    b200::set_error("b200_enc_parameter_sets: bad arguments");
+    return B200_ERR_ARG;
+  }
+  b200_enc_params p;
+  b200_enc_params_default(&p);
+  memcpy(&p, up, std::min<size_t>((size_t)up->struct_size, sizeof(p)));
+  b200::StreamLayout l;
+  l.w = p.width; l.h = p.height; l.deblock = p.deblock; l.qp_delta = p.qp_delta; l.fps_num = p.fps_num; l.fps_den = p.fps_den;
+  l.sao = p.sao; l.tile_cols = tile_cols; l.tile_rows = tile_rows; l.wpp = wpp ? 1 : 0; l.scaling_list = p.scaling_list ? 1 : 0;
+  l.conf_right = p.src_width ? p.width - p.src_width : 0; l.conf_bottom = p.src_height ? p.height - p.src_height : 0;
+  if (l.w <= 0 || l.h <= 0 || (l.w & 7) || (l.h & 7) || l.conf_right < 0 || l.conf_right > 6 || l.conf_bottom < 0 || l.conf_bottom > 6 ||
+      ((l.conf_right | l.conf_bottom) & 1)) {
+    b200::set_error("b200_enc_parameter_sets: bad picture size");
+    return B200_ERR_ARG;
+  }
+  std::vector<uint8_t> ps;
+  b200::write_parameter_sets(l, ps);
+  if ((size_t)cap < ps.size()) return -(int)ps.size();
+  memcpy(out, ps.data(), ps.size());
+  return (int)ps.size();
+}
+
 void *b200_enc_open_params(const b200_enc_params *up)
 {
   if (!up || up->struct_size < (int)(9 * sizeof(int))) { b200::set_error("b200_enc_open_params: bad arguments"); return nullptr; }
