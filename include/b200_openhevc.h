@@ -122,8 +122,14 @@ typedef struct b200_stream_info {
   int scaling_list;                /* 0 off, 1 default lists, 2 lists carried in the SPS, 3 in the PPS */
   int max_tr_depth_inter, max_tr_depth_intra;
   int max_dec_pic_buffering;
-  int decodable;                   /* 1 = within the decoding scope stated at the top of this header */
-  char reason[96];                 /* why not, when decodable == 0 */
+  int decodable;                   /* 1 = within the decoding scope stated at the top of this header (parameter sets and
+                                      every slice header found in the buffer) */
+  char reason[96];                 /* why not, when decodable == 0 (the first reason met) */
+  /* slice segment headers found after the parameter sets (none: slices = 0 and the fields below are 0) */
+  int slices;                      /* slice NAL units whose header was parsed */
+  int slice_type, slice_qp;        /* of the last one: 0 B, 1 P, 2 I; SliceQpY */
+  int entry_points;                /* ... its number of entry points (substreams - 1) */
+  int num_ref_idx_l0, rps_pictures;/* ... active reference indices, pictures in its reference picture set */
 } b200_stream_info;
 /* Returns 0 when an SPS and the PPS that refers to it were found and parsed (the last pair in the buffer counts),
  * B200_ERR_ARG otherwise (b200_last_error() says why).  scaling_table: NULL, or 1552 bytes that receive the scaling

@@ -729,6 +729,9 @@ int b200_dec_probe(const uint8_t *buf, size_t n, b200_stream_info *info, uint8_t
   if (!buf || !info || info->struct_size < (int)(3 * sizeof(int))) { b200::set_error("b200_dec_probe: bad arguments"); return B200_ERR_ARG; }
   std::unique_ptr<Decoder> d(new Decoder());
   int last_pps = -1;
+  b200_stream_info o;
+  memset(&o, 0, sizeof(o));
+  const char *why = nullptr;
   size_t pos = 0;
   auto next_sc = [&](size_t from) { for (size_t k = from; k + 3 <= n; k++) if (buf[k] == 0 && buf[k + 1] == 0 && buf[k + 2] == 1) return k; return n; };
   for (pos = next_sc(0); pos < n;) {
@@ -746,6 +749,27 @@ int b200_dec_probe(const uint8_t *buf, size_t n, b200_stream_info *info, uint8_t
         d->pps_tab[t.id] = t;
         last_pps = t.id;
       }
+      if (type <= 9 || (type >= 16 && type <= 21)) {           // a slice segment: its header against the sets it names
+        const std::vector<uint8_t> r = b200::unescape(buf + start + 2, end - start - 2);
+        b200::BitReader pb(r.data(), r.size());
+        pb.u(1);
+        if (type >= 16 && type <= 23) pb.u(1);
+        const uint32_t pid = pb.ue();
+        if (pb.bad || pid > 63 || !d->pps_tab[pid].valid || !d->sps_tab[d->pps_tab[pid].sps_id].valid) {
+          b200::set_error("b200_dec_probe: slice before its parameter sets");
+          return B200_ERR_ARG;
+        }
+        const b200::Pps &sp = d->pps_tab[pid];
+        const b200::Sps &ss = d->sps_tab[sp.sps_id];
+        b200::SliceHeader sh;
+        std::string err;
+        if (!b200::parse_slice_header_rbsp(r.data(), r.size(), type, ss, sp, sh, err)) { b200::set_error("b200_dec_probe: %s", err.c_str()); return B200_ERR_ARG; }
+        last_pps = (int)pid;
+        o.slices++;
+        o.slice_type = sh.slice_type; o.slice_qp = sh.qp; o.entry_points = (int)sh.entry.size();
+        o.num_ref_idx_l0 = sh.slice_type == 2 ? 0 : sh.num_ref_idx_l0; o.rps_pictures = sh.rps.num_delta();
+        if (!why) why = d->unsupported(ss, sp, sh);
+      }
     }
     pos = next;
   }
@@ -755,8 +779,6 @@ int b200_dec_probe(const uint8_t *buf, size_t n, b200_stream_info *info, uint8_t
   }
   const b200::Pps &p = d->pps_tab[last_pps];
   const b200::Sps &s = d->sps_tab[p.sps_id];
-  b200_stream_info o;
-  memset(&o, 0, sizeof(o));
   o.coded_width = s.width; o.coded_height = s.height;
   o.width = s.width - s.conf_left - s.conf_right; o.height = s.height - s.conf_top - s.conf_bottom;
   o.crop_left = s.conf_left; o.crop_top = s.conf_top;
@@ -767,9 +789,11 @@ int b200_dec_probe(const uint8_t *buf, size_t n, b200_stream_info *info, uint8_t
   o.scaling_list = !s.scaling_list ? 0 : (p.scaling_list ? 3 : (s.scaling_list_data ? 2 : 1));
   o.max_tr_depth_inter = s.max_tr_depth_inter; o.max_tr_depth_intra = s.max_tr_depth_intra;
   o.max_dec_pic_buffering = s.max_dec_pic_buffering;
-  b200::SliceHeader sh;                              // a slice that uses nothing beyond the parameter sets
-  sh.slice_type = 1; sh.num_ref_idx_l0 = 1;
-  const char *why = d->unsupported(s, p, sh);
+  if (!o.slices) {
+    b200::SliceHeader sh;                            // a slice that uses nothing beyond the parameter sets
+    sh.slice_type = 1; sh.num_ref_idx_l0 = 1;
+    why = d->unsupported(s, p, sh);
+  }
   o.decodable = why ? 0 : 1;
   if (why) snprintf(o.reason, sizeof(o.reason), "%s", why);
   if (scaling_table && o.scaling_list) {

@@ -56,7 +56,8 @@ class StreamInfo(C.Structure):
     _fields_ = [(n, C.c_int) for n in ("struct_size", "width", "height", "coded_width", "coded_height", "crop_left", "crop_top",
                                        "fps_num", "fps_den", "tile_cols", "tile_rows", "wpp", "sao", "sign_hiding", "qp_delta",
                                        "tmvp", "strong_intra", "cabac_init_present", "scaling_list", "max_tr_depth_inter",
-                                       "max_tr_depth_intra", "max_dec_pic_buffering", "decodable")] + [("reason", C.c_char * 96)]
+                                       "max_tr_depth_intra", "max_dec_pic_buffering", "decodable")] + [("reason", C.c_char * 96)] + [
+                    (n, C.c_int) for n in ("slices", "slice_type", "slice_qp", "entry_points", "num_ref_idx_l0", "rps_pictures")]
 
 
 def probe(annexb: bytes, with_scaling_table: bool = False):

@@ -78,3 +78,37 @@ def test_streams_outside_the_scope_are_named():
         probe(bytes(hdr[:pps_at]))                 # no PPS
     with pytest.raises(B200Error):
         probe(b"\x00\x00\x01\x42\x01" + bytes(3))  # truncated SPS
+
+
+@pytest.mark.parametrize("w,h,n,tiles,kw,expect", [
+    (416, 240, 3, None, {}, {"entry_points": 3, "num_ref_idx_l0": 1, "rps_pictures": 1}),
+    (416, 240, 4, None, {"refs": 3, "tmvp": 1}, {"entry_points": 3, "num_ref_idx_l0": 3, "rps_pictures": 3}),
+    (416, 240, 2, None, {"no_wpp": 1, "sao": 2, "tr_depth": 2}, {"entry_points": 0}),
+    (640, 256, 2, (3, 2), {}, {"entry_points": 5}),                                   # one substream per tile
+    (640, 256, 2, (2, 2), {"wpp": 1}, {"entry_points": 7}),                           # WPP rows inside the tiles: 2 x (2 + 2) substreams
+    (416, 240, 3, None, {"tr_depth": 2, "tu4": 1, "intra_sizes": 7, "chroma_modes": 1, "sign_hiding": 1, "strong_intra": 1, "cb_qp_offset": 2,
+                         "cr_qp_offset": -2, "beta_offset_div2": 1, "tc_offset_div2": 1, "sao": 2, "intra_in_p": 1, "refs": 2, "tmvp": 1,
+                         "qp_delta": 1, "cabac_init": 1, "scaling_list": 2}, {"entry_points": 3, "num_ref_idx_l0": 2}),
+])
+def test_slice_headers_of_the_decoder_test_matrix_are_within_scope(w, h, n, tiles, kw, expect):
+    """The decoder's host side (parameter-set activation, slice header parsing, the scope check) on whole oracle
+    streams: every slice header is parsed and found decodable; entry points, reference indices and the reference
+    picture set are what the stream was coded with."""
+    qp = 29
+    enc = OracleTiledEncoder(w, h, tiles[0], tile_rows=tiles[1], qp=qp, intra_period=0, **kw) if tiles else OracleEncoder(w, h, qp=qp, intra_period=0, **kw)
+    stream = b"".join(enc.encode(f) for f in frames_of("sports", w, h, n))
+    enc.close()
+    info = probe(stream)
+    assert info["decodable"] == 1, info["reason"]
+    assert info["slices"] == n and info["slice_type"] == 1 and info["slice_qp"] == qp
+    for k, v in expect.items():
+        # the last picture of a stream with `refs` pictures in flight has min(refs, pictures before it) references
+        assert info[k] == (min(v, n - 1) if k in ("num_ref_idx_l0", "rps_pictures") else v), (k, info[k])
+
+
+def test_an_intra_picture_alone_reports_an_i_slice():
+    enc = OracleEncoder(192, 136, qp=35)
+    info = probe(enc.encode(frames_of("camera", 192, 136, 1)[0]))
+    enc.close()
+    assert info["slices"] == 1 and info["slice_type"] == 2 and info["slice_qp"] == 35 and info["num_ref_idx_l0"] == 0
+    assert info["entry_points"] == 2 and info["decodable"] == 1
