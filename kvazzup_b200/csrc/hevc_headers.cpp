@@ -206,8 +206,10 @@ bool parse_sps_rbsp(const uint8_t *rbsp, size_t n, Sps &sps, std::string &err)
   sps.width = (int)b.ue(); sps.height = (int)b.ue();
   if (b.u(1)) {
     const int sw = sps.chroma_format_idc == 1 || sps.chroma_format_idc == 2 ? 2 : 1, shh = sps.chroma_format_idc == 1 ? 2 : 1;
-    sps.conf_left = sw * (int)b.ue(); sps.conf_right = sw * (int)b.ue();
-    sps.conf_top = shh * (int)b.ue(); sps.conf_bottom = shh * (int)b.ue();
+    // offsets come from the network: bound them before they are multiplied (the window is checked against the picture later)
+    auto off = [&]() { const uint32_t v = b.ue(); if (v > 8192) { b.bad = true; return 0; } return (int)v; };
+    sps.conf_left = sw * off(); sps.conf_right = sw * off();
+    sps.conf_top = shh * off(); sps.conf_bottom = shh * off();
   }
   sps.bit_depth_luma = 8 + (int)b.ue(); sps.bit_depth_chroma = 8 + (int)b.ue();
   sps.log2_max_poc = 4 + (int)b.ue();

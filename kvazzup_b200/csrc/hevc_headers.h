@@ -33,9 +33,11 @@ struct BitReader {
   void skip(int bits) { pos += (size_t)bits; if (pos > n * 8) bad = true; }
   uint32_t ue()
   {
+    // values of 2^30 and more are refused: no syntax element this decoder reads comes near, and what callers add to
+    // or multiply with a value (+ 8, * 2) then stays inside an int
     int z = 0;
-    while (!bad && u(1) == 0 && z < 32) z++;
-    if (z >= 32) { bad = true; return 0; }
+    while (!bad && u(1) == 0 && z < 30) z++;
+    if (z >= 30) { bad = true; return 0; }
     return z ? ((1u << z) - 1 + u(z)) : 0;
   }
   int32_t se()
