@@ -185,6 +185,7 @@ int b200_rtp_receive(b200_rtp_receiver *r, const uint8_t *pkt, size_t len)
     if (len < hdr + 4) return -1;
     hdr += 4 + 4 * (((size_t)pkt[hdr + 2] << 8) | pkt[hdr + 3]);
   }
+  if (len < hdr + kNalHeader) return -1;                     // CSRC list / extension longer than the packet (also keeps len - hdr below from wrapping)
   size_t end = len;
   if (pkt[0] & 0x20) {                                       // padding
     if (pkt[len - 1] == 0 || pkt[len - 1] > len - hdr) return -1;

@@ -151,3 +151,41 @@ def test_receiver_survives_garbage_and_truncations():
     out = [x for p in s.push_frame(au, 9000) for x in (r.receive(p) or [])]
     assert [o[0] for o in out][-1:] == split_nals(au)
     assert rtp.annexb_split(bytes(rng.integers(0, 2, size=5000, dtype=np.uint8))) is not None     # dense start codes
+
+
+def test_csrc_list_and_padding_longer_than_the_packet_are_refused():
+    """Found by tools/fuzz/rtp_harness.cpp under AddressSanitizer: a 17-byte packet that announces four CSRC entries
+    (28-byte header) and a padding count larger than the packet made the payload offset wrap and the NAL header be
+    read beyond the packet.  Such packets are malformed: -1, state untouched."""
+    r = rtp.RtpReceiver(3)
+    pkt = bytearray(17)
+    pkt[0] = 0x80 | 0x20 | 4                        # version 2, padding, CC = 4
+    pkt[8:12] = (3).to_bytes(4, "big")              # the expected SSRC
+    pkt[16] = 200                                   # padding count
+    assert r.receive(bytes(pkt)) is None
+    pkt[0] = 0x80 | 0x10 | 15                       # extension flag with a CSRC list that already ends beyond the packet
+    assert r.receive(bytes(pkt)) is None
+    assert r.lost == 0
+
+
+def test_rtp_shim_survives_the_sanitizer_fuzz(tmp_path):
+    """The whole shim (packetiser, depacketiser, splitter, intra / inter probes) under AddressSanitizer +
+    UndefinedBehaviorSanitizer: packets lost, truncated, bit-flipped, reordered, duplicated, relabelled as aggregation
+    or fragmentation units, random datagrams, output buffers of random sizes."""
+    import shutil
+    import subprocess
+    from pathlib import Path
+    root = Path(__file__).resolve().parents[1]
+    gxx = shutil.which("g++")
+    if not gxx:
+        pytest.skip("g++ not available")
+    exe = tmp_path / "rtp_harness"
+    b = subprocess.run([gxx, "-std=c++17", "-O1", "-g", "-fsanitize=address,undefined", "-fno-sanitize-recover=undefined",
+                        "-I", str(root / "include"), str(root / "tools/fuzz/rtp_harness.cpp"), str(root / "kvazzup_b200/csrc/rtp_shim.cpp"),
+                        "-o", str(exe)], capture_output=True, text=True)
+    if b.returncode != 0 and "sanitize" in b.stderr:
+        pytest.skip("sanitizer runtime not available")
+    assert b.returncode == 0, b.stderr
+    out = subprocess.run([str(exe), "5", "250"], capture_output=True, text=True, timeout=300)
+    assert out.returncode == 0, (out.stdout + out.stderr)[-2000:]
+    assert out.stdout.startswith("rounds 250")
