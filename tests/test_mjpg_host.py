@@ -42,3 +42,31 @@ def test_probe_accepts_the_committed_frames_and_survives_corruption():
             rc, w, h, s = probe(lib, bytes(bad))
             assert rc in (0, -1, -2), (name, trial, rc)      # accepted or refused; what matters is getting here
     assert probe(lib, b"")[0] < 0 and probe(lib, b"\xff\xd8")[0] < 0
+
+
+def test_host_pass_survives_mutated_frames_under_asan_ubsan(tmp_path):
+    """Marker parsing, Huffman table construction and the entropy-coded scan (the host half of the MJPG path) under
+    AddressSanitizer + UndefinedBehaviorSanitizer on mutated golden frames (tools/fuzz/mjpg_harness.cpp)."""
+    import os
+    import shutil
+    import subprocess
+    import sys
+    from pathlib import Path
+    root = Path(__file__).resolve().parents[1]
+    nvcc = shutil.which("nvcc") or "/usr/local/cuda/bin/nvcc"
+    if not Path(nvcc).exists():
+        pytest.skip("nvcc not available")
+    exe = tmp_path / "mjpg_harness"
+    b = subprocess.run([nvcc, "-gencode", "arch=compute_100a,code=sm_100a", "-O1", "-g", "-std=c++17", "-Xcompiler=-fsanitize=address",
+                        "-Xcompiler=-fsanitize=undefined", "-Xcompiler=-fno-sanitize-recover=undefined", "-I", str(root / "include"),
+                        str(root / "tools/fuzz/mjpg_harness.cpp"), str(root / "kvazzup_b200/csrc/mjpg.cu"), str(root / "kvazzup_b200/csrc/runtime.cu"),
+                        "-o", str(exe)], capture_output=True, text=True)
+    if b.returncode != 0 and "sanitize" in b.stderr + b.stdout:
+        pytest.skip("sanitizer runtime not available")
+    assert b.returncode == 0, (b.stdout + b.stderr)[-2000:]
+    cases = tmp_path / "cases.bin"
+    subprocess.run([sys.executable, str(root / "tools/fuzz/gen_mjpg_cases.py"), str(cases), "4000", "9"], check=True)
+    out = subprocess.run([str(exe), str(cases)], capture_output=True, text=True, timeout=300,
+                         env=dict(os.environ, ASAN_OPTIONS="protect_shadow_gap=0"))
+    assert out.returncode == 0, (out.stdout + out.stderr)[-2000:]
+    assert out.stdout.startswith("cases 4000")
