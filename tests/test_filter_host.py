@@ -35,6 +35,21 @@ def test_filter_runtime_semantics(tmp_path):
     assert r.returncode == 0 and r.stdout.strip().endswith("OK"), r.stdout + r.stderr
 
 
+@pytest.mark.parametrize("sanitizer", ["thread", "address,undefined"])
+def test_filter_runtime_semantics_under_sanitizers(tmp_path, sanitizer):
+    """The same program under ThreadSanitizer (the runtime is one thread per filter, bounded queues with a drop
+    policy, fan-out copies) and under AddressSanitizer + UndefinedBehaviorSanitizer: no report, same verdict."""
+    exe = str(tmp_path / "filter_semantics_san")
+    cmd = ["g++", "-O1", "-g", "-std=c++17", "-fsanitize=" + sanitizer, "-fno-sanitize-recover=all", "-I" + str(ROOT / "include"),
+           str(ROOT / "tests/cpp/filter_semantics.cpp"), "-o", exe, "-lpthread"]
+    b = subprocess.run(cmd, capture_output=True, text=True)
+    if b.returncode != 0 and "sanitize" in b.stderr:
+        pytest.skip("sanitizer runtime not available")
+    assert b.returncode == 0, b.stderr
+    r = subprocess.run([exe], capture_output=True, text=True, timeout=120)
+    assert r.returncode == 0 and r.stdout.strip().endswith("OK") and "Sanitizer" not in r.stderr, r.stdout + r.stderr[-2000:]
+
+
 def test_loopback_program_builds_against_the_library(tmp_path):
     build("tools/loopback_pipeline.cpp", str(tmp_path / "loopback_pipeline"), link_lib=True)
 
